@@ -1,0 +1,262 @@
+/*
+ * drmlt_b200.h -- C ABI of the B200-native Markov-chain light-transport hot path.
+ *
+ * This is the drop-in boundary for the reference's `pssmlt` / `drmlt` integrator
+ * plugins (reference: src/integrators/drmlt/drmlt.cpp:176-618,
+ * src/integrators/pssmlt/pssmlt.cpp:164-552).  A thin Mitsuba-side plugin
+ * (drmlt-mitsuba_b200/shim/) flattens `Scene` into the POD buffers below and calls
+ * `dr_render()`; everything behind this header runs on the GPU (sm_100a).
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; the caller owns all
+ * host buffers, the library owns device memory; every entry point returns a
+ * dr_status (0 = ok) and never throws; `dr_last_error()` gives the message of the
+ * last failure on the calling thread.  There is NO CPU fallback: when no CUDA
+ * device is usable the calls fail with DR_ERR_NO_DEVICE.
+ */
+#ifndef DRMLT_B200_H
+#define DRMLT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DR_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ status */
+typedef enum dr_status {
+    DR_OK = 0,
+    DR_ERR_INVALID_ARG = 1,   /* bad parameter combination (mirrors the reference's Log(EError,..)) */
+    DR_ERR_NO_DEVICE = 2,     /* CUDA runtime / device missing: no CPU fallback exists */
+    DR_ERR_CUDA = 3,          /* a CUDA call failed */
+    DR_ERR_ZERO_LUMINANCE = 4,/* bootstrap mean luminance is zero (pathsampler.cpp:939-941) */
+    DR_ERR_CANCELLED = 5,     /* dr_cancel() was called (Integrator::cancel, drmlt.cpp:386-391) */
+    DR_ERR_UNSUPPORTED = 6
+} dr_status;
+
+/* ------------------------------------------------------------------- scene */
+
+/* BSDF models on the hot path */
+typedef enum dr_bsdf_type {
+    DR_BSDF_DIFFUSE = 0,        /* src/bsdfs/diffuse.cpp:109-150 */
+    DR_BSDF_DIELECTRIC = 1,     /* src/bsdfs/dielectric.cpp:227-400 */
+    DR_BSDF_CONDUCTOR = 2,      /* src/bsdfs/conductor.cpp:223-285 */
+    DR_BSDF_ROUGHCONDUCTOR = 3  /* src/bsdfs/roughconductor.cpp:250-412 */
+} dr_bsdf_type;
+
+#define DR_MAT_TWOSIDED       1u  /* wrapped in <bsdf type="twosided"> (src/bsdfs/twosided.cpp) */
+#define DR_MAT_GGX            2u  /* roughconductor distribution=ggx (else beckmann) */
+#define DR_MAT_SAMPLE_VISIBLE 4u  /* roughconductor sampleVisible=true */
+
+typedef struct dr_material {
+    int32_t  type;              /* dr_bsdf_type */
+    uint32_t flags;             /* DR_MAT_* */
+    float    reflectance[3];    /* diffuse reflectance | specularReflectance */
+    float    transmittance[3];  /* dielectric specularTransmittance */
+    float    eta[3];            /* conductor eta (RGB) | dielectric intIOR/extIOR in eta[0] */
+    float    k[3];              /* conductor k (RGB) */
+    float    alpha;             /* roughconductor alpha (isotropic) */
+    float    _pad;
+} dr_material;                  /* 64 bytes */
+
+/* One area emitter = one emissive triangle mesh (src/emitters/area.cpp:67-215).
+ * Its triangles are the contiguous range [first_tri, first_tri + n_tris). */
+typedef struct dr_emitter {
+    uint32_t first_tri;
+    uint32_t n_tris;
+    float    radiance[3];
+    float    sampling_weight;   /* Emitter::getSamplingWeight(), default 1 (scene.cpp:380-383) */
+} dr_emitter;
+
+#define DR_TRI_SMOOTH 1u        /* interpolate vertex normals (mesh has normals) */
+
+/* Pinhole camera (src/sensors/perspective.cpp:107-460) */
+typedef struct dr_camera {
+    float   to_world[16];       /* row-major 4x4 camera-to-world, no scale */
+    float   xfov_deg;           /* horizontal field of view in degrees */
+    float   near_clip, far_clip;
+    int32_t film_width, film_height;   /* film size == crop size (no crop window) */
+} dr_camera;
+
+typedef struct dr_scene_desc {
+    uint32_t n_vertices, n_triangles, n_materials, n_emitters;
+    const float    *positions;     /* 3 * n_vertices */
+    const float    *normals;       /* 3 * n_vertices, or NULL (then no triangle may be DR_TRI_SMOOTH) */
+    const uint32_t *indices;       /* 3 * n_triangles */
+    const uint32_t *tri_material;  /* n_triangles, index into materials */
+    const int32_t  *tri_emitter;   /* n_triangles, index into emitters or -1 */
+    const uint32_t *tri_flags;     /* n_triangles, DR_TRI_* (may be NULL = 0) */
+    const dr_material *materials;
+    const dr_emitter  *emitters;
+    dr_camera camera;
+} dr_scene_desc;
+
+/* ------------------------------------------------------------------ config */
+
+typedef enum dr_integrator { DR_INTEGRATOR_PSSMLT = 0, DR_INTEGRATOR_DRMLT = 1 } dr_integrator;
+typedef enum dr_technique  { DR_TECH_PATH = 0, DR_TECH_BDPT = 1, DR_TECH_MMLT = 2 } dr_technique;
+typedef enum dr_type       { DR_TYPE_GREEN = 0, DR_TYPE_MIRA = 1, DR_TYPE_ORBITAL = 2 } dr_type;
+typedef enum dr_filter     { DR_FILTER_GAUSSIAN = 0, DR_FILTER_BOX = 1 } dr_filter;
+
+/* Parameter names, meaning and defaults follow DRMLT::DRMLT(props) (drmlt.cpp:178-351)
+ * and PSSMLT::PSSMLT(props) (pssmlt.cpp:166-308).  Fill with dr_config_default()
+ * and then override, or build from "-D key=value" strings with dr_config_set(). */
+typedef struct dr_config {
+    int32_t integrator;        /* dr_integrator : -D integrator=pssmlt|drmlt */
+    int32_t technique;         /* dr_technique  : technique=path|bdpt|mmlt (required) */
+    int32_t type;              /* dr_type       : type=green|mira|orbital|mirasym (drmlt, required) */
+    int32_t max_depth;         /* maxDepth (-1 = unset; MMLT/path/bdpt here require > 0) */
+    int32_t rr_depth;          /* rrDepth = 5 */
+    int32_t direct_sampling;   /* directSampling = true (forced false for MMLT) */
+    int32_t direct_samples;    /* directSamples = 16; separateDirect = directSamples >= 0 */
+    int32_t luminance_samples; /* luminanceSamples = 100000 */
+    float   p_large;           /* pLarge = 0.3 */
+    int32_t work_units;        /* workUnits = -1 (auto) */
+    int32_t kelemen_style_weights;  /* kelemenStyleWeights = true (forced false for MMLT) */
+    int32_t two_stage;         /* twoStage = false (only false is supported: section 8(f) "next") */
+    int32_t timeout;           /* timeout = 0 seconds */
+    float   average_luminance; /* averageLuminance = -1 (use bootstrap estimate) */
+    int32_t light_image;       /* lightImage = true */
+    int32_t acceptance_map;    /* acceptanceMap = false (drmlt) */
+    int32_t timid_after_large; /* timidAfterLarge = false (drmlt) */
+    int32_t fix_emitter_path;  /* fixEmitterPath = false (drmlt, MMLT only) */
+    int32_t use_mixture;       /* useMixture = false (drmlt) */
+    float   sigma;             /* sigma = 1/64 */
+    float   scale_second;      /* scaleSecond = 0.1 (<= 1) */
+    int32_t kelemen_style_mutation; /* kelemenStyleMutation = true (pssmlt) */
+    float   mutation_size_low;      /* mutationSizeLow = 1/1024 (pssmlt) */
+    float   mutation_size_high;     /* mutationSizeHigh = 1/64 (pssmlt) */
+    /* carried by other scene objects in the reference */
+    int32_t sample_count;      /* sensor sampler's sampleCount = mutations per pixel (drmlt.cpp:400) */
+    int32_t rfilter;           /* film reconstruction filter: gaussian (stddev .5) | box */
+    /* GPU execution knobs (no reference equivalent) */
+    int32_t n_chains;          /* Markov chains resident per GPU; 0 = auto */
+    uint64_t seed;             /* counter-based RNG key (reference: /dev/urandom, random.cpp:473-489) */
+    int32_t rank, world_size;  /* chain / bootstrap shard of this process (1 GPU: 0, 1) */
+    float   ray_epsilon;       /* 0 = 1e-4f (Mitsuba single precision, constants.h:29) */
+    float   shadow_epsilon;    /* 0 = 1e-3f (constants.h:30) */
+} dr_config;
+
+void      dr_config_default(dr_config *cfg);
+/* "technique"="mmlt", "sigma"="0.015625", "acceptanceMap"="true", ... (names as in the reference XML). */
+dr_status dr_config_set(dr_config *cfg, const char *key, const char *value);
+/* Applies the reference's constructor-time rules (MMLT forces directSampling=false and
+ * kelemenStyleWeights=false; fixEmitterPath needs MMLT; scaleSecond <= 1; ...). */
+dr_status dr_config_validate(dr_config *cfg);
+
+/* ------------------------------------------------------------------- stats */
+
+/* Numerators / denominators of the reference's StatsCounters
+ * (drmlt_proc.cpp:34-49,715-768; pssmlt_proc.cpp:33-40). */
+typedef struct dr_stats {
+    uint64_t mutations;                 /* ++mutationCtr */
+    uint64_t first_accept,  first_base;        /* firstLevelRatio */
+    uint64_t large_accept,  large_base;        /* largeStepRatio */
+    uint64_t bold_accept,   bold_base;         /* boldStepRatio (pssmlt: smallStepRatio) */
+    uint64_t second_accept, second_base;       /* secondLevelRatio */
+    uint64_t second_large_accept, second_large_base;
+    uint64_t second_bold_accept,  second_bold_base;
+    uint64_t accept, accept_base;              /* acceptanceRate */
+    uint64_t paths, rays;               /* path evaluations / rays cast in the chain phase */
+    uint64_t bootstrap_paths, bootstrap_rays;
+    double   luminance;                 /* normalization b actually used */
+    double   bootstrap_ms, chains_ms, total_ms;  /* device-timed phases */
+    uint64_t kernel_launches;           /* launches of this library's kernels */
+} dr_stats;
+
+/* ------------------------------------------------------------- entry points */
+
+typedef struct dr_scene_t *dr_scene;
+typedef struct dr_job_t   *dr_job;
+
+int         dr_abi_version(void);
+const char *dr_last_error(void);
+int         dr_device_count(void);
+
+/* Flatten -> BVH build (host) -> upload.  Replaces Scene::initialize + ShapeKDTree build
+ * (scene.cpp:332-394, skdtree.cpp) for this path. */
+dr_status dr_scene_create(const dr_scene_desc *desc, int device, dr_scene *out);
+void      dr_scene_destroy(dr_scene scene);
+
+/* Whole job on one GPU, HOST buffers: DRMLT::render / PSSMLT::render (drmlt.cpp:393-611) +
+ * develop (drmlt_proc.cpp:813-854).  `image_rgb` receives the developed W*H*3 float image
+ * (what the reference hands to film->setBitmap); in acceptanceMap mode it holds the R/G counts. */
+dr_status dr_render(dr_scene scene, const dr_config *cfg, float *image_rgb, dr_stats *stats);
+void      dr_cancel(dr_scene scene);
+
+/* ---- staged API (multi-GPU drivers, tests, benchmarks) -------------------
+ * One job = one rank's share of a render.  Sequence:
+ *   dr_job_create -> dr_job_bootstrap -> [all-reduce sum_lum/count across ranks] ->
+ *   dr_job_seed_chains(b) -> dr_job_run(...)* -> dr_job_film / dr_job_develop.        */
+dr_status dr_job_create(dr_scene scene, const dr_config *cfg, dr_job *out);
+void      dr_job_destroy(dr_job job);
+/* Bootstrap on this rank: generateSeeds (pathsampler.cpp:859-960).  Returns the local
+ * luminance sum and the number of (non-NaN) samples; b = max_depth_factor * sum / count. */
+dr_status dr_job_bootstrap(dr_job job, double *sum_luminance, double *count);
+/* Resample chain seeds from the local seed pool (luminance CDF) and replay them. */
+dr_status dr_job_seed_chains(dr_job job, double b);
+/* Advance every chain by `mutations_per_chain` iterations of the MLT loop. */
+dr_status dr_job_run(dr_job job, int64_t mutations_per_chain);
+/* Device pointers of the accumulation film (W*H*3 floats, un-normalised) -- the buffer
+ * a multi-GPU driver hands to ncclReduce. */
+dr_status dr_job_film_device(dr_job job, float **film_dev, int64_t *n_floats);
+/* Develop: image = film * (b / mean pixel luminance)  (drmlt_proc.cpp:823-849).  Host out. */
+dr_status dr_job_develop(dr_job job, float *image_rgb);
+dr_status dr_job_stats(dr_job job, dr_stats *stats);
+int64_t   dr_job_num_chains(dr_job job);
+int64_t   dr_job_total_mutations(dr_job job);   /* W*H*sampleCount share of this rank */
+
+/* ---- replay / parity entry points ---------------------------------------- */
+
+typedef struct dr_ray { float o[3]; float mint; float d[3]; float maxt; } dr_ray;
+typedef struct dr_hit { float t, u, v; int32_t prim; } dr_hit;   /* prim = -1: miss */
+
+/* Closest-hit over `n` rays (Scene::rayIntersect, skdtree.cpp:111-138).  Host buffers.
+ * `shadow`!=0: any-hit only (t/u/v undefined, prim >= 0 means occluded). */
+dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n, int shadow, dr_hit *hits);
+
+#define DR_MAX_SPLATS 12
+typedef struct dr_path_result {
+    float   luminance;          /* SplatList::luminance (un-normalised) */
+    int32_t n_splats;
+    int32_t s, t;               /* MMLT strategy (pathsampler.cpp:104-129), else -1 */
+    float   mis_weight;         /* MMLT: Path::miWeight of the (s,t) strategy; else 0 */
+    float   pos[DR_MAX_SPLATS][2];
+    float   value[DR_MAX_SPLATS][3];   /* un-normalised RGB contributions */
+    int32_t n_rays;
+} dr_path_result;
+
+/* PathSampler::sampleSplats (pathsampler.cpp:79-571) on `n` replayed primary-sample
+ * vectors.  u_* are [n][dim_*] row-major; depth[i] is the MMLT depth (ignored otherwise). */
+dr_status dr_eval_paths(dr_scene scene, const dr_config *cfg,
+                        const float *u_sensor, int dim_sensor,
+                        const float *u_emitter, int dim_emitter,
+                        const float *u_direct, int dim_direct,
+                        const int32_t *depth, int64_t n, dr_path_result *out);
+
+/* Per-mutation record of one chain (accept/reject parity under identical uniforms) */
+typedef struct dr_step_record {
+    float   L_x, L_y, L_z;      /* current / stage-1 / stage-2 luminance (L_z = 0 if no stage 2) */
+    float   a1, a2;
+    uint8_t large_step, accept1, did_second, accept2;
+} dr_step_record;
+
+/* Run `n_chains` chains for `steps` mutations each from bootstrap indices `seed_index[i]`
+ * (MMLT depth `depth[i]`), recording every decision.  Film contributions are discarded
+ * unless `film` (host, W*H*3) is given.  Uses the same counter-based uniforms as dr_job_run. */
+dr_status dr_chain_steps(dr_scene scene, const dr_config *cfg, double b,
+                         const uint64_t *seed_index, const int32_t *depth, const uint64_t *chain_id,
+                         int64_t n_chains, int64_t steps, dr_step_record *records, float *film);
+
+/* Bootstrap luminances of samples [first, first+n) (before the x maxDepth MMLT scaling). */
+dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfg,
+                                 uint64_t first, int64_t n, float *luminance, int32_t *depth);
+
+/* Primary-sample dimensions per sampler (findMaxDimensions, pssmlt_utils.h:27-77). */
+void dr_max_dimensions(const dr_config *cfg, int depth, int *sensor, int *emitter, int *direct);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRMLT_B200_H */

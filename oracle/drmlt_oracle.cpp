@@ -1,0 +1,263 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  PARITY UNPINNED (no reference
+// golden vectors exist for this path).
+//
+// C entry points of the CPU restatement, loaded with ctypes by tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference leg.  Mirrors the replay entry points of
+// include/drmlt_b200.h so that parity tests call both sides with the same buffers.
+#include "orc_mlt.hpp"
+#include <thread>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+
+using namespace orc;
+
+struct OrcScene { Scene sc; };
+
+static void applyEps(Scene &sc, const dr_config *cfg) {
+    // The oracle defaults to the double-precision constants of the reference's default build
+    // (constants.h:25-27); parity tests pass the float-build values the GPU uses.
+    sc.epsilon = cfg && cfg->ray_epsilon > 0 ? (Float) cfg->ray_epsilon : 1e-7;
+    sc.shadowEpsilon = cfg && cfg->shadow_epsilon > 0 ? (Float) cfg->shadow_epsilon : 1e-5;
+}
+
+extern "C" {
+
+void *orc_scene_create(const dr_scene_desc *desc) {
+    OrcScene *s = new OrcScene();
+    s->sc.load(*desc);
+    return s;
+}
+void orc_scene_destroy(void *h) { delete (OrcScene *) h; }
+
+void orc_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out) {
+    uint32_t c[4] = { c0, c1, c2, c3 };
+    Philox::gen(c, seed);
+    for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+float orc_uniform(uint64_t seed, uint32_t stream, uint64_t a, uint32_t b, uint32_t j) { return keyedUniform(seed, stream, a, b, j); }
+
+void orc_max_dimensions(const dr_config *cfg, int depth, int *sensor, int *emitter, int *direct) {
+    MaxDim md = findMaxDimensions(cfg->max_depth, cfg->rr_depth, depth, cfg->technique, cfg->direct_sampling != 0);
+    *sensor = md.sensor; *emitter = md.emitter; *direct = md.direct;
+}
+
+int orc_trace_rays(void *h, const dr_ray *rays, int64_t n, int shadow, float ray_epsilon, dr_hit *hits) {
+    Scene &sc = ((OrcScene *) h)->sc;
+    dr_config tmp; memset(&tmp, 0, sizeof(tmp)); tmp.ray_epsilon = ray_epsilon;
+    applyEps(sc, &tmp);
+    for (int64_t i = 0; i < n; ++i) {
+        Ray r; r.o = Vec3(rays[i].o[0], rays[i].o[1], rays[i].o[2]); r.d = Vec3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+        r.mint = rays[i].mint; r.maxt = rays[i].maxt;
+        Float mint = r.mint, maxt = r.maxt;
+        Float t = 0, u = 0, v = 0; int prim = -1;
+        bool hit = maxt > mint && sc.traverse(r, mint, maxt, shadow != 0, t, u, v, prim);
+        hits[i].prim = hit ? prim : -1;
+        hits[i].t = hit ? (float) t : 0; hits[i].u = hit ? (float) u : 0; hits[i].v = hit ? (float) v : 0;
+    }
+    return 0;
+}
+
+static void fillResult(const SplatList &list, uint64_t rays, dr_path_result *out) {
+    memset(out, 0, sizeof(*out));
+    out->luminance = (float) list.luminance;
+    out->n_splats = (int32_t) std::min(list.size(), (size_t) DR_MAX_SPLATS);
+    out->s = list.s; out->t = list.t;
+    out->mis_weight = (float) list.misWeight;
+    for (int k = 0; k < out->n_splats; ++k) {
+        out->pos[k][0] = (float) list.splats[k].first.x; out->pos[k][1] = (float) list.splats[k].first.y;
+        out->value[k][0] = (float) list.splats[k].second.r; out->value[k][1] = (float) list.splats[k].second.g;
+        out->value[k][2] = (float) list.splats[k].second.b;
+    }
+    out->n_rays = (int32_t) rays;
+}
+
+// double-precision outputs for tolerance analysis: lum[n], rgb of splat 0 [n][3], mis[n]
+int orc_eval_paths(void *h, const dr_config *cfg, const float *u_sensor, int dim_sensor, const float *u_emitter, int dim_emitter,
+                   const float *u_direct, int dim_direct, const int32_t *depth, int64_t n, dr_path_result *out, double *lum_out) {
+    Scene &sc = ((OrcScene *) h)->sc;
+    applyEps(sc, cfg);
+    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+        SplatList list;
+        for (;;) {
+            int64_t i = next.fetch_add(256);
+            if (i >= n) break;
+            for (int64_t j = i; j < std::min(n, i + 256); ++j) {
+                ArraySampler se(u_sensor + j * dim_sensor, dim_sensor), em(u_emitter + j * dim_emitter, dim_emitter),
+                    di(u_direct + j * dim_direct, dim_direct);
+                PathSampler ps(&sc, pathConfigOf(*cfg), &em, &se, &di);
+                ps.sampleSplats(list, depth ? depth[j] : -1);
+                fillResult(list, ps.ctx.rays, &out[j]);
+                if (lum_out) lum_out[j] = list.luminance;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work);
+    for (auto &t : th) t.join();
+    return 0;
+}
+
+int orc_bootstrap_luminance(void *h, const dr_config *cfg, uint64_t first, int64_t n, float *luminance, int32_t *depth, double *lum64) {
+    Scene &sc = ((OrcScene *) h)->sc;
+    applyEps(sc, cfg);
+    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+        SplatList list;
+        for (;;) {
+            int64_t i = next.fetch_add(256);
+            if (i >= n) break;
+            for (int64_t j = i; j < std::min(n, i + 256); ++j) {
+                bootstrapSample(sc, *cfg, first + (uint64_t) j, list);
+                luminance[j] = (float) list.luminance;
+                if (lum64) lum64[j] = list.luminance;
+                if (depth) depth[j] = bootstrapDepth(*cfg, first + (uint64_t) j);
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work);
+    for (auto &t : th) t.join();
+    return 0;
+}
+
+// Chains with recorded decisions (mirror of dr_chain_steps).  film (optional) is W*H*3 doubles->floats.
+int orc_chain_steps(void *h, const dr_config *cfg, double b, const uint64_t *seed_index, const int32_t *depth,
+                    const uint64_t *chain_id, int64_t n_chains, int64_t steps, dr_step_record *records, float *film_out,
+                    dr_stats *stats_out, int threads) {
+    Scene &sc = ((OrcScene *) h)->sc;
+    applyEps(sc, cfg);
+    unsigned nt = threads > 0 ? (unsigned) threads : std::max(1u, std::thread::hardware_concurrency());
+    nt = (unsigned) std::min<int64_t>(nt, std::max<int64_t>(1, n_chains));
+    std::vector<Film> films(film_out ? nt : 0);
+    for (auto &f : films) f.init(sc.cam.resX, sc.cam.resY, cfg->rfilter);
+    std::vector<ChainStats> tstats(nt);
+    std::atomic<int64_t> next(0);
+    auto work = [&](unsigned tid) {
+        ChainRunner runner(sc, *cfg, b, film_out ? &films[tid] : nullptr);
+        std::vector<StepRecord> recs(records ? steps : 0);
+        for (;;) {
+            int64_t i = next.fetch_add(1);
+            if (i >= n_chains) break;
+            runner.run(chain_id[i], seed_index[i], depth ? depth[i] : -1, (uint64_t) steps, records ? recs.data() : nullptr);
+            if (records)
+                for (int64_t m = 0; m < steps; ++m) {
+                    dr_step_record &o = records[i * steps + m];
+                    const StepRecord &r = recs[m];
+                    o.L_x = (float) r.L_x; o.L_y = (float) r.L_y; o.L_z = (float) r.L_z; o.a1 = (float) r.a1; o.a2 = (float) r.a2;
+                    o.large_step = r.large; o.accept1 = r.acc1; o.did_second = r.did2; o.accept2 = r.acc2;
+                }
+        }
+        tstats[tid] = runner.stats;
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+    ChainStats total;
+    for (auto &s : tstats) total.add(s);
+    if (film_out) {
+        size_t n = (size_t) sc.cam.resX * sc.cam.resY * 3;
+        for (size_t i = 0; i < n; ++i) {
+            double acc = 0;
+            for (auto &f : films) acc += f.data[i];
+            film_out[i] = (float) acc;
+        }
+    }
+    if (stats_out) {
+        memset(stats_out, 0, sizeof(*stats_out));
+        stats_out->mutations = total.mutations;
+        stats_out->first_accept = total.first_accept; stats_out->first_base = total.first_base;
+        stats_out->large_accept = total.large_accept; stats_out->large_base = total.large_base;
+        stats_out->bold_accept = total.bold_accept; stats_out->bold_base = total.bold_base;
+        stats_out->second_accept = total.second_accept; stats_out->second_base = total.second_base;
+        stats_out->second_large_accept = total.second_large_accept; stats_out->second_large_base = total.second_large_base;
+        stats_out->second_bold_accept = total.second_bold_accept; stats_out->second_bold_base = total.second_bold_base;
+        stats_out->accept = total.accept; stats_out->accept_base = total.accept_base;
+        stats_out->paths = total.paths; stats_out->rays = total.rays;
+        stats_out->luminance = b;
+    }
+    return 0;
+}
+
+// Whole render on the CPU (the reported CPU baseline; "port" of DRMLT::render / PSSMLT::render,
+// drmlt.cpp:393-611).  n_boot bootstrap samples -> b and the seed CDF -> n_chains chains of
+// `steps` mutations each, one chain per work item, `threads` host threads.
+int orc_render(void *h, const dr_config *cfg, int64_t n_boot, int64_t n_chains, int64_t steps, int threads,
+               float *image_rgb, dr_stats *stats_out, double *seconds_chains) {
+    Scene &sc = ((OrcScene *) h)->sc;
+    applyEps(sc, cfg);
+    std::vector<float> lum(n_boot);
+    std::vector<int32_t> dep(n_boot);
+    std::vector<double> lum64(n_boot);
+    orc_bootstrap_luminance(h, cfg, 0, n_boot, lum.data(), dep.data(), lum64.data());
+    // generateSeeds: running mean over non-NaN samples, x maxDepth for MMLT (pathsampler.cpp:922-934)
+    double sum = 0, tok = 0;
+    DiscreteDistribution seedPDF;
+    std::vector<int64_t> pool;
+    for (int64_t i = 0; i < n_boot; ++i) {
+        if (std::isnan(lum64[i])) continue;
+        tok += 1; sum += lum64[i];
+        if (lum64[i] != 0) { pool.push_back(i); seedPDF.append(lum64[i]); }
+    }
+    double b = tok > 0 ? sum / tok : 0;
+    if (cfg->technique == DR_TECH_MMLT) b *= cfg->max_depth;
+    if (b == 0 || pool.empty()) return DR_ERR_ZERO_LUMINANCE;
+    seedPDF.normalize();
+    if (cfg->average_luminance != -1.0f) b = cfg->average_luminance;
+    if (cfg->acceptance_map) b = 1.0;
+    std::vector<uint64_t> seedIdx(n_chains), chainId(n_chains);
+    std::vector<int32_t> depth(n_chains);
+    for (int64_t c = 0; c < n_chains; ++c) {
+        Float u = keyedUniform(cfg->seed, S_RESAMPLE, (uint64_t) c, 0, 0);
+        int64_t s = pool[seedPDF.sample(u)];
+        seedIdx[c] = (uint64_t) s; chainId[c] = (uint64_t) c; depth[c] = dep[s];
+    }
+    std::vector<float> film((size_t) sc.cam.resX * sc.cam.resY * 3);
+    auto t0 = std::chrono::steady_clock::now();
+    orc_chain_steps(h, cfg, b, seedIdx.data(), depth.data(), chainId.data(), n_chains, steps, nullptr, film.data(), stats_out, threads);
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds_chains) *seconds_chains = std::chrono::duration<double>(t1 - t0).count();
+    if (image_rgb) {
+        Film f; f.init(sc.cam.resX, sc.cam.resY, cfg->rfilter);
+        for (size_t i = 0; i < film.size(); ++i) f.data[i] = film[i];
+        develop(f, b, cfg->acceptance_map != 0, image_rgb);
+    }
+    if (stats_out) stats_out->luminance = b;
+    return 0;
+}
+
+// Film splat of explicit (pos, rgb) pairs -- parity of ImageBlock::put + the filter table.
+int orc_splat(int w, int h, int rfilter, const float *pos, const float *rgb, int64_t n, float *film_out) {
+    Film f; f.init(w, h, rfilter);
+    for (int64_t i = 0; i < n; ++i) f.put(Vec2(pos[2 * i], pos[2 * i + 1]), RGB(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]));
+    for (size_t i = 0; i < f.data.size(); ++i) film_out[i] = (float) f.data[i];
+    return 0;
+}
+
+// BSDF leaf access for chi-square / consistency tests (modelled on src/tests/test_chisquare.cpp)
+void orc_bsdf_sample(const dr_material *m, const double *wi, int mode, double u1, double u2, double *wo, double *weight, double *pdf, int *sampledType) {
+    BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), mode);
+    Float p = 0;
+    RGB w = bsdfSample(*m, b, p, Vec2(u1, u2), 1e-7);
+    wo[0] = b.wo.x; wo[1] = b.wo.y; wo[2] = b.wo.z;
+    weight[0] = w.r; weight[1] = w.g; weight[2] = w.b;
+    *pdf = p; *sampledType = b.sampledType;
+}
+void orc_bsdf_eval(const dr_material *m, const double *wi, const double *wo, int mode, int measure, double *value, double *pdf) {
+    BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), Vec3(wo[0], wo[1], wo[2]), mode);
+    RGB v = bsdfEval(*m, b, measure);
+    value[0] = v.r; value[1] = v.g; value[2] = v.b;
+    *pdf = bsdfPdf(*m, b, measure);
+}
+
+// transition kernels (transition.h) for known-answer tests
+double orc_kelemen_sample(double s1, double s2, double xi) { return KelemenKernel(s1, s2).sample(xi); }
+double orc_kelemen_pdf(double s1, double s2, double du) { return KelemenKernel(s1, s2).pdf(du); }
+double orc_gaussian_sample(double sigma, double xi1, double xi2) { return GaussianKernel{ sigma }.sample(xi1, xi2); }
+double orc_cauchy_sample(double rho, double xi) { return WrappedCauchyKernel(rho).sample(xi); }
+double orc_wrap(double y) { return wrapReflect(y); }
+
+} // extern "C"

@@ -1,0 +1,365 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).
+//
+// orc_bsdf.hpp: the five BSDF plugins on the hot path, in the local shading frame.
+// Restates src/bsdfs/diffuse.cpp:109-150, src/bsdfs/dielectric.cpp:220-340,
+// src/bsdfs/conductor.cpp:223-285, src/bsdfs/roughconductor.cpp:250-412,
+// src/bsdfs/microfacet.h:191-700 (Beckmann + GGX, sampleAll / sampleVisible),
+// src/bsdfs/twosided.cpp:107-195.
+#pragma once
+#include "orc_math.hpp"
+#include "../include/drmlt_b200.h"
+
+namespace orc {
+
+enum ETransportMode { ERadiance = 0, EImportance = 1 };
+enum EMeasure { EInvalidMeasure = 0, ESolidAngle = 1, ELength = 2, EArea = 3, EDiscrete = 4 };
+enum EBSDFType {
+    EDiffuseReflection = 0x1, EGlossyReflection = 0x2, EDeltaReflection = 0x4, EDeltaTransmission = 0x8,
+    ESmooth = EDiffuseReflection | EGlossyReflection, EDelta = EDeltaReflection | EDeltaTransmission
+};
+
+struct BSDFRecord {
+    Vec3 wi, wo;
+    int mode;
+    int sampledType = 0;
+    Float eta = 1.0;
+    BSDFRecord(const Vec3 &wi_, int mode_) : wi(wi_), mode(mode_) {}
+    BSDFRecord(const Vec3 &wi_, const Vec3 &wo_, int mode_) : wi(wi_), wo(wo_), mode(mode_) {}
+    void reverse() { std::swap(wi, wo); mode = 1 - mode; }   // include/mitsuba/render/bsdf.h reverse()
+};
+
+inline RGB rgb3(const float *v) { return RGB(v[0], v[1], v[2]); }
+
+inline bool bsdfHasSmooth(const dr_material &m) { return m.type == DR_BSDF_DIFFUSE || m.type == DR_BSDF_ROUGHCONDUCTOR; }
+inline bool bsdfNonSymmetric(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC; }   // dielectric.cpp:201
+// BSDF::ETransmission | BSDF::EBackSide test used by DirectSamplingRecord (records.inl:160-164)
+inline bool bsdfTransmissiveOrBackside(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }
+inline int bsdfMeasure(int sampledType) { return (sampledType & EDelta) ? EDiscrete : ESolidAngle; }
+
+// ---------------------------------------------------------------- microfacet.h
+struct Microfacet {
+    bool ggx, sampleVis;
+    Float alpha;
+    Microfacet(const dr_material &m)
+        : ggx((m.flags & DR_MAT_GGX) != 0), sampleVis((m.flags & DR_MAT_SAMPLE_VISIBLE) != 0),
+          alpha(std::max((Float) m.alpha, (Float) 1e-4)) {}   // microfacet.h:67-72
+
+    Float eval(const Vec3 &m) const {   // :191-237
+        if (Frame::cosTheta(m) <= 0) return 0.0;
+        Float cosTheta2 = Frame::cosTheta2(m);
+        Float beckmannExponent = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
+        Float result;
+        if (!ggx) {
+            result = std::exp(-beckmannExponent) / (PI * alpha * alpha * cosTheta2 * cosTheta2);
+        } else {
+            Float root = (1.0 + beckmannExponent) * cosTheta2;
+            result = 1.0 / (PI * alpha * alpha * root * root);
+        }
+        if (result * Frame::cosTheta(m) < 1e-20) result = 0;
+        return result;
+    }
+    Float smithG1(const Vec3 &v, const Vec3 &m) const {   // :476-513
+        if (dot(v, m) * Frame::cosTheta(v) <= 0) return 0.0;
+        Float tanTheta = std::abs(Frame::tanTheta(v));
+        if (tanTheta == 0.0) return 1.0;
+        if (!ggx) {
+            Float a = 1.0 / (alpha * tanTheta);
+            if (a >= 1.6) return 1.0;
+            Float aSqr = a * a;
+            return (3.535 * a + 2.181 * aSqr) / (1.0 + 2.276 * a + 2.577 * aSqr);
+        } else {
+            Float root = alpha * tanTheta;
+            return 2.0 / (1.0 + std::hypot((Float) 1.0, root));
+        }
+    }
+    Float G(const Vec3 &wi, const Vec3 &wo, const Vec3 &m) const { return smithG1(wi, m) * smithG1(wo, m); }
+    Float pdfAll(const Vec3 &m) const { return eval(m) * Frame::cosTheta(m); }
+    Float pdfVisible(const Vec3 &wi, const Vec3 &m) const {   // :469-473
+        if (Frame::cosTheta(wi) == 0) return 0.0;
+        return smithG1(wi, m) * absDot(wi, m) * eval(m) / std::abs(Frame::cosTheta(wi));
+    }
+    Float pdf(const Vec3 &wi, const Vec3 &m) const { return sampleVis ? pdfVisible(wi, m) : pdfAll(m); }
+
+    Vec3 sampleAll(const Vec2 &sample, Float &pdf) const {   // :287-397 (isotropic)
+        Float sinPhiM = std::sin(2.0 * PI * sample.y), cosPhiM = std::cos(2.0 * PI * sample.y);
+        Float alphaSqr = alpha * alpha, cosThetaM;
+        if (!ggx) {
+            Float tanThetaMSqr = alphaSqr * -std::log(1.0 - sample.x);
+            cosThetaM = 1.0 / std::sqrt(1.0 + tanThetaMSqr);
+            pdf = (1.0 - sample.x) / (PI * alpha * alpha * cosThetaM * cosThetaM * cosThetaM);
+        } else {
+            Float tanThetaMSqr = alphaSqr * sample.x / (1.0 - sample.x);
+            cosThetaM = 1.0 / std::sqrt(1.0 + tanThetaMSqr);
+            Float temp = 1 + tanThetaMSqr / alphaSqr;
+            pdf = INV_PI / (alpha * alpha * cosThetaM * cosThetaM * cosThetaM * temp * temp);
+        }
+        if (pdf < 1e-20) pdf = 0;
+        Float sinThetaM = std::sqrt(std::max((Float) 0, 1 - cosThetaM * cosThetaM));
+        return Vec3(sinThetaM * cosPhiM, sinThetaM * sinPhiM, cosThetaM);
+    }
+
+    // Numerical inverse of erf used by the Beckmann visible-normal sampler (src/libcore/math.cpp:25-80,
+    // Giles' single-precision polynomial as used by the reference)
+    static Float erfinv(Float x) {
+        Float w = -std::log((1.0 - x) * (1.0 + x));
+        Float p;
+        if (w < 5.0) {
+            w = w - 2.5;
+            p = 2.81022636e-08;
+            p = 3.43273939e-07 + p * w; p = -3.5233877e-06 + p * w; p = -4.39150654e-06 + p * w;
+            p = 0.00021858087 + p * w; p = -0.00125372503 + p * w; p = -0.00417768164 + p * w;
+            p = 0.246640727 + p * w; p = 1.50140941 + p * w;
+        } else {
+            w = std::sqrt(w) - 3.0;
+            p = -0.000200214257;
+            p = 0.000100950558 + p * w; p = 0.00134934322 + p * w; p = -0.00367342844 + p * w;
+            p = 0.00573950773 + p * w; p = -0.0076224613 + p * w; p = 0.00943887047 + p * w;
+            p = 1.00167406 + p * w; p = 2.83297682 + p * w;
+        }
+        return p * x;
+    }
+    static Float erfApprox(Float x) {   // src/libcore/math.cpp erf(): A&S 7.1.26-style rational
+        Float a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027, a5 = 1.061405429, p = 0.3275911;
+        Float sign = signum(x);
+        x = std::abs(x);
+        Float t = 1.0 / (1.0 + p * x);
+        Float y = 1.0 - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * std::exp(-x * x);
+        return sign * y;
+    }
+
+    Vec2 sampleVisible11(Float thetaI, Vec2 sample, Float epsilon) const {   // :573-690
+        const Float SQRT_PI_INV = 1 / std::sqrt(PI);
+        Vec2 slope;
+        if (!ggx) {
+            if (thetaI < 1e-4) {
+                Float r = std::sqrt(-std::log(1.0 - sample.x));
+                return Vec2(r * std::cos(2 * PI * sample.y), r * std::sin(2 * PI * sample.y));
+            }
+            Float tanThetaI = std::tan(thetaI), cotThetaI = 1 / tanThetaI;
+            Float a = -1, c = erfApprox(cotThetaI);
+            Float sample_x = std::max(sample.x, (Float) 1e-6);
+            Float fit = 1 + thetaI * (-0.876 + thetaI * (0.4265 - 0.0594 * thetaI));
+            Float b = c - (1 + c) * std::pow(1 - sample_x, fit);
+            Float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * std::exp(-cotThetaI * cotThetaI));
+            int it = 0;
+            while (++it < 10) {
+                if (!(b >= a && b <= c)) b = 0.5 * (a + c);
+                Float invErf = erfinv(b);
+                Float value = normalization * (1 + b + SQRT_PI_INV * tanThetaI * std::exp(-invErf * invErf)) - sample_x;
+                Float derivative = normalization * (1 - invErf * tanThetaI);
+                if (std::abs(value) < 1e-5) break;
+                if (value > 0) c = b; else a = b;
+                b -= value / derivative;
+            }
+            slope.x = erfinv(b);
+            slope.y = erfinv(2.0 * std::max(sample.y, (Float) 1e-6) - 1.0);
+        } else {
+            if (thetaI < 1e-4) {
+                Float r = safe_sqrt(sample.x / (1 - sample.x));
+                return Vec2(r * std::cos(2 * PI * sample.y), r * std::sin(2 * PI * sample.y));
+            }
+            Float tanThetaI = std::tan(thetaI);
+            Float a = 1 / tanThetaI;
+            Float G1 = 2.0 / (1.0 + safe_sqrt(1.0 + 1.0 / (a * a)));
+            Float A = 2.0 * sample.x / G1 - 1.0;
+            if (std::abs(A) == 1) A -= signum(A) * epsilon;
+            Float tmp = 1.0 / (A * A - 1.0);
+            Float B = tanThetaI;
+            Float D = safe_sqrt(B * B * tmp * tmp - (A * A - B * B) * tmp);
+            Float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+            slope.x = (A < 0.0 || slope_x_2 > 1.0 / tanThetaI) ? slope_x_1 : slope_x_2;
+            Float S;
+            if (sample.y > 0.5) { S = 1.0; sample.y = 2.0 * (sample.y - 0.5); }
+            else { S = -1.0; sample.y = 2.0 * (0.5 - sample.y); }
+            Float z = (sample.y * (sample.y * (sample.y * (-0.365728915865723) + 0.790235037209296) - 0.424965825137544) + 0.000152998850436920) /
+                      (sample.y * (sample.y * (sample.y * (sample.y * 0.169507819808272 - 0.397203533833404) - 0.232500544458471) + 1) - 0.539825872510702);
+            slope.y = S * z * std::sqrt(1.0 + slope.x * slope.x);
+        }
+        return slope;
+    }
+    Vec3 sampleVisible(const Vec3 &_wi, const Vec2 &sample, Float epsilon) const {   // :417-466
+        Vec3 wi = normalize(Vec3(alpha * _wi.x, alpha * _wi.y, _wi.z));
+        Float theta = 0, phi = 0;
+        if (wi.z < 0.99999) { theta = std::acos(wi.z); phi = std::atan2(wi.y, wi.x); }
+        Float sinPhi = std::sin(phi), cosPhi = std::cos(phi);
+        Vec2 slope = sampleVisible11(theta, sample, epsilon);
+        slope = Vec2(cosPhi * slope.x - sinPhi * slope.y, sinPhi * slope.x + cosPhi * slope.y);
+        slope.x *= alpha; slope.y *= alpha;
+        Float normalization = 1.0 / std::sqrt(slope.x * slope.x + slope.y * slope.y + 1.0);
+        return Vec3(-slope.x * normalization, -slope.y * normalization, normalization);
+    }
+    Vec3 sample(const Vec3 &wi, const Vec2 &s, Float &pdf, Float epsilon) const {   // :243-252
+        if (sampleVis) { Vec3 m = sampleVisible(wi, s, epsilon); pdf = pdfVisible(wi, m); return m; }
+        return sampleAll(s, pdf);
+    }
+};
+
+// ---------------------------------------------------------------- nested (one-sided) models
+namespace detail {
+
+inline Vec3 reflectZ(const Vec3 &wi) { return Vec3(-wi.x, -wi.y, wi.z); }
+inline Vec3 reflectM(const Vec3 &wi, const Vec3 &m) { return m * (2 * dot(wi, m)) - wi; }
+
+inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
+    switch (m.type) {
+    case DR_BSDF_DIFFUSE:   // diffuse.cpp:109-117
+        if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
+        return rgb3(m.reflectance) * (INV_PI * Frame::cosTheta(b.wo));
+    case DR_BSDF_CONDUCTOR:   // conductor.cpp:223-237
+        if (measure != EDiscrete || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0 ||
+            std::abs(dot(reflectZ(b.wi), b.wo) - 1) > DELTA_EPSILON) return RGB(0.0);
+        return rgb3(m.reflectance) * fresnelConductorExact(Frame::cosTheta(b.wi), rgb3(m.eta), rgb3(m.k));
+    case DR_BSDF_ROUGHCONDUCTOR: {   // roughconductor.cpp:258-297
+        if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
+        Vec3 H = normalize(b.wo + b.wi);
+        Microfacet distr(m);
+        const Float D = distr.eval(H);
+        if (D == 0) return RGB(0.0);
+        const RGB F = fresnelConductorExact(dot(b.wi, H), rgb3(m.eta), rgb3(m.k)) * rgb3(m.reflectance);
+        const Float G = distr.G(b.wi, b.wo, H);
+        Float model = D * G / (4.0 * Frame::cosTheta(b.wi));
+        return F * model;
+    }
+    case DR_BSDF_DIELECTRIC: {   // dielectric.cpp:227-253
+        if (measure != EDiscrete) return RGB(0.0);
+        Float eta = m.eta[0], invEta = 1 / eta, cosThetaT;
+        Float F = fresnelDielectricExt(Frame::cosTheta(b.wi), cosThetaT, eta);
+        if (Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) >= 0) {
+            if (std::abs(dot(reflectZ(b.wi), b.wo) - 1) > DELTA_EPSILON) return RGB(0.0);
+            return rgb3(m.reflectance) * F;
+        } else {
+            Float scale = -(cosThetaT < 0 ? invEta : eta);
+            Vec3 refr(scale * b.wi.x, scale * b.wi.y, cosThetaT);
+            if (std::abs(dot(refr, b.wo) - 1) > DELTA_EPSILON) return RGB(0.0);
+            Float factor = (b.mode == ERadiance) ? (cosThetaT < 0 ? invEta : eta) : 1.0;
+            return rgb3(m.transmittance) * (factor * factor * (1 - F));
+        }
+    }
+    }
+    return RGB(0.0);
+}
+
+inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
+    switch (m.type) {
+    case DR_BSDF_DIFFUSE:   // diffuse.cpp:119-126
+        if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return 0.0;
+        return squareToCosineHemispherePdf(b.wo);
+    case DR_BSDF_CONDUCTOR:   // conductor.cpp:239-252
+        if (measure != EDiscrete || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0 ||
+            std::abs(dot(reflectZ(b.wi), b.wo) - 1) > DELTA_EPSILON) return 0.0;
+        return 1.0;
+    case DR_BSDF_ROUGHCONDUCTOR: {   // roughconductor.cpp:299-324
+        if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return 0.0;
+        Vec3 H = normalize(b.wo + b.wi);
+        Microfacet distr(m);
+        if (distr.sampleVis)
+            return distr.eval(H) * distr.smithG1(b.wi, H) / (4.0 * Frame::cosTheta(b.wi));
+        else
+            return distr.pdf(b.wi, H) / (4 * absDot(b.wo, H));
+    }
+    case DR_BSDF_DIELECTRIC: {   // dielectric.cpp:255-276
+        if (measure != EDiscrete) return 0.0;
+        Float eta = m.eta[0], invEta = 1 / eta, cosThetaT;
+        Float F = fresnelDielectricExt(Frame::cosTheta(b.wi), cosThetaT, eta);
+        if (Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) >= 0) {
+            if (std::abs(dot(reflectZ(b.wi), b.wo) - 1) > DELTA_EPSILON) return 0.0;
+            return F;
+        } else {
+            Float scale = -(cosThetaT < 0 ? invEta : eta);
+            Vec3 refr(scale * b.wi.x, scale * b.wi.y, cosThetaT);
+            if (std::abs(dot(refr, b.wo) - 1) > DELTA_EPSILON) return 0.0;
+            return 1 - F;
+        }
+    }
+    }
+    return 0.0;
+}
+
+inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const Vec2 &sample, Float epsilon) {
+    switch (m.type) {
+    case DR_BSDF_DIFFUSE:   // diffuse.cpp:139-149
+        if (Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
+        b.wo = squareToCosineHemisphere(sample);
+        b.eta = 1.0; b.sampledType = EDiffuseReflection;
+        pdf = squareToCosineHemispherePdf(b.wo);
+        return rgb3(m.reflectance);
+    case DR_BSDF_CONDUCTOR:   // conductor.cpp:270-285
+        if (Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
+        b.sampledType = EDeltaReflection; b.wo = reflectZ(b.wi); b.eta = 1.0; pdf = 1;
+        return rgb3(m.reflectance) * fresnelConductorExact(Frame::cosTheta(b.wi), rgb3(m.eta), rgb3(m.k));
+    case DR_BSDF_ROUGHCONDUCTOR: {   // roughconductor.cpp:371-417
+        if (Frame::cosTheta(b.wi) < 0) return RGB(0.0);
+        Microfacet distr(m);
+        Float temporaryPdf = 0;
+        Vec3 mm = distr.sample(b.wi, sample, temporaryPdf, epsilon);
+        if (temporaryPdf == 0) return RGB(0.0);
+        b.wo = reflectM(b.wi, mm);
+        b.eta = 1.0; b.sampledType = EGlossyReflection;
+        if (Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
+        RGB F = fresnelConductorExact(dot(b.wi, mm), rgb3(m.eta), rgb3(m.k)) * rgb3(m.reflectance);
+        Float weight;
+        if (distr.sampleVis) weight = distr.smithG1(b.wo, mm);
+        else weight = distr.eval(mm) * distr.G(b.wi, b.wo, mm) * dot(b.wi, mm) / (temporaryPdf * Frame::cosTheta(b.wi));
+        if (weight > 0) {
+            pdf = temporaryPdf / (4.0 * dot(b.wo, mm));
+            return F * weight;
+        }
+        return RGB(0.0);
+    }
+    case DR_BSDF_DIELECTRIC: {   // dielectric.cpp:278-330 (both components enabled)
+        Float eta = m.eta[0], invEta = 1 / eta, cosThetaT;
+        Float F = fresnelDielectricExt(Frame::cosTheta(b.wi), cosThetaT, eta);
+        if (sample.x <= F) {
+            b.sampledType = EDeltaReflection; b.wo = reflectZ(b.wi); b.eta = 1.0; pdf = F;
+            return rgb3(m.reflectance);
+        } else {
+            b.sampledType = EDeltaTransmission;
+            Float scale = -(cosThetaT < 0 ? invEta : eta);
+            b.wo = Vec3(scale * b.wi.x, scale * b.wi.y, cosThetaT);
+            b.eta = cosThetaT < 0 ? eta : invEta;
+            pdf = 1 - F;
+            Float factor = (b.mode == ERadiance) ? (cosThetaT < 0 ? invEta : eta) : 1.0;
+            return rgb3(m.transmittance) * (factor * factor);
+        }
+    }
+    }
+    return RGB(0.0);
+}
+
+} // namespace detail
+
+// ---------------------------------------------------------------- public: with the twosided adapter
+inline RGB bsdfEval(const dr_material &m, const BSDFRecord &bRec, int measure = ESolidAngle) {
+    if (m.flags & DR_MAT_TWOSIDED) {   // twosided.cpp:107-127
+        BSDFRecord b(bRec);
+        if (Frame::cosTheta(b.wi) > 0) return detail::evalNested(m, b, measure);
+        b.wi.z *= -1; b.wo.z *= -1;
+        return detail::evalNested(m, b, measure);
+    }
+    return detail::evalNested(m, bRec, measure);
+}
+inline Float bsdfPdf(const dr_material &m, const BSDFRecord &bRec, int measure = ESolidAngle) {
+    if (m.flags & DR_MAT_TWOSIDED) {   // twosided.cpp:129-141
+        BSDFRecord b(bRec);
+        if (b.wi.z > 0) return detail::pdfNested(m, b, measure);
+        b.wi.z *= -1; b.wo.z *= -1;
+        return detail::pdfNested(m, b, measure);
+    }
+    return detail::pdfNested(m, bRec, measure);
+}
+inline RGB bsdfSample(const dr_material &m, BSDFRecord &bRec, Float &pdf, const Vec2 &sample, Float epsilon) {
+    pdf = 0;
+    if (m.flags & DR_MAT_TWOSIDED) {   // twosided.cpp:166-186
+        bool flipped = false;
+        if (Frame::cosTheta(bRec.wi) < 0) { bRec.wi.z *= -1; flipped = true; }
+        RGB result = detail::sampleNested(m, bRec, pdf, sample, epsilon);
+        if (flipped) {
+            bRec.wi.z *= -1;
+            if (!result.isZero() && pdf != 0) bRec.wo.z *= -1;
+        }
+        return result;
+    }
+    return detail::sampleNested(m, bRec, pdf, sample, epsilon);
+}
+
+} // namespace orc

@@ -1,0 +1,618 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).
+//
+// orc_mlt.hpp: primary-sample-space samplers, transition kernels, the PSSMLT and DRMLT chain
+// loops, bootstrap, splatting and develop.  Restates
+//   src/integrators/drmlt/tools/transition.h:23-190         (Gaussian/Kelemen/Identity/WrappedCauchy)
+//   src/integrators/drmlt/drmlt_sampler.{h,cpp}             (DRMLTSampler + Green/Mira/Orbital)
+//   src/integrators/drmlt/drmlt_proc.cpp:161-380, 386-771   (processMixture, process), :813-854 (develop)
+//   src/integrators/pssmlt/pssmlt_sampler.{h,cpp}, pssmlt_proc.cpp:110-285, :326-365
+//   src/integrators/pssmlt_utils.h:27-77                    (findMaxDimensions)
+//   src/libbidir/pathsampler.cpp:859-960                    (generateSeeds)
+//   include/mitsuba/render/imageblock.h:149-196, src/libcore/rfilter.cpp:37-55 (film splat)
+//
+// Uniform addressing: every uniform is addressed by KEY (orc_rng.hpp), so a sampler's whole
+// proposal vector is a pure function of (chain, mutation, stage, sampler, coordinate).  The
+// reference fills a sampler's vector lazily, at its first primarySample(0) of a stage
+// (drmlt_sampler.cpp:252-254), from one sequential SFMT stream; with keyed uniforms lazy and
+// eager fills give the same vectors, and a sampler the path never touches cannot influence
+// the chain, so the restatement fills eagerly.
+#pragma once
+#include "orc_sampler.hpp"
+#include "orc_rng.hpp"
+#include <memory>
+#include <functional>
+
+namespace orc {
+
+// ------------------------------------------------------------------ findMaxDimensions (pssmlt_utils.h:27-77)
+// No media and no rough dielectrics in scope: offsetMedium = offsetRoughDielectric = 0.
+struct MaxDim { int sensor, emitter, direct; };
+inline MaxDim findMaxDimensions(int maxDepth, int rrDepth, int depth, int technique, bool useDirectSampling) {
+    int offsetRR = rrDepth < maxDepth ? 1 : 0;
+    if (technique == DR_TECH_MMLT) {
+        int maxDim = (depth + 2) * 3;
+        if (maxDim % 2 == 1) maxDim++;
+        return MaxDim{ maxDim, maxDim, 1 };
+    } else if (technique == DR_TECH_PATH) {
+        int maxDim = (maxDepth + 2) * (4 + offsetRR);
+        if (maxDim % 2 == 1) maxDim++;
+        return MaxDim{ maxDim, 0, 0 };
+    } else {
+        int maxDim = (maxDepth + 2) * (2 + offsetRR);
+        if (maxDim % 2 == 1) maxDim++;
+        return MaxDim{ maxDim, maxDim, useDirectSampling ? maxDepth : 0 };
+    }
+}
+
+// ------------------------------------------------------------------ transition kernels (transition.h)
+struct KelemenKernel {
+    Float s1, s2, logRatio;
+    KelemenKernel(Float a, Float b) : s1(a), s2(b) { logRatio = -std::log(b / a); }
+    Float sample(Float xi) const {   // transition.h:96-110
+        int sign;
+        if (xi < 0.5) { sign = 1; xi *= 2.0; } else { sign = -1; xi = 2.0 * (xi - 0.5); }
+        Float dv = s2 * std::exp((1 - xi) * logRatio);
+        return dv * sign;
+    }
+    Float pdf(Float du) const {      // :112-117
+        Float d = std::abs(du);
+        if (d < s1 || d > s2) return 0.0;
+        return 1.0 / (2.0 * d * (-logRatio));
+    }
+    Float logPdf(Float du) const { return std::log(pdf(du)); }
+};
+struct GaussianKernel {
+    Float sigma;
+    Float sample(Float xi1, Float xi2) const {   // :63-68 Box-Muller
+        Float tmp = std::sqrt(-2.0 * std::log(1 - xi1));
+        return tmp * std::cos(2.0 * PI * xi2) * sigma;
+    }
+};
+struct WrappedCauchyKernel {
+    Float rho, dispersion;
+    explicit WrappedCauchyKernel(Float r) : rho(r), dispersion(2.0 * r / (1.0 + r * r)) {}
+    Float sample(Float xi) const {   // :162-178
+        int sign = 1;
+        if (xi < 0.5) { sign = 1; xi *= 2.0; } else { sign = -1; xi = 2.0 * (xi - 0.5); }
+        Float V = std::cos(2.0 * PI * xi);
+        Float angle = (V + dispersion) / (1.0 + dispersion * V);
+        return sign * safe_acos(angle);
+    }
+};
+
+// Float-precision uniform source addressed by key.  `mut` is the mutation index of the chain.
+struct KeyedSource {
+    uint64_t seed = 0, chain = 0;
+    uint32_t mut = 0;
+    Float coin(int which) const { return keyedUniform(seed, S_COIN, chain, mut, (uint32_t) which); }
+    Float stage(int stageIdx, int sampler, int coord, int draw) const {
+        return keyedUniform(seed, (stageIdx == 0 ? S_STAGE1 : S_STAGE2) + sampler, chain, mut, (uint32_t) (2 * coord + draw));
+    }
+    static Float boot(uint64_t seed, uint64_t index, int sampler, int coord) {
+        return keyedUniform(seed, S_BOOT, index, (uint32_t) sampler, (uint32_t) coord);
+    }
+};
+
+// drmlt_sampler.h:140-144
+inline Float wrapReflect(Float y) { return y > 1 ? 2.0 - y : (y <= 0 ? std::abs(y) : y); }
+
+enum EKernel { K_KELEMEN, K_GAUSSIAN, K_ORBITAL, K_IDENTITY };
+
+// DRMLTSampler and subclasses (drmlt_sampler.{h,cpp}), eager fill, keyed uniforms.
+struct DRMLTSampler : Sampler {
+    int type;                 // dr_type
+    int samplerId;            // 0 sensor, 1 emitter, 2 direct
+    const KeyedSource *src = nullptr;
+    size_t maxDim = 0;
+    bool largeStep = false;
+    bool isFirst = true, isLightTracing = false, isReverse = false;
+    bool identityAll = false;        // setStagesToIdentity(): MMLT direct sampler (drmlt_proc.cpp:133-136)
+    bool stage2Identity = false;     // handleLightTracing(): fixEmitterPath on the emitter sampler (:137-140)
+    Float sigma, scaleSecond;
+    const Float s1 = 1.0 / 1024.0, s2 = 1.0 / 64.0, kelemenScale = 1.9;   // drmlt_sampler.h:201-205
+    std::vector<Float> uCurrent, uProp1, uProp2;
+    size_t sampleIndex = 0, dimStage1 = 0, dimStage2 = 0;
+    bool filled1 = false, filled2 = false;
+    bool arrayMode = false;          // replay of an explicit vector (seed replay): read uCurrent directly
+
+    bool kernelIsIdentity() const {
+        if (identityAll) return true;
+        if (isFirst) return false;
+        if (stage2Identity) return !isLightTracing;   // stage2 = Identity, stageLT = real kernel
+        return false;
+    }
+    void setLargeStep(bool v) { largeStep = v; }
+    void nextStage(bool lightTracing = false) { sampleIndex = 0; isFirst = false; isLightTracing = lightTracing; }
+    void setReverse(bool v) { sampleIndex = 0; isReverse = v; }
+    void resetStage() {
+        sampleIndex = 0; isFirst = true; isReverse = false; isLightTracing = false;
+        uProp1.clear(); uProp2.clear(); filled1 = filled2 = false; dimStage1 = dimStage2 = 0;
+    }
+    void accept(bool acceptFirst) {   // drmlt_sampler.cpp:189-199
+        ensureFilled(acceptFirst);
+        uCurrent = acceptFirst ? uProp1 : uProp2;
+        uCurrent.resize(maxDim);      // orbital with odd maxDim pushes one extra coordinate
+        for (Float &v : uCurrent) v = wrapReflect(v);
+        resetStage();
+    }
+    void reject() { resetStage(); }
+
+    // fillSpace (drmlt_sampler.cpp:313-394)
+    void fill(bool first) {
+        std::vector<Float> &uProposed = first ? uProp1 : uProp2;
+        uProposed.clear();
+        const int st = first ? 0 : 1;
+        KelemenKernel kel(type == DR_TYPE_ORBITAL ? s1 * kelemenScale : s1, type == DR_TYPE_ORBITAL ? s2 * kelemenScale : s2);
+        GaussianKernel gauss{ scaleSecond * sigma };
+        WrappedCauchyKernel cauchy(std::exp(-0.25));
+        bool savedFirst = isFirst; isFirst = first;
+        const bool identity = kernelIsIdentity();
+        isFirst = savedFirst;
+        for (size_t i = 0; i < maxDim; i++) {
+            if (largeStep) {
+                uProposed.push_back(src->stage(st, samplerId, (int) i, 0));
+            } else if (identity) {
+                uProposed.push_back(uCurrent[i]);
+            } else if (type != DR_TYPE_ORBITAL) {
+                if (first) uProposed.push_back(uCurrent[i] + kel.sample(src->stage(st, samplerId, (int) i, 0)));
+                else uProposed.push_back(uCurrent[i] + gauss.sample(src->stage(st, samplerId, (int) i, 0), src->stage(st, samplerId, (int) i, 1)));
+            } else if (first) {   // orbital first stage: 2-D radial Kelemen (:351-359)
+                Float d = kel.sample(src->stage(st, samplerId, (int) i, 0));
+                Float a = src->stage(st, samplerId, (int) i, 1) * 2.0 * PI;
+                Float x1 = i + 1 < uCurrent.size() ? uCurrent[i + 1] : 0.0;
+                uProposed.push_back(uCurrent[i] + d * std::cos(a));
+                uProposed.push_back(x1 + d * std::sin(a));
+                i++;
+            } else {              // orbital second stage (:361-392)
+                Float theta_i = cauchy.sample(src->stage(st, samplerId, (int) i, 0));
+                Float x1 = i + 1 < uCurrent.size() ? uCurrent[i + 1] : 0.0;
+                Float du1 = uProp1[i] - uCurrent[i];
+                Float du2 = uProp1[i + 1] - x1;
+                Float norm = std::sqrt(du1 * du1 + du2 * du2);
+                Float mu_i = safe_acos(-du1 / norm);
+                if (-du2 < 0) mu_i = 2.0 * PI - mu_i;
+                Float c1 = uProp1[i] + std::cos(theta_i + mu_i) * norm;
+                Float c2 = uProp1[i + 1] + std::sin(theta_i + mu_i) * norm;
+                uProposed.push_back(c1);
+                uProposed.push_back(c2);
+                i++;
+            }
+        }
+        (first ? filled1 : filled2) = true;
+    }
+    void ensureFilled(bool first) {
+        if (first ? !filled1 : !filled2) {
+            if (!first && !filled1) fill(true);
+            fill(first);
+        }
+    }
+    // primarySample (drmlt_sampler.cpp:231-307)
+    Float primarySample(size_t k) {
+        if (arrayMode) return k < uCurrent.size() ? wrapReflect(uCurrent[k]) : 0.5;
+        (isFirst ? dimStage1 : dimStage2) = std::max(k, isFirst ? dimStage1 : dimStage2);
+        if (type == DR_TYPE_GREEN && isReverse) {
+            ensureFilled(true); ensureFilled(false);
+            Float du = uProp1[k] - uCurrent[k];
+            return wrapReflect(uProp2[k] - du);
+        }
+        ensureFilled(isFirst);
+        const std::vector<Float> &uProposed = isFirst ? uProp1 : uProp2;
+        if (k >= uProposed.size()) return 0.5;   // the reference logs EError here (:257-259)
+        return wrapReflect(uProposed[k]);
+    }
+    Float next1D() override { return primarySample(sampleIndex++); }
+
+    // MiraDRMLTSampler::getTransitionRatio (drmlt_sampler.cpp:400-414).  dimStage* hold the largest
+    // INDEX touched, so the last used coordinate is skipped exactly as in the reference.
+    Float getTransitionRatio() {
+        if (identityAll) return 1.0;   // stage1->isIdentity()
+        ensureFilled(true); ensureFilled(false);
+        KelemenKernel kel(s1, s2);
+        size_t dimStage = std::max(dimStage1, dimStage2);
+        Float num = 0.0, denum = 0.0;
+        for (size_t i = 0; i < dimStage; i++) {
+            num += kel.logPdf(uProp2[i] - uProp1[i]);
+            denum += kel.logPdf(uCurrent[i] - uProp1[i]);
+        }
+        return std::exp(num - denum);
+    }
+};
+
+// PSSMLTSampler (pssmlt_sampler.{h,cpp}), eager fill, keyed uniforms.
+struct PSSMLTSampler : Sampler {
+    int samplerId;
+    const KeyedSource *src = nullptr;
+    size_t maxDim = 0;
+    bool largeStep = false, useKelemen = true;
+    Float s1, s2, logRatio, sigma;
+    std::vector<Float> u, backup;
+    size_t sampleIndex = 0;
+    bool filled = false, arrayMode = false;
+    void configure(Float s1_, Float s2_, Float sigma_) { s1 = s1_; s2 = s2_; sigma = sigma_; logRatio = -std::log(s2 / s1); }
+    Float mutate(Float value, int coord) const {   // pssmlt_sampler.h:117-147
+        if (useKelemen) {
+            Float sample = src->stage(0, samplerId, coord, 0);
+            bool add;
+            if (sample < 0.5) { add = true; sample *= 2.0; } else { add = false; sample = 2.0 * (sample - 0.5); }
+            Float dv = s2 * std::exp(sample * logRatio);
+            if (add) { value += dv; if (value > 1) value -= 1; }
+            else { value -= dv; if (value < 0) value += 1; }
+        } else {
+            Float tmp1 = std::sqrt(-2 * std::log(1 - src->stage(0, samplerId, coord, 0)));
+            Float dv = tmp1 * std::cos(2 * PI * src->stage(0, samplerId, coord, 1));
+            Float r = std::fmod(value + sigma * dv, 1.0);
+            value = (r < 0.0) ? r + 1.0 : r;
+        }
+        return value;
+    }
+    void setLargeStep(bool v) { largeStep = v; }
+    void ensureFilled() {   // primarySample(0) (pssmlt_sampler.cpp:124-166)
+        if (filled) return;
+        backup = u;
+        for (size_t k = 0; k < maxDim; k++) {
+            if (largeStep) u[k] = src->stage(0, samplerId, (int) k, 0);
+            else u[k] = mutate(u[k], (int) k);
+        }
+        filled = true;
+    }
+    Float primarySample(size_t i) {
+        if (arrayMode) return i < u.size() ? u[i] : 0.5;
+        ensureFilled();
+        return i < u.size() ? u[i] : 0.5;
+    }
+    Float next1D() override { return primarySample(sampleIndex++); }
+    void accept() { ensureFilled(); backup.clear(); sampleIndex = 0; filled = false; }
+    void reject() { if (filled) u = backup; backup.clear(); sampleIndex = 0; filled = false; }
+};
+
+// ------------------------------------------------------------------ film (imageblock.h:149-196)
+struct Film {
+    int w, h;
+    Float radius, scaleFactor;
+    Float values[32];
+    std::vector<Float> data;   // w*h*3
+    void init(int w_, int h_, int rfilter) {
+        w = w_; h = h_; data.assign((size_t) w * h * 3, 0.0);
+        // gaussian.cpp:30-60 (stddev 0.5, radius 2) / box.cpp:30-46 (radius 0.5 + 1e-5); rfilter.cpp:37-55
+        Float stddev = 0.5;
+        radius = rfilter == DR_FILTER_BOX ? 0.5 + 1e-5 : 4 * stddev;
+        Float sum = 0.0;
+        for (int i = 0; i < 31; ++i) {
+            Float x = (radius * i) / 31;
+            Float v;
+            if (rfilter == DR_FILTER_BOX) v = std::abs(x) <= radius ? 1.0 : 0.0;
+            else {
+                Float alpha = -1.0 / (2.0 * stddev * stddev);
+                v = std::max((Float) 0.0, std::exp(alpha * x * x) - std::exp(alpha * radius * radius));
+            }
+            values[i] = v; sum += v;
+        }
+        values[31] = 0.0;
+        scaleFactor = 31 / radius;
+        sum *= 2 * radius / 31;
+        for (int i = 0; i < 31; ++i) values[i] /= sum;
+    }
+    Float evalDiscretized(Float x) const { return values[std::min((int) std::abs(x * scaleFactor), 31)]; }
+    bool put(const Vec2 &_pos, const RGB &value) {
+        if (!value.isValid()) return false;
+        const Float px = _pos.x - 0.5, py = _pos.y - 0.5;
+        const int minx = std::max((int) std::ceil(px - radius), 0), miny = std::max((int) std::ceil(py - radius), 0);
+        const int maxx = std::min((int) std::floor(px + radius), w - 1), maxy = std::min((int) std::floor(py + radius), h - 1);
+        for (int y = miny; y <= maxy; ++y) {
+            const Float wy = evalDiscretized(y - py);
+            for (int x = minx; x <= maxx; ++x) {
+                const Float wgt = evalDiscretized(x - px) * wy;
+                Float *dest = &data[((size_t) y * w + x) * 3];
+                dest[0] += wgt * value.r; dest[1] += wgt * value.g; dest[2] += wgt * value.b;
+            }
+        }
+        return true;
+    }
+};
+
+struct ChainStats {
+    uint64_t mutations = 0, first_accept = 0, first_base = 0, large_accept = 0, large_base = 0, bold_accept = 0, bold_base = 0,
+             second_accept = 0, second_base = 0, second_large_accept = 0, second_large_base = 0,
+             second_bold_accept = 0, second_bold_base = 0, accept = 0, accept_base = 0, paths = 0, rays = 0;
+    void add(const ChainStats &o) {
+        mutations += o.mutations; first_accept += o.first_accept; first_base += o.first_base;
+        large_accept += o.large_accept; large_base += o.large_base; bold_accept += o.bold_accept; bold_base += o.bold_base;
+        second_accept += o.second_accept; second_base += o.second_base;
+        second_large_accept += o.second_large_accept; second_large_base += o.second_large_base;
+        second_bold_accept += o.second_bold_accept; second_bold_base += o.second_bold_base;
+        accept += o.accept; accept_base += o.accept_base; paths += o.paths; rays += o.rays;
+    }
+};
+
+inline PathSamplerConfig pathConfigOf(const dr_config &c) {
+    PathSamplerConfig p;
+    p.technique = c.technique; p.maxDepth = c.max_depth; p.rrDepth = c.rr_depth;
+    p.excludeDirectIllum = c.direct_samples >= 0;   // separateDirect (drmlt.cpp:233)
+    p.lightImage = c.light_image != 0;
+    return p;
+}
+
+// One bootstrap path sample `index` (generateSeeds body, pathsampler.cpp:879-920): all three
+// samplers replay the BOOT stream; MMLT depth = (index % maxDepth) + 1.
+struct BootSampler : Sampler {
+    uint64_t seed, index; int samplerId; int pos = 0;
+    Float next1D() override { return KeyedSource::boot(seed, index, samplerId, pos++); }
+};
+inline int bootstrapDepth(const dr_config &c, uint64_t index) {
+    return c.technique == DR_TECH_MMLT ? (int) (index % (uint64_t) c.max_depth) + 1 : -1;
+}
+inline void bootstrapSample(const Scene &sc, const dr_config &c, uint64_t index, SplatList &list, uint64_t *rays = nullptr) {
+    BootSampler se, em, di;
+    se.seed = em.seed = di.seed = c.seed; se.index = em.index = di.index = index;
+    se.samplerId = 0; em.samplerId = 1; di.samplerId = 2;
+    PathSampler ps(&sc, pathConfigOf(c), &em, &se, &di);
+    ps.sampleSplats(list, bootstrapDepth(c, index));
+    if (rays) *rays += ps.ctx.rays;
+}
+
+struct StepRecord { Float L_x, L_y, L_z, a1, a2; bool large, acc1, did2, acc2; };
+
+// ------------------------------------------------------------------ DRMLTRenderer::process (+ processMixture)
+struct ChainRunner {
+    const Scene &sc;
+    dr_config cfg;
+    Float b;                    // m_config.luminance
+    Film *film;                 // may be null
+    ChainStats stats;
+    ChainRunner(const Scene &s, const dr_config &c, Float b_, Film *f) : sc(s), cfg(c), b(b_), film(f) {}
+
+    static bool invalidStrict(Float x) { return std::isnan(x) || std::isinf(x) || x <= 0; }   // drmlt_proc.cpp:428
+    static bool invalidLoose(Float x) { return std::isnan(x) || std::isinf(x) || x < 0; }     // :181
+    static Float metropolisClamp(Float x) { return std::min((Float) 1.0, x); }                // :425 (NaN -> 1)
+
+    void splat(const SplatList &l, Float weight) {
+        if (!film || cfg.acceptance_map || !(weight > 0)) return;
+        for (size_t k = 0; k < l.size(); ++k) {
+            RGB value = l.splats[k].second * weight;
+            if (value.isValid()) film->put(l.splats[k].first, value);
+        }
+    }
+    void splatAcceptanceOnly(const SplatList &l, int stage) {   // drmlt_proc.cpp:443-450
+        if (!film || !cfg.acceptance_map) return;
+        for (size_t k = 0; k < l.size(); ++k)
+            film->put(l.splats[k].first, stage == 0 ? RGB(1, 0, 0) : RGB(0, 1, 0));
+    }
+
+    // chain `chainId`, seeded from bootstrap sample `seedIndex`; records (optional) has nMutations entries
+    void runDRMLT(uint64_t chainId, uint64_t seedIndex, int depth, uint64_t nMutations, StepRecord *records) {
+        KeyedSource src; src.seed = cfg.seed; src.chain = chainId;
+        MaxDim md = findMaxDimensions(cfg.max_depth, cfg.rr_depth, depth, cfg.technique, cfg.direct_sampling != 0);
+        DRMLTSampler sensorS, emitterS, directS;
+        DRMLTSampler *all[3] = { &sensorS, &emitterS, &directS };
+        size_t dims[3] = { (size_t) md.sensor, (size_t) md.emitter, (size_t) md.direct };
+        for (int i = 0; i < 3; ++i) {
+            DRMLTSampler &s = *all[i];
+            s.type = cfg.type; s.samplerId = i; s.src = &src; s.maxDim = dims[i];
+            s.sigma = cfg.sigma; s.scaleSecond = cfg.scale_second;
+            // seed replay + fillReplay (drmlt_proc.cpp:467-504): current = BOOT vector of the seed
+            s.uCurrent.resize(dims[i]);
+            for (size_t k = 0; k < dims[i]; ++k) s.uCurrent[k] = KeyedSource::boot(cfg.seed, seedIndex, i, (int) k);
+        }
+        if (cfg.technique == DR_TECH_MMLT) {
+            directS.identityAll = true;
+            if (cfg.fix_emitter_path) emitterS.stage2Identity = true;
+        }
+        PathSampler ps(&sc, pathConfigOf(cfg), &emitterS, &sensorS, &directS);
+        SplatList current, prop1, prop2, reverse;
+        for (auto s : all) { s->arrayMode = true; s->sampleIndex = 0; }
+        ps.sampleSplats(current, depth);
+        for (auto s : all) { s->arrayMode = false; s->resetStage(); }
+        ++stats.paths;
+        if (cfg.acceptance_map) {}   // luminance override only affects develop
+        current.normalize();
+
+        const bool mixture = cfg.use_mixture != 0;
+        for (uint64_t m = 0; m < nMutations; ++m) {
+            src.mut = (uint32_t) m;
+            StepRecord rec = { current.luminance, 0, 0, 0, 0, false, false, false, false };
+            Float a1 = 0, a2 = 0; bool acc1 = false, acc2 = false;
+            bool largeStep = src.coin(0) < cfg.p_large;
+            for (auto s : all) s->setLargeStep(largeStep);
+            ps.sampleSplats(prop1, depth);
+            prop1.normalize();
+            ++stats.mutations; ++stats.paths;
+            auto flipCoin = [&](Float x, int which) { return (x >= 1) || (src.coin(which) < x); };
+
+            if (mixture) {   // processMixture (drmlt_proc.cpp:161-380)
+                Float a = 0; bool accept = false;
+                if (!invalidLoose(prop1.luminance)) { a = metropolisClamp(prop1.luminance / current.luminance); accept = flipCoin(a, 1); }
+                bool doSecond = false;
+                if (!largeStep) doSecond = flipCoin(0.5, 3);
+                SplatList *proposed = &prop1;
+                if (doSecond) {
+                    sensorS.nextStage(); directS.nextStage();
+                    if (cfg.fix_emitter_path) emitterS.nextStage(current.t == 1); else emitterS.nextStage();
+                    ps.sampleSplats(prop2, depth); prop2.normalize(); ++stats.paths;
+                    proposed = &prop2;
+                    if (invalidLoose(prop2.luminance)) { a = 0; accept = false; }
+                    else { a = metropolisClamp(prop2.luminance / current.luminance); accept = flipCoin(a, 2); }
+                }
+                splat(current, 1.0 - a);
+                splat(*proposed, a);
+                rec.large = largeStep; rec.L_y = prop1.luminance; rec.L_z = doSecond ? prop2.luminance : 0;
+                rec.did2 = doSecond; rec.a1 = doSecond ? 0 : a; rec.a2 = doSecond ? a : 0;
+                rec.acc1 = accept && !doSecond; rec.acc2 = accept && doSecond;
+                stats.accept_base++;
+                if (!doSecond) { stats.first_base++; if (largeStep) stats.large_base++; else stats.bold_base++; }
+                else stats.second_base++;
+                if (accept) {
+                    stats.accept++;
+                    if (!doSecond) { stats.first_accept++; if (largeStep) stats.large_accept++; else stats.bold_accept++; }
+                    else stats.second_accept++;
+                    std::swap(current, *proposed);
+                    for (auto s : all) s->accept(!doSecond);
+                } else {
+                    for (auto s : all) s->reject();
+                }
+                if (records) records[m] = rec;
+                continue;
+            }
+
+            // first stage (drmlt_proc.cpp:543-550)
+            if (!invalidStrict(prop1.luminance)) { a1 = metropolisClamp(prop1.luminance / current.luminance); acc1 = flipCoin(a1, 1); }
+            bool doSecond = !acc1;
+            if (!cfg.timid_after_large) doSecond = doSecond && !largeStep;
+            prop2.clear();
+            if (doSecond) {
+                sensorS.nextStage(); directS.nextStage();
+                if (cfg.fix_emitter_path) emitterS.nextStage(current.t == 1); else emitterS.nextStage();
+                ps.sampleSplats(prop2, depth); prop2.normalize(); ++stats.paths;
+                if (!invalidStrict(prop2.luminance)) {
+                    if (cfg.type == DR_TYPE_GREEN) {   // :588-621
+                        for (auto s : all) s->setReverse(true);
+                        ps.sampleSplats(reverse, depth); reverse.normalize(); ++stats.paths;
+                        Float aReverse = invalidStrict(reverse.luminance) ? 0.0 : metropolisClamp(reverse.luminance / prop2.luminance);
+                        if (aReverse == 1) { a2 = 0; acc2 = false; }
+                        else {
+                            Float lumRatio = prop2.luminance / current.luminance;
+                            a2 = metropolisClamp(lumRatio * (1.0 - aReverse) / (1.0 - a1));
+                            acc2 = flipCoin(a2, 2);
+                        }
+                        for (auto s : all) s->setReverse(false);
+                    } else if (cfg.type == DR_TYPE_MIRA) {   // :625-650
+                        Float aReverse = metropolisClamp(prop1.luminance / prop2.luminance);
+                        if (aReverse >= 1) { a2 = 0; acc2 = false; }
+                        else {
+                            Float transitionRatio = largeStep ? 1.0 :
+                                sensorS.getTransitionRatio() * emitterS.getTransitionRatio() * directS.getTransitionRatio();
+                            if (invalidStrict(transitionRatio)) { a2 = 0; acc2 = false; }
+                            else {
+                                Float lumRatio = prop2.luminance / current.luminance;
+                                a2 = metropolisClamp(lumRatio * transitionRatio * (1.0 - aReverse) / (1.0 - a1));
+                                acc2 = flipCoin(a2, 2);
+                            }
+                        }
+                    } else {   // orbital :655-669
+                        if (prop2.luminance < prop1.luminance) { a2 = 0; acc2 = false; }
+                        else if (prop2.luminance >= current.luminance) { a2 = 1.0; acc2 = true; }
+                        else {
+                            a2 = (prop2.luminance - prop1.luminance) / (current.luminance - prop1.luminance);
+                            acc2 = flipCoin(a2, 2);
+                        }
+                    }
+                }
+            }
+            // expectation weights (:676-688)
+            Float w1 = a1, w2 = (1.0 - a1) * a2, wc = 1.0 - w1 - w2;
+            splat(current, wc); splat(prop1, w1); splat(prop2, w2);
+            rec.large = largeStep; rec.L_y = prop1.luminance; rec.L_z = doSecond ? prop2.luminance : 0;
+            rec.a1 = a1; rec.a2 = a2; rec.acc1 = acc1; rec.did2 = doSecond; rec.acc2 = acc2;
+            if (records) records[m] = rec;
+
+            if (acc1 || acc2) {   // :691-742
+                // NB: after the swap proposed.* holds the OLD current state, and that is what the reference
+                // hands to splatAcceptanceOnly (drmlt_proc.cpp:695-708): the map is binned at the state left.
+                if (acc1) { std::swap(prop1, current); if (!largeStep) splatAcceptanceOnly(prop1, 0); }
+                else { std::swap(prop2, current); splatAcceptanceOnly(prop2, 1); }
+                for (auto s : all) s->accept(acc1);
+                stats.accept_base++; stats.accept++;
+                if (acc1) {
+                    stats.first_base++; stats.first_accept++;
+                    if (largeStep) { stats.large_base++; stats.large_accept++; } else { stats.bold_base++; stats.bold_accept++; }
+                } else {
+                    stats.accept_base++; stats.first_base++; stats.second_base++; stats.second_accept++;
+                    if (largeStep) { stats.large_base++; stats.second_large_base++; stats.second_large_accept++; }
+                    else { stats.bold_base++; stats.second_bold_base++; stats.second_bold_accept++; }
+                }
+            } else {              // :746-769
+                for (auto s : all) s->reject();
+                stats.accept_base++; stats.first_base++;
+                if (largeStep) { stats.large_base++; if (doSecond) { stats.second_base++; stats.second_large_base++; stats.accept_base++; } }
+                else { stats.bold_base++; if (doSecond) { stats.second_base++; stats.second_bold_base++; stats.accept_base++; } }
+            }
+        }
+        stats.rays += ps.ctx.rays;
+    }
+
+    // PSSMLTRenderer::process (pssmlt_proc.cpp:110-285)
+    void runPSSMLT(uint64_t chainId, uint64_t seedIndex, int depth, uint64_t nMutations, StepRecord *records) {
+        KeyedSource src; src.seed = cfg.seed; src.chain = chainId;
+        MaxDim md = findMaxDimensions(cfg.max_depth, cfg.rr_depth, depth, cfg.technique, cfg.direct_sampling != 0);
+        PSSMLTSampler sensorS, emitterS, directS;
+        PSSMLTSampler *all[3] = { &sensorS, &emitterS, &directS };
+        size_t dims[3] = { (size_t) md.sensor, (size_t) md.emitter, (size_t) md.direct };
+        for (int i = 0; i < 3; ++i) {
+            PSSMLTSampler &s = *all[i];
+            s.samplerId = i; s.src = &src; s.maxDim = dims[i]; s.useKelemen = cfg.kelemen_style_mutation != 0;
+            s.configure(cfg.mutation_size_low, cfg.mutation_size_high, cfg.sigma);
+            s.u.resize(dims[i]);
+            for (size_t k = 0; k < dims[i]; ++k) s.u[k] = KeyedSource::boot(cfg.seed, seedIndex, i, (int) k);
+        }
+        PathSampler ps(&sc, pathConfigOf(cfg), &emitterS, &sensorS, &directS);
+        SplatList current, proposed;
+        for (auto s : all) { s->arrayMode = true; s->sampleIndex = 0; }
+        ps.sampleSplats(current, depth);
+        for (auto s : all) { s->arrayMode = false; s->sampleIndex = 0; }
+        ++stats.paths;
+        current.normalize();
+        Float cumulativeWeight = 0;
+        const bool kelemenW = cfg.kelemen_style_weights != 0;
+        for (uint64_t m = 0; m < nMutations; ++m) {
+            src.mut = (uint32_t) m;
+            bool largeStep = src.coin(0) < cfg.p_large;
+            for (auto s : all) s->setLargeStep(largeStep);
+            ps.sampleSplats(proposed, depth);
+            proposed.normalize();
+            ++stats.mutations; ++stats.paths;
+            Float a = std::min((Float) 1.0, proposed.luminance / current.luminance);
+            if (std::isnan(proposed.luminance) || proposed.luminance < 0) a = 0;
+            bool accept; Float currentWeight, proposedWeight;
+            if (a > 0) {
+                if (kelemenW) {
+                    currentWeight = (1 - a) * current.luminance / (current.luminance / b + cfg.p_large);
+                    proposedWeight = (a + (largeStep ? 1 : 0)) * proposed.luminance / (proposed.luminance / b + cfg.p_large);
+                } else { currentWeight = 1 - a; proposedWeight = a; }
+                accept = (a == 1) || (src.coin(1) < a);
+            } else {
+                currentWeight = kelemenW ? current.luminance / (current.luminance / b + cfg.p_large) : 1;
+                proposedWeight = 0; accept = false;
+            }
+            cumulativeWeight += currentWeight;
+            StepRecord rec = { current.luminance, proposed.luminance, 0, a, 0, largeStep, accept, false, false };
+            if (records) records[m] = rec;
+            stats.accept_base++;
+            if (largeStep) stats.large_base++; else stats.bold_base++;
+            if (accept) {
+                splatNonZero(current, cumulativeWeight);
+                cumulativeWeight = proposedWeight;
+                std::swap(proposed, current);
+                for (auto s : all) s->accept();
+                stats.accept++;
+                if (largeStep) stats.large_accept++; else stats.bold_accept++;
+            } else {
+                splatNonZero(proposed, proposedWeight);
+                for (auto s : all) s->reject();
+            }
+        }
+        splatNonZero(current, cumulativeWeight);
+        stats.rays += ps.ctx.rays;
+    }
+    void splatNonZero(const SplatList &l, Float weight) {   // pssmlt_proc.cpp:229-233
+        if (!film) return;
+        for (size_t k = 0; k < l.size(); ++k) {
+            RGB value = l.splats[k].second * weight;
+            if (!value.isZero()) film->put(l.splats[k].first, value);
+        }
+    }
+    void run(uint64_t chainId, uint64_t seedIndex, int depth, uint64_t nMutations, StepRecord *records) {
+        if (cfg.integrator == DR_INTEGRATOR_PSSMLT) runPSSMLT(chainId, seedIndex, depth, nMutations, records);
+        else runDRMLT(chainId, seedIndex, depth, nMutations, records);
+    }
+};
+
+// develop (drmlt_proc.cpp:813-854): image = accum * (b / mean pixel luminance)
+inline void develop(const Film &film, Float b, bool acceptanceMap, float *out) {
+    size_t n = (size_t) film.w * film.h;
+    Float avg = 0;
+    for (size_t i = 0; i < n; ++i) avg += RGB(film.data[3 * i], film.data[3 * i + 1], film.data[3 * i + 2]).luminance();
+    avg /= (Float) n;
+    Float factor = acceptanceMap ? 1.0 : b / avg;
+    for (size_t i = 0; i < 3 * n; ++i) out[i] = (float) (film.data[i] * factor);
+}
+
+} // namespace orc
