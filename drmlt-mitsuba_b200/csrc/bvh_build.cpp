@@ -1,0 +1,130 @@
+// bvh_build.cpp -- host-side binned-SAH BVH2 build, flattened into the 64-byte node layout of
+// scene.h.  Replaces the reference's SAH kd-tree construction (include/mitsuba/render/gkdtree.h)
+// for this path; what matters for parity is only the set of triangles, not the tree.
+#include "scene.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -lo[a]; } }
+    void grow(const Box &b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+int as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+float as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+
+} // namespace
+
+void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out) {
+    const int NB = 16, LEAF = 4;
+    std::vector<Box> box(nTris);
+    std::vector<float> cen(3 * (size_t) nTris);
+    out.order.resize(nTris);
+    for (uint32_t i = 0; i < nTris; ++i) {
+        out.order[i] = i;
+        Box b; b.reset();
+        for (int v = 0; v < 3; ++v)
+            for (int a = 0; a < 3; ++a) {
+                float x = P[3 * (size_t) I[3 * (size_t) i + v] + a];
+                b.lo[a] = std::min(b.lo[a], x); b.hi[a] = std::max(b.hi[a], x);
+            }
+        box[i] = b;
+        for (int a = 0; a < 3; ++a) cen[3 * (size_t) i + a] = 0.5f * (b.lo[a] + b.hi[a]);
+    }
+    out.nodes.clear();
+    out.rootIsLeaf = nTris <= (uint32_t) LEAF;
+    if (out.rootIsLeaf) {
+        // one pseudo node whose child0 is the leaf and child1 an empty box
+        Box b; b.reset();
+        for (uint32_t i = 0; i < nTris; ++i) b.grow(box[i]);
+        float inf = std::numeric_limits<float>::infinity();
+        out.nodes.push_back(make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]));
+        out.nodes.push_back(make_float4(b.hi[1], b.hi[2], inf, inf));
+        out.nodes.push_back(make_float4(inf, -inf, -inf, -inf));
+        out.nodes.push_back(make_float4(as_float(~(int) ((0u << 2) | (nTris ? nTris - 1 : 0))), as_float(~0), 0.f, 0.f));
+        out.rootIsLeaf = 0;   // handled uniformly through the pseudo node
+        return;
+    }
+    struct Task { int node; int child; uint32_t first, count; };
+    std::vector<Task> stack;
+    // node records are patched when the children are known
+    auto alloc_node = [&]() { int n = (int) (out.nodes.size() / 4); out.nodes.resize(out.nodes.size() + 4); return n; };
+    int root = alloc_node();
+    (void) root;
+    // process(range) -> fills node `node`
+    struct Range { int node; uint32_t first, count; };
+    std::vector<Range> work;
+    work.push_back({ 0, 0, nTris });
+    while (!work.empty()) {
+        Range r = work.back(); work.pop_back();
+        // centroid bounds
+        float clo[3], chi[3];
+        for (int a = 0; a < 3; ++a) { clo[a] = std::numeric_limits<float>::infinity(); chi[a] = -clo[a]; }
+        for (uint32_t i = r.first; i < r.first + r.count; ++i) {
+            const float *c = &cen[3 * (size_t) out.order[i]];
+            for (int a = 0; a < 3; ++a) { clo[a] = std::min(clo[a], c[a]); chi[a] = std::max(chi[a], c[a]); }
+        }
+        int bestAxis = -1, bestSplit = -1; float bestCost = std::numeric_limits<float>::infinity();
+        for (int a = 0; a < 3; ++a) {
+            float ext = chi[a] - clo[a];
+            if (!(ext > 0.f)) continue;
+            uint32_t cnt[NB] = { 0 }; Box bb[NB];
+            for (int b = 0; b < NB; ++b) bb[b].reset();
+            float scale = NB / ext;
+            for (uint32_t i = r.first; i < r.first + r.count; ++i) {
+                uint32_t p = out.order[i];
+                int b = std::min(NB - 1, (int) ((cen[3 * (size_t) p + a] - clo[a]) * scale));
+                cnt[b]++; bb[b].grow(box[p]);
+            }
+            float rArea[NB]; uint32_t rCnt[NB];
+            Box acc; acc.reset(); uint32_t c2 = 0;
+            for (int b = NB - 1; b > 0; --b) { acc.grow(bb[b]); c2 += cnt[b]; rCnt[b] = c2; rArea[b] = c2 ? acc.area() : 0.f; }
+            acc.reset(); uint32_t c1 = 0;
+            for (int b = 0; b < NB - 1; ++b) {
+                acc.grow(bb[b]); c1 += cnt[b];
+                if (c1 == 0 || rCnt[b + 1] == 0) continue;
+                float cost = c1 * acc.area() + rCnt[b + 1] * rArea[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = b; }
+            }
+        }
+        uint32_t mid;
+        if (bestAxis >= 0) {
+            float ext = chi[bestAxis] - clo[bestAxis], scale = NB / ext;
+            uint32_t *beg = out.order.data() + r.first, *end = beg + r.count;
+            uint32_t *m = std::partition(beg, end, [&](uint32_t p) {
+                int b = std::min(NB - 1, (int) ((cen[3 * (size_t) p + bestAxis] - clo[bestAxis]) * scale));
+                return b <= bestSplit;
+            });
+            mid = (uint32_t) (m - out.order.data());
+        } else {
+            mid = r.first + r.count / 2;
+        }
+        if (mid == r.first || mid == r.first + r.count) mid = r.first + r.count / 2;
+        uint32_t firsts[2] = { r.first, mid }, counts[2] = { mid - r.first, r.first + r.count - mid };
+        Box cb[2]; int code[2];
+        for (int c = 0; c < 2; ++c) {
+            cb[c].reset();
+            for (uint32_t i = firsts[c]; i < firsts[c] + counts[c]; ++i) cb[c].grow(box[out.order[i]]);
+            if (counts[c] <= (uint32_t) LEAF) {
+                code[c] = ~(int) ((firsts[c] << 2) | (counts[c] - 1));
+            } else {
+                code[c] = alloc_node();
+                work.push_back({ code[c], firsts[c], counts[c] });
+            }
+        }
+        float4 *n = &out.nodes[4 * (size_t) r.node];
+        n[0] = make_float4(cb[0].lo[0], cb[0].lo[1], cb[0].lo[2], cb[0].hi[0]);
+        n[1] = make_float4(cb[0].hi[1], cb[0].hi[2], cb[1].lo[0], cb[1].lo[1]);
+        n[2] = make_float4(cb[1].lo[2], cb[1].hi[0], cb[1].hi[1], cb[1].hi[2]);
+        n[3] = make_float4(as_float(code[0]), as_float(code[1]), 0.f, 0.f);
+    }
+}

@@ -1,0 +1,77 @@
+// scene.h -- GPU-resident scene: BVH, triangles, materials, emitters, camera.
+//
+// Data layout in HBM (all read-only during rendering, 16-byte vector loads):
+//   nodes   : 64 B / inner node = 4 x float4
+//               n0 = (lo0.x lo0.y lo0.z hi0.x)  n1 = (hi0.y hi0.z lo1.x lo1.y)
+//               n2 = (lo1.z hi1.x hi1.y hi1.z)  n3 = (child0, child1, -, -) as int bits
+//             child >= 0: inner node index; child < 0: leaf, ~child = (firstTri << 2) | (count - 1), count <= 4
+//   tris    : 48 B / triangle in LEAF ORDER = 3 x float4
+//               t0 = (p0.x p0.y p0.z e1.x) t1 = (e1.y e1.z e2.x e2.y) t2 = (e2.z, prim, matflags, emitter)
+//             prim = index in the caller's triangle order, matflags = material | (DR_TRI_SMOOTH << 31 .. )
+//   normals : 48 B / triangle in leaf order (only read for smooth triangles at the closest hit)
+//   em_tris : 96 B / emitter triangle in EMITTER order: p0,e1,e2 + n0,n1,n2 (position sampling)
+//   em_cdf  : double prefix sums of the per-emitter triangle areas (pmf.h DiscreteDistribution)
+// Replaces ShapeKDTree + TriAccel (src/librender/skdtree.cpp, include/mitsuba/render/triaccel.h) for this path.
+#pragma once
+#include "common.cuh"
+#include "../../include/drmlt_b200.h"
+#include <vector>
+#include <string>
+
+struct DevMaterial {      // 64 B, mirrors dr_material
+    int32_t type; uint32_t flags;
+    float reflectance[3], transmittance[3], eta[3], k[3];
+    float alpha, pad;
+};
+
+struct DevEmitter {       // 48 B
+    float radiance[3];
+    float area, invArea;
+    float pdfDiscrete;    // emitterPDF[e]
+    uint32_t firstEmTri;  // offset into em_tris
+    uint32_t nTris;
+    uint32_t cdfOffset;   // offset into em_cdf (nTris + 1 entries)
+    uint32_t pad[3];
+};
+
+struct DevCamera {
+    float m[12];          // rows of the 3x4 camera-to-world matrix
+    float3 pos, dir;
+    float tanHalf, aspect, nearClip, farClip;
+    float resX, resY, rectX, rectY, normalization;
+};
+
+struct DevScene {
+    const float4 *nodes;
+    const float4 *tris;
+    const float4 *normals;
+    const float4 *emTris;
+    const double *emCdf;
+    const double *emitterCdf;       // nEmitters + 1 (selection by sampling weight)
+    const DevEmitter *emitters;
+    const DevMaterial *materials;
+    int nEmitters, nTris, nNodes;
+    int rootIsLeaf;                  // degenerate scenes with <= 4 triangles
+    DevCamera cam;
+    float epsilon, shadowEpsilon;
+};
+
+// Host-side BVH build output (bvh_build.cpp)
+struct BuiltBVH {
+    std::vector<float4> nodes;       // 4 per node
+    std::vector<uint32_t> order;     // leaf order -> caller's triangle index
+    int rootIsLeaf = 0;
+};
+void build_bvh(const float *positions, const uint32_t *indices, uint32_t nTris, BuiltBVH &out);
+
+struct dr_scene_t {
+    int device = 0;
+    DevScene dev;                    // pointers are device pointers
+    std::vector<void *> allocations;
+    int filmW = 0, filmH = 0;
+    uint32_t nTris = 0, nNodes = 0;
+    volatile int cancel = 0;
+    size_t bytes = 0;
+};
+
+void dr_set_error(const char *fmt, ...);
