@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- chain mutations/s of the drmlt hot path on N B200s (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference --steps K --warmup W    (CPU arm: the oracle port on all host cores)
+
+Workload (config.workload): C5 -- procedural occluded-light "door" scene, ~1M triangles, 1280x720,
+drmlt type=orbital technique=mmlt, maxDepth 8, directSamples=-1, synthetic data generated here.
+A step = every resident chain of every rank advances `--mutations` iterations of the MLT loop
+(dr_job_run); per-GPU work is fixed as N grows (weak scaling; chains are independent, so there is
+no data-path collective -- b all-reduce and film reduce happen once per job and are part of e2e).
+`value` = mutations of all ranks / max-over-ranks device time (CUDA events on the launching stream,
+scene + chain state resident in HBM).  `e2e` = the same metric through the public whole-job call
+(scene re-upload H2D + bootstrap + b all-reduce + chains + film reduce + develop + image D2H).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "chain_mutations_per_sec"
+UNIT = "mutations/s"
+PARAMS = dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)
+
+
+def workload_name(scene_name, data):
+    return "C5 %s scene %d tris %dx%d drmlt orbital mmlt maxDepth=8 directSamples=-1" % (
+        scene_name, data.n_triangles, data.film[0], data.film[1])
+
+
+def build_scene(args):
+    from drmlt_mitsuba_b200 import scenes
+    if args.scene == "door":
+        return scenes.door_scene()
+    return scenes.SCENES[args.scene]()
+
+
+def ray_bytes(n_tris):
+    """B_ray(T) = 64*ceil(log2(T/4)) + 4*48 + 64."""
+    return 64 * int(np.ceil(np.log2(max(n_tris, 8) / 4.0))) + 4 * 48 + 64
+
+
+def mutation_bytes(n_tris, paths_per_mut, rays_per_path, dims, footprint):
+    """B_mut = p*d*B_ray + B_state + B_splat; dims = D_s + D_e + D_d of the chain."""
+    b_state = 2 * dims * 4 * (1 + paths_per_mut)
+    b_splat = 3 * 16 * footprint * 3
+    return paths_per_mut * rays_per_path * ray_bytes(n_tris) + b_state + b_splat
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------- CPU arm
+def oracle_scene(data):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    oracle_lib.build()
+    return oracle_lib, oracle_lib.OracleScene(data)
+
+
+def cpu_config(seed=99):
+    """The oracle in the reference's default precision (double, Epsilon 1e-7) on the same parameters."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from drmlt_mitsuba_b200 import abi
+    return oracle_lib.default_config(integrator=abi.DR_INTEGRATOR_DRMLT, technique=abi.DR_TECH_MMLT, type=abi.DR_TYPE_ORBITAL,
+                                     max_depth=8, direct_samples=-1, direct_sampling=0, kelemen_style_weights=0, seed=seed)
+
+
+def cpu_sample(orc, cfg, threads, target_s, n_boot=40000):
+    """A bounded sample of the workload on the host cores: bootstrap, then `threads*4` chains."""
+    lum, dep = orc.bootstrap(cfg, 0, n_boot)
+    seeds = np.nonzero(lum > 0)[0]
+    b = float(lum.mean() * 8)
+    n_chains = threads * 4
+    rng = np.random.RandomState(1)
+    p = lum[seeds] / lum[seeds].sum()
+    pick = seeds[rng.choice(len(seeds), n_chains, p=p)]
+    ids = np.arange(n_chains, dtype=np.uint64)
+
+    def run(steps):
+        t0 = time.perf_counter()
+        _, _, st = orc.chain_steps(cfg, b, pick.astype(np.uint64), dep[pick], ids, steps, want_film=True, threads=threads, want_records=False)
+        return st.mutations / (time.perf_counter() - t0), st
+    rate, _ = run(200)                                            # calibration
+    steps = int(max(200, min(2_000_000, rate * target_s / n_chains)))
+    rate, st = run(steps)
+    return rate, n_chains, steps, st
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    data = build_scene(args)
+    _, orc = oracle_scene(data)
+    cfg = cpu_config()
+    threads = os.cpu_count() or 1
+    per_step_s = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    rates, info = [], None
+    for i in range(args.warmup + args.steps):
+        rate, n_chains, steps, st = cpu_sample(orc, cfg, threads, per_step_s)
+        if i >= args.warmup:
+            rates.append(rate)
+        info = (n_chains, steps)
+    value = float(np.mean(rates))
+    sample = "%d chains x %d mutations per step, oracle port (double precision) of DRMLTRenderer::process, %d threads" % (info[0], info[1], threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * info[0] * info[1] / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.scene, data)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    from drmlt_mitsuba_b200 import abi, distributed
+    from drmlt_mitsuba_b200.integrator import Job, Scene, make_config
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    __graft_entry__.build()
+
+    data = build_scene(args)
+    t0 = time.perf_counter()
+    scene = Scene(data, device=local)
+    scene_create_s = time.perf_counter() - t0
+    scene_bytes = scene.reupload()
+
+    params = dict(PARAMS, seed=args.seed, sampleCount=args.spp * world)   # weak scaling: W*H*spp mutations per GPU
+    if args.chains:
+        params["chains"] = args.chains
+    cfg = make_config(rank=rank, worldSize=world, **params)
+    job = Job(scene, cfg)
+    s, c = job.bootstrap()
+    b = distributed.all_reduce_normalization(s, c, True, cfg.max_depth, dist if world > 1 else None, dev)
+    job.seed_chains(b)
+    n_chains = job.num_chains
+    M = args.mutations
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        job.run(M)
+    barrier()
+    st0 = job.stats()
+    wall0 = time.perf_counter()
+    with ClockSampler(local) as clk:
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            job.run(M)                                              # device-timed inside (events on the launching stream)
+        barrier()
+    wall = time.perf_counter() - wall0
+    st1 = job.stats()
+    dev_ms = st1.chains_ms - st0.chains_ms
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    muts_rank = st1.mutations - st0.mutations
+    muts_all = muts_rank * world
+    value = muts_all / (max_ms * 1e-3)
+    launches = int(st1.kernel_launches - st0.kernel_launches)
+
+    # ---- roofline of the dominant kernel (k_chain_step): algorithmic bytes per launch / launch duration
+    paths_per_mut = (st1.paths - st0.paths) / max(1, muts_rank)
+    rays_per_path = (st1.rays - st0.rays) / max(1, st1.paths - st0.paths)
+    mean_depth = 4.5                                                # depths 1..8 equally likely
+    dims = 2 * (3 * (mean_depth + 2)) + 1
+    b_mut = mutation_bytes(data.n_triangles, paths_per_mut, rays_per_path, dims, 16)
+    ms_per_launch = dev_ms / max(1, launches)
+    muts_per_launch = muts_rank / max(1, launches)
+    achieved = b_mut * muts_per_launch / (ms_per_launch * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "measured"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_chain_step_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_chain_step", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "bytes_per_mutation": b_mut, "paths_per_mutation": paths_per_mut,
+                "rays_per_path": rays_per_path, "mrays_per_s": (st1.rays - st0.rays) * world / (max_ms * 1e-3) / 1e6,
+                "ms_per_launch": ms_per_launch, "mutations_per_launch": muts_per_launch}
+    job.close()
+
+    # ---- e2e: whole job through the public API with host buffers
+    e2e_params = dict(PARAMS, seed=args.seed + 1, sampleCount=args.e2e_spp * world)
+    if args.chains:
+        e2e_params["chains"] = args.chains
+    barrier()
+    e0 = time.perf_counter()
+    h2d = scene.reupload()
+    img, est, eb = distributed.render(scene, e2e_params, dist if world > 1 else None, rank, world)
+    barrier()
+    e_wall = time.perf_counter() - e0
+    te = torch.tensor([float(est.mutations)], dtype=torch.float64, device=dev)
+    tw = torch.tensor([e_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    W, H = data.film
+    e2e = {"value": float(te.item()) / float(tw.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(W * H * 3 * 4), "seconds": float(tw.item()), "mutations": int(te.item()),
+           "what": "dr_scene_reupload + bootstrap + b all-reduce + chains + film reduce + develop + image D2H; sampleCount=%d" % (args.e2e_spp * world)}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            try:
+                _, orc = oracle_scene(data)
+                threads = os.cpu_count() or 1
+                rate, nch, steps, _ = cpu_sample(orc, cpu_config(), threads, args.cpu_seconds)
+                cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": "%d chains x %d mutations of the same workload, oracle port (double) of DRMLTRenderer::process" % (nch, steps)}
+            except Exception as ex:                                   # the baseline is reported, never required
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": workload_name(args.scene, data), "chains_per_gpu": int(n_chains), "mutations_per_chain_per_step": M,
+                           "l2": "flushed between timed steps (512 MiB device write)", "b": b, "scene_create_s": scene_create_s,
+                           "scene_bytes": int(scene_bytes), "wall_s_timed_region": wall},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line:
+        print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scene", default="door")
+    ap.add_argument("--mutations", type=int, default=64, help="mutations per chain per step")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = auto)")
+    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--e2e-spp", type=int, default=16, dest="e2e_spp")
+    ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
+    ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

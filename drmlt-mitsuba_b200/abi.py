@@ -95,7 +95,7 @@ class dr_step_record(C.Structure):
 # every symbol include/drmlt_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "dr_abi_version", "dr_last_error", "dr_device_count", "dr_config_default", "dr_config_set",
-    "dr_config_validate", "dr_scene_create", "dr_scene_destroy", "dr_render", "dr_cancel",
+    "dr_config_validate", "dr_scene_create", "dr_scene_destroy", "dr_scene_reupload", "dr_render", "dr_cancel",
     "dr_job_create", "dr_job_destroy", "dr_job_bootstrap", "dr_job_seed_chains", "dr_job_run",
     "dr_job_film_device", "dr_job_develop", "dr_job_stats", "dr_job_num_chains", "dr_job_total_mutations",
     "dr_trace_rays", "dr_eval_paths", "dr_chain_steps", "dr_bootstrap_luminance", "dr_max_dimensions",
@@ -131,6 +131,7 @@ def load_library(path=None):
     lib.dr_scene_create.argtypes = [P(dr_scene_desc), C.c_int, P(C.c_void_p)]
     lib.dr_scene_destroy.argtypes = [C.c_void_p]
     lib.dr_scene_destroy.restype = None
+    lib.dr_scene_reupload.argtypes = [C.c_void_p, P(C.c_int64)]
     lib.dr_render.argtypes = [C.c_void_p, P(dr_config), P(C.c_float), P(dr_stats)]
     lib.dr_cancel.argtypes = [C.c_void_p]
     lib.dr_cancel.restype = None

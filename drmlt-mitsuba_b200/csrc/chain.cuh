@@ -85,7 +85,7 @@ DR_D float metropolis_clamp(float x) { return x < 1.0f ? x : 1.0f; }            
 
 // ---------------------------------------------------------------- bootstrap (generateSeeds body)
 __global__ void __launch_bounds__(128)
-k_bootstrap(DevScene sc, PathCfg pc, PssParams pp, unsigned long long first, long long n, float *lum, unsigned long long *counters) {
+k_bootstrap(const __grid_constant__ DevScene sc, const __grid_constant__ PathCfg pc, const __grid_constant__ PssParams pp, unsigned long long first, long long n, float *lum, unsigned long long *counters) {
     const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
     uint32_t rays = 0;
     if (i < n) {
@@ -203,7 +203,7 @@ __global__ void k_resample(const double *cdf, long long n, unsigned long long se
 
 // ---------------------------------------------------------------- chain initialisation (seed replay)
 __global__ void __launch_bounds__(128)
-k_init_chains(DevScene sc, PathCfg pc, PssParams pp, ChainArrays ca, unsigned long long *counters) {
+k_init_chains(const __grid_constant__ DevScene sc, const __grid_constant__ PathCfg pc, const __grid_constant__ PssParams pp, const __grid_constant__ ChainArrays ca, unsigned long long *counters) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ca.n) return;
     const unsigned long long sidx = ca.seedIdx[j];
@@ -276,7 +276,8 @@ DR_D void commit_state(const Pss &pss, float *Xbase, size_t n, const int offs[3]
 }
 
 __global__ void __launch_bounds__(128)
-k_chain_step(DevScene sc, PathCfg pc, PssParams pp, ChainParams cp, FilmParams fp, ChainArrays ca, float4 *film,
+k_chain_step(const __grid_constant__ DevScene sc, const __grid_constant__ PathCfg pc, const __grid_constant__ PssParams pp,
+             const __grid_constant__ ChainParams cp, const __grid_constant__ FilmParams fp, const __grid_constant__ ChainArrays ca, float4 *film,
              unsigned long long *counters, dr_step_record *records, int recordStride, int steps) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t st[ST_COUNT];
@@ -499,7 +500,7 @@ k_chain_step(DevScene sc, PathCfg pc, PssParams pp, ChainParams cp, FilmParams f
 }
 
 // PSSMLT's "last splat" of the accumulated current state (pssmlt_proc.cpp:274-279); resets the weight
-__global__ void k_flush_pssmlt(ChainArrays ca, FilmParams fp, float4 *film) {
+__global__ void k_flush_pssmlt(const __grid_constant__ ChainArrays ca, const __grid_constant__ FilmParams fp, float4 *film) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ca.n) return;
     float4 v = ca.val[j];
@@ -527,7 +528,7 @@ __global__ void k_develop(const float4 *film, long long n, float factor, float *
 }
 
 // ---------------------------------------------------------------- replay kernels
-__global__ void k_trace(DevScene sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits) {
+__global__ void k_trace(const __grid_constant__ DevScene sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits) {
     const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
     if (i >= n) return;
     const dr_ray r = rays[i];
@@ -541,7 +542,7 @@ __global__ void k_trace(DevScene sc, const dr_ray *rays, long long n, int shadow
 }
 
 __global__ void __launch_bounds__(128)
-k_eval_paths(DevScene sc, PathCfg pc, PssParams pp, const float *us, int ds, const float *ue, int de, const float *ud, int dd,
+k_eval_paths(const __grid_constant__ DevScene sc, const __grid_constant__ PathCfg pc, const __grid_constant__ PssParams pp, const float *us, int ds, const float *ue, int de, const float *ud, int dd,
              const int *depth, long long n, dr_path_result *out) {
     const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -1,0 +1,945 @@
+// drmlt_b200.cu -- host side of the C ABI (include/drmlt_b200.h): configuration, scene upload,
+// bootstrap / chain orchestration, develop and the replay entry points.
+//
+// Host-side counterparts in the reference: DRMLT::DRMLT / PSSMLT::PSSMLT (parameter parsing,
+// src/integrators/drmlt/drmlt.cpp:178-351, src/integrators/pssmlt/pssmlt.cpp:166-308),
+// DRMLT::render / PSSMLT::render (work sizing + bootstrap orchestration, drmlt.cpp:393-611) and
+// DRMLTProcess::develop (drmlt_proc.cpp:813-854).  There is no CPU fallback: every entry point
+// that computes needs a CUDA device and fails with DR_ERR_NO_DEVICE / DR_ERR_CUDA otherwise.
+#include "chain.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_error[1024] = "";
+void dr_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            dr_set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);            \
+            return DR_ERR_CUDA;                                                                           \
+        }                                                                                                 \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+
+extern "C" int dr_abi_version(void) { return DR_ABI_VERSION; }
+extern "C" const char *dr_last_error(void) { return g_error; }
+extern "C" int dr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------ configuration
+extern "C" void dr_config_default(dr_config *c) {
+    memset(c, 0, sizeof(*c));
+    c->integrator = DR_INTEGRATOR_DRMLT;
+    c->technique = -1;                 // required (drmlt.cpp:194-203)
+    c->type = -1;                      // required for drmlt (drmlt.cpp:313-322)
+    c->max_depth = -1;
+    c->rr_depth = 5;
+    c->direct_sampling = 1;
+    c->direct_samples = 16;
+    c->luminance_samples = 100000;
+    c->p_large = 0.3f;
+    c->work_units = -1;
+    c->kelemen_style_weights = 1;
+    c->two_stage = 0;
+    c->timeout = 0;
+    c->average_luminance = -1.0f;
+    c->light_image = 1;
+    c->acceptance_map = 0;
+    c->timid_after_large = 0;
+    c->fix_emitter_path = 0;
+    c->use_mixture = 0;
+    c->sigma = 1.0f / 64.0f;
+    c->scale_second = 0.1f;
+    c->kelemen_style_mutation = 1;
+    c->mutation_size_low = 1.0f / 1024.0f;
+    c->mutation_size_high = 1.0f / 64.0f;
+    c->sample_count = 4;               // IndependentSampler default sampleCount (samplers/independent.cpp)
+    c->rfilter = DR_FILTER_GAUSSIAN;
+    c->n_chains = 0;
+    c->seed = 0x5eed5eedull;
+    c->rank = 0;
+    c->world_size = 1;
+    c->ray_epsilon = 0.f;
+    c->shadow_epsilon = 0.f;
+}
+
+static bool parse_bool(const char *v, int *out) {
+    if (!strcmp(v, "true") || !strcmp(v, "1")) { *out = 1; return true; }
+    if (!strcmp(v, "false") || !strcmp(v, "0")) { *out = 0; return true; }
+    return false;
+}
+static bool parse_int(const char *v, long long *out) {
+    char *end = nullptr;
+    long long x = strtoll(v, &end, 10);
+    if (end == v || *end) return false;
+    *out = x;
+    return true;
+}
+static bool parse_float(const char *v, float *out) {
+    char *end = nullptr;
+    double x = strtod(v, &end);
+    if (end == v || *end) return false;
+    *out = (float) x;
+    return true;
+}
+
+extern "C" dr_status dr_config_set(dr_config *c, const char *key, const char *value) {
+    if (!c || !key || !value) { dr_set_error("dr_config_set: null argument"); return DR_ERR_INVALID_ARG; }
+    struct BoolKey { const char *name; int32_t dr_config::*field; };
+    struct IntKey { const char *name; int32_t dr_config::*field; };
+    struct FloatKey { const char *name; float dr_config::*field; };
+    static const BoolKey bools[] = {
+        { "directSampling", &dr_config::direct_sampling }, { "kelemenStyleWeights", &dr_config::kelemen_style_weights },
+        { "twoStage", &dr_config::two_stage }, { "lightImage", &dr_config::light_image },
+        { "acceptanceMap", &dr_config::acceptance_map }, { "timidAfterLarge", &dr_config::timid_after_large },
+        { "fixEmitterPath", &dr_config::fix_emitter_path }, { "useMixture", &dr_config::use_mixture },
+        { "kelemenStyleMutation", &dr_config::kelemen_style_mutation },
+    };
+    static const IntKey ints[] = {
+        { "maxDepth", &dr_config::max_depth }, { "rrDepth", &dr_config::rr_depth }, { "directSamples", &dr_config::direct_samples },
+        { "luminanceSamples", &dr_config::luminance_samples }, { "workUnits", &dr_config::work_units },
+        { "timeout", &dr_config::timeout }, { "sampleCount", &dr_config::sample_count }, { "chains", &dr_config::n_chains },
+        { "rank", &dr_config::rank }, { "worldSize", &dr_config::world_size },
+    };
+    static const FloatKey floats[] = {
+        { "pLarge", &dr_config::p_large }, { "averageLuminance", &dr_config::average_luminance }, { "sigma", &dr_config::sigma },
+        { "scaleSecond", &dr_config::scale_second }, { "mutationSizeLow", &dr_config::mutation_size_low },
+        { "mutationSizeHigh", &dr_config::mutation_size_high }, { "rayEpsilon", &dr_config::ray_epsilon },
+        { "shadowEpsilon", &dr_config::shadow_epsilon },
+    };
+    if (!strcmp(key, "integrator")) {
+        if (!strcmp(value, "pssmlt")) c->integrator = DR_INTEGRATOR_PSSMLT;
+        else if (!strcmp(value, "drmlt")) c->integrator = DR_INTEGRATOR_DRMLT;
+        else { dr_set_error("Unknown integrator \"%s\" (pssmlt|drmlt)", value); return DR_ERR_INVALID_ARG; }
+        return DR_OK;
+    }
+    if (!strcmp(key, "technique")) {   // drmlt.cpp:194-203
+        if (!strcmp(value, "path")) c->technique = DR_TECH_PATH;
+        else if (!strcmp(value, "bdpt")) c->technique = DR_TECH_BDPT;
+        else if (!strcmp(value, "mmlt")) c->technique = DR_TECH_MMLT;
+        else { dr_set_error("Unknown technique type"); return DR_ERR_INVALID_ARG; }
+        return DR_OK;
+    }
+    if (!strcmp(key, "type")) {        // drmlt.cpp:313-322 ("mirasym" selects the orbital sampler)
+        if (!strcmp(value, "green")) c->type = DR_TYPE_GREEN;
+        else if (!strcmp(value, "mira")) c->type = DR_TYPE_MIRA;
+        else if (!strcmp(value, "orbital") || !strcmp(value, "mirasym")) c->type = DR_TYPE_ORBITAL;
+        else { dr_set_error("Unknown implementation type"); return DR_ERR_INVALID_ARG; }
+        return DR_OK;
+    }
+    if (!strcmp(key, "rfilter")) {
+        if (!strcmp(value, "gaussian")) c->rfilter = DR_FILTER_GAUSSIAN;
+        else if (!strcmp(value, "box")) c->rfilter = DR_FILTER_BOX;
+        else { dr_set_error("Unsupported reconstruction filter \"%s\" (gaussian|box)", value); return DR_ERR_UNSUPPORTED; }
+        return DR_OK;
+    }
+    if (!strcmp(key, "seed")) {
+        char *end = nullptr;
+        unsigned long long x = strtoull(value, &end, 0);
+        if (end == value || *end) { dr_set_error("seed: not an integer: \"%s\"", value); return DR_ERR_INVALID_ARG; }
+        c->seed = x;
+        return DR_OK;
+    }
+    for (const BoolKey &k : bools)
+        if (!strcmp(key, k.name)) {
+            int v;
+            if (!parse_bool(value, &v)) { dr_set_error("%s: not a boolean: \"%s\"", key, value); return DR_ERR_INVALID_ARG; }
+            c->*(k.field) = v;
+            return DR_OK;
+        }
+    for (const IntKey &k : ints)
+        if (!strcmp(key, k.name)) {
+            long long v;
+            if (!parse_int(value, &v)) { dr_set_error("%s: not an integer: \"%s\"", key, value); return DR_ERR_INVALID_ARG; }
+            c->*(k.field) = (int32_t) v;
+            return DR_OK;
+        }
+    for (const FloatKey &k : floats)
+        if (!strcmp(key, k.name)) {
+            float v;
+            if (!parse_float(value, &v)) { dr_set_error("%s: not a number: \"%s\"", key, value); return DR_ERR_INVALID_ARG; }
+            c->*(k.field) = v;
+            return DR_OK;
+        }
+    // accepted and ignored: parameters of the reference that only matter for features outside this path
+    if (!strcmp(key, "firstStage") || !strcmp(key, "firstStageSizeReduction")) return DR_OK;
+    dr_set_error("Unknown parameter \"%s\"", key);
+    return DR_ERR_INVALID_ARG;
+}
+
+extern "C" dr_status dr_config_validate(dr_config *c) {
+    if (!c) { dr_set_error("dr_config_validate: null"); return DR_ERR_INVALID_ARG; }
+    if (c->integrator != DR_INTEGRATOR_PSSMLT && c->integrator != DR_INTEGRATOR_DRMLT) { dr_set_error("Unknown integrator"); return DR_ERR_INVALID_ARG; }
+    if (c->technique < DR_TECH_PATH || c->technique > DR_TECH_MMLT) { dr_set_error("Unknown technique type"); return DR_ERR_INVALID_ARG; }
+    if (c->integrator == DR_INTEGRATOR_DRMLT && (c->type < DR_TYPE_GREEN || c->type > DR_TYPE_ORBITAL)) {
+        dr_set_error("Unknown implementation type"); return DR_ERR_INVALID_ARG;
+    }
+    if (c->technique == DR_TECH_MMLT && c->max_depth == -1) { dr_set_error("Impossible to use MMLT with no max depth"); return DR_ERR_INVALID_ARG; }
+    if (c->technique == DR_TECH_MMLT) { c->direct_sampling = 0; c->kelemen_style_weights = 0; }   // drmlt.cpp:229-231, 266-268
+    if (c->fix_emitter_path && c->technique != DR_TECH_MMLT) { dr_set_error("Impossible to use fixEmitterPath without MMLT"); return DR_ERR_INVALID_ARG; }
+    if (c->integrator == DR_INTEGRATOR_DRMLT && c->scale_second > 1.0f) { dr_set_error("scaleSecond is bigger than the first stage"); return DR_ERR_INVALID_ARG; }
+    if (!(c->p_large >= 0.f && c->p_large <= 1.f)) { dr_set_error("pLarge must be in [0, 1]"); return DR_ERR_INVALID_ARG; }
+    if (c->sample_count <= 0) { dr_set_error("sampleCount must be positive"); return DR_ERR_INVALID_ARG; }
+    if (c->world_size < 1 || c->rank < 0 || c->rank >= c->world_size) { dr_set_error("rank/worldSize out of range"); return DR_ERR_INVALID_ARG; }
+    // limits of the GPU path
+    if (c->max_depth <= 0 || c->max_depth + 3 > DR_MAXK) {
+        dr_set_error("maxDepth must be in [1, %d] on the GPU path (got %d)", DR_MAXK - 3, c->max_depth); return DR_ERR_UNSUPPORTED;
+    }
+    if (c->two_stage) { dr_set_error("twoStage=true is not supported (importance map, SURVEY 8f)"); return DR_ERR_UNSUPPORTED; }
+    if (c->technique == DR_TECH_BDPT && c->direct_sampling) {
+        // the reference overflows its direct sampler in this mode
+        dr_set_error("technique=bdpt requires directSampling=false on the GPU path"); return DR_ERR_UNSUPPORTED;
+    }
+    if (c->acceptance_map && c->integrator == DR_INTEGRATOR_DRMLT && c->rfilter != DR_FILTER_BOX) {
+        dr_set_error("acceptanceMap requires the box reconstruction filter (drmlt_proc.cpp:75-79)"); return DR_ERR_INVALID_ARG;
+    }
+    if (c->rfilter != DR_FILTER_GAUSSIAN && c->rfilter != DR_FILTER_BOX) { dr_set_error("Unsupported rfilter"); return DR_ERR_UNSUPPORTED; }
+    return DR_OK;
+}
+
+static void max_dimensions(const dr_config *c, int depth, int *se, int *em, int *di) {   // pssmlt_utils.h:27-77
+    const int offsetRR = c->rr_depth < c->max_depth ? 1 : 0;
+    int m;
+    if (c->technique == DR_TECH_MMLT) { m = (depth + 2) * 3; if (m & 1) m++; *se = m; *em = m; *di = 1; }
+    else if (c->technique == DR_TECH_PATH) { m = (c->max_depth + 2) * (4 + offsetRR); if (m & 1) m++; *se = m; *em = 0; *di = 0; }
+    else { m = (c->max_depth + 2) * (2 + offsetRR); if (m & 1) m++; *se = m; *em = m; *di = c->direct_sampling ? c->max_depth : 0; }
+}
+extern "C" void dr_max_dimensions(const dr_config *cfg, int depth, int *sensor, int *emitter, int *direct) {
+    max_dimensions(cfg, depth, sensor, emitter, direct);
+}
+
+// ------------------------------------------------------------------ scene
+struct HostUpload { void *dev; std::vector<char> host; };
+
+struct SceneImpl : dr_scene_t {
+    std::vector<HostUpload> uploads;     // host staging copies (kept for dr_scene_reupload)
+    unsigned int *dOrder = nullptr;      // leaf order -> caller's triangle index
+    size_t uploadBytes = 0;
+};
+
+template <class T>
+static dr_status upload(SceneImpl *s, const std::vector<T> &v, const T **devOut) {
+    HostUpload u;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    u.host.assign(bytes, 0);
+    if (!v.empty()) memcpy(u.host.data(), v.data(), v.size() * sizeof(T));
+    CK(cudaMalloc(&u.dev, bytes));
+    s->allocations.push_back(u.dev);
+    CK(cudaMemcpy(u.dev, u.host.data(), bytes, cudaMemcpyHostToDevice));
+    s->bytes += bytes;
+    s->uploadBytes += bytes;
+    *devOut = (const T *) u.dev;
+    s->uploads.push_back(std::move(u));
+    return DR_OK;
+}
+
+static float as_float_bits(int i) { float f; memcpy(&f, &i, 4); return f; }
+
+extern "C" void dr_scene_destroy(dr_scene scene) {
+    if (!scene) return;
+    SceneImpl *s = static_cast<SceneImpl *>(scene);
+    cudaSetDevice(s->device);
+    for (void *p : s->allocations) cudaFree(p);
+    delete s;
+}
+
+extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scene *out) {
+    if (!d || !out) { dr_set_error("dr_scene_create: null argument"); return DR_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (!d->positions || !d->indices || !d->tri_material || !d->tri_emitter || !d->materials || d->n_triangles == 0 ||
+        d->n_vertices == 0 || d->n_materials == 0) {
+        dr_set_error("dr_scene_create: empty scene or missing buffers"); return DR_ERR_INVALID_ARG;
+    }
+    if (d->n_triangles >= (1u << 29)) { dr_set_error("dr_scene_create: too many triangles"); return DR_ERR_UNSUPPORTED; }
+    if (d->n_emitters && !d->emitters) { dr_set_error("dr_scene_create: emitters missing"); return DR_ERR_INVALID_ARG; }
+    if (d->camera.film_width <= 0 || d->camera.film_height <= 0) { dr_set_error("dr_scene_create: bad film size"); return DR_ERR_INVALID_ARG; }
+    for (uint32_t i = 0; i < d->n_triangles; ++i) {
+        if (d->tri_material[i] >= d->n_materials) { dr_set_error("triangle %u: material index out of range", i); return DR_ERR_INVALID_ARG; }
+        if (d->tri_emitter[i] >= (int32_t) d->n_emitters) { dr_set_error("triangle %u: emitter index out of range", i); return DR_ERR_INVALID_ARG; }
+        for (int v = 0; v < 3; ++v)
+            if (d->indices[3 * (size_t) i + v] >= d->n_vertices) { dr_set_error("triangle %u: vertex index out of range", i); return DR_ERR_INVALID_ARG; }
+    }
+    for (uint32_t m = 0; m < d->n_materials; ++m)
+        if (d->materials[m].type < DR_BSDF_DIFFUSE || d->materials[m].type > DR_BSDF_ROUGHCONDUCTOR) {
+            dr_set_error("material %u: unsupported BSDF type %d", m, d->materials[m].type); return DR_ERR_UNSUPPORTED;
+        }
+    for (uint32_t e = 0; e < d->n_emitters; ++e) {
+        const dr_emitter &em = d->emitters[e];
+        if (em.n_tris == 0 || (uint64_t) em.first_tri + em.n_tris > d->n_triangles) { dr_set_error("emitter %u: triangle range out of bounds", e); return DR_ERR_INVALID_ARG; }
+        for (uint32_t t = 0; t < em.n_tris; ++t)
+            if (d->tri_emitter[em.first_tri + t] != (int32_t) e) { dr_set_error("emitter %u: tri_emitter mismatch at triangle %u", e, em.first_tri + t); return DR_ERR_INVALID_ARG; }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        dr_set_error("no CUDA device available (there is no CPU fallback)");
+        return DR_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { dr_set_error("device %d out of range (%d devices)", device, ndev); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(device));
+
+    SceneImpl *s = new SceneImpl();
+    s->device = device;
+    s->filmW = d->camera.film_width; s->filmH = d->camera.film_height;
+    s->nTris = d->n_triangles;
+    dr_status st = DR_OK;
+    auto fail = [&](dr_status code) { dr_scene_destroy(s); return code; };
+
+    BuiltBVH bvh;
+    build_bvh(d->positions, d->indices, d->n_triangles, bvh);
+    s->nNodes = (uint32_t) (bvh.nodes.size() / 4);
+
+    // triangles and shading normals in leaf order
+    const size_t nT = d->n_triangles;
+    std::vector<float4> tris(3 * nT), normals;
+    bool anySmooth = false;
+    for (size_t i = 0; i < nT; ++i)
+        if (d->normals && d->tri_flags && (d->tri_flags[i] & DR_TRI_SMOOTH)) { anySmooth = true; break; }
+    if (anySmooth) normals.assign(3 * nT, make_float4(0, 0, 0, 0));
+    auto P = [&](uint32_t v) { return f3(d->positions[3 * (size_t) v], d->positions[3 * (size_t) v + 1], d->positions[3 * (size_t) v + 2]); };
+    auto N = [&](uint32_t v) { return f3(d->normals[3 * (size_t) v], d->normals[3 * (size_t) v + 1], d->normals[3 * (size_t) v + 2]); };
+    for (size_t slot = 0; slot < nT; ++slot) {
+        const uint32_t prim = bvh.order[slot];
+        const uint32_t i0 = d->indices[3 * (size_t) prim], i1 = d->indices[3 * (size_t) prim + 1], i2 = d->indices[3 * (size_t) prim + 2];
+        const float3 p0 = P(i0), e1 = P(i1) - p0, e2 = P(i2) - p0;
+        const bool smooth = anySmooth && (d->tri_flags[prim] & DR_TRI_SMOOTH);
+        const uint32_t mf = d->tri_material[prim] | (smooth ? 0x80000000u : 0u);
+        tris[3 * slot] = make_float4(p0.x, p0.y, p0.z, e1.x);
+        tris[3 * slot + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+        tris[3 * slot + 2] = make_float4(e2.z, as_float_bits((int) prim), as_float_bits((int) mf), as_float_bits(d->tri_emitter[prim]));
+        if (smooth) {
+            const float3 n0 = N(i0), n1 = N(i1), n2 = N(i2);
+            normals[3 * slot] = make_float4(n0.x, n0.y, n0.z, n1.x);
+            normals[3 * slot + 1] = make_float4(n1.y, n1.z, n2.x, n2.y);
+            normals[3 * slot + 2] = make_float4(n2.z, 0, 0, 0);
+        }
+    }
+    // emitters: triangles in emitter order + area CDFs (trimesh.cpp:405-420, pmf.h)
+    std::vector<float4> emTris;
+    std::vector<double> emCdf, emitterCdf;
+    std::vector<DevEmitter> emitters(d->n_emitters);
+    double weightSum = 0.0;
+    for (uint32_t e = 0; e < d->n_emitters; ++e) weightSum += (double) d->emitters[e].sampling_weight;
+    emitterCdf.push_back(0.0);
+    for (uint32_t e = 0; e < d->n_emitters; ++e) {
+        const dr_emitter &em = d->emitters[e];
+        DevEmitter &de = emitters[e];
+        memset(&de, 0, sizeof(de));
+        de.firstEmTri = (uint32_t) (emTris.size() / 6);
+        de.nTris = em.n_tris;
+        de.cdfOffset = (uint32_t) emCdf.size();
+        const size_t cdfStart = emCdf.size();
+        emCdf.push_back(0.0);
+        for (uint32_t t = 0; t < em.n_tris; ++t) {
+            const uint32_t prim = em.first_tri + t;
+            const uint32_t i0 = d->indices[3 * (size_t) prim], i1 = d->indices[3 * (size_t) prim + 1], i2 = d->indices[3 * (size_t) prim + 2];
+            const float3 p0 = P(i0), p1 = P(i1), p2 = P(i2), e1 = p1 - p0, e2 = p2 - p0;
+            // area in double from the float positions (Triangle::surfaceArea, triangle.cpp:62-68)
+            const double ax = (double) p1.x - p0.x, ay = (double) p1.y - p0.y, az = (double) p1.z - p0.z;
+            const double bx = (double) p2.x - p0.x, by = (double) p2.y - p0.y, bz = (double) p2.z - p0.z;
+            const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+            emCdf.push_back(emCdf.back() + 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz));
+            const bool smooth = anySmooth && (d->tri_flags[prim] & DR_TRI_SMOOTH);
+            emTris.push_back(make_float4(p0.x, p0.y, p0.z, e1.x));
+            emTris.push_back(make_float4(e1.y, e1.z, e2.x, e2.y));
+            emTris.push_back(make_float4(e2.z, as_float_bits(smooth ? 1 : 0), 0, 0));
+            if (smooth) {
+                const float3 n0 = N(i0), n1 = N(i1), n2 = N(i2);
+                emTris.push_back(make_float4(n0.x, n0.y, n0.z, n1.x));
+                emTris.push_back(make_float4(n1.y, n1.z, n2.x, n2.y));
+                emTris.push_back(make_float4(n2.z, 0, 0, 0));
+            } else {
+                for (int k = 0; k < 3; ++k) emTris.push_back(make_float4(0, 0, 0, 0));
+            }
+        }
+        const double area = emCdf.back();
+        if (!(area > 0.0)) { dr_set_error("emitter %u has zero area", e); return fail(DR_ERR_INVALID_ARG); }
+        for (size_t k = cdfStart; k < emCdf.size(); ++k) emCdf[k] *= 1.0 / area;   // DiscreteDistribution::normalize
+        emCdf.back() = 1.0;
+        de.radiance[0] = em.radiance[0]; de.radiance[1] = em.radiance[1]; de.radiance[2] = em.radiance[2];
+        de.area = (float) area; de.invArea = (float) (1.0 / area);
+        de.pdfDiscrete = weightSum > 0.0 ? (float) ((double) em.sampling_weight / weightSum) : 0.f;
+        emitterCdf.push_back(emitterCdf.back() + (double) em.sampling_weight);
+    }
+    if (d->n_emitters && weightSum > 0.0) {
+        for (double &v : emitterCdf) v *= 1.0 / weightSum;
+        emitterCdf.back() = 1.0;
+    }
+    std::vector<DevMaterial> mats(d->n_materials);
+    static_assert(sizeof(DevMaterial) == sizeof(dr_material), "material layout");
+    memcpy(mats.data(), d->materials, sizeof(dr_material) * d->n_materials);
+
+    DevScene &ds = s->dev;
+    memset(&ds, 0, sizeof(ds));
+    const unsigned int *dOrder = nullptr;
+    if ((st = upload(s, bvh.nodes, &ds.nodes)) || (st = upload(s, tris, &ds.tris)) || (st = upload(s, normals, &ds.normals)) ||
+        (st = upload(s, emTris, &ds.emTris)) || (st = upload(s, emCdf, &ds.emCdf)) || (st = upload(s, emitterCdf, &ds.emitterCdf)) ||
+        (st = upload(s, emitters, &ds.emitters)) || (st = upload(s, mats, &ds.materials)) || (st = upload(s, bvh.order, &dOrder)))
+        return fail(st);
+    s->dOrder = const_cast<unsigned int *>(dOrder);
+    ds.nEmitters = (int) d->n_emitters; ds.nTris = (int) d->n_triangles; ds.nNodes = (int) s->nNodes; ds.rootIsLeaf = 0;
+    ds.epsilon = 1e-4f; ds.shadowEpsilon = 1e-3f;     // constants.h:29-30 (single precision)
+
+    // pinhole camera (perspective.cpp:126-173)
+    const dr_camera &c = d->camera;
+    DevCamera &dc = ds.cam;
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 4; ++k) dc.m[4 * r + k] = c.to_world[4 * r + k];
+    dc.pos = f3(c.to_world[3], c.to_world[7], c.to_world[11]);
+    dc.dir = f3(c.to_world[2], c.to_world[6], c.to_world[10]);
+    const double tanHalf = std::tan(0.5 * (double) c.xfov_deg * 3.14159265358979323846 / 180.0);
+    const double aspect = (double) c.film_width / (double) c.film_height;
+    dc.tanHalf = (float) tanHalf; dc.aspect = (float) aspect;
+    dc.nearClip = c.near_clip; dc.farClip = c.far_clip;
+    dc.resX = (float) c.film_width; dc.resY = (float) c.film_height;
+    dc.rectX = (float) tanHalf; dc.rectY = (float) (tanHalf / aspect);
+    dc.normalization = (float) (1.0 / (2.0 * tanHalf * 2.0 * tanHalf / aspect));
+    *out = s;
+    return DR_OK;
+}
+
+// Repeat the host->device copies of the flattened scene (what a plugin pays per render job).
+extern "C" dr_status dr_scene_reupload(dr_scene scene, int64_t *bytes) {
+    if (!scene) { dr_set_error("dr_scene_reupload: null scene"); return DR_ERR_INVALID_ARG; }
+    SceneImpl *s = static_cast<SceneImpl *>(scene);
+    CK(cudaSetDevice(s->device));
+    for (HostUpload &u : s->uploads) CK(cudaMemcpy(u.dev, u.host.data(), u.host.size(), cudaMemcpyHostToDevice));
+    if (bytes) *bytes = (int64_t) s->uploadBytes;
+    return DR_OK;
+}
+
+extern "C" void dr_cancel(dr_scene scene) { if (scene) scene->cancel = 1; }
+
+// ------------------------------------------------------------------ launch parameters
+struct Params { PathCfg pc; PssParams pp; ChainParams cp; FilmParams fp; };
+
+static void make_params(const dr_config &c, int W, int H, double b, Params &p) {
+    memset(&p, 0, sizeof(p));
+    p.pc.technique = c.technique; p.pc.maxDepth = c.max_depth; p.pc.rrDepth = c.rr_depth;
+    p.pc.excludeDirect = c.direct_samples >= 0;        // separateDirect (drmlt.cpp:242)
+    p.pc.lightImage = c.light_image != 0;
+    PssParams &pp = p.pp;
+    pp.seed = c.seed; pp.integrator = c.integrator; pp.type = c.type;
+    const double s1 = 1.0 / 1024.0, s2 = 1.0 / 64.0;   // drmlt_sampler.h:201-202
+    const double scale = (c.integrator == DR_INTEGRATOR_DRMLT && c.type == DR_TYPE_ORBITAL) ? 1.9 : 1.0;   // :203-205
+    pp.kel_s2 = (float) (s2 * scale);
+    pp.kel_logRatio = (float) -std::log((s2 * scale) / (s1 * scale));
+    pp.sigma2 = c.scale_second * c.sigma;
+    const double rho = std::exp(-0.25);
+    pp.cauchy_disp = (float) (2.0 * rho / (1.0 + rho * rho));
+    pp.pss_kelemen = c.kelemen_style_mutation;
+    pp.pss_s2 = c.mutation_size_high;
+    pp.pss_logRatio = (float) -std::log((double) c.mutation_size_high / (double) c.mutation_size_low);
+    pp.pss_sigma = c.sigma;
+    pp.identity1 = pp.identity2 = 0;
+    if (c.integrator == DR_INTEGRATOR_DRMLT && c.technique == DR_TECH_MMLT) {
+        pp.identity1 = 1u << SMP_DIRECT;                // setStagesToIdentity (drmlt_proc.cpp:133-136)
+        if (c.fix_emitter_path) pp.identity2 = 1u << SMP_EMITTER;   // handleLightTracing (:137-140)
+    }
+    ChainParams &cp = p.cp;
+    cp.pLarge = c.p_large; cp.b = (float) b;
+    cp.acceptanceMap = c.integrator == DR_INTEGRATOR_DRMLT && c.acceptance_map;
+    cp.timidAfterLarge = c.timid_after_large; cp.fixEmitterPath = c.fix_emitter_path; cp.useMixture = c.use_mixture;
+    cp.kelemenWeights = c.kelemen_style_weights;
+    cp.kel_s1 = (float) s1; cp.kel_s2 = (float) s2; cp.kel_logRatio = (float) -std::log(s2 / s1);
+    // reconstruction filter table (rfilter.cpp:37-55; gaussian.cpp:30-60 stddev 0.5 radius 2; box.cpp radius 0.5 + 1e-5)
+    FilmParams &fp = p.fp;
+    fp.w = W; fp.h = H;
+    const double stddev = 0.5, radius = c.rfilter == DR_FILTER_BOX ? (double) (0.5f + 1e-5f) : 4 * stddev;
+    double vals[32], sum = 0.0;
+    for (int i = 0; i < 31; ++i) {
+        const double x = (radius * i) / 31;
+        double v;
+        if (c.rfilter == DR_FILTER_BOX) v = std::fabs(x) <= radius ? 1.0 : 0.0;
+        else { const double alpha = -1.0 / (2.0 * stddev * stddev); v = std::max(0.0, std::exp(alpha * x * x) - std::exp(alpha * radius * radius)); }
+        vals[i] = v; sum += v;
+    }
+    vals[31] = 0.0;
+    sum *= 2 * radius / 31;
+    for (int i = 0; i < 31; ++i) vals[i] /= sum;
+    for (int i = 0; i < 32; ++i) fp.values[i] = (float) vals[i];
+    fp.radius = (float) radius; fp.scaleFactor = (float) (31 / radius);
+}
+
+static DevScene scene_for(const dr_scene scene, const dr_config &c) {
+    DevScene ds = scene->dev;
+    if (c.ray_epsilon > 0.f) ds.epsilon = c.ray_epsilon;
+    if (c.shadow_epsilon > 0.f) ds.shadowEpsilon = c.shadow_epsilon;
+    return ds;
+}
+
+static dr_status check_technique(const dr_config &c) {
+    if (c.technique == DR_TECH_BDPT) { dr_set_error("technique=bdpt is not implemented on the GPU path yet"); return DR_ERR_UNSUPPORTED; }
+    return DR_OK;
+}
+
+// ------------------------------------------------------------------ job
+struct dr_job_t {
+    dr_scene scene = nullptr;
+    dr_config cfg;
+    Params par;
+    DevScene ds;
+    ChainArrays ca;
+    float4 *film = nullptr;
+    unsigned long long *counters = nullptr;     // ST_COUNT chain counters + 2 bootstrap counters
+    float *bootLum = nullptr;
+    double *cdf = nullptr, *blockSums = nullptr, *red = nullptr;
+    float *devImage = nullptr;
+    long long nBoot = 0;
+    unsigned long long bootFirst = 0;
+    int nChains = 0;
+    long long totalMutations = 0, mutationsDone = 0;
+    double b = 0.0;
+    bool bootstrapped = false, seeded = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double bootstrapMs = 0.0, chainsMs = 0.0, totalMs = 0.0;
+    uint64_t launches = 0;
+    std::vector<void *> allocations;
+    int stepsPerLaunch = 64;
+};
+
+template <class T>
+static dr_status job_alloc(dr_job j, T **p, size_t count) {
+    CK(cudaMalloc((void **) p, std::max<size_t>(count * sizeof(T), 16)));
+    j->allocations.push_back(*p);
+    CK(cudaMemsetAsync(*p, 0, std::max<size_t>(count * sizeof(T), 16), j->stream));
+    return DR_OK;
+}
+
+extern "C" void dr_job_destroy(dr_job j) {
+    if (!j) return;
+    cudaSetDevice(j->scene->device);
+    if (j->stream) cudaStreamSynchronize(j->stream);
+    for (void *p : j->allocations) cudaFree(p);
+    if (j->ev0) cudaEventDestroy(j->ev0);
+    if (j->ev1) cudaEventDestroy(j->ev1);
+    if (j->stream) cudaStreamDestroy(j->stream);
+    delete j;
+}
+
+static int auto_chains(long long totalMutations) {
+    // enough resident chains to fill 148 SMs several times over, but at least ~64 mutations per chain
+    long long n = totalMutations / 256;
+    n = std::max<long long>(4096, std::min<long long>(n, 131072));
+    n = std::min<long long>(n, std::max<long long>(128, totalMutations));
+    return (int) ((n + 127) / 128 * 128);
+}
+
+static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int nChains, dr_job *out) {
+    if (!scene || !cfgIn || !out) { dr_set_error("dr_job_create: null argument"); return DR_ERR_INVALID_ARG; }
+    *out = nullptr;
+    dr_config cfg = *cfgIn;
+    dr_status st = dr_config_validate(&cfg);
+    if (st) return st;
+    if ((st = check_technique(cfg))) return st;
+    CK(cudaSetDevice(scene->device));
+    dr_job j = new dr_job_t();
+    j->scene = scene; j->cfg = cfg;
+    j->ds = scene_for(scene, cfg);
+    const int W = scene->filmW, H = scene->filmH;
+    make_params(cfg, W, H, 1.0, j->par);
+    auto fail = [&](dr_status code) { dr_job_destroy(j); return code; };
+    if (cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&j->ev0) != cudaSuccess ||
+        cudaEventCreate(&j->ev1) != cudaSuccess) { dr_set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(DR_ERR_CUDA); }
+    // this rank's share of W*H*sampleCount mutations (drmlt.cpp:475-476)
+    const long long total = (long long) W * H * cfg.sample_count;
+    j->totalMutations = total / cfg.world_size + (cfg.rank < total % cfg.world_size ? 1 : 0);
+    j->nChains = nChains > 0 ? nChains : (cfg.n_chains > 0 ? cfg.n_chains : auto_chains(j->totalMutations));
+    // primary-sample storage: worst case over the MMLT depths
+    int dS, dE, dD;
+    max_dimensions(&cfg, cfg.max_depth, &dS, &dE, &dD);
+    ChainArrays &ca = j->ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.n = j->nChains; ca.dimS = dS; ca.dimE = dE; ca.dimD = dD;
+    const size_t n = (size_t) j->nChains;
+    if ((st = job_alloc(j, &ca.X, (size_t) (dS + dE + dD) * n)) || (st = job_alloc(j, &ca.L, n)) || (st = job_alloc(j, &ca.pos, n)) ||
+        (st = job_alloc(j, &ca.val, n)) || (st = job_alloc(j, &ca.tcur, n)) || (st = job_alloc(j, &ca.depth, n)) ||
+        (st = job_alloc(j, &ca.chainId, n)) || (st = job_alloc(j, &ca.seedIdx, n)) || (st = job_alloc(j, &ca.mutDone, n)) ||
+        (st = job_alloc(j, &j->film, (size_t) W * H)) || (st = job_alloc(j, &j->counters, (size_t) ST_COUNT + 2)) ||
+        (st = job_alloc(j, &j->red, 4)) || (st = job_alloc(j, &j->devImage, (size_t) W * H * 3)))
+        return fail(st);
+    CK(cudaStreamSynchronize(j->stream));
+    *out = j;
+    return DR_OK;
+}
+
+extern "C" dr_status dr_job_create(dr_scene scene, const dr_config *cfg, dr_job *out) { return job_create_common(scene, cfg, 0, out); }
+
+// luminanceSamples sizing of DRMLT::render (drmlt.cpp:446-473), with the reference's CPU work-unit
+// count standing in for "workUnits" and a floor of 4 bootstrap samples per resident chain.
+static long long bootstrap_samples(const dr_job j) {
+    const dr_config &c = j->cfg;
+    const long long desired = c.technique == DR_TECH_PATH ? 200000 : 100000;
+    const long long total = (long long) j->scene->filmW * j->scene->filmH * c.sample_count;
+    long long workUnits = c.work_units > 0 ? c.work_units : std::max<long long>(1, (desired - 1 + total) / desired);
+    long long n = c.luminance_samples;
+    const long long times = c.technique == DR_TECH_MMLT ? 50 : 10;
+    n = std::max(n, workUnits * times);
+    n = std::max(n, 4ll * j->nChains * c.world_size);
+    if (c.technique == DR_TECH_MMLT) n *= c.max_depth;
+    return n;
+}
+
+extern "C" dr_status dr_job_bootstrap(dr_job j, double *sumOut, double *countOut) {
+    if (!j) { dr_set_error("dr_job_bootstrap: null job"); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(j->scene->device));
+    const dr_config &c = j->cfg;
+    const long long all = bootstrap_samples(j);
+    long long per = (all + c.world_size - 1) / c.world_size;
+    if (c.technique == DR_TECH_MMLT) per = (per + c.max_depth - 1) / c.max_depth * c.max_depth;   // whole depth cycles per rank
+    j->nBoot = per;
+    j->bootFirst = (unsigned long long) per * (unsigned long long) c.rank;
+    dr_status st;
+    if (!j->bootLum) {
+        const long long nb = (per + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+        if ((st = job_alloc(j, &j->bootLum, (size_t) per)) || (st = job_alloc(j, &j->cdf, (size_t) per + 1)) ||
+            (st = job_alloc(j, &j->blockSums, (size_t) nb + 1)))
+            return st;
+    }
+    CK(cudaMemsetAsync(j->red, 0, 4 * sizeof(double), j->stream));
+    CK(cudaEventRecord(j->ev0, j->stream));
+    const int T = 128;
+    k_bootstrap<<<(unsigned) ((per + T - 1) / T), T, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->bootFirst, per, j->bootLum, j->counters + ST_COUNT);
+    CKL();
+    k_lum_reduce<<<148 * 4, 256, 0, j->stream>>>(j->bootLum, per, j->red);
+    CKL();
+    const long long nb = (per + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+    k_scan_blocks<<<(unsigned) nb, SCAN_BLOCK, 0, j->stream>>>(j->bootLum, per, j->cdf, j->blockSums);
+    CKL();
+    k_scan_sums<<<1, 1024, 0, j->stream>>>(j->blockSums, (int) nb);
+    CKL();
+    k_scan_add<<<(unsigned) ((per + 255) / 256), 256, 0, j->stream>>>(j->cdf, per, j->blockSums);
+    CKL();
+    j->launches += 5;
+    CK(cudaEventRecord(j->ev1, j->stream));
+    double red[2];
+    CK(cudaMemcpyAsync(red, j->red, sizeof(red), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, j->ev0, j->ev1));
+    j->bootstrapMs += ms;
+    j->bootstrapped = true;
+    if (sumOut) *sumOut = red[0];
+    if (countOut) *countOut = red[1];
+    return DR_OK;
+}
+
+extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
+    if (!j) { dr_set_error("dr_job_seed_chains: null job"); return DR_ERR_INVALID_ARG; }
+    if (!j->bootstrapped) { dr_set_error("dr_job_seed_chains: call dr_job_bootstrap first"); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(j->scene->device));
+    const dr_config &c = j->cfg;
+    if (c.average_luminance != -1.0f) b = c.average_luminance;        // drmlt.cpp:555-558
+    if (c.integrator == DR_INTEGRATOR_DRMLT && c.acceptance_map) b = 1.0;   // :550-552
+    if (!(b > 0.0) || !std::isfinite(b)) {
+        dr_set_error("The average image luminance appears to be zero! This could indicate a problem with the scene setup.");
+        return DR_ERR_ZERO_LUMINANCE;                                   // pathsampler.cpp:939-941
+    }
+    double total = 0.0;
+    CK(cudaMemcpyAsync(&total, j->cdf + j->nBoot, sizeof(double), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    if (!(total > 0.0)) { dr_set_error("bootstrap found no path with non-zero luminance on rank %d", c.rank); return DR_ERR_ZERO_LUMINANCE; }
+    j->b = b;
+    j->par.cp.b = (float) b;
+    const int n = j->nChains, T = 128;
+    const unsigned long long firstChain = (unsigned long long) c.rank * (unsigned long long) n;
+    CK(cudaEventRecord(j->ev0, j->stream));
+    k_resample<<<(n + T - 1) / T, T, 0, j->stream>>>(j->cdf, j->nBoot, c.seed, firstChain, n, j->bootFirst, c.max_depth, c.technique,
+                                                   j->ca.seedIdx, j->ca.chainId, j->ca.depth);
+    CKL();
+    if (c.technique == DR_TECH_MMLT) {
+        // bucket chains by MMLT depth so that the chains of a warp have the same trip counts
+        std::vector<unsigned long long> seedIdx(n), chainId(n);
+        std::vector<int> depth(n), perm(n);
+        CK(cudaMemcpyAsync(seedIdx.data(), j->ca.seedIdx, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaMemcpyAsync(chainId.data(), j->ca.chainId, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaMemcpyAsync(depth.data(), j->ca.depth, n * sizeof(int), cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaStreamSynchronize(j->stream));
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b2) { return depth[a] < depth[b2]; });
+        std::vector<unsigned long long> s2(n), c2(n);
+        std::vector<int> d2(n);
+        for (int i = 0; i < n; ++i) { s2[i] = seedIdx[perm[i]]; c2[i] = chainId[perm[i]]; d2[i] = depth[perm[i]]; }
+        CK(cudaMemcpyAsync(j->ca.seedIdx, s2.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, j->stream));
+        CK(cudaMemcpyAsync(j->ca.chainId, c2.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, j->stream));
+        CK(cudaMemcpyAsync(j->ca.depth, d2.data(), n * sizeof(int), cudaMemcpyHostToDevice, j->stream));
+        CK(cudaStreamSynchronize(j->stream));
+    }
+    k_init_chains<<<(n + T - 1) / T, T, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->ca, j->counters);
+    CKL();
+    j->launches += 2;
+    CK(cudaEventRecord(j->ev1, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, j->ev0, j->ev1));
+    j->bootstrapMs += ms;
+    j->seeded = true;
+    return DR_OK;
+}
+
+static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, int recordStride, bool withFilm) {
+    const int n = j->nChains, T = 128;
+    long long done = 0;
+    while (done < steps) {
+        if (j->scene->cancel) { dr_set_error("cancelled"); return DR_ERR_CANCELLED; }
+        const int chunk = (int) std::min<long long>(records ? steps : j->stepsPerLaunch, steps - done);
+        k_chain_step<<<(n + T - 1) / T, T, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->par.cp, j->par.fp, j->ca, withFilm ? j->film : nullptr,
+                                                         j->counters, records, recordStride, chunk);
+        CKL();
+        ++j->launches;
+        done += chunk;
+    }
+    return DR_OK;
+}
+
+extern "C" dr_status dr_job_run(dr_job j, int64_t mutationsPerChain) {
+    if (!j) { dr_set_error("dr_job_run: null job"); return DR_ERR_INVALID_ARG; }
+    if (!j->seeded) { dr_set_error("dr_job_run: call dr_job_seed_chains first"); return DR_ERR_INVALID_ARG; }
+    if (mutationsPerChain < 0) { dr_set_error("dr_job_run: negative mutation count"); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(j->scene->device));
+    CK(cudaEventRecord(j->ev0, j->stream));
+    dr_status st = run_chains(j, mutationsPerChain, nullptr, 0, true);
+    if (st) { cudaStreamSynchronize(j->stream); return st; }
+    CK(cudaEventRecord(j->ev1, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, j->ev0, j->ev1));
+    j->chainsMs += ms;
+    j->mutationsDone += mutationsPerChain * (long long) j->nChains;
+    return DR_OK;
+}
+
+extern "C" dr_status dr_job_film_device(dr_job j, float **filmDev, int64_t *nFloats) {
+    if (!j || !filmDev || !nFloats) { dr_set_error("dr_job_film_device: null argument"); return DR_ERR_INVALID_ARG; }
+    *filmDev = reinterpret_cast<float *>(j->film);
+    *nFloats = (int64_t) j->scene->filmW * j->scene->filmH * 4;     // RGBA, A unused (16-byte vector atomics)
+    return DR_OK;
+}
+
+// PSSMLT keeps the weight of the current state and splats it when the state is replaced; the
+// last state is splatted when the chain ends (pssmlt_proc.cpp:274-279).
+static dr_status flush_pssmlt(dr_job j) {
+    if (j->cfg.integrator != DR_INTEGRATOR_PSSMLT) return DR_OK;
+    const int T = 128;
+    k_flush_pssmlt<<<(j->nChains + T - 1) / T, T, 0, j->stream>>>(j->ca, j->par.fp, j->film);
+    CKL();
+    ++j->launches;
+    return DR_OK;
+}
+
+extern "C" dr_status dr_job_develop(dr_job j, float *imageRgb) {
+    if (!j || !imageRgb) { dr_set_error("dr_job_develop: null argument"); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(j->scene->device));
+    dr_status st = flush_pssmlt(j);
+    if (st) return st;
+    const long long n = (long long) j->scene->filmW * j->scene->filmH;
+    CK(cudaMemsetAsync(j->red + 2, 0, sizeof(double), j->stream));
+    k_film_luminance<<<148 * 4, 256, 0, j->stream>>>(j->film, n, j->red + 2);
+    CKL();
+    double lumSum = 0.0;
+    CK(cudaMemcpyAsync(&lumSum, j->red + 2, sizeof(double), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    const bool accMap = j->par.cp.acceptanceMap;
+    const double avg = lumSum / (double) n;
+    const float factor = accMap ? 1.0f : (avg > 0.0 ? (float) (j->b / avg) : 0.f);
+    k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, j->stream>>>(j->film, n, factor, j->devImage);
+    CKL();
+    j->launches += 2;
+    CK(cudaMemcpyAsync(imageRgb, j->devImage, (size_t) n * 3 * sizeof(float), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    return DR_OK;
+}
+
+extern "C" dr_status dr_job_stats(dr_job j, dr_stats *s) {
+    if (!j || !s) { dr_set_error("dr_job_stats: null argument"); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(j->scene->device));
+    unsigned long long c[ST_COUNT + 2];
+    CK(cudaMemcpyAsync(c, j->counters, sizeof(c), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    memset(s, 0, sizeof(*s));
+    s->mutations = c[ST_MUT];
+    s->first_accept = c[ST_FIRST_A]; s->first_base = c[ST_FIRST_B];
+    s->large_accept = c[ST_LARGE_A]; s->large_base = c[ST_LARGE_B];
+    s->bold_accept = c[ST_BOLD_A]; s->bold_base = c[ST_BOLD_B];
+    s->second_accept = c[ST_SECOND_A]; s->second_base = c[ST_SECOND_B];
+    s->second_large_accept = c[ST_SECOND_LARGE_A]; s->second_large_base = c[ST_SECOND_LARGE_B];
+    s->second_bold_accept = c[ST_SECOND_BOLD_A]; s->second_bold_base = c[ST_SECOND_BOLD_B];
+    s->accept = c[ST_ACC_A]; s->accept_base = c[ST_ACC_B];
+    s->paths = c[ST_PATHS]; s->rays = c[ST_RAYS];
+    s->bootstrap_paths = (uint64_t) (j->bootstrapped ? j->nBoot : 0); s->bootstrap_rays = c[ST_COUNT + 1];
+    s->luminance = j->b;
+    s->bootstrap_ms = j->bootstrapMs; s->chains_ms = j->chainsMs; s->total_ms = j->totalMs;
+    s->kernel_launches = j->launches;
+    return DR_OK;
+}
+
+extern "C" int64_t dr_job_num_chains(dr_job j) { return j ? j->nChains : 0; }
+extern "C" int64_t dr_job_total_mutations(dr_job j) { return j ? j->totalMutations : 0; }
+
+extern "C" dr_status dr_render(dr_scene scene, const dr_config *cfg, float *imageRgb, dr_stats *stats) {
+    if (!scene || !cfg || !imageRgb) { dr_set_error("dr_render: null argument"); return DR_ERR_INVALID_ARG; }
+    scene->cancel = 0;
+    dr_job j = nullptr;
+    dr_status st = dr_job_create(scene, cfg, &j);
+    if (st) return st;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, j->stream);
+    double sum = 0.0, count = 0.0;
+    if (!(st = dr_job_bootstrap(j, &sum, &count))) {
+        double b = count > 0.0 ? sum / count : 0.0;                              // pathsampler.cpp:922-934
+        if (j->cfg.technique == DR_TECH_MMLT) b *= j->cfg.max_depth;
+        if (!(st = dr_job_seed_chains(j, b))) {
+            const long long per = std::max<long long>(1, j->totalMutations / j->nChains);   // nMutations (drmlt.cpp:475-476)
+            if (!(st = dr_job_run(j, per))) st = dr_job_develop(j, imageRgb);
+        }
+    }
+    cudaEventRecord(t1, j->stream);
+    cudaEventSynchronize(t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    j->totalMs = ms;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    if (!st && stats) st = dr_job_stats(j, stats);
+    dr_job_destroy(j);
+    return st;
+}
+
+// ------------------------------------------------------------------ replay / parity entry points
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    dr_status alloc(size_t bytes) { CK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); return DR_OK; }
+    template <class T> T *as() { return (T *) p; }
+};
+
+extern "C" dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n, int shadow, dr_hit *hits) {
+    if (!scene || (n > 0 && (!rays || !hits)) || n < 0) { dr_set_error("dr_trace_rays: bad argument"); return DR_ERR_INVALID_ARG; }
+    if (n == 0) return DR_OK;
+    SceneImpl *s = static_cast<SceneImpl *>(scene);
+    CK(cudaSetDevice(s->device));
+    DevBuf dr, dh;
+    dr_status st;
+    if ((st = dr.alloc(n * sizeof(dr_ray))) || (st = dh.alloc(n * sizeof(dr_hit)))) return st;
+    CK(cudaMemcpy(dr.p, rays, n * sizeof(dr_ray), cudaMemcpyHostToDevice));
+    k_trace<<<(unsigned) ((n + 127) / 128), 128>>>(s->dev, dr.as<dr_ray>(), n, shadow, s->dOrder, dh.as<dr_hit>());
+    CKL();
+    CK(cudaMemcpy(hits, dh.p, n * sizeof(dr_hit), cudaMemcpyDeviceToHost));
+    return DR_OK;
+}
+
+extern "C" dr_status dr_eval_paths(dr_scene scene, const dr_config *cfgIn, const float *us, int ds_, const float *ue, int de, const float *ud, int dd,
+                                   const int32_t *depth, int64_t n, dr_path_result *out) {
+    if (!scene || !cfgIn || n < 0 || (n > 0 && !out)) { dr_set_error("dr_eval_paths: bad argument"); return DR_ERR_INVALID_ARG; }
+    dr_config cfg = *cfgIn;
+    dr_status st = dr_config_validate(&cfg);
+    if (st) return st;
+    if ((st = check_technique(cfg))) return st;
+    if (cfg.technique == DR_TECH_MMLT && !depth) { dr_set_error("dr_eval_paths: MMLT needs a depth per path"); return DR_ERR_INVALID_ARG; }
+    if ((ds_ > 0 && !us) || (de > 0 && !ue) || (dd > 0 && !ud)) { dr_set_error("dr_eval_paths: missing primary-sample buffer"); return DR_ERR_INVALID_ARG; }
+    if (n == 0) return DR_OK;
+    CK(cudaSetDevice(scene->device));
+    Params par;
+    make_params(cfg, scene->filmW, scene->filmH, 1.0, par);
+    DevBuf bs, be, bd, bdep, bout;
+    if ((st = bs.alloc((size_t) n * ds_ * 4)) || (st = be.alloc((size_t) n * de * 4)) || (st = bd.alloc((size_t) n * dd * 4)) ||
+        (st = bdep.alloc((size_t) n * 4)) || (st = bout.alloc((size_t) n * sizeof(dr_path_result))))
+        return st;
+    if (ds_) CK(cudaMemcpy(bs.p, us, (size_t) n * ds_ * 4, cudaMemcpyHostToDevice));
+    if (de) CK(cudaMemcpy(be.p, ue, (size_t) n * de * 4, cudaMemcpyHostToDevice));
+    if (dd) CK(cudaMemcpy(bd.p, ud, (size_t) n * dd * 4, cudaMemcpyHostToDevice));
+    if (depth) CK(cudaMemcpy(bdep.p, depth, (size_t) n * 4, cudaMemcpyHostToDevice));
+    k_eval_paths<<<(unsigned) ((n + 127) / 128), 128>>>(scene_for(scene, cfg), par.pc, par.pp, bs.as<float>(), ds_, be.as<float>(), de, bd.as<float>(), dd,
+                                                       depth ? bdep.as<int>() : nullptr, n, bout.as<dr_path_result>());
+    CKL();
+    CK(cudaMemcpy(out, bout.p, (size_t) n * sizeof(dr_path_result), cudaMemcpyDeviceToHost));
+    return DR_OK;
+}
+
+extern "C" dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfgIn, uint64_t first, int64_t n, float *luminance, int32_t *depth) {
+    if (!scene || !cfgIn || n < 0 || (n > 0 && !luminance)) { dr_set_error("dr_bootstrap_luminance: bad argument"); return DR_ERR_INVALID_ARG; }
+    dr_config cfg = *cfgIn;
+    dr_status st = dr_config_validate(&cfg);
+    if (st) return st;
+    if ((st = check_technique(cfg))) return st;
+    if (n == 0) return DR_OK;
+    CK(cudaSetDevice(scene->device));
+    Params par;
+    make_params(cfg, scene->filmW, scene->filmH, 1.0, par);
+    DevBuf bl, bc;
+    if ((st = bl.alloc((size_t) n * 4)) || (st = bc.alloc(2 * sizeof(unsigned long long)))) return st;
+    CK(cudaMemset(bc.p, 0, 2 * sizeof(unsigned long long)));
+    k_bootstrap<<<(unsigned) ((n + 127) / 128), 128>>>(scene_for(scene, cfg), par.pc, par.pp, first, n, bl.as<float>(), bc.as<unsigned long long>());
+    CKL();
+    CK(cudaMemcpy(luminance, bl.p, (size_t) n * 4, cudaMemcpyDeviceToHost));
+    if (depth)
+        for (int64_t i = 0; i < n; ++i)
+            depth[i] = cfg.technique == DR_TECH_MMLT ? (int32_t) ((first + (uint64_t) i) % (uint64_t) cfg.max_depth) + 1 : -1;
+    return DR_OK;
+}
+
+extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, double b, const uint64_t *seedIndex, const int32_t *depth,
+                                    const uint64_t *chainId, int64_t nChains, int64_t steps, dr_step_record *records, float *film) {
+    if (!scene || !cfgIn || nChains < 0 || steps < 0 || (nChains > 0 && (!seedIndex || !chainId))) { dr_set_error("dr_chain_steps: bad argument"); return DR_ERR_INVALID_ARG; }
+    if (nChains == 0) return DR_OK;
+    if (nChains > (1 << 24) || steps > (1 << 24)) { dr_set_error("dr_chain_steps: too large"); return DR_ERR_INVALID_ARG; }
+    dr_job j = nullptr;
+    dr_status st = job_create_common(scene, cfgIn, (int) nChains, &j);
+    if (st) return st;
+    if (j->cfg.technique == DR_TECH_MMLT && !depth) { dr_job_destroy(j); dr_set_error("dr_chain_steps: MMLT needs a depth per chain"); return DR_ERR_INVALID_ARG; }
+    auto done = [&](dr_status code) { cudaStreamSynchronize(j->stream); dr_job_destroy(j); return code; };
+    if (j->cfg.average_luminance != -1.0f) b = j->cfg.average_luminance;
+    if (j->cfg.integrator == DR_INTEGRATOR_DRMLT && j->cfg.acceptance_map) b = 1.0;
+    j->b = b; j->par.cp.b = (float) b;
+    const int n = (int) nChains, T = 128;
+    std::vector<int> dep(n, -1);
+    if (depth) for (int i = 0; i < n; ++i) dep[i] = depth[i];
+    if (j->cfg.technique != DR_TECH_MMLT) std::fill(dep.begin(), dep.end(), -1);
+    else for (int i = 0; i < n; ++i) if (dep[i] < 1 || dep[i] > j->cfg.max_depth) return done((dr_set_error("dr_chain_steps: depth out of range"), DR_ERR_INVALID_ARG));
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
+    if (cudaMemcpyAsync(j->ca.seedIdx, seedIndex, n * sizeof(uint64_t), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
+        cudaMemcpyAsync(j->ca.chainId, chainId, n * sizeof(uint64_t), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
+        cudaMemcpyAsync(j->ca.depth, dep.data(), n * sizeof(int), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
+        cudaStreamSynchronize(j->stream) != cudaSuccess) {
+        dr_set_error("dr_chain_steps: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return done(DR_ERR_CUDA);
+    }
+    k_init_chains<<<(n + T - 1) / T, T, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->ca, j->counters);
+    if (cudaGetLastError() != cudaSuccess) { dr_set_error("k_init_chains launch failed"); return done(DR_ERR_CUDA); }
+    DevBuf drec;
+    if (records && steps > 0) {
+        if ((st = drec.alloc((size_t) n * steps * sizeof(dr_step_record)))) return done(st);
+        cudaMemsetAsync(drec.p, 0, (size_t) n * steps * sizeof(dr_step_record), j->stream);
+    }
+    j->seeded = true;
+    if (steps > 0 && (st = run_chains(j, steps, records ? drec.as<dr_step_record>() : nullptr, (int) steps, film != nullptr))) return done(st);
+    if (film && (st = flush_pssmlt(j))) return done(st);
+    if (cudaStreamSynchronize(j->stream) != cudaSuccess) { dr_set_error("dr_chain_steps: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return done(DR_ERR_CUDA); }
+    if (records && steps > 0 && cudaMemcpy(records, drec.p, (size_t) n * steps * sizeof(dr_step_record), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        dr_set_error("dr_chain_steps: record download failed"); return done(DR_ERR_CUDA);
+    }
+    if (film) {
+        const size_t np = (size_t) scene->filmW * scene->filmH;
+        std::vector<float4> f4(np);
+        if (cudaMemcpy(f4.data(), j->film, np * sizeof(float4), cudaMemcpyDeviceToHost) != cudaSuccess) { dr_set_error("dr_chain_steps: film download failed"); return done(DR_ERR_CUDA); }
+        for (size_t i = 0; i < np; ++i) { film[3 * i] = f4[i].x; film[3 * i + 1] = f4[i].y; film[3 * i + 2] = f4[i].z; }
+    }
+    return done(DR_OK);
+}

@@ -1,0 +1,75 @@
+"""Multi-GPU driver: one process per GPU, chains sharded across ranks.
+
+The path shards into independent units (chains never interact, drmlt_proc.cpp:856-883), so the
+data path has no collective.  Exactly two exchanges exist, both mirroring what the reference does
+between its init threads / work units:
+  1. b: every rank bootstraps its own sample range; {sum luminance, sample count} are summed with
+     ONE all-reduce (the reference averages the per-thread means, drmlt.cpp:530-545);
+  2. film: the per-rank accumulation films are summed onto rank 0 with ONE reduce at the end
+     (the reference's processResult adds full-frame blocks under a mutex, drmlt_proc.cpp:856-867).
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is only the transport.
+"""
+import numpy as np
+
+
+def shard_range(total, world_size, rank):
+    """Contiguous share [first, first + n) of `total` units for `rank` (remainder to the low ranks)."""
+    base, rem = divmod(int(total), int(world_size))
+    n = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, n
+
+
+def normalization_from_sums(lum_sum, count, is_mmlt, max_depth):
+    """b = mean luminance over all non-NaN bootstrap samples, x maxDepth for MMLT (pathsampler.cpp:922-934)."""
+    b = lum_sum / count if count > 0 else 0.0
+    return b * max_depth if is_mmlt else b
+
+
+def all_reduce_normalization(lum_sum, count, is_mmlt, max_depth, dist=None, device="cpu"):
+    """One all-reduce of {sum, count} -> the global b (identical on every rank)."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        import torch
+        t = torch.tensor([lum_sum, count], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        lum_sum, count = float(t[0].item()), float(t[1].item())
+    return normalization_from_sums(lum_sum, count, is_mmlt, max_depth)
+
+
+def reduce_film(film_tensor, dist=None, dst=0):
+    """One reduce(sum) of the accumulation film onto rank `dst`, in place."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(film_tensor, dst=dst, op=dist.ReduceOp.SUM)
+    return film_tensor
+
+
+def render(scene, params, dist=None, rank=0, world_size=1, mutations_per_chain=None):
+    """A whole job on `world_size` GPUs: returns (image on rank 0 else None, job stats, b).
+    `params` are reference-style parameters (see integrator.make_config)."""
+    import torch
+    from . import abi
+    from .integrator import DeviceFilm, Job, make_config
+
+    cfg = make_config(rank=rank, worldSize=world_size, **params)
+    job = Job(scene, cfg)
+    s, c = job.bootstrap()
+    dev = "cuda:%d" % scene.device
+    b = all_reduce_normalization(s, c, cfg.technique == abi.DR_TECH_MMLT, cfg.max_depth, dist, dev)
+    job.seed_chains(b)
+    per = mutations_per_chain if mutations_per_chain is not None else max(1, job.total_mutations // job.num_chains)
+    job.run(per)
+    if world_size > 1:
+        film = torch.as_tensor(DeviceFilm(job), device=dev)
+        reduce_film(film, dist, 0)
+        torch.cuda.synchronize()
+    img = job.develop() if rank == 0 else None
+    st = job.stats()
+    job.close()
+    return img, st, b
+
+
+def relmse(img, ref, eps=1e-2):
+    """relMSE = mean((I - R)^2 / (R^2 + eps))."""
+    img = np.asarray(img, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.mean((img - ref) ** 2 / (ref ** 2 + eps)))

@@ -1,0 +1,187 @@
+"""Python-side handles over the C ABI (include/drmlt_b200.h) used by tests and bench.py.
+
+`make_config` takes the reference's own parameter names (the `-D key=value` strings of
+`mitsuba scene.xml -D integrator=drmlt -D technique=mmlt ...`, drmlt.cpp:178-351) and goes through
+`dr_config_set` / `dr_config_validate`, so unknown keys and illegal combinations fail exactly where
+the reference's constructor logs EError.  Everything here is plumbing: all computation happens in
+csrc/libdrmlt_b200.so on the GPU; there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+def _fp(a, ty=C.c_float):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+def _fmt(v):
+    if isinstance(v, bool):
+        return b"true" if v else b"false"
+    if isinstance(v, float):
+        return repr(float(v)).encode()
+    return str(v).encode()
+
+
+def make_config(**params):
+    """dr_config from reference-style parameters, e.g. make_config(integrator="drmlt",
+    technique="mmlt", type="orbital", maxDepth=8, sigma=1/64, acceptanceMap=True)."""
+    lib = abi.load_library()
+    cfg = abi.dr_config()
+    lib.dr_config_default(C.byref(cfg))
+    for k, v in params.items():
+        abi.check(lib, lib.dr_config_set(C.byref(cfg), k.encode(), _fmt(v)))
+    abi.check(lib, lib.dr_config_validate(C.byref(cfg)))
+    return cfg
+
+
+class Scene:
+    """GPU-resident flattened scene (dr_scene)."""
+
+    def __init__(self, data, device=0):
+        self.lib = abi.load_library()
+        self.data = data
+        self.device = device
+        desc = data.desc()
+        h = C.c_void_p()
+        abi.check(self.lib, self.lib.dr_scene_create(C.byref(desc), device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dr_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def film(self):
+        return self.data.film
+
+    def reupload(self):
+        n = C.c_int64(0)
+        abi.check(self.lib, self.lib.dr_scene_reupload(self.h, C.byref(n)))
+        return n.value
+
+    # ---- whole job, host buffers (DRMLT::render / PSSMLT::render)
+    def render(self, cfg, out=None):
+        W, H = self.film
+        img = out if out is not None else np.zeros((H, W, 3), np.float32)
+        st = abi.dr_stats()
+        abi.check(self.lib, self.lib.dr_render(self.h, C.byref(cfg), _fp(img), C.byref(st)))
+        return img, st
+
+    # ---- replay entry points
+    def trace(self, rays, shadow=False):
+        n = len(rays)
+        hits = (abi.dr_hit * n)()
+        abi.check(self.lib, self.lib.dr_trace_rays(self.h, rays, n, int(shadow), hits))
+        return hits
+
+    def eval_paths(self, cfg, us, ue, ud, depth):
+        us, ue, ud = [np.ascontiguousarray(x, np.float32) for x in (us, ue, ud)]
+        n = us.shape[0]
+        depth = np.ascontiguousarray(depth, np.int32)
+        out = (abi.dr_path_result * n)()
+        abi.check(self.lib, self.lib.dr_eval_paths(self.h, C.byref(cfg), _fp(us), us.shape[1], _fp(ue), ue.shape[1],
+                                                   _fp(ud), ud.shape[1], _fp(depth, C.c_int32), n, out))
+        return out
+
+    def bootstrap_luminance(self, cfg, first, n):
+        lum = np.zeros(n, np.float32)
+        dep = np.zeros(n, np.int32)
+        abi.check(self.lib, self.lib.dr_bootstrap_luminance(self.h, C.byref(cfg), first, n, _fp(lum), _fp(dep, C.c_int32)))
+        return lum, dep
+
+    def chain_steps(self, cfg, b, seed_index, depth, chain_id, steps, want_film=False):
+        n = len(seed_index)
+        seed_index = np.ascontiguousarray(seed_index, np.uint64)
+        chain_id = np.ascontiguousarray(chain_id, np.uint64)
+        depth = np.ascontiguousarray(depth, np.int32)
+        rec = (abi.dr_step_record * (n * steps))()
+        W, H = self.film
+        film = np.zeros((H, W, 3), np.float32) if want_film else None
+        abi.check(self.lib, self.lib.dr_chain_steps(self.h, C.byref(cfg), b, _fp(seed_index, C.c_uint64), _fp(depth, C.c_int32),
+                                                    _fp(chain_id, C.c_uint64), n, steps, rec, _fp(film) if want_film else None))
+        return (rec, film) if want_film else rec
+
+
+class Job:
+    """One rank's share of a render (dr_job): bootstrap -> [all-reduce] -> seed -> run* -> develop."""
+
+    def __init__(self, scene, cfg):
+        self.lib = scene.lib
+        self.scene = scene
+        self.cfg = cfg
+        h = C.c_void_p()
+        abi.check(self.lib, self.lib.dr_job_create(scene.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dr_job_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bootstrap(self):
+        s, c = C.c_double(0), C.c_double(0)
+        abi.check(self.lib, self.lib.dr_job_bootstrap(self.h, C.byref(s), C.byref(c)))
+        return s.value, c.value
+
+    def normalization(self, lum_sum, count):
+        """b = mean luminance (x maxDepth for MMLT): pathsampler.cpp:922-934."""
+        b = lum_sum / count if count > 0 else 0.0
+        if self.cfg.technique == abi.DR_TECH_MMLT:
+            b *= self.cfg.max_depth
+        return b
+
+    def seed_chains(self, b):
+        abi.check(self.lib, self.lib.dr_job_seed_chains(self.h, b))
+
+    def run(self, mutations_per_chain):
+        abi.check(self.lib, self.lib.dr_job_run(self.h, int(mutations_per_chain)))
+
+    def film_device(self):
+        p, n = C.c_void_p(), C.c_int64(0)
+        abi.check(self.lib, self.lib.dr_job_film_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def develop(self):
+        W, H = self.scene.film
+        img = np.zeros((H, W, 3), np.float32)
+        abi.check(self.lib, self.lib.dr_job_develop(self.h, _fp(img)))
+        return img
+
+    def stats(self):
+        st = abi.dr_stats()
+        abi.check(self.lib, self.lib.dr_job_stats(self.h, C.byref(st)))
+        return st
+
+    @property
+    def num_chains(self):
+        return self.lib.dr_job_num_chains(self.h)
+
+    @property
+    def total_mutations(self):
+        return self.lib.dr_job_total_mutations(self.h)
+
+
+class DeviceFilm:
+    """Zero-copy view of a job's accumulation film for torch (`torch.as_tensor(DeviceFilm(job), device=...)`):
+    the buffer a multi-GPU driver hands to the NCCL reduce."""
+
+    def __init__(self, job):
+        ptr, n = job.film_device()
+        self._keep = job
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}

@@ -178,6 +178,10 @@ int         dr_device_count(void);
  * (scene.cpp:332-394, skdtree.cpp) for this path. */
 dr_status dr_scene_create(const dr_scene_desc *desc, int device, dr_scene *out);
 void      dr_scene_destroy(dr_scene scene);
+/* Repeat the host->device copies of the flattened scene buffers (BVH nodes, triangles, normals,
+ * emitter tables, materials) from the staging copies kept by dr_scene_create; `bytes` receives
+ * the number of bytes copied.  This is the per-job upload a plugin pays when the scene changed. */
+dr_status dr_scene_reupload(dr_scene scene, int64_t *bytes);
 
 /* Whole job on one GPU, HOST buffers: DRMLT::render / PSSMLT::render (drmlt.cpp:393-611) +
  * develop (drmlt_proc.cpp:813-854).  `image_rgb` receives the developed W*H*3 float image

@@ -92,12 +92,12 @@ class OracleScene:
                                 fptr(depth, C.c_int32), n, out, fptr(lum, C.c_double))
         return out, lum
 
-    def chain_steps(self, cfg, b, seed_index, depth, chain_id, steps, want_film=False, threads=0):
+    def chain_steps(self, cfg, b, seed_index, depth, chain_id, steps, want_film=False, threads=0, want_records=True):
         n = len(seed_index)
         seed_index = np.ascontiguousarray(seed_index, np.uint64)
         chain_id = np.ascontiguousarray(chain_id, np.uint64)
         depth = np.ascontiguousarray(depth, np.int32)
-        rec = (abi.dr_step_record * (n * steps))()
+        rec = (abi.dr_step_record * (n * steps))() if want_records else None
         W, H = self.data.film
         film = np.zeros((H, W, 3), np.float32) if want_film else None
         st = abi.dr_stats()

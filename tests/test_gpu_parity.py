@@ -1,0 +1,418 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star):
+  * rays: same primitive, t within 1e-5 relative (floating-point ties on shared edges excepted);
+  * f(u): per-path contribution within 1e-4 relative for >= 99.9 % of replayed primary-sample vectors;
+  * accept/reject: bit-exact under identical uniforms except where the acceptance ratio lies
+    within 1e-5 of the threshold (float32 GPU vs float64 oracle);
+  * b within 0.5 %, per-stage acceptance rates within 1 % absolute.
+The oracle is run with the float-build epsilons the GPU uses (constants.h:29-30).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from drmlt_mitsuba_b200 import abi, scenes
+from drmlt_mitsuba_b200.integrator import Job, Scene, make_config
+
+pytestmark = pytest.mark.gpu
+
+REC = np.dtype([("L_x", "<f4"), ("L_y", "<f4"), ("L_z", "<f4"), ("a1", "<f4"), ("a2", "<f4"),
+                ("large", "u1"), ("acc1", "u1"), ("did2", "u1"), ("acc2", "u1")])
+
+
+def recs(buf):
+    return np.frombuffer(buf, dtype=REC)
+
+
+def ocfg(cfg):
+    o = abi.dr_config.from_buffer_copy(cfg)
+    o.ray_epsilon, o.shadow_epsilon = 1e-4, 1e-3
+    return o
+
+
+SCENE_MAKERS = {
+    "cornell": lambda: scenes.cornell_box(film=(128, 128), tess=8),
+    "glossy": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3),
+    "caustic": lambda: scenes.caustic_scene(film=(128, 128), grid=48),
+    "door": lambda: scenes.door_scene(film=(160, 90), floor_grid=64, n_spheres=16, sphere_subdiv=2),
+}
+_cache = {}
+
+
+def pair(name):
+    if name not in _cache:
+        data = SCENE_MAKERS[name]()
+        _cache[name] = (Scene(data), oracle_lib.OracleScene(data), data)
+    return _cache[name]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib, oracle):
+    yield
+    _cache.clear()
+
+
+# ------------------------------------------------------------------ (c) intersection
+def _random_rays(data, n, seed):
+    rng = np.random.RandomState(seed)
+    P = data.arrays()[0]
+    lo, hi = P.min(0), P.max(0)
+    o = lo + (hi - lo) * rng.rand(n, 3)
+    d = rng.randn(n, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = (abi.dr_ray * n)()
+    arr = np.frombuffer(rays, dtype=np.float32).reshape(n, 8)
+    arr[:, 0:3] = o
+    arr[:, 3] = 1e-4
+    arr[:, 4:7] = d
+    arr[:, 7] = np.where(rng.rand(n) < 0.2, rng.rand(n) * 2.0, np.inf)
+    return rays
+
+
+@pytest.mark.parametrize("name", ["cornell", "glossy", "caustic", "door"])
+def test_ray_casting_matches_oracle(name):
+    gpu, orc, data = pair(name)
+    n = 100000
+    rays = _random_rays(data, n, 1)
+    hg = np.frombuffer(gpu.trace(rays), dtype=[("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<i4")])
+    hc = np.frombuffer(orc.trace(rays), dtype=hg.dtype)
+    hit_same = (hg["prim"] >= 0) == (hc["prim"] >= 0)
+    assert hit_same.mean() > 0.9999
+    both = (hg["prim"] >= 0) & (hc["prim"] >= 0)
+    rel = np.abs(hg["t"][both] - hc["t"][both]) / np.maximum(hc["t"][both], 1e-6)
+    assert (rel < 1e-4).mean() > 0.9999          # same surface point even where the primitive differs on a shared edge
+    same_prim = hg["prim"][both] == hc["prim"][both]
+    assert same_prim.mean() > 0.999
+    ok = same_prim & (rel < 1e-5)
+    assert ok.mean() > 0.998
+    # barycentrics of the common hits
+    du = np.abs(hg["u"][both][same_prim] - hc["u"][both][same_prim])
+    assert np.percentile(du, 99.9) < 1e-3
+    # any-hit agrees with closest-hit existence
+    sg = np.frombuffer(gpu.trace(rays, shadow=True), dtype=hg.dtype)
+    assert ((sg["prim"] >= 0) == (hc["prim"] >= 0)).mean() > 0.9999
+
+
+def test_ray_edge_cases():
+    gpu, orc, data = pair("cornell")
+    rays = (abi.dr_ray * 4)()
+    # empty interval, axis-parallel direction with zero components, ray starting outside pointing away, grazing the floor plane
+    vals = [((0, 0, 0), 1e-4, (0, 0, -1), 1e-5), ((0, 0, 0), 1e-4, (0, -1, 0), np.inf), ((0, 0, 5), 1e-4, (0, 0, 1), np.inf),
+            ((0, -1, 0.5), 1e-4, (1, 0, 0), np.inf)]
+    for r, (o, mint, d, maxt) in zip(rays, vals):
+        r.o[:] = o; r.d[:] = d; r.mint = mint; r.maxt = maxt
+    hg, hc = gpu.trace(rays), orc.trace(rays)
+    for a, b in zip(hg, hc):
+        assert (a.prim >= 0) == (b.prim >= 0)
+        if a.prim >= 0:
+            assert a.t == pytest.approx(b.t, rel=1e-5)
+    assert hg[0].prim == -1 and hg[1].prim >= 0 and hg[2].prim == -1
+    assert len(gpu.trace((abi.dr_ray * 0)())) == 0
+
+
+# ------------------------------------------------------------------ (b) path contribution f(u), MIS
+CASES = [
+    ("cornell", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1)),
+    ("cornell", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=16)),
+    ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, lightImage=False)),
+    ("glossy", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("glossy", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1)),
+    ("caustic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1, fixEmitterPath=True)),
+    ("door", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("door", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1)),
+]
+
+
+def _case_id(c):
+    return "%s-%s-%s" % (c[0], c[1]["technique"], c[1].get("type", "pss"))
+
+
+def _compare_f(lg, lc, what):
+    lg = lg.astype(np.float64)
+    support = (lg > 0) == (lc > 0)
+    both = (lg > 0) & (lc > 0)
+    rel = np.abs(lg[both] - lc[both]) / lc[both]
+    ok = np.ones(len(lc), bool)
+    ok[~support] = False
+    ok[np.nonzero(both)[0][rel >= 1e-4]] = False
+    frac = ok.mean()
+    assert both.sum() > 50, what
+    assert frac >= 0.999, "%s: only %.5f of paths within 1e-4 (support mismatches %d, worst rel %.3g)" % (
+        what, frac, (~support).sum(), rel.max() if len(rel) else 0)
+    return frac
+
+
+@pytest.mark.parametrize("case", CASES, ids=_case_id)
+def test_path_contribution_replayed_u(case):
+    """Identical primary-sample vectors replayed from the host (dr_eval_paths)."""
+    name, params = case
+    gpu, orc, _ = pair(name)
+    cfg = make_config(seed=3, **params)
+    n = 40000
+    rng = np.random.RandomState(5)
+    md = cfg.max_depth
+    depth = rng.randint(1, md + 1, n).astype(np.int32)
+    ds, de, dd = (50, 2, 2) if cfg.technique == abi.DR_TECH_PATH else (3 * (md + 2), 3 * (md + 2), 1)
+    us, ue, ud = [rng.rand(n, k).astype(np.float32) for k in (ds, de, dd)]
+    og = gpu.eval_paths(cfg, us, ue, ud, depth)
+    oc, lum64 = orc.eval_paths(ocfg(cfg), us, ue, ud, depth)
+    g = np.frombuffer(og, dtype=np.uint8).reshape(n, C.sizeof(abi.dr_path_result))
+    c = np.frombuffer(oc, dtype=np.uint8).reshape(n, C.sizeof(abi.dr_path_result))
+    lg = g[:, 0:4].copy().view("<f4")[:, 0]
+    _compare_f(lg, lum64, _case_id(case))
+    if cfg.technique == abi.DR_TECH_MMLT:
+        sg, tg = g[:, 8:12].copy().view("<i4")[:, 0], g[:, 12:16].copy().view("<i4")[:, 0]
+        sc_, tc = c[:, 8:12].copy().view("<i4")[:, 0], c[:, 12:16].copy().view("<i4")[:, 0]
+        assert np.array_equal(sg, sc_) and np.array_equal(tg, tc)
+        mg, mc = g[:, 16:20].copy().view("<f4")[:, 0], c[:, 16:20].copy().view("<f4")[:, 0]
+        both = (lg > 0) & (lum64 > 0)
+        assert (np.abs(mg[both] - mc[both]) <= 1e-4 * mc[both]).mean() >= 0.999     # MIS weights
+    # splat positions and RGB of the contributing paths
+    both = (lg > 0) & (lum64 > 0)
+    pg, pc = g[:, 20:28].copy().view("<f4"), c[:, 20:28].copy().view("<f4")
+    assert (np.abs(pg[both] - pc[both]).max(axis=1) < 2e-2).mean() >= 0.999          # pixels (film is 128 px wide)
+    off = 20 + 8 * abi.DR_MAX_SPLATS
+    vg, vc = g[:, off:off + 12].copy().view("<f4"), c[:, off:off + 12].copy().view("<f4")
+    assert (np.abs(vg[both] - vc[both]) <= 1e-4 * np.abs(vc[both]) + 1e-7 * np.abs(vc[both]).max(axis=1, keepdims=True)).all(axis=1).mean() >= 0.999
+    # ray counts: identical control flow
+    rg, rc = g[:, -4:].copy().view("<i4")[:, 0], c[:, -4:].copy().view("<i4")[:, 0]
+    assert (rg == rc).mean() >= 0.999
+
+
+@pytest.mark.parametrize("case", CASES, ids=_case_id)
+def test_bootstrap_luminance_and_b(case):
+    """Keyed bootstrap samples: per-sample parity and b within 0.5 % (here: same samples, so far tighter)."""
+    name, params = case
+    gpu, orc, _ = pair(name)
+    cfg = make_config(seed=17, **params)
+    n = 60000
+    lg, dg = gpu.bootstrap_luminance(cfg, 1000, n)
+    lc, dc = orc.bootstrap(ocfg(cfg), 1000, n)
+    assert np.array_equal(dg, dc)
+    _compare_f(lg, lc, _case_id(case))
+    bg, bc = np.nansum(lg.astype(np.float64)), np.nansum(lc)
+    assert bg == pytest.approx(bc, rel=5e-3)
+
+
+# ------------------------------------------------------------------ (d) accept / reject decisions
+CHAIN_CASES = [
+    ("cornell", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1)),
+    ("cornell", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1, kelemenStyleMutation=False, kelemenStyleWeights=False)),
+    ("cornell", dict(integrator="pssmlt", technique="mmlt", maxDepth=6, directSamples=-1)),
+    ("cornell", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1, scaleSecond=0.1)),
+    ("cornell", dict(integrator="drmlt", type="green", technique="path", maxDepth=8, directSamples=-1)),
+    ("cornell", dict(integrator="drmlt", type="orbital", technique="path", maxDepth=8, directSamples=-1)),
+    ("cornell", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1, useMixture=True)),
+    ("cornell", dict(integrator="drmlt", type="mira", technique="mmlt", maxDepth=6, directSamples=-1, timidAfterLarge=True)),
+    ("cornell", dict(integrator="drmlt", type="green", technique="mmlt", maxDepth=6, directSamples=-1)),
+    ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("caustic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1, fixEmitterPath=True)),
+    ("glossy", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("door", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+]
+
+
+def _chain_id(c):
+    p = c[1]
+    extra = "".join("-" + k for k in ("useMixture", "timidAfterLarge", "fixEmitterPath") if p.get(k))
+    if p.get("kelemenStyleMutation") is False:
+        extra += "-gauss"
+    return "%s-%s-%s-%s%s" % (c[0], p["integrator"], p["technique"], p.get("type", "na"), extra)
+
+
+def _first_divergence(rg, rc, steps):
+    """Per chain: index of the first mutation whose decisions differ (steps if none)."""
+    n = len(rg) // steps
+    dec = np.stack([rg[k] == rc[k] for k in ("large", "acc1", "did2", "acc2")]).all(0).reshape(n, steps)
+    first = np.where(dec.all(1), steps, np.argmin(dec, axis=1))
+    return first
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=_chain_id)
+def test_chain_decisions_under_identical_uniforms(case):
+    name, params = case
+    gpu, orc, _ = pair(name)
+    cfg = make_config(seed=29, **params)
+    o = ocfg(cfg)
+    lum, dep = orc.bootstrap(o, 0, 20000)
+    seeds = np.nonzero(lum > 0)[0][:256].astype(np.uint64)
+    assert len(seeds) >= 64
+    depth = dep[seeds.astype(np.int64)]
+    ids = np.arange(len(seeds), dtype=np.uint64) + 1000
+    steps = 64
+    rg = recs(gpu.chain_steps(cfg, 0.5, seeds, depth, ids, steps))
+    rc_buf, _, st = orc.chain_steps(o, 0.5, seeds, depth, ids, steps)
+    rc = recs(rc_buf)
+    n = len(seeds)
+    first = _first_divergence(rg, rc, steps)
+    # A chain whose decision flipped because the acceptance ratio sat within float rounding of the coin
+    # legitimately follows another trajectory afterwards; everything BEFORE the first flip must agree,
+    # and the flip itself must be a near-threshold event.
+    diverged = np.nonzero(first < steps)[0]
+    assert len(diverged) <= max(2, n // 50), "%d of %d chains diverged" % (len(diverged), n)
+    G, Cc = rg.reshape(n, steps), rc.reshape(n, steps)
+    for c in diverged:
+        m = first[c]
+        g, r = G[c, m], Cc[c, m]
+        close = (abs(float(g["a1"]) - float(r["a1"])) < 1e-3) and (abs(float(g["a2"]) - float(r["a2"])) < 1e-3)
+        assert close, "chain %d step %d: decisions differ far from the threshold: gpu %s oracle %s" % (c, m, g, r)
+    # before divergence: luminances and acceptance probabilities agree
+    mask = (np.arange(steps)[None, :] < first[:, None])
+    for k in ("L_x", "L_y", "L_z"):
+        a, b = G[k][mask].astype(np.float64), Cc[k][mask].astype(np.float64)
+        nz = b > 0
+        assert ((a > 0) == nz).mean() > 0.999
+        assert (np.abs(a[nz] - b[nz]) <= 2e-4 * b[nz]).mean() > 0.998, k
+    for k in ("a1", "a2"):
+        assert np.percentile(np.abs(G[k][mask] - Cc[k][mask]), 99.8) < 1e-3, k
+    # overall agreement of the raw decision stream
+    agree = np.stack([rg[k] == rc[k] for k in ("large", "acc1", "did2", "acc2")]).all(0).mean()
+    assert agree > 0.97
+
+
+@pytest.mark.parametrize("case", [CHAIN_CASES[0], CHAIN_CASES[3], CHAIN_CASES[9], CHAIN_CASES[10]], ids=_chain_id)
+def test_film_of_recorded_chains(case):
+    """Splatting (ImageBlock::put) of the same chains: the accumulated films agree."""
+    name, params = case
+    gpu, orc, _ = pair(name)
+    cfg = make_config(seed=31, **params)
+    o = ocfg(cfg)
+    lum, dep = orc.bootstrap(o, 0, 20000)
+    seeds = np.nonzero(lum > 0)[0][:512].astype(np.uint64)
+    depth = dep[seeds.astype(np.int64)]
+    ids = np.arange(len(seeds), dtype=np.uint64)
+    _, fg = gpu.chain_steps(cfg, 0.5, seeds, depth, ids, 48, want_film=True)
+    _, fc, st = orc.chain_steps(o, 0.5, seeds, depth, ids, 48, want_film=True)
+    assert fc.sum() > 0
+    # a handful of near-threshold flips move single splats; compare blurred mass and the total
+    assert fg.sum() == pytest.approx(fc.sum(), rel=2e-2)
+    diff = np.abs(fg - fc).sum() / fc.sum()
+    assert diff < 0.08, diff
+
+
+def test_acceptance_map_mode():
+    gpu, orc, _ = pair("cornell")
+    cfg = make_config(seed=37, integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1,
+                      scaleSecond=0.1, acceptanceMap=True, rfilter="box")
+    o = ocfg(cfg)
+    lum, dep = orc.bootstrap(o, 0, 20000)
+    seeds = np.nonzero(lum > 0)[0][:512].astype(np.uint64)
+    ids = np.arange(len(seeds), dtype=np.uint64)
+    rg, fg = gpu.chain_steps(cfg, 1.0, seeds, dep[seeds.astype(np.int64)], ids, 48, want_film=True)
+    rc, fc, st = orc.chain_steps(o, 1.0, seeds, dep[seeds.astype(np.int64)], ids, 48, want_film=True)
+    w = 1.0 / (2 * (0.5 + 1e-5)) ** 2
+    r = recs(rg)
+    # R counts stage-1 accepts of non-large steps, G counts stage-2 accepts, B stays empty (drmlt_proc.cpp:443-450)
+    assert fg[..., 0].sum() / w == pytest.approx(((r["acc1"] == 1) & (r["large"] == 0)).sum(), rel=1e-3)
+    assert fg[..., 1].sum() / w == pytest.approx((r["acc2"] == 1).sum(), rel=1e-3)
+    assert fg[..., 2].sum() == 0
+    assert fg[..., :2].sum() == pytest.approx(fc[..., :2].sum(), rel=3e-2)
+
+
+# ------------------------------------------------------------------ (a) bootstrap, whole jobs, statistics
+@pytest.mark.parametrize("case", [CHAIN_CASES[0], CHAIN_CASES[3], CHAIN_CASES[9], CHAIN_CASES[10]], ids=_chain_id)
+def test_job_b_and_acceptance_rates(case):
+    """dr_job_* against the oracle's whole-render port on the same keyed streams: b within 0.5 %,
+    per-stage acceptance rates within 1 % absolute."""
+    name, params = case
+    gpu, orc, data = pair(name)
+    cfg = make_config(seed=41, sampleCount=16, chains=4096, luminanceSamples=20000, **params)
+    job = Job(gpu, cfg)
+    s, c = job.bootstrap()
+    b = job.normalization(s, c)
+    st_boot = job.stats()
+    n_boot = st_boot.bootstrap_paths
+    job.seed_chains(b)
+    steps = 40
+    job.run(steps)
+    sg = job.stats()
+    img = job.develop()
+    r, img_c, sc_, sec = orc.render(ocfg(cfg), n_boot, 4096, steps)
+    assert r == 0
+    assert b == pytest.approx(sc_.luminance, rel=5e-3)
+    assert sg.mutations == 4096 * steps == sc_.mutations
+
+    def rate(st, a, base):
+        return getattr(st, a) / max(1, getattr(st, base))
+    for a, base in (("first_accept", "first_base"), ("large_accept", "large_base"), ("bold_accept", "bold_base"),
+                    ("second_accept", "second_base"), ("accept", "accept_base")):
+        assert abs(rate(sg, a, base) - rate(sc_, a, base)) < 0.01, (a, rate(sg, a, base), rate(sc_, a, base))
+    # developed images: same normalisation (mean luminance = b) and close in L1 (same chains, same uniforms)
+    lum_g = (img * np.array([0.212671, 0.715160, 0.072169])).sum(-1).mean()
+    assert lum_g == pytest.approx(b, rel=1e-3)
+    assert np.abs(img - img_c).sum() / img_c.sum() < 0.15
+    assert sg.rays == pytest.approx(sc_.rays, rel=2e-2)
+    job.close()
+
+
+def test_render_entry_point_and_errors():
+    gpu, orc, data = pair("cornell")
+    cfg = make_config(seed=43, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, sampleCount=8, chains=2048)
+    img, st = gpu.render(cfg)
+    W, H = data.film
+    assert img.shape == (H, W, 3) and np.isfinite(img).all() and (img >= 0).all()
+    assert st.mutations == 2048 * (W * H * 8 // 2048)
+    assert st.kernel_launches > 0 and st.chains_ms > 0 and st.bootstrap_ms > 0
+    lum = (img * np.array([0.212671, 0.715160, 0.072169])).sum(-1).mean()
+    assert lum == pytest.approx(st.luminance, rel=1e-3)
+    # averageLuminance overrides b (drmlt.cpp:555-558)
+    cfg2 = make_config(seed=43, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, sampleCount=2,
+                       chains=1024, averageLuminance=2.5)
+    img2, st2 = gpu.render(cfg2)
+    assert st2.luminance == pytest.approx(2.5)
+    # a scene without emitters has zero luminance: EError in the reference (pathsampler.cpp:939-941)
+    dark = scenes.SceneData("dark", (32, 32))
+    m = dark.add_material(abi.DR_BSDF_DIFFUSE)
+    dark.add_quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0), m)
+    dark.set_camera((0, 0, 3), (0, 0, 0), (0, 1, 0), 40.0)
+    ds = Scene(dark)
+    with pytest.raises(abi.DrmltError) as e:
+        ds.render(make_config(integrator="pssmlt", technique="path", maxDepth=4, directSamples=-1))
+    assert e.value.status == 4
+    with pytest.raises(abi.DrmltError):
+        ds.render(make_config(integrator="drmlt", type="green", technique="bdpt", maxDepth=4, directSamples=-1, directSampling=False))
+
+
+def test_full_size_properties():
+    """BASELINE sizes (C5: ~1M triangles, 1280x720): size-independent properties of a whole job."""
+    data = scenes.door_scene()
+    assert 0.95e6 < data.n_triangles < 1.1e6
+    gpu = Scene(data)
+    cfg = make_config(seed=47, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1, sampleCount=4)
+    job = Job(gpu, cfg)
+    s, c = job.bootstrap()
+    b = job.normalization(s, c)
+    assert b > 0
+    job.seed_chains(b)
+    n = job.num_chains
+    job.run(8)
+    s1 = job.stats()
+    ptr, nfl = job.film_device()
+    assert nfl == 1280 * 720 * 4
+    img1 = job.develop()
+    job.run(8)
+    s2 = job.stats()
+    img2 = job.develop()
+    # counters are exact and additive; every mutation deposits unit luminance, so develop() keeps mean luminance = b
+    assert s1.mutations == n * 8 and s2.mutations == n * 16
+    assert s2.first_base == s2.mutations and s2.large_base + s2.bold_base == s2.mutations
+    assert s2.accept_base == s2.mutations + s2.second_base
+    Y = np.array([0.212671, 0.715160, 0.072169])
+    for img in (img1, img2):
+        assert np.isfinite(img).all() and (img >= 0).all()
+        assert (img * Y).sum(-1).mean() == pytest.approx(b, rel=1e-3)
+    # determinism: the same job again gives identical counters (uniforms are keyed, not drawn in launch order)
+    job2 = Job(gpu, cfg)
+    s_, c_ = job2.bootstrap()
+    assert (s_, c_) == (s, c)
+    job2.seed_chains(b)
+    job2.run(16)
+    t2 = job2.stats()
+    for f in ("mutations", "first_accept", "second_accept", "second_base", "large_accept", "rays", "paths"):
+        assert getattr(t2, f) == getattr(s2, f), f
+    # ray budget: a depth-d MMLT path costs at most d rays
+    assert s2.rays <= 8 * s2.paths
+    job.close(); job2.close()

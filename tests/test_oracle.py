@@ -1,0 +1,293 @@
+"""CPU tests of the oracle (oracle/): known answers and the reference's own run-time invariants.
+
+The reference ships no golden vectors for this path, so the oracle is pinned by:
+published known answers (Philox4x32-10), closed-form values of the transition kernels
+(transition.h), the invariants the reference asserts at run time (seed replay, 0 <= a <= 1,
+MMLT depth consistency), analytic checks (PT == BDPT == MMLT normalisation, energy conservation)
+and BSDF sample/eval/pdf consistency modelled on src/tests/test_chisquare.cpp.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from drmlt_mitsuba_b200 import abi, scenes
+
+
+# ------------------------------------------------------------------ RNG
+def test_philox_known_answers(oracle):
+    # Random123 kat_vectors, philox4x32-10
+    kats = [
+        ((0, 0, 0, 0), 0, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, 0xffffffffffffffff, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), 0x299f31d0a4093822, (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    out = (C.c_uint32 * 4)()
+    for ctr, key, want in kats:
+        oracle.orc_philox(key, *ctr, out)
+        assert tuple(out) == want
+
+
+def test_keyed_uniform_range_and_addressing(oracle):
+    vals = np.array([oracle.orc_uniform(42, 1, i, 0, j) for i in range(64) for j in range(8)])
+    assert vals.min() >= 0.0 and vals.max() < 1.0
+    assert abs(vals.mean() - 0.5) < 0.06
+    # the uniform is (word >> 8) * 2^-24 of the addressed Philox word
+    out = (C.c_uint32 * 4)()
+    oracle.orc_philox(42, 5, 0, 2, (3 << 24) | (6 >> 2), out)
+    assert oracle.orc_uniform(42, 3, 5, 2, 6) == np.float32((out[6 & 3] >> 8) * 2.0 ** -24)
+
+
+# ------------------------------------------------------------------ transition kernels (transition.h:23-190)
+def test_kelemen_kernel_closed_form(oracle):
+    s1, s2 = 1 / 1024, 1 / 64
+    assert oracle.orc_kelemen_sample(s1, s2, 0.0) == pytest.approx(s1, rel=1e-12)            # xi -> 0: +s1
+    assert oracle.orc_kelemen_sample(s1, s2, 0.5) == pytest.approx(-s1, rel=1e-12)           # second half: negative
+    assert oracle.orc_kelemen_sample(s1, s2, 0.5 - 1e-12) == pytest.approx(s2, rel=1e-9)
+    assert oracle.orc_kelemen_sample(s1, s2, 0.25) == pytest.approx(math.sqrt(s1 * s2), rel=1e-12)
+    # pdf = 1 / (2 |d| ln(s2/s1)) on [s1, s2], zero outside; integrates to one
+    assert oracle.orc_kelemen_pdf(s1, s2, s1 / 2) == 0.0 and oracle.orc_kelemen_pdf(s1, s2, 2 * s2) == 0.0
+    d = 0.004
+    assert oracle.orc_kelemen_pdf(s1, s2, -d) == pytest.approx(1 / (2 * d * math.log(s2 / s1)), rel=1e-12)
+    xs = np.exp(np.linspace(math.log(s1), math.log(s2), 20001))
+    p = np.array([oracle.orc_kelemen_pdf(s1, s2, x) for x in xs])
+    assert 2 * np.trapezoid(p, xs) == pytest.approx(1.0, rel=1e-4)   # end points may round outside [s1, s2]
+
+
+def test_gaussian_and_cauchy_kernels(oracle):
+    sigma = 0.1 / 64
+    assert oracle.orc_gaussian_sample(sigma, 0.0, 0.3) == 0.0
+    u1, u2 = 0.7, 0.2
+    want = math.sqrt(-2 * math.log(1 - u1)) * math.cos(2 * math.pi * u2) * sigma
+    assert oracle.orc_gaussian_sample(sigma, u1, u2) == pytest.approx(want, rel=1e-12)
+    rho = math.exp(-0.25)
+    # wrapped Cauchy by CDF inversion: symmetric, in [-pi, pi], median of |theta| = 2 atan((1-rho)/(1+rho))
+    xs = (np.arange(20000) + 0.5) / 20000
+    th = np.array([oracle.orc_cauchy_sample(rho, x) for x in xs])
+    assert np.all(np.abs(th) <= math.pi + 1e-12)
+    assert abs(np.mean(th)) < 1e-9
+    assert np.median(np.abs(th)) == pytest.approx(2 * math.atan((1 - rho) / (1 + rho)), rel=2e-3)
+
+
+def test_wrap_reflect(oracle):
+    for y, want in [(0.25, 0.25), (1.25, 0.75), (-0.25, 0.25), (0.0, 0.0), (1.0, 1.0), (2.0, 0.0)]:
+        assert oracle.orc_wrap(y) == pytest.approx(want)
+
+
+# ------------------------------------------------------------------ findMaxDimensions (pssmlt_utils.h:27-77)
+def test_max_dimensions(oracle):
+    def dims(**kw):
+        depth = kw.pop("depth", -1)
+        cfg = oracle_lib.default_config(**kw)
+        s, e, d = C.c_int(), C.c_int(), C.c_int()
+        oracle.orc_max_dimensions(C.byref(cfg), depth, C.byref(s), C.byref(e), C.byref(d))
+        return s.value, e.value, d.value
+    assert dims(technique=abi.DR_TECH_PATH, max_depth=8) == (50, 0, 0)
+    assert dims(technique=abi.DR_TECH_BDPT, max_depth=8, direct_sampling=0) == (30, 30, 0)    # C3
+    assert dims(technique=abi.DR_TECH_BDPT, max_depth=8, direct_sampling=1) == (30, 30, 8)
+    for d in range(1, 9):
+        m = 3 * (d + 2)
+        m += m & 1
+        assert dims(technique=abi.DR_TECH_MMLT, max_depth=8, depth=d) == (m, m, 1)
+    assert dims(technique=abi.DR_TECH_PATH, max_depth=4, rr_depth=5) == (24, 0, 0)            # no RR dimension
+
+
+# ------------------------------------------------------------------ BSDFs (modelled on test_chisquare.cpp)
+def _mat(type_, flags=0, alpha=0.2):
+    m = abi.dr_material()
+    m.type, m.flags = type_, flags
+    m.reflectance[:] = (0.8, 0.7, 0.6)
+    m.transmittance[:] = (1, 1, 1)
+    m.eta[:] = (0.2, 0.92, 1.1) if type_ in (abi.DR_BSDF_CONDUCTOR, abi.DR_BSDF_ROUGHCONDUCTOR) else (1.5, 0, 0)
+    m.k[:] = (3.9, 2.45, 2.14)
+    m.alpha = alpha
+    return m
+
+
+def _sample(oracle, m, wi, mode, u1, u2):
+    wo, w, pdf, ty = (C.c_double * 3)(), (C.c_double * 3)(), C.c_double(), C.c_int()
+    oracle.orc_bsdf_sample(C.byref(m), (C.c_double * 3)(*wi), mode, u1, u2, wo, w, C.byref(pdf), C.byref(ty))
+    return np.array(wo), np.array(w), pdf.value, ty.value
+
+
+def _eval(oracle, m, wi, wo, mode, measure):
+    v, pdf = (C.c_double * 3)(), C.c_double()
+    oracle.orc_bsdf_eval(C.byref(m), (C.c_double * 3)(*wi), (C.c_double * 3)(*wo), mode, measure, v, C.byref(pdf))
+    return np.array(v), pdf.value
+
+
+@pytest.mark.parametrize("name,mat", [
+    ("diffuse", _mat(abi.DR_BSDF_DIFFUSE)),
+    ("twosided-diffuse", _mat(abi.DR_BSDF_DIFFUSE, abi.DR_MAT_TWOSIDED)),
+    ("rough-ggx-vis", _mat(abi.DR_BSDF_ROUGHCONDUCTOR, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE)),
+    ("rough-ggx-all", _mat(abi.DR_BSDF_ROUGHCONDUCTOR, abi.DR_MAT_GGX)),
+    ("rough-beckmann-vis", _mat(abi.DR_BSDF_ROUGHCONDUCTOR, abi.DR_MAT_SAMPLE_VISIBLE, alpha=0.3)),
+    ("rough-beckmann-all", _mat(abi.DR_BSDF_ROUGHCONDUCTOR, 0, alpha=0.3)),
+])
+def test_smooth_bsdf_sample_matches_eval_over_pdf(oracle, name, mat):
+    rng = np.random.RandomState(3)
+    wi = np.array([0.3, -0.2, 0.0]); wi[2] = math.sqrt(1 - wi[0] ** 2 - wi[1] ** 2)
+    n_ok = 0
+    for _ in range(400):
+        u1, u2 = rng.rand(2)
+        wo, w, pdf, ty = _sample(oracle, mat, wi, 0, u1, u2)
+        if not w.any():
+            continue
+        f, p = _eval(oracle, mat, wi, wo, 0, 1)
+        assert p == pytest.approx(pdf, rel=1e-6), name
+        tol = 2e-2 if "beckmann-vis" in name else 1e-6   # Newton inversion is approximate (microfacet.h:573-644)
+        assert np.allclose(f / p, w, rtol=tol, atol=1e-9), name
+        n_ok += 1
+    assert n_ok > 300
+
+
+@pytest.mark.parametrize("flags", [abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE, abi.DR_MAT_GGX, 0])
+def test_rough_conductor_pdf_integrates_to_one(oracle, flags):
+    mat = _mat(abi.DR_BSDF_ROUGHCONDUCTOR, flags, alpha=0.4)
+    wi = np.array([0.5, 0.1, 0.0]); wi[2] = math.sqrt(1 - 0.26)
+    n = 200
+    th = (np.arange(n) + 0.5) / n * (math.pi / 2)
+    ph = (np.arange(2 * n) + 0.5) / (2 * n) * 2 * math.pi
+    total = 0.0
+    for t in th:
+        for p in ph[::4]:
+            wo = (math.sin(t) * math.cos(p), math.sin(t) * math.sin(p), math.cos(t))
+            total += _eval(oracle, mat, wi, wo, 0, 1)[1] * math.sin(t)
+    total *= (math.pi / 2 / n) * (2 * math.pi / (2 * n) * 4)
+    # sampleAll loses the mass of microfacet normals facing away from wi / below the horizon
+    assert 0.8 < total <= 1.01
+
+
+def test_dielectric_is_delta_and_energy_conserving(oracle):
+    mat = _mat(abi.DR_BSDF_DIELECTRIC)
+    wi = np.array([0.6, 0.0, 0.8])
+    wo_r, w_r, pdf_r, ty_r = _sample(oracle, mat, wi, 1, 0.0, 0.5)       # u <= F: reflection
+    wo_t, w_t, pdf_t, ty_t = _sample(oracle, mat, wi, 1, 0.999, 0.5)     # refraction
+    assert ty_r == 4 and ty_t == 8
+    assert pdf_r + pdf_t == pytest.approx(1.0)
+    assert np.allclose(wo_r, [-0.6, 0.0, 0.8])
+    # Snell: sin_t = sin_i / eta
+    assert math.hypot(wo_t[0], wo_t[1]) == pytest.approx(0.6 / 1.5, rel=1e-12) and wo_t[2] < 0
+    # radiance transport scales by 1/eta^2 entering the denser medium (dielectric.cpp:318-320)
+    _, w_rad, _, _ = _sample(oracle, mat, wi, 0, 0.999, 0.5)
+    assert np.allclose(w_rad, 1 / 1.5 ** 2)
+    f, p = _eval(oracle, mat, wi, wo_t, 1, 4)
+    assert p == pytest.approx(pdf_t) and np.allclose(f / p, w_t)
+
+
+# ------------------------------------------------------------------ film (imageblock.h:149-196, rfilter.cpp:37-55)
+def test_film_splat_box_and_gaussian(oracle):
+    W = H = 8
+    film = np.zeros((H, W, 3), np.float32)
+    pos = np.array([[3.5, 2.5]], np.float32)
+    rgb = np.array([[1.0, 2.0, 3.0]], np.float32)
+    oracle.orc_splat(W, H, abi.DR_FILTER_BOX, oracle_lib.fptr(pos), oracle_lib.fptr(rgb), 1, oracle_lib.fptr(film))
+    assert np.count_nonzero(film[..., 0]) == 1
+    w = 1.0 / (2 * (0.5 + 1e-5)) ** 2
+    assert film[2, 3, 1] == pytest.approx(2.0 * w, rel=1e-5)
+    film[:] = 0
+    pos = np.array([[3.7, 2.2]], np.float32)
+    oracle.orc_splat(W, H, abi.DR_FILTER_GAUSSIAN, oracle_lib.fptr(pos), oracle_lib.fptr(rgb), 1, oracle_lib.fptr(film))
+    assert np.count_nonzero(film[..., 0]) == 16                       # radius 2 => 4x4 footprint
+    assert film[..., 0].sum() == pytest.approx(1.0, rel=0.08)         # tabulated, normalised filter
+    assert np.allclose(film[..., 2], 3 * film[..., 0])
+    # negative or non-finite values are rejected (imageblock.h:151-160)
+    bad = np.array([[1.0, -1.0, 0.0]], np.float32)
+    before = film.copy()
+    oracle.orc_splat(W, H, abi.DR_FILTER_GAUSSIAN, oracle_lib.fptr(pos), oracle_lib.fptr(bad), 1, oracle_lib.fptr(film))
+    assert before.any() and np.array_equal(film, np.zeros_like(film))
+
+
+# ------------------------------------------------------------------ path sampling invariants
+@pytest.fixture(scope="module")
+def cornell(oracle):
+    return oracle_lib.OracleScene(scenes.cornell_box(film=(64, 64), tess=2))
+
+
+def _cfg(**kw):
+    kw.setdefault("max_depth", 6)
+    kw.setdefault("direct_samples", -1)
+    kw.setdefault("direct_sampling", 0)
+    return oracle_lib.default_config(**kw)
+
+
+def test_normalisation_agrees_across_techniques(cornell):
+    """b from PT, BDPT and MMLT are unbiased estimators of the same integral once they cover the
+    same path space.  With separateDirect (directSamples >= 0) all three drop depth <= 2
+    (pathsampler.cpp:279-284, :559-561) and must agree.  With directSamples = -1 PT and MMLT still
+    agree (both skip the directly visible emitter: path.cpp:152 / pathsampler.cpp:131-135) while
+    BDPT additionally sees the emitter directly (s=0, t=2), a depth-independent surplus."""
+    n = 60000
+    for ds, md in ((0, 6), (-1, 4)):
+        b = {}
+        for name, tech in (("path", abi.DR_TECH_PATH), ("bdpt", abi.DR_TECH_BDPT), ("mmlt", abi.DR_TECH_MMLT)):
+            cfg = _cfg(technique=tech, seed=11, direct_samples=ds, max_depth=md)
+            k = md if tech == abi.DR_TECH_MMLT else 1
+            lum, _ = cornell.bootstrap(cfg, 0, n * k)
+            b[name] = lum.mean() * k
+        assert b["path"] == pytest.approx(b["mmlt"], rel=0.03), (ds, b)
+        if ds == 0:
+            assert b["bdpt"] == pytest.approx(b["mmlt"], rel=0.03), (ds, b)
+        else:
+            assert b["bdpt"] > b["mmlt"] * 1.5, (ds, b)
+
+
+def test_seed_replay_invariant_and_acceptance_bounds(cornell):
+    """drmlt_proc.cpp:509-512: the replayed seed must reproduce the bootstrap luminance;
+    flipCoin asserts 0 <= a <= 1 (drmlt_proc.cpp:419-422)."""
+    for integ, tech, typ in ((abi.DR_INTEGRATOR_DRMLT, abi.DR_TECH_MMLT, abi.DR_TYPE_ORBITAL),
+                             (abi.DR_INTEGRATOR_DRMLT, abi.DR_TECH_PATH, abi.DR_TYPE_MIRA),
+                             (abi.DR_INTEGRATOR_DRMLT, abi.DR_TECH_BDPT, abi.DR_TYPE_GREEN),
+                             (abi.DR_INTEGRATOR_PSSMLT, abi.DR_TECH_PATH, abi.DR_TYPE_MIRA)):
+        cfg = _cfg(integrator=integ, technique=tech, type=typ, seed=5)
+        lum, dep = cornell.bootstrap(cfg, 0, 3000)
+        seeds = np.nonzero(lum > 0)[0][:48]
+        rec, _, st = cornell.chain_steps(cfg, 1.0, seeds, dep[seeds], np.arange(len(seeds)), 40)
+        r = np.ctypeslib.as_array(rec).view(np.recarray) if False else rec
+        for c, s in enumerate(seeds):
+            first = r[c * 40]
+            assert first.L_x == pytest.approx(lum[s], rel=1e-6)
+        a1 = np.array([x.a1 for x in r]); a2 = np.array([x.a2 for x in r])
+        assert a1.min() >= 0 and a1.max() <= 1 and a2.min() >= 0 and a2.max() <= 1
+        assert st.mutations == len(seeds) * 40
+        # a second stage is only attempted after a rejected first stage
+        assert not any(x.did_second and x.accept1 for x in r)
+        assert not any(x.accept2 and not x.did_second for x in r)
+
+
+def test_mmlt_depth_consistency(cornell):
+    """pathsampler.cpp:176-185: an MMLT sample of depth d has s + t = d + 1 (light image on)."""
+    cfg = _cfg(technique=abi.DR_TECH_MMLT, seed=9)
+    n = 600
+    rng = np.random.RandomState(0)
+    depth = rng.randint(1, 7, n).astype(np.int32)
+    us, ue, ud = rng.rand(n, 24).astype(np.float32), rng.rand(n, 24).astype(np.float32), rng.rand(n, 1).astype(np.float32)
+    out, lum = cornell.eval_paths(cfg, us, ue, ud, depth)
+    for i in range(n):
+        assert out[i].s + out[i].t == depth[i] + 1
+        assert out[i].n_splats in (0, 1)
+        if out[i].n_splats:
+            assert 0 < out[i].mis_weight <= 1.0 + 1e-9
+            assert out[i].n_rays <= depth[i]          # a depth-d MMLT path costs at most d rays
+    assert (lum > 0).sum() > n // 20
+
+
+def test_chain_determinism_and_stats_bookkeeping(cornell):
+    cfg = _cfg(technique=abi.DR_TECH_MMLT, type=abi.DR_TYPE_ORBITAL, seed=21)
+    lum, dep = cornell.bootstrap(cfg, 0, 3000)
+    seeds = np.nonzero(lum > 0)[0][:32]
+    ids = np.arange(32)
+    r1, f1, s1 = cornell.chain_steps(cfg, 1.0, seeds, dep[seeds], ids, 64, want_film=True, threads=1)
+    r2, f2, s2 = cornell.chain_steps(cfg, 1.0, seeds, dep[seeds], ids, 64, want_film=True, threads=4)
+    assert bytes(r1) == bytes(r2)
+    assert np.allclose(f1, f2, rtol=1e-5, atol=1e-7)
+    # Appendix A.6 bookkeeping identities
+    assert s1.first_base == s1.mutations
+    assert s1.large_base + s1.bold_base == s1.mutations
+    assert s1.accept_base == s1.mutations + s1.second_base
+    assert s1.accept == s1.first_accept + s1.second_accept
+    # every mutation deposits exactly unit luminance (expectation weights sum to one, splats normalised)
+    lum_film = (f1 * np.array([0.212671, 0.715160, 0.072169])).sum()
+    assert lum_film == pytest.approx(s1.mutations, rel=0.12)   # gaussian filter mass 1 up to tabulation, border loss
