@@ -6,6 +6,7 @@
 // Branching is on the material type (a small enum) -- no virtual dispatch.
 #pragma once
 #include "scene.h"
+#include "real.cuh"
 
 enum { MODE_RADIANCE = 0, MODE_IMPORTANCE = 1 };
 enum { MEAS_INVALID = 0, MEAS_SOLID_ANGLE = 1, MEAS_AREA = 3, MEAS_DISCRETE = 4 };
@@ -13,8 +14,8 @@ enum { BT_DIFFUSE_R = 1, BT_GLOSSY_R = 2, BT_DELTA_R = 4, BT_DELTA_T = 8, BT_SMO
 
 struct Mat {   // material fetched into registers
     int type; uint32_t flags;
-    float3 refl, trans, eta, k;
-    float alpha;
+    R3 refl, trans, eta, k;
+    Real alpha;
 };
 
 DR_D Mat load_material(const DevScene &sc, int id) {
@@ -22,8 +23,8 @@ DR_D Mat load_material(const DevScene &sc, int id) {
     const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
     Mat m;
     m.type = __float_as_int(a.x); m.flags = (uint32_t) __float_as_int(a.y);
-    m.refl = f3(a.z, a.w, b.x); m.trans = f3(b.y, b.z, b.w);
-    m.eta = f3(c.x, c.y, c.z); m.k = f3(c.w, d.x, d.y);
+    m.refl = r3(a.z, a.w, b.x); m.trans = r3(b.y, b.z, b.w);
+    m.eta = r3(c.x, c.y, c.z); m.k = r3(c.w, d.x, d.y);
     m.alpha = d.z;
     return m;
 }
@@ -32,314 +33,314 @@ DR_D bool mat_non_symmetric(int type) { return type == DR_BSDF_DIELECTRIC; }
 DR_D bool mat_transmissive_or_backside(const Mat &m) { return m.type == DR_BSDF_DIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }
 
 // ---- warps (src/libcore/warp.cpp:44-100)
-DR_D float2 square_to_disk_concentric(float sx, float sy) {
-    float r1 = 2.0f * sx - 1.0f, r2 = 2.0f * sy - 1.0f;
-    float phi, r;
-    if (r1 == 0.f && r2 == 0.f) { r = phi = 0.f; }
-    else if (r1 * r1 > r2 * r2) { r = r1; phi = (DR_PI / 4.0f) * (r2 / r1); }
-    else { r = r2; phi = (DR_PI / 2.0f) - (r1 / r2) * (DR_PI / 4.0f); }
-    float s, c;
-    sincosf(phi, &s, &c);
-    return make_float2(r * c, r * s);
+DR_D R2 square_to_disk_concentric(Real sx, Real sy) {
+    Real ra = 2.0 * sx - 1.0, rb = 2.0 * sy - 1.0;
+    Real phi, r;
+    if (ra == 0. && rb == 0.) { r = phi = 0.; }
+    else if (ra * ra > rb * rb) { r = ra; phi = (R_PI / 4.0) * (rb / ra); }
+    else { r = rb; phi = (R_PI / 2.0) - (ra / rb) * (R_PI / 4.0); }
+    Real s, c;
+    sincos(phi, &s, &c);
+    return r2(r * c, r * s);
 }
-DR_D float3 square_to_cosine_hemisphere(float sx, float sy) {
-    float2 p = square_to_disk_concentric(sx, sy);
-    float z = safe_sqrtf(1.0f - p.x * p.x - p.y * p.y);
-    if (z == 0.f) z = 1e-10f;
-    return f3(p.x, p.y, z);
+DR_D R3 square_to_cosine_hemisphere(Real sx, Real sy) {
+    R2 p = square_to_disk_concentric(sx, sy);
+    Real z = safe_sqrt(1.0 - p.x * p.x - p.y * p.y);
+    if (z == 0.) z = 1e-10;
+    return r3(p.x, p.y, z);
 }
 
 // ---- Fresnel (src/libcore/util.cpp:659-693, 765-789)
-DR_D float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
-    if (eta == 1.f) { cosThetaT_ = -cosThetaI_; return 0.0f; }
-    float scale = (cosThetaI_ > 0.f) ? 1.0f / eta : eta;
-    float cosThetaTSqr = 1.0f - (1.0f - cosThetaI_ * cosThetaI_) * (scale * scale);
-    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
-    float cosThetaI = fabsf(cosThetaI_), cosThetaT = sqrtf(cosThetaTSqr);
-    float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
-    float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
-    cosThetaT_ = (cosThetaI_ > 0.f) ? -cosThetaT : cosThetaT;
-    return 0.5f * (Rs * Rs + Rp * Rp);
+DR_D Real fresnel_dielectric_ext(Real cosThetaI_, Real &cosThetaT_, Real eta) {
+    if (eta == 1.) { cosThetaT_ = -cosThetaI_; return 0.0; }
+    Real scale = (cosThetaI_ > 0.) ? 1.0 / eta : eta;
+    Real cosThetaTSqr = 1.0 - (1.0 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0) { cosThetaT_ = 0.0; return 1.0; }
+    Real cosThetaI = fabs(cosThetaI_), cosThetaT = sqrt(cosThetaTSqr);
+    Real Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    Real Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0.) ? -cosThetaT : cosThetaT;
+    return 0.5 * (Rs * Rs + Rp * Rp);
 }
-DR_D float fresnel_conductor_1(float cosThetaI, float eta, float k) {
-    float cosThetaI2 = cosThetaI * cosThetaI, sinThetaI2 = 1.f - cosThetaI2, sinThetaI4 = sinThetaI2 * sinThetaI2;
-    float temp1 = eta * eta - k * k - sinThetaI2;
-    float a2pb2 = safe_sqrtf(temp1 * temp1 + 4.f * k * k * eta * eta);
-    float a = safe_sqrtf(0.5f * (a2pb2 + temp1));
-    float term1 = a2pb2 + cosThetaI2, term2 = 2.f * a * cosThetaI;
-    float Rs2 = (term1 - term2) / (term1 + term2);
-    float term3 = a2pb2 * cosThetaI2 + sinThetaI4, term4 = term2 * sinThetaI2;
-    float Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
-    return 0.5f * (Rp2 + Rs2);
+DR_D Real fresnel_conductor_1(Real cosThetaI, Real eta, Real k) {
+    Real cosThetaI2 = cosThetaI * cosThetaI, sinThetaI2 = 1. - cosThetaI2, sinThetaI4 = sinThetaI2 * sinThetaI2;
+    Real temp1 = eta * eta - k * k - sinThetaI2;
+    Real a2pb2 = safe_sqrt(temp1 * temp1 + 4. * k * k * eta * eta);
+    Real a = safe_sqrt(0.5 * (a2pb2 + temp1));
+    Real term1 = a2pb2 + cosThetaI2, term2 = 2. * a * cosThetaI;
+    Real Rs2 = (term1 - term2) / (term1 + term2);
+    Real term3 = a2pb2 * cosThetaI2 + sinThetaI4, term4 = term2 * sinThetaI2;
+    Real Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
+    return 0.5 * (Rp2 + Rs2);
 }
-DR_D float3 fresnel_conductor(float cosThetaI, float3 eta, float3 k) {
-    return f3(fresnel_conductor_1(cosThetaI, eta.x, k.x), fresnel_conductor_1(cosThetaI, eta.y, k.y),
+DR_D R3 fresnel_conductor(Real cosThetaI, R3 eta, R3 k) {
+    return r3(fresnel_conductor_1(cosThetaI, eta.x, k.x), fresnel_conductor_1(cosThetaI, eta.y, k.y),
               fresnel_conductor_1(cosThetaI, eta.z, k.z));
 }
 
 // ---- isotropic microfacet distribution (src/bsdfs/microfacet.h)
 struct Microfacet {
     bool ggx, visible;
-    float alpha;
-    DR_D Microfacet(const Mat &m) : ggx(m.flags & DR_MAT_GGX), visible(m.flags & DR_MAT_SAMPLE_VISIBLE), alpha(fmaxf(m.alpha, 1e-4f)) {}
-    DR_D float eval(float3 m) const {
-        if (m.z <= 0.f) return 0.0f;
-        float cosTheta2 = m.z * m.z;
-        float e = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
-        float result;
-        if (!ggx) result = expf(-e) / (DR_PI * alpha * alpha * cosTheta2 * cosTheta2);
-        else { float root = (1.0f + e) * cosTheta2; result = 1.0f / (DR_PI * alpha * alpha * root * root); }
-        if (result * m.z < 1e-20f) result = 0.f;
+    Real alpha;
+    DR_D Microfacet(const Mat &m) : ggx(m.flags & DR_MAT_GGX), visible(m.flags & DR_MAT_SAMPLE_VISIBLE), alpha(fmax(m.alpha, 1e-4)) {}
+    DR_D Real eval(R3 m) const {
+        if (m.z <= 0.) return 0.0;
+        Real cosTheta2 = m.z * m.z;
+        Real e = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
+        Real result;
+        if (!ggx) result = exp(-e) / (R_PI * alpha * alpha * cosTheta2 * cosTheta2);
+        else { Real root = (1.0 + e) * cosTheta2; result = 1.0 / (R_PI * alpha * alpha * root * root); }
+        if (result * m.z < 1e-20) result = 0.;
         return result;
     }
-    DR_D float smithG1(float3 v, float3 m) const {
-        if (dot(v, m) * v.z <= 0.f) return 0.0f;
-        float temp = 1.f - v.z * v.z;
-        float tanTheta = temp <= 0.f ? 0.f : fabsf(sqrtf(temp) / v.z);
-        if (tanTheta == 0.0f) return 1.0f;
+    DR_D Real smithG1(R3 v, R3 m) const {
+        if (dot(v, m) * v.z <= 0.) return 0.0;
+        Real temp = 1. - v.z * v.z;
+        Real tanTheta = temp <= 0. ? 0. : fabs(sqrt(temp) / v.z);
+        if (tanTheta == 0.0) return 1.0;
         if (!ggx) {
-            float a = 1.0f / (alpha * tanTheta);
-            if (a >= 1.6f) return 1.0f;
-            float aSqr = a * a;
-            return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
+            Real a = 1.0 / (alpha * tanTheta);
+            if (a >= 1.6) return 1.0;
+            Real aSqr = a * a;
+            return (3.535 * a + 2.181 * aSqr) / (1.0 + 2.276 * a + 2.577 * aSqr);
         } else {
-            float root = alpha * tanTheta;
-            return 2.0f / (1.0f + sqrtf(1.0f + root * root));
+            Real root = alpha * tanTheta;
+            return 2.0 / (1.0 + sqrt(1.0 + root * root));
         }
     }
-    DR_D float G(float3 wi, float3 wo, float3 m) const { return smithG1(wi, m) * smithG1(wo, m); }
-    DR_D float pdf_all(float3 m) const { return eval(m) * m.z; }
-    DR_D float pdf_visible(float3 wi, float3 m) const {
-        if (wi.z == 0.f) return 0.0f;
-        return smithG1(wi, m) * absdot(wi, m) * eval(m) / fabsf(wi.z);
+    DR_D Real G(R3 wi, R3 wo, R3 m) const { return smithG1(wi, m) * smithG1(wo, m); }
+    DR_D Real pdf_all(R3 m) const { return eval(m) * m.z; }
+    DR_D Real pdf_visible(R3 wi, R3 m) const {
+        if (wi.z == 0.) return 0.0;
+        return smithG1(wi, m) * absdot(wi, m) * eval(m) / fabs(wi.z);
     }
-    DR_D float pdf(float3 wi, float3 m) const { return visible ? pdf_visible(wi, m) : pdf_all(m); }
-    DR_D float3 sample_all(float sx, float sy, float &pdf) const {
-        float sinPhiM, cosPhiM;
-        sincosf(2.0f * DR_PI * sy, &sinPhiM, &cosPhiM);
-        float alphaSqr = alpha * alpha, cosThetaM;
+    DR_D Real pdf(R3 wi, R3 m) const { return visible ? pdf_visible(wi, m) : pdf_all(m); }
+    DR_D R3 sample_all(Real sx, Real sy, Real &pdf) const {
+        Real sinPhiM, cosPhiM;
+        sincos(2.0 * R_PI * sy, &sinPhiM, &cosPhiM);
+        Real alphaSqr = alpha * alpha, cosThetaM;
         if (!ggx) {
-            float tanThetaMSqr = alphaSqr * -logf(1.0f - sx);
-            cosThetaM = 1.0f / sqrtf(1.0f + tanThetaMSqr);
-            pdf = (1.0f - sx) / (DR_PI * alpha * alpha * cosThetaM * cosThetaM * cosThetaM);
+            Real tanThetaMSqr = alphaSqr * -log(1.0 - sx);
+            cosThetaM = 1.0 / sqrt(1.0 + tanThetaMSqr);
+            pdf = (1.0 - sx) / (R_PI * alpha * alpha * cosThetaM * cosThetaM * cosThetaM);
         } else {
-            float tanThetaMSqr = alphaSqr * sx / (1.0f - sx);
-            cosThetaM = 1.0f / sqrtf(1.0f + tanThetaMSqr);
-            float temp = 1.f + tanThetaMSqr / alphaSqr;
-            pdf = DR_INV_PI / (alpha * alpha * cosThetaM * cosThetaM * cosThetaM * temp * temp);
+            Real tanThetaMSqr = alphaSqr * sx / (1.0 - sx);
+            cosThetaM = 1.0 / sqrt(1.0 + tanThetaMSqr);
+            Real temp = 1. + tanThetaMSqr / alphaSqr;
+            pdf = R_INV_PI / (alpha * alpha * cosThetaM * cosThetaM * cosThetaM * temp * temp);
         }
-        if (pdf < 1e-20f) pdf = 0.f;
-        float sinThetaM = sqrtf(fmaxf(0.f, 1.f - cosThetaM * cosThetaM));
-        return f3(sinThetaM * cosPhiM, sinThetaM * sinPhiM, cosThetaM);
+        if (pdf < 1e-20) pdf = 0.;
+        Real sinThetaM = sqrt(fmax(0., 1. - cosThetaM * cosThetaM));
+        return r3(sinThetaM * cosPhiM, sinThetaM * sinPhiM, cosThetaM);
     }
-    static DR_D float erfinv_giles(float x) {   // src/libcore/math.cpp:25-52
-        float w = -logf((1.0f - x) * (1.0f + x)), p;
-        if (w < 5.0f) {
-            w = w - 2.5f;
-            p = 2.81022636e-08f; p = 3.43273939e-07f + p * w; p = -3.5233877e-06f + p * w; p = -4.39150654e-06f + p * w;
-            p = 0.00021858087f + p * w; p = -0.00125372503f + p * w; p = -0.00417768164f + p * w;
-            p = 0.246640727f + p * w; p = 1.50140941f + p * w;
+    static DR_D Real erfinv_giles(Real x) {   // src/libcore/math.cpp:25-52
+        Real w = -log((1.0 - x) * (1.0 + x)), p;
+        if (w < 5.0) {
+            w = w - 2.5;
+            p = 2.81022636e-08; p = 3.43273939e-07 + p * w; p = -3.5233877e-06 + p * w; p = -4.39150654e-06 + p * w;
+            p = 0.00021858087 + p * w; p = -0.00125372503 + p * w; p = -0.00417768164 + p * w;
+            p = 0.246640727 + p * w; p = 1.50140941 + p * w;
         } else {
-            w = sqrtf(w) - 3.0f;
-            p = -0.000200214257f; p = 0.000100950558f + p * w; p = 0.00134934322f + p * w; p = -0.00367342844f + p * w;
-            p = 0.00573950773f + p * w; p = -0.0076224613f + p * w; p = 0.00943887047f + p * w;
-            p = 1.00167406f + p * w; p = 2.83297682f + p * w;
+            w = sqrt(w) - 3.0;
+            p = -0.000200214257; p = 0.000100950558 + p * w; p = 0.00134934322 + p * w; p = -0.00367342844 + p * w;
+            p = 0.00573950773 + p * w; p = -0.0076224613 + p * w; p = 0.00943887047 + p * w;
+            p = 1.00167406 + p * w; p = 2.83297682 + p * w;
         }
         return p * x;
     }
-    static DR_D float erf_as(float x) {   // math.cpp:54-70 (A&S 7.1.26)
-        float sign = signbit(x) ? -1.f : 1.f;
-        x = fabsf(x);
-        float t = 1.0f / (1.0f + 0.3275911f * x);
-        float y = 1.0f - (((((1.061405429f * t + -1.453152027f) * t) + 1.421413741f) * t + -0.284496736f) * t + 0.254829592f) * t * expf(-x * x);
+    static DR_D Real erf_as(Real x) {   // math.cpp:54-70 (A&S 7.1.26)
+        Real sign = signbit(x) ? -1. : 1.;
+        x = fabs(x);
+        Real t = 1.0 / (1.0 + 0.3275911 * x);
+        Real y = 1.0 - (((((1.061405429 * t + -1.453152027) * t) + 1.421413741) * t + -0.284496736) * t + 0.254829592) * t * exp(-x * x);
         return sign * y;
     }
-    DR_D float2 sample_visible11(float thetaI, float sx, float sy, float epsilon) const {
-        const float SQRT_PI_INV = 0.5641895835477563f;
-        float2 slope;
+    DR_D R2 sample_visible11(Real thetaI, Real sx, Real sy, Real epsilon) const {
+        const Real SQRT_PI_INV = 0.5641895835477563;
+        R2 slope;
         if (!ggx) {
-            if (thetaI < 1e-4f) {
-                float r = sqrtf(-logf(1.0f - sx)), s, c;
-                sincosf(2.f * DR_PI * sy, &s, &c);
-                return make_float2(r * c, r * s);
+            if (thetaI < 1e-4) {
+                Real r = sqrt(-log(1.0 - sx)), s, c;
+                sincos(2. * R_PI * sy, &s, &c);
+                return r2(r * c, r * s);
             }
-            float tanThetaI = tanf(thetaI), cotThetaI = 1.f / tanThetaI;
-            float a = -1.f, c = erf_as(cotThetaI);
-            float sample_x = fmaxf(sx, 1e-6f);
-            float fit = 1.f + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
-            float b = c - (1.f + c) * powf(1.f - sample_x, fit);
-            float normalization = 1.f / (1.f + c + SQRT_PI_INV * tanThetaI * expf(-cotThetaI * cotThetaI));
+            Real tanThetaI = tan(thetaI), cotThetaI = 1. / tanThetaI;
+            Real a = -1., c = erf_as(cotThetaI);
+            Real sample_x = fmax(sx, 1e-6);
+            Real fit = 1. + thetaI * (-0.876 + thetaI * (0.4265 - 0.0594 * thetaI));
+            Real b = c - (1. + c) * pow(1. - sample_x, fit);
+            Real normalization = 1. / (1. + c + SQRT_PI_INV * tanThetaI * exp(-cotThetaI * cotThetaI));
             int it = 0;
             while (++it < 10) {
-                if (!(b >= a && b <= c)) b = 0.5f * (a + c);
-                float invErf = erfinv_giles(b);
-                float value = normalization * (1.f + b + SQRT_PI_INV * tanThetaI * expf(-invErf * invErf)) - sample_x;
-                float derivative = normalization * (1.f - invErf * tanThetaI);
-                if (fabsf(value) < 1e-5f) break;
-                if (value > 0.f) c = b; else a = b;
+                if (!(b >= a && b <= c)) b = 0.5 * (a + c);
+                Real invErf = erfinv_giles(b);
+                Real value = normalization * (1. + b + SQRT_PI_INV * tanThetaI * exp(-invErf * invErf)) - sample_x;
+                Real derivative = normalization * (1. - invErf * tanThetaI);
+                if (fabs(value) < 1e-5) break;
+                if (value > 0.) c = b; else a = b;
                 b -= value / derivative;
             }
             slope.x = erfinv_giles(b);
-            slope.y = erfinv_giles(2.0f * fmaxf(sy, 1e-6f) - 1.0f);
+            slope.y = erfinv_giles(2.0 * fmax(sy, 1e-6) - 1.0);
         } else {
-            if (thetaI < 1e-4f) {
-                float r = safe_sqrtf(sx / (1.f - sx)), s, c;
-                sincosf(2.f * DR_PI * sy, &s, &c);
-                return make_float2(r * c, r * s);
+            if (thetaI < 1e-4) {
+                Real r = safe_sqrt(sx / (1. - sx)), s, c;
+                sincos(2. * R_PI * sy, &s, &c);
+                return r2(r * c, r * s);
             }
-            float tanThetaI = tanf(thetaI);
-            float a = 1.f / tanThetaI;
-            float G1 = 2.0f / (1.0f + safe_sqrtf(1.0f + 1.0f / (a * a)));
-            float A = 2.0f * sx / G1 - 1.0f;
-            if (fabsf(A) == 1.f) A -= (signbit(A) ? -1.f : 1.f) * epsilon;
-            float tmp = 1.0f / (A * A - 1.0f);
-            float B = tanThetaI;
-            float D = safe_sqrtf(B * B * tmp * tmp - (A * A - B * B) * tmp);
-            float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
-            slope.x = (A < 0.0f || slope_x_2 > 1.0f / tanThetaI) ? slope_x_1 : slope_x_2;
-            float S;
-            if (sy > 0.5f) { S = 1.0f; sy = 2.0f * (sy - 0.5f); }
-            else { S = -1.0f; sy = 2.0f * (0.5f - sy); }
-            float z = (sy * (sy * (sy * (-0.365728915865723f) + 0.790235037209296f) - 0.424965825137544f) + 0.000152998850436920f) /
-                      (sy * (sy * (sy * (sy * 0.169507819808272f - 0.397203533833404f) - 0.232500544458471f) + 1.f) - 0.539825872510702f);
-            slope.y = S * z * sqrtf(1.0f + slope.x * slope.x);
+            Real tanThetaI = tan(thetaI);
+            Real a = 1. / tanThetaI;
+            Real G1 = 2.0 / (1.0 + safe_sqrt(1.0 + 1.0 / (a * a)));
+            Real A = 2.0 * sx / G1 - 1.0;
+            if (fabs(A) == 1.) A -= (signbit(A) ? -1. : 1.) * epsilon;
+            Real tmp = 1.0 / (A * A - 1.0);
+            Real B = tanThetaI;
+            Real D = safe_sqrt(B * B * tmp * tmp - (A * A - B * B) * tmp);
+            Real slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+            slope.x = (A < 0.0 || slope_x_2 > 1.0 / tanThetaI) ? slope_x_1 : slope_x_2;
+            Real S;
+            if (sy > 0.5) { S = 1.0; sy = 2.0 * (sy - 0.5); }
+            else { S = -1.0; sy = 2.0 * (0.5 - sy); }
+            Real z = (sy * (sy * (sy * (-0.365728915865723) + 0.790235037209296) - 0.424965825137544) + 0.000152998850436920) /
+                      (sy * (sy * (sy * (sy * 0.169507819808272 - 0.397203533833404) - 0.232500544458471) + 1.) - 0.539825872510702);
+            slope.y = S * z * sqrt(1.0 + slope.x * slope.x);
         }
         return slope;
     }
-    DR_D float3 sample_visible(float3 _wi, float sx, float sy, float epsilon) const {
-        float3 wi = normalize(f3(alpha * _wi.x, alpha * _wi.y, _wi.z));
-        float theta = 0.f, phi = 0.f;
-        if (wi.z < 0.99999f) { theta = acosf(wi.z); phi = atan2f(wi.y, wi.x); }
-        float sinPhi, cosPhi;
-        sincosf(phi, &sinPhi, &cosPhi);
-        float2 slope = sample_visible11(theta, sx, sy, epsilon);
-        slope = make_float2(cosPhi * slope.x - sinPhi * slope.y, sinPhi * slope.x + cosPhi * slope.y);
+    DR_D R3 sample_visible(R3 _wi, Real sx, Real sy, Real epsilon) const {
+        R3 wi = normalize(r3(alpha * _wi.x, alpha * _wi.y, _wi.z));
+        Real theta = 0., phi = 0.;
+        if (wi.z < 0.99999) { theta = acos(wi.z); phi = atan2(wi.y, wi.x); }
+        Real sinPhi, cosPhi;
+        sincos(phi, &sinPhi, &cosPhi);
+        R2 slope = sample_visible11(theta, sx, sy, epsilon);
+        slope = r2(cosPhi * slope.x - sinPhi * slope.y, sinPhi * slope.x + cosPhi * slope.y);
         slope.x *= alpha; slope.y *= alpha;
-        float normalization = 1.0f / sqrtf(slope.x * slope.x + slope.y * slope.y + 1.0f);
-        return f3(-slope.x * normalization, -slope.y * normalization, normalization);
+        Real normalization = 1.0 / sqrt(slope.x * slope.x + slope.y * slope.y + 1.0);
+        return r3(-slope.x * normalization, -slope.y * normalization, normalization);
     }
-    DR_D float3 sample(float3 wi, float sx, float sy, float &pdf, float epsilon) const {
-        if (visible) { float3 m = sample_visible(wi, sx, sy, epsilon); pdf = pdf_visible(wi, m); return m; }
+    DR_D R3 sample(R3 wi, Real sx, Real sy, Real &pdf, Real epsilon) const {
+        if (visible) { R3 m = sample_visible(wi, sx, sy, epsilon); pdf = pdf_visible(wi, m); return m; }
         return sample_all(sx, sy, pdf);
     }
 };
 
-DR_D float3 reflect_z(float3 wi) { return f3(-wi.x, -wi.y, wi.z); }
+DR_D R3 reflect_z(R3 wi) { return r3(-wi.x, -wi.y, wi.z); }
 
 // ---- nested (one-sided) evaluation
-DR_D float3 bsdf_eval_nested(const Mat &m, float3 wi, float3 wo, int mode, int measure) {
+DR_D R3 bsdf_eval_nested(const Mat &m, R3 wi, R3 wo, int mode, int measure) {
     switch (m.type) {
     case DR_BSDF_DIFFUSE:
-        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0.f || wo.z <= 0.f) return f3(0.f);
-        return m.refl * (DR_INV_PI * wo.z);
+        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0. || wo.z <= 0.) return r3(0.);
+        return m.refl * (R_INV_PI * wo.z);
     case DR_BSDF_CONDUCTOR:
-        if (measure != MEAS_DISCRETE || wi.z <= 0.f || wo.z <= 0.f || fabsf(dot(reflect_z(wi), wo) - 1.f) > DR_DELTA_EPS) return f3(0.f);
+        if (measure != MEAS_DISCRETE || wi.z <= 0. || wo.z <= 0. || fabs(dot(reflect_z(wi), wo) - 1.) > R_DELTA_EPS) return r3(0.);
         return m.refl * fresnel_conductor(wi.z, m.eta, m.k);
     case DR_BSDF_ROUGHCONDUCTOR: {
-        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0.f || wo.z <= 0.f) return f3(0.f);
-        float3 H = normalize(wo + wi);
+        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0. || wo.z <= 0.) return r3(0.);
+        R3 H = normalize(wo + wi);
         Microfacet distr(m);
-        const float D = distr.eval(H);
-        if (D == 0.f) return f3(0.f);
-        const float3 F = fresnel_conductor(dot(wi, H), m.eta, m.k) * m.refl;
-        const float G = distr.G(wi, wo, H);
-        return F * (D * G / (4.0f * wi.z));
+        const Real D = distr.eval(H);
+        if (D == 0.) return r3(0.);
+        const R3 F = fresnel_conductor(dot(wi, H), m.eta, m.k) * m.refl;
+        const Real G = distr.G(wi, wo, H);
+        return F * (D * G / (4.0 * wi.z));
     }
     case DR_BSDF_DIELECTRIC: {
-        if (measure != MEAS_DISCRETE) return f3(0.f);
-        float eta = m.eta.x, invEta = 1.f / eta, cosThetaT;
-        float F = fresnel_dielectric_ext(wi.z, cosThetaT, eta);
-        if (wi.z * wo.z >= 0.f) {
-            if (fabsf(dot(reflect_z(wi), wo) - 1.f) > DR_DELTA_EPS) return f3(0.f);
+        if (measure != MEAS_DISCRETE) return r3(0.);
+        Real eta = m.eta.x, invEta = 1. / eta, cosThetaT;
+        Real F = fresnel_dielectric_ext(wi.z, cosThetaT, eta);
+        if (wi.z * wo.z >= 0.) {
+            if (fabs(dot(reflect_z(wi), wo) - 1.) > R_DELTA_EPS) return r3(0.);
             return m.refl * F;
         } else {
-            float scale = -(cosThetaT < 0.f ? invEta : eta);
-            float3 refr = f3(scale * wi.x, scale * wi.y, cosThetaT);
-            if (fabsf(dot(refr, wo) - 1.f) > DR_DELTA_EPS) return f3(0.f);
-            float factor = (mode == MODE_RADIANCE) ? (cosThetaT < 0.f ? invEta : eta) : 1.0f;
-            return m.trans * (factor * factor * (1.f - F));
+            Real scale = -(cosThetaT < 0. ? invEta : eta);
+            R3 refr = r3(scale * wi.x, scale * wi.y, cosThetaT);
+            if (fabs(dot(refr, wo) - 1.) > R_DELTA_EPS) return r3(0.);
+            Real factor = (mode == MODE_RADIANCE) ? (cosThetaT < 0. ? invEta : eta) : 1.0;
+            return m.trans * (factor * factor * (1. - F));
         }
     }
     }
-    return f3(0.f);
+    return r3(0.);
 }
 
-DR_D float bsdf_pdf_nested(const Mat &m, float3 wi, float3 wo, int measure) {
+DR_D Real bsdf_pdf_nested(const Mat &m, R3 wi, R3 wo, int measure) {
     switch (m.type) {
     case DR_BSDF_DIFFUSE:
-        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0.f || wo.z <= 0.f) return 0.f;
-        return DR_INV_PI * wo.z;
+        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0. || wo.z <= 0.) return 0.;
+        return R_INV_PI * wo.z;
     case DR_BSDF_CONDUCTOR:
-        if (measure != MEAS_DISCRETE || wi.z <= 0.f || wo.z <= 0.f || fabsf(dot(reflect_z(wi), wo) - 1.f) > DR_DELTA_EPS) return 0.f;
-        return 1.0f;
+        if (measure != MEAS_DISCRETE || wi.z <= 0. || wo.z <= 0. || fabs(dot(reflect_z(wi), wo) - 1.) > R_DELTA_EPS) return 0.;
+        return 1.0;
     case DR_BSDF_ROUGHCONDUCTOR: {
-        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0.f || wo.z <= 0.f) return 0.f;
-        float3 H = normalize(wo + wi);
+        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0. || wo.z <= 0.) return 0.;
+        R3 H = normalize(wo + wi);
         Microfacet distr(m);
-        if (distr.visible) return distr.eval(H) * distr.smithG1(wi, H) / (4.0f * wi.z);
-        return distr.pdf(wi, H) / (4.f * absdot(wo, H));
+        if (distr.visible) return distr.eval(H) * distr.smithG1(wi, H) / (4.0 * wi.z);
+        return distr.pdf(wi, H) / (4. * absdot(wo, H));
     }
     case DR_BSDF_DIELECTRIC: {
-        if (measure != MEAS_DISCRETE) return 0.f;
-        float eta = m.eta.x, invEta = 1.f / eta, cosThetaT;
-        float F = fresnel_dielectric_ext(wi.z, cosThetaT, eta);
-        if (wi.z * wo.z >= 0.f) {
-            if (fabsf(dot(reflect_z(wi), wo) - 1.f) > DR_DELTA_EPS) return 0.f;
+        if (measure != MEAS_DISCRETE) return 0.;
+        Real eta = m.eta.x, invEta = 1. / eta, cosThetaT;
+        Real F = fresnel_dielectric_ext(wi.z, cosThetaT, eta);
+        if (wi.z * wo.z >= 0.) {
+            if (fabs(dot(reflect_z(wi), wo) - 1.) > R_DELTA_EPS) return 0.;
             return F;
         } else {
-            float scale = -(cosThetaT < 0.f ? invEta : eta);
-            float3 refr = f3(scale * wi.x, scale * wi.y, cosThetaT);
-            if (fabsf(dot(refr, wo) - 1.f) > DR_DELTA_EPS) return 0.f;
-            return 1.f - F;
+            Real scale = -(cosThetaT < 0. ? invEta : eta);
+            R3 refr = r3(scale * wi.x, scale * wi.y, cosThetaT);
+            if (fabs(dot(refr, wo) - 1.) > R_DELTA_EPS) return 0.;
+            return 1. - F;
         }
     }
     }
-    return 0.f;
+    return 0.;
 }
 
-struct BsdfSample { float3 wo; float3 weight; float pdf; int sampledType; float eta; };
+struct BsdfSample { R3 wo; R3 weight; Real pdf; int sampledType; Real eta; };
 
-DR_D void bsdf_sample_nested(const Mat &m, float3 wi, int mode, float sx, float sy, float epsilon, BsdfSample &r) {
-    r.weight = f3(0.f); r.pdf = 0.f; r.sampledType = 0; r.eta = 1.f; r.wo = f3(0.f, 0.f, 1.f);
+DR_D void bsdf_sample_nested(const Mat &m, R3 wi, int mode, Real sx, Real sy, Real epsilon, BsdfSample &r) {
+    r.weight = r3(0.); r.pdf = 0.; r.sampledType = 0; r.eta = 1.; r.wo = r3(0., 0., 1.);
     switch (m.type) {
     case DR_BSDF_DIFFUSE:
-        if (wi.z <= 0.f) return;
+        if (wi.z <= 0.) return;
         r.wo = square_to_cosine_hemisphere(sx, sy);
-        r.sampledType = BT_DIFFUSE_R; r.pdf = DR_INV_PI * r.wo.z; r.weight = m.refl;
+        r.sampledType = BT_DIFFUSE_R; r.pdf = R_INV_PI * r.wo.z; r.weight = m.refl;
         return;
     case DR_BSDF_CONDUCTOR:
-        if (wi.z <= 0.f) return;
-        r.sampledType = BT_DELTA_R; r.wo = reflect_z(wi); r.pdf = 1.f;
+        if (wi.z <= 0.) return;
+        r.sampledType = BT_DELTA_R; r.wo = reflect_z(wi); r.pdf = 1.;
         r.weight = m.refl * fresnel_conductor(wi.z, m.eta, m.k);
         return;
     case DR_BSDF_ROUGHCONDUCTOR: {
-        if (wi.z < 0.f) return;
+        if (wi.z < 0.) return;
         Microfacet distr(m);
-        float tpdf = 0.f;
-        float3 mm = distr.sample(wi, sx, sy, tpdf, epsilon);
-        if (tpdf == 0.f) return;
-        r.wo = mm * (2.f * dot(wi, mm)) - wi;
+        Real tpdf = 0.;
+        R3 mm = distr.sample(wi, sx, sy, tpdf, epsilon);
+        if (tpdf == 0.) return;
+        r.wo = mm * (2. * dot(wi, mm)) - wi;
         r.sampledType = BT_GLOSSY_R;
-        if (r.wo.z <= 0.f) return;
-        float3 F = fresnel_conductor(dot(wi, mm), m.eta, m.k) * m.refl;
-        float weight;
+        if (r.wo.z <= 0.) return;
+        R3 F = fresnel_conductor(dot(wi, mm), m.eta, m.k) * m.refl;
+        Real weight;
         if (distr.visible) weight = distr.smithG1(r.wo, mm);
         else weight = distr.eval(mm) * distr.G(wi, r.wo, mm) * dot(wi, mm) / (tpdf * wi.z);
-        if (weight > 0.f) { r.pdf = tpdf / (4.0f * dot(r.wo, mm)); r.weight = F * weight; }
+        if (weight > 0.) { r.pdf = tpdf / (4.0 * dot(r.wo, mm)); r.weight = F * weight; }
         return;
     }
     case DR_BSDF_DIELECTRIC: {
-        float eta = m.eta.x, invEta = 1.f / eta, cosThetaT;
-        float F = fresnel_dielectric_ext(wi.z, cosThetaT, eta);
+        Real eta = m.eta.x, invEta = 1. / eta, cosThetaT;
+        Real F = fresnel_dielectric_ext(wi.z, cosThetaT, eta);
         if (sx <= F) {
             r.sampledType = BT_DELTA_R; r.wo = reflect_z(wi); r.pdf = F; r.weight = m.refl;
         } else {
             r.sampledType = BT_DELTA_T;
-            float scale = -(cosThetaT < 0.f ? invEta : eta);
-            r.wo = f3(scale * wi.x, scale * wi.y, cosThetaT);
-            r.eta = cosThetaT < 0.f ? eta : invEta;
-            r.pdf = 1.f - F;
-            float factor = (mode == MODE_RADIANCE) ? (cosThetaT < 0.f ? invEta : eta) : 1.0f;
+            Real scale = -(cosThetaT < 0. ? invEta : eta);
+            r.wo = r3(scale * wi.x, scale * wi.y, cosThetaT);
+            r.eta = cosThetaT < 0. ? eta : invEta;
+            r.pdf = 1. - F;
+            Real factor = (mode == MODE_RADIANCE) ? (cosThetaT < 0. ? invEta : eta) : 1.0;
             r.weight = m.trans * (factor * factor);
         }
         return;
@@ -348,17 +349,17 @@ DR_D void bsdf_sample_nested(const Mat &m, float3 wi, int mode, float sx, float 
 }
 
 // ---- public: twosided adapter (twosided.cpp:107-186)
-DR_D float3 bsdf_eval(const Mat &m, float3 wi, float3 wo, int mode, int measure) {
-    if ((m.flags & DR_MAT_TWOSIDED) && !(wi.z > 0.f)) { wi.z = -wi.z; wo.z = -wo.z; }
+DR_D R3 bsdf_eval(const Mat &m, R3 wi, R3 wo, int mode, int measure) {
+    if ((m.flags & DR_MAT_TWOSIDED) && !(wi.z > 0.)) { wi.z = -wi.z; wo.z = -wo.z; }
     return bsdf_eval_nested(m, wi, wo, mode, measure);
 }
-DR_D float bsdf_pdf(const Mat &m, float3 wi, float3 wo, int measure) {
-    if ((m.flags & DR_MAT_TWOSIDED) && !(wi.z > 0.f)) { wi.z = -wi.z; wo.z = -wo.z; }
+DR_D Real bsdf_pdf(const Mat &m, R3 wi, R3 wo, int measure) {
+    if ((m.flags & DR_MAT_TWOSIDED) && !(wi.z > 0.)) { wi.z = -wi.z; wo.z = -wo.z; }
     return bsdf_pdf_nested(m, wi, wo, measure);
 }
-DR_D void bsdf_sample(const Mat &m, float3 wi, int mode, float sx, float sy, float epsilon, BsdfSample &r) {
+DR_D void bsdf_sample(const Mat &m, R3 wi, int mode, Real sx, Real sy, Real epsilon, BsdfSample &r) {
     bool flipped = false;
-    if ((m.flags & DR_MAT_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; flipped = true; }
+    if ((m.flags & DR_MAT_TWOSIDED) && wi.z < 0.) { wi.z = -wi.z; flipped = true; }
     bsdf_sample_nested(m, wi, mode, sx, sy, epsilon, r);
-    if (flipped && !is_zero(r.weight) && r.pdf != 0.f) r.wo.z = -r.wo.z;
+    if (flipped && !is_zero(r.weight) && r.pdf != 0.) r.wo.z = -r.wo.z;
 }

@@ -318,12 +318,12 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     for (size_t slot = 0; slot < nT; ++slot) {
         const uint32_t prim = bvh.order[slot];
         const uint32_t i0 = d->indices[3 * (size_t) prim], i1 = d->indices[3 * (size_t) prim + 1], i2 = d->indices[3 * (size_t) prim + 2];
-        const float3 p0 = P(i0), e1 = P(i1) - p0, e2 = P(i2) - p0;
+        const float3 p0 = P(i0), p1 = P(i1), p2 = P(i2);
         const bool smooth = anySmooth && (d->tri_flags[prim] & DR_TRI_SMOOTH);
         const uint32_t mf = d->tri_material[prim] | (smooth ? 0x80000000u : 0u);
-        tris[3 * slot] = make_float4(p0.x, p0.y, p0.z, e1.x);
-        tris[3 * slot + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
-        tris[3 * slot + 2] = make_float4(e2.z, as_float_bits((int) prim), as_float_bits((int) mf), as_float_bits(d->tri_emitter[prim]));
+        tris[3 * slot] = make_float4(p0.x, p0.y, p0.z, p1.x);
+        tris[3 * slot + 1] = make_float4(p1.y, p1.z, p2.x, p2.y);
+        tris[3 * slot + 2] = make_float4(p2.z, as_float_bits((int) prim), as_float_bits((int) mf), as_float_bits(d->tri_emitter[prim]));
         if (smooth) {
             const float3 n0 = N(i0), n1 = N(i1), n2 = N(i2);
             normals[3 * slot] = make_float4(n0.x, n0.y, n0.z, n1.x);
@@ -350,16 +350,16 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
         for (uint32_t t = 0; t < em.n_tris; ++t) {
             const uint32_t prim = em.first_tri + t;
             const uint32_t i0 = d->indices[3 * (size_t) prim], i1 = d->indices[3 * (size_t) prim + 1], i2 = d->indices[3 * (size_t) prim + 2];
-            const float3 p0 = P(i0), p1 = P(i1), p2 = P(i2), e1 = p1 - p0, e2 = p2 - p0;
+            const float3 p0 = P(i0), p1 = P(i1), p2 = P(i2);
             // area in double from the float positions (Triangle::surfaceArea, triangle.cpp:62-68)
             const double ax = (double) p1.x - p0.x, ay = (double) p1.y - p0.y, az = (double) p1.z - p0.z;
             const double bx = (double) p2.x - p0.x, by = (double) p2.y - p0.y, bz = (double) p2.z - p0.z;
             const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
             emCdf.push_back(emCdf.back() + 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz));
             const bool smooth = anySmooth && (d->tri_flags[prim] & DR_TRI_SMOOTH);
-            emTris.push_back(make_float4(p0.x, p0.y, p0.z, e1.x));
-            emTris.push_back(make_float4(e1.y, e1.z, e2.x, e2.y));
-            emTris.push_back(make_float4(e2.z, as_float_bits(smooth ? 1 : 0), 0, 0));
+            emTris.push_back(make_float4(p0.x, p0.y, p0.z, p1.x));
+            emTris.push_back(make_float4(p1.y, p1.z, p2.x, p2.y));
+            emTris.push_back(make_float4(p2.z, as_float_bits(smooth ? 1 : 0), 0, 0));
             if (smooth) {
                 const float3 n0 = N(i0), n1 = N(i1), n2 = N(i2);
                 emTris.push_back(make_float4(n0.x, n0.y, n0.z, n1.x));
@@ -374,8 +374,8 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
         for (size_t k = cdfStart; k < emCdf.size(); ++k) emCdf[k] *= 1.0 / area;   // DiscreteDistribution::normalize
         emCdf.back() = 1.0;
         de.radiance[0] = em.radiance[0]; de.radiance[1] = em.radiance[1]; de.radiance[2] = em.radiance[2];
-        de.area = (float) area; de.invArea = (float) (1.0 / area);
-        de.pdfDiscrete = weightSum > 0.0 ? (float) ((double) em.sampling_weight / weightSum) : 0.f;
+        de.area = area; de.invArea = 1.0 / area;
+        de.pdfDiscrete = weightSum > 0.0 ? (double) em.sampling_weight * (1.0 / weightSum) : 0.0;
         emitterCdf.push_back(emitterCdf.back() + (double) em.sampling_weight);
     }
     if (d->n_emitters && weightSum > 0.0) {
@@ -400,16 +400,16 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     // pinhole camera (perspective.cpp:126-173)
     const dr_camera &c = d->camera;
     DevCamera &dc = ds.cam;
-    for (int r = 0; r < 3; ++r) for (int k = 0; k < 4; ++k) dc.m[4 * r + k] = c.to_world[4 * r + k];
-    dc.pos = f3(c.to_world[3], c.to_world[7], c.to_world[11]);
-    dc.dir = f3(c.to_world[2], c.to_world[6], c.to_world[10]);
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 4; ++k) dc.m[4 * r + k] = (double) c.to_world[4 * r + k];
+    dc.pos[0] = c.to_world[3]; dc.pos[1] = c.to_world[7]; dc.pos[2] = c.to_world[11];
+    dc.dir[0] = c.to_world[2]; dc.dir[1] = c.to_world[6]; dc.dir[2] = c.to_world[10];
     const double tanHalf = std::tan(0.5 * (double) c.xfov_deg * 3.14159265358979323846 / 180.0);
     const double aspect = (double) c.film_width / (double) c.film_height;
-    dc.tanHalf = (float) tanHalf; dc.aspect = (float) aspect;
+    dc.tanHalf = tanHalf; dc.aspect = aspect;
     dc.nearClip = c.near_clip; dc.farClip = c.far_clip;
-    dc.resX = (float) c.film_width; dc.resY = (float) c.film_height;
-    dc.rectX = (float) tanHalf; dc.rectY = (float) (tanHalf / aspect);
-    dc.normalization = (float) (1.0 / (2.0 * tanHalf * 2.0 * tanHalf / aspect));
+    dc.resX = c.film_width; dc.resY = c.film_height;
+    dc.rectX = tanHalf; dc.rectY = tanHalf / aspect;
+    dc.normalization = 1.0 / (2.0 * dc.rectX * 2.0 * dc.rectY);
     *out = s;
     return DR_OK;
 }
@@ -438,14 +438,14 @@ static void make_params(const dr_config &c, int W, int H, double b, Params &p) {
     pp.seed = c.seed; pp.integrator = c.integrator; pp.type = c.type;
     const double s1 = 1.0 / 1024.0, s2 = 1.0 / 64.0;   // drmlt_sampler.h:201-202
     const double scale = (c.integrator == DR_INTEGRATOR_DRMLT && c.type == DR_TYPE_ORBITAL) ? 1.9 : 1.0;   // :203-205
-    pp.kel_s2 = (float) (s2 * scale);
-    pp.kel_logRatio = (float) -std::log((s2 * scale) / (s1 * scale));
-    pp.sigma2 = c.scale_second * c.sigma;
+    pp.kel_s2 = s2 * scale;
+    pp.kel_logRatio = -std::log((s2 * scale) / (s1 * scale));
+    pp.sigma2 = (double) c.scale_second * (double) c.sigma;
     const double rho = std::exp(-0.25);
-    pp.cauchy_disp = (float) (2.0 * rho / (1.0 + rho * rho));
+    pp.cauchy_disp = 2.0 * rho / (1.0 + rho * rho);
     pp.pss_kelemen = c.kelemen_style_mutation;
     pp.pss_s2 = c.mutation_size_high;
-    pp.pss_logRatio = (float) -std::log((double) c.mutation_size_high / (double) c.mutation_size_low);
+    pp.pss_logRatio = -std::log((double) c.mutation_size_high / (double) c.mutation_size_low);
     pp.pss_sigma = c.sigma;
     pp.identity1 = pp.identity2 = 0;
     if (c.integrator == DR_INTEGRATOR_DRMLT && c.technique == DR_TECH_MMLT) {
@@ -453,11 +453,11 @@ static void make_params(const dr_config &c, int W, int H, double b, Params &p) {
         if (c.fix_emitter_path) pp.identity2 = 1u << SMP_EMITTER;   // handleLightTracing (:137-140)
     }
     ChainParams &cp = p.cp;
-    cp.pLarge = c.p_large; cp.b = (float) b;
+    cp.pLarge = c.p_large; cp.b = b;
     cp.acceptanceMap = c.integrator == DR_INTEGRATOR_DRMLT && c.acceptance_map;
     cp.timidAfterLarge = c.timid_after_large; cp.fixEmitterPath = c.fix_emitter_path; cp.useMixture = c.use_mixture;
     cp.kelemenWeights = c.kelemen_style_weights;
-    cp.kel_s1 = (float) s1; cp.kel_s2 = (float) s2; cp.kel_logRatio = (float) -std::log(s2 / s1);
+    cp.kel_s1 = s1; cp.kel_s2 = s2; cp.kel_logRatio = -std::log(s2 / s1);
     // reconstruction filter table (rfilter.cpp:37-55; gaussian.cpp:30-60 stddev 0.5 radius 2; box.cpp radius 0.5 + 1e-5)
     FilmParams &fp = p.fp;
     fp.w = W; fp.h = H;
@@ -496,8 +496,11 @@ struct dr_job_t {
     Params par;
     DevScene ds;
     ChainArrays ca;
+    LaneMem lm;
     float4 *film = nullptr;
-    unsigned long long *counters = nullptr;     // ST_COUNT chain counters + 2 bootstrap counters
+    unsigned long long *counters = nullptr;     // [0, ST_COUNT): chain phase, [ST_COUNT, 2 ST_COUNT): bootstrap
+    unsigned int *active = nullptr;             // lanes with work left after the last logic round
+    unsigned int *activeHost = nullptr;         // pinned mirror
     float *bootLum = nullptr;
     double *cdf = nullptr, *blockSums = nullptr, *red = nullptr;
     float *devImage = nullptr;
@@ -505,14 +508,15 @@ struct dr_job_t {
     unsigned long long bootFirst = 0;
     int nChains = 0;
     long long totalMutations = 0, mutationsDone = 0;
+    uint32_t mutTarget = 0;
     double b = 0.0;
     bool bootstrapped = false, seeded = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double bootstrapMs = 0.0, chainsMs = 0.0, totalMs = 0.0;
-    uint64_t launches = 0;
+    uint64_t launches = 0, rounds = 0;
     std::vector<void *> allocations;
-    int stepsPerLaunch = 64;
+    int roundsPerPoll = 16;
 };
 
 template <class T>
@@ -528,6 +532,7 @@ extern "C" void dr_job_destroy(dr_job j) {
     cudaSetDevice(j->scene->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
     for (void *p : j->allocations) cudaFree(p);
+    if (j->activeHost) cudaFreeHost(j->activeHost);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);
     if (j->stream) cudaStreamDestroy(j->stream);
@@ -535,14 +540,27 @@ extern "C" void dr_job_destroy(dr_job j) {
 }
 
 static int auto_chains(long long totalMutations) {
-    // enough resident chains to fill 148 SMs several times over, but at least ~64 mutations per chain
-    long long n = totalMutations / 256;
-    n = std::max<long long>(4096, std::min<long long>(n, 131072));
+    // enough lanes to fill 148 SMs x 2048 resident threads several times over, but >= 32 mutations per chain
+    long long n = totalMutations / 32;
+    n = std::max<long long>(4096, std::min<long long>(n, 1 << 20));
     n = std::min<long long>(n, std::max<long long>(128, totalMutations));
     return (int) ((n + 127) / 128 * 128);
 }
 
-static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int nChains, dr_job *out) {
+// lane memory of the wavefront machine for `n` lanes
+static dr_status alloc_lanes(dr_job j, int n) {
+    LaneMem &lm = j->lm;
+    memset(&lm, 0, sizeof(lm));
+    lm.n = n;
+    dr_status st;
+    if ((st = job_alloc(j, &lm.w, (size_t) W_COUNT * n)) || (st = job_alloc(j, &lm.mis, (size_t) 3 * (DR_MAXK + 1) * n)) ||
+        (st = job_alloc(j, &lm.rayO, (size_t) n)) || (st = job_alloc(j, &lm.rayD, (size_t) n)) || (st = job_alloc(j, &lm.hit, (size_t) n)) ||
+        (st = job_alloc(j, &lm.rayKind, (size_t) n)))
+        return st;
+    return DR_OK;
+}
+
+static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int nLanes, bool chains, dr_job *out) {
     if (!scene || !cfgIn || !out) { dr_set_error("dr_job_create: null argument"); return DR_ERR_INVALID_ARG; }
     *out = nullptr;
     dr_config cfg = *cfgIn;
@@ -557,33 +575,70 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     make_params(cfg, W, H, 1.0, j->par);
     auto fail = [&](dr_status code) { dr_job_destroy(j); return code; };
     if (cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&j->ev0) != cudaSuccess ||
-        cudaEventCreate(&j->ev1) != cudaSuccess) { dr_set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(DR_ERR_CUDA); }
+        cudaEventCreate(&j->ev1) != cudaSuccess || cudaMallocHost((void **) &j->activeHost, sizeof(unsigned int)) != cudaSuccess) {
+        dr_set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(DR_ERR_CUDA);
+    }
     // this rank's share of W*H*sampleCount mutations (drmlt.cpp:475-476)
     const long long total = (long long) W * H * cfg.sample_count;
     j->totalMutations = total / cfg.world_size + (cfg.rank < total % cfg.world_size ? 1 : 0);
-    j->nChains = nChains > 0 ? nChains : (cfg.n_chains > 0 ? cfg.n_chains : auto_chains(j->totalMutations));
-    // primary-sample storage: worst case over the MMLT depths
-    int dS, dE, dD;
-    max_dimensions(&cfg, cfg.max_depth, &dS, &dE, &dD);
+    j->nChains = nLanes > 0 ? nLanes : (cfg.n_chains > 0 ? cfg.n_chains : auto_chains(j->totalMutations));
+    const size_t n = (size_t) j->nChains;
     ChainArrays &ca = j->ca;
     memset(&ca, 0, sizeof(ca));
-    ca.n = j->nChains; ca.dimS = dS; ca.dimE = dE; ca.dimD = dD;
-    const size_t n = (size_t) j->nChains;
-    if ((st = job_alloc(j, &ca.X, (size_t) (dS + dE + dD) * n)) || (st = job_alloc(j, &ca.L, n)) || (st = job_alloc(j, &ca.pos, n)) ||
-        (st = job_alloc(j, &ca.val, n)) || (st = job_alloc(j, &ca.tcur, n)) || (st = job_alloc(j, &ca.depth, n)) ||
-        (st = job_alloc(j, &ca.chainId, n)) || (st = job_alloc(j, &ca.seedIdx, n)) || (st = job_alloc(j, &ca.mutDone, n)) ||
-        (st = job_alloc(j, &j->film, (size_t) W * H)) || (st = job_alloc(j, &j->counters, (size_t) ST_COUNT + 2)) ||
-        (st = job_alloc(j, &j->red, 4)) || (st = job_alloc(j, &j->devImage, (size_t) W * H * 3)))
+    ca.n = j->nChains;
+    if ((st = alloc_lanes(j, j->nChains)) || (st = job_alloc(j, &j->counters, (size_t) 2 * ST_COUNT)) || (st = job_alloc(j, &j->active, 1)) ||
+        (st = job_alloc(j, &j->red, 4)))
         return fail(st);
+    if (chains) {
+        // primary-sample storage: worst case over the MMLT depths
+        int dS, dE, dD;
+        max_dimensions(&cfg, cfg.max_depth, &dS, &dE, &dD);
+        ca.dimS = dS; ca.dimE = dE; ca.dimD = dD;
+        if ((st = job_alloc(j, &ca.X, (size_t) (dS + dE + dD) * n)) || (st = job_alloc(j, &ca.depth, n)) || (st = job_alloc(j, &ca.chainId, n)) ||
+            (st = job_alloc(j, &ca.seedIdx, n)) || (st = job_alloc(j, &j->film, (size_t) W * H)) || (st = job_alloc(j, &j->devImage, (size_t) W * H * 3)))
+            return fail(st);
+    }
     CK(cudaStreamSynchronize(j->stream));
     *out = j;
     return DR_OK;
 }
 
-extern "C" dr_status dr_job_create(dr_scene scene, const dr_config *cfg, dr_job *out) { return job_create_common(scene, cfg, 0, out); }
+extern "C" dr_status dr_job_create(dr_scene scene, const dr_config *cfg, dr_job *out) { return job_create_common(scene, cfg, 0, true, out); }
+
+// Run the wavefront machine until no lane has work left: rounds of (k_logic, k_trace).  The number of
+// lanes still active is polled every `roundsPerPoll` rounds through a pinned counter.
+static dr_status run_wavefront(dr_job j, const JobParams &job, unsigned long long *counters, bool withFilm) {
+    const int n = j->lm.n;
+    const int TL = 128, TT = 256;
+    const unsigned gl = (unsigned) ((n + TL - 1) / TL), gt = (unsigned) ((n + TT - 1) / TT);
+    for (;;) {
+        if (j->scene->cancel) { cudaStreamSynchronize(j->stream); dr_set_error("cancelled"); return DR_ERR_CANCELLED; }
+        for (int r = 0; r < j->roundsPerPoll; ++r) {
+            if (r == j->roundsPerPoll - 1) CK(cudaMemsetAsync(j->active, 0, sizeof(unsigned int), j->stream));
+            k_logic<<<gl, TL, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->par.cp, j->par.fp, j->ca, j->lm, job, withFilm ? j->film : nullptr,
+                                               counters, j->active);
+            k_trace<<<gt, TT, 0, j->stream>>>(j->ds, j->lm);
+        }
+        CKL();
+        j->launches += 2ull * j->roundsPerPoll;
+        j->rounds += j->roundsPerPoll;
+        CK(cudaMemcpyAsync(j->activeHost, j->active, sizeof(unsigned int), cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaStreamSynchronize(j->stream));
+        if (*j->activeHost == 0) break;
+    }
+    return DR_OK;
+}
+
+static dr_status setup_lanes(dr_job j, const JobParams &job) {
+    const int n = j->lm.n, T = 128;
+    k_setup_lanes<<<(n + T - 1) / T, T, 0, j->stream>>>(j->par.pp, j->ca, j->lm, job);
+    CKL();
+    ++j->launches;
+    return DR_OK;
+}
 
 // luminanceSamples sizing of DRMLT::render (drmlt.cpp:446-473), with the reference's CPU work-unit
-// count standing in for "workUnits" and a floor of 4 bootstrap samples per resident chain.
+// count standing in for "workUnits" and a floor of 2 bootstrap samples per resident chain.
 static long long bootstrap_samples(const dr_job j) {
     const dr_config &c = j->cfg;
     const long long desired = c.technique == DR_TECH_PATH ? 200000 : 100000;
@@ -592,7 +647,7 @@ static long long bootstrap_samples(const dr_job j) {
     long long n = c.luminance_samples;
     const long long times = c.technique == DR_TECH_MMLT ? 50 : 10;
     n = std::max(n, workUnits * times);
-    n = std::max(n, 4ll * j->nChains * c.world_size);
+    n = std::max(n, 2ll * j->nChains * c.world_size);
     if (c.technique == DR_TECH_MMLT) n *= c.max_depth;
     return n;
 }
@@ -607,27 +662,28 @@ extern "C" dr_status dr_job_bootstrap(dr_job j, double *sumOut, double *countOut
     j->nBoot = per;
     j->bootFirst = (unsigned long long) per * (unsigned long long) c.rank;
     dr_status st;
+    const long long nb = (per + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
     if (!j->bootLum) {
-        const long long nb = (per + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
         if ((st = job_alloc(j, &j->bootLum, (size_t) per)) || (st = job_alloc(j, &j->cdf, (size_t) per + 1)) ||
             (st = job_alloc(j, &j->blockSums, (size_t) nb + 1)))
             return st;
     }
     CK(cudaMemsetAsync(j->red, 0, 4 * sizeof(double), j->stream));
     CK(cudaEventRecord(j->ev0, j->stream));
-    const int T = 128;
-    k_bootstrap<<<(unsigned) ((per + T - 1) / T), T, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->bootFirst, per, j->bootLum, j->counters + ST_COUNT);
-    CKL();
+    // the bootstrap paths run through the same wavefront machine as the chains (JOB_BOOT)
+    JobParams job;
+    memset(&job, 0, sizeof(job));
+    job.type = JOB_BOOT; job.nItems = per; job.first = j->bootFirst; job.lumOut = j->bootLum;
+    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters + ST_COUNT, false))) return st;
     k_lum_reduce<<<148 * 4, 256, 0, j->stream>>>(j->bootLum, per, j->red);
     CKL();
-    const long long nb = (per + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
     k_scan_blocks<<<(unsigned) nb, SCAN_BLOCK, 0, j->stream>>>(j->bootLum, per, j->cdf, j->blockSums);
     CKL();
     k_scan_sums<<<1, 1024, 0, j->stream>>>(j->blockSums, (int) nb);
     CKL();
     k_scan_add<<<(unsigned) ((per + 255) / 256), 256, 0, j->stream>>>(j->cdf, per, j->blockSums);
     CKL();
-    j->launches += 5;
+    j->launches += 4;
     CK(cudaEventRecord(j->ev1, j->stream));
     double red[2];
     CK(cudaMemcpyAsync(red, j->red, sizeof(red), cudaMemcpyDeviceToHost, j->stream));
@@ -657,15 +713,16 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
     CK(cudaStreamSynchronize(j->stream));
     if (!(total > 0.0)) { dr_set_error("bootstrap found no path with non-zero luminance on rank %d", c.rank); return DR_ERR_ZERO_LUMINANCE; }
     j->b = b;
-    j->par.cp.b = (float) b;
+    j->par.cp.b = b;
     const int n = j->nChains, T = 128;
     const unsigned long long firstChain = (unsigned long long) c.rank * (unsigned long long) n;
     CK(cudaEventRecord(j->ev0, j->stream));
     k_resample<<<(n + T - 1) / T, T, 0, j->stream>>>(j->cdf, j->nBoot, c.seed, firstChain, n, j->bootFirst, c.max_depth, c.technique,
                                                    j->ca.seedIdx, j->ca.chainId, j->ca.depth);
     CKL();
+    ++j->launches;
     if (c.technique == DR_TECH_MMLT) {
-        // bucket chains by MMLT depth so that the chains of a warp have the same trip counts
+        // bucket chains by MMLT depth so that the lanes of a warp walk paths of the same length
         std::vector<unsigned long long> seedIdx(n), chainId(n);
         std::vector<int> depth(n), perm(n);
         CK(cudaMemcpyAsync(seedIdx.data(), j->ca.seedIdx, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
@@ -682,9 +739,13 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
         CK(cudaMemcpyAsync(j->ca.depth, d2.data(), n * sizeof(int), cudaMemcpyHostToDevice, j->stream));
         CK(cudaStreamSynchronize(j->stream));
     }
-    k_init_chains<<<(n + T - 1) / T, T, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->ca, j->counters);
-    CKL();
-    j->launches += 2;
+    // seed replay: the lanes evaluate their seed vector (PH_INIT) in the first rounds of the next run
+    JobParams job;
+    memset(&job, 0, sizeof(job));
+    job.type = JOB_CHAIN; job.mutTarget = 0;
+    dr_status st;
+    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters, true))) return st;
+    j->mutTarget = 0;
     CK(cudaEventRecord(j->ev1, j->stream));
     CK(cudaStreamSynchronize(j->stream));
     float ms = 0.f;
@@ -695,24 +756,20 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
 }
 
 static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, int recordStride, bool withFilm) {
-    const int n = j->nChains, T = 128;
-    long long done = 0;
-    while (done < steps) {
-        if (j->scene->cancel) { dr_set_error("cancelled"); return DR_ERR_CANCELLED; }
-        const int chunk = (int) std::min<long long>(records ? steps : j->stepsPerLaunch, steps - done);
-        k_chain_step<<<(n + T - 1) / T, T, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->par.cp, j->par.fp, j->ca, withFilm ? j->film : nullptr,
-                                                         j->counters, records, recordStride, chunk);
-        CKL();
-        ++j->launches;
-        done += chunk;
-    }
-    return DR_OK;
+    JobParams job;
+    memset(&job, 0, sizeof(job));
+    job.type = JOB_CHAIN;
+    job.mut0 = j->mutTarget;
+    j->mutTarget += (uint32_t) steps;
+    job.mutTarget = j->mutTarget;
+    job.records = records; job.recordStride = recordStride;
+    return run_wavefront(j, job, j->counters, withFilm);
 }
 
 extern "C" dr_status dr_job_run(dr_job j, int64_t mutationsPerChain) {
     if (!j) { dr_set_error("dr_job_run: null job"); return DR_ERR_INVALID_ARG; }
     if (!j->seeded) { dr_set_error("dr_job_run: call dr_job_seed_chains first"); return DR_ERR_INVALID_ARG; }
-    if (mutationsPerChain < 0) { dr_set_error("dr_job_run: negative mutation count"); return DR_ERR_INVALID_ARG; }
+    if (mutationsPerChain < 0 || mutationsPerChain > (1ll << 30)) { dr_set_error("dr_job_run: mutation count out of range"); return DR_ERR_INVALID_ARG; }
     CK(cudaSetDevice(j->scene->device));
     CK(cudaEventRecord(j->ev0, j->stream));
     dr_status st = run_chains(j, mutationsPerChain, nullptr, 0, true);
@@ -738,7 +795,7 @@ extern "C" dr_status dr_job_film_device(dr_job j, float **filmDev, int64_t *nFlo
 static dr_status flush_pssmlt(dr_job j) {
     if (j->cfg.integrator != DR_INTEGRATOR_PSSMLT) return DR_OK;
     const int T = 128;
-    k_flush_pssmlt<<<(j->nChains + T - 1) / T, T, 0, j->stream>>>(j->ca, j->par.fp, j->film);
+    k_flush_pssmlt<<<(j->nChains + T - 1) / T, T, 0, j->stream>>>(j->lm, j->par.fp, j->film);
     CKL();
     ++j->launches;
     return DR_OK;
@@ -770,7 +827,7 @@ extern "C" dr_status dr_job_develop(dr_job j, float *imageRgb) {
 extern "C" dr_status dr_job_stats(dr_job j, dr_stats *s) {
     if (!j || !s) { dr_set_error("dr_job_stats: null argument"); return DR_ERR_INVALID_ARG; }
     CK(cudaSetDevice(j->scene->device));
-    unsigned long long c[ST_COUNT + 2];
+    unsigned long long c[2 * ST_COUNT];
     CK(cudaMemcpyAsync(c, j->counters, sizeof(c), cudaMemcpyDeviceToHost, j->stream));
     CK(cudaStreamSynchronize(j->stream));
     memset(s, 0, sizeof(*s));
@@ -783,7 +840,7 @@ extern "C" dr_status dr_job_stats(dr_job j, dr_stats *s) {
     s->second_bold_accept = c[ST_SECOND_BOLD_A]; s->second_bold_base = c[ST_SECOND_BOLD_B];
     s->accept = c[ST_ACC_A]; s->accept_base = c[ST_ACC_B];
     s->paths = c[ST_PATHS]; s->rays = c[ST_RAYS];
-    s->bootstrap_paths = (uint64_t) (j->bootstrapped ? j->nBoot : 0); s->bootstrap_rays = c[ST_COUNT + 1];
+    s->bootstrap_paths = c[ST_COUNT + ST_PATHS]; s->bootstrap_rays = c[ST_COUNT + ST_RAYS];
     s->luminance = j->b;
     s->bootstrap_ms = j->bootstrapMs; s->chains_ms = j->chainsMs; s->total_ms = j->totalMs;
     s->kernel_launches = j->launches;
@@ -839,80 +896,90 @@ extern "C" dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n
     dr_status st;
     if ((st = dr.alloc(n * sizeof(dr_ray))) || (st = dh.alloc(n * sizeof(dr_hit)))) return st;
     CK(cudaMemcpy(dr.p, rays, n * sizeof(dr_ray), cudaMemcpyHostToDevice));
-    k_trace<<<(unsigned) ((n + 127) / 128), 128>>>(s->dev, dr.as<dr_ray>(), n, shadow, s->dOrder, dh.as<dr_hit>());
+    k_trace_rays<<<(unsigned) ((n + 127) / 128), 128>>>(s->dev, dr.as<dr_ray>(), n, shadow, s->dOrder, dh.as<dr_hit>());
     CKL();
     CK(cudaMemcpy(hits, dh.p, n * sizeof(dr_hit), cudaMemcpyDeviceToHost));
     return DR_OK;
 }
 
+static int replay_lanes(int64_t n) { return (int) std::min<int64_t>((n + 127) / 128 * 128, 1 << 18); }
+
 extern "C" dr_status dr_eval_paths(dr_scene scene, const dr_config *cfgIn, const float *us, int ds_, const float *ue, int de, const float *ud, int dd,
                                    const int32_t *depth, int64_t n, dr_path_result *out) {
     if (!scene || !cfgIn || n < 0 || (n > 0 && !out)) { dr_set_error("dr_eval_paths: bad argument"); return DR_ERR_INVALID_ARG; }
-    dr_config cfg = *cfgIn;
-    dr_status st = dr_config_validate(&cfg);
+    if ((ds_ > 0 && !us) || (de > 0 && !ue) || (dd > 0 && !ud) || ds_ < 0 || de < 0 || dd < 0) { dr_set_error("dr_eval_paths: missing primary-sample buffer"); return DR_ERR_INVALID_ARG; }
+    if (n == 0) { dr_config c = *cfgIn; return dr_config_validate(&c); }
+    dr_job j = nullptr;
+    dr_status st = job_create_common(scene, cfgIn, replay_lanes(n), false, &j);
     if (st) return st;
-    if ((st = check_technique(cfg))) return st;
-    if (cfg.technique == DR_TECH_MMLT && !depth) { dr_set_error("dr_eval_paths: MMLT needs a depth per path"); return DR_ERR_INVALID_ARG; }
-    if ((ds_ > 0 && !us) || (de > 0 && !ue) || (dd > 0 && !ud)) { dr_set_error("dr_eval_paths: missing primary-sample buffer"); return DR_ERR_INVALID_ARG; }
-    if (n == 0) return DR_OK;
-    CK(cudaSetDevice(scene->device));
-    Params par;
-    make_params(cfg, scene->filmW, scene->filmH, 1.0, par);
+    auto done = [&](dr_status code) { cudaStreamSynchronize(j->stream); dr_job_destroy(j); return code; };
+    if (j->cfg.technique == DR_TECH_MMLT) {
+        if (!depth) return done((dr_set_error("dr_eval_paths: MMLT needs a depth per path"), DR_ERR_INVALID_ARG));
+        for (int64_t i = 0; i < n; ++i)
+            if (depth[i] < 1 || depth[i] > j->cfg.max_depth) return done((dr_set_error("dr_eval_paths: depth out of range"), DR_ERR_INVALID_ARG));
+    }
     DevBuf bs, be, bd, bdep, bout;
     if ((st = bs.alloc((size_t) n * ds_ * 4)) || (st = be.alloc((size_t) n * de * 4)) || (st = bd.alloc((size_t) n * dd * 4)) ||
         (st = bdep.alloc((size_t) n * 4)) || (st = bout.alloc((size_t) n * sizeof(dr_path_result))))
-        return st;
-    if (ds_) CK(cudaMemcpy(bs.p, us, (size_t) n * ds_ * 4, cudaMemcpyHostToDevice));
-    if (de) CK(cudaMemcpy(be.p, ue, (size_t) n * de * 4, cudaMemcpyHostToDevice));
-    if (dd) CK(cudaMemcpy(bd.p, ud, (size_t) n * dd * 4, cudaMemcpyHostToDevice));
-    if (depth) CK(cudaMemcpy(bdep.p, depth, (size_t) n * 4, cudaMemcpyHostToDevice));
-    k_eval_paths<<<(unsigned) ((n + 127) / 128), 128>>>(scene_for(scene, cfg), par.pc, par.pp, bs.as<float>(), ds_, be.as<float>(), de, bd.as<float>(), dd,
-                                                       depth ? bdep.as<int>() : nullptr, n, bout.as<dr_path_result>());
-    CKL();
-    CK(cudaMemcpy(out, bout.p, (size_t) n * sizeof(dr_path_result), cudaMemcpyDeviceToHost));
-    return DR_OK;
+        return done(st);
+    cudaError_t e = cudaSuccess;
+    if (ds_) e = cudaMemcpy(bs.p, us, (size_t) n * ds_ * 4, cudaMemcpyHostToDevice);
+    if (de && e == cudaSuccess) e = cudaMemcpy(be.p, ue, (size_t) n * de * 4, cudaMemcpyHostToDevice);
+    if (dd && e == cudaSuccess) e = cudaMemcpy(bd.p, ud, (size_t) n * dd * 4, cudaMemcpyHostToDevice);
+    if (depth && e == cudaSuccess) e = cudaMemcpy(bdep.p, depth, (size_t) n * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return done((dr_set_error("dr_eval_paths: upload failed: %s", cudaGetErrorString(e)), DR_ERR_CUDA));
+    JobParams job;
+    memset(&job, 0, sizeof(job));
+    job.type = JOB_EVAL; job.nItems = n;
+    job.us = bs.as<float>(); job.ue = be.as<float>(); job.ud = bd.as<float>(); job.ds = ds_; job.de = de; job.dd = dd;
+    job.depthIn = depth ? bdep.as<int>() : nullptr; job.out = bout.as<dr_path_result>();
+    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters, false))) return done(st);
+    if (cudaMemcpy(out, bout.p, (size_t) n * sizeof(dr_path_result), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return done((dr_set_error("dr_eval_paths: download failed"), DR_ERR_CUDA));
+    return done(DR_OK);
 }
 
 extern "C" dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfgIn, uint64_t first, int64_t n, float *luminance, int32_t *depth) {
     if (!scene || !cfgIn || n < 0 || (n > 0 && !luminance)) { dr_set_error("dr_bootstrap_luminance: bad argument"); return DR_ERR_INVALID_ARG; }
-    dr_config cfg = *cfgIn;
-    dr_status st = dr_config_validate(&cfg);
+    if (n == 0) { dr_config c = *cfgIn; return dr_config_validate(&c); }
+    dr_job j = nullptr;
+    dr_status st = job_create_common(scene, cfgIn, replay_lanes(n), false, &j);
     if (st) return st;
-    if ((st = check_technique(cfg))) return st;
-    if (n == 0) return DR_OK;
-    CK(cudaSetDevice(scene->device));
-    Params par;
-    make_params(cfg, scene->filmW, scene->filmH, 1.0, par);
-    DevBuf bl, bc;
-    if ((st = bl.alloc((size_t) n * 4)) || (st = bc.alloc(2 * sizeof(unsigned long long)))) return st;
-    CK(cudaMemset(bc.p, 0, 2 * sizeof(unsigned long long)));
-    k_bootstrap<<<(unsigned) ((n + 127) / 128), 128>>>(scene_for(scene, cfg), par.pc, par.pp, first, n, bl.as<float>(), bc.as<unsigned long long>());
-    CKL();
-    CK(cudaMemcpy(luminance, bl.p, (size_t) n * 4, cudaMemcpyDeviceToHost));
+    auto done = [&](dr_status code) { cudaStreamSynchronize(j->stream); dr_job_destroy(j); return code; };
+    DevBuf bl;
+    if ((st = bl.alloc((size_t) n * 4))) return done(st);
+    JobParams job;
+    memset(&job, 0, sizeof(job));
+    job.type = JOB_BOOT; job.nItems = n; job.first = first; job.lumOut = bl.as<float>();
+    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters + ST_COUNT, false))) return done(st);
+    if (cudaMemcpy(luminance, bl.p, (size_t) n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return done((dr_set_error("dr_bootstrap_luminance: download failed"), DR_ERR_CUDA));
     if (depth)
         for (int64_t i = 0; i < n; ++i)
-            depth[i] = cfg.technique == DR_TECH_MMLT ? (int32_t) ((first + (uint64_t) i) % (uint64_t) cfg.max_depth) + 1 : -1;
-    return DR_OK;
+            depth[i] = j->cfg.technique == DR_TECH_MMLT ? (int32_t) ((first + (uint64_t) i) % (uint64_t) j->cfg.max_depth) + 1 : -1;
+    return done(DR_OK);
 }
 
 extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, double b, const uint64_t *seedIndex, const int32_t *depth,
                                     const uint64_t *chainId, int64_t nChains, int64_t steps, dr_step_record *records, float *film) {
     if (!scene || !cfgIn || nChains < 0 || steps < 0 || (nChains > 0 && (!seedIndex || !chainId))) { dr_set_error("dr_chain_steps: bad argument"); return DR_ERR_INVALID_ARG; }
-    if (nChains == 0) return DR_OK;
+    if (nChains == 0) { dr_config c = *cfgIn; return dr_config_validate(&c); }
     if (nChains > (1 << 24) || steps > (1 << 24)) { dr_set_error("dr_chain_steps: too large"); return DR_ERR_INVALID_ARG; }
     dr_job j = nullptr;
-    dr_status st = job_create_common(scene, cfgIn, (int) nChains, &j);
+    dr_status st = job_create_common(scene, cfgIn, (int) nChains, true, &j);
     if (st) return st;
-    if (j->cfg.technique == DR_TECH_MMLT && !depth) { dr_job_destroy(j); dr_set_error("dr_chain_steps: MMLT needs a depth per chain"); return DR_ERR_INVALID_ARG; }
     auto done = [&](dr_status code) { cudaStreamSynchronize(j->stream); dr_job_destroy(j); return code; };
+    if (j->cfg.technique == DR_TECH_MMLT && !depth) return done((dr_set_error("dr_chain_steps: MMLT needs a depth per chain"), DR_ERR_INVALID_ARG));
     if (j->cfg.average_luminance != -1.0f) b = j->cfg.average_luminance;
     if (j->cfg.integrator == DR_INTEGRATOR_DRMLT && j->cfg.acceptance_map) b = 1.0;
-    j->b = b; j->par.cp.b = (float) b;
-    const int n = (int) nChains, T = 128;
+    j->b = b; j->par.cp.b = b;
+    const int n = (int) nChains;
     std::vector<int> dep(n, -1);
-    if (depth) for (int i = 0; i < n; ++i) dep[i] = depth[i];
-    if (j->cfg.technique != DR_TECH_MMLT) std::fill(dep.begin(), dep.end(), -1);
-    else for (int i = 0; i < n; ++i) if (dep[i] < 1 || dep[i] > j->cfg.max_depth) return done((dr_set_error("dr_chain_steps: depth out of range"), DR_ERR_INVALID_ARG));
+    if (j->cfg.technique == DR_TECH_MMLT)
+        for (int i = 0; i < n; ++i) {
+            dep[i] = depth[i];
+            if (dep[i] < 1 || dep[i] > j->cfg.max_depth) return done((dr_set_error("dr_chain_steps: depth out of range"), DR_ERR_INVALID_ARG));
+        }
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
     if (cudaMemcpyAsync(j->ca.seedIdx, seedIndex, n * sizeof(uint64_t), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
         cudaMemcpyAsync(j->ca.chainId, chainId, n * sizeof(uint64_t), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
@@ -921,13 +988,15 @@ extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, doub
         dr_set_error("dr_chain_steps: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return done(DR_ERR_CUDA);
     }
-    k_init_chains<<<(n + T - 1) / T, T, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->ca, j->counters);
-    if (cudaGetLastError() != cudaSuccess) { dr_set_error("k_init_chains launch failed"); return done(DR_ERR_CUDA); }
     DevBuf drec;
     if (records && steps > 0) {
         if ((st = drec.alloc((size_t) n * steps * sizeof(dr_step_record)))) return done(st);
         cudaMemsetAsync(drec.p, 0, (size_t) n * steps * sizeof(dr_step_record), j->stream);
     }
+    JobParams job;
+    memset(&job, 0, sizeof(job));
+    job.type = JOB_CHAIN; job.mutTarget = 0;
+    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters, film != nullptr))) return done(st);   // seed replay
     j->seeded = true;
     if (steps > 0 && (st = run_chains(j, steps, records ? drec.as<dr_step_record>() : nullptr, (int) steps, film != nullptr))) return done(st);
     if (film && (st = flush_pssmlt(j))) return done(st);

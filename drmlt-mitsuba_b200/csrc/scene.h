@@ -6,10 +6,12 @@
 //               n2 = (lo1.z hi1.x hi1.y hi1.z)  n3 = (child0, child1, -, -) as int bits
 //             child >= 0: inner node index; child < 0: leaf, ~child = (firstTri << 2) | (count - 1), count <= 4
 //   tris    : 48 B / triangle in LEAF ORDER = 3 x float4
-//               t0 = (p0.x p0.y p0.z e1.x) t1 = (e1.y e1.z e2.x e2.y) t2 = (e2.z, prim, matflags, emitter)
-//             prim = index in the caller's triangle order, matflags = material | (DR_TRI_SMOOTH << 31 .. )
+//               t0 = (p0.x p0.y p0.z p1.x) t1 = (p1.y p1.z p2.x p2.y) t2 = (p2.z, prim, matflags, emitter)
+//             the exact float vertices (edges are formed on the fly, so the double-precision
+//             re-intersection of the shading stage sees the same triangle as the reference);
+//             prim = index in the caller's triangle order, matflags = material | smooth << 31
 //   normals : 48 B / triangle in leaf order (only read for smooth triangles at the closest hit)
-//   em_tris : 96 B / emitter triangle in EMITTER order: p0,e1,e2 + n0,n1,n2 (position sampling)
+//   em_tris : 96 B / emitter triangle in EMITTER order: p0,p1,p2,smooth + n0,n1,n2 (position sampling)
 //   em_cdf  : double prefix sums of the per-emitter triangle areas (pmf.h DiscreteDistribution)
 // Replaces ShapeKDTree + TriAccel (src/librender/skdtree.cpp, include/mitsuba/render/triaccel.h) for this path.
 #pragma once
@@ -24,21 +26,21 @@ struct DevMaterial {      // 64 B, mirrors dr_material
     float alpha, pad;
 };
 
-struct DevEmitter {       // 48 B
+struct DevEmitter {       // 64 B
+    double area, invArea;
+    double pdfDiscrete;   // emitterPDF[e]
     float radiance[3];
-    float area, invArea;
-    float pdfDiscrete;    // emitterPDF[e]
     uint32_t firstEmTri;  // offset into em_tris
     uint32_t nTris;
     uint32_t cdfOffset;   // offset into em_cdf (nTris + 1 entries)
-    uint32_t pad[3];
+    uint32_t pad[4];
 };
 
-struct DevCamera {
-    float m[12];          // rows of the 3x4 camera-to-world matrix
-    float3 pos, dir;
-    float tanHalf, aspect, nearClip, farClip;
-    float resX, resY, rectX, rectY, normalization;
+struct DevCamera {        // derived in double from the float parameters of dr_camera (perspective.cpp:126-173)
+    double m[12];         // rows of the 3x4 camera-to-world matrix
+    double pos[3], dir[3];
+    double tanHalf, aspect, nearClip, farClip;
+    double resX, resY, rectX, rectY, normalization;
 };
 
 struct DevScene {

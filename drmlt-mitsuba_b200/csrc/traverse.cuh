@@ -27,7 +27,7 @@ DR_D float adaptive_mint(const DevScene &sc, float3 o, float mint) {
 
 DR_D bool tri_test(const float4 t0, const float4 t1, const float4 t2, float3 o, float3 d,
                    float tmin, float tmax, float &t, float &u, float &v) {
-    const float3 p0 = f3(t0.x, t0.y, t0.z), e1 = f3(t0.w, t1.x, t1.y), e2 = f3(t1.z, t1.w, t2.x);
+    const float3 p0 = f3(t0.x, t0.y, t0.z), e1 = f3(t0.w, t1.x, t1.y) - p0, e2 = f3(t1.z, t1.w, t2.x) - p0;
     const float3 pvec = cross(d, e2);
     const float det = dot(e1, pvec);
     if (det == 0.f) return false;
@@ -44,7 +44,9 @@ template <bool ANYHIT>
 DR_D bool traverse(const DevScene &sc, float3 o, float3 d, float tmin, float tmax, Hit &hit, uint32_t *nodeVisits = nullptr) {
     hit.tri = -1;
     if (!(tmax > tmin)) return false;
-    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    // zero direction components: clamp so that 1/d stays finite (no 0 * inf = NaN in the slab test)
+    const float3 inv = f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
+                          1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
     const float3 oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
     int stack[DR_STACK];
     int sp = 0;

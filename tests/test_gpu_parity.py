@@ -177,9 +177,11 @@ def test_path_contribution_replayed_u(case):
     off = 20 + 8 * abi.DR_MAX_SPLATS
     vg, vc = g[:, off:off + 12].copy().view("<f4"), c[:, off:off + 12].copy().view("<f4")
     assert (np.abs(vg[both] - vc[both]) <= 1e-4 * np.abs(vc[both]) + 1e-7 * np.abs(vc[both]).max(axis=1, keepdims=True)).all(axis=1).mean() >= 0.999
-    # ray counts: identical control flow
+    # ray counts: identical control flow on contributing paths; a path that dies during the sensor walk
+    # skips its emitter walk on the GPU (the reference walks both before testing, pathsampler.cpp:139-159)
     rg, rc = g[:, -4:].copy().view("<i4")[:, 0], c[:, -4:].copy().view("<i4")[:, 0]
-    assert (rg == rc).mean() >= 0.999
+    assert (rg[both] == rc[both]).mean() >= 0.999
+    assert (rg <= rc).mean() >= 0.999
 
 
 @pytest.mark.parametrize("case", CASES, ids=_case_id)
@@ -265,7 +267,8 @@ def test_chain_decisions_under_identical_uniforms(case):
         a, b = G[k][mask].astype(np.float64), Cc[k][mask].astype(np.float64)
         nz = b > 0
         assert ((a > 0) == nz).mean() > 0.999
-        assert (np.abs(a[nz] - b[nz]) <= 2e-4 * b[nz]).mean() > 0.998, k
+        if nz.any():
+            assert (np.abs(a[nz] - b[nz]) <= 2e-4 * b[nz]).mean() > 0.998, k
     for k in ("a1", "a2"):
         assert np.percentile(np.abs(G[k][mask] - Cc[k][mask]), 99.8) < 1e-3, k
     # overall agreement of the raw decision stream
