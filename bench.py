@@ -228,29 +228,58 @@ def run_gpu(args):
     value = muts_all / (max_ms * 1e-3)
     launches = int(st1.kernel_launches - st0.kernel_launches)
 
-    # ---- roofline of the dominant kernel (k_chain_step): algorithmic bytes per launch / launch duration
+    # ---- per-stage device time: one extra step with CUDA events around every stage of every round (the timed
+    #      steps above run without them), on the same resident job
+    job.profile(True)
+    flush.fill_(1)
+    torch.cuda.synchronize()
+    p0 = job.stats()
+    job.run(M)
+    p1 = job.stats()
+    job.profile(False)
+    stage_ms = {"k_trace": p1.trace_ms - p0.trace_ms, "k_walk+k_connect": p1.walk_ms - p0.walk_ms, "k_chain": p1.chain_ms - p0.chain_ms}
+    stage_launches = {"k_trace": p1.trace_launches - p0.trace_launches, "k_walk+k_connect": p1.walk_launches - p0.walk_launches,
+                      "k_chain": p1.chain_launches - p0.chain_launches}
+    prof_rounds = max(1, p1.rounds - p0.rounds)
+    prof_rays, prof_paths, prof_muts = p1.rays - p0.rays, p1.paths - p0.paths, p1.mutations - p0.mutations
+    tot_stage = sum(stage_ms.values()) or 1.0
+
+    # ---- roofline.  Algorithmic bytes per unit of each stage (DESIGN.md "Algorithmic bytes"):
+    #   k_trace : B_ray(T) per ray = 64*ceil(log2(T/4)) + 4*48 + 64
+    #   k_walk  : lane records of one vertex step, read + written = 1 056 B per ray that hits
+    #   k_chain : lane records + coordinate buffers of one finished path, read + written = 1 664 B per path
     paths_per_mut = (st1.paths - st0.paths) / max(1, muts_rank)
     rays_per_path = (st1.rays - st0.rays) / max(1, st1.paths - st0.paths)
     mean_depth = 4.5                                                # depths 1..8 equally likely
     dims = 2 * (3 * (mean_depth + 2)) + 1
     b_mut = mutation_bytes(data.n_triangles, paths_per_mut, rays_per_path, dims, 16)
-    ms_per_launch = dev_ms / max(1, launches)
-    muts_per_launch = muts_rank / max(1, launches)
-    achieved = b_mut * muts_per_launch / (ms_per_launch * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback"
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "measured"
     except Exception:
         pass
-    traffic = None
+    traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_chain_step_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_chain_step", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "bytes_per_mutation": b_mut, "paths_per_mutation": paths_per_mut,
-                "rays_per_path": rays_per_path, "mrays_per_s": (st1.rays - st0.rays) * world / (max_ms * 1e-3) / 1e6,
-                "ms_per_launch": ms_per_launch, "mutations_per_launch": muts_per_launch}
+    unit_bytes = {"k_trace": (ray_bytes(data.n_triangles), prof_rays), "k_walk+k_connect": (1056, prof_rays), "k_chain": (1664, prof_paths)}
+    stages = {}
+    for k, ms in stage_ms.items():
+        bpu, units = unit_bytes[k]
+        stages[k] = {"ms": ms, "share": ms / tot_stage, "launches": int(stage_launches[k]),
+                     "achieved_gbs": bpu * units / (ms * 1e-3) / 1e9 if ms > 0 else None, "bytes_per_unit": bpu, "units": int(units)}
+    dom = max(stage_ms, key=stage_ms.get)
+    dom_launch_ms = stage_ms[dom] / max(1, stage_launches[dom])
+    achieved = stages[dom]["achieved_gbs"] or 0.0
+    step_gbs = b_mut * muts_rank / (dev_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic.get(dom), "ms_per_launch": dom_launch_ms,
+                "units_per_launch": stages[dom]["units"] / max(1, stage_launches[dom]), "bytes_per_unit": stages[dom]["bytes_per_unit"],
+                "stages": stages, "whole_step": {"bytes_per_mutation": b_mut, "achieved": step_gbs, "frac": step_gbs / peak},
+                "paths_per_mutation": paths_per_mut, "rays_per_path": rays_per_path,
+                "mrays_per_s": (st1.rays - st0.rays) * world / (max_ms * 1e-3) / 1e6,
+                "rounds_per_step": prof_rounds, "profiled_step_mutations": int(prof_muts)}
     job.close()
 
     # ---- e2e: whole job through the public API with host buffers

@@ -61,9 +61,16 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
     int root = alloc_node();
     (void) root;
     // process(range) -> fills node `node`
-    struct Range { int node; uint32_t first, count; };
+    struct Range { int node; uint32_t first, count; int depth; };
     std::vector<Range> work;
-    work.push_back({ 0, 0, nTris });
+    work.push_back({ 0, 0, nTris, 1 });
+    // Child boxes are padded by a few 1e-6 of the scene extent: the traversal tests them with the float-cast ray,
+    // whose origin / direction differ from the double ray by one float ulp.
+    Box sceneBox; sceneBox.reset();
+    for (uint32_t i = 0; i < nTris; ++i) sceneBox.grow(box[i]);
+    const float pad = 4e-6f * std::max(std::max(sceneBox.hi[0] - sceneBox.lo[0], sceneBox.hi[1] - sceneBox.lo[1]),
+                                       std::max(sceneBox.hi[2] - sceneBox.lo[2], 1e-30f));
+    out.maxDepth = 1;
     while (!work.empty()) {
         Range r = work.back(); work.pop_back();
         // centroid bounds
@@ -118,8 +125,10 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
                 code[c] = ~(int) ((firsts[c] << 2) | (counts[c] - 1));
             } else {
                 code[c] = alloc_node();
-                work.push_back({ code[c], firsts[c], counts[c] });
+                work.push_back({ code[c], firsts[c], counts[c], r.depth + 1 });
+                out.maxDepth = std::max(out.maxDepth, r.depth + 1);
             }
+            for (int a = 0; a < 3; ++a) { cb[c].lo[a] -= pad; cb[c].hi[a] += pad; }
         }
         float4 *n = &out.nodes[4 * (size_t) r.node];
         n[0] = make_float4(cb[0].lo[0], cb[0].lo[1], cb[0].lo[2], cb[0].hi[0]);

@@ -6,7 +6,8 @@
 // DRMLT::render / PSSMLT::render (work sizing + bootstrap orchestration, drmlt.cpp:393-611) and
 // DRMLTProcess::develop (drmlt_proc.cpp:813-854).  There is no CPU fallback: every entry point
 // that computes needs a CUDA device and fails with DR_ERR_NO_DEVICE / DR_ERR_CUDA otherwise.
-#include "chain.cuh"
+#include "machine.cuh"
+#include "util_kernels.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -268,6 +269,7 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
         dr_set_error("dr_scene_create: empty scene or missing buffers"); return DR_ERR_INVALID_ARG;
     }
     if (d->n_triangles >= (1u << 29)) { dr_set_error("dr_scene_create: too many triangles"); return DR_ERR_UNSUPPORTED; }
+    if (d->n_materials >= (1u << 24)) { dr_set_error("dr_scene_create: too many materials"); return DR_ERR_UNSUPPORTED; }
     if (d->n_emitters && !d->emitters) { dr_set_error("dr_scene_create: emitters missing"); return DR_ERR_INVALID_ARG; }
     if (d->camera.film_width <= 0 || d->camera.film_height <= 0) { dr_set_error("dr_scene_create: bad film size"); return DR_ERR_INVALID_ARG; }
     for (uint32_t i = 0; i < d->n_triangles; ++i) {
@@ -299,11 +301,13 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     s->device = device;
     s->filmW = d->camera.film_width; s->filmH = d->camera.film_height;
     s->nTris = d->n_triangles;
+    for (uint32_t i = 0; i < d->n_triangles; ++i) s->typeMask |= 1u << d->materials[d->tri_material[i]].type;
     dr_status st = DR_OK;
     auto fail = [&](dr_status code) { dr_scene_destroy(s); return code; };
 
     BuiltBVH bvh;
     build_bvh(d->positions, d->indices, d->n_triangles, bvh);
+    if (bvh.maxDepth >= DR_STACK) { dr_set_error("dr_scene_create: BVH depth %d exceeds the traversal stack (%d)", bvh.maxDepth, DR_STACK); return fail(DR_ERR_UNSUPPORTED); }
     s->nNodes = (uint32_t) (bvh.nodes.size() / 4);
 
     // triangles and shading normals in leaf order
@@ -320,7 +324,8 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
         const uint32_t i0 = d->indices[3 * (size_t) prim], i1 = d->indices[3 * (size_t) prim + 1], i2 = d->indices[3 * (size_t) prim + 2];
         const float3 p0 = P(i0), p1 = P(i1), p2 = P(i2);
         const bool smooth = anySmooth && (d->tri_flags[prim] & DR_TRI_SMOOTH);
-        const uint32_t mf = d->tri_material[prim] | (smooth ? 0x80000000u : 0u);
+        // material index | BSDF model << 24 (routes the hit to its walk queue) | smooth << 31
+        const uint32_t mf = d->tri_material[prim] | ((uint32_t) d->materials[d->tri_material[prim]].type << 24) | (smooth ? 0x80000000u : 0u);
         tris[3 * slot] = make_float4(p0.x, p0.y, p0.z, p1.x);
         tris[3 * slot + 1] = make_float4(p1.y, p1.z, p2.x, p2.y);
         tris[3 * slot + 2] = make_float4(p2.z, as_float_bits((int) prim), as_float_bits((int) mf), as_float_bits(d->tri_emitter[prim]));
@@ -427,14 +432,14 @@ extern "C" dr_status dr_scene_reupload(dr_scene scene, int64_t *bytes) {
 extern "C" void dr_cancel(dr_scene scene) { if (scene) scene->cancel = 1; }
 
 // ------------------------------------------------------------------ launch parameters
-struct Params { PathCfg pc; PssParams pp; ChainParams cp; FilmParams fp; };
-
-static void make_params(const dr_config &c, int W, int H, double b, Params &p) {
-    memset(&p, 0, sizeof(p));
+// Fills the constant part of a Machine from the configuration.  `evalDims` (JOB_EVAL): the coordinate
+// buffers are laid out for the replayed vectors' own dimensions.
+static void make_params(const dr_config &c, int W, int H, double b, const int *evalDims, Machine &p) {
     p.pc.technique = c.technique; p.pc.maxDepth = c.max_depth; p.pc.rrDepth = c.rr_depth;
     p.pc.excludeDirect = c.direct_samples >= 0;        // separateDirect (drmlt.cpp:242)
     p.pc.lightImage = c.light_image != 0;
     PssParams &pp = p.pp;
+    memset(&pp, 0, sizeof(pp));
     pp.seed = c.seed; pp.integrator = c.integrator; pp.type = c.type;
     const double s1 = 1.0 / 1024.0, s2 = 1.0 / 64.0;   // drmlt_sampler.h:201-202
     const double scale = (c.integrator == DR_INTEGRATOR_DRMLT && c.type == DR_TYPE_ORBITAL) ? 1.9 : 1.0;   // :203-205
@@ -452,12 +457,22 @@ static void make_params(const dr_config &c, int W, int H, double b, Params &p) {
         pp.identity1 = 1u << SMP_DIRECT;                // setStagesToIdentity (drmlt_proc.cpp:133-136)
         if (c.fix_emitter_path) pp.identity2 = 1u << SMP_EMITTER;   // handleLightTracing (:137-140)
     }
+    // subset mode (pss.cuh): exact whenever the strategy coordinate can only change in a large step and no
+    // stage reads the current state after such a change
+    pp.subset = c.integrator == DR_INTEGRATOR_DRMLT && c.technique == DR_TECH_MMLT && !(c.type == DR_TYPE_GREEN && c.timid_after_large);
     ChainParams &cp = p.cp;
+    memset(&cp, 0, sizeof(cp));
     cp.pLarge = c.p_large; cp.b = b;
     cp.acceptanceMap = c.integrator == DR_INTEGRATOR_DRMLT && c.acceptance_map;
     cp.timidAfterLarge = c.timid_after_large; cp.fixEmitterPath = c.fix_emitter_path; cp.useMixture = c.use_mixture;
     cp.kelemenWeights = c.kelemen_style_weights;
     cp.kel_s1 = s1; cp.kel_s2 = s2; cp.kel_logRatio = -std::log(s2 / s1);
+    max_dimensions(&c, c.max_depth, &cp.dimS, &cp.dimE, &cp.dimD);   // worst case over the MMLT depths
+    int lay[3] = { cp.dimS, cp.dimE, cp.dimD };
+    if (evalDims) for (int s = 0; s < 3; ++s) lay[s] = std::max(lay[s], evalDims[s]);
+    int off = 0;
+    for (int s = 0; s < 3; ++s) { pp.off[s] = off; off += (lay[s] + 1) & ~1; }
+    pp.nU = std::max(off, 2);
     // reconstruction filter table (rfilter.cpp:37-55; gaussian.cpp:30-60 stddev 0.5 radius 2; box.cpp radius 0.5 + 1e-5)
     FilmParams &fp = p.fp;
     fp.w = W; fp.h = H;
@@ -490,19 +505,19 @@ static dr_status check_technique(const dr_config &c) {
 }
 
 // ------------------------------------------------------------------ job
+enum { STAGE_TRACE = 0, STAGE_WALK, STAGE_CHAIN, STAGE_COUNT };
+
 struct dr_job_t {
     dr_scene scene = nullptr;
     dr_config cfg;
-    Params par;
-    DevScene ds;
-    ChainArrays ca;
-    LaneMem lm;
+    Machine M;                                  // constant part: scene, parameters, lane memory, queues
+    int *depth = nullptr;                       // [n] MMLT depth of every chain (or -1)
+    unsigned long long *chainId = nullptr, *seedIdx = nullptr;
     float4 *film = nullptr;
     unsigned long long *counters = nullptr;     // [0, ST_COUNT): chain phase, [ST_COUNT, 2 ST_COUNT): bootstrap
-    unsigned int *active = nullptr;             // lanes with work left after the last logic round
-    unsigned int *activeHost = nullptr;         // pinned mirror
+    uint32_t *countsHost = nullptr;             // pinned mirror of the queue counters
     float *bootLum = nullptr;
-    double *cdf = nullptr, *blockSums = nullptr, *red = nullptr;
+    double *cdf = nullptr, *blockSums = nullptr, *red = nullptr, *redScratch = nullptr;
     float *devImage = nullptr;
     long long nBoot = 0;
     unsigned long long bootFirst = 0;
@@ -517,6 +532,11 @@ struct dr_job_t {
     uint64_t launches = 0, rounds = 0;
     std::vector<void *> allocations;
     int roundsPerPoll = 16;
+    // optional per-stage device timing (dr_job_profile): events around every stage of every round
+    bool profile = false;
+    std::vector<cudaEvent_t> profEvents;
+    double stageMs[STAGE_COUNT] = { 0, 0, 0 };
+    uint64_t stageLaunches[STAGE_COUNT] = { 0, 0, 0 };
 };
 
 template <class T>
@@ -532,7 +552,8 @@ extern "C" void dr_job_destroy(dr_job j) {
     cudaSetDevice(j->scene->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
     for (void *p : j->allocations) cudaFree(p);
-    if (j->activeHost) cudaFreeHost(j->activeHost);
+    if (j->countsHost) cudaFreeHost(j->countsHost);
+    for (cudaEvent_t e : j->profEvents) cudaEventDestroy(e);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);
     if (j->stream) cudaStreamDestroy(j->stream);
@@ -540,27 +561,31 @@ extern "C" void dr_job_destroy(dr_job j) {
 }
 
 static int auto_chains(long long totalMutations) {
-    // enough lanes to fill 148 SMs x 2048 resident threads several times over, but >= 32 mutations per chain
+    // enough lanes to keep every stage kernel's queue several waves deep on 148 SMs, but >= 32 mutations per chain
     long long n = totalMutations / 32;
     n = std::max<long long>(4096, std::min<long long>(n, 1 << 20));
     n = std::min<long long>(n, std::max<long long>(128, totalMutations));
     return (int) ((n + 127) / 128 * 128);
 }
 
-// lane memory of the wavefront machine for `n` lanes
+// lane memory and work queues of the wavefront machine for `n` lanes
 static dr_status alloc_lanes(dr_job j, int n) {
-    LaneMem &lm = j->lm;
+    LaneMem &lm = j->M.lm;
     memset(&lm, 0, sizeof(lm));
-    lm.n = n;
+    lm.n = n; lm.nU = j->M.pp.nU;
+    Queues &q = j->M.q;
+    q.n = n;
     dr_status st;
-    if ((st = job_alloc(j, &lm.w, (size_t) W_COUNT * n)) || (st = job_alloc(j, &lm.mis, (size_t) 3 * (DR_MAXK + 1) * n)) ||
-        (st = job_alloc(j, &lm.rayO, (size_t) n)) || (st = job_alloc(j, &lm.rayD, (size_t) n)) || (st = job_alloc(j, &lm.hit, (size_t) n)) ||
-        (st = job_alloc(j, &lm.rayKind, (size_t) n)))
+    if ((st = job_alloc(j, &lm.core, (size_t) n)) || (st = job_alloc(j, &lm.vt, (size_t) n)) || (st = job_alloc(j, &lm.vs, (size_t) n)) ||
+        (st = job_alloc(j, &lm.vtp, (size_t) n)) || (st = job_alloc(j, &lm.vsp, (size_t) n)) || (st = job_alloc(j, &lm.chain, (size_t) n)) ||
+        (st = job_alloc(j, &lm.mis, (size_t) MIS_WORDS * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
+        (st = job_alloc(j, &lm.ray, (size_t) 2 * n)) || (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)) ||
+        (st = job_alloc(j, &q.items, (size_t) Q_COUNT * n)) || (st = job_alloc(j, &q.count, (size_t) Q_COUNT)))
         return st;
     return DR_OK;
 }
 
-static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int nLanes, bool chains, dr_job *out) {
+static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int nLanes, bool chains, const int *evalDims, dr_job *out) {
     if (!scene || !cfgIn || !out) { dr_set_error("dr_job_create: null argument"); return DR_ERR_INVALID_ARG; }
     *out = nullptr;
     dr_config cfg = *cfgIn;
@@ -570,32 +595,27 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     CK(cudaSetDevice(scene->device));
     dr_job j = new dr_job_t();
     j->scene = scene; j->cfg = cfg;
-    j->ds = scene_for(scene, cfg);
+    memset(&j->M, 0, sizeof(j->M));
+    j->M.sc = scene_for(scene, cfg);
     const int W = scene->filmW, H = scene->filmH;
-    make_params(cfg, W, H, 1.0, j->par);
+    make_params(cfg, W, H, 1.0, evalDims, j->M);
     auto fail = [&](dr_status code) { dr_job_destroy(j); return code; };
     if (cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&j->ev0) != cudaSuccess ||
-        cudaEventCreate(&j->ev1) != cudaSuccess || cudaMallocHost((void **) &j->activeHost, sizeof(unsigned int)) != cudaSuccess) {
+        cudaEventCreate(&j->ev1) != cudaSuccess || cudaMallocHost((void **) &j->countsHost, sizeof(uint32_t) * Q_COUNT) != cudaSuccess) {
         dr_set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(DR_ERR_CUDA);
     }
+    j->profile = getenv("DRMLT_PROFILE_STAGES") != nullptr;
     // this rank's share of W*H*sampleCount mutations (drmlt.cpp:475-476)
     const long long total = (long long) W * H * cfg.sample_count;
     j->totalMutations = total / cfg.world_size + (cfg.rank < total % cfg.world_size ? 1 : 0);
     j->nChains = nLanes > 0 ? nLanes : (cfg.n_chains > 0 ? cfg.n_chains : auto_chains(j->totalMutations));
     const size_t n = (size_t) j->nChains;
-    ChainArrays &ca = j->ca;
-    memset(&ca, 0, sizeof(ca));
-    ca.n = j->nChains;
-    if ((st = alloc_lanes(j, j->nChains)) || (st = job_alloc(j, &j->counters, (size_t) 2 * ST_COUNT)) || (st = job_alloc(j, &j->active, 1)) ||
-        (st = job_alloc(j, &j->red, 4)))
+    if ((st = alloc_lanes(j, j->nChains)) || (st = job_alloc(j, &j->counters, (size_t) 2 * ST_COUNT)) || (st = job_alloc(j, &j->red, 4)) ||
+        (st = job_alloc(j, &j->redScratch, (size_t) lum_reduce_scratch_doubles())))
         return fail(st);
     if (chains) {
-        // primary-sample storage: worst case over the MMLT depths
-        int dS, dE, dD;
-        max_dimensions(&cfg, cfg.max_depth, &dS, &dE, &dD);
-        ca.dimS = dS; ca.dimE = dE; ca.dimD = dD;
-        if ((st = job_alloc(j, &ca.X, (size_t) (dS + dE + dD) * n)) || (st = job_alloc(j, &ca.depth, n)) || (st = job_alloc(j, &ca.chainId, n)) ||
-            (st = job_alloc(j, &ca.seedIdx, n)) || (st = job_alloc(j, &j->film, (size_t) W * H)) || (st = job_alloc(j, &j->devImage, (size_t) W * H * 3)))
+        if ((st = job_alloc(j, &j->depth, n)) || (st = job_alloc(j, &j->chainId, n)) || (st = job_alloc(j, &j->seedIdx, n)) ||
+            (st = job_alloc(j, &j->film, (size_t) W * H)) || (st = job_alloc(j, &j->devImage, (size_t) W * H * 3)))
             return fail(st);
     }
     CK(cudaStreamSynchronize(j->stream));
@@ -603,35 +623,67 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     return DR_OK;
 }
 
-extern "C" dr_status dr_job_create(dr_scene scene, const dr_config *cfg, dr_job *out) { return job_create_common(scene, cfg, 0, true, out); }
+extern "C" dr_status dr_job_create(dr_scene scene, const dr_config *cfg, dr_job *out) { return job_create_common(scene, cfg, 0, true, nullptr, out); }
 
-// Run the wavefront machine until no lane has work left: rounds of (k_logic, k_trace).  The number of
-// lanes still active is polled every `roundsPerPoll` rounds through a pinned counter.
-static dr_status run_wavefront(dr_job j, const JobParams &job, unsigned long long *counters, bool withFilm) {
-    const int n = j->lm.n;
-    const int TL = 128, TT = 256;
-    const unsigned gl = (unsigned) ((n + TL - 1) / TL), gt = (unsigned) ((n + TT - 1) / TT);
+static Machine machine_for(dr_job j, const JobParams &job, unsigned long long *counters, bool withFilm) {
+    Machine M = j->M;
+    M.job = job; M.film = withFilm ? j->film : nullptr; M.counters = counters; M.parity = (int) (j->rounds & 1);
+    return M;
+}
+
+// Run the wavefront machine until no lane has work left.  One round = trace (closest, shadow) -> walk per BSDF
+// model + connect (MMLT) | path tracer (technique=path) -> chain.  The queue counters are polled every
+// `roundsPerPoll` rounds through a pinned mirror.
+static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long *counters, bool withFilm) {
+    Machine M = machine_for(j, job, counters, withFilm);
+    LaunchCfg lc; lc.stream = j->stream; lc.nLanes = j->nChains;
+    const bool mmlt = j->cfg.technique == DR_TECH_MMLT;
+    const unsigned typeMask = static_cast<SceneImpl *>(j->scene)->typeMask;
+    const int walkLaunches = mmlt ? __builtin_popcount(typeMask & 15u) + 1 : 1;
+    auto mark = [&]() {
+        if (!j->profile) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, j->stream); j->profEvents.push_back(e);
+    };
     for (;;) {
         if (j->scene->cancel) { cudaStreamSynchronize(j->stream); dr_set_error("cancelled"); return DR_ERR_CANCELLED; }
         for (int r = 0; r < j->roundsPerPoll; ++r) {
-            if (r == j->roundsPerPoll - 1) CK(cudaMemsetAsync(j->active, 0, sizeof(unsigned int), j->stream));
-            k_logic<<<gl, TL, 0, j->stream>>>(j->ds, j->par.pc, j->par.pp, j->par.cp, j->par.fp, j->ca, j->lm, job, withFilm ? j->film : nullptr,
-                                               counters, j->active);
-            k_trace<<<gt, TT, 0, j->stream>>>(j->ds, j->lm);
+            M.parity = (int) (j->rounds & 1);
+            mark();
+            launch_trace(M, lc);
+            mark();
+            if (mmlt) launch_walk(M, lc, typeMask); else launch_pt(M, lc);
+            mark();
+            launch_chain(M, lc);
+            mark();
+            ++j->rounds;
         }
         CKL();
-        j->launches += 2ull * j->roundsPerPoll;
-        j->rounds += j->roundsPerPoll;
-        CK(cudaMemcpyAsync(j->activeHost, j->active, sizeof(unsigned int), cudaMemcpyDeviceToHost, j->stream));
+        j->launches += (uint64_t) j->roundsPerPoll * (3 + walkLaunches + 1);
+        CK(cudaMemcpyAsync(j->countsHost, M.q.count, sizeof(uint32_t) * Q_COUNT, cudaMemcpyDeviceToHost, j->stream));
         CK(cudaStreamSynchronize(j->stream));
-        if (*j->activeHost == 0) break;
+        if (j->profile) {
+            for (size_t i = 0; i + 3 < j->profEvents.size(); i += 4)
+                for (int s = 0; s < STAGE_COUNT; ++s) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, j->profEvents[i + s], j->profEvents[i + s + 1]);
+                    j->stageMs[s] += ms;
+                }
+            j->stageLaunches[STAGE_TRACE] += 3ull * j->roundsPerPoll; j->stageLaunches[STAGE_WALK] += (uint64_t) walkLaunches * j->roundsPerPoll;
+            j->stageLaunches[STAGE_CHAIN] += j->roundsPerPoll;
+            for (cudaEvent_t e : j->profEvents) cudaEventDestroy(e);
+            j->profEvents.clear();
+        }
+        const int p = (int) (j->rounds & 1);                      // queues the next round would consume
+        if (j->countsHost[Q_RAYC + p] == 0 && j->countsHost[Q_RAYS + p] == 0 && j->countsHost[Q_CHAIN + p] == 0) break;
     }
     return DR_OK;
 }
 
 static dr_status setup_lanes(dr_job j, const JobParams &job) {
-    const int n = j->lm.n, T = 128;
-    k_setup_lanes<<<(n + T - 1) / T, T, 0, j->stream>>>(j->par.pp, j->ca, j->lm, job);
+    Machine M = machine_for(j, job, j->counters, false);
+    LaunchCfg lc; lc.stream = j->stream; lc.nLanes = j->nChains;
+    CK(cudaMemsetAsync(M.q.count, 0, sizeof(uint32_t) * Q_COUNT, j->stream));
+    launch_setup(M, lc, j->depth, j->chainId, j->seedIdx);
     CKL();
     ++j->launches;
     return DR_OK;
@@ -662,7 +714,7 @@ extern "C" dr_status dr_job_bootstrap(dr_job j, double *sumOut, double *countOut
     j->nBoot = per;
     j->bootFirst = (unsigned long long) per * (unsigned long long) c.rank;
     dr_status st;
-    const long long nb = (per + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+    const long long nb = scan_blocks(per);
     if (!j->bootLum) {
         if ((st = job_alloc(j, &j->bootLum, (size_t) per)) || (st = job_alloc(j, &j->cdf, (size_t) per + 1)) ||
             (st = job_alloc(j, &j->blockSums, (size_t) nb + 1)))
@@ -674,16 +726,11 @@ extern "C" dr_status dr_job_bootstrap(dr_job j, double *sumOut, double *countOut
     JobParams job;
     memset(&job, 0, sizeof(job));
     job.type = JOB_BOOT; job.nItems = per; job.first = j->bootFirst; job.lumOut = j->bootLum;
-    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters + ST_COUNT, false))) return st;
-    k_lum_reduce<<<148 * 4, 256, 0, j->stream>>>(j->bootLum, per, j->red);
+    if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters + ST_COUNT, false))) return st;
+    launch_lum_reduce(j->bootLum, per, j->redScratch, j->red, j->stream);
+    launch_scan(j->bootLum, per, j->cdf, j->blockSums, j->stream);
     CKL();
-    k_scan_blocks<<<(unsigned) nb, SCAN_BLOCK, 0, j->stream>>>(j->bootLum, per, j->cdf, j->blockSums);
-    CKL();
-    k_scan_sums<<<1, 1024, 0, j->stream>>>(j->blockSums, (int) nb);
-    CKL();
-    k_scan_add<<<(unsigned) ((per + 255) / 256), 256, 0, j->stream>>>(j->cdf, per, j->blockSums);
-    CKL();
-    j->launches += 4;
+    j->launches += 5;
     CK(cudaEventRecord(j->ev1, j->stream));
     double red[2];
     CK(cudaMemcpyAsync(red, j->red, sizeof(red), cudaMemcpyDeviceToHost, j->stream));
@@ -713,38 +760,37 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
     CK(cudaStreamSynchronize(j->stream));
     if (!(total > 0.0)) { dr_set_error("bootstrap found no path with non-zero luminance on rank %d", c.rank); return DR_ERR_ZERO_LUMINANCE; }
     j->b = b;
-    j->par.cp.b = b;
-    const int n = j->nChains, T = 128;
+    j->M.cp.b = b;
+    const int n = j->nChains;
     const unsigned long long firstChain = (unsigned long long) c.rank * (unsigned long long) n;
     CK(cudaEventRecord(j->ev0, j->stream));
-    k_resample<<<(n + T - 1) / T, T, 0, j->stream>>>(j->cdf, j->nBoot, c.seed, firstChain, n, j->bootFirst, c.max_depth, c.technique,
-                                                   j->ca.seedIdx, j->ca.chainId, j->ca.depth);
+    launch_resample(j->cdf, j->nBoot, c.seed, firstChain, n, j->bootFirst, c.max_depth, c.technique, j->seedIdx, j->chainId, j->depth, j->stream);
     CKL();
     ++j->launches;
     if (c.technique == DR_TECH_MMLT) {
-        // bucket chains by MMLT depth so that the lanes of a warp walk paths of the same length
+        // bucket chains by MMLT depth so that neighbouring lanes walk paths of the same length
         std::vector<unsigned long long> seedIdx(n), chainId(n);
         std::vector<int> depth(n), perm(n);
-        CK(cudaMemcpyAsync(seedIdx.data(), j->ca.seedIdx, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
-        CK(cudaMemcpyAsync(chainId.data(), j->ca.chainId, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
-        CK(cudaMemcpyAsync(depth.data(), j->ca.depth, n * sizeof(int), cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaMemcpyAsync(seedIdx.data(), j->seedIdx, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaMemcpyAsync(chainId.data(), j->chainId, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaMemcpyAsync(depth.data(), j->depth, n * sizeof(int), cudaMemcpyDeviceToHost, j->stream));
         CK(cudaStreamSynchronize(j->stream));
         std::iota(perm.begin(), perm.end(), 0);
         std::stable_sort(perm.begin(), perm.end(), [&](int a, int b2) { return depth[a] < depth[b2]; });
         std::vector<unsigned long long> s2(n), c2(n);
         std::vector<int> d2(n);
         for (int i = 0; i < n; ++i) { s2[i] = seedIdx[perm[i]]; c2[i] = chainId[perm[i]]; d2[i] = depth[perm[i]]; }
-        CK(cudaMemcpyAsync(j->ca.seedIdx, s2.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, j->stream));
-        CK(cudaMemcpyAsync(j->ca.chainId, c2.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, j->stream));
-        CK(cudaMemcpyAsync(j->ca.depth, d2.data(), n * sizeof(int), cudaMemcpyHostToDevice, j->stream));
+        CK(cudaMemcpyAsync(j->seedIdx, s2.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, j->stream));
+        CK(cudaMemcpyAsync(j->chainId, c2.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, j->stream));
+        CK(cudaMemcpyAsync(j->depth, d2.data(), n * sizeof(int), cudaMemcpyHostToDevice, j->stream));
         CK(cudaStreamSynchronize(j->stream));
     }
-    // seed replay: the lanes evaluate their seed vector (PH_INIT) in the first rounds of the next run
+    // seed replay: the lanes evaluate their seed vector (PH_INIT); mutTarget = 0 parks them afterwards
     JobParams job;
     memset(&job, 0, sizeof(job));
     job.type = JOB_CHAIN; job.mutTarget = 0;
     dr_status st;
-    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters, true))) return st;
+    if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters, true))) return st;
     j->mutTarget = 0;
     CK(cudaEventRecord(j->ev1, j->stream));
     CK(cudaStreamSynchronize(j->stream));
@@ -763,7 +809,12 @@ static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, 
     j->mutTarget += (uint32_t) steps;
     job.mutTarget = j->mutTarget;
     job.records = records; job.recordStride = recordStride;
-    return run_wavefront(j, job, j->counters, withFilm);
+    Machine M = machine_for(j, job, j->counters, withFilm);
+    LaunchCfg lc; lc.stream = j->stream; lc.nLanes = j->nChains;
+    launch_resume(M, lc);                                          // parked chains start their next mutation
+    CKL();
+    ++j->launches;
+    return run_machine(j, job, j->counters, withFilm);
 }
 
 extern "C" dr_status dr_job_run(dr_job j, int64_t mutationsPerChain) {
@@ -794,8 +845,11 @@ extern "C" dr_status dr_job_film_device(dr_job j, float **filmDev, int64_t *nFlo
 // last state is splatted when the chain ends (pssmlt_proc.cpp:274-279).
 static dr_status flush_pssmlt(dr_job j) {
     if (j->cfg.integrator != DR_INTEGRATOR_PSSMLT) return DR_OK;
-    const int T = 128;
-    k_flush_pssmlt<<<(j->nChains + T - 1) / T, T, 0, j->stream>>>(j->lm, j->par.fp, j->film);
+    JobParams job;
+    memset(&job, 0, sizeof(job));
+    Machine M = machine_for(j, job, j->counters, true);
+    LaunchCfg lc; lc.stream = j->stream; lc.nLanes = j->nChains;
+    launch_flush_pssmlt(M, lc);
     CKL();
     ++j->launches;
     return DR_OK;
@@ -808,15 +862,15 @@ extern "C" dr_status dr_job_develop(dr_job j, float *imageRgb) {
     if (st) return st;
     const long long n = (long long) j->scene->filmW * j->scene->filmH;
     CK(cudaMemsetAsync(j->red + 2, 0, sizeof(double), j->stream));
-    k_film_luminance<<<148 * 4, 256, 0, j->stream>>>(j->film, n, j->red + 2);
+    launch_film_luminance(j->film, n, j->red + 2, j->stream);
     CKL();
     double lumSum = 0.0;
     CK(cudaMemcpyAsync(&lumSum, j->red + 2, sizeof(double), cudaMemcpyDeviceToHost, j->stream));
     CK(cudaStreamSynchronize(j->stream));
-    const bool accMap = j->par.cp.acceptanceMap;
+    const bool accMap = j->M.cp.acceptanceMap;
     const double avg = lumSum / (double) n;
     const float factor = accMap ? 1.0f : (avg > 0.0 ? (float) (j->b / avg) : 0.f);
-    k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, j->stream>>>(j->film, n, factor, j->devImage);
+    launch_develop(j->film, n, factor, j->devImage, j->stream);
     CKL();
     j->launches += 2;
     CK(cudaMemcpyAsync(imageRgb, j->devImage, (size_t) n * 3 * sizeof(float), cudaMemcpyDeviceToHost, j->stream));
@@ -844,9 +898,13 @@ extern "C" dr_status dr_job_stats(dr_job j, dr_stats *s) {
     s->luminance = j->b;
     s->bootstrap_ms = j->bootstrapMs; s->chains_ms = j->chainsMs; s->total_ms = j->totalMs;
     s->kernel_launches = j->launches;
+    s->rounds = j->rounds;
+    s->trace_ms = j->stageMs[STAGE_TRACE]; s->walk_ms = j->stageMs[STAGE_WALK]; s->chain_ms = j->stageMs[STAGE_CHAIN];
+    s->trace_launches = j->stageLaunches[STAGE_TRACE]; s->walk_launches = j->stageLaunches[STAGE_WALK]; s->chain_launches = j->stageLaunches[STAGE_CHAIN];
     return DR_OK;
 }
 
+extern "C" void dr_job_profile(dr_job j, int on) { if (j) j->profile = on != 0; }
 extern "C" int64_t dr_job_num_chains(dr_job j) { return j ? j->nChains : 0; }
 extern "C" int64_t dr_job_total_mutations(dr_job j) { return j ? j->totalMutations : 0; }
 
@@ -896,7 +954,7 @@ extern "C" dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n
     dr_status st;
     if ((st = dr.alloc(n * sizeof(dr_ray))) || (st = dh.alloc(n * sizeof(dr_hit)))) return st;
     CK(cudaMemcpy(dr.p, rays, n * sizeof(dr_ray), cudaMemcpyHostToDevice));
-    k_trace_rays<<<(unsigned) ((n + 127) / 128), 128>>>(s->dev, dr.as<dr_ray>(), n, shadow, s->dOrder, dh.as<dr_hit>());
+    launch_trace_rays(s->dev, dr.as<dr_ray>(), n, shadow, s->dOrder, dh.as<dr_hit>(), 0);
     CKL();
     CK(cudaMemcpy(hits, dh.p, n * sizeof(dr_hit), cudaMemcpyDeviceToHost));
     return DR_OK;
@@ -908,9 +966,11 @@ extern "C" dr_status dr_eval_paths(dr_scene scene, const dr_config *cfgIn, const
                                    const int32_t *depth, int64_t n, dr_path_result *out) {
     if (!scene || !cfgIn || n < 0 || (n > 0 && !out)) { dr_set_error("dr_eval_paths: bad argument"); return DR_ERR_INVALID_ARG; }
     if ((ds_ > 0 && !us) || (de > 0 && !ue) || (dd > 0 && !ud) || ds_ < 0 || de < 0 || dd < 0) { dr_set_error("dr_eval_paths: missing primary-sample buffer"); return DR_ERR_INVALID_ARG; }
+    if (ds_ > 255 || de > 255 || dd > 255) { dr_set_error("dr_eval_paths: at most 255 coordinates per sampler"); return DR_ERR_INVALID_ARG; }
     if (n == 0) { dr_config c = *cfgIn; return dr_config_validate(&c); }
     dr_job j = nullptr;
-    dr_status st = job_create_common(scene, cfgIn, replay_lanes(n), false, &j);
+    const int evalDims[3] = { ds_, de, dd };
+    dr_status st = job_create_common(scene, cfgIn, replay_lanes(n), false, evalDims, &j);
     if (st) return st;
     auto done = [&](dr_status code) { cudaStreamSynchronize(j->stream); dr_job_destroy(j); return code; };
     if (j->cfg.technique == DR_TECH_MMLT) {
@@ -933,7 +993,7 @@ extern "C" dr_status dr_eval_paths(dr_scene scene, const dr_config *cfgIn, const
     job.type = JOB_EVAL; job.nItems = n;
     job.us = bs.as<float>(); job.ue = be.as<float>(); job.ud = bd.as<float>(); job.ds = ds_; job.de = de; job.dd = dd;
     job.depthIn = depth ? bdep.as<int>() : nullptr; job.out = bout.as<dr_path_result>();
-    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters, false))) return done(st);
+    if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters, false))) return done(st);
     if (cudaMemcpy(out, bout.p, (size_t) n * sizeof(dr_path_result), cudaMemcpyDeviceToHost) != cudaSuccess)
         return done((dr_set_error("dr_eval_paths: download failed"), DR_ERR_CUDA));
     return done(DR_OK);
@@ -943,7 +1003,7 @@ extern "C" dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfg
     if (!scene || !cfgIn || n < 0 || (n > 0 && !luminance)) { dr_set_error("dr_bootstrap_luminance: bad argument"); return DR_ERR_INVALID_ARG; }
     if (n == 0) { dr_config c = *cfgIn; return dr_config_validate(&c); }
     dr_job j = nullptr;
-    dr_status st = job_create_common(scene, cfgIn, replay_lanes(n), false, &j);
+    dr_status st = job_create_common(scene, cfgIn, replay_lanes(n), false, nullptr, &j);
     if (st) return st;
     auto done = [&](dr_status code) { cudaStreamSynchronize(j->stream); dr_job_destroy(j); return code; };
     DevBuf bl;
@@ -951,7 +1011,7 @@ extern "C" dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfg
     JobParams job;
     memset(&job, 0, sizeof(job));
     job.type = JOB_BOOT; job.nItems = n; job.first = first; job.lumOut = bl.as<float>();
-    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters + ST_COUNT, false))) return done(st);
+    if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters + ST_COUNT, false))) return done(st);
     if (cudaMemcpy(luminance, bl.p, (size_t) n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
         return done((dr_set_error("dr_bootstrap_luminance: download failed"), DR_ERR_CUDA));
     if (depth)
@@ -966,13 +1026,13 @@ extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, doub
     if (nChains == 0) { dr_config c = *cfgIn; return dr_config_validate(&c); }
     if (nChains > (1 << 24) || steps > (1 << 24)) { dr_set_error("dr_chain_steps: too large"); return DR_ERR_INVALID_ARG; }
     dr_job j = nullptr;
-    dr_status st = job_create_common(scene, cfgIn, (int) nChains, true, &j);
+    dr_status st = job_create_common(scene, cfgIn, (int) nChains, true, nullptr, &j);
     if (st) return st;
     auto done = [&](dr_status code) { cudaStreamSynchronize(j->stream); dr_job_destroy(j); return code; };
     if (j->cfg.technique == DR_TECH_MMLT && !depth) return done((dr_set_error("dr_chain_steps: MMLT needs a depth per chain"), DR_ERR_INVALID_ARG));
     if (j->cfg.average_luminance != -1.0f) b = j->cfg.average_luminance;
     if (j->cfg.integrator == DR_INTEGRATOR_DRMLT && j->cfg.acceptance_map) b = 1.0;
-    j->b = b; j->par.cp.b = b;
+    j->b = b; j->M.cp.b = b;
     const int n = (int) nChains;
     std::vector<int> dep(n, -1);
     if (j->cfg.technique == DR_TECH_MMLT)
@@ -981,9 +1041,9 @@ extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, doub
             if (dep[i] < 1 || dep[i] > j->cfg.max_depth) return done((dr_set_error("dr_chain_steps: depth out of range"), DR_ERR_INVALID_ARG));
         }
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
-    if (cudaMemcpyAsync(j->ca.seedIdx, seedIndex, n * sizeof(uint64_t), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
-        cudaMemcpyAsync(j->ca.chainId, chainId, n * sizeof(uint64_t), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
-        cudaMemcpyAsync(j->ca.depth, dep.data(), n * sizeof(int), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
+    if (cudaMemcpyAsync(j->seedIdx, seedIndex, n * sizeof(uint64_t), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
+        cudaMemcpyAsync(j->chainId, chainId, n * sizeof(uint64_t), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
+        cudaMemcpyAsync(j->depth, dep.data(), n * sizeof(int), cudaMemcpyHostToDevice, j->stream) != cudaSuccess ||
         cudaStreamSynchronize(j->stream) != cudaSuccess) {
         dr_set_error("dr_chain_steps: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return done(DR_ERR_CUDA);
@@ -996,7 +1056,7 @@ extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, doub
     JobParams job;
     memset(&job, 0, sizeof(job));
     job.type = JOB_CHAIN; job.mutTarget = 0;
-    if ((st = setup_lanes(j, job)) || (st = run_wavefront(j, job, j->counters, film != nullptr))) return done(st);   // seed replay
+    if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters, film != nullptr))) return done(st);   // seed replay
     j->seeded = true;
     if (steps > 0 && (st = run_chains(j, steps, records ? drec.as<dr_step_record>() : nullptr, (int) steps, film != nullptr))) return done(st);
     if (film && (st = flush_pssmlt(j))) return done(st);

@@ -1,0 +1,560 @@
+// k_chain.cu -- the chain kernel of the wavefront machine (machine.cuh) and the lane set-up kernels.
+//
+// k_chain consumes the lanes whose path has just ended (or which have no path yet).  In ONE thread per
+// lane it (1) turns the finished path into a result (Path::miWeight, src/libbidir/path.cpp:763-1028, and the
+// single MMLT splat, pathsampler.cpp:288-313), (2) runs the chain-level step: delayed-rejection acceptance
+// (DRMLTRenderer::process, src/integrators/drmlt/drmlt_proc.cpp:539-769; processMixture :161-380;
+// PSSMLTRenderer::process, src/integrators/pssmlt/pssmlt_proc.cpp:175-272), expectation-weighted film splats,
+// commit of the accepted primary-sample vector and statistics, and (3) mutates the next proposal into the
+// lane's coordinate buffer (pss.cuh) and emits the first ray of its path.
+#include "machine.cuh"
+
+namespace {
+
+DR_D bool invalid_strict(Real x) { return isnan(x) || isinf(x) || x <= 0.; }   // drmlt_proc.cpp:428
+DR_D bool invalid_loose(Real x) { return isnan(x) || isinf(x) || x < 0.; }     // drmlt_proc.cpp:181
+DR_D Real metropolis_clamp(Real x) { return x < 1.0 ? x : 1.0; }               // std::min(1, x): NaN -> 1
+
+DR_D void result_clear(PathResult &r) { r.lum = 0.; r.n = 0; r.val = r3(0.); r.pos = r2(0., 0.); r.mis = 0.; r.s = r.t = -1; }
+
+DR_D float3 normalized_value(const PathResult &r) {          // SplatList::normalize (pathsampler.cpp:1001-1028)
+    const Real inv = r.lum > 0. ? 1.0 / r.lum : 1.0;
+    return to_f3(r.val * inv);
+}
+
+// MMLT strategy from the direct sampler's coordinate (pathsampler.cpp:104-129)
+DR_D void mmlt_strategy(const PathCfg &pc, int depth, Real decision, int &s, int &t) {
+    int nStrats;
+    if (pc.lightImage) { nStrats = depth + 1; s = min((int) (nStrats * decision), nStrats - 1); t = nStrats - s; }
+    else { nStrats = depth; s = min((int) (nStrats * decision), nStrats - 1); t = 1 + (nStrats - s); }
+}
+
+// number of coordinate PAIRS of each sampler that a proposal with strategy (s, t) must carry
+DR_D void pair_extent(const Machine &M, const int dims[3], int s, int t, int ext[3]) {
+    if (M.pp.subset) { ext[0] = t; ext[1] = s; ext[2] = 1; }
+    else { ext[0] = (dims[0] + 1) >> 1; ext[1] = (dims[1] + 1) >> 1; ext[2] = (dims[2] + 1) >> 1; }
+}
+
+// MiraDRMLTSampler::getTransitionRatio over the three samplers (drmlt_sampler.cpp:400-414).
+// dimStage holds the largest INDEX touched, so the last used coordinate is skipped.
+DR_D Real mira_transition_ratio(const Machine &M, const MutCtx &mc, const double *ub, const uint8_t posY[3], const int posZ[3]) {
+    const ChainParams &cp = M.cp;
+    const int nU = M.lm.nU;
+    Real ratio = 1.0;
+    for (int s = 0; s < 3; ++s) {
+        if (mc.identity1(s)) continue;
+        Real num = 0., den = 0.;
+        const int dimStage = max(max((int) posY[s] - 1, 0), max(posZ[s] - 1, 0));
+        for (int i = 0; i < dimStage; i += 2) {
+            const int slot = M.pp.off[s] + i;
+            const R2 x = ub_load(ub + UB_X * nU, slot), y = ub_load(ub + UB_Y * nU, slot), z = ub_load(ub + UB_Z * nU, slot);
+            num += kelemen_logpdf(z.x - y.x, cp.kel_s1, cp.kel_s2, cp.kel_logRatio);
+            den += kelemen_logpdf(x.x - y.x, cp.kel_s1, cp.kel_s2, cp.kel_logRatio);
+            if (i + 1 < dimStage) {
+                num += kelemen_logpdf(z.y - y.y, cp.kel_s1, cp.kel_s2, cp.kel_logRatio);
+                den += kelemen_logpdf(x.y - y.y, cp.kel_s1, cp.kel_s2, cp.kel_logRatio);
+            }
+        }
+        ratio *= exp(num - den);
+    }
+    return ratio;
+}
+
+// write the accepted proposal back as the new current state (DRMLTSampler::accept, drmlt_sampler.cpp:189-199)
+DR_D void commit_state(const Machine &M, const MutCtx &mc, double *ub, const int dims[3], int from, bool first, int s_, int t_, bool drmlt) {
+    const int nU = M.lm.nU;
+    int ext[3];
+    pair_extent(M, dims, s_, t_, ext);
+    for (int s = 0; s < 3; ++s) {
+        if (!mc.largeStep && (first ? mc.identity1(s) : mc.identity2(s))) continue;
+        for (int p = 0; p < ext[s]; ++p) {
+            const int slot = M.pp.off[s] + 2 * p;
+            R2 v = ub_load(ub + from * nU, slot);
+            if (drmlt) { v.x = wrap_reflect(v.x); v.y = wrap_reflect(v.y); }
+            ub_store(ub + UB_X * nU, slot, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ proposals
+// Fill the lane's coordinate buffer for the path that is about to start and select it (Core::ubuf).
+DR_D void fill_proposal(const Machine &M, int lane, Core &c, const MutCtx &mc, long long item) {
+    const PssParams &pp = M.pp;
+    const int nU = M.lm.nU;
+    double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * nU;
+    int dims[3];
+    chain_dims(M.pc, M.cp, c.depth, dims);
+    const bool mmlt = M.pc.technique == DR_TECH_MMLT;
+    if (M.job.type == JOB_EVAL) {                  // replayed host vectors (float) -> X
+        c.ubuf = UB_X;
+        const float *src[3] = { M.job.us + item * M.job.ds, M.job.ue + item * M.job.de, M.job.ud + item * M.job.dd };
+        const int n[3] = { M.job.ds, M.job.de, M.job.dd };
+        for (int s = 0; s < 3; ++s)
+            for (int k = 0; k < n[s]; ++k) ub[pp.off[s] + k] = (double) src[s][k];
+        return;
+    }
+    if (M.job.type == JOB_BOOT) {                  // bootstrap sample `index`: keyed uniforms -> X
+        c.ubuf = UB_X;
+        const unsigned long long index = M.job.first + (unsigned long long) item;
+        auto boot_pair = [&](int s, int p) {
+            const float4 u = keyed_uniform4(pp.seed, S_BOOT, index, (uint32_t) s, (uint32_t) (p >> 1));
+            return (p & 1) ? r2(u.z, u.w) : r2(u.x, u.y);
+        };
+        int ext[3] = { (dims[0] + 1) >> 1, (dims[1] + 1) >> 1, (dims[2] + 1) >> 1 };
+        if (mmlt) {                                // only what strategy (s, t) can consume
+            const R2 d = boot_pair(SMP_DIRECT, 0);
+            ub_store(ub, pp.off[SMP_DIRECT], d);
+            int s_, t_;
+            mmlt_strategy(M.pc, c.depth, d.x, s_, t_);
+            ext[0] = min(ext[0], t_); ext[1] = min(ext[1], s_); ext[2] = 0;
+        }
+        for (int s = 0; s < 3; ++s)
+            for (int p = 0; p < ext[s]; ++p) ub_store(ub, pp.off[s] + 2 * p, boot_pair(s, p));
+        return;
+    }
+    // ---- Markov chain
+    if (c.phase == PH_INIT) { c.ubuf = UB_X; return; }        // seed replay: the bootstrap vector is already in X
+    const int dst = c.phase == PH_STAGE1 ? UB_Y : (c.phase == PH_STAGE2 ? UB_Z : UB_R);
+    c.ubuf = (uint8_t) dst;
+    auto make_pair = [&](int s, int p) {
+        const int slot = pp.off[s] + 2 * p;
+        const R2 x = ub_load(ub + UB_X * nU, slot);
+        R2 v;
+        if (c.phase == PH_STAGE1) v = propose_stage1(mc, s, p, x);
+        else {
+            const R2 y = ub_load(ub + UB_Y * nU, slot);
+            if (c.phase == PH_STAGE2) v = propose_stage2(mc, s, p, x, y);
+            else { const R2 z = ub_load(ub + UB_Z * nU, slot); v = r2(z.x - (y.x - x.x), z.y - (y.y - x.y)); }   // y* = z - (y - x), drmlt_sampler.cpp:293-296
+        }
+        ub_store(ub + dst * nU, slot, v);
+        return v;
+    };
+    int ext[3] = { (dims[0] + 1) >> 1, (dims[1] + 1) >> 1, (dims[2] + 1) >> 1 };
+    if (pp.subset) {
+        const R2 d = make_pair(SMP_DIRECT, 0);
+        int s_, t_;
+        mmlt_strategy(M.pc, c.depth, wrap_reflect(d.x), s_, t_);
+        ext[0] = t_; ext[1] = s_; ext[2] = 0;
+    }
+    for (int s = 0; s < 3; ++s)
+        for (int p = 0; p < ext[s]; ++p) make_pair(s, p);
+}
+
+// ------------------------------------------------------------------ path start
+// returns the queue the lane goes to (Q_RAYC, Q_CONNECT) or -1 when the path is already over (empty result)
+DR_D int path_start(const Machine &M, int lane, Core &c) {
+    const DevScene &sc = M.sc;
+    UReader rd;
+    c.pos0 = c.pos1 = c.pos2 = 0; c.nrays = 0;
+    reader_open(M, c, lane, rd);
+    int dest;
+    if (M.pc.technique == DR_TECH_MMLT) {                     // pathsampler.cpp:84-159
+        const int depth = c.depth, k = depth + 2;
+        double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
+        int s, t;
+        mmlt_strategy(M.pc, depth, rd.next1D(SMP_DIRECT), s, t);
+        c.s = (uint8_t) s; c.t = (uint8_t) t;
+        if (depth == 1) { reader_close(rd, c); c.pstate = PS_EMPTY; return -1; }
+        c.connectable = 0; c.flags = 0; c.weight = r3(1.);
+        (void) rd.next2D(SMP_SENSOR);                         // sampleSensorPosition consumes 2 (vertex.cpp:79)
+        mis_put(mis, MIS_RAD, k, 1.0);
+        mis_put(mis, MIS_RAD, k - 1, 1.0);                    // supernode pdf[ERadiance] (perspective.cpp:305)
+        Vtx vt;
+        vt.p = cam_pos(sc.cam); vt.ng = vt.ns = cam_dir(sc.cam); vt.ss = r3(0.); vt.type = V_SENSOR_SAMPLE; vt.degenerate = 0; vt.mat = -1; vt.emitter = -1;
+        c.connectable |= 1u << (k - 1);                       // sensor sample: never discrete, not degenerate
+        rec_store(M.lm.vt + lane, vt);
+        c.j = 1;
+        if (t >= 2) {                                         // vertex.cpp:126-151, perspective.cpp:318-345
+            const R2 u = rd.next2D(SMP_SENSOR);
+            const R3 dl = cam_sample_to_dir(sc.cam, u.x, u.y);
+            c.pdfFwd = sc.cam.normalization / (dl.z * dl.z * dl.z);
+            c.pdfBwd = 1.0;
+            c.pstate = PS_SENSOR_HIT;
+            emit_ray(M, lane, c, vt.p, cam_xform_dir(sc.cam, dl), sc.epsilon, INFINITY);
+            dest = Q_RAYC;
+        } else {
+            dest = mmlt_emitter_start(M, lane, c, rd, mis);
+        }
+    } else {                                                  // PathSampler EUnidirectional (pathsampler.cpp:529-567)
+        const R2 u0 = rd.next2D(SMP_SENSOR);
+        const R2 samplePos = r2(u0.x * sc.cam.resX, u0.y * sc.cam.resY);
+        c.spos = make_float2((float) samplePos.x, (float) samplePos.y);
+        const R3 dl = cam_sample_to_dir(sc.cam, samplePos.x / sc.cam.resX, samplePos.y / sc.cam.resY);
+        const Real invZ = 1.0 / dl.z;
+        PtExtra px;
+        px.Li = r3(0.); px.pending = r3(0.); px.refN = r3(0.); px.eta = 1.0; px.bsPdf = 0.; px.dIn = r3(0.);
+        c.weight = r3(1.);
+        c.flags = F_PT_FIRST | (M.pc.excludeDirect ? 0u : (F_PT_EMITTED | F_PT_DIRECT));
+        c.j = 1; c.s = c.t = 0;
+        c.pstate = PS_PT_HIT;
+        rec_store(reinterpret_cast<PtExtra *>(M.lm.vs + lane), px);
+        emit_ray(M, lane, c, cam_pos(sc.cam), cam_xform_dir(sc.cam, dl), sc.cam.nearClip * invZ, sc.cam.farClip * invZ);
+        dest = Q_RAYC;
+    }
+    reader_close(rd, c);
+    return dest;
+}
+
+// ------------------------------------------------------------------ path end -> result
+DR_D void path_result(const Machine &M, int lane, Core &c, PathResult &out) {
+    result_clear(out);
+    if (M.pc.technique == DR_TECH_MMLT) { out.s = c.s; out.t = c.t; }
+    if (c.pstate == PS_CONNECT_SHADOW) {
+        const int tri = __float_as_int(M.lm.hit[lane].w);
+        if (tri >= 0) return;                                 // occluded
+        if (M.pc.excludeDirect && c.depth <= 2) return;       // pathsampler.cpp:279-284
+        if (c.flags & F_SPOS_FAIL) return;
+        c.pstate = PS_FINISH;
+    }
+    if (c.pstate == PS_FINISH) {                              // pathsampler.cpp:288-313
+        const int depth = c.depth, k = depth + 2, s = c.s, t = c.t;
+        const double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
+        MisArrays A;
+        A.connectable = c.connectable;
+#pragma unroll
+        for (int i = 0; i <= DR_MAXK; ++i) {
+            const bool in = i <= k;
+            A.pdfImp[i] = in ? mis_get(mis, MIS_IMP, i) : 0.; A.pdfRad[i] = in ? mis_get(mis, MIS_RAD, i) : 0.; A.conv[i] = in ? mis_get(mis, MIS_CONV, i) : 0.;
+        }
+        const Real w = mis_weight(A, s, t, M.pc.lightImage != 0);
+        const int nStrats = M.pc.lightImage ? depth + 1 : depth;
+        const R3 value = c.weight * (w * (Real) nStrats);
+        out.mis = w; out.n = 1; out.pos = r2(c.spos.x, c.spos.y); out.val = value; out.lum = luminance(value);
+    } else if (c.pstate == PS_PT_DONE) {
+        PtExtra px;
+        rec_load(px, reinterpret_cast<const PtExtra *>(M.lm.vs + lane));
+        out.n = 1; out.pos = r2(c.spos.x, c.spos.y); out.val = px.Li; out.lum = luminance(px.Li);
+    }
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ the chain kernel
+#define CHAIN_MAX_PATHS 4      // paths one lane may complete in one launch without emitting a ray (dead-on-arrival paths)
+
+__global__ void __launch_bounds__(128)
+k_chain(const __grid_constant__ Machine M) {
+    const JobParams &job = M.job;
+    const PssParams &pp = M.pp;
+    const ChainParams &cp = M.cp;
+    const FilmParams &fp = M.fp;
+    float4 *film = M.film;
+    const bool drmlt = pp.integrator == DR_INTEGRATOR_DRMLT;
+    uint32_t st[ST_COUNT];
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; ++i) st[i] = 0;
+    const uint32_t cnt = M.q.count[Q_CHAIN + M.parity];
+    const uint32_t *items = M.q.items + (size_t) (Q_CHAIN + M.parity) * M.q.n;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
+        const int lane = (int) items[qi];
+        Core c;
+        rec_load(c, M.lm.core + lane);
+        int dest = -1;
+        for (int completed = 0;;) {
+            long long item = 0;
+            MutCtx mc;
+            mc.pp = &pp; mc.chain = c.chainId; mc.mut = c.mut; mc.largeStep = false; mc.lightTracing = false;
+            if (job.type != JOB_CHAIN) item = (long long) lane + (long long) c.mut * M.lm.n;
+            else {
+                mc.largeStep = c.phase != PH_INIT && c.large == 1u;
+                mc.lightTracing = c.phase == PH_STAGE2 && cp.fixEmitterPath && c.tx == 1;   // nextStage(current->t == 1)
+            }
+            if (c.pstate != PS_START) {
+                // ================= a path is complete: job-level step =================
+                PathResult r;
+                path_result(M, lane, c, r);
+                ++st[ST_PATHS];
+                ++completed;
+                if (job.type == JOB_BOOT) {
+                    job.lumOut[item] = (float) r.lum;
+                    ++c.mut;
+                    c.pstate = ((long long) lane + (long long) c.mut * M.lm.n < job.nItems) ? PS_START : PS_IDLE;
+                } else if (job.type == JOB_EVAL) {
+                    dr_path_result o;
+                    memset(&o, 0, sizeof(o));
+                    o.luminance = (float) r.lum; o.n_splats = r.n; o.s = r.s; o.t = r.t; o.mis_weight = (float) r.mis;
+                    o.pos[0][0] = (float) r.pos.x; o.pos[0][1] = (float) r.pos.y;
+                    o.value[0][0] = (float) r.val.x; o.value[0][1] = (float) r.val.y; o.value[0][2] = (float) r.val.z;
+                    o.n_rays = c.nrays;
+                    job.out[item] = o;
+                    ++c.mut;
+                    c.pstate = ((long long) lane + (long long) c.mut * M.lm.n < job.nItems) ? PS_START : PS_IDLE;
+                } else {
+                    ChainCore cc;
+                    rec_load(cc, M.lm.chain + lane);
+                    double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * M.lm.nU;
+                    int dims[3];
+                    chain_dims(M.pc, cp, c.depth, dims);
+                    bool mutationDone = false;
+                    Real a2 = 0.; bool acc2 = false;
+                    const bool largeStep = c.large == 1u;
+                    const float2 rpos = make_float2((float) r.pos.x, (float) r.pos.y);
+                    if (c.phase == PH_INIT) {
+                        // seed replay (drmlt_proc.cpp:467-512): the bootstrap vector becomes the current state
+                        cc.Lx = r.lum; cc.posx = rpos; cc.valx = normalized_value(r);
+                        cc.cumW = 0.; c.tx = (int8_t) r.t;
+                        c.phase = PH_STAGE1; c.large = 2u;
+                        c.pstate = c.mut < job.mutTarget ? PS_START : PS_IDLE;
+                    } else if (!drmlt) {
+                        // ---------------- PSSMLT (pssmlt_proc.cpp:175-272)
+                        ++st[ST_MUT];
+                        const Real yL = r.lum;
+                        Real a = fmin(1.0, yL / cc.Lx);
+                        if (isnan(yL) || yL < 0.) a = 0.;
+                        a = isnan(a) ? 1.0 : a;                              // std::min(1, NaN) = 1
+                        bool accept; Real currentWeight, proposedWeight;
+                        if (a > 0.) {
+                            if (cp.kelemenWeights) {
+                                currentWeight = (1. - a) * cc.Lx / (cc.Lx / cp.b + cp.pLarge);
+                                proposedWeight = (a + (largeStep ? 1. : 0.)) * yL / (yL / cp.b + cp.pLarge);
+                            } else { currentWeight = 1. - a; proposedWeight = a; }
+                            accept = (a == 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 1u) < a);
+                        } else {
+                            currentWeight = cp.kelemenWeights ? cc.Lx / (cc.Lx / cp.b + cp.pLarge) : 1.;
+                            proposedWeight = 0.; accept = false;
+                        }
+                        cc.cumW += currentWeight;
+                        if (job.records) {
+                            dr_step_record &rec = job.records[(size_t) lane * job.recordStride + (c.mut - job.mut0)];
+                            rec.L_x = (float) cc.Lx; rec.L_y = (float) yL; rec.L_z = 0.f; rec.a1 = (float) a; rec.a2 = 0.f;
+                            rec.large_step = largeStep; rec.accept1 = accept; rec.did_second = 0; rec.accept2 = 0;
+                        }
+                        ++st[ST_ACC_B];
+                        if (largeStep) ++st[ST_LARGE_B]; else ++st[ST_BOLD_B];
+                        const float3 yval = normalized_value(r);
+                        if (accept) {
+                            const float3 v = cc.valx * (float) cc.cumW;
+                            if (film && !is_zero(v)) film_put(film, fp, cc.posx, v);
+                            cc.cumW = proposedWeight;
+                            commit_state(M, mc, ub, dims, UB_Y, true, r.s, r.t, false);
+                            cc.Lx = yL; cc.posx = rpos; cc.valx = yval; c.tx = (int8_t) r.t;
+                            ++st[ST_ACC_A];
+                            if (largeStep) ++st[ST_LARGE_A]; else ++st[ST_BOLD_A];
+                        } else {
+                            const float3 v = yval * (float) proposedWeight;
+                            if (film && r.n && !is_zero(v)) film_put(film, fp, rpos, v);
+                        }
+                        mutationDone = true;
+                    } else if (c.phase == PH_STAGE1) {
+                        // ---------------- DRMLT first stage (drmlt_proc.cpp:539-558; mixture :284-299)
+                        ++st[ST_MUT];
+                        cc.yL = r.lum; cc.ypos = rpos; cc.yval = normalized_value(r); cc.yn = (uint8_t) r.n; cc.yt = (int8_t) r.t; cc.ys = (int8_t) r.s;
+                        cc.posY[0] = c.pos0; cc.posY[1] = c.pos1; cc.posY[2] = c.pos2;
+                        cc.a1 = 0.; cc.acc1 = 0; cc.zL = 0.; cc.zn = 0;
+                        bool doSecond;
+                        if (cp.useMixture) {
+                            if (!invalid_loose(cc.yL)) {
+                                cc.a1 = metropolis_clamp(cc.yL / cc.Lx);
+                                cc.acc1 = (cc.a1 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 1u) < cc.a1);
+                            }
+                            doSecond = !largeStep && ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 3u) < 0.5);
+                        } else {
+                            if (!invalid_strict(cc.yL)) {
+                                cc.a1 = metropolis_clamp(cc.yL / cc.Lx);
+                                cc.acc1 = (cc.a1 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 1u) < cc.a1);
+                            }
+                            doSecond = !cc.acc1 && (cp.timidAfterLarge || !largeStep);
+                        }
+                        if (doSecond) { c.phase = PH_STAGE2; c.pstate = PS_START; }
+                        else mutationDone = true;
+                    } else if (c.phase == PH_STAGE2) {
+                        cc.zL = r.lum; cc.zpos = rpos; cc.zval = normalized_value(r); cc.zn = (uint8_t) r.n; cc.zt = (int8_t) r.t; cc.zs = (int8_t) r.s;
+                        mutationDone = true;
+                        if (cp.useMixture) {   // drmlt_proc.cpp:317-324: plain MH on the replaced proposal
+                            cc.a1 = 0.; cc.acc1 = 0;
+                            if (!invalid_loose(cc.zL)) {
+                                a2 = metropolis_clamp(cc.zL / cc.Lx);
+                                acc2 = (a2 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 2u) < a2);
+                            }
+                        } else if (!invalid_strict(cc.zL)) {
+                            if (pp.type == DR_TYPE_GREEN) { c.phase = PH_REVERSE; c.pstate = PS_START; mutationDone = false; }
+                            else if (pp.type == DR_TYPE_MIRA) {   // drmlt_proc.cpp:625-650
+                                const Real aReverse = metropolis_clamp(cc.yL / cc.zL);
+                                if (!(aReverse >= 1.)) {
+                                    const int posZ[3] = { c.pos0, c.pos1, c.pos2 };
+                                    const Real T = largeStep ? 1.0 : mira_transition_ratio(M, mc, ub, cc.posY, posZ);
+                                    if (!invalid_strict(T)) {
+                                        a2 = metropolis_clamp((cc.zL / cc.Lx) * T * (1.0 - aReverse) / (1.0 - cc.a1));
+                                        acc2 = (a2 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 2u) < a2);
+                                    }
+                                }
+                            } else {                               // orbital, drmlt_proc.cpp:655-669
+                                if (cc.zL < cc.yL) { a2 = 0.; }
+                                else if (cc.zL >= cc.Lx) { a2 = 1.0; acc2 = true; }
+                                else {
+                                    a2 = (cc.zL - cc.yL) / (cc.Lx - cc.yL);
+                                    acc2 = (a2 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 2u) < a2);
+                                }
+                            }
+                        }
+                    } else {                   // Green's reverse path (drmlt_proc.cpp:588-621)
+                        const Real Lr = r.lum;
+                        const Real aReverse = invalid_strict(Lr) ? 0. : metropolis_clamp(Lr / cc.zL);
+                        if (aReverse != 1.) {
+                            a2 = metropolis_clamp((cc.zL / cc.Lx) * (1. - aReverse) / (1. - cc.a1));
+                            acc2 = (a2 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 2u) < a2);
+                        }
+                        mutationDone = true;
+                    }
+
+                    if (mutationDone && drmlt) {
+                        // ---- splat with expectation weights (drmlt_proc.cpp:676-688; mixture :327-333)
+                        const bool did2 = c.phase != PH_STAGE1;
+                        const bool acc1 = cc.acc1 != 0;
+                        const Real a1 = cc.a1;
+                        if (job.records) {
+                            dr_step_record &rec = job.records[(size_t) lane * job.recordStride + (c.mut - job.mut0)];
+                            rec.L_x = (float) cc.Lx; rec.L_y = (float) cc.yL; rec.L_z = did2 ? (float) cc.zL : 0.f; rec.a1 = (float) a1; rec.a2 = (float) a2;
+                            rec.large_step = largeStep; rec.accept1 = acc1; rec.did_second = did2; rec.accept2 = acc2;
+                        }
+                        if (film && !cp.acceptanceMap) {
+                            Real wy, wz, wx;
+                            if (cp.useMixture) { wy = did2 ? 0. : a1; wz = did2 ? a2 : 0.; wx = 1.0 - (did2 ? a2 : a1); }
+                            else { wy = a1; wz = (1.0 - a1) * a2; wx = 1.0 - wy - wz; }
+                            if (wx > 0.) film_put(film, fp, cc.posx, cc.valx * (float) wx);
+                            if (wy > 0. && cc.yn) film_put(film, fp, cc.ypos, cc.yval * (float) wy);
+                            if (wz > 0. && cc.zn) film_put(film, fp, cc.zpos, cc.zval * (float) wz);
+                        }
+                        // the stage-2 kernels of the commit see the stage-2 context
+                        MutCtx mc2 = mc;
+                        mc2.lightTracing = cp.fixEmitterPath && c.tx == 1;
+                        // ---- accept / reject, statistics (drmlt_proc.cpp:691-769; mixture :335-378)
+                        if (cp.useMixture) {
+                            const bool accept = did2 ? acc2 : acc1;
+                            ++st[ST_ACC_B];
+                            if (!did2) { ++st[ST_FIRST_B]; if (largeStep) ++st[ST_LARGE_B]; else ++st[ST_BOLD_B]; } else ++st[ST_SECOND_B];
+                            if (accept) {
+                                ++st[ST_ACC_A];
+                                if (!did2) { ++st[ST_FIRST_A]; if (largeStep) ++st[ST_LARGE_A]; else ++st[ST_BOLD_A]; } else ++st[ST_SECOND_A];
+                                if (did2) {
+                                    commit_state(M, mc2, ub, dims, UB_Z, false, cc.zs, cc.zt, true);
+                                    cc.Lx = cc.zL; cc.posx = cc.zpos; cc.valx = cc.zval; c.tx = cc.zt;
+                                } else {
+                                    commit_state(M, mc, ub, dims, UB_Y, true, cc.ys, cc.yt, true);
+                                    cc.Lx = cc.yL; cc.posx = cc.ypos; cc.valx = cc.yval; c.tx = cc.yt;
+                                }
+                            }
+                        } else if (acc1 || acc2) {
+                            // acceptance map: binned at the state that is being LEFT (proposed.* after the swap, :695-708)
+                            if (film && cp.acceptanceMap && (acc1 ? !largeStep : true))
+                                film_put(film, fp, cc.posx, acc1 ? make_float3(1.f, 0.f, 0.f) : make_float3(0.f, 1.f, 0.f));
+                            if (acc1) {
+                                commit_state(M, mc, ub, dims, UB_Y, true, cc.ys, cc.yt, true);
+                                cc.Lx = cc.yL; cc.posx = cc.ypos; cc.valx = cc.yval; c.tx = cc.yt;
+                            } else {
+                                commit_state(M, mc2, ub, dims, UB_Z, false, cc.zs, cc.zt, true);
+                                cc.Lx = cc.zL; cc.posx = cc.zpos; cc.valx = cc.zval; c.tx = cc.zt;
+                            }
+                            ++st[ST_ACC_B]; ++st[ST_ACC_A];
+                            if (acc1) {
+                                ++st[ST_FIRST_B]; ++st[ST_FIRST_A];
+                                if (largeStep) { ++st[ST_LARGE_B]; ++st[ST_LARGE_A]; } else { ++st[ST_BOLD_B]; ++st[ST_BOLD_A]; }
+                            } else {
+                                ++st[ST_ACC_B]; ++st[ST_FIRST_B]; ++st[ST_SECOND_B]; ++st[ST_SECOND_A];
+                                if (largeStep) { ++st[ST_LARGE_B]; ++st[ST_SECOND_LARGE_B]; ++st[ST_SECOND_LARGE_A]; }
+                                else { ++st[ST_BOLD_B]; ++st[ST_SECOND_BOLD_B]; ++st[ST_SECOND_BOLD_A]; }
+                            }
+                        } else {
+                            ++st[ST_ACC_B]; ++st[ST_FIRST_B];
+                            if (largeStep) { ++st[ST_LARGE_B]; if (did2) { ++st[ST_SECOND_B]; ++st[ST_SECOND_LARGE_B]; ++st[ST_ACC_B]; } }
+                            else { ++st[ST_BOLD_B]; if (did2) { ++st[ST_SECOND_B]; ++st[ST_SECOND_BOLD_B]; ++st[ST_ACC_B]; } }
+                        }
+                    }
+                    if (mutationDone) {
+                        ++c.mut;
+                        c.phase = PH_STAGE1; c.large = 2u;
+                        c.pstate = c.mut < job.mutTarget ? PS_START : PS_IDLE;
+                    }
+                    rec_store(M.lm.chain + lane, cc);
+                }
+                if (c.pstate == PS_IDLE) break;
+                if (completed >= CHAIN_MAX_PATHS) { dest = Q_CHAIN + (M.parity ^ 1); break; }   // start the next path next round
+                continue;
+            }
+            // ================= start the next path =================
+            if (job.type == JOB_CHAIN) {
+                if (c.phase == PH_STAGE1 && c.large == 2u) {   // new mutation: draw the large-step coin (drmlt_proc.cpp:533)
+                    c.large = (Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 0u) < cp.pLarge ? 1u : 0u;
+                    mc.largeStep = c.large == 1u;
+                }
+            } else {
+                item = (long long) lane + (long long) c.mut * M.lm.n;
+                if (job.type == JOB_BOOT) {
+                    const unsigned long long index = job.first + (unsigned long long) item;
+                    c.depth = M.pc.technique == DR_TECH_MMLT ? (uint8_t) ((index % (unsigned long long) M.pc.maxDepth) + 1) : 0;
+                } else c.depth = job.depthIn ? (uint8_t) job.depthIn[item] : 0;
+            }
+            fill_proposal(M, lane, c, mc, item);
+            dest = path_start(M, lane, c);
+            if (dest >= 0) break;                             // a ray is in flight (or the lane goes to the connection)
+        }
+        rec_store(M.lm.core + lane, c);
+        if (dest == Q_RAYC) q_push(M.q, Q_RAYC + (M.parity ^ 1), (uint32_t) lane);
+        else if (dest == Q_CONNECT) q_push(M.q, Q_CHAIN + (M.parity ^ 1), (uint32_t) lane);   // cannot happen for depth >= 2; kept safe
+        else if (dest >= 0) q_push(M.q, dest, (uint32_t) lane);
+    }
+    stats_flush(st, M.counters);
+}
+
+// ------------------------------------------------------------------ lane set-up
+// JOB_CHAIN: seed replay + fillReplay (drmlt_proc.cpp:467-504): current = the seed's bootstrap vector; the lane then
+// evaluates it (PH_INIT) before its first mutation.  JOB_BOOT / JOB_EVAL: lane l starts at item l.
+__global__ void k_setup_lanes(const __grid_constant__ Machine M, const int *depthIn, const unsigned long long *chainIdIn, const unsigned long long *seedIdxIn) {
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= M.lm.n) return;
+    Core c;
+    memset(&c, 0, sizeof(c));
+    c.tx = -1; c.large = 2u; c.phase = PH_STAGE1;
+    bool queued;
+    if (M.job.type == JOB_CHAIN) {
+        const unsigned long long sidx = seedIdxIn[lane];
+        c.chainId = chainIdIn[lane]; c.seedIdx = sidx;
+        c.depth = M.pc.technique == DR_TECH_MMLT ? (uint8_t) depthIn[lane] : 0;
+        double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * M.lm.nU;
+        const int alloc[3] = { M.cp.dimS, M.cp.dimE, M.cp.dimD };
+        for (int k = 0; k < M.lm.nU; ++k) ub[k] = 0.0;
+        for (int s = 0; s < 3; ++s)
+            for (int k = 0; k < alloc[s]; ++k)
+                ub[M.pp.off[s] + k] = (double) keyed_uniform(M.pp.seed, S_BOOT, sidx, (uint32_t) s, (uint32_t) k);
+        c.phase = PH_INIT;
+        c.pstate = PS_START;
+        queued = true;
+    } else {
+        queued = lane < M.job.nItems;
+        c.pstate = queued ? PS_START : PS_IDLE;
+    }
+    rec_store(M.lm.core + lane, c);
+    if (queued) q_push(M.q, Q_CHAIN + M.parity, (uint32_t) lane);
+}
+
+// dr_job_run raised the mutation target: idle chains start their next mutation
+__global__ void k_resume_lanes(const __grid_constant__ Machine M) {
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= M.lm.n) return;
+    Core *c = M.lm.core + lane;
+    if (c->pstate == PS_IDLE && c->mut < M.job.mutTarget) {
+        c->pstate = PS_START; c->phase = PH_STAGE1; c->large = 2u;
+        q_push(M.q, Q_CHAIN + M.parity, (uint32_t) lane);
+    }
+}
+
+// PSSMLT's "last splat" of the accumulated current state (pssmlt_proc.cpp:274-279); resets the weight
+__global__ void k_flush_pssmlt(const __grid_constant__ Machine M) {
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= M.lm.n) return;
+    ChainCore cc;
+    rec_load(cc, M.lm.chain + lane);
+    const float3 v = cc.valx * (float) cc.cumW;
+    if (!is_zero(v)) film_put(M.film, M.fp, cc.posx, v);
+    cc.cumW = 0.;
+    rec_store(M.lm.chain + lane, cc);
+}
+
+static unsigned grid_for(int n, int threads) { return (unsigned) std::max(1, std::min((n + threads - 1) / threads, 148 * 16)); }
+
+void launch_chain(const Machine &M, const LaunchCfg &lc) { k_chain<<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M); }
+void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId, const unsigned long long *seedIdx) {
+    k_setup_lanes<<<(unsigned) ((lc.nLanes + 127) / 128), 128, 0, lc.stream>>>(M, depth, chainId, seedIdx);
+}
+void launch_resume(const Machine &M, const LaunchCfg &lc) { k_resume_lanes<<<(unsigned) ((lc.nLanes + 127) / 128), 128, 0, lc.stream>>>(M); }
+void launch_flush_pssmlt(const Machine &M, const LaunchCfg &lc) { k_flush_pssmlt<<<(unsigned) ((lc.nLanes + 127) / 128), 128, 0, lc.stream>>>(M); }

@@ -1,0 +1,142 @@
+// k_pt.cu -- technique=path: the unidirectional path tracer as a resumable wavefront stage.
+// PathSampler EUnidirectional (src/libbidir/pathsampler.cpp:529-567) + MIPathTracer::Li
+// (src/integrators/path/path.cpp:123-312) with strictNormals=false, hideEmitters=false, minDepth=0,
+// directTracing=false.  Core::weight = throughput, Core::j = depth counter; the emitter-side vertex slot of
+// the lane holds PtExtra, the sensor-side slot the current shading point.
+#include "machine.cuh"
+
+__global__ void __launch_bounds__(128)
+k_pt(const __grid_constant__ Machine M) {
+    const DevScene &sc = M.sc;
+    const PathCfg &pc = M.pc;
+    const uint32_t cnt = M.q.count[Q_PT];
+    const uint32_t *items = M.q.items + (size_t) Q_PT * M.q.n;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
+        const int lane = (int) items[qi];
+        Core c;
+        rec_load(c, M.lm.core + lane);
+        PtExtra px;
+        rec_load(px, reinterpret_cast<const PtExtra *>(M.lm.vs + lane));
+        Hit hit;
+        { const float4 h = M.lm.hit[lane]; hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.tri = __float_as_int(h.w); }
+        UReader rd;
+        reader_open(M, c, lane, rd);
+        Vtx v;
+        int dest = Q_CHAIN + M.parity;
+        enum { GO_HIT, GO_SHADE, GO_BSDF, GO_DONE } go = c.pstate == PS_PT_NEE ? GO_BSDF : GO_HIT;
+        if (c.pstate == PS_PT_NEE) {                         // the shadow ray of the direct-illumination sample arrived
+            if (hit.tri < 0) px.Li += px.pending;
+            rec_load(v, M.lm.vt + lane);
+            c.d = px.dIn;                                    // incoming direction at v
+        }
+        for (bool running = true; running;) {
+            switch (go) {
+            case GO_HIT: {                                   // the camera ray or a BSDF-sampled ray arrived
+                if (hit.tri < 0) { go = GO_DONE; break; }
+                Vtx prev;
+                if (!(c.flags & F_PT_FIRST)) rec_load(prev, M.lm.vt + lane);
+                const R3 o = (c.flags & F_PT_FIRST) ? cam_pos(sc.cam) : prev.p;
+                const R3 d = c.d;
+                Real tHit;
+                fill_vertex(sc, hit, o, d, v, tHit);
+                if (!(c.flags & F_PT_FIRST)) {
+                    // emitter hit by the BSDF-sampled ray: MIS against direct sampling (path.cpp:242-290)
+                    if (v.emitter >= 0) {
+                        const R3 value = dot(v.ns, -d) > 0. ? emitter_radiance(sc, v.emitter) : r3(0.);
+                        Real lumPdf = 0.;
+                        // pdfEmitterDirect (scene.cpp:1057-1060, area.cpp:172-180, shape.cpp:116-126) with dRec.setQuery(ray, its)
+                        if (!(c.flags & F_DELTA) && dot(d, px.refN) >= 0. && dot(d, v.ns) < 0.) {
+                            const DevEmitter &em = sc.emitters[v.emitter];
+                            lumPdf = em.invArea * (tHit * tHit) / absdot(d, v.ns) * em.pdfDiscrete;
+                        }
+                        if ((c.flags & F_PT_DIRECT) && (c.flags & F_PT_NONSPEC))
+                            px.Li += c.weight * value * ((px.bsPdf * px.bsPdf) / (px.bsPdf * px.bsPdf + lumPdf * lumPdf));
+                    }
+                    c.flags = (c.flags & ~F_PT_EMITTED) | F_PT_DIRECT;   // rRec.type = ERadianceNoEmission
+                    if (c.j++ >= pc.rrDepth) {               // Russian roulette (path.cpp:297-306)
+                        const Real q = fmin(max3(c.weight) * px.eta * px.eta, 0.95);
+                        if (rd.next1D(SMP_SENSOR) >= q) { go = GO_DONE; break; }
+                        c.weight = c.weight / q;
+                    }
+                }
+                c.flags &= ~F_PT_FIRST;
+                go = GO_SHADE;
+                break;
+            }
+            case GO_SHADE: {                                 // top of the loop body for the vertex v (in registers)
+                const R3 d = c.d;
+                const Mat m = load_material(sc, v.mat);
+                if (v.emitter >= 0 && (c.flags & F_PT_EMITTED) && (c.flags & F_PT_NONSPEC) && dot(v.ns, -d) > 0.)
+                    px.Li += c.weight * emitter_radiance(sc, v.emitter);
+                if (c.j >= pc.maxDepth && pc.maxDepth > 0) { go = GO_DONE; break; }
+                const R3 wi = to_local(v, -d);
+                px.refN = mat_transmissive_or_backside(m) ? r3(0.) : v.ns;    // records.inl:160-164
+                rec_store(M.lm.vt + lane, v);
+                px.dIn = d;
+                // ---- direct illumination (scene.cpp:879-904, area.cpp:156-170, shape.cpp:102-114)
+                if ((c.flags & F_PT_DIRECT) && mat_has_smooth(m.type) && sc.nEmitters > 0) {
+                    const R2 u = rd.next2D(SMP_SENSOR);
+                    EmitterPoint ep;
+                    sample_emitter_point(sc, u.x, u.y, ep);
+                    R3 dd = ep.p - v.p;
+                    const Real distSq = dot(dd, dd), dist = sqrt(distSq);
+                    dd = dd / dist;
+                    const Real dp = absdot(dd, ep.n);
+                    Real pdf = sc.emitters[ep.emitter].invArea * (dp != 0. ? distSq / dp : 0.);
+                    if (dot(dd, px.refN) >= 0. && dot(dd, ep.n) < 0. && pdf != 0.) {
+                        const R3 value = emitter_radiance(sc, ep.emitter) / pdf / ep.emPdf;
+                        pdf *= ep.emPdf;
+                        const R3 wo = to_local(v, dd);
+                        const R3 bsdfVal = bsdf_eval(m, wi, wo, MODE_RADIANCE, MEAS_SOLID_ANGLE);
+                        px.pending = r3(0.);
+                        if (!is_zero(bsdfVal)) {
+                            const Real bp = bsdf_pdf(m, wi, wo, MEAS_SOLID_ANGLE);
+                            px.pending = c.weight * value * bsdfVal * ((pdf * pdf) / (pdf * pdf + bp * bp));
+                        }
+                        c.pstate = PS_PT_NEE;
+                        emit_ray(M, lane, c, v.p, dd, sc.epsilon, dist * (1. - sc.shadowEpsilon));
+                        dest = Q_RAYS + (M.parity ^ 1);
+                        running = false;
+                        break;
+                    }
+                }
+                go = GO_BSDF;
+                break;
+            }
+            case GO_BSDF: {                                  // BSDF sampling (path.cpp:222-240)
+                const R3 d = c.d;
+                const Mat m = load_material(sc, v.mat);
+                const R3 wi = to_local(v, -d);
+                const R2 ub = rd.next2D(SMP_SENSOR);
+                BsdfSample bs;
+                bsdf_sample(m, wi, MODE_RADIANCE, ub.x, ub.y, sc.epsilon, bs);
+                if (is_zero(bs.weight)) { go = GO_DONE; break; }
+                if (!(bs.sampledType & BT_DELTA)) c.flags |= F_PT_NONSPEC;
+                c.flags = (bs.sampledType & BT_DELTA) ? (c.flags | F_DELTA) : (c.flags & ~F_DELTA);
+                // throughput and eta are only read again if the ray hits something (path.cpp:268-274)
+                c.weight *= bs.weight;
+                px.eta *= bs.eta;
+                px.bsPdf = bs.pdf;
+                c.pstate = PS_PT_HIT;
+                emit_ray(M, lane, c, v.p, to_world(v, bs.wo), sc.epsilon, INFINITY);
+                dest = Q_RAYC + (M.parity ^ 1);
+                running = false;
+                break;
+            }
+            default:
+                c.pstate = PS_PT_DONE;
+                running = false;
+                break;
+            }
+        }
+        reader_close(rd, c);
+        rec_store(reinterpret_cast<PtExtra *>(M.lm.vs + lane), px);
+        rec_store(M.lm.core + lane, c);
+        q_push(M.q, dest, (uint32_t) lane);
+    }
+}
+
+void launch_pt(const Machine &M, const LaunchCfg &lc) {
+    const unsigned g = (unsigned) std::max(1, std::min((lc.nLanes + 127) / 128, 148 * 16));
+    k_pt<<<g, 128, 0, lc.stream>>>(M);
+}

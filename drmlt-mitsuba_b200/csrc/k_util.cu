@@ -1,22 +1,39 @@
-// chain.cuh -- data-parallel helpers around the wavefront machine (wave.cuh): the normalisation
-// constant b and the luminance CDF of the bootstrap (warp-shuffle reduce and scan), seed
-// resampling, develop, and the ray-cast replay kernel.  Behavioural parity targets:
+// k_util.cu -- data-parallel helpers around the wavefront machine: the normalisation constant b and the
+// luminance CDF of the bootstrap (warp-shuffle reduce and scan), seed resampling, develop.
+// Behavioural parity targets:
 //   PathSampler::generateSeeds               src/libbidir/pathsampler.cpp:859-960
 //   DiscreteDistribution                     include/mitsuba/core/pmf.h:60-200
 //   DRMLTProcess::develop                    src/integrators/drmlt/drmlt_proc.cpp:813-854
-#pragma once
-#include "wave.cuh"
+#include "util_kernels.h"
+#include "common.cuh"
+#include "../../include/drmlt_b200.h"
 
 // ---------------------------------------------------------------- b and the luminance CDF
-// sum / count of the non-NaN luminances: warp shuffle reduce -> one atomic per warp (double)
-__global__ void k_lum_reduce(const float *lum, long long n, double *out /* [2]: sum, count */) {
+// sum / count of the non-NaN luminances, bit-reproducible: fixed grid, fixed-order tree inside a block
+// (warp shuffle, then warp 0 over the warp totals), then ONE thread adds the block partials in block order.
+#define RED_BLOCKS (148 * 4)
+__global__ void __launch_bounds__(256)
+k_lum_reduce(const float *lum, long long n, double *partial /* [RED_BLOCKS][2] */) {
+    __shared__ double ws[8], wc[8];
     double s = 0.0, c = 0.0;
     for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
         const float v = lum[i];
         if (!isnan(v)) { s += (double) v; c += 1.0; }
     }
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); c += __shfl_down_sync(0xffffffffu, c, o); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], c); }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ws[warp] = s; wc[warp] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tc = 0.0;
+        for (int w = 0; w < 8; ++w) { ts += ws[w]; tc += wc[w]; }
+        partial[2 * blockIdx.x] = ts; partial[2 * blockIdx.x + 1] = tc;
+    }
+}
+__global__ void k_lum_final(const double *partial, double *out /* [2]: sum, count */) {
+    double ts = 0.0, tc = 0.0;
+    for (int b = 0; b < RED_BLOCKS; ++b) { ts += partial[2 * b]; tc += partial[2 * b + 1]; }
+    out[0] = ts; out[1] = tc;
 }
 
 // Inclusive scan of max(lum,0) in double, three passes (block scan, scan of block totals, add).
@@ -117,17 +134,23 @@ __global__ void k_develop(const float4 *film, long long n, float factor, float *
     rgb[3 * i] = p.x * factor; rgb[3 * i + 1] = p.y * factor; rgb[3 * i + 2] = p.z * factor;
 }
 
-// ---------------------------------------------------------------- replay kernels
-__global__ void k_trace_rays(const __grid_constant__ DevScene sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits) {
-    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const dr_ray r = rays[i];
-    Hit h;
-    const float3 o = f3(r.o[0], r.o[1], r.o[2]), d = f3(r.d[0], r.d[1], r.d[2]);
-    bool hit = shadow ? traverse<true>(sc, o, d, r.mint, r.maxt, h) : traverse<false>(sc, o, d, r.mint, r.maxt, h);
-    dr_hit out;
-    out.prim = hit ? (int) order[h.tri] : -1;
-    out.t = hit ? h.t : 0.f; out.u = hit ? h.u : 0.f; out.v = hit ? h.v : 0.f;
-    hits[i] = out;
-}
 
+// ---------------------------------------------------------------- launchers
+int lum_reduce_scratch_doubles() { return 2 * RED_BLOCKS; }
+void launch_lum_reduce(const float *lum, long long n, double *scratch, double *out, cudaStream_t s) {
+    k_lum_reduce<<<RED_BLOCKS, 256, 0, s>>>(lum, n, scratch);
+    k_lum_final<<<1, 1, 0, s>>>(scratch, out);
+}
+void launch_scan(const float *lum, long long n, double *cdf, double *blockSums, cudaStream_t s) {
+    const long long nb = scan_blocks(n);
+    k_scan_blocks<<<(unsigned) nb, SCAN_BLOCK, 0, s>>>(lum, n, cdf, blockSums);
+    k_scan_sums<<<1, 1024, 0, s>>>(blockSums, (int) nb);
+    k_scan_add<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(cdf, n, blockSums);
+}
+long long scan_blocks(long long n) { return (n + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS); }
+void launch_resample(const double *cdf, long long n, unsigned long long seed, unsigned long long firstChain, int nChains, unsigned long long bootFirst,
+                     int maxDepth, int technique, unsigned long long *seedIdx, unsigned long long *chainId, int *depth, cudaStream_t s) {
+    k_resample<<<(nChains + 127) / 128, 128, 0, s>>>(cdf, n, seed, firstChain, nChains, bootFirst, maxDepth, technique, seedIdx, chainId, depth);
+}
+void launch_film_luminance(const float4 *film, long long n, double *out, cudaStream_t s) { k_film_luminance<<<148 * 4, 256, 0, s>>>(film, n, out); }
+void launch_develop(const float4 *film, long long n, float factor, float *rgb, cudaStream_t s) { k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(film, n, factor, rgb); }

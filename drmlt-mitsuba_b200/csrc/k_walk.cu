@@ -1,0 +1,216 @@
+// k_walk.cu -- MMLT wavefront stages that turn a closest hit into the next path vertex (k_walk) and that
+// connect the two subpath ends (k_connect).  See machine.cuh for the machine, path.cuh for the building blocks.
+//
+// k_walk is instantiated once per BSDF model: the traversal kernel routes every hit to the walk queue of
+// the material class it found, so each instance runs one BSDF's sampling code on full warps.
+// Behavioural parity: PathVertex::sampleNext (src/libbidir/vertex.cpp:153-350), PathEdge::sampleNext
+// (edge.cpp:27-84), the MMLT branch of PathSampler::sampleSplats (pathsampler.cpp:139-295),
+// PathVertex::eval / evalPdf (vertex.cpp:958-1205), PathEdge::evalCached (edge.cpp:221-271).
+#include "machine.cuh"
+
+template <int BSDF>
+__global__ void __launch_bounds__(128)
+k_walk(const __grid_constant__ Machine M) {
+    const DevScene &sc = M.sc;
+    const uint32_t cnt = M.q.count[Q_WALK + BSDF];
+    const uint32_t *items = M.q.items + (size_t) (Q_WALK + BSDF) * M.q.n;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
+        const int lane = (int) items[qi];
+        Core c;
+        rec_load(c, M.lm.core + lane);
+        const bool emitterSide = c.pstate == PS_EMITTER_HIT;
+        Vtx *vArr = emitterSide ? M.lm.vs : M.lm.vt;
+        PredRec *pArr = emitterSide ? M.lm.vsp : M.lm.vtp;
+        double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
+        const int k = c.depth + 2;                           // s + t + 1
+        Hit hit;
+        { const float4 h = M.lm.hit[lane]; hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.tri = __float_as_int(h.w); }
+        int dest = Q_CHAIN + M.parity;                       // default: the path ends here (empty result)
+        do {
+            Vtx v; PredRec vp;
+            rec_load(v, vArr + lane);
+            int j = c.j;
+            if (j >= 2) rec_load(vp, pArr + lane);
+            const R3 d = c.d;
+            Vtx nv; Real tHit;
+            fill_vertex(sc, hit, v.p, d, nv, tHit);
+            if (tHit == 0.) { c.pstate = PS_EMPTY; break; }
+            Mat nm = load_material(sc, nv.mat);
+            nm.type = BSDF;                                  // compile-time constant for the BSDF switch
+            nv.degenerate = !(mat_has_smooth(BSDF) || nv.emitter >= 0);
+            // solid angle -> area (vertex.cpp:334-347); delta interactions keep their discrete pdfs
+            const Real cosNext = absdot(d, nv.ng);
+            Real pdfFwd = c.pdfFwd, pdfBwd = c.pdfBwd;
+            if (!(c.flags & F_DELTA)) {
+                pdfFwd = pdfFwd / (tHit * tHit) * cosNext;
+                if (j >= 2) {
+                    R3 pd = v.p - vp.p;
+                    const Real plen = length(pd);
+                    pd = pd / plen;
+                    pdfBwd = pdfBwd / (plen * plen) * absdot(pd, vp.ng);
+                }
+            }
+            const Real conv = tHit * tHit / fabs(absdot(d, v.ng) * cosNext);
+            if (!emitterSide) {
+                const int g = k - j;
+                mis_put(mis, MIS_RAD, g - 1, pdfFwd);        // density of vertex j + 1
+                mis_put(mis, MIS_IMP, g + 1, pdfBwd);        // density of vertex j - 1
+                mis_put(mis, MIS_CONV, g - 1, conv);         // edge (g-1, g)
+                if (j == 1) {                                // pixel of the path (pathsampler.cpp:309-312)
+                    R2 sp = r2(0., 0.);
+                    cam_sample_position(sc.cam, nv.p - cam_pos(sc.cam), sp);
+                    c.spos = make_float2((float) sp.x, (float) sp.y);
+                }
+            } else {
+                mis_put(mis, MIS_IMP, j + 1, pdfFwd);
+                mis_put(mis, MIS_RAD, j - 1, pdfBwd);
+                mis_put(mis, MIS_CONV, j, conv);             // edge (j, j+1)
+            }
+            vp.p = v.p; vp.ng = v.ng;
+            v = nv;
+            ++j;
+            c.j = (uint8_t) j;
+            rec_store(vArr + lane, v);
+            rec_store(pArr + lane, vp);
+            const int steps = emitterSide ? c.s : c.t;
+            UReader rd;
+            reader_open(M, c, lane, rd);
+            if (j < steps) {                                 // BSDF sampling step at vertex j (vertex.cpp:153-271)
+                WalkStep ws;
+                const R2 u = rd.next2D(emitterSide ? SMP_EMITTER : SMP_SENSOR);
+                reader_close(rd, c);
+                if (!surface_sample_next(sc, v, nm, normalize(vp.p - v.p), emitterSide ? MODE_IMPORTANCE : MODE_RADIANCE, u, ws)) { c.pstate = PS_EMPTY; break; }
+                const int bit = emitterSide ? j : k - j;
+                if (!ws.delta && !v.degenerate) { c.connectable |= 1u << bit; c.flags |= F_ANYCONN; }
+                c.flags = ws.delta ? (c.flags | F_DELTA) : (c.flags & ~F_DELTA);
+                c.weight *= ws.weightFwd;
+                c.pdfFwd = ws.pdfFwd; c.pdfBwd = ws.pdfBwd;
+                emit_ray(M, lane, c, v.p, ws.wo, sc.epsilon, INFINITY);
+                dest = Q_RAYC + (M.parity ^ 1);
+                break;
+            }
+            // last vertex of this subpath: its measure stays invalid => connectable iff not degenerate
+            if (!v.degenerate) { c.connectable |= 1u << (emitterSide ? (int) c.s : k - (int) c.t); c.flags |= F_ANYCONN; }
+            if (!emitterSide) {
+                const int q = mmlt_emitter_start(M, lane, c, rd, mis);
+                dest = q == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : (q == Q_CONNECT ? Q_CONNECT : Q_CHAIN + M.parity);
+            } else {
+                c.pstate = PS_CONNECT;
+                dest = Q_CONNECT;
+            }
+            reader_close(rd, c);
+        } while (false);
+        rec_store(M.lm.core + lane, c);
+        q_push(M.q, dest, (uint32_t) lane);
+    }
+}
+
+// ------------------------------------------------------------------ connection (pathsampler.cpp:161-295)
+__global__ void __launch_bounds__(128)
+k_connect(const __grid_constant__ Machine M) {
+    const DevScene &sc = M.sc;
+    const PathCfg &pc = M.pc;
+    const uint32_t cnt = M.q.count[Q_CONNECT];
+    const uint32_t *items = M.q.items + (size_t) Q_CONNECT * M.q.n;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
+        const int lane = (int) items[qi];
+        Core c;
+        rec_load(c, M.lm.core + lane);
+        double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
+        int dest = Q_CHAIN + M.parity;
+        c.pstate = PS_EMPTY;
+        do {
+            if (!(c.flags & F_ANYCONN)) break;               // pathsampler.cpp:161-174
+            const int s = c.s, t = c.t, depth = c.depth;
+            Vtx vt; PredRec vtp;
+            rec_load(vt, M.lm.vt + lane);
+            if (t >= 2) rec_load(vtp, M.lm.vtp + lane);
+            if (s == 0) {                                    // pure sensor path: vt must be on an emitter (:213-224)
+                if (vt.type != V_SURFACE || vt.emitter < 0) break;
+                const R3 n = vt.ns;                          // cast(): pRec.n = its.shFrame.n (records.inl:154-155)
+                R3 wo = vtp.p - vt.p;
+                const Real dist = length(wo);
+                wo = wo / dist;
+                const Real dp = dot(wo, n);
+                if (!(dp > 0.)) break;                       // evalDirection (area.cpp:140-148) / |n.wo| = 1/pi
+                c.weight = c.weight * emitter_radiance(sc, vt.emitter);   // radiance * pi * (1/pi)
+                const DevEmitter &em = sc.emitters[vt.emitter];
+                c.connectable |= 1u << 1;                    // emitter sample: area measure, not degenerate
+                mis_put(mis, MIS_IMP, 1, em.invArea * em.pdfDiscrete);                       // vs->evalPdf: pdfEmitterPosition
+                mis_put(mis, MIS_IMP, 2, R_INV_PI * dp / (dist * dist) * absdot(wo, vtp.ng));   // vt->evalPdf(vs, vtPred, EImportance)
+                // connection edge of a supernode: length 0, generalized geometric term = 1 (edge.cpp:229-234, 561-571)
+                if (pc.excludeDirect && depth <= 2) break;
+                c.pstate = PS_FINISH;
+                break;
+            }
+            Vtx vs; PredRec vsp;
+            rec_load(vs, M.lm.vs + lane);
+            if (s >= 2) rec_load(vsp, M.lm.vsp + lane);
+            if (vs.degenerate || vt.degenerate) break;       // :253-257
+            R3 d = vs.p - vt.p;                              // from vt towards vs
+            const Real len = length(d);
+            if (len == 0.) break;
+            d = d / len;
+            R3 fs, ft;
+            Mat ms, mt;
+            if (s == 1) {                                    // vs->eval(vsPred, vt, EImportance)
+                const Real dp = dot(-d, vs.ns);
+                fs = r3(dp > 0. ? R_INV_PI : 0.);
+            } else {
+                ms = load_material(sc, vs.mat);
+                fs = surface_eval(sc, vs, ms, normalize(vsp.p - vs.p), -d, MODE_IMPORTANCE);
+            }
+            if (t == 1) {
+                const Real imp = cam_importance(sc.cam, cam_inv_dir(sc.cam, d));
+                const Real dp = absdot(vt.ns, d);
+                ft = r3(dp != 0. ? imp / dp : imp);
+            } else {
+                mt = load_material(sc, vt.mat);
+                ft = surface_eval(sc, vt, mt, normalize(vtp.p - vt.p), d, MODE_RADIANCE);
+            }
+            R3 value = c.weight * fs * ft;
+            if (is_zero(value)) break;
+            // generalized geometric term (edge.cpp:245-267), applied before the visibility test: an occluded
+            // connection is dropped whatever its value
+            value *= absdot(vs.ns, d) * absdot(vt.ns, d) / (len * len);
+            c.weight = value;
+            // the four densities next to the connection (path.cpp:835-859)
+            c.connectable |= (1u << s) | (1u << (s + 1));    // measure forced to EArea (:263-265)
+            if (s == 1) {
+                const Real dp = dot(-d, vs.ns);
+                mis_put(mis, MIS_IMP, s + 1, R_INV_PI * fmax(dp, 0.) / (len * len) * absdot(d, vt.ng));
+                mis_put(mis, MIS_RAD, s - 1, 1.0);
+            } else {
+                mis_put(mis, MIS_IMP, s + 1, surface_pdf_area(vs, ms, vsp.p, vt.p, vt.ng));
+                mis_put(mis, MIS_RAD, s - 1, surface_pdf_area(vs, ms, vt.p, vsp.p, vsp.ng));
+            }
+            if (t == 1) {
+                mis_put(mis, MIS_RAD, s, cam_importance(sc.cam, cam_inv_dir(sc.cam, d)) / (len * len) * absdot(d, vs.ng));
+                mis_put(mis, MIS_IMP, s + 2, 1.0);
+                R2 sp = r2(0., 0.);
+                if (!cam_sample_position(sc.cam, vs.p - vt.p, sp)) c.flags |= F_SPOS_FAIL;   // :298-303
+                c.spos = make_float2((float) sp.x, (float) sp.y);
+            } else {
+                mis_put(mis, MIS_RAD, s, surface_pdf_area(vt, mt, vtp.p, vs.p, vs.ng));
+                mis_put(mis, MIS_IMP, s + 2, surface_pdf_area(vt, mt, vs.p, vtp.p, vtp.ng));
+            }
+            // pathConnectAndCollapse (edge.cpp:572-606): vt and vs are always "on surface" here
+            c.pstate = PS_CONNECT_SHADOW;
+            emit_ray(M, lane, c, vt.p, d, sc.epsilon, len * (1. - sc.shadowEpsilon));
+            dest = Q_RAYS + (M.parity ^ 1);
+        } while (false);
+        rec_store(M.lm.core + lane, c);
+        q_push(M.q, dest, (uint32_t) lane);
+    }
+}
+
+static unsigned grid_for(int n, int threads) { return (unsigned) std::max(1, std::min((n + threads - 1) / threads, 148 * 16)); }
+
+void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask) {
+    const unsigned g = grid_for(lc.nLanes, 128);
+    if (typeMask & (1u << DR_BSDF_DIFFUSE)) k_walk<DR_BSDF_DIFFUSE><<<g, 128, 0, lc.stream>>>(M);
+    if (typeMask & (1u << DR_BSDF_DIELECTRIC)) k_walk<DR_BSDF_DIELECTRIC><<<g, 128, 0, lc.stream>>>(M);
+    if (typeMask & (1u << DR_BSDF_CONDUCTOR)) k_walk<DR_BSDF_CONDUCTOR><<<g, 128, 0, lc.stream>>>(M);
+    if (typeMask & (1u << DR_BSDF_ROUGHCONDUCTOR)) k_walk<DR_BSDF_ROUGHCONDUCTOR><<<g, 128, 0, lc.stream>>>(M);
+    k_connect<<<g, 128, 0, lc.stream>>>(M);
+}

@@ -1,0 +1,294 @@
+// machine.cuh -- the staged wavefront machine that runs the Markov chains: lane records, work
+// queues, job description.  (Kernels: k_chain.cu, k_walk.cu, k_pt.cu, k_trace.cu.)
+//
+// Every chain ("lane") has at most ONE ray in flight.  Lanes move between small, specialised kernels
+// through device-side work queues of lane indices, so that each kernel runs convergent code on full
+// warps, with a register budget that fits its own stage only:
+//
+//   k_trace<closest|shadow>  float32 BVH traversal of the queued rays; a closest hit is routed to the
+//                            walk queue of the BSDF model of the triangle it found (sort by material)
+//   k_walk<bsdf>             hit -> path vertex (double re-intersection), MIS bookkeeping, BSDF sample of
+//                            the next direction (sensor or emitter subpath)            -> next ray / connect
+//   k_connect                MMLT connection of the two subpath ends (PathVertex::eval, geometric term,
+//                            the four densities next to the connection)                 -> shadow ray
+//   k_pt                     technique=path: MIPathTracer::Li as a resumable state machine
+//   k_chain                  a path has ended: MIS weight, then the chain-level step fused in the same
+//                            thread -- delayed-rejection acceptance (mira / green / orbital / mixture, or
+//                            PSSMLT), expectation-weighted film splats, commit of the accepted
+//                            primary-sample vector, statistics -- then the NEXT proposal is mutated and
+//                            its first ray is emitted
+//
+// One round = { trace closest, trace shadow, walk x materials, connect, chain }; every ray emitted in
+// round r is traced in round r + 1.  Lanes progress at their own pace: a lane whose first stage was
+// accepted starts its next mutation while its neighbour traces a second-stage path.  The same machine
+// runs three kinds of jobs: Markov chains (JOB_CHAIN), the bootstrap (JOB_BOOT,
+// PathSampler::generateSeeds) and replayed primary-sample vectors (JOB_EVAL, parity tests).
+//
+// Behavioural parity targets:
+//   PathSampler::sampleSplats                src/libbidir/pathsampler.cpp:79-571 (MMLT :84-320, PT :529-567)
+//   MIPathTracer::Li                         src/integrators/path/path.cpp:123-312
+//   DRMLTRenderer::process / processMixture  src/integrators/drmlt/drmlt_proc.cpp:161-380, 386-771
+//   PSSMLTRenderer::process                  src/integrators/pssmlt/pssmlt_proc.cpp:110-285
+#pragma once
+#include "path.cuh"
+
+// ------------------------------------------------------------------ lane records (AoS: one record per lane per array,
+// every record a multiple of 16 bytes, so a lane picked from a queue is fetched with a few 128-bit loads)
+enum { PS_IDLE = 0, PS_START, PS_SENSOR_HIT, PS_EMITTER_HIT, PS_CONNECT, PS_CONNECT_SHADOW, PS_FINISH, PS_EMPTY,
+       PS_PT_HIT, PS_PT_NEE, PS_PT_DONE };
+enum { PH_STAGE1 = 0, PH_STAGE2 = 1, PH_REVERSE = 2, PH_INIT = 3 };
+enum { F_DELTA = 1u, F_ANYCONN = 2u, F_SPOS_FAIL = 4u, F_PT_FIRST = 8u, F_PT_EMITTED = 16u, F_PT_DIRECT = 32u, F_PT_NONSPEC = 64u };
+
+struct alignas(16) Core {     // 128 bytes
+    uint8_t pstate, s, t, j;          // path in flight: state, strategy, vertices walked on the current side
+    uint8_t depth, phase, large, ubuf;   // MMLT depth | chain phase | large-step coin (2 = not drawn) | active coordinate buffer
+    int8_t tx; uint8_t nrays, pos0, pos1;   // t of the current state | rays cast | reader positions (sensor, emitter)
+    uint8_t pos2, pad0, pad1, pad2;   // reader position (direct)
+    uint32_t flags, connectable;
+    uint32_t mut;                     // JOB_CHAIN: mutation counter | JOB_BOOT / JOB_EVAL: items done by this lane
+    uint32_t pad3;
+    float2 spos;                      // pixel of the path in flight
+    uint64_t chainId;                 // RNG key of the chain
+    uint64_t seedIdx;                 // bootstrap sample the chain started from
+    uint64_t pad4;
+    R3 weight;                        // MMLT: product of walk weights, then the connection value | PT: throughput
+    R3 d;                             // direction of the ray in flight (double; the traversal gets its float cast)
+    Real pdfFwd, pdfBwd;              // densities of the step in flight (solid angle or discrete)
+};
+static_assert(sizeof(Core) == 128, "Core layout");
+
+struct alignas(16) PredRec { R3 p, ng; };                  // 48 bytes
+struct alignas(16) PtExtra { R3 Li, pending, refN; Real eta, bsPdf; R3 dIn; };   // 112 bytes (aliases the emitter-side vertex)
+struct alignas(16) ChainCore {        // 128 bytes
+    Real Lx, a1, cumW;
+    Real yL, zL;
+    float2 posx, ypos, zpos;
+    float3 valx, yval, zval;
+    uint8_t acc1, yn, zn, pad0;
+    int8_t yt, zt, ys, zs;
+    uint8_t posY[3], pad1;            // reader positions at the end of the stage-1 path (m_dimStage1, drmlt_sampler.cpp:237-238)
+    uint32_t pad2[4];
+};
+static_assert(sizeof(ChainCore) == 128 && sizeof(Vtx) == 112 && sizeof(PtExtra) == sizeof(Vtx), "lane layout");
+
+enum { MIS_IMP = 0, MIS_RAD = 16, MIS_CONV = 32, MIS_WORDS = 48 };
+static_assert(DR_MAXK + 1 <= 16, "MIS arrays");
+
+struct LaneMem {
+    Core *core;               // [n]
+    Vtx *vt, *vs;             // [n] last vertex of the sensor / emitter subpath
+    PredRec *vtp, *vsp;       // [n] position and geometric normal of their predecessors
+    ChainCore *chain;         // [n]
+    double *mis;              // [n][48]: pdfImp[16], pdfRad[16], conv[16]
+    double *ubuf;             // [n][UB_COUNT][nU] coordinate buffers X, Y, Z, R
+    float4 *ray;              // [n][2] (o, tmin), (d, tmax): the ray in flight, float32 for the traversal
+    double *rayd;             // [n][8] o, d, tmin, tmax of the same ray un-rounded (deciding triangle tests)
+    float4 *hit;              // [n] (t, u, v, leaf-order triangle or -1)
+    int n, nU;
+};
+
+// whole-record copies through 128-bit accesses
+template <class T> DR_D void rec_load(T &dst, const T *src) {
+    static_assert(sizeof(T) % 16 == 0, "record size");
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(&dst);
+#pragma unroll
+    for (int i = 0; i < (int) (sizeof(T) / 16); ++i) d[i] = s[i];
+}
+template <class T> DR_D void rec_store(T *dst, const T &src) {
+    static_assert(sizeof(T) % 16 == 0, "record size");
+    const uint4 *s = reinterpret_cast<const uint4 *>(&src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < (int) (sizeof(T) / 16); ++i) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------ work queues
+// Q_RAYC / Q_RAYS / Q_CHAIN are double-buffered by round parity: kernels of round r consume [r & 1] and
+// produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).
+enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 4 */, Q_CONNECT = 10, Q_PT = 11, Q_COUNT = 12 };
+struct Queues {
+    uint32_t *items;          // [Q_COUNT][n]
+    uint32_t *count;          // [Q_COUNT]
+    int n;
+};
+// Opportunistic warp-aggregated append: the threads of the warp that push to the same queue at the same
+// time share one atomic.
+DR_D void q_push(const Queues &q, int which, uint32_t lane) {
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, which);
+    const int leader = __ffs(peers) - 1;
+    const unsigned self = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if ((int) self == leader) base = atomicAdd(&q.count[which], (uint32_t) __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    q.items[(size_t) which * q.n + base + __popc(peers & ((1u << self) - 1u))] = lane;
+}
+
+// ------------------------------------------------------------------ jobs
+enum { JOB_CHAIN = 0, JOB_BOOT = 1, JOB_EVAL = 2 };
+struct JobParams {
+    int type;
+    uint32_t mutTarget;                 // JOB_CHAIN: lanes run until they have done this many mutations
+    long long nItems;                   // JOB_BOOT / JOB_EVAL: lane l evaluates items l, l + n, l + 2n, ...
+    unsigned long long first;           // JOB_BOOT: bootstrap sample index of item 0
+    float *lumOut;                      // JOB_BOOT: luminance of every item
+    const float *us, *ue, *ud;          // JOB_EVAL: replayed primary-sample vectors [nItems][d*]
+    int ds, de, dd;
+    const int *depthIn;                 // JOB_EVAL: MMLT depth per item
+    dr_path_result *out;                // JOB_EVAL
+    dr_step_record *records;            // JOB_CHAIN (parity): one record per mutation
+    int recordStride;
+    uint32_t mut0;
+};
+
+struct FilmParams {
+    int w, h;
+    float radius, scaleFactor;
+    float values[32];          // rfilter.cpp:37-55 discretised filter (MTS_FILTER_RESOLUTION = 31)
+};
+
+struct ChainParams {
+    Real pLarge;
+    Real b;                    // m_config.luminance
+    int acceptanceMap, timidAfterLarge, fixEmitterPath, useMixture, kelemenWeights;
+    Real kel_s1, kel_s2, kel_logRatio;     // un-scaled Kelemen bounds for Mira's transition ratio
+    int dimS, dimE, dimD;      // allocated coordinates per sampler (maxDepth worst case)
+};
+
+enum { ST_MUT = 0, ST_FIRST_A, ST_FIRST_B, ST_LARGE_A, ST_LARGE_B, ST_BOLD_A, ST_BOLD_B, ST_SECOND_A, ST_SECOND_B,
+       ST_SECOND_LARGE_A, ST_SECOND_LARGE_B, ST_SECOND_BOLD_A, ST_SECOND_BOLD_B, ST_ACC_A, ST_ACC_B, ST_PATHS, ST_RAYS, ST_COUNT };
+
+// everything a stage kernel needs, passed as ONE __grid_constant__ argument
+struct Machine {
+    DevScene sc;
+    PathCfg pc;
+    PssParams pp;
+    ChainParams cp;
+    FilmParams fp;
+    LaneMem lm;
+    Queues q;
+    JobParams job;
+    float4 *film;
+    unsigned long long *counters;
+    int parity;               // round & 1
+};
+
+// ------------------------------------------------------------------ MIS arrays of a lane
+DR_D void mis_put(double *mis, int arr, int i, Real v) { mis[arr + i] = v; }
+DR_D Real mis_get(const double *mis, int arr, int i) { return mis[arr + i]; }
+
+// findMaxDimensions (pssmlt_utils.h:27-77): MMLT vectors depend on the chain's depth
+DR_D void chain_dims(const PathCfg &pc, const ChainParams &cp, int depth, int dims[3]) {
+    if (pc.technique == DR_TECH_MMLT) {
+        int m = (depth + 2) * 3; if (m & 1) m++;
+        dims[0] = m; dims[1] = m; dims[2] = 1;
+    } else { dims[0] = cp.dimS; dims[1] = cp.dimE; dims[2] = cp.dimD; }
+}
+
+// coordinate reader over the lane's active buffer
+DR_D void reader_open(const Machine &M, const Core &c, int lane, UReader &rd) {
+    rd.buf = M.lm.ubuf + ((size_t) lane * UB_COUNT + c.ubuf) * M.lm.nU;
+    rd.off[0] = M.pp.off[0]; rd.off[1] = M.pp.off[1]; rd.off[2] = M.pp.off[2];
+    if (M.job.type == JOB_EVAL) { rd.lim[0] = M.job.ds; rd.lim[1] = M.job.de; rd.lim[2] = M.job.dd; }
+    else {
+        int dims[3];
+        chain_dims(M.pc, M.cp, c.depth, dims);
+        rd.lim[0] = dims[0] + (dims[0] & 1); rd.lim[1] = dims[1] + (dims[1] & 1); rd.lim[2] = dims[2] + (dims[2] & 1);
+    }
+    rd.pos[0] = c.pos0; rd.pos[1] = c.pos1; rd.pos[2] = c.pos2;
+    rd.reflect = M.job.type == JOB_CHAIN && M.pp.integrator == DR_INTEGRATOR_DRMLT;
+}
+DR_D void reader_close(const UReader &rd, Core &c) { c.pos0 = (uint8_t) rd.pos[0]; c.pos1 = (uint8_t) rd.pos[1]; c.pos2 = (uint8_t) rd.pos[2]; }
+
+// queue the next ray of a lane; mint == epsilon gets the adaptive scaling of skdtree.cpp:126-129
+DR_D void emit_ray(const Machine &M, int lane, Core &c, R3 o, R3 d, Real tmin, Real tmax) {
+    if (tmin == (Real) M.sc.epsilon) tmin *= fmax(fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z)), (Real) M.sc.epsilon);
+    M.lm.ray[2 * (size_t) lane] = make_float4((float) o.x, (float) o.y, (float) o.z, (float) tmin);
+    M.lm.ray[2 * (size_t) lane + 1] = make_float4((float) d.x, (float) d.y, (float) d.z, (float) tmax);
+    double2 *rd = reinterpret_cast<double2 *>(M.lm.rayd + 8 * (size_t) lane);
+    rd[0] = make_double2(o.x, o.y); rd[1] = make_double2(o.z, d.x); rd[2] = make_double2(d.y, d.z); rd[3] = make_double2(tmin, tmax);
+    c.d = d;
+    ++c.nrays;
+}
+
+// ------------------------------------------------------------------ film
+// Splat of one (position, RGB) pair through the tabulated reconstruction filter
+// (ImageBlock::put, include/mitsuba/render/imageblock.h:149-196): one 16-byte vector atomic per touched pixel.
+DR_D void film_put(float4 *film, const FilmParams &fp, float2 pos, float3 value) {
+    if (!rgb_valid(value)) return;
+    const float px = pos.x - 0.5f, py = pos.y - 0.5f;
+    const int minx = max((int) ceilf(px - fp.radius), 0), miny = max((int) ceilf(py - fp.radius), 0);
+    const int maxx = min((int) floorf(px + fp.radius), fp.w - 1), maxy = min((int) floorf(py + fp.radius), fp.h - 1);
+    for (int y = miny; y <= maxy; ++y) {
+        const float wy = fp.values[min((int) fabsf((y - py) * fp.scaleFactor), 31)];
+        for (int x = minx; x <= maxx; ++x) {
+            const float w = fp.values[min((int) fabsf((x - px) * fp.scaleFactor), 31)] * wy;
+            if (w == 0.f) continue;
+            atomicAdd(film + (size_t) y * fp.w + x, make_float4(w * value.x, w * value.y, w * value.z, 0.f));
+        }
+    }
+}
+
+// per-warp statistics -> global counters (the reference's StatsCounter, statistics.h:80-110)
+DR_D void stats_flush(const uint32_t *st, unsigned long long *counters) {
+    unsigned int any = 0;
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; ++i) any |= st[i];
+    if (__any_sync(0xffffffffu, any != 0)) {
+#pragma unroll
+        for (int i = 0; i < ST_COUNT; ++i) {
+            unsigned int v = st[i];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counters[i], (unsigned long long) v);
+        }
+    }
+}
+
+// MMLT: sample the emitter end of the path (PS_EMITTER_START of the state machine): emitter subpath vertex 1,
+// then either the emission ray (s >= 2) or straight to the connection.  Returns the queue the lane goes to
+// (Q_RAYC or Q_CONNECT), or -1 when the path is dead.
+DR_D int mmlt_emitter_start(const Machine &M, int lane, Core &c, UReader &rd, double *mis) {
+    const DevScene &sc = M.sc;
+    c.flags &= ~F_DELTA;
+    mis_put(mis, MIS_IMP, 0, 1.0);
+    c.connectable |= 1u;                          // area lights: supernode not degenerate, never discrete
+    if (c.s >= 1) {
+        if (sc.nEmitters == 0) { c.pstate = PS_EMPTY; return -1; }   // nothing to sample: the path is dead
+        EmitterPoint ep;
+        const R2 u0 = rd.next2D(SMP_EMITTER);
+        sample_emitter_point(sc, u0.x, u0.y, ep);
+        const DevEmitter &em = sc.emitters[ep.emitter];
+        c.weight *= emitter_radiance(sc, ep.emitter) * (R_PI * em.area / ep.emPdf);   // m_power / emPdf
+        mis_put(mis, MIS_IMP, 1, ep.pdfArea);
+        Vtx vs;
+        vs.p = ep.p; vs.ng = vs.ns = ep.n; vs.ss = r3(0.); vs.type = V_EMITTER_SAMPLE; vs.degenerate = 0; vs.emitter = ep.emitter; vs.mat = -1;
+        c.connectable |= 1u << 1;
+        rec_store(M.lm.vs + lane, vs);
+        c.j = 1;
+        if (c.s >= 2) {                           // vertex.cpp:99-124, area.cpp:130-138
+            const R2 u = rd.next2D(SMP_EMITTER);
+            const R3 local = square_to_cosine_hemisphere(u.x, u.y);
+            R3 fs, ft;
+            coordinate_system(vs.ns, fs, ft);
+            c.pdfFwd = R_INV_PI * local.z; c.pdfBwd = 1.0;
+            c.pstate = PS_EMITTER_HIT;
+            emit_ray(M, lane, c, vs.p, fs * local.x + ft * local.y + vs.ns * local.z, sc.epsilon, INFINITY);
+            return Q_RAYC;
+        }
+    }
+    c.pstate = PS_CONNECT;
+    return Q_CONNECT;
+}
+
+// ------------------------------------------------------------------ host-callable launchers (one per translation unit)
+struct LaunchCfg { cudaStream_t stream; int nLanes; };
+void launch_trace(const Machine &M, const LaunchCfg &lc);                 // k_trace.cu: closest + shadow queues
+void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask);   // k_walk.cu: walk queues of the BSDF types present, then connect
+void launch_pt(const Machine &M, const LaunchCfg &lc);                    // k_pt.cu
+void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu
+void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId,
+                  const unsigned long long *seedIdx);                     // k_chain.cu: initialise lanes for M.job and queue them
+void launch_resume(const Machine &M, const LaunchCfg &lc);                // k_chain.cu: re-queue idle chains whose target was raised
+void launch_flush_pssmlt(const Machine &M, const LaunchCfg &lc);          // k_chain.cu
+void launch_trace_rays(const DevScene &sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits, cudaStream_t stream);

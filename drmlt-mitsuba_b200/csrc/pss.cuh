@@ -1,12 +1,21 @@
-// pss.cuh -- primary-sample-space state of one Markov chain and its lazily evaluated proposals.
+// pss.cuh -- primary-sample-space state of one Markov chain: transition kernels, proposal
+// vectors and the coordinate reader of the path samplers.
 //
 // The reference keeps three std::vector<Float> per sampler (current, stage-1 proposal, stage-2
-// proposal; src/integrators/drmlt/drmlt_sampler.h:207-210) and fills a whole proposal vector at the
-// first query of a stage (drmlt_sampler.cpp:313-394, pssmlt_sampler.cpp:124-166).  Here only the
-// CURRENT vector lives in HBM (SoA of doubles: coordinate-major, chain-minor, so a warp of chains
-// reads one coordinate with two coalesced 128-byte transactions).  Proposal coordinates are pure functions of
-// (current value, keyed uniforms) and are recomputed in registers when the path sampler asks for
-// them; nothing but the accepted vector is ever written back.
+// proposal; src/integrators/drmlt/drmlt_sampler.h:207-210) and fills a whole proposal vector at
+// the first query of a stage (drmlt_sampler.cpp:313-394, pssmlt_sampler.cpp:124-166).  Here every
+// chain owns four coordinate buffers in HBM -- X (current), Y (stage 1), Z (stage 2), R (Green's
+// reverse state) -- each `nU` doubles, contiguous per chain, read and written as 16-byte pairs.
+// A proposal is filled ONCE, by the chain kernel, when a path starts; the wavefront stages that
+// walk the path only read pairs back (no transcendental math in the ray-bound kernels), and an
+// accepted proposal is committed by copying its pairs into X.
+//
+// drmlt + mmlt: the strategy coordinate uses the identity kernel (drmlt_proc.cpp:133-136), so (s,t)
+// only changes in a large step, which redraws every coordinate.  A path of strategy (s,t) can only
+// consume sensor coordinates [0, 2t) and emitter coordinates [0, 2s); all other coordinates can never
+// influence anything before they are redrawn, so only that subset is filled and committed
+// ("subset mode"; exact, not an approximation).  Everything else (pssmlt, technique=path/bdpt,
+// green + timidAfterLarge whose reverse state reads x after a strategy change) uses full vectors.
 //
 // Transition kernels: src/integrators/drmlt/tools/transition.h:23-190 (Kelemen, Gaussian,
 // WrappedCauchy, Identity), PSSMLTSampler::mutate (pssmlt_sampler.h:117-147).
@@ -14,8 +23,8 @@
 #include "real.cuh"
 #include "../../include/drmlt_b200.h"
 
-enum { PSS_ARRAY = 0, PSS_BOOT = 1, PSS_STAGE1 = 2, PSS_STAGE2 = 3, PSS_REVERSE = 4 };
 enum { SMP_SENSOR = 0, SMP_EMITTER = 1, SMP_DIRECT = 2 };
+enum { UB_X = 0, UB_Y = 1, UB_Z = 2, UB_R = 3, UB_COUNT = 4 };
 
 struct PssParams {          // per-launch constants
     uint64_t seed;
@@ -25,6 +34,9 @@ struct PssParams {          // per-launch constants
     Real cauchy_disp;                 // 2 rho / (1 + rho^2), rho = exp(-1/4)
     int pss_kelemen; Real pss_s2, pss_logRatio, pss_sigma;   // PSSMLT
     uint32_t identity1, identity2;     // bit s: sampler s uses the identity kernel in stage 1 / stage 2
+    int subset;                        // subset mode (see above)
+    int off[3];                        // first slot of each sampler inside a coordinate buffer (even)
+    int nU;                            // doubles per buffer (even)
 };
 
 DR_D Real wrap_reflect(Real y) { return y > 1. ? 2. - y : (y <= 0. ? fabs(y) : y); }   // drmlt_sampler.h:140-144
@@ -63,94 +75,81 @@ DR_D Real pssmlt_mutate(Real value, Real xi1, Real xi2, const PssParams &pp) {  
     return value;
 }
 
-struct Pss {
-    const PssParams *pp;
-    const void *xs[3];        // coordinate (s,k) of this chain lives at xs[s][k * stride] (double state, or float replay input)
-    bool f32;                 // xs point to float arrays (dr_eval_paths replays host vectors)
-    size_t stride;
-    int dim[3];
-    uint64_t chain;           // chain id (stages) or bootstrap sample index (PSS_BOOT)
-    uint32_t mut;
-    int mode;
-    bool largeStep;
-    bool lightTracing;        // nextStage(current->t == 1): emitter sampler keeps its real stage-2 kernel
-    int pos[3];
-    int maxIdx[3];            // largest index touched in this stage (m_dimStage*, drmlt_sampler.cpp:237-238)
-    int cacheKey; R2 cacheVal;
+// 16-byte pair access to a coordinate buffer
+DR_D R2 ub_load(const double *buf, int slot) { const double2 v = *reinterpret_cast<const double2 *>(buf + slot); return r2(v.x, v.y); }
+DR_D void ub_store(double *buf, int slot, R2 v) { *reinterpret_cast<double2 *>(buf + slot) = make_double2(v.x, v.y); }
 
-    DR_D void begin(int mode_) {
-        mode = mode_;
-        pos[0] = pos[1] = pos[2] = 0;
-        maxIdx[0] = maxIdx[1] = maxIdx[2] = 0;
-        cacheKey = -1;
-    }
-    DR_D Real xat(int s, int k) const {
-        if (k >= dim[s]) return 0.0;
-        return f32 ? (Real) static_cast<const float *>(xs[s])[(size_t) k * stride] : static_cast<const double *>(xs[s])[(size_t) k * stride];
-    }
+// What a proposal needs to know about the mutation it belongs to.
+struct MutCtx {
+    const PssParams *pp;
+    uint64_t chain;          // chain id
+    uint32_t mut;            // mutation counter of the chain
+    bool largeStep;
+    bool lightTracing;       // nextStage(current->t == 1): the emitter sampler keeps its real stage-2 kernel
     DR_D bool identity1(int s) const { return (pp->identity1 >> s) & 1u; }
     DR_D bool identity2(int s) const {
-        if ((pp->identity1 >> s) & 1u) return true;               // setStagesToIdentity
+        if ((pp->identity1 >> s) & 1u) return true;               // setStagesToIdentity (drmlt_proc.cpp:133-136)
         if ((pp->identity2 >> s) & 1u) return !lightTracing;      // handleLightTracing: stage2 = Identity, stageLT = real kernel
         return false;
     }
-    // un-wrapped stage-1 proposal of the coordinate pair (2p, 2p+1)
-    DR_D R2 prop1(int s, int p) const {
-        const Real x0 = xat(s, 2 * p), x1 = xat(s, 2 * p + 1);
-        if (!largeStep && identity1(s)) return r2(x0, x1);
-        const float4 u = keyed_uniform4(pp->seed, S_STAGE1 + s, chain, mut, (uint32_t) p);
-        if (largeStep) return r2(u.x, u.z);
-        if (pp->integrator == DR_INTEGRATOR_PSSMLT)
-            return r2(pssmlt_mutate(x0, u.x, u.y, *pp), pssmlt_mutate(x1, u.z, u.w, *pp));
-        if (pp->type != DR_TYPE_ORBITAL)
-            return r2(x0 + kelemen_sample(u.x, pp->kel_s2, pp->kel_logRatio), x1 + kelemen_sample(u.z, pp->kel_s2, pp->kel_logRatio));
-        const Real d = kelemen_sample(u.x, pp->kel_s2, pp->kel_logRatio);   // drmlt_sampler.cpp:351-359
-        Real sa, ca;
-        sincospi(2.0 * u.y, &sa, &ca);
-        return r2(x0 + d * ca, x1 + d * sa);
-    }
-    // un-wrapped stage-2 proposal
-    DR_D R2 prop2(int s, int p) const {
-        const Real x0 = xat(s, 2 * p), x1 = xat(s, 2 * p + 1);
-        if (!largeStep && identity2(s)) return r2(x0, x1);
-        const float4 u = keyed_uniform4(pp->seed, S_STAGE2 + s, chain, mut, (uint32_t) p);
-        if (largeStep) return r2(u.x, u.z);   // release-build behaviour of fillSpace with m_largeStep still set
-        if (pp->type != DR_TYPE_ORBITAL)
-            return r2(x0 + gaussian_sample(u.x, u.y, pp->sigma2), x1 + gaussian_sample(u.z, u.w, pp->sigma2));
-        const R2 y = prop1(s, p);                  // drmlt_sampler.cpp:361-392
-        const Real theta = cauchy_sample(u.x, pp->cauchy_disp);
-        const Real du1 = y.x - x0, du2 = y.y - x1;
-        const Real norm = sqrt(du1 * du1 + du2 * du2);
-        Real mu = safe_acos(-du1 / norm);
-        if (-du2 < 0.) mu = 2. * R_PI - mu;
-        Real sa, ca;
-        sincos(theta + mu, &sa, &ca);
-        return r2(y.x + ca * norm, y.y + sa * norm);
-    }
-    DR_D R2 pair_value(int s, int p) const {
-        switch (mode) {
-        case PSS_ARRAY: return r2(xat(s, 2 * p), xat(s, 2 * p + 1));
-        case PSS_BOOT: {
-            const float4 u = keyed_uniform4(pp->seed, S_BOOT, chain, (uint32_t) s, (uint32_t) (p >> 1));
-            return (p & 1) ? r2(u.z, u.w) : r2(u.x, u.y);
-        }
-        case PSS_STAGE1: return prop1(s, p);
-        case PSS_STAGE2: return prop2(s, p);
-        default: {   // PSS_REVERSE: y* = z - (y - x) (drmlt_sampler.cpp:293-296)
-            const R2 y = prop1(s, p), z = prop2(s, p);
-            return r2(z.x - (y.x - xat(s, 2 * p)), z.y - (y.y - xat(s, 2 * p + 1)));
-        }
-        }
-    }
+};
+
+// un-wrapped stage-1 proposal of the coordinate pair p of sampler s (drmlt_sampler.cpp:313-359, pssmlt_sampler.cpp:124-166)
+DR_D R2 propose_stage1(const MutCtx &m, int s, int p, R2 x) {
+    const PssParams &pp = *m.pp;
+    if (!m.largeStep && m.identity1(s)) return x;
+    const float4 u = keyed_uniform4(pp.seed, S_STAGE1 + s, m.chain, m.mut, (uint32_t) p);
+    if (m.largeStep) return r2(u.x, u.z);
+    if (pp.integrator == DR_INTEGRATOR_PSSMLT)
+        return r2(pssmlt_mutate(x.x, u.x, u.y, pp), pssmlt_mutate(x.y, u.z, u.w, pp));
+    if (pp.type != DR_TYPE_ORBITAL)
+        return r2(x.x + kelemen_sample(u.x, pp.kel_s2, pp.kel_logRatio), x.y + kelemen_sample(u.z, pp.kel_s2, pp.kel_logRatio));
+    const Real d = kelemen_sample(u.x, pp.kel_s2, pp.kel_logRatio);   // drmlt_sampler.cpp:351-359
+    Real sa, ca;
+    sincospi(2.0 * u.y, &sa, &ca);
+    return r2(x.x + d * ca, x.y + d * sa);
+}
+// un-wrapped stage-2 proposal (drmlt_sampler.cpp:313-332, 361-392); y = the stage-1 proposal of the same pair
+DR_D R2 propose_stage2(const MutCtx &m, int s, int p, R2 x, R2 y) {
+    const PssParams &pp = *m.pp;
+    if (!m.largeStep && m.identity2(s)) return x;
+    const float4 u = keyed_uniform4(pp.seed, S_STAGE2 + s, m.chain, m.mut, (uint32_t) p);
+    if (m.largeStep) return r2(u.x, u.z);   // release-build behaviour of fillSpace with m_largeStep still set
+    if (pp.type != DR_TYPE_ORBITAL)
+        return r2(x.x + gaussian_sample(u.x, u.y, pp.sigma2), x.y + gaussian_sample(u.z, u.w, pp.sigma2));
+    const Real theta = cauchy_sample(u.x, pp.cauchy_disp);
+    const Real du1 = y.x - x.x, du2 = y.y - x.y;
+    const Real norm = sqrt(du1 * du1 + du2 * du2);
+    Real mu = safe_acos(-du1 / norm);
+    if (-du2 < 0.) mu = 2. * R_PI - mu;
+    Real sa, ca;
+    sincos(theta + mu, &sa, &ca);
+    return r2(y.x + ca * norm, y.y + sa * norm);
+}
+
+// Sequential reader of the active coordinate buffer of one chain (Sampler::next1D/next2D of the three
+// DRMLTSampler / PSSMLTSampler instances).  pos[] survives between wavefront stages in the lane record.
+struct UReader {
+    const double *buf;        // active buffer of this chain
+    int off[3], lim[3];       // first slot / number of readable coordinates per sampler
+    int pos[3];
+    bool reflect;             // DRMLT stores un-wrapped values and reflects on read
     DR_D Real next1D(int s) {
         const int k = pos[s]++;
-        maxIdx[s] = max(maxIdx[s], k);
-        if (k >= dim[s] + (dim[s] & 1)) return 0.5;    // the reference raises EError here
-        const int key = (s << 16) | (k >> 1);
-        if (key != cacheKey) { cacheVal = pair_value(s, k >> 1); cacheKey = key; }
-        const Real v = (k & 1) ? cacheVal.y : cacheVal.x;
-        // DRMLT stores un-wrapped values and reflects on read; PSSMLT / bootstrap values are in [0,1)
-        return (pp->integrator == DR_INTEGRATOR_DRMLT) ? wrap_reflect(v) : v;
+        if (k >= lim[s]) return 0.5;                  // the reference raises EError here
+        const Real v = buf[off[s] + k];
+        return reflect ? wrap_reflect(v) : v;
     }
-    DR_D R2 next2D(int s) { Real a = next1D(s); Real b = next1D(s); return r2(a, b); }
+    DR_D R2 next2D(int s) {
+        const int k = pos[s];
+        pos[s] = k + 2;
+        if (k + 1 >= lim[s] || (k & 1)) {             // odd position or running off the end: scalar path
+            pos[s] = k;
+            const Real a = next1D(s), b = next1D(s);
+            return r2(a, b);
+        }
+        R2 v = ub_load(buf, off[s] + k);
+        if (reflect) { v.x = wrap_reflect(v.x); v.y = wrap_reflect(v.y); }
+        return v;
+    }
 };

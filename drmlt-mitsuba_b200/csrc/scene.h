@@ -9,7 +9,7 @@
 //               t0 = (p0.x p0.y p0.z p1.x) t1 = (p1.y p1.z p2.x p2.y) t2 = (p2.z, prim, matflags, emitter)
 //             the exact float vertices (edges are formed on the fly, so the double-precision
 //             re-intersection of the shading stage sees the same triangle as the reference);
-//             prim = index in the caller's triangle order, matflags = material | smooth << 31
+//             prim = index in the caller's triangle order, matflags = material | bsdf model << 24 | smooth << 31
 //   normals : 48 B / triangle in leaf order (only read for smooth triangles at the closest hit)
 //   em_tris : 96 B / emitter triangle in EMITTER order: p0,p1,p2,smooth + n0,n1,n2 (position sampling)
 //   em_cdf  : double prefix sums of the per-emitter triangle areas (pmf.h DiscreteDistribution)
@@ -63,6 +63,7 @@ struct BuiltBVH {
     std::vector<float4> nodes;       // 4 per node
     std::vector<uint32_t> order;     // leaf order -> caller's triangle index
     int rootIsLeaf = 0;
+    int maxDepth = 1;                // inner-node levels (bounds the traversal stack)
 };
 void build_bvh(const float *positions, const uint32_t *indices, uint32_t nTris, BuiltBVH &out);
 
@@ -72,6 +73,7 @@ struct dr_scene_t {
     std::vector<void *> allocations;
     int filmW = 0, filmH = 0;
     uint32_t nTris = 0, nNodes = 0;
+    unsigned typeMask = 0;           // BSDF models present (bit = dr_bsdf_type)
     volatile int cancel = 0;
     size_t bytes = 0;
 };

@@ -5,7 +5,9 @@
 // path (ld.global.nc).  Replaces ShapeKDTree::rayIntersect + rayIntersectHavran + TriAccel
 // (src/librender/skdtree.cpp:111-215, include/mitsuba/render/sahkdtree3.h:179-320,
 // include/mitsuba/render/triaccel.h:91-157) for this path: same closest hit in [mint, maxt]
-// (inclusive), same adaptive ray epsilon.
+// (inclusive), same adaptive ray epsilon.  Float32 arithmetic only PRUNES: boxes are tested conservatively and
+// a triangle that passes the float test within a tolerance band is decided by a double-precision test on the
+// un-rounded ray, so hit / miss decisions do not depend on float rounding.
 #pragma once
 #include "scene.h"
 
@@ -14,7 +16,8 @@ struct Hit {
     int tri;        // leaf-order triangle index, -1 = miss
 };
 
-#define DR_STACK 48
+#define DR_STACK 64
+#define DR_TRI_TOL 2e-3f     /* candidate band of the float32 triangle test (barycentric units) */
 
 DR_D float4 ldg4(const float4 *p) { return __ldg(p); }
 
@@ -25,25 +28,46 @@ DR_D float adaptive_mint(const DevScene &sc, float3 o, float mint) {
     return mint;
 }
 
-DR_D bool tri_test(const float4 t0, const float4 t1, const float4 t2, float3 o, float3 d,
-                   float tmin, float tmax, float &t, float &u, float &v) {
+// Candidate test in float32 with a tolerance band around the triangle's edges and the ray interval ...
+DR_D bool tri_candidate(const float4 t0, const float4 t1, const float4 t2, float3 o, float3 d, float tmin, float tmax) {
     const float3 p0 = f3(t0.x, t0.y, t0.z), e1 = f3(t0.w, t1.x, t1.y) - p0, e2 = f3(t1.z, t1.w, t2.x) - p0;
     const float3 pvec = cross(d, e2);
     const float det = dot(e1, pvec);
     if (det == 0.f) return false;
     const float inv = 1.0f / det;
     const float3 tvec = o - p0;
-    u = dot(tvec, pvec) * inv;
+    const float u = dot(tvec, pvec) * inv;
     const float3 qvec = cross(tvec, e1);
-    v = dot(d, qvec) * inv;
-    t = dot(e2, qvec) * inv;
-    return u >= 0.f && v >= 0.f && u + v <= 1.0f && t >= tmin && t <= tmax;
+    const float v = dot(d, qvec) * inv;
+    const float t = dot(e2, qvec) * inv;
+    const float tolT = 1e-5f + 1e-5f * fabsf(t);
+    return u >= -DR_TRI_TOL && v >= -DR_TRI_TOL && u + v <= 1.0f + DR_TRI_TOL && t >= tmin - tolT && t <= tmax + tolT;
+}
+// ... and the deciding test in double on the un-rounded ray (o, d, tmin, tmax = rd[0..7]): the hit / miss decision, t
+// and the barycentrics are those of the reference's double-precision triangle test (triaccel.h:91-157: inclusive
+// [mint, maxt], u, v >= 0, u + v <= 1), independent of float32 rounding in the traversal.
+DR_D bool tri_verify(const float4 t0, const float4 t1, const float4 t2, const double *rd, double tmax, double &t, double &u, double &v) {
+    const double p0x = t0.x, p0y = t0.y, p0z = t0.z;
+    const double e1x = (double) t0.w - p0x, e1y = (double) t1.x - p0y, e1z = (double) t1.y - p0z;
+    const double e2x = (double) t1.z - p0x, e2y = (double) t1.w - p0y, e2z = (double) t2.x - p0z;
+    const double ox = rd[0], oy = rd[1], oz = rd[2], dx = rd[3], dy = rd[4], dz = rd[5];
+    const double pvx = dy * e2z - dz * e2y, pvy = dz * e2x - dx * e2z, pvz = dx * e2y - dy * e2x;
+    const double det = e1x * pvx + e1y * pvy + e1z * pvz;
+    if (det == 0.0) return false;
+    const double inv = 1.0 / det;
+    const double tvx = ox - p0x, tvy = oy - p0y, tvz = oz - p0z;
+    u = (tvx * pvx + tvy * pvy + tvz * pvz) * inv;
+    const double qx = tvy * e1z - tvz * e1y, qy = tvz * e1x - tvx * e1z, qz = tvx * e1y - tvy * e1x;
+    v = (dx * qx + dy * qy + dz * qz) * inv;
+    t = (e2x * qx + e2y * qy + e2z * qz) * inv;
+    return u >= 0.0 && v >= 0.0 && u + v <= 1.0 && t >= rd[6] && t <= tmax;
 }
 
 template <bool ANYHIT>
-DR_D bool traverse(const DevScene &sc, float3 o, float3 d, float tmin, float tmax, Hit &hit, uint32_t *nodeVisits = nullptr) {
+DR_D bool traverse(const DevScene &sc, float3 o, float3 d, float tmin, float tmax, const double *rd, Hit &hit, uint32_t *nodeVisits = nullptr) {
     hit.tri = -1;
-    if (!(tmax > tmin)) return false;
+    if (!(rd[7] > rd[6])) return false;
+    double bestT = rd[7];
     // zero direction components: clamp so that 1/d stays finite (no 0 * inf = NaN in the slab test)
     const float3 inv = f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
                           1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
@@ -67,12 +91,13 @@ DR_D bool traverse(const DevScene &sc, float3 o, float3 d, float tmin, float tma
             a2 = n2.x * inv.z - oi.z; b2 = n2.w * inv.z - oi.z;
             float near1 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tmin));
             float far1 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), tmax));
-            // conservative: widen by a few ulps so that float slab rounding never culls a true hit
-            const bool h0 = near0 <= far0 * 1.0000004f, h1 = near1 <= far1 * 1.0000004f;
+            // conservative: the boxes are padded at upload and the comparison is widened by a few ulps, so that float
+            // slab rounding (of the test and of the float-cast ray) never culls a true hit
+            const bool h0 = near0 <= far0 * 1.000002f, h1 = near1 <= far1 * 1.000002f;
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 const bool swap = near1 < near0;
-                stack[sp++] = swap ? c0 : c1;
+                if (sp < DR_STACK) stack[sp++] = swap ? c0 : c1;
                 cur = swap ? c1 : c0;
                 continue;
             } else if (h0) { cur = c0; continue; }
@@ -83,11 +108,14 @@ DR_D bool traverse(const DevScene &sc, float3 o, float3 d, float tmin, float tma
             for (int i = 0; i < count; ++i) {
                 const float4 *tp = sc.tris + 3 * (size_t) (first + i);
                 const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1), t2 = ldg4(tp + 2);
-                float t, u, v;
-                if (tri_test(t0, t1, t2, o, d, tmin, tmax, t, u, v)) {
-                    hit.t = t; hit.u = u; hit.v = v; hit.tri = first + i;
-                    if (ANYHIT) return true;
-                    tmax = t;
+                if (tri_candidate(t0, t1, t2, o, d, tmin, tmax)) {
+                    double t, u, v;
+                    if (tri_verify(t0, t1, t2, rd, bestT, t, u, v)) {
+                        hit.t = (float) t; hit.u = (float) u; hit.v = (float) v; hit.tri = first + i;
+                        if (ANYHIT) return true;
+                        bestT = t;
+                        tmax = __double2float_ru(t);
+                    }
                 }
             }
         }

@@ -1,0 +1,11 @@
+// util_kernels.h -- host-callable launchers of k_util.cu
+#pragma once
+#include <cuda_runtime.h>
+long long scan_blocks(long long n);
+int lum_reduce_scratch_doubles();
+void launch_lum_reduce(const float *lum, long long n, double *scratch, double *out /* [2]: sum, count */, cudaStream_t s);   // 2 launches, bit-reproducible
+void launch_scan(const float *lum, long long n, double *cdf /* n + 1 */, double *blockSums, cudaStream_t s);   // 3 launches
+void launch_resample(const double *cdf, long long n, unsigned long long seed, unsigned long long firstChain, int nChains, unsigned long long bootFirst,
+                     int maxDepth, int technique, unsigned long long *seedIdx, unsigned long long *chainId, int *depth, cudaStream_t s);
+void launch_film_luminance(const float4 *film, long long n, double *out, cudaStream_t s);
+void launch_develop(const float4 *film, long long n, float factor, float *rgb, cudaStream_t s);

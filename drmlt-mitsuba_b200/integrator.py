@@ -152,6 +152,10 @@ class Job:
     def run(self, mutations_per_chain):
         abi.check(self.lib, self.lib.dr_job_run(self.h, int(mutations_per_chain)))
 
+    def profile(self, on=True):
+        """Stage profiling: CUDA events around every stage of every round; sums appear in stats()."""
+        self.lib.dr_job_profile(self.h, 1 if on else 0)
+
     def film_device(self):
         p, n = C.c_void_p(), C.c_int64(0)
         abi.check(self.lib, self.lib.dr_job_film_device(self.h, C.byref(p), C.byref(n)))

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DR_ABI_VERSION 1
+#define DR_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ status */
 typedef enum dr_status {
@@ -163,6 +163,10 @@ typedef struct dr_stats {
     double   luminance;                 /* normalization b actually used */
     double   bootstrap_ms, chains_ms, total_ms;  /* device-timed phases */
     uint64_t kernel_launches;           /* launches of this library's kernels */
+    uint64_t rounds;                    /* wavefront rounds (one ray per active chain and round) */
+    /* per-stage device time, only filled while stage profiling is on (dr_job_profile) */
+    double   trace_ms, walk_ms, chain_ms;
+    uint64_t trace_launches, walk_launches, chain_launches;
 } dr_stats;
 
 /* ------------------------------------------------------------- entry points */
@@ -208,6 +212,9 @@ dr_status dr_job_film_device(dr_job job, float **film_dev, int64_t *n_floats);
 /* Develop: image = film * (b / mean pixel luminance)  (drmlt_proc.cpp:823-849).  Host out. */
 dr_status dr_job_develop(dr_job job, float *image_rgb);
 dr_status dr_job_stats(dr_job job, dr_stats *stats);
+/* Stage profiling: CUDA events around every stage of every wavefront round (trace | walk+connect or
+ * path tracer | chain); the sums appear in dr_stats.  Off by default (env DRMLT_PROFILE_STAGES=1 turns it on). */
+void      dr_job_profile(dr_job job, int on);
 int64_t   dr_job_num_chains(dr_job job);
 int64_t   dr_job_total_mutations(dr_job job);   /* W*H*sampleCount share of this rank */
 

@@ -130,8 +130,22 @@ def _case_id(c):
     return "%s-%s-%s" % (c[0], c[1]["technique"], c[1].get("type", "pss"))
 
 
+# Contributions more than 18 orders of magnitude below the brightest one are rounding noise, not light: they arise
+# when a connection direction lies IN the plane of a flat wall, so that a cosine that is exactly zero in real
+# arithmetic evaluates to +-1e-16 and its sign -- different in any two implementations -- decides whether the
+# side checks of PathVertex::eval pass.  They are treated as zero on both sides (they are ~1e-30, the
+# dimmest genuine contribution of these scenes is ~1e-6).
+NOISE = 1e-18
+
+
+def _denoise(l, ref):
+    l = np.asarray(l, np.float64).copy()
+    l[np.abs(l) < NOISE * np.nanmax(ref)] = 0.0
+    return l
+
+
 def _compare_f(lg, lc, what):
-    lg = lg.astype(np.float64)
+    lg, lc = _denoise(lg, lc), _denoise(lc, lc)
     support = (lg > 0) == (lc > 0)
     both = (lg > 0) & (lc > 0)
     rel = np.abs(lg[both] - lc[both]) / lc[both]
@@ -240,7 +254,7 @@ def test_chain_decisions_under_identical_uniforms(case):
     cfg = make_config(seed=29, **params)
     o = ocfg(cfg)
     lum, dep = orc.bootstrap(o, 0, 20000)
-    seeds = np.nonzero(lum > 0)[0][:256].astype(np.uint64)
+    seeds = np.nonzero(_denoise(lum, lum) > 0)[0][:256].astype(np.uint64)
     assert len(seeds) >= 64
     depth = dep[seeds.astype(np.int64)]
     ids = np.arange(len(seeds), dtype=np.uint64) + 1000
@@ -265,6 +279,7 @@ def test_chain_decisions_under_identical_uniforms(case):
     mask = (np.arange(steps)[None, :] < first[:, None])
     for k in ("L_x", "L_y", "L_z"):
         a, b = G[k][mask].astype(np.float64), Cc[k][mask].astype(np.float64)
+        a, b = _denoise(a, b), _denoise(b, b)
         nz = b > 0
         assert ((a > 0) == nz).mean() > 0.999
         if nz.any():
@@ -284,7 +299,7 @@ def test_film_of_recorded_chains(case):
     cfg = make_config(seed=31, **params)
     o = ocfg(cfg)
     lum, dep = orc.bootstrap(o, 0, 20000)
-    seeds = np.nonzero(lum > 0)[0][:512].astype(np.uint64)
+    seeds = np.nonzero(_denoise(lum, lum) > 0)[0][:512].astype(np.uint64)
     depth = dep[seeds.astype(np.int64)]
     ids = np.arange(len(seeds), dtype=np.uint64)
     _, fg = gpu.chain_steps(cfg, 0.5, seeds, depth, ids, 48, want_film=True)
@@ -302,7 +317,7 @@ def test_acceptance_map_mode():
                       scaleSecond=0.1, acceptanceMap=True, rfilter="box")
     o = ocfg(cfg)
     lum, dep = orc.bootstrap(o, 0, 20000)
-    seeds = np.nonzero(lum > 0)[0][:512].astype(np.uint64)
+    seeds = np.nonzero(_denoise(lum, lum) > 0)[0][:512].astype(np.uint64)
     ids = np.arange(len(seeds), dtype=np.uint64)
     rg, fg = gpu.chain_steps(cfg, 1.0, seeds, dep[seeds.astype(np.int64)], ids, 48, want_film=True)
     rc, fc, st = orc.chain_steps(o, 1.0, seeds, dep[seeds.astype(np.int64)], ids, 48, want_film=True)

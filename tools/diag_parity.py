@@ -13,6 +13,8 @@ import test_gpu_parity as T
 
 for case in T.CASES:
     name, params = case
+    if len(sys.argv) > 1 and name not in sys.argv[1:]:
+        continue
     gpu, orc, data = T.pair(name)
     cfg = make_config(seed=3, **params)
     n = 40000
@@ -48,6 +50,8 @@ for case in T.CASES:
         for i in idx:
             print("   ex %d: depth %d s %d t %d gpu %.7g cpu %.7g rel %.2e mis %.6g/%.6g rays %d/%d" % (i, depth[i], s[i], t[i], lg[i], lum64[i], rel[i], mg[i], mc[i], rg[i], rc[i]))
     if supp.any():
-        idx = np.nonzero(supp)[0][:4]
+        print('   supp: gpu zero %d, cpu zero %d; by depth' % ((supp & (lg == 0)).sum(), (supp & (lum64 == 0)).sum()), np.bincount(depth[supp], minlength=9), 's', np.bincount(s[supp].clip(0), minlength=9), 'gpu lum percentiles', np.percentile(lg[supp & (lg > 0)], [0, 50, 100]) if (supp & (lg > 0)).any() else None, 'cpu', np.percentile(lum64[supp & (lum64 > 0)], [0, 50, 100]) if (supp & (lum64 > 0)).any() else None)
+        print('   all contributing lum percentiles', np.percentile(lum64[both], [0, 1, 50, 99, 100]))
+        idx = np.nonzero(supp)[0][:12]
         for i in idx:
             print("   supp %d: depth %d s %d t %d gpu %.7g cpu %.7g rays %d/%d" % (i, depth[i], s[i], t[i], lg[i], lum64[i], rg[i], rc[i]))
