@@ -515,7 +515,11 @@ struct dr_job_t {
     unsigned long long *chainId = nullptr, *seedIdx = nullptr;
     float4 *film = nullptr;
     unsigned long long *counters = nullptr;     // [0, ST_COUNT): chain phase, [ST_COUNT, 2 ST_COUNT): bootstrap
-    uint32_t *countsHost = nullptr;             // pinned mirror of the queue counters
+    // Wavefront groups: the lanes are split into independent groups, each with its own work queues and stream, so
+    // that the latency-bound tail of one group's stage kernels overlaps with the other groups' kernels.
+    struct Group { Queues q; cudaStream_t stream = nullptr; cudaEvent_t evJoin = nullptr; uint32_t *countsHost = nullptr; int begin = 0, end = 0; };
+    cudaEvent_t evFork = nullptr;
+    std::vector<Group> groups;
     float *bootLum = nullptr;
     double *cdf = nullptr, *blockSums = nullptr, *red = nullptr, *redScratch = nullptr;
     float *devImage = nullptr;
@@ -552,7 +556,8 @@ extern "C" void dr_job_destroy(dr_job j) {
     cudaSetDevice(j->scene->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
     for (void *p : j->allocations) cudaFree(p);
-    if (j->countsHost) cudaFreeHost(j->countsHost);
+    for (auto &g : j->groups) { if (g.countsHost) cudaFreeHost(g.countsHost); if (g.evJoin) cudaEventDestroy(g.evJoin); if (g.stream) cudaStreamDestroy(g.stream); }
+    if (j->evFork) cudaEventDestroy(j->evFork);
     for (cudaEvent_t e : j->profEvents) cudaEventDestroy(e);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);
@@ -573,15 +578,29 @@ static dr_status alloc_lanes(dr_job j, int n) {
     LaneMem &lm = j->M.lm;
     memset(&lm, 0, sizeof(lm));
     lm.n = n; lm.nU = j->M.pp.nU;
-    Queues &q = j->M.q;
-    q.n = n;
     dr_status st;
     if ((st = job_alloc(j, &lm.core, (size_t) n)) || (st = job_alloc(j, &lm.vt, (size_t) n)) || (st = job_alloc(j, &lm.vs, (size_t) n)) ||
         (st = job_alloc(j, &lm.vtp, (size_t) n)) || (st = job_alloc(j, &lm.vsp, (size_t) n)) || (st = job_alloc(j, &lm.chain, (size_t) n)) ||
         (st = job_alloc(j, &lm.mis, (size_t) MIS_WORDS * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
-        (st = job_alloc(j, &lm.ray, (size_t) 2 * n)) || (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)) ||
-        (st = job_alloc(j, &q.items, (size_t) Q_COUNT * n)) || (st = job_alloc(j, &q.count, (size_t) Q_COUNT)))
+        (st = job_alloc(j, &lm.ray, (size_t) 2 * n)) || (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)))
         return st;
+    // groups of at least 64K lanes, at most 8 (DRMLT_GROUPS overrides)
+    int G = std::max(1, std::min(8, n / 65536));
+    if (getenv("DRMLT_GROUPS")) G = std::max(1, std::min(64, atoi(getenv("DRMLT_GROUPS"))));
+    G = std::min(G, std::max(1, n / 32));
+    j->groups.resize(G);
+    for (int g = 0; g < G; ++g) {
+        dr_job_t::Group &gr = j->groups[g];
+        gr.begin = (int) ((long long) n * g / G); gr.end = (int) ((long long) n * (g + 1) / G);
+        gr.q.n = gr.end - gr.begin;
+        if ((st = job_alloc(j, &gr.q.items, (size_t) Q_COUNT * gr.q.n)) || (st = job_alloc(j, &gr.q.count, (size_t) Q_COUNT + 2)))   // + head counters of the two ray queues
+            return st;
+        if (cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&gr.evJoin, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost((void **) &gr.countsHost, sizeof(uint32_t) * Q_COUNT) != cudaSuccess) {
+            dr_set_error("group stream creation failed: %s", cudaGetErrorString(cudaGetLastError())); return DR_ERR_CUDA;
+        }
+    }
+    trace_init();
+    if (cudaEventCreateWithFlags(&j->evFork, cudaEventDisableTiming) != cudaSuccess) { dr_set_error("event creation failed"); return DR_ERR_CUDA; }
     return DR_OK;
 }
 
@@ -599,9 +618,11 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     j->M.sc = scene_for(scene, cfg);
     const int W = scene->filmW, H = scene->filmH;
     make_params(cfg, W, H, 1.0, evalDims, j->M);
+    j->M.traceRefill = getenv("DRMLT_TRACE_REFILL") ? atoi(getenv("DRMLT_TRACE_REFILL")) : 24;
+    j->M.traceDescend = getenv("DRMLT_TRACE_DESCEND") ? atoi(getenv("DRMLT_TRACE_DESCEND")) : 8;
     auto fail = [&](dr_status code) { dr_job_destroy(j); return code; };
     if (cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&j->ev0) != cudaSuccess ||
-        cudaEventCreate(&j->ev1) != cudaSuccess || cudaMallocHost((void **) &j->countsHost, sizeof(uint32_t) * Q_COUNT) != cudaSuccess) {
+        cudaEventCreate(&j->ev1) != cudaSuccess) {
         dr_set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(DR_ERR_CUDA);
     }
     j->profile = getenv("DRMLT_PROFILE_STAGES") != nullptr;
@@ -625,67 +646,133 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
 
 extern "C" dr_status dr_job_create(dr_scene scene, const dr_config *cfg, dr_job *out) { return job_create_common(scene, cfg, 0, true, nullptr, out); }
 
-static Machine machine_for(dr_job j, const JobParams &job, unsigned long long *counters, bool withFilm) {
+static Machine machine_for(dr_job j, int group, const JobParams &job, unsigned long long *counters, bool withFilm) {
     Machine M = j->M;
+    const dr_job_t::Group &gr = j->groups[group];
+    M.q = gr.q; M.laneBegin = gr.begin; M.laneEnd = gr.end;
     M.job = job; M.film = withFilm ? j->film : nullptr; M.counters = counters; M.parity = (int) (j->rounds & 1);
     return M;
+}
+// the job's main stream waits for everything queued on the group streams, and vice versa
+static dr_status join_groups(dr_job j) {
+    for (auto &g : j->groups) CK(cudaStreamSynchronize(g.stream));
+    return DR_OK;
 }
 
 // Run the wavefront machine until no lane has work left.  One round = trace (closest, shadow) -> walk per BSDF
 // model + connect (MMLT) | path tracer (technique=path) -> chain.  The queue counters are polled every
 // `roundsPerPoll` rounds through a pinned mirror.
+// One round of one group on stream `st`.
+static void launch_round(dr_job j, Machine &M, int g, cudaStream_t st, bool mmlt, unsigned typeMask, bool marks) {
+    LaunchCfg lc; lc.stream = st; lc.nLanes = j->groups[g].end - j->groups[g].begin;
+    auto mark = [&]() { if (marks) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); j->profEvents.push_back(e); } };
+    mark();
+    launch_trace(M, lc);
+    mark();
+    if (mmlt) launch_walk(M, lc, typeMask); else launch_pt(M, lc);
+    mark();
+    launch_chain(M, lc);
+    mark();
+}
+
+// Run the wavefront machine until no lane has work left.  One round = trace (closest, shadow) -> walk per BSDF
+// model + connect (MMLT) | path tracer (technique=path) -> chain, per group.  `roundsPerPoll` rounds of all groups
+// are captured ONCE into a CUDA graph (one branch per group, so the groups' kernels overlap) and replayed until the
+// queue counters, copied to a pinned mirror at the end of every replay, show that every queue is empty.
 static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long *counters, bool withFilm) {
-    Machine M = machine_for(j, job, counters, withFilm);
-    LaunchCfg lc; lc.stream = j->stream; lc.nLanes = j->nChains;
+    const int G = (int) j->groups.size();
+    std::vector<Machine> Ms;
+    for (int g = 0; g < G; ++g) Ms.push_back(machine_for(j, g, job, counters, withFilm));
     const bool mmlt = j->cfg.technique == DR_TECH_MMLT;
     const unsigned typeMask = static_cast<SceneImpl *>(j->scene)->typeMask;
     const int walkLaunches = mmlt ? __builtin_popcount(typeMask & 15u) + 1 : 1;
-    auto mark = [&]() {
-        if (!j->profile) return;
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, j->stream); j->profEvents.push_back(e);
-    };
-    for (;;) {
-        if (j->scene->cancel) { cudaStreamSynchronize(j->stream); dr_set_error("cancelled"); return DR_ERR_CANCELLED; }
-        for (int r = 0; r < j->roundsPerPoll; ++r) {
-            M.parity = (int) (j->rounds & 1);
-            mark();
-            launch_trace(M, lc);
-            mark();
-            if (mmlt) launch_walk(M, lc, typeMask); else launch_pt(M, lc);
-            mark();
-            launch_chain(M, lc);
-            mark();
-            ++j->rounds;
+    const int beginLaunches = job.type == JOB_CHAIN ? (j->cfg.integrator == DR_INTEGRATOR_DRMLT ? 3 : 2) : 1;
+    const int R = j->roundsPerPoll;                             // even: a replay starts at the parity it was captured with
+    CK(cudaStreamSynchronize(j->stream));                       // everything queued on the main stream is visible to the groups
+    cudaStream_t s0 = j->groups[0].stream;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const bool useGraph = !j->profile && !getenv("DRMLT_NO_GRAPH");
+    auto cleanup = [&]() { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); };
+    if (useGraph) {
+        const uint64_t round0 = j->rounds;
+        CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+        cudaEventRecord(j->evFork, s0);
+        for (int g = 1; g < G; ++g) cudaStreamWaitEvent(j->groups[g].stream, j->evFork, 0);
+        for (int r = 0; r < R; ++r)
+            for (int g = 0; g < G; ++g) {
+                Ms[g].parity = (int) ((round0 + r) & 1);
+                launch_round(j, Ms[g], g, j->groups[g].stream, mmlt, typeMask, false);
+            }
+        for (int g = 0; g < G; ++g)
+            cudaMemcpyAsync(j->groups[g].countsHost, j->groups[g].q.count, sizeof(uint32_t) * Q_COUNT, cudaMemcpyDeviceToHost, j->groups[g].stream);
+        for (int g = 1; g < G; ++g) { cudaEventRecord(j->groups[g].evJoin, j->groups[g].stream); cudaStreamWaitEvent(s0, j->groups[g].evJoin, 0); }
+        if (cudaStreamEndCapture(s0, &graph) != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            dr_set_error("CUDA graph capture of the wavefront rounds failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cleanup();
+            return DR_ERR_CUDA;
         }
-        CKL();
-        j->launches += (uint64_t) j->roundsPerPoll * (3 + walkLaunches + 1);
-        CK(cudaMemcpyAsync(j->countsHost, M.q.count, sizeof(uint32_t) * Q_COUNT, cudaMemcpyDeviceToHost, j->stream));
-        CK(cudaStreamSynchronize(j->stream));
-        if (j->profile) {
+    }
+    for (;;) {
+        if (j->scene->cancel) { join_groups(j); cleanup(); dr_set_error("cancelled"); return DR_ERR_CANCELLED; }
+        if (useGraph) {
+            if (cudaGraphLaunch(exec, s0) != cudaSuccess || cudaStreamSynchronize(s0) != cudaSuccess) {
+                dr_set_error("wavefront rounds failed: %s", cudaGetErrorString(cudaGetLastError()));
+                cleanup();
+                return DR_ERR_CUDA;
+            }
+            j->rounds += R;
+        } else {
+            for (int r = 0; r < R; ++r) {
+                for (int g = 0; g < G; ++g) {
+                    Ms[g].parity = (int) (j->rounds & 1);
+                    // stage profiling serialises the groups on one stream so that the event intervals are kernel times
+                    launch_round(j, Ms[g], g, j->profile ? s0 : j->groups[g].stream, mmlt, typeMask, j->profile);
+                }
+                ++j->rounds;
+            }
+            CKL();
+            for (int g = 0; g < G; ++g)
+                CK(cudaMemcpyAsync(j->groups[g].countsHost, j->groups[g].q.count, sizeof(uint32_t) * Q_COUNT, cudaMemcpyDeviceToHost,
+                                   j->profile ? s0 : j->groups[g].stream));
+            dr_status st = join_groups(j);
+            if (st) return st;
+        }
+        j->launches += (uint64_t) R * G * (3 + walkLaunches + 1 + beginLaunches);
+        if (!j->profEvents.empty()) {
             for (size_t i = 0; i + 3 < j->profEvents.size(); i += 4)
                 for (int s = 0; s < STAGE_COUNT; ++s) {
                     float ms = 0.f;
                     cudaEventElapsedTime(&ms, j->profEvents[i + s], j->profEvents[i + s + 1]);
                     j->stageMs[s] += ms;
                 }
-            j->stageLaunches[STAGE_TRACE] += 3ull * j->roundsPerPoll; j->stageLaunches[STAGE_WALK] += (uint64_t) walkLaunches * j->roundsPerPoll;
-            j->stageLaunches[STAGE_CHAIN] += j->roundsPerPoll;
+            j->stageLaunches[STAGE_TRACE] += 3ull * R * G; j->stageLaunches[STAGE_WALK] += (uint64_t) walkLaunches * R * G;
+            j->stageLaunches[STAGE_CHAIN] += (uint64_t) R * G * (1 + beginLaunches);
             for (cudaEvent_t e : j->profEvents) cudaEventDestroy(e);
             j->profEvents.clear();
         }
         const int p = (int) (j->rounds & 1);                      // queues the next round would consume
-        if (j->countsHost[Q_RAYC + p] == 0 && j->countsHost[Q_RAYS + p] == 0 && j->countsHost[Q_CHAIN + p] == 0) break;
+        bool busy = false;
+        for (int g = 0; g < G; ++g) {
+            const uint32_t *c = j->groups[g].countsHost;
+            busy |= c[Q_RAYC + p] != 0 || c[Q_RAYS + p] != 0 || c[Q_CHAIN + p] != 0;
+        }
+        if (!busy) break;
     }
+    cleanup();
     return DR_OK;
 }
 
 static dr_status setup_lanes(dr_job j, const JobParams &job) {
-    Machine M = machine_for(j, job, j->counters, false);
-    LaunchCfg lc; lc.stream = j->stream; lc.nLanes = j->nChains;
-    CK(cudaMemsetAsync(M.q.count, 0, sizeof(uint32_t) * Q_COUNT, j->stream));
-    launch_setup(M, lc, j->depth, j->chainId, j->seedIdx);
+    CK(cudaStreamSynchronize(j->stream));
+    for (int g = 0; g < (int) j->groups.size(); ++g) {
+        Machine M = machine_for(j, g, job, j->counters, false);
+        LaunchCfg lc; lc.stream = j->groups[g].stream; lc.nLanes = M.laneEnd - M.laneBegin;
+        CK(cudaMemsetAsync(M.q.count, 0, sizeof(uint32_t) * (Q_COUNT + 2), lc.stream));
+        launch_setup(M, lc, j->depth, j->chainId, j->seedIdx);
+        ++j->launches;
+    }
     CKL();
-    ++j->launches;
     return DR_OK;
 }
 
@@ -809,11 +896,14 @@ static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, 
     j->mutTarget += (uint32_t) steps;
     job.mutTarget = j->mutTarget;
     job.records = records; job.recordStride = recordStride;
-    Machine M = machine_for(j, job, j->counters, withFilm);
-    LaunchCfg lc; lc.stream = j->stream; lc.nLanes = j->nChains;
-    launch_resume(M, lc);                                          // parked chains start their next mutation
+    CK(cudaStreamSynchronize(j->stream));
+    for (int g = 0; g < (int) j->groups.size(); ++g) {             // parked chains start their next mutation
+        Machine M = machine_for(j, g, job, j->counters, withFilm);
+        LaunchCfg lc; lc.stream = j->groups[g].stream; lc.nLanes = M.laneEnd - M.laneBegin;
+        launch_resume(M, lc);
+        ++j->launches;
+    }
     CKL();
-    ++j->launches;
     return run_machine(j, job, j->counters, withFilm);
 }
 
@@ -847,12 +937,15 @@ static dr_status flush_pssmlt(dr_job j) {
     if (j->cfg.integrator != DR_INTEGRATOR_PSSMLT) return DR_OK;
     JobParams job;
     memset(&job, 0, sizeof(job));
-    Machine M = machine_for(j, job, j->counters, true);
-    LaunchCfg lc; lc.stream = j->stream; lc.nLanes = j->nChains;
-    launch_flush_pssmlt(M, lc);
+    CK(cudaStreamSynchronize(j->stream));
+    for (int g = 0; g < (int) j->groups.size(); ++g) {
+        Machine M = machine_for(j, g, job, j->counters, true);
+        LaunchCfg lc; lc.stream = j->groups[g].stream; lc.nLanes = M.laneEnd - M.laneBegin;
+        launch_flush_pssmlt(M, lc);
+        ++j->launches;
+    }
     CKL();
-    ++j->launches;
-    return DR_OK;
+    return join_groups(j);
 }
 
 extern "C" dr_status dr_job_develop(dr_job j, float *imageRgb) {

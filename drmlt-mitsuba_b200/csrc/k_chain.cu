@@ -5,8 +5,8 @@
 // single MMLT splat, pathsampler.cpp:288-313), (2) runs the chain-level step: delayed-rejection acceptance
 // (DRMLTRenderer::process, src/integrators/drmlt/drmlt_proc.cpp:539-769; processMixture :161-380;
 // PSSMLTRenderer::process, src/integrators/pssmlt/pssmlt_proc.cpp:175-272), expectation-weighted film splats,
-// commit of the accepted primary-sample vector and statistics, and (3) mutates the next proposal into the
-// lane's coordinate buffer (pss.cuh) and emits the first ray of its path.
+// commit of the accepted primary-sample vector and statistics, and (3) hands the lane to the k_begin class
+// (k_begin.cu) that mutates its next proposal and emits the first ray of the next path.
 #include "machine.cuh"
 
 namespace {
@@ -20,19 +20,6 @@ DR_D void result_clear(PathResult &r) { r.lum = 0.; r.n = 0; r.val = r3(0.); r.p
 DR_D float3 normalized_value(const PathResult &r) {          // SplatList::normalize (pathsampler.cpp:1001-1028)
     const Real inv = r.lum > 0. ? 1.0 / r.lum : 1.0;
     return to_f3(r.val * inv);
-}
-
-// MMLT strategy from the direct sampler's coordinate (pathsampler.cpp:104-129)
-DR_D void mmlt_strategy(const PathCfg &pc, int depth, Real decision, int &s, int &t) {
-    int nStrats;
-    if (pc.lightImage) { nStrats = depth + 1; s = min((int) (nStrats * decision), nStrats - 1); t = nStrats - s; }
-    else { nStrats = depth; s = min((int) (nStrats * decision), nStrats - 1); t = 1 + (nStrats - s); }
-}
-
-// number of coordinate PAIRS of each sampler that a proposal with strategy (s, t) must carry
-DR_D void pair_extent(const Machine &M, const int dims[3], int s, int t, int ext[3]) {
-    if (M.pp.subset) { ext[0] = t; ext[1] = s; ext[2] = 1; }
-    else { ext[0] = (dims[0] + 1) >> 1; ext[1] = (dims[1] + 1) >> 1; ext[2] = (dims[2] + 1) >> 1; }
 }
 
 // MiraDRMLTSampler::getTransitionRatio over the three samplers (drmlt_sampler.cpp:400-414).
@@ -76,125 +63,6 @@ DR_D void commit_state(const Machine &M, const MutCtx &mc, double *ub, const int
     }
 }
 
-// ------------------------------------------------------------------ proposals
-// Fill the lane's coordinate buffer for the path that is about to start and select it (Core::ubuf).
-DR_D void fill_proposal(const Machine &M, int lane, Core &c, const MutCtx &mc, long long item) {
-    const PssParams &pp = M.pp;
-    const int nU = M.lm.nU;
-    double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * nU;
-    int dims[3];
-    chain_dims(M.pc, M.cp, c.depth, dims);
-    const bool mmlt = M.pc.technique == DR_TECH_MMLT;
-    if (M.job.type == JOB_EVAL) {                  // replayed host vectors (float) -> X
-        c.ubuf = UB_X;
-        const float *src[3] = { M.job.us + item * M.job.ds, M.job.ue + item * M.job.de, M.job.ud + item * M.job.dd };
-        const int n[3] = { M.job.ds, M.job.de, M.job.dd };
-        for (int s = 0; s < 3; ++s)
-            for (int k = 0; k < n[s]; ++k) ub[pp.off[s] + k] = (double) src[s][k];
-        return;
-    }
-    if (M.job.type == JOB_BOOT) {                  // bootstrap sample `index`: keyed uniforms -> X
-        c.ubuf = UB_X;
-        const unsigned long long index = M.job.first + (unsigned long long) item;
-        auto boot_pair = [&](int s, int p) {
-            const float4 u = keyed_uniform4(pp.seed, S_BOOT, index, (uint32_t) s, (uint32_t) (p >> 1));
-            return (p & 1) ? r2(u.z, u.w) : r2(u.x, u.y);
-        };
-        int ext[3] = { (dims[0] + 1) >> 1, (dims[1] + 1) >> 1, (dims[2] + 1) >> 1 };
-        if (mmlt) {                                // only what strategy (s, t) can consume
-            const R2 d = boot_pair(SMP_DIRECT, 0);
-            ub_store(ub, pp.off[SMP_DIRECT], d);
-            int s_, t_;
-            mmlt_strategy(M.pc, c.depth, d.x, s_, t_);
-            ext[0] = min(ext[0], t_); ext[1] = min(ext[1], s_); ext[2] = 0;
-        }
-        for (int s = 0; s < 3; ++s)
-            for (int p = 0; p < ext[s]; ++p) ub_store(ub, pp.off[s] + 2 * p, boot_pair(s, p));
-        return;
-    }
-    // ---- Markov chain
-    if (c.phase == PH_INIT) { c.ubuf = UB_X; return; }        // seed replay: the bootstrap vector is already in X
-    const int dst = c.phase == PH_STAGE1 ? UB_Y : (c.phase == PH_STAGE2 ? UB_Z : UB_R);
-    c.ubuf = (uint8_t) dst;
-    auto make_pair = [&](int s, int p) {
-        const int slot = pp.off[s] + 2 * p;
-        const R2 x = ub_load(ub + UB_X * nU, slot);
-        R2 v;
-        if (c.phase == PH_STAGE1) v = propose_stage1(mc, s, p, x);
-        else {
-            const R2 y = ub_load(ub + UB_Y * nU, slot);
-            if (c.phase == PH_STAGE2) v = propose_stage2(mc, s, p, x, y);
-            else { const R2 z = ub_load(ub + UB_Z * nU, slot); v = r2(z.x - (y.x - x.x), z.y - (y.y - x.y)); }   // y* = z - (y - x), drmlt_sampler.cpp:293-296
-        }
-        ub_store(ub + dst * nU, slot, v);
-        return v;
-    };
-    int ext[3] = { (dims[0] + 1) >> 1, (dims[1] + 1) >> 1, (dims[2] + 1) >> 1 };
-    if (pp.subset) {
-        const R2 d = make_pair(SMP_DIRECT, 0);
-        int s_, t_;
-        mmlt_strategy(M.pc, c.depth, wrap_reflect(d.x), s_, t_);
-        ext[0] = t_; ext[1] = s_; ext[2] = 0;
-    }
-    for (int s = 0; s < 3; ++s)
-        for (int p = 0; p < ext[s]; ++p) make_pair(s, p);
-}
-
-// ------------------------------------------------------------------ path start
-// returns the queue the lane goes to (Q_RAYC, Q_CONNECT) or -1 when the path is already over (empty result)
-DR_D int path_start(const Machine &M, int lane, Core &c) {
-    const DevScene &sc = M.sc;
-    UReader rd;
-    c.pos0 = c.pos1 = c.pos2 = 0; c.nrays = 0;
-    reader_open(M, c, lane, rd);
-    int dest;
-    if (M.pc.technique == DR_TECH_MMLT) {                     // pathsampler.cpp:84-159
-        const int depth = c.depth, k = depth + 2;
-        double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
-        int s, t;
-        mmlt_strategy(M.pc, depth, rd.next1D(SMP_DIRECT), s, t);
-        c.s = (uint8_t) s; c.t = (uint8_t) t;
-        if (depth == 1) { reader_close(rd, c); c.pstate = PS_EMPTY; return -1; }
-        c.connectable = 0; c.flags = 0; c.weight = r3(1.);
-        (void) rd.next2D(SMP_SENSOR);                         // sampleSensorPosition consumes 2 (vertex.cpp:79)
-        mis_put(mis, MIS_RAD, k, 1.0);
-        mis_put(mis, MIS_RAD, k - 1, 1.0);                    // supernode pdf[ERadiance] (perspective.cpp:305)
-        Vtx vt;
-        vt.p = cam_pos(sc.cam); vt.ng = vt.ns = cam_dir(sc.cam); vt.ss = r3(0.); vt.type = V_SENSOR_SAMPLE; vt.degenerate = 0; vt.mat = -1; vt.emitter = -1;
-        c.connectable |= 1u << (k - 1);                       // sensor sample: never discrete, not degenerate
-        rec_store(M.lm.vt + lane, vt);
-        c.j = 1;
-        if (t >= 2) {                                         // vertex.cpp:126-151, perspective.cpp:318-345
-            const R2 u = rd.next2D(SMP_SENSOR);
-            const R3 dl = cam_sample_to_dir(sc.cam, u.x, u.y);
-            c.pdfFwd = sc.cam.normalization / (dl.z * dl.z * dl.z);
-            c.pdfBwd = 1.0;
-            c.pstate = PS_SENSOR_HIT;
-            emit_ray(M, lane, c, vt.p, cam_xform_dir(sc.cam, dl), sc.epsilon, INFINITY);
-            dest = Q_RAYC;
-        } else {
-            dest = mmlt_emitter_start(M, lane, c, rd, mis);
-        }
-    } else {                                                  // PathSampler EUnidirectional (pathsampler.cpp:529-567)
-        const R2 u0 = rd.next2D(SMP_SENSOR);
-        const R2 samplePos = r2(u0.x * sc.cam.resX, u0.y * sc.cam.resY);
-        c.spos = make_float2((float) samplePos.x, (float) samplePos.y);
-        const R3 dl = cam_sample_to_dir(sc.cam, samplePos.x / sc.cam.resX, samplePos.y / sc.cam.resY);
-        const Real invZ = 1.0 / dl.z;
-        PtExtra px;
-        px.Li = r3(0.); px.pending = r3(0.); px.refN = r3(0.); px.eta = 1.0; px.bsPdf = 0.; px.dIn = r3(0.);
-        c.weight = r3(1.);
-        c.flags = F_PT_FIRST | (M.pc.excludeDirect ? 0u : (F_PT_EMITTED | F_PT_DIRECT));
-        c.j = 1; c.s = c.t = 0;
-        c.pstate = PS_PT_HIT;
-        rec_store(reinterpret_cast<PtExtra *>(M.lm.vs + lane), px);
-        emit_ray(M, lane, c, cam_pos(sc.cam), cam_xform_dir(sc.cam, dl), sc.cam.nearClip * invZ, sc.cam.farClip * invZ);
-        dest = Q_RAYC;
-    }
-    reader_close(rd, c);
-    return dest;
-}
-
 // ------------------------------------------------------------------ path end -> result
 DR_D void path_result(const Machine &M, int lane, Core &c, PathResult &out) {
     result_clear(out);
@@ -230,9 +98,8 @@ DR_D void path_result(const Machine &M, int lane, Core &c, PathResult &out) {
 } // namespace
 
 // ------------------------------------------------------------------ the chain kernel
-#define CHAIN_MAX_PATHS 4      // paths one lane may complete in one launch without emitting a ray (dead-on-arrival paths)
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CHAIN_MINB)
 k_chain(const __grid_constant__ Machine M) {
     const JobParams &job = M.job;
     const PssParams &pp = M.pp;
@@ -250,7 +117,7 @@ k_chain(const __grid_constant__ Machine M) {
         Core c;
         rec_load(c, M.lm.core + lane);
         int dest = -1;
-        for (int completed = 0;;) {
+        for (;;) {
             long long item = 0;
             MutCtx mc;
             mc.pp = &pp; mc.chain = c.chainId; mc.mut = c.mut; mc.largeStep = false; mc.lightTracing = false;
@@ -264,7 +131,6 @@ k_chain(const __grid_constant__ Machine M) {
                 PathResult r;
                 path_result(M, lane, c, r);
                 ++st[ST_PATHS];
-                ++completed;
                 if (job.type == JOB_BOOT) {
                     job.lumOut[item] = (float) r.lum;
                     ++c.mut;
@@ -468,30 +334,13 @@ k_chain(const __grid_constant__ Machine M) {
                     rec_store(M.lm.chain + lane, cc);
                 }
                 if (c.pstate == PS_IDLE) break;
-                if (completed >= CHAIN_MAX_PATHS) { dest = Q_CHAIN + (M.parity ^ 1); break; }   // start the next path next round
-                continue;
             }
-            // ================= start the next path =================
-            if (job.type == JOB_CHAIN) {
-                if (c.phase == PH_STAGE1 && c.large == 2u) {   // new mutation: draw the large-step coin (drmlt_proc.cpp:533)
-                    c.large = (Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 0u) < cp.pLarge ? 1u : 0u;
-                    mc.largeStep = c.large == 1u;
-                }
-            } else {
-                item = (long long) lane + (long long) c.mut * M.lm.n;
-                if (job.type == JOB_BOOT) {
-                    const unsigned long long index = job.first + (unsigned long long) item;
-                    c.depth = M.pc.technique == DR_TECH_MMLT ? (uint8_t) ((index % (unsigned long long) M.pc.maxDepth) + 1) : 0;
-                } else c.depth = job.depthIn ? (uint8_t) job.depthIn[item] : 0;
-            }
-            fill_proposal(M, lane, c, mc, item);
-            dest = path_start(M, lane, c);
-            if (dest >= 0) break;                             // a ray is in flight (or the lane goes to the connection)
+            // ================= hand the lane to the kernel that starts its next path =================
+            dest = Q_BEGIN + (job.type != JOB_CHAIN ? BEGIN_OTHER : (c.phase == PH_STAGE1 ? BEGIN_STAGE1 : (c.phase == PH_STAGE2 ? BEGIN_STAGE2 : BEGIN_OTHER)));
+            break;
         }
         rec_store(M.lm.core + lane, c);
-        if (dest == Q_RAYC) q_push(M.q, Q_RAYC + (M.parity ^ 1), (uint32_t) lane);
-        else if (dest == Q_CONNECT) q_push(M.q, Q_CHAIN + (M.parity ^ 1), (uint32_t) lane);   // cannot happen for depth >= 2; kept safe
-        else if (dest >= 0) q_push(M.q, dest, (uint32_t) lane);
+        if (dest >= 0) q_push(M.q, dest, (uint32_t) lane);
     }
     stats_flush(st, M.counters);
 }
@@ -500,8 +349,8 @@ k_chain(const __grid_constant__ Machine M) {
 // JOB_CHAIN: seed replay + fillReplay (drmlt_proc.cpp:467-504): current = the seed's bootstrap vector; the lane then
 // evaluates it (PH_INIT) before its first mutation.  JOB_BOOT / JOB_EVAL: lane l starts at item l.
 __global__ void k_setup_lanes(const __grid_constant__ Machine M, const int *depthIn, const unsigned long long *chainIdIn, const unsigned long long *seedIdxIn) {
-    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= M.lm.n) return;
+    const int lane = M.laneBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= M.laneEnd) return;
     Core c;
     memset(&c, 0, sizeof(c));
     c.tx = -1; c.large = 2u; c.phase = PH_STAGE1;
@@ -529,8 +378,8 @@ __global__ void k_setup_lanes(const __grid_constant__ Machine M, const int *dept
 
 // dr_job_run raised the mutation target: idle chains start their next mutation
 __global__ void k_resume_lanes(const __grid_constant__ Machine M) {
-    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= M.lm.n) return;
+    const int lane = M.laneBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= M.laneEnd) return;
     Core *c = M.lm.core + lane;
     if (c->pstate == PS_IDLE && c->mut < M.job.mutTarget) {
         c->pstate = PS_START; c->phase = PH_STAGE1; c->large = 2u;
@@ -540,8 +389,8 @@ __global__ void k_resume_lanes(const __grid_constant__ Machine M) {
 
 // PSSMLT's "last splat" of the accumulated current state (pssmlt_proc.cpp:274-279); resets the weight
 __global__ void k_flush_pssmlt(const __grid_constant__ Machine M) {
-    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= M.lm.n) return;
+    const int lane = M.laneBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= M.laneEnd) return;
     ChainCore cc;
     rec_load(cc, M.lm.chain + lane);
     const float3 v = cc.valx * (float) cc.cumW;
@@ -552,7 +401,10 @@ __global__ void k_flush_pssmlt(const __grid_constant__ Machine M) {
 
 static unsigned grid_for(int n, int threads) { return (unsigned) std::max(1, std::min((n + threads - 1) / threads, 148 * 16)); }
 
-void launch_chain(const Machine &M, const LaunchCfg &lc) { k_chain<<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M); }
+void launch_chain(const Machine &M, const LaunchCfg &lc) {
+    k_chain<<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M);
+    launch_begin(M, lc);
+}
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId, const unsigned long long *seedIdx) {
     k_setup_lanes<<<(unsigned) ((lc.nLanes + 127) / 128), 128, 0, lc.stream>>>(M, depth, chainId, seedIdx);
 }

@@ -5,28 +5,74 @@
 // chain queue (MMLT), everything to the path-tracer queue for technique=path.
 #include "machine.cuh"
 
+// Persistent warps with dynamic ray fetch: incoherent rays of one warp finish after very different numbers of node
+// visits, so lanes whose ray is done pull the next ray from the queue (one warp-aggregated atomic on the queue's head
+// counter) as soon as fewer than REFILL lanes of the warp are still traversing.
+
 template <bool SHADOW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, TRACE_MINB)
 k_trace(const __grid_constant__ Machine M) {
     const int qid = (SHADOW ? Q_RAYS : Q_RAYC) + M.parity;
     const uint32_t cnt = M.q.count[qid];
     const uint32_t *items = M.q.items + (size_t) qid * M.q.n;
+    uint32_t *head = M.q.count + Q_COUNT + (SHADOW ? 1 : 0);
     if (blockIdx.x == 0 && threadIdx.x == 0 && cnt) atomicAdd(&M.counters[ST_RAYS], (unsigned long long) cnt);
     const bool pt = M.pc.technique != DR_TECH_MMLT;
-    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
-        const int lane = (int) items[qi];
-        const float4 a = M.lm.ray[2 * (size_t) lane], b = M.lm.ray[2 * (size_t) lane + 1];
-        Hit h;
-        const bool found = traverse<SHADOW>(M.sc, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, M.lm.rayd + 8 * (size_t) lane, h);
-        M.lm.hit[lane] = make_float4(h.t, h.u, h.v, __int_as_float(found ? h.tri : -1));
-        int dest;
-        if (pt) dest = Q_PT;
-        else if (SHADOW || !found) dest = Q_CHAIN + M.parity;
-        else {
-            const uint32_t mf = (uint32_t) __float_as_int(__ldg(&M.sc.tris[3 * (size_t) h.tri + 2].z));
-            dest = Q_WALK + (int) ((mf >> 24) & 3u);
+    const unsigned self = threadIdx.x & 31u;
+    int stack[DR_STACK];
+    Traversal<SHADOW> tr;
+    tr.done = true;
+    int lane = -1;
+    bool exhausted = false;                                  // warp-uniform: the queue has no rays left
+    for (;;) {
+        // ---- refill the idle lanes of this warp
+        if (!exhausted) {
+            const unsigned idle = __ballot_sync(0xffffffffu, lane < 0);
+            if (idle) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if ((int) self == leader) base = atomicAdd(head, (uint32_t) __popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (lane < 0) {
+                    const uint32_t qi = base + __popc(idle & ((1u << self) - 1u));
+                    if (qi < cnt) {
+                        lane = (int) items[qi];
+                        const float4 a = M.lm.ray[2 * (size_t) lane], b = M.lm.ray[2 * (size_t) lane + 1];
+                        tr.begin(stack, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, M.lm.rayd + 8 * (size_t) lane);
+                    }
+                }
+                exhausted = base + (uint32_t) __popc(idle) >= cnt;
+            }
         }
-        q_push(M.q, dest, (uint32_t) lane);
+        if (!__any_sync(0xffffffffu, lane >= 0)) break;
+        // ---- while-while traversal: (A) every busy lane descends inner nodes until it holds a leaf -- lanes that found
+        //      one wait, and the phase ends once fewer than TRACE_DESCEND lanes are still descending; (B) the lanes that
+        //      hold a leaf intersect its triangles together.  Repeat until too few lanes are busy (refill) or all are done.
+        for (;;) {
+            for (;;) {
+                const bool descending = lane >= 0 && !tr.done && tr.cur >= 0;
+                if (descending) tr.node_step(M.sc);
+                const unsigned still = __ballot_sync(0xffffffffu, lane >= 0 && !tr.done && tr.cur >= 0);
+                const unsigned leafy = __ballot_sync(0xffffffffu, lane >= 0 && !tr.done && tr.cur < 0);
+                if (still == 0 || (leafy != 0 && __popc(still) < M.traceDescend)) break;
+            }
+            if (lane >= 0 && !tr.done && tr.cur < 0) tr.leaf_step(M.sc);
+            if (lane >= 0 && tr.done) {
+                const bool found = tr.hit.tri >= 0;
+                M.lm.hit[lane] = make_float4(tr.hit.t, tr.hit.u, tr.hit.v, __int_as_float(found ? tr.hit.tri : -1));
+                int dest;
+                if (pt) dest = Q_PT;
+                else if (SHADOW || !found) dest = Q_CHAIN + M.parity;
+                else {
+                    const uint32_t mf = (uint32_t) __float_as_int(__ldg(&M.sc.tris[3 * (size_t) tr.hit.tri + 2].z));
+                    dest = Q_WALK + (int) ((mf >> 24) & 3u);
+                }
+                q_push(M.q, dest, (uint32_t) lane);
+                lane = -1;
+            }
+            const int busy = __popc(__ballot_sync(0xffffffffu, lane >= 0));
+            if (busy == 0 || (!exhausted && busy < M.traceRefill)) break;
+        }
     }
 }
 
@@ -52,14 +98,26 @@ __global__ void k_round_begin(uint32_t *count, int parity) {
     if (t < Q_COUNT) {
         const bool nextParity = (t < Q_WALK) && ((t & 1) == (parity ^ 1));
         if (nextParity || t >= Q_WALK) count[t] = 0;
-    }
+    } else if (t < Q_COUNT + 2) count[t] = 0;               // head counters of the two ray queues (dynamic fetch)
+}
+
+// persistent kernels: exactly as many CTAs as are resident at once (SMs x occupancy)
+static int gridC = 0, gridS = 0;
+void trace_init() {                                          // outside any stream capture
+    if (gridC) return;
+    int dev = 0, sms = 148, bc = 4, bs = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_trace<false>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_trace<true>, 128, 0);
+    gridC = sms * std::max(bc, 1); gridS = sms * std::max(bs, 1);
 }
 
 void launch_trace(const Machine &M, const LaunchCfg &lc) {
     k_round_begin<<<1, 32, 0, lc.stream>>>(M.q.count, M.parity);
-    const unsigned g = (unsigned) std::max(1, std::min((lc.nLanes + 255) / 256, 148 * 8));
-    k_trace<false><<<g, 256, 0, lc.stream>>>(M);
-    k_trace<true><<<g, 256, 0, lc.stream>>>(M);
+    const int need = std::max(1, (lc.nLanes + 127) / 128);
+    k_trace<false><<<(unsigned) std::min(gridC, need), 128, 0, lc.stream>>>(M);
+    k_trace<true><<<(unsigned) std::min(gridS, need), 128, 0, lc.stream>>>(M);
 }
 void launch_trace_rays(const DevScene &sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits, cudaStream_t stream) {
     k_trace_rays<<<(unsigned) ((n + 127) / 128), 128, 0, stream>>>(sc, rays, n, shadow, order, hits);

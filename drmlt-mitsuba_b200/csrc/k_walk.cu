@@ -9,7 +9,7 @@
 #include "machine.cuh"
 
 template <int BSDF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, WALK_MINB)
 k_walk(const __grid_constant__ Machine M) {
     const DevScene &sc = M.sc;
     const uint32_t cnt = M.q.count[Q_WALK + BSDF];
@@ -73,10 +73,10 @@ k_walk(const __grid_constant__ Machine M) {
             rec_store(vArr + lane, v);
             rec_store(pArr + lane, vp);
             const int steps = emitterSide ? c.s : c.t;
-            UReader rd;
-            reader_open(M, c, lane, rd);
             if (j < steps) {                                 // BSDF sampling step at vertex j (vertex.cpp:153-271)
                 WalkStep ws;
+                UReader rd;
+                reader_open(M, c, lane, rd);
                 const R2 u = rd.next2D(emitterSide ? SMP_EMITTER : SMP_SENSOR);
                 reader_close(rd, c);
                 if (!surface_sample_next(sc, v, nm, normalize(vp.p - v.p), emitterSide ? MODE_IMPORTANCE : MODE_RADIANCE, u, ws)) { c.pstate = PS_EMPTY; break; }
@@ -91,14 +91,8 @@ k_walk(const __grid_constant__ Machine M) {
             }
             // last vertex of this subpath: its measure stays invalid => connectable iff not degenerate
             if (!v.degenerate) { c.connectable |= 1u << (emitterSide ? (int) c.s : k - (int) c.t); c.flags |= F_ANYCONN; }
-            if (!emitterSide) {
-                const int q = mmlt_emitter_start(M, lane, c, rd, mis);
-                dest = q == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : (q == Q_CONNECT ? Q_CONNECT : Q_CHAIN + M.parity);
-            } else {
-                c.pstate = PS_CONNECT;
-                dest = Q_CONNECT;
-            }
-            reader_close(rd, c);
+            if (!emitterSide) dest = mmlt_emitter_launch(M, lane, c) == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : Q_CONNECT;
+            else { c.pstate = PS_CONNECT; dest = Q_CONNECT; }
         } while (false);
         rec_store(M.lm.core + lane, c);
         q_push(M.q, dest, (uint32_t) lane);
@@ -106,7 +100,7 @@ k_walk(const __grid_constant__ Machine M) {
 }
 
 // ------------------------------------------------------------------ connection (pathsampler.cpp:161-295)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CONNECT_MINB)
 k_connect(const __grid_constant__ Machine M) {
     const DevScene &sc = M.sc;
     const PathCfg &pc = M.pc;

@@ -32,6 +32,24 @@
 #pragma once
 #include "path.cuh"
 
+// Resident CTAs (of 128 threads) per SM that each stage kernel is compiled for.  Every stage is bound by the latency of
+// dependent gathers (ncu: long-scoreboard stalls dominate), so registers are traded for resident warps.
+#ifndef TRACE_MINB
+#define TRACE_MINB 8
+#endif
+#ifndef WALK_MINB
+#define WALK_MINB 5
+#endif
+#ifndef CONNECT_MINB
+#define CONNECT_MINB 4
+#endif
+#ifndef CHAIN_MINB
+#define CHAIN_MINB 5
+#endif
+#ifndef BEGIN_MINB
+#define BEGIN_MINB 6
+#endif
+
 // ------------------------------------------------------------------ lane records (AoS: one record per lane per array,
 // every record a multiple of 16 bytes, so a lane picked from a queue is fetched with a few 128-bit loads)
 enum { PS_IDLE = 0, PS_START, PS_SENSOR_HIT, PS_EMITTER_HIT, PS_CONNECT, PS_CONNECT_SHADOW, PS_FINISH, PS_EMPTY,
@@ -57,8 +75,8 @@ struct alignas(16) Core {     // 128 bytes
 };
 static_assert(sizeof(Core) == 128, "Core layout");
 
-struct alignas(16) PredRec { R3 p, ng; };                  // 48 bytes
-struct alignas(16) PtExtra { R3 Li, pending, refN; Real eta, bsPdf; R3 dIn; };   // 112 bytes (aliases the emitter-side vertex)
+struct alignas(16) PredRec { R3 p, ng; Real pad[2]; };     // 64 bytes (two 32-byte sectors: no partial-sector writes)
+struct alignas(16) PtExtra { R3 Li, pending, refN; Real eta, bsPdf; R3 dIn; Real pad[2]; };   // 128 bytes (aliases the emitter-side vertex)
 struct alignas(16) ChainCore {        // 128 bytes
     Real Lx, a1, cumW;
     Real yL, zL;
@@ -69,7 +87,7 @@ struct alignas(16) ChainCore {        // 128 bytes
     uint8_t posY[3], pad1;            // reader positions at the end of the stage-1 path (m_dimStage1, drmlt_sampler.cpp:237-238)
     uint32_t pad2[4];
 };
-static_assert(sizeof(ChainCore) == 128 && sizeof(Vtx) == 112 && sizeof(PtExtra) == sizeof(Vtx), "lane layout");
+static_assert(sizeof(ChainCore) == 128 && sizeof(Vtx) == 128 && sizeof(PtExtra) == sizeof(Vtx) && sizeof(PredRec) == 64, "lane layout");
 
 enum { MIS_IMP = 0, MIS_RAD = 16, MIS_CONV = 32, MIS_WORDS = 48 };
 static_assert(DR_MAXK + 1 <= 16, "MIS arrays");
@@ -105,8 +123,12 @@ template <class T> DR_D void rec_store(T *dst, const T &src) {
 
 // ------------------------------------------------------------------ work queues
 // Q_RAYC / Q_RAYS / Q_CHAIN are double-buffered by round parity: kernels of round r consume [r & 1] and
-// produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).
-enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 4 */, Q_CONNECT = 10, Q_PT = 11, Q_COUNT = 12 };
+// produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT, Q_PT and
+// Q_BEGIN are produced and consumed inside one round.
+enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 4 */, Q_CONNECT = 10, Q_PT = 11,
+       Q_BEGIN = 12 /* + BEGIN_* class, 3 */, Q_COUNT = 15 };
+// classes of "start the next path" work: each runs one kind of proposal arithmetic on full warps
+enum { BEGIN_STAGE1 = 0, BEGIN_STAGE2 = 1, BEGIN_OTHER = 2 };
 struct Queues {
     uint32_t *items;          // [Q_COUNT][n]
     uint32_t *count;          // [Q_COUNT]
@@ -172,6 +194,8 @@ struct Machine {
     float4 *film;
     unsigned long long *counters;
     int parity;               // round & 1
+    int laneBegin, laneEnd;   // lanes of this wavefront group (set-up kernels; the stage kernels only see queue items)
+    int traceRefill, traceDescend;   // k_trace tuning: refill below this many busy lanes / leave the descend phase below this many
 };
 
 // ------------------------------------------------------------------ MIS arrays of a lane
@@ -184,6 +208,19 @@ DR_D void chain_dims(const PathCfg &pc, const ChainParams &cp, int depth, int di
         int m = (depth + 2) * 3; if (m & 1) m++;
         dims[0] = m; dims[1] = m; dims[2] = 1;
     } else { dims[0] = cp.dimS; dims[1] = cp.dimE; dims[2] = cp.dimD; }
+}
+
+// MMLT strategy from the direct sampler's coordinate (pathsampler.cpp:104-129)
+DR_D void mmlt_strategy(const PathCfg &pc, int depth, Real decision, int &s, int &t) {
+    int nStrats;
+    if (pc.lightImage) { nStrats = depth + 1; s = min((int) (nStrats * decision), nStrats - 1); t = nStrats - s; }
+    else { nStrats = depth; s = min((int) (nStrats * decision), nStrats - 1); t = 1 + (nStrats - s); }
+}
+
+// number of coordinate PAIRS of each sampler that a proposal with strategy (s, t) must carry
+DR_D void pair_extent(const Machine &M, const int dims[3], int s, int t, int ext[3]) {
+    if (M.pp.subset) { ext[0] = t; ext[1] = s; ext[2] = 1; }
+    else { ext[0] = (dims[0] + 1) >> 1; ext[1] = (dims[1] + 1) >> 1; ext[2] = (dims[2] + 1) >> 1; }
 }
 
 // coordinate reader over the lane's active buffer
@@ -245,35 +282,56 @@ DR_D void stats_flush(const uint32_t *st, unsigned long long *counters) {
     }
 }
 
-// MMLT: sample the emitter end of the path (PS_EMITTER_START of the state machine): emitter subpath vertex 1,
-// then either the emission ray (s >= 2) or straight to the connection.  Returns the queue the lane goes to
-// (Q_RAYC or Q_CONNECT), or -1 when the path is dead.
-DR_D int mmlt_emitter_start(const Machine &M, int lane, Core &c, UReader &rd, double *mis) {
+// MMLT emitter end of the path, part 1 (k_begin, when the path starts): sample emitter subpath vertex 1 and, for
+// s >= 2, the emission direction (Scene::sampleEmitterPosition scene.cpp:1066-1082, vertex.cpp:99-124,
+// area.cpp:130-138).  Nothing here depends on the sensor subpath, so it is done up front, where every lane of the
+// warp does the same thing; the results wait in the lane's emitter-side records:
+//   vs = the emitter sample (vs.ss holds the position-sampling weight m_power / emPdf),
+//   vsp.p = emission direction, vsp.ng.x = its solid-angle density.
+// Returns false when there is nothing to sample (the path is dead).
+DR_D bool mmlt_emitter_sample(const Machine &M, int lane, Core &c, UReader &rd, double *mis) {
     const DevScene &sc = M.sc;
-    c.flags &= ~F_DELTA;
     mis_put(mis, MIS_IMP, 0, 1.0);
+    if (c.s == 0) return true;
+    if (sc.nEmitters == 0) return false;
+    EmitterPoint ep;
+    const R2 u0 = rd.next2D(SMP_EMITTER);
+    sample_emitter_point(sc, u0.x, u0.y, ep);
+    const DevEmitter &em = sc.emitters[ep.emitter];
+    mis_put(mis, MIS_IMP, 1, ep.pdfArea);
+    Vtx vs;
+    vs.p = ep.p; vs.ng = vs.ns = ep.n; vs.type = V_EMITTER_SAMPLE; vs.degenerate = 0; vs.emitter = ep.emitter; vs.mat = -1;
+    vs.ss = emitter_radiance(sc, ep.emitter) * (R_PI * em.area / ep.emPdf);   // m_power / emPdf
+    rec_store(M.lm.vs + lane, vs);
+    if (c.s >= 2) {
+        const R2 u = rd.next2D(SMP_EMITTER);
+        const R3 local = square_to_cosine_hemisphere(u.x, u.y);
+        R3 fs, ft;
+        coordinate_system(vs.ns, fs, ft);
+        PredRec e;
+        e.p = fs * local.x + ft * local.y + vs.ns * local.z;
+        e.ng = r3(R_INV_PI * local.z, 0., 0.);
+        rec_store(M.lm.vsp + lane, e);
+    }
+    return true;
+}
+// Part 2 (when the sensor subpath is complete): switch the lane to its emitter subpath -- launch the emission ray
+// (s >= 2) or go straight to the connection.  Returns the queue the lane goes to (Q_RAYC or Q_CONNECT).
+DR_D int mmlt_emitter_launch(const Machine &M, int lane, Core &c) {
+    c.flags &= ~F_DELTA;
     c.connectable |= 1u;                          // area lights: supernode not degenerate, never discrete
     if (c.s >= 1) {
-        if (sc.nEmitters == 0) { c.pstate = PS_EMPTY; return -1; }   // nothing to sample: the path is dead
-        EmitterPoint ep;
-        const R2 u0 = rd.next2D(SMP_EMITTER);
-        sample_emitter_point(sc, u0.x, u0.y, ep);
-        const DevEmitter &em = sc.emitters[ep.emitter];
-        c.weight *= emitter_radiance(sc, ep.emitter) * (R_PI * em.area / ep.emPdf);   // m_power / emPdf
-        mis_put(mis, MIS_IMP, 1, ep.pdfArea);
         Vtx vs;
-        vs.p = ep.p; vs.ng = vs.ns = ep.n; vs.ss = r3(0.); vs.type = V_EMITTER_SAMPLE; vs.degenerate = 0; vs.emitter = ep.emitter; vs.mat = -1;
+        rec_load(vs, M.lm.vs + lane);
+        c.weight *= vs.ss;
         c.connectable |= 1u << 1;
-        rec_store(M.lm.vs + lane, vs);
         c.j = 1;
-        if (c.s >= 2) {                           // vertex.cpp:99-124, area.cpp:130-138
-            const R2 u = rd.next2D(SMP_EMITTER);
-            const R3 local = square_to_cosine_hemisphere(u.x, u.y);
-            R3 fs, ft;
-            coordinate_system(vs.ns, fs, ft);
-            c.pdfFwd = R_INV_PI * local.z; c.pdfBwd = 1.0;
+        if (c.s >= 2) {
+            PredRec e;
+            rec_load(e, M.lm.vsp + lane);
+            c.pdfFwd = e.ng.x; c.pdfBwd = 1.0;
             c.pstate = PS_EMITTER_HIT;
-            emit_ray(M, lane, c, vs.p, fs * local.x + ft * local.y + vs.ns * local.z, sc.epsilon, INFINITY);
+            emit_ray(M, lane, c, vs.p, e.p, M.sc.epsilon, INFINITY);
             return Q_RAYC;
         }
     }
@@ -283,10 +341,12 @@ DR_D int mmlt_emitter_start(const Machine &M, int lane, Core &c, UReader &rd, do
 
 // ------------------------------------------------------------------ host-callable launchers (one per translation unit)
 struct LaunchCfg { cudaStream_t stream; int nLanes; };
+void trace_init();                                                        // k_trace.cu: occupancy query, once, outside stream capture
 void launch_trace(const Machine &M, const LaunchCfg &lc);                 // k_trace.cu: closest + shadow queues
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask);   // k_walk.cu: walk queues of the BSDF types present, then connect
 void launch_pt(const Machine &M, const LaunchCfg &lc);                    // k_pt.cu
-void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu
+void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu, then the three k_begin classes (k_begin.cu)
+void launch_begin(const Machine &M, const LaunchCfg &lc);                 // k_begin.cu
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId,
                   const unsigned long long *seedIdx);                     // k_chain.cu: initialise lanes for M.job and queue them
 void launch_resume(const Machine &M, const LaunchCfg &lc);                // k_chain.cu: re-queue idle chains whose target was raised

@@ -32,11 +32,12 @@ struct PathResult {           // single-splat techniques (path, mmlt)
 
 enum { V_EMITTER_SAMPLE = 3, V_SENSOR_SAMPLE = 4, V_SURFACE = 5 };
 
-struct Vtx {                  // 28 words, stored verbatim in lane memory between wavefront stages
+struct Vtx {                  // 128 bytes (one cache line), stored verbatim in lane memory between wavefront stages
     R3 p, ng, ns, ss;         // position, geometric normal, shading normal, shading tangent s (t = ns x ss)
     int mat, emitter;
     int type;
     int degenerate;
+    int pad[4];
 };
 
 DR_D R3 to_local(const Vtx &v, R3 w) { return r3(dot(w, v.ss), dot(w, cross(v.ns, v.ss)), dot(w, v.ns)); }

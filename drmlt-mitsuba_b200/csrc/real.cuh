@@ -30,7 +30,7 @@ DR_HD R3 operator-(R3 a) { return r3(-a.x, -a.y, -a.z); }
 DR_HD R3 operator*(R3 a, Real s) { return r3(a.x * s, a.y * s, a.z * s); }
 DR_HD R3 operator*(Real s, R3 a) { return r3(a.x * s, a.y * s, a.z * s); }
 DR_HD R3 operator*(R3 a, R3 b) { return r3(a.x * b.x, a.y * b.y, a.z * b.z); }
-DR_HD R3 operator/(R3 a, Real s) { return r3(a.x / s, a.y / s, a.z / s); }
+DR_HD R3 operator/(R3 a, Real s) { const Real r = 1.0 / s; return r3(a.x * r, a.y * r, a.z * r); }   // TVector3::operator/ (vector.h)
 DR_HD R3 operator/(R3 a, R3 b) { return r3(a.x / b.x, a.y / b.y, a.z / b.z); }
 DR_HD R3 &operator+=(R3 &a, R3 b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
 DR_HD R3 &operator*=(R3 &a, R3 b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; return a; }

@@ -28,20 +28,24 @@ DR_D float adaptive_mint(const DevScene &sc, float3 o, float mint) {
     return mint;
 }
 
-// Candidate test in float32 with a tolerance band around the triangle's edges and the ray interval ...
-DR_D bool tri_candidate(const float4 t0, const float4 t1, const float4 t2, float3 o, float3 d, float tmin, float tmax) {
+// Float32 triangle test with a tolerance band: 0 = miss, 1 = clear hit (inside the triangle and the ray interval by
+// more than the band: float rounding cannot change the decision, nor the order against the best hit so far),
+// 2 = borderline (decided in double by tri_verify).
+DR_D int tri_classify(const float4 t0, const float4 t1, const float4 t2, float3 o, float3 d, float tmin, float tmax, float &t, float &u, float &v) {
     const float3 p0 = f3(t0.x, t0.y, t0.z), e1 = f3(t0.w, t1.x, t1.y) - p0, e2 = f3(t1.z, t1.w, t2.x) - p0;
     const float3 pvec = cross(d, e2);
     const float det = dot(e1, pvec);
-    if (det == 0.f) return false;
+    if (det == 0.f) return 0;
     const float inv = 1.0f / det;
     const float3 tvec = o - p0;
-    const float u = dot(tvec, pvec) * inv;
+    u = dot(tvec, pvec) * inv;
     const float3 qvec = cross(tvec, e1);
-    const float v = dot(d, qvec) * inv;
-    const float t = dot(e2, qvec) * inv;
+    v = dot(d, qvec) * inv;
+    t = dot(e2, qvec) * inv;
     const float tolT = 1e-5f + 1e-5f * fabsf(t);
-    return u >= -DR_TRI_TOL && v >= -DR_TRI_TOL && u + v <= 1.0f + DR_TRI_TOL && t >= tmin - tolT && t <= tmax + tolT;
+    if (!(u >= -DR_TRI_TOL && v >= -DR_TRI_TOL && u + v <= 1.0f + DR_TRI_TOL && t >= tmin - tolT && t <= tmax + tolT)) return 0;
+    const bool clear = u >= DR_TRI_TOL && v >= DR_TRI_TOL && u + v <= 1.0f - DR_TRI_TOL && t >= tmin + tolT && t <= tmax - tolT;
+    return clear ? 1 : 2;
 }
 // ... and the deciding test in double on the un-rounded ray (o, d, tmin, tmax = rd[0..7]): the hit / miss decision, t
 // and the barycentrics are those of the reference's double-precision triangle test (triaccel.h:91-157: inclusive
@@ -63,64 +67,102 @@ DR_D bool tri_verify(const float4 t0, const float4 t1, const float4 t2, const do
     return u >= 0.0 && v >= 0.0 && u + v <= 1.0 && t >= rd[6] && t <= tmax;
 }
 
+// One ray's traversal state; step() processes ONE inner node or ONE leaf, so that a persistent kernel can
+// interleave "fetch a new ray for the lanes that finished" with the traversal of the others.
 template <bool ANYHIT>
-DR_D bool traverse(const DevScene &sc, float3 o, float3 d, float tmin, float tmax, const double *rd, Hit &hit, uint32_t *nodeVisits = nullptr) {
-    hit.tri = -1;
-    if (!(rd[7] > rd[6])) return false;
-    double bestT = rd[7];
-    // zero direction components: clamp so that 1/d stays finite (no 0 * inf = NaN in the slab test)
-    const float3 inv = f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
-                          1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
-    const float3 oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-    int stack[DR_STACK];
-    int sp = 0;
-    int cur = 0;   // inner node index, or leaf code (< 0)
-    while (true) {
-        if (cur >= 0) {
+struct Traversal {
+    float3 o, d, inv, oi;
+    float tmin, tmax;
+    const double *rd;         // un-rounded ray: o, d, tmin, tmax
+    double bestT;
+    bool bestExact;
+    Hit hit;
+    int *stack;               // DR_STACK entries of thread-private memory, owned by the caller
+    int sp, cur;              // cur: inner node index, or leaf code (< 0)
+    bool done;
+
+    DR_D void begin(int *stack_, float3 o_, float3 d_, float tmin_, float tmax_, const double *rd_) {
+        stack = stack_;
+        o = o_; d = d_; tmin = tmin_; tmax = tmax_; rd = rd_;
+        hit.tri = -1; hit.t = hit.u = hit.v = 0.f;
+        bestT = rd[7]; bestExact = true;
+        // zero direction components: clamp so that 1/d stays finite (no 0 * inf = NaN in the slab test)
+        inv = f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
+                 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
+        oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+        sp = 0; cur = 0;
+        done = !(rd[7] > rd[6]);
+    }
+    DR_D void pop() { if (sp == 0) done = true; else cur = stack[--sp]; }
+    DR_D void step(const DevScene &sc) { if (cur >= 0) node_step(sc); else leaf_step(sc); }
+    DR_D void node_step(const DevScene &sc) {
+        {
             const float4 *n = sc.nodes + 4 * (size_t) cur;
             const float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2), n3 = ldg4(n + 3);
-            if (nodeVisits) ++*nodeVisits;
             // child 0: lo = (n0.x n0.y n0.z) hi = (n0.w n1.x n1.y); child 1: lo = (n1.z n1.w n2.x) hi = (n2.y n2.z n2.w)
             float a0 = n0.x * inv.x - oi.x, b0 = n0.w * inv.x - oi.x;
             float a1 = n0.y * inv.y - oi.y, b1 = n1.x * inv.y - oi.y;
             float a2 = n0.z * inv.z - oi.z, b2 = n1.y * inv.z - oi.z;
-            float near0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tmin));
-            float far0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), tmax));
+            const float near0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tmin));
+            const float far0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), tmax));
             a0 = n1.z * inv.x - oi.x; b0 = n2.y * inv.x - oi.x;
             a1 = n1.w * inv.y - oi.y; b1 = n2.z * inv.y - oi.y;
             a2 = n2.x * inv.z - oi.z; b2 = n2.w * inv.z - oi.z;
-            float near1 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tmin));
-            float far1 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), tmax));
+            const float near1 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tmin));
+            const float far1 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), tmax));
             // conservative: the boxes are padded at upload and the comparison is widened by a few ulps, so that float
             // slab rounding (of the test and of the float-cast ray) never culls a true hit
             const bool h0 = near0 <= far0 * 1.000002f, h1 = near1 <= far1 * 1.000002f;
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 const bool swap = near1 < near0;
-                if (sp < DR_STACK) stack[sp++] = swap ? c0 : c1;
+                stack[sp++] = swap ? c0 : c1;             // depth < DR_STACK is checked when the scene is created
                 cur = swap ? c1 : c0;
-                continue;
-            } else if (h0) { cur = c0; continue; }
-            else if (h1) { cur = c1; continue; }
-        } else {
-            const int code = ~cur;
-            const int first = code >> 2, count = (code & 3) + 1;
-            for (int i = 0; i < count; ++i) {
-                const float4 *tp = sc.tris + 3 * (size_t) (first + i);
-                const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1), t2 = ldg4(tp + 2);
-                if (tri_candidate(t0, t1, t2, o, d, tmin, tmax)) {
-                    double t, u, v;
-                    if (tri_verify(t0, t1, t2, rd, bestT, t, u, v)) {
-                        hit.t = (float) t; hit.u = (float) u; hit.v = (float) v; hit.tri = first + i;
-                        if (ANYHIT) return true;
-                        bestT = t;
-                        tmax = __double2float_ru(t);
-                    }
+            } else if (h0) cur = c0;
+            else if (h1) cur = c1;
+            else pop();
+        }
+    }
+    DR_D void leaf_step(const DevScene &sc) {
+        const int code = ~cur;
+        const int first = code >> 2, count = (code & 3) + 1;
+        for (int i = 0; i < count; ++i) {
+            const float4 *tp = sc.tris + 3 * (size_t) (first + i);
+            const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1), t2 = ldg4(tp + 2);
+            float tf, uf, vf;
+            const int cls = tri_classify(t0, t1, t2, o, d, tmin, tmax, tf, uf, vf);
+            if (cls == 1) {
+                hit.t = tf; hit.u = uf; hit.v = vf; hit.tri = first + i;
+                if (ANYHIT) { done = true; return; }
+                bestT = (double) tf; bestExact = false;
+                tmax = tf;
+            } else if (cls == 2) {                       // rare: decide in double on the un-rounded ray
+                double t, u, v;
+                if (!ANYHIT && !bestExact && hit.tri >= 0 && tf >= tmax - (2e-5f + 2e-5f * fabsf(tf))) {
+                    // the best hit so far was accepted on its float t, which is too close to this candidate's: make it exact
+                    const float4 *bp = sc.tris + 3 * (size_t) hit.tri;
+                    double bu, bv;
+                    if (!tri_verify(ldg4(bp), ldg4(bp + 1), ldg4(bp + 2), rd, rd[7], bestT, bu, bv)) bestT = (double) hit.t;
+                    bestExact = true;
+                }
+                if (tri_verify(t0, t1, t2, rd, bestT, t, u, v)) {
+                    hit.t = (float) t; hit.u = (float) u; hit.v = (float) v; hit.tri = first + i;
+                    if (ANYHIT) { done = true; return; }
+                    bestT = t; bestExact = true;
+                    tmax = __double2float_ru(t);
                 }
             }
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
+        pop();
     }
+};
+
+template <bool ANYHIT>
+DR_D bool traverse(const DevScene &sc, float3 o, float3 d, float tmin, float tmax, const double *rd, Hit &hit) {
+    int stack[DR_STACK];
+    Traversal<ANYHIT> tr;
+    tr.begin(stack, o, d, tmin, tmax, rd);
+    while (!tr.done) tr.step(sc);
+    hit = tr.hit;
     return hit.tri >= 0;
 }

@@ -1,0 +1,275 @@
+// mts_plugin.cpp -- Mitsuba 0.6 integrator plugins `drmlt` and `pssmlt` backed by libdrmlt_b200.so.
+//
+// This is the reference-side half of the drop-in boundary.  Built once per plugin
+// name inside a drmlt-mitsuba source tree (it needs Mitsuba's headers and links libmitsuba-core /
+// libmitsuba-render, which are absent from the build image of this repository -- see INTEGRATION.md):
+//
+//   g++ -std=c++11 -shared -fPIC -DDR_PLUGIN_DRMLT  mts_plugin.cpp -I<mitsuba>/include -I<repo>/include \
+//       -L<repo>/drmlt-mitsuba_b200/csrc -ldrmlt_b200 -lmitsuba-core -lmitsuba-render -o plugins/drmlt.so
+//   g++ ... -DDR_PLUGIN_PSSMLT ... -o plugins/pssmlt.so
+//
+// It replaces src/integrators/drmlt/drmlt.cpp:176-621 and src/integrators/pssmlt/pssmlt.cpp:164-556 as the
+// object PluginManager::createObject instantiates for <integrator type="drmlt|pssmlt"> (plugin.cpp:180-196):
+// same class names, same parameters (they are forwarded verbatim to dr_config_set, which knows the
+// reference's names and defaults), same output convention (film->setBitmap + queue->signalRefresh,
+// drmlt_proc.cpp:850-853).  Scene loading (XML, meshes), the film and its file output stay Mitsuba's.
+#include <mitsuba/render/scene.h>
+#include <mitsuba/render/renderjob.h>
+#include <mitsuba/render/renderqueue.h>
+#include <mitsuba/render/trimesh.h>
+#include <mitsuba/render/bsdf.h>
+#include <mitsuba/render/emitter.h>
+#include <mitsuba/render/sensor.h>
+#include <mitsuba/render/film.h>
+#include <mitsuba/core/bitmap.h>
+#include <mitsuba/core/plugin.h>
+#include <mitsuba/core/sched.h>
+#include <drmlt_b200.h>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <vector>
+
+MTS_NAMESPACE_BEGIN
+
+namespace {
+
+// ---- BSDF flattening ------------------------------------------------------------------------------
+// Parameters come from the Properties the BSDF was constructed with (ConfigurableObject::getProperties,
+// include/mitsuba/core/cobject.h:77) -- exact values.  The `twosided` adapter owns its nested BSDF privately
+// (src/bsdfs/twosided.cpp:85-100) and exposes no getter, so the nested model is recovered from toString()
+// (twosided.cpp: "nestedBRDF[0] = <nested toString>"), which prints spectra with 6 significant digits.
+struct ToStringParser {
+    const std::string &s;
+    explicit ToStringParser(const std::string &str) : s(str) {}
+    std::string className(size_t from = 0) const {
+        size_t b = s.find_first_not_of(" \n\t", from), e = s.find('[', b);
+        return s.substr(b, e - b);
+    }
+    // "key = [a, b, c]" or "key = ConstantSpectrumTexture[value=[a, b, c]]" / "ConstantFloatTexture[value=a]"
+    bool spectrum(const char *key, size_t from, float out[3]) const {
+        size_t p = s.find(std::string(key) + " = ", from);
+        if (p == std::string::npos) return false;
+        size_t lb = s.find('[', p);
+        if (s.compare(lb + 1, 6, "value=") == 0 || s.find("Texture[", p) < lb + 1) lb = s.find('[', lb + 1);
+        float a, b, c;
+        if (sscanf(s.c_str() + lb, "[%f, %f, %f]", &a, &b, &c) != 3) return false;
+        out[0] = a; out[1] = b; out[2] = c;
+        return true;
+    }
+    bool scalar(const char *key, size_t from, float &out) const {
+        size_t p = s.find(std::string(key) + " = ", from);
+        if (p == std::string::npos) return false;
+        p += strlen(key) + 3;
+        size_t v = s.find("value=", p), nl = s.find('\n', p);
+        if (v != std::string::npos && v < nl) p = v + 6;
+        return sscanf(s.c_str() + p, "%f", &out) == 1;
+    }
+};
+
+void toRGB(const Spectrum &sp, float out[3]) {
+    Float r, g, b;
+    sp.toLinearRGB(r, g, b);
+    out[0] = (float) r; out[1] = (float) g; out[2] = (float) b;
+}
+
+bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why) {
+    memset(&m, 0, sizeof(m));
+    m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 1.f;
+    m.transmittance[0] = m.transmittance[1] = m.transmittance[2] = 1.f;
+    const std::string cls = bsdf->getClass()->getName();
+    const Properties &props = bsdf->getProperties();
+    const std::string str = bsdf->toString();
+    ToStringParser ts(str);
+    size_t from = 0;
+    std::string model = cls;
+    bool nested = false;
+    if (cls == "TwoSidedBRDF") {
+        m.flags |= DR_MAT_TWOSIDED;
+        from = str.find("nestedBRDF[0] = ");
+        if (from == std::string::npos) { why = "cannot parse twosided"; return false; }
+        from += strlen("nestedBRDF[0] = ");
+        model = ts.className(from);
+        nested = true;
+    }
+    if (model == "SmoothDiffuse") {                       // src/bsdfs/diffuse.cpp
+        m.type = DR_BSDF_DIFFUSE;
+        if (!nested) toRGB(props.getSpectrum(props.hasProperty("reflectance") ? "reflectance" : "diffuseReflectance", Spectrum(.5f)), m.reflectance);
+        else if (!ts.spectrum("reflectance", from, m.reflectance)) { why = "textured diffuse reflectance"; return false; }
+    } else if (model == "SmoothDielectric") {             // src/bsdfs/dielectric.cpp
+        m.type = DR_BSDF_DIELECTRIC;
+        float eta = 0.f;
+        if (!ts.scalar("eta", from, eta)) { why = "cannot parse dielectric eta"; return false; }
+        m.eta[0] = eta;                                   // intIOR / extIOR, as printed by SmoothDielectric::toString
+        ts.spectrum("specularReflectance", from, m.reflectance);
+        ts.spectrum("specularTransmittance", from, m.transmittance);
+    } else if (model == "SmoothConductor" || model == "RoughConductor") {   // conductor.cpp / roughconductor.cpp
+        m.type = model == "SmoothConductor" ? DR_BSDF_CONDUCTOR : DR_BSDF_ROUGHCONDUCTOR;
+        if (!ts.spectrum("eta", from, m.eta) || !ts.spectrum("k", from, m.k)) { why = "cannot parse conductor eta/k"; return false; }
+        ts.spectrum("specularReflectance", from, m.reflectance);
+        if (m.type == DR_BSDF_ROUGHCONDUCTOR) {
+            float au = 0.f, av = 0.f;
+            if (!ts.scalar("alphaU", from, au) || !ts.scalar("alphaV", from, av) || au != av) { why = "anisotropic or textured roughness"; return false; }
+            m.alpha = au;
+            size_t d = str.find("distribution = ", from);
+            if (d == std::string::npos) { why = "no distribution"; return false; }
+            if (str.compare(d + 15, 3, "ggx") == 0) m.flags |= DR_MAT_GGX;
+            else if (str.compare(d + 15, 8, "beckmann") != 0) { why = "phong distribution"; return false; }
+            size_t v = str.find("sampleVisible = ", from);
+            if (v != std::string::npos && str[v + 16] == '1') m.flags |= DR_MAT_SAMPLE_VISIBLE;
+        }
+    } else { why = "unsupported BSDF " + model; return false; }
+    return true;
+}
+
+} // namespace
+
+#if defined(DR_PLUGIN_PSSMLT)
+#define DR_CLASS PSSMLT
+#define DR_NAME "pssmlt"
+#else
+#define DR_CLASS DRMLT
+#define DR_NAME "drmlt"
+#endif
+
+class DR_CLASS : public Integrator {
+public:
+    DR_CLASS(const Properties &props) : Integrator(props), m_scene(NULL) {
+        dr_config_default(&m_config);
+        check(dr_config_set(&m_config, "integrator", DR_NAME));
+        // forward every parameter under the reference's own name (drmlt.cpp:193-349, pssmlt.cpp:181-307)
+        std::vector<std::string> names;
+        props.putPropertyNames(names);
+        for (size_t i = 0; i < names.size(); ++i) {
+            const std::string &k = names[i];
+            std::ostringstream v;
+            switch (props.getType(k)) {
+                case Properties::EBoolean: v << (props.getBoolean(k) ? "true" : "false"); break;
+                case Properties::EInteger: v << props.getInteger(k); break;
+                case Properties::EFloat: v.precision(17); v << props.getFloat(k); break;
+                case Properties::EString: v << props.getString(k); break;
+                default: continue;
+            }
+            check(dr_config_set(&m_config, k.c_str(), v.str().c_str()));
+        }
+    }
+    DR_CLASS(Stream *stream, InstanceManager *manager) : Integrator(stream, manager), m_scene(NULL) {
+        Log(EError, "Network rendering is not supported by the B200 plugin");
+    }
+    void serialize(Stream *stream, InstanceManager *manager) const {
+        Integrator::serialize(stream, manager);
+        Log(EError, "Network rendering is not supported by the B200 plugin");
+    }
+
+    bool preprocess(const Scene *scene, RenderQueue *, const RenderJob *, int, int, int) {
+        if (scene->getSubsurfaceIntegrators().size() > 0)       // drmlt.cpp:377-378
+            Log(EError, "Subsurface integrators are not supported by MLT!");
+        if (scene->getSampler()->getClass()->getName() != "IndependentSampler")   // drmlt.cpp:380-381
+            Log(EError, "Metropolis light transport requires the independent sampler");
+        return true;
+    }
+
+    bool render(Scene *scene, RenderQueue *queue, const RenderJob *job, int, int, int) {
+        ref<Sensor> sensor = scene->getSensor();
+        ref<Film> film = sensor->getFilm();
+        const Vector2i size = film->getCropSize();
+        m_config.sample_count = (int32_t) sensor->getSampler()->getSampleCount();   // drmlt.cpp:400
+        const std::string rf = film->getReconstructionFilter()->getClass()->getName();
+        check(dr_config_set(&m_config, "rfilter", rf == "BoxFilter" ? "box" : "gaussian"));
+        if (rf != "BoxFilter" && rf != "GaussianFilter") Log(EWarn, "Reconstruction filter %s: using gaussian", rf.c_str());
+        check(dr_config_validate(&m_config));
+
+        // ---- flatten Scene -> dr_scene_desc
+        std::vector<float> P, N;
+        std::vector<uint32_t> I, triMat, triFlags;
+        std::vector<int32_t> triEm;
+        std::vector<dr_material> mats;
+        std::vector<dr_emitter> ems;
+        bool anyNormals = false;
+        const std::vector<TriMesh *> &meshes = scene->getMeshes();
+        if (meshes.size() != scene->getShapes().size())
+            Log(EError, "Only triangle meshes are supported on the GPU path (tessellate analytic shapes)");
+        for (size_t mi = 0; mi < meshes.size(); ++mi) {
+            const TriMesh *mesh = meshes[mi];
+            if (mesh->getVertexTexcoords()) Log(EWarn, "Mesh \"%s\" has texture coordinates: the shading tangent follows dpdu, not p1-p0", mesh->getName().c_str());
+            dr_material mat; std::string why;
+            if (!mesh->getBSDF() || !flattenBSDF(mesh->getBSDF(), mat, why)) Log(EError, "Mesh \"%s\": %s", mesh->getName().c_str(), why.c_str());
+            mats.push_back(mat);
+            const uint32_t base = (uint32_t) (P.size() / 3), firstTri = (uint32_t) triMat.size();
+            const Point *pos = mesh->getVertexPositions();
+            const Normal *nrm = mesh->getVertexNormals();
+            for (size_t v = 0; v < mesh->getVertexCount(); ++v) {
+                P.push_back((float) pos[v].x); P.push_back((float) pos[v].y); P.push_back((float) pos[v].z);
+                N.push_back(nrm ? (float) nrm[v].x : 0.f); N.push_back(nrm ? (float) nrm[v].y : 0.f); N.push_back(nrm ? (float) nrm[v].z : 0.f);
+            }
+            anyNormals |= nrm != NULL;
+            int32_t em = -1;
+            if (mesh->isEmitter()) {
+                const Emitter *e = mesh->getEmitter();
+                if (e->getClass()->getName() != "AreaLight") Log(EError, "Only area emitters are supported (pathsampler.cpp:65-71)");
+                dr_emitter de;
+                de.first_tri = firstTri; de.n_tris = (uint32_t) mesh->getTriangleCount();
+                toRGB(e->getProperties().getSpectrum("radiance", Spectrum::getD65()), de.radiance);   // area.cpp:77
+                de.sampling_weight = (float) e->getSamplingWeight();
+                em = (int32_t) ems.size();
+                ems.push_back(de);
+            }
+            const Triangle *tri = mesh->getTriangles();
+            for (size_t t = 0; t < mesh->getTriangleCount(); ++t) {
+                for (int k = 0; k < 3; ++k) I.push_back(base + tri[t].idx[k]);
+                triMat.push_back((uint32_t) mi); triEm.push_back(em); triFlags.push_back(nrm ? DR_TRI_SMOOTH : 0u);
+            }
+        }
+        if (scene->getEmitters().size() != ems.size()) Log(EError, "Only area emitters attached to triangle meshes are supported");
+        const PerspectiveCamera *cam = dynamic_cast<const PerspectiveCamera *>(sensor.get());
+        if (!cam || sensor->getClass()->getName() != "PerspectiveCameraImpl") Log(EError, "Only the perspective (pinhole) sensor is supported");
+        dr_scene_desc desc;
+        memset(&desc, 0, sizeof(desc));
+        desc.n_vertices = (uint32_t) (P.size() / 3); desc.n_triangles = (uint32_t) triMat.size();
+        desc.n_materials = (uint32_t) mats.size(); desc.n_emitters = (uint32_t) ems.size();
+        desc.positions = P.data(); desc.normals = anyNormals ? N.data() : NULL; desc.indices = I.data();
+        desc.tri_material = triMat.data(); desc.tri_emitter = triEm.data(); desc.tri_flags = triFlags.data();
+        desc.materials = mats.data(); desc.emitters = ems.empty() ? NULL : ems.data();
+        const Matrix4x4 &tw = cam->getWorldTransform()->eval(0).getMatrix();
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) desc.camera.to_world[4 * r + c] = (float) tw(r, c);
+        desc.camera.xfov_deg = (float) cam->getXFov();
+        desc.camera.near_clip = (float) cam->getNearClip(); desc.camera.far_clip = (float) cam->getFarClip();
+        desc.camera.film_width = size.x; desc.camera.film_height = size.y;
+
+        const char *dev = getenv("DRMLT_DEVICE");
+        check(dr_scene_create(&desc, dev ? atoi(dev) : 0, &m_scene));
+
+        // ---- render on the GPU, hand the developed image to the film (drmlt_proc.cpp:850-853)
+        std::vector<float> image((size_t) size.x * size.y * 3);
+        dr_stats st;
+        const dr_status status = dr_render(m_scene, &m_config, image.data(), &st);
+        dr_scene sceneHandle = m_scene;
+        m_scene = NULL;
+        dr_scene_destroy(sceneHandle);
+        if (status == DR_ERR_CANCELLED) return false;
+        check(status);
+        ref<Bitmap> bitmap = new Bitmap(Bitmap::ESpectrum, Bitmap::EFloat, size);
+        Spectrum *target = (Spectrum *) bitmap->getData();
+        for (size_t i = 0; i < (size_t) size.x * size.y; ++i)
+            target[i].fromLinearRGB(image[3 * i], image[3 * i + 1], image[3 * i + 2]);
+        film->setBitmap(bitmap);
+        queue->signalRefresh(job);
+        // same figures as the reference's StatsCounters (drmlt_proc.cpp:34-49)
+        Log(EInfo, "Normalization factor b = %f; %llu mutations, first stage accepted %.2f %%, second stage %.2f %%, %.1f ms on the GPU",
+            st.luminance, (unsigned long long) st.mutations, st.first_base ? 100.0 * st.first_accept / st.first_base : 0.0,
+            st.second_base ? 100.0 * st.second_accept / st.second_base : 0.0, st.total_ms);
+        return true;
+    }
+
+    void cancel() { if (m_scene) dr_cancel(m_scene); }           // Integrator::cancel (drmlt.cpp:386-391), any thread
+
+    MTS_DECLARE_CLASS()
+private:
+    void check(dr_status st) const { if (st != DR_OK) Log(EError, "%s", dr_last_error()); }   // EError throws (renderjob.cpp:110-114)
+    dr_config m_config;
+    dr_scene m_scene;
+};
+
+MTS_IMPLEMENT_CLASS_S(DR_CLASS, false, Integrator)
+MTS_EXPORT_PLUGIN(DR_CLASS, "B200 " DR_NAME " integrator");
+MTS_NAMESPACE_END

@@ -41,10 +41,10 @@ struct Vec3 {
     Vec3 operator-(const Vec3 &o) const { return Vec3(x - o.x, y - o.y, z - o.z); }
     Vec3 operator-() const { return Vec3(-x, -y, -z); }
     Vec3 operator*(Float s) const { return Vec3(x * s, y * s, z * s); }
-    Vec3 operator/(Float s) const { return Vec3(x / s, y / s, z / s); }
+    Vec3 operator/(Float s) const { const Float r = (Float) 1 / s; return Vec3(x * r, y * r, z * r); }   // TVector3::operator/ (vector.h:535-542)
     Vec3 &operator+=(const Vec3 &o) { x += o.x; y += o.y; z += o.z; return *this; }
     Vec3 &operator*=(Float s) { x *= s; y *= s; z *= s; return *this; }
-    Vec3 &operator/=(Float s) { x /= s; y /= s; z /= s; return *this; }
+    Vec3 &operator/=(Float s) { const Float r = (Float) 1 / s; x *= r; y *= r; z *= r; return *this; }   // vector.h:545-556
 };
 inline Vec3 operator*(Float s, const Vec3 &v) { return v * s; }
 inline Float dot(const Vec3 &a, const Vec3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -67,11 +67,11 @@ struct RGB {
     RGB operator*(const RGB &o) const { return RGB(r * o.r, g * o.g, b * o.b); }
     RGB operator/(const RGB &o) const { return RGB(r / o.r, g / o.g, b / o.b); }
     RGB operator*(Float s) const { return RGB(r * s, g * s, b * s); }
-    RGB operator/(Float s) const { return RGB(r / s, g / s, b / s); }
+    RGB operator/(Float s) const { const Float rc = (Float) 1 / s; return RGB(r * rc, g * rc, b * rc); }   // TSpectrum::operator/ (spectrum.h:415-425)
     RGB &operator+=(const RGB &o) { r += o.r; g += o.g; b += o.b; return *this; }
     RGB &operator*=(const RGB &o) { r *= o.r; g *= o.g; b *= o.b; return *this; }
     RGB &operator*=(Float s) { r *= s; g *= s; b *= s; return *this; }
-    RGB &operator/=(Float s) { r /= s; g /= s; b /= s; return *this; }
+    RGB &operator/=(Float s) { const Float rc = (Float) 1 / s; r *= rc; g *= rc; b *= rc; return *this; }
     bool isZero() const { return r == 0 && g == 0 && b == 0; }
     Float max() const { return std::max(r, std::max(g, b)); }
     // include/mitsuba/core/spectrum.h:734-736

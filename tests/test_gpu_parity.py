@@ -182,10 +182,10 @@ def test_path_contribution_replayed_u(case):
         sc_, tc = c[:, 8:12].copy().view("<i4")[:, 0], c[:, 12:16].copy().view("<i4")[:, 0]
         assert np.array_equal(sg, sc_) and np.array_equal(tg, tc)
         mg, mc = g[:, 16:20].copy().view("<f4")[:, 0], c[:, 16:20].copy().view("<f4")[:, 0]
-        both = (lg > 0) & (lum64 > 0)
+        both = (_denoise(lg, lum64) > 0) & (_denoise(lum64, lum64) > 0)
         assert (np.abs(mg[both] - mc[both]) <= 1e-4 * mc[both]).mean() >= 0.999     # MIS weights
     # splat positions and RGB of the contributing paths
-    both = (lg > 0) & (lum64 > 0)
+    both = (_denoise(lg, lum64) > 0) & (_denoise(lum64, lum64) > 0)
     pg, pc = g[:, 20:28].copy().view("<f4"), c[:, 20:28].copy().view("<f4")
     assert (np.abs(pg[both] - pc[both]).max(axis=1) < 2e-2).mean() >= 0.999          # pixels (film is 128 px wide)
     off = 20 + 8 * abi.DR_MAX_SPLATS
