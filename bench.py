@@ -284,8 +284,6 @@ def run_gpu(args):
 
     # ---- e2e: whole job through the public API with host buffers
     e2e_params = dict(PARAMS, seed=args.seed + 1, sampleCount=args.e2e_spp * world)
-    if args.chains:
-        e2e_params["chains"] = args.chains
     barrier()
     e0 = time.perf_counter()
     h2d = scene.reupload()
@@ -300,6 +298,7 @@ def run_gpu(args):
     W, H = data.film
     e2e = {"value": float(te.item()) / float(tw.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(W * H * 3 * 4), "seconds": float(tw.item()), "mutations": int(te.item()),
+           "rank0_phases_ms": {"bootstrap_and_seeding": est.bootstrap_ms, "chains": est.chains_ms},
            "what": "dr_scene_reupload + bootstrap + b all-reduce + chains + film reduce + develop + image D2H; sampleCount=%d" % (args.e2e_spp * world)}
 
     line = None
@@ -337,9 +336,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scene", default="door")
     ap.add_argument("--mutations", type=int, default=64, help="mutations per chain per step")
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = auto)")
+    ap.add_argument("--chains", type=int, default=4194304, help="chains resident per GPU in the timed steps (0 = auto)")
     ap.add_argument("--spp", type=int, default=64)
-    ap.add_argument("--e2e-spp", type=int, default=16, dest="e2e_spp")
+    ap.add_argument("--e2e-spp", type=int, default=64, dest="e2e_spp", help="sampleCount of the whole-job e2e render (64 = the C5 workload)")
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")

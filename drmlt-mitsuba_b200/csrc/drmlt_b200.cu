@@ -227,7 +227,7 @@ extern "C" void dr_max_dimensions(const dr_config *cfg, int depth, int *sensor, 
 }
 
 // ------------------------------------------------------------------ scene
-struct HostUpload { void *dev; std::vector<char> host; };
+struct HostUpload { void *dev; char *host; size_t bytes; };   // host: pinned staging copy (kept for dr_scene_reupload)
 
 struct SceneImpl : dr_scene_t {
     std::vector<HostUpload> uploads;     // host staging copies (kept for dr_scene_reupload)
@@ -239,15 +239,18 @@ template <class T>
 static dr_status upload(SceneImpl *s, const std::vector<T> &v, const T **devOut) {
     HostUpload u;
     size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-    u.host.assign(bytes, 0);
-    if (!v.empty()) memcpy(u.host.data(), v.data(), v.size() * sizeof(T));
-    CK(cudaMalloc(&u.dev, bytes));
-    s->allocations.push_back(u.dev);
-    CK(cudaMemcpy(u.dev, u.host.data(), bytes, cudaMemcpyHostToDevice));
+    u.bytes = bytes;
+    CK(cudaMallocHost((void **) &u.host, bytes));
+    s->uploads.push_back(u);
+    HostUpload &up = s->uploads.back();
+    memset(up.host, 0, bytes);
+    if (!v.empty()) memcpy(up.host, v.data(), v.size() * sizeof(T));
+    CK(cudaMalloc(&up.dev, bytes));
+    s->allocations.push_back(up.dev);
+    CK(cudaMemcpy(up.dev, up.host, bytes, cudaMemcpyHostToDevice));
     s->bytes += bytes;
     s->uploadBytes += bytes;
-    *devOut = (const T *) u.dev;
-    s->uploads.push_back(std::move(u));
+    *devOut = (const T *) up.dev;
     return DR_OK;
 }
 
@@ -258,6 +261,7 @@ extern "C" void dr_scene_destroy(dr_scene scene) {
     SceneImpl *s = static_cast<SceneImpl *>(scene);
     cudaSetDevice(s->device);
     for (void *p : s->allocations) cudaFree(p);
+    for (HostUpload &u : s->uploads) if (u.host) cudaFreeHost(u.host);
     delete s;
 }
 
@@ -424,7 +428,8 @@ extern "C" dr_status dr_scene_reupload(dr_scene scene, int64_t *bytes) {
     if (!scene) { dr_set_error("dr_scene_reupload: null scene"); return DR_ERR_INVALID_ARG; }
     SceneImpl *s = static_cast<SceneImpl *>(scene);
     CK(cudaSetDevice(s->device));
-    for (HostUpload &u : s->uploads) CK(cudaMemcpy(u.dev, u.host.data(), u.host.size(), cudaMemcpyHostToDevice));
+    for (HostUpload &u : s->uploads) CK(cudaMemcpyAsync(u.dev, u.host, u.bytes, cudaMemcpyHostToDevice, 0));
+    CK(cudaStreamSynchronize(0));
     if (bytes) *bytes = (int64_t) s->uploadBytes;
     return DR_OK;
 }
@@ -568,7 +573,7 @@ extern "C" void dr_job_destroy(dr_job j) {
 static int auto_chains(long long totalMutations) {
     // enough lanes to keep every stage kernel's queue several waves deep on 148 SMs, but >= 32 mutations per chain
     long long n = totalMutations / 32;
-    n = std::max<long long>(4096, std::min<long long>(n, 1 << 20));
+    n = std::max<long long>(4096, std::min<long long>(n, 1 << 22));
     n = std::min<long long>(n, std::max<long long>(128, totalMutations));
     return (int) ((n + 127) / 128 * 128);
 }
@@ -582,7 +587,7 @@ static dr_status alloc_lanes(dr_job j, int n) {
     if ((st = job_alloc(j, &lm.core, (size_t) n)) || (st = job_alloc(j, &lm.vt, (size_t) n)) || (st = job_alloc(j, &lm.vs, (size_t) n)) ||
         (st = job_alloc(j, &lm.vtp, (size_t) n)) || (st = job_alloc(j, &lm.vsp, (size_t) n)) || (st = job_alloc(j, &lm.chain, (size_t) n)) ||
         (st = job_alloc(j, &lm.mis, (size_t) MIS_WORDS * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
-        (st = job_alloc(j, &lm.ray, (size_t) 2 * n)) || (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)))
+        (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)))
         return st;
     // groups of at least 64K lanes, at most 8 (DRMLT_GROUPS overrides)
     int G = std::max(1, std::min(8, n / 65536));
@@ -593,7 +598,7 @@ static dr_status alloc_lanes(dr_job j, int n) {
         dr_job_t::Group &gr = j->groups[g];
         gr.begin = (int) ((long long) n * g / G); gr.end = (int) ((long long) n * (g + 1) / G);
         gr.q.n = gr.end - gr.begin;
-        if ((st = job_alloc(j, &gr.q.items, (size_t) Q_COUNT * gr.q.n)) || (st = job_alloc(j, &gr.q.count, (size_t) Q_COUNT + 2)))   // + head counters of the two ray queues
+        if ((st = job_alloc(j, &gr.q.items, (size_t) Q_COUNT * gr.q.n)) || (st = job_alloc(j, &gr.q.rays, (size_t) 4 * 2 * gr.q.n)) || (st = job_alloc(j, &gr.q.count, (size_t) Q_COUNT + 2)))   // + head counters of the two ray queues
             return st;
         if (cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&gr.evJoin, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost((void **) &gr.countsHost, sizeof(uint32_t) * Q_COUNT) != cudaSuccess) {
             dr_set_error("group stream creation failed: %s", cudaGetErrorString(cudaGetLastError())); return DR_ERR_CUDA;
@@ -776,8 +781,9 @@ static dr_status setup_lanes(dr_job j, const JobParams &job) {
     return DR_OK;
 }
 
-// luminanceSamples sizing of DRMLT::render (drmlt.cpp:446-473), with the reference's CPU work-unit
-// count standing in for "workUnits" and a floor of 2 bootstrap samples per resident chain.
+// luminanceSamples sizing of DRMLT::render (drmlt.cpp:446-473), with the reference's CPU work-unit count standing in
+// for "workUnits", and a floor of one bootstrap sample per four resident chains (of all ranks) so that the seed pool
+// does not degenerate when hundreds of thousands of chains are resampled from it.
 static long long bootstrap_samples(const dr_job j) {
     const dr_config &c = j->cfg;
     const long long desired = c.technique == DR_TECH_PATH ? 200000 : 100000;
@@ -786,7 +792,7 @@ static long long bootstrap_samples(const dr_job j) {
     long long n = c.luminance_samples;
     const long long times = c.technique == DR_TECH_MMLT ? 50 : 10;
     n = std::max(n, workUnits * times);
-    n = std::max(n, 2ll * j->nChains * c.world_size);
+    n = std::max(n, (long long) j->nChains * c.world_size / 4);
     if (c.technique == DR_TECH_MMLT) n *= c.max_depth;
     return n;
 }
@@ -854,24 +860,6 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
     launch_resample(j->cdf, j->nBoot, c.seed, firstChain, n, j->bootFirst, c.max_depth, c.technique, j->seedIdx, j->chainId, j->depth, j->stream);
     CKL();
     ++j->launches;
-    if (c.technique == DR_TECH_MMLT) {
-        // bucket chains by MMLT depth so that neighbouring lanes walk paths of the same length
-        std::vector<unsigned long long> seedIdx(n), chainId(n);
-        std::vector<int> depth(n), perm(n);
-        CK(cudaMemcpyAsync(seedIdx.data(), j->seedIdx, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
-        CK(cudaMemcpyAsync(chainId.data(), j->chainId, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
-        CK(cudaMemcpyAsync(depth.data(), j->depth, n * sizeof(int), cudaMemcpyDeviceToHost, j->stream));
-        CK(cudaStreamSynchronize(j->stream));
-        std::iota(perm.begin(), perm.end(), 0);
-        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b2) { return depth[a] < depth[b2]; });
-        std::vector<unsigned long long> s2(n), c2(n);
-        std::vector<int> d2(n);
-        for (int i = 0; i < n; ++i) { s2[i] = seedIdx[perm[i]]; c2[i] = chainId[perm[i]]; d2[i] = depth[perm[i]]; }
-        CK(cudaMemcpyAsync(j->seedIdx, s2.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, j->stream));
-        CK(cudaMemcpyAsync(j->chainId, c2.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, j->stream));
-        CK(cudaMemcpyAsync(j->depth, d2.data(), n * sizeof(int), cudaMemcpyHostToDevice, j->stream));
-        CK(cudaStreamSynchronize(j->stream));
-    }
     // seed replay: the lanes evaluate their seed vector (PH_INIT); mutTarget = 0 parks them afterwards
     JobParams job;
     memset(&job, 0, sizeof(job));

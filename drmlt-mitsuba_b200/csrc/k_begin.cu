@@ -77,7 +77,7 @@ DR_D void fill_proposal(const Machine &M, int lane, Core &c, const MutCtx &mc, l
 
 // ------------------------------------------------------------------ path start
 // returns the queue the lane goes to (Q_RAYC, Q_CONNECT) or -1 when the path is already over (empty result)
-DR_D int path_start(const Machine &M, int lane, Core &c) {
+DR_D int path_start(const Machine &M, int lane, Core &c, RayF &ray) {
     const DevScene &sc = M.sc;
     UReader rd;
     c.pos0 = c.pos1 = c.pos2 = 0; c.nrays = 0;
@@ -106,10 +106,10 @@ DR_D int path_start(const Machine &M, int lane, Core &c) {
             c.pdfFwd = sc.cam.normalization / (dl.z * dl.z * dl.z);
             c.pdfBwd = 1.0;
             c.pstate = PS_SENSOR_HIT;
-            emit_ray(M, lane, c, vt.p, cam_xform_dir(sc.cam, dl), sc.epsilon, INFINITY);
+            emit_ray(M, lane, c, vt.p, cam_xform_dir(sc.cam, dl), sc.epsilon, INFINITY, ray);
             dest = Q_RAYC;
         } else {
-            dest = mmlt_emitter_launch(M, lane, c);
+            dest = mmlt_emitter_launch(M, lane, c, ray);
         }
     } else {                                                  // PathSampler EUnidirectional (pathsampler.cpp:529-567)
         const R2 u0 = rd.next2D(SMP_SENSOR);
@@ -124,7 +124,7 @@ DR_D int path_start(const Machine &M, int lane, Core &c) {
         c.j = 1; c.s = c.t = 0;
         c.pstate = PS_PT_HIT;
         rec_store(reinterpret_cast<PtExtra *>(M.lm.vs + lane), px);
-        emit_ray(M, lane, c, cam_pos(sc.cam), cam_xform_dir(sc.cam, dl), sc.cam.nearClip * invZ, sc.cam.farClip * invZ);
+        emit_ray(M, lane, c, cam_pos(sc.cam), cam_xform_dir(sc.cam, dl), sc.cam.nearClip * invZ, sc.cam.farClip * invZ, ray);
         dest = Q_RAYC;
     }
     reader_close(rd, c);
@@ -162,11 +162,12 @@ k_begin(const __grid_constant__ Machine M) {
             } else c.depth = job.depthIn ? (uint8_t) job.depthIn[item] : 0;
         }
         fill_proposal(M, lane, c, mc, item);
-        const int dest = path_start(M, lane, c);
+        RayF ray;
+        const int dest = path_start(M, lane, c, ray);
         if (dest != Q_RAYC) c.pstate = PS_EMPTY;                  // (a connection without any ray cannot occur for depth >= 2)
         rec_store(M.lm.core + lane, c);
         // a dead-on-arrival path (MMLT depth 1, no emitter) goes back to the chain kernel in the next round
-        q_push(M.q, dest == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : Q_CHAIN + (M.parity ^ 1), (uint32_t) lane);
+        q_push_ray(M.q, dest == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : Q_CHAIN + (M.parity ^ 1), (uint32_t) lane, ray);
     }
 }
 

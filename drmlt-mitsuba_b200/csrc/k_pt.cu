@@ -23,6 +23,7 @@ k_pt(const __grid_constant__ Machine M) {
         reader_open(M, c, lane, rd);
         Vtx v;
         int dest = Q_CHAIN + M.parity;
+        RayF ray;
         enum { GO_HIT, GO_SHADE, GO_BSDF, GO_DONE } go = c.pstate == PS_PT_NEE ? GO_BSDF : GO_HIT;
         if (c.pstate == PS_PT_NEE) {                         // the shadow ray of the direct-illumination sample arrived
             if (hit.tri < 0) px.Li += px.pending;
@@ -94,7 +95,7 @@ k_pt(const __grid_constant__ Machine M) {
                             px.pending = c.weight * value * bsdfVal * ((pdf * pdf) / (pdf * pdf + bp * bp));
                         }
                         c.pstate = PS_PT_NEE;
-                        emit_ray(M, lane, c, v.p, dd, sc.epsilon, dist * (1. - sc.shadowEpsilon));
+                        emit_ray(M, lane, c, v.p, dd, sc.epsilon, dist * (1. - sc.shadowEpsilon), ray);
                         dest = Q_RAYS + (M.parity ^ 1);
                         running = false;
                         break;
@@ -118,7 +119,7 @@ k_pt(const __grid_constant__ Machine M) {
                 px.eta *= bs.eta;
                 px.bsPdf = bs.pdf;
                 c.pstate = PS_PT_HIT;
-                emit_ray(M, lane, c, v.p, to_world(v, bs.wo), sc.epsilon, INFINITY);
+                emit_ray(M, lane, c, v.p, to_world(v, bs.wo), sc.epsilon, INFINITY, ray);
                 dest = Q_RAYC + (M.parity ^ 1);
                 running = false;
                 break;
@@ -132,7 +133,7 @@ k_pt(const __grid_constant__ Machine M) {
         reader_close(rd, c);
         rec_store(reinterpret_cast<PtExtra *>(M.lm.vs + lane), px);
         rec_store(M.lm.core + lane, c);
-        q_push(M.q, dest, (uint32_t) lane);
+        q_push_ray(M.q, dest, (uint32_t) lane, ray);
     }
 }
 

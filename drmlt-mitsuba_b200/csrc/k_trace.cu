@@ -15,6 +15,7 @@ k_trace(const __grid_constant__ Machine M) {
     const int qid = (SHADOW ? Q_RAYS : Q_RAYC) + M.parity;
     const uint32_t cnt = M.q.count[qid];
     const uint32_t *items = M.q.items + (size_t) qid * M.q.n;
+    const float4 *rays = M.q.rays + 2 * (size_t) qid * M.q.n;
     uint32_t *head = M.q.count + Q_COUNT + (SHADOW ? 1 : 0);
     if (blockIdx.x == 0 && threadIdx.x == 0 && cnt) atomicAdd(&M.counters[ST_RAYS], (unsigned long long) cnt);
     const bool pt = M.pc.technique != DR_TECH_MMLT;
@@ -35,9 +36,9 @@ k_trace(const __grid_constant__ Machine M) {
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (lane < 0) {
                     const uint32_t qi = base + __popc(idle & ((1u << self) - 1u));
-                    if (qi < cnt) {
+                    if (qi < cnt) {                          // three independent, coalesced loads: no dependent gather
+                        const float4 a = rays[2 * (size_t) qi], b = rays[2 * (size_t) qi + 1];
                         lane = (int) items[qi];
-                        const float4 a = M.lm.ray[2 * (size_t) lane], b = M.lm.ray[2 * (size_t) lane + 1];
                         tr.begin(stack, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, M.lm.rayd + 8 * (size_t) lane);
                     }
                 }

@@ -26,6 +26,7 @@ k_walk(const __grid_constant__ Machine M) {
         Hit hit;
         { const float4 h = M.lm.hit[lane]; hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.tri = __float_as_int(h.w); }
         int dest = Q_CHAIN + M.parity;                       // default: the path ends here (empty result)
+        RayF ray;
         do {
             Vtx v; PredRec vp;
             rec_load(v, vArr + lane);
@@ -85,17 +86,17 @@ k_walk(const __grid_constant__ Machine M) {
                 c.flags = ws.delta ? (c.flags | F_DELTA) : (c.flags & ~F_DELTA);
                 c.weight *= ws.weightFwd;
                 c.pdfFwd = ws.pdfFwd; c.pdfBwd = ws.pdfBwd;
-                emit_ray(M, lane, c, v.p, ws.wo, sc.epsilon, INFINITY);
+                emit_ray(M, lane, c, v.p, ws.wo, sc.epsilon, INFINITY, ray);
                 dest = Q_RAYC + (M.parity ^ 1);
                 break;
             }
             // last vertex of this subpath: its measure stays invalid => connectable iff not degenerate
             if (!v.degenerate) { c.connectable |= 1u << (emitterSide ? (int) c.s : k - (int) c.t); c.flags |= F_ANYCONN; }
-            if (!emitterSide) dest = mmlt_emitter_launch(M, lane, c) == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : Q_CONNECT;
+            if (!emitterSide) dest = mmlt_emitter_launch(M, lane, c, ray) == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : Q_CONNECT;
             else { c.pstate = PS_CONNECT; dest = Q_CONNECT; }
         } while (false);
         rec_store(M.lm.core + lane, c);
-        q_push(M.q, dest, (uint32_t) lane);
+        q_push_ray(M.q, dest, (uint32_t) lane, ray);
     }
 }
 
@@ -112,6 +113,7 @@ k_connect(const __grid_constant__ Machine M) {
         rec_load(c, M.lm.core + lane);
         double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
         int dest = Q_CHAIN + M.parity;
+        RayF ray;
         c.pstate = PS_EMPTY;
         do {
             if (!(c.flags & F_ANYCONN)) break;               // pathsampler.cpp:161-174
@@ -190,11 +192,11 @@ k_connect(const __grid_constant__ Machine M) {
             }
             // pathConnectAndCollapse (edge.cpp:572-606): vt and vs are always "on surface" here
             c.pstate = PS_CONNECT_SHADOW;
-            emit_ray(M, lane, c, vt.p, d, sc.epsilon, len * (1. - sc.shadowEpsilon));
+            emit_ray(M, lane, c, vt.p, d, sc.epsilon, len * (1. - sc.shadowEpsilon), ray);
             dest = Q_RAYS + (M.parity ^ 1);
         } while (false);
         rec_store(M.lm.core + lane, c);
-        q_push(M.q, dest, (uint32_t) lane);
+        q_push_ray(M.q, dest, (uint32_t) lane, ray);
     }
 }
 

@@ -99,7 +99,6 @@ struct LaneMem {
     ChainCore *chain;         // [n]
     double *mis;              // [n][48]: pdfImp[16], pdfRad[16], conv[16]
     double *ubuf;             // [n][UB_COUNT][nU] coordinate buffers X, Y, Z, R
-    float4 *ray;              // [n][2] (o, tmin), (d, tmax): the ray in flight, float32 for the traversal
     double *rayd;             // [n][8] o, d, tmin, tmax of the same ray un-rounded (deciding triangle tests)
     float4 *hit;              // [n] (t, u, v, leaf-order triangle or -1)
     int n, nU;
@@ -129,14 +128,17 @@ enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 4 */, Q_C
        Q_BEGIN = 12 /* + BEGIN_* class, 3 */, Q_COUNT = 15 };
 // classes of "start the next path" work: each runs one kind of proposal arithmetic on full warps
 enum { BEGIN_STAGE1 = 0, BEGIN_STAGE2 = 1, BEGIN_OTHER = 2 };
+struct RayF { float4 a, b; };                               // (o, tmin), (d, tmax): float32 cast of a ray, for the traversal
 struct Queues {
     uint32_t *items;          // [Q_COUNT][n]
-    uint32_t *count;          // [Q_COUNT]
+    uint32_t *count;          // [Q_COUNT] (+ 2 head counters of the ray queues)
+    float4 *rays;             // [4][n][2]: the float32 rays of the four ray queues (Q_RAYC x2, Q_RAYS x2), parallel to
+                              // items -- the traversal kernels read their input with coalesced, independent loads
     int n;
 };
 // Opportunistic warp-aggregated append: the threads of the warp that push to the same queue at the same
 // time share one atomic.
-DR_D void q_push(const Queues &q, int which, uint32_t lane) {
+DR_D uint32_t q_push(const Queues &q, int which, uint32_t lane) {
     const unsigned act = __activemask();
     const unsigned peers = __match_any_sync(act, which);
     const int leader = __ffs(peers) - 1;
@@ -144,7 +146,17 @@ DR_D void q_push(const Queues &q, int which, uint32_t lane) {
     uint32_t base = 0;
     if ((int) self == leader) base = atomicAdd(&q.count[which], (uint32_t) __popc(peers));
     base = __shfl_sync(peers, base, leader);
-    q.items[(size_t) which * q.n + base + __popc(peers & ((1u << self) - 1u))] = lane;
+    const uint32_t slot = base + __popc(peers & ((1u << self) - 1u));
+    q.items[(size_t) which * q.n + slot] = lane;
+    return slot;
+}
+// append a lane and, when the destination is a ray queue, its ray
+DR_D void q_push_ray(const Queues &q, int which, uint32_t lane, const RayF &ray) {
+    const uint32_t slot = q_push(q, which, lane);
+    if (which < Q_CHAIN) {
+        float4 *r = q.rays + 2 * ((size_t) which * q.n + slot);
+        r[0] = ray.a; r[1] = ray.b;
+    }
 }
 
 // ------------------------------------------------------------------ jobs
@@ -238,11 +250,11 @@ DR_D void reader_open(const Machine &M, const Core &c, int lane, UReader &rd) {
 }
 DR_D void reader_close(const UReader &rd, Core &c) { c.pos0 = (uint8_t) rd.pos[0]; c.pos1 = (uint8_t) rd.pos[1]; c.pos2 = (uint8_t) rd.pos[2]; }
 
-// queue the next ray of a lane; mint == epsilon gets the adaptive scaling of skdtree.cpp:126-129
-DR_D void emit_ray(const Machine &M, int lane, Core &c, R3 o, R3 d, Real tmin, Real tmax) {
+// the next ray of a lane (un-rounded copy -> lane record, float32 cast -> `ray`, queued by q_push_ray); mint == epsilon gets the adaptive scaling of skdtree.cpp:126-129
+DR_D void emit_ray(const Machine &M, int lane, Core &c, R3 o, R3 d, Real tmin, Real tmax, RayF &ray) {
     if (tmin == (Real) M.sc.epsilon) tmin *= fmax(fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z)), (Real) M.sc.epsilon);
-    M.lm.ray[2 * (size_t) lane] = make_float4((float) o.x, (float) o.y, (float) o.z, (float) tmin);
-    M.lm.ray[2 * (size_t) lane + 1] = make_float4((float) d.x, (float) d.y, (float) d.z, (float) tmax);
+    ray.a = make_float4((float) o.x, (float) o.y, (float) o.z, (float) tmin);
+    ray.b = make_float4((float) d.x, (float) d.y, (float) d.z, (float) tmax);
     double2 *rd = reinterpret_cast<double2 *>(M.lm.rayd + 8 * (size_t) lane);
     rd[0] = make_double2(o.x, o.y); rd[1] = make_double2(o.z, d.x); rd[2] = make_double2(d.y, d.z); rd[3] = make_double2(tmin, tmax);
     c.d = d;
@@ -317,7 +329,7 @@ DR_D bool mmlt_emitter_sample(const Machine &M, int lane, Core &c, UReader &rd, 
 }
 // Part 2 (when the sensor subpath is complete): switch the lane to its emitter subpath -- launch the emission ray
 // (s >= 2) or go straight to the connection.  Returns the queue the lane goes to (Q_RAYC or Q_CONNECT).
-DR_D int mmlt_emitter_launch(const Machine &M, int lane, Core &c) {
+DR_D int mmlt_emitter_launch(const Machine &M, int lane, Core &c, RayF &ray) {
     c.flags &= ~F_DELTA;
     c.connectable |= 1u;                          // area lights: supernode not degenerate, never discrete
     if (c.s >= 1) {
@@ -331,7 +343,7 @@ DR_D int mmlt_emitter_launch(const Machine &M, int lane, Core &c) {
             rec_load(e, M.lm.vsp + lane);
             c.pdfFwd = e.ng.x; c.pdfBwd = 1.0;
             c.pstate = PS_EMITTER_HIT;
-            emit_ray(M, lane, c, vs.p, e.p, M.sc.epsilon, INFINITY);
+            emit_ray(M, lane, c, vs.p, e.p, M.sc.epsilon, INFINITY, ray);
             return Q_RAYC;
         }
     }

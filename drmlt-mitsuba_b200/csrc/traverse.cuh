@@ -85,13 +85,13 @@ struct Traversal {
         stack = stack_;
         o = o_; d = d_; tmin = tmin_; tmax = tmax_; rd = rd_;
         hit.tri = -1; hit.t = hit.u = hit.v = 0.f;
-        bestT = rd[7]; bestExact = true;
+        bestT = 0.0; bestExact = true;                // no hit yet: the limit of the exact test is rd[7]
         // zero direction components: clamp so that 1/d stays finite (no 0 * inf = NaN in the slab test)
         inv = f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
                  1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
         oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
         sp = 0; cur = 0;
-        done = !(rd[7] > rd[6]);
+        done = !(tmax > tmin);
     }
     DR_D void pop() { if (sp == 0) done = true; else cur = stack[--sp]; }
     DR_D void step(const DevScene &sc) { if (cur >= 0) node_step(sc); else leaf_step(sc); }
@@ -145,7 +145,7 @@ struct Traversal {
                     if (!tri_verify(ldg4(bp), ldg4(bp + 1), ldg4(bp + 2), rd, rd[7], bestT, bu, bv)) bestT = (double) hit.t;
                     bestExact = true;
                 }
-                if (tri_verify(t0, t1, t2, rd, bestT, t, u, v)) {
+                if (tri_verify(t0, t1, t2, rd, hit.tri >= 0 ? bestT : rd[7], t, u, v)) {
                     hit.t = (float) t; hit.u = (float) u; hit.v = (float) v; hit.tri = first + i;
                     if (ANYHIT) { done = true; return; }
                     bestT = t; bestExact = true;
