@@ -314,7 +314,7 @@ def run_gpu(args):
             except Exception as ex:                                   # the baseline is reported, never required
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.scene, data), "chains_per_gpu": int(n_chains), "mutations_per_chain_per_step": M,
                            "l2": "flushed between timed steps (512 MiB device write)", "b": b, "scene_create_s": scene_create_s,
