@@ -163,6 +163,9 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
+    # libraries (NCCL's version banner, ...) may write to stdout; the contract is ONE JSON line there
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import __graft_entry__
@@ -287,6 +290,7 @@ def run_gpu(args):
     barrier()
     e0 = time.perf_counter()
     h2d = scene.reupload()
+    reupload_ms = (time.perf_counter() - e0) * 1e3
     img, est, eb = distributed.render(scene, e2e_params, dist if world > 1 else None, rank, world)
     barrier()
     e_wall = time.perf_counter() - e0
@@ -298,7 +302,8 @@ def run_gpu(args):
     W, H = data.film
     e2e = {"value": float(te.item()) / float(tw.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(W * H * 3 * 4), "seconds": float(tw.item()), "mutations": int(te.item()),
-           "rank0_phases_ms": {"bootstrap_and_seeding": est.bootstrap_ms, "chains": est.chains_ms},
+           "rank0_phases_ms": dict(getattr(distributed.render, "last_timing", {}), scene_reupload_ms=reupload_ms,
+                                   device_bootstrap_and_seeding_ms=est.bootstrap_ms, device_chains_ms=est.chains_ms),
            "what": "dr_scene_reupload + bootstrap + b all-reduce + chains + film reduce + develop + image D2H; sampleCount=%d" % (args.e2e_spp * world)}
 
     line = None
@@ -324,7 +329,7 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     if line:
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     return 0
 
 

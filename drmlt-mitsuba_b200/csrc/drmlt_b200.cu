@@ -505,7 +505,7 @@ static DevScene scene_for(const dr_scene scene, const dr_config &c) {
 }
 
 static dr_status check_technique(const dr_config &c) {
-    if (c.technique == DR_TECH_BDPT) { dr_set_error("technique=bdpt is not implemented on the GPU path yet"); return DR_ERR_UNSUPPORTED; }
+    if (c.technique == DR_TECH_BDPT && c.max_depth + 2 > BD_MAXV) { dr_set_error("technique=bdpt: maxDepth must be <= %d", BD_MAXV - 2); return DR_ERR_UNSUPPORTED; }
     return DR_OK;
 }
 
@@ -588,6 +588,10 @@ static dr_status alloc_lanes(dr_job j, int n) {
         (st = job_alloc(j, &lm.vtp, (size_t) n)) || (st = job_alloc(j, &lm.vsp, (size_t) n)) || (st = job_alloc(j, &lm.chain, (size_t) n)) ||
         (st = job_alloc(j, &lm.mis, (size_t) MIS_WORDS * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
         (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)))
+        return st;
+    if (j->cfg.technique == DR_TECH_BDPT &&      // both subpaths and the splat lists are kept per lane
+        ((st = job_alloc(j, &lm.bv, (size_t) 2 * BD_MAXV * n)) || (st = job_alloc(j, &lm.bx, (size_t) 2 * BD_MAXV * n)) ||
+         (st = job_alloc(j, &lm.bacc, (size_t) n)) || (st = job_alloc(j, &lm.bsplat, (size_t) 4 * BD_MAXS * 2 * n))))
         return st;
     // groups of at least 64K lanes, at most 8 (DRMLT_GROUPS overrides)
     int G = std::max(1, std::min(8, n / 65536));
@@ -674,7 +678,7 @@ static void launch_round(dr_job j, Machine &M, int g, cudaStream_t st, bool mmlt
     mark();
     launch_trace(M, lc);
     mark();
-    if (mmlt) launch_walk(M, lc, typeMask); else launch_pt(M, lc);
+    if (mmlt) launch_walk(M, lc, typeMask); else if (j->cfg.technique == DR_TECH_BDPT) launch_bdpt(M, lc); else launch_pt(M, lc);
     mark();
     launch_chain(M, lc);
     mark();

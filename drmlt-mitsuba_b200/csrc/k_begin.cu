@@ -7,7 +7,7 @@
 // Behavioural parity: DRMLTSampler::fillSpace / OrbitalDRMLTSampler (src/integrators/drmlt/drmlt_sampler.cpp:313-394),
 // PSSMLTSampler::primarySample (src/integrators/pssmlt/pssmlt_sampler.cpp:124-166), the first steps of
 // PathSampler::sampleSplats (src/libbidir/pathsampler.cpp:84-146, 529-567).
-#include "machine.cuh"
+#include "bdpt.cuh"
 
 namespace {
 
@@ -111,6 +111,8 @@ DR_D int path_start(const Machine &M, int lane, Core &c, RayF &ray) {
         } else {
             dest = mmlt_emitter_launch(M, lane, c, ray);
         }
+    } else if (M.pc.technique == DR_TECH_BDPT) {              // pathsampler.cpp:321-341
+        dest = bdpt_path_start(M, lane, c, rd, ray);
     } else {                                                  // PathSampler EUnidirectional (pathsampler.cpp:529-567)
         const R2 u0 = rd.next2D(SMP_SENSOR);
         const R2 samplePos = r2(u0.x * sc.cam.resX, u0.y * sc.cam.resY);

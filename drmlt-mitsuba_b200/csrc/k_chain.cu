@@ -15,12 +15,33 @@ DR_D bool invalid_strict(Real x) { return isnan(x) || isinf(x) || x <= 0.; }   /
 DR_D bool invalid_loose(Real x) { return isnan(x) || isinf(x) || x < 0.; }     // drmlt_proc.cpp:181
 DR_D Real metropolis_clamp(Real x) { return x < 1.0 ? x : 1.0; }               // std::min(1, x): NaN -> 1
 
-DR_D void result_clear(PathResult &r) { r.lum = 0.; r.n = 0; r.val = r3(0.); r.pos = r2(0., 0.); r.mis = 0.; r.s = r.t = -1; }
+DR_D void result_clear(PathResult &r) { r.lum = 0.; r.n = 0; r.nl = 0; r.val = r3(0.); r.pos = r2(0., 0.); r.mis = 0.; r.s = r.t = -1; }
 
 DR_D float3 normalized_value(const PathResult &r) {          // SplatList::normalize (pathsampler.cpp:1001-1028)
     const Real inv = r.lum > 0. ? 1.0 / r.lum : 1.0;
     return to_f3(r.val * inv);
 }
+
+// ---- light-image splat lists of technique=bdpt (list 0 = x, 1 = y, 2 = z, 3 = the path that just ended)
+DR_D float4 *splat_list(const Machine &M, int lane, int list) { return M.lm.bsplat + ((size_t) lane * 4 + list) * BD_MAXS * 2; }
+// copy list `src` to `dst`, scaling the values (SplatList::normalize when src = 3)
+DR_D void splat_list_copy(const Machine &M, int lane, int dst, int src, int n, float scale) {
+    const float4 *s = splat_list(M, lane, src);
+    float4 *d = splat_list(M, lane, dst);
+    for (int i = 0; i < n; ++i) {
+        const float4 v = s[2 * i + 1];
+        d[2 * i] = s[2 * i];
+        d[2 * i + 1] = make_float4(v.x * scale, v.y * scale, v.z * scale, 0.f);
+    }
+}
+DR_D void splat_list_put(const Machine &M, int lane, int list, int n, float weight) {
+    const float4 *s = splat_list(M, lane, list);
+    for (int i = 0; i < n; ++i) {
+        const float4 p = s[2 * i], v = s[2 * i + 1];
+        film_put(M.film, M.fp, make_float2(p.x, p.y), make_float3(v.x * weight, v.y * weight, v.z * weight));
+    }
+}
+DR_D float inv_lum(const PathResult &r) { return r.lum > 0. ? (float) (1.0 / r.lum) : 1.f; }
 
 // MiraDRMLTSampler::getTransitionRatio over the three samplers (drmlt_sampler.cpp:400-414).
 // dimStage holds the largest INDEX touched, so the last used coordinate is skipped.
@@ -88,6 +109,12 @@ DR_D void path_result(const Machine &M, int lane, Core &c, PathResult &out) {
         const int nStrats = M.pc.lightImage ? depth + 1 : depth;
         const R3 value = c.weight * (w * (Real) nStrats);
         out.mis = w; out.n = 1; out.pos = r2(c.spos.x, c.spos.y); out.val = value; out.lum = luminance(value);
+    } else if (c.pstate == PS_BD_DONE) {                      // splat 0 + light-image splats (the lane's in-flight list)
+        BdAcc acc;
+        rec_load(acc, M.lm.bacc + lane);
+        out.n = acc.has0; out.nl = acc.nl;
+        out.s = acc.ns; out.t = acc.nt;                       // diagnostic: index of the last vertex of each subpath
+        out.pos = r2(acc.pos0.x, acc.pos0.y); out.val = acc.val0; out.lum = acc.lum;
     } else if (c.pstate == PS_PT_DONE) {
         PtExtra px;
         rec_load(px, reinterpret_cast<const PtExtra *>(M.lm.vs + lane));
@@ -141,6 +168,15 @@ k_chain(const __grid_constant__ Machine M) {
                     o.luminance = (float) r.lum; o.n_splats = r.n; o.s = r.s; o.t = r.t; o.mis_weight = (float) r.mis;
                     o.pos[0][0] = (float) r.pos.x; o.pos[0][1] = (float) r.pos.y;
                     o.value[0][0] = (float) r.val.x; o.value[0][1] = (float) r.val.y; o.value[0][2] = (float) r.val.z;
+                    if (r.nl) {                               // bdpt: light-image splats follow splat 0 (if it exists)
+                        const float4 *sl = splat_list(M, lane, 3);
+                        for (int i = 0; i < r.nl && r.n + i < DR_MAX_SPLATS; ++i) {
+                            const float4 sp = sl[2 * i], sv = sl[2 * i + 1];
+                            o.pos[r.n + i][0] = sp.x; o.pos[r.n + i][1] = sp.y;
+                            o.value[r.n + i][0] = sv.x; o.value[r.n + i][1] = sv.y; o.value[r.n + i][2] = sv.z;
+                        }
+                        o.n_splats = r.n + r.nl;
+                    }
                     o.n_rays = c.nrays;
                     job.out[item] = o;
                     ++c.mut;
@@ -158,6 +194,8 @@ k_chain(const __grid_constant__ Machine M) {
                     if (c.phase == PH_INIT) {
                         // seed replay (drmlt_proc.cpp:467-512): the bootstrap vector becomes the current state
                         cc.Lx = r.lum; cc.posx = rpos; cc.valx = normalized_value(r);
+                        cc.xl = (uint8_t) r.nl;
+                        if (r.nl) splat_list_copy(M, lane, 0, 3, r.nl, inv_lum(r));
                         cc.cumW = 0.; c.tx = (int8_t) r.t;
                         c.phase = PH_STAGE1; c.large = 2u;
                         c.pstate = c.mut < job.mutTarget ? PS_START : PS_IDLE;
@@ -191,20 +229,26 @@ k_chain(const __grid_constant__ Machine M) {
                         if (accept) {
                             const float3 v = cc.valx * (float) cc.cumW;
                             if (film && !is_zero(v)) film_put(film, fp, cc.posx, v);
+                            if (film && cc.xl) splat_list_put(M, lane, 0, cc.xl, (float) cc.cumW);
                             cc.cumW = proposedWeight;
                             commit_state(M, mc, ub, dims, UB_Y, true, r.s, r.t, false);
                             cc.Lx = yL; cc.posx = rpos; cc.valx = yval; c.tx = (int8_t) r.t;
+                            cc.xl = (uint8_t) r.nl;
+                            if (r.nl) splat_list_copy(M, lane, 0, 3, r.nl, inv_lum(r));
                             ++st[ST_ACC_A];
                             if (largeStep) ++st[ST_LARGE_A]; else ++st[ST_BOLD_A];
                         } else {
                             const float3 v = yval * (float) proposedWeight;
                             if (film && r.n && !is_zero(v)) film_put(film, fp, rpos, v);
+                            if (film && r.nl && proposedWeight > 0.) splat_list_put(M, lane, 3, r.nl, (float) proposedWeight * inv_lum(r));
                         }
                         mutationDone = true;
                     } else if (c.phase == PH_STAGE1) {
                         // ---------------- DRMLT first stage (drmlt_proc.cpp:539-558; mixture :284-299)
                         ++st[ST_MUT];
                         cc.yL = r.lum; cc.ypos = rpos; cc.yval = normalized_value(r); cc.yn = (uint8_t) r.n; cc.yt = (int8_t) r.t; cc.ys = (int8_t) r.s;
+                        cc.yl = (uint8_t) r.nl; cc.zl = 0;
+                        if (r.nl) splat_list_copy(M, lane, 1, 3, r.nl, inv_lum(r));
                         cc.posY[0] = c.pos0; cc.posY[1] = c.pos1; cc.posY[2] = c.pos2;
                         cc.a1 = 0.; cc.acc1 = 0; cc.zL = 0.; cc.zn = 0;
                         bool doSecond;
@@ -225,6 +269,8 @@ k_chain(const __grid_constant__ Machine M) {
                         else mutationDone = true;
                     } else if (c.phase == PH_STAGE2) {
                         cc.zL = r.lum; cc.zpos = rpos; cc.zval = normalized_value(r); cc.zn = (uint8_t) r.n; cc.zt = (int8_t) r.t; cc.zs = (int8_t) r.s;
+                        cc.zl = (uint8_t) r.nl;
+                        if (r.nl) splat_list_copy(M, lane, 2, 3, r.nl, inv_lum(r));
                         mutationDone = true;
                         if (cp.useMixture) {   // drmlt_proc.cpp:317-324: plain MH on the replaced proposal
                             cc.a1 = 0.; cc.acc1 = 0;
@@ -277,9 +323,9 @@ k_chain(const __grid_constant__ Machine M) {
                             Real wy, wz, wx;
                             if (cp.useMixture) { wy = did2 ? 0. : a1; wz = did2 ? a2 : 0.; wx = 1.0 - (did2 ? a2 : a1); }
                             else { wy = a1; wz = (1.0 - a1) * a2; wx = 1.0 - wy - wz; }
-                            if (wx > 0.) film_put(film, fp, cc.posx, cc.valx * (float) wx);
-                            if (wy > 0. && cc.yn) film_put(film, fp, cc.ypos, cc.yval * (float) wy);
-                            if (wz > 0. && cc.zn) film_put(film, fp, cc.zpos, cc.zval * (float) wz);
+                            if (wx > 0.) { film_put(film, fp, cc.posx, cc.valx * (float) wx); if (cc.xl) splat_list_put(M, lane, 0, cc.xl, (float) wx); }
+                            if (wy > 0.) { if (cc.yn) film_put(film, fp, cc.ypos, cc.yval * (float) wy); if (cc.yl) splat_list_put(M, lane, 1, cc.yl, (float) wy); }
+                            if (wz > 0.) { if (cc.zn) film_put(film, fp, cc.zpos, cc.zval * (float) wz); if (cc.zl) splat_list_put(M, lane, 2, cc.zl, (float) wz); }
                         }
                         // the stage-2 kernels of the commit see the stage-2 context
                         MutCtx mc2 = mc;
@@ -294,10 +340,10 @@ k_chain(const __grid_constant__ Machine M) {
                                 if (!did2) { ++st[ST_FIRST_A]; if (largeStep) ++st[ST_LARGE_A]; else ++st[ST_BOLD_A]; } else ++st[ST_SECOND_A];
                                 if (did2) {
                                     commit_state(M, mc2, ub, dims, UB_Z, false, cc.zs, cc.zt, true);
-                                    cc.Lx = cc.zL; cc.posx = cc.zpos; cc.valx = cc.zval; c.tx = cc.zt;
+                                    cc.Lx = cc.zL; cc.posx = cc.zpos; cc.valx = cc.zval; c.tx = cc.zt; cc.xl = cc.zl; if (cc.zl) splat_list_copy(M, lane, 0, 2, cc.zl, 1.f);
                                 } else {
                                     commit_state(M, mc, ub, dims, UB_Y, true, cc.ys, cc.yt, true);
-                                    cc.Lx = cc.yL; cc.posx = cc.ypos; cc.valx = cc.yval; c.tx = cc.yt;
+                                    cc.Lx = cc.yL; cc.posx = cc.ypos; cc.valx = cc.yval; c.tx = cc.yt; cc.xl = cc.yl; if (cc.yl) splat_list_copy(M, lane, 0, 1, cc.yl, 1.f);
                                 }
                             }
                         } else if (acc1 || acc2) {
@@ -306,10 +352,10 @@ k_chain(const __grid_constant__ Machine M) {
                                 film_put(film, fp, cc.posx, acc1 ? make_float3(1.f, 0.f, 0.f) : make_float3(0.f, 1.f, 0.f));
                             if (acc1) {
                                 commit_state(M, mc, ub, dims, UB_Y, true, cc.ys, cc.yt, true);
-                                cc.Lx = cc.yL; cc.posx = cc.ypos; cc.valx = cc.yval; c.tx = cc.yt;
+                                cc.Lx = cc.yL; cc.posx = cc.ypos; cc.valx = cc.yval; c.tx = cc.yt; cc.xl = cc.yl; if (cc.yl) splat_list_copy(M, lane, 0, 1, cc.yl, 1.f);
                             } else {
                                 commit_state(M, mc2, ub, dims, UB_Z, false, cc.zs, cc.zt, true);
-                                cc.Lx = cc.zL; cc.posx = cc.zpos; cc.valx = cc.zval; c.tx = cc.zt;
+                                cc.Lx = cc.zL; cc.posx = cc.zpos; cc.valx = cc.zval; c.tx = cc.zt; cc.xl = cc.zl; if (cc.zl) splat_list_copy(M, lane, 0, 2, cc.zl, 1.f);
                             }
                             ++st[ST_ACC_B]; ++st[ST_ACC_A];
                             if (acc1) {
@@ -395,6 +441,7 @@ __global__ void k_flush_pssmlt(const __grid_constant__ Machine M) {
     rec_load(cc, M.lm.chain + lane);
     const float3 v = cc.valx * (float) cc.cumW;
     if (!is_zero(v)) film_put(M.film, M.fp, cc.posx, v);
+    if (cc.xl && cc.cumW > 0.) splat_list_put(M, lane, 0, cc.xl, (float) cc.cumW);
     cc.cumW = 0.;
     rec_store(M.lm.chain + lane, cc);
 }

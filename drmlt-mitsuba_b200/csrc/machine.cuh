@@ -53,7 +53,7 @@
 // ------------------------------------------------------------------ lane records (AoS: one record per lane per array,
 // every record a multiple of 16 bytes, so a lane picked from a queue is fetched with a few 128-bit loads)
 enum { PS_IDLE = 0, PS_START, PS_SENSOR_HIT, PS_EMITTER_HIT, PS_CONNECT, PS_CONNECT_SHADOW, PS_FINISH, PS_EMPTY,
-       PS_PT_HIT, PS_PT_NEE, PS_PT_DONE };
+       PS_PT_HIT, PS_PT_NEE, PS_PT_DONE, PS_BD_EHIT, PS_BD_SHIT, PS_BD_SHADOW, PS_BD_DONE };
 enum { PH_STAGE1 = 0, PH_STAGE2 = 1, PH_REVERSE = 2, PH_INIT = 3 };
 enum { F_DELTA = 1u, F_ANYCONN = 2u, F_SPOS_FAIL = 4u, F_PT_FIRST = 8u, F_PT_EMITTED = 16u, F_PT_DIRECT = 32u, F_PT_NONSPEC = 64u };
 
@@ -82,12 +82,36 @@ struct alignas(16) ChainCore {        // 128 bytes
     Real yL, zL;
     float2 posx, ypos, zpos;
     float3 valx, yval, zval;
-    uint8_t acc1, yn, zn, pad0;
+    uint8_t acc1, yn, zn, xl;         // yn / zn: splat 0 of y / z exists | xl, yl, zl: light-image splats of x / y / z (bdpt)
     int8_t yt, zt, ys, zs;
-    uint8_t posY[3], pad1;            // reader positions at the end of the stage-1 path (m_dimStage1, drmlt_sampler.cpp:237-238)
-    uint32_t pad2[4];
+    uint8_t posY[3], yl;              // reader positions at the end of the stage-1 path (m_dimStage1, drmlt_sampler.cpp:237-238)
+    uint8_t zl, pad0[3];
+    uint32_t pad2[3];
 };
 static_assert(sizeof(ChainCore) == 128 && sizeof(Vtx) == 128 && sizeof(PtExtra) == sizeof(Vtx) && sizeof(PredRec) == 64, "lane layout");
+
+// ---- technique=bdpt: both subpaths are kept (every vertex can be a connection end point)
+#define BD_MAXV (DR_MAXK)             // vertices per subpath, supernode = index 0 (maxDepth + 2 <= BD_MAXV)
+#define BD_MAXS DR_MAX_SPLATS         // splats of one path: splat 0 + light-image splats
+enum { BD_E = 0, BD_S = 1 };          // emitter / sensor subpath
+struct alignas(16) BExtra {           // 64 bytes per subpath vertex v
+    R3 prefix;                        // product of the sampling weights (and Russian-roulette weights) of vertices 0 .. v-1
+    Real fwd;                         // area density of v when generated from v-1 (pdf[mode] of v-1)
+    Real bwd;                         // area density of v when generated from v+1 (pdf[1-mode] of v+1)
+    Real conv;                        // len^2 / |cos cos| of edge (v, v+1), geometric normals (path.cpp:875-899)
+    uint32_t discrete, pad[3];        // v sampled a delta direction (measure == EDiscrete)
+};
+struct alignas(16) BdAcc {            // 128 bytes: the splat list being built (aliases nothing; own array)
+    R3 val0;                          // splat 0: accumulated value of all t >= 2 strategies
+    Real lum;                         // SplatList::luminance
+    float2 pos0;
+    int has0, nl;                     // splat 0 exists (sensor subpath has >= 2 vertices) | light-image splats so far
+    int ns, nt;                       // last vertex index of the emitter / sensor subpath
+    int pad[2];
+    Real pdfs[4];                     // the four densities next to the connection in flight (path.cpp:835-859)
+    Real pad2[4];
+};
+static_assert(sizeof(BExtra) == 64 && sizeof(BdAcc) == 128, "bdpt records");
 
 enum { MIS_IMP = 0, MIS_RAD = 16, MIS_CONV = 32, MIS_WORDS = 48 };
 static_assert(DR_MAXK + 1 <= 16, "MIS arrays");
@@ -100,6 +124,11 @@ struct LaneMem {
     double *mis;              // [n][48]: pdfImp[16], pdfRad[16], conv[16]
     double *ubuf;             // [n][UB_COUNT][nU] coordinate buffers X, Y, Z, R
     double *rayd;             // [n][8] o, d, tmin, tmax of the same ray un-rounded (deciding triangle tests)
+    // technique=bdpt only (else null)
+    Vtx *bv;                  // [n][2][BD_MAXV] subpath vertices
+    BExtra *bx;               // [n][2][BD_MAXV]
+    BdAcc *bacc;              // [n]
+    float4 *bsplat;           // [n][4][BD_MAXS][2]: light-image splats (pos.xy | rgb) of the lists x, y, z and of the path in flight
     float4 *hit;              // [n] (t, u, v, leaf-order triangle or -1)
     int n, nU;
 };
@@ -357,6 +386,7 @@ void trace_init();                                                        // k_t
 void launch_trace(const Machine &M, const LaunchCfg &lc);                 // k_trace.cu: closest + shadow queues
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask);   // k_walk.cu: walk queues of the BSDF types present, then connect
 void launch_pt(const Machine &M, const LaunchCfg &lc);                    // k_pt.cu
+void launch_bdpt(const Machine &M, const LaunchCfg &lc);                  // k_bdpt.cu
 void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu, then the three k_begin classes (k_begin.cu)
 void launch_begin(const Machine &M, const LaunchCfg &lc);                 // k_begin.cu
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId,

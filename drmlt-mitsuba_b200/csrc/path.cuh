@@ -23,7 +23,8 @@ struct PathCfg {
 
 struct PathResult {           // single-splat techniques (path, mmlt)
     Real lum;                // SplatList::luminance, un-normalised
-    int n;                    // number of splats (0 or 1)
+    int n;                    // splat 0 exists (0 or 1)
+    int nl;                   // bdpt: light-image splats in the lane's in-flight list
     R2 pos;
     R3 val;
     int s, t;

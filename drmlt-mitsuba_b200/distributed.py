@@ -50,21 +50,40 @@ def render(scene, params, dist=None, rank=0, world_size=1, mutations_per_chain=N
     from . import abi
     from .integrator import DeviceFilm, Job, make_config
 
+    import time
+    t0 = time.perf_counter()
+    timing = {}
+
+    def lap(name):
+        nonlocal t0
+        t1 = time.perf_counter()
+        timing[name] = timing.get(name, 0.0) + (t1 - t0) * 1e3
+        t0 = t1
+
     cfg = make_config(rank=rank, worldSize=world_size, **params)
     job = Job(scene, cfg)
+    lap("job_create_ms")
     s, c = job.bootstrap()
+    lap("bootstrap_ms")
     dev = "cuda:%d" % scene.device
     b = all_reduce_normalization(s, c, cfg.technique == abi.DR_TECH_MMLT, cfg.max_depth, dist, dev)
+    lap("allreduce_b_ms")
     job.seed_chains(b)
+    lap("seed_chains_ms")
     per = mutations_per_chain if mutations_per_chain is not None else max(1, job.total_mutations // job.num_chains)
     job.run(per)
+    lap("chains_ms")
     if world_size > 1:
         film = torch.as_tensor(DeviceFilm(job), device=dev)
         reduce_film(film, dist, 0)
         torch.cuda.synchronize()
+    lap("film_reduce_ms")
     img = job.develop() if rank == 0 else None
+    lap("develop_ms")
     st = job.stats()
     job.close()
+    lap("job_destroy_ms")
+    render.last_timing = timing
     return img, st, b
 
 

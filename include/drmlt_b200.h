@@ -231,7 +231,7 @@ dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n, int shado
 typedef struct dr_path_result {
     float   luminance;          /* SplatList::luminance (un-normalised) */
     int32_t n_splats;
-    int32_t s, t;               /* MMLT strategy (pathsampler.cpp:104-129), else -1 */
+    int32_t s, t;               /* MMLT strategy (pathsampler.cpp:104-129) | BDPT: last vertex index of the emitter / sensor subpath | else -1 */
     float   mis_weight;         /* MMLT: Path::miWeight of the (s,t) strategy; else 0 */
     float   pos[DR_MAX_SPLATS][2];
     float   value[DR_MAX_SPLATS][3];   /* un-normalised RGB contributions */

@@ -121,6 +121,8 @@ struct PathSampler {
         sensorSubpath.initialize(ERadiance);
         randomWalk(ctx, emitterSubpath, emitterSampler, emitterDepth, cfg.rrDepth, EImportance);
         randomWalk(ctx, sensorSubpath, sensorSampler, sensorDepth, cfg.rrDepth, ERadiance);
+        list.s = (int) emitterSubpath.vertexCount() - 1;   // diagnostic: index of the last vertex of each subpath
+        list.t = (int) sensorSubpath.vertexCount() - 1;
 
         std::vector<RGB> importanceWeights(emitterSubpath.vertexCount()), radianceWeights(sensorSubpath.vertexCount());
         importanceWeights[0] = radianceWeights[0] = RGB(1.0);

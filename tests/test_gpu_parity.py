@@ -123,6 +123,10 @@ CASES = [
     ("caustic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1, fixEmitterPath=True)),
     ("door", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
     ("door", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1)),
+    # C3: bidirectional path tracing with MIS (directSampling=false: SURVEY Appendix C.1)
+    ("cornell", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
+    ("glossy", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=8, directSamples=-1, directSampling=False)),
+    ("caustic", dict(integrator="pssmlt", technique="bdpt", maxDepth=8, directSamples=-1, directSampling=False, lightImage=False)),
 ]
 
 
@@ -191,6 +195,20 @@ def test_path_contribution_replayed_u(case):
     off = 20 + 8 * abi.DR_MAX_SPLATS
     vg, vc = g[:, off:off + 12].copy().view("<f4"), c[:, off:off + 12].copy().view("<f4")
     assert (np.abs(vg[both] - vc[both]) <= 1e-4 * np.abs(vc[both]) + 1e-7 * np.abs(vc[both]).max(axis=1, keepdims=True)).all(axis=1).mean() >= 0.999
+    if cfg.technique == abi.DR_TECH_BDPT:
+        # the whole splat list: same number of splats (splat 0 + light-image splats), same pixels, same values
+        ng_, nc_ = g[:, 4:8].copy().view("<i4")[:, 0], c[:, 4:8].copy().view("<i4")[:, 0]
+        assert (ng_[both] == nc_[both]).mean() >= 0.999
+        same = both & (ng_ == nc_)
+        K = abi.DR_MAX_SPLATS
+        PG, PC = g[:, 20:20 + 8 * K].copy().view("<f4").reshape(n, K, 2), c[:, 20:20 + 8 * K].copy().view("<f4").reshape(n, K, 2)
+        VG, VC = g[:, off:off + 12 * K].copy().view("<f4").reshape(n, K, 3), c[:, off:off + 12 * K].copy().view("<f4").reshape(n, K, 3)
+        okp = (np.abs(PG[same] - PC[same]).max(axis=(1, 2)) < 2e-2)
+        scale = np.abs(VC[same]).max(axis=(1, 2), keepdims=True)
+        okv = (np.abs(VG[same] - VC[same]) <= 1e-4 * np.abs(VC[same]) + 1e-6 * scale).all(axis=(1, 2))
+        assert okp.mean() >= 0.999 and okv.mean() >= 0.999, (okp.mean(), okv.mean())
+        if cfg.light_image:
+            assert (nc_[both] > 1).any()                 # light-image splats do occur
     # ray counts: identical control flow on contributing paths; a path that dies during the sensor walk
     # skips its emitter walk on the GPU (the reference walks both before testing, pathsampler.cpp:139-159)
     rg, rc = g[:, -4:].copy().view("<i4")[:, 0], c[:, -4:].copy().view("<i4")[:, 0]
@@ -228,6 +246,9 @@ CHAIN_CASES = [
     ("caustic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1, fixEmitterPath=True)),
     ("glossy", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
     ("door", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("glossy", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
+    ("cornell", dict(integrator="pssmlt", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
+    ("cornell", dict(integrator="drmlt", type="mira", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False, timidAfterLarge=True)),
 ]
 
 
@@ -291,7 +312,7 @@ def test_chain_decisions_under_identical_uniforms(case):
     assert agree > 0.97
 
 
-@pytest.mark.parametrize("case", [CHAIN_CASES[0], CHAIN_CASES[3], CHAIN_CASES[9], CHAIN_CASES[10]], ids=_chain_id)
+@pytest.mark.parametrize("case", [CHAIN_CASES[0], CHAIN_CASES[3], CHAIN_CASES[9], CHAIN_CASES[10], CHAIN_CASES[13], CHAIN_CASES[14]], ids=_chain_id)
 def test_film_of_recorded_chains(case):
     """Splatting (ImageBlock::put) of the same chains: the accumulated films agree."""
     name, params = case
@@ -331,7 +352,7 @@ def test_acceptance_map_mode():
 
 
 # ------------------------------------------------------------------ (a) bootstrap, whole jobs, statistics
-@pytest.mark.parametrize("case", [CHAIN_CASES[0], CHAIN_CASES[3], CHAIN_CASES[9], CHAIN_CASES[10]], ids=_chain_id)
+@pytest.mark.parametrize("case", [CHAIN_CASES[0], CHAIN_CASES[3], CHAIN_CASES[9], CHAIN_CASES[10], CHAIN_CASES[13]], ids=_chain_id)
 def test_job_b_and_acceptance_rates(case):
     """dr_job_* against the oracle's whole-render port on the same keyed streams: b within 0.5 %,
     per-stage acceptance rates within 1 % absolute."""
