@@ -37,8 +37,8 @@ k_trace(const __grid_constant__ Machine M) {
                 if (lane < 0) {
                     const uint32_t qi = base + __popc(idle & ((1u << self) - 1u));
                     if (qi < cnt) {                          // three independent, coalesced loads: no dependent gather
-                        const float4 a = rays[2 * (size_t) qi], b = rays[2 * (size_t) qi + 1];
-                        lane = (int) items[qi];
+                        const float4 a = __ldcs(rays + 2 * (size_t) qi), b = __ldcs(rays + 2 * (size_t) qi + 1);
+                        lane = (int) __ldcs(items + qi);
                         tr.begin(stack, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, M.lm.rayd + 8 * (size_t) lane);
                     }
                 }
@@ -60,7 +60,7 @@ k_trace(const __grid_constant__ Machine M) {
             if (lane >= 0 && !tr.done && tr.cur < 0) tr.leaf_step(M.sc);
             if (lane >= 0 && tr.done) {
                 const bool found = tr.hit.tri >= 0;
-                M.lm.hit[lane] = make_float4(tr.hit.t, tr.hit.u, tr.hit.v, __int_as_float(found ? tr.hit.tri : -1));
+                __stcs(M.lm.hit + lane, make_float4(tr.hit.t, tr.hit.u, tr.hit.v, __int_as_float(found ? tr.hit.tri : -1)));
                 int dest;
                 if (pt) dest = Q_PT;
                 else if (SHADOW || !found) dest = Q_CHAIN + M.parity;

@@ -34,6 +34,13 @@
 
 // Resident CTAs (of 128 threads) per SM that each stage kernel is compiled for.  Every stage is bound by the latency of
 // dependent gathers (ncu: long-scoreboard stalls dominate), so registers are traded for resident warps.
+#ifdef DR_NO_STREAMING
+#define DR_REC_LD(p) (*(p))
+#define DR_REC_ST(p, v) (*(p) = (v))
+#else
+#define DR_REC_LD(p) __ldcs(p)
+#define DR_REC_ST(p, v) __stcs(p, v)
+#endif
 #ifndef TRACE_MINB
 #define TRACE_MINB 8
 #endif
@@ -133,20 +140,22 @@ struct LaneMem {
     int n, nU;
 };
 
-// whole-record copies through 128-bit accesses
+// whole-record copies through 128-bit accesses.  Lane records are touched once per round and are far larger than L2
+// in total, so they use the streaming (evict-first) cache operators: the BVH and triangle lines that every ray shares
+// are what should stay resident in L2.
 template <class T> DR_D void rec_load(T &dst, const T *src) {
     static_assert(sizeof(T) % 16 == 0, "record size");
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
     uint4 *d = reinterpret_cast<uint4 *>(&dst);
 #pragma unroll
-    for (int i = 0; i < (int) (sizeof(T) / 16); ++i) d[i] = s[i];
+    for (int i = 0; i < (int) (sizeof(T) / 16); ++i) d[i] = DR_REC_LD(s + i);
 }
 template <class T> DR_D void rec_store(T *dst, const T &src) {
     static_assert(sizeof(T) % 16 == 0, "record size");
     const uint4 *s = reinterpret_cast<const uint4 *>(&src);
     uint4 *d = reinterpret_cast<uint4 *>(dst);
 #pragma unroll
-    for (int i = 0; i < (int) (sizeof(T) / 16); ++i) d[i] = s[i];
+    for (int i = 0; i < (int) (sizeof(T) / 16); ++i) DR_REC_ST(d + i, s[i]);
 }
 
 // ------------------------------------------------------------------ work queues

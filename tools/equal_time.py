@@ -1,0 +1,106 @@
+"""Equal-time relMSE (BASELINE.json: "relMSE at equal time"): the GPU path and the CPU oracle on all host cores render the
+same scene for the same wall-clock budget; both are compared with a long converged render.
+
+    python tools/equal_time.py [--scene door] [--seconds 10] [--film 320x180] [--out profiles/…json]
+
+relMSE = mean((I - R)^2 / (R^2 + 1e-2))  (SURVEY.md section 8d).  The reference image R is a GPU render with ~40x the
+mutations of the timed GPU run and another seed; because the timed GPU run and R share an implementation, the oracle
+also renders a long image R_cpu (different code, double precision) and relMSE(R, R_cpu) is reported as the noise floor
+of the comparison.  Wall-clock budgets include everything a user pays: bootstrap, seeding, chains, develop."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def relmse(img, ref, eps=1e-2):
+    img, ref = np.asarray(img, np.float64), np.asarray(ref, np.float64)
+    return float(np.mean((img - ref) ** 2 / (ref ** 2 + eps)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="door")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--film", default="320x180")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "equal_time.json"))
+    args = ap.parse_args()
+    import __graft_entry__
+    __graft_entry__.build()
+    import oracle_lib
+    from drmlt_mitsuba_b200 import abi, scenes
+    from drmlt_mitsuba_b200.integrator import Scene, make_config
+
+    W, H = [int(x) for x in args.film.split("x")]
+    if args.scene == "door":
+        data = scenes.door_scene(film=(W, H))
+    else:
+        data = scenes.SCENES[args.scene](film=(W, H))
+    params = dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)
+    gpu = Scene(data)
+
+    def gpu_render(spp, seed):
+        cfg = make_config(seed=seed, sampleCount=spp, **params)
+        t0 = time.perf_counter()
+        img, st = gpu.render(cfg)
+        return img, time.perf_counter() - t0, st
+
+    # ---- calibrate and run the GPU for the budget
+    _, t1, st1 = gpu_render(8, 1)
+    _, t2, st2 = gpu_render(64, 2)
+    rate = (st2.mutations - st1.mutations) / max(1e-6, t2 - t1)            # marginal mutations / s
+    fixed = max(0.0, t1 - st1.mutations / rate)
+    spp = max(1, int((args.seconds - fixed) * rate / (W * H)))
+    img_gpu, t_gpu, st_gpu = gpu_render(spp, 3)
+    # ---- long reference renders
+    ref_spp = spp * 40
+    ref, t_ref, st_ref = gpu_render(ref_spp, 1234567)
+
+    # ---- CPU oracle on all host cores for the same budget
+    orc = oracle_lib.OracleScene(data)
+    threads = os.cpu_count() or 1
+    ocfg = oracle_lib.default_config(integrator=abi.DR_INTEGRATOR_DRMLT, technique=abi.DR_TECH_MMLT, type=abi.DR_TYPE_ORBITAL, max_depth=8,
+                                     direct_samples=-1, direct_sampling=0, kelemen_style_weights=0, seed=5, ray_epsilon=1e-4, shadow_epsilon=1e-3)
+    n_boot, n_chains = 100000 * 8 // 4, threads * 8                         # reference sizing: luminanceSamples x maxDepth (a quarter, it is timed)
+
+    def cpu_render(steps, seed):
+        ocfg.seed = seed
+        t0 = time.perf_counter()
+        r, img, st, sec = orc.render(ocfg, n_boot, n_chains, steps, threads)
+        assert r == 0
+        return img, time.perf_counter() - t0, st
+
+    _, c1, s1 = cpu_render(200, 7)
+    _, c2, s2 = cpu_render(2000, 8)
+    crate = (s2.mutations - s1.mutations) / max(1e-6, c2 - c1)
+    cfixed = max(0.0, c1 - s1.mutations / crate)
+    steps = max(1, int((args.seconds - cfixed) * crate / n_chains))
+    img_cpu, t_cpu, st_cpu = cpu_render(steps, 9)
+    # long CPU render as an independent check of the reference image (bounded: ~6x the budget)
+    img_cpu_long, t_cpu_long, st_cpu_long = cpu_render(steps * 6, 10)
+
+    out = {"scene": args.scene, "triangles": int(data.n_triangles), "film": [W, H], "params": params, "budget_s": args.seconds,
+           "gpu": {"seconds": t_gpu, "mutations": int(st_gpu.mutations), "spp": spp, "relMSE": relmse(img_gpu, ref), "b": st_gpu.luminance},
+           "cpu_oracle": {"seconds": t_cpu, "mutations": int(st_cpu.mutations), "threads": threads, "relMSE": relmse(img_cpu, ref), "b": st_cpu.luminance,
+                          "kind": "oracle port (double), not the reference binary"},
+           "reference_image": {"spp": ref_spp, "mutations": int(st_ref.mutations), "seconds": t_ref, "mean": float(ref.mean())},
+           "cross_check": {"cpu_long_seconds": t_cpu_long, "cpu_long_mutations": int(st_cpu_long.mutations),
+                           "relMSE_cpu_long_vs_reference": relmse(img_cpu_long, ref), "mean_cpu_long": float(img_cpu_long.mean()),
+                           "mean_gpu": float(img_gpu.mean()), "mean_cpu": float(img_cpu.mean())},
+           "eps": 1e-2}
+    out["relMSE_ratio_cpu_over_gpu"] = out["cpu_oracle"]["relMSE"] / max(out["gpu"]["relMSE"], 1e-300)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
