@@ -550,7 +550,14 @@ struct dr_job_t {
 
 template <class T>
 static dr_status job_alloc(dr_job j, T **p, size_t count) {
-    CK(cudaMalloc((void **) p, std::max<size_t>(count * sizeof(T), 16)));
+    const cudaError_t e = cudaMalloc((void **) p, std::max<size_t>(count * sizeof(T), 16));
+    if (e != cudaSuccess) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        dr_set_error("cudaMalloc of %zu bytes failed: %s (%zu of %zu bytes free)", count * sizeof(T), cudaGetErrorString(e), fr, tot);
+        cudaGetLastError();
+        return DR_ERR_CUDA;
+    }
     j->allocations.push_back(*p);
     CK(cudaMemsetAsync(*p, 0, std::max<size_t>(count * sizeof(T), 16), j->stream));
     return DR_OK;

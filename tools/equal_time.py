@@ -3,7 +3,7 @@ same scene for the same wall-clock budget; both are compared with a long converg
 
     python tools/equal_time.py [--scene door] [--seconds 10] [--film 320x180] [--out profiles/…json]
 
-relMSE = mean((I - R)^2 / (R^2 + 1e-2))  (SURVEY.md section 8d).  The reference image R is a GPU render with ~40x the
+relMSE = mean((I - R)^2 / (R^2 + 1e-2))  (SURVEY.md section 8d).  The reference image R is a GPU render with --ref-factor times the
 mutations of the timed GPU run and another seed; because the timed GPU run and R share an implementation, the oracle
 also renders a long image R_cpu (different code, double precision) and relMSE(R, R_cpu) is reported as the noise floor
 of the comparison.  Wall-clock budgets include everything a user pays: bootstrap, seeding, chains, develop."""
@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--scene", default="door")
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--film", default="320x180")
+    ap.add_argument("--ref-factor", type=int, default=8, dest="ref_factor", help="the reference image gets this many times the mutations of the timed GPU run")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "equal_time.json"))
     args = ap.parse_args()
     import __graft_entry__
@@ -53,14 +54,14 @@ def main():
         return img, time.perf_counter() - t0, st
 
     # ---- calibrate and run the GPU for the budget
-    _, t1, st1 = gpu_render(8, 1)
-    _, t2, st2 = gpu_render(64, 2)
+    _, t1, st1 = gpu_render(256, 1)
+    _, t2, st2 = gpu_render(1024, 2)
     rate = (st2.mutations - st1.mutations) / max(1e-6, t2 - t1)            # marginal mutations / s
     fixed = max(0.0, t1 - st1.mutations / rate)
     spp = max(1, int((args.seconds - fixed) * rate / (W * H)))
     img_gpu, t_gpu, st_gpu = gpu_render(spp, 3)
     # ---- long reference renders
-    ref_spp = spp * 40
+    ref_spp = spp * args.ref_factor
     ref, t_ref, st_ref = gpu_render(ref_spp, 1234567)
 
     # ---- CPU oracle on all host cores for the same budget

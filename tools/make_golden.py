@@ -35,7 +35,7 @@ CASES = [
      dict(integrator=abi.DR_INTEGRATOR_DRMLT, type=abi.DR_TYPE_ORBITAL, technique=abi.DR_TECH_MMLT, max_depth=8, direct_samples=-1, direct_sampling=0,
           kelemen_style_weights=0), (30, 30, 1)),
 ]
-N_PATHS, N_BOOT, N_CHAINS, N_STEPS = 192, 3000, 6, 24
+N_PATHS, N_BOOT, N_CHAINS, N_STEPS = 640, 3000, 6, 24
 
 
 def config(over):
