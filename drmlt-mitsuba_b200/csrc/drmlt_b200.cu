@@ -548,9 +548,23 @@ struct dr_job_t {
     uint64_t stageLaunches[STAGE_COUNT] = { 0, 0, 0 };
 };
 
+// Device memory of a job comes from the device's stream-ordered pool (cudaMallocAsync) with an unbounded release
+// threshold: a long-lived process (the plugin renders frame after frame) pays for the ~7 GB of lane memory once.
+// Only what is read before it is written gets cleared (`zero`).
+static void pool_init(int device) {
+    static bool done[64] = { false };
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
 template <class T>
-static dr_status job_alloc(dr_job j, T **p, size_t count) {
-    const cudaError_t e = cudaMalloc((void **) p, std::max<size_t>(count * sizeof(T), 16));
+static dr_status job_alloc(dr_job j, T **p, size_t count, bool zero = false) {
+    const cudaError_t e = cudaMallocAsync((void **) p, std::max<size_t>(count * sizeof(T), 16), j->stream);
     if (e != cudaSuccess) {
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
@@ -559,7 +573,7 @@ static dr_status job_alloc(dr_job j, T **p, size_t count) {
         return DR_ERR_CUDA;
     }
     j->allocations.push_back(*p);
-    CK(cudaMemsetAsync(*p, 0, std::max<size_t>(count * sizeof(T), 16), j->stream));
+    if (zero) CK(cudaMemsetAsync(*p, 0, std::max<size_t>(count * sizeof(T), 16), j->stream));
     return DR_OK;
 }
 
@@ -567,7 +581,8 @@ extern "C" void dr_job_destroy(dr_job j) {
     if (!j) return;
     cudaSetDevice(j->scene->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
-    for (void *p : j->allocations) cudaFree(p);
+    for (void *p : j->allocations) cudaFreeAsync(p, j->stream);
+    if (j->stream) cudaStreamSynchronize(j->stream);
     for (auto &g : j->groups) { if (g.countsHost) cudaFreeHost(g.countsHost); if (g.evJoin) cudaEventDestroy(g.evJoin); if (g.stream) cudaStreamDestroy(g.stream); }
     if (j->evFork) cudaEventDestroy(j->evFork);
     for (cudaEvent_t e : j->profEvents) cudaEventDestroy(e);
@@ -578,8 +593,9 @@ extern "C" void dr_job_destroy(dr_job j) {
 }
 
 static int auto_chains(long long totalMutations) {
-    // enough lanes to keep every stage kernel's queue several waves deep on 148 SMs, but >= 32 mutations per chain
-    long long n = totalMutations / 32;
+    // enough lanes to keep every stage kernel's queue several waves deep on 148 SMs, but >= 64 mutations per chain:
+    // at equal mutation count, chains shorter than that lose statistical efficiency (profiles/r01_g_chain_length_study.json)
+    long long n = totalMutations / 64;
     n = std::max<long long>(4096, std::min<long long>(n, 1 << 22));
     n = std::min<long long>(n, std::max<long long>(128, totalMutations));
     return (int) ((n + 127) / 128 * 128);
@@ -592,8 +608,8 @@ static dr_status alloc_lanes(dr_job j, int n) {
     lm.n = n; lm.nU = j->M.pp.nU;
     dr_status st;
     if ((st = job_alloc(j, &lm.core, (size_t) n)) || (st = job_alloc(j, &lm.vt, (size_t) n)) || (st = job_alloc(j, &lm.vs, (size_t) n)) ||
-        (st = job_alloc(j, &lm.vtp, (size_t) n)) || (st = job_alloc(j, &lm.vsp, (size_t) n)) || (st = job_alloc(j, &lm.chain, (size_t) n)) ||
-        (st = job_alloc(j, &lm.mis, (size_t) MIS_WORDS * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
+        (st = job_alloc(j, &lm.vtp, (size_t) n)) || (st = job_alloc(j, &lm.vsp, (size_t) n)) || (st = job_alloc(j, &lm.chain, (size_t) n, true)) ||
+        (st = job_alloc(j, &lm.mis, (size_t) MIS_WORDS * n, true)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
         (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)))
         return st;
     if (j->cfg.technique == DR_TECH_BDPT &&      // both subpaths and the splat lists are kept per lane
@@ -609,7 +625,7 @@ static dr_status alloc_lanes(dr_job j, int n) {
         dr_job_t::Group &gr = j->groups[g];
         gr.begin = (int) ((long long) n * g / G); gr.end = (int) ((long long) n * (g + 1) / G);
         gr.q.n = gr.end - gr.begin;
-        if ((st = job_alloc(j, &gr.q.items, (size_t) Q_COUNT * gr.q.n)) || (st = job_alloc(j, &gr.q.rays, (size_t) 4 * 2 * gr.q.n)) || (st = job_alloc(j, &gr.q.count, (size_t) Q_COUNT + 2)))   // + head counters of the two ray queues
+        if ((st = job_alloc(j, &gr.q.items, (size_t) Q_COUNT * gr.q.n)) || (st = job_alloc(j, &gr.q.rays, (size_t) 4 * 2 * gr.q.n)) || (st = job_alloc(j, &gr.q.count, (size_t) Q_COUNT + 2, true)))   // + head counters of the two ray queues
             return st;
         if (cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&gr.evJoin, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost((void **) &gr.countsHost, sizeof(uint32_t) * Q_COUNT) != cudaSuccess) {
             dr_set_error("group stream creation failed: %s", cudaGetErrorString(cudaGetLastError())); return DR_ERR_CUDA;
@@ -641,18 +657,19 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
         cudaEventCreate(&j->ev1) != cudaSuccess) {
         dr_set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(DR_ERR_CUDA);
     }
+    pool_init(scene->device);
     j->profile = getenv("DRMLT_PROFILE_STAGES") != nullptr;
     // this rank's share of W*H*sampleCount mutations (drmlt.cpp:475-476)
     const long long total = (long long) W * H * cfg.sample_count;
     j->totalMutations = total / cfg.world_size + (cfg.rank < total % cfg.world_size ? 1 : 0);
     j->nChains = nLanes > 0 ? nLanes : (cfg.n_chains > 0 ? cfg.n_chains : auto_chains(j->totalMutations));
     const size_t n = (size_t) j->nChains;
-    if ((st = alloc_lanes(j, j->nChains)) || (st = job_alloc(j, &j->counters, (size_t) 2 * ST_COUNT)) || (st = job_alloc(j, &j->red, 4)) ||
+    if ((st = alloc_lanes(j, j->nChains)) || (st = job_alloc(j, &j->counters, (size_t) 2 * ST_COUNT, true)) || (st = job_alloc(j, &j->red, 4, true)) ||
         (st = job_alloc(j, &j->redScratch, (size_t) lum_reduce_scratch_doubles())))
         return fail(st);
     if (chains) {
         if ((st = job_alloc(j, &j->depth, n)) || (st = job_alloc(j, &j->chainId, n)) || (st = job_alloc(j, &j->seedIdx, n)) ||
-            (st = job_alloc(j, &j->film, (size_t) W * H)) || (st = job_alloc(j, &j->devImage, (size_t) W * H * 3)))
+            (st = job_alloc(j, &j->film, (size_t) W * H, true)) || (st = job_alloc(j, &j->devImage, (size_t) W * H * 3)))
             return fail(st);
     }
     CK(cudaStreamSynchronize(j->stream));
@@ -794,7 +811,7 @@ static dr_status setup_lanes(dr_job j, const JobParams &job) {
 
 // luminanceSamples sizing of DRMLT::render (drmlt.cpp:446-473), with the reference's CPU work-unit count standing in
 // for "workUnits", and a floor of one bootstrap sample per four resident chains (of all ranks) so that the seed pool
-// does not degenerate when hundreds of thousands of chains are resampled from it.
+// does not degenerate when hundreds of thousands of chains are resampled from it, and of 1/8 of the mutation budget.
 static long long bootstrap_samples(const dr_job j) {
     const dr_config &c = j->cfg;
     const long long desired = c.technique == DR_TECH_PATH ? 200000 : 100000;
@@ -805,6 +822,10 @@ static long long bootstrap_samples(const dr_job j) {
     n = std::max(n, workUnits * times);
     n = std::max(n, (long long) j->nChains * c.world_size / 4);
     if (c.technique == DR_TECH_MMLT) n *= c.max_depth;
+    // The image is scaled by b, so the relative error of b is a floor of the image error.  On the GPU a bootstrap path
+    // costs about as much as a mutation: spend 1/8 of the mutation budget on it (profiles/r01_g_chain_length_study.json:
+    // 16 M instead of 0.8 M bootstrap paths lower relMSE 4-10x at 59 M mutations for +0.2 s).
+    n = std::max(n, total / 8);
     return n;
 }
 
