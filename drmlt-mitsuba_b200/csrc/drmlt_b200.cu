@@ -608,8 +608,8 @@ static dr_status alloc_lanes(dr_job j, int n) {
     lm.n = n; lm.nU = j->M.pp.nU;
     dr_status st;
     if ((st = job_alloc(j, &lm.core, (size_t) n)) || (st = job_alloc(j, &lm.vt, (size_t) n)) || (st = job_alloc(j, &lm.vs, (size_t) n)) ||
-        (st = job_alloc(j, &lm.vtp, (size_t) n)) || (st = job_alloc(j, &lm.vsp, (size_t) n)) || (st = job_alloc(j, &lm.chain, (size_t) n, true)) ||
-        (st = job_alloc(j, &lm.mis, (size_t) MIS_WORDS * n, true)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
+        (st = job_alloc(j, &lm.geo, (size_t) 4 * n)) || (st = job_alloc(j, &lm.chain, (size_t) n, true)) ||
+        (st = job_alloc(j, &lm.misrec, (size_t) 2 * MR_MAXV * MR_WORDS * n)) || (st = job_alloc(j, &lm.conn, (size_t) 4 * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
         (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)))
         return st;
     if (j->cfg.technique == DR_TECH_BDPT &&      // both subpaths and the splat lists are kept per lane

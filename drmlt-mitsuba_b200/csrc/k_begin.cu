@@ -85,20 +85,23 @@ DR_D int path_start(const Machine &M, int lane, Core &c, RayF &ray) {
     int dest;
     if (M.pc.technique == DR_TECH_MMLT) {                     // pathsampler.cpp:84-159
         const int depth = c.depth, k = depth + 2;
-        double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
         int s, t;
         mmlt_strategy(M.pc, depth, rd.next1D(SMP_DIRECT), s, t);
         c.s = (uint8_t) s; c.t = (uint8_t) t;
         if (depth == 1) { reader_close(rd, c); c.pstate = PS_EMPTY; return -1; }
         c.connectable = 0; c.flags = 0; c.weight = r3(1.);
-        if (!mmlt_emitter_sample(M, lane, c, rd, mis)) { reader_close(rd, c); c.pstate = PS_EMPTY; return -1; }
+        if (!mmlt_emitter_sample(M, lane, c, rd)) { reader_close(rd, c); c.pstate = PS_EMPTY; return -1; }
         (void) rd.next2D(SMP_SENSOR);                         // sampleSensorPosition consumes 2 (vertex.cpp:79)
-        mis_put(mis, MIS_RAD, k, 1.0);
-        mis_put(mis, MIS_RAD, k - 1, 1.0);                    // supernode pdf[ERadiance] (perspective.cpp:305)
+        // (pdfRad of the sensor supernode and of the sensor sample are 1: perspective.cpp:305; path_result knows)
         Vtx vt;
         vt.p = cam_pos(sc.cam); vt.ng = vt.ns = cam_dir(sc.cam); vt.ss = r3(0.); vt.type = V_SENSOR_SAMPLE; vt.degenerate = 0; vt.mat = -1; vt.emitter = -1;
         c.connectable |= 1u << (k - 1);                       // sensor sample: never discrete, not degenerate
         rec_store(M.lm.vt + lane, vt);
+        if (t >= 2) {
+            PredRec g1;
+            g1.p = vt.p; g1.ng = vt.ng; g1.pad[0] = g1.pad[1] = 0.;
+            rec_store(geo_slot(M, lane, SIDE_S, 1), g1);
+        }
         c.j = 1;
         if (t >= 2) {                                         // vertex.cpp:126-151, perspective.cpp:318-345
             const R2 u = rd.next2D(SMP_SENSOR);

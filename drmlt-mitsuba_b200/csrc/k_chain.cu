@@ -97,13 +97,30 @@ DR_D void path_result(const Machine &M, int lane, Core &c, PathResult &out) {
     }
     if (c.pstate == PS_FINISH) {                              // pathsampler.cpp:288-313
         const int depth = c.depth, k = depth + 2, s = c.s, t = c.t;
-        const double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
+        // assemble pdfImp / pdfRad / conv of the full path (vertex i <= s: emitter subpath vertex i, else sensor subpath
+        // vertex k - i) from the per-step records of the two walks and the four densities of the connection
         MisArrays A;
         A.connectable = c.connectable;
 #pragma unroll
-        for (int i = 0; i <= DR_MAXK; ++i) {
-            const bool in = i <= k;
-            A.pdfImp[i] = in ? mis_get(mis, MIS_IMP, i) : 0.; A.pdfRad[i] = in ? mis_get(mis, MIS_RAD, i) : 0.; A.conv[i] = in ? mis_get(mis, MIS_CONV, i) : 0.;
+        for (int i = 0; i <= DR_MAXK; ++i) { A.pdfImp[i] = 0.; A.pdfRad[i] = 0.; A.conv[i] = 0.; }
+        A.pdfImp[0] = 1.0; A.pdfRad[k] = 1.0; A.pdfRad[k - 1] = 1.0;       // supernodes; sensor sample (perspective.cpp:305)
+        for (int j = 0; j < s; ++j) {                         // emitter walk step j produced vertex j + 1
+            const double4 r = *reinterpret_cast<const double4 *>(misrec_slot(M, lane, SIDE_E, j));
+            A.pdfImp[j + 1] = r.x;
+            if (j >= 1) { A.pdfRad[j - 1] = r.y; A.conv[j] = r.z; }
+        }
+        for (int j = 1; j < t; ++j) {                         // sensor walk step j produced vertex j + 1 (global index k - j - 1)
+            const double4 r = *reinterpret_cast<const double4 *>(misrec_slot(M, lane, SIDE_S, j));
+            A.pdfRad[k - j - 1] = r.x;
+            A.pdfImp[k - j + 1] = r.y;
+            A.conv[k - j - 1] = r.z;
+        }
+        {
+            const double4 q = *reinterpret_cast<const double4 *>(M.lm.conn + 4 * (size_t) lane);
+            A.pdfImp[s + 1] = q.x;
+            if (s >= 1) A.pdfRad[s - 1] = q.y;
+            if (s >= 1) A.pdfRad[s] = q.z;                     // (s = 0: pdfRad[0] is not used by the sweep)
+            if (s + 2 <= k) A.pdfImp[s + 2] = q.w;
         }
         const Real w = mis_weight(A, s, t, M.pc.lightImage != 0);
         const int nStrats = M.pc.lightImage ? depth + 1 : depth;

@@ -19,19 +19,17 @@ k_walk(const __grid_constant__ Machine M) {
         Core c;
         rec_load(c, M.lm.core + lane);
         const bool emitterSide = c.pstate == PS_EMITTER_HIT;
-        Vtx *vArr = emitterSide ? M.lm.vs : M.lm.vt;
-        PredRec *pArr = emitterSide ? M.lm.vsp : M.lm.vtp;
-        double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
+        const int side = emitterSide ? SIDE_E : SIDE_S;
         const int k = c.depth + 2;                           // s + t + 1
         Hit hit;
         { const float4 h = M.lm.hit[lane]; hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.tri = __float_as_int(h.w); }
         int dest = Q_CHAIN + M.parity;                       // default: the path ends here (empty result)
         RayF ray;
         do {
-            Vtx v; PredRec vp;
-            rec_load(v, vArr + lane);
+            PredRec v, vp;                                   // vertex j (origin of the ray) and its predecessor: position + geometric normal
             int j = c.j;
-            if (j >= 2) rec_load(vp, pArr + lane);
+            rec_load(v, geo_slot(M, lane, side, j));
+            if (j >= 2) rec_load(vp, geo_slot(M, lane, side, j - 1));
             const R3 d = c.d;
             Vtx nv; Real tHit;
             fill_vertex(sc, hit, v.p, d, nv, tHit);
@@ -51,47 +49,38 @@ k_walk(const __grid_constant__ Machine M) {
                     pdfBwd = pdfBwd / (plen * plen) * absdot(pd, vp.ng);
                 }
             }
-            const Real conv = tHit * tHit / fabs(absdot(d, v.ng) * cosNext);
-            if (!emitterSide) {
-                const int g = k - j;
-                mis_put(mis, MIS_RAD, g - 1, pdfFwd);        // density of vertex j + 1
-                mis_put(mis, MIS_IMP, g + 1, pdfBwd);        // density of vertex j - 1
-                mis_put(mis, MIS_CONV, g - 1, conv);         // edge (g-1, g)
-                if (j == 1) {                                // pixel of the path (pathsampler.cpp:309-312)
-                    R2 sp = r2(0., 0.);
-                    cam_sample_position(sc.cam, nv.p - cam_pos(sc.cam), sp);
-                    c.spos = make_float2((float) sp.x, (float) sp.y);
-                }
-            } else {
-                mis_put(mis, MIS_IMP, j + 1, pdfFwd);
-                mis_put(mis, MIS_RAD, j - 1, pdfBwd);
-                mis_put(mis, MIS_CONV, j, conv);             // edge (j, j+1)
+            misrec_store(M, lane, side, j, pdfFwd, pdfBwd, tHit * tHit / fabs(absdot(d, v.ng) * cosNext));
+            if (!emitterSide && j == 1) {                    // pixel of the path (pathsampler.cpp:309-312)
+                R2 sp = r2(0., 0.);
+                cam_sample_position(sc.cam, nv.p - cam_pos(sc.cam), sp);
+                c.spos = make_float2((float) sp.x, (float) sp.y);
             }
-            vp.p = v.p; vp.ng = v.ng;
-            v = nv;
             ++j;
             c.j = (uint8_t) j;
-            rec_store(vArr + lane, v);
-            rec_store(pArr + lane, vp);
+            PredRec ng_;
+            ng_.p = nv.p; ng_.ng = nv.ng; ng_.pad[0] = ng_.pad[1] = 0.;
             const int steps = emitterSide ? c.s : c.t;
             if (j < steps) {                                 // BSDF sampling step at vertex j (vertex.cpp:153-271)
+                rec_store(geo_slot(M, lane, side, j), ng_);  // only position + geometric normal of an inner vertex are needed again
                 WalkStep ws;
                 UReader rd;
                 reader_open(M, c, lane, rd);
                 const R2 u = rd.next2D(emitterSide ? SMP_EMITTER : SMP_SENSOR);
                 reader_close(rd, c);
-                if (!surface_sample_next(sc, v, nm, normalize(vp.p - v.p), emitterSide ? MODE_IMPORTANCE : MODE_RADIANCE, u, ws)) { c.pstate = PS_EMPTY; break; }
+                if (!surface_sample_next(sc, nv, nm, normalize(v.p - nv.p), emitterSide ? MODE_IMPORTANCE : MODE_RADIANCE, u, ws)) { c.pstate = PS_EMPTY; break; }
                 const int bit = emitterSide ? j : k - j;
-                if (!ws.delta && !v.degenerate) { c.connectable |= 1u << bit; c.flags |= F_ANYCONN; }
+                if (!ws.delta && !nv.degenerate) { c.connectable |= 1u << bit; c.flags |= F_ANYCONN; }
                 c.flags = ws.delta ? (c.flags | F_DELTA) : (c.flags & ~F_DELTA);
                 c.weight *= ws.weightFwd;
                 c.pdfFwd = ws.pdfFwd; c.pdfBwd = ws.pdfBwd;
-                emit_ray(M, lane, c, v.p, ws.wo, sc.epsilon, INFINITY, ray);
+                emit_ray(M, lane, c, nv.p, ws.wo, sc.epsilon, INFINITY, ray);
                 dest = Q_RAYC + (M.parity ^ 1);
                 break;
             }
-            // last vertex of this subpath: its measure stays invalid => connectable iff not degenerate
-            if (!v.degenerate) { c.connectable |= 1u << (emitterSide ? (int) c.s : k - (int) c.t); c.flags |= F_ANYCONN; }
+            // last vertex of this subpath: the connection needs its full record; its measure stays invalid => connectable iff
+            // not degenerate
+            rec_store((emitterSide ? M.lm.vs : M.lm.vt) + lane, nv);
+            if (!nv.degenerate) { c.connectable |= 1u << (emitterSide ? (int) c.s : k - (int) c.t); c.flags |= F_ANYCONN; }
             if (!emitterSide) dest = mmlt_emitter_launch(M, lane, c, ray) == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : Q_CONNECT;
             else { c.pstate = PS_CONNECT; dest = Q_CONNECT; }
         } while (false);
@@ -111,7 +100,7 @@ k_connect(const __grid_constant__ Machine M) {
         const int lane = (int) items[qi];
         Core c;
         rec_load(c, M.lm.core + lane);
-        double *mis = M.lm.mis + (size_t) lane * MIS_WORDS;
+        Real conn[4] = { 0., 0., 0., 0. };                   // pdfImp[s+1], pdfRad[s-1], pdfRad[s], pdfImp[s+2]
         int dest = Q_CHAIN + M.parity;
         RayF ray;
         c.pstate = PS_EMPTY;
@@ -120,7 +109,7 @@ k_connect(const __grid_constant__ Machine M) {
             const int s = c.s, t = c.t, depth = c.depth;
             Vtx vt; PredRec vtp;
             rec_load(vt, M.lm.vt + lane);
-            if (t >= 2) rec_load(vtp, M.lm.vtp + lane);
+            if (t >= 2) rec_load(vtp, geo_slot(M, lane, SIDE_S, t - 1));
             if (s == 0) {                                    // pure sensor path: vt must be on an emitter (:213-224)
                 if (vt.type != V_SURFACE || vt.emitter < 0) break;
                 const R3 n = vt.ns;                          // cast(): pRec.n = its.shFrame.n (records.inl:154-155)
@@ -132,8 +121,8 @@ k_connect(const __grid_constant__ Machine M) {
                 c.weight = c.weight * emitter_radiance(sc, vt.emitter);   // radiance * pi * (1/pi)
                 const DevEmitter &em = sc.emitters[vt.emitter];
                 c.connectable |= 1u << 1;                    // emitter sample: area measure, not degenerate
-                mis_put(mis, MIS_IMP, 1, em.invArea * em.pdfDiscrete);                       // vs->evalPdf: pdfEmitterPosition
-                mis_put(mis, MIS_IMP, 2, R_INV_PI * dp / (dist * dist) * absdot(wo, vtp.ng));   // vt->evalPdf(vs, vtPred, EImportance)
+                conn[0] = em.invArea * em.pdfDiscrete;                                       // vs->evalPdf: pdfEmitterPosition
+                conn[3] = R_INV_PI * dp / (dist * dist) * absdot(wo, vtp.ng);                 // vt->evalPdf(vs, vtPred, EImportance)
                 // connection edge of a supernode: length 0, generalized geometric term = 1 (edge.cpp:229-234, 561-571)
                 if (pc.excludeDirect && depth <= 2) break;
                 c.pstate = PS_FINISH;
@@ -141,7 +130,7 @@ k_connect(const __grid_constant__ Machine M) {
             }
             Vtx vs; PredRec vsp;
             rec_load(vs, M.lm.vs + lane);
-            if (s >= 2) rec_load(vsp, M.lm.vsp + lane);
+            if (s >= 2) rec_load(vsp, geo_slot(M, lane, SIDE_E, s - 1));
             if (vs.degenerate || vt.degenerate) break;       // :253-257
             R3 d = vs.p - vt.p;                              // from vt towards vs
             const Real len = length(d);
@@ -174,27 +163,28 @@ k_connect(const __grid_constant__ Machine M) {
             c.connectable |= (1u << s) | (1u << (s + 1));    // measure forced to EArea (:263-265)
             if (s == 1) {
                 const Real dp = dot(-d, vs.ns);
-                mis_put(mis, MIS_IMP, s + 1, R_INV_PI * fmax(dp, 0.) / (len * len) * absdot(d, vt.ng));
-                mis_put(mis, MIS_RAD, s - 1, 1.0);
+                conn[0] = R_INV_PI * fmax(dp, 0.) / (len * len) * absdot(d, vt.ng);
+                conn[1] = 1.0;
             } else {
-                mis_put(mis, MIS_IMP, s + 1, surface_pdf_area(vs, ms, vsp.p, vt.p, vt.ng));
-                mis_put(mis, MIS_RAD, s - 1, surface_pdf_area(vs, ms, vt.p, vsp.p, vsp.ng));
+                conn[0] = surface_pdf_area(vs, ms, vsp.p, vt.p, vt.ng);
+                conn[1] = surface_pdf_area(vs, ms, vt.p, vsp.p, vsp.ng);
             }
             if (t == 1) {
-                mis_put(mis, MIS_RAD, s, cam_importance(sc.cam, cam_inv_dir(sc.cam, d)) / (len * len) * absdot(d, vs.ng));
-                mis_put(mis, MIS_IMP, s + 2, 1.0);
+                conn[2] = cam_importance(sc.cam, cam_inv_dir(sc.cam, d)) / (len * len) * absdot(d, vs.ng);
+                conn[3] = 1.0;
                 R2 sp = r2(0., 0.);
                 if (!cam_sample_position(sc.cam, vs.p - vt.p, sp)) c.flags |= F_SPOS_FAIL;   // :298-303
                 c.spos = make_float2((float) sp.x, (float) sp.y);
             } else {
-                mis_put(mis, MIS_RAD, s, surface_pdf_area(vt, mt, vtp.p, vs.p, vs.ng));
-                mis_put(mis, MIS_IMP, s + 2, surface_pdf_area(vt, mt, vs.p, vtp.p, vtp.ng));
+                conn[2] = surface_pdf_area(vt, mt, vtp.p, vs.p, vs.ng);
+                conn[3] = surface_pdf_area(vt, mt, vs.p, vtp.p, vtp.ng);
             }
             // pathConnectAndCollapse (edge.cpp:572-606): vt and vs are always "on surface" here
             c.pstate = PS_CONNECT_SHADOW;
             emit_ray(M, lane, c, vt.p, d, sc.epsilon, len * (1. - sc.shadowEpsilon), ray);
             dest = Q_RAYS + (M.parity ^ 1);
         } while (false);
+        if (c.pstate != PS_EMPTY) *reinterpret_cast<double4 *>(M.lm.conn + 4 * (size_t) lane) = make_double4(conn[0], conn[1], conn[2], conn[3]);
         rec_store(M.lm.core + lane, c);
         q_push_ray(M.q, dest, (uint32_t) lane, ray);
     }

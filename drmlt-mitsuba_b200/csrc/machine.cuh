@@ -120,15 +120,23 @@ struct alignas(16) BdAcc {            // 128 bytes: the splat list being built (
 };
 static_assert(sizeof(BExtra) == 64 && sizeof(BdAcc) == 128, "bdpt records");
 
-enum { MIS_IMP = 0, MIS_RAD = 16, MIS_CONV = 32, MIS_WORDS = 48 };
-static_assert(DR_MAXK + 1 <= 16, "MIS arrays");
+// MIS bookkeeping of the MMLT walks: ONE 32-byte record per walk step, written as a whole sector.
+//   misrec[side][j] = { fwdNext, bwdPrev, conv, - }: written when vertex j of `side` (0 sensor, 1 emitter) has produced
+//   vertex j + 1:  fwdNext = area density of vertex j+1 generated from j, bwdPrev = area density of vertex j-1 generated
+//   from j (reverse direction), conv = len^2 / |cos cos| of edge (j, j+1) with geometric normals (path.cpp:875-899).
+//   conn[0..3] = the four densities next to the connection, recomputed by k_connect (path.cpp:835-859):
+//   pdfImp[s+1], pdfRad[s-1], pdfRad[s], pdfImp[s+2].
+enum { MR_FWD = 0, MR_BWD = 1, MR_CONV = 2, MR_WORDS = 4, MR_MAXV = 16, SIDE_S = 0, SIDE_E = 1 };
+static_assert(DR_MAXK + 1 <= MR_MAXV, "MIS records");
 
 struct LaneMem {
     Core *core;               // [n]
     Vtx *vt, *vs;             // [n] last vertex of the sensor / emitter subpath
-    PredRec *vtp, *vsp;       // [n] position and geometric normal of their predecessors
+    PredRec *geo;             // [n][2 sides][2]: position + geometric normal of the last two vertices of each subpath;
+                              //   vertex j lives in slot j & 1 (the walk overwrites j-1 with j+1: no copies)
     ChainCore *chain;         // [n]
-    double *mis;              // [n][48]: pdfImp[16], pdfRad[16], conv[16]
+    double *misrec;           // [n][2 sides][MR_MAXV][MR_WORDS]: per-step MIS records (see MR_*)
+    double *conn;             // [n][4]: densities next to the connection
     double *ubuf;             // [n][UB_COUNT][nU] coordinate buffers X, Y, Z, R
     double *rayd;             // [n][8] o, d, tmin, tmax of the same ray un-rounded (deciding triangle tests)
     // technique=bdpt only (else null)
@@ -249,8 +257,12 @@ struct Machine {
 };
 
 // ------------------------------------------------------------------ MIS arrays of a lane
-DR_D void mis_put(double *mis, int arr, int i, Real v) { mis[arr + i] = v; }
-DR_D Real mis_get(const double *mis, int arr, int i) { return mis[arr + i]; }
+DR_D PredRec *geo_slot(const Machine &M, int lane, int side, int j) { return M.lm.geo + ((size_t) lane * 2 + side) * 2 + (j & 1); }
+DR_D double *misrec_slot(const Machine &M, int lane, int side, int j) { return M.lm.misrec + (((size_t) lane * 2 + side) * MR_MAXV + j) * MR_WORDS; }
+DR_D void misrec_store(const Machine &M, int lane, int side, int j, Real fwdNext, Real bwdPrev, Real conv) {
+    double4 v = make_double4(fwdNext, bwdPrev, conv, 0.0);
+    *reinterpret_cast<double4 *>(misrec_slot(M, lane, side, j)) = v;      // one aligned 32-byte sector
+}
 
 // findMaxDimensions (pssmlt_utils.h:27-77): MMLT vectors depend on the chain's depth
 DR_D void chain_dims(const PathCfg &pc, const ChainParams &cp, int depth, int dims[3]) {
@@ -336,32 +348,35 @@ DR_D void stats_flush(const uint32_t *st, unsigned long long *counters) {
 // s >= 2, the emission direction (Scene::sampleEmitterPosition scene.cpp:1066-1082, vertex.cpp:99-124,
 // area.cpp:130-138).  Nothing here depends on the sensor subpath, so it is done up front, where every lane of the
 // warp does the same thing; the results wait in the lane's emitter-side records:
-//   vs = the emitter sample (vs.ss holds the position-sampling weight m_power / emPdf),
-//   vsp.p = emission direction, vsp.ng.x = its solid-angle density.
+//   vs = the emitter sample (vs.ss holds the position-sampling weight m_power / emPdf), its position / normal also in
+//   geo[emitter][1];  geo[emitter][0] = { emission direction, its solid-angle density } until vertex 2 overwrites it;
+//   misrec[emitter][0].fwdNext = area density of the emitter sample.
 // Returns false when there is nothing to sample (the path is dead).
-DR_D bool mmlt_emitter_sample(const Machine &M, int lane, Core &c, UReader &rd, double *mis) {
+DR_D bool mmlt_emitter_sample(const Machine &M, int lane, Core &c, UReader &rd) {
     const DevScene &sc = M.sc;
-    mis_put(mis, MIS_IMP, 0, 1.0);
     if (c.s == 0) return true;
     if (sc.nEmitters == 0) return false;
     EmitterPoint ep;
     const R2 u0 = rd.next2D(SMP_EMITTER);
     sample_emitter_point(sc, u0.x, u0.y, ep);
     const DevEmitter &em = sc.emitters[ep.emitter];
-    mis_put(mis, MIS_IMP, 1, ep.pdfArea);
+    misrec_store(M, lane, SIDE_E, 0, ep.pdfArea, 1.0, 0.0);
     Vtx vs;
     vs.p = ep.p; vs.ng = vs.ns = ep.n; vs.type = V_EMITTER_SAMPLE; vs.degenerate = 0; vs.emitter = ep.emitter; vs.mat = -1;
     vs.ss = emitter_radiance(sc, ep.emitter) * (R_PI * em.area / ep.emPdf);   // m_power / emPdf
     rec_store(M.lm.vs + lane, vs);
     if (c.s >= 2) {
+        PredRec g1;
+        g1.p = vs.p; g1.ng = vs.ng; g1.pad[0] = g1.pad[1] = 0.;
+        rec_store(geo_slot(M, lane, SIDE_E, 1), g1);
         const R2 u = rd.next2D(SMP_EMITTER);
         const R3 local = square_to_cosine_hemisphere(u.x, u.y);
         R3 fs, ft;
         coordinate_system(vs.ns, fs, ft);
         PredRec e;
         e.p = fs * local.x + ft * local.y + vs.ns * local.z;
-        e.ng = r3(R_INV_PI * local.z, 0., 0.);
-        rec_store(M.lm.vsp + lane, e);
+        e.ng = r3(R_INV_PI * local.z, 0., 0.); e.pad[0] = e.pad[1] = 0.;
+        rec_store(geo_slot(M, lane, SIDE_E, 0), e);
     }
     return true;
 }
@@ -378,7 +393,7 @@ DR_D int mmlt_emitter_launch(const Machine &M, int lane, Core &c, RayF &ray) {
         c.j = 1;
         if (c.s >= 2) {
             PredRec e;
-            rec_load(e, M.lm.vsp + lane);
+            rec_load(e, geo_slot(M, lane, SIDE_E, 0));
             c.pdfFwd = e.ng.x; c.pdfBwd = 1.0;
             c.pstate = PS_EMITTER_HIT;
             emit_ray(M, lane, c, vs.p, e.p, M.sc.epsilon, INFINITY, ray);
