@@ -610,7 +610,7 @@ static dr_status alloc_lanes(dr_job j, int n) {
     if ((st = job_alloc(j, &lm.core, (size_t) n)) || (st = job_alloc(j, &lm.vt, (size_t) n)) || (st = job_alloc(j, &lm.vs, (size_t) n)) ||
         (st = job_alloc(j, &lm.geo, (size_t) 4 * n)) || (st = job_alloc(j, &lm.chain, (size_t) n, true)) ||
         (st = job_alloc(j, &lm.misrec, (size_t) 2 * MR_MAXV * MR_WORDS * n)) || (st = job_alloc(j, &lm.conn, (size_t) 4 * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
-        (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)) || (st = job_alloc(j, &lm.hit, (size_t) n)))
+        (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)))
         return st;
     if (j->cfg.technique == DR_TECH_BDPT &&      // both subpaths and the splat lists are kept per lane
         ((st = job_alloc(j, &lm.bv, (size_t) 2 * BD_MAXV * n)) || (st = job_alloc(j, &lm.bx, (size_t) 2 * BD_MAXV * n)) ||
@@ -625,7 +625,7 @@ static dr_status alloc_lanes(dr_job j, int n) {
         dr_job_t::Group &gr = j->groups[g];
         gr.begin = (int) ((long long) n * g / G); gr.end = (int) ((long long) n * (g + 1) / G);
         gr.q.n = gr.end - gr.begin;
-        if ((st = job_alloc(j, &gr.q.items, (size_t) Q_COUNT * gr.q.n)) || (st = job_alloc(j, &gr.q.rays, (size_t) 4 * 2 * gr.q.n)) || (st = job_alloc(j, &gr.q.count, (size_t) Q_COUNT + 2, true)))   // + head counters of the two ray queues
+        if ((st = job_alloc(j, &gr.q.items, (size_t) Q_COUNT * gr.q.n)) || (st = job_alloc(j, &gr.q.rays, (size_t) 4 * 2 * gr.q.n)) || (st = job_alloc(j, &gr.q.aux, (size_t) Q_COUNT * gr.q.n, true)) || (st = job_alloc(j, &gr.q.count, (size_t) Q_COUNT + 2, true)))   // + head counters of the two ray queues
             return st;
         if (cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&gr.evJoin, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost((void **) &gr.countsHost, sizeof(uint32_t) * Q_COUNT) != cudaSuccess) {
             dr_set_error("group stream creation failed: %s", cudaGetErrorString(cudaGetLastError())); return DR_ERR_CUDA;

@@ -196,7 +196,7 @@ k_bdpt(const __grid_constant__ Machine M) {
         BdAcc acc;
         rec_load(acc, M.lm.bacc + lane);
         Hit hit;
-        { const float4 h = M.lm.hit[lane]; hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.tri = __float_as_int(h.w); }
+        hit.t = hit.u = hit.v = 0.f; hit.tri = __ldcs(M.q.aux + (size_t) Q_PT * M.q.n + qi);
         UReader rd;
         reader_open(M, c, lane, rd);
         RayF ray;

@@ -85,11 +85,10 @@ DR_D void commit_state(const Machine &M, const MutCtx &mc, double *ub, const int
 }
 
 // ------------------------------------------------------------------ path end -> result
-DR_D void path_result(const Machine &M, int lane, Core &c, PathResult &out) {
+DR_D void path_result(const Machine &M, int lane, int tri, Core &c, PathResult &out) {
     result_clear(out);
     if (M.pc.technique == DR_TECH_MMLT) { out.s = c.s; out.t = c.t; }
     if (c.pstate == PS_CONNECT_SHADOW) {
-        const int tri = __float_as_int(M.lm.hit[lane].w);
         if (tri >= 0) return;                                 // occluded
         if (M.pc.excludeDirect && c.depth <= 2) return;       // pathsampler.cpp:279-284
         if (c.flags & F_SPOS_FAIL) return;
@@ -173,7 +172,7 @@ k_chain(const __grid_constant__ Machine M) {
             if (c.pstate != PS_START) {
                 // ================= a path is complete: job-level step =================
                 PathResult r;
-                path_result(M, lane, c, r);
+                path_result(M, lane, __ldcs(M.q.aux + (size_t) (Q_CHAIN + M.parity) * M.q.n + qi), c, r);
                 ++st[ST_PATHS];
                 if (job.type == JOB_BOOT) {
                     job.lumOut[item] = (float) r.lum;

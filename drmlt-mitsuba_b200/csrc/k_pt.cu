@@ -18,7 +18,7 @@ k_pt(const __grid_constant__ Machine M) {
         PtExtra px;
         rec_load(px, reinterpret_cast<const PtExtra *>(M.lm.vs + lane));
         Hit hit;
-        { const float4 h = M.lm.hit[lane]; hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.tri = __float_as_int(h.w); }
+        hit.t = hit.u = hit.v = 0.f; hit.tri = __ldcs(M.q.aux + (size_t) Q_PT * M.q.n + qi);
         UReader rd;
         reader_open(M, c, lane, rd);
         Vtx v;

@@ -60,7 +60,6 @@ k_trace(const __grid_constant__ Machine M) {
             if (lane >= 0 && !tr.done && tr.cur < 0) tr.leaf_step(M.sc);
             if (lane >= 0 && tr.done) {
                 const bool found = tr.hit.tri >= 0;
-                __stcs(M.lm.hit + lane, make_float4(tr.hit.t, tr.hit.u, tr.hit.v, __int_as_float(found ? tr.hit.tri : -1)));
                 int dest;
                 if (pt) dest = Q_PT;
                 else if (SHADOW || !found) dest = Q_CHAIN + M.parity;
@@ -68,7 +67,7 @@ k_trace(const __grid_constant__ Machine M) {
                     const uint32_t mf = (uint32_t) __float_as_int(__ldg(&M.sc.tris[3 * (size_t) tr.hit.tri + 2].z));
                     dest = Q_WALK + (int) ((mf >> 24) & 3u);
                 }
-                q_push(M.q, dest, (uint32_t) lane);
+                q_push_hit(M.q, dest, (uint32_t) lane, found ? tr.hit.tri : -1);
                 lane = -1;
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, lane >= 0));

@@ -22,7 +22,7 @@ k_walk(const __grid_constant__ Machine M) {
         const int side = emitterSide ? SIDE_E : SIDE_S;
         const int k = c.depth + 2;                           // s + t + 1
         Hit hit;
-        { const float4 h = M.lm.hit[lane]; hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.tri = __float_as_int(h.w); }
+        hit.t = hit.u = hit.v = 0.f; hit.tri = __ldcs(M.q.aux + (size_t) (Q_WALK + BSDF) * M.q.n + qi);
         int dest = Q_CHAIN + M.parity;                       // default: the path ends here (empty result)
         RayF ray;
         do {

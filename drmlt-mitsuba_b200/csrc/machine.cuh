@@ -144,7 +144,6 @@ struct LaneMem {
     BExtra *bx;               // [n][2][BD_MAXV]
     BdAcc *bacc;              // [n]
     float4 *bsplat;           // [n][4][BD_MAXS][2]: light-image splats (pos.xy | rgb) of the lists x, y, z and of the path in flight
-    float4 *hit;              // [n] (t, u, v, leaf-order triangle or -1)
     int n, nU;
 };
 
@@ -180,6 +179,8 @@ struct Queues {
     uint32_t *count;          // [Q_COUNT] (+ 2 head counters of the ray queues)
     float4 *rays;             // [4][n][2]: the float32 rays of the four ray queues (Q_RAYC x2, Q_RAYS x2), parallel to
                               // items -- the traversal kernels read their input with coalesced, independent loads
+    int *aux;                 // [Q_COUNT][n]: result of the traversal that queued the lane (leaf-order triangle, -1 = miss),
+                              // parallel to items: the consumer reads it coalesced instead of gathering a per-lane record
     int n;
 };
 // Opportunistic warp-aggregated append: the threads of the warp that push to the same queue at the same
@@ -195,6 +196,11 @@ DR_D uint32_t q_push(const Queues &q, int which, uint32_t lane) {
     const uint32_t slot = base + __popc(peers & ((1u << self) - 1u));
     q.items[(size_t) which * q.n + slot] = lane;
     return slot;
+}
+// append a lane together with the traversal result that sends it there
+DR_D void q_push_hit(const Queues &q, int which, uint32_t lane, int tri) {
+    const uint32_t slot = q_push(q, which, lane);
+    q.aux[(size_t) which * q.n + slot] = tri;
 }
 // append a lane and, when the destination is a ray queue, its ray
 DR_D void q_push_ray(const Queues &q, int which, uint32_t lane, const RayF &ray) {

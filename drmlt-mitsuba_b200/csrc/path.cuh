@@ -83,7 +83,7 @@ DR_D void fill_vertex(const DevScene &sc, const Hit &hit, R3 o, R3 d, Vtx &v, Re
     const R3 p0 = r3(t0.x, t0.y, t0.z), p1 = r3(t0.w, t1.x, t1.y), p2 = r3(t1.z, t1.w, t2.x);
     const uint32_t mf = (uint32_t) __float_as_int(t2.z);
     const R3 e1 = p1 - p0, e2 = p2 - p0;
-    Real t = hit.t, bu = hit.u, bv = hit.v;
+    Real t = 0., bu = 0., bv = 0.;                  // det == 0 cannot pass the traversal's tests; t = 0 then ends the path
     {
         const R3 pvec = cross(d, e2);
         const Real det = dot(e1, pvec);
