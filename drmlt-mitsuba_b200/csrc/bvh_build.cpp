@@ -25,7 +25,7 @@ float as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 } // namespace
 
 void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out) {
-    const int NB = 16, LEAF = 4;
+    const int NB = 16, LEAF = 2;
     std::vector<Box> box(nTris);
     std::vector<float> cen(3 * (size_t) nTris);
     out.order.resize(nTris);
