@@ -771,7 +771,7 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
             dr_status st = join_groups(j);
             if (st) return st;
         }
-        j->launches += (uint64_t) R * G * (3 + walkLaunches + 1 + beginLaunches);
+        j->launches += (uint64_t) R * G * (2 + walkLaunches + 1 + beginLaunches);
         if (!j->profEvents.empty()) {
             for (size_t i = 0; i + 3 < j->profEvents.size(); i += 4)
                 for (int s = 0; s < STAGE_COUNT; ++s) {
@@ -779,7 +779,7 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
                     cudaEventElapsedTime(&ms, j->profEvents[i + s], j->profEvents[i + s + 1]);
                     j->stageMs[s] += ms;
                 }
-            j->stageLaunches[STAGE_TRACE] += 3ull * R * G; j->stageLaunches[STAGE_WALK] += (uint64_t) walkLaunches * R * G;
+            j->stageLaunches[STAGE_TRACE] += 2ull * R * G; j->stageLaunches[STAGE_WALK] += (uint64_t) walkLaunches * R * G;
             j->stageLaunches[STAGE_CHAIN] += (uint64_t) R * G * (1 + beginLaunches);
             for (cudaEvent_t e : j->profEvents) cudaEventDestroy(e);
             j->profEvents.clear();

@@ -9,20 +9,20 @@
 // visits, so lanes whose ray is done pull the next ray from the queue (one warp-aggregated atomic on the queue's head
 // counter) as soon as fewer than REFILL lanes of the warp are still traversing.
 
-template <bool SHADOW>
+// One kernel traces both ray queues of the round (closest-hit rays first, then the shadow rays of the connections):
+// the handful of shadow rays no longer pays for a launch and a latency-bound tail of its own.
 __global__ void __launch_bounds__(128, TRACE_MINB)
 k_trace(const __grid_constant__ Machine M) {
-    const int qid = (SHADOW ? Q_RAYS : Q_RAYC) + M.parity;
-    const uint32_t cnt = M.q.count[qid];
-    const uint32_t *items = M.q.items + (size_t) qid * M.q.n;
-    const float4 *rays = M.q.rays + 2 * (size_t) qid * M.q.n;
-    uint32_t *head = M.q.count + Q_COUNT + (SHADOW ? 1 : 0);
+    const uint32_t cntC = M.q.count[Q_RAYC + M.parity], cntS = M.q.count[Q_RAYS + M.parity], cnt = cntC + cntS;
+    const uint32_t *itemsC = M.q.items + (size_t) (Q_RAYC + M.parity) * M.q.n, *itemsS = M.q.items + (size_t) (Q_RAYS + M.parity) * M.q.n;
+    const float4 *raysC = M.q.rays + 2 * (size_t) (Q_RAYC + M.parity) * M.q.n, *raysS = M.q.rays + 2 * (size_t) (Q_RAYS + M.parity) * M.q.n;
+    uint32_t *head = M.q.count + Q_COUNT;
     if (blockIdx.x == 0 && threadIdx.x == 0 && cnt) atomicAdd(&M.counters[ST_RAYS], (unsigned long long) cnt);
     const bool pt = M.pc.technique != DR_TECH_MMLT;
     const unsigned self = threadIdx.x & 31u;
     int stack[DR_STACK];
-    Traversal<SHADOW> tr;
-    tr.done = true;
+    Traversal tr;
+    tr.done = true; tr.anyhit = false;
     int lane = -1;
     bool exhausted = false;                                  // warp-uniform: the queue has no rays left
     for (;;) {
@@ -37,9 +37,12 @@ k_trace(const __grid_constant__ Machine M) {
                 if (lane < 0) {
                     const uint32_t qi = base + __popc(idle & ((1u << self) - 1u));
                     if (qi < cnt) {                          // three independent, coalesced loads: no dependent gather
-                        const float4 a = __ldcs(rays + 2 * (size_t) qi), b = __ldcs(rays + 2 * (size_t) qi + 1);
-                        lane = (int) __ldcs(items + qi);
-                        tr.begin(stack, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, M.lm.rayd + 8 * (size_t) lane);
+                        const bool shadow = qi >= cntC;
+                        const uint32_t k = shadow ? qi - cntC : qi;
+                        const float4 *rays = shadow ? raysS : raysC;
+                        const float4 a = __ldcs(rays + 2 * (size_t) k), b = __ldcs(rays + 2 * (size_t) k + 1);
+                        lane = (int) __ldcs((shadow ? itemsS : itemsC) + k);
+                        tr.begin(stack, shadow, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, M.lm.rayd + 8 * (size_t) lane);
                     }
                 }
                 exhausted = base + (uint32_t) __popc(idle) >= cnt;
@@ -62,7 +65,7 @@ k_trace(const __grid_constant__ Machine M) {
                 const bool found = tr.hit.tri >= 0;
                 int dest;
                 if (pt) dest = Q_PT;
-                else if (SHADOW || !found) dest = Q_CHAIN + M.parity;
+                else if (tr.anyhit || !found) dest = Q_CHAIN + M.parity;
                 else {
                     const uint32_t mf = (uint32_t) __float_as_int(__ldg(&M.sc.tris[3 * (size_t) tr.hit.tri + 2].z));
                     dest = Q_WALK + (int) ((mf >> 24) & 3u);
@@ -102,22 +105,20 @@ __global__ void k_round_begin(uint32_t *count, int parity) {
 }
 
 // persistent kernels: exactly as many CTAs as are resident at once (SMs x occupancy)
-static int gridC = 0, gridS = 0;
+static int gridC = 0;
 void trace_init() {                                          // outside any stream capture
     if (gridC) return;
-    int dev = 0, sms = 148, bc = 4, bs = 4;
+    int dev = 0, sms = 148, bc = 4;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_trace<false>, 128, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_trace<true>, 128, 0);
-    gridC = sms * std::max(bc, 1); gridS = sms * std::max(bs, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_trace, 128, 0);
+    gridC = sms * std::max(bc, 1);
 }
 
 void launch_trace(const Machine &M, const LaunchCfg &lc) {
     k_round_begin<<<1, 32, 0, lc.stream>>>(M.q.count, M.parity);
     const int need = std::max(1, (lc.nLanes + 127) / 128);
-    k_trace<false><<<(unsigned) std::min(gridC, need), 128, 0, lc.stream>>>(M);
-    k_trace<true><<<(unsigned) std::min(gridS, need), 128, 0, lc.stream>>>(M);
+    k_trace<<<(unsigned) std::min(gridC, need), 128, 0, lc.stream>>>(M);
 }
 void launch_trace_rays(const DevScene &sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits, cudaStream_t stream) {
     k_trace_rays<<<(unsigned) ((n + 127) / 128), 128, 0, stream>>>(sc, rays, n, shadow, order, hits);

@@ -69,8 +69,8 @@ DR_D bool tri_verify(const float4 t0, const float4 t1, const float4 t2, const do
 
 // One ray's traversal state; step() processes ONE inner node or ONE leaf, so that a persistent kernel can
 // interleave "fetch a new ray for the lanes that finished" with the traversal of the others.
-template <bool ANYHIT>
 struct Traversal {
+    bool anyhit;              // shadow ray: the first hit ends the traversal
     float3 o, d, inv, oi;
     float tmin, tmax;
     const double *rd;         // un-rounded ray: o, d, tmin, tmax
@@ -81,8 +81,8 @@ struct Traversal {
     int sp, cur;              // cur: inner node index, or leaf code (< 0)
     bool done;
 
-    DR_D void begin(int *stack_, float3 o_, float3 d_, float tmin_, float tmax_, const double *rd_) {
-        stack = stack_;
+    DR_D void begin(int *stack_, bool anyhit_, float3 o_, float3 d_, float tmin_, float tmax_, const double *rd_) {
+        stack = stack_; anyhit = anyhit_;
         o = o_; d = d_; tmin = tmin_; tmax = tmax_; rd = rd_;
         hit.tri = -1; hit.t = hit.u = hit.v = 0.f;
         bestT = 0.0; bestExact = true;                // no hit yet: the limit of the exact test is rd[7]
@@ -133,12 +133,12 @@ struct Traversal {
             const int cls = tri_classify(t0, t1, t2, o, d, tmin, tmax, tf, uf, vf);
             if (cls == 1) {
                 hit.t = tf; hit.u = uf; hit.v = vf; hit.tri = first + i;
-                if (ANYHIT) { done = true; return; }
+                if (anyhit) { done = true; return; }
                 bestT = (double) tf; bestExact = false;
                 tmax = tf;
             } else if (cls == 2) {                       // rare: decide in double on the un-rounded ray
                 double t, u, v;
-                if (!ANYHIT && !bestExact && hit.tri >= 0 && tf >= tmax - (2e-5f + 2e-5f * fabsf(tf))) {
+                if (!anyhit && !bestExact && hit.tri >= 0 && tf >= tmax - (2e-5f + 2e-5f * fabsf(tf))) {
                     // the best hit so far was accepted on its float t, which is too close to this candidate's: make it exact
                     const float4 *bp = sc.tris + 3 * (size_t) hit.tri;
                     double bu, bv;
@@ -147,7 +147,7 @@ struct Traversal {
                 }
                 if (tri_verify(t0, t1, t2, rd, hit.tri >= 0 ? bestT : rd[7], t, u, v)) {
                     hit.t = (float) t; hit.u = (float) u; hit.v = (float) v; hit.tri = first + i;
-                    if (ANYHIT) { done = true; return; }
+                    if (anyhit) { done = true; return; }
                     bestT = t; bestExact = true;
                     tmax = __double2float_ru(t);
                 }
@@ -160,8 +160,8 @@ struct Traversal {
 template <bool ANYHIT>
 DR_D bool traverse(const DevScene &sc, float3 o, float3 d, float tmin, float tmax, const double *rd, Hit &hit) {
     int stack[DR_STACK];
-    Traversal<ANYHIT> tr;
-    tr.begin(stack, o, d, tmin, tmax, rd);
+    Traversal tr;
+    tr.begin(stack, ANYHIT, o, d, tmin, tmax, rd);
     while (!tr.done) tr.step(sc);
     hit = tr.hit;
     return hit.tri >= 0;
