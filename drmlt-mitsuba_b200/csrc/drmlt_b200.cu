@@ -718,8 +718,8 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
     for (int g = 0; g < G; ++g) Ms.push_back(machine_for(j, g, job, counters, withFilm));
     const bool mmlt = j->cfg.technique == DR_TECH_MMLT;
     const unsigned typeMask = static_cast<SceneImpl *>(j->scene)->typeMask;
-    const int walkLaunches = mmlt ? __builtin_popcount(typeMask & 15u) + 1 : 1;
-    const int beginLaunches = job.type == JOB_CHAIN ? (j->cfg.integrator == DR_INTEGRATOR_DRMLT ? 3 : 2) : 1;
+    const int walkLaunches = mmlt ? 2 : 1;
+    const int beginLaunches = 1;
     const int R = j->roundsPerPoll;                             // even: a replay starts at the parity it was captured with
     CK(cudaStreamSynchronize(j->stream));                       // everything queued on the main stream is visible to the groups
     cudaStream_t s0 = j->groups[0].stream;

@@ -140,13 +140,10 @@ DR_D int path_start(const Machine &M, int lane, Core &c, RayF &ray) {
 } // namespace
 
 template <int CLS>
-__global__ void __launch_bounds__(128, BEGIN_MINB)
-k_begin(const __grid_constant__ Machine M) {
+DR_D void begin_lane(const Machine &M, uint32_t qi) {
     const JobParams &job = M.job;
-    const uint32_t cnt = M.q.count[Q_BEGIN + CLS];
-    const uint32_t *items = M.q.items + (size_t) (Q_BEGIN + CLS) * M.q.n;
-    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
-        const int lane = (int) items[qi];
+    {
+        const int lane = (int) M.q.items[(size_t) (Q_BEGIN + CLS) * M.q.n + qi];
         Core c;
         rec_load(c, M.lm.core + lane);
         if (CLS == BEGIN_STAGE1) c.phase = PH_STAGE1;             // compile-time phase for the proposal switch
@@ -176,11 +173,22 @@ k_begin(const __grid_constant__ Machine M) {
     }
 }
 
-void launch_begin(const Machine &M, const LaunchCfg &lc) {
-    const unsigned g = (unsigned) std::max(1, std::min((lc.nLanes + 127) / 128, 148 * 16));
-    if (M.job.type == JOB_CHAIN) {
-        k_begin<BEGIN_STAGE1><<<g, 128, 0, lc.stream>>>(M);
-        if (M.pp.integrator == DR_INTEGRATOR_DRMLT) k_begin<BEGIN_STAGE2><<<g, 128, 0, lc.stream>>>(M);
+// the three classes in one launch, every warp on one class (multiq_locate)
+__global__ void __launch_bounds__(128, BEGIN_MINB)
+k_begin(const __grid_constant__ Machine M) {
+    const uint32_t cnt[3] = { M.q.count[Q_BEGIN + BEGIN_STAGE1], M.q.count[Q_BEGIN + BEGIN_STAGE2], M.q.count[Q_BEGIN + BEGIN_OTHER] };
+    const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;; w += nWarps) {
+        int cls; uint32_t qi;
+        if (!multiq_locate<3>(cnt, w, cls, qi)) break;
+        if (qi >= cnt[cls]) continue;
+        if (cls == BEGIN_STAGE1) begin_lane<BEGIN_STAGE1>(M, qi);
+        else if (cls == BEGIN_STAGE2) begin_lane<BEGIN_STAGE2>(M, qi);
+        else begin_lane<BEGIN_OTHER>(M, qi);
     }
-    k_begin<BEGIN_OTHER><<<g, 128, 0, lc.stream>>>(M);
+}
+
+void launch_begin(const Machine &M, const LaunchCfg &lc) {
+    const unsigned g = (unsigned) std::max(1, std::min((lc.nLanes + 127) / 128 + 3, 148 * 16));
+    k_begin<<<g, 128, 0, lc.stream>>>(M);
 }

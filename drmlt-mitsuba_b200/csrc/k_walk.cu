@@ -9,13 +9,10 @@
 #include "machine.cuh"
 
 template <int BSDF>
-__global__ void __launch_bounds__(128, WALK_MINB)
-k_walk(const __grid_constant__ Machine M) {
+DR_D void walk_lane(const Machine &M, uint32_t qi) {
     const DevScene &sc = M.sc;
-    const uint32_t cnt = M.q.count[Q_WALK + BSDF];
-    const uint32_t *items = M.q.items + (size_t) (Q_WALK + BSDF) * M.q.n;
-    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
-        const int lane = (int) items[qi];
+    {
+        const int lane = (int) M.q.items[(size_t) (Q_WALK + BSDF) * M.q.n + qi];
         Core c;
         rec_load(c, M.lm.core + lane);
         const bool emitterSide = c.pstate == PS_EMITTER_HIT;
@@ -192,11 +189,25 @@ k_connect(const __grid_constant__ Machine M) {
 
 static unsigned grid_for(int n, int threads) { return (unsigned) std::max(1, std::min((n + threads - 1) / threads, 148 * 16)); }
 
+// the walk queues of all BSDF models in one launch, every warp on one model (multiq_locate)
+__global__ void __launch_bounds__(128, WALK_MINB)
+k_walk(const __grid_constant__ Machine M) {
+    const uint32_t cnt[4] = { M.q.count[Q_WALK + 0], M.q.count[Q_WALK + 1], M.q.count[Q_WALK + 2], M.q.count[Q_WALK + 3] };
+    const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;; w += nWarps) {
+        int cls; uint32_t qi;
+        if (!multiq_locate<4>(cnt, w, cls, qi)) break;
+        if (qi >= cnt[cls]) continue;
+        if (cls == DR_BSDF_DIFFUSE) walk_lane<DR_BSDF_DIFFUSE>(M, qi);
+        else if (cls == DR_BSDF_DIELECTRIC) walk_lane<DR_BSDF_DIELECTRIC>(M, qi);
+        else if (cls == DR_BSDF_CONDUCTOR) walk_lane<DR_BSDF_CONDUCTOR>(M, qi);
+        else walk_lane<DR_BSDF_ROUGHCONDUCTOR>(M, qi);
+    }
+}
+
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask) {
-    const unsigned g = grid_for(lc.nLanes, 128);
-    if (typeMask & (1u << DR_BSDF_DIFFUSE)) k_walk<DR_BSDF_DIFFUSE><<<g, 128, 0, lc.stream>>>(M);
-    if (typeMask & (1u << DR_BSDF_DIELECTRIC)) k_walk<DR_BSDF_DIELECTRIC><<<g, 128, 0, lc.stream>>>(M);
-    if (typeMask & (1u << DR_BSDF_CONDUCTOR)) k_walk<DR_BSDF_CONDUCTOR><<<g, 128, 0, lc.stream>>>(M);
-    if (typeMask & (1u << DR_BSDF_ROUGHCONDUCTOR)) k_walk<DR_BSDF_ROUGHCONDUCTOR><<<g, 128, 0, lc.stream>>>(M);
+    (void) typeMask;
+    const unsigned g = grid_for(lc.nLanes + 4 * 128, 128);
+    k_walk<<<g, 128, 0, lc.stream>>>(M);
     k_connect<<<g, 128, 0, lc.stream>>>(M);
 }

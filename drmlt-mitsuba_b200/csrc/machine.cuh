@@ -211,6 +211,20 @@ DR_D void q_push_ray(const Queues &q, int which, uint32_t lane, const RayF &ray)
     }
 }
 
+// Several queues in ONE launch: the global warp index space is the concatenation of the queues, each rounded up to
+// whole warps, so that every warp works on one queue (one kind of work) and the classes run side by side instead of
+// each paying for a launch and a latency-bound tail of its own.  Returns false when `warp` is past the end.
+template <int K>
+DR_D bool multiq_locate(const uint32_t (&cnt)[K], uint32_t warp, int &cls, uint32_t &qi) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t w = (cnt[k] + 31u) >> 5;
+        if (warp < w) { cls = k; qi = (warp << 5) + (threadIdx.x & 31u); return true; }
+        warp -= w;
+    }
+    return false;
+}
+
 // ------------------------------------------------------------------ jobs
 enum { JOB_CHAIN = 0, JOB_BOOT = 1, JOB_EVAL = 2 };
 struct JobParams {
