@@ -33,7 +33,8 @@
 #include "path.cuh"
 
 // Resident CTAs (of 128 threads) per SM that each stage kernel is compiled for.  Every stage is bound by the latency of
-// dependent gathers (ncu: long-scoreboard stalls dominate), so registers are traded for resident warps.
+// dependent gathers (ncu: long-scoreboard stalls dominate), so registers are traded for resident warps -- up to the point
+// where spills start to cost (measured: 4 / 4 / 5 CTAs for walk / chain / begin; 3 or 5 are within 1 %).
 #ifdef DR_NO_STREAMING
 #define DR_REC_LD(p) (*(p))
 #define DR_REC_ST(p, v) (*(p) = (v))
@@ -45,16 +46,16 @@
 #define TRACE_MINB 8
 #endif
 #ifndef WALK_MINB
-#define WALK_MINB 5
+#define WALK_MINB 4
 #endif
 #ifndef CONNECT_MINB
 #define CONNECT_MINB 4
 #endif
 #ifndef CHAIN_MINB
-#define CHAIN_MINB 5
+#define CHAIN_MINB 4
 #endif
 #ifndef BEGIN_MINB
-#define BEGIN_MINB 6
+#define BEGIN_MINB 5
 #endif
 
 // ------------------------------------------------------------------ lane records (AoS: one record per lane per array,
