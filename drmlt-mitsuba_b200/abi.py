@@ -72,7 +72,7 @@ class dr_stats(C.Structure):
         ("luminance", C.c_double), ("bootstrap_ms", C.c_double), ("chains_ms", C.c_double),
         ("total_ms", C.c_double), ("kernel_launches", C.c_uint64), ("rounds", C.c_uint64),
         ("trace_ms", C.c_double), ("walk_ms", C.c_double), ("chain_ms", C.c_double),
-        ("trace_launches", C.c_uint64), ("walk_launches", C.c_uint64), ("chain_launches", C.c_uint64)]
+        ("trace_launches", C.c_uint64), ("walk_launches", C.c_uint64), ("chain_launches", C.c_uint64), ("direct_ms", C.c_double)]
 
 
 class dr_ray(C.Structure):
@@ -99,7 +99,7 @@ EXPORTED_SYMBOLS = [
     "dr_abi_version", "dr_last_error", "dr_device_count", "dr_config_default", "dr_config_set",
     "dr_config_validate", "dr_scene_create", "dr_scene_destroy", "dr_scene_reupload", "dr_render", "dr_cancel",
     "dr_job_create", "dr_job_destroy", "dr_job_bootstrap", "dr_job_seed_chains", "dr_job_run",
-    "dr_job_film_device", "dr_job_develop", "dr_job_stats", "dr_job_profile", "dr_job_num_chains", "dr_job_total_mutations",
+    "dr_job_film_device", "dr_job_develop", "dr_job_stats", "dr_job_profile", "dr_job_direct", "dr_direct_image", "dr_job_num_chains", "dr_job_total_mutations",
     "dr_trace_rays", "dr_eval_paths", "dr_chain_steps", "dr_bootstrap_luminance", "dr_max_dimensions",
 ]
 
@@ -146,6 +146,8 @@ def load_library(path=None):
     lib.dr_job_film_device.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_int64)]
     lib.dr_job_develop.argtypes = [C.c_void_p, P(C.c_float)]
     lib.dr_job_stats.argtypes = [C.c_void_p, P(dr_stats)]
+    lib.dr_job_direct.argtypes = [C.c_void_p]
+    lib.dr_direct_image.argtypes = [C.c_void_p, P(dr_config), P(C.c_float), P(C.c_double)]
     lib.dr_job_profile.argtypes = [C.c_void_p, C.c_int]
     lib.dr_job_profile.restype = None
     lib.dr_job_num_chains.argtypes = [C.c_void_p]

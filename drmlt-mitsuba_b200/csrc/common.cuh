@@ -61,7 +61,7 @@ DR_HD void coordinate_system(float3 a, float3 &b, float3 &c) {
 // Same address space as oracle/orc_rng.hpp (DESIGN.md "uniform address space"):
 //   word(stream,a,b,j) = philox(ctr={lo(a),hi(a),b,(stream<<24)|(j>>2)}, key=seed)[j&3]
 //   uniform = (word >> 8) * 2^-24
-enum { S_BOOT = 1, S_RESAMPLE = 2, S_COIN = 3, S_STAGE1 = 4, S_STAGE2 = 7 };
+enum { S_BOOT = 1, S_RESAMPLE = 2, S_COIN = 3, S_STAGE1 = 4, S_STAGE2 = 7, S_DIRECT = 10 };
 
 DR_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__

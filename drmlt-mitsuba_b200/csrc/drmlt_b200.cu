@@ -528,6 +528,9 @@ struct dr_job_t {
     float *bootLum = nullptr;
     double *cdf = nullptr, *blockSums = nullptr, *red = nullptr, *redScratch = nullptr;
     float *devImage = nullptr;
+    float4 *directFilm = nullptr;               // weighted film of the separate direct-illumination pass
+    float *directImage = nullptr;               // ... developed (null until dr_job_direct ran)
+    bool haveDirect = false;
     long long nBoot = 0;
     unsigned long long bootFirst = 0;
     int nChains = 0;
@@ -537,7 +540,7 @@ struct dr_job_t {
     bool bootstrapped = false, seeded = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double bootstrapMs = 0.0, chainsMs = 0.0, totalMs = 0.0;
+    double bootstrapMs = 0.0, chainsMs = 0.0, totalMs = 0.0, directMs = 0.0;
     uint64_t launches = 0, rounds = 0;
     std::vector<void *> allocations;
     int roundsPerPoll = 16;
@@ -983,11 +986,43 @@ extern "C" dr_status dr_job_develop(dr_job j, float *imageRgb) {
     const bool accMap = j->M.cp.acceptanceMap;
     const double avg = lumSum / (double) n;
     const float factor = accMap ? 1.0f : (avg > 0.0 ? (float) (j->b / avg) : 0.f);
-    launch_develop(j->film, n, factor, j->devImage, j->stream);
+    launch_develop(j->film, n, factor, (j->haveDirect && !accMap) ? j->directImage : nullptr, j->devImage, j->stream);
     CKL();
     j->launches += 2;
     CK(cudaMemcpyAsync(imageRgb, j->devImage, (size_t) n * 3 * sizeof(float), cudaMemcpyDeviceToHost, j->stream));
     CK(cudaStreamSynchronize(j->stream));
+    return DR_OK;
+}
+
+// pixelSamples x shadingSamples split of directSamples (util.cpp:44-54)
+static void direct_split(int directSamples, int *pixelSamples, int *shadingSamples) {
+    int p = std::max(directSamples, 1), s = 1;
+    while (p > 8) { p /= 2; s *= 2; }
+    *pixelSamples = p; *shadingSamples = s;
+}
+
+// The separate direct-illumination image (renderDirectComponent, src/libbidir/util.cpp:30-94); develop adds it.
+extern "C" dr_status dr_job_direct(dr_job j) {
+    if (!j) { dr_set_error("dr_job_direct: null job"); return DR_ERR_INVALID_ARG; }
+    if (j->cfg.direct_samples <= 0) return DR_OK;               // directSamples = 0: direct light is excluded and not rendered (drmlt.cpp:479)
+    if (!j->film) { dr_set_error("dr_job_direct: not a render job"); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(j->scene->device));
+    const long long n = (long long) j->scene->filmW * j->scene->filmH;
+    dr_status st;
+    if (!j->directFilm && ((st = job_alloc(j, &j->directFilm, (size_t) n)) || (st = job_alloc(j, &j->directImage, (size_t) 3 * n)))) return st;
+    CK(cudaMemsetAsync(j->directFilm, 0, sizeof(float4) * n, j->stream));
+    int ps, ss;
+    direct_split(j->cfg.direct_samples, &ps, &ss);
+    CK(cudaEventRecord(j->ev0, j->stream));
+    launch_direct(j->M.sc, j->M.fp, j->cfg.seed, ps, ss, j->directFilm, j->directImage, nullptr, j->stream);
+    CKL();
+    j->launches += 2;
+    CK(cudaEventRecord(j->ev1, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, j->ev0, j->ev1));
+    j->directMs += ms;
+    j->haveDirect = true;
     return DR_OK;
 }
 
@@ -1012,6 +1047,7 @@ extern "C" dr_status dr_job_stats(dr_job j, dr_stats *s) {
     s->bootstrap_ms = j->bootstrapMs; s->chains_ms = j->chainsMs; s->total_ms = j->totalMs;
     s->kernel_launches = j->launches;
     s->rounds = j->rounds;
+    s->direct_ms = j->directMs;
     s->trace_ms = j->stageMs[STAGE_TRACE]; s->walk_ms = j->stageMs[STAGE_WALK]; s->chain_ms = j->stageMs[STAGE_CHAIN];
     s->trace_launches = j->stageLaunches[STAGE_TRACE]; s->walk_launches = j->stageLaunches[STAGE_WALK]; s->chain_launches = j->stageLaunches[STAGE_CHAIN];
     return DR_OK;
@@ -1036,7 +1072,7 @@ extern "C" dr_status dr_render(dr_scene scene, const dr_config *cfg, float *imag
         if (j->cfg.technique == DR_TECH_MMLT) b *= j->cfg.max_depth;
         if (!(st = dr_job_seed_chains(j, b))) {
             const long long per = std::max<long long>(1, j->totalMutations / j->nChains);   // nMutations (drmlt.cpp:475-476)
-            if (!(st = dr_job_run(j, per))) st = dr_job_develop(j, imageRgb);
+            if (!(st = dr_job_run(j, per)) && !(st = dr_job_direct(j))) st = dr_job_develop(j, imageRgb);
         }
     }
     cudaEventRecord(t1, j->stream);
@@ -1070,6 +1106,30 @@ extern "C" dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n
     launch_trace_rays(s->dev, dr.as<dr_ray>(), n, shadow, s->dOrder, dh.as<dr_hit>(), 0);
     CKL();
     CK(cudaMemcpy(hits, dh.p, n * sizeof(dr_hit), cudaMemcpyDeviceToHost));
+    return DR_OK;
+}
+
+extern "C" dr_status dr_direct_image(dr_scene scene, const dr_config *cfgIn, float *imageRgb, double *li) {
+    if (!scene || !cfgIn || !imageRgb) { dr_set_error("dr_direct_image: bad argument"); return DR_ERR_INVALID_ARG; }
+    dr_config cfg = *cfgIn;
+    dr_status st = dr_config_validate(&cfg);
+    if (st) return st;
+    if (cfg.direct_samples <= 0) { dr_set_error("dr_direct_image: directSamples must be positive"); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(scene->device));
+    const long long n = (long long) scene->filmW * scene->filmH;
+    int ps, ss;
+    direct_split(cfg.direct_samples, &ps, &ss);
+    Machine M;
+    memset(&M, 0, sizeof(M));
+    M.sc = scene_for(scene, cfg);
+    make_params(cfg, scene->filmW, scene->filmH, 1.0, nullptr, M);
+    DevBuf film, rgb, dli;
+    if ((st = film.alloc(sizeof(float4) * n)) || (st = rgb.alloc(sizeof(float) * 3 * n)) || (li && (st = dli.alloc(sizeof(double) * 3 * n * ps)))) return st;
+    CK(cudaMemset(film.p, 0, sizeof(float4) * n));
+    launch_direct(M.sc, M.fp, cfg.seed, ps, ss, film.as<float4>(), rgb.as<float>(), li ? dli.as<double>() : nullptr, 0);
+    CKL();
+    CK(cudaMemcpy(imageRgb, rgb.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (li) CK(cudaMemcpy(li, dli.p, sizeof(double) * 3 * n * ps, cudaMemcpyDeviceToHost));
     return DR_OK;
 }
 

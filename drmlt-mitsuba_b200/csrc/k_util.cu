@@ -127,11 +127,13 @@ __global__ void k_film_luminance(const float4 *film, long long n, double *out) {
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
-__global__ void k_develop(const float4 *film, long long n, float factor, float *rgb) {
+__global__ void k_develop(const float4 *film, long long n, float factor, const float *direct, float *rgb) {
     const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = film[i];
-    rgb[3 * i] = p.x * factor; rgb[3 * i + 1] = p.y * factor; rgb[3 * i + 2] = p.z * factor;
+    float r = p.x * factor, g = p.y * factor, b = p.z * factor;
+    if (direct) { r += direct[3 * i]; g += direct[3 * i + 1]; b += direct[3 * i + 2]; }      // value += direct[i] (drmlt_proc.cpp:846-847)
+    rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
 }
 
 
@@ -153,4 +155,6 @@ void launch_resample(const double *cdf, long long n, unsigned long long seed, un
     k_resample<<<(nChains + 127) / 128, 128, 0, s>>>(cdf, n, seed, firstChain, nChains, bootFirst, maxDepth, technique, seedIdx, chainId, depth);
 }
 void launch_film_luminance(const float4 *film, long long n, double *out, cudaStream_t s) { k_film_luminance<<<148 * 4, 256, 0, s>>>(film, n, out); }
-void launch_develop(const float4 *film, long long n, float factor, float *rgb, cudaStream_t s) { k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(film, n, factor, rgb); }
+void launch_develop(const float4 *film, long long n, float factor, const float *direct, float *rgb, cudaStream_t s) {
+    k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(film, n, factor, direct, rgb);
+}

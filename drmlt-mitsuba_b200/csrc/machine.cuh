@@ -438,4 +438,6 @@ void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const
                   const unsigned long long *seedIdx);                     // k_chain.cu: initialise lanes for M.job and queue them
 void launch_resume(const Machine &M, const LaunchCfg &lc);                // k_chain.cu: re-queue idle chains whose target was raised
 void launch_flush_pssmlt(const Machine &M, const LaunchCfg &lc);          // k_chain.cu
+void launch_direct(const DevScene &sc, const FilmParams &fp, unsigned long long seed, int pixelSamples, int shadingSamples, float4 *film, float *rgb,
+                   double *li, cudaStream_t stream);                       // k_direct.cu: weighted film -> normalised rgb
 void launch_trace_rays(const DevScene &sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits, cudaStream_t stream);

@@ -8,4 +8,4 @@ void launch_scan(const float *lum, long long n, double *cdf /* n + 1 */, double 
 void launch_resample(const double *cdf, long long n, unsigned long long seed, unsigned long long firstChain, int nChains, unsigned long long bootFirst,
                      int maxDepth, int technique, unsigned long long *seedIdx, unsigned long long *chainId, int *depth, cudaStream_t s);
 void launch_film_luminance(const float4 *film, long long n, double *out, cudaStream_t s);
-void launch_develop(const float4 *film, long long n, float factor, float *rgb, cudaStream_t s);
+void launch_develop(const float4 *film, long long n, float factor, const float *direct /* or null */, float *rgb, cudaStream_t s);

@@ -78,6 +78,9 @@ def render(scene, params, dist=None, rank=0, world_size=1, mutations_per_chain=N
         reduce_film(film, dist, 0)
         torch.cuda.synchronize()
     lap("film_reduce_ms")
+    if rank == 0:
+        job.direct()                       # separate direct-illumination image (directSamples > 0), added by develop
+    lap("direct_ms")
     img = job.develop() if rank == 0 else None
     lap("develop_ms")
     st = job.stats()

@@ -99,6 +99,17 @@ class Scene:
         abi.check(self.lib, self.lib.dr_bootstrap_luminance(self.h, C.byref(cfg), first, n, _fp(lum), _fp(dep, C.c_int32)))
         return lum, dep
 
+    def direct_image(self, cfg, want_li=False):
+        """The separate direct-illumination image (directSamples > 0); optionally the radiance of every pixel sample."""
+        W, H = self.film
+        ps = max(int(cfg.direct_samples), 1)
+        while ps > 8:
+            ps //= 2
+        img = np.zeros((H, W, 3), np.float32)
+        li = np.zeros((H, W, ps, 3), np.float64) if want_li else None
+        abi.check(self.lib, self.lib.dr_direct_image(self.h, C.byref(cfg), _fp(img), _fp(li, C.c_double) if want_li else None))
+        return (img, li) if want_li else img
+
     def chain_steps(self, cfg, b, seed_index, depth, chain_id, steps, want_film=False):
         n = len(seed_index)
         seed_index = np.ascontiguousarray(seed_index, np.uint64)
@@ -151,6 +162,10 @@ class Job:
 
     def run(self, mutations_per_chain):
         abi.check(self.lib, self.lib.dr_job_run(self.h, int(mutations_per_chain)))
+
+    def direct(self):
+        """Render the separate direct-illumination image (no-op unless directSamples > 0); develop() adds it."""
+        abi.check(self.lib, self.lib.dr_job_direct(self.h))
 
     def profile(self, on=True):
         """Stage profiling: CUDA events around every stage of every round; sums appear in stats()."""

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DR_ABI_VERSION 2
+#define DR_ABI_VERSION 3
 
 /* ------------------------------------------------------------------ status */
 typedef enum dr_status {
@@ -167,6 +167,7 @@ typedef struct dr_stats {
     /* per-stage device time, only filled while stage profiling is on (dr_job_profile) */
     double   trace_ms, walk_ms, chain_ms;
     uint64_t trace_launches, walk_launches, chain_launches;
+    double   direct_ms;                 /* separate direct-illumination pass (directSamples > 0) */
 } dr_stats;
 
 /* ------------------------------------------------------------- entry points */
@@ -206,6 +207,10 @@ dr_status dr_job_bootstrap(dr_job job, double *sum_luminance, double *count);
 dr_status dr_job_seed_chains(dr_job job, double b);
 /* Advance every chain by `mutations_per_chain` iterations of the MLT loop. */
 dr_status dr_job_run(dr_job job, int64_t mutations_per_chain);
+/* The separate direct-illumination image of the reference's default configuration (directSamples > 0:
+ * BidirectionalUtils::renderDirectComponent, src/libbidir/util.cpp:30-94, with the `direct` integrator,
+ * src/integrators/direct/direct.cpp:144-305); dr_job_develop adds it (drmlt_proc.cpp:846-847).  No-op for directSamples <= 0. */
+dr_status dr_job_direct(dr_job job);
 /* Device pointers of the accumulation film (W*H*3 floats, un-normalised) -- the buffer
  * a multi-GPU driver hands to ncclReduce. */
 dr_status dr_job_film_device(dr_job job, float **film_dev, int64_t *n_floats);
@@ -263,6 +268,10 @@ dr_status dr_chain_steps(dr_scene scene, const dr_config *cfg, double b,
 /* Bootstrap luminances of samples [first, first+n) (before the x maxDepth MMLT scaling). */
 dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfg,
                                  uint64_t first, int64_t n, float *luminance, int32_t *depth);
+
+/* The direct-illumination image alone (parity entry point).  `li` (optional): un-filtered radiance of every pixel
+ * sample, [H][W][pixelSamples][3] doubles, pixelSamples x shadingSamples being the split of directSamples (util.cpp:44-54). */
+dr_status dr_direct_image(dr_scene scene, const dr_config *cfg, float *image_rgb, double *li);
 
 /* Primary-sample dimensions per sampler (findMaxDimensions, pssmlt_utils.h:27-77). */
 void dr_max_dimensions(const dr_config *cfg, int depth, int *sensor, int *emitter, int *direct);

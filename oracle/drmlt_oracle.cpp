@@ -185,6 +185,7 @@ int orc_chain_steps(void *h, const dr_config *cfg, double b, const uint64_t *see
 // Whole render on the CPU (the reported CPU baseline; "port" of DRMLT::render / PSSMLT::render,
 // drmlt.cpp:393-611).  n_boot bootstrap samples -> b and the seed CDF -> n_chains chains of
 // `steps` mutations each, one chain per work item, `threads` host threads.
+int orc_direct_image(void *h, const dr_config *cfg, float *image_rgb, double *li_out);
 int orc_render(void *h, const dr_config *cfg, int64_t n_boot, int64_t n_chains, int64_t steps, int threads,
                float *image_rgb, dr_stats *stats_out, double *seconds_chains) {
     Scene &sc = ((OrcScene *) h)->sc;
@@ -224,6 +225,11 @@ int orc_render(void *h, const dr_config *cfg, int64_t n_boot, int64_t n_chains, 
         Film f; f.init(sc.cam.resX, sc.cam.resY, cfg->rfilter);
         for (size_t i = 0; i < film.size(); ++i) f.data[i] = film[i];
         develop(f, b, cfg->acceptance_map != 0, image_rgb);
+        if (cfg->direct_samples > 0 && !cfg->acceptance_map) {   // value += direct[i] (drmlt_proc.cpp:846-847)
+            std::vector<float> direct(film.size());
+            orc_direct_image(h, cfg, direct.data(), nullptr);
+            for (size_t i = 0; i < film.size(); ++i) image_rgb[i] += direct[i];
+        }
     }
     if (stats_out) stats_out->luminance = b;
     return 0;
@@ -259,5 +265,57 @@ double orc_kelemen_pdf(double s1, double s2, double du) { return KelemenKernel(s
 double orc_gaussian_sample(double sigma, double xi1, double xi2) { return GaussianKernel{ sigma }.sample(xi1, xi2); }
 double orc_cauchy_sample(double rho, double xi) { return WrappedCauchyKernel(rho).sample(xi); }
 double orc_wrap(double y) { return wrapReflect(y); }
+
+// The separate direct-illumination image (BidirectionalUtils::renderDirectComponent, src/libbidir/util.cpp:30-94):
+// pixelSamples x shadingSamples split of directSamples, SamplingIntegrator::renderBlock (src/librender/integrator.cpp)
+// with the film's reconstruction filter and weight normalisation.  The reference draws its samples from an `ldsampler`
+// seeded from /dev/urandom; here sample j of pixel p uses the keyed uniforms (S_DIRECT, p, j, .): same estimator.
+// li_out (optional): the un-filtered radiance of every pixel sample [h][w][pixelSamples][3].
+int orc_direct_image(void *h, const dr_config *cfg, float *image_rgb, double *li_out) {
+    Scene &sc = ((OrcScene *) h)->sc;
+    applyEps(sc, cfg);
+    int pixelSamples = std::max(cfg->direct_samples, 1), shadingSamples = 1;
+    while (pixelSamples > 8) { pixelSamples /= 2; shadingSamples *= 2; }
+    const int W = (int) sc.cam.resX, H = (int) sc.cam.resY;
+    Film f; f.init(W, H, cfg->rfilter);
+    std::vector<Float> weight((size_t) W * H, 0.0);
+    PathCtx ctx; ctx.scene = &sc;
+    std::vector<Vec2> u(2 * shadingSamples);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const uint64_t p = (uint64_t) y * W + x;
+            for (int j = 0; j < pixelSamples; ++j) {
+                const Vec2 jitter(keyedUniform(cfg->seed, S_DIRECT, p, (uint32_t) j, 0), keyedUniform(cfg->seed, S_DIRECT, p, (uint32_t) j, 1));
+                for (int i = 0; i < 2 * shadingSamples; ++i)
+                    u[i] = Vec2(keyedUniform(cfg->seed, S_DIRECT, p, (uint32_t) j, 2 + 2 * i), keyedUniform(cfg->seed, S_DIRECT, p, (uint32_t) j, 3 + 2 * i));
+                const Vec2 samplePos(x + jitter.x, y + jitter.y);
+                Vec3 dl = sc.cam.sampleToDir(samplePos.x / sc.cam.resX, samplePos.y / sc.cam.resY);
+                Float invZ = 1.0 / dl.z;
+                Ray ray; ray.o = sc.cam.pos; ray.d = sc.cam.xformDir(dl);
+                ray.mint = sc.cam.nearClip * invZ; ray.maxt = sc.cam.farClip * invZ;
+                const RGB Li = directLi(ctx, ray, shadingSamples, u.data());
+                if (li_out) { double *o = li_out + (((size_t) p) * pixelSamples + j) * 3; o[0] = Li.r; o[1] = Li.g; o[2] = Li.b; }
+                // ImageBlock::put(pos, spec, alpha): weighted value + weight channel (imageblock.h:149-196)
+                if (!Li.isValid()) continue;
+                const Float px = samplePos.x - 0.5, py = samplePos.y - 0.5;
+                const int minx = std::max((int) std::ceil(px - f.radius), 0), miny = std::max((int) std::ceil(py - f.radius), 0);
+                const int maxx = std::min((int) std::floor(px + f.radius), W - 1), maxy = std::min((int) std::floor(py + f.radius), H - 1);
+                for (int yy = miny; yy <= maxy; ++yy) {
+                    const Float wy = f.evalDiscretized(yy - py);
+                    for (int xx = minx; xx <= maxx; ++xx) {
+                        const Float wgt = f.evalDiscretized(xx - px) * wy;
+                        Float *dest = &f.data[((size_t) yy * W + xx) * 3];
+                        dest[0] += wgt * Li.r; dest[1] += wgt * Li.g; dest[2] += wgt * Li.b;
+                        weight[(size_t) yy * W + xx] += wgt;
+                    }
+                }
+            }
+        }
+    for (size_t i = 0; i < (size_t) W * H; ++i) {             // HDRFilm::develop: divide by the accumulated filter weight
+        const Float inv = weight[i] > 0 ? 1.0 / weight[i] : 0.0;
+        for (int c = 0; c < 3; ++c) image_rgb[3 * i + c] = (float) (f.data[3 * i + c] * inv);
+    }
+    return 0;
+}
 
 } // extern "C"

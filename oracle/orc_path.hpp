@@ -675,4 +675,51 @@ inline RGB pathTracerLi(PathCtx &ctx, Sampler *sampler, Ray ray, int maxDepth, i
     return Li;
 }
 
+
+// MIDirectIntegrator::Li (src/integrators/direct/direct.cpp:144-305) for a camera ray, with the plugin defaults
+// strictNormals=false, hideEmitters=false and emitterSamples = bsdfSamples = shadingSamples; `u` supplies the
+// 2-D samples: first the emitter samples, then the BSDF samples.
+inline RGB directLi(PathCtx &ctx, Ray ray, int shadingSamples, const Vec2 *u) {
+    const Scene &sc = *ctx.scene;
+    Intersection its;
+    RGB Li(0.0);
+    if (!sc.rayIntersect(ray, its, &ctx.rays)) return Li;
+    if (its.emitter >= 0 && dot(its.sh.n, -ray.d) > 0) Li += sc.emitters[its.emitter].radiance;   // its.Le(-ray.d), area.cpp:112-117
+    const dr_material &bsdf = sc.mats[its.material];
+    const int nE = shadingSamples, nB = shadingSamples;
+    const Float fracLum = nE / (Float) (nE + nB), fracBSDF = nB / (Float) (nE + nB), weightLum = 1.0 / nE, weightBSDF = 1.0 / nB;
+    auto mi = [](Float a, Float b) { a *= a; b *= b; return a / (a + b); };
+    DirectRec dRec;
+    dRec.ref = its.p;
+    dRec.refN = bsdfTransmissiveOrBackside(bsdf) ? Vec3(0.0) : its.sh.n;
+    if (bsdfHasSmooth(bsdf) && !sc.emitters.empty()) {
+        for (int i = 0; i < nE; ++i) {
+            RGB value = sampleEmitterDirect(ctx, dRec, u[i], true);
+            if (value.isZero()) continue;
+            BSDFRecord bRec(its.wi, its.toLocal(dRec.d), ERadiance);
+            const RGB bsdfVal = bsdfEval(bsdf, bRec);
+            if (bsdfVal.isZero()) continue;
+            const Float bPdf = bsdfPdf(bsdf, bRec);        // area lights are on a surface
+            Li += value * bsdfVal * (mi(dRec.pdf * fracLum, bPdf * fracBSDF) * weightLum);
+        }
+    }
+    for (int i = 0; i < nB; ++i) {
+        Float bPdf;
+        BSDFRecord bRec(its.wi, ERadiance);
+        RGB bsdfVal = bsdfSample(bsdf, bRec, bPdf, u[nE + i], sc.epsilon);
+        if (bsdfVal.isZero()) continue;
+        const Vec3 wo = its.toWorld(bRec.wo);
+        Ray bsdfRay = sc.makeRay(its.p, wo);
+        Intersection bIts;
+        if (!sc.rayIntersect(bsdfRay, bIts, &ctx.rays)) continue;
+        if (bIts.emitter < 0) continue;
+        const RGB value = (dot(bIts.sh.n, -bsdfRay.d) > 0) ? sc.emitters[bIts.emitter].radiance : RGB(0.0);
+        dRec.p = bIts.p; dRec.n = bIts.sh.n; dRec.measure = ESolidAngle;      // dRec.setQuery (records.inl:170-178)
+        dRec.emitter = bIts.emitter; dRec.d = bsdfRay.d; dRec.dist = bIts.t;
+        const Float lumPdf = (!(bRec.sampledType & EDelta)) ? pdfEmitterDirect(sc, dRec) : 0;
+        Li += value * bsdfVal * (mi(bPdf * fracBSDF, lumPdf * fracLum) * weightBSDF);
+    }
+    return Li;
+}
+
 } // namespace orc

@@ -41,7 +41,7 @@ struct Philox {
     }
 };
 
-enum Stream { S_BOOT = 1, S_RESAMPLE = 2, S_COIN = 3, S_STAGE1 = 4, S_STAGE2 = 7 };
+enum Stream { S_BOOT = 1, S_RESAMPLE = 2, S_COIN = 3, S_STAGE1 = 4, S_STAGE2 = 7, S_DIRECT = 10 };
 
 inline float keyedUniform(uint64_t seed, uint32_t stream, uint64_t a, uint32_t b, uint32_t j) {
     uint32_t c[4] = { (uint32_t) a, (uint32_t) (a >> 32), b, (stream << 24) | (j >> 2) };

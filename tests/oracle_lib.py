@@ -42,6 +42,7 @@ def load():
                                     C.c_int64, C.c_int64, P(abi.dr_step_record), P(C.c_float), P(abi.dr_stats), C.c_int]
     lib.orc_render.argtypes = [C.c_void_p, P(abi.dr_config), C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                P(C.c_float), P(abi.dr_stats), P(C.c_double)]
+    lib.orc_direct_image.argtypes = [C.c_void_p, P(abi.dr_config), P(C.c_float), P(C.c_double)]
     lib.orc_splat.argtypes = [C.c_int, C.c_int, C.c_int, P(C.c_float), P(C.c_float), C.c_int64, P(C.c_float)]
     lib.orc_bsdf_sample.argtypes = [P(abi.dr_material), P(C.c_double), C.c_int, C.c_double, C.c_double,
                                     P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int)]
@@ -105,6 +106,16 @@ class OracleScene:
                                  fptr(chain_id, C.c_uint64), n, steps, rec, fptr(film) if want_film else None,
                                  C.byref(st), threads)
         return rec, film, st
+
+    def direct_image(self, cfg, want_li=False):
+        W, H = self.data.film
+        ps = max(int(cfg.direct_samples), 1)
+        while ps > 8:
+            ps //= 2
+        img = np.zeros((H, W, 3), np.float32)
+        li = np.zeros((H, W, ps, 3), np.float64) if want_li else None
+        self.lib.orc_direct_image(self.h, C.byref(cfg), fptr(img), fptr(li, C.c_double) if want_li else None)
+        return (img, li) if want_li else img
 
     def render(self, cfg, n_boot, n_chains, steps, threads=0):
         W, H = self.data.film

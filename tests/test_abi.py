@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), "libdrmlt_b200.so does not export %s" % name
     assert sorted(abi.EXPORTED_SYMBOLS) == declared
-    assert lib.dr_abi_version() == 2
+    assert lib.dr_abi_version() == 3
 
 
 def test_struct_layouts_match_header(lib):

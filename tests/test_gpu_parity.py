@@ -387,6 +387,41 @@ def test_job_b_and_acceptance_rates(case):
     job.close()
 
 
+@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16)])
+def test_direct_illumination_pass(name, samples):
+    """the separate direct image (renderDirectComponent + the `direct` integrator) on keyed samples."""
+    gpu, orc, data = pair(name)
+    cfg = make_config(seed=53, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=samples)
+    ig, lg = gpu.direct_image(cfg, want_li=True)
+    ic, lc = orc.direct_image(ocfg(cfg), want_li=True)
+    assert lg.shape == lc.shape and lg.shape[2] == (8 if samples == 16 else 4)
+    a, b = lg.reshape(-1, 3), lc.reshape(-1, 3)
+    scale = np.abs(b).max(axis=1)
+    lit = scale > 0
+    assert lit.mean() > 0.2
+    ok = (np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-9 * b.max()).all(axis=1)
+    assert ok.mean() >= 0.999, ok.mean()                      # per pixel-sample radiance, every shading sample included
+    assert np.abs(ig - ic).max() <= 2e-3 * ic.max() and ig.mean() == pytest.approx(ic.mean(), rel=1e-4)
+
+
+def test_default_parameters_render_direct_plus_mlt():
+    """With the reference's default directSamples the image is MLT(depth > 2) + the separate direct image."""
+    gpu, orc, data = pair("cornell")
+    base = dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, sampleCount=64, chains=4096, seed=59)
+    img_all, st_all = gpu.render(make_config(directSamples=-1, **base))
+    img_sep, st_sep = gpu.render(make_config(directSamples=16, **base))
+    assert st_sep.direct_ms > 0 and st_all.direct_ms == 0
+    assert st_sep.luminance < st_all.luminance                # b of the MLT part no longer contains direct light
+    direct = gpu.direct_image(make_config(directSamples=16, **base))
+    assert direct.mean() > 0
+    # (the two images are not comparable as a whole: the direct integrator also shows the directly visible emitter,
+    #  which MMLT never renders -- depth-1 paths are empty, pathsampler.cpp:131-135)
+    assert np.isfinite(img_sep).all() and (img_sep >= direct - 1e-6).all()
+    # the MLT part alone (image minus direct) carries exactly b (develop keeps mean luminance = b)
+    Y = np.array([0.212671, 0.715160, 0.072169])
+    assert ((img_sep - direct) * Y).sum(-1).mean() == pytest.approx(st_sep.luminance, rel=2e-3)
+
+
 def test_render_entry_point_and_errors():
     gpu, orc, data = pair("cornell")
     cfg = make_config(seed=43, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, sampleCount=8, chains=2048)
