@@ -17,6 +17,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <chrono>
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_error[1024] = "";
@@ -531,6 +532,9 @@ struct dr_job_t {
     float4 *directFilm = nullptr;               // weighted film of the separate direct-illumination pass
     float *directImage = nullptr;               // ... developed (null until dr_job_direct ran)
     bool haveDirect = false;
+    // timeout (drmlt.cpp:296, drmlt_proc.cpp:519-521, 870-877): the chain phase stops issuing rounds after `timeout` seconds
+    std::chrono::steady_clock::time_point deadline;
+    bool hasDeadline = false, timedOut = false;
     long long nBoot = 0;
     unsigned long long bootFirst = 0;
     int nChains = 0;
@@ -751,6 +755,7 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
     }
     for (;;) {
         if (j->scene->cancel) { join_groups(j); cleanup(); dr_set_error("cancelled"); return DR_ERR_CANCELLED; }
+        if (job.type == JOB_CHAIN && j->hasDeadline && std::chrono::steady_clock::now() >= j->deadline) { j->timedOut = true; break; }
         if (useGraph) {
             if (cudaGraphLaunch(exec, s0) != cudaSuccess || cudaStreamSynchronize(s0) != cudaSuccess) {
                 dr_set_error("wavefront rounds failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -933,6 +938,11 @@ static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, 
 extern "C" dr_status dr_job_run(dr_job j, int64_t mutationsPerChain) {
     if (!j) { dr_set_error("dr_job_run: null job"); return DR_ERR_INVALID_ARG; }
     if (!j->seeded) { dr_set_error("dr_job_run: call dr_job_seed_chains first"); return DR_ERR_INVALID_ARG; }
+    if (j->cfg.timeout > 0 && !j->hasDeadline) {               // the reference's timer starts with the chain phase
+        j->deadline = std::chrono::steady_clock::now() + std::chrono::seconds(j->cfg.timeout);
+        j->hasDeadline = true;
+    }
+    if (j->timedOut) return DR_OK;
     if (mutationsPerChain < 0 || mutationsPerChain > (1ll << 30)) { dr_set_error("dr_job_run: mutation count out of range"); return DR_ERR_INVALID_ARG; }
     CK(cudaSetDevice(j->scene->device));
     CK(cudaEventRecord(j->ev0, j->stream));

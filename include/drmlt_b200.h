@@ -115,7 +115,7 @@ typedef struct dr_config {
     int32_t work_units;        /* workUnits = -1 (auto) */
     int32_t kelemen_style_weights;  /* kelemenStyleWeights = true (forced false for MMLT) */
     int32_t two_stage;         /* twoStage = false (only false is supported: section 8(f) "next") */
-    int32_t timeout;           /* timeout = 0 seconds */
+    int32_t timeout;           /* timeout = 0 seconds; > 0: the chain phase stops after that many seconds (drmlt_proc.cpp:519-521) */
     float   average_luminance; /* averageLuminance = -1 (use bootstrap estimate) */
     int32_t light_image;       /* lightImage = true */
     int32_t acceptance_map;    /* acceptanceMap = false (drmlt) */

@@ -422,6 +422,22 @@ def test_default_parameters_render_direct_plus_mlt():
     assert ((img_sep - direct) * Y).sum(-1).mean() == pytest.approx(st_sep.luminance, rel=2e-3)
 
 
+def test_timeout_stops_the_chain_phase():
+    """timeout (drmlt.cpp:296): an equal-time stop -- fewer mutations than requested, still a valid developed image."""
+    import time
+    gpu, orc, data = pair("cornell")
+    W, H = data.film
+    cfg = make_config(seed=61, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, sampleCount=200000,
+                      chains=65536, timeout=1)
+    t0 = time.perf_counter()
+    img, st = gpu.render(cfg)
+    dt = time.perf_counter() - t0
+    assert dt < 6.0
+    assert 0 < st.mutations < W * H * 200000
+    Y = np.array([0.212671, 0.715160, 0.072169])
+    assert np.isfinite(img).all() and (img * Y).sum(-1).mean() == pytest.approx(st.luminance, rel=1e-3)
+
+
 def test_render_entry_point_and_errors():
     gpu, orc, data = pair("cornell")
     cfg = make_config(seed=43, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, sampleCount=8, chains=2048)
