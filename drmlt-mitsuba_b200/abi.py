@@ -60,7 +60,12 @@ class dr_config(C.Structure):
                 ("kelemen_style_mutation", C.c_int32), ("mutation_size_low", C.c_float),
                 ("mutation_size_high", C.c_float), ("sample_count", C.c_int32), ("rfilter", C.c_int32),
                 ("n_chains", C.c_int32), ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32),
-                ("ray_epsilon", C.c_float), ("shadow_epsilon", C.c_float)]
+                ("ray_epsilon", C.c_float), ("shadow_epsilon", C.c_float),
+                ("first_stage", C.c_int32), ("first_stage_size_reduction", C.c_int32),
+                ("film_width", C.c_int32), ("film_height", C.c_int32),
+                ("crop_offset_x", C.c_int32), ("crop_offset_y", C.c_int32),
+                ("crop_width", C.c_int32), ("crop_height", C.c_int32),
+                ("importance_map", C.POINTER(C.c_float))]
 
 
 class dr_stats(C.Structure):
@@ -72,7 +77,8 @@ class dr_stats(C.Structure):
         ("luminance", C.c_double), ("bootstrap_ms", C.c_double), ("chains_ms", C.c_double),
         ("total_ms", C.c_double), ("kernel_launches", C.c_uint64), ("rounds", C.c_uint64),
         ("trace_ms", C.c_double), ("walk_ms", C.c_double), ("chain_ms", C.c_double),
-        ("trace_launches", C.c_uint64), ("walk_launches", C.c_uint64), ("chain_launches", C.c_uint64), ("direct_ms", C.c_double)]
+        ("trace_launches", C.c_uint64), ("walk_launches", C.c_uint64), ("chain_launches", C.c_uint64), ("direct_ms", C.c_double),
+        ("first_stage_ms", C.c_double)]
 
 
 class dr_ray(C.Structure):
@@ -94,6 +100,8 @@ class dr_step_record(C.Structure):
                 ("large_step", C.c_uint8), ("accept1", C.c_uint8), ("did_second", C.c_uint8), ("accept2", C.c_uint8)]
 
 
+dr_refresh_fn = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_double, C.POINTER(dr_stats), C.c_void_p)
+
 # every symbol include/drmlt_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "dr_abi_version", "dr_last_error", "dr_device_count", "dr_config_default", "dr_config_set",
@@ -101,6 +109,7 @@ EXPORTED_SYMBOLS = [
     "dr_job_create", "dr_job_destroy", "dr_job_bootstrap", "dr_job_seed_chains", "dr_job_run",
     "dr_job_film_device", "dr_job_develop", "dr_job_stats", "dr_job_profile", "dr_job_direct", "dr_direct_image", "dr_job_num_chains", "dr_job_total_mutations",
     "dr_trace_rays", "dr_eval_paths", "dr_chain_steps", "dr_bootstrap_luminance", "dr_max_dimensions",
+    "dr_render_progressive", "dr_film_size", "dr_first_stage_config", "dr_resample_luminance", "dr_importance_map",
 ]
 
 _lib = None
@@ -162,6 +171,11 @@ def load_library(path=None):
     lib.dr_bootstrap_luminance.argtypes = [C.c_void_p, P(dr_config), C.c_uint64, C.c_int64, P(C.c_float), P(C.c_int32)]
     lib.dr_max_dimensions.argtypes = [P(dr_config), C.c_int, P(C.c_int), P(C.c_int), P(C.c_int)]
     lib.dr_max_dimensions.restype = None
+    lib.dr_render_progressive.argtypes = [C.c_void_p, P(dr_config), P(C.c_float), P(dr_stats), C.c_double, dr_refresh_fn, C.c_void_p]
+    lib.dr_film_size.argtypes = [C.c_void_p, P(dr_config), P(C.c_int32), P(C.c_int32)]
+    lib.dr_first_stage_config.argtypes = [C.c_void_p, P(dr_config), P(dr_config)]
+    lib.dr_resample_luminance.argtypes = [C.c_void_p, P(C.c_float), C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(C.c_float)]
+    lib.dr_importance_map.argtypes = [C.c_void_p, P(dr_config), P(C.c_float), P(dr_stats)]
     if path == LIB_PATH:
         _lib = lib
     return lib

@@ -80,6 +80,12 @@ extern "C" void dr_config_default(dr_config *c) {
     c->world_size = 1;
     c->ray_epsilon = 0.f;
     c->shadow_epsilon = 0.f;
+    c->first_stage = 0;
+    c->first_stage_size_reduction = 16;
+    c->film_width = c->film_height = 0;
+    c->crop_offset_x = c->crop_offset_y = 0;
+    c->crop_width = c->crop_height = 0;
+    c->importance_map = nullptr;
 }
 
 static bool parse_bool(const char *v, int *out) {
@@ -112,13 +118,18 @@ extern "C" dr_status dr_config_set(dr_config *c, const char *key, const char *va
         { "twoStage", &dr_config::two_stage }, { "lightImage", &dr_config::light_image },
         { "acceptanceMap", &dr_config::acceptance_map }, { "timidAfterLarge", &dr_config::timid_after_large },
         { "fixEmitterPath", &dr_config::fix_emitter_path }, { "useMixture", &dr_config::use_mixture },
-        { "kelemenStyleMutation", &dr_config::kelemen_style_mutation },
+        { "kelemenStyleMutation", &dr_config::kelemen_style_mutation }, { "firstStage", &dr_config::first_stage },
     };
     static const IntKey ints[] = {
         { "maxDepth", &dr_config::max_depth }, { "rrDepth", &dr_config::rr_depth }, { "directSamples", &dr_config::direct_samples },
         { "luminanceSamples", &dr_config::luminance_samples }, { "workUnits", &dr_config::work_units },
         { "timeout", &dr_config::timeout }, { "sampleCount", &dr_config::sample_count }, { "chains", &dr_config::n_chains },
         { "rank", &dr_config::rank }, { "worldSize", &dr_config::world_size },
+        { "firstStageSizeReduction", &dr_config::first_stage_size_reduction },
+        // film plugin parameters (src/librender/film.cpp:30-48)
+        { "width", &dr_config::film_width }, { "height", &dr_config::film_height },
+        { "cropOffsetX", &dr_config::crop_offset_x }, { "cropOffsetY", &dr_config::crop_offset_y },
+        { "cropWidth", &dr_config::crop_width }, { "cropHeight", &dr_config::crop_height },
     };
     static const FloatKey floats[] = {
         { "pLarge", &dr_config::p_large }, { "averageLuminance", &dr_config::average_luminance }, { "sigma", &dr_config::sigma },
@@ -180,8 +191,6 @@ extern "C" dr_status dr_config_set(dr_config *c, const char *key, const char *va
             c->*(k.field) = v;
             return DR_OK;
         }
-    // accepted and ignored: parameters of the reference that only matter for features outside this path
-    if (!strcmp(key, "firstStage") || !strcmp(key, "firstStageSizeReduction")) return DR_OK;
     dr_set_error("Unknown parameter \"%s\"", key);
     return DR_ERR_INVALID_ARG;
 }
@@ -204,7 +213,10 @@ extern "C" dr_status dr_config_validate(dr_config *c) {
     if (c->max_depth <= 0 || c->max_depth + 3 > DR_MAXK) {
         dr_set_error("maxDepth must be in [1, %d] on the GPU path (got %d)", DR_MAXK - 3, c->max_depth); return DR_ERR_UNSUPPORTED;
     }
-    if (c->two_stage) { dr_set_error("twoStage=true is not supported (importance map, SURVEY 8f)"); return DR_ERR_UNSUPPORTED; }
+    if (c->two_stage && c->first_stage_size_reduction <= 0) { dr_set_error("firstStageSizeReduction must be positive"); return DR_ERR_INVALID_ARG; }   // Assert, drmlt.cpp:409
+    if (c->film_width < 0 || c->film_height < 0 || c->crop_offset_x < 0 || c->crop_offset_y < 0 || c->crop_width < 0 || c->crop_height < 0) {
+        dr_set_error("Invalid crop window specification!"); return DR_ERR_INVALID_ARG;       // film.cpp:44-48
+    }
     if (c->technique == DR_TECH_BDPT && c->direct_sampling) {
         // the reference overflows its direct sampler in this mode
         dr_set_error("technique=bdpt requires directSampling=false on the GPU path"); return DR_ERR_UNSUPPORTED;
@@ -414,12 +426,9 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     dc.pos[0] = c.to_world[3]; dc.pos[1] = c.to_world[7]; dc.pos[2] = c.to_world[11];
     dc.dir[0] = c.to_world[2]; dc.dir[1] = c.to_world[6]; dc.dir[2] = c.to_world[10];
     const double tanHalf = std::tan(0.5 * (double) c.xfov_deg * 3.14159265358979323846 / 180.0);
-    const double aspect = (double) c.film_width / (double) c.film_height;
-    dc.tanHalf = tanHalf; dc.aspect = aspect;
+    dc.tanHalf = tanHalf;
     dc.nearClip = c.near_clip; dc.farClip = c.far_clip;
-    dc.resX = c.film_width; dc.resY = c.film_height;
-    dc.rectX = tanHalf; dc.rectY = tanHalf / aspect;
-    dc.normalization = 1.0 / (2.0 * dc.rectX * 2.0 * dc.rectY);
+    camera_set_window(dc, c.film_width, c.film_height, 0, 0, c.film_width, c.film_height);
     *out = s;
     return DR_OK;
 }
@@ -498,10 +507,26 @@ static void make_params(const dr_config &c, int W, int H, double b, const int *e
     fp.radius = (float) radius; fp.scaleFactor = (float) (31 / radius);
 }
 
-static DevScene scene_for(const dr_scene scene, const dr_config &c) {
+// Film and crop window of a job (Film::Film, src/librender/film.cpp:30-48): the configuration may override the
+// camera's film size (the nested first-stage pass does) and select a crop window; every image buffer has the crop size.
+struct FilmWindow { int filmW, filmH, cropX, cropY, W, H; };
+static dr_status film_window(const dr_scene scene, const dr_config &c, FilmWindow &fw) {
+    fw.filmW = c.film_width > 0 ? c.film_width : scene->filmW;
+    fw.filmH = c.film_height > 0 ? c.film_height : scene->filmH;
+    fw.cropX = c.crop_offset_x; fw.cropY = c.crop_offset_y;
+    fw.W = c.crop_width > 0 ? c.crop_width : fw.filmW;
+    fw.H = c.crop_height > 0 ? c.crop_height : fw.filmH;
+    if (fw.cropX < 0 || fw.cropY < 0 || fw.W <= 0 || fw.H <= 0 || fw.cropX + fw.W > fw.filmW || fw.cropY + fw.H > fw.filmH) {
+        dr_set_error("Invalid crop window specification!"); return DR_ERR_INVALID_ARG;
+    }
+    return DR_OK;
+}
+
+static DevScene scene_for(const dr_scene scene, const dr_config &c, const FilmWindow &fw) {
     DevScene ds = scene->dev;
     if (c.ray_epsilon > 0.f) ds.epsilon = c.ray_epsilon;
     if (c.shadow_epsilon > 0.f) ds.shadowEpsilon = c.shadow_epsilon;
+    camera_set_window(ds.cam, fw.filmW, fw.filmH, fw.cropX, fw.cropY, fw.W, fw.H);
     return ds;
 }
 
@@ -516,6 +541,8 @@ enum { STAGE_TRACE = 0, STAGE_WALK, STAGE_CHAIN, STAGE_COUNT };
 struct dr_job_t {
     dr_scene scene = nullptr;
     dr_config cfg;
+    int W = 0, H = 0;                           // size of the rendered image = crop window of the film
+    float *importance = nullptr;                // [W*H] two-stage importance map on the device (null: none)
     Machine M;                                  // constant part: scene, parameters, lane memory, queues
     int *depth = nullptr;                       // [n] MMLT depth of every chain (or -1)
     unsigned long long *chainId = nullptr, *seedIdx = nullptr;
@@ -654,8 +681,11 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     dr_job j = new dr_job_t();
     j->scene = scene; j->cfg = cfg;
     memset(&j->M, 0, sizeof(j->M));
-    j->M.sc = scene_for(scene, cfg);
-    const int W = scene->filmW, H = scene->filmH;
+    FilmWindow fw;
+    if ((st = film_window(scene, cfg, fw))) { delete j; return st; }
+    j->M.sc = scene_for(scene, cfg, fw);
+    const int W = fw.W, H = fw.H;
+    j->W = W; j->H = H;
     make_params(cfg, W, H, 1.0, evalDims, j->M);
     j->M.traceRefill = getenv("DRMLT_TRACE_REFILL") ? atoi(getenv("DRMLT_TRACE_REFILL")) : 24;
     j->M.traceDescend = getenv("DRMLT_TRACE_DESCEND") ? atoi(getenv("DRMLT_TRACE_DESCEND")) : 8;
@@ -678,7 +708,16 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
         if ((st = job_alloc(j, &j->depth, n)) || (st = job_alloc(j, &j->chainId, n)) || (st = job_alloc(j, &j->seedIdx, n)) ||
             (st = job_alloc(j, &j->film, (size_t) W * H, true)) || (st = job_alloc(j, &j->devImage, (size_t) W * H * 3)))
             return fail(st);
+        if (cfg.importance_map && !cfg.first_stage) {      // m_config.importanceMap: splats are divided by it (pathsampler.cpp:1001-1020)
+            if ((st = job_alloc(j, &j->importance, (size_t) W * H))) return fail(st);
+            if (cudaMemcpyAsync(j->importance, cfg.importance_map, sizeof(float) * (size_t) W * H, cudaMemcpyHostToDevice, j->stream) != cudaSuccess) {
+                dr_set_error("importance map upload failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(DR_ERR_CUDA);
+            }
+            j->M.cp.importance = j->importance;
+            if (cfg.integrator == DR_INTEGRATOR_PSSMLT) j->M.cp.kelemenWeights = 0;    // pssmlt_proc.cpp:205
+        }
     }
+    j->cfg.importance_map = nullptr;                       // the host buffer is not referenced after creation
     CK(cudaStreamSynchronize(j->stream));
     *out = j;
     return DR_OK;
@@ -823,7 +862,7 @@ static dr_status setup_lanes(dr_job j, const JobParams &job) {
 static long long bootstrap_samples(const dr_job j) {
     const dr_config &c = j->cfg;
     const long long desired = c.technique == DR_TECH_PATH ? 200000 : 100000;
-    const long long total = (long long) j->scene->filmW * j->scene->filmH * c.sample_count;
+    const long long total = (long long) j->W * j->H * c.sample_count;
     long long workUnits = c.work_units > 0 ? c.work_units : std::max<long long>(1, (desired - 1 + total) / desired);
     long long n = c.luminance_samples;
     const long long times = c.technique == DR_TECH_MMLT ? 50 : 10;
@@ -957,10 +996,16 @@ extern "C" dr_status dr_job_run(dr_job j, int64_t mutationsPerChain) {
     return DR_OK;
 }
 
+static dr_status flush_pssmlt(dr_job j);
 extern "C" dr_status dr_job_film_device(dr_job j, float **filmDev, int64_t *nFloats) {
     if (!j || !filmDev || !nFloats) { dr_set_error("dr_job_film_device: null argument"); return DR_ERR_INVALID_ARG; }
+    if (j->seeded) {                                            // the film handed to a reduce must hold PSSMLT's pending last splats
+        CK(cudaSetDevice(j->scene->device));
+        dr_status st = flush_pssmlt(j);
+        if (st) return st;
+    }
     *filmDev = reinterpret_cast<float *>(j->film);
-    *nFloats = (int64_t) j->scene->filmW * j->scene->filmH * 4;     // RGBA, A unused (16-byte vector atomics)
+    *nFloats = (int64_t) j->W * j->H * 4;     // RGBA, A unused (16-byte vector atomics)
     return DR_OK;
 }
 
@@ -986,9 +1031,9 @@ extern "C" dr_status dr_job_develop(dr_job j, float *imageRgb) {
     CK(cudaSetDevice(j->scene->device));
     dr_status st = flush_pssmlt(j);
     if (st) return st;
-    const long long n = (long long) j->scene->filmW * j->scene->filmH;
+    const long long n = (long long) j->W * j->H;
     CK(cudaMemsetAsync(j->red + 2, 0, sizeof(double), j->stream));
-    launch_film_luminance(j->film, n, j->red + 2, j->stream);
+    launch_film_luminance(j->film, j->importance, n, j->red + 2, j->stream);
     CKL();
     double lumSum = 0.0;
     CK(cudaMemcpyAsync(&lumSum, j->red + 2, sizeof(double), cudaMemcpyDeviceToHost, j->stream));
@@ -996,7 +1041,7 @@ extern "C" dr_status dr_job_develop(dr_job j, float *imageRgb) {
     const bool accMap = j->M.cp.acceptanceMap;
     const double avg = lumSum / (double) n;
     const float factor = accMap ? 1.0f : (avg > 0.0 ? (float) (j->b / avg) : 0.f);
-    launch_develop(j->film, n, factor, (j->haveDirect && !accMap) ? j->directImage : nullptr, j->devImage, j->stream);
+    launch_develop(j->film, j->importance, n, factor, (j->haveDirect && !accMap) ? j->directImage : nullptr, j->devImage, j->stream);
     CKL();
     j->launches += 2;
     CK(cudaMemcpyAsync(imageRgb, j->devImage, (size_t) n * 3 * sizeof(float), cudaMemcpyDeviceToHost, j->stream));
@@ -1015,9 +1060,10 @@ static void direct_split(int directSamples, int *pixelSamples, int *shadingSampl
 extern "C" dr_status dr_job_direct(dr_job j) {
     if (!j) { dr_set_error("dr_job_direct: null job"); return DR_ERR_INVALID_ARG; }
     if (j->cfg.direct_samples <= 0) return DR_OK;               // directSamples = 0: direct light is excluded and not rendered (drmlt.cpp:479)
+    if (j->cfg.two_stage && j->cfg.first_stage) return DR_OK;   // the nested pass renders no direct image (`!nested`, drmlt.cpp:478)
     if (!j->film) { dr_set_error("dr_job_direct: not a render job"); return DR_ERR_INVALID_ARG; }
     CK(cudaSetDevice(j->scene->device));
-    const long long n = (long long) j->scene->filmW * j->scene->filmH;
+    const long long n = (long long) j->W * j->H;
     dr_status st;
     if (!j->directFilm && ((st = job_alloc(j, &j->directFilm, (size_t) n)) || (st = job_alloc(j, &j->directImage, (size_t) 3 * n)))) return st;
     CK(cudaMemsetAsync(j->directFilm, 0, sizeof(float4) * n, j->stream));
@@ -1067,9 +1113,141 @@ extern "C" void dr_job_profile(dr_job j, int on) { if (j) j->profile = on != 0; 
 extern "C" int64_t dr_job_num_chains(dr_job j) { return j ? j->nChains : 0; }
 extern "C" int64_t dr_job_total_mutations(dr_job j) { return j ? j->totalMutations : 0; }
 
-extern "C" dr_status dr_render(dr_scene scene, const dr_config *cfg, float *imageRgb, dr_stats *stats) {
-    if (!scene || !cfg || !imageRgb) { dr_set_error("dr_render: null argument"); return DR_ERR_INVALID_ARG; }
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    dr_status alloc(size_t bytes) { CK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); return DR_OK; }
+    template <class T> T *as() { return (T *) p; }
+};
+
+// ------------------------------------------------------------------ two-stage MLT (src/libbidir/util.cpp:96-199)
+extern "C" dr_status dr_film_size(dr_scene scene, const dr_config *cfg, int32_t *width, int32_t *height) {
+    if (!scene || !cfg || !width || !height) { dr_set_error("dr_film_size: null argument"); return DR_ERR_INVALID_ARG; }
+    FilmWindow fw;
+    dr_status st = film_window(scene, *cfg, fw);
+    if (st) return st;
+    *width = fw.W; *height = fw.H;
+    return DR_OK;
+}
+
+extern "C" dr_status dr_first_stage_config(dr_scene scene, const dr_config *cfgIn, dr_config *nested) {
+    if (!scene || !cfgIn || !nested) { dr_set_error("dr_first_stage_config: null argument"); return DR_ERR_INVALID_ARG; }
+    dr_config c = *cfgIn;
+    dr_status st = dr_config_validate(&c);
+    if (st) return st;
+    const int f = c.first_stage_size_reduction;
+    if (f <= 0) { dr_set_error("firstStageSizeReduction must be positive"); return DR_ERR_INVALID_ARG; }
+    FilmWindow fw;
+    if ((st = film_window(scene, c, fw))) return st;
+    c.two_stage = 1; c.first_stage = 1;                                   // integratorProps + firstStage=true (util.cpp:151)
+    c.film_width = std::max(1, fw.filmW / f); c.film_height = std::max(1, fw.filmH / f);   // :104-110
+    c.crop_width = std::max(1, fw.W / f); c.crop_height = std::max(1, fw.H / f);
+    c.crop_offset_x = fw.cropX / f;
+    c.crop_offset_y = fw.cropX / f;                                       // sic: the reference passes reducedCropOffset.x for Y too (:128)
+    const long long spp = (long long) c.sample_count * f;                 // "higher number of mutations/pixel" (:134-136)
+    if (spp > 0x7fffffffll) { dr_set_error("dr_first_stage_config: sampleCount * firstStageSizeReduction overflows"); return DR_ERR_INVALID_ARG; }
+    c.sample_count = (int32_t) spp;
+    c.importance_map = nullptr;
+    c.n_chains = 0;                                                       // sized for the small nested job
+    *nested = c;
+    return DR_OK;
+}
+
+// Resampler::Resampler (include/mitsuba/core/rfilter.h:123-177), resampling mode, gaussian filter (stddev 0.5, radius 2)
+struct ResampleTable { int taps = 0; std::vector<int> start; std::vector<double> weights; };
+static void resample_table(int sourceRes, int targetRes, ResampleTable &t) {
+    const double stddev = 0.5, radius = 4 * stddev, alpha = -1.0 / (2.0 * stddev * stddev);
+    auto eval = [&](double x) { return std::max(0.0, std::exp(alpha * x * x) - std::exp(alpha * radius * radius)); };   // gaussian.cpp:52-57
+    double filterRadius = radius, scale = 1.0, invScale = 1.0;
+    if (targetRes < sourceRes) { scale = (double) sourceRes / (double) targetRes; invScale = 1 / scale; filterRadius *= scale; }
+    t.taps = (int) std::ceil(filterRadius * 2);
+    t.start.resize(targetRes); t.weights.resize((size_t) t.taps * targetRes);
+    for (int i = 0; i < targetRes; i++) {
+        const double center = (i + 0.5) / targetRes * sourceRes;
+        t.start[i] = (int) std::floor(center - filterRadius + 0.5);
+        double sum = 0;
+        for (int j = 0; j < t.taps; j++) {
+            const double pos = t.start[i] + j + 0.5 - center;
+            const double w = eval(pos * invScale);
+            t.weights[(size_t) i * t.taps + j] = w;
+            sum += w;
+        }
+        const double normalization = 1.0 / sum;
+        for (int j = 0; j < t.taps; j++) t.weights[(size_t) i * t.taps + j] *= normalization;
+    }
+}
+
+extern "C" dr_status dr_resample_luminance(dr_scene scene, const float *imageRgb, int32_t w, int32_t h, int32_t W, int32_t H, float *map) {
+    if (!scene || !imageRgb || !map || w <= 0 || h <= 0 || W <= 0 || H <= 0) { dr_set_error("dr_resample_luminance: bad argument"); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(scene->device));
+    DevBuf rgb, lum, tmp, out, outF, dStart, dWeights;
+    dr_status st;
+    if ((st = rgb.alloc(sizeof(float) * 3 * (size_t) w * h)) || (st = lum.alloc(sizeof(double) * (size_t) w * h)) || (st = outF.alloc(sizeof(float) * (size_t) W * H))) return st;
+    CK(cudaMemcpy(rgb.p, imageRgb, sizeof(float) * 3 * (size_t) w * h, cudaMemcpyHostToDevice));
+    launch_rgb_luminance(rgb.as<float>(), (long long) w * h, lum.as<double>(), 0);     // nestedFilm->develop into an ELuminance bitmap (util.cpp:184-188)
+    const double *cur = lum.as<double>();
+    int curW = w;
+    auto pass = [&](int srcRes, int tgtRes, int other, int alongX, DevBuf &dst) -> dr_status {
+        ResampleTable t;
+        resample_table(srcRes, tgtRes, t);
+        DevBuf ds_, dw_;
+        dr_status s2;
+        if ((s2 = ds_.alloc(sizeof(int) * t.start.size())) || (s2 = dw_.alloc(sizeof(double) * t.weights.size())) || (s2 = dst.alloc(sizeof(double) * (size_t) tgtRes * other))) return s2;
+        CK(cudaMemcpy(ds_.p, t.start.data(), sizeof(int) * t.start.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dw_.p, t.weights.data(), sizeof(double) * t.weights.size(), cudaMemcpyHostToDevice));
+        launch_resample_axis(cur, srcRes, tgtRes, other, alongX, ds_.as<int>(), dw_.as<double>(), t.taps, dst.as<double>(), 0);
+        CKL();
+        CK(cudaDeviceSynchronize());                               // the tables are freed when this scope ends
+        return DR_OK;
+    };
+    // mitsuba::resample (src/libcore/bitmap.cpp:2230-2329): along x first (into a [h][W] temporary), then along y
+    if (w != W) { if ((st = pass(w, W, h, 1, tmp))) return st; cur = tmp.as<double>(); curW = W; }
+    if (h != H) { if ((st = pass(h, H, curW, 0, out))) return st; cur = out.as<double>(); }
+    launch_double_to_float(cur, (long long) W * H, outF.as<float>(), 0);
+    CKL();
+    CK(cudaMemcpy(map, outF.p, sizeof(float) * (size_t) W * H, cudaMemcpyDeviceToHost));
+    return DR_OK;
+}
+
+extern "C" dr_status dr_importance_map(dr_scene scene, const dr_config *cfg, float *map, dr_stats *nestedStats) {
+    if (!scene || !cfg || !map) { dr_set_error("dr_importance_map: null argument"); return DR_ERR_INVALID_ARG; }
+    dr_config nested;
+    dr_status st = dr_first_stage_config(scene, cfg, &nested);
+    if (st) return st;
+    int32_t w, h, W, H;
+    if ((st = dr_film_size(scene, &nested, &w, &h)) || (st = dr_film_size(scene, cfg, &W, &H))) return st;
+    std::vector<float> img((size_t) 3 * w * h);
+    if ((st = dr_render(scene, &nested, img.data(), nestedStats))) return st;      // "Executing first MLT stage" (drmlt.cpp:406-418)
+    return dr_resample_luminance(scene, img.data(), w, h, W, H, map);
+}
+
+extern "C" dr_status dr_render(dr_scene scene, const dr_config *cfgIn, float *imageRgb, dr_stats *stats) {
+    return dr_render_progressive(scene, cfgIn, imageRgb, stats, 0.0, nullptr, nullptr);
+}
+
+// dr_render with periodic develops of the partial result: what DRMLTProcess::processResult does for interactive jobs
+// (develop + signalRefresh every <= 2 s, drmlt_proc.cpp:856-867) and what `mitsuba -r <sec>` dumps through Scene::flush
+// (src/librender/scene.cpp:468-511).  The chain phase runs in slices of about `refreshSeconds`; after each slice the
+// film is developed into `imageRgb` and `fn` is called; a non-zero return cancels the job like Integrator::cancel.
+extern "C" dr_status dr_render_progressive(dr_scene scene, const dr_config *cfgIn, float *imageRgb, dr_stats *stats,
+                                           double refreshSeconds, dr_refresh_fn fn, void *user) {
+    if (!scene || !cfgIn || !imageRgb) { dr_set_error("dr_render: null argument"); return DR_ERR_INVALID_ARG; }
     scene->cancel = 0;
+    dr_config cfgLocal = *cfgIn;
+    const dr_config *cfg = &cfgLocal;
+    std::vector<float> importance;
+    double firstStageMs = 0.0;
+    if (cfgLocal.two_stage && !cfgLocal.first_stage && !cfgLocal.importance_map) {
+        int32_t W, H;
+        dr_status s0 = dr_film_size(scene, cfg, &W, &H);
+        if (s0) return s0;
+        importance.resize((size_t) W * H);
+        dr_stats ns;
+        const auto t0 = std::chrono::steady_clock::now();
+        if ((s0 = dr_importance_map(scene, cfg, importance.data(), &ns))) return s0;
+        firstStageMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        cfgLocal.importance_map = importance.data();
+    }
     dr_job j = nullptr;
     dr_status st = dr_job_create(scene, cfg, &j);
     if (st) return st;
@@ -1080,9 +1258,31 @@ extern "C" dr_status dr_render(dr_scene scene, const dr_config *cfg, float *imag
     if (!(st = dr_job_bootstrap(j, &sum, &count))) {
         double b = count > 0.0 ? sum / count : 0.0;                              // pathsampler.cpp:922-934
         if (j->cfg.technique == DR_TECH_MMLT) b *= j->cfg.max_depth;
-        if (!(st = dr_job_seed_chains(j, b))) {
+        // the direct image is rendered before the chains start (drmlt.cpp:478-488), so partial develops include it
+        if (!(st = dr_job_direct(j)) && !(st = dr_job_seed_chains(j, b))) {
             const long long per = std::max<long long>(1, j->totalMutations / j->nChains);   // nMutations (drmlt.cpp:475-476)
-            if (!(st = dr_job_run(j, per)) && !(st = dr_job_direct(j))) st = dr_job_develop(j, imageRgb);
+            if (!fn || !(refreshSeconds > 0.0)) st = dr_job_run(j, per);
+            else {
+                const auto start = std::chrono::steady_clock::now();
+                long long done = 0, slice = std::min<long long>(per, 4);
+                while (!st && done < per && !j->timedOut) {
+                    const auto s0 = std::chrono::steady_clock::now();
+                    slice = std::min(slice, per - done);
+                    if ((st = dr_job_run(j, slice))) break;
+                    done += slice;
+                    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
+                    // next slice: about refreshSeconds of work at the measured rate (at most 4x growth per step)
+                    const double want = sec > 0.0 ? (double) slice * refreshSeconds / sec : (double) slice * 4.0;
+                    slice = (long long) std::max(1.0, std::min(want, (double) slice * 4.0));
+                    if (done < per && !j->timedOut) {
+                        dr_stats ps;
+                        if ((st = dr_job_develop(j, imageRgb)) || (st = dr_job_stats(j, &ps))) break;
+                        const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+                        if (fn(imageRgb, j->W, j->H, elapsed, &ps, user)) { dr_set_error("cancelled"); st = DR_ERR_CANCELLED; }
+                    }
+                }
+            }
+            if (!st) st = dr_job_develop(j, imageRgb);
         }
     }
     cudaEventRecord(t1, j->stream);
@@ -1091,18 +1291,12 @@ extern "C" dr_status dr_render(dr_scene scene, const dr_config *cfg, float *imag
     cudaEventElapsedTime(&ms, t0, t1);
     j->totalMs = ms;
     cudaEventDestroy(t0); cudaEventDestroy(t1);
-    if (!st && stats) st = dr_job_stats(j, stats);
+    if (!st && stats) { st = dr_job_stats(j, stats); stats->first_stage_ms = firstStageMs; }
     dr_job_destroy(j);
     return st;
 }
 
 // ------------------------------------------------------------------ replay / parity entry points
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    dr_status alloc(size_t bytes) { CK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); return DR_OK; }
-    template <class T> T *as() { return (T *) p; }
-};
 
 extern "C" dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n, int shadow, dr_hit *hits) {
     if (!scene || (n > 0 && (!rays || !hits)) || n < 0) { dr_set_error("dr_trace_rays: bad argument"); return DR_ERR_INVALID_ARG; }
@@ -1126,13 +1320,15 @@ extern "C" dr_status dr_direct_image(dr_scene scene, const dr_config *cfgIn, flo
     if (st) return st;
     if (cfg.direct_samples <= 0) { dr_set_error("dr_direct_image: directSamples must be positive"); return DR_ERR_INVALID_ARG; }
     CK(cudaSetDevice(scene->device));
-    const long long n = (long long) scene->filmW * scene->filmH;
+    FilmWindow fw;
+    if ((st = film_window(scene, cfg, fw))) return st;
+    const long long n = (long long) fw.W * fw.H;
     int ps, ss;
     direct_split(cfg.direct_samples, &ps, &ss);
     Machine M;
     memset(&M, 0, sizeof(M));
-    M.sc = scene_for(scene, cfg);
-    make_params(cfg, scene->filmW, scene->filmH, 1.0, nullptr, M);
+    M.sc = scene_for(scene, cfg, fw);
+    make_params(cfg, fw.W, fw.H, 1.0, nullptr, M);
     DevBuf film, rgb, dli;
     if ((st = film.alloc(sizeof(float4) * n)) || (st = rgb.alloc(sizeof(float) * 3 * n)) || (li && (st = dli.alloc(sizeof(double) * 3 * n * ps)))) return st;
     CK(cudaMemset(film.p, 0, sizeof(float4) * n));
@@ -1248,7 +1444,7 @@ extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, doub
         dr_set_error("dr_chain_steps: record download failed"); return done(DR_ERR_CUDA);
     }
     if (film) {
-        const size_t np = (size_t) scene->filmW * scene->filmH;
+        const size_t np = (size_t) j->W * j->H;
         std::vector<float4> f4(np);
         if (cudaMemcpy(f4.data(), j->film, np * sizeof(float4), cudaMemcpyDeviceToHost) != cudaSuccess) { dr_set_error("dr_chain_steps: film download failed"); return done(DR_ERR_CUDA); }
         for (size_t i = 0; i < np; ++i) { film[3 * i] = f4[i].x; film[3 * i + 1] = f4[i].y; film[3 * i + 2] = f4[i].z; }

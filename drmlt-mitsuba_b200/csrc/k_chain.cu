@@ -138,6 +138,32 @@ DR_D void path_result(const Machine &M, int lane, int tri, Core &c, PathResult &
     }
 }
 
+// SplatList::normalize(importanceMap), first half (pathsampler.cpp:1001-1020): two-stage MLT divides every non-zero
+// splat by the importance of its pixel and re-derives the list's luminance from the re-weighted splats.  The chain then
+// runs on that luminance; develop multiplies the importance back (drmlt_proc.cpp:823-849).
+DR_D Real importance_at(const Machine &M, Real px, Real py) {
+    const int x = min(max(0, (int) px), M.fp.w - 1), y = min(max(0, (int) py), M.fp.h - 1);
+    return (Real) __ldg(M.cp.importance + (size_t) y * M.fp.w + x);
+}
+DR_D void importance_apply(const Machine &M, int lane, PathResult &r) {
+    Real lum = 0.;
+    if (r.n && !is_zero(r.val)) {
+        r.val = r.val * (1.0 / importance_at(M, r.pos.x, r.pos.y));
+        lum += luminance(r.val);
+    }
+    if (r.nl) {                                                   // bdpt: the light-image splats of the path in flight
+        float4 *sl = splat_list(M, lane, 3);
+        for (int i = 0; i < r.nl; ++i) {
+            const float4 p = sl[2 * i], v = sl[2 * i + 1];
+            if (v.x == 0.f && v.y == 0.f && v.z == 0.f) continue;
+            const R3 w = r3((Real) v.x, (Real) v.y, (Real) v.z) * (1.0 / importance_at(M, (Real) p.x, (Real) p.y));
+            sl[2 * i + 1] = make_float4((float) w.x, (float) w.y, (float) w.z, 0.f);
+            lum += luminance(w);
+        }
+    }
+    r.lum = lum;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------ the chain kernel
@@ -198,6 +224,7 @@ k_chain(const __grid_constant__ Machine M) {
                     ++c.mut;
                     c.pstate = ((long long) lane + (long long) c.mut * M.lm.n < job.nItems) ? PS_START : PS_IDLE;
                 } else {
+                    if (cp.importance) importance_apply(M, lane, r);
                     ChainCore cc;
                     rec_load(cc, M.lm.chain + lane);
                     double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * M.lm.nU;

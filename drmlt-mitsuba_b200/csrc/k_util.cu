@@ -118,24 +118,53 @@ __global__ void k_resample(const double *cdf, long long n, unsigned long long se
 }
 
 // ---------------------------------------------------------------- develop (drmlt_proc.cpp:813-854)
-__global__ void k_film_luminance(const float4 *film, long long n, double *out) {
+__global__ void k_film_luminance(const float4 *film, const float *importance, long long n, double *out) {
     double s = 0.0;
     for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
         const float4 p = film[i];
-        s += (double) luminance(f3(p.x, p.y, p.z));
+        double l = (double) luminance(f3(p.x, p.y, p.z));
+        if (importance) l *= (double) importance[i];         // avgLuminance += accum[i].getLuminance() * importanceMap[i] (:825-827)
+        s += l;
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
-__global__ void k_develop(const float4 *film, long long n, float factor, const float *direct, float *rgb) {
+__global__ void k_develop(const float4 *film, const float *importance, long long n, float factor, const float *direct, float *rgb) {
     const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = film[i];
-    float r = p.x * factor, g = p.y * factor, b = p.z * factor;
+    const float correction = importance ? factor * importance[i] : factor;                   // correction *= importanceMap[i] (:843-844)
+    float r = p.x * correction, g = p.y * correction, b = p.z * correction;
     if (direct) { r += direct[3 * i]; g += direct[3 * i + 1]; b += direct[3 * i + 2]; }      // value += direct[i] (drmlt_proc.cpp:846-847)
     rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
 }
 
+// ---------------------------------------------------------------- two-stage MLT: importance map (src/libbidir/util.cpp:180-196)
+// Developed first-stage image -> luminance (Spectrum::getLuminance, spectrum.h:640-650) -> separable up/down-sampling with
+// precomputed, normalised filter taps (Resampler, include/mitsuba/core/rfilter.h:123-198; the tables are built on the
+// host by dr_resample_luminance), clamped boundary (EClamp, :437-458), result clamped to [0, inf) after EACH pass
+// (resampleAndClamp, :232-280).  One thread per output pixel.
+__global__ void k_rgb_luminance(const float *rgb, long long n, double *lum) {
+    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (i < n) lum[i] = (double) rgb[3 * i] * 0.212671 + (double) rgb[3 * i + 1] * 0.715160 + (double) rgb[3 * i + 2] * 0.072169;
+}
+// pass along x: src [h][ws] -> dst [h][wt];  pass along y: src [hs][w] -> dst [ht][w]
+__global__ void k_resample_axis(const double *src, int srcRes, int tgtRes, int other, int alongX, const int *start, const double *weights, int taps, double *dst) {
+    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (i >= (long long) tgtRes * other) return;
+    const int t = alongX ? (int) (i % tgtRes) : (int) (i / other), o = alongX ? (int) (i / tgtRes) : (int) (i % other);
+    double result = 0.0;
+    for (int j = 0; j < taps; ++j) {
+        const int pos = min(max(start[t] + j, 0), srcRes - 1);
+        const double v = alongX ? src[(size_t) o * srcRes + pos] : src[(size_t) pos * other + o];
+        result += v * weights[(size_t) t * taps + j];
+    }
+    dst[alongX ? (size_t) o * tgtRes + t : (size_t) t * other + o] = fmax(0.0, result);       // min(max, max(min, result)), max = inf
+}
+__global__ void k_double_to_float(const double *src, long long n, float *dst) {
+    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float) src[i];
+}
 
 // ---------------------------------------------------------------- launchers
 int lum_reduce_scratch_doubles() { return 2 * RED_BLOCKS; }
@@ -154,7 +183,13 @@ void launch_resample(const double *cdf, long long n, unsigned long long seed, un
                      int maxDepth, int technique, unsigned long long *seedIdx, unsigned long long *chainId, int *depth, cudaStream_t s) {
     k_resample<<<(nChains + 127) / 128, 128, 0, s>>>(cdf, n, seed, firstChain, nChains, bootFirst, maxDepth, technique, seedIdx, chainId, depth);
 }
-void launch_film_luminance(const float4 *film, long long n, double *out, cudaStream_t s) { k_film_luminance<<<148 * 4, 256, 0, s>>>(film, n, out); }
-void launch_develop(const float4 *film, long long n, float factor, const float *direct, float *rgb, cudaStream_t s) {
-    k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(film, n, factor, direct, rgb);
+void launch_film_luminance(const float4 *film, const float *importance, long long n, double *out, cudaStream_t s) { k_film_luminance<<<148 * 4, 256, 0, s>>>(film, importance, n, out); }
+void launch_develop(const float4 *film, const float *importance, long long n, float factor, const float *direct, float *rgb, cudaStream_t s) {
+    k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(film, importance, n, factor, direct, rgb);
 }
+void launch_rgb_luminance(const float *rgb, long long n, double *lum, cudaStream_t s) { k_rgb_luminance<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(rgb, n, lum); }
+void launch_resample_axis(const double *src, int srcRes, int tgtRes, int other, int alongX, const int *start, const double *weights, int taps, double *dst, cudaStream_t s) {
+    const long long n = (long long) tgtRes * other;
+    k_resample_axis<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(src, srcRes, tgtRes, other, alongX, start, weights, taps, dst);
+}
+void launch_double_to_float(const double *src, long long n, float *dst, cudaStream_t s) { k_double_to_float<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(src, n, dst); }

@@ -255,6 +255,7 @@ struct ChainParams {
     int acceptanceMap, timidAfterLarge, fixEmitterPath, useMixture, kelemenWeights;
     Real kel_s1, kel_s2, kel_logRatio;     // un-scaled Kelemen bounds for Mira's transition ratio
     int dimS, dimE, dimD;      // allocated coordinates per sampler (maxDepth worst case)
+    const float *importance;   // two-stage MLT: m_config.importanceMap at film resolution (null: single stage)
 };
 
 enum { ST_MUT = 0, ST_FIRST_A, ST_FIRST_B, ST_LARGE_A, ST_LARGE_B, ST_BOLD_A, ST_BOLD_B, ST_SECOND_A, ST_SECOND_B,

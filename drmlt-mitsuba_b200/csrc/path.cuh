@@ -53,21 +53,22 @@ DR_D R3 cam_xform_dir(const DevCamera &c, R3 v) {
 DR_D R3 cam_inv_dir(const DevCamera &c, R3 v) {
     return r3(c.m[0] * v.x + c.m[4] * v.y + c.m[8] * v.z, c.m[1] * v.x + c.m[5] * v.y + c.m[9] * v.z, c.m[2] * v.x + c.m[6] * v.y + c.m[10] * v.z);
 }
-DR_D R3 cam_sample_to_dir(const DevCamera &c, Real sx, Real sy) {   // :150-157, :336-339
-    return normalize(r3((1. - 2. * sx) * c.tanHalf, (1. - 2. * sy) * c.tanHalf / c.aspect, 1.0));
+DR_D R3 cam_sample_to_dir(const DevCamera &c, Real sx, Real sy) {   // :132-157, :336-339 (sample in [0,1]^2 over the crop window)
+    const Real fx = c.relOffX + sx * c.relSizeX, fy = c.relOffY + sy * c.relSizeY;
+    return normalize(r3((1. - 2. * fx) * c.tanHalf, (1. - 2. * fy) * c.tanHalf / c.aspect, 1.0));
 }
 DR_D Real cam_importance(const DevCamera &c, R3 d) {   // :191-245
     if (d.z <= 0.) return 0.0;
     Real inv = 1.0 / d.z;
     Real px = d.x * inv, py = d.y * inv;
-    if (px < -c.rectX || px > c.rectX || py < -c.rectY || py > c.rectY) return 0.0;
+    if (px < c.rectMinX || px > c.rectMaxX || py < c.rectMinY || py > c.rectMaxY) return 0.0;
     return c.normalization * inv * inv * inv;
 }
 DR_D bool cam_sample_position(const DevCamera &c, R3 dWorld, R2 &pos) {   // :367-385
     R3 l = cam_inv_dir(c, dWorld);
     if (l.z <= 0.) return false;
-    Real sx = 0.5 * (1. - l.x / (l.z * c.tanHalf));
-    Real sy = 0.5 * (1. - l.y * c.aspect / (l.z * c.tanHalf));
+    Real sx = (0.5 * (1. - l.x / (l.z * c.tanHalf)) - c.relOffX) / c.relSizeX;
+    Real sy = (0.5 * (1. - l.y * c.aspect / (l.z * c.tanHalf)) - c.relOffY) / c.relSizeY;
     if (sx < 0. || sx > 1. || sy < 0. || sy > 1.) return false;
     pos = r2(sx * c.resX, sy * c.resY);
     return true;

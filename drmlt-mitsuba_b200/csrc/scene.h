@@ -39,9 +39,24 @@ struct DevEmitter {       // 64 B
 struct DevCamera {        // derived in double from the float parameters of dr_camera (perspective.cpp:126-173)
     double m[12];         // rows of the 3x4 camera-to-world matrix
     double pos[3], dir[3];
-    double tanHalf, aspect, nearClip, farClip;
-    double resX, resY, rectX, rectY, normalization;
+    double tanHalf, aspect, nearClip, farClip;   // aspect of the FULL film
+    double resX, resY;    // crop size = resolution of the sensor (perspective.cpp:126-130)
+    double relOffX, relOffY, relSizeX, relSizeY;   // crop window as fractions of the film (:132-135)
+    double rectMinX, rectMaxX, rectMinY, rectMaxY; // m_imageRect: the crop window on the plane z = 1 (:162-169)
+    double normalization;
 };
+// film + crop window -> the sensor's derived quantities (PerspectiveCameraImpl::configure, perspective.cpp:126-173)
+inline void camera_set_window(DevCamera &dc, int filmW, int filmH, int cropX, int cropY, int cropW, int cropH) {
+    dc.aspect = (double) filmW / (double) filmH;
+    dc.resX = cropW; dc.resY = cropH;
+    dc.relSizeX = (double) cropW / (double) filmW; dc.relSizeY = (double) cropH / (double) filmH;
+    dc.relOffX = (double) cropX / (double) filmW; dc.relOffY = (double) cropY / (double) filmH;
+    const double x0 = (1.0 - 2.0 * dc.relOffX) * dc.tanHalf, x1 = (1.0 - 2.0 * (dc.relOffX + dc.relSizeX)) * dc.tanHalf;
+    const double y0 = (1.0 - 2.0 * dc.relOffY) * dc.tanHalf / dc.aspect, y1 = (1.0 - 2.0 * (dc.relOffY + dc.relSizeY)) * dc.tanHalf / dc.aspect;
+    dc.rectMinX = x0 < x1 ? x0 : x1; dc.rectMaxX = x0 < x1 ? x1 : x0;
+    dc.rectMinY = y0 < y1 ? y0 : y1; dc.rectMaxY = y0 < y1 ? y1 : y0;
+    dc.normalization = 1.0 / ((dc.rectMaxX - dc.rectMinX) * (dc.rectMaxY - dc.rectMinY));
+}
 
 struct DevScene {
     const float4 *nodes;

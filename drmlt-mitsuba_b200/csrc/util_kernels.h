@@ -7,5 +7,9 @@ void launch_lum_reduce(const float *lum, long long n, double *scratch, double *o
 void launch_scan(const float *lum, long long n, double *cdf /* n + 1 */, double *blockSums, cudaStream_t s);   // 3 launches
 void launch_resample(const double *cdf, long long n, unsigned long long seed, unsigned long long firstChain, int nChains, unsigned long long bootFirst,
                      int maxDepth, int technique, unsigned long long *seedIdx, unsigned long long *chainId, int *depth, cudaStream_t s);
-void launch_film_luminance(const float4 *film, long long n, double *out, cudaStream_t s);
-void launch_develop(const float4 *film, long long n, float factor, const float *direct /* or null */, float *rgb, cudaStream_t s);
+void launch_film_luminance(const float4 *film, const float *importance /* or null */, long long n, double *out, cudaStream_t s);
+void launch_develop(const float4 *film, const float *importance /* or null */, long long n, float factor, const float *direct /* or null */, float *rgb, cudaStream_t s);
+// two-stage MLT importance map (util.cpp:180-196): luminance of an RGB image, one separable resampling pass, narrowing copy
+void launch_rgb_luminance(const float *rgb, long long n, double *lum, cudaStream_t s);
+void launch_resample_axis(const double *src, int srcRes, int tgtRes, int other, int alongX, const int *start, const double *weights, int taps, double *dst, cudaStream_t s);
+void launch_double_to_float(const double *src, long long n, float *dst, cudaStream_t s);

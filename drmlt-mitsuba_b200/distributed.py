@@ -7,6 +7,9 @@ between its init threads / work units:
      ONE all-reduce (the reference averages the per-thread means, drmlt.cpp:530-545);
   2. film: the per-rank accumulation films are summed onto rank 0 with ONE reduce at the end
      (the reference's processResult adds full-frame blocks under a mutex, drmlt_proc.cpp:856-867).
+Two-stage MLT (twoStage=true, src/libbidir/util.cpp:96-199) runs the nested low-resolution job first, sharded the same
+way; its (small) film is ALL-reduced so that every rank develops the same first-stage image and derives the same
+importance map without a broadcast.
 `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is only the transport.
 """
 import numpy as np
@@ -36,19 +39,40 @@ def all_reduce_normalization(lum_sum, count, is_mmlt, max_depth, dist=None, devi
     return normalization_from_sums(lum_sum, count, is_mmlt, max_depth)
 
 
-def reduce_film(film_tensor, dist=None, dst=0):
-    """One reduce(sum) of the accumulation film onto rank `dst`, in place."""
+def reduce_film(film_tensor, dist=None, dst=0, all_ranks=False):
+    """One reduce(sum) of the accumulation film onto rank `dst` (or onto every rank: the first-stage film of
+    two-stage MLT), in place."""
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.reduce(film_tensor, dst=dst, op=dist.ReduceOp.SUM)
+        if all_ranks:
+            dist.all_reduce(film_tensor, op=dist.ReduceOp.SUM)
+        else:
+            dist.reduce(film_tensor, dst=dst, op=dist.ReduceOp.SUM)
     return film_tensor
 
 
 def render(scene, params, dist=None, rank=0, world_size=1, mutations_per_chain=None):
     """A whole job on `world_size` GPUs: returns (image on rank 0 else None, job stats, b).
     `params` are reference-style parameters (see integrator.make_config)."""
+    from .integrator import make_config, set_importance_map
+    import time
+    cfg = make_config(rank=rank, worldSize=world_size, **params)
+    first_stage_ms = 0.0
+    if cfg.two_stage and not cfg.first_stage:
+        # mltLuminancePass (util.cpp:96-199): nested job on all ranks, all-reduced film, identical map everywhere
+        t0 = time.perf_counter()
+        nested = scene.first_stage_config(cfg)
+        img_n, _, _ = _render_cfg(scene, nested, dist, rank, world_size, None, all_ranks=True)
+        set_importance_map(cfg, scene.resample_luminance(img_n, scene.film_size(cfg)))
+        first_stage_ms = (time.perf_counter() - t0) * 1e3
+    out = _render_cfg(scene, cfg, dist, rank, world_size, mutations_per_chain, all_ranks=False)
+    render.last_timing = dict(_render_cfg.last_timing, first_stage_ms=first_stage_ms)
+    return out
+
+
+def _render_cfg(scene, cfg, dist, rank, world_size, mutations_per_chain, all_ranks):
     import torch
     from . import abi
-    from .integrator import DeviceFilm, Job, make_config
+    from .integrator import DeviceFilm, Job
 
     import time
     t0 = time.perf_counter()
@@ -60,7 +84,6 @@ def render(scene, params, dist=None, rank=0, world_size=1, mutations_per_chain=N
         timing[name] = timing.get(name, 0.0) + (t1 - t0) * 1e3
         t0 = t1
 
-    cfg = make_config(rank=rank, worldSize=world_size, **params)
     job = Job(scene, cfg)
     lap("job_create_ms")
     s, c = job.bootstrap()
@@ -75,18 +98,18 @@ def render(scene, params, dist=None, rank=0, world_size=1, mutations_per_chain=N
     lap("chains_ms")
     if world_size > 1:
         film = torch.as_tensor(DeviceFilm(job), device=dev)
-        reduce_film(film, dist, 0)
+        reduce_film(film, dist, 0, all_ranks)
         torch.cuda.synchronize()
     lap("film_reduce_ms")
     if rank == 0:
         job.direct()                       # separate direct-illumination image (directSamples > 0), added by develop
     lap("direct_ms")
-    img = job.develop() if rank == 0 else None
+    img = job.develop() if (rank == 0 or all_ranks) else None
     lap("develop_ms")
     st = job.stats()
     job.close()
     lap("job_destroy_ms")
-    render.last_timing = timing
+    _render_cfg.last_timing = timing
     return img, st, b
 
 

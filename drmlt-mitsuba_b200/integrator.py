@@ -25,6 +25,19 @@ def _fmt(v):
     return str(v).encode()
 
 
+def set_importance_map(cfg, importance):
+    """Attach a (H, W) float32 importance map (m_config.importanceMap) to a configuration; None detaches it.
+    The array is kept alive by the configuration object."""
+    if importance is None:
+        cfg.importance_map = None
+        cfg._importance_keep = None
+        return cfg
+    arr = np.ascontiguousarray(importance, np.float32)
+    cfg._importance_keep = arr
+    cfg.importance_map = _fp(arr)
+    return cfg
+
+
 def make_config(**params):
     """dr_config from reference-style parameters, e.g. make_config(integrator="drmlt",
     technique="mmlt", type="orbital", maxDepth=8, sigma=1/64, acceptanceMap=True)."""
@@ -64,6 +77,34 @@ class Scene:
     def film(self):
         return self.data.film
 
+    def film_size(self, cfg):
+        """(W, H) of the image a job with this configuration renders: the crop window of the (possibly overridden) film."""
+        w, h = C.c_int32(0), C.c_int32(0)
+        abi.check(self.lib, self.lib.dr_film_size(self.h, C.byref(cfg), C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    # ---- two-stage MLT (BidirectionalUtils::mltLuminancePass, src/libbidir/util.cpp:96-199)
+    def first_stage_config(self, cfg):
+        nested = abi.dr_config()
+        abi.check(self.lib, self.lib.dr_first_stage_config(self.h, C.byref(cfg), C.byref(nested)))
+        return nested
+
+    def resample_luminance(self, image_rgb, size):
+        """Developed first-stage image (h, w, 3) -> importance map (H, W) for size = (W, H)."""
+        img = np.ascontiguousarray(image_rgb, np.float32)
+        h, w = img.shape[:2]
+        W, H = size
+        out = np.zeros((H, W), np.float32)
+        abi.check(self.lib, self.lib.dr_resample_luminance(self.h, _fp(img), w, h, W, H, _fp(out)))
+        return out
+
+    def importance_map(self, cfg):
+        W, H = self.film_size(cfg)
+        out = np.zeros((H, W), np.float32)
+        st = abi.dr_stats()
+        abi.check(self.lib, self.lib.dr_importance_map(self.h, C.byref(cfg), _fp(out), C.byref(st)))
+        return out, st
+
     def reupload(self):
         n = C.c_int64(0)
         abi.check(self.lib, self.lib.dr_scene_reupload(self.h, C.byref(n)))
@@ -71,10 +112,25 @@ class Scene:
 
     # ---- whole job, host buffers (DRMLT::render / PSSMLT::render)
     def render(self, cfg, out=None):
-        W, H = self.film
+        W, H = self.film_size(cfg)
         img = out if out is not None else np.zeros((H, W, 3), np.float32)
         st = abi.dr_stats()
         abi.check(self.lib, self.lib.dr_render(self.h, C.byref(cfg), _fp(img), C.byref(st)))
+        return img, st
+
+    def render_progressive(self, cfg, refresh_seconds, on_refresh):
+        """dr_render with a develop of the partial image about every `refresh_seconds`:
+        on_refresh(image (H, W, 3) view, seconds, stats) -> truthy cancels the job."""
+        W, H = self.film_size(cfg)
+        img = np.zeros((H, W, 3), np.float32)
+        st = abi.dr_stats()
+
+        def _cb(ptr, w, h, seconds, stats, user):
+            view = np.ctypeslib.as_array(ptr, shape=(h, w, 3))
+            return 1 if on_refresh(view, seconds, stats.contents) else 0
+
+        cb = abi.dr_refresh_fn(_cb)
+        abi.check(self.lib, self.lib.dr_render_progressive(self.h, C.byref(cfg), _fp(img), C.byref(st), float(refresh_seconds), cb, None))
         return img, st
 
     # ---- replay entry points
@@ -101,7 +157,7 @@ class Scene:
 
     def direct_image(self, cfg, want_li=False):
         """The separate direct-illumination image (directSamples > 0); optionally the radiance of every pixel sample."""
-        W, H = self.film
+        W, H = self.film_size(cfg)
         ps = max(int(cfg.direct_samples), 1)
         while ps > 8:
             ps //= 2
@@ -116,7 +172,7 @@ class Scene:
         chain_id = np.ascontiguousarray(chain_id, np.uint64)
         depth = np.ascontiguousarray(depth, np.int32)
         rec = (abi.dr_step_record * (n * steps))()
-        W, H = self.film
+        W, H = self.film_size(cfg)
         film = np.zeros((H, W, 3), np.float32) if want_film else None
         abi.check(self.lib, self.lib.dr_chain_steps(self.h, C.byref(cfg), b, _fp(seed_index, C.c_uint64), _fp(depth, C.c_int32),
                                                     _fp(chain_id, C.c_uint64), n, steps, rec, _fp(film) if want_film else None))
@@ -177,7 +233,7 @@ class Job:
         return p.value, n.value
 
     def develop(self):
-        W, H = self.scene.film
+        W, H = self.scene.film_size(self.cfg)
         img = np.zeros((H, W, 3), np.float32)
         abi.check(self.lib, self.lib.dr_job_develop(self.h, _fp(img)))
         return img

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DR_ABI_VERSION 3
+#define DR_ABI_VERSION 4
 
 /* ------------------------------------------------------------------ status */
 typedef enum dr_status {
@@ -114,7 +114,7 @@ typedef struct dr_config {
     float   p_large;           /* pLarge = 0.3 */
     int32_t work_units;        /* workUnits = -1 (auto) */
     int32_t kelemen_style_weights;  /* kelemenStyleWeights = true (forced false for MMLT) */
-    int32_t two_stage;         /* twoStage = false (only false is supported: section 8(f) "next") */
+    int32_t two_stage;         /* twoStage = false; true: low-resolution first pass -> importance map (util.cpp:96-199) */
     int32_t timeout;           /* timeout = 0 seconds; > 0: the chain phase stops after that many seconds (drmlt_proc.cpp:519-521) */
     float   average_luminance; /* averageLuminance = -1 (use bootstrap estimate) */
     int32_t light_image;       /* lightImage = true */
@@ -136,6 +136,16 @@ typedef struct dr_config {
     int32_t rank, world_size;  /* chain / bootstrap shard of this process (1 GPU: 0, 1) */
     float   ray_epsilon;       /* 0 = 1e-4f (Mitsuba single precision, constants.h:29) */
     float   shadow_epsilon;    /* 0 = 1e-3f (constants.h:30) */
+    /* two-stage MLT (drmlt.cpp:278-293, 401-418; BidirectionalUtils::mltLuminancePass, src/libbidir/util.cpp:96-199) */
+    int32_t first_stage;                 /* firstStage = false (internal in the reference: this job IS the nested pass) */
+    int32_t first_stage_size_reduction;  /* firstStageSizeReduction = 16 */
+    /* film window, carried by the film plugin in the reference (src/librender/film.cpp:30-67): 0 = use dr_camera's film */
+    int32_t film_width, film_height;     /* full film size override (the nested pass renders at size / firstStageSizeReduction) */
+    int32_t crop_offset_x, crop_offset_y;/* cropOffsetX/Y = 0 */
+    int32_t crop_width, crop_height;     /* cropWidth/Height = film size; the rendered image and all buffers have the CROP size */
+    /* m_config.importanceMap (drmlt.h:57, internal): host pointer to crop_width*crop_height floats, or NULL.
+     * With twoStage=true and NULL here, dr_render computes it with dr_importance_map first. */
+    const float *importance_map;
 } dr_config;
 
 void      dr_config_default(dr_config *cfg);
@@ -168,6 +178,7 @@ typedef struct dr_stats {
     double   trace_ms, walk_ms, chain_ms;
     uint64_t trace_launches, walk_launches, chain_launches;
     double   direct_ms;                 /* separate direct-illumination pass (directSamples > 0) */
+    double   first_stage_ms;            /* two-stage MLT: wall time of the nested first-stage pass (dr_render only) */
 } dr_stats;
 
 /* ------------------------------------------------------------- entry points */
@@ -193,6 +204,14 @@ dr_status dr_scene_reupload(dr_scene scene, int64_t *bytes);
  * (what the reference hands to film->setBitmap); in acceptanceMap mode it holds the R/G counts. */
 dr_status dr_render(dr_scene scene, const dr_config *cfg, float *image_rgb, dr_stats *stats);
 void      dr_cancel(dr_scene scene);
+/* dr_render with periodic develops of the partial result -- DRMLTProcess::processResult's develop + signalRefresh for
+ * interactive jobs (drmlt_proc.cpp:856-867) and the images `mitsuba -r <sec>` dumps through Scene::flush
+ * (src/librender/scene.cpp:468-511).  The chain phase runs in slices of about `refresh_seconds`; after each slice the
+ * film is developed into `image_rgb` and `fn(image_rgb, width, height, seconds since the chains started, stats, user)`
+ * is called from the calling thread; a non-zero return cancels the job (DR_ERR_CANCELLED). */
+typedef int (*dr_refresh_fn)(const float *image_rgb, int32_t width, int32_t height, double seconds, const dr_stats *stats, void *user);
+dr_status dr_render_progressive(dr_scene scene, const dr_config *cfg, float *image_rgb, dr_stats *stats,
+                                double refresh_seconds, dr_refresh_fn fn, void *user);
 
 /* ---- staged API (multi-GPU drivers, tests, benchmarks) -------------------
  * One job = one rank's share of a render.  Sequence:
@@ -222,6 +241,21 @@ dr_status dr_job_stats(dr_job job, dr_stats *stats);
 void      dr_job_profile(dr_job job, int on);
 int64_t   dr_job_num_chains(dr_job job);
 int64_t   dr_job_total_mutations(dr_job job);   /* W*H*sampleCount share of this rank */
+
+/* ---- two-stage MLT ------------------------------------------------------- */
+
+/* Size of the image a job with this configuration renders (the crop window of the film). */
+dr_status dr_film_size(dr_scene scene, const dr_config *cfg, int32_t *width, int32_t *height);
+/* Configuration of the nested first-stage job (util.cpp:100-159): firstStage = true, film and crop window divided by
+ * firstStageSizeReduction (at least 1 pixel), sampleCount multiplied by it, no importance map. */
+dr_status dr_first_stage_config(dr_scene scene, const dr_config *cfg, dr_config *nested);
+/* Developed first-stage image (w*h*3 floats, host) -> luminance (spectrum.h:640-650) -> up-sampled to W*H with the
+ * gaussian reconstruction filter, clamped boundary, values clamped to [0, inf) (util.cpp:180-196,
+ * Resampler include/mitsuba/core/rfilter.h:107-324).  Runs on the GPU of `scene`. */
+dr_status dr_resample_luminance(dr_scene scene, const float *image_rgb, int32_t w, int32_t h, int32_t W, int32_t H, float *map);
+/* BidirectionalUtils::mltLuminancePass on this GPU: nested render with dr_first_stage_config, then
+ * dr_resample_luminance.  `map` receives crop_width*crop_height floats of the job described by `cfg`. */
+dr_status dr_importance_map(dr_scene scene, const dr_config *cfg, float *map, dr_stats *nested_stats);
 
 /* ---- replay / parity entry points ---------------------------------------- */
 

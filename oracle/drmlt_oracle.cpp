@@ -19,6 +19,11 @@ static void applyEps(Scene &sc, const dr_config *cfg) {
     // (constants.h:25-27); parity tests pass the float-build values the GPU uses.
     sc.epsilon = cfg && cfg->ray_epsilon > 0 ? (Float) cfg->ray_epsilon : 1e-7;
     sc.shadowEpsilon = cfg && cfg->shadow_epsilon > 0 ? (Float) cfg->shadow_epsilon : 1e-5;
+    // film / crop window of the job (Film::Film, src/librender/film.cpp:30-48): 0 = the camera's film, no crop
+    int fW = cfg && cfg->film_width > 0 ? cfg->film_width : sc.cam.filmW, fH = cfg && cfg->film_height > 0 ? cfg->film_height : sc.cam.filmH;
+    int cX = cfg ? cfg->crop_offset_x : 0, cY = cfg ? cfg->crop_offset_y : 0;
+    int cW = cfg && cfg->crop_width > 0 ? cfg->crop_width : fW, cH = cfg && cfg->crop_height > 0 ? cfg->crop_height : fH;
+    sc.cam.setWindow(fW, fH, cX, cY, cW, cH);
 }
 
 extern "C" {
@@ -186,9 +191,31 @@ int orc_chain_steps(void *h, const dr_config *cfg, double b, const uint64_t *see
 // drmlt.cpp:393-611).  n_boot bootstrap samples -> b and the seed CDF -> n_chains chains of
 // `steps` mutations each, one chain per work item, `threads` host threads.
 int orc_direct_image(void *h, const dr_config *cfg, float *image_rgb, double *li_out);
-int orc_render(void *h, const dr_config *cfg, int64_t n_boot, int64_t n_chains, int64_t steps, int threads,
+void orc_first_stage_config(void *h, const dr_config *cfg, dr_config *nested);
+void orc_resample_luminance(const float *image_rgb, int w, int h, int W, int H, float *map);
+int orc_render(void *h, const dr_config *cfgIn, int64_t n_boot, int64_t n_chains, int64_t steps, int threads,
                float *image_rgb, dr_stats *stats_out, double *seconds_chains) {
     Scene &sc = ((OrcScene *) h)->sc;
+    dr_config cfgLocal = *cfgIn;
+    const dr_config *cfg = &cfgLocal;
+    std::vector<float> importance;
+    if (cfgLocal.two_stage && !cfgLocal.first_stage && !cfgLocal.importance_map) {
+        // BidirectionalUtils::mltLuminancePass (util.cpp:96-199): nested render at reduced size with sizeFactor x the
+        // mutations per pixel (= total mutations / sizeFactor), developed, luminance, up-sampled
+        dr_config nested;
+        orc_first_stage_config(h, cfg, &nested);
+        applyEps(sc, &nested);
+        const int w = (int) sc.cam.resX, hh = (int) sc.cam.resY;
+        std::vector<float> img((size_t) 3 * w * hh);
+        int rc = orc_render(h, &nested, n_boot, n_chains, std::max<int64_t>(1, steps / std::max(1, cfgLocal.first_stage_size_reduction)), threads,
+                            img.data(), nullptr, nullptr);
+        if (rc) return rc;
+        applyEps(sc, cfg);
+        const int W = (int) sc.cam.resX, H = (int) sc.cam.resY;
+        importance.resize((size_t) W * H);
+        orc_resample_luminance(img.data(), w, hh, W, H, importance.data());
+        cfgLocal.importance_map = importance.data();
+    }
     applyEps(sc, cfg);
     std::vector<float> lum(n_boot);
     std::vector<int32_t> dep(n_boot);
@@ -224,8 +251,8 @@ int orc_render(void *h, const dr_config *cfg, int64_t n_boot, int64_t n_chains, 
     if (image_rgb) {
         Film f; f.init(sc.cam.resX, sc.cam.resY, cfg->rfilter);
         for (size_t i = 0; i < film.size(); ++i) f.data[i] = film[i];
-        develop(f, b, cfg->acceptance_map != 0, image_rgb);
-        if (cfg->direct_samples > 0 && !cfg->acceptance_map) {   // value += direct[i] (drmlt_proc.cpp:846-847)
+        develop(f, b, cfg->acceptance_map != 0, image_rgb, cfg->first_stage ? nullptr : cfg->importance_map);
+        if (cfg->direct_samples > 0 && !cfg->acceptance_map && !(cfg->two_stage && cfg->first_stage)) {   // `!nested` (drmlt.cpp:478)   // value += direct[i] (drmlt_proc.cpp:846-847)
             std::vector<float> direct(film.size());
             orc_direct_image(h, cfg, direct.data(), nullptr);
             for (size_t i = 0; i < film.size(); ++i) image_rgb[i] += direct[i];
@@ -233,6 +260,31 @@ int orc_render(void *h, const dr_config *cfg, int64_t n_boot, int64_t n_chains, 
     }
     if (stats_out) stats_out->luminance = b;
     return 0;
+}
+
+// Nested first-stage configuration (util.cpp:100-159); mirrors dr_first_stage_config.
+void orc_first_stage_config(void *h, const dr_config *cfg, dr_config *nested) {
+    Scene &sc = ((OrcScene *) h)->sc;
+    applyEps(sc, cfg);
+    const int f = std::max(1, cfg->first_stage_size_reduction);
+    const int fW = cfg->film_width > 0 ? cfg->film_width : sc.cam.filmW, fH = cfg->film_height > 0 ? cfg->film_height : sc.cam.filmH;
+    dr_config c = *cfg;
+    c.two_stage = 1; c.first_stage = 1;
+    c.film_width = std::max(1, fW / f); c.film_height = std::max(1, fH / f);
+    c.crop_width = std::max(1, (int) sc.cam.resX / f); c.crop_height = std::max(1, (int) sc.cam.resY / f);
+    c.crop_offset_x = cfg->crop_offset_x / f;
+    c.crop_offset_y = cfg->crop_offset_x / f;            // sic (util.cpp:128)
+    c.sample_count = cfg->sample_count * f;
+    c.importance_map = nullptr;
+    c.n_chains = 0;
+    *nested = c;
+}
+void orc_resample_luminance(const float *image_rgb, int w, int h, int W, int H, float *map) { resampleLuminance(image_rgb, w, h, W, H, map); }
+// develop of an accumulated film (W*H*3 floats) with an optional importance map (drmlt_proc.cpp:813-854)
+void orc_develop(const float *film_rgb, int w, int h, double b, int acceptance_map, const float *importance, float *image_rgb) {
+    Film f; f.init(w, h, DR_FILTER_BOX);
+    for (size_t i = 0; i < f.data.size(); ++i) f.data[i] = film_rgb[i];
+    develop(f, b, acceptance_map != 0, image_rgb, importance);
 }
 
 // Film splat of explicit (pos, rgb) pairs -- parity of ImageBlock::put + the filter table.

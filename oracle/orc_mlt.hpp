@@ -359,7 +359,12 @@ struct ChainRunner {
     Float b;                    // m_config.luminance
     Film *film;                 // may be null
     ChainStats stats;
-    ChainRunner(const Scene &s, const dr_config &c, Float b_, Film *f) : sc(s), cfg(c), b(b_), film(f) {}
+    const float *imp = nullptr; // m_config.importanceMap (two-stage MLT), at the job's image size
+    int impW = 0, impH = 0;
+    ChainRunner(const Scene &s, const dr_config &c, Float b_, Film *f) : sc(s), cfg(c), b(b_), film(f) {
+        if (c.importance_map && !c.first_stage) { imp = c.importance_map; impW = (int) s.cam.resX; impH = (int) s.cam.resY; }
+    }
+    void norm(SplatList &l) const { l.normalize(imp, impW, impH); }
 
     static bool invalidStrict(Float x) { return std::isnan(x) || std::isinf(x) || x <= 0; }   // drmlt_proc.cpp:428
     static bool invalidLoose(Float x) { return std::isnan(x) || std::isinf(x) || x < 0; }     // :181
@@ -404,7 +409,7 @@ struct ChainRunner {
         for (auto s : all) { s->arrayMode = false; s->resetStage(); }
         ++stats.paths;
         if (cfg.acceptance_map) {}   // luminance override only affects develop
-        current.normalize();
+        norm(current);
 
         const bool mixture = cfg.use_mixture != 0;
         for (uint64_t m = 0; m < nMutations; ++m) {
@@ -414,7 +419,7 @@ struct ChainRunner {
             bool largeStep = src.coin(0) < cfg.p_large;
             for (auto s : all) s->setLargeStep(largeStep);
             ps.sampleSplats(prop1, depth);
-            prop1.normalize();
+            norm(prop1);
             ++stats.mutations; ++stats.paths;
             auto flipCoin = [&](Float x, int which) { return (x >= 1) || (src.coin(which) < x); };
 
@@ -427,7 +432,7 @@ struct ChainRunner {
                 if (doSecond) {
                     sensorS.nextStage(); directS.nextStage();
                     if (cfg.fix_emitter_path) emitterS.nextStage(current.t == 1); else emitterS.nextStage();
-                    ps.sampleSplats(prop2, depth); prop2.normalize(); ++stats.paths;
+                    ps.sampleSplats(prop2, depth); norm(prop2); ++stats.paths;
                     proposed = &prop2;
                     if (invalidLoose(prop2.luminance)) { a = 0; accept = false; }
                     else { a = metropolisClamp(prop2.luminance / current.luminance); accept = flipCoin(a, 2); }
@@ -461,11 +466,11 @@ struct ChainRunner {
             if (doSecond) {
                 sensorS.nextStage(); directS.nextStage();
                 if (cfg.fix_emitter_path) emitterS.nextStage(current.t == 1); else emitterS.nextStage();
-                ps.sampleSplats(prop2, depth); prop2.normalize(); ++stats.paths;
+                ps.sampleSplats(prop2, depth); norm(prop2); ++stats.paths;
                 if (!invalidStrict(prop2.luminance)) {
                     if (cfg.type == DR_TYPE_GREEN) {   // :588-621
                         for (auto s : all) s->setReverse(true);
-                        ps.sampleSplats(reverse, depth); reverse.normalize(); ++stats.paths;
+                        ps.sampleSplats(reverse, depth); norm(reverse); ++stats.paths;
                         Float aReverse = invalidStrict(reverse.luminance) ? 0.0 : metropolisClamp(reverse.luminance / prop2.luminance);
                         if (aReverse == 1) { a2 = 0; acc2 = false; }
                         else {
@@ -549,15 +554,15 @@ struct ChainRunner {
         ps.sampleSplats(current, depth);
         for (auto s : all) { s->arrayMode = false; s->sampleIndex = 0; }
         ++stats.paths;
-        current.normalize();
+        norm(current);
         Float cumulativeWeight = 0;
-        const bool kelemenW = cfg.kelemen_style_weights != 0;
+        const bool kelemenW = cfg.kelemen_style_weights != 0 && !imp;   // pssmlt_proc.cpp:205
         for (uint64_t m = 0; m < nMutations; ++m) {
             src.mut = (uint32_t) m;
             bool largeStep = src.coin(0) < cfg.p_large;
             for (auto s : all) s->setLargeStep(largeStep);
             ps.sampleSplats(proposed, depth);
-            proposed.normalize();
+            norm(proposed);
             ++stats.mutations; ++stats.paths;
             Float a = std::min((Float) 1.0, proposed.luminance / current.luminance);
             if (std::isnan(proposed.luminance) || proposed.luminance < 0) a = 0;
@@ -606,13 +611,83 @@ struct ChainRunner {
 };
 
 // develop (drmlt_proc.cpp:813-854): image = accum * (b / mean pixel luminance)
-inline void develop(const Film &film, Float b, bool acceptanceMap, float *out) {
+inline void develop(const Film &film, Float b, bool acceptanceMap, float *out, const float *importanceMap = nullptr) {
     size_t n = (size_t) film.w * film.h;
     Float avg = 0;
-    for (size_t i = 0; i < n; ++i) avg += RGB(film.data[3 * i], film.data[3 * i + 1], film.data[3 * i + 2]).luminance();
+    for (size_t i = 0; i < n; ++i) {
+        Float l = RGB(film.data[3 * i], film.data[3 * i + 1], film.data[3 * i + 2]).luminance();
+        avg += importanceMap ? l * importanceMap[i] : l;      // :825-830
+    }
     avg /= (Float) n;
     Float factor = acceptanceMap ? 1.0 : b / avg;
-    for (size_t i = 0; i < 3 * n; ++i) out[i] = (float) (film.data[i] * factor);
+    for (size_t i = 0; i < n; ++i) {
+        Float correction = importanceMap ? factor * importanceMap[i] : factor;   // :841-844
+        for (int c = 0; c < 3; ++c) out[3 * i + c] = (float) (film.data[3 * i + c] * correction);
+    }
+}
+
+// ------------------------------------------------------------------ two-stage MLT: importance map
+// Resampler (include/mitsuba/core/rfilter.h:107-324) in resampling mode with the gaussian filter (gaussian.cpp:30-60),
+// EClamp boundary (:437-458) and resampleAndClamp to [0, inf) (:232-280).
+struct Resampler {
+    int sourceRes, targetRes, taps;
+    std::vector<int> start;
+    std::vector<Float> weights;
+    static Float gaussianEval(Float x) {
+        const Float stddev = 0.5, radius = 4 * stddev, alpha = -1.0 / (2.0 * stddev * stddev);
+        return std::max((Float) 0.0, std::exp(alpha * x * x) - std::exp(alpha * radius * radius));
+    }
+    Resampler(int src, int tgt) : sourceRes(src), targetRes(tgt) {
+        Float filterRadius = 2.0, scale = 1.0, invScale = 1.0;
+        if (targetRes < sourceRes) { scale = (Float) sourceRes / (Float) targetRes; invScale = 1 / scale; filterRadius *= scale; }
+        taps = (int) std::ceil(filterRadius * 2);
+        start.resize(targetRes); weights.resize((size_t) taps * targetRes);
+        for (int i = 0; i < targetRes; i++) {
+            Float center = (i + 0.5) / targetRes * sourceRes;
+            start[i] = (int) std::floor(center - filterRadius + 0.5);
+            Float sum = 0;
+            for (int j = 0; j < taps; j++) {
+                Float pos = start[i] + j + 0.5 - center;
+                Float weight = gaussianEval(pos * invScale);
+                weights[(size_t) i * taps + j] = weight;
+                sum += weight;
+            }
+            Float normalization = 1.0 / sum;
+            for (int j = 0; j < taps; j++) weights[(size_t) i * taps + j] *= normalization;
+        }
+    }
+    // one line: source[stride * k] -> target[tstride * i]
+    void resampleAndClamp(const Float *source, size_t stride, Float *target, size_t tstride) const {
+        for (int i = 0; i < targetRes; ++i) {
+            Float result = 0;
+            for (int j = 0; j < taps; ++j) {
+                int pos = std::min(std::max(start[i] + j, 0), sourceRes - 1);
+                result += source[stride * pos] * weights[(size_t) i * taps + j];
+            }
+            target[tstride * i] = std::max((Float) 0.0, result);
+        }
+    }
+};
+// mltLuminancePass, last part (util.cpp:180-196): developed RGB -> luminance -> Bitmap::resample (bitmap.cpp:2230-2329)
+inline void resampleLuminance(const float *rgb, int w, int h, int W, int H, float *map) {
+    std::vector<Float> lum((size_t) w * h);
+    for (size_t i = 0; i < lum.size(); ++i) lum[i] = RGB(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]).luminance();
+    std::vector<Float> tmp, out;
+    const Float *cur = lum.data();
+    int curW = w;
+    if (w != W) {
+        Resampler r(w, W);
+        tmp.resize((size_t) W * h);
+        for (int y = 0; y < h; ++y) r.resampleAndClamp(cur + (size_t) y * w, 1, tmp.data() + (size_t) y * W, 1);
+        cur = tmp.data(); curW = W;
+    }
+    if (h != H) {
+        Resampler r(h, H);
+        out.resize((size_t) W * H);
+        for (int x = 0; x < curW; ++x) r.resampleAndClamp(cur + x, curW, out.data() + x, curW);
+        cur = out.data();
+    }
+    for (size_t i = 0; i < (size_t) W * H; ++i) map[i] = (float) cur[i];
 }
 
 } // namespace orc

@@ -584,7 +584,19 @@ struct SplatList {
     void accum(size_t i, const RGB &value) { splats[i].second += value; luminance += value.luminance(); ++nSamples; }
     void clear() { luminance = 0; nSamples = 0; splats.clear(); misWeight = 0; }
     size_t size() const { return splats.size(); }
-    void normalize() {   // pathsampler.cpp:1001-1028 (no importance map)
+    // pathsampler.cpp:1001-1028; importanceMap (two-stage MLT): w*h floats or null
+    void normalize(const float *importanceMap = nullptr, int w = 0, int h = 0) {
+        if (importanceMap) {
+            luminance = 0.0;
+            for (auto &sp : splats) {
+                if (sp.second.isZero()) continue;
+                int x = std::min(std::max(0, (int) sp.first.x), w - 1), y = std::min(std::max(0, (int) sp.first.y), h - 1);
+                Float lumValue = importanceMap[x + (size_t) y * w];
+                Float recip = 1.0 / lumValue;             // Spectrum::operator/= (spectrum.h:447-456)
+                sp.second *= recip;
+                luminance += sp.second.luminance();
+            }
+        }
         if (luminance > 0) {
             Float inv = 1.0 / luminance;
             for (auto &sp : splats) sp.second *= inv;

@@ -90,9 +90,23 @@ struct Camera {
     Float toWorld[16];
     Vec3 pos, dir;          // trafo(0), trafo((0,0,1))
     Float tanHalf, aspect, nearClip, farClip;
-    Float resX, resY;
-    Float rectX, rectY;     // half extents of the image rectangle at z = 1
+    Float resX, resY;       // crop size = the sensor's resolution (perspective.cpp:126-130)
+    Float relOffX = 0, relOffY = 0, relSizeX = 1, relSizeY = 1;   // crop window as fractions of the film (:132-135)
+    Float rectMinX, rectMaxX, rectMinY, rectMaxY;   // m_imageRect at z = 1 (:162-169)
     Float normalization;
+    int filmW = 0, filmH = 0;   // film size given by dr_camera (a configuration may override it, see setWindow)
+    // PerspectiveCameraImpl::configure (perspective.cpp:126-173) for a film / crop window (Film::Film, film.cpp:30-48)
+    void setWindow(int fW, int fH, int cropX, int cropY, int cropW, int cropH) {
+        aspect = (Float) fW / (Float) fH;
+        resX = cropW; resY = cropH;
+        relSizeX = (Float) cropW / (Float) fW; relSizeY = (Float) cropH / (Float) fH;
+        relOffX = (Float) cropX / (Float) fW; relOffY = (Float) cropY / (Float) fH;
+        Float x0 = (1 - 2 * relOffX) * tanHalf, x1 = (1 - 2 * (relOffX + relSizeX)) * tanHalf;
+        Float y0 = (1 - 2 * relOffY) * tanHalf / aspect, y1 = (1 - 2 * (relOffY + relSizeY)) * tanHalf / aspect;
+        rectMinX = std::min(x0, x1); rectMaxX = std::max(x0, x1);
+        rectMinY = std::min(y0, y1); rectMaxY = std::max(y0, y1);
+        normalization = 1.0 / ((rectMaxX - rectMinX) * (rectMaxY - rectMinY));   // :167-173
+    }
     Vec3 xformDir(const Vec3 &v) const {
         return Vec3(toWorld[0] * v.x + toWorld[1] * v.y + toWorld[2] * v.z,
                     toWorld[4] * v.x + toWorld[5] * v.y + toWorld[6] * v.z,
@@ -105,7 +119,8 @@ struct Camera {
     }
     // perspective.cpp:150-157 m_sampleToCamera applied to (sx, sy, 0), normalised
     Vec3 sampleToDir(Float sx, Float sy) const {
-        return normalize(Vec3((1 - 2 * sx) * tanHalf, (1 - 2 * sy) * tanHalf / aspect, 1.0));
+        Float fx = relOffX + sx * relSizeX, fy = relOffY + sy * relSizeY;   // sample over the crop window -> film fraction
+        return normalize(Vec3((1 - 2 * fx) * tanHalf, (1 - 2 * fy) * tanHalf / aspect, 1.0));
     }
     // perspective.cpp:191-245
     Float importance(const Vec3 &d) const {
@@ -113,15 +128,15 @@ struct Camera {
         if (cosTheta <= 0) return 0.0;
         Float invCosTheta = 1.0 / cosTheta;
         Float px = d.x * invCosTheta, py = d.y * invCosTheta;
-        if (px < -rectX || px > rectX || py < -rectY || py > rectY) return 0.0;
+        if (px < rectMinX || px > rectMaxX || py < rectMinY || py > rectMaxY) return 0.0;
         return normalization * invCosTheta * invCosTheta * invCosTheta;
     }
     // perspective.cpp:367-385 (dWorld need not be normalised)
     bool getSamplePosition(const Vec3 &dWorld, Vec2 &pos) const {
         Vec3 local = invDir(dWorld);
         if (local.z <= 0) return false;
-        Float sx = 0.5 * (1 - local.x / (local.z * tanHalf));
-        Float sy = 0.5 * (1 - local.y * aspect / (local.z * tanHalf));
+        Float sx = (0.5 * (1 - local.x / (local.z * tanHalf)) - relOffX) / relSizeX;
+        Float sy = (0.5 * (1 - local.y * aspect / (local.z * tanHalf)) - relOffY) / relSizeY;
         if (sx < 0 || sx > 1 || sy < 0 || sy > 1) return false;
         pos = Vec2(sx * resX, sy * resY);
         return true;
@@ -240,11 +255,9 @@ inline void Scene::load(const dr_scene_desc &d) {
     cam.pos = Vec3(c.to_world[3], c.to_world[7], c.to_world[11]);
     cam.dir = cam.xformDir(Vec3(0, 0, 1));
     cam.tanHalf = std::tan(0.5 * (Float) c.xfov_deg * PI / 180.0);
-    cam.aspect = (Float) c.film_width / (Float) c.film_height;
     cam.nearClip = c.near_clip; cam.farClip = c.far_clip;
-    cam.resX = c.film_width; cam.resY = c.film_height;
-    cam.rectX = cam.tanHalf; cam.rectY = cam.tanHalf / cam.aspect;
-    cam.normalization = 1.0 / (2 * cam.rectX * 2 * cam.rectY);   // perspective.cpp:167-173
+    cam.filmW = c.film_width; cam.filmH = c.film_height;
+    cam.setWindow(c.film_width, c.film_height, 0, 0, c.film_width, c.film_height);
     buildBVH();
 }
 

@@ -43,6 +43,12 @@ def load():
     lib.orc_render.argtypes = [C.c_void_p, P(abi.dr_config), C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                P(C.c_float), P(abi.dr_stats), P(C.c_double)]
     lib.orc_direct_image.argtypes = [C.c_void_p, P(abi.dr_config), P(C.c_float), P(C.c_double)]
+    lib.orc_first_stage_config.argtypes = [C.c_void_p, P(abi.dr_config), P(abi.dr_config)]
+    lib.orc_first_stage_config.restype = None
+    lib.orc_resample_luminance.argtypes = [P(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_float)]
+    lib.orc_resample_luminance.restype = None
+    lib.orc_develop.argtypes = [P(C.c_float), C.c_int, C.c_int, C.c_double, C.c_int, P(C.c_float), P(C.c_float)]
+    lib.orc_develop.restype = None
     lib.orc_splat.argtypes = [C.c_int, C.c_int, C.c_int, P(C.c_float), P(C.c_float), C.c_int64, P(C.c_float)]
     lib.orc_bsdf_sample.argtypes = [P(abi.dr_material), P(C.c_double), C.c_int, C.c_double, C.c_double,
                                     P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int)]
@@ -76,6 +82,17 @@ class OracleScene:
         except Exception:
             pass
 
+    def film_size(self, cfg):
+        """Crop window of the (possibly overridden) film: Film::Film, src/librender/film.cpp:30-48."""
+        fw = cfg.film_width if cfg.film_width > 0 else self.data.film[0]
+        fh = cfg.film_height if cfg.film_height > 0 else self.data.film[1]
+        return (cfg.crop_width if cfg.crop_width > 0 else fw, cfg.crop_height if cfg.crop_height > 0 else fh)
+
+    def first_stage_config(self, cfg):
+        nested = abi.dr_config()
+        self.lib.orc_first_stage_config(self.h, C.byref(cfg), C.byref(nested))
+        return nested
+
     def bootstrap(self, cfg, first, n):
         lum = np.zeros(n, np.float32)
         dep = np.zeros(n, np.int32)
@@ -99,7 +116,7 @@ class OracleScene:
         chain_id = np.ascontiguousarray(chain_id, np.uint64)
         depth = np.ascontiguousarray(depth, np.int32)
         rec = (abi.dr_step_record * (n * steps))() if want_records else None
-        W, H = self.data.film
+        W, H = self.film_size(cfg)
         film = np.zeros((H, W, 3), np.float32) if want_film else None
         st = abi.dr_stats()
         self.lib.orc_chain_steps(self.h, C.byref(cfg), b, fptr(seed_index, C.c_uint64), fptr(depth, C.c_int32),
@@ -108,7 +125,7 @@ class OracleScene:
         return rec, film, st
 
     def direct_image(self, cfg, want_li=False):
-        W, H = self.data.film
+        W, H = self.film_size(cfg)
         ps = max(int(cfg.direct_samples), 1)
         while ps > 8:
             ps //= 2
@@ -118,7 +135,7 @@ class OracleScene:
         return (img, li) if want_li else img
 
     def render(self, cfg, n_boot, n_chains, steps, threads=0):
-        W, H = self.data.film
+        W, H = self.film_size(cfg)
         img = np.zeros((H, W, 3), np.float32)
         st = abi.dr_stats()
         sec = C.c_double(0)
@@ -130,6 +147,27 @@ class OracleScene:
         hits = (abi.dr_hit * n)()
         self.lib.orc_trace_rays(self.h, rays, n, int(shadow), eps, hits)
         return hits
+
+
+def resample_luminance(image_rgb, size):
+    """Oracle of dr_resample_luminance: (h, w, 3) developed first-stage image -> (H, W) importance map."""
+    lib = load()
+    img = np.ascontiguousarray(image_rgb, np.float32)
+    h, w = img.shape[:2]
+    W, H = size
+    out = np.zeros((H, W), np.float32)
+    lib.orc_resample_luminance(fptr(img), w, h, W, H, fptr(out))
+    return out
+
+
+def develop(film_rgb, b, acceptance_map=False, importance=None):
+    lib = load()
+    film = np.ascontiguousarray(film_rgb, np.float32)
+    H, W = film.shape[:2]
+    out = np.zeros((H, W, 3), np.float32)
+    imp = np.ascontiguousarray(importance, np.float32) if importance is not None else None
+    lib.orc_develop(fptr(film), W, H, b, int(acceptance_map), fptr(imp) if imp is not None else None, fptr(out))
+    return out
 
 
 def default_config(**kw):
@@ -146,6 +184,7 @@ def default_config(**kw):
     c.sample_count, c.rfilter = 64, abi.DR_FILTER_GAUSSIAN
     c.n_chains, c.seed, c.rank, c.world_size = 0, 1234, 0, 1
     c.ray_epsilon = c.shadow_epsilon = 0.0
+    c.first_stage, c.first_stage_size_reduction = 0, 16
     for k, v in kw.items():
         setattr(c, k, v)
     return c

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), "libdrmlt_b200.so does not export %s" % name
     assert sorted(abi.EXPORTED_SYMBOLS) == declared
-    assert lib.dr_abi_version() == 3
+    assert lib.dr_abi_version() == 4
 
 
 def test_struct_layouts_match_header(lib):
@@ -53,6 +53,14 @@ def test_config_parameter_names_of_the_reference(lib):
     cfg = make_config(integrator="pssmlt", technique="path", maxDepth=8, kelemenStyleMutation=False, sigma=0.02)
     assert cfg.integrator == abi.DR_INTEGRATOR_PSSMLT and cfg.kelemen_style_mutation == 0
     assert make_config(integrator="drmlt", technique="path", type="mirasym", maxDepth=5).type == abi.DR_TYPE_ORBITAL
+    # two-stage MLT (drmlt.cpp:278-293) and the film plugin's window (film.cpp:30-48)
+    cfg = abi.dr_config()
+    lib.dr_config_default(C.byref(cfg))
+    assert cfg.two_stage == 0 and cfg.first_stage == 0 and cfg.first_stage_size_reduction == 16 and not cfg.importance_map
+    cfg = make_config(integrator="drmlt", technique="path", type="mira", maxDepth=5, twoStage=True, firstStageSizeReduction=8,
+                      width=640, height=360, cropOffsetX=10, cropOffsetY=20, cropWidth=100, cropHeight=50)
+    assert (cfg.two_stage, cfg.first_stage_size_reduction, cfg.film_width, cfg.film_height) == (1, 8, 640, 360)
+    assert (cfg.crop_offset_x, cfg.crop_offset_y, cfg.crop_width, cfg.crop_height) == (10, 20, 100, 50)
 
 
 @pytest.mark.parametrize("params,needle", [
@@ -65,6 +73,8 @@ def test_config_parameter_names_of_the_reference(lib):
     (dict(integrator="drmlt", type="mira", maxDepth=8), "Unknown technique"),                # technique is required
     (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, acceptanceMap=True), "box reconstruction filter"),
     (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, bogus=1), "Unknown parameter"),
+    (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, twoStage=True, firstStageSizeReduction=0), "firstStageSizeReduction"),
+    (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, cropOffsetX=-1), "Invalid crop window"),
     (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, sigma="abc"), "not a number"),
 ])
 def test_config_errors_mirror_the_reference(lib, params, needle):

@@ -111,3 +111,30 @@ def test_two_ranks_gloo_all_reduce_b_and_film_reduce(oracle):
         film += f.astype(np.float32)
     assert film.sum() > 0
     np.testing.assert_allclose(out["film"], film, rtol=1e-5, atol=1e-7)
+
+
+def _worker_two_stage(rank, world, port, out):
+    """First stage of two-stage MLT on two ranks: each rank's nested film shard is ALL-reduced, then every rank derives
+    the importance map on its own (no broadcast)."""
+    import oracle_lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(100 + rank)
+        film = torch.from_numpy(rng.rand(6, 8, 3).astype(np.float32))
+        distributed.reduce_film(film, dist, 0, all_ranks=True)
+        out["map%d" % rank] = oracle_lib.resample_luminance(film.numpy(), (32, 24))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_first_stage_film_all_reduce(oracle):
+    import oracle_lib
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_two_stage, args=(2, _free_port(), out), nprocs=2, join=True)
+    total = sum(np.random.RandomState(100 + r).rand(6, 8, 3).astype(np.float32) for r in range(2))
+    ref = oracle_lib.resample_luminance(total, (32, 24))
+    assert np.array_equal(out["map0"], out["map1"])
+    np.testing.assert_allclose(out["map0"], ref, rtol=1e-6)

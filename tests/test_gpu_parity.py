@@ -14,7 +14,7 @@ import pytest
 
 import oracle_lib
 from drmlt_mitsuba_b200 import abi, scenes
-from drmlt_mitsuba_b200.integrator import Job, Scene, make_config
+from drmlt_mitsuba_b200.integrator import DeviceFilm, Job, Scene, make_config, set_importance_map
 
 pytestmark = pytest.mark.gpu
 
@@ -127,11 +127,18 @@ CASES = [
     ("cornell", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
     ("glossy", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=8, directSamples=-1, directSampling=False)),
     ("caustic", dict(integrator="pssmlt", technique="bdpt", maxDepth=8, directSamples=-1, directSampling=False, lightImage=False)),
+    # film plugin parameters (film.cpp:30-48, perspective.cpp:126-173): crop window, and a film size other than dr_camera's
+    ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1,
+                     cropOffsetX=24, cropOffsetY=40, cropWidth=64, cropHeight=48)),
+    ("cornell", dict(integrator="pssmlt", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False,
+                     width=96, height=64, cropOffsetX=8, cropOffsetY=0, cropWidth=80, cropHeight=60)),
+    ("glossy", dict(integrator="pssmlt", technique="path", maxDepth=6, directSamples=-1, width=16, height=16)),
 ]
 
 
 def _case_id(c):
-    return "%s-%s-%s" % (c[0], c[1]["technique"], c[1].get("type", "pss"))
+    extra = ("-crop" if "cropWidth" in c[1] else "") + ("-film" if "width" in c[1] else "")
+    return "%s-%s-%s%s" % (c[0], c[1]["technique"], c[1].get("type", "pss"), extra)
 
 
 # Contributions more than 18 orders of magnitude below the brightest one are rounding noise, not light: they arise
@@ -271,8 +278,12 @@ def _first_divergence(rg, rc, steps):
 @pytest.mark.parametrize("case", CHAIN_CASES, ids=_chain_id)
 def test_chain_decisions_under_identical_uniforms(case):
     name, params = case
-    gpu, orc, _ = pair(name)
     cfg = make_config(seed=29, **params)
+    _check_chain_decisions(name, cfg)
+
+
+def _check_chain_decisions(name, cfg):
+    gpu, orc, _ = pair(name)
     o = ocfg(cfg)
     lum, dep = orc.bootstrap(o, 0, 20000)
     seeds = np.nonzero(_denoise(lum, lum) > 0)[0][:256].astype(np.uint64)
@@ -330,6 +341,133 @@ def test_film_of_recorded_chains(case):
     assert fg.sum() == pytest.approx(fc.sum(), rel=2e-2)
     diff = np.abs(fg - fc).sum() / fc.sum()
     assert diff < 0.08, diff
+
+
+# ------------------------------------------------------------------ two-stage MLT
+def _smooth_map(W, H, seed):
+    """A strictly positive importance map with a 20x dynamic range."""
+    rng = np.random.RandomState(seed)
+    y, x = np.mgrid[0:H, 0:W].astype(np.float64)
+    m = 0.05 + (0.5 + 0.5 * np.sin(x / W * 7.0 + rng.rand() * 6)) * (0.5 + 0.5 * np.cos(y / H * 5.0 + rng.rand() * 6))
+    return m.astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [((20, 12), (160, 90)), ((64, 48), (16, 12)), ((33, 17), (33, 40)), ((8, 8), (128, 8)), ((5, 7), (5, 7)), ((1, 1), (16, 16))])
+def test_resample_luminance_matches_oracle(shape):
+    """mltLuminancePass, last part (util.cpp:180-196): luminance + Bitmap::resample with the gaussian filter."""
+    (w, h), (W, H) = shape
+    gpu, _, _ = pair("cornell")
+    rng = np.random.RandomState(w * 131 + H)
+    img = (rng.rand(h, w, 3) ** 3).astype(np.float32) * 4.0
+    mg = gpu.resample_luminance(img, (W, H))
+    mc = oracle_lib.resample_luminance(img, (W, H))
+    assert mg.shape == (H, W) and (mg >= 0).all()
+    assert np.abs(mg - mc).max() <= 1e-6 * mc.max()
+    # normalised taps: a constant image stays constant
+    flat = gpu.resample_luminance(np.full((h, w, 3), 0.25, np.float32), (W, H))
+    assert np.allclose(flat, 0.25, rtol=1e-6)
+
+
+TWO_STAGE_CASES = [
+    ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, twoStage=True)),
+    ("cornell", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1, twoStage=True)),
+    ("cornell", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False, twoStage=True)),
+    ("glossy", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1, twoStage=True)),
+]
+
+
+@pytest.mark.parametrize("case", TWO_STAGE_CASES, ids=_chain_id)
+def test_two_stage_chain_decisions(case):
+    """SplatList::normalize(importanceMap) (pathsampler.cpp:1001-1020): with the SAME importance map on both sides the
+    chains take the same decisions; PSSMLT drops its Kelemen weights (pssmlt_proc.cpp:205)."""
+    name, params = case
+    gpu, _, _ = pair(name)
+    cfg = make_config(seed=29, **params)
+    W, H = gpu.film_size(cfg)
+    set_importance_map(cfg, _smooth_map(W, H, 3))
+    _check_chain_decisions(name, cfg)
+
+
+def test_two_stage_luminance_is_reweighted():
+    """L of a state under an importance map = L / map[pixel] for single-splat techniques."""
+    gpu, orc, _ = pair("cornell")
+    cfg = make_config(seed=5, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1)
+    lum, dep = orc.bootstrap(ocfg(cfg), 0, 8000)
+    seeds = np.nonzero(_denoise(lum, lum) > 0)[0][:128].astype(np.uint64)
+    depth = dep[seeds.astype(np.int64)]
+    ids = np.arange(len(seeds), dtype=np.uint64)
+    r0 = recs(gpu.chain_steps(cfg, 0.5, seeds, depth, ids, 1))
+    cfg2 = make_config(seed=5, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, twoStage=True)
+    set_importance_map(cfg2, np.full((128, 128), 0.25, np.float32))
+    r1 = recs(gpu.chain_steps(cfg2, 0.5, seeds, depth, ids, 1))
+    assert np.allclose(r1["L_x"], 4.0 * r0["L_x"], rtol=1e-6)
+    assert np.allclose(r1["L_y"], 4.0 * r0["L_y"], rtol=1e-6)
+    assert np.array_equal(r1["acc1"], r0["acc1"])            # a constant map changes no ratio
+
+
+@pytest.mark.parametrize("case", [TWO_STAGE_CASES[0], TWO_STAGE_CASES[1]], ids=_chain_id)
+def test_two_stage_develop_matches_oracle(case):
+    """develop with an importance map (drmlt_proc.cpp:823-849): image = film * (b / mean(lum * map)) * map."""
+    import torch
+    name, params = case
+    gpu, _, _ = pair(name)
+    cfg = make_config(seed=41, sampleCount=4, chains=2048, **params)
+    W, H = gpu.film_size(cfg)
+    imp = _smooth_map(W, H, 9)
+    set_importance_map(cfg, imp)
+    job = Job(gpu, cfg)
+    s, c = job.bootstrap()
+    b = job.normalization(s, c)
+    job.seed_chains(b)
+    job.run(32)
+    img = job.develop()                                       # (flushes PSSMLT's pending weights first)
+    raw = torch.as_tensor(DeviceFilm(job), device="cuda:0").cpu().numpy().reshape(H, W, 4)[:, :, :3]
+    ref = oracle_lib.develop(raw, b, False, imp)
+    assert np.isfinite(img).all() and img.sum() > 0
+    assert np.abs(img - ref).max() <= 2e-5 * ref.max()
+    lum = (img.astype(np.float64) * [0.212671, 0.715160, 0.072169]).sum(-1)
+    assert lum.mean() == pytest.approx(b, rel=1e-4)           # develop keeps mean luminance = b
+    job.close()
+
+
+def test_two_stage_render_end_to_end():
+    """dr_render with twoStage=true: nested low-resolution pass -> importance map -> main pass.  The importance map is the
+    blurred luminance of the first-stage image; the developed image keeps mean luminance b and agrees with the single-stage
+    render in expectation."""
+    gpu, orc, _ = pair("cornell")
+    base = dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, sampleCount=32, seed=77)
+    cfg2 = make_config(twoStage=True, firstStageSizeReduction=8, **base)
+    nested = gpu.first_stage_config(cfg2)
+    assert (nested.film_width, nested.film_height, nested.crop_width, nested.crop_height) == (16, 16, 16, 16)
+    assert nested.sample_count == 32 * 8 and nested.first_stage == 1 and nested.two_stage == 1
+    on = orc.first_stage_config(ocfg(cfg2))
+    assert (on.film_width, on.film_height, on.crop_width, on.crop_height, on.sample_count) == (16, 16, 16, 16, 256)
+    imp, nst = gpu.importance_map(cfg2)
+    assert imp.shape == (128, 128) and np.isfinite(imp).all() and (imp >= 0).all() and imp.mean() > 0
+    assert nst.mutations > 0 and nst.direct_ms == 0.0
+    img1, st1 = gpu.render(make_config(**base))
+    img2, st2 = gpu.render(cfg2)
+    assert st2.first_stage_ms > 0 and st1.first_stage_ms == 0
+    lum = lambda im: (im.astype(np.float64) * [0.212671, 0.715160, 0.072169]).sum(-1)
+    assert lum(img2).mean() == pytest.approx(st2.luminance, rel=1e-3)
+    assert st2.luminance == pytest.approx(st1.luminance, rel=0.03)       # b does not depend on the importance map (pathsampler.cpp:899-901)
+    # the importance map tracks the image: correlation with the blurred single-stage luminance
+    l1 = lum(img1).reshape(16, 8, 16, 8).mean(axis=(1, 3))
+    i1 = imp.astype(np.float64).reshape(16, 8, 16, 8).mean(axis=(1, 3))
+    assert np.corrcoef(l1.ravel(), i1.ravel())[0, 1] > 0.9
+    # the two renders agree at low resolution
+    l2 = lum(img2).reshape(16, 8, 16, 8).mean(axis=(1, 3))
+    assert np.abs(l2 - l1).sum() / l1.sum() < 0.15
+    # a job with a crop window + the default direct pass renders at the crop size
+    cfg3 = make_config(integrator="drmlt", type="mira", technique="path", maxDepth=6, sampleCount=8, seed=3,
+                       cropOffsetX=32, cropOffsetY=16, cropWidth=64, cropHeight=96)
+    img3, st3 = gpu.render(cfg3)
+    assert img3.shape == (96, 64, 3) and np.isfinite(img3).all() and st3.direct_ms > 0
+    full, _ = gpu.render(make_config(integrator="drmlt", type="mira", technique="path", maxDepth=6, sampleCount=8, seed=3))
+    a, b_ = lum(img3).mean(), lum(full[16:112, 32:96]).mean()
+    assert a == pytest.approx(b_, rel=0.1)                    # the crop shows the same part of the scene
+    with pytest.raises(abi.DrmltError):
+        gpu.render(make_config(integrator="drmlt", type="mira", technique="path", maxDepth=6, cropOffsetX=100, cropWidth=64))
 
 
 def test_acceptance_map_mode():

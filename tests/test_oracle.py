@@ -291,3 +291,108 @@ def test_chain_determinism_and_stats_bookkeeping(cornell):
     # every mutation deposits exactly unit luminance (expectation weights sum to one, splats normalised)
     lum_film = (f1 * np.array([0.212671, 0.715160, 0.072169])).sum()
     assert lum_film == pytest.approx(s1.mutations, rel=0.12)   # gaussian filter mass 1 up to tabulation, border loss
+
+
+# ------------------------------------------------------------------ two-stage MLT, crop windows
+def _np_resample_axis(src, tgt_res):
+    """Independent numpy restatement of Resampler (rfilter.h:123-177, 232-280) along axis 0, gaussian filter, EClamp."""
+    src_res = src.shape[0]
+    radius, scale = 2.0, 1.0
+    if tgt_res < src_res:
+        scale = src_res / tgt_res
+        radius *= scale
+    taps = int(math.ceil(radius * 2))
+    out = np.zeros((tgt_res,) + src.shape[1:])
+    for i in range(tgt_res):
+        center = (i + 0.5) / tgt_res * src_res
+        start = int(math.floor(center - radius + 0.5))
+        pos = (start + np.arange(taps) + 0.5 - center) / scale
+        w = np.maximum(0.0, np.exp(-2.0 * pos * pos) - math.exp(-2.0 * 4.0))
+        w /= w.sum()
+        idx = np.clip(start + np.arange(taps), 0, src_res - 1)
+        out[i] = np.maximum(0.0, np.tensordot(w, src[idx], axes=(0, 0)))
+    return out
+
+
+@pytest.mark.parametrize("shape", [((20, 12), (160, 90)), ((64, 48), (16, 12)), ((9, 5), (9, 11)), ((3, 3), (3, 3))])
+def test_importance_map_resampler(oracle, shape):
+    (w, h), (W, H) = shape
+    rng = np.random.RandomState(7)
+    img = rng.rand(h, w, 3).astype(np.float32)
+    m = oracle_lib.resample_luminance(img, (W, H))
+    lum = (img.astype(np.float64) * [0.212671, 0.715160, 0.072169]).sum(-1)
+    ref = lum
+    if w != W:
+        ref = _np_resample_axis(ref.T, W).T
+    if h != H:
+        ref = _np_resample_axis(ref, H)
+    assert m.shape == (H, W)
+    assert np.allclose(m, ref, rtol=1e-6, atol=1e-7)
+    flat = oracle_lib.resample_luminance(np.full((h, w, 3), 2.0, np.float32), (W, H))
+    assert np.allclose(flat, 2.0, rtol=1e-6)                  # taps are normalised (rfilter.h:171-176)
+
+
+def test_importance_map_reweights_the_chain(cornell):
+    """SplatList::normalize(importanceMap) (pathsampler.cpp:1001-1020): L -> L / map[pixel]; a constant map changes no
+    decision; develop multiplies the map back (drmlt_proc.cpp:823-849)."""
+    cfg = _cfg(technique=abi.DR_TECH_MMLT, type=abi.DR_TYPE_ORBITAL, seed=21)
+    lum, dep = cornell.bootstrap(cfg, 0, 3000)
+    seeds = np.nonzero(lum > 0)[0][:32]
+    ids = np.arange(32)
+    r0, f0, _ = cornell.chain_steps(cfg, 1.0, seeds, dep[seeds], ids, 32, want_film=True, threads=2)
+    imp = np.full((64, 64), 0.5, np.float32)
+    cfg2 = _cfg(technique=abi.DR_TECH_MMLT, type=abi.DR_TYPE_ORBITAL, seed=21, two_stage=1)
+    cfg2.importance_map = oracle_lib.fptr(imp)
+    r1, f1, _ = cornell.chain_steps(cfg2, 1.0, seeds, dep[seeds], ids, 32, want_film=True, threads=2)
+    for a, b in zip(r0, r1):
+        assert b.L_x == pytest.approx(2.0 * a.L_x, rel=1e-6) and b.L_y == pytest.approx(2.0 * a.L_y, rel=1e-6)
+        assert (a.accept1, a.did_second, a.accept2) == (b.accept1, b.did_second, b.accept2)
+    assert np.allclose(f0, f1, rtol=1e-5, atol=1e-7)          # splats are normalised to unit luminance either way
+    # develop: the mean luminance of the developed image is b, with or without a map
+    rng = np.random.RandomState(1)
+    imp2 = (0.1 + rng.rand(64, 64)).astype(np.float32)
+    for m in (None, imp2):
+        img = oracle_lib.develop(f0, 0.37, False, m)
+        l = (img.astype(np.float64) * [0.212671, 0.715160, 0.072169]).sum(-1)
+        assert l.mean() == pytest.approx(0.37, rel=1e-5)
+    # a non-constant map does change the chain
+    cfg2.importance_map = oracle_lib.fptr(imp2)
+    r2, _, _ = cornell.chain_steps(cfg2, 1.0, seeds, dep[seeds], ids, 32, threads=2)
+    assert bytes(r2) != bytes(r1)
+
+
+def test_two_stage_render_and_crop_window(cornell):
+    """orc_render with twoStage: nested pass at size / firstStageSizeReduction with sampleCount x reduction (util.cpp:100-136);
+    crop windows shift the sensor's sample space (perspective.cpp:132-157)."""
+    cfg = _cfg(technique=abi.DR_TECH_PATH, type=abi.DR_TYPE_MIRA, seed=4, max_depth=5, two_stage=1, first_stage_size_reduction=4,
+               rfilter=abi.DR_FILTER_BOX)
+    nested = cornell.first_stage_config(cfg)
+    assert (nested.film_width, nested.film_height, nested.crop_width, nested.crop_height) == (16, 16, 16, 16)
+    assert nested.sample_count == cfg.sample_count * 4 and nested.first_stage == 1
+    rc, img2, st2, _ = cornell.render(cfg, 20000, 256, 96, threads=8)
+    assert rc == 0 and img2.shape == (64, 64, 3) and np.isfinite(img2).all()
+    cfg1 = _cfg(technique=abi.DR_TECH_PATH, type=abi.DR_TYPE_MIRA, seed=4, max_depth=5, rfilter=abi.DR_FILTER_BOX)
+    rc, img1, st1, _ = cornell.render(cfg1, 20000, 256, 96, threads=8)
+    lum = lambda im: (im.astype(np.float64) * [0.212671, 0.715160, 0.072169]).sum(-1)
+    assert lum(img2).mean() == pytest.approx(st2.luminance, rel=1e-4)
+    assert st2.luminance == pytest.approx(st1.luminance, rel=1e-9)      # same bootstrap: b ignores the map
+    a, b = lum(img1).reshape(8, 8, 8, 8).mean(axis=(1, 3)), lum(img2).reshape(8, 8, 8, 8).mean(axis=(1, 3))
+    assert np.abs(a - b).sum() / a.sum() < 0.35
+    # crop window: replayed paths land at (full-film pixel - crop offset); outside the window they contribute nothing
+    n = 4000
+    rng = np.random.RandomState(3)
+    us = rng.rand(n, 40).astype(np.float32)
+    z = np.zeros((n, 2), np.float32)
+    full = _cfg(technique=abi.DR_TECH_PATH, seed=1, max_depth=5)
+    crop = _cfg(technique=abi.DR_TECH_PATH, seed=1, max_depth=5, crop_offset_x=16, crop_offset_y=8, crop_width=32, crop_height=40)
+    us_crop = us.copy()                                        # the same film points, expressed in crop sample space
+    us_crop[:, 0] = (us[:, 0] * 64 - 16) / 32
+    us_crop[:, 1] = (us[:, 1] * 64 - 8) / 40
+    inside = (us_crop[:, 0] >= 0) & (us_crop[:, 0] < 1) & (us_crop[:, 1] >= 0) & (us_crop[:, 1] < 1)
+    of, lf = cornell.eval_paths(full, us[inside], z[inside], z[inside], np.zeros(inside.sum(), np.int32))
+    oc, lc = cornell.eval_paths(crop, us_crop[inside], z[inside], z[inside], np.zeros(inside.sum(), np.int32))
+    nz = lf > 0
+    assert nz.sum() > 100 and np.allclose(lc[nz], lf[nz], rtol=2e-4)
+    for i in np.nonzero(nz)[0][:200]:
+        assert oc[i].pos[0][0] == pytest.approx(of[i].pos[0][0] - 16, abs=2e-3)
+        assert oc[i].pos[0][1] == pytest.approx(of[i].pos[0][1] - 8, abs=2e-3)
