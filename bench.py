@@ -193,6 +193,8 @@ def run_gpu(args):
     params = dict(PARAMS, seed=args.seed, sampleCount=args.spp * world)   # weak scaling: W*H*spp mutations per GPU
     if args.chains:
         params["chains"] = args.chains
+    if args.lanes:
+        params["lanes"] = args.lanes
     cfg = make_config(rank=rank, worldSize=world, **params)
     job = Job(scene, cfg)
     s, c = job.bootstrap()
@@ -287,6 +289,10 @@ def run_gpu(args):
 
     # ---- e2e: whole job through the public API with host buffers
     e2e_params = dict(PARAMS, seed=args.seed + 1, sampleCount=args.e2e_spp * world)
+    if args.e2e_chains:
+        e2e_params["chains"] = args.e2e_chains
+    if args.e2e_lanes:
+        e2e_params["lanes"] = args.e2e_lanes
     barrier()
     e0 = time.perf_counter()
     h2d = scene.reupload()
@@ -342,6 +348,9 @@ def main():
     ap.add_argument("--scene", default="door")
     ap.add_argument("--mutations", type=int, default=64, help="mutations per chain per step")
     ap.add_argument("--chains", type=int, default=4194304, help="chains resident per GPU in the timed steps (0 = auto)")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes of the wavefront machine in the timed steps (0 = one per chain; fewer: work-unit queue)")
+    ap.add_argument("--e2e-chains", type=int, default=0, dest="e2e_chains")
+    ap.add_argument("--e2e-lanes", type=int, default=0, dest="e2e_lanes")
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--e2e-spp", type=int, default=64, dest="e2e_spp", help="sampleCount of the whole-job e2e render (64 = the C5 workload)")
     ap.add_argument("--seed", type=int, default=2024)

@@ -86,6 +86,7 @@ extern "C" void dr_config_default(dr_config *c) {
     c->crop_offset_x = c->crop_offset_y = 0;
     c->crop_width = c->crop_height = 0;
     c->importance_map = nullptr;
+    c->n_lanes = 0;
 }
 
 static bool parse_bool(const char *v, int *out) {
@@ -125,7 +126,7 @@ extern "C" dr_status dr_config_set(dr_config *c, const char *key, const char *va
         { "luminanceSamples", &dr_config::luminance_samples }, { "workUnits", &dr_config::work_units },
         { "timeout", &dr_config::timeout }, { "sampleCount", &dr_config::sample_count }, { "chains", &dr_config::n_chains },
         { "rank", &dr_config::rank }, { "worldSize", &dr_config::world_size },
-        { "firstStageSizeReduction", &dr_config::first_stage_size_reduction },
+        { "firstStageSizeReduction", &dr_config::first_stage_size_reduction }, { "lanes", &dr_config::n_lanes },
         // film plugin parameters (src/librender/film.cpp:30-48)
         { "width", &dr_config::film_width }, { "height", &dr_config::film_height },
         { "cropOffsetX", &dr_config::crop_offset_x }, { "cropOffsetY", &dr_config::crop_offset_y },
@@ -537,6 +538,8 @@ static dr_status check_technique(const dr_config &c) {
 
 // ------------------------------------------------------------------ job
 enum { STAGE_TRACE = 0, STAGE_WALK, STAGE_CHAIN, STAGE_COUNT };
+struct dr_job_t;
+static void resample_chains(dr_job_t *j, unsigned long long firstChain);
 
 struct dr_job_t {
     dr_scene scene = nullptr;
@@ -546,6 +549,7 @@ struct dr_job_t {
     Machine M;                                  // constant part: scene, parameters, lane memory, queues
     int *depth = nullptr;                       // [n] MMLT depth of every chain (or -1)
     unsigned long long *chainId = nullptr, *seedIdx = nullptr;
+
     float4 *film = nullptr;
     unsigned long long *counters = nullptr;     // [0, ST_COUNT): chain phase, [ST_COUNT, 2 ST_COUNT): bootstrap
     // Wavefront groups: the lanes are split into independent groups, each with its own work queues and stream, so
@@ -564,7 +568,10 @@ struct dr_job_t {
     bool hasDeadline = false, timedOut = false;
     long long nBoot = 0;
     unsigned long long bootFirst = 0;
-    int nChains = 0;
+    int nChains = 0;                            // Markov chains of the job (the reference's work units)
+    int nLanes = 0;                             // lanes of the wavefront machine; < nChains: the lanes pull chains from a queue
+    unsigned int *chainCursor = nullptr;        // work-unit queue: next chain index
+    uint32_t epoch = 0;                         // work-unit queue: batches run so far (chain ids of batch e start at e * nChains * worldSize)
     long long totalMutations = 0, mutationsDone = 0;
     uint32_t mutTarget = 0;
     double b = 0.0;
@@ -700,8 +707,13 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     const long long total = (long long) W * H * cfg.sample_count;
     j->totalMutations = total / cfg.world_size + (cfg.rank < total % cfg.world_size ? 1 : 0);
     j->nChains = nLanes > 0 ? nLanes : (cfg.n_chains > 0 ? cfg.n_chains : auto_chains(j->totalMutations));
+    // lanes: explicit (`lanes`), else one per chain.  With fewer lanes than chains the lanes pull chains from a queue.
+    j->nLanes = j->nChains;
+    if (nLanes <= 0 && cfg.n_lanes > 0 && cfg.n_lanes < j->nChains) j->nLanes = std::max(128, (cfg.n_lanes + 127) / 128 * 128);
+    if (j->nLanes > j->nChains) j->nLanes = j->nChains;
     const size_t n = (size_t) j->nChains;
-    if ((st = alloc_lanes(j, j->nChains)) || (st = job_alloc(j, &j->counters, (size_t) 2 * ST_COUNT, true)) || (st = job_alloc(j, &j->red, 4, true)) ||
+    if (j->nLanes < j->nChains && (st = job_alloc(j, &j->chainCursor, 1, true))) return fail(st);
+    if ((st = alloc_lanes(j, j->nLanes)) || (st = job_alloc(j, &j->counters, (size_t) 2 * ST_COUNT, true)) || (st = job_alloc(j, &j->red, 4, true)) ||
         (st = job_alloc(j, &j->redScratch, (size_t) lum_reduce_scratch_doubles())))
         return fail(st);
     if (chains) {
@@ -916,6 +928,13 @@ extern "C" dr_status dr_job_bootstrap(dr_job j, double *sumOut, double *countOut
     return DR_OK;
 }
 
+// seedPDF.sample per chain (pathsampler.cpp:946-954)
+static void resample_chains(dr_job_t *j, unsigned long long firstChain) {
+    const dr_config &c = j->cfg;
+    launch_resample(j->cdf, j->nBoot, c.seed, firstChain, j->nChains, j->bootFirst, c.max_depth, c.technique, j->seedIdx, j->chainId, j->depth, j->stream);
+    ++j->launches;
+}
+
 extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
     if (!j) { dr_set_error("dr_job_seed_chains: null job"); return DR_ERR_INVALID_ARG; }
     if (!j->bootstrapped) { dr_set_error("dr_job_seed_chains: call dr_job_bootstrap first"); return DR_ERR_INVALID_ARG; }
@@ -936,15 +955,17 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
     const int n = j->nChains;
     const unsigned long long firstChain = (unsigned long long) c.rank * (unsigned long long) n;
     CK(cudaEventRecord(j->ev0, j->stream));
-    launch_resample(j->cdf, j->nBoot, c.seed, firstChain, n, j->bootFirst, c.max_depth, c.technique, j->seedIdx, j->chainId, j->depth, j->stream);
+    resample_chains(j, firstChain);
     CKL();
-    ++j->launches;
-    // seed replay: the lanes evaluate their seed vector (PH_INIT); mutTarget = 0 parks them afterwards
-    JobParams job;
-    memset(&job, 0, sizeof(job));
-    job.type = JOB_CHAIN; job.mutTarget = 0;
-    dr_status st;
-    if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters, true))) return st;
+    j->epoch = 0;
+    if (!j->chainCursor) {
+        // resident chains: the lanes evaluate their seed vector (PH_INIT); mutTarget = 0 parks them afterwards
+        JobParams job;
+        memset(&job, 0, sizeof(job));
+        job.type = JOB_CHAIN; job.mutTarget = 0;
+        dr_status st;
+        if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters, true))) return st;
+    }                                          // (work-unit queue: a chain replays its seed when a lane takes it up)
     j->mutTarget = 0;
     CK(cudaEventRecord(j->ev1, j->stream));
     CK(cudaStreamSynchronize(j->stream));
@@ -955,7 +976,38 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
     return DR_OK;
 }
 
+// Work-unit queue: chains [first, first + count) of the current batch, `steps` mutations each, through the job's lanes.
+static dr_status run_chain_range(dr_job j, long long first, long long count, long long steps) {
+    JobParams job;
+    memset(&job, 0, sizeof(job));
+    job.type = JOB_CHAIN;
+    job.mut0 = 0; job.mutTarget = (uint32_t) steps;
+    job.chainCursor = j->chainCursor; job.chainFirst = (unsigned int) first; job.chainEnd = (unsigned int) (first + count);
+    job.qDepth = j->depth; job.qChainId = j->chainId; job.qSeedIdx = j->seedIdx;
+    const unsigned int cursor0 = (unsigned int) (first + std::min<long long>(count, j->nLanes));   // the lanes start with the first chains
+    CK(cudaMemcpyAsync(j->chainCursor, &cursor0, sizeof(cursor0), cudaMemcpyHostToDevice, j->stream));
+    dr_status st;
+    if ((st = setup_lanes(j, job))) return st;
+    return run_machine(j, job, j->counters, true);
+}
+
+// a fresh batch of chains for the work-unit queue: batch e uses chain ids (and resampling uniforms) e * nChains * worldSize + ...
+static dr_status next_batch(dr_job j) {
+    if (j->epoch > 0) {
+        const dr_config &c = j->cfg;
+        const unsigned long long firstChain = ((unsigned long long) j->epoch * c.world_size + c.rank) * (unsigned long long) j->nChains;
+        resample_chains(j, firstChain);
+        CKL();
+    }
+    ++j->epoch;
+    return DR_OK;
+}
+
 static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, int recordStride, bool withFilm) {
+    if (j->chainCursor) {                                          // work-unit queue: one batch = every chain once
+        dr_status st = next_batch(j);
+        return st ? st : run_chain_range(j, 0, j->nChains, steps);
+    }
     JobParams job;
     memset(&job, 0, sizeof(job));
     job.type = JOB_CHAIN;
@@ -974,7 +1026,12 @@ static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, 
     return run_machine(j, job, j->counters, withFilm);
 }
 
-extern "C" dr_status dr_job_run(dr_job j, int64_t mutationsPerChain) {
+static dr_status job_run_impl(dr_job j, int64_t mutationsPerChain, long long rangeFirst, long long rangeCount);
+extern "C" dr_status dr_job_run(dr_job j, int64_t mutationsPerChain) { return job_run_impl(j, mutationsPerChain, 0, -1); }
+
+// rangeCount < 0: resident chains advance, or (work-unit queue) a whole new batch runs; else chains
+// [rangeFirst, rangeFirst + rangeCount) of the current batch run (work-unit queue only; used by progressive renders)
+static dr_status job_run_impl(dr_job j, int64_t mutationsPerChain, long long rangeFirst, long long rangeCount) {
     if (!j) { dr_set_error("dr_job_run: null job"); return DR_ERR_INVALID_ARG; }
     if (!j->seeded) { dr_set_error("dr_job_run: call dr_job_seed_chains first"); return DR_ERR_INVALID_ARG; }
     if (j->cfg.timeout > 0 && !j->hasDeadline) {               // the reference's timer starts with the chain phase
@@ -985,14 +1042,14 @@ extern "C" dr_status dr_job_run(dr_job j, int64_t mutationsPerChain) {
     if (mutationsPerChain < 0 || mutationsPerChain > (1ll << 30)) { dr_set_error("dr_job_run: mutation count out of range"); return DR_ERR_INVALID_ARG; }
     CK(cudaSetDevice(j->scene->device));
     CK(cudaEventRecord(j->ev0, j->stream));
-    dr_status st = run_chains(j, mutationsPerChain, nullptr, 0, true);
+    dr_status st = rangeCount < 0 ? run_chains(j, mutationsPerChain, nullptr, 0, true) : run_chain_range(j, rangeFirst, rangeCount, mutationsPerChain);
     if (st) { cudaStreamSynchronize(j->stream); return st; }
     CK(cudaEventRecord(j->ev1, j->stream));
     CK(cudaStreamSynchronize(j->stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, j->ev0, j->ev1));
     j->chainsMs += ms;
-    j->mutationsDone += mutationsPerChain * (long long) j->nChains;
+    j->mutationsDone += mutationsPerChain * (rangeCount < 0 ? (long long) j->nChains : rangeCount);
     return DR_OK;
 }
 
@@ -1263,18 +1320,22 @@ extern "C" dr_status dr_render_progressive(dr_scene scene, const dr_config *cfgI
             const long long per = std::max<long long>(1, j->totalMutations / j->nChains);   // nMutations (drmlt.cpp:475-476)
             if (!fn || !(refreshSeconds > 0.0)) st = dr_job_run(j, per);
             else {
+                // slices: mutations of the resident chains, or (work-unit queue) ranges of the batch's chains
+                const bool queue = j->chainCursor != nullptr;
+                const long long whole = queue ? j->nChains : per;
+                if (queue) st = next_batch(j);
                 const auto start = std::chrono::steady_clock::now();
-                long long done = 0, slice = std::min<long long>(per, 4);
-                while (!st && done < per && !j->timedOut) {
+                long long done = 0, slice = queue ? std::min<long long>(whole, std::max<long long>(j->nLanes, whole / 64)) : std::min<long long>(per, 4);
+                while (!st && done < whole && !j->timedOut) {
                     const auto s0 = std::chrono::steady_clock::now();
-                    slice = std::min(slice, per - done);
-                    if ((st = dr_job_run(j, slice))) break;
+                    slice = std::min(slice, whole - done);
+                    if ((st = queue ? job_run_impl(j, per, done, slice) : dr_job_run(j, slice))) break;
                     done += slice;
                     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
                     // next slice: about refreshSeconds of work at the measured rate (at most 4x growth per step)
                     const double want = sec > 0.0 ? (double) slice * refreshSeconds / sec : (double) slice * 4.0;
-                    slice = (long long) std::max(1.0, std::min(want, (double) slice * 4.0));
-                    if (done < per && !j->timedOut) {
+                    slice = (long long) std::max(queue ? (double) j->nLanes : 1.0, std::min(want, (double) slice * 4.0));
+                    if (done < whole && !j->timedOut) {
                         dr_stats ps;
                         if ((st = dr_job_develop(j, imageRgb)) || (st = dr_job_stats(j, &ps))) break;
                         const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();

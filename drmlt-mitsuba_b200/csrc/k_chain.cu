@@ -164,6 +164,24 @@ DR_D void importance_apply(const Machine &M, int lane, PathResult &r) {
     r.lum = lum;
 }
 
+// A lane takes up chain `idx` of the job: seed replay + fillReplay (drmlt_proc.cpp:467-504) -- current = the seed's
+// bootstrap vector; the lane then evaluates it (PH_INIT) before its first mutation.
+DR_D void chain_init(const Machine &M, int lane, Core &c, const int *depthIn, const unsigned long long *chainIdIn, const unsigned long long *seedIdxIn, size_t idx) {
+    memset(&c, 0, sizeof(c));
+    c.tx = -1; c.large = 2u;
+    const unsigned long long sidx = seedIdxIn[idx];
+    c.chainId = chainIdIn[idx]; c.seedIdx = sidx;
+    c.depth = M.pc.technique == DR_TECH_MMLT ? (uint8_t) depthIn[idx] : 0;
+    double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * M.lm.nU;
+    const int alloc[3] = { M.cp.dimS, M.cp.dimE, M.cp.dimD };
+    for (int k = 0; k < M.lm.nU; ++k) ub[k] = 0.0;
+    for (int s = 0; s < 3; ++s)
+        for (int k = 0; k < alloc[s]; ++k)
+            ub[M.pp.off[s] + k] = (double) keyed_uniform(M.pp.seed, S_BOOT, sidx, (uint32_t) s, (uint32_t) k);
+    c.phase = PH_INIT;
+    c.pstate = PS_START;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------ the chain kernel
@@ -420,6 +438,17 @@ k_chain(const __grid_constant__ Machine M) {
                         c.phase = PH_STAGE1; c.large = 2u;
                         c.pstate = c.mut < job.mutTarget ? PS_START : PS_IDLE;
                     }
+                    if (c.pstate == PS_IDLE && job.chainCursor) {
+                        // work-unit queue: this chain is complete; the lane takes the next one (generateWork, drmlt_proc.cpp:869-883)
+                        if (!drmlt) {                              // PSSMLT's last splat of the accumulated state (pssmlt_proc.cpp:274-279)
+                            const float3 v = cc.valx * (float) cc.cumW;
+                            if (film && !is_zero(v)) film_put(film, fp, cc.posx, v);
+                            if (film && cc.xl && cc.cumW > 0.) splat_list_put(M, lane, 0, cc.xl, (float) cc.cumW);
+                            cc.cumW = 0.;
+                        }
+                        const unsigned int idx = atomicAdd(job.chainCursor, 1u);
+                        if (idx < job.chainEnd) chain_init(M, lane, c, job.qDepth, job.qChainId, job.qSeedIdx, idx);
+                    }
                     rec_store(M.lm.chain + lane, cc);
                 }
                 if (c.pstate == PS_IDLE) break;
@@ -445,18 +474,11 @@ __global__ void k_setup_lanes(const __grid_constant__ Machine M, const int *dept
     c.tx = -1; c.large = 2u; c.phase = PH_STAGE1;
     bool queued;
     if (M.job.type == JOB_CHAIN) {
-        const unsigned long long sidx = seedIdxIn[lane];
-        c.chainId = chainIdIn[lane]; c.seedIdx = sidx;
-        c.depth = M.pc.technique == DR_TECH_MMLT ? (uint8_t) depthIn[lane] : 0;
-        double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * M.lm.nU;
-        const int alloc[3] = { M.cp.dimS, M.cp.dimE, M.cp.dimD };
-        for (int k = 0; k < M.lm.nU; ++k) ub[k] = 0.0;
-        for (int s = 0; s < 3; ++s)
-            for (int k = 0; k < alloc[s]; ++k)
-                ub[M.pp.off[s] + k] = (double) keyed_uniform(M.pp.seed, S_BOOT, sidx, (uint32_t) s, (uint32_t) k);
-        c.phase = PH_INIT;
-        c.pstate = PS_START;
-        queued = true;
+        // resident chains: chain = lane; work-unit queue: the lanes start with the first chains of the range
+        const size_t idx = M.job.chainCursor ? (size_t) M.job.chainFirst + lane : (size_t) lane;
+        queued = !M.job.chainCursor || idx < M.job.chainEnd;
+        if (queued) chain_init(M, lane, c, depthIn, chainIdIn, seedIdxIn, idx);
+        else c.pstate = PS_IDLE;
     } else {
         queued = lane < M.job.nItems;
         c.pstate = queued ? PS_START : PS_IDLE;

@@ -241,6 +241,13 @@ struct JobParams {
     dr_step_record *records;            // JOB_CHAIN (parity): one record per mutation
     int recordStride;
     uint32_t mut0;
+    // JOB_CHAIN, work-unit queue (null cursor: chains are resident, one per lane): a lane whose chain has done its
+    // `mutTarget` mutations takes the next chain of [.., chainEnd) from the cursor -- the reference's work units handed
+    // out by DRMLTProcess::generateWork (drmlt_proc.cpp:869-883), one seed + nMutations mutations each
+    unsigned int *chainCursor;
+    unsigned int chainFirst, chainEnd;
+    const int *qDepth;                  // [chains] MMLT depth | chain id (RNG key) | bootstrap sample of every chain
+    const unsigned long long *qChainId, *qSeedIdx;
 };
 
 struct FilmParams {

@@ -173,6 +173,10 @@ public:
         ref<Sensor> sensor = scene->getSensor();
         ref<Film> film = sensor->getFilm();
         const Vector2i size = film->getCropSize();
+        // film + crop window (src/librender/film.cpp:30-48): the camera carries the full film, the job renders the crop
+        m_config.film_width = film->getSize().x; m_config.film_height = film->getSize().y;
+        m_config.crop_offset_x = film->getCropOffset().x; m_config.crop_offset_y = film->getCropOffset().y;
+        m_config.crop_width = size.x; m_config.crop_height = size.y;
         m_config.sample_count = (int32_t) sensor->getSampler()->getSampleCount();   // drmlt.cpp:400
         const std::string rf = film->getReconstructionFilter()->getClass()->getName();
         check(dr_config_set(&m_config, "rfilter", rf == "BoxFilter" ? "box" : "gaussian"));
@@ -234,7 +238,7 @@ public:
         for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) desc.camera.to_world[4 * r + c] = (float) tw(r, c);
         desc.camera.xfov_deg = (float) cam->getXFov();
         desc.camera.near_clip = (float) cam->getNearClip(); desc.camera.far_clip = (float) cam->getFarClip();
-        desc.camera.film_width = size.x; desc.camera.film_height = size.y;
+        desc.camera.film_width = film->getSize().x; desc.camera.film_height = film->getSize().y;
 
         const char *dev = getenv("DRMLT_DEVICE");
         check(dr_scene_create(&desc, dev ? atoi(dev) : 0, &m_scene));
@@ -242,23 +246,34 @@ public:
         // ---- render on the GPU, hand the developed image to the film (drmlt_proc.cpp:850-853)
         std::vector<float> image((size_t) size.x * size.y * 3);
         dr_stats st;
-        const dr_status status = dr_render(m_scene, &m_config, image.data(), &st);
+        // interactive jobs and `mitsuba -r` see partial results: develop + signalRefresh every <= 2 s (drmlt_proc.cpp:856-867);
+        // Scene::flush (scene.cpp:468-511) then dumps whatever bitmap the film holds, plus _time.csv / _stats.txt
+        RefreshCtx ctx = { film.get(), queue, job, size };
+        const dr_status status = dr_render_progressive(m_scene, &m_config, image.data(), &st, 2.0, &DR_CLASS::refresh, &ctx);
         dr_scene sceneHandle = m_scene;
         m_scene = NULL;
         dr_scene_destroy(sceneHandle);
         if (status == DR_ERR_CANCELLED) return false;
         check(status);
-        ref<Bitmap> bitmap = new Bitmap(Bitmap::ESpectrum, Bitmap::EFloat, size);
-        Spectrum *target = (Spectrum *) bitmap->getData();
-        for (size_t i = 0; i < (size_t) size.x * size.y; ++i)
-            target[i].fromLinearRGB(image[3 * i], image[3 * i + 1], image[3 * i + 2]);
-        film->setBitmap(bitmap);
-        queue->signalRefresh(job);
+        refresh(image.data(), size.x, size.y, 0.0, &st, &ctx);
         // same figures as the reference's StatsCounters (drmlt_proc.cpp:34-49)
         Log(EInfo, "Normalization factor b = %f; %llu mutations, first stage accepted %.2f %%, second stage %.2f %%, %.1f ms on the GPU",
             st.luminance, (unsigned long long) st.mutations, st.first_base ? 100.0 * st.first_accept / st.first_base : 0.0,
             st.second_base ? 100.0 * st.second_accept / st.second_base : 0.0, st.total_ms);
         return true;
+    }
+
+    struct RefreshCtx { Film *film; RenderQueue *queue; const RenderJob *job; Vector2i size; };
+    // DRMLTProcess::develop, last lines (drmlt_proc.cpp:850-853): hand the developed image to the film and signal a refresh
+    static int refresh(const float *image, int32_t w, int32_t h, double, const dr_stats *, void *user) {
+        RefreshCtx *ctx = static_cast<RefreshCtx *>(user);
+        ref<Bitmap> bitmap = new Bitmap(Bitmap::ESpectrum, Bitmap::EFloat, Vector2i(w, h));
+        Spectrum *target = (Spectrum *) bitmap->getData();
+        for (size_t i = 0; i < (size_t) w * h; ++i)
+            target[i].fromLinearRGB(image[3 * i], image[3 * i + 1], image[3 * i + 2]);
+        ctx->film->setBitmap(bitmap);
+        ctx->queue->signalRefresh(ctx->job);
+        return 0;
     }
 
     void cancel() { if (m_scene) dr_cancel(m_scene); }           // Integrator::cancel (drmlt.cpp:386-391), any thread

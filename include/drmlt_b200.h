@@ -131,7 +131,7 @@ typedef struct dr_config {
     int32_t sample_count;      /* sensor sampler's sampleCount = mutations per pixel (drmlt.cpp:400) */
     int32_t rfilter;           /* film reconstruction filter: gaussian (stddev .5) | box */
     /* GPU execution knobs (no reference equivalent) */
-    int32_t n_chains;          /* Markov chains resident per GPU; 0 = auto */
+    int32_t n_chains;          /* Markov chains (the reference's work units) per GPU; 0 = auto */
     uint64_t seed;             /* counter-based RNG key (reference: /dev/urandom, random.cpp:473-489) */
     int32_t rank, world_size;  /* chain / bootstrap shard of this process (1 GPU: 0, 1) */
     float   ray_epsilon;       /* 0 = 1e-4f (Mitsuba single precision, constants.h:29) */
@@ -143,6 +143,12 @@ typedef struct dr_config {
     int32_t film_width, film_height;     /* full film size override (the nested pass renders at size / firstStageSizeReduction) */
     int32_t crop_offset_x, crop_offset_y;/* cropOffsetX/Y = 0 */
     int32_t crop_width, crop_height;     /* cropWidth/Height = film size; the rendered image and all buffers have the CROP size */
+    /* GPU execution knob: lanes of the wavefront machine.  0 or >= n_chains: one lane per chain (chains stay resident and
+     * dr_job_run advances all of them).  Fewer lanes than chains: the lanes pull chains from a work-unit queue (the
+     * reference's DRMLTProcess::generateWork, drmlt_proc.cpp:869-883); every dr_job_run then runs a fresh batch of
+     * n_chains chains, `mutations_per_chain` mutations each, from newly resampled seeds. */
+    int32_t n_lanes;
+    int32_t _reserved0;
     /* m_config.importanceMap (drmlt.h:57, internal): host pointer to crop_width*crop_height floats, or NULL.
      * With twoStage=true and NULL here, dr_render computes it with dr_importance_map first. */
     const float *importance_map;

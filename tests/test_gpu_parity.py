@@ -576,6 +576,72 @@ def test_timeout_stops_the_chain_phase():
     assert np.isfinite(img).all() and (img * Y).sum(-1).mean() == pytest.approx(st.luminance, rel=1e-3)
 
 
+@pytest.mark.parametrize("params", [
+    dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1),
+    dict(integrator="pssmlt", technique="path", maxDepth=6, directSamples=-1),
+    dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False),
+], ids=["drmlt-mmlt", "pssmlt-path", "drmlt-bdpt"])
+def test_work_unit_queue_equals_resident_chains(params):
+    """Fewer lanes than chains: the lanes pull chains from a queue (generateWork, drmlt_proc.cpp:869-883).  A chain is
+    (seed, chain id, nMutations) whichever lane runs it, so the counters are IDENTICAL and the film differs only by the
+    order of float atomics."""
+    gpu, _, _ = pair("cornell")
+    base = dict(sampleCount=16, seed=123, chains=8192, **params)
+    img_r, st_r = gpu.render(make_config(**base))
+    img_q, st_q = gpu.render(make_config(lanes=1024, **base))
+    for k in ("mutations", "first_accept", "first_base", "large_accept", "second_accept", "second_base", "accept", "accept_base", "paths", "rays"):
+        assert getattr(st_q, k) == getattr(st_r, k), k
+    assert st_q.mutations == 8192 * (128 * 128 * 16 // 8192)
+    np.testing.assert_allclose(img_q, img_r, rtol=5e-3, atol=5e-4)
+    # the staged API: every dr_job_run is a fresh batch of chains (new ids, new seeds) -> different film, same statistics
+    cfg = make_config(lanes=1024, **base)
+    job = Job(gpu, cfg)
+    s, c = job.bootstrap()
+    job.seed_chains(job.normalization(s, c))
+    job.run(8)
+    m1 = job.stats().mutations
+    job.run(8)
+    m2 = job.stats().mutations
+    assert m1 == 8192 * 8 and m2 == 2 * m1
+    assert job.num_chains == 8192
+    job.close()
+
+
+def test_progressive_render_refreshes():
+    """dr_render_progressive: partial develops while the chains run (processResult's develop + signalRefresh for
+    interactive jobs, drmlt_proc.cpp:856-867; the images of `mitsuba -r`, scene.cpp:468-511) and cancel from the callback."""
+    gpu, _, _ = pair("cornell")
+    cfg = make_config(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=4, sampleCount=256, seed=8, chains=8192)
+    seen = []
+
+    def on_refresh(img, seconds, st):
+        lum = (img.astype(np.float64) * [0.212671, 0.715160, 0.072169]).sum(-1).mean()
+        seen.append((seconds, int(st.mutations), lum, bool(np.isfinite(img).all())))
+        return False
+
+    img, st = gpu.render_progressive(cfg, 0.02, on_refresh)
+    assert len(seen) >= 2 and all(ok for *_, ok in seen)
+    muts = [m for _, m, _, _ in seen]
+    secs = [s_ for s_, _, _, _ in seen]
+    assert muts == sorted(muts) and muts[0] > 0 and muts[-1] < st.mutations
+    assert secs == sorted(secs)
+    assert st.mutations == 8192 * (128 * 128 * 256 // 8192)   # the slices add up to the whole budget
+    ref, st_ref = gpu.render(cfg)
+    assert st_ref.mutations == st.mutations
+    np.testing.assert_allclose(img, ref, rtol=2e-3, atol=2e-4)   # same chains and uniforms: slicing only reorders float atomics
+    # cancel from the callback
+    with pytest.raises(abi.DrmltError) as e:
+        gpu.render_progressive(cfg, 0.02, lambda *a: True)
+    assert e.value.status == 5
+    # work-unit queue: the slices are ranges of chains
+    cfgq = make_config(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=4, sampleCount=256, seed=8, chains=65536, lanes=2048)
+    seen.clear()
+    imgq, stq = gpu.render_progressive(cfgq, 0.02, on_refresh)
+    assert len(seen) >= 2 and stq.mutations == 65536 * (128 * 128 * 256 // 65536)
+    refq, _ = gpu.render(cfgq)
+    np.testing.assert_allclose(imgq, refq, rtol=5e-3, atol=5e-4)
+
+
 def test_render_entry_point_and_errors():
     gpu, orc, data = pair("cornell")
     cfg = make_config(seed=43, integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, sampleCount=8, chains=2048)
