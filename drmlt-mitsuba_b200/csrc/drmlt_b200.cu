@@ -657,8 +657,12 @@ static dr_status alloc_lanes(dr_job j, int n) {
         ((st = job_alloc(j, &lm.bv, (size_t) 2 * BD_MAXV * n)) || (st = job_alloc(j, &lm.bx, (size_t) 2 * BD_MAXV * n)) ||
          (st = job_alloc(j, &lm.bacc, (size_t) n)) || (st = job_alloc(j, &lm.bsplat, (size_t) 4 * BD_MAXS * 2 * n))))
         return st;
-    // groups of at least 64K lanes, at most 8 (DRMLT_GROUPS overrides)
-    int G = std::max(1, std::min(8, n / 65536));
+    // groups of about 1 M lanes -- the persistent traversal kernel needs several rays per resident thread to amortise
+    // its latency-bound tail, while >= 3 groups are needed for the stages of different groups to overlap (measured at
+    // 4 M lanes: 1 group 110 M mutations/s, 2: 136, 3: 144, 4: 146, 6: 143, 8: 140; at 8 M lanes 8 groups: 148) --
+    // but never fewer than 64K lanes per group, at most 8 groups (DRMLT_GROUPS overrides)
+    int G = std::max(3, std::min(8, n >> 20));
+    G = std::max(1, std::min(G, n / 65536));
     if (getenv("DRMLT_GROUPS")) G = std::max(1, std::min(64, atoi(getenv("DRMLT_GROUPS"))));
     G = std::min(G, std::max(1, n / 32));
     j->groups.resize(G);
