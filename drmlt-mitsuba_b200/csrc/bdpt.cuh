@@ -23,7 +23,8 @@ DR_D bool bd_sample_surface(const Machine &M, int lane, Core &c, UReader &rd, in
     const Mat m = load_material(M.sc, v.mat);
     WalkStep ws;
     const R2 u = rd.next2D(side == BD_E ? SMP_EMITTER : SMP_SENSOR);
-    if (!surface_sample_next(M.sc, v, m, normalize(predP - v.p), mode, u, ws)) return false;
+    const Real uz = mat_uses_sampler(m.type) ? rd.next1D(side == BD_E ? SMP_EMITTER : SMP_SENSOR) : 0.5;   // bRec.sampler->next1D()
+    if (!surface_sample_next(M.sc, v, m, normalize(predP - v.p), mode, u, uz, ws)) return false;
     if (mode == MODE_RADIANCE && ws.eta != 1.) c.weight *= ws.eta * ws.eta;     // vertex.cpp:264-266
     c.weight *= ws.weightFwd;
     Real rrWeight;

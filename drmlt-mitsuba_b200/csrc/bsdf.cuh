@@ -1,7 +1,7 @@
 // bsdf.cuh -- device BSDF models in the local shading frame (z = shading normal).
 //
 // Behavioural parity targets: src/bsdfs/diffuse.cpp:109-150, dielectric.cpp:227-330,
-// conductor.cpp:223-285, roughconductor.cpp:258-417 with src/bsdfs/microfacet.h (Beckmann/GGX,
+// conductor.cpp:223-285, roughconductor.cpp:258-417, roughdielectric.cpp:270-611 with src/bsdfs/microfacet.h (Beckmann/GGX,
 // isotropic, sampleAll and sampleVisible), wrapped by twosided.cpp:107-186 when DR_MAT_TWOSIDED.
 // Branching is on the material type (a small enum) -- no virtual dispatch.
 #pragma once
@@ -10,7 +10,7 @@
 
 enum { MODE_RADIANCE = 0, MODE_IMPORTANCE = 1 };
 enum { MEAS_INVALID = 0, MEAS_SOLID_ANGLE = 1, MEAS_AREA = 3, MEAS_DISCRETE = 4 };
-enum { BT_DIFFUSE_R = 1, BT_GLOSSY_R = 2, BT_DELTA_R = 4, BT_DELTA_T = 8, BT_SMOOTH = 3, BT_DELTA = 12 };
+enum { BT_DIFFUSE_R = 1, BT_GLOSSY_R = 2, BT_DELTA_R = 4, BT_DELTA_T = 8, BT_GLOSSY_T = 16, BT_SMOOTH = 19, BT_DELTA = 12 };
 
 struct Mat {   // material fetched into registers
     int type; uint32_t flags;
@@ -28,9 +28,11 @@ DR_D Mat load_material(const DevScene &sc, int id) {
     m.alpha = d.z;
     return m;
 }
-DR_D bool mat_has_smooth(int type) { return type == DR_BSDF_DIFFUSE || type == DR_BSDF_ROUGHCONDUCTOR; }
-DR_D bool mat_non_symmetric(int type) { return type == DR_BSDF_DIELECTRIC; }
-DR_D bool mat_transmissive_or_backside(const Mat &m) { return m.type == DR_BSDF_DIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }
+DR_D bool mat_has_smooth(int type) { return type == DR_BSDF_DIFFUSE || type == DR_BSDF_ROUGHCONDUCTOR || type == DR_BSDF_ROUGHDIELECTRIC; }
+DR_D bool mat_non_symmetric(int type) { return type == DR_BSDF_DIELECTRIC || type == DR_BSDF_ROUGHDIELECTRIC; }
+DR_D bool mat_transmissive_or_backside(const Mat &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }
+// BSDF::EUsesSampler: sample() draws one more number from the vertex's sampler (roughdielectric.cpp:464, 555)
+DR_D bool mat_uses_sampler(int type) { return type == DR_BSDF_ROUGHDIELECTRIC; }
 
 // ---- warps (src/libcore/warp.cpp:44-100)
 DR_D R2 square_to_disk_concentric(Real sx, Real sy) {
@@ -83,6 +85,7 @@ struct Microfacet {
     bool ggx, visible;
     Real alpha;
     DR_D Microfacet(const Mat &m) : ggx(m.flags & DR_MAT_GGX), visible(m.flags & DR_MAT_SAMPLE_VISIBLE), alpha(fmax(m.alpha, 1e-4)) {}
+    DR_D void scale_alpha(Real v) { alpha *= v; }      // microfacet.h:178-183
     DR_D Real eval(R3 m) const {
         if (m.z <= 0.) return 0.0;
         Real cosTheta2 = m.z * m.z;
@@ -246,6 +249,27 @@ DR_D R3 bsdf_eval_nested(const Mat &m, R3 wi, R3 wo, int mode, int measure) {
         const Real G = distr.G(wi, wo, H);
         return F * (D * G / (4.0 * wi.z));
     }
+    case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:270-348
+        if (measure != MEAS_SOLID_ANGLE || wi.z == 0.) return r3(0.);
+        const Real mEta = m.eta.x, mInvEta = 1. / mEta;
+        const bool reflect = wi.z * wo.z > 0.;
+        R3 H;
+        if (reflect) H = normalize(wo + wi);
+        else H = normalize(wi + wo * (wi.z > 0. ? mEta : mInvEta));
+        H = H * copysign(1.0, H.z);
+        Microfacet distr(m);
+        const Real D = distr.eval(H);
+        if (D == 0.) return r3(0.);
+        Real cosThetaT;
+        const Real F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, mEta);
+        const Real G = distr.G(wi, wo, H);
+        if (reflect) return m.refl * (F * D * G / (4.0 * fabs(wi.z)));
+        const Real eta = wi.z > 0. ? mEta : mInvEta;
+        const Real sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+        const Real value = ((1. - F) * D * G * eta * eta * dot(wi, H) * dot(wo, H)) / (wi.z * sqrtDenom * sqrtDenom);
+        const Real factor = (mode == MODE_RADIANCE) ? (wi.z > 0. ? mInvEta : mEta) : 1.0;
+        return m.trans * fabs(value * factor * factor);
+    }
     case DR_BSDF_DIELECTRIC: {
         if (measure != MEAS_DISCRETE) return r3(0.);
         Real eta = m.eta.x, invEta = 1. / eta, cosThetaT;
@@ -280,6 +304,30 @@ DR_D Real bsdf_pdf_nested(const Mat &m, R3 wi, R3 wo, int measure) {
         if (distr.visible) return distr.eval(H) * distr.smithG1(wi, H) / (4.0 * wi.z);
         return distr.pdf(wi, H) / (4. * absdot(wo, H));
     }
+    case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:350-420 (both components enabled)
+        if (measure != MEAS_SOLID_ANGLE) return 0.;
+        const Real mEta = m.eta.x, mInvEta = 1. / mEta;
+        const bool reflect = wi.z * wo.z > 0.;
+        R3 H;
+        Real dwh_dwo;
+        if (reflect) {
+            H = normalize(wo + wi);
+            dwh_dwo = 1.0 / (4.0 * dot(wo, H));
+        } else {
+            const Real eta = wi.z > 0. ? mEta : mInvEta;
+            H = normalize(wi + wo * eta);
+            const Real sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+            dwh_dwo = (eta * eta * dot(wo, H)) / (sqrtDenom * sqrtDenom);
+        }
+        H = H * copysign(1.0, H.z);
+        Microfacet sampleDistr(m);
+        if (!sampleDistr.visible) sampleDistr.scale_alpha(1.2 - 0.2 * sqrt(fabs(wi.z)));
+        Real prob = sampleDistr.pdf(wi * copysign(1.0, wi.z), H);
+        Real cosThetaT;
+        const Real F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, mEta);
+        prob *= reflect ? F : (1. - F);
+        return fabs(prob * dwh_dwo);
+    }
     case DR_BSDF_DIELECTRIC: {
         if (measure != MEAS_DISCRETE) return 0.;
         Real eta = m.eta.x, invEta = 1. / eta, cosThetaT;
@@ -300,9 +348,51 @@ DR_D Real bsdf_pdf_nested(const Mat &m, R3 wi, R3 wo, int measure) {
 
 struct BsdfSample { R3 wo; R3 weight; Real pdf; int sampledType; Real eta; };
 
-DR_D void bsdf_sample_nested(const Mat &m, R3 wi, int mode, Real sx, Real sy, Real epsilon, BsdfSample &r) {
+// `sz`: the number an EUsesSampler BSDF draws from bRec.sampler inside sample() (roughdielectric.cpp:555)
+DR_D void bsdf_sample_nested(const Mat &m, R3 wi, int mode, Real sx, Real sy, Real sz, Real epsilon, BsdfSample &r) {
     r.weight = r3(0.); r.pdf = 0.; r.sampledType = 0; r.eta = 1.; r.wo = r3(0., 0., 1.);
     switch (m.type) {
+    case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:514-611 (both components enabled)
+        const Real mEta = m.eta.x, mInvEta = 1. / mEta;
+        Microfacet distr(m);
+        Microfacet sampleDistr(distr);
+        if (!distr.visible) sampleDistr.scale_alpha(1.2 - 0.2 * sqrt(fabs(wi.z)));
+        Real microfacetPDF = 0.;
+        const R3 mm = sampleDistr.sample(wi * copysign(1.0, wi.z), sx, sy, microfacetPDF, epsilon);
+        if (microfacetPDF == 0.) return;
+        float temporaryPdf = (float) microfacetPDF;              // sic: single precision in the reference (:543)
+        Real cosThetaT;
+        const Real F = fresnel_dielectric_ext(dot(wi, mm), cosThetaT, mEta);
+        R3 weight = r3(1.);
+        bool sampleReflection = true;
+        if (sz > F) { sampleReflection = false; temporaryPdf *= (float) (1. - F); }
+        else temporaryPdf *= (float) F;
+        Real dwh_dwo;
+        if (sampleReflection) {
+            r.wo = mm * (2. * dot(wi, mm)) - wi;
+            r.eta = 1.; r.sampledType = BT_GLOSSY_R;
+            if (wi.z * r.wo.z <= 0.) return;
+            weight = weight * m.refl;
+            dwh_dwo = 1.0 / (4.0 * dot(r.wo, mm));
+        } else {
+            if (cosThetaT == 0.) return;
+            const Real e = cosThetaT < 0. ? mInvEta : mEta;      // refract(): util.cpp:775-780
+            r.wo = mm * (dot(wi, mm) * e + cosThetaT) - wi * e;
+            r.eta = cosThetaT < 0. ? mEta : mInvEta;
+            r.sampledType = BT_GLOSSY_T;
+            if (wi.z * r.wo.z >= 0.) return;
+            const Real factor = (mode == MODE_RADIANCE) ? (cosThetaT < 0. ? mInvEta : mEta) : 1.0;
+            weight = weight * m.trans * (factor * factor);
+            const Real sqrtDenom = dot(wi, mm) + r.eta * dot(r.wo, mm);
+            dwh_dwo = (r.eta * r.eta * dot(r.wo, mm)) / (sqrtDenom * sqrtDenom);
+        }
+        if (distr.visible) weight = weight * distr.smithG1(r.wo, mm);
+        else weight = weight * fabs(distr.eval(mm) * distr.G(wi, r.wo, mm) * dot(wi, mm) / (microfacetPDF * wi.z));
+        temporaryPdf *= (float) fabs(dwh_dwo);
+        r.pdf = (Real) temporaryPdf;
+        r.weight = weight;
+        return;
+    }
     case DR_BSDF_DIFFUSE:
         if (wi.z <= 0.) return;
         r.wo = square_to_cosine_hemisphere(sx, sy);
@@ -357,9 +447,9 @@ DR_D Real bsdf_pdf(const Mat &m, R3 wi, R3 wo, int measure) {
     if ((m.flags & DR_MAT_TWOSIDED) && !(wi.z > 0.)) { wi.z = -wi.z; wo.z = -wo.z; }
     return bsdf_pdf_nested(m, wi, wo, measure);
 }
-DR_D void bsdf_sample(const Mat &m, R3 wi, int mode, Real sx, Real sy, Real epsilon, BsdfSample &r) {
+DR_D void bsdf_sample(const Mat &m, R3 wi, int mode, Real sx, Real sy, Real sz, Real epsilon, BsdfSample &r) {
     bool flipped = false;
     if ((m.flags & DR_MAT_TWOSIDED) && wi.z < 0.) { wi.z = -wi.z; flipped = true; }
-    bsdf_sample_nested(m, wi, mode, sx, sy, epsilon, r);
+    bsdf_sample_nested(m, wi, mode, sx, sy, sz, epsilon, r);
     if (flipped && !is_zero(r.weight) && r.pdf != 0.) r.wo.z = -r.wo.z;
 }

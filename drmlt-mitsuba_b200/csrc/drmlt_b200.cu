@@ -229,8 +229,9 @@ extern "C" dr_status dr_config_validate(dr_config *c) {
     return DR_OK;
 }
 
-static void max_dimensions(const dr_config *c, int depth, int *se, int *em, int *di) {   // pssmlt_utils.h:27-77
-    const int offsetRR = c->rr_depth < c->max_depth ? 1 : 0;
+// hasRoughDielectric: some shape's BSDF draws a third number per sample (offsetRoughDielectric, pssmlt_utils.h:35-52)
+static void max_dimensions(const dr_config *c, int depth, int *se, int *em, int *di, bool hasRoughDielectric = false) {   // pssmlt_utils.h:27-77
+    const int offsetRR = (c->rr_depth < c->max_depth ? 1 : 0) + (hasRoughDielectric ? 1 : 0);
     int m;
     if (c->technique == DR_TECH_MMLT) { m = (depth + 2) * 3; if (m & 1) m++; *se = m; *em = m; *di = 1; }
     else if (c->technique == DR_TECH_PATH) { m = (c->max_depth + 2) * (4 + offsetRR); if (m & 1) m++; *se = m; *em = 0; *di = 0; }
@@ -297,7 +298,7 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
             if (d->indices[3 * (size_t) i + v] >= d->n_vertices) { dr_set_error("triangle %u: vertex index out of range", i); return DR_ERR_INVALID_ARG; }
     }
     for (uint32_t m = 0; m < d->n_materials; ++m)
-        if (d->materials[m].type < DR_BSDF_DIFFUSE || d->materials[m].type > DR_BSDF_ROUGHCONDUCTOR) {
+        if (d->materials[m].type < DR_BSDF_DIFFUSE || d->materials[m].type > DR_BSDF_ROUGHDIELECTRIC) {
             dr_set_error("material %u: unsupported BSDF type %d", m, d->materials[m].type); return DR_ERR_UNSUPPORTED;
         }
     for (uint32_t e = 0; e < d->n_emitters; ++e) {
@@ -450,8 +451,9 @@ extern "C" void dr_cancel(dr_scene scene) { if (scene) scene->cancel = 1; }
 // ------------------------------------------------------------------ launch parameters
 // Fills the constant part of a Machine from the configuration.  `evalDims` (JOB_EVAL): the coordinate
 // buffers are laid out for the replayed vectors' own dimensions.
-static void make_params(const dr_config &c, int W, int H, double b, const int *evalDims, Machine &p) {
+static void make_params(const dr_config &c, int W, int H, double b, const int *evalDims, Machine &p, unsigned typeMask = 0) {
     p.pc.technique = c.technique; p.pc.maxDepth = c.max_depth; p.pc.rrDepth = c.rr_depth;
+    p.pc.hasRoughDielectric = (typeMask >> DR_BSDF_ROUGHDIELECTRIC) & 1u;
     p.pc.excludeDirect = c.direct_samples >= 0;        // separateDirect (drmlt.cpp:242)
     p.pc.lightImage = c.light_image != 0;
     PssParams &pp = p.pp;
@@ -483,7 +485,7 @@ static void make_params(const dr_config &c, int W, int H, double b, const int *e
     cp.timidAfterLarge = c.timid_after_large; cp.fixEmitterPath = c.fix_emitter_path; cp.useMixture = c.use_mixture;
     cp.kelemenWeights = c.kelemen_style_weights;
     cp.kel_s1 = s1; cp.kel_s2 = s2; cp.kel_logRatio = -std::log(s2 / s1);
-    max_dimensions(&c, c.max_depth, &cp.dimS, &cp.dimE, &cp.dimD);   // worst case over the MMLT depths
+    max_dimensions(&c, c.max_depth, &cp.dimS, &cp.dimE, &cp.dimD, p.pc.hasRoughDielectric != 0);   // worst case over the MMLT depths
     int lay[3] = { cp.dimS, cp.dimE, cp.dimD };
     if (evalDims) for (int s = 0; s < 3; ++s) lay[s] = std::max(lay[s], evalDims[s]);
     int off = 0;
@@ -697,7 +699,7 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     j->M.sc = scene_for(scene, cfg, fw);
     const int W = fw.W, H = fw.H;
     j->W = W; j->H = H;
-    make_params(cfg, W, H, 1.0, evalDims, j->M);
+    make_params(cfg, W, H, 1.0, evalDims, j->M, static_cast<SceneImpl *>(scene)->typeMask);
     j->M.traceRefill = getenv("DRMLT_TRACE_REFILL") ? atoi(getenv("DRMLT_TRACE_REFILL")) : 24;
     j->M.traceDescend = getenv("DRMLT_TRACE_DESCEND") ? atoi(getenv("DRMLT_TRACE_DESCEND")) : 8;
     auto fail = [&](dr_status code) { dr_job_destroy(j); return code; };
@@ -1393,7 +1395,7 @@ extern "C" dr_status dr_direct_image(dr_scene scene, const dr_config *cfgIn, flo
     Machine M;
     memset(&M, 0, sizeof(M));
     M.sc = scene_for(scene, cfg, fw);
-    make_params(cfg, fw.W, fw.H, 1.0, nullptr, M);
+    make_params(cfg, fw.W, fw.H, 1.0, nullptr, M, static_cast<SceneImpl *>(scene)->typeMask);
     DevBuf film, rgb, dli;
     if ((st = film.alloc(sizeof(float4) * n)) || (st = rgb.alloc(sizeof(float) * 3 * n)) || (li && (st = dli.alloc(sizeof(double) * 3 * n * ps)))) return st;
     CK(cudaMemset(film.p, 0, sizeof(float4) * n));

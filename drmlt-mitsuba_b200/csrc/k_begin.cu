@@ -41,7 +41,7 @@ DR_D void fill_proposal(const Machine &M, int lane, Core &c, const MutCtx &mc, l
             ub_store(ub, pp.off[SMP_DIRECT], d);
             int s_, t_;
             mmlt_strategy(M.pc, c.depth, d.x, s_, t_);
-            ext[0] = min(ext[0], t_); ext[1] = min(ext[1], s_); ext[2] = 0;
+            ext[0] = min(ext[0], subset_pairs(M, t_)); ext[1] = min(ext[1], subset_pairs(M, s_)); ext[2] = 0;
         }
         for (int s = 0; s < 3; ++s)
             for (int p = 0; p < ext[s]; ++p) ub_store(ub, pp.off[s] + 2 * p, boot_pair(s, p));
@@ -69,7 +69,7 @@ DR_D void fill_proposal(const Machine &M, int lane, Core &c, const MutCtx &mc, l
         const R2 d = make_pair(SMP_DIRECT, 0);
         int s_, t_;
         mmlt_strategy(M.pc, c.depth, wrap_reflect(d.x), s_, t_);
-        ext[0] = t_; ext[1] = s_; ext[2] = 0;
+        ext[0] = subset_pairs(M, t_); ext[1] = subset_pairs(M, s_); ext[2] = 0;
     }
     for (int s = 0; s < 3; ++s)
         for (int p = 0; p < ext[s]; ++p) make_pair(s, p);

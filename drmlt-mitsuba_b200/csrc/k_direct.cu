@@ -76,7 +76,7 @@ k_direct(const __grid_constant__ DevScene sc, const __grid_constant__ FilmParams
         }
         for (int i = 0; i < nB; ++i) {                      // BSDF sampling (direct.cpp:245-300)
             BsdfSample bs;
-            bsdf_sample(m, wi, MODE_RADIANCE, U(2 + 2 * (nE + i)), U(3 + 2 * (nE + i)), sc.epsilon, bs);
+            bsdf_sample(m, wi, MODE_RADIANCE, U(2 + 2 * (nE + i)), U(3 + 2 * (nE + i)), mat_uses_sampler(m.type) ? U(2 + 4 * nE + i) : 0.5, sc.epsilon, bs);
             if (is_zero(bs.weight)) continue;
             const R3 wo = to_world(v, bs.wo);
             Hit h2;

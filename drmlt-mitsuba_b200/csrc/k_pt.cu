@@ -109,8 +109,9 @@ k_pt(const __grid_constant__ Machine M) {
                 const Mat m = load_material(sc, v.mat);
                 const R3 wi = to_local(v, -d);
                 const R2 ub = rd.next2D(SMP_SENSOR);
+                const Real uz = mat_uses_sampler(m.type) ? rd.next1D(SMP_SENSOR) : 0.5;      // bRec.sampler->next1D() (roughdielectric.cpp:555)
                 BsdfSample bs;
-                bsdf_sample(m, wi, MODE_RADIANCE, ub.x, ub.y, sc.epsilon, bs);
+                bsdf_sample(m, wi, MODE_RADIANCE, ub.x, ub.y, uz, sc.epsilon, bs);
                 if (is_zero(bs.weight)) { go = GO_DONE; break; }
                 if (!(bs.sampledType & BT_DELTA)) c.flags |= F_PT_NONSPEC;
                 c.flags = (bs.sampledType & BT_DELTA) ? (c.flags | F_DELTA) : (c.flags & ~F_DELTA);

@@ -68,7 +68,7 @@ k_trace(const __grid_constant__ Machine M) {
                 else if (tr.anyhit || !found) dest = Q_CHAIN + M.parity;
                 else {
                     const uint32_t mf = (uint32_t) __float_as_int(__ldg(&M.sc.tris[3 * (size_t) tr.hit.tri + 2].z));
-                    dest = Q_WALK + (int) ((mf >> 24) & 3u);
+                    dest = Q_WALK + (int) ((mf >> 24) & 7u);
                 }
                 q_push_hit(M.q, dest, (uint32_t) lane, found ? tr.hit.tri : -1);
                 lane = -1;

@@ -170,8 +170,8 @@ template <class T> DR_D void rec_store(T *dst, const T &src) {
 // Q_RAYC / Q_RAYS / Q_CHAIN are double-buffered by round parity: kernels of round r consume [r & 1] and
 // produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT, Q_PT and
 // Q_BEGIN are produced and consumed inside one round.
-enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 4 */, Q_CONNECT = 10, Q_PT = 11,
-       Q_BEGIN = 12 /* + BEGIN_* class, 3 */, Q_COUNT = 15 };
+enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 5 */, Q_CONNECT = 11, Q_PT = 12,
+       Q_BEGIN = 13 /* + BEGIN_* class, 3 */, Q_COUNT = 16 };
 // classes of "start the next path" work: each runs one kind of proposal arithmetic on full warps
 enum { BEGIN_STAGE1 = 0, BEGIN_STAGE2 = 1, BEGIN_OTHER = 2 };
 struct RayF { float4 a, b; };                               // (o, tmin), (d, tmax): float32 cast of a ray, for the traversal
@@ -308,9 +308,12 @@ DR_D void mmlt_strategy(const PathCfg &pc, int depth, Real decision, int &s, int
     else { nStrats = depth; s = min((int) (nStrats * decision), nStrats - 1); t = 1 + (nStrats - s); }
 }
 
+// coordinate pairs a subpath of n vertices can consume: 2n coordinates, or up to 3n - 2 when BSDF samples may draw a
+// third number (rough dielectrics)
+DR_D int subset_pairs(const Machine &M, int n) { return M.pc.hasRoughDielectric ? (3 * n) / 2 : n; }
 // number of coordinate PAIRS of each sampler that a proposal with strategy (s, t) must carry
 DR_D void pair_extent(const Machine &M, const int dims[3], int s, int t, int ext[3]) {
-    if (M.pp.subset) { ext[0] = t; ext[1] = s; ext[2] = 1; }
+    if (M.pp.subset) { ext[0] = subset_pairs(M, t); ext[1] = subset_pairs(M, s); ext[2] = 1; }
     else { ext[0] = (dims[0] + 1) >> 1; ext[1] = (dims[1] + 1) >> 1; ext[2] = (dims[2] + 1) >> 1; }
 }
 

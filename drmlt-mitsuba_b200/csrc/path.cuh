@@ -19,6 +19,7 @@ struct PathCfg {
     int technique, maxDepth, rrDepth;
     int excludeDirect;        // separateDirect (directSamples >= 0)
     int lightImage;
+    int hasRoughDielectric;   // some triangle's BSDF draws an extra number per sample (pssmlt_utils.h:35-45)
 };
 
 struct PathResult {           // single-splat techniques (path, mmlt)
@@ -185,10 +186,11 @@ DR_D Real surface_pdf_area(const Vtx &v, const Mat &m, R3 fromPos, R3 toPos, R3 
 
 // One BSDF sampling step of a random walk (vertex.cpp:153-271 + :334-347), shared by both subpaths.
 struct WalkStep { R3 wo; R3 weightFwd; Real pdfFwd, pdfBwd; bool delta; Real eta; };
-DR_D bool surface_sample_next(const DevScene &sc, const Vtx &v, const Mat &m, R3 wiW, int mode, R2 u, WalkStep &ws) {
+// uz: the extra number of an EUsesSampler BSDF (mat_uses_sampler), drawn by the caller right after u
+DR_D bool surface_sample_next(const DevScene &sc, const Vtx &v, const Mat &m, R3 wiW, int mode, R2 u, Real uz, WalkStep &ws) {
     const R3 wi = to_local(v, wiW);
     BsdfSample bs;
-    bsdf_sample(m, wi, mode, u.x, u.y, sc.epsilon, bs);
+    bsdf_sample(m, wi, mode, u.x, u.y, uz, sc.epsilon, bs);
     if (is_zero(bs.weight)) return false;
     const int measure = (bs.sampledType & BT_DELTA) ? MEAS_DISCRETE : MEAS_SOLID_ANGLE;
     ws.wo = to_world(v, bs.wo);

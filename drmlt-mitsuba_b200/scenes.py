@@ -187,8 +187,10 @@ def cornell_box(film=(256, 256), tess=8):
     return s
 
 
-def glossy_scene(film=(512, 512), subdiv=5):
-    """C3: room + three GGX rough-conductor spheres + one dielectric sphere, ~100k triangles."""
+def glossy_scene(film=(512, 512), subdiv=5, rough_glass=None):
+    """C3: room + three GGX rough-conductor spheres + one dielectric sphere, ~100k triangles.
+    rough_glass = (alpha, flags): the glass sphere and a frosted pane in front of the back wall become `roughdielectric`
+    (SURVEY 8f rank 4)."""
     s = SceneData("glossy", film)
     white = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.73, 0.73, 0.73))
     red = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.63, 0.065, 0.05))
@@ -199,7 +201,16 @@ def glossy_scene(film=(512, 512), subdiv=5):
         m = s.add_material(abi.DR_BSDF_ROUGHCONDUCTOR, flags=abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE,
                            reflectance=(1, 1, 1), eta=cu_eta, k=cu_k, alpha=alpha)
         s.add_icosphere((-0.6 + 0.6 * i, -0.7, -0.3 + 0.1 * i), 0.3, subdiv, m)
-    glass = s.add_material(abi.DR_BSDF_DIELECTRIC, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5, 0, 0))
+    if rough_glass is None:
+        glass = s.add_material(abi.DR_BSDF_DIELECTRIC, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5, 0, 0))
+    else:
+        s.name = "glossy-roughglass"
+        glass = s.add_material(abi.DR_BSDF_ROUGHDIELECTRIC, flags=rough_glass[1], reflectance=(1, 1, 1), transmittance=(1, 1, 1),
+                               eta=(1.5, 0, 0), alpha=rough_glass[0])
+        # a thin frosted pane (two faces, outward normals) between the camera and the back wall
+        z0, z1 = -0.55, -0.5
+        s.add_quad((-0.9, -0.2, z1), (0.9, -0.2, z1), (0.9, 0.8, z1), (-0.9, 0.8, z1), glass)
+        s.add_quad((0.9, -0.2, z0), (-0.9, -0.2, z0), (-0.9, 0.8, z0), (0.9, 0.8, z0), glass)
     s.add_icosphere((0.1, -0.65, 0.45), 0.35, subdiv, glass)
     s.set_camera((0, 0, 3.9), (0, 0, 0), (0, 1, 0), 39.0)
     return s

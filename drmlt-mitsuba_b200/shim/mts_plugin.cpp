@@ -118,6 +118,22 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why) {
             size_t v = str.find("sampleVisible = ", from);
             if (v != std::string::npos && str[v + 16] == '1') m.flags |= DR_MAT_SAMPLE_VISIBLE;
         }
+    } else if (model == "RoughDielectric") {              // src/bsdfs/roughdielectric.cpp (toString :659-672)
+        if (nested) { why = "twosided rough dielectric"; return false; }
+        m.type = DR_BSDF_ROUGHDIELECTRIC;
+        float eta = 0.f, au = 0.f, av = 0.f;
+        if (!ts.scalar("eta", from, eta)) { why = "cannot parse rough dielectric eta"; return false; }
+        m.eta[0] = eta;                                   // intIOR / extIOR
+        if (!ts.scalar("alphaU", from, au) || !ts.scalar("alphaV", from, av) || au != av) { why = "anisotropic or textured roughness"; return false; }
+        m.alpha = au;
+        ts.spectrum("specularReflectance", from, m.reflectance);
+        ts.spectrum("specularTransmittance", from, m.transmittance);
+        size_t d = str.find("distribution = ", from);
+        if (d == std::string::npos) { why = "no distribution"; return false; }
+        if (str.compare(d + 15, 3, "ggx") == 0) m.flags |= DR_MAT_GGX;
+        else if (str.compare(d + 15, 8, "beckmann") != 0) { why = "phong distribution"; return false; }
+        size_t v = str.find("sampleVisible = ", from);
+        if (v != std::string::npos && str[v + 16] == '1') m.flags |= DR_MAT_SAMPLE_VISIBLE;
     } else { why = "unsupported BSDF " + model; return false; }
     return true;
 }

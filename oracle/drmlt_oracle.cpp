@@ -43,7 +43,7 @@ void orc_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c
 float orc_uniform(uint64_t seed, uint32_t stream, uint64_t a, uint32_t b, uint32_t j) { return keyedUniform(seed, stream, a, b, j); }
 
 void orc_max_dimensions(const dr_config *cfg, int depth, int *sensor, int *emitter, int *direct) {
-    MaxDim md = findMaxDimensions(cfg->max_depth, cfg->rr_depth, depth, cfg->technique, cfg->direct_sampling != 0);
+    MaxDim md = findMaxDimensions(cfg->max_depth, cfg->rr_depth, depth, cfg->technique, cfg->direct_sampling != 0, false);
     *sensor = md.sensor; *emitter = md.emitter; *direct = md.direct;
 }
 
@@ -304,6 +304,15 @@ void orc_bsdf_sample(const dr_material *m, const double *wi, int mode, double u1
     weight[0] = w.r; weight[1] = w.g; weight[2] = w.b;
     *pdf = p; *sampledType = b.sampledType;
 }
+// ... with the extra number EUsesSampler BSDFs draw from bRec.sampler (roughdielectric.cpp:555)
+void orc_bsdf_sample3(const dr_material *m, const double *wi, int mode, double u1, double u2, double u3, double *wo, double *weight, double *pdf, int *sampledType, double *eta) {
+    BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), mode);
+    Float p = 0;
+    RGB w = bsdfSample(*m, b, p, Vec2(u1, u2), 1e-7, u3);
+    wo[0] = b.wo.x; wo[1] = b.wo.y; wo[2] = b.wo.z;
+    weight[0] = w.r; weight[1] = w.g; weight[2] = w.b;
+    *pdf = p; *sampledType = b.sampledType; *eta = b.eta;
+}
 void orc_bsdf_eval(const dr_material *m, const double *wi, const double *wo, int mode, int measure, double *value, double *pdf) {
     BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), Vec3(wo[0], wo[1], wo[2]), mode);
     RGB v = bsdfEval(*m, b, measure);
@@ -333,6 +342,7 @@ int orc_direct_image(void *h, const dr_config *cfg, float *image_rgb, double *li
     std::vector<Float> weight((size_t) W * H, 0.0);
     PathCtx ctx; ctx.scene = &sc;
     std::vector<Vec2> u(2 * shadingSamples);
+    std::vector<Float> extra(shadingSamples);
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
             const uint64_t p = (uint64_t) y * W + x;
@@ -345,7 +355,8 @@ int orc_direct_image(void *h, const dr_config *cfg, float *image_rgb, double *li
                 Float invZ = 1.0 / dl.z;
                 Ray ray; ray.o = sc.cam.pos; ray.d = sc.cam.xformDir(dl);
                 ray.mint = sc.cam.nearClip * invZ; ray.maxt = sc.cam.farClip * invZ;
-                const RGB Li = directLi(ctx, ray, shadingSamples, u.data());
+                for (int i = 0; i < shadingSamples; ++i) extra[i] = keyedUniform(cfg->seed, S_DIRECT, p, (uint32_t) j, 2 + 4 * shadingSamples + i);
+                const RGB Li = directLi(ctx, ray, shadingSamples, u.data(), extra.data());
                 if (li_out) { double *o = li_out + (((size_t) p) * pixelSamples + j) * 3; o[0] = Li.r; o[1] = Li.g; o[2] = Li.b; }
                 // ImageBlock::put(pos, spec, alpha): weighted value + weight channel (imageblock.h:149-196)
                 if (!Li.isValid()) continue;

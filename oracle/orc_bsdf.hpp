@@ -14,8 +14,8 @@ namespace orc {
 enum ETransportMode { ERadiance = 0, EImportance = 1 };
 enum EMeasure { EInvalidMeasure = 0, ESolidAngle = 1, ELength = 2, EArea = 3, EDiscrete = 4 };
 enum EBSDFType {
-    EDiffuseReflection = 0x1, EGlossyReflection = 0x2, EDeltaReflection = 0x4, EDeltaTransmission = 0x8,
-    ESmooth = EDiffuseReflection | EGlossyReflection, EDelta = EDeltaReflection | EDeltaTransmission
+    EDiffuseReflection = 0x1, EGlossyReflection = 0x2, EDeltaReflection = 0x4, EDeltaTransmission = 0x8, EGlossyTransmission = 0x10,
+    ESmooth = EDiffuseReflection | EGlossyReflection | EGlossyTransmission, EDelta = EDeltaReflection | EDeltaTransmission
 };
 
 struct BSDFRecord {
@@ -30,10 +30,12 @@ struct BSDFRecord {
 
 inline RGB rgb3(const float *v) { return RGB(v[0], v[1], v[2]); }
 
-inline bool bsdfHasSmooth(const dr_material &m) { return m.type == DR_BSDF_DIFFUSE || m.type == DR_BSDF_ROUGHCONDUCTOR; }
-inline bool bsdfNonSymmetric(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC; }   // dielectric.cpp:201
+inline bool bsdfHasSmooth(const dr_material &m) { return m.type == DR_BSDF_DIFFUSE || m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC; }
+inline bool bsdfNonSymmetric(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC; }   // dielectric.cpp:201, roughdielectric.cpp:253
+// BSDF::EUsesSampler: sample() draws one more number from the vertex's sampler (roughdielectric.cpp:464, 555)
+inline bool bsdfUsesSampler(const dr_material &m) { return m.type == DR_BSDF_ROUGHDIELECTRIC; }
 // BSDF::ETransmission | BSDF::EBackSide test used by DirectSamplingRecord (records.inl:160-164)
-inline bool bsdfTransmissiveOrBackside(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }
+inline bool bsdfTransmissiveOrBackside(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }
 inline int bsdfMeasure(int sampledType) { return (sampledType & EDelta) ? EDiscrete : ESolidAngle; }
 
 // ---------------------------------------------------------------- microfacet.h
@@ -43,6 +45,7 @@ struct Microfacet {
     Microfacet(const dr_material &m)
         : ggx((m.flags & DR_MAT_GGX) != 0), sampleVis((m.flags & DR_MAT_SAMPLE_VISIBLE) != 0),
           alpha(std::max((Float) m.alpha, (Float) 1e-4)) {}   // microfacet.h:67-72
+    void scaleAlpha(Float value) { alpha *= value; }          // :178-183
 
     Float eval(const Vec3 &m) const {   // :191-237
         if (Frame::cosTheta(m) <= 0) return 0.0;
@@ -220,6 +223,31 @@ inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
         Float model = D * G / (4.0 * Frame::cosTheta(b.wi));
         return F * model;
     }
+    case DR_BSDF_ROUGHDIELECTRIC: {   // roughdielectric.cpp:270-348
+        if (measure != ESolidAngle || Frame::cosTheta(b.wi) == 0) return RGB(0.0);
+        const Float mEta = m.eta[0], mInvEta = 1 / mEta;
+        const bool reflect = Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) > 0;
+        Vec3 H;
+        if (reflect) H = normalize(b.wo + b.wi);
+        else { Float eta = Frame::cosTheta(b.wi) > 0 ? mEta : mInvEta; H = normalize(b.wi + b.wo * eta); }
+        H = H * std::copysign(1.0, Frame::cosTheta(H));
+        Microfacet distr(m);
+        const Float D = distr.eval(H);
+        if (D == 0) return RGB(0.0);
+        Float cosThetaT;
+        const Float F = fresnelDielectricExt(dot(b.wi, H), cosThetaT, mEta);
+        const Float G = distr.G(b.wi, b.wo, H);
+        if (reflect) {
+            Float value = F * D * G / (4.0 * std::abs(Frame::cosTheta(b.wi)));
+            return rgb3(m.reflectance) * value;
+        } else {
+            Float eta = Frame::cosTheta(b.wi) > 0.0 ? mEta : mInvEta;
+            Float sqrtDenom = dot(b.wi, H) + eta * dot(b.wo, H);
+            Float value = ((1 - F) * D * G * eta * eta * dot(b.wi, H) * dot(b.wo, H)) / (Frame::cosTheta(b.wi) * sqrtDenom * sqrtDenom);
+            Float factor = (b.mode == ERadiance) ? (Frame::cosTheta(b.wi) > 0 ? mInvEta : mEta) : 1.0;
+            return rgb3(m.transmittance) * std::abs(value * factor * factor);
+        }
+    }
     case DR_BSDF_DIELECTRIC: {   // dielectric.cpp:227-253
         if (measure != EDiscrete) return RGB(0.0);
         Float eta = m.eta[0], invEta = 1 / eta, cosThetaT;
@@ -257,6 +285,30 @@ inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
         else
             return distr.pdf(b.wi, H) / (4 * absDot(b.wo, H));
     }
+    case DR_BSDF_ROUGHDIELECTRIC: {   // roughdielectric.cpp:350-420 (both components enabled)
+        if (measure != ESolidAngle) return 0.0;
+        const Float mEta = m.eta[0], mInvEta = 1 / mEta;
+        const bool reflect = Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) > 0;
+        Vec3 H;
+        Float dwh_dwo;
+        if (reflect) {
+            H = normalize(b.wo + b.wi);
+            dwh_dwo = 1.0 / (4.0 * dot(b.wo, H));
+        } else {
+            Float eta = Frame::cosTheta(b.wi) > 0 ? mEta : mInvEta;
+            H = normalize(b.wi + b.wo * eta);
+            Float sqrtDenom = dot(b.wi, H) + eta * dot(b.wo, H);
+            dwh_dwo = (eta * eta * dot(b.wo, H)) / (sqrtDenom * sqrtDenom);
+        }
+        H = H * std::copysign(1.0, Frame::cosTheta(H));
+        Microfacet sampleDistr(m);
+        if (!sampleDistr.sampleVis) sampleDistr.scaleAlpha(1.2 - 0.2 * std::sqrt(std::abs(Frame::cosTheta(b.wi))));
+        Float prob = sampleDistr.pdf(b.wi * std::copysign(1.0, Frame::cosTheta(b.wi)), H);
+        Float cosThetaT;
+        Float F = fresnelDielectricExt(dot(b.wi, H), cosThetaT, mEta);
+        prob *= reflect ? F : (1 - F);
+        return std::abs(prob * dwh_dwo);
+    }
     case DR_BSDF_DIELECTRIC: {   // dielectric.cpp:255-276
         if (measure != EDiscrete) return 0.0;
         Float eta = m.eta[0], invEta = 1 / eta, cosThetaT;
@@ -275,8 +327,49 @@ inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
     return 0.0;
 }
 
-inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const Vec2 &sample, Float epsilon) {
+// `extra`: the number sample() draws from bRec.sampler (EUsesSampler BSDFs; roughdielectric.cpp:555)
+inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const Vec2 &sample, Float epsilon, Float extra) {
     switch (m.type) {
+    case DR_BSDF_ROUGHDIELECTRIC: {   // roughdielectric.cpp:514-611 (both components enabled)
+        const Float mEta = m.eta[0], mInvEta = 1 / mEta;
+        Microfacet distr(m);
+        Microfacet sampleDistr(distr);
+        if (!distr.sampleVis) sampleDistr.scaleAlpha(1.2 - 0.2 * std::sqrt(std::abs(Frame::cosTheta(b.wi))));
+        Float microfacetPDF;
+        const Vec3 mm = sampleDistr.sample(b.wi * std::copysign(1.0, Frame::cosTheta(b.wi)), sample, microfacetPDF, epsilon);
+        if (microfacetPDF == 0) return RGB(0.0);
+        float temporaryPdf = (float) microfacetPDF;              // sic: single precision in the reference (:543)
+        Float cosThetaT;
+        Float F = fresnelDielectricExt(dot(b.wi, mm), cosThetaT, mEta);
+        RGB weight(1.0);
+        bool sampleReflection = true;
+        if (extra > F) { sampleReflection = false; temporaryPdf *= 1 - F; }
+        else temporaryPdf *= F;
+        Float dwh_dwo;
+        if (sampleReflection) {
+            b.wo = reflectM(b.wi, mm);
+            b.eta = 1.0; b.sampledType = EGlossyReflection;
+            if (Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
+            weight = weight * rgb3(m.reflectance);
+            dwh_dwo = 1.0 / (4.0 * dot(b.wo, mm));
+        } else {
+            if (cosThetaT == 0) return RGB(0.0);
+            Float e = cosThetaT < 0 ? mInvEta : mEta;            // refract(): util.cpp:775-780 (eta inverted when cosThetaT < 0)
+            b.wo = mm * (dot(b.wi, mm) * e + cosThetaT) - b.wi * e;
+            b.eta = cosThetaT < 0 ? mEta : mInvEta;
+            b.sampledType = EGlossyTransmission;
+            if (Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) >= 0) return RGB(0.0);
+            Float factor = (b.mode == ERadiance) ? (cosThetaT < 0 ? mInvEta : mEta) : 1.0;
+            weight = weight * rgb3(m.transmittance) * (factor * factor);
+            Float sqrtDenom = dot(b.wi, mm) + b.eta * dot(b.wo, mm);
+            dwh_dwo = (b.eta * b.eta * dot(b.wo, mm)) / (sqrtDenom * sqrtDenom);
+        }
+        if (distr.sampleVis) weight = weight * distr.smithG1(b.wo, mm);
+        else weight = weight * std::abs(distr.eval(mm) * distr.G(b.wi, b.wo, mm) * dot(b.wi, mm) / (microfacetPDF * Frame::cosTheta(b.wi)));
+        temporaryPdf *= std::abs(dwh_dwo);
+        pdf = temporaryPdf;
+        return weight;
+    }
     case DR_BSDF_DIFFUSE:   // diffuse.cpp:139-149
         if (Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
         b.wo = squareToCosineHemisphere(sample);
@@ -347,19 +440,19 @@ inline Float bsdfPdf(const dr_material &m, const BSDFRecord &bRec, int measure =
     }
     return detail::pdfNested(m, bRec, measure);
 }
-inline RGB bsdfSample(const dr_material &m, BSDFRecord &bRec, Float &pdf, const Vec2 &sample, Float epsilon) {
+inline RGB bsdfSample(const dr_material &m, BSDFRecord &bRec, Float &pdf, const Vec2 &sample, Float epsilon, Float extra = 0.5) {
     pdf = 0;
     if (m.flags & DR_MAT_TWOSIDED) {   // twosided.cpp:166-186
         bool flipped = false;
         if (Frame::cosTheta(bRec.wi) < 0) { bRec.wi.z *= -1; flipped = true; }
-        RGB result = detail::sampleNested(m, bRec, pdf, sample, epsilon);
+        RGB result = detail::sampleNested(m, bRec, pdf, sample, epsilon, extra);
         if (flipped) {
             bRec.wi.z *= -1;
             if (!result.isZero() && pdf != 0) bRec.wo.z *= -1;
         }
         return result;
     }
-    return detail::sampleNested(m, bRec, pdf, sample, epsilon);
+    return detail::sampleNested(m, bRec, pdf, sample, epsilon, extra);
 }
 
 } // namespace orc

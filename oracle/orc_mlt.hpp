@@ -25,10 +25,10 @@
 namespace orc {
 
 // ------------------------------------------------------------------ findMaxDimensions (pssmlt_utils.h:27-77)
-// No media and no rough dielectrics in scope: offsetMedium = offsetRoughDielectric = 0.
+// No media in scope: offsetMedium = 0.  hasRoughDielectric: some shape's BSDF is a RoughDielectric (:35-45).
 struct MaxDim { int sensor, emitter, direct; };
-inline MaxDim findMaxDimensions(int maxDepth, int rrDepth, int depth, int technique, bool useDirectSampling) {
-    int offsetRR = rrDepth < maxDepth ? 1 : 0;
+inline MaxDim findMaxDimensions(int maxDepth, int rrDepth, int depth, int technique, bool useDirectSampling, bool hasRoughDielectric) {
+    int offsetRR = (rrDepth < maxDepth ? 1 : 0) + (hasRoughDielectric ? 1 : 0);
     if (technique == DR_TECH_MMLT) {
         int maxDim = (depth + 2) * 3;
         if (maxDim % 2 == 1) maxDim++;
@@ -386,7 +386,7 @@ struct ChainRunner {
     // chain `chainId`, seeded from bootstrap sample `seedIndex`; records (optional) has nMutations entries
     void runDRMLT(uint64_t chainId, uint64_t seedIndex, int depth, uint64_t nMutations, StepRecord *records) {
         KeyedSource src; src.seed = cfg.seed; src.chain = chainId;
-        MaxDim md = findMaxDimensions(cfg.max_depth, cfg.rr_depth, depth, cfg.technique, cfg.direct_sampling != 0);
+        MaxDim md = findMaxDimensions(cfg.max_depth, cfg.rr_depth, depth, cfg.technique, cfg.direct_sampling != 0, sc.hasRoughDielectric);
         DRMLTSampler sensorS, emitterS, directS;
         DRMLTSampler *all[3] = { &sensorS, &emitterS, &directS };
         size_t dims[3] = { (size_t) md.sensor, (size_t) md.emitter, (size_t) md.direct };
@@ -537,7 +537,7 @@ struct ChainRunner {
     // PSSMLTRenderer::process (pssmlt_proc.cpp:110-285)
     void runPSSMLT(uint64_t chainId, uint64_t seedIndex, int depth, uint64_t nMutations, StepRecord *records) {
         KeyedSource src; src.seed = cfg.seed; src.chain = chainId;
-        MaxDim md = findMaxDimensions(cfg.max_depth, cfg.rr_depth, depth, cfg.technique, cfg.direct_sampling != 0);
+        MaxDim md = findMaxDimensions(cfg.max_depth, cfg.rr_depth, depth, cfg.technique, cfg.direct_sampling != 0, sc.hasRoughDielectric);
         PSSMLTSampler sensorS, emitterS, directS;
         PSSMLTSampler *all[3] = { &sensorS, &emitterS, &directS };
         size_t dims[3] = { (size_t) md.sensor, (size_t) md.emitter, (size_t) md.direct };

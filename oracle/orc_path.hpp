@@ -269,7 +269,10 @@ inline bool vertexSampleNext(PathCtx &ctx, PathVertex &cur, Sampler *sampler, co
         Vec3 wi = normalize(pred->getPosition() - its.p);
         BSDFRecord bRec(its.toLocal(wi), mode);
         Vec2 rndPoint = sampler->next2D();
-        cur.weight[mode] = bsdfSample(bsdf, bRec, cur.pdf[mode], rndPoint, sc.epsilon);
+        // EUsesSampler BSDFs draw one more number inside sample() (roughdielectric.cpp:555); drawing it up front is
+        // equivalent: the only exit before the draw returns a zero weight, which ends the walk
+        Float extra = bsdfUsesSampler(bsdf) ? sampler->next1D() : 0.5;
+        cur.weight[mode] = bsdfSample(bsdf, bRec, cur.pdf[mode], rndPoint, sc.epsilon, extra);
         if (cur.weight[mode].isZero()) return false;
         cur.measure = bsdfMeasure(bRec.sampledType);
         Vec3 wo = its.toWorld(bRec.wo);
@@ -650,7 +653,9 @@ inline RGB pathTracerLi(PathCtx &ctx, Sampler *sampler, Ray ray, int maxDepth, i
         }
         Float bsdfPdfV;
         BSDFRecord bRec(its.wi, ERadiance);
-        RGB bsdfWeight = bsdfSample(bsdf, bRec, bsdfPdfV, sampler->next2D(), sc.epsilon);
+        const Vec2 bsdfPoint = sampler->next2D();
+        const Float bsdfExtra = bsdfUsesSampler(bsdf) ? sampler->next1D() : 0.5;      // bRec.sampler->next1D() (roughdielectric.cpp:555)
+        RGB bsdfWeight = bsdfSample(bsdf, bRec, bsdfPdfV, bsdfPoint, sc.epsilon, bsdfExtra);
         if (bsdfWeight.isZero()) break;
         non_specular |= !(bRec.sampledType & EDelta);
         const Vec3 wo = its.toWorld(bRec.wo);
@@ -691,7 +696,8 @@ inline RGB pathTracerLi(PathCtx &ctx, Sampler *sampler, Ray ray, int maxDepth, i
 // MIDirectIntegrator::Li (src/integrators/direct/direct.cpp:144-305) for a camera ray, with the plugin defaults
 // strictNormals=false, hideEmitters=false and emitterSamples = bsdfSamples = shadingSamples; `u` supplies the
 // 2-D samples: first the emitter samples, then the BSDF samples.
-inline RGB directLi(PathCtx &ctx, Ray ray, int shadingSamples, const Vec2 *u) {
+// `extra` (optional): one more number per BSDF sample for EUsesSampler BSDFs (bRec.sampler->next1D(), roughdielectric.cpp:555)
+inline RGB directLi(PathCtx &ctx, Ray ray, int shadingSamples, const Vec2 *u, const Float *extra = nullptr) {
     const Scene &sc = *ctx.scene;
     Intersection its;
     RGB Li(0.0);
@@ -718,7 +724,7 @@ inline RGB directLi(PathCtx &ctx, Ray ray, int shadingSamples, const Vec2 *u) {
     for (int i = 0; i < nB; ++i) {
         Float bPdf;
         BSDFRecord bRec(its.wi, ERadiance);
-        RGB bsdfVal = bsdfSample(bsdf, bRec, bPdf, u[nE + i], sc.epsilon);
+        RGB bsdfVal = bsdfSample(bsdf, bRec, bPdf, u[nE + i], sc.epsilon, extra ? extra[i] : 0.5);
         if (bsdfVal.isZero()) continue;
         const Vec3 wo = its.toWorld(bRec.wo);
         Ray bsdfRay = sc.makeRay(its.p, wo);

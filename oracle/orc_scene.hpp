@@ -156,6 +156,7 @@ struct Scene {
     std::vector<uint32_t> idx, triMat, triFlags;
     std::vector<int32_t> triEmitter;
     std::vector<dr_material> mats;
+    bool hasRoughDielectric = false;   // pssmlt_utils.h:35-45
     std::vector<EmitterRec> emitters;
     DiscreteDistribution emitterPDF;   // scene.cpp:380-383 (sampling weights)
     std::vector<TriAccel> accel;
@@ -229,6 +230,7 @@ inline void Scene::load(const dr_scene_desc &d) {
     if (d.tri_flags) triFlags.assign(d.tri_flags, d.tri_flags + d.n_triangles);
     else triFlags.assign(d.n_triangles, 0);
     mats.assign(d.materials, d.materials + d.n_materials);
+    for (uint32_t i = 0; i < d.n_triangles; ++i) hasRoughDielectric |= mats[d.tri_material[i]].type == DR_BSDF_ROUGHDIELECTRIC;
     emitters.resize(d.n_emitters);
     emitterPDF.clear();
     for (uint32_t e = 0; e < d.n_emitters; ++e) {

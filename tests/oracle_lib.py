@@ -52,6 +52,8 @@ def load():
     lib.orc_splat.argtypes = [C.c_int, C.c_int, C.c_int, P(C.c_float), P(C.c_float), C.c_int64, P(C.c_float)]
     lib.orc_bsdf_sample.argtypes = [P(abi.dr_material), P(C.c_double), C.c_int, C.c_double, C.c_double,
                                     P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int)]
+    lib.orc_bsdf_sample3.argtypes = [P(abi.dr_material), P(C.c_double), C.c_int, C.c_double, C.c_double, C.c_double,
+                                     P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int), P(C.c_double)]
     lib.orc_bsdf_eval.argtypes = [P(abi.dr_material), P(C.c_double), P(C.c_double), C.c_int, C.c_int,
                                   P(C.c_double), P(C.c_double)]
     for name in ("orc_kelemen_sample", "orc_kelemen_pdf", "orc_gaussian_sample"):

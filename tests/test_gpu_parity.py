@@ -36,6 +36,9 @@ SCENE_MAKERS = {
     "cornell": lambda: scenes.cornell_box(film=(128, 128), tess=8),
     "glossy": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3),
     "caustic": lambda: scenes.caustic_scene(film=(128, 128), grid=48),
+    # rough dielectric sphere + frosted pane: GGX with visible-normal sampling, Beckmann with sampleAll
+    "roughglass": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.15, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE)),
+    "roughglass-beckmann": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.3, 0)),
     "door": lambda: scenes.door_scene(film=(160, 90), floor_grid=64, n_spheres=16, sphere_subdiv=2),
 }
 _cache = {}
@@ -127,6 +130,12 @@ CASES = [
     ("cornell", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
     ("glossy", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=8, directSamples=-1, directSampling=False)),
     ("caustic", dict(integrator="pssmlt", technique="bdpt", maxDepth=8, directSamples=-1, directSampling=False, lightImage=False)),
+    # roughdielectric: one extra primary sample per BSDF sample (roughdielectric.cpp:555, pssmlt_utils.h:35-52)
+    ("roughglass", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("roughglass", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1)),
+    ("roughglass", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
+    ("roughglass-beckmann", dict(integrator="drmlt", type="mira", technique="mmlt", maxDepth=6, directSamples=16)),
+    ("roughglass-beckmann", dict(integrator="drmlt", type="mira", technique="path", maxDepth=6, directSamples=-1)),
     # film plugin parameters (film.cpp:30-48, perspective.cpp:126-173): crop window, and a film size other than dr_camera's
     ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1,
                      cropOffsetX=24, cropOffsetY=40, cropWidth=64, cropHeight=48)),
@@ -180,7 +189,7 @@ def test_path_contribution_replayed_u(case):
     rng = np.random.RandomState(5)
     md = cfg.max_depth
     depth = rng.randint(1, md + 1, n).astype(np.int32)
-    ds, de, dd = (50, 2, 2) if cfg.technique == abi.DR_TECH_PATH else (3 * (md + 2), 3 * (md + 2), 1)
+    ds, de, dd = (6 * (md + 2), 2, 2) if cfg.technique == abi.DR_TECH_PATH else (3 * (md + 2), 3 * (md + 2), 1)
     us, ue, ud = [rng.rand(n, k).astype(np.float32) for k in (ds, de, dd)]
     og = gpu.eval_paths(cfg, us, ue, ud, depth)
     oc, lum64 = orc.eval_paths(ocfg(cfg), us, ue, ud, depth)
@@ -219,8 +228,13 @@ def test_path_contribution_replayed_u(case):
     # ray counts: identical control flow on contributing paths; a path that dies during the sensor walk
     # skips its emitter walk on the GPU (the reference walks both before testing, pathsampler.cpp:139-159)
     rg, rc = g[:, -4:].copy().view("<i4")[:, 0], c[:, -4:].copy().view("<i4")[:, 0]
-    assert (rg[both] == rc[both]).mean() >= 0.999
-    assert (rg <= rc).mean() >= 0.999
+    # bdpt + rough dielectric: every path makes ~20 connections, and a connection through a microfacet at grazing
+    # incidence has a value that vanishes continuously ((1 - F) G -> 0) while smithG1's sign test (microfacet.h:477-482)
+    # flips on rounding noise: one shadow ray more or less in ~0.4 % of the paths, contributions equal to 1e-8
+    # (measured: 168 of 40 000 paths, +-1 ray, both directions)
+    fuzzy = cfg.technique == abi.DR_TECH_BDPT and name.startswith("roughglass")
+    assert (rg[both] == rc[both]).mean() >= (0.99 if fuzzy else 0.999)
+    assert (rg <= rc).mean() >= (0.995 if fuzzy else 0.999)
 
 
 @pytest.mark.parametrize("case", CASES, ids=_case_id)
@@ -256,6 +270,10 @@ CHAIN_CASES = [
     ("glossy", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
     ("cornell", dict(integrator="pssmlt", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
     ("cornell", dict(integrator="drmlt", type="mira", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False, timidAfterLarge=True)),
+    ("roughglass", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("roughglass", dict(integrator="drmlt", type="mira", technique="mmlt", maxDepth=6, directSamples=-1)),
+    ("roughglass-beckmann", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1)),
+    ("roughglass", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False)),
 ]
 
 
@@ -525,7 +543,7 @@ def test_job_b_and_acceptance_rates(case):
     job.close()
 
 
-@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16)])
+@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16), ("roughglass", 16), ("roughglass-beckmann", 4)])
 def test_direct_illumination_pass(name, samples):
     """the separate direct image (renderDirectComponent + the `direct` integrator) on keyed samples."""
     gpu, orc, data = pair(name)

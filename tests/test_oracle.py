@@ -396,3 +396,81 @@ def test_two_stage_render_and_crop_window(cornell):
     for i in np.nonzero(nz)[0][:200]:
         assert oc[i].pos[0][0] == pytest.approx(of[i].pos[0][0] - 16, abs=2e-3)
         assert oc[i].pos[0][1] == pytest.approx(of[i].pos[0][1] - 8, abs=2e-3)
+
+
+# ------------------------------------------------------------------ rough dielectric
+def _sample3(oracle, m, wi, mode, u1, u2, u3):
+    wo, w, pdf, ty, eta = (C.c_double * 3)(), (C.c_double * 3)(), C.c_double(), C.c_int(), C.c_double()
+    oracle.orc_bsdf_sample3(C.byref(m), (C.c_double * 3)(*wi), mode, u1, u2, u3, wo, w, C.byref(pdf), C.byref(ty), C.byref(eta))
+    return np.array(wo), np.array(w), pdf.value, ty.value, eta.value
+
+
+@pytest.mark.parametrize("name,flags,alpha", [("ggx-vis", abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE, 0.2), ("ggx-all", abi.DR_MAT_GGX, 0.2),
+                                              ("beckmann-vis", abi.DR_MAT_SAMPLE_VISIBLE, 0.3), ("beckmann-all", 0, 0.3)])
+@pytest.mark.parametrize("side", [1, -1])
+def test_rough_dielectric_sample_eval_pdf_consistency(oracle, name, flags, alpha, side):
+    """roughdielectric.cpp:270-611: sample() = eval() / pdf() for the sampled direction, in both transport modes, from
+    either side; reflection keeps the hemisphere (eta = 1), refraction changes it (eta = intIOR/extIOR or its inverse); the
+    pdf returned by sample() passed through a float (sic, :543)."""
+    mat = _mat(abi.DR_BSDF_ROUGHDIELECTRIC, flags, alpha=alpha)
+    mat.reflectance[:] = (1, 1, 1)
+    rng = np.random.RandomState(11)
+    wi = np.array([0.3, -0.2, 0.0]); wi[2] = side * math.sqrt(1 - wi[0] ** 2 - wi[1] ** 2)
+    n_r = n_t = 0
+    for mode in (0, 1):
+        for _ in range(300):
+            u1, u2, u3 = rng.rand(3)
+            wo, w, pdf, ty, eta = _sample3(oracle, mat, wi, mode, u1, u2, u3)
+            if not w.any():
+                continue
+            f, p = _eval(oracle, mat, wi, wo, mode, 1)
+            assert p == pytest.approx(pdf, rel=2e-6), name          # float rounding of temporaryPdf
+            tol = 2e-2 if name == "beckmann-vis" else 1e-5
+            assert np.allclose(f / p, w, rtol=tol, atol=1e-9), (name, mode)
+            if wo[2] * wi[2] > 0:
+                n_r += 1
+                assert ty == 0x2 and eta == 1.0
+            else:
+                n_t += 1
+                assert ty == 0x10 and eta == pytest.approx(1.5 if wi[2] > 0 else 1 / 1.5)
+    assert n_r > 10 and n_t > 200
+
+
+def test_rough_dielectric_reciprocity_and_smooth_limit(oracle):
+    """f(wi, wo) in radiance mode and f(wo, wi) in importance mode differ by the eta^2 radiance scaling only
+    (roughdielectric.cpp:339-345); for alpha -> 0 the lobe collapses onto the smooth dielectric's directions."""
+    mat = _mat(abi.DR_BSDF_ROUGHDIELECTRIC, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE, alpha=0.25)
+    rng = np.random.RandomState(2)
+    wi = np.array([0.1, 0.4, 0.0]); wi[2] = math.sqrt(1 - 0.17)
+    for _ in range(50):
+        wo, w, pdf, ty, eta = _sample3(oracle, mat, wi, 1, *rng.rand(3))
+        if not w.any():
+            continue
+        f_imp, _ = _eval(oracle, mat, wi, wo, 1, 1)           # importance transport: no eta^2 factor
+        f_rad, _ = _eval(oracle, mat, wi, wo, 0, 1)
+        if ty == 0x10:
+            assert np.allclose(f_rad, f_imp * (1 / 1.5) ** 2, rtol=1e-9)
+        else:
+            assert np.allclose(f_rad, f_imp, rtol=1e-12)
+    smooth = _mat(abi.DR_BSDF_DIELECTRIC)
+    sharp = _mat(abi.DR_BSDF_ROUGHDIELECTRIC, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE, alpha=1e-4)
+    for u3 in (0.001, 0.9):
+        wo_r, w_r, _, _, _ = _sample3(oracle, sharp, wi, 0, 0.37, 0.61, u3)
+        wo_s, w_s, _, _ = _sample(oracle, smooth, wi, 0, u3, 0.5)
+        assert np.allclose(wo_r, wo_s, atol=2e-3)
+
+
+def test_rough_dielectric_normalisation_agrees_across_techniques(oracle):
+    """With a rough dielectric in the scene (one extra primary sample per BSDF sample, non-symmetric BSDF, eta^2 radiance
+    scaling) the unidirectional, bidirectional and MMLT estimators of b still integrate the same path space."""
+    data = scenes.glossy_scene(film=(64, 64), subdiv=2, rough_glass=(0.2, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE))
+    orc = oracle_lib.OracleScene(data)
+    b, err = {}, {}
+    for name, tech in (("path", abi.DR_TECH_PATH), ("bdpt", abi.DR_TECH_BDPT), ("mmlt", abi.DR_TECH_MMLT)):
+        cfg = _cfg(technique=tech, seed=9, direct_samples=0, max_depth=6)
+        k = 6 if tech == abi.DR_TECH_MMLT else 1
+        lum, _ = orc.bootstrap(cfg, 0, 150000 * k)
+        b[name], err[name] = lum.mean() * k, lum.std() * k / math.sqrt(len(lum))
+    for a_, c_ in (("path", "bdpt"), ("mmlt", "bdpt"), ("path", "mmlt")):
+        assert abs(b[a_] - b[c_]) < 4 * math.hypot(err[a_], err[c_]), (b, err)
+    assert err["bdpt"] < 0.02 * b["bdpt"]
