@@ -161,6 +161,15 @@ def run_reference(args):
     return 0
 
 
+def scaled_traffic(traffic, stage, units_per_launch):
+    """DRAM bytes (ncu dram__bytes_read.sum + dram__bytes_write.sum) of one launch of `stage`, scaled from the captured
+    launch of profiles/traffic.json to the units (rays or paths) one launch of THIS run processes."""
+    if stage not in traffic:
+        return None
+    cap = traffic.get("paths_in_captured_launch" if stage == "k_chain" else "rays_in_captured_launch")
+    return int(traffic[stage] * units_per_launch / cap) if cap else traffic[stage]
+
+
 # ---------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     # libraries (NCCL's version banner, ...) may write to stdout; the contract is ONE JSON line there
@@ -279,7 +288,8 @@ def run_gpu(args):
     achieved = stages[dom]["achieved_gbs"] or 0.0
     step_gbs = b_mut * muts_rank / (dev_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic.get(dom), "ms_per_launch": dom_launch_ms,
+                "frac": achieved / peak, "traffic": scaled_traffic(traffic, dom, stages[dom]["units"] / max(1, stage_launches[dom])),
+                "traffic_source": traffic.get("source"), "ms_per_launch": dom_launch_ms,
                 "units_per_launch": stages[dom]["units"] / max(1, stage_launches[dom]), "bytes_per_unit": stages[dom]["bytes_per_unit"],
                 "stages": stages, "whole_step": {"bytes_per_mutation": b_mut, "achieved": step_gbs, "frac": step_gbs / peak},
                 "paths_per_mutation": paths_per_mut, "rays_per_path": rays_per_path,

@@ -42,7 +42,8 @@ for r in rows:
 sel = [l for l in launches if kern in l["name"] and l["rows"]]
 L = sel[which]
 fn = [f for f in lines if kern.split("<")[0] in f]
-fn = fn[0] if len(fn) == 1 else [f for f in fn if (("ILi%s" % kern.split("<")[1].rstrip(">")) in f or ("ILb%s" % kern.split("<")[1].rstrip(">")) in f)][0] if "<" in kern else fn[0]
+exact = [f for f in fn if ("%d%s7Machine" % (len(kern), kern)) in f]      # k_trace(Machine), not k_trace_rays(...)
+fn = exact[0] if exact else fn[0] if len(fn) == 1 else [f for f in fn if (("ILi%s" % kern.split("<")[1].rstrip(">")) in f or ("ILb%s" % kern.split("<")[1].rstrip(">")) in f)][0] if "<" in kern else fn[0]
 table = lines[fn]
 hdr = L["hdr"]
 ia, ii, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
