@@ -560,6 +560,7 @@ struct dr_job_t {
     cudaEvent_t evFork = nullptr;
     std::vector<Group> groups;
     float *bootLum = nullptr;
+    float *bootLumTarget = nullptr;             // two-stage MLT: importance-re-weighted luminances, the seed CDF is built on these
     double *cdf = nullptr, *blockSums = nullptr, *red = nullptr, *redScratch = nullptr;
     float *devImage = nullptr;
     float4 *directFilm = nullptr;               // weighted film of the separate direct-illumination pass
@@ -906,6 +907,7 @@ extern "C" dr_status dr_job_bootstrap(dr_job j, double *sumOut, double *countOut
     dr_status st;
     const long long nb = scan_blocks(per);
     if (!j->bootLum) {
+        if (j->importance && (st = job_alloc(j, &j->bootLumTarget, (size_t) per))) return st;
         if ((st = job_alloc(j, &j->bootLum, (size_t) per)) || (st = job_alloc(j, &j->cdf, (size_t) per + 1)) ||
             (st = job_alloc(j, &j->blockSums, (size_t) nb + 1)))
             return st;
@@ -916,9 +918,15 @@ extern "C" dr_status dr_job_bootstrap(dr_job j, double *sumOut, double *countOut
     JobParams job;
     memset(&job, 0, sizeof(job));
     job.type = JOB_BOOT; job.nItems = per; job.first = j->bootFirst; job.lumOut = j->bootLum;
+    job.lumTargetOut = j->bootLumTarget;
     if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters + ST_COUNT, false))) return st;
     launch_lum_reduce(j->bootLum, per, j->redScratch, j->red, j->stream);
-    launch_scan(j->bootLum, per, j->cdf, j->blockSums, j->stream);
+    // b comes from the un-weighted luminances (generateSeeds copies the luminance before normalize(importanceMap),
+    // pathsampler.cpp:899-901).  The seed CDF is built on the chains' TARGET: with an importance map that is the re-weighted
+    // luminance.  The reference seeds ~ the un-weighted luminance and lets its ~100 000-mutation work units forget the start;
+    // chains of ~64 mutations must start in their stationary distribution (seeding ~ L under a target ~ L / importance
+    // biased the cornell box by 2-14 %, measured).
+    launch_scan(j->bootLumTarget ? j->bootLumTarget : j->bootLum, per, j->cdf, j->blockSums, j->stream);
     CKL();
     j->launches += 5;
     CK(cudaEventRecord(j->ev1, j->stream));

@@ -220,6 +220,10 @@ k_chain(const __grid_constant__ Machine M) {
                 ++st[ST_PATHS];
                 if (job.type == JOB_BOOT) {
                     job.lumOut[item] = (float) r.lum;
+                    if (job.lumTargetOut) {                   // the density the chains will actually sample (importance_apply)
+                        if (cp.importance) importance_apply(M, lane, r);
+                        job.lumTargetOut[item] = (float) r.lum;
+                    }
                     ++c.mut;
                     c.pstate = ((long long) lane + (long long) c.mut * M.lm.n < job.nItems) ? PS_START : PS_IDLE;
                 } else if (job.type == JOB_EVAL) {

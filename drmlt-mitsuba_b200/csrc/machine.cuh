@@ -234,6 +234,7 @@ struct JobParams {
     long long nItems;                   // JOB_BOOT / JOB_EVAL: lane l evaluates items l, l + n, l + 2n, ...
     unsigned long long first;           // JOB_BOOT: bootstrap sample index of item 0
     float *lumOut;                      // JOB_BOOT: luminance of every item
+    float *lumTargetOut;                // JOB_BOOT, two-stage MLT: luminance after the importance re-weighting (the chains' target)
     const float *us, *ue, *ud;          // JOB_EVAL: replayed primary-sample vectors [nItems][d*]
     int ds, de, dd;
     const int *depthIn;                 // JOB_EVAL: MMLT depth per item

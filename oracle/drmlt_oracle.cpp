@@ -225,10 +225,24 @@ int orc_render(void *h, const dr_config *cfgIn, int64_t n_boot, int64_t n_chains
     double sum = 0, tok = 0;
     DiscreteDistribution seedPDF;
     std::vector<int64_t> pool;
+    // Two-stage MLT: b from the un-weighted luminances (pathsampler.cpp:899-901); the seed pool is weighted by the chains'
+    // TARGET, the importance-re-weighted luminance -- the short chains of the GPU design must start in their stationary
+    // distribution (the reference seeds ~ the un-weighted luminance and relies on ~100 000-mutation work units); mirrors dr_job_bootstrap.
+    std::vector<double> target(lum64);
+    if (cfg->importance_map && !cfg->first_stage) {
+        const int W = (int) sc.cam.resX, H = (int) sc.cam.resY;
+        SplatList list;
+        for (int64_t i = 0; i < n_boot; ++i) {
+            if (!(lum64[i] > 0)) continue;
+            bootstrapSample(sc, *cfg, (uint64_t) i, list);
+            list.normalize(cfg->importance_map, W, H);
+            target[i] = list.luminance;
+        }
+    }
     for (int64_t i = 0; i < n_boot; ++i) {
         if (std::isnan(lum64[i])) continue;
         tok += 1; sum += lum64[i];
-        if (lum64[i] != 0) { pool.push_back(i); seedPDF.append(lum64[i]); }
+        if (lum64[i] != 0 && target[i] > 0 && std::isfinite(target[i])) { pool.push_back(i); seedPDF.append(target[i]); }
     }
     double b = tok > 0 ? sum / tok : 0;
     if (cfg->technique == DR_TECH_MMLT) b *= cfg->max_depth;
