@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdrmlt_b200.so")
 
 DR_OK = 0
-DR_BSDF_DIFFUSE, DR_BSDF_DIELECTRIC, DR_BSDF_CONDUCTOR, DR_BSDF_ROUGHCONDUCTOR, DR_BSDF_ROUGHDIELECTRIC = 0, 1, 2, 3, 4
-DR_MAT_TWOSIDED, DR_MAT_GGX, DR_MAT_SAMPLE_VISIBLE = 1, 2, 4
+DR_BSDF_DIFFUSE, DR_BSDF_DIELECTRIC, DR_BSDF_CONDUCTOR, DR_BSDF_ROUGHCONDUCTOR, DR_BSDF_ROUGHDIELECTRIC, DR_BSDF_PLASTIC = 0, 1, 2, 3, 4, 5
+DR_MAT_TWOSIDED, DR_MAT_GGX, DR_MAT_SAMPLE_VISIBLE, DR_MAT_NONLINEAR = 1, 2, 4, 8
 DR_TRI_SMOOTH = 1
 DR_INTEGRATOR_PSSMLT, DR_INTEGRATOR_DRMLT = 0, 1
 DR_TECH_PATH, DR_TECH_BDPT, DR_TECH_MMLT = 0, 1, 2

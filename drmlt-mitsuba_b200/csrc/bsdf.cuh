@@ -1,7 +1,7 @@
 // bsdf.cuh -- device BSDF models in the local shading frame (z = shading normal).
 //
 // Behavioural parity targets: src/bsdfs/diffuse.cpp:109-150, dielectric.cpp:227-330,
-// conductor.cpp:223-285, roughconductor.cpp:258-417, roughdielectric.cpp:270-611 with src/bsdfs/microfacet.h (Beckmann/GGX,
+// conductor.cpp:223-285, roughconductor.cpp:258-417, roughdielectric.cpp:270-611, plastic.cpp:240-420 with src/bsdfs/microfacet.h (Beckmann/GGX,
 // isotropic, sampleAll and sampleVisible), wrapped by twosided.cpp:107-186 when DR_MAT_TWOSIDED.
 // Branching is on the material type (a small enum) -- no virtual dispatch.
 #pragma once
@@ -28,7 +28,7 @@ DR_D Mat load_material(const DevScene &sc, int id) {
     m.alpha = d.z;
     return m;
 }
-DR_D bool mat_has_smooth(int type) { return type == DR_BSDF_DIFFUSE || type == DR_BSDF_ROUGHCONDUCTOR || type == DR_BSDF_ROUGHDIELECTRIC; }
+DR_D bool mat_has_smooth(int type) { return type == DR_BSDF_DIFFUSE || type == DR_BSDF_ROUGHCONDUCTOR || type == DR_BSDF_ROUGHDIELECTRIC || type == DR_BSDF_PLASTIC; }
 DR_D bool mat_non_symmetric(int type) { return type == DR_BSDF_DIELECTRIC || type == DR_BSDF_ROUGHDIELECTRIC; }
 DR_D bool mat_transmissive_or_backside(const Mat &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }
 // BSDF::EUsesSampler: sample() draws one more number from the vertex's sampler (roughdielectric.cpp:464, 555)
@@ -230,6 +230,20 @@ struct Microfacet {
 
 DR_D R3 reflect_z(R3 wi) { return r3(-wi.x, -wi.y, wi.z); }
 
+// ---- smooth plastic (plastic.cpp): m.refl = diffuseReflectance, m.trans = specularReflectance, m.eta.x = eta; the library
+// derives m.k.x = m_fdrInt (fresnelDiffuseReflectance(1 / eta), util.cpp:822-867) and m.k.y = m_specularSamplingWeight
+// (plastic.cpp:196-203) when the scene is created.
+DR_D Real plastic_prob_specular(const Mat &m, Real Fi) {            // plastic.cpp:291-295
+    const Real w = m.k.y;
+    return (Fi * w) / (Fi * w + (1. - Fi) * (1. - w));
+}
+DR_D R3 plastic_diffuse(const Mat &m) {                             // :266-271
+    R3 diff = m.refl;
+    if (m.flags & DR_MAT_NONLINEAR) { diff.x /= 1. - diff.x * m.k.x; diff.y /= 1. - diff.y * m.k.x; diff.z /= 1. - diff.z * m.k.x; }
+    else diff = diff / (1. - m.k.x);
+    return diff;
+}
+
 // ---- nested (one-sided) evaluation
 DR_D R3 bsdf_eval_nested(const Mat &m, R3 wi, R3 wo, int mode, int measure) {
     switch (m.type) {
@@ -248,6 +262,18 @@ DR_D R3 bsdf_eval_nested(const Mat &m, R3 wi, R3 wo, int mode, int measure) {
         const R3 F = fresnel_conductor(dot(wi, H), m.eta, m.k) * m.refl;
         const Real G = distr.G(wi, wo, H);
         return F * (D * G / (4.0 * wi.z));
+    }
+    case DR_BSDF_PLASTIC: {                                          // plastic.cpp:240-277
+        if (wo.z <= 0. || wi.z <= 0.) return r3(0.);
+        Real cosThetaT;
+        const Real Fi = fresnel_dielectric_ext(wi.z, cosThetaT, m.eta.x);
+        if (measure == MEAS_DISCRETE) {
+            if (fabs(dot(reflect_z(wi), wo) - 1.) < R_DELTA_EPS) return m.trans * Fi;
+        } else if (measure == MEAS_SOLID_ANGLE) {
+            const Real Fo = fresnel_dielectric_ext(wo.z, cosThetaT, m.eta.x);
+            return plastic_diffuse(m) * (R_INV_PI * wo.z * (1. / (m.eta.x * m.eta.x)) * (1. - Fi) * (1. - Fo));
+        }
+        return r3(0.);
     }
     case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:270-348
         if (measure != MEAS_SOLID_ANGLE || wi.z == 0.) return r3(0.);
@@ -304,6 +330,15 @@ DR_D Real bsdf_pdf_nested(const Mat &m, R3 wi, R3 wo, int measure) {
         if (distr.visible) return distr.eval(H) * distr.smithG1(wi, H) / (4.0 * wi.z);
         return distr.pdf(wi, H) / (4. * absdot(wo, H));
     }
+    case DR_BSDF_PLASTIC: {                                          // plastic.cpp:279-307
+        if (wo.z <= 0. || wi.z <= 0.) return 0.;
+        Real cosThetaT;
+        const Real probSpecular = plastic_prob_specular(m, fresnel_dielectric_ext(wi.z, cosThetaT, m.eta.x));
+        if (measure == MEAS_DISCRETE) {
+            if (fabs(dot(reflect_z(wi), wo) - 1.) < R_DELTA_EPS) return probSpecular;
+        } else if (measure == MEAS_SOLID_ANGLE) return R_INV_PI * wo.z * (1. - probSpecular);
+        return 0.;
+    }
     case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:350-420 (both components enabled)
         if (measure != MEAS_SOLID_ANGLE) return 0.;
         const Real mEta = m.eta.x, mInvEta = 1. / mEta;
@@ -352,6 +387,24 @@ struct BsdfSample { R3 wo; R3 weight; Real pdf; int sampledType; Real eta; };
 DR_D void bsdf_sample_nested(const Mat &m, R3 wi, int mode, Real sx, Real sy, Real sz, Real epsilon, BsdfSample &r) {
     r.weight = r3(0.); r.pdf = 0.; r.sampledType = 0; r.eta = 1.; r.wo = r3(0., 0., 1.);
     switch (m.type) {
+    case DR_BSDF_PLASTIC: {                                          // plastic.cpp:368-412
+        if (wi.z <= 0.) return;
+        Real cosThetaT;
+        const Real Fi = fresnel_dielectric_ext(wi.z, cosThetaT, m.eta.x);
+        const Real probSpecular = plastic_prob_specular(m, Fi);
+        r.eta = 1.;
+        if (sx < probSpecular) {
+            r.sampledType = BT_DELTA_R; r.wo = reflect_z(wi); r.pdf = probSpecular;
+            r.weight = m.trans * (Fi / probSpecular);
+        } else {
+            r.sampledType = BT_DIFFUSE_R;
+            r.wo = square_to_cosine_hemisphere((sx - probSpecular) / (1. - probSpecular), sy);
+            const Real Fo = fresnel_dielectric_ext(r.wo.z, cosThetaT, m.eta.x);
+            r.pdf = (1. - probSpecular) * (R_INV_PI * r.wo.z);
+            r.weight = plastic_diffuse(m) * ((1. / (m.eta.x * m.eta.x)) * (1. - Fi) * (1. - Fo) / (1. - probSpecular));
+        }
+        return;
+    }
     case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:514-611 (both components enabled)
         const Real mEta = m.eta.x, mInvEta = 1. / mEta;
         Microfacet distr(m);

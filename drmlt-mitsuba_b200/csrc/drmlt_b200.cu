@@ -271,6 +271,28 @@ static dr_status upload(SceneImpl *s, const std::vector<T> &v, const T **devOut)
 
 static float as_float_bits(int i) { float f; memcpy(&f, &i, 4); return f; }
 
+// fresnelDiffuseReflectance(eta, fast = false) (src/libcore/util.cpp:815-867): integral of the unpolarised Fresnel
+// reflectance F(sqrt(xi), eta) over xi in [0, 1].  The reference integrates with an adaptive Gauss-Lobatto rule to a relative
+// error of 1e-5; here: xi = x^2, composite Simpson in x (the integrand's kink at the critical angle is resolved by the 2^16
+// intervals), error < 1e-8.
+static double fresnel_dielectric_host(double cosThetaI, double eta) {        // util.cpp:659-693
+    if (eta == 1.0) return 0.0;
+    const double scale = cosThetaI > 0 ? 1.0 / eta : eta;
+    const double cosThetaTSqr = 1.0 - (1.0 - cosThetaI * cosThetaI) * (scale * scale);
+    if (cosThetaTSqr <= 0.0) return 1.0;
+    const double ci = std::fabs(cosThetaI), ct = std::sqrt(cosThetaTSqr);
+    const double Rs = (ci - eta * ct) / (ci + eta * ct), Rp = (eta * ci - ct) / (eta * ci + ct);
+    return 0.5 * (Rs * Rs + Rp * Rp);
+}
+static double fresnel_diffuse_reflectance(double eta) {
+    const int n = 1 << 16;
+    const double h = 1.0 / n;
+    auto f = [&](double x) { return fresnel_dielectric_host(x, eta) * 2.0 * x; };
+    double s = f(0.0) + f(1.0);
+    for (int i = 1; i < n; ++i) s += f(i * h) * ((i & 1) ? 4.0 : 2.0);
+    return s * h / 3.0;
+}
+
 extern "C" void dr_scene_destroy(dr_scene scene) {
     if (!scene) return;
     SceneImpl *s = static_cast<SceneImpl *>(scene);
@@ -298,7 +320,7 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
             if (d->indices[3 * (size_t) i + v] >= d->n_vertices) { dr_set_error("triangle %u: vertex index out of range", i); return DR_ERR_INVALID_ARG; }
     }
     for (uint32_t m = 0; m < d->n_materials; ++m)
-        if (d->materials[m].type < DR_BSDF_DIFFUSE || d->materials[m].type > DR_BSDF_ROUGHDIELECTRIC) {
+        if (d->materials[m].type < DR_BSDF_DIFFUSE || d->materials[m].type > DR_BSDF_PLASTIC) {
             dr_set_error("material %u: unsupported BSDF type %d", m, d->materials[m].type); return DR_ERR_UNSUPPORTED;
         }
     for (uint32_t e = 0; e < d->n_emitters; ++e) {
@@ -409,6 +431,14 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     std::vector<DevMaterial> mats(d->n_materials);
     static_assert(sizeof(DevMaterial) == sizeof(dr_material), "material layout");
     memcpy(mats.data(), d->materials, sizeof(dr_material) * d->n_materials);
+    for (DevMaterial &m : mats)
+        if (m.type == DR_BSDF_PLASTIC) {                    // SmoothPlastic::configure (plastic.cpp:188-205)
+            m.k[0] = (float) fresnel_diffuse_reflectance(1.0 / (double) m.eta[0]);
+            const double Y[3] = { 0.212671, 0.715160, 0.072169 };
+            double dAvg = 0, sAvg = 0;
+            for (int c = 0; c < 3; ++c) { dAvg += Y[c] * m.reflectance[c]; sAvg += Y[c] * m.transmittance[c]; }
+            m.k[1] = (float) (sAvg / (dAvg + sAvg));
+        }
 
     DevScene &ds = s->dev;
     memset(&ds, 0, sizeof(ds));

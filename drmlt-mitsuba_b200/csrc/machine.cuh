@@ -170,8 +170,8 @@ template <class T> DR_D void rec_store(T *dst, const T &src) {
 // Q_RAYC / Q_RAYS / Q_CHAIN are double-buffered by round parity: kernels of round r consume [r & 1] and
 // produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT, Q_PT and
 // Q_BEGIN are produced and consumed inside one round.
-enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 5 */, Q_CONNECT = 11, Q_PT = 12,
-       Q_BEGIN = 13 /* + BEGIN_* class, 3 */, Q_COUNT = 16 };
+enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 6 */, Q_CONNECT = 12, Q_PT = 13,
+       Q_BEGIN = 14 /* + BEGIN_* class, 3 */, Q_COUNT = 17 };
 // classes of "start the next path" work: each runs one kind of proposal arithmetic on full warps
 enum { BEGIN_STAGE1 = 0, BEGIN_STAGE2 = 1, BEGIN_OTHER = 2 };
 struct RayF { float4 a, b; };                               // (o, tmin), (d, tmax): float32 cast of a ray, for the traversal

@@ -174,15 +174,21 @@ def _room(s, white, red, green, tess, light_half=0.25, radiance=(15.0, 15.0, 15.
     s.add_quad((-h, 0.995, -h), (h, 0.995, -h), (h, 0.995, h), (-h, 0.995, h), light_mat, radiance=radiance)   # faces -y
 
 
-def cornell_box(film=(256, 256), tess=8):
-    """C1 / C2: Cornell box, area light, one-sided diffuse walls, ~1k triangles."""
-    s = SceneData("cornell", film)
+def cornell_box(film=(256, 256), tess=8, plastic=False):
+    """C1 / C2: Cornell box, area light, one-sided diffuse walls, ~1k triangles.
+    plastic=True: the two boxes are `plastic` (one linear, one nonlinear + twosided)."""
+    s = SceneData("cornell-plastic" if plastic else "cornell", film)
     white = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.73, 0.73, 0.73))
     red = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.63, 0.065, 0.05))
     green = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.14, 0.45, 0.091))
     _room(s, white, red, green, tess)
-    s.add_box((0.33, -0.7, 0.35), (0.3, 0.3, 0.3), -17.0, white, tess=4)
-    s.add_box((-0.33, -0.4, -0.3), (0.3, 0.6, 0.3), 17.0, white, tess=4)
+    box1 = box2 = white
+    if plastic:       # reflectance = diffuseReflectance, transmittance = specularReflectance (include/drmlt_b200.h)
+        box1 = s.add_material(abi.DR_BSDF_PLASTIC, reflectance=(0.1, 0.27, 0.36), transmittance=(1, 1, 1), eta=(1.49, 0, 0))
+        box2 = s.add_material(abi.DR_BSDF_PLASTIC, flags=abi.DR_MAT_NONLINEAR | abi.DR_MAT_TWOSIDED, reflectance=(0.6, 0.5, 0.2),
+                              transmittance=(0.9, 0.9, 1.0), eta=(1.9, 0, 0))
+    s.add_box((0.33, -0.7, 0.35), (0.3, 0.3, 0.3), -17.0, box1, tess=4)
+    s.add_box((-0.33, -0.4, -0.3), (0.3, 0.6, 0.3), 17.0, box2, tess=4)
     s.set_camera((0, 0, 3.9), (0, 0, 0), (0, 1, 0), 39.0)
     return s
 

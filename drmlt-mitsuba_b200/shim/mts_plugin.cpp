@@ -118,6 +118,16 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why) {
             size_t v = str.find("sampleVisible = ", from);
             if (v != std::string::npos && str[v + 16] == '1') m.flags |= DR_MAT_SAMPLE_VISIBLE;
         }
+    } else if (model == "SmoothPlastic") {                // src/bsdfs/plastic.cpp (toString :479-493)
+        m.type = DR_BSDF_PLASTIC;
+        float eta = 0.f;
+        if (!ts.scalar("eta", from, eta)) { why = "cannot parse plastic eta"; return false; }
+        m.eta[0] = eta;                                   // intIOR / extIOR
+        m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 0.5f;                  // diffuseReflectance default (plastic.cpp:160)
+        if (!ts.spectrum("diffuseReflectance", from, m.reflectance)) { why = "textured plastic diffuseReflectance"; return false; }
+        ts.spectrum("specularReflectance", from, m.transmittance);                      // dr_material: transmittance = specularReflectance
+        size_t nl = str.find("nonlinear = ", from);
+        if (nl != std::string::npos && str[nl + 12] == '1') m.flags |= DR_MAT_NONLINEAR;
     } else if (model == "RoughDielectric") {              // src/bsdfs/roughdielectric.cpp (toString :659-672)
         if (nested) { why = "twosided rough dielectric"; return false; }
         m.type = DR_BSDF_ROUGHDIELECTRIC;

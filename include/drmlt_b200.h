@@ -43,20 +43,22 @@ typedef enum dr_bsdf_type {
     DR_BSDF_DIELECTRIC = 1,     /* src/bsdfs/dielectric.cpp:227-400 */
     DR_BSDF_CONDUCTOR = 2,      /* src/bsdfs/conductor.cpp:223-285 */
     DR_BSDF_ROUGHCONDUCTOR = 3, /* src/bsdfs/roughconductor.cpp:250-412 */
-    DR_BSDF_ROUGHDIELECTRIC = 4 /* src/bsdfs/roughdielectric.cpp:270-611 (isotropic alpha; uses one extra primary sample per BSDF sample) */
+    DR_BSDF_ROUGHDIELECTRIC = 4,/* src/bsdfs/roughdielectric.cpp:270-611 (isotropic alpha; uses one extra primary sample per BSDF sample) */
+    DR_BSDF_PLASTIC = 5         /* src/bsdfs/plastic.cpp:240-420: delta specular coating over a diffuse base */
 } dr_bsdf_type;
 
 #define DR_MAT_TWOSIDED       1u  /* wrapped in <bsdf type="twosided"> (src/bsdfs/twosided.cpp) */
 #define DR_MAT_GGX            2u  /* roughconductor / roughdielectric distribution=ggx (else beckmann) */
 #define DR_MAT_SAMPLE_VISIBLE 4u  /* roughconductor / roughdielectric sampleVisible=true */
+#define DR_MAT_NONLINEAR      8u  /* plastic nonlinear=true (plastic.cpp:162, 268-271) */
 
 typedef struct dr_material {
     int32_t  type;              /* dr_bsdf_type */
     uint32_t flags;             /* DR_MAT_* */
-    float    reflectance[3];    /* diffuse reflectance | specularReflectance */
-    float    transmittance[3];  /* dielectric specularTransmittance */
-    float    eta[3];            /* conductor eta (RGB) | dielectric, roughdielectric: intIOR/extIOR in eta[0] */
-    float    k[3];              /* conductor k (RGB) */
+    float    reflectance[3];    /* diffuse reflectance | specularReflectance | plastic: diffuseReflectance */
+    float    transmittance[3];  /* dielectric specularTransmittance | plastic: specularReflectance */
+    float    eta[3];            /* conductor eta (RGB) | dielectric, roughdielectric, plastic: intIOR/extIOR in eta[0] */
+    float    k[3];              /* conductor k (RGB) (plastic: ignored; the library derives its constants here) */
     float    alpha;             /* roughconductor / roughdielectric alpha (isotropic) */
     float    _pad;
 } dr_material;                  /* 64 bytes */

@@ -313,6 +313,7 @@ int orc_splat(int w, int h, int rfilter, const float *pos, const float *rgb, int
 void orc_bsdf_sample(const dr_material *m, const double *wi, int mode, double u1, double u2, double *wo, double *weight, double *pdf, int *sampledType) {
     BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), mode);
     Float p = 0;
+    dr_material mm = *m; detail::preparePlastic(mm); m = &mm;
     RGB w = bsdfSample(*m, b, p, Vec2(u1, u2), 1e-7);
     wo[0] = b.wo.x; wo[1] = b.wo.y; wo[2] = b.wo.z;
     weight[0] = w.r; weight[1] = w.g; weight[2] = w.b;
@@ -329,6 +330,7 @@ void orc_bsdf_sample3(const dr_material *m, const double *wi, int mode, double u
 }
 void orc_bsdf_eval(const dr_material *m, const double *wi, const double *wo, int mode, int measure, double *value, double *pdf) {
     BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), Vec3(wo[0], wo[1], wo[2]), mode);
+    dr_material mm = *m; detail::preparePlastic(mm); m = &mm;
     RGB v = bsdfEval(*m, b, measure);
     value[0] = v.r; value[1] = v.g; value[2] = v.b;
     *pdf = bsdfPdf(*m, b, measure);

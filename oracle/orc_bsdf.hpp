@@ -30,7 +30,7 @@ struct BSDFRecord {
 
 inline RGB rgb3(const float *v) { return RGB(v[0], v[1], v[2]); }
 
-inline bool bsdfHasSmooth(const dr_material &m) { return m.type == DR_BSDF_DIFFUSE || m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC; }
+inline bool bsdfHasSmooth(const dr_material &m) { return m.type == DR_BSDF_DIFFUSE || m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC || m.type == DR_BSDF_PLASTIC; }
 inline bool bsdfNonSymmetric(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC; }   // dielectric.cpp:201, roughdielectric.cpp:253
 // BSDF::EUsesSampler: sample() draws one more number from the vertex's sampler (roughdielectric.cpp:464, 555)
 inline bool bsdfUsesSampler(const dr_material &m) { return m.type == DR_BSDF_ROUGHDIELECTRIC; }
@@ -203,6 +203,42 @@ namespace detail {
 inline Vec3 reflectZ(const Vec3 &wi) { return Vec3(-wi.x, -wi.y, wi.z); }
 inline Vec3 reflectM(const Vec3 &wi, const Vec3 &m) { return m * (2 * dot(wi, m)) - wi; }
 
+// ---------------------------------------------------------------- smooth plastic (plastic.cpp)
+// fresnelDiffuseReflectance(eta, fast = false) (util.cpp:815-867): integral over xi in [0,1] of F(sqrt(xi), eta); the
+// reference uses an adaptive Gauss-Lobatto rule (relative error 1e-5), here composite Simpson in x = sqrt(xi).
+inline Float fresnelDiffuseReflectance(Float eta) {
+    const int n = 1 << 16;
+    const Float h = 1.0 / n;
+    auto f = [&](Float x) { Float ct; return fresnelDielectricExt(x, ct, eta) * 2.0 * x; };
+    Float s = f(0.0) + f(1.0);
+    for (int i = 1; i < n; ++i) s += f(i * h) * ((i & 1) ? 4.0 : 2.0);
+    return s * h / 3.0;
+}
+// SmoothPlastic::configure (plastic.cpp:188-205): m_fdrInt -> k[0], m_specularSamplingWeight -> k[1]
+inline void preparePlastic(dr_material &m) {
+    if (m.type != DR_BSDF_PLASTIC) return;
+    m.k[0] = (float) fresnelDiffuseReflectance(1.0 / (Float) m.eta[0]);
+    Float dAvg = rgb3(m.reflectance).luminance(), sAvg = rgb3(m.transmittance).luminance();
+    m.k[1] = (float) (sAvg / (dAvg + sAvg));
+}
+struct Plastic {       // SmoothPlastic::configure (plastic.cpp:188-205); dr_material: reflectance = diffuse, transmittance = specular
+    Float eta, invEta2, fdrInt, specularSamplingWeight;
+    RGB diffuse, specular;
+    bool nonlinear;
+    explicit Plastic(const dr_material &m) {
+        eta = m.eta[0]; invEta2 = 1 / (eta * eta);
+        // derived once per material by preparePlastic (below), stored as floats like the library's device copy
+        fdrInt = m.k[0]; specularSamplingWeight = m.k[1];
+        diffuse = rgb3(m.reflectance); specular = rgb3(m.transmittance);
+        nonlinear = (m.flags & DR_MAT_NONLINEAR) != 0;
+    }
+    Float probSpecular(Float Fi) const { return (Fi * specularSamplingWeight) / (Fi * specularSamplingWeight + (1 - Fi) * (1 - specularSamplingWeight)); }
+    RGB diff() const {
+        if (nonlinear) return RGB(diffuse.r / (1 - diffuse.r * fdrInt), diffuse.g / (1 - diffuse.g * fdrInt), diffuse.b / (1 - diffuse.b * fdrInt));
+        return diffuse * (1.0 / (1 - fdrInt)) ;
+    }
+};
+
 inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
     switch (m.type) {
     case DR_BSDF_DIFFUSE:   // diffuse.cpp:109-117
@@ -222,6 +258,19 @@ inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
         const Float G = distr.G(b.wi, b.wo, H);
         Float model = D * G / (4.0 * Frame::cosTheta(b.wi));
         return F * model;
+    }
+    case DR_BSDF_PLASTIC: {   // plastic.cpp:240-277
+        if (Frame::cosTheta(b.wo) <= 0 || Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
+        Plastic p(m);
+        Float ct;
+        Float Fi = fresnelDielectricExt(Frame::cosTheta(b.wi), ct, p.eta);
+        if (measure == EDiscrete) {
+            if (std::abs(dot(reflectZ(b.wi), b.wo) - 1) < DELTA_EPSILON) return p.specular * Fi;
+        } else if (measure == ESolidAngle) {
+            Float Fo = fresnelDielectricExt(Frame::cosTheta(b.wo), ct, p.eta);
+            return p.diff() * (squareToCosineHemispherePdf(b.wo) * p.invEta2 * (1 - Fi) * (1 - Fo));
+        }
+        return RGB(0.0);
     }
     case DR_BSDF_ROUGHDIELECTRIC: {   // roughdielectric.cpp:270-348
         if (measure != ESolidAngle || Frame::cosTheta(b.wi) == 0) return RGB(0.0);
@@ -285,6 +334,16 @@ inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
         else
             return distr.pdf(b.wi, H) / (4 * absDot(b.wo, H));
     }
+    case DR_BSDF_PLASTIC: {   // plastic.cpp:279-307
+        if (Frame::cosTheta(b.wo) <= 0 || Frame::cosTheta(b.wi) <= 0) return 0.0;
+        Plastic p(m);
+        Float ct;
+        Float probSpecular = p.probSpecular(fresnelDielectricExt(Frame::cosTheta(b.wi), ct, p.eta));
+        if (measure == EDiscrete) {
+            if (std::abs(dot(reflectZ(b.wi), b.wo) - 1) < DELTA_EPSILON) return probSpecular;
+        } else if (measure == ESolidAngle) return squareToCosineHemispherePdf(b.wo) * (1 - probSpecular);
+        return 0.0;
+    }
     case DR_BSDF_ROUGHDIELECTRIC: {   // roughdielectric.cpp:350-420 (both components enabled)
         if (measure != ESolidAngle) return 0.0;
         const Float mEta = m.eta[0], mInvEta = 1 / mEta;
@@ -330,6 +389,24 @@ inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
 // `extra`: the number sample() draws from bRec.sampler (EUsesSampler BSDFs; roughdielectric.cpp:555)
 inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const Vec2 &sample, Float epsilon, Float extra) {
     switch (m.type) {
+    case DR_BSDF_PLASTIC: {   // plastic.cpp:368-412 (both components enabled)
+        if (Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
+        Plastic p(m);
+        Float ct;
+        Float Fi = fresnelDielectricExt(Frame::cosTheta(b.wi), ct, p.eta);
+        Float probSpecular = p.probSpecular(Fi);
+        b.eta = 1.0;
+        if (sample.x < probSpecular) {
+            b.sampledType = EDeltaReflection; b.wo = reflectZ(b.wi); pdf = probSpecular;
+            return p.specular * (Fi / probSpecular);
+        } else {
+            b.sampledType = EDiffuseReflection;
+            b.wo = squareToCosineHemisphere(Vec2((sample.x - probSpecular) / (1 - probSpecular), sample.y));
+            Float Fo = fresnelDielectricExt(Frame::cosTheta(b.wo), ct, p.eta);
+            pdf = (1 - probSpecular) * squareToCosineHemispherePdf(b.wo);
+            return p.diff() * (p.invEta2 * (1 - Fi) * (1 - Fo) / (1 - probSpecular));
+        }
+    }
     case DR_BSDF_ROUGHDIELECTRIC: {   // roughdielectric.cpp:514-611 (both components enabled)
         const Float mEta = m.eta[0], mInvEta = 1 / mEta;
         Microfacet distr(m);

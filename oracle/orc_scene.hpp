@@ -151,6 +151,8 @@ struct EmitterRec {
     RGB power() const { return radiance * (PI * area); }   // area.cpp:205
 };
 
+namespace detail { inline void preparePlastic(dr_material &m); }   // orc_bsdf.hpp: constants SmoothPlastic::configure derives
+
 struct Scene {
     std::vector<Vec3> P, N;
     std::vector<uint32_t> idx, triMat, triFlags;
@@ -230,6 +232,7 @@ inline void Scene::load(const dr_scene_desc &d) {
     if (d.tri_flags) triFlags.assign(d.tri_flags, d.tri_flags + d.n_triangles);
     else triFlags.assign(d.n_triangles, 0);
     mats.assign(d.materials, d.materials + d.n_materials);
+    for (dr_material &m : mats) detail::preparePlastic(m);
     for (uint32_t i = 0; i < d.n_triangles; ++i) hasRoughDielectric |= mats[d.tri_material[i]].type == DR_BSDF_ROUGHDIELECTRIC;
     emitters.resize(d.n_emitters);
     emitterPDF.clear();

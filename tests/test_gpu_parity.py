@@ -39,6 +39,7 @@ SCENE_MAKERS = {
     # rough dielectric sphere + frosted pane: GGX with visible-normal sampling, Beckmann with sampleAll
     "roughglass": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.15, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE)),
     "roughglass-beckmann": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.3, 0)),
+    "plastic": lambda: scenes.cornell_box(film=(128, 128), tess=8, plastic=True),
     "door": lambda: scenes.door_scene(film=(160, 90), floor_grid=64, n_spheres=16, sphere_subdiv=2),
 }
 _cache = {}
@@ -136,6 +137,10 @@ CASES = [
     ("roughglass", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
     ("roughglass-beckmann", dict(integrator="drmlt", type="mira", technique="mmlt", maxDepth=6, directSamples=16)),
     ("roughglass-beckmann", dict(integrator="drmlt", type="mira", technique="path", maxDepth=6, directSamples=-1)),
+    # plastic: delta coating + diffuse base in one BSDF (plastic.cpp:240-420)
+    ("plastic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("plastic", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=16)),
+    ("plastic", dict(integrator="drmlt", type="mira", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
     # film plugin parameters (film.cpp:30-48, perspective.cpp:126-173): crop window, and a film size other than dr_camera's
     ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1,
                      cropOffsetX=24, cropOffsetY=40, cropWidth=64, cropHeight=48)),
@@ -274,6 +279,9 @@ CHAIN_CASES = [
     ("roughglass", dict(integrator="drmlt", type="mira", technique="mmlt", maxDepth=6, directSamples=-1)),
     ("roughglass-beckmann", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=-1)),
     ("roughglass", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False)),
+    ("plastic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("plastic", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1)),
+    ("plastic", dict(integrator="pssmlt", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False)),
 ]
 
 
@@ -552,7 +560,7 @@ def test_job_b_and_acceptance_rates(case):
     job.close()
 
 
-@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16), ("roughglass", 16), ("roughglass-beckmann", 4)])
+@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16), ("roughglass", 16), ("roughglass-beckmann", 4), ("plastic", 16)])
 def test_direct_illumination_pass(name, samples):
     """the separate direct image (renderDirectComponent + the `direct` integrator) on keyed samples."""
     gpu, orc, data = pair(name)

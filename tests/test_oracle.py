@@ -474,3 +474,68 @@ def test_rough_dielectric_normalisation_agrees_across_techniques(oracle):
     for a_, c_ in (("path", "bdpt"), ("mmlt", "bdpt"), ("path", "mmlt")):
         assert abs(b[a_] - b[c_]) < 4 * math.hypot(err[a_], err[c_]), (b, err)
     assert err["bdpt"] < 0.02 * b["bdpt"]
+
+
+# ------------------------------------------------------------------ smooth plastic
+def _plastic(flags=0):
+    m = _mat(abi.DR_BSDF_PLASTIC, flags)
+    m.reflectance[:] = (0.5, 0.3, 0.2)        # diffuseReflectance
+    m.transmittance[:] = (1.0, 0.9, 0.8)      # specularReflectance
+    m.eta[:] = (1.49, 0, 0)
+    return m
+
+
+@pytest.mark.parametrize("flags", [0, abi.DR_MAT_NONLINEAR, abi.DR_MAT_TWOSIDED])
+def test_plastic_components_and_consistency(oracle, flags):
+    """plastic.cpp:240-412: a delta specular coating (discrete measure) over a diffuse base (solid angle); sample() = eval() /
+    pdf() in the measure of the sampled component; the specular lobe is picked with the Fresnel-weighted probability."""
+    mat = _plastic(flags)
+    rng = np.random.RandomState(4)
+    wi = np.array([0.5, -0.3, 0.0]); wi[2] = math.sqrt(1 - 0.34)
+    n_s = n_d = 0
+    for _ in range(600):
+        u1, u2 = rng.rand(2)
+        wo, w, pdf, ty = _sample(oracle, mat, wi, 0, u1, u2)
+        assert w.any() and pdf > 0
+        measure = 4 if ty == 0x4 else 1
+        f, p = _eval(oracle, mat, wi, wo, 0, measure)
+        assert p == pytest.approx(pdf, rel=1e-9)
+        assert np.allclose(f / p, w, rtol=1e-9)
+        other, _ = _eval(oracle, mat, wi, wo, 0, 1 if measure == 4 else 4)
+        if ty == 0x4:
+            n_s += 1
+            assert np.allclose(wo, [-wi[0], -wi[1], wi[2]])
+        else:
+            n_d += 1
+            assert ty == 0x1 and wo[2] > 0
+            if np.dot(wo, [-wi[0], -wi[1], wi[2]]) < 0.99:             # (the delta test tolerates DeltaEpsilon = 1e-3, plastic.cpp:261)
+                assert not other.any()                               # a generic direction has no specular component
+    # specular sampling probability: Fi w / (Fi w + (1 - Fi)(1 - w)) (plastic.cpp:291-295)
+    _, p_spec = _eval(oracle, mat, wi, [-wi[0], -wi[1], wi[2]], 0, 4)
+    assert n_s / 600 == pytest.approx(p_spec, abs=0.06)
+    assert n_s > 10 and n_d > 300
+    below = np.array([0.5, -0.3, -wi[2]])
+    if not flags & abi.DR_MAT_TWOSIDED:
+        assert not _sample(oracle, mat, below, 0, 0.3, 0.3)[1].any()  # one-sided
+    else:
+        assert _sample(oracle, mat, below, 0, 0.3, 0.3)[1].any()
+
+
+def test_plastic_energy_and_fresnel_diffuse_reflectance(oracle):
+    """The diffuse base is normalised by 1 / (1 - fdrInt) with fdrInt = fresnelDiffuseReflectance(1 / eta)
+    (util.cpp:822-867, approx. 0.6 for eta 1.5): a white base under a white coating reflects (almost) all light."""
+    m = _plastic()
+    m.reflectance[:] = (1, 1, 1); m.transmittance[:] = (1, 1, 1)
+    rng = np.random.RandomState(6)
+    wi = np.array([0.0, 0.0, 1.0])
+    tot = np.zeros(3)
+    n = 4000
+    for _ in range(n):
+        _, w, _, _ = _sample(oracle, m, wi, 0, *rng.rand(2))
+        tot += w
+    assert np.all(np.abs(tot / n - 1.0) < 0.03)
+    # fdrInt through the diffuse value at normal incidence: f = diff / (1 - fdr) * cos/pi / eta^2 * (1 - F)^2
+    F0 = ((1.49 - 1) / (1.49 + 1)) ** 2
+    f, _ = _eval(oracle, m, wi, [0, 0, 1.0], 0, 1)
+    fdr = 1 - (1 / math.pi) / 1.49 ** 2 * (1 - F0) ** 2 / f[0]
+    assert fdr == pytest.approx(0.5925, abs=3e-3)

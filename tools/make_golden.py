@@ -41,6 +41,9 @@ CASES = [
     ("roughglass_pssmlt_path_crop", lambda: scenes.glossy_scene(film=(64, 64), subdiv=2, rough_glass=(0.3, 0)),
      dict(integrator=abi.DR_INTEGRATOR_PSSMLT, technique=abi.DR_TECH_PATH, max_depth=6, direct_samples=-1,
           film_width=96, film_height=64, crop_offset_x=16, crop_offset_y=8, crop_width=64, crop_height=48), (48, 2, 2)),
+    ("plastic_drmlt_orbital_mmlt", lambda: scenes.cornell_box(film=(64, 64), tess=4, plastic=True),
+     dict(integrator=abi.DR_INTEGRATOR_DRMLT, type=abi.DR_TYPE_ORBITAL, technique=abi.DR_TECH_MMLT, max_depth=6, direct_samples=-1, direct_sampling=0,
+          kelemen_style_weights=0), (24, 24, 1)),
 ]
 N_PATHS, N_BOOT, N_CHAINS, N_STEPS = 640, 3000, 6, 24
 
