@@ -137,3 +137,63 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
         n[3] = make_float4(as_float(code[0]), as_float(code[1]), 0.f, 0.f);
     }
 }
+
+// ------------------------------------------------------------------ BVH2 -> BVH4
+// Collapse: the children of a 4-wide node are the grandchildren of the binary node, expanding the inner child of largest
+// surface area first (three quarters of the binary nodes disappear; a ray does half as many dependent node fetches).
+// 128-byte node = 8 x float4, structure of arrays over the four children:
+//   lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] child[4] (int bits: >= 0 inner node, < 0 leaf code, DR_NO_CHILD empty) -
+void collapse_bvh4(BuiltBVH &bvh) {
+    const std::vector<float4> n2 = bvh.nodes;
+    std::vector<float4> n4;
+    struct Child { float lo[3], hi[3]; int code; };
+    auto children2 = [&](int node, Child out[2]) {
+        const float4 *n = &n2[4 * (size_t) node];
+        out[0] = { { n[0].x, n[0].y, n[0].z }, { n[0].w, n[1].x, n[1].y }, as_int(n[3].x) };
+        out[1] = { { n[1].z, n[1].w, n[2].x }, { n[2].y, n[2].z, n[2].w }, as_int(n[3].y) };
+    };
+    auto area = [](const Child &c) {
+        const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    struct Todo { int node2, node4, depth; };
+    std::vector<Todo> work;
+    n4.resize(8);
+    work.push_back({ 0, 0, 1 });
+    int maxDepth = 1;
+    while (!work.empty()) {
+        const Todo t = work.back(); work.pop_back();
+        maxDepth = std::max(maxDepth, t.depth);
+        Child ch[4];
+        int k = 2;
+        children2(t.node2, ch);
+        while (k < 4) {
+            int best = -1; float bestArea = -1.f;
+            for (int i = 0; i < k; ++i)
+                if (ch[i].code >= 0 && std::isfinite(ch[i].lo[0]) && area(ch[i]) > bestArea) { bestArea = area(ch[i]); best = i; }
+            if (best < 0) break;
+            Child two[2];
+            children2(ch[best].code, two);
+            ch[best] = two[0];
+            ch[k++] = two[1];
+        }
+        float v[7][4];
+        for (int i = 0; i < 4; ++i) {
+            const bool empty = i >= k || (ch[i].code < 0 && ch[i].code == ~0 && !std::isfinite(ch[i].lo[0]));   // pseudo-root's empty child
+            int code = empty ? DR_NO_CHILD : ch[i].code;
+            if (!empty && code >= 0) {
+                const int idx = (int) (n4.size() / 8);
+                n4.resize(n4.size() + 8);
+                work.push_back({ code, idx, t.depth + 1 });
+                code = idx;
+            }
+            for (int a = 0; a < 3; ++a) { v[a][i] = empty ? 1e30f : ch[i].lo[a]; v[3 + a][i] = empty ? 1e30f : ch[i].hi[a]; }
+            v[6][i] = as_float(code);
+        }
+        float4 *n = &n4[8 * (size_t) t.node4];
+        for (int r = 0; r < 7; ++r) n[r] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+        n[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    bvh.nodes.swap(n4);
+    bvh.maxDepth = 3 * maxDepth + 1;          // a step pushes up to three children
+}

@@ -348,8 +348,11 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
 
     BuiltBVH bvh;
     build_bvh(d->positions, d->indices, d->n_triangles, bvh);
+#ifdef DR_BVH4
+    collapse_bvh4(bvh);
+#endif
     if (bvh.maxDepth >= DR_STACK) { dr_set_error("dr_scene_create: BVH depth %d exceeds the traversal stack (%d)", bvh.maxDepth, DR_STACK); return fail(DR_ERR_UNSUPPORTED); }
-    s->nNodes = (uint32_t) (bvh.nodes.size() / 4);
+    s->nNodes = (uint32_t) (bvh.nodes.size() / DR_NODE_F4);
 
     // triangles and shading normals in leaf order
     const size_t nT = d->n_triangles;

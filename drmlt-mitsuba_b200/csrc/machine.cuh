@@ -34,7 +34,9 @@
 
 // Resident CTAs (of 128 threads) per SM that each stage kernel is compiled for.  Every stage is bound by the latency of
 // dependent gathers (ncu: long-scoreboard stalls dominate), so registers are traded for resident warps -- up to the point
-// where spills start to cost (measured: 4 / 4 / 5 CTAs for walk / chain / begin; 3 or 5 are within 1 %).
+// where spills start to cost (measured: 4 / 4 / 5 CTAs for walk / chain / begin; 3 or 5 are within 1 %; traversal with
+// 4-wide nodes: 6 CTAs = 85 registers, no spills -- 8 CTAs spill 64 B and are 3 % slower, 10 / 12 CTAs 18 / 37 % slower,
+// 4 CTAs 6 % slower).
 #ifdef DR_NO_STREAMING
 #define DR_REC_LD(p) (*(p))
 #define DR_REC_ST(p, v) (*(p) = (v))
@@ -43,7 +45,7 @@
 #define DR_REC_ST(p, v) __stcs(p, v)
 #endif
 #ifndef TRACE_MINB
-#define TRACE_MINB 8
+#define TRACE_MINB 6
 #endif
 #ifndef WALK_MINB
 #define WALK_MINB 4

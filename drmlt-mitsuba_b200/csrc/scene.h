@@ -1,10 +1,11 @@
 // scene.h -- GPU-resident scene: BVH, triangles, materials, emitters, camera.
 //
 // Data layout in HBM (all read-only during rendering, 16-byte vector loads):
-//   nodes   : 64 B / inner node = 4 x float4
-//               n0 = (lo0.x lo0.y lo0.z hi0.x)  n1 = (hi0.y hi0.z lo1.x lo1.y)
-//               n2 = (lo1.z hi1.x hi1.y hi1.z)  n3 = (child0, child1, -, -) as int bits
-//             child >= 0: inner node index; child < 0: leaf, ~child = (firstTri << 2) | (count - 1), count <= 4
+//   nodes   : 128 B / inner node of the 4-wide BVH = 8 x float4, structure of arrays over the four children:
+//               lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] child[4] (int bits) -
+//             child >= 0: inner node index; child < 0: leaf, ~child = (firstTri << 2) | (count - 1), count <= 2;
+//             DR_NO_CHILD: empty slot.  (Built as a binary SAH tree and collapsed, bvh_build.cpp; -DDR_BVH2 keeps the
+//             binary layout: 64 B = (lo0.x lo0.y lo0.z hi0.x) (hi0.y hi0.z lo1.x lo1.y) (lo1.z hi1.x hi1.y hi1.z) (child0, child1, -, -).)
 //   tris    : 48 B / triangle in LEAF ORDER = 3 x float4
 //               t0 = (p0.x p0.y p0.z p1.x) t1 = (p1.y p1.z p2.x p2.y) t2 = (p2.z, prim, matflags, emitter)
 //             the exact float vertices (edges are formed on the fly, so the double-precision
@@ -15,6 +16,9 @@
 //   em_cdf  : double prefix sums of the per-emitter triangle areas (pmf.h DiscreteDistribution)
 // Replaces ShapeKDTree + TriAccel (src/librender/skdtree.cpp, include/mitsuba/render/triaccel.h) for this path.
 #pragma once
+#ifndef DR_BVH2
+#define DR_BVH4 1            /* 4-wide nodes (collapse_bvh4, bvh_build.cpp); -DDR_BVH2 keeps the binary tree */
+#endif
 #include "common.cuh"
 #include "../../include/drmlt_b200.h"
 #include <vector>
@@ -81,6 +85,8 @@ struct BuiltBVH {
     int maxDepth = 1;                // inner-node levels (bounds the traversal stack)
 };
 void build_bvh(const float *positions, const uint32_t *indices, uint32_t nTris, BuiltBVH &out);
+#define DR_NO_CHILD ((int) 0x80000000)       /* empty child slot of a 4-wide node */
+void collapse_bvh4(BuiltBVH &bvh);           // BVH2 (4 float4 per node) -> BVH4 (8 float4 per node); bvh_build.cpp
 
 struct dr_scene_t {
     int device = 0;

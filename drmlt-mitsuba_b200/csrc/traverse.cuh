@@ -1,8 +1,8 @@
-// traverse.cuh -- BVH2 ray traversal: closest hit and any hit.
+// traverse.cuh -- BVH ray traversal (4-wide nodes; binary with -DDR_BVH2): closest hit and any hit.
 //
 // One ray per thread, ordered while-while traversal with a short per-thread stack; every node
-// visit is four 16-byte loads (64 B), every triangle test three (48 B), through the read-only
-// path (ld.global.nc).  Replaces ShapeKDTree::rayIntersect + rayIntersectHavran + TriAccel
+// visit is seven 16-byte loads (six box planes x four children + the four child codes), every
+// triangle test three (48 B), through the read-only path (ld.global.nc).  Replaces ShapeKDTree::rayIntersect + rayIntersectHavran + TriAccel
 // (src/librender/skdtree.cpp:111-215, include/mitsuba/render/sahkdtree3.h:179-320,
 // include/mitsuba/render/triaccel.h:91-157) for this path: same closest hit in [mint, maxt]
 // (inclusive), same adaptive ray epsilon.  Float32 arithmetic only PRUNES: boxes are tested conservatively and
@@ -17,6 +17,11 @@ struct Hit {
 };
 
 #define DR_STACK 64
+#ifdef DR_BVH4
+#define DR_NODE_F4 8         /* float4 per node */
+#else
+#define DR_NODE_F4 4
+#endif
 #define DR_TRI_TOL 2e-3f     /* candidate band of the float32 triangle test (barycentric units) */
 
 DR_D float4 ldg4(const float4 *p) { return __ldg(p); }
@@ -95,6 +100,35 @@ struct Traversal {
     }
     DR_D void pop() { if (sp == 0) done = true; else cur = stack[--sp]; }
     DR_D void step(const DevScene &sc) { if (cur >= 0) node_step(sc); else leaf_step(sc); }
+#ifdef DR_BVH4
+    // 4-wide node: seven 16-byte loads (six box planes x four children, four child codes), four independent slab tests,
+    // the hit children sorted by entry distance: the nearest is visited next, the others are pushed far to near.
+    DR_D void node_step(const DevScene &sc) {
+        const float4 *n = sc.nodes + 8 * (size_t) cur;
+        const float4 lx = ldg4(n), ly = ldg4(n + 1), lz = ldg4(n + 2), hx = ldg4(n + 3), hy = ldg4(n + 4), hz = ldg4(n + 5), cc = ldg4(n + 6);
+        float key[4]; int code[4];
+#define DR_SLAB(i, c)                                                                                         \
+        {                                                                                                     \
+            const float a0 = lx.c * inv.x - oi.x, b0 = hx.c * inv.x - oi.x;                                   \
+            const float a1 = ly.c * inv.y - oi.y, b1 = hy.c * inv.y - oi.y;                                   \
+            const float a2 = lz.c * inv.z - oi.z, b2 = hz.c * inv.z - oi.z;                                   \
+            const float nr = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tmin));          \
+            const float fr = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), tmax));          \
+            code[i] = __float_as_int(cc.c);                                                                   \
+            key[i] = (nr <= fr * 1.000002f && code[i] != DR_NO_CHILD) ? nr : INFINITY;                        \
+        }
+        DR_SLAB(0, x) DR_SLAB(1, y) DR_SLAB(2, z) DR_SLAB(3, w)
+#undef DR_SLAB
+#define DR_CSWAP(i, j) { if (key[j] < key[i]) { const float tk = key[i]; key[i] = key[j]; key[j] = tk; const int tc = code[i]; code[i] = code[j]; code[j] = tc; } }
+        DR_CSWAP(0, 1) DR_CSWAP(2, 3) DR_CSWAP(0, 2) DR_CSWAP(1, 3) DR_CSWAP(1, 2)
+#undef DR_CSWAP
+        if (key[0] == INFINITY) { pop(); return; }
+        if (key[3] != INFINITY) stack[sp++] = code[3];
+        if (key[2] != INFINITY) stack[sp++] = code[2];
+        if (key[1] != INFINITY) stack[sp++] = code[1];
+        cur = code[0];
+    }
+#else
     DR_D void node_step(const DevScene &sc) {
         {
             const float4 *n = sc.nodes + 4 * (size_t) cur;
@@ -123,6 +157,7 @@ struct Traversal {
             else pop();
         }
     }
+#endif
     DR_D void leaf_step(const DevScene &sc) {
         const int code = ~cur;
         const int first = code >> 2, count = (code & 3) + 1;
