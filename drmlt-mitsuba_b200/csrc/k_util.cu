@@ -107,7 +107,13 @@ __global__ void k_resample(const double *cdf, long long n, unsigned long long se
     if (c >= nChains) return;
     const unsigned long long id = firstChain + (unsigned long long) c;
     const double total = cdf[n];
+#ifdef DR_INDEPENDENT_RESAMPLING
     const double v = (double) keyed_uniform(seed, S_RESAMPLE, id, 0u, 0u) * total;
+#else
+    // stratified over the chains of this rank: chain c draws from the c-th of nChains equal slices of the CDF, so a seed of
+    // relative luminance w starts floor(w nChains) or ceil(w nChains) chains instead of a binomially distributed number
+    const double v = ((double) c + (double) keyed_uniform(seed, S_RESAMPLE, id, 0u, 0u)) / (double) nChains * total;
+#endif
     long long lo = 0, hi = n + 1;
     while (lo < hi) { long long mid = (lo + hi) >> 1; if (cdf[mid] < v) lo = mid + 1; else hi = mid; }
     long long index = min(n - 1, max(0ll, lo - 1));

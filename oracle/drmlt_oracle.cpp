@@ -253,7 +253,8 @@ int orc_render(void *h, const dr_config *cfgIn, int64_t n_boot, int64_t n_chains
     std::vector<uint64_t> seedIdx(n_chains), chainId(n_chains);
     std::vector<int32_t> depth(n_chains);
     for (int64_t c = 0; c < n_chains; ++c) {
-        Float u = keyedUniform(cfg->seed, S_RESAMPLE, (uint64_t) c, 0, 0);
+        // one stratum of the seed CDF per chain (the reference draws independently, pathsampler.cpp:946-954); mirrors k_resample
+        Float u = ((Float) c + (Float) keyedUniform(cfg->seed, S_RESAMPLE, (uint64_t) c, 0, 0)) / (Float) n_chains;
         int64_t s = pool[seedPDF.sample(u)];
         seedIdx[c] = (uint64_t) s; chainId[c] = (uint64_t) c; depth[c] = dep[s];
     }
