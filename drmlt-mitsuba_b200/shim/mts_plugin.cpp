@@ -275,7 +275,8 @@ public:
         // interactive jobs and `mitsuba -r` see partial results: develop + signalRefresh every <= 2 s (drmlt_proc.cpp:856-867);
         // Scene::flush (scene.cpp:468-511) then dumps whatever bitmap the film holds, plus _time.csv / _stats.txt
         RefreshCtx ctx = { film.get(), queue, job, size };
-        const dr_status status = dr_render_progressive(m_scene, &m_config, image.data(), &st, 2.0, &DR_CLASS::refresh, &ctx);
+        // (`mitsuba -r` marks the job interactive: mitsuba.cpp:395; non-interactive jobs only develop at the end, drmlt.cpp:608)
+        const dr_status status = dr_render_progressive(m_scene, &m_config, image.data(), &st, job->isInteractive() ? 2.0 : 0.0, &DR_CLASS::refresh, &ctx);
         dr_scene sceneHandle = m_scene;
         m_scene = NULL;
         dr_scene_destroy(sceneHandle);
