@@ -1,11 +1,13 @@
-// bvh_build.cpp -- host-side binned-SAH BVH2 build, flattened into the 64-byte node layout of
-// scene.h.  Replaces the reference's SAH kd-tree construction (include/mitsuba/render/gkdtree.h)
+// bvh_build.cpp -- host-side binned-SAH BVH build (binary tree, subtrees built by a thread pool, then collapsed to
+// 4-wide nodes), flattened into the node layout of scene.h.  Replaces the reference's SAH kd-tree construction (include/mitsuba/render/gkdtree.h)
 // for this path; what matters for parity is only the set of triangles, not the tree.
 #include "scene.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <atomic>
+#include <thread>
 
 namespace {
 
@@ -54,26 +56,17 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
         out.rootIsLeaf = 0;   // handled uniformly through the pseudo node
         return;
     }
-    struct Task { int node; int child; uint32_t first, count; };
-    std::vector<Task> stack;
-    // node records are patched when the children are known
-    auto alloc_node = [&]() { int n = (int) (out.nodes.size() / 4); out.nodes.resize(out.nodes.size() + 4); return n; };
-    int root = alloc_node();
-    (void) root;
-    // process(range) -> fills node `node`
-    struct Range { int node; uint32_t first, count; int depth; };
-    std::vector<Range> work;
-    work.push_back({ 0, 0, nTris, 1 });
     // Child boxes are padded by a few 1e-6 of the scene extent: the traversal tests them with the float-cast ray,
     // whose origin / direction differ from the double ray by one float ulp.
     Box sceneBox; sceneBox.reset();
     for (uint32_t i = 0; i < nTris; ++i) sceneBox.grow(box[i]);
     const float pad = 4e-6f * std::max(std::max(sceneBox.hi[0] - sceneBox.lo[0], sceneBox.hi[1] - sceneBox.lo[1]),
                                        std::max(sceneBox.hi[2] - sceneBox.lo[2], 1e-30f));
-    out.maxDepth = 1;
-    while (!work.empty()) {
-        Range r = work.back(); work.pop_back();
-        // centroid bounds
+    struct Range { int node; uint32_t first, count; int depth; };
+    // Binned-SAH split of one range: partitions out.order[first, first + count) in place, fills node `r.node` of `nodes` and
+    // returns the child ranges that need nodes of their own (allocated at the end of `nodes`).  Ranges are disjoint, so
+    // subtrees can be built concurrently as long as each thread appends to its own node array.
+    auto split = [&](const Range &r, std::vector<float4> &nodes, std::vector<Range> &work, int &maxDepth) {
         float clo[3], chi[3];
         for (int a = 0; a < 3; ++a) { clo[a] = std::numeric_limits<float>::infinity(); chi[a] = -clo[a]; }
         for (uint32_t i = r.first; i < r.first + r.count; ++i) {
@@ -124,17 +117,67 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
             if (counts[c] <= (uint32_t) LEAF) {
                 code[c] = ~(int) ((firsts[c] << 2) | (counts[c] - 1));
             } else {
-                code[c] = alloc_node();
+                code[c] = (int) (nodes.size() / 4);
+                nodes.resize(nodes.size() + 4);
                 work.push_back({ code[c], firsts[c], counts[c], r.depth + 1 });
-                out.maxDepth = std::max(out.maxDepth, r.depth + 1);
+                maxDepth = std::max(maxDepth, r.depth + 1);
             }
             for (int a = 0; a < 3; ++a) { cb[c].lo[a] -= pad; cb[c].hi[a] += pad; }
         }
-        float4 *n = &out.nodes[4 * (size_t) r.node];
+        float4 *n = &nodes[4 * (size_t) r.node];
         n[0] = make_float4(cb[0].lo[0], cb[0].lo[1], cb[0].lo[2], cb[0].hi[0]);
         n[1] = make_float4(cb[0].hi[1], cb[0].hi[2], cb[1].lo[0], cb[1].lo[1]);
         n[2] = make_float4(cb[1].lo[2], cb[1].hi[0], cb[1].hi[1], cb[1].hi[2]);
         n[3] = make_float4(as_float(code[0]), as_float(code[1]), 0.f, 0.f);
+    };
+    // Phase A (serial): the top of the tree, until the open ranges are small enough to be handed out as subtree tasks.
+    out.nodes.resize(4);
+    out.maxDepth = 1;
+    const uint32_t taskSize = std::max<uint32_t>(4096, nTris / 64);
+    std::vector<Range> work, tasks;
+    work.push_back({ 0, 0, nTris, 1 });
+    while (!work.empty()) {
+        Range r = work.back(); work.pop_back();
+        if (r.count <= taskSize && r.node != 0) { tasks.push_back(r); continue; }
+        split(r, out.nodes, work, out.maxDepth);
+    }
+    // Phase B (parallel): every task builds its subtree into a private node array whose node 0 is the subtree root.
+    struct Sub { std::vector<float4> nodes; int maxDepth = 1; };
+    std::vector<Sub> subs(tasks.size());
+    std::atomic<size_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= tasks.size()) break;
+            Sub &sb = subs[k];
+            sb.nodes.resize(4);
+            std::vector<Range> w;
+            w.push_back({ 0, tasks[k].first, tasks[k].count, tasks[k].depth });
+            sb.maxDepth = tasks[k].depth;
+            while (!w.empty()) { Range r = w.back(); w.pop_back(); split(r, sb.nodes, w, sb.maxDepth); }
+        }
+    };
+    const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nThreads && t < tasks.size(); ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    // Stitch: the subtree root goes into the node reserved for it, its other nodes are appended; inner child codes move along.
+    for (size_t k = 0; k < tasks.size(); ++k) {
+        const Sub &sb = subs[k];
+        const int offset = (int) (out.nodes.size() / 4) - 1;      // private node i >= 1 -> global node offset + i
+        const size_t nLocal = sb.nodes.size() / 4;
+        out.nodes.resize(out.nodes.size() + 4 * (nLocal - 1));
+        for (size_t i = 0; i < nLocal; ++i) {
+            float4 n3 = sb.nodes[4 * i + 3];
+            int c0 = as_int(n3.x), c1 = as_int(n3.y);
+            if (c0 >= 0) c0 += offset;
+            if (c1 >= 0) c1 += offset;
+            n3.x = as_float(c0); n3.y = as_float(c1);
+            float4 *dst = &out.nodes[4 * (i == 0 ? (size_t) tasks[k].node : (size_t) (offset + (int) i))];
+            dst[0] = sb.nodes[4 * i]; dst[1] = sb.nodes[4 * i + 1]; dst[2] = sb.nodes[4 * i + 2]; dst[3] = n3;
+        }
+        out.maxDepth = std::max(out.maxDepth, sb.maxDepth);
     }
 }
 
