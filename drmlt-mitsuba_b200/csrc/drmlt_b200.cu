@@ -683,10 +683,13 @@ static dr_status alloc_lanes(dr_job j, int n) {
     LaneMem &lm = j->M.lm;
     memset(&lm, 0, sizeof(lm));
     lm.n = n; lm.nU = j->M.pp.nU;
+    // coordinate buffers: X and Y always, Z for drmlt's second stage, R for Green's reverse state; MIS records: one per walk step
+    lm.ubCount = j->cfg.integrator != DR_INTEGRATOR_DRMLT ? 2 : (j->cfg.type == DR_TYPE_GREEN ? 4 : 3);
+    lm.mrSlots = std::min((int) MR_MAXV, j->cfg.max_depth + 3);
     dr_status st;
     if ((st = job_alloc(j, &lm.core, (size_t) n)) || (st = job_alloc(j, &lm.vt, (size_t) n)) || (st = job_alloc(j, &lm.vs, (size_t) n)) ||
         (st = job_alloc(j, &lm.geo, (size_t) 4 * n)) || (st = job_alloc(j, &lm.chain, (size_t) n, true)) ||
-        (st = job_alloc(j, &lm.misrec, (size_t) 2 * MR_MAXV * MR_WORDS * n)) || (st = job_alloc(j, &lm.conn, (size_t) 4 * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) UB_COUNT * lm.nU * n)) ||
+        (st = job_alloc(j, &lm.misrec, (size_t) 2 * lm.mrSlots * MR_WORDS * n)) || (st = job_alloc(j, &lm.conn, (size_t) 4 * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) lm.ubCount * lm.nU * n)) ||
         (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)))
         return st;
     if (j->cfg.technique == DR_TECH_BDPT &&      // both subpaths and the splat lists are kept per lane

@@ -16,7 +16,7 @@ namespace {
 DR_D void fill_proposal(const Machine &M, int lane, Core &c, const MutCtx &mc, long long item) {
     const PssParams &pp = M.pp;
     const int nU = M.lm.nU;
-    double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * nU;
+    double *ub = M.lm.ubuf + (size_t) lane * M.lm.ubCount * nU;
     int dims[3];
     chain_dims(M.pc, M.cp, c.depth, dims);
     const bool mmlt = M.pc.technique == DR_TECH_MMLT;

@@ -172,7 +172,7 @@ DR_D void chain_init(const Machine &M, int lane, Core &c, const int *depthIn, co
     const unsigned long long sidx = seedIdxIn[idx];
     c.chainId = chainIdIn[idx]; c.seedIdx = sidx;
     c.depth = M.pc.technique == DR_TECH_MMLT ? (uint8_t) depthIn[idx] : 0;
-    double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * M.lm.nU;
+    double *ub = M.lm.ubuf + (size_t) lane * M.lm.ubCount * M.lm.nU;
     const int alloc[3] = { M.cp.dimS, M.cp.dimE, M.cp.dimD };
     for (int k = 0; k < M.lm.nU; ++k) ub[k] = 0.0;
     for (int s = 0; s < 3; ++s)
@@ -249,7 +249,7 @@ k_chain(const __grid_constant__ Machine M) {
                     if (cp.importance) importance_apply(M, lane, r);
                     ChainCore cc;
                     rec_load(cc, M.lm.chain + lane);
-                    double *ub = M.lm.ubuf + (size_t) lane * UB_COUNT * M.lm.nU;
+                    double *ub = M.lm.ubuf + (size_t) lane * M.lm.ubCount * M.lm.nU;
                     int dims[3];
                     chain_dims(M.pc, cp, c.depth, dims);
                     bool mutationDone = false;

@@ -138,9 +138,10 @@ struct LaneMem {
     PredRec *geo;             // [n][2 sides][2]: position + geometric normal of the last two vertices of each subpath;
                               //   vertex j lives in slot j & 1 (the walk overwrites j-1 with j+1: no copies)
     ChainCore *chain;         // [n]
-    double *misrec;           // [n][2 sides][MR_MAXV][MR_WORDS]: per-step MIS records (see MR_*)
+    double *misrec;           // [n][2 sides][mrSlots][MR_WORDS]: per-step MIS records (see MR_*); mrSlots = maxDepth + 2 <= MR_MAXV
     double *conn;             // [n][4]: densities next to the connection
-    double *ubuf;             // [n][UB_COUNT][nU] coordinate buffers X, Y, Z, R
+    double *ubuf;             // [n][ubCount][nU] coordinate buffers X, Y (pssmlt), Z (drmlt), R (green): only the buffers the
+                              //   integrator can touch are allocated
     double *rayd;             // [n][8] o, d, tmin, tmax of the same ray un-rounded (deciding triangle tests)
     // technique=bdpt only (else null)
     Vtx *bv;                  // [n][2][BD_MAXV] subpath vertices
@@ -148,6 +149,7 @@ struct LaneMem {
     BdAcc *bacc;              // [n]
     float4 *bsplat;           // [n][4][BD_MAXS][2]: light-image splats (pos.xy | rgb) of the lists x, y, z and of the path in flight
     int n, nU;
+    int ubCount, mrSlots;
 };
 
 // whole-record copies through 128-bit accesses.  Lane records are touched once per round and are far larger than L2
@@ -290,7 +292,7 @@ struct Machine {
 
 // ------------------------------------------------------------------ MIS arrays of a lane
 DR_D PredRec *geo_slot(const Machine &M, int lane, int side, int j) { return M.lm.geo + ((size_t) lane * 2 + side) * 2 + (j & 1); }
-DR_D double *misrec_slot(const Machine &M, int lane, int side, int j) { return M.lm.misrec + (((size_t) lane * 2 + side) * MR_MAXV + j) * MR_WORDS; }
+DR_D double *misrec_slot(const Machine &M, int lane, int side, int j) { return M.lm.misrec + (((size_t) lane * 2 + side) * M.lm.mrSlots + j) * MR_WORDS; }
 DR_D void misrec_store(const Machine &M, int lane, int side, int j, Real fwdNext, Real bwdPrev, Real conv) {
     double4 v = make_double4(fwdNext, bwdPrev, conv, 0.0);
     *reinterpret_cast<double4 *>(misrec_slot(M, lane, side, j)) = v;      // one aligned 32-byte sector
@@ -322,7 +324,7 @@ DR_D void pair_extent(const Machine &M, const int dims[3], int s, int t, int ext
 
 // coordinate reader over the lane's active buffer
 DR_D void reader_open(const Machine &M, const Core &c, int lane, UReader &rd) {
-    rd.buf = M.lm.ubuf + ((size_t) lane * UB_COUNT + c.ubuf) * M.lm.nU;
+    rd.buf = M.lm.ubuf + ((size_t) lane * M.lm.ubCount + c.ubuf) * M.lm.nU;
     rd.off[0] = M.pp.off[0]; rd.off[1] = M.pp.off[1]; rd.off[2] = M.pp.off[2];
     if (M.job.type == JOB_EVAL) { rd.lim[0] = M.job.ds; rd.lim[1] = M.job.de; rd.lim[2] = M.job.dd; }
     else {
