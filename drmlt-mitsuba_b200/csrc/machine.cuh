@@ -34,7 +34,8 @@
 
 // Resident CTAs (of 128 threads) per SM that each stage kernel is compiled for.  Every stage is bound by the latency of
 // dependent gathers (ncu: long-scoreboard stalls dominate), so registers are traded for resident warps -- up to the point
-// where spills start to cost (measured: 4 / 4 / 5 CTAs for walk / chain / begin; 3 or 5 are within 1 %; traversal with
+// where spills start to cost (measured at the end of round 1: 4 / 3 / 3 / 4 CTAs for walk / connect / chain / begin, each within 2 % of
+// its neighbours; traversal with
 // 4-wide nodes: 6 CTAs = 85 registers, no spills -- 8 CTAs spill 64 B and are 3 % slower, 10 / 12 CTAs 18 / 37 % slower,
 // 4 CTAs 6 % slower).
 #ifdef DR_NO_STREAMING
@@ -51,13 +52,13 @@
 #define WALK_MINB 4
 #endif
 #ifndef CONNECT_MINB
-#define CONNECT_MINB 4
+#define CONNECT_MINB 3
 #endif
 #ifndef CHAIN_MINB
-#define CHAIN_MINB 4
+#define CHAIN_MINB 3
 #endif
 #ifndef BEGIN_MINB
-#define BEGIN_MINB 5
+#define BEGIN_MINB 4
 #endif
 
 // ------------------------------------------------------------------ lane records (AoS: one record per lane per array,
