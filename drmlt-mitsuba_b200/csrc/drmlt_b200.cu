@@ -737,7 +737,7 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     const int W = fw.W, H = fw.H;
     j->W = W; j->H = H;
     make_params(cfg, W, H, 1.0, evalDims, j->M, static_cast<SceneImpl *>(scene)->typeMask);
-    j->M.traceRefill = getenv("DRMLT_TRACE_REFILL") ? atoi(getenv("DRMLT_TRACE_REFILL")) : 24;
+    j->M.traceRefill = getenv("DRMLT_TRACE_REFILL") ? atoi(getenv("DRMLT_TRACE_REFILL")) : 12;   // measured with the 4-wide BVH: 8 / 12 / 16 / 24 / 28 -> k_trace 924 / 910 / 910 / 932 / 935 ms
     j->M.traceDescend = getenv("DRMLT_TRACE_DESCEND") ? atoi(getenv("DRMLT_TRACE_DESCEND")) : 8;
     auto fail = [&](dr_status code) { dr_job_destroy(j); return code; };
     if (cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&j->ev0) != cudaSuccess ||
