@@ -10,7 +10,7 @@ DR_D BExtra *bxp(const Machine &M, int lane, int side, int v) { return M.lm.bx +
 DR_D bool bd_roulette(const Machine &M, Core &c, UReader &rd, int sampler, int i, Real &rrWeight) {
     rrWeight = 1.0;
     if (i < M.pc.rrDepth) return true;
-    const Real q = fmin(max3(c.weight), 0.95);
+    const Real q = fmin(max3(c.weight), (Real) 0.95f);
     if (rd.next1D(sampler) > q) return false;
     rrWeight = 1.0 / q;
     c.weight *= rrWeight;

@@ -48,7 +48,7 @@ DR_D R2 square_to_disk_concentric(Real sx, Real sy) {
 DR_D R3 square_to_cosine_hemisphere(Real sx, Real sy) {
     R2 p = square_to_disk_concentric(sx, sy);
     Real z = safe_sqrt(1.0 - p.x * p.x - p.y * p.y);
-    if (z == 0.) z = 1e-10;
+    if (z == 0.) z = 1e-10f;
     return r3(p.x, p.y, z);
 }
 
@@ -84,7 +84,7 @@ DR_D R3 fresnel_conductor(Real cosThetaI, R3 eta, R3 k) {
 struct Microfacet {
     bool ggx, visible;
     Real alpha;
-    DR_D Microfacet(const Mat &m) : ggx(m.flags & DR_MAT_GGX), visible(m.flags & DR_MAT_SAMPLE_VISIBLE), alpha(fmax(m.alpha, 1e-4)) {}
+    DR_D Microfacet(const Mat &m) : ggx(m.flags & DR_MAT_GGX), visible(m.flags & DR_MAT_SAMPLE_VISIBLE), alpha(fmax((Real) m.alpha, (Real) 1e-4f)) {}
     DR_D void scale_alpha(Real v) { alpha *= v; }      // microfacet.h:178-183
     DR_D Real eval(R3 m) const {
         if (m.z <= 0.) return 0.0;
@@ -93,7 +93,7 @@ struct Microfacet {
         Real result;
         if (!ggx) result = exp(-e) / (R_PI * alpha * alpha * cosTheta2 * cosTheta2);
         else { Real root = (1.0 + e) * cosTheta2; result = 1.0 / (R_PI * alpha * alpha * root * root); }
-        if (result * m.z < 1e-20) result = 0.;
+        if (result * m.z < 1e-20f) result = 0.;
         return result;
     }
     DR_D Real smithG1(R3 v, R3 m) const {
@@ -103,9 +103,9 @@ struct Microfacet {
         if (tanTheta == 0.0) return 1.0;
         if (!ggx) {
             Real a = 1.0 / (alpha * tanTheta);
-            if (a >= 1.6) return 1.0;
+            if (a >= 1.6f) return 1.0;
             Real aSqr = a * a;
-            return (3.535 * a + 2.181 * aSqr) / (1.0 + 2.276 * a + 2.577 * aSqr);
+            return (3.535f * a + 2.181f * aSqr) / (1.0 + 2.276f * a + 2.577f * aSqr);
         } else {
             Real root = alpha * tanTheta;
             return 2.0 / (1.0 + sqrt(1.0 + root * root));
@@ -132,7 +132,7 @@ struct Microfacet {
             Real temp = 1. + tanThetaMSqr / alphaSqr;
             pdf = R_INV_PI / (alpha * alpha * cosThetaM * cosThetaM * cosThetaM * temp * temp);
         }
-        if (pdf < 1e-20) pdf = 0.;
+        if (pdf < 1e-20f) pdf = 0.;
         Real sinThetaM = sqrt(fmax(0., 1. - cosThetaM * cosThetaM));
         return r3(sinThetaM * cosPhiM, sinThetaM * sinPhiM, cosThetaM);
     }
@@ -162,15 +162,15 @@ struct Microfacet {
         const Real SQRT_PI_INV = 0.5641895835477563;
         R2 slope;
         if (!ggx) {
-            if (thetaI < 1e-4) {
+            if (thetaI < 1e-4f) {
                 Real r = sqrt(-log(1.0 - sx)), s, c;
                 sincos(2. * R_PI * sy, &s, &c);
                 return r2(r * c, r * s);
             }
             Real tanThetaI = tan(thetaI), cotThetaI = 1. / tanThetaI;
             Real a = -1., c = erf_as(cotThetaI);
-            Real sample_x = fmax(sx, 1e-6);
-            Real fit = 1. + thetaI * (-0.876 + thetaI * (0.4265 - 0.0594 * thetaI));
+            Real sample_x = fmax(sx, (Real) 1e-6f);
+            Real fit = 1. + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
             Real b = c - (1. + c) * pow(1. - sample_x, fit);
             Real normalization = 1. / (1. + c + SQRT_PI_INV * tanThetaI * exp(-cotThetaI * cotThetaI));
             int it = 0;
@@ -179,14 +179,14 @@ struct Microfacet {
                 Real invErf = erfinv_giles(b);
                 Real value = normalization * (1. + b + SQRT_PI_INV * tanThetaI * exp(-invErf * invErf)) - sample_x;
                 Real derivative = normalization * (1. - invErf * tanThetaI);
-                if (fabs(value) < 1e-5) break;
+                if (fabs(value) < 1e-5f) break;
                 if (value > 0.) c = b; else a = b;
                 b -= value / derivative;
             }
             slope.x = erfinv_giles(b);
-            slope.y = erfinv_giles(2.0 * fmax(sy, 1e-6) - 1.0);
+            slope.y = erfinv_giles(2.0 * fmax(sy, (Real) 1e-6f) - 1.0);
         } else {
-            if (thetaI < 1e-4) {
+            if (thetaI < 1e-4f) {
                 Real r = safe_sqrt(sx / (1. - sx)), s, c;
                 sincos(2. * R_PI * sy, &s, &c);
                 return r2(r * c, r * s);
@@ -356,7 +356,7 @@ DR_D Real bsdf_pdf_nested(const Mat &m, R3 wi, R3 wo, int measure) {
         }
         H = H * copysign(1.0, H.z);
         Microfacet sampleDistr(m);
-        if (!sampleDistr.visible) sampleDistr.scale_alpha(1.2 - 0.2 * sqrt(fabs(wi.z)));
+        if (!sampleDistr.visible) sampleDistr.scale_alpha(1.2f - 0.2f * sqrt(fabs(wi.z)));
         Real prob = sampleDistr.pdf(wi * copysign(1.0, wi.z), H);
         Real cosThetaT;
         const Real F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, mEta);
@@ -409,7 +409,7 @@ DR_D void bsdf_sample_nested(const Mat &m, R3 wi, int mode, Real sx, Real sy, Re
         const Real mEta = m.eta.x, mInvEta = 1. / mEta;
         Microfacet distr(m);
         Microfacet sampleDistr(distr);
-        if (!distr.visible) sampleDistr.scale_alpha(1.2 - 0.2 * sqrt(fabs(wi.z)));
+        if (!distr.visible) sampleDistr.scale_alpha(1.2f - 0.2f * sqrt(fabs(wi.z)));
         Real microfacetPDF = 0.;
         const R3 mm = sampleDistr.sample(wi * copysign(1.0, wi.z), sx, sy, microfacetPDF, epsilon);
         if (microfacetPDF == 0.) return;

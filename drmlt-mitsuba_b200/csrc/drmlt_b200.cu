@@ -437,7 +437,7 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     for (DevMaterial &m : mats)
         if (m.type == DR_BSDF_PLASTIC) {                    // SmoothPlastic::configure (plastic.cpp:188-205)
             m.k[0] = (float) fresnel_diffuse_reflectance(1.0 / (double) m.eta[0]);
-            const double Y[3] = { 0.212671, 0.715160, 0.072169 };
+            const double Y[3] = { 0.212671f, 0.715160f, 0.072169f };   // float literals, as spectrum.h:734-736
             double dAvg = 0, sAvg = 0;
             for (int c = 0; c < 3; ++c) { dAvg += Y[c] * m.reflectance[c]; sAvg += Y[c] * m.transmittance[c]; }
             m.k[1] = (float) (sAvg / (dAvg + sAvg));
@@ -493,7 +493,7 @@ static void make_params(const dr_config &c, int W, int H, double b, const int *e
     memset(&pp, 0, sizeof(pp));
     pp.seed = c.seed; pp.integrator = c.integrator; pp.type = c.type;
     const double s1 = 1.0 / 1024.0, s2 = 1.0 / 64.0;   // drmlt_sampler.h:201-202
-    const double scale = (c.integrator == DR_INTEGRATOR_DRMLT && c.type == DR_TYPE_ORBITAL) ? 1.9 : 1.0;   // :203-205
+    const double scale = (c.integrator == DR_INTEGRATOR_DRMLT && c.type == DR_TYPE_ORBITAL) ? (double) 1.9f : 1.0;   // :203-205
     pp.kel_s2 = s2 * scale;
     pp.kel_logRatio = -std::log((s2 * scale) / (s1 * scale));
     pp.sigma2 = (double) c.scale_second * (double) c.sigma;

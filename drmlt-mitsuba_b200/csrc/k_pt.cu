@@ -55,7 +55,7 @@ k_pt(const __grid_constant__ Machine M) {
                     }
                     c.flags = (c.flags & ~F_PT_EMITTED) | F_PT_DIRECT;   // rRec.type = ERadianceNoEmission
                     if (c.j++ >= pc.rrDepth) {               // Russian roulette (path.cpp:297-306)
-                        const Real q = fmin(max3(c.weight) * px.eta * px.eta, 0.95);
+                        const Real q = fmin(max3(c.weight) * px.eta * px.eta, (Real) 0.95f);
                         if (rd.next1D(SMP_SENSOR) >= q) { go = GO_DONE; break; }
                         c.weight = c.weight / q;
                     }

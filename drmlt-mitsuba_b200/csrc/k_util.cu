@@ -152,7 +152,7 @@ __global__ void k_develop(const float4 *film, const float *importance, long long
 // (resampleAndClamp, :232-280).  One thread per output pixel.
 __global__ void k_rgb_luminance(const float *rgb, long long n, double *lum) {
     const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-    if (i < n) lum[i] = (double) rgb[3 * i] * 0.212671 + (double) rgb[3 * i + 1] * 0.715160 + (double) rgb[3 * i + 2] * 0.072169;
+    if (i < n) lum[i] = (double) rgb[3 * i] * 0.212671f + (double) rgb[3 * i + 1] * 0.715160f + (double) rgb[3 * i + 2] * 0.072169f;
 }
 // pass along x: src [h][ws] -> dst [h][wt];  pass along y: src [hs][w] -> dst [ht][w]
 __global__ void k_resample_axis(const double *src, int srcRes, int tgtRes, int other, int alongX, const int *start, const double *weights, int taps, double *dst) {

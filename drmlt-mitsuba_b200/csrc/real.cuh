@@ -42,7 +42,7 @@ DR_HD Real length(R3 a) { return sqrt(dot(a, a)); }
 DR_HD R3 normalize(R3 a) { return a / sqrt(dot(a, a)); }
 DR_HD bool is_zero(R3 a) { return a.x == 0.0 && a.y == 0.0 && a.z == 0.0; }
 DR_HD Real max3(R3 a) { return fmax(a.x, fmax(a.y, a.z)); }
-DR_HD Real luminance(R3 c) { return c.x * 0.212671 + c.y * 0.715160 + c.z * 0.072169; }   // spectrum.h:734-736
+DR_HD Real luminance(R3 c) { return c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f; }   // spectrum.h:734-736
 DR_HD bool rgb_valid(R3 c) { return isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && c.x >= 0.0 && c.y >= 0.0 && c.z >= 0.0; }
 DR_HD Real safe_sqrt(Real v) { return sqrt(fmax(v, 0.0)); }
 DR_HD Real safe_acos(Real v) { return acos(fmin(1.0, fmax(-1.0, v))); }

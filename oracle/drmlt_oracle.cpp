@@ -337,6 +337,57 @@ void orc_bsdf_eval(const dr_material *m, const double *wi, const double *wo, int
     *pdf = bsdfPdf(*m, b, measure);
 }
 
+
+// ---- numerical leaves, exported one by one so that tests/test_ref_pins.py can hold them against the reference's own
+// code (oracle/_ref/libref_leaf.so, built by oracle/ref/Makefile from the sources under /root/reference) and against
+// the fixture that library produced (tests/golden/ref_leaf.npz).
+void orc_squareToCosineHemisphere(double u, double v, double *out) { Vec3 d = squareToCosineHemisphere(Vec2(u, v)); out[0] = d.x; out[1] = d.y; out[2] = d.z; }
+void orc_squareToUniformDiskConcentric(double u, double v, double *out) { Vec2 p = squareToUniformDiskConcentric(Vec2(u, v)); out[0] = p.x; out[1] = p.y; }
+void orc_squareToUniformTriangle(double u, double v, double *out) { Vec2 p = squareToUniformTriangle(Vec2(u, v)); out[0] = p.x; out[1] = p.y; }
+double orc_fresnelDielectricExt(double cosThetaI, double eta, double *cosThetaT) { Float ct; Float r = fresnelDielectricExt(cosThetaI, ct, eta); *cosThetaT = ct; return r; }
+void orc_fresnelConductorExact(double cosThetaI, const double *eta, const double *k, double *out) {
+    RGB r = fresnelConductorExact(cosThetaI, RGB(eta[0], eta[1], eta[2]), RGB(k[0], k[1], k[2]));
+    out[0] = r.r; out[1] = r.g; out[2] = r.b;
+}
+double orc_fresnelDiffuseReflectance(double eta) { return detail::fresnelDiffuseReflectance(eta); }
+void orc_coordinateSystem(const double *a, double *b, double *c) {
+    Vec3 B, Cv; coordinateSystem(Vec3(a[0], a[1], a[2]), B, Cv);
+    b[0] = B.x; b[1] = B.y; b[2] = B.z; c[0] = Cv.x; c[1] = Cv.y; c[2] = Cv.z;
+}
+double orc_luminance(const double *rgb) { return RGB(rgb[0], rgb[1], rgb[2]).luminance(); }
+int orc_triAccel(const double *p0, const double *p1, const double *p2, const double *o, const double *d, double mint, double maxt, double *uvt) {
+    TriAccel ta;
+    if (triLoad(ta, Vec3(p0[0], p0[1], p0[2]), Vec3(p1[0], p1[1], p1[2]), Vec3(p2[0], p2[1], p2[2])) != 0) return -1;
+    Ray ray; ray.o = Vec3(o[0], o[1], o[2]); ray.d = Vec3(d[0], d[1], d[2]); ray.mint = mint; ray.maxt = maxt;
+    Float u = 0, v = 0, t = 0;
+    bool hit = triIntersect(ta, ray, mint, maxt, u, v, t);
+    uvt[0] = u; uvt[1] = v; uvt[2] = t;
+    return hit ? 1 : 0;
+}
+double orc_pmf(const double *weights, int n, const double *xi, int m, int32_t *index, double *reused, double *pmf_out) {
+    DiscreteDistribution dist;
+    for (int i = 0; i < n; ++i) dist.append(weights[i]);
+    Float sum = dist.normalize();
+    for (int i = 0; i < n; ++i) pmf_out[i] = dist[i];
+    for (int j = 0; j < m; ++j) { Float s = xi[j]; index[j] = (int32_t) dist.sampleReuse(s); reused[j] = s; }
+    return sum;
+}
+void orc_microfacet(int type, double alpha, int sampleVisible, const double *wi, const double *m_in, double u, double v, double *out) {
+    dr_material mat{}; mat.alpha = (float) alpha; mat.flags = (type ? DR_MAT_GGX : 0) | (sampleVisible ? DR_MAT_SAMPLE_VISIBLE : 0);
+    Microfacet distr(mat);
+    distr.alpha = std::max((Float) alpha, (Float) 1e-4);   // the material record stores alpha as float; the leaf test passes a double
+    Vec3 Wi(wi[0], wi[1], wi[2]), M(m_in[0], m_in[1], m_in[2]);
+    out[0] = distr.eval(M);
+    out[1] = distr.pdf(Wi, M);
+    Vec3 Wo = M * (2 * dot(Wi, M)) - Wi;
+    out[2] = distr.G(Wi, Wo, M);
+    out[3] = distr.smithG1(Wi, M);
+    Float pdf;
+    Vec3 s = distr.sample(Wi, Vec2(u, v), pdf, 1e-7);
+    out[4] = s.x; out[5] = s.y; out[6] = s.z; out[7] = pdf;
+}
+double orc_kelemen_logpdf(double s1, double s2, double du) { return KelemenKernel(s1, s2).logPdf(du); }
+
 // transition kernels (transition.h) for known-answer tests
 double orc_kelemen_sample(double s1, double s2, double xi) { return KelemenKernel(s1, s2).sample(xi); }
 double orc_kelemen_pdf(double s1, double s2, double du) { return KelemenKernel(s1, s2).pdf(du); }

@@ -44,7 +44,7 @@ struct Microfacet {
     Float alpha;
     Microfacet(const dr_material &m)
         : ggx((m.flags & DR_MAT_GGX) != 0), sampleVis((m.flags & DR_MAT_SAMPLE_VISIBLE) != 0),
-          alpha(std::max((Float) m.alpha, (Float) 1e-4)) {}   // microfacet.h:67-72
+          alpha(std::max((Float) m.alpha, (Float) 1e-4f)) {}   // microfacet.h:67-72
     void scaleAlpha(Float value) { alpha *= value; }          // :178-183
 
     Float eval(const Vec3 &m) const {   // :191-237
@@ -58,7 +58,7 @@ struct Microfacet {
             Float root = (1.0 + beckmannExponent) * cosTheta2;
             result = 1.0 / (PI * alpha * alpha * root * root);
         }
-        if (result * Frame::cosTheta(m) < 1e-20) result = 0;
+        if (result * Frame::cosTheta(m) < 1e-20f) result = 0;
         return result;
     }
     Float smithG1(const Vec3 &v, const Vec3 &m) const {   // :476-513
@@ -67,9 +67,9 @@ struct Microfacet {
         if (tanTheta == 0.0) return 1.0;
         if (!ggx) {
             Float a = 1.0 / (alpha * tanTheta);
-            if (a >= 1.6) return 1.0;
+            if (a >= 1.6f) return 1.0;
             Float aSqr = a * a;
-            return (3.535 * a + 2.181 * aSqr) / (1.0 + 2.276 * a + 2.577 * aSqr);
+            return (3.535f * a + 2.181f * aSqr) / (1.0 + 2.276f * a + 2.577f * aSqr);
         } else {
             Float root = alpha * tanTheta;
             return 2.0 / (1.0 + std::hypot((Float) 1.0, root));
@@ -96,7 +96,7 @@ struct Microfacet {
             Float temp = 1 + tanThetaMSqr / alphaSqr;
             pdf = INV_PI / (alpha * alpha * cosThetaM * cosThetaM * cosThetaM * temp * temp);
         }
-        if (pdf < 1e-20) pdf = 0;
+        if (pdf < 1e-20f) pdf = 0;
         Float sinThetaM = std::sqrt(std::max((Float) 0, 1 - cosThetaM * cosThetaM));
         return Vec3(sinThetaM * cosPhiM, sinThetaM * sinPhiM, cosThetaM);
     }
@@ -134,14 +134,14 @@ struct Microfacet {
         const Float SQRT_PI_INV = 1 / std::sqrt(PI);
         Vec2 slope;
         if (!ggx) {
-            if (thetaI < 1e-4) {
+            if (thetaI < 1e-4f) {
                 Float r = std::sqrt(-std::log(1.0 - sample.x));
                 return Vec2(r * std::cos(2 * PI * sample.y), r * std::sin(2 * PI * sample.y));
             }
             Float tanThetaI = std::tan(thetaI), cotThetaI = 1 / tanThetaI;
             Float a = -1, c = erfApprox(cotThetaI);
-            Float sample_x = std::max(sample.x, (Float) 1e-6);
-            Float fit = 1 + thetaI * (-0.876 + thetaI * (0.4265 - 0.0594 * thetaI));
+            Float sample_x = std::max(sample.x, (Float) 1e-6f);
+            Float fit = 1 + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
             Float b = c - (1 + c) * std::pow(1 - sample_x, fit);
             Float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * std::exp(-cotThetaI * cotThetaI));
             int it = 0;
@@ -150,14 +150,14 @@ struct Microfacet {
                 Float invErf = erfinv(b);
                 Float value = normalization * (1 + b + SQRT_PI_INV * tanThetaI * std::exp(-invErf * invErf)) - sample_x;
                 Float derivative = normalization * (1 - invErf * tanThetaI);
-                if (std::abs(value) < 1e-5) break;
+                if (std::abs(value) < 1e-5f) break;
                 if (value > 0) c = b; else a = b;
                 b -= value / derivative;
             }
             slope.x = erfinv(b);
-            slope.y = erfinv(2.0 * std::max(sample.y, (Float) 1e-6) - 1.0);
+            slope.y = erfinv(2.0 * std::max(sample.y, (Float) 1e-6f) - 1.0);
         } else {
-            if (thetaI < 1e-4) {
+            if (thetaI < 1e-4f) {
                 Float r = safe_sqrt(sample.x / (1 - sample.x));
                 return Vec2(r * std::cos(2 * PI * sample.y), r * std::sin(2 * PI * sample.y));
             }
@@ -361,7 +361,7 @@ inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
         }
         H = H * std::copysign(1.0, Frame::cosTheta(H));
         Microfacet sampleDistr(m);
-        if (!sampleDistr.sampleVis) sampleDistr.scaleAlpha(1.2 - 0.2 * std::sqrt(std::abs(Frame::cosTheta(b.wi))));
+        if (!sampleDistr.sampleVis) sampleDistr.scaleAlpha(1.2f - 0.2f * std::sqrt(std::abs(Frame::cosTheta(b.wi))));
         Float prob = sampleDistr.pdf(b.wi * std::copysign(1.0, Frame::cosTheta(b.wi)), H);
         Float cosThetaT;
         Float F = fresnelDielectricExt(dot(b.wi, H), cosThetaT, mEta);
@@ -411,7 +411,7 @@ inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const V
         const Float mEta = m.eta[0], mInvEta = 1 / mEta;
         Microfacet distr(m);
         Microfacet sampleDistr(distr);
-        if (!distr.sampleVis) sampleDistr.scaleAlpha(1.2 - 0.2 * std::sqrt(std::abs(Frame::cosTheta(b.wi))));
+        if (!distr.sampleVis) sampleDistr.scaleAlpha(1.2f - 0.2f * std::sqrt(std::abs(Frame::cosTheta(b.wi))));
         Float microfacetPDF;
         const Vec3 mm = sampleDistr.sample(b.wi * std::copysign(1.0, Frame::cosTheta(b.wi)), sample, microfacetPDF, epsilon);
         if (microfacetPDF == 0) return RGB(0.0);

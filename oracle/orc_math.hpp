@@ -75,7 +75,7 @@ struct RGB {
     bool isZero() const { return r == 0 && g == 0 && b == 0; }
     Float max() const { return std::max(r, std::max(g, b)); }
     // include/mitsuba/core/spectrum.h:734-736
-    Float luminance() const { return r * 0.212671 + g * 0.715160 + b * 0.072169; }
+    Float luminance() const { return r * 0.212671f + g * 0.715160f + b * 0.072169f; }
     // spectrum.h:467 isValid(): finite and non-negative
     bool isValid() const {
         return std::isfinite(r) && std::isfinite(g) && std::isfinite(b) && r >= 0 && g >= 0 && b >= 0;
@@ -144,7 +144,7 @@ inline Vec2 squareToUniformDiskConcentric(const Vec2 &sample) {
 inline Vec3 squareToCosineHemisphere(const Vec2 &sample) {
     Vec2 p = squareToUniformDiskConcentric(sample);
     Float z = safe_sqrt(1.0 - p.x * p.x - p.y * p.y);
-    if (z == 0) z = 1e-10;
+    if (z == 0) z = 1e-10f;
     return Vec3(p.x, p.y, z);
 }
 inline Float squareToCosineHemispherePdf(const Vec3 &d) { return INV_PI * Frame::cosTheta(d); }

@@ -109,7 +109,7 @@ struct DRMLTSampler : Sampler {
     bool identityAll = false;        // setStagesToIdentity(): MMLT direct sampler (drmlt_proc.cpp:133-136)
     bool stage2Identity = false;     // handleLightTracing(): fixEmitterPath on the emitter sampler (:137-140)
     Float sigma, scaleSecond;
-    const Float s1 = 1.0 / 1024.0, s2 = 1.0 / 64.0, kelemenScale = 1.9;   // drmlt_sampler.h:201-205
+    const Float s1 = 1.0 / 1024.0, s2 = 1.0 / 64.0, kelemenScale = 1.9f;   // drmlt_sampler.h:201-205
     std::vector<Float> uCurrent, uProp1, uProp2;
     size_t sampleIndex = 0, dimStage1 = 0, dimStage2 = 0;
     bool filled1 = false, filled2 = false;

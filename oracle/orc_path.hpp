@@ -305,7 +305,7 @@ inline bool vertexSampleNext(PathCtx &ctx, PathVertex &cur, Sampler *sampler, co
     if (throughput) {   // :307-322
         (*throughput) *= cur.weight[mode];
         if (russianRoulette) {
-            Float q = std::min(throughput->max(), (Float) 0.95);
+            Float q = std::min(throughput->max(), (Float) 0.95f);
             if (sampler->next1D() > q) { cur.measure = EInvalidMeasure; return false; }
             cur.rrWeight = 1.0 / q;
             (*throughput) *= cur.rrWeight;
@@ -684,7 +684,7 @@ inline RGB pathTracerLi(PathCtx &ctx, Sampler *sampler, Ray ray, int maxDepth, i
         if (!its.valid()) break;
         typeEmitted = false; typeDirect = true;   // rRec.type = ERadianceNoEmission
         if (depth++ >= rrDepth) {
-            Float q = std::min(throughput.max() * eta * eta, (Float) 0.95);
+            Float q = std::min(throughput.max() * eta * eta, (Float) 0.95f);
             if (sampler->next1D() >= q) break;
             throughput = throughput / q;
         }
