@@ -84,7 +84,9 @@ DR_D R3 fresnel_conductor(Real cosThetaI, R3 eta, R3 k) {
 struct Microfacet {
     bool ggx, visible;
     Real alpha;
-    DR_D Microfacet(const Mat &m) : ggx(m.flags & DR_MAT_GGX), visible(m.flags & DR_MAT_SAMPLE_VISIBLE), alpha(fmax((Real) m.alpha, (Real) 1e-4f)) {}
+    DR_D Microfacet(const Mat &m) : ggx(m.flags & DR_MAT_GGX), visible(m.flags & DR_MAT_SAMPLE_VISIBLE), alpha(fmax(average3((Real) m.alpha), (Real) 1e-4f)) {}
+    // the reference averages the alpha texture's Spectrum with a FLOAT third (spectrum.h:481-486, roughconductor.cpp:273)
+    DR_D static Real average3(Real a) { Real r = 0.; r += a; r += a; r += a; return r * (Real) (1.0f / 3); }
     DR_D void scale_alpha(Real v) { alpha *= v; }      // microfacet.h:178-183
     DR_D Real eval(R3 m) const {
         if (m.z <= 0.) return 0.0;

@@ -324,6 +324,7 @@ void orc_bsdf_sample(const dr_material *m, const double *wi, int mode, double u1
 void orc_bsdf_sample3(const dr_material *m, const double *wi, int mode, double u1, double u2, double u3, double *wo, double *weight, double *pdf, int *sampledType, double *eta) {
     BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), mode);
     Float p = 0;
+    dr_material mm = *m; detail::preparePlastic(mm); m = &mm;
     RGB w = bsdfSample(*m, b, p, Vec2(u1, u2), 1e-7, u3);
     wo[0] = b.wo.x; wo[1] = b.wo.y; wo[2] = b.wo.z;
     weight[0] = w.r; weight[1] = w.g; weight[2] = w.b;
@@ -375,7 +376,7 @@ double orc_pmf(const double *weights, int n, const double *xi, int m, int32_t *i
 void orc_microfacet(int type, double alpha, int sampleVisible, const double *wi, const double *m_in, double u, double v, double *out) {
     dr_material mat{}; mat.alpha = (float) alpha; mat.flags = (type ? DR_MAT_GGX : 0) | (sampleVisible ? DR_MAT_SAMPLE_VISIBLE : 0);
     Microfacet distr(mat);
-    distr.alpha = std::max((Float) alpha, (Float) 1e-4);   // the material record stores alpha as float; the leaf test passes a double
+    distr.alpha = std::max((Float) alpha, (Float) 1e-4f);   // the material record stores alpha as float; the leaf test passes a double
     Vec3 Wi(wi[0], wi[1], wi[2]), M(m_in[0], m_in[1], m_in[2]);
     out[0] = distr.eval(M);
     out[1] = distr.pdf(Wi, M);

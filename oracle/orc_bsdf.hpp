@@ -44,7 +44,10 @@ struct Microfacet {
     Float alpha;
     Microfacet(const dr_material &m)
         : ggx((m.flags & DR_MAT_GGX) != 0), sampleVis((m.flags & DR_MAT_SAMPLE_VISIBLE) != 0),
-          alpha(std::max((Float) m.alpha, (Float) 1e-4f)) {}   // microfacet.h:67-72
+          alpha(std::max(average3((Float) m.alpha), (Float) 1e-4f)) {}   // microfacet.h:67-72
+    // alpha is a ConstantFloatTexture evaluated to a Spectrum and averaged: (a + a + a) * (1.0f / 3), a FLOAT third
+    // (roughconductor.cpp:273, spectrum.h:481-486) -- the effective roughness is alpha * (1 + 3e-8)
+    static Float average3(Float a) { Float r = 0.0; r += a; r += a; r += a; return r * (1.0f / 3); }
     void scaleAlpha(Float value) { alpha *= value; }          // :178-183
 
     Float eval(const Vec3 &m) const {   // :191-237

@@ -1,0 +1,350 @@
+/* oracle/_ref path driver -- TEST INFRASTRUCTURE ONLY (never linked into or called by the product).
+ *
+ * C entry points around the reference's OWN path code, compiled from where it lies under /root/reference by the
+ * Makefile next to this file into oracle/_ref/libref_path.so:
+ *   libbidir  pathsampler.cpp (PathSampler::sampleSplats: MMLT / BDPT / PT), path.cpp (randomWalk, miWeight),
+ *             vertex.cpp, edge.cpp, common.cpp, rsampler.cpp, ...
+ *   librender scene.cpp, skdtree.cpp (SAH kd-tree), trimesh.cpp, shape.cpp, emitter.cpp, sensor.cpp, bsdf.cpp, ...
+ *   libcore   everything the above needs
+ *   plugins   bsdfs/{diffuse,dielectric,conductor,roughconductor,roughdielectric,plastic,twosided}.cpp,
+ *             emitters/area.cpp, sensors/perspective.cpp, rfilters/{gaussian,box}.cpp, samplers/independent.cpp,
+ *             integrators/path/path.cpp   (each with its CreateInstance renamed CreateInstance_<plugin>)
+ * What is NOT the reference's: the arithmetic-free Boost/Eigen stand-ins in stubs/, the TLS stand-in in
+ * ref_runtime.cpp, the plugin table and film below, and aborting stubs for symbols of files that cannot be compiled
+ * here and are never reached (Bitmap, SpecularManifold, hardware renderer).  The XML loader is not used: the scene
+ * is assembled from the same flattened description (include/drmlt_b200.h: dr_scene_desc) the product and the oracle
+ * take, through the reference's own object interfaces (Properties, addChild, configure, Scene::initialize).
+ *
+ * Uniforms are REPLAYED: the three samplers PathSampler draws from are Sampler subclasses that hand out the
+ * caller's primary-sample vectors in order (what PSSMLTSampler / DRMLTSampler::next1D/next2D do with
+ * primarySample(i), drmlt_sampler.cpp:416-425).
+ */
+#include <mitsuba/render/scene.h>
+#include <mitsuba/render/trimesh.h>
+#include <mitsuba/render/film.h>
+#include <mitsuba/render/sampler.h>
+#include <mitsuba/render/bsdf.h>
+#include <mitsuba/render/emitter.h>
+#include <mitsuba/render/sensor.h>
+#include <mitsuba/core/plugin.h>
+#include <mitsuba/core/statistics.h>
+#include <mitsuba/core/fstream.h>
+#include <mitsuba/core/sched.h>
+#include <mitsuba/core/appender.h>
+#include <mitsuba/bidir/pathsampler.h>
+#include <map>
+#include <tuple>
+#include <execinfo.h>
+#include <signal.h>
+#include "../../include/drmlt_b200.h"
+
+using namespace mitsuba;
+#define TR(msg) do { if (getenv("REF_TRACE")) fprintf(stderr, "[ref] %s\n", msg); } while (0)
+
+#define REF_PLUGINS(X) X(diffuse) X(dielectric) X(conductor) X(roughconductor) X(roughdielectric) X(plastic) X(twosided) \
+    X(area) X(perspective) X(gaussian) X(box) X(independent) X(path)
+#define X(name) extern "C" void *CreateInstance_##name(const Properties &props);
+REF_PLUGINS(X)
+#undef X
+
+/* ---- plugin table instead of dlopen("plugins/<name>.so") (libcore/plugin.cpp:180-196) */
+MTS_NAMESPACE_BEGIN
+ref<PluginManager> PluginManager::m_instance = NULL;
+PluginManager::PluginManager() {}
+PluginManager::~PluginManager() {}
+void PluginManager::staticInitialization() { m_instance = new PluginManager(); }
+void PluginManager::staticShutdown() { m_instance = NULL; }
+void PluginManager::ensurePluginLoaded(const std::string &) {}
+std::vector<std::string> PluginManager::getLoadedPlugins() const { return std::vector<std::string>(); }
+ConfigurableObject *PluginManager::createObject(const Properties &props) {
+    const std::string name = props.getPluginName();
+#define X(n) if (name == #n) return (ConfigurableObject *) CreateInstance_##n(props);
+    REF_PLUGINS(X)
+#undef X
+    SLog(EError, "oracle/_ref: plugin \"%s\" is not linked in", name.c_str());
+    return NULL;
+}
+ConfigurableObject *PluginManager::createObject(const Class *classType, const Properties &props) {
+    ConfigurableObject *o = createObject(props);
+    if (!o->getClass()->derivesFrom(classType))
+        SLog(EError, "oracle/_ref: plugin \"%s\" has the wrong class", props.getPluginName().c_str());
+    return o;
+}
+MTS_IMPLEMENT_CLASS(PluginManager, false, Object)
+
+/* ---- a film that only carries size, crop window and reconstruction filter (the hdrfilm plugin needs OpenEXR) */
+class PinFilm : public Film {
+public:
+    PinFilm(const Properties &props) : Film(props) {}
+    void clear() {}
+    void put(const ImageBlock *) {}
+    void setBitmap(const Bitmap *, Float) {}
+    void addBitmap(const Bitmap *, Float) {}
+    void setDestinationFile(const fs::path &, uint32_t) {}
+    void develop(const Scene *, Float) {}
+    bool develop(const Point2i &, const Vector2i &, const Point2i &, Bitmap *) const { return false; }
+    bool destinationExists(const fs::path &) const { return false; }
+    bool hasAlpha() const { return false; }
+    MTS_DECLARE_CLASS()
+};
+MTS_IMPLEMENT_CLASS(PinFilm, false, Film)
+
+/* ---- replayed uniforms */
+class ReplaySampler : public Sampler {
+public:
+    ReplaySampler() : Sampler(Properties()), m_u(NULL), m_n(0), m_i(0) {}
+    void set(const float *u, int n) { m_u = u; m_n = n; m_i = 0; }
+    ref<Sampler> clone() { return new ReplaySampler(); }
+    void generate(const Point2i &) { m_i = 0; }
+    void advance() { m_i = 0; }
+    void setSampleIndex(size_t) { m_i = 0; }
+    Float next1D() { if (m_i >= m_n) { overflow = true; return 0.5; } return (Float) m_u[m_i++]; }
+    Point2 next2D() { Float a = next1D(); Float b = next1D(); return Point2(a, b); }
+    void request1DArray(size_t) { SLog(EError, "ReplaySampler: sample arrays are not used on this path"); }
+    void request2DArray(size_t) { SLog(EError, "ReplaySampler: sample arrays are not used on this path"); }
+    std::string toString() const { return "ReplaySampler[]"; }
+    bool overflow = false;
+    int consumed() const { return m_i; }
+    MTS_DECLARE_CLASS()
+private:
+    const float *m_u; int m_n, m_i;
+};
+MTS_IMPLEMENT_CLASS(ReplaySampler, false, Sampler)
+MTS_NAMESPACE_END
+
+namespace {
+
+struct RefScene {
+    ref<Scene> scene;
+    std::vector<ref<BSDF> > bsdfs;      // one per dr_material
+    int filmW = 0, filmH = 0;
+};
+
+void onSegv(int) { void *bt[64]; int n = backtrace(bt, 64); backtrace_symbols_fd(bt, n, 2); _exit(139); }
+bool g_init = false;
+void initOnce() {
+    if (g_init) return;
+    g_init = true;
+    if (getenv("REF_TRACE")) signal(SIGSEGV, onSegv);
+    /* the start-up sequence of src/mitsuba/mitsuba.cpp (main): class table, threads, logger, spectra, scheduler */
+    Class::staticInitialization();
+    Object::staticInitialization();
+    PluginManager::staticInitialization();
+    Statistics::staticInitialization();
+    Thread::staticInitialization();
+    Logger::staticInitialization();
+    FileStream::staticInitialization();
+    Spectrum::staticInitialization();
+    Scheduler::staticInitialization();
+    Thread::getThread()->getLogger()->setLogLevel(EWarn);
+}
+
+Spectrum rgbSpectrum(const float *v) { Spectrum s; s.fromLinearRGB(v[0], v[1], v[2]); return s; }
+
+ref<BSDF> makeBSDF(const dr_material &m) {
+    PluginManager *pm = PluginManager::getInstance();
+    const char *names[] = { "diffuse", "dielectric", "conductor", "roughconductor", "roughdielectric", "plastic" };
+    Properties p(names[m.type]);
+    switch (m.type) {
+        case DR_BSDF_DIFFUSE: p.setSpectrum("reflectance", rgbSpectrum(m.reflectance)); break;
+        case DR_BSDF_DIELECTRIC:
+        case DR_BSDF_ROUGHDIELECTRIC:
+            p.setFloat("intIOR", (Float) m.eta[0]); p.setFloat("extIOR", 1.0);
+            p.setSpectrum("specularReflectance", rgbSpectrum(m.reflectance));
+            p.setSpectrum("specularTransmittance", rgbSpectrum(m.transmittance));
+            break;
+        case DR_BSDF_CONDUCTOR:
+        case DR_BSDF_ROUGHCONDUCTOR:
+            p.setString("material", "none");      // eta / k are given explicitly (no data/ior lookup)
+            p.setSpectrum("eta", rgbSpectrum(m.eta)); p.setSpectrum("k", rgbSpectrum(m.k)); p.setFloat("extEta", 1.0);
+            p.setSpectrum("specularReflectance", rgbSpectrum(m.reflectance));
+            break;
+        case DR_BSDF_PLASTIC:
+            p.setFloat("intIOR", (Float) m.eta[0]); p.setFloat("extIOR", 1.0);
+            p.setSpectrum("diffuseReflectance", rgbSpectrum(m.reflectance));
+            p.setSpectrum("specularReflectance", rgbSpectrum(m.transmittance));
+            p.setBoolean("nonlinear", (m.flags & DR_MAT_NONLINEAR) != 0);
+            break;
+    }
+    if (m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC) {
+        p.setString("distribution", (m.flags & DR_MAT_GGX) ? "ggx" : "beckmann");
+        p.setFloat("alpha", (Float) m.alpha);
+        p.setBoolean("sampleVisible", (m.flags & DR_MAT_SAMPLE_VISIBLE) != 0);
+    }
+    ref<BSDF> bsdf = static_cast<BSDF *>(pm->createObject(MTS_CLASS(BSDF), p));
+    bsdf->configure();
+    if (m.flags & DR_MAT_TWOSIDED) {
+        ref<BSDF> two = static_cast<BSDF *>(pm->createObject(MTS_CLASS(BSDF), Properties("twosided")));
+        two->addChild(bsdf);
+        two->configure();
+        return two;
+    }
+    return bsdf;
+}
+
+}  // namespace
+
+extern "C" {
+
+static void *scene_create(const dr_scene_desc *d, int rfilter);
+void *ref_scene_create(const dr_scene_desc *d, int rfilter) {
+    try { return scene_create(d, rfilter); }
+    catch (const std::exception &e) { fprintf(stderr, "oracle/_ref: %s\n", e.what()); return NULL; }
+}
+static void *scene_create(const dr_scene_desc *d, int rfilter) {
+    initOnce();
+    TR("init done");
+    PluginManager *pm = PluginManager::getInstance();
+    RefScene *rs = new RefScene();
+    rs->scene = new Scene(Properties("scene"));
+
+    /* sensor: perspective, fov along x, film + reconstruction filter (perspective.cpp:125-187, film.cpp:30-48) */
+    const dr_camera &c = d->camera;
+    Matrix4x4 mtx;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) mtx(i, j) = (Float) c.to_world[4 * i + j];
+    Properties sp("perspective");
+    sp.setTransform("toWorld", Transform(mtx));
+    sp.setFloat("fov", (Float) c.xfov_deg);
+    sp.setString("fovAxis", "x");
+    sp.setFloat("nearClip", (Float) c.near_clip);
+    sp.setFloat("farClip", (Float) c.far_clip);
+    TR("scene object");
+    ref<Sensor> sensor = static_cast<Sensor *>(pm->createObject(MTS_CLASS(Sensor), sp));
+    TR("sensor created");
+    Properties fp("pinfilm");
+    fp.setInteger("width", c.film_width); fp.setInteger("height", c.film_height);
+    ref<Film> film = new PinFilm(fp);
+    ref<ConfigurableObject> rf = pm->createObject(MTS_CLASS(ReconstructionFilter), Properties(rfilter == DR_FILTER_BOX ? "box" : "gaussian"));
+    rf->configure();
+    film->addChild(rf);
+    rf->setParent(film);
+    film->configure();
+    sensor->addChild(film);
+    film->setParent(sensor);
+    ref<ConfigurableObject> smp = pm->createObject(MTS_CLASS(Sampler), Properties("independent"));
+    smp->configure();
+    sensor->addChild(smp);
+    smp->setParent(sensor);
+    TR("sensor children");
+    sensor->configure();
+    TR("sensor configured");
+    rs->scene->addChild(sensor);
+    rs->filmW = c.film_width; rs->filmH = c.film_height;
+
+    for (uint32_t i = 0; i < d->n_materials; ++i) rs->bsdfs.push_back(makeBSDF(d->materials[i]));
+
+    /* one TriMesh per (material, emitter, smooth) group, in triangle order (trimesh.h:71-77) */
+    typedef std::tuple<uint32_t, int32_t, bool> Key;
+    std::map<Key, std::vector<uint32_t> > groups;
+    for (uint32_t t = 0; t < d->n_triangles; ++t) {
+        bool smooth = d->tri_flags && (d->tri_flags[t] & DR_TRI_SMOOTH) && d->normals;
+        groups[Key(d->tri_material[t], d->tri_emitter[t], smooth)].push_back(t);
+    }
+    TR("bsdfs");
+    for (auto &g : groups) {
+        const std::vector<uint32_t> &tris = g.second;
+        const bool smooth = std::get<2>(g.first);
+        std::map<uint32_t, uint32_t> remap;
+        for (uint32_t t : tris) for (int k = 0; k < 3; ++k) { uint32_t v = d->indices[3 * t + k]; if (!remap.count(v)) { uint32_t n = (uint32_t) remap.size(); remap[v] = n; } }
+        ref<TriMesh> mesh = new TriMesh("mesh", tris.size(), remap.size(), smooth, false, false, false, !smooth);
+        for (auto &kv : remap) {
+            mesh->getVertexPositions()[kv.second] = Point(d->positions[3 * kv.first], d->positions[3 * kv.first + 1], d->positions[3 * kv.first + 2]);
+            if (smooth) mesh->getVertexNormals()[kv.second] = Normal(d->normals[3 * kv.first], d->normals[3 * kv.first + 1], d->normals[3 * kv.first + 2]);
+        }
+        for (size_t i = 0; i < tris.size(); ++i) for (int k = 0; k < 3; ++k) mesh->getTriangles()[i].idx[k] = remap[d->indices[3 * tris[i] + k]];
+        mesh->addChild(rs->bsdfs[std::get<0>(g.first)]);
+        rs->bsdfs[std::get<0>(g.first)]->setParent(mesh);
+        int32_t e = std::get<1>(g.first);
+        if (e >= 0) {
+            Properties ep("area");
+            ep.setSpectrum("radiance", rgbSpectrum(d->emitters[e].radiance));
+            ep.setFloat("samplingWeight", (Float) d->emitters[e].sampling_weight);
+            ref<ConfigurableObject> em = pm->createObject(MTS_CLASS(Emitter), ep);
+            mesh->addChild(em);
+            em->setParent(mesh);       // what the scene loader does after every addChild (scenehandler.cpp)
+        }
+        mesh->configure();
+        rs->scene->addChild(mesh);
+    }
+    TR("meshes");
+    /* Scene::configure would otherwise instantiate the "direct" plugin (scene.cpp:273-277); PathSampler never uses it */
+    ref<ConfigurableObject> integ = pm->createObject(MTS_CLASS(Integrator), Properties("path"));
+    integ->configure();
+    rs->scene->addChild(integ);
+    rs->scene->configure();
+    TR("scene configured");
+    rs->scene->initialize();           // builds the SAH kd-tree (skdtree.cpp), emitter / area distributions
+    TR("scene initialized");
+    return rs;
+}
+
+void ref_scene_destroy(void *h) { delete (RefScene *) h; }
+
+/* PathSampler::sampleSplats on replayed primary-sample vectors (pathsampler.cpp:79-571). */
+int ref_eval_paths(void *h, int technique, int max_depth, int rr_depth, int sample_direct, int light_image,
+                   const float *u_sensor, int dim_sensor, const float *u_emitter, int dim_emitter,
+                   const float *u_direct, int dim_direct, const int32_t *depth, int64_t n,
+                   dr_path_result *out, double *lum_out, int32_t *consumed /* 3 per path, may be NULL */) {
+    RefScene *rs = (RefScene *) h;
+    ref<ReplaySampler> se = new ReplaySampler(), em = new ReplaySampler(), di = new ReplaySampler();
+    PathSampler::ETechnique tech = technique == DR_TECH_MMLT ? PathSampler::EMMLT
+                                 : technique == DR_TECH_BDPT ? PathSampler::EBidirectional : PathSampler::EUnidirectional;
+    ref<PathSampler> ps = new PathSampler(tech, rs->scene, em, se, di, max_depth, rr_depth, false, sample_direct != 0, light_image != 0);
+    SplatList list;
+    for (int64_t j = 0; j < n; ++j) {
+        se->set(u_sensor + j * dim_sensor, dim_sensor);
+        em->set(u_emitter + j * dim_emitter, dim_emitter);
+        di->set(u_direct + j * dim_direct, dim_direct);
+        ps->sampleSplats(Point2i(-1), list, depth ? depth[j] : -1);
+        dr_path_result &r = out[j];
+        memset(&r, 0, sizeof(r));
+        r.luminance = (float) list.luminance;
+        r.s = list.s; r.t = list.t;
+        r.n_splats = (int32_t) std::min(list.splats.size(), (size_t) DR_MAX_SPLATS);
+        for (int k = 0; k < r.n_splats; ++k) {
+            r.pos[k][0] = (float) list.splats[k].first.x; r.pos[k][1] = (float) list.splats[k].first.y;
+            Float R, G, B; list.splats[k].second.toLinearRGB(R, G, B);
+            r.value[k][0] = (float) R; r.value[k][1] = (float) G; r.value[k][2] = (float) B;
+        }
+        if (lum_out) lum_out[j] = list.luminance;
+        if (consumed) { consumed[3 * j] = se->consumed(); consumed[3 * j + 1] = em->consumed(); consumed[3 * j + 2] = di->consumed(); }
+    }
+    return (se->overflow || em->overflow || di->overflow) ? 1 : 0;
+}
+
+/* BSDF::sample / eval / pdf of the reference's plugins in the local frame (what orc_bsdf_sample / orc_bsdf_eval
+ * expose of the oracle); `extra` is the number an EUsesSampler BSDF draws from bRec.sampler (roughdielectric.cpp:555). */
+static void makeIts(Intersection &its) {
+    its.p = Point(0, 0, 0); its.t = 1; its.time = 0;
+    its.geoFrame = its.shFrame = Frame(Vector(1, 0, 0), Vector(0, 1, 0), Normal(0, 0, 1));
+    its.uv = Point2(0.5, 0.5); its.dpdu = Vector(1, 0, 0); its.dpdv = Vector(0, 1, 0); its.hasUVPartials = false;
+}
+void ref_bsdf_sample(const dr_material *m, const double *wi, int mode, double u1, double u2, double extra,
+                     double *wo, double *weight, double *pdf, int *sampledType, double *eta) {
+    initOnce();
+    ref<BSDF> bsdf = makeBSDF(*m);
+    Intersection its; makeIts(its);
+    its.wi = Vector(wi[0], wi[1], wi[2]);
+    float ex = (float) extra;
+    ref<ReplaySampler> smp = new ReplaySampler();
+    smp->set(&ex, 1);
+    BSDFSamplingRecord bRec(its, smp, mode == 0 ? ERadiance : EImportance);
+    Float p = 0;
+    Spectrum w = bsdf->sample(bRec, p, Point2(u1, u2));
+    wo[0] = bRec.wo.x; wo[1] = bRec.wo.y; wo[2] = bRec.wo.z;
+    Float R, G, B; w.toLinearRGB(R, G, B);
+    weight[0] = R; weight[1] = G; weight[2] = B;
+    *pdf = p; *sampledType = (int) bRec.sampledType; *eta = bRec.eta;
+}
+void ref_bsdf_eval(const dr_material *m, const double *wi, const double *wo, int mode, int measure, double *value, double *pdf) {
+    initOnce();
+    ref<BSDF> bsdf = makeBSDF(*m);
+    Intersection its; makeIts(its);
+    BSDFSamplingRecord bRec(its, Vector(wi[0], wi[1], wi[2]), Vector(wo[0], wo[1], wo[2]), mode == 0 ? ERadiance : EImportance);
+    Spectrum v = bsdf->eval(bRec, (EMeasure) measure);
+    Float R, G, B; v.toLinearRGB(R, G, B);
+    value[0] = R; value[1] = G; value[2] = B;
+    *pdf = bsdf->pdf(bRec, (EMeasure) measure);
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+"""Seeded cases for the reference's own BSDF plugins and PathSampler (oracle/_ref/libref_path.so, built by
+oracle/ref/Makefile from /root/reference) against the oracle restatement.  Test infrastructure only."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from drmlt_mitsuba_b200 import abi  # noqa: E402
+
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libref_path.so")
+ORACLE = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_path.npz")
+D = C.c_double
+PD = C.POINTER(D)
+
+# reference BSDF type bits (bsdf.h:230-242) -> the oracle's compact encoding (orc_bsdf.hpp:16-19)
+TYPE_MAP = {0: 0, 0x2: 0x1, 0x8: 0x2, 0x20: 0x4, 0x40: 0x8, 0x10: 0x10}
+
+
+def material(type_, flags=0, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5, 0, 0), k=(0, 0, 0), alpha=0.1):
+    m = abi.dr_material()
+    m.type, m.flags, m.alpha = type_, flags, alpha
+    m.reflectance[:], m.transmittance[:], m.eta[:], m.k[:] = reflectance, transmittance, eta, k
+    return m
+
+
+def bsdf_materials():
+    T, G, V, N = abi.DR_MAT_TWOSIDED, abi.DR_MAT_GGX, abi.DR_MAT_SAMPLE_VISIBLE, abi.DR_MAT_NONLINEAR
+    cu = dict(eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421))
+    return {
+        "diffuse": material(0, reflectance=(0.5, 0.6, 0.7)),
+        "diffuse_twosided": material(0, T, reflectance=(0.73, 0.2, 0.1)),
+        "dielectric": material(1, reflectance=(1, 0.9, 0.8), transmittance=(0.7, 0.8, 0.9), eta=(1.5, 0, 0)),
+        "conductor": material(2, reflectance=(1, 0.9, 0.8), **cu),
+        "roughconductor_beckmann": material(3, 0, reflectance=(0.9, 0.9, 0.9), alpha=0.2, **cu),
+        "roughconductor_beckmann_visible": material(3, V, alpha=0.15, **cu),
+        "roughconductor_ggx": material(3, G, alpha=0.3, **cu),
+        "roughconductor_ggx_visible": material(3, G | V, alpha=0.05, **cu),
+        "roughdielectric_beckmann": material(4, 0, eta=(1.5, 0, 0), alpha=0.2),
+        "roughdielectric_ggx_visible": material(4, G | V, eta=(1.33, 0, 0), alpha=0.1, transmittance=(0.9, 0.95, 1.0)),
+        "roughdielectric_beckmann_visible": material(4, V, eta=(1.5, 0, 0), alpha=0.3),
+        "plastic": material(5, 0, reflectance=(0.5, 0.3, 0.2), transmittance=(1, 1, 1), eta=(1.49, 0, 0)),
+        "plastic_nonlinear": material(5, N, reflectance=(0.2, 0.3, 0.7), transmittance=(0.9, 0.9, 0.9), eta=(1.9, 0, 0)),
+    }
+
+
+def _dirs(rng, n, both=True):
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    if not both:
+        v[:, 2] = np.abs(v[:, 2])
+    return np.ascontiguousarray(v)
+
+
+def run_bsdf(lib, prefix, n=600, seed=7):
+    """sample() and eval()/pdf() of every material on seeded directions; -> dict name -> array."""
+    is_ref = prefix == "ref_"
+    smp = getattr(lib, "ref_bsdf_sample" if is_ref else "orc_bsdf_sample3")
+    smp.restype = None
+    smp.argtypes = [C.c_void_p, PD, C.c_int, D, D, D, PD, PD, PD, C.POINTER(C.c_int), PD]
+    ev = getattr(lib, prefix + "bsdf_eval")
+    ev.restype = None
+    ev.argtypes = [C.c_void_p, PD, PD, C.c_int, C.c_int, PD, PD]
+    out = {}
+    for name, m in bsdf_materials().items():
+        rng = np.random.default_rng(seed)
+        two_sided_ok = m.type in (1, 4) or (m.flags & abi.DR_MAT_TWOSIDED)
+        wi = _dirs(rng, n, both=bool(two_sided_ok))
+        wo_e = _dirs(rng, n, both=True)
+        u = rng.random((n, 3))
+        mp = C.byref(m)
+        res = np.zeros((n, 2, 14))
+        for i in range(n):
+            for mode in (0, 1):
+                wo, w, pdf, ty, eta = (D * 3)(), (D * 3)(), D(), C.c_int(), D()
+                smp(mp, wi[i].ctypes.data_as(PD), mode, u[i, 0], u[i, 1], u[i, 2], wo, w, C.byref(pdf), C.byref(ty), C.byref(eta))
+                t = TYPE_MAP[ty.value] if is_ref else ty.value
+                zero = pdf.value == 0 or (w[0] == 0 and w[1] == 0 and w[2] == 0)      # a failed sample: outputs undefined
+                res[i, mode, :9] = [0] * 9 if zero else [wo[0], wo[1], wo[2], w[0], w[1], w[2], pdf.value, t, eta.value]
+                v, p = (D * 3)(), D()
+                ev(mp, wi[i].ctypes.data_as(PD), wo_e[i].ctypes.data_as(PD), mode, 1, v, C.byref(p))      # ESolidAngle
+                res[i, mode, 9:13] = [v[0], v[1], v[2], p.value]
+                if not zero and not (t & (0x4 | 0x8)):      # pdf of the sampled direction (smooth lobes)
+                    v2, p2 = (D * 3)(), D()
+                    ev(mp, wi[i].ctypes.data_as(PD), wo, mode, 1, v2, C.byref(p2))
+                    res[i, mode, 13] = p2.value
+        out["bsdf_" + name] = res
+    return out
+
+
+# ---------------------------------------------------------------- PathSampler::sampleSplats on replayed vectors
+from drmlt_mitsuba_b200 import scenes  # noqa: E402
+from drmlt_mitsuba_b200.integrator import make_config  # noqa: E402
+
+SCENES = {
+    "cornell": lambda: scenes.cornell_box(film=(128, 128), tess=8),
+    "glossy": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3),
+    "caustic": lambda: scenes.caustic_scene(film=(128, 128), grid=48),
+    "roughglass": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.15, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE)),
+    "roughglass-beckmann": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.3, 0)),
+    "plastic": lambda: scenes.cornell_box(film=(128, 128), tess=8, plastic=True),
+}
+# (scene, technique, maxDepth): C1..C4-shaped configurations of SURVEY 8 plus the 8f BSDFs
+PATH_CASES = [("cornell", "mmlt", 6), ("cornell", "bdpt", 5), ("cornell", "path", 8),
+              ("glossy", "mmlt", 8), ("glossy", "bdpt", 6), ("glossy", "path", 6),
+              ("caustic", "mmlt", 8), ("caustic", "path", 8),
+              ("roughglass", "mmlt", 8), ("roughglass", "path", 6), ("roughglass-beckmann", "bdpt", 5),
+              ("plastic", "mmlt", 8), ("plastic", "bdpt", 6), ("plastic", "path", 8)]
+N_PATHS = 6000
+
+
+def case_key(case):
+    return "path_%s_%s_%d" % case
+
+
+def case_config(case):
+    name, tech, md = case
+    params = dict(integrator="drmlt", type="orbital", technique=tech, maxDepth=md, directSamples=-1)
+    if tech == "bdpt":
+        params["directSampling"] = False       # the reference overflows its direct sampler otherwise
+    return make_config(seed=3, **params)
+
+
+def case_inputs(case, n=N_PATHS):
+    """The replayed primary-sample vectors of a case: a pure function of (case, n)."""
+    name, tech, md = case
+    rng = np.random.RandomState(1234 + 17 * PATH_CASES.index(case))
+    depth = rng.randint(1, md + 1, n).astype(np.int32)
+    ds, de, dd = (6 * (md + 2), 2, 2) if tech == "path" else (3 * (md + 2), 3 * (md + 2), 1)
+    us, ue, ud = [rng.rand(n, k).astype(np.float32) for k in (ds, de, dd)]
+    return us, ue, ud, depth
+
+
+def unpack(results, n):
+    """dr_path_result array -> dict of arrays (luminance f32, n_splats, s, t, pos0, value0)."""
+    r = np.frombuffer(results, dtype=np.uint8).reshape(n, C.sizeof(abi.dr_path_result))
+    off = 20 + 8 * abi.DR_MAX_SPLATS
+    return dict(n_splats=r[:, 4:8].copy().view("<i4")[:, 0], s=r[:, 8:12].copy().view("<i4")[:, 0], t=r[:, 12:16].copy().view("<i4")[:, 0],
+                pos0=r[:, 20:28].copy().view("<f4"), value0=r[:, off:off + 12].copy().view("<f4"))
+
+
+_ref_scenes = {}
+
+
+def run_paths_ref(lib, case, n=N_PATHS):
+    """The reference's own PathSampler on the case's vectors -> dict of arrays (lum in double)."""
+    P = C.POINTER
+    lib.ref_scene_create.restype = C.c_void_p
+    lib.ref_scene_create.argtypes = [P(abi.dr_scene_desc), C.c_int]
+    lib.ref_eval_paths.argtypes = [C.c_void_p] + [C.c_int] * 5 + [P(C.c_float), C.c_int] * 3 + [P(C.c_int32), C.c_int64, P(abi.dr_path_result), P(C.c_double), P(C.c_int32)]
+    cfg = case_config(case)
+    if case[0] not in _ref_scenes:
+        data = SCENES[case[0]]()
+        d = data.desc()
+        h = lib.ref_scene_create(C.byref(d), cfg.rfilter)
+        assert h, "oracle/_ref could not build the scene"
+        _ref_scenes[case[0]] = (h, data, d)
+    h = _ref_scenes[case[0]][0]
+    us, ue, ud, depth = case_inputs(case, n)
+    out = (abi.dr_path_result * n)()
+    lum = np.zeros(n, np.float64)
+    f = lambda a, ty=C.c_float: a.ctypes.data_as(P(ty))     # noqa: E731
+    rc = lib.ref_eval_paths(h, cfg.technique, cfg.max_depth, cfg.rr_depth, cfg.direct_sampling, cfg.light_image,
+                            f(us), us.shape[1], f(ue), ue.shape[1], f(ud), ud.shape[1], f(depth, C.c_int32), n, out, f(lum, C.c_double), None)
+    assert rc == 0, "the reference asked for more primary samples than findMaxDimensions provides"
+    res = unpack(out, n)
+    res["lum"] = lum
+    return res

@@ -1,5 +1,7 @@
-"""Writes tests/golden/ref_leaf.npz: outputs of the REFERENCE'S OWN leaf code (oracle/_ref/libref_leaf.so, compiled by
+"""Writes tests/golden/ref_leaf.npz and tests/golden/ref_path.npz: outputs of the REFERENCE'S OWN leaf code (oracle/_ref/libref_leaf.so, compiled by
 oracle/ref/Makefile from the sources under /root/reference) on the seeded inputs of tests/ref_leaf_cases.py.
+ref_path.npz holds the same for oracle/_ref/libref_path.so: the reference's BSDF plugins (sample / eval / pdf) and
+PathSampler::sampleSplats (MMLT / BDPT / PT) on the replayed vectors of tests/ref_path_cases.py.
 Run in the container that has /root/reference; the fixture travels, the reference does not."""
 import os
 import subprocess
@@ -15,3 +17,19 @@ subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle", "ref")])
 out = R.run_cases(R.load(R.REF_LEAF), "ref_")
 np.savez_compressed(R.GOLDEN, **out)
 print("wrote", R.GOLDEN, {k: v.shape for k, v in out.items()})
+
+import ctypes as C  # noqa: E402
+import ref_path_cases as RP  # noqa: E402
+
+lib = C.CDLL(RP.REF_PATH)
+out = RP.run_bsdf(lib, "ref_")
+for case in RP.PATH_CASES:
+    r = RP.run_paths_ref(lib, case)
+    k = RP.case_key(case)
+    out[k + "_lum"] = r["lum"]
+    out[k + "_st"] = np.stack([r["s"], r["t"], r["n_splats"]], 1).astype(np.int8)
+    out[k + "_pos0"] = r["pos0"]
+    out[k + "_value0"] = r["value0"]
+    print(k, "contributing", int((r["lum"] > 0).sum()), "of", len(r["lum"]))
+np.savez_compressed(RP.GOLDEN, **out)
+print("wrote", RP.GOLDEN, os.path.getsize(RP.GOLDEN), "bytes")
