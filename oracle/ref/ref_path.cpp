@@ -32,6 +32,10 @@
 #include <mitsuba/core/sched.h>
 #include <mitsuba/core/appender.h>
 #include <mitsuba/bidir/pathsampler.h>
+#include <mitsuba/render/renderjob.h>
+#include <mitsuba/render/renderqueue.h>
+#include <mitsuba/core/bitmap.h>
+#include <mitsuba/core/timer.h>
 #include <map>
 #include <tuple>
 #include <execinfo.h>
@@ -42,7 +46,7 @@ using namespace mitsuba;
 #define TR(msg) do { if (getenv("REF_TRACE")) fprintf(stderr, "[ref] %s\n", msg); } while (0)
 
 #define REF_PLUGINS(X) X(diffuse) X(dielectric) X(conductor) X(roughconductor) X(roughdielectric) X(plastic) X(twosided) \
-    X(area) X(perspective) X(gaussian) X(box) X(independent) X(path)
+    X(area) X(perspective) X(gaussian) X(box) X(independent) X(path) X(drmlt) X(pssmlt)
 #define X(name) extern "C" void *CreateInstance_##name(const Properties &props);
 REF_PLUGINS(X)
 #undef X
@@ -78,7 +82,14 @@ public:
     PinFilm(const Properties &props) : Film(props) {}
     void clear() {}
     void put(const ImageBlock *) {}
-    void setBitmap(const Bitmap *, Float) {}
+    /* what DRMLTProcess::develop / PSSMLTProcess::develop hand over (drmlt_proc.cpp:850-853): spectrum float pixels */
+    void setBitmap(const Bitmap *bitmap, Float multiplier) {
+        const Vector2i sz = bitmap->getSize();
+        image.resize((size_t) sz.x * sz.y * 3);
+        const Float *src = bitmap->getFloatData();
+        for (size_t i = 0; i < image.size(); ++i) image[i] = (float) (src[i] * multiplier);
+    }
+    std::vector<float> image;
     void addBitmap(const Bitmap *, Float) {}
     void setDestinationFile(const fs::path &, uint32_t) {}
     void develop(const Scene *, Float) {}
@@ -116,6 +127,7 @@ namespace {
 
 struct RefScene {
     ref<Scene> scene;
+    ref<PinFilm> film;
     std::vector<ref<BSDF> > bsdfs;      // one per dr_material
     int filmW = 0, filmH = 0;
 };
@@ -136,7 +148,7 @@ void initOnce() {
     FileStream::staticInitialization();
     Spectrum::staticInitialization();
     Scheduler::staticInitialization();
-    Thread::getThread()->getLogger()->setLogLevel(EWarn);
+    Thread::getThread()->getLogger()->setLogLevel(getenv("REF_LOG") ? EDebug : EWarn);
 }
 
 Spectrum rgbSpectrum(const float *v) { Spectrum s; s.fromLinearRGB(v[0], v[1], v[2]); return s; }
@@ -186,12 +198,12 @@ ref<BSDF> makeBSDF(const dr_material &m) {
 
 extern "C" {
 
-static void *scene_create(const dr_scene_desc *d, int rfilter);
+static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties *integrator = NULL, int sampleCount = 1);
 void *ref_scene_create(const dr_scene_desc *d, int rfilter) {
     try { return scene_create(d, rfilter); }
     catch (const std::exception &e) { fprintf(stderr, "oracle/_ref: %s\n", e.what()); return NULL; }
 }
-static void *scene_create(const dr_scene_desc *d, int rfilter) {
+static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties *integrator, int sampleCount) {
     initOnce();
     TR("init done");
     PluginManager *pm = PluginManager::getInstance();
@@ -213,7 +225,8 @@ static void *scene_create(const dr_scene_desc *d, int rfilter) {
     TR("sensor created");
     Properties fp("pinfilm");
     fp.setInteger("width", c.film_width); fp.setInteger("height", c.film_height);
-    ref<Film> film = new PinFilm(fp);
+    ref<PinFilm> film = new PinFilm(fp);
+    rs->film = film;
     ref<ConfigurableObject> rf = pm->createObject(MTS_CLASS(ReconstructionFilter), Properties(rfilter == DR_FILTER_BOX ? "box" : "gaussian"));
     rf->configure();
     film->addChild(rf);
@@ -221,7 +234,9 @@ static void *scene_create(const dr_scene_desc *d, int rfilter) {
     film->configure();
     sensor->addChild(film);
     film->setParent(sensor);
-    ref<ConfigurableObject> smp = pm->createObject(MTS_CLASS(Sampler), Properties("independent"));
+    Properties smpProps("independent");
+    smpProps.setInteger("sampleCount", sampleCount);     // = mutations per pixel (drmlt.cpp:400)
+    ref<ConfigurableObject> smp = pm->createObject(MTS_CLASS(Sampler), smpProps);
     smp->configure();
     sensor->addChild(smp);
     smp->setParent(sensor);
@@ -268,7 +283,7 @@ static void *scene_create(const dr_scene_desc *d, int rfilter) {
     }
     TR("meshes");
     /* Scene::configure would otherwise instantiate the "direct" plugin (scene.cpp:273-277); PathSampler never uses it */
-    ref<ConfigurableObject> integ = pm->createObject(MTS_CLASS(Integrator), Properties("path"));
+    ref<ConfigurableObject> integ = pm->createObject(MTS_CLASS(Integrator), integrator ? *integrator : Properties("path"));
     integ->configure();
     rs->scene->addChild(integ);
     rs->scene->configure();
@@ -310,6 +325,72 @@ int ref_eval_paths(void *h, int technique, int max_depth, int rr_depth, int samp
         if (consumed) { consumed[3 * j] = se->consumed(); consumed[3 * j + 1] = em->consumed(); consumed[3 * j + 2] = di->consumed(); }
     }
     return (se->overflow || em->overflow || di->overflow) ? 1 : 0;
+}
+
+/* The reference's OWN integrator, end to end: DRMLT::render / PSSMLT::render (drmlt.cpp:393-611) through a RenderJob on
+ * `threads` local workers, as src/mitsuba/mitsuba.cpp runs it.  Returns the developed image, the wall time of the job
+ * and the integrator's statistics counters (acceptance rates) as text.  The reference seeds its generators from
+ * /dev/urandom (random.cpp:473-489): results are comparable statistically, not sample by sample. */
+int ref_render(const dr_scene_desc *d, const dr_config *c, int sample_count, int threads, float *image_rgb,
+               double *seconds, double *scene_seconds, char *stats, int stats_len) {
+    try {
+        initOnce();
+        Properties ip(c->integrator == DR_INTEGRATOR_DRMLT ? "drmlt" : "pssmlt");
+        ip.setString("technique", c->technique == DR_TECH_MMLT ? "mmlt" : c->technique == DR_TECH_BDPT ? "bdpt" : "path");
+        if (c->integrator == DR_INTEGRATOR_DRMLT) {
+            const char *types[] = { "green", "mira", "orbital", "mirasym" };
+            ip.setString("type", types[c->type]);
+            ip.setBoolean("acceptanceMap", c->acceptance_map != 0);
+            ip.setBoolean("timidAfterLarge", c->timid_after_large != 0);
+            ip.setBoolean("fixEmitterPath", c->fix_emitter_path != 0);
+            ip.setBoolean("useMixture", c->use_mixture != 0);
+            ip.setFloat("scaleSecond", (Float) c->scale_second);
+        } else {
+            ip.setBoolean("kelemenStyleMutation", c->kelemen_style_mutation != 0);
+            ip.setFloat("mutationSizeLow", (Float) c->mutation_size_low);
+            ip.setFloat("mutationSizeHigh", (Float) c->mutation_size_high);
+        }
+        ip.setInteger("maxDepth", c->max_depth);
+        ip.setInteger("rrDepth", c->rr_depth);
+        ip.setBoolean("directSampling", c->direct_sampling != 0);
+        ip.setInteger("directSamples", c->direct_samples);
+        ip.setInteger("luminanceSamples", c->luminance_samples);
+        ip.setFloat("pLarge", (Float) c->p_large);
+        ip.setInteger("workUnits", c->work_units);
+        ip.setBoolean("kelemenStyleWeights", c->kelemen_style_weights != 0);
+        ip.setBoolean("lightImage", c->light_image != 0);
+        ip.setFloat("sigma", (Float) c->sigma);
+        ip.setInteger("timeout", c->timeout);
+
+        Scheduler *sched = Scheduler::getInstance();
+        for (int i = 0; i < threads; ++i) sched->registerWorker(new LocalWorker(i, formatString("wrk%i", i)));
+        sched->start();
+        ref<Timer> timer = new Timer();
+        RefScene *rs = (RefScene *) scene_create(d, c->rfilter, &ip, sample_count);
+        *scene_seconds = timer->getMilliseconds() / 1000.0;
+        Statistics::getInstance()->resetAll();
+        ref<RenderQueue> queue = new RenderQueue();
+        int sceneResID = sched->registerResource(rs->scene);
+        ref<RenderJob> job = new RenderJob("rend", rs->scene, queue, sceneResID, -1, -1, false, false);
+        timer->reset();
+        TR("job start");
+        job->start();
+        TR("job started");
+        queue->waitLeft(0);
+        TR("queue waited");
+        queue->join();
+        TR("queue joined");
+        *seconds = timer->getMilliseconds() / 1000.0;
+        sched->unregisterResource(sceneResID);
+        sched->stop();                       // as src/mitsuba/mitsuba.cpp does after its jobs; workers are re-registered per call
+        for (size_t i = sched->getWorkerCount(); i-- > 0; ) sched->unregisterWorker(sched->getWorker((int) i));
+        const std::string st = Statistics::getInstance()->getStats();
+        snprintf(stats, stats_len, "%s", st.c_str());
+        if (rs->film->image.empty()) { delete rs; return 2; }
+        memcpy(image_rgb, rs->film->image.data(), rs->film->image.size() * sizeof(float));
+        delete rs;
+        return 0;
+    } catch (const std::exception &e) { fprintf(stderr, "oracle/_ref: %s\n", e.what()); return 1; }
 }
 
 /* BSDF::sample / eval / pdf of the reference's plugins in the local frame (what orc_bsdf_sample / orc_bsdf_eval

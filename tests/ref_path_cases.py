@@ -170,3 +170,104 @@ def run_paths_ref(lib, case, n=N_PATHS):
     res = unpack(out, n)
     res["lum"] = lum
     return res
+
+
+NOISE = 1e-18      # contributions 18 orders below the brightest are rounding noise (tests/test_gpu_parity.py)
+
+
+def compare_paths(lum, st, pos0, value0, want_lum, want_st, want_pos0, want_value0, what, mmlt):
+    """f(u), strategy, splat count, pixel and RGB of one implementation against the reference's."""
+    top = want_lum.max()
+    a = np.where(np.abs(lum) < NOISE * top, 0.0, lum)
+    b = np.where(np.abs(want_lum) < NOISE * top, 0.0, want_lum)
+    support = (a > 0) == (b > 0)
+    both = (a > 0) & (b > 0)
+    assert both.sum() > 500, what
+    rel = np.abs(a[both] - b[both]) / b[both]
+    ok = support.copy()
+    ok[np.nonzero(both)[0][rel >= 1e-4]] = False
+    assert ok.mean() >= 0.999, "%s: %.5f of the paths within 1e-4 (support mismatches %d, worst %.3g)" % (what, ok.mean(), (~support).sum(), rel.max())
+    if mmlt:
+        assert np.array_equal(st[:, :2], want_st[:, :2]), what + ": MMLT strategies differ"
+    assert (st[both, 2] == want_st[both, 2]).mean() >= 0.999, what + ": splat counts differ"
+    assert (np.abs(pos0[both] - want_pos0[both]).max(axis=1) < 2e-2).mean() >= 0.999, what + ": pixels differ"
+    scale = np.abs(want_value0[both]).max(axis=1, keepdims=True)
+    okv = (np.abs(value0[both] - want_value0[both]) <= 1e-4 * np.abs(want_value0[both]) + 1e-6 * scale).all(axis=1)
+    assert okv.mean() >= 0.999, what + ": splat RGB differs"
+    return rel
+
+
+# ---------------------------------------------------------------- the reference's own integrators, end to end
+import re  # noqa: E402
+
+GOLDEN_RENDER = os.path.join(ROOT, "tests", "golden", "ref_render.npz")
+RENDER_SCENE = lambda: scenes.cornell_box(film=(64, 64), tess=4)     # noqa: E731
+# name -> (integrator parameters, mutations per pixel).  The reference needs at least one work unit of 1e5 (2e5 for
+# technique=path) mutations per core (drmlt.cpp:430-450, 498-546), hence the high sample counts on a small film.
+RENDER_CASES = {
+    "drmlt_orbital_mmlt": (dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1), 1024),
+    "drmlt_mira_path": (dict(integrator="drmlt", type="mira", technique="path", maxDepth=6, directSamples=-1), 1024),
+    "drmlt_green_bdpt": (dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False), 512),
+    "pssmlt_path": (dict(integrator="pssmlt", technique="path", maxDepth=6, directSamples=-1), 1024),
+    "pssmlt_mmlt": (dict(integrator="pssmlt", technique="mmlt", maxDepth=6, directSamples=-1), 1024),
+}
+
+
+def parse_stats(text):
+    """Statistics::getStats() text -> {counter name: percent} (StatsCounter EPercentage lines, statistics.cpp)."""
+    out = {}
+    for m in re.finditer(r"-\s+(.+?)\s*:\s*([0-9.]+) %", text):
+        out[m.group(1).strip()] = float(m.group(2))
+    return out
+
+
+def run_render_ref(lib, params, spp, threads=8, data=None):
+    P = C.POINTER
+    lib.ref_render.argtypes = [P(abi.dr_scene_desc), P(abi.dr_config), C.c_int, C.c_int, P(C.c_float), P(C.c_double), P(C.c_double), C.c_char_p, C.c_int]
+    data = data or RENDER_SCENE()
+    cfg = make_config(sampleCount=spp, seed=1, **params)
+    d = data.desc()
+    W, H = data.film
+    img = np.zeros((H, W, 3), np.float32)
+    sec, ssec, buf = C.c_double(), C.c_double(), C.create_string_buffer(1 << 16)
+    rc = lib.ref_render(C.byref(d), C.byref(cfg), spp, threads, img.ctypes.data_as(P(C.c_float)), C.byref(sec), C.byref(ssec), buf, len(buf))
+    assert rc == 0, "oracle/_ref: the reference render failed"
+    return img, sec.value, ssec.value, parse_stats(buf.value.decode())
+
+
+def luminance(img):
+    return img[..., 0] * np.float32(0.212671) + img[..., 1] * np.float32(0.715160) + img[..., 2] * np.float32(0.072169)
+
+
+def rel_mse(img, ref, eps=1e-2):
+    """relMSE = mean((I - R)^2 / (R^2 + eps)) on luminance."""
+    a, b = luminance(img.astype(np.float64)), luminance(ref.astype(np.float64))
+    return float(np.mean((a - b) ** 2 / (b ** 2 + eps)))
+
+# the reference's statistics counters (drmlt_proc.cpp:34-49, pssmlt_proc.cpp:33-40) -> dr_stats numerator / denominator
+STATS_MAP = {
+    "Accepted 1st-stage mutations": ("first_accept", "first_base"),
+    "Accepted 2nd-stage mutations": ("second_accept", "second_base"),
+    "Accepted 2nd-stage mutations after bold mutation": ("second_bold_accept", "second_bold_base"),
+    "Accepted bold mutation in the 1st-stage mutations": ("bold_accept", "bold_base"),
+    "Accepted large mutations in the 1st-stage mutations": ("large_accept", "large_base"),
+    "Overall acceptance rate": ("accept", "accept_base"),
+    "Accepted large steps": ("large_accept", "large_base"),
+    "Accepted small steps": ("bold_accept", "bold_base"),
+}
+
+
+def check_rates_and_b(name, st, b, golden):
+    """north_star: per-stage acceptance rates within 1 % absolute and b within 0.5 % of the reference's.  The reference
+    seeds from /dev/urandom; the fixture keeps three of its runs, and their own spread (up to 2 % absolute for MMLT,
+    whose ~40 work units each stay at one path depth) is added to the bound."""
+    names, runs = golden[name + "_stats_names"], golden[name + "_stats"]
+    out = {}
+    for k, vals in zip(names, runs.T):
+        a, base = STATS_MAP[str(k)]
+        ours = 100.0 * getattr(st, a) / max(1, getattr(st, base))
+        out[str(k)] = (ours, vals.mean())
+        assert abs(ours - vals.mean()) <= 1.0 + (vals.max() - vals.min()), (name, str(k), ours, vals)
+    bs = golden[name + "_b"]
+    assert abs(b - bs.mean()) <= 0.005 * bs.mean() + (bs.max() - bs.min()) / 2, (name, b, bs)
+    return out

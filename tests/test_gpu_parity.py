@@ -779,3 +779,55 @@ def test_full_size_properties():
     # ray budget: a depth-d MMLT path costs at most d rays
     assert s2.rays <= 8 * s2.paths
     job.close(); job2.close()
+
+
+# ------------------------------------------------------------------ the CUDA path against the REFERENCE ITSELF
+# tests/golden/ref_path.npz holds the outputs of the reference's own PathSampler::sampleSplats (oracle/_ref/libref_path.so,
+# compiled from /root/reference by oracle/ref/Makefile; fixture written by tools/make_ref_golden.py) on seeded
+# primary-sample vectors.  north_star: f(u) within 1e-4 relative for >= 99.9 % of the paths.
+import ref_path_cases as RP  # noqa: E402
+compare_paths = RP.compare_paths
+
+_ref_gpu_scenes = {}
+
+
+@pytest.mark.parametrize("case", RP.PATH_CASES, ids=RP.case_key)
+def test_cuda_paths_match_reference_path_sampler(case):
+    gold = np.load(RP.GOLDEN)
+    k = RP.case_key(case)
+    if case[0] not in _ref_gpu_scenes:
+        _ref_gpu_scenes[case[0]] = Scene(RP.SCENES[case[0]]())
+    cfg = RP.case_config(case)          # the product's default epsilons (float build) against the reference's double build
+    us, ue, ud, depth = RP.case_inputs(case)
+    out = _ref_gpu_scenes[case[0]].eval_paths(cfg, us, ue, ud, depth)
+    n = len(depth)
+    r = RP.unpack(out, n)
+    lum = np.frombuffer(out, dtype=np.uint8).reshape(n, C.sizeof(abi.dr_path_result))[:, 0:4].copy().view("<f4")[:, 0].astype(np.float64)
+    rel = compare_paths(lum, np.stack([r["s"], r["t"], r["n_splats"]], 1), r["pos0"], r["value0"],
+                        gold[k + "_lum"], gold[k + "_st"].astype(np.int32), gold[k + "_pos0"], gold[k + "_value0"], k, case[1] == "mmlt")
+    assert np.median(rel) < 2e-7, k      # float32 storage of dr_path_result.luminance
+
+
+@pytest.mark.parametrize("name", list(RP.RENDER_CASES))
+def test_cuda_job_statistics_match_reference_integrators(name):
+    """Whole jobs on the GPU against three end-to-end runs of the reference's own integrators (tests/golden/ref_render.npz):
+    per-stage acceptance rates within 1 % absolute, b within 0.5 % (+ the reference's own run-to-run spread)."""
+    gold = dict(np.load(RP.GOLDEN_RENDER))
+    params, spp = RP.RENDER_CASES[name]
+    gpu = Scene(RP.RENDER_SCENE())
+    img, st = gpu.render(make_config(seed=5, sampleCount=spp, **params))
+    assert st.mutations >= 64 * 64 * spp * 0.99
+    RP.check_rates_and_b(name, st, st.luminance, gold)
+    assert RP.luminance(img).mean() == pytest.approx(st.luminance, rel=2e-3)
+
+
+def test_cuda_equal_mutation_relmse_against_the_reference_integrator():
+    """north_star: relMSE against a long converged REFERENCE render, at equal mutation count, is not worse than the
+    reference's own (three reference runs at 1 024 mutations / pixel are in the fixture; they spread over 4x)."""
+    gold = dict(np.load(RP.GOLDEN_RENDER))
+    params, spp = RP.RENDER_CASES["drmlt_orbital_mmlt"]
+    gpu = Scene(RP.RENDER_SCENE())
+    errs = [RP.rel_mse(gpu.render(make_config(seed=s, sampleCount=spp, **params))[0], gold["converged_drmlt_orbital_mmlt"]) for s in (1, 2, 3)]
+    runs = gold["drmlt_orbital_mmlt_relmse_runs"]
+    print("relMSE vs converged reference render: CUDA", errs, "reference", runs)
+    assert np.median(errs) <= 1.25 * np.median(runs) and max(errs) <= 1.25 * runs.max()

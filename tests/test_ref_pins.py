@@ -92,7 +92,6 @@ import oracle_lib  # noqa: E402
 import ref_path_cases as RP  # noqa: E402
 
 needs_ref_path = pytest.mark.skipif(not os.path.exists(RP.REF_PATH), reason="oracle/_ref not built (needs /root/reference)")
-NOISE = 1e-18      # contributions 18 orders below the brightest are rounding noise (tests/test_gpu_parity.py)
 
 
 @pytest.fixture(scope="module")
@@ -140,26 +139,7 @@ def test_oracle_bsdfs_reproduce_reference_fixture(golden_path):
         assert err.max() <= max(_bsdf_tolerance(name), 1e-9), "%s: worst difference %g" % (name, err.max())
 
 
-def compare_paths(lum, st, pos0, value0, want_lum, want_st, want_pos0, want_value0, what, mmlt):
-    """f(u), strategy, splat count, pixel and RGB of one implementation against the reference's."""
-    top = want_lum.max()
-    a = np.where(np.abs(lum) < NOISE * top, 0.0, lum)
-    b = np.where(np.abs(want_lum) < NOISE * top, 0.0, want_lum)
-    support = (a > 0) == (b > 0)
-    both = (a > 0) & (b > 0)
-    assert both.sum() > 500, what
-    rel = np.abs(a[both] - b[both]) / b[both]
-    ok = support.copy()
-    ok[np.nonzero(both)[0][rel >= 1e-4]] = False
-    assert ok.mean() >= 0.999, "%s: %.5f of the paths within 1e-4 (support mismatches %d, worst %.3g)" % (what, ok.mean(), (~support).sum(), rel.max())
-    if mmlt:
-        assert np.array_equal(st[:, :2], want_st[:, :2]), what + ": MMLT strategies differ"
-    assert (st[both, 2] == want_st[both, 2]).mean() >= 0.999, what + ": splat counts differ"
-    assert (np.abs(pos0[both] - want_pos0[both]).max(axis=1) < 2e-2).mean() >= 0.999, what + ": pixels differ"
-    scale = np.abs(want_value0[both]).max(axis=1, keepdims=True)
-    okv = (np.abs(value0[both] - want_value0[both]) <= 1e-4 * np.abs(want_value0[both]) + 1e-6 * scale).all(axis=1)
-    assert okv.mean() >= 0.999, what + ": splat RGB differs"
-    return rel
+compare_paths = RP.compare_paths
 
 
 _oracle_scenes = {}
@@ -194,3 +174,35 @@ def test_fixture_is_what_the_reference_path_sampler_computes(case, golden_path):
     r = RP.run_paths_ref(C.CDLL(RP.REF_PATH), case)
     assert np.allclose(r["lum"], golden_path[k + "_lum"], rtol=1e-9, atol=0)
     assert np.array_equal(np.stack([r["s"], r["t"], r["n_splats"]], 1), golden_path[k + "_st"])
+
+
+# ================================================================ whole jobs: the reference's DRMLT / PSSMLT integrators
+# tests/golden/ref_render.npz: three end-to-end runs per configuration of the reference's own integrators
+# (DRMLT::render / PSSMLT::render through a RenderJob, oracle/ref/ref_path.cpp:ref_render) -- statistics counters, b,
+# developed image -- plus a 16x longer render as converged image.
+@pytest.fixture(scope="module")
+def golden_render():
+    return dict(np.load(RP.GOLDEN_RENDER))
+
+
+@pytest.mark.parametrize("name", ["drmlt_mira_path", "pssmlt_mmlt"])
+def test_oracle_job_statistics_match_reference_integrators(name, golden_render):
+    params, spp = RP.RENDER_CASES[name]
+    spp //= 4                                   # a quarter of the reference's mutations keeps the CPU suite short
+    orc = oracle_lib.OracleScene(RP.RENDER_SCENE())
+    cfg = RP.make_config(sampleCount=spp, seed=11, **params)
+    cfg.ray_epsilon = cfg.shadow_epsilon = 0
+    r, img, st, sec = orc.render(cfg, 300000, 4096, 64 * 64 * spp // 4096, 0)
+    assert r == 0
+    RP.check_rates_and_b(name, st, st.luminance, golden_render)
+
+
+def test_reference_render_fixture_is_consistent(golden_render):
+    # develop scales the film so that its mean luminance is b (drmlt_proc.cpp:823-849): every run's image carries its b
+    for name in RP.RENDER_CASES:
+        assert golden_render[name + "_stats"].shape[0] == 3
+        assert RP.luminance(golden_render[name + "_image"]).mean() == pytest.approx(golden_render[name + "_b"][0], rel=1e-6)
+    # path tracing, BDPT and MMLT estimate the same image: their b agree (the BDPT case has maxDepth 5 and a light image)
+    assert golden_render["drmlt_mira_path_b"].mean() == pytest.approx(golden_render["pssmlt_mmlt_b"].mean(), rel=1e-2)
+    runs = golden_render["drmlt_orbital_mmlt_relmse_runs"]
+    assert (runs > 0).all() and runs.max() < 0.05

@@ -33,3 +33,27 @@ for case in RP.PATH_CASES:
     print(k, "contributing", int((r["lum"] > 0).sum()), "of", len(r["lum"]))
 np.savez_compressed(RP.GOLDEN, **out)
 print("wrote", RP.GOLDEN, os.path.getsize(RP.GOLDEN), "bytes")
+
+# ---- the reference's own DRMLT / PSSMLT integrators end to end (statistics counters, b, images)
+rout = {}
+RUNS = 3            # the reference seeds from /dev/urandom: keep its own run-to-run spread next to the values
+for name, (params, spp) in RP.RENDER_CASES.items():
+    runs = [RP.run_render_ref(lib, params, spp) for _ in range(RUNS)]
+    names = sorted(runs[0][3])
+    rout[name + "_image"] = runs[0][0]
+    rout[name + "_stats_names"] = np.array(names)
+    rout[name + "_stats"] = np.array([[r[3][k] for k in names] for r in runs])
+    rout[name + "_b"] = np.array([RP.luminance(r[0]).mean() for r in runs])
+    rout[name + "_mutations_per_s"] = np.array([64 * 64 * spp / r[1] for r in runs])
+    print(name, "b =", rout[name + "_b"], dict(zip(names, rout[name + "_stats"].T.round(2).tolist())))
+# a long render of the first case as the converged image of the equal-mutation relMSE test
+params, spp = RP.RENDER_CASES["drmlt_orbital_mmlt"]
+img, sec, _, _ = RP.run_render_ref(lib, params, 16 * spp)
+rout["converged_drmlt_orbital_mmlt"] = img
+# ... and two more runs at the test's sample count: the reference's own run-to-run spread of relMSE
+rout["drmlt_orbital_mmlt_relmse_runs"] = np.array([RP.rel_mse(rout["drmlt_orbital_mmlt_image"], img)] +
+                                                  [RP.rel_mse(RP.run_render_ref(lib, params, spp)[0], img) for _ in range(2)])
+print("converged in %.1f s; relMSE of the reference's own runs at %d spp:" % (sec, spp), rout["drmlt_orbital_mmlt_relmse_runs"])
+np.savez_compressed(RP.GOLDEN_RENDER, **rout)
+print("wrote", RP.GOLDEN_RENDER, os.path.getsize(RP.GOLDEN_RENDER), "bytes")
+os._exit(0)        # the reference's scheduler threads are not torn down
