@@ -2,7 +2,8 @@
 """bench.py -- chain mutations/s of the drmlt hot path on N B200s (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
-  python bench.py --impl reference --steps K --warmup W    (CPU arm: the oracle port on all host cores)
+  python bench.py --impl reference --steps K --warmup W    (CPU arm: the reference's own DRMLT integrator, oracle/_ref, on all host
+                                                            cores; the oracle port only if oracle/_ref is absent)
 
 Workload (config.workload): C5 -- procedural occluded-light "door" scene, ~1M triangles, 1280x720,
 drmlt type=orbital technique=mmlt, maxDepth 8, directSamples=-1, synthetic data generated here.
@@ -135,10 +136,61 @@ def cpu_sample(orc, cfg, threads, target_s, n_boot=40000):
     return rate, n_chains, steps, st
 
 
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_path.so")
+
+
+def reference_sample(scene, spp, timeout_s=600):
+    """One bounded run of the REFERENCE'S OWN DRMLT integrator (oracle/_ref, compiled from the reference's sources) on all
+    host cores, in a subprocess (tools/ref_sample.py).  None if oracle/_ref is absent or the run fails."""
+    if not os.path.exists(REF_LIB):
+        return None
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_sample.py"), "--scene", scene, "--spp", str(spp)],
+                             capture_output=True, text=True, timeout=timeout_s).stdout
+        for ln in out.splitlines():                     # the reference's progress bar shares the line
+            if "REF_SAMPLE " in ln:
+                return json.loads(ln[ln.index("REF_SAMPLE ") + len("REF_SAMPLE "):])
+    except Exception:
+        pass
+    return None
+
+
+def reference_baseline(r):
+    return {"value": r["mutations_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+            "sample": "the reference's own DRMLT::render (oracle/_ref, double precision, SAH kd-tree) on the same scene: %d mutations/pixel = "
+                      "%d mutations in %.1f s render time incl. its bootstrap, %d worker threads; kd-tree build %.1f s not counted"
+                      % (r["spp"], r["mutations"], r["render_s"], r["threads"], r["scene_build_s"]),
+            "acceptance_percent": r["stats_percent"]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if os.path.exists(REF_LIB):
+        # the real reference: warm-up steps at a small sample, timed steps sized to <= ~2 minutes in total
+        runs = []
+        for i in range(args.warmup + args.steps):
+            timed = i >= args.warmup
+            spp = args.ref_spp if timed else 2
+            r = reference_sample(args.scene, spp)
+            if r is None:
+                runs = None
+                break
+            if timed:
+                runs.append(r)
+        if runs:
+            data = build_scene(args)
+            value = float(sum(r["mutations"] for r in runs) / sum(r["render_s"] for r in runs))
+            base = reference_baseline(runs[-1])
+            base["value"] = value
+            line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": 1e3 * float(np.mean([r["render_s"] for r in runs])), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.scene, data), "mutations_per_pixel_per_step": runs[-1]["spp"]},
+                    "cpu_baseline": base,
+                    "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            print(json.dumps(line))
+            return 0
     data = build_scene(args)
     _, orc = oracle_scene(data)
     cfg = cpu_config()
@@ -327,11 +379,16 @@ def run_gpu(args):
         cpu = None
         if not args.no_cpu:
             try:
+                ref = reference_sample(args.scene, args.ref_spp)
+                if ref is not None:
+                    raise StopIteration
                 _, orc = oracle_scene(data)
                 threads = os.cpu_count() or 1
                 rate, nch, steps, _ = cpu_sample(orc, cpu_config(), threads, args.cpu_seconds)
                 cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                        "sample": "%d chains x %d mutations of the same workload, oracle port (double) of DRMLTRenderer::process" % (nch, steps)}
+            except StopIteration:
+                cpu = reference_baseline(ref)
             except Exception as ex:                                   # the baseline is reported, never required
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -366,6 +423,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--ref-spp", type=int, default=8, dest="ref_spp", help="mutations per pixel of one bounded run of the reference's own integrator")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
