@@ -423,7 +423,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
-    ap.add_argument("--ref-spp", type=int, default=8, dest="ref_spp", help="mutations per pixel of one bounded run of the reference's own integrator")
+    ap.add_argument("--ref-spp", type=int, default=16, dest="ref_spp", help="mutations per pixel of one bounded run of the reference's own integrator")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

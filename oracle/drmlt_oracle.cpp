@@ -1,5 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  PARITY UNPINNED (no reference
-// golden vectors exist for this path).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_math.hpp header for what pins it: the reference's own
+// sources compiled into oracle/_ref, tests/test_ref_pins.py).
 //
 // C entry points of the CPU restatement, loaded with ctypes by tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference leg.  Mirrors the replay entry points of

@@ -2,12 +2,21 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 // load this code, and only as the checker / reported CPU baseline.
 //
-// PARITY UNPINNED: the reference ships no test, golden vector or known-answer fixture for the
-// pssmlt/drmlt/PathSampler path and the reference cannot be built in this
-// container (Boost/Eigen/Xerces/OpenEXR absent), so this restatement is pinned only by the
-// reference's own run-time invariants (seed replay, 0<=a<=1, depth consistency), analytic checks
-// (white furnace, PT == BDPT == MMLT normalisation) and chi-square tests modelled on
-// src/tests/test_chisquare.cpp.
+// PARITY PINS.  The reference ships no test, golden vector or known-answer fixture for the pssmlt / drmlt / PathSampler
+// path and its own build cannot run here (Boost/Eigen/Xerces/OpenEXR absent).  Its SOURCES do
+// compile, though, from where they lie under /root/reference, once a few arithmetic-free Boost/Eigen headers are stood in
+// for (oracle/ref/): oracle/_ref/libref_leaf.so and libref_path.so are the reference's own libcore + librender + libbidir +
+// BSDF / emitter / sensor / integrator plugins.  This restatement is pinned against them (tests/test_ref_pins.py, fixtures
+// tests/golden/ref_*.npz written by tools/make_ref_golden.py):
+//   * numerical leaves (warps, Fresnel, TriAccel, DiscreteDistribution, microfacet, transition kernels): bit for bit;
+//   * BSDF plugins sample / eval / pdf: bit for bit (GGX 2 ulp; plastic 1e-7, its derived constants are stored as float);
+//   * PathSampler::sampleSplats (MMLT / BDPT / PT) on replayed primary-sample vectors, 14 scene x technique cases:
+//     f(u), strategy, splat count, pixel, RGB -- 1e-12 where only diffuse surfaces are hit, >= 99.95 % within 1e-4 else;
+//   * whole jobs of the reference's DRMLT / PSSMLT integrators: acceptance-rate counters, b, equal-mutation relMSE.
+// NOT pinned sample by sample: the chain step's accept / reject sequence -- the reference draws from SFMT streams seeded
+// from /dev/urandom in call order, this restatement (like the product) addresses uniforms by key.
+// That -ffp-contract=off is set in the Makefile is what makes the bit-for-bit comparisons possible (the reference's
+// default x86-64 build has no FMA contraction).
 //
 // orc_math.hpp: vectors, RGB spectrum, frames, warps.  Float = double (the reference's default
 // CMake build is double precision: data/cmake/MitsubaBuildOptions.cmake:48-70).

@@ -3,7 +3,8 @@
 PROVENANCE.  The reference ships no golden vectors for this path and cannot be built or imported in this image
 (SURVEY.md F5/F6), so these vectors are produced by the CPU oracle (oracle/, a restatement of the reference's
 algorithm) -- they pin the oracle against regressions and give the CUDA path a fixture that travels to the GPU box;
-they are NOT outputs of the reference binary ("parity unpinned").
+they are NOT outputs of the reference.  Outputs of the reference's own compiled code are in tests/golden/ref_*.npz
+(tools/make_ref_golden.py), and the oracle is pinned to those by tests/test_ref_pins.py.
 
     python tools/make_golden.py            # rewrites tests/golden/vectors.npz
 """
