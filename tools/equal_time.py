@@ -1,5 +1,6 @@
-"""Equal-time relMSE (BASELINE.json: "relMSE at equal time"): the GPU path and the CPU oracle on all host cores render the
-same scene for the same wall-clock budget; both are compared with a long converged render.
+"""Equal-time relMSE (BASELINE.json: "relMSE at equal time"): the GPU path, the reference's own DRMLT integrator (oracle/_ref) and
+the CPU oracle, the latter two on all host cores, render the same scene for the same time budget; all are compared with a long
+converged render.
 
     python tools/equal_time.py [--scene door] [--seconds 10] [--film 320x180] [--out profiles/…json]
 
@@ -87,6 +88,38 @@ def main():
     # long CPU render as an independent check of the reference image (bounded: ~6x the budget)
     img_cpu_long, t_cpu_long, st_cpu_long = cpu_render(steps * 6, 10)
 
+    # ---- the reference's OWN integrator (oracle/_ref, tools/ref_sample.py) on all host cores for the same budget of render time
+    # (its bootstrap included, its kd-tree build excluded -- as the BVH build is for the GPU)
+    import subprocess
+    import tempfile
+
+    def ref_render(spp_, tag):
+        path = os.path.join(tempfile.gettempdir(), "equal_time_ref_%s.npy" % tag)
+        outp = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_sample.py"), "--scene", args.scene, "--film", "%dx%d" % (W, H),
+                               "--spp", str(spp_), "--out-image", path], capture_output=True, text=True, timeout=1200).stdout
+        for ln in outp.splitlines():
+            if "REF_SAMPLE " in ln:
+                return np.load(path), json.loads(ln[ln.index("REF_SAMPLE ") + len("REF_SAMPLE "):])
+        raise RuntimeError("tools/ref_sample.py produced no result")
+
+    real = None
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_path.so")):
+        try:
+            lo = max(2, -(-(threads + 1) * 100000 // (W * H)))
+            _, r1 = ref_render(lo, "a")
+            _, r2 = ref_render(4 * r1["spp"], "b")
+            rrate = (r2["mutations"] - r1["mutations"]) / max(1e-6, r2["render_s"] - r1["render_s"])
+            rfixed = max(0.0, r1["render_s"] - r1["mutations"] / rrate)
+            rspp = max(r1["spp"], int((args.seconds - rfixed) * rrate / (W * H)))
+            img_real, r3 = ref_render(rspp, "c")
+            img_real_long, r4 = ref_render(6 * rspp, "d")
+            real = {"seconds": r3["render_s"], "mutations": r3["mutations"], "spp": r3["spp"], "threads": r3["threads"], "relMSE": relmse(img_real, ref),
+                    "b": r3["mean_luminance"], "acceptance_percent": r3["stats_percent"], "kind": "the reference's own DRMLT::render (oracle/_ref)",
+                    "long_run": {"seconds": r4["render_s"], "mutations": r4["mutations"], "relMSE_vs_reference_image": relmse(img_real_long, ref),
+                                 "mean": float(img_real_long.mean())}}
+        except Exception as ex:
+            real = {"failed": repr(ex)}
+
     out = {"scene": args.scene, "triangles": int(data.n_triangles), "film": [W, H], "params": params, "budget_s": args.seconds,
            "gpu": {"seconds": t_gpu, "mutations": int(st_gpu.mutations), "spp": spp, "relMSE": relmse(img_gpu, ref), "b": st_gpu.luminance},
            "cpu_oracle": {"seconds": t_cpu, "mutations": int(st_cpu.mutations), "threads": threads, "relMSE": relmse(img_cpu, ref), "b": st_cpu.luminance,
@@ -96,6 +129,9 @@ def main():
                            "relMSE_cpu_long_vs_reference": relmse(img_cpu_long, ref), "mean_cpu_long": float(img_cpu_long.mean()),
                            "mean_gpu": float(img_gpu.mean()), "mean_cpu": float(img_cpu.mean())},
            "eps": 1e-2}
+    out["cpu_reference"] = real
+    if real and "relMSE" in real:
+        out["relMSE_ratio_reference_over_gpu"] = real["relMSE"] / max(out["gpu"]["relMSE"], 1e-300)
     out["relMSE_ratio_cpu_over_gpu"] = out["cpu_oracle"]["relMSE"] / max(out["gpu"]["relMSE"], 1e-300)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:

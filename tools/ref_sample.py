@@ -21,10 +21,16 @@ def main():
     ap.add_argument("--scene", default="door")
     ap.add_argument("--spp", type=int, default=8)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--film", default="", help="WxH (door scene only; default: the scene's own film)")
+    ap.add_argument("--out-image", default="", dest="out_image", help="write the developed image to this .npy file")
     args = ap.parse_args()
     import ref_path_cases as RP
     from drmlt_mitsuba_b200 import scenes
-    data = scenes.door_scene() if args.scene == "door" else scenes.SCENES[args.scene]()
+    film = tuple(int(x) for x in args.film.split("x")) if args.film else None
+    if args.scene == "door":
+        data = scenes.door_scene(film=film) if film else scenes.door_scene()
+    else:
+        data = scenes.SCENES[args.scene](film=film) if film else scenes.SCENES[args.scene]()
     W, H = data.film
     # the reference hands out one seed per work unit of 1e5 mutations and floor(workUnits / cores) seeds per init thread
     # (drmlt.cpp:430-450, 498-546): fewer work units than cores would render nothing
@@ -34,6 +40,9 @@ def main():
     img, sec, scene_sec, stats = RP.run_render_ref(lib, params, spp, threads=args.threads, data=data)
     out = {"mutations_per_s": W * H * spp / sec, "render_s": sec, "scene_build_s": scene_sec, "spp": spp, "threads": args.threads,
            "mutations": W * H * spp, "mean_luminance": float(RP.luminance(img).mean()), "stats_percent": stats}
+    if args.out_image:
+        import numpy as np
+        np.save(args.out_image, img)
     sys.stdout.write("\nREF_SAMPLE " + json.dumps(out) + "\n")
     sys.stdout.flush()
     os._exit(0)          # the reference's worker threads are not torn down
