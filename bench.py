@@ -374,6 +374,16 @@ def run_gpu(args):
                                    device_bootstrap_and_seeding_ms=est.bootstrap_ms, device_chains_ms=est.chains_ms),
            "what": "dr_scene_reupload + bootstrap + b all-reduce + chains + film reduce + develop + image D2H; sampleCount=%d" % (args.e2e_spp * world)}
 
+    def pct(a, b):
+        return round(100.0 * a / max(1, b), 2)
+    # the reference's statistics counters (drmlt_proc.cpp:34-49) of rank 0's job, comparable with cpu_baseline.acceptance_percent
+    e2e["acceptance_percent"] = {"Accepted 1st-stage mutations": pct(est.first_accept, est.first_base),
+                                 "Accepted 2nd-stage mutations": pct(est.second_accept, est.second_base),
+                                 "Accepted bold mutation in the 1st-stage mutations": pct(est.bold_accept, est.bold_base),
+                                 "Accepted large mutations in the 1st-stage mutations": pct(est.large_accept, est.large_base),
+                                 "Overall acceptance rate": pct(est.accept, est.accept_base)}
+    e2e["b"] = est.luminance
+
     line = None
     if rank == 0:
         cpu = None
