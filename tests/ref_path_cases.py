@@ -103,14 +103,22 @@ SCENES = {
     "roughglass": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.15, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE)),
     "roughglass-beckmann": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.3, 0)),
     "plastic": lambda: scenes.cornell_box(film=(128, 128), tess=8, plastic=True),
+    # the bench's C5 "door" scene at test size (occluded light, displaced floor, spheres)
+    "door": lambda: scenes.door_scene(film=(160, 90), floor_grid=64, n_spheres=16, sphere_subdiv=2),
 }
 # (scene, technique, maxDepth): C1..C4-shaped configurations of SURVEY 8 plus the 8f BSDFs
 PATH_CASES = [("cornell", "mmlt", 6), ("cornell", "bdpt", 5), ("cornell", "path", 8),
               ("glossy", "mmlt", 8), ("glossy", "bdpt", 6), ("glossy", "path", 6),
               ("caustic", "mmlt", 8), ("caustic", "path", 8),
               ("roughglass", "mmlt", 8), ("roughglass", "path", 6), ("roughglass-beckmann", "bdpt", 5),
-              ("plastic", "mmlt", 8), ("plastic", "bdpt", 6), ("plastic", "path", 8)]
+              ("plastic", "mmlt", 8), ("plastic", "bdpt", 6), ("plastic", "path", 8),
+              ("door", "mmlt", 8), ("door", "path", 8)]
 N_PATHS = 6000
+N_PATHS_OF = {"door": 48000}      # the door scene's light is occluded: ~1.5 % (MMLT) / 6 % (PT) of uniform vectors contribute
+
+
+def n_paths(case):
+    return N_PATHS_OF.get(case[0], N_PATHS)
 
 
 def case_key(case):
@@ -125,9 +133,10 @@ def case_config(case):
     return make_config(seed=3, **params)
 
 
-def case_inputs(case, n=N_PATHS):
+def case_inputs(case, n=None):
     """The replayed primary-sample vectors of a case: a pure function of (case, n)."""
     name, tech, md = case
+    n = n or n_paths(case)
     rng = np.random.RandomState(1234 + 17 * PATH_CASES.index(case))
     depth = rng.randint(1, md + 1, n).astype(np.int32)
     ds, de, dd = (6 * (md + 2), 2, 2) if tech == "path" else (3 * (md + 2), 3 * (md + 2), 1)
@@ -146,7 +155,7 @@ def unpack(results, n):
 _ref_scenes = {}
 
 
-def run_paths_ref(lib, case, n=N_PATHS):
+def run_paths_ref(lib, case, n=None):
     """The reference's own PathSampler on the case's vectors -> dict of arrays (lum in double)."""
     P = C.POINTER
     lib.ref_scene_create.restype = C.c_void_p
@@ -160,6 +169,7 @@ def run_paths_ref(lib, case, n=N_PATHS):
         assert h, "oracle/_ref could not build the scene"
         _ref_scenes[case[0]] = (h, data, d)
     h = _ref_scenes[case[0]][0]
+    n = n or n_paths(case)
     us, ue, ud, depth = case_inputs(case, n)
     out = (abi.dr_path_result * n)()
     lum = np.zeros(n, np.float64)
