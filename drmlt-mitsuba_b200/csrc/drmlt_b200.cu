@@ -458,6 +458,16 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     const dr_camera &c = d->camera;
     DevCamera &dc = ds.cam;
     for (int r = 0; r < 3; ++r) for (int k = 0; k < 4; ++k) dc.m[4 * r + k] = (double) c.to_world[4 * r + k];
+    {   // world -> camera directions: Transform::inverse (transform.h) of the caller's float matrix, which is a rotation only to ~6e-8
+        const double *a = dc.m;
+        const double c00 = a[5] * a[10] - a[6] * a[9], c01 = a[6] * a[8] - a[4] * a[10], c02 = a[4] * a[9] - a[5] * a[8];
+        const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+        if (!(std::fabs(det) > 1e-12)) { dr_set_error("dr_scene_create: camera to_world is singular"); return fail(DR_ERR_INVALID_ARG); }
+        const double id = 1.0 / det;
+        dc.inv[0] = c00 * id; dc.inv[1] = (a[2] * a[9] - a[1] * a[10]) * id; dc.inv[2] = (a[1] * a[6] - a[2] * a[5]) * id;
+        dc.inv[3] = c01 * id; dc.inv[4] = (a[0] * a[10] - a[2] * a[8]) * id; dc.inv[5] = (a[2] * a[4] - a[0] * a[6]) * id;
+        dc.inv[6] = c02 * id; dc.inv[7] = (a[1] * a[8] - a[0] * a[9]) * id; dc.inv[8] = (a[0] * a[5] - a[1] * a[4]) * id;
+    }
     dc.pos[0] = c.to_world[3]; dc.pos[1] = c.to_world[7]; dc.pos[2] = c.to_world[11];
     dc.dir[0] = c.to_world[2]; dc.dir[1] = c.to_world[6]; dc.dir[2] = c.to_world[10];
     const double tanHalf = std::tan(0.5 * (double) c.xfov_deg * 3.14159265358979323846 / 180.0);

@@ -52,7 +52,7 @@ DR_D R3 cam_xform_dir(const DevCamera &c, R3 v) {
     return r3(c.m[0] * v.x + c.m[1] * v.y + c.m[2] * v.z, c.m[4] * v.x + c.m[5] * v.y + c.m[6] * v.z, c.m[8] * v.x + c.m[9] * v.y + c.m[10] * v.z);
 }
 DR_D R3 cam_inv_dir(const DevCamera &c, R3 v) {
-    return r3(c.m[0] * v.x + c.m[4] * v.y + c.m[8] * v.z, c.m[1] * v.x + c.m[5] * v.y + c.m[9] * v.z, c.m[2] * v.x + c.m[6] * v.y + c.m[10] * v.z);
+    return r3(c.inv[0] * v.x + c.inv[1] * v.y + c.inv[2] * v.z, c.inv[3] * v.x + c.inv[4] * v.y + c.inv[5] * v.z, c.inv[6] * v.x + c.inv[7] * v.y + c.inv[8] * v.z);
 }
 DR_D R3 cam_sample_to_dir(const DevCamera &c, Real sx, Real sy) {   // :132-157, :336-339 (sample in [0,1]^2 over the crop window)
     const Real fx = c.relOffX + sx * c.relSizeX, fy = c.relOffY + sy * c.relSizeY;

@@ -42,6 +42,7 @@ struct DevEmitter {       // 64 B
 
 struct DevCamera {        // derived in double from the float parameters of dr_camera (perspective.cpp:126-173)
     double m[12];         // rows of the 3x4 camera-to-world matrix
+    double inv[9];        // inverse of its 3x3 block, rows (the reference inverts the matrix, it does not assume a rotation)
     double pos[3], dir[3];
     double tanHalf, aspect, nearClip, farClip;   // aspect of the FULL film
     double resX, resY;    // crop size = resolution of the sensor (perspective.cpp:126-130)

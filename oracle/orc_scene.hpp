@@ -88,6 +88,7 @@ struct BVHNode {
 
 struct Camera {
     Float toWorld[16];
+    Float inv[9];           // inverse of the 3x3 block (the reference inverts the matrix: Transform::inverse, transform.h)
     Vec3 pos, dir;          // trafo(0), trafo((0,0,1))
     Float tanHalf, aspect, nearClip, farClip;
     Float resX, resY;       // crop size = the sensor's resolution (perspective.cpp:126-130)
@@ -112,10 +113,16 @@ struct Camera {
                     toWorld[4] * v.x + toWorld[5] * v.y + toWorld[6] * v.z,
                     toWorld[8] * v.x + toWorld[9] * v.y + toWorld[10] * v.z);
     }
-    Vec3 invDir(const Vec3 &v) const {   // rigid transform: inverse rotation = transpose
-        return Vec3(toWorld[0] * v.x + toWorld[4] * v.y + toWorld[8] * v.z,
-                    toWorld[1] * v.x + toWorld[5] * v.y + toWorld[9] * v.z,
-                    toWorld[2] * v.x + toWorld[6] * v.y + toWorld[10] * v.z);
+    Vec3 invDir(const Vec3 &v) const {   // world -> camera direction
+        return Vec3(inv[0] * v.x + inv[1] * v.y + inv[2] * v.z, inv[3] * v.x + inv[4] * v.y + inv[5] * v.z, inv[6] * v.x + inv[7] * v.y + inv[8] * v.z);
+    }
+    void invert() {
+        const Float *a = toWorld;
+        const Float c00 = a[5] * a[10] - a[6] * a[9], c01 = a[6] * a[8] - a[4] * a[10], c02 = a[4] * a[9] - a[5] * a[8];
+        const Float id = 1.0 / (a[0] * c00 + a[1] * c01 + a[2] * c02);
+        inv[0] = c00 * id; inv[1] = (a[2] * a[9] - a[1] * a[10]) * id; inv[2] = (a[1] * a[6] - a[2] * a[5]) * id;
+        inv[3] = c01 * id; inv[4] = (a[0] * a[10] - a[2] * a[8]) * id; inv[5] = (a[2] * a[4] - a[0] * a[6]) * id;
+        inv[6] = c02 * id; inv[7] = (a[1] * a[8] - a[0] * a[9]) * id; inv[8] = (a[0] * a[5] - a[1] * a[4]) * id;
     }
     // perspective.cpp:150-157 m_sampleToCamera applied to (sx, sy, 0), normalised
     Vec3 sampleToDir(Float sx, Float sy) const {
@@ -257,6 +264,7 @@ inline void Scene::load(const dr_scene_desc &d) {
 
     const dr_camera &c = d.camera;
     for (int i = 0; i < 16; ++i) cam.toWorld[i] = c.to_world[i];
+    cam.invert();
     cam.pos = Vec3(c.to_world[3], c.to_world[7], c.to_world[11]);
     cam.dir = cam.xformDir(Vec3(0, 0, 1));
     cam.tanHalf = std::tan(0.5 * (Float) c.xfov_deg * PI / 180.0);
