@@ -23,6 +23,12 @@ import ref_leaf_cases as R
 TOL = {"fresnelDiffuseReflectance": 1e-5, "microfacet_ggx_all": 4e-15, "microfacet_ggx_visible": 4e-15}
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _oracle_built():
+    import oracle_lib as _ol
+    _ol.load()          # builds oracle/_build/liboracle.so if it is missing (fresh checkout)
+
+
 @pytest.fixture(scope="module")
 def golden():
     return dict(np.load(R.GOLDEN))
