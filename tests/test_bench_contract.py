@@ -1,0 +1,35 @@
+"""The CPU arm of bench.py (`--impl reference`) prints the contract's JSON line.  With oracle/_ref present it times the
+reference's own DRMLT integrator (cpu_baseline.kind "reference"), otherwise the oracle port ("port").  Runs on the small
+Cornell scene so that the CPU suite stays short; the GPU arm is covered by the driver's own bench run."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scene", "cornell", "--steps", "1", "--warmup", "0",
+                          "--ref-spp", "16"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+                "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "chain_mutations_per_sec" and line["unit"] == "mutations/s"
+    assert line["value"] > 1e4 and line["gpu_launches"] == 0
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    cb = line["cpu_baseline"]
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_path.so"))
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
+    if have_ref:      # the reference's statistics counters travel with the line
+        assert 0 < cb["acceptance_percent"]["Overall acceptance rate"] < 100
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ""
