@@ -507,7 +507,7 @@ static void make_params(const dr_config &c, int W, int H, double b, const int *e
     pp.kel_s2 = s2 * scale;
     pp.kel_logRatio = -std::log((s2 * scale) / (s1 * scale));
     pp.sigma2 = (double) c.scale_second * (double) c.sigma;
-    const double rho = std::exp(-0.25);
+    const double rho = std::exp(-0.25f);   // a FLOAT exponential, as m_rho (drmlt_sampler.h:204)
     pp.cauchy_disp = 2.0 * rho / (1.0 + rho * rho);
     pp.pss_kelemen = c.kelemen_style_mutation;
     pp.pss_s2 = c.mutation_size_high;

@@ -389,6 +389,24 @@ void orc_microfacet(int type, double alpha, int sampleVisible, const double *wi,
 }
 double orc_kelemen_logpdf(double s1, double s2, double du) { return KelemenKernel(s1, s2).logPdf(du); }
 
+
+// DRMLTSampler (drmlt_sampler.cpp:189-414) on an explicit current state and an explicit stream of uniforms consumed in call
+// order: stage-1 proposal, stage-2 proposal (after setLargeStep(false), as timidAfterLarge does), Green's reverse state
+// y* = z - (y - x), Mira's transition ratio.  Held against the reference's own sampler by tests/test_ref_pins.py.
+int orc_drmlt_sampler(int type, int maxDim, double sigma, double scaleSecond, int largeStep, const double *uCurrent,
+                      const double *stream, double *prop1, double *prop2, double *reverse, double *ratio) {
+    KeyedSource src; src.seq = stream; src.seqPos = 0;
+    DRMLTSampler s; s.type = type; s.samplerId = 0; s.src = &src; s.maxDim = (size_t) maxDim; s.sigma = sigma; s.scaleSecond = scaleSecond;
+    s.uCurrent.assign(uCurrent, uCurrent + maxDim);
+    s.setLargeStep(largeStep != 0);
+    for (int k = 0; k < maxDim; ++k) prop1[k] = s.primarySample((size_t) k);
+    s.nextStage(); s.setLargeStep(false);
+    for (int k = 0; k < maxDim; ++k) prop2[k] = s.primarySample((size_t) k);
+    if (type == DR_TYPE_GREEN) { s.setReverse(true); for (int k = 0; k < maxDim; ++k) reverse[k] = s.primarySample((size_t) k); }
+    *ratio = type == DR_TYPE_MIRA ? s.getTransitionRatio() : 1.0;
+    return (int) src.seqPos;
+}
+
 // transition kernels (transition.h) for known-answer tests
 double orc_kelemen_sample(double s1, double s2, double xi) { return KelemenKernel(s1, s2).sample(xi); }
 double orc_kelemen_pdf(double s1, double s2, double du) { return KelemenKernel(s1, s2).pdf(du); }

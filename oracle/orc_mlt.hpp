@@ -85,7 +85,12 @@ struct KeyedSource {
     uint64_t seed = 0, chain = 0;
     uint32_t mut = 0;
     Float coin(int which) const { return keyedUniform(seed, S_COIN, chain, mut, (uint32_t) which); }
+    // sequential mode (tests/test_ref_pins.py): the stage uniforms come, in call order, from a recorded stream of the
+    // reference's own generator, so that the sampler arithmetic can be held against drmlt_sampler.cpp draw by draw
+    const double *seq = nullptr;
+    mutable size_t seqPos = 0;
     Float stage(int stageIdx, int sampler, int coord, int draw) const {
+        if (seq) return seq[seqPos++];
         return keyedUniform(seed, (stageIdx == 0 ? S_STAGE1 : S_STAGE2) + sampler, chain, mut, (uint32_t) (2 * coord + draw));
     }
     static Float boot(uint64_t seed, uint64_t index, int sampler, int coord) {
@@ -144,7 +149,7 @@ struct DRMLTSampler : Sampler {
         const int st = first ? 0 : 1;
         KelemenKernel kel(type == DR_TYPE_ORBITAL ? s1 * kelemenScale : s1, type == DR_TYPE_ORBITAL ? s2 * kelemenScale : s2);
         GaussianKernel gauss{ scaleSecond * sigma };
-        WrappedCauchyKernel cauchy(std::exp(-0.25));
+        WrappedCauchyKernel cauchy(std::exp(-0.25f));   // a FLOAT exponential: m_rho = std::exp(-0.25f) (drmlt_sampler.h:204)
         bool savedFirst = isFirst; isFirst = first;
         const bool identity = kernelIsIdentity();
         isFirst = savedFirst;
@@ -155,7 +160,10 @@ struct DRMLTSampler : Sampler {
                 uProposed.push_back(uCurrent[i]);
             } else if (type != DR_TYPE_ORBITAL) {
                 if (first) uProposed.push_back(uCurrent[i] + kel.sample(src->stage(st, samplerId, (int) i, 0)));
-                else uProposed.push_back(uCurrent[i] + gauss.sample(src->stage(st, samplerId, (int) i, 0), src->stage(st, samplerId, (int) i, 1)));
+                else {
+                    const Float xi1 = src->stage(st, samplerId, (int) i, 0), xi2 = src->stage(st, samplerId, (int) i, 1);   // in this order (transition.h:63-66)
+                    uProposed.push_back(uCurrent[i] + gauss.sample(xi1, xi2));
+                }
             } else if (first) {   // orbital first stage: 2-D radial Kelemen (:351-359)
                 Float d = kel.sample(src->stage(st, samplerId, (int) i, 0));
                 Float a = src->stage(st, samplerId, (int) i, 1) * 2.0 * PI;

@@ -198,6 +198,8 @@ ref<BSDF> makeBSDF(const dr_material &m) {
 
 extern "C" {
 
+void ref_init() { initOnce(); }
+
 static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties *integrator = NULL, int sampleCount = 1);
 void *ref_scene_create(const dr_scene_desc *d, int rfilter) {
     try { return scene_create(d, rfilter); }

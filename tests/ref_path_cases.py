@@ -281,3 +281,46 @@ def check_rates_and_b(name, st, b, golden):
     bs = golden[name + "_b"]
     assert abs(b - bs.mean()) <= 0.005 * bs.mean() + (bs.max() - bs.min()) / 2, (name, b, bs)
     return out
+
+
+# ---------------------------------------------------------------- the reference's DRMLT samplers (Green / Mira / Orbital)
+GOLDEN_SAMPLER = os.path.join(ROOT, "tests", "golden", "ref_sampler.npz")
+SAMPLER_DIM, SAMPLER_SEEDS = 30, 24
+
+
+def run_sampler_ref(lib):
+    """ref_drmlt_sampler (oracle/ref/ref_sampler.cpp) for every type x {small, large} step x seed ->
+    dict of arrays: current state, the uniform stream the sampler consumed, stage-1 / stage-2 proposals, Green's reverse
+    state, Mira's transition ratio."""
+    lib.ref_drmlt_sampler.argtypes = [C.c_int, C.c_int, D, D, C.c_int, C.c_uint64, PD, PD, C.c_int, PD, PD, PD, PD]
+    md, ns = SAMPLER_DIM, 6 * SAMPLER_DIM
+    p = lambda a: a.ctypes.data_as(PD)      # noqa: E731
+    out = {}
+    for type_ in (0, 1, 2):
+        for large in (0, 1):
+            rows = []
+            for seed in range(SAMPLER_SEEDS):
+                uc, st, p1, p2, rv, ra = np.zeros(md), np.zeros(ns), np.zeros(md), np.zeros(md), np.zeros(md), D()
+                rc = lib.ref_drmlt_sampler(type_, md, 1.0 / 64, 0.1, large, 1000 * type_ + 100 * large + seed + 1, p(uc), p(st), ns, p(p1), p(p2), p(rv), C.byref(ra))
+                assert rc == 0
+                rows.append(np.concatenate([uc, st, p1, p2, rv, [ra.value]]))
+            out["sampler_%d_%d" % (type_, large)] = np.array(rows)
+    return out
+
+
+def run_sampler_oracle(lib, ref_rows):
+    """The oracle's DRMLTSampler on the current states and uniform streams recorded from the reference."""
+    lib.orc_drmlt_sampler.argtypes = [C.c_int, C.c_int, D, D, C.c_int, PD, PD, PD, PD, PD, PD]
+    md, ns = SAMPLER_DIM, 6 * SAMPLER_DIM
+    p = lambda a: a.ctypes.data_as(PD)      # noqa: E731
+    out = {}
+    for key, rows in ref_rows.items():
+        type_, large = int(key.split("_")[1]), int(key.split("_")[2])
+        res = []
+        for row in rows:
+            uc, st = np.ascontiguousarray(row[:md]), np.ascontiguousarray(row[md:md + ns])
+            p1, p2, rv, ra = np.zeros(md), np.zeros(md), np.zeros(md), D()
+            lib.orc_drmlt_sampler(type_, md, 1.0 / 64, 0.1, large, p(uc), p(st), p(p1), p(p2), p(rv), C.byref(ra))
+            res.append(np.concatenate([uc, st, p1, p2, rv, [ra.value]]))
+        out[key] = np.array(res)
+    return out

@@ -212,3 +212,38 @@ def test_reference_render_fixture_is_consistent(golden_render):
     assert golden_render["drmlt_mira_path_b"].mean() == pytest.approx(golden_render["pssmlt_mmlt_b"].mean(), rel=1e-2)
     runs = golden_render["drmlt_orbital_mmlt_relmse_runs"]
     assert (runs > 0).all() and runs.max() < 0.05
+
+
+# ================================================================ the delayed-rejection samplers themselves
+# drmlt_sampler.cpp (Green / Mira / Orbital) compiled into oracle/_ref (oracle/ref/ref_sampler.cpp).  The reference's Random is
+# seeded explicitly and a twin generator records the uniforms the sampler consumes; the oracle's sampler, fed the same current
+# state and the same stream in call order, must produce the same stage-1 and stage-2 proposals (Kelemen, Gaussian, the 2-D
+# radial Kelemen and the pairwise orbital rotation with its wrapped-Cauchy angle), the same Green reverse state
+# y* = z - (y - x) and the same Mira transition ratio -- bit for bit.
+def _same(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+@needs_ref_path
+def test_oracle_drmlt_samplers_equal_reference_samplers_bit_for_bit():
+    ref = RP.run_sampler_ref(C.CDLL(RP.REF_PATH))
+    got = RP.run_sampler_oracle(C.CDLL(RP.ORACLE), ref)
+    for key in sorted(ref):
+        assert _same(got[key], ref[key]), key
+
+
+def test_oracle_drmlt_samplers_reproduce_reference_fixture():
+    gold = dict(np.load(RP.GOLDEN_SAMPLER))
+    assert len(gold) == 6
+    got = RP.run_sampler_oracle(C.CDLL(RP.ORACLE), gold)
+    md = RP.SAMPLER_DIM
+    for key in sorted(gold):
+        g, w = got[key], gold[key]
+        assert g.shape == w.shape and np.isnan(g).tolist() == np.isnan(w).tolist(), key
+        assert np.allclose(g, w, rtol=1e-9, atol=1e-12, equal_nan=True), key       # other libm variants may round the last bits
+        # large steps redraw every coordinate uniformly; small steps stay within the kernels' reach of the current state
+        p1 = w[:, 7 * md:8 * md]
+        if key.endswith("_0"):
+            assert np.abs(p1 - w[:, :md]).max() < 2 * 1.9 / 64 + 1e-12, key
+        else:
+            assert 0.2 < np.abs(p1 - w[:, :md]).mean() < 0.45, key

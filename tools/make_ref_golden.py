@@ -34,6 +34,10 @@ for case in RP.PATH_CASES:
 np.savez_compressed(RP.GOLDEN, **out)
 print("wrote", RP.GOLDEN, os.path.getsize(RP.GOLDEN), "bytes")
 
+# ---- the reference's own DRMLT samplers (Green / Mira / Orbital) on recorded uniform streams
+np.savez_compressed(RP.GOLDEN_SAMPLER, **RP.run_sampler_ref(lib))
+print("wrote", RP.GOLDEN_SAMPLER, os.path.getsize(RP.GOLDEN_SAMPLER), "bytes")
+
 # ---- the reference's own DRMLT / PSSMLT integrators end to end (statistics counters, b, images)
 rout = {}
 RUNS = 3            # the reference seeds from /dev/urandom: keep its own run-to-run spread next to the values
