@@ -407,6 +407,24 @@ int orc_drmlt_sampler(int type, int maxDim, double sigma, double scaleSecond, in
     return (int) src.seqPos;
 }
 
+// PSSMLTSampler (pssmlt_sampler.cpp:93-166, pssmlt_sampler.h:117-147) on an explicit current state and an explicit stream of
+// uniforms consumed in call order, over a SEQUENCE of mutations: per mutation setLargeStep -> primarySample(0..maxDim-1) ->
+// accept / reject (eager fill, Kelemen / Gaussian mutation, backup / restore).  Held against the reference's own sampler
+// by tests/test_ref_pins.py.
+int orc_pssmlt_sampler(int kelemen, int maxDim, double s1, double s2, double sigma, int nMut, const int *large, const int *accepted,
+                       const double *uCurrent, const double *stream, double *proposals) {
+    KeyedSource src; src.seq = stream; src.seqPos = 0;
+    PSSMLTSampler s; s.samplerId = 0; s.src = &src; s.maxDim = (size_t) maxDim; s.useKelemen = kelemen != 0;
+    s.configure(s1, s2, sigma);
+    s.u.assign(uCurrent, uCurrent + maxDim);
+    for (int m = 0; m < nMut; ++m) {
+        s.setLargeStep(large[m] != 0);
+        for (int k = 0; k < maxDim; ++k) proposals[(size_t) m * maxDim + k] = s.primarySample((size_t) k);
+        if (accepted[m]) s.accept(); else s.reject();
+    }
+    return (int) src.seqPos;
+}
+
 // transition kernels (transition.h) for known-answer tests
 double orc_kelemen_sample(double s1, double s2, double xi) { return KelemenKernel(s1, s2).sample(xi); }
 double orc_kelemen_pdf(double s1, double s2, double du) { return KelemenKernel(s1, s2).pdf(du); }

@@ -324,3 +324,56 @@ def run_sampler_oracle(lib, ref_rows):
             res.append(np.concatenate([uc, st, p1, p2, rv, [ra.value]]))
         out[key] = np.array(res)
     return out
+
+
+# ---------------------------------------------------------------- the reference's PSSMLT sampler over a sequence of mutations
+GOLDEN_PSS_SAMPLER = os.path.join(ROOT, "tests", "golden", "ref_pssmlt_sampler.npz")
+PSS_DIM, PSS_MUT, PSS_SEEDS = 50, 12, 16            # maxDim of C1 (pssmlt_utils.h:27-77: 50 for path, maxDepth 8)
+PSS_S1, PSS_S2, PSS_SIGMA = 1.0 / 1024, 1.0 / 64, 1.0 / 64
+PI32 = C.POINTER(C.c_int32)
+
+
+def pss_pattern(seed):
+    """Which mutations are large steps and which are accepted: a pure function of the seed (pLarge 0.3, ~half accepted)."""
+    rng = np.random.RandomState(4242 + seed)
+    return (rng.rand(PSS_MUT) < 0.3).astype(np.int32), (rng.rand(PSS_MUT) < 0.5).astype(np.int32)
+
+
+def run_pss_sampler_ref(lib):
+    """ref_pssmlt_sampler (oracle/ref/ref_pssmlt_sampler.cpp) for {Kelemen, Gaussian} x seed -> rows
+    [current state | recorded uniform stream | proposals of every mutation]."""
+    lib.ref_pssmlt_sampler.argtypes = [C.c_int, C.c_int, D, D, D, C.c_uint64, C.c_int, PI32, PI32, PD, PD, C.c_int, PD]
+    md, ns = PSS_DIM, 2 * PSS_DIM * PSS_MUT
+    p = lambda a: a.ctypes.data_as(PD)      # noqa: E731
+    out = {}
+    for kelemen in (1, 0):
+        rows = []
+        for seed in range(PSS_SEEDS):
+            large, acc = pss_pattern(seed)
+            uc, st, pr = np.zeros(md), np.zeros(ns), np.zeros(md * PSS_MUT)
+            rc = lib.ref_pssmlt_sampler(kelemen, md, PSS_S1, PSS_S2, PSS_SIGMA, 7000 + 100 * kelemen + seed, PSS_MUT,
+                                        large.ctypes.data_as(PI32), acc.ctypes.data_as(PI32), p(uc), p(st), ns, p(pr))
+            assert rc == 0
+            rows.append(np.concatenate([uc, st, pr]))
+        out["pss_%d" % kelemen] = np.array(rows)
+    return out
+
+
+def run_pss_sampler_oracle(lib, ref_rows):
+    """The oracle's PSSMLTSampler on the current states and uniform streams recorded from the reference."""
+    lib.orc_pssmlt_sampler.argtypes = [C.c_int, C.c_int, D, D, D, C.c_int, PI32, PI32, PD, PD, PD]
+    md, ns = PSS_DIM, 2 * PSS_DIM * PSS_MUT
+    p = lambda a: a.ctypes.data_as(PD)      # noqa: E731
+    out, used = {}, {}
+    for key, rows in ref_rows.items():
+        kelemen = int(key.split("_")[1])
+        res, cnt = [], []
+        for seed, row in enumerate(rows):
+            large, acc = pss_pattern(seed)
+            uc, st = np.ascontiguousarray(row[:md]), np.ascontiguousarray(row[md:md + ns])
+            pr = np.zeros(md * PSS_MUT)
+            cnt.append(lib.orc_pssmlt_sampler(kelemen, md, PSS_S1, PSS_S2, PSS_SIGMA, PSS_MUT, large.ctypes.data_as(PI32),
+                                              acc.ctypes.data_as(PI32), p(uc), p(st), p(pr)))
+            res.append(np.concatenate([uc, st, pr]))
+        out[key], used[key] = np.array(res), cnt
+    return out, used

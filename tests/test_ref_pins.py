@@ -247,3 +247,33 @@ def test_oracle_drmlt_samplers_reproduce_reference_fixture():
             assert np.abs(p1 - w[:, :md]).max() < 2 * 1.9 / 64 + 1e-12, key
         else:
             assert 0.2 < np.abs(p1 - w[:, :md]).mean() < 0.45, key
+
+
+# ================================================================ the PSSMLT sampler over a sequence of mutations
+# pssmlt_sampler.{h,cpp} compiled into oracle/_ref (oracle/ref/ref_pssmlt_sampler.cpp): seed replay, then 12 mutations with a
+# fixed large-step / accept pattern.  The oracle's PSSMLTSampler, fed the same current state and the recorded stream in call
+# order, must propose the same states in every mutation -- eager fill of all maxDim coordinates, Kelemen (one uniform) and
+# Gaussian (two uniforms, Box-Muller) mutation with their wraps, uniform large steps, restore on reject -- bit for bit.
+@needs_ref_path
+def test_oracle_pssmlt_sampler_equals_reference_sampler_bit_for_bit():
+    ref = RP.run_pss_sampler_ref(C.CDLL(RP.REF_PATH))
+    got, _ = RP.run_pss_sampler_oracle(C.CDLL(RP.ORACLE), ref)
+    for key in sorted(ref):
+        assert _same(got[key], ref[key]), key
+
+
+def test_oracle_pssmlt_sampler_reproduces_reference_fixture():
+    gold = dict(np.load(RP.GOLDEN_PSS_SAMPLER))
+    assert sorted(gold) == ["pss_0", "pss_1"]
+    got, used = RP.run_pss_sampler_oracle(C.CDLL(RP.ORACLE), gold)
+    md, nm = RP.PSS_DIM, RP.PSS_MUT
+    for key in sorted(gold):
+        g, w = got[key], gold[key]
+        assert g.shape == w.shape
+        assert np.allclose(g, w, rtol=1e-9, atol=1e-12), key       # other libm variants may round the last bits
+        props = w[:, md + 2 * md * nm:].reshape(len(w), nm, md)
+        assert props.min() >= 0.0 and props.max() <= 1.0, key
+        for seed in range(len(w)):
+            large, _ = RP.pss_pattern(seed)
+            draws = 1 if key == "pss_1" else 2                     # uniforms per coordinate of a small step
+            assert used[key][seed] == md * int(large.sum() + draws * (nm - large.sum())), (key, seed)

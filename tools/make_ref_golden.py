@@ -37,6 +37,8 @@ print("wrote", RP.GOLDEN, os.path.getsize(RP.GOLDEN), "bytes")
 # ---- the reference's own DRMLT samplers (Green / Mira / Orbital) on recorded uniform streams
 np.savez_compressed(RP.GOLDEN_SAMPLER, **RP.run_sampler_ref(lib))
 print("wrote", RP.GOLDEN_SAMPLER, os.path.getsize(RP.GOLDEN_SAMPLER), "bytes")
+np.savez_compressed(RP.GOLDEN_PSS_SAMPLER, **RP.run_pss_sampler_ref(lib))
+print("wrote", RP.GOLDEN_PSS_SAMPLER, os.path.getsize(RP.GOLDEN_PSS_SAMPLER), "bytes")
 
 # ---- the reference's own DRMLT / PSSMLT integrators end to end (statistics counters, b, images)
 rout = {}
