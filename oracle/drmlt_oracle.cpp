@@ -407,6 +407,37 @@ int orc_drmlt_sampler(int type, int maxDim, double sigma, double scaleSecond, in
     return (int) src.seqPos;
 }
 
+// The same sampler over a SEQUENCE of mutations, driven as DRMLTRenderer::process drives it (drmlt_proc.cpp:541-760): outcome 0 =
+// accept the first stage, 1 = second stage accepted, 2 = second stage rejected; mode 1 = handleLightTracing() (emitter sampler
+// under fixEmitterPath), mode 2 = setStagesToIdentity() (MMLT direct sampler).  NaN marks what a mutation did not produce.
+int orc_drmlt_sampler_seq(int type, int mode, int maxDim, double sigma, double scaleSecond, int nMut, const int *large, const int *outcome,
+                          const int *lightTracing, const double *uCurrent, const double *stream,
+                          double *prop1, double *prop2, double *reverse, double *ratio) {
+    KeyedSource src; src.seq = stream; src.seqPos = 0;
+    DRMLTSampler s; s.type = type; s.samplerId = 0; s.src = &src; s.maxDim = (size_t) maxDim; s.sigma = sigma; s.scaleSecond = scaleSecond;
+    s.stage2Identity = mode == 1; s.identityAll = mode == 2;
+    s.uCurrent.assign(uCurrent, uCurrent + maxDim);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int m = 0; m < nMut; ++m) {
+        double *p1 = prop1 + (size_t) m * maxDim, *p2 = prop2 + (size_t) m * maxDim, *rv = reverse + (size_t) m * maxDim;
+        for (int k = 0; k < maxDim; ++k) p1[k] = p2[k] = rv[k] = nan;
+        ratio[m] = nan;
+        s.setLargeStep(large[m] != 0);
+        for (int k = 0; k < maxDim; ++k) p1[k] = s.primarySample((size_t) k);
+        if (outcome[m] == 0) { s.accept(true); continue; }
+        s.nextStage(lightTracing[m] != 0); s.setLargeStep(false);
+        for (int k = 0; k < maxDim; ++k) p2[k] = s.primarySample((size_t) k);
+        if (type == DR_TYPE_GREEN) {
+            s.setReverse(true);
+            for (int k = 0; k < maxDim; ++k) rv[k] = s.primarySample((size_t) k);
+            s.setReverse(false);
+        }
+        ratio[m] = type == DR_TYPE_MIRA ? s.getTransitionRatio() : 1.0;
+        if (outcome[m] == 1) s.accept(false); else s.reject();
+    }
+    return (int) src.seqPos;
+}
+
 // PSSMLTSampler (pssmlt_sampler.cpp:93-166, pssmlt_sampler.h:117-147) on an explicit current state and an explicit stream of
 // uniforms consumed in call order, over a SEQUENCE of mutations: per mutation setLargeStep -> primarySample(0..maxDim-1) ->
 // accept / reject (eager fill, Kelemen / Gaussian mutation, backup / restore).  Held against the reference's own sampler

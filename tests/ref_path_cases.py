@@ -377,3 +377,50 @@ def run_pss_sampler_oracle(lib, ref_rows):
             res.append(np.concatenate([uc, st, pr]))
         out[key], used[key] = np.array(res), cnt
     return out, used
+
+
+# ---------------------------------------------------------------- the DRMLT samplers over a sequence of mutations
+GOLDEN_SAMPLER_SEQ = os.path.join(ROOT, "tests", "golden", "ref_sampler_seq.npz")
+SEQ_DIM, SEQ_MUT, SEQ_SEEDS = 30, 10, 8
+
+
+def seq_pattern(seed):
+    """Per mutation: large step?, outcome (0 first stage accepted / 1 second accepted / 2 second rejected), light-tracing stage?"""
+    rng = np.random.RandomState(977 + seed)
+    return ((rng.rand(SEQ_MUT) < 0.3).astype(np.int32), rng.randint(0, 3, SEQ_MUT).astype(np.int32), (rng.rand(SEQ_MUT) < 0.5).astype(np.int32))
+
+
+def _seq_run(fn, is_ref, type_, mode, seed, uc=None, st=None):
+    md, nm, ns = SEQ_DIM, SEQ_MUT, 6 * SEQ_DIM * SEQ_MUT
+    p = lambda a: a.ctypes.data_as(PD)      # noqa: E731
+    pi = lambda a: a.ctypes.data_as(PI32)   # noqa: E731
+    large, outc, lt = seq_pattern(seed)
+    if mode != 1:
+        lt = np.zeros_like(lt)          # nextStage(true) only reaches a sampler after handleLightTracing() (drmlt_proc.cpp:566-571)
+    p1, p2, rv, ra = np.zeros(md * nm), np.zeros(md * nm), np.zeros(md * nm), np.zeros(nm)
+    if is_ref:
+        uc, st = np.zeros(md), np.zeros(ns)
+        rc = fn(type_, mode, md, 1.0 / 64, 0.1, 5000 + 1000 * type_ + 100 * mode + seed, nm, pi(large), pi(outc), pi(lt), p(uc), p(st), ns, p(p1), p(p2), p(rv), p(ra))
+        assert rc == 0
+    else:
+        rc = fn(type_, mode, md, 1.0 / 64, 0.1, nm, pi(large), pi(outc), pi(lt), p(uc), p(st), p(p1), p(p2), p(rv), p(ra))
+        assert 0 < rc <= ns
+    return np.concatenate([uc, st, p1, p2, rv, ra])
+
+
+def run_sampler_seq_ref(lib):
+    """ref_drmlt_sampler_seq for every type x mode (0 plain, 1 handleLightTracing, 2 setStagesToIdentity) x seed."""
+    lib.ref_drmlt_sampler_seq.argtypes = [C.c_int, C.c_int, C.c_int, D, D, C.c_uint64, C.c_int, PI32, PI32, PI32, PD, PD, C.c_int, PD, PD, PD, PD]
+    return {"seq_%d_%d" % (t, m): np.array([_seq_run(lib.ref_drmlt_sampler_seq, True, t, m, s) for s in range(SEQ_SEEDS)])
+            for t in (0, 1, 2) for m in (0, 1, 2)}
+
+
+def run_sampler_seq_oracle(lib, ref_rows):
+    lib.orc_drmlt_sampler_seq.argtypes = [C.c_int, C.c_int, C.c_int, D, D, C.c_int, PI32, PI32, PI32, PD, PD, PD, PD, PD, PD]
+    md, ns = SEQ_DIM, 6 * SEQ_DIM * SEQ_MUT
+    out = {}
+    for key, rows in ref_rows.items():
+        t, m = int(key.split("_")[1]), int(key.split("_")[2])
+        out[key] = np.array([_seq_run(lib.orc_drmlt_sampler_seq, False, t, m, s, np.ascontiguousarray(r[:md]), np.ascontiguousarray(r[md:md + ns]))
+                             for s, r in enumerate(rows)])
+    return out

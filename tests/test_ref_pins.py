@@ -277,3 +277,42 @@ def test_oracle_pssmlt_sampler_reproduces_reference_fixture():
             large, _ = RP.pss_pattern(seed)
             draws = 1 if key == "pss_1" else 2                     # uniforms per coordinate of a small step
             assert used[key][seed] == md * int(large.sum() + draws * (nm - large.sum())), (key, seed)
+
+
+# ================================================================ the DRMLT samplers over a sequence of mutations
+# ref_drmlt_sampler_seq (oracle/ref/ref_sampler.cpp) drives Green / Mira / Orbital the way DRMLTRenderer::process does
+# (drmlt_proc.cpp:541-760) for 10 consecutive mutations with a fixed pattern of large steps and outcomes (first stage accepted,
+# second stage accepted, second stage rejected), plain, after handleLightTracing() (the emitter sampler under fixEmitterPath,
+# with light-tracing second stages) and after setStagesToIdentity() (the MMLT direct sampler).  Every proposal of every
+# mutation, Green's reverse states and Mira's ratios must agree bit for bit: the state carried from mutation to mutation
+# (accept's wrap, reject's reset) is then the reference's too.
+@needs_ref_path
+def test_oracle_drmlt_sampler_sequences_equal_reference_bit_for_bit():
+    ref = RP.run_sampler_seq_ref(C.CDLL(RP.REF_PATH))
+    got = RP.run_sampler_seq_oracle(C.CDLL(RP.ORACLE), ref)
+    for key in sorted(ref):
+        assert _same(got[key], ref[key]), key
+
+
+def test_oracle_drmlt_sampler_sequences_reproduce_reference_fixture():
+    gold = dict(np.load(RP.GOLDEN_SAMPLER_SEQ))
+    assert len(gold) == 9
+    got = RP.run_sampler_seq_oracle(C.CDLL(RP.ORACLE), gold)
+    md, nm = RP.SEQ_DIM, RP.SEQ_MUT
+    off = md + 6 * md * nm
+    for key in sorted(gold):
+        g, w = got[key], gold[key]
+        assert g.shape == w.shape and np.isnan(g).tolist() == np.isnan(w).tolist(), key
+        assert np.allclose(g, w, rtol=1e-9, atol=1e-12, equal_nan=True), key       # other libm variants may round the last bits
+        type_, mode = int(key.split("_")[1]), int(key.split("_")[2])
+        for seed in range(len(w)):
+            _, outc, _ = RP.seq_pattern(seed)
+            p1 = w[seed, off:off + md * nm].reshape(nm, md)
+            p2 = w[seed, off + md * nm:off + 2 * md * nm].reshape(nm, md)
+            rv = w[seed, off + 2 * md * nm:off + 3 * md * nm].reshape(nm, md)
+            assert not np.isnan(p1).any()
+            assert np.isnan(p2).all(axis=1).tolist() == (outc == 0).tolist(), (key, seed)      # a second stage exactly where one was taken
+            assert np.isnan(rv).all(axis=1).tolist() == ((outc == 0) | (type_ != 0)).tolist(), (key, seed)
+            large = RP.seq_pattern(seed)[0]
+            if mode == 2 and not large[0]:       # identity stages: a small step proposes the current state itself
+                assert np.array_equal(p1[0], w[seed, :md]), (key, seed)

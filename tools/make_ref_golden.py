@@ -39,6 +39,8 @@ np.savez_compressed(RP.GOLDEN_SAMPLER, **RP.run_sampler_ref(lib))
 print("wrote", RP.GOLDEN_SAMPLER, os.path.getsize(RP.GOLDEN_SAMPLER), "bytes")
 np.savez_compressed(RP.GOLDEN_PSS_SAMPLER, **RP.run_pss_sampler_ref(lib))
 print("wrote", RP.GOLDEN_PSS_SAMPLER, os.path.getsize(RP.GOLDEN_PSS_SAMPLER), "bytes")
+np.savez_compressed(RP.GOLDEN_SAMPLER_SEQ, **RP.run_sampler_seq_ref(lib))
+print("wrote", RP.GOLDEN_SAMPLER_SEQ, os.path.getsize(RP.GOLDEN_SAMPLER_SEQ), "bytes")
 
 # ---- the reference's own DRMLT / PSSMLT integrators end to end (statistics counters, b, images)
 rout = {}
