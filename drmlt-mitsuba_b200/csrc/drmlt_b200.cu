@@ -537,7 +537,7 @@ static void make_params(const dr_config &c, int W, int H, double b, const int *e
     // reconstruction filter table (rfilter.cpp:37-55; gaussian.cpp:30-60 stddev 0.5 radius 2; box.cpp radius 0.5 + 1e-5)
     FilmParams &fp = p.fp;
     fp.w = W; fp.h = H;
-    const double stddev = 0.5, radius = c.rfilter == DR_FILTER_BOX ? (double) (0.5f + 1e-5f) : 4 * stddev;
+    const double stddev = 0.5, radius = c.rfilter == DR_FILTER_BOX ? 0.5 + (double) 1e-5f : 4 * stddev;   // Float 0.5 + a float literal (box.cpp:38)
     double vals[32], sum = 0.0;
     for (int i = 0; i < 31; ++i) {
         const double x = (radius * i) / 31;
@@ -548,7 +548,8 @@ static void make_params(const dr_config &c, int W, int H, double b, const int *e
     }
     vals[31] = 0.0;
     sum *= 2 * radius / 31;
-    for (int i = 0; i < 31; ++i) vals[i] /= sum;
+    const double normalization = 1.0 / sum;          // multiplied in, as rfilter.cpp:52-54
+    for (int i = 0; i < 31; ++i) vals[i] *= normalization;
     for (int i = 0; i < 32; ++i) fp.values[i] = (float) vals[i];
     fp.radius = (float) radius; fp.scaleFactor = (float) (31 / radius);
 }

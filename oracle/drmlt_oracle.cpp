@@ -310,6 +310,16 @@ int orc_splat(int w, int h, int rfilter, const float *pos, const float *rgb, int
     return 0;
 }
 
+// The same in double, with the per-splat verdict of put (false = rejected as non-finite / negative): held against the
+// reference's own ImageBlock::put by tests/test_ref_pins.py.
+int orc_splat_f64(int w, int h, int rfilter, const float *pos, const float *rgb, int64_t n, double *film_out, int *accepted) {
+    Film f; f.init(w, h, rfilter);
+    for (int64_t i = 0; i < n; ++i)
+        accepted[i] = f.put(Vec2(pos[2 * i], pos[2 * i + 1]), RGB(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2])) ? 1 : 0;
+    for (size_t i = 0; i < f.data.size(); ++i) film_out[i] = f.data[i];
+    return 0;
+}
+
 // BSDF leaf access for chi-square / consistency tests (modelled on src/tests/test_chisquare.cpp)
 void orc_bsdf_sample(const dr_material *m, const double *wi, int mode, double u1, double u2, double *wo, double *weight, double *pdf, int *sampledType) {
     BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), mode);

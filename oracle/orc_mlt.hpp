@@ -283,7 +283,7 @@ struct Film {
         w = w_; h = h_; data.assign((size_t) w * h * 3, 0.0);
         // gaussian.cpp:30-60 (stddev 0.5, radius 2) / box.cpp:30-46 (radius 0.5 + 1e-5); rfilter.cpp:37-55
         Float stddev = 0.5;
-        radius = rfilter == DR_FILTER_BOX ? 0.5 + 1e-5 : 4 * stddev;
+        radius = rfilter == DR_FILTER_BOX ? 0.5 + (Float) 1e-5f : 4 * stddev;   // a FLOAT literal added to Float 0.5 (box.cpp:38)
         Float sum = 0.0;
         for (int i = 0; i < 31; ++i) {
             Float x = (radius * i) / 31;
@@ -298,7 +298,8 @@ struct Film {
         values[31] = 0.0;
         scaleFactor = 31 / radius;
         sum *= 2 * radius / 31;
-        for (int i = 0; i < 31; ++i) values[i] /= sum;
+        const Float normalization = 1.0 / sum;          // multiplied in, as rfilter.cpp:52-54
+        for (int i = 0; i < 31; ++i) values[i] *= normalization;
     }
     Float evalDiscretized(Float x) const { return values[std::min((int) std::abs(x * scaleFactor), 31)]; }
     bool put(const Vec2 &_pos, const RGB &value) {

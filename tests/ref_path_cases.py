@@ -424,3 +424,32 @@ def run_sampler_seq_oracle(lib, ref_rows):
         out[key] = np.array([_seq_run(lib.orc_drmlt_sampler_seq, False, t, m, s, np.ascontiguousarray(r[:md]), np.ascontiguousarray(r[md:md + ns]))
                              for s, r in enumerate(rows)])
     return out
+
+
+# ---------------------------------------------------------------- the reference's ImageBlock::put with its own filter plugins
+GOLDEN_FILM = os.path.join(ROOT, "tests", "golden", "ref_film.npz")
+FILM_W, FILM_H, FILM_N = 37, 23, 4000
+PF32 = C.POINTER(C.c_float)
+
+
+def film_inputs():
+    """Splat positions (inside, on pixel / half-pixel lattices, up to 3 pixels outside) and values (incl. NaN, inf, negative)."""
+    rng = np.random.RandomState(5)
+    pos = (rng.rand(FILM_N, 2) * [FILM_W + 6, FILM_H + 6] - 3).astype(np.float32)
+    pos[:50] = np.round(pos[:50] * 2) / 2
+    rgb = (rng.rand(FILM_N, 3) ** 4 * 10).astype(np.float32)
+    rgb[5, 1], rgb[6, 0], rgb[7, 2] = np.nan, np.inf, -1e-3
+    return pos, rgb
+
+
+def run_film(fn, is_ref):
+    """{gaussian, box} -> film [h][w][3] in double + the verdict of every put."""
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, PF32, PF32, C.c_int64, PD, PI32]
+    pos, rgb = film_inputs()
+    out = {}
+    for name, gaussian in (("gaussian", 1), ("box", 0)):
+        film, ok = np.zeros((FILM_H, FILM_W, 3)), np.zeros(FILM_N, np.int32)
+        sel = gaussian if is_ref else (abi.DR_FILTER_GAUSSIAN if gaussian else abi.DR_FILTER_BOX)
+        assert fn(FILM_W, FILM_H, sel, pos.ctypes.data_as(PF32), rgb.ctypes.data_as(PF32), FILM_N, film.ctypes.data_as(PD), ok.ctypes.data_as(PI32)) == 0
+        out["film_" + name], out["ok_" + name] = film, ok
+    return out

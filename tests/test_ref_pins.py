@@ -316,3 +316,29 @@ def test_oracle_drmlt_sampler_sequences_reproduce_reference_fixture():
             large = RP.seq_pattern(seed)[0]
             if mode == 2 and not large[0]:       # identity stages: a small step proposes the current state itself
                 assert np.array_equal(p1[0], w[seed, :md]), (key, seed)
+
+
+# ================================================================ the film: ImageBlock::put with the reference's filter plugins
+# oracle/ref/ref_film.cpp: a block created as DRMLTProcess::createWorkResult creates it, 4000 splats (inside, on pixel and
+# half-pixel lattices, up to 3 pixels outside the film; NaN / inf / negative values) -> the oracle's Film::put accumulates
+# the same doubles and rejects the same splats.  (Pinning found: the box radius is Float 0.5 + the FLOAT literal 1e-5f,
+# box.cpp:38, and the filter table is normalised by multiplication, rfilter.cpp:52-54.)
+@needs_ref_path
+def test_oracle_film_equals_reference_imageblock_bit_for_bit():
+    lib_ref = C.CDLL(RP.REF_PATH)
+    ref, got = RP.run_film(lib_ref.ref_splat, True), RP.run_film(C.CDLL(RP.ORACLE).orc_splat_f64, False)
+    for key in sorted(ref):
+        assert np.array_equal(got[key], ref[key]), key
+
+
+def test_oracle_film_reproduces_reference_fixture():
+    gold = dict(np.load(RP.GOLDEN_FILM))
+    got = RP.run_film(C.CDLL(RP.ORACLE).orc_splat_f64, False)
+    pos, rgb = RP.film_inputs()
+    for name in ("gaussian", "box"):
+        assert np.array_equal(got["ok_" + name], gold["ok_" + name])
+        assert gold["ok_" + name][5:8].tolist() == [0, 0, 0] and gold["ok_" + name].sum() == RP.FILM_N - 3
+        assert np.allclose(got["film_" + name], gold["film_" + name], rtol=1e-12, atol=0), name
+    # a normalised filter keeps the energy of splats whose footprint lies inside the film
+    inside = (pos[:, 0] > 3) & (pos[:, 0] < RP.FILM_W - 3) & (pos[:, 1] > 3) & (pos[:, 1] < RP.FILM_H - 3) & (gold["ok_box"] == 1)
+    assert inside.sum() > 1000

@@ -42,6 +42,10 @@ print("wrote", RP.GOLDEN_PSS_SAMPLER, os.path.getsize(RP.GOLDEN_PSS_SAMPLER), "b
 np.savez_compressed(RP.GOLDEN_SAMPLER_SEQ, **RP.run_sampler_seq_ref(lib))
 print("wrote", RP.GOLDEN_SAMPLER_SEQ, os.path.getsize(RP.GOLDEN_SAMPLER_SEQ), "bytes")
 
+# ---- the reference's own ImageBlock::put with its gaussian / box filter plugins
+np.savez_compressed(RP.GOLDEN_FILM, **RP.run_film(lib.ref_splat, True))
+print("wrote", RP.GOLDEN_FILM, os.path.getsize(RP.GOLDEN_FILM), "bytes")
+
 # ---- the reference's own DRMLT / PSSMLT integrators end to end (statistics counters, b, images)
 rout = {}
 RUNS = 3            # the reference seeds from /dev/urandom: keep its own run-to-run spread next to the values
