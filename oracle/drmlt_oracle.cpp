@@ -46,6 +46,11 @@ void orc_max_dimensions(const dr_config *cfg, int depth, int *sensor, int *emitt
     MaxDim md = findMaxDimensions(cfg->max_depth, cfg->rr_depth, depth, cfg->technique, cfg->direct_sampling != 0, false);
     *sensor = md.sensor; *emitter = md.emitter; *direct = md.direct;
 }
+// ... with the scene's own hasRoughDielectric (pssmlt_utils.h:35-45); held against the reference by tests/test_ref_pins.py
+void orc_max_dimensions_scene(void *h, const dr_config *cfg, int depth, int *out3) {
+    MaxDim md = findMaxDimensions(cfg->max_depth, cfg->rr_depth, depth, cfg->technique, cfg->direct_sampling != 0, ((OrcScene *) h)->sc.hasRoughDielectric);
+    out3[0] = md.sensor; out3[1] = md.emitter; out3[2] = md.direct;
+}
 
 int orc_trace_rays(void *h, const dr_ray *rays, int64_t n, int shadow, float ray_epsilon, dr_hit *hits) {
     Scene &sc = ((OrcScene *) h)->sc;

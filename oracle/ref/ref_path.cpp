@@ -41,6 +41,7 @@
 #include <execinfo.h>
 #include <signal.h>
 #include "../../include/drmlt_b200.h"
+#include "src/integrators/pssmlt_utils.h"     // findMaxDimensions, as the integrators include it (drmlt.cpp, pssmlt.cpp)
 
 using namespace mitsuba;
 #define TR(msg) do { if (getenv("REF_TRACE")) fprintf(stderr, "[ref] %s\n", msg); } while (0)
@@ -296,6 +297,18 @@ static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties 
 }
 
 void ref_scene_destroy(void *h) { delete (RefScene *) h; }
+
+// findMaxDimensions (pssmlt_utils.h:27-77) on the scene built from the caller's dr_scene_desc: the primary-sample space sizes of
+// the three samplers, which depend on the scene (a RoughDielectric BSDF anywhere adds a dimension per vertex).
+int ref_max_dimensions(void *h, int max_depth, int rr_depth, int depth, int technique, int direct_sampling, int *out3) {
+    try {
+        const PathSampler::ETechnique tech = technique == DR_TECH_MMLT ? PathSampler::EMMLT
+            : technique == DR_TECH_PATH ? PathSampler::EUnidirectional : PathSampler::EBidirectional;
+        MaxDim md = findMaxDimensions(((RefScene *) h)->scene.get(), max_depth, rr_depth, depth, tech, direct_sampling != 0);
+        out3[0] = md.sensor; out3[1] = md.emitter; out3[2] = md.direct;
+        return 0;
+    } catch (const std::exception &e) { fprintf(stderr, "oracle/_ref: %s\n", e.what()); return 1; }
+}
 
 /* PathSampler::sampleSplats on replayed primary-sample vectors (pathsampler.cpp:79-571). */
 int ref_eval_paths(void *h, int technique, int max_depth, int rr_depth, int sample_direct, int light_image,

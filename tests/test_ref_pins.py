@@ -342,3 +342,41 @@ def test_oracle_film_reproduces_reference_fixture():
     # a normalised filter keeps the energy of splats whose footprint lies inside the film
     inside = (pos[:, 0] > 3) & (pos[:, 0] < RP.FILM_W - 3) & (pos[:, 1] > 3) & (pos[:, 1] < RP.FILM_H - 3) & (gold["ok_box"] == 1)
     assert inside.sum() > 1000
+
+
+# ================================================================ findMaxDimensions on the scene (pssmlt_utils.h:27-77)
+# The reference derives the primary-sample space sizes from the scene it was given: a RoughDielectric BSDF on any shape adds
+# one dimension per vertex, Russian roulette another.  Same scene description -> the reference's own function vs the oracle's.
+@needs_ref_path
+@pytest.mark.parametrize("scene_name", ["cornell", "roughglass"])
+def test_oracle_max_dimensions_equal_reference_on_the_scene(scene_name):
+    import oracle_lib
+    from drmlt_mitsuba_b200 import abi
+    from drmlt_mitsuba_b200.integrator import make_config
+    P = C.POINTER
+    lib = C.CDLL(RP.REF_PATH)
+    lib.ref_scene_create.restype = C.c_void_p
+    lib.ref_scene_create.argtypes = [P(abi.dr_scene_desc), C.c_int]
+    lib.ref_max_dimensions.argtypes = [C.c_void_p] + [C.c_int] * 5 + [P(C.c_int)]
+    data = RP.SCENES[scene_name]()
+    d = data.desc()
+    h = lib.ref_scene_create(C.byref(d), abi.DR_FILTER_GAUSSIAN)
+    assert h
+    orc = oracle_lib.OracleScene(data)
+    orc.lib.orc_max_dimensions_scene.argtypes = [C.c_void_p, P(abi.dr_config), C.c_int, P(C.c_int)]
+    seen = set()
+    for tech_name, tech in (("path", abi.DR_TECH_PATH), ("bdpt", abi.DR_TECH_BDPT), ("mmlt", abi.DR_TECH_MMLT)):
+        for max_depth in (3, 8, 11):
+            for rr_depth in (5, 20):
+                for direct in (False, True):
+                    cfg = make_config(integrator="drmlt", type="mira", technique=tech_name, maxDepth=max_depth, rrDepth=rr_depth, directSampling=False)
+                    cfg.direct_sampling = int(direct and tech_name == "bdpt")     # the product refuses it; the sizes are still defined
+                    for depth in range(1, max_depth + 1):
+                        a, b = (C.c_int * 3)(), (C.c_int * 3)()
+                        assert lib.ref_max_dimensions(h, max_depth, rr_depth, depth, tech, int(cfg.direct_sampling), a) == 0
+                        orc.lib.orc_max_dimensions_scene(orc.h, C.byref(cfg), depth, b)
+                        assert list(a) == list(b), (tech_name, max_depth, rr_depth, direct, depth, list(a), list(b))
+                        seen.add(tuple(a))
+    assert len(seen) > 12
+    if scene_name == "roughglass":
+        assert (10 * 6, 0, 0) in seen          # path, maxDepth 8, RR and rough dielectric: (8 + 2) * (4 + 1 + 1)
