@@ -27,7 +27,8 @@ float as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 } // namespace
 
 void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out) {
-    const int NB = 16, LEAF = 2;
+    const int NB = 16;
+    const int LEAF = getenv("DRMLT_BVH_LEAF") ? std::max(1, std::min(4, atoi(getenv("DRMLT_BVH_LEAF")))) : 2;   // triangles per leaf (the leaf code holds count - 1 in two bits)
     std::vector<Box> box(nTris);
     std::vector<float> cen(3 * (size_t) nTris);
     out.order.resize(nTris);

@@ -582,6 +582,10 @@ static dr_status check_technique(const dr_config &c) {
     return DR_OK;
 }
 
+// tuning knobs of the launch geometry (read per call, so a sweep can change them between jobs of one process)
+int stage_ctas_per_sm() { const char *e = getenv("DRMLT_STAGE_CTAS"); return e ? std::max(1, atoi(e)) : 16; }
+int trace_ctas_per_sm() { const char *e = getenv("DRMLT_TRACE_CTAS"); return e ? std::max(0, atoi(e)) : 0; }
+
 // ------------------------------------------------------------------ job
 enum { STAGE_TRACE = 0, STAGE_WALK, STAGE_CHAIN, STAGE_COUNT };
 struct dr_job_t;

@@ -270,6 +270,6 @@ k_bdpt(const __grid_constant__ Machine M) {
 }
 
 void launch_bdpt(const Machine &M, const LaunchCfg &lc) {
-    const unsigned g = (unsigned) std::max(1, std::min((lc.nLanes + 127) / 128, 148 * 16));
+    const unsigned g = stage_grid(lc.nLanes, 128);
     k_bdpt<<<g, 128, 0, lc.stream>>>(M);
 }

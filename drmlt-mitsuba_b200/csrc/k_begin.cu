@@ -189,6 +189,6 @@ k_begin(const __grid_constant__ Machine M) {
 }
 
 void launch_begin(const Machine &M, const LaunchCfg &lc) {
-    const unsigned g = (unsigned) std::max(1, std::min((lc.nLanes + 127) / 128 + 3, 148 * 16));
+    const unsigned g = stage_grid(lc.nLanes + 3 * 128, 128);
     k_begin<<<g, 128, 0, lc.stream>>>(M);
 }

@@ -515,7 +515,7 @@ __global__ void k_flush_pssmlt(const __grid_constant__ Machine M) {
     rec_store(M.lm.chain + lane, cc);
 }
 
-static unsigned grid_for(int n, int threads) { return (unsigned) std::max(1, std::min((n + threads - 1) / threads, 148 * 16)); }
+static unsigned grid_for(int n, int threads) { return stage_grid(n, threads); }
 
 void launch_chain(const Machine &M, const LaunchCfg &lc) {
     k_chain<<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M);

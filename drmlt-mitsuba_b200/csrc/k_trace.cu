@@ -4,6 +4,7 @@
 // found (the model is packed into the triangle record at scene creation), a miss or a shadow-ray result to the
 // chain queue (MMLT), everything to the path-tracer queue for technique=path.
 #include "machine.cuh"
+#include <algorithm>
 
 // Persistent warps with dynamic ray fetch: incoherent rays of one warp finish after very different numbers of node
 // visits, so lanes whose ray is done pull the next ray from the queue (one warp-aggregated atomic on the queue's head
@@ -107,11 +108,11 @@ __global__ void k_round_begin(uint32_t *count, int parity) {
 // persistent kernels: exactly as many CTAs as are resident at once (SMs x occupancy)
 static int gridC = 0;
 void trace_init() {                                          // outside any stream capture
-    if (gridC) return;
     int dev = 0, sms = 148, bc = 4;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_trace, 128, 0);
+    if (trace_ctas_per_sm() > 0) bc = std::min(bc, trace_ctas_per_sm());
     gridC = sms * std::max(bc, 1);
 }
 

@@ -188,7 +188,7 @@ k_connect(const __grid_constant__ Machine M) {
     }
 }
 
-static unsigned grid_for(int n, int threads) { return (unsigned) std::max(1, std::min((n + threads - 1) / threads, 148 * 16)); }
+static unsigned grid_for(int n, int threads) { return stage_grid(n, threads); }
 
 // the walk queues of all BSDF models in one launch, every warp on one model (multiq_locate)
 __global__ void __launch_bounds__(128, WALK_MINB)

@@ -444,6 +444,11 @@ DR_D int mmlt_emitter_launch(const Machine &M, int lane, Core &c, RayF &ray) {
 
 // ------------------------------------------------------------------ host-callable launchers (one per translation unit)
 struct LaunchCfg { cudaStream_t stream; int nLanes; };
+// Grid of a stage kernel (grid-stride loops over a queue): enough CTAs for `n` items, capped at `stageCtasPerSm` CTAs per SM so
+// that the stage kernels of different wavefront groups share the SMs instead of each flooding the device (DRMLT_STAGE_CTAS).
+int stage_ctas_per_sm();                                                  // drmlt_b200.cu
+int trace_ctas_per_sm();                                                  // drmlt_b200.cu: 0 = the occupancy limit
+inline unsigned stage_grid(int n, int threads) { return (unsigned) std::max(1, std::min((n + threads - 1) / threads, 148 * stage_ctas_per_sm())); }
 void trace_init();                                                        // k_trace.cu: occupancy query, once, outside stream capture
 void launch_trace(const Machine &M, const LaunchCfg &lc);                 // k_trace.cu: closest + shadow queues
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask);   // k_walk.cu: walk queues of the BSDF types present, then connect
