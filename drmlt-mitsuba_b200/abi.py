@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdrmlt_b200.so")
+# DRMLT_B200_LIB: another build of the same library (tools/build_variant.sh, A/B tuning runs)
+LIB_PATH = os.environ.get("DRMLT_B200_LIB") or os.path.join(_HERE, "csrc", "libdrmlt_b200.so")
 
 DR_OK = 0
 DR_BSDF_DIFFUSE, DR_BSDF_DIELECTRIC, DR_BSDF_CONDUCTOR, DR_BSDF_ROUGHCONDUCTOR, DR_BSDF_ROUGHDIELECTRIC, DR_BSDF_PLASTIC = 0, 1, 2, 3, 4, 5

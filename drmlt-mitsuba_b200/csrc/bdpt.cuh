@@ -1,4 +1,4 @@
-// bdpt.cuh -- pieces of the BDPT stage shared by k_begin.cu (path start) and k_bdpt.cu (walks and connections).
+// bdpt.cuh -- pieces of the BDPT stage shared by begin.cuh (path start) and k_bdpt.cu (walks and connections).
 #pragma once
 #include "machine.cuh"
 
@@ -78,7 +78,7 @@ DR_D bool bd_sensor_start(const Machine &M, int lane, Core &c, UReader &rd, BdAc
 }
 
 
-// Start of a BDPT path (called by k_begin): emitter supernode -> emitter sample -> first emitter ray, or -- when the
+// Start of a BDPT path (called by begin_path): emitter supernode -> emitter sample -> first emitter ray, or -- when the
 // emitter subpath cannot be extended -- the start of the sensor subpath.  Returns the queue (Q_RAYC) or -1.
 DR_D int bdpt_path_start(const Machine &M, int lane, Core &c, UReader &rd, RayF &ray) {
     const DevScene &sc = M.sc;

@@ -1,15 +1,15 @@
-// k_begin.cu -- start of a path: the proposal is mutated into the lane's coordinate buffer (pss.cuh) and the first
-// ray of its path is emitted.  One kernel instance per class of work, fed by its own queue (machine.cuh Q_BEGIN),
-// so that a warp runs ONE kind of transition-kernel arithmetic:
-//   BEGIN_STAGE1  first-stage proposal  (large step: uniforms | Kelemen | orbital: radial Kelemen + angle)
-//   BEGIN_STAGE2  second-stage proposal (Gaussian | orbital rotation by a wrapped-Cauchy angle)
-//   BEGIN_OTHER   seed replay, Green's reverse state, bootstrap samples, replayed vectors
+// begin.cuh -- start of a path, fused into the chain kernel (k_chain.cu): the proposal is mutated into the lane's coordinate
+// buffer (pss.cuh) and the first ray of its path is emitted, in the same thread that has just finished the chain-level step
+// (one Core round trip, one queue hand-off and one dependent launch per path less than a kernel of its own).
+//   stage 1   first-stage proposal  (large step: uniforms | Kelemen | orbital: radial Kelemen + angle)
+//   stage 2   second-stage proposal (Gaussian | orbital rotation by a wrapped-Cauchy angle)
+//   other     seed replay, Green's reverse state, bootstrap samples, replayed vectors
 // Behavioural parity: DRMLTSampler::fillSpace / OrbitalDRMLTSampler (src/integrators/drmlt/drmlt_sampler.cpp:313-394),
 // PSSMLTSampler::primarySample (src/integrators/pssmlt/pssmlt_sampler.cpp:124-166), the first steps of
 // PathSampler::sampleSplats (src/libbidir/pathsampler.cpp:84-146, 529-567).
+#pragma once
 #include "bdpt.cuh"
 
-namespace {
 
 // ------------------------------------------------------------------ proposals
 // Fill the lane's coordinate buffer for the path that is about to start and select it (Core::ubuf).
@@ -137,58 +137,28 @@ DR_D int path_start(const Machine &M, int lane, Core &c, RayF &ray) {
 }
 
 
-} // namespace
 
-template <int CLS>
-DR_D void begin_lane(const Machine &M, uint32_t qi) {
+// Start the next path of a lane whose state says PS_START: returns the queue the lane goes to with `ray` (a ray queue of the
+// next round, or the next round's chain queue for a path that is over before its first ray -- MMLT depth 1, no emitter).
+DR_D int begin_path(const Machine &M, int lane, Core &c, RayF &ray) {
     const JobParams &job = M.job;
-    {
-        const int lane = (int) M.q.items[(size_t) (Q_BEGIN + CLS) * M.q.n + qi];
-        Core c;
-        rec_load(c, M.lm.core + lane);
-        if (CLS == BEGIN_STAGE1) c.phase = PH_STAGE1;             // compile-time phase for the proposal switch
-        if (CLS == BEGIN_STAGE2) c.phase = PH_STAGE2;
-        long long item = 0;
-        MutCtx mc;
-        mc.pp = &M.pp; mc.chain = c.chainId; mc.mut = c.mut; mc.largeStep = false; mc.lightTracing = false;
-        if (job.type == JOB_CHAIN) {
-            if (CLS == BEGIN_STAGE1 && c.large == 2u)             // new mutation: draw the large-step coin (drmlt_proc.cpp:533)
-                c.large = (Real) keyed_uniform(M.pp.seed, S_COIN, c.chainId, c.mut, 0u) < M.cp.pLarge ? 1u : 0u;
-            mc.largeStep = c.phase != PH_INIT && c.large == 1u;
-            mc.lightTracing = c.phase == PH_STAGE2 && M.cp.fixEmitterPath && c.tx == 1;   // nextStage(current->t == 1)
-        } else {
-            item = (long long) lane + (long long) c.mut * M.lm.n;
-            if (job.type == JOB_BOOT) {
-                const unsigned long long index = job.first + (unsigned long long) item;
-                c.depth = M.pc.technique == DR_TECH_MMLT ? (uint8_t) ((index % (unsigned long long) M.pc.maxDepth) + 1) : 0;
-            } else c.depth = job.depthIn ? (uint8_t) job.depthIn[item] : 0;
-        }
-        fill_proposal(M, lane, c, mc, item);
-        RayF ray;
-        const int dest = path_start(M, lane, c, ray);
-        if (dest != Q_RAYC) c.pstate = PS_EMPTY;                  // (a connection without any ray cannot occur for depth >= 2)
-        rec_store(M.lm.core + lane, c);
-        // a dead-on-arrival path (MMLT depth 1, no emitter) goes back to the chain kernel in the next round
-        q_push_ray(M.q, dest == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : Q_CHAIN + (M.parity ^ 1), (uint32_t) lane, ray);
+    long long item = 0;
+    MutCtx mc;
+    mc.pp = &M.pp; mc.chain = c.chainId; mc.mut = c.mut; mc.largeStep = false; mc.lightTracing = false;
+    if (job.type == JOB_CHAIN) {
+        if (c.phase == PH_STAGE1 && c.large == 2u)                // new mutation: draw the large-step coin (drmlt_proc.cpp:533)
+            c.large = (Real) keyed_uniform(M.pp.seed, S_COIN, c.chainId, c.mut, 0u) < M.cp.pLarge ? 1u : 0u;
+        mc.largeStep = c.phase != PH_INIT && c.large == 1u;
+        mc.lightTracing = c.phase == PH_STAGE2 && M.cp.fixEmitterPath && c.tx == 1;   // nextStage(current->t == 1)
+    } else {
+        item = (long long) lane + (long long) c.mut * M.lm.n;
+        if (job.type == JOB_BOOT) {
+            const unsigned long long index = job.first + (unsigned long long) item;
+            c.depth = M.pc.technique == DR_TECH_MMLT ? (uint8_t) ((index % (unsigned long long) M.pc.maxDepth) + 1) : 0;
+        } else c.depth = job.depthIn ? (uint8_t) job.depthIn[item] : 0;
     }
-}
-
-// the three classes in one launch, every warp on one class (multiq_locate)
-__global__ void __launch_bounds__(128, BEGIN_MINB)
-k_begin(const __grid_constant__ Machine M) {
-    const uint32_t cnt[3] = { M.q.count[Q_BEGIN + BEGIN_STAGE1], M.q.count[Q_BEGIN + BEGIN_STAGE2], M.q.count[Q_BEGIN + BEGIN_OTHER] };
-    const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;; w += nWarps) {
-        int cls; uint32_t qi;
-        if (!multiq_locate<3>(cnt, w, cls, qi)) break;
-        if (qi >= cnt[cls]) continue;
-        if (cls == BEGIN_STAGE1) begin_lane<BEGIN_STAGE1>(M, qi);
-        else if (cls == BEGIN_STAGE2) begin_lane<BEGIN_STAGE2>(M, qi);
-        else begin_lane<BEGIN_OTHER>(M, qi);
-    }
-}
-
-void launch_begin(const Machine &M, const LaunchCfg &lc) {
-    const unsigned g = stage_grid(lc.nLanes + 3 * 128, 128);
-    k_begin<<<g, 128, 0, lc.stream>>>(M);
+    fill_proposal(M, lane, c, mc, item);
+    const int dest = path_start(M, lane, c, ray);
+    if (dest != Q_RAYC) c.pstate = PS_EMPTY;                      // (a connection without any ray cannot occur for depth >= 2)
+    return dest == Q_RAYC ? Q_RAYC + (M.parity ^ 1) : Q_CHAIN + (M.parity ^ 1);
 }

@@ -835,7 +835,6 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
     const bool mmlt = j->cfg.technique == DR_TECH_MMLT;
     const unsigned typeMask = static_cast<SceneImpl *>(j->scene)->typeMask;
     const int walkLaunches = mmlt ? 2 : 1;
-    const int beginLaunches = 1;
     const int R = j->roundsPerPoll;                             // even: a replay starts at the parity it was captured with
     CK(cudaStreamSynchronize(j->stream));                       // everything queued on the main stream is visible to the groups
     cudaStream_t s0 = j->groups[0].stream;
@@ -888,7 +887,7 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
             dr_status st = join_groups(j);
             if (st) return st;
         }
-        j->launches += (uint64_t) R * G * (2 + walkLaunches + 1 + beginLaunches);
+        j->launches += (uint64_t) R * G * (1 + walkLaunches + 1);
         if (!j->profEvents.empty()) {
             for (size_t i = 0; i + 3 < j->profEvents.size(); i += 4)
                 for (int s = 0; s < STAGE_COUNT; ++s) {
@@ -896,8 +895,8 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
                     cudaEventElapsedTime(&ms, j->profEvents[i + s], j->profEvents[i + s + 1]);
                     j->stageMs[s] += ms;
                 }
-            j->stageLaunches[STAGE_TRACE] += 2ull * R * G; j->stageLaunches[STAGE_WALK] += (uint64_t) walkLaunches * R * G;
-            j->stageLaunches[STAGE_CHAIN] += (uint64_t) R * G * (1 + beginLaunches);
+            j->stageLaunches[STAGE_TRACE] += 1ull * R * G; j->stageLaunches[STAGE_WALK] += (uint64_t) walkLaunches * R * G;
+            j->stageLaunches[STAGE_CHAIN] += (uint64_t) R * G;
             for (cudaEvent_t e : j->profEvents) cudaEventDestroy(e);
             j->profEvents.clear();
         }

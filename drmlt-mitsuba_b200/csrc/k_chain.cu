@@ -5,9 +5,9 @@
 // single MMLT splat, pathsampler.cpp:288-313), (2) runs the chain-level step: delayed-rejection acceptance
 // (DRMLTRenderer::process, src/integrators/drmlt/drmlt_proc.cpp:539-769; processMixture :161-380;
 // PSSMLTRenderer::process, src/integrators/pssmlt/pssmlt_proc.cpp:175-272), expectation-weighted film splats,
-// commit of the accepted primary-sample vector and statistics, and (3) hands the lane to the k_begin class
-// (k_begin.cu) that mutates its next proposal and emits the first ray of the next path.
-#include "machine.cuh"
+// commit of the accepted primary-sample vector and statistics, and (3) mutates the lane's next proposal and
+// emits the first ray of the next path (begin.cuh).
+#include "begin.cuh"
 
 namespace {
 
@@ -197,6 +197,7 @@ k_chain(const __grid_constant__ Machine M) {
     uint32_t st[ST_COUNT];
 #pragma unroll
     for (int i = 0; i < ST_COUNT; ++i) st[i] = 0;
+    queues_recycle(M.q);
     const uint32_t cnt = M.q.count[Q_CHAIN + M.parity];
     const uint32_t *items = M.q.items + (size_t) (Q_CHAIN + M.parity) * M.q.n;
     for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
@@ -457,12 +458,15 @@ k_chain(const __grid_constant__ Machine M) {
                 }
                 if (c.pstate == PS_IDLE) break;
             }
-            // ================= hand the lane to the kernel that starts its next path =================
-            dest = Q_BEGIN + (job.type != JOB_CHAIN ? BEGIN_OTHER : (c.phase == PH_STAGE1 ? BEGIN_STAGE1 : (c.phase == PH_STAGE2 ? BEGIN_STAGE2 : BEGIN_OTHER)));
             break;
         }
-        rec_store(M.lm.core + lane, c);
-        if (dest >= 0) q_push(M.q, dest, (uint32_t) lane);
+        // ================= start the lane's next path: mutate the proposal, emit its first ray (begin.cuh) =================
+        if (c.pstate == PS_START) {
+            RayF ray;
+            dest = begin_path(M, lane, c, ray);
+            rec_store(M.lm.core + lane, c);
+            q_push_ray(M.q, dest, (uint32_t) lane, ray);
+        } else rec_store(M.lm.core + lane, c);
     }
     stats_flush(st, M.counters);
 }
@@ -519,7 +523,6 @@ static unsigned grid_for(int n, int threads) { return stage_grid(n, threads); }
 
 void launch_chain(const Machine &M, const LaunchCfg &lc) {
     k_chain<<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M);
-    launch_begin(M, lc);
 }
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId, const unsigned long long *seedIdx) {
     k_setup_lanes<<<(unsigned) ((lc.nLanes + 127) / 128), 128, 0, lc.stream>>>(M, depth, chainId, seedIdx);

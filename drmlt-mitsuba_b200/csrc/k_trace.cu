@@ -19,6 +19,7 @@ k_trace(const __grid_constant__ Machine M) {
     const float4 *raysC = M.q.rays + 2 * (size_t) (Q_RAYC + M.parity) * M.q.n, *raysS = M.q.rays + 2 * (size_t) (Q_RAYS + M.parity) * M.q.n;
     uint32_t *head = M.q.count + Q_COUNT;
     if (blockIdx.x == 0 && threadIdx.x == 0 && cnt) atomicAdd(&M.counters[ST_RAYS], (unsigned long long) cnt);
+    trace_recycle(M.q, M.parity);
     const bool pt = M.pc.technique != DR_TECH_MMLT;
     const unsigned self = threadIdx.x & 31u;
     int stack[DR_STACK];
@@ -95,16 +96,6 @@ __global__ void k_trace_rays(const __grid_constant__ DevScene sc, const dr_ray *
     hits[i] = out;
 }
 
-// start of a round: empty the queues this round produces into (next-parity ray / chain queues, and the
-// in-round walk / connect / path-tracer queues)
-__global__ void k_round_begin(uint32_t *count, int parity) {
-    const int t = threadIdx.x;
-    if (t < Q_COUNT) {
-        const bool nextParity = (t < Q_WALK) && ((t & 1) == (parity ^ 1));
-        if (nextParity || t >= Q_WALK) count[t] = 0;
-    } else if (t < Q_COUNT + 2) count[t] = 0;               // head counters of the two ray queues (dynamic fetch)
-}
-
 // persistent kernels: exactly as many CTAs as are resident at once (SMs x occupancy)
 static int gridC = 0;
 void trace_init() {                                          // outside any stream capture
@@ -117,7 +108,6 @@ void trace_init() {                                          // outside any stre
 }
 
 void launch_trace(const Machine &M, const LaunchCfg &lc) {
-    k_round_begin<<<1, 32, 0, lc.stream>>>(M.q.count, M.parity);
     const int need = std::max(1, (lc.nLanes + 127) / 128);
     k_trace<<<(unsigned) std::min(gridC, need), 128, 0, lc.stream>>>(M);
 }

@@ -57,9 +57,6 @@
 #ifndef CHAIN_MINB
 #define CHAIN_MINB 3
 #endif
-#ifndef BEGIN_MINB
-#define BEGIN_MINB 4
-#endif
 
 // ------------------------------------------------------------------ lane records (AoS: one record per lane per array,
 // every record a multiple of 16 bytes, so a lane picked from a queue is fetched with a few 128-bit loads)
@@ -173,12 +170,9 @@ template <class T> DR_D void rec_store(T *dst, const T &src) {
 
 // ------------------------------------------------------------------ work queues
 // Q_RAYC / Q_RAYS / Q_CHAIN are double-buffered by round parity: kernels of round r consume [r & 1] and
-// produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT, Q_PT and
-// Q_BEGIN are produced and consumed inside one round.
-enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 6 */, Q_CONNECT = 12, Q_PT = 13,
-       Q_BEGIN = 14 /* + BEGIN_* class, 3 */, Q_COUNT = 17 };
-// classes of "start the next path" work: each runs one kind of proposal arithmetic on full warps
-enum { BEGIN_STAGE1 = 0, BEGIN_STAGE2 = 1, BEGIN_OTHER = 2 };
+// produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT and Q_PT
+// are produced and consumed inside one round.
+enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 6 */, Q_CONNECT = 12, Q_PT = 13, Q_COUNT = 14 };
 struct RayF { float4 a, b; };                               // (o, tmin), (d, tmax): float32 cast of a ray, for the traversal
 struct Queues {
     uint32_t *items;          // [Q_COUNT][n]
@@ -215,6 +209,19 @@ DR_D void q_push_ray(const Queues &q, int which, uint32_t lane, const RayF &ray)
         float4 *r = q.rays + 2 * ((size_t) which * q.n + slot);
         r[0] = ray.a; r[1] = ray.b;
     }
+}
+
+// The queue counters are emptied by the kernels of the round themselves (no launch of its own).  k_chain, the last kernel
+// of round r, empties the in-round walk / connect / path-tracer queues (their consumers ran before it) and the head
+// counters of the dynamic ray fetch; k_trace, the first kernel of round r + 1, empties the ray / chain queues that round r
+// consumed -- the ones round r + 1 produces into once the traversal is done (trace_recycle).
+DR_D void queues_recycle(const Queues &q) {
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0 && t >= Q_WALK && t < Q_COUNT + 2) q.count[t] = 0;
+}
+DR_D void trace_recycle(const Queues &q, int parity) {
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0 && t < Q_WALK && (t & 1) == (parity ^ 1)) q.count[t] = 0;
 }
 
 // Several queues in ONE launch: the global warp index space is the concatenation of the queues, each rounded up to
@@ -352,7 +359,7 @@ DR_D void emit_ray(const Machine &M, int lane, Core &c, R3 o, R3 d, Real tmin, R
 // ------------------------------------------------------------------ film
 // Splat of one (position, RGB) pair through the tabulated reconstruction filter
 // (ImageBlock::put, include/mitsuba/render/imageblock.h:149-196): one 16-byte vector atomic per touched pixel.
-DR_D void film_put(float4 *film, const FilmParams &fp, float2 pos, float3 value) {
+static __device__ __noinline__ void film_put(float4 *film, const FilmParams &fp, float2 pos, float3 value) {
     if (!rgb_valid(value)) return;
     const float px = pos.x - 0.5f, py = pos.y - 0.5f;
     const int minx = max((int) ceilf(px - fp.radius), 0), miny = max((int) ceilf(py - fp.radius), 0);
@@ -382,7 +389,7 @@ DR_D void stats_flush(const uint32_t *st, unsigned long long *counters) {
     }
 }
 
-// MMLT emitter end of the path, part 1 (k_begin, when the path starts): sample emitter subpath vertex 1 and, for
+// MMLT emitter end of the path, part 1 (begin_path, when the path starts): sample emitter subpath vertex 1 and, for
 // s >= 2, the emission direction (Scene::sampleEmitterPosition scene.cpp:1066-1082, vertex.cpp:99-124,
 // area.cpp:130-138).  Nothing here depends on the sensor subpath, so it is done up front, where every lane of the
 // warp does the same thing; the results wait in the lane's emitter-side records:
@@ -454,8 +461,7 @@ void launch_trace(const Machine &M, const LaunchCfg &lc);                 // k_t
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask);   // k_walk.cu: walk queues of the BSDF types present, then connect
 void launch_pt(const Machine &M, const LaunchCfg &lc);                    // k_pt.cu
 void launch_bdpt(const Machine &M, const LaunchCfg &lc);                  // k_bdpt.cu
-void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu, then the three k_begin classes (k_begin.cu)
-void launch_begin(const Machine &M, const LaunchCfg &lc);                 // k_begin.cu
+void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu (chain step + start of the next path)
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId,
                   const unsigned long long *seedIdx);                     // k_chain.cu: initialise lanes for M.job and queue them
 void launch_resume(const Machine &M, const LaunchCfg &lc);                // k_chain.cu: re-queue idle chains whose target was raised
