@@ -192,6 +192,61 @@ int orc_chain_steps(void *h, const dr_config *cfg, double b, const uint64_t *see
     return 0;
 }
 
+// ONE chain on recorded uniform streams of the reference (oracle/ref/ref_sampler.cpp: ref_drmlt_chain / ref_pssmlt_chain): the seed is
+// replayed from `boot_stream` (the ReplayableSampler's stream from the seed's sample index on), everything else -- fillReplay,
+// the large-step coins, the samplers' lazy fills in touch order, the acceptance coins -- is consumed, in the reference's call
+// order, from `worker_stream`.  film_out is W*H*3 DOUBLES (the work unit's ImageBlock); returns the number of worker uniforms
+// consumed (< 0: a stream was too short).
+// table_out / table_in (optional): the replay table in keyed address space (orc_mlt.hpp KeyedSource), table_dim coordinates
+// per sampler, 3 * dim + steps * (4 + 12 * dim) doubles; with table_in the streams are not used (pass null).
+long long orc_chain_stream(void *h, const dr_config *cfg, double b, int depth, const double *boot_stream, long long n_boot,
+                           const double *worker_stream, long long n_worker, long long steps, dr_step_record *records,
+                           double *film_out, dr_stats *stats_out, double *table_out, const double *table_in, int table_dim) {
+    Scene &sc = ((OrcScene *) h)->sc;
+    applyEps(sc, cfg);
+    Film film;
+    film.init(sc.cam.resX, sc.cam.resY, cfg->rfilter);
+    ChainRunner runner(sc, *cfg, b, film_out ? &film : nullptr);
+    // the streams are read through padded copies, so that an (erroneous) over-read is detected instead of crashing
+    std::vector<double> boot, work;
+    if (!table_in) {
+        boot.assign(boot_stream, boot_stream + n_boot); work.assign(worker_stream, worker_stream + n_worker);
+        const size_t pad = 4096;
+        boot.resize(boot.size() + pad, 0.5); work.resize(work.size() + pad, 0.5);
+        runner.bootStream = boot.data(); runner.workerStream = work.data();
+    }
+    if (table_out) {
+        const size_t n = 3 * (size_t) table_dim + (size_t) steps * (4 + 12 * (size_t) table_dim);
+        for (size_t i = 0; i < n; ++i) table_out[i] = std::numeric_limits<double>::quiet_NaN();
+    }
+    runner.tableOut = table_in ? nullptr : table_out; runner.tableIn = table_in; runner.tableDim = table_dim;
+    std::vector<StepRecord> recs(records ? steps : 0);
+    runner.run(0, 0, depth, (uint64_t) steps, records ? recs.data() : nullptr);
+    if (records)
+        for (long long m = 0; m < steps; ++m) {
+            dr_step_record &o = records[m];
+            const StepRecord &r = recs[m];
+            o.L_x = (float) r.L_x; o.L_y = (float) r.L_y; o.L_z = (float) r.L_z; o.a1 = (float) r.a1; o.a2 = (float) r.a2;
+            o.large_step = r.large; o.accept1 = r.acc1; o.did_second = r.did2; o.accept2 = r.acc2;
+        }
+    if (film_out) for (size_t i = 0; i < film.data.size(); ++i) film_out[i] = film.data[i];
+    if (stats_out) {
+        const ChainStats &t = runner.stats;
+        memset(stats_out, 0, sizeof(*stats_out));
+        stats_out->mutations = t.mutations;
+        stats_out->first_accept = t.first_accept; stats_out->first_base = t.first_base;
+        stats_out->large_accept = t.large_accept; stats_out->large_base = t.large_base;
+        stats_out->bold_accept = t.bold_accept; stats_out->bold_base = t.bold_base;
+        stats_out->second_accept = t.second_accept; stats_out->second_base = t.second_base;
+        stats_out->second_large_accept = t.second_large_accept; stats_out->second_large_base = t.second_large_base;
+        stats_out->second_bold_accept = t.second_bold_accept; stats_out->second_bold_base = t.second_bold_base;
+        stats_out->accept = t.accept; stats_out->accept_base = t.accept_base;
+        stats_out->paths = t.paths; stats_out->rays = t.rays; stats_out->luminance = b;
+    }
+    if (!table_in && runner.streamUsed > (size_t) n_worker) return -1;
+    return (long long) runner.streamUsed;
+}
+
 // Whole render on the CPU (the reported CPU baseline; "port" of DRMLT::render / PSSMLT::render,
 // drmlt.cpp:393-611).  n_boot bootstrap samples -> b and the seed CDF -> n_chains chains of
 // `steps` mutations each, one chain per work item, `threads` host threads.

@@ -81,18 +81,49 @@ struct WrappedCauchyKernel {
 };
 
 // Float-precision uniform source addressed by key.  `mut` is the mutation index of the chain.
+//
+// Replay table (whole chains of the reference on the CUDA path, dr_chain_replay): a sequential stream says nothing about WHICH
+// uniform a value is; the keyed address does.  While a chain runs in sequential mode every value it consumes is also written to
+// `table` at its keyed address, and a chain can run FROM such a table instead of Philox (tableIn).  Layout (doubles, NaN = never
+// drawn), D = tableDim:  [3][D] the replayed seed state per sampler | per mutation: [4] coins, [3][2 D] stage-1 draws (sampler,
+// 2 * coordinate + draw), [3][2 D] stage-2 draws.
 struct KeyedSource {
     uint64_t seed = 0, chain = 0;
     uint32_t mut = 0;
-    Float coin(int which) const { return keyedUniform(seed, S_COIN, chain, mut, (uint32_t) which); }
-    // sequential mode (tests/test_ref_pins.py): the stage uniforms come, in call order, from a recorded stream of the
-    // reference's own generator, so that the sampler arithmetic can be held against drmlt_sampler.cpp draw by draw
+    // sequential mode (tests/test_ref_pins.py): the uniforms come, in call order, from a recorded stream of the
+    // reference's own generator, so that the arithmetic can be held against the reference draw by draw
     const double *seq = nullptr;
     mutable size_t seqPos = 0;
+    double *table = nullptr;             // written in sequential mode
+    const double *tableIn = nullptr;     // read instead of Philox
+    int tableDim = 0;
+    size_t tableMutStride() const { return 4 + 12 * (size_t) tableDim; }
+    size_t coinAddr(int which) const { return 3 * (size_t) tableDim + mut * tableMutStride() + (size_t) which; }
+    size_t stageAddr(int stageIdx, int sampler, int coord, int draw) const {
+        return 3 * (size_t) tableDim + mut * tableMutStride() + 4 + ((size_t) (stageIdx * 3 + sampler) * 2 * tableDim) + (size_t) (2 * coord + draw);
+    }
+    Float coin(int which) const {
+        if (seq) { const double v = seq[seqPos++]; if (table) table[coinAddr(which)] = v; return (Float) v; }
+        if (tableIn) return (Float) tableIn[coinAddr(which)];
+        return (Float) keyedUniform(seed, S_COIN, chain, mut, (uint32_t) which);
+    }
     Float stage(int stageIdx, int sampler, int coord, int draw) const {
-        if (seq) return seq[seqPos++];
+        if (seq) { const double v = seq[seqPos++]; if (table && coord < tableDim) table[stageAddr(stageIdx, sampler, coord, draw)] = v; return (Float) v; }
+        if (tableIn) return (Float) tableIn[stageAddr(stageIdx, sampler, coord, draw)];
         return keyedUniform(seed, (stageIdx == 0 ? S_STAGE1 : S_STAGE2) + sampler, chain, mut, (uint32_t) (2 * coord + draw));
     }
+    // the reference fills a proposal lazily, at the sampler's first query of a stage: sequential and table runs must not draw
+    // (or read) anything for a sampler the path never touches
+    bool lazy() const { return seq || tableIn; }
+    // a value that becomes part of the chain's STATE without being a mutation draw (fillReplay, drmlt_sampler.h:127-131; a new
+    // dimension of PSSMLTSampler, pssmlt_sampler.cpp:137-139): recorded in the table's seed-state section
+    Float fresh(int sampler, int coord) const {
+        const double v = seq[seqPos++];
+        if (table && coord < tableDim) table[(size_t) sampler * tableDim + coord] = v;
+        return (Float) v;
+    }
+    // table mode: a NaN draw = this coordinate is not mutated in this step
+    static bool missing(Float v) { return std::isnan(v); }
     static Float boot(uint64_t seed, uint64_t index, int sampler, int coord) {
         return keyedUniform(seed, S_BOOT, index, (uint32_t) sampler, (uint32_t) coord);
     }
@@ -119,6 +150,10 @@ struct DRMLTSampler : Sampler {
     size_t sampleIndex = 0, dimStage1 = 0, dimStage2 = 0;
     bool filled1 = false, filled2 = false;
     bool arrayMode = false;          // replay of an explicit vector (seed replay): read uCurrent directly
+    // stream mode (whole chains of the reference replayed, tests/test_ref_pins.py): seed replay pulls the three samplers'
+    // values, in call order, from ONE interleaved stream (drmlt_sampler.cpp:245-249, drmlt_proc.cpp:470-485)
+    const double *replaySeq = nullptr;
+    size_t *replayPos = nullptr;
 
     bool kernelIsIdentity() const {
         if (identityAll) return true;
@@ -134,6 +169,10 @@ struct DRMLTSampler : Sampler {
         uProp1.clear(); uProp2.clear(); filled1 = filled2 = false; dimStage1 = dimStage2 = 0;
     }
     void accept(bool acceptFirst) {   // drmlt_sampler.cpp:189-199
+        // a sampler the path never touched holds an EMPTY proposal, which the reference copies over its current state (SURVEY
+        // C.14) -- values that nothing reads before the next large step refills them; a sequential stream must not be advanced
+        // for it, so the (unobservable) current state is simply kept
+        if (src && src->lazy() && !(acceptFirst ? filled1 : filled2)) { resetStage(); return; }
         ensureFilled(acceptFirst);
         uCurrent = acceptFirst ? uProp1 : uProp2;
         uCurrent.resize(maxDim);      // orbital with odd maxDim pushes one extra coordinate
@@ -190,13 +229,21 @@ struct DRMLTSampler : Sampler {
     }
     void ensureFilled(bool first) {
         if (first ? !filled1 : !filled2) {
-            if (!first && !filled1) fill(true);
+            // keyed uniforms: a second stage can always look at the first-stage proposal.  The reference's lazy fill never draws a
+            // first-stage vector on behalf of a second stage (a sampler first touched in stage 2 -- a strategy change by a large-step
+            // second stage, timidAfterLarge -- is filled with uniforms that need none)
+            if (!first && !filled1 && !(src && src->lazy())) fill(true);
             fill(first);
         }
     }
     // primarySample (drmlt_sampler.cpp:231-307)
     Float primarySample(size_t k) {
         if (arrayMode) return k < uCurrent.size() ? wrapReflect(uCurrent[k]) : 0.5;
+        if (replaySeq) {                 // m_replay: one draw per call, kept as the state (drmlt_sampler.cpp:245-249)
+            if (k == 0) uCurrent.clear();
+            uCurrent.push_back((Float) replaySeq[(*replayPos)++]);
+            return wrapReflect(uCurrent[k]);
+        }
         (isFirst ? dimStage1 : dimStage2) = std::max(k, isFirst ? dimStage1 : dimStage2);
         if (type == DR_TYPE_GREEN && isReverse) {
             ensureFilled(true); ensureFilled(false);
@@ -214,6 +261,7 @@ struct DRMLTSampler : Sampler {
     // INDEX touched, so the last used coordinate is skipped exactly as in the reference.
     Float getTransitionRatio() {
         if (identityAll) return 1.0;   // stage1->isIdentity()
+        if (src && src->lazy() && std::max(dimStage1, dimStage2) == 0) return 1.0;   // untouched: empty sums, no draws
         ensureFilled(true); ensureFilled(false);
         KelemenKernel kel(s1, s2);
         size_t dimStage = std::max(dimStage1, dimStage2);
@@ -238,6 +286,7 @@ struct PSSMLTSampler : Sampler {
     bool filled = false, arrayMode = false;
     void configure(Float s1_, Float s2_, Float sigma_) { s1 = s1_; s2 = s2_; sigma = sigma_; logRatio = -std::log(s2 / s1); }
     Float mutate(Float value, int coord) const {   // pssmlt_sampler.h:117-147
+        if (src->tableIn && KeyedSource::missing(src->stage(0, samplerId, coord, 0))) return value;   // not mutated in the recorded step
         if (useKelemen) {
             Float sample = src->stage(0, samplerId, coord, 0);
             bool add;
@@ -254,23 +303,31 @@ struct PSSMLTSampler : Sampler {
         return value;
     }
     void setLargeStep(bool v) { largeStep = v; }
+    const double *replaySeq = nullptr;   // stream mode: seed replay from ONE interleaved stream (pssmlt_sampler.cpp:126-129)
+    size_t *replayPos = nullptr;
     void ensureFilled() {   // primarySample(0) (pssmlt_sampler.cpp:124-166)
         if (filled) return;
         backup = u;
+        const size_t have = u.size();    // keyed uniforms: the state is padded up front, have == maxDim
         for (size_t k = 0; k < maxDim; k++) {
-            if (largeStep) u[k] = src->stage(0, samplerId, (int) k, 0);
+            if (k >= have) u.push_back(src->fresh(samplerId, (int) k));      // a NEW dimension: a fresh value, not a mutation (:137-139)
+            else if (largeStep) { const Float v = src->stage(0, samplerId, (int) k, 0); if (!(src->tableIn && KeyedSource::missing(v))) u[k] = v; }
             else u[k] = mutate(u[k], (int) k);
         }
         filled = true;
     }
     Float primarySample(size_t i) {
         if (arrayMode) return i < u.size() ? u[i] : 0.5;
+        if (replaySeq) { u.push_back((Float) replaySeq[(*replayPos)++]); return u[i]; }
         ensureFilled();
         return i < u.size() ? u[i] : 0.5;
     }
     Float next1D() override { return primarySample(sampleIndex++); }
-    void accept() { ensureFilled(); backup.clear(); sampleIndex = 0; filled = false; }
-    void reject() { if (filled) u = backup; backup.clear(); sampleIndex = 0; filled = false; }
+    void accept() { if (!(src && src->lazy())) ensureFilled(); backup.clear(); sampleIndex = 0; filled = false; }
+    void reject() {          // dimensions created by this step were never backed up: they stay (pssmlt_sampler.cpp:108-113)
+        if (filled) for (size_t k = 0; k < backup.size(); ++k) u[k] = backup[k];
+        backup.clear(); sampleIndex = 0; filled = false;
+    }
 };
 
 // ------------------------------------------------------------------ film (imageblock.h:149-196)
@@ -393,8 +450,18 @@ struct ChainRunner {
     }
 
     // chain `chainId`, seeded from bootstrap sample `seedIndex`; records (optional) has nMutations entries
+    // Stream mode: the seed's replay stream and the worker's stream of a recorded chain of the reference (oracle/ref/ref_sampler.cpp);
+    // every uniform is then consumed in the reference's call order.  streamUsed reports the worker uniforms consumed.
+    const double *bootStream = nullptr, *workerStream = nullptr;
+    size_t streamUsed = 0;
+    // replay table (KeyedSource): written while a stream is replayed / read instead of Philox
+    double *tableOut = nullptr;
+    const double *tableIn = nullptr;
+    int tableDim = 0;
+
     void runDRMLT(uint64_t chainId, uint64_t seedIndex, int depth, uint64_t nMutations, StepRecord *records) {
         KeyedSource src; src.seed = cfg.seed; src.chain = chainId;
+        src.seq = workerStream; src.table = tableOut; src.tableIn = tableIn; src.tableDim = tableDim;
         MaxDim md = findMaxDimensions(cfg.max_depth, cfg.rr_depth, depth, cfg.technique, cfg.direct_sampling != 0, sc.hasRoughDielectric);
         DRMLTSampler sensorS, emitterS, directS;
         DRMLTSampler *all[3] = { &sensorS, &emitterS, &directS };
@@ -405,7 +472,8 @@ struct ChainRunner {
             s.sigma = cfg.sigma; s.scaleSecond = cfg.scale_second;
             // seed replay + fillReplay (drmlt_proc.cpp:467-504): current = BOOT vector of the seed
             s.uCurrent.resize(dims[i]);
-            for (size_t k = 0; k < dims[i]; ++k) s.uCurrent[k] = KeyedSource::boot(cfg.seed, seedIndex, i, (int) k);
+            for (size_t k = 0; k < dims[i]; ++k)
+                s.uCurrent[k] = tableIn ? (Float) tableIn[(size_t) i * tableDim + k] : KeyedSource::boot(cfg.seed, seedIndex, i, (int) k);
         }
         if (cfg.technique == DR_TECH_MMLT) {
             directS.identityAll = true;
@@ -413,9 +481,17 @@ struct ChainRunner {
         }
         PathSampler ps(&sc, pathConfigOf(cfg), &emitterS, &sensorS, &directS);
         SplatList current, prop1, prop2, reverse;
-        for (auto s : all) { s->arrayMode = true; s->sampleIndex = 0; }
+        size_t bootPos = 0;
+        if (bootStream) for (auto s : all) { s->uCurrent.clear(); s->replaySeq = bootStream; s->replayPos = &bootPos; s->sampleIndex = 0; }
+        else for (auto s : all) { s->arrayMode = true; s->sampleIndex = 0; }
         ps.sampleSplats(current, depth);
-        for (auto s : all) { s->arrayMode = false; s->resetStage(); }
+        for (auto s : all) { s->arrayMode = false; s->replaySeq = nullptr; s->resetStage(); }
+        if (bootStream)                  // accept(true) wraps the replayed values, fillReplay pads with the worker's uniforms (drmlt_proc.cpp:493-504)
+            for (auto s : all) {
+                for (Float &v : s->uCurrent) v = wrapReflect(v);
+                while (s->uCurrent.size() < s->maxDim) s->uCurrent.push_back(src.fresh(s->samplerId, (int) s->uCurrent.size()));
+                if (src.table) for (size_t k = 0; k < s->uCurrent.size() && (int) k < src.tableDim; ++k) src.table[(size_t) s->samplerId * src.tableDim + k] = s->uCurrent[k];
+            }
         ++stats.paths;
         if (cfg.acceptance_map) {}   // luminance override only affects develop
         norm(current);
@@ -541,11 +617,13 @@ struct ChainRunner {
             }
         }
         stats.rays += ps.ctx.rays;
+        streamUsed = src.seqPos;
     }
 
     // PSSMLTRenderer::process (pssmlt_proc.cpp:110-285)
     void runPSSMLT(uint64_t chainId, uint64_t seedIndex, int depth, uint64_t nMutations, StepRecord *records) {
         KeyedSource src; src.seed = cfg.seed; src.chain = chainId;
+        src.seq = workerStream; src.table = tableOut; src.tableIn = tableIn; src.tableDim = tableDim; src.table = tableOut; src.tableIn = tableIn; src.tableDim = tableDim;
         MaxDim md = findMaxDimensions(cfg.max_depth, cfg.rr_depth, depth, cfg.technique, cfg.direct_sampling != 0, sc.hasRoughDielectric);
         PSSMLTSampler sensorS, emitterS, directS;
         PSSMLTSampler *all[3] = { &sensorS, &emitterS, &directS };
@@ -555,13 +633,18 @@ struct ChainRunner {
             s.samplerId = i; s.src = &src; s.maxDim = dims[i]; s.useKelemen = cfg.kelemen_style_mutation != 0;
             s.configure(cfg.mutation_size_low, cfg.mutation_size_high, cfg.sigma);
             s.u.resize(dims[i]);
-            for (size_t k = 0; k < dims[i]; ++k) s.u[k] = KeyedSource::boot(cfg.seed, seedIndex, i, (int) k);
+            for (size_t k = 0; k < dims[i]; ++k)
+                s.u[k] = tableIn ? (Float) tableIn[(size_t) i * tableDim + k] : KeyedSource::boot(cfg.seed, seedIndex, i, (int) k);
         }
         PathSampler ps(&sc, pathConfigOf(cfg), &emitterS, &sensorS, &directS);
         SplatList current, proposed;
-        for (auto s : all) { s->arrayMode = true; s->sampleIndex = 0; }
+        size_t bootPos = 0;
+        if (bootStream) for (auto s : all) { s->u.clear(); s->replaySeq = bootStream; s->replayPos = &bootPos; s->sampleIndex = 0; }
+        else for (auto s : all) { s->arrayMode = true; s->sampleIndex = 0; }
         ps.sampleSplats(current, depth);
-        for (auto s : all) { s->arrayMode = false; s->sampleIndex = 0; }
+        for (auto s : all) { s->arrayMode = false; s->replaySeq = nullptr; s->sampleIndex = 0; }
+        if (bootStream && tableOut)      // the replayed part of the seed state (new dimensions are added by KeyedSource::fresh)
+            for (auto s : all) for (size_t k = 0; k < s->u.size() && (int) k < tableDim; ++k) tableOut[(size_t) s->samplerId * tableDim + k] = s->u[k];
         ++stats.paths;
         norm(current);
         Float cumulativeWeight = 0;
@@ -605,6 +688,7 @@ struct ChainRunner {
         }
         splatNonZero(current, cumulativeWeight);
         stats.rays += ps.ctx.rays;
+        streamUsed = src.seqPos;
     }
     void splatNonZero(const SplatList &l, Float weight) {   // pssmlt_proc.cpp:229-233
         if (!film) return;

@@ -297,6 +297,7 @@ static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties 
 }
 
 void ref_scene_destroy(void *h) { delete (RefScene *) h; }
+void *ref_scene_ptr(void *h) { return ((RefScene *) h)->scene.get(); }     // the mitsuba::Scene, for the drivers in other translation units
 
 // findMaxDimensions (pssmlt_utils.h:27-77) on the scene built from the caller's dr_scene_desc: the primary-sample space sizes of
 // the three samplers, which depend on the scene (a RoughDielectric BSDF anywhere adds a dimension per vertex).

@@ -453,3 +453,199 @@ def run_film(fn, is_ref):
         assert fn(FILM_W, FILM_H, sel, pos.ctypes.data_as(PF32), rgb.ctypes.data_as(PF32), FILM_N, film.ctypes.data_as(PD), ok.ctypes.data_as(PI32)) == 0
         out["film_" + name], out["ok_" + name] = film, ok
     return out
+
+
+# ---------------------------------------------------------------- WHOLE CHAINS of the reference, replayed
+# ref_drmlt_chain / ref_pssmlt_chain (oracle/ref/ref_sampler.cpp, ref_pssmlt_sampler.cpp) run the reference's own
+# DRMLTRenderer::process / PSSMLTRenderer::process (drmlt_proc.cpp:386-771, :161-380; pssmlt_proc.cpp:110-285) on one work unit with
+# explicitly seeded generators, for every prefix 0..K of the chain, and hand out the two uniform streams the chain consumes.
+# The oracle's chain step (orc_chain_stream) consumes those streams in the reference's call order; the CUDA path replays the
+# same chain from the table of keyed uniforms the oracle derives from the streams (dr_chain_replay).
+GOLDEN_CHAIN = os.path.join(ROOT, "tests", "golden", "ref_chain.npz")
+CHAIN_K = 24                       # mutations per replayed chain
+CHAIN_PICKS = (0, 5)               # two seeds per case
+CHAIN_NBOOT, CHAIN_NSEEDS = 3000, 8
+CHAIN_STREAM = (512, 16384)        # recorded lengths: seed-replay stream, worker stream
+CHAIN_TABLE_DIM = 64               # coordinates per sampler in the replay table (>= findMaxDimensions of every case, even)
+CHAIN_SCENES = {
+    "cornell": lambda: scenes.cornell_box(film=(24, 24), tess=2),
+    "glossy": lambda: scenes.glossy_scene(film=(24, 24), subdiv=1, rough_glass=(0.15, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE)),
+}
+# (name, scene, parameters): every delayed-rejection type x technique, the flags of drmlt_proc.cpp, PSSMLT Kelemen / Gaussian
+CHAIN_REPLAY_CASES = [
+    ("mira_path", "cornell", dict(integrator="drmlt", type="mira", technique="path", maxDepth=6)),
+    ("mira_bdpt", "cornell", dict(integrator="drmlt", type="mira", technique="bdpt", maxDepth=5, directSampling=False)),
+    ("mira_mmlt", "cornell", dict(integrator="drmlt", type="mira", technique="mmlt", maxDepth=6)),
+    ("green_path", "cornell", dict(integrator="drmlt", type="green", technique="path", maxDepth=6)),
+    ("green_bdpt", "cornell", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=5, directSampling=False)),
+    ("green_mmlt", "cornell", dict(integrator="drmlt", type="green", technique="mmlt", maxDepth=6)),
+    ("orbital_path", "cornell", dict(integrator="drmlt", type="orbital", technique="path", maxDepth=6)),
+    ("orbital_bdpt", "cornell", dict(integrator="drmlt", type="orbital", technique="bdpt", maxDepth=5, directSampling=False)),
+    ("orbital_mmlt", "cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8)),
+    ("orbital_mmlt_glossy", "glossy", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6)),
+    ("mira_path_glossy", "glossy", dict(integrator="drmlt", type="mira", technique="path", maxDepth=5)),
+    ("mixture_mmlt", "cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, useMixture=True)),
+    ("mixture_path", "cornell", dict(integrator="drmlt", type="mira", technique="path", maxDepth=6, useMixture=True)),
+    ("timid_orbital_mmlt", "cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, timidAfterLarge=True)),
+    ("timid_green_mmlt", "cornell", dict(integrator="drmlt", type="green", technique="mmlt", maxDepth=6, timidAfterLarge=True)),
+    ("fixemitter_orbital_mmlt", "cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, fixEmitterPath=True)),
+    ("fixemitter_mira_mmlt", "cornell", dict(integrator="drmlt", type="mira", technique="mmlt", maxDepth=6, fixEmitterPath=True)),
+    ("accmap_mira_path", "cornell", dict(integrator="drmlt", type="mira", technique="path", maxDepth=6, acceptanceMap=True, rfilter="box")),
+    ("pssmlt_kelemen_path", "cornell", dict(integrator="pssmlt", technique="path", maxDepth=6)),
+    ("pssmlt_kelemen_mmlt", "cornell", dict(integrator="pssmlt", technique="mmlt", maxDepth=6)),
+    ("pssmlt_kelemen_bdpt", "cornell", dict(integrator="pssmlt", technique="bdpt", maxDepth=5, directSampling=False)),
+    ("pssmlt_gaussian_path", "cornell", dict(integrator="pssmlt", technique="path", maxDepth=6, kelemenStyleMutation=False)),
+    ("pssmlt_veach_weights_path", "glossy", dict(integrator="pssmlt", technique="path", maxDepth=5, kelemenStyleWeights=False)),
+]
+CHAIN_B = 0.37                     # m_config.luminance of the replayed work units (PSSMLT's Kelemen weights use it)
+PU64 = C.POINTER(C.c_uint64)
+
+
+def chain_case_config(params):
+    return make_config(seed=1, sampleCount=1, directSamples=-1, **params)
+
+
+def chain_projections(shape):
+    """Three fixed weight images: a film is pinned per prefix through its projections on them (a few doubles instead of a frame)."""
+    rng = np.random.RandomState(77)
+    return rng.rand(3, *shape)
+
+
+def run_chain_ref(lib, case, pick):
+    """One replayed chain of the reference -> dict: seed, the two streams, per-prefix counters and film projections, final film."""
+    name, scene_name, params = case
+    P = C.POINTER
+    cfg = chain_case_config(params)
+    data = CHAIN_SCENES[scene_name]()
+    d = data.desc()
+    W, H = data.film
+    K = CHAIN_K
+    pssmlt = cfg.integrator == abi.DR_INTEGRATOR_PSSMLT
+    nc = 6 if pssmlt else 14
+    films, ctr = np.zeros((K + 1, H, W, 3)), np.zeros((K + 1, nc), np.uint64)
+    boot, work = np.zeros(CHAIN_STREAM[0]), np.zeros(CHAIN_STREAM[1])
+    dep, sidx, slum, nxt = C.c_int32(), C.c_uint64(), D(), D()
+    seeds = (1000 + 7 * CHAIN_REPLAY_CASES.index(case) + pick, 2000 + 13 * CHAIN_REPLAY_CASES.index(case) + pick)
+    common = [seeds[0], seeds[1], CHAIN_NBOOT, CHAIN_NSEEDS, pick, K, C.byref(dep), C.byref(sidx), C.byref(slum),
+              boot.ctypes.data_as(PD), len(boot), work.ctypes.data_as(PD), len(work), films.ctypes.data_as(PD), ctr.ctypes.data_as(PU64), C.byref(nxt)]
+    tail = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_int32), PU64, PD, PD, C.c_int, PD, C.c_int, PD, PU64, PD]
+    if pssmlt:
+        lib.ref_pssmlt_chain.argtypes = [P(abi.dr_scene_desc), P(abi.dr_config), D] + tail
+        rc = lib.ref_pssmlt_chain(C.byref(d), C.byref(cfg), CHAIN_B, *common)
+    else:
+        # timidAfterLarge trips the reference's (always live) assertions at the first rejected large step: the assertion-free
+        # twin of the same translation unit replays the arithmetic behind them (oracle/ref/ref_sampler.cpp)
+        fn = lib.ref_drmlt_chain_ndebug if cfg.timid_after_large else lib.ref_drmlt_chain
+        fn.argtypes = [P(abi.dr_scene_desc), P(abi.dr_config)] + tail
+        rc = fn(C.byref(d), C.byref(cfg), *common)
+    assert rc == 0, "oracle/_ref: the reference chain failed (%s)" % name
+    used = np.nonzero(work == nxt.value)[0]
+    assert len(used) == 1, "worker stream too short for %s" % name
+    proj = np.einsum("khwc,jhw->kjc", films, chain_projections((H, W)))
+    return dict(depth=np.int32(dep.value), sample_index=np.uint64(sidx.value), seed_lum=np.float64(slum.value), used=np.int64(used[0]),
+                boot=boot, work=work[:used[0] + 8].copy(), counters=ctr, proj=proj, film=films[K].copy())
+
+
+def chain_decisions_from_counters(ctr, pssmlt):
+    """Per mutation (large step, first accepted, second stage ran, second accepted) from the per-prefix statistics counters
+    (value, base pairs: drmlt_proc.cpp:34-49 in order; pssmlt_proc.cpp:33-40)."""
+    d = np.diff(ctr.astype(np.int64), axis=0)
+    if pssmlt:      # largeStepRatio, smallStepRatio, acceptanceRate
+        return np.stack([d[:, 1], d[:, 4], np.zeros_like(d[:, 0]), np.zeros_like(d[:, 0])], axis=1)
+    # firstLevel, largeStep, boldStep, secondLevel, secondLevelLarge, secondLevelBold, acceptanceRate
+    return np.stack([d[:, 3], d[:, 0], d[:, 7], d[:, 6]], axis=1)
+
+
+def oracle_chain_fn(lib):
+    P = C.POINTER
+    lib.orc_chain_stream.restype = C.c_longlong
+    lib.orc_chain_stream.argtypes = [C.c_void_p, P(abi.dr_config), D, C.c_int, PD, C.c_longlong, PD, C.c_longlong, C.c_longlong,
+                                     P(abi.dr_step_record), PD, P(abi.dr_stats), PD, PD, C.c_int]
+    return lib.orc_chain_stream
+
+
+def chain_table_size(steps=CHAIN_K, dim=CHAIN_TABLE_DIM):
+    return 3 * dim + steps * (4 + 12 * dim)
+
+
+def run_chain_oracle(orc, case, ref, steps=CHAIN_K, table_in=None, want_table=False):
+    """The oracle's chain step on the recorded streams of `ref` (or from a replay table) -> dict like run_chain_ref's."""
+    name, scene_name, params = case
+    cfg = chain_case_config(params)
+    cfg.ray_epsilon = cfg.shadow_epsilon = 0.0          # the reference's own epsilons (double build)
+    W, H = orc.data.film
+    fn = oracle_chain_fn(orc.lib)
+    pssmlt = cfg.integrator == abi.DR_INTEGRATOR_PSSMLT
+    film, st = np.zeros((H, W, 3)), abi.dr_stats()
+    rec = (abi.dr_step_record * max(steps, 1))()
+    table = np.zeros(chain_table_size(steps)) if (want_table and table_in is None) else None
+    boot, work = np.ascontiguousarray(ref["boot"]), np.ascontiguousarray(ref["work"])
+    used = fn(orc.h, C.byref(cfg), CHAIN_B if pssmlt else 1.0, int(ref["depth"]),
+              boot.ctypes.data_as(PD) if table_in is None else None, len(boot), work.ctypes.data_as(PD) if table_in is None else None, len(work),
+              steps, rec, film.ctypes.data_as(PD), C.byref(st), table.ctypes.data_as(PD) if table is not None else None,
+              table_in.ctypes.data_as(PD) if table_in is not None else None, CHAIN_TABLE_DIM)
+    r = np.frombuffer(rec, dtype=np.uint8).reshape(-1, C.sizeof(abi.dr_step_record))[:steps]
+    dec = r[:, 20:24].astype(np.int64)                   # large_step, accept1, did_second, accept2
+    return dict(used=used, film=film, decisions=dec, stats=st, table=table, records=rec,
+                L=r[:, 0:20].copy().view("<f4").reshape(-1, 5))
+
+
+def chain_key(case, pick):
+    return "chain_%s_%d" % (case[0], pick)
+
+
+def run_chain_ref_all(lib):
+    """Every replayed chain of the reference -> flat dict of arrays (tests/golden/ref_chain.npz)."""
+    out = {}
+    for case in CHAIN_REPLAY_CASES:
+        for pick in CHAIN_PICKS:
+            r = run_chain_ref(lib, case, pick)
+            k = chain_key(case, pick)
+            out[k + "_seed"] = np.array([float(r["depth"]), float(r["sample_index"]), float(r["seed_lum"]), float(r["used"])])
+            out[k + "_boot"], out[k + "_work"] = r["boot"], r["work"]
+            out[k + "_counters"], out[k + "_proj"], out[k + "_film"] = r["counters"], r["proj"], r["film"]
+    return out
+
+
+def chain_from_golden(gold, case, pick):
+    k = chain_key(case, pick)
+    seed = gold[k + "_seed"]
+    return dict(depth=np.int32(seed[0]), sample_index=np.uint64(seed[1]), seed_lum=seed[2], used=np.int64(seed[3]),
+                boot=gold[k + "_boot"], work=gold[k + "_work"], counters=gold[k + "_counters"], proj=gold[k + "_proj"], film=gold[k + "_film"])
+
+
+_chain_orcs = {}
+
+
+def chain_oracle_scene(scene_name):
+    import oracle_lib
+    if scene_name not in _chain_orcs:
+        _chain_orcs[scene_name] = oracle_lib.OracleScene(CHAIN_SCENES[scene_name]())
+    return _chain_orcs[scene_name]
+
+
+def check_chain_oracle_vs_ref(case, ref):
+    """The oracle's chain step on the recorded streams against the reference's chain: the number of uniforms consumed, every
+    decision (from the reference's per-prefix statistics counters), and the work unit's film after EVERY mutation (projections;
+    pins the splat weights a1, (1 - a1) a2 and the splat positions of each step), plus the final film pixel by pixel."""
+    orc = chain_oracle_scene(case[1])
+    pssmlt = case[2]["integrator"] == "pssmlt"
+    o = run_chain_oracle(orc, case, ref, want_table=True)
+    assert o["used"] == ref["used"], (case[0], "uniforms consumed", o["used"], int(ref["used"]))
+    want = chain_decisions_from_counters(ref["counters"], pssmlt)
+    got = o["decisions"]
+    if pssmlt:
+        got = np.stack([got[:, 0], got[:, 1], 0 * got[:, 0], 0 * got[:, 0]], axis=1)
+    assert np.array_equal(want, got), (case[0], "decisions", np.nonzero((want != got).any(axis=1))[0][:4])
+    scale = max(np.abs(ref["film"]).max(), 1e-30)
+    assert np.abs(o["film"] - ref["film"]).max() <= 1e-12 * scale, (case[0], "final film")
+    W, H = orc.data.film
+    w = chain_projections((H, W))
+    for k in range(CHAIN_K + 1):
+        fk = run_chain_oracle(orc, case, ref, steps=k)["film"]
+        pk = np.einsum("hwc,jhw->jc", fk, w)
+        assert np.abs(pk - ref["proj"][k]).max() <= 1e-11 * max(np.abs(ref["proj"][k]).max(), 1e-30), (case[0], "film after mutation", k)
+    # the same chain from the replay table (keyed address space) the CUDA path is fed with
+    t = run_chain_oracle(orc, case, ref, table_in=o["table"])
+    assert np.array_equal(t["decisions"], o["decisions"]) and np.abs(t["film"] - o["film"]).max() <= 1e-13 * scale, (case[0], "replay table")
+    return o

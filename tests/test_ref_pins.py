@@ -380,3 +380,38 @@ def test_oracle_max_dimensions_equal_reference_on_the_scene(scene_name):
     assert len(seen) > 12
     if scene_name == "roughglass":
         assert (10 * 6, 0, 0) in seen          # path, maxDepth 8, RR and rough dielectric: (8 + 2) * (4 + 1 + 1)
+
+
+# ================================================================ whole chains of DRMLTRenderer::process / PSSMLTRenderer::process
+# ref_drmlt_chain / ref_pssmlt_chain (oracle/ref/ref_sampler.cpp, ref_pssmlt_sampler.cpp) compile drmlt_proc.cpp / pssmlt_proc.cpp into
+# the driver's translation unit and run the renderer's prepare() + process() on one SeedWorkUnit with explicitly seeded generators;
+# twin generators hand out the uniforms the chain consumes.  The oracle's chain step, fed those streams in call order, must consume
+# exactly as many uniforms, take every decision alike (large step, first accepted, second stage, second accepted -- read off the
+# reference's statistics counters after every prefix of the chain) and leave the same film after every mutation: the
+# north_star's "given identical uniform streams, accept / reject decisions must be bit-exact", for mira / green / orbital x
+# path / bdpt / mmlt, mixture, timidAfterLarge, fixEmitterPath, acceptanceMap and PSSMLT Kelemen / Gaussian / Veach weights.
+@needs_ref_path
+@pytest.mark.parametrize("case", RP.CHAIN_REPLAY_CASES, ids=lambda c: c[0])
+def test_oracle_chain_equals_reference_chain(case):
+    lib = C.CDLL(RP.REF_PATH)
+    for pick in RP.CHAIN_PICKS:
+        RP.check_chain_oracle_vs_ref(case, RP.run_chain_ref(lib, case, pick))
+
+
+@pytest.fixture(scope="module")
+def golden_chain():
+    return dict(np.load(RP.GOLDEN_CHAIN))
+
+
+@pytest.mark.parametrize("case", RP.CHAIN_REPLAY_CASES, ids=lambda c: c[0])
+def test_oracle_chain_reproduces_reference_fixture(case, golden_chain):
+    for pick in RP.CHAIN_PICKS:
+        RP.check_chain_oracle_vs_ref(case, RP.chain_from_golden(golden_chain, case, pick))
+
+
+@needs_ref_path
+def test_reference_chain_fixture_is_current(golden_chain):
+    live = RP.run_chain_ref_all(C.CDLL(RP.REF_PATH))
+    assert sorted(live) == sorted(golden_chain)
+    for k, v in live.items():
+        assert np.array_equal(v, golden_chain[k]), k
