@@ -144,10 +144,10 @@ DR_D int begin_path(const Machine &M, int lane, Core &c, RayF &ray) {
     const JobParams &job = M.job;
     long long item = 0;
     MutCtx mc;
-    mc.pp = &M.pp; mc.chain = c.chainId; mc.mut = c.mut; mc.largeStep = false; mc.lightTracing = false;
+    mc.pp = &M.pp; mc.chain = c.chainId; mc.mut = c.mut; mc.largeStep = false; mc.lightTracing = false; mc.table = replay_table(M, lane);
     if (job.type == JOB_CHAIN) {
         if (c.phase == PH_STAGE1 && c.large == 2u)                // new mutation: draw the large-step coin (drmlt_proc.cpp:533)
-            c.large = (Real) keyed_uniform(M.pp.seed, S_COIN, c.chainId, c.mut, 0u) < M.cp.pLarge ? 1u : 0u;
+            c.large = chain_coin(M, lane, c, 0) < M.cp.pLarge ? 1u : 0u;
         mc.largeStep = c.phase != PH_INIT && c.large == 1u;
         mc.lightTracing = c.phase == PH_STAGE2 && M.cp.fixEmitterPath && c.tx == 1;   // nextStage(current->t == 1)
     } else {

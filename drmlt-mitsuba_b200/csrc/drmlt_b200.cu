@@ -619,6 +619,9 @@ struct dr_job_t {
     bool hasDeadline = false, timedOut = false;
     long long nBoot = 0;
     unsigned long long bootFirst = 0;
+    const double *replay = nullptr;             // dr_chain_replay: the chains' uniform tables on the device
+    long long replayStride = 0;
+    int replayDim = 0;
     int nChains = 0;                            // Markov chains of the job (the reference's work units)
     int nLanes = 0;                             // lanes of the wavefront machine; < nChains: the lanes pull chains from a queue
     unsigned int *chainCursor = nullptr;        // work-unit queue: next chain index
@@ -1079,6 +1082,7 @@ static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, 
     j->mutTarget += (uint32_t) steps;
     job.mutTarget = j->mutTarget;
     job.records = records; job.recordStride = recordStride;
+    job.replay = j->replay; job.replayStride = j->replayStride; job.replayDim = j->replayDim;
     CK(cudaStreamSynchronize(j->stream));
     for (int g = 0; g < (int) j->groups.size(); ++g) {             // parked chains start their next mutation
         Machine M = machine_for(j, g, job, j->counters, withFilm);
@@ -1524,8 +1528,29 @@ extern "C" dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfg
     return done(DR_OK);
 }
 
+static dr_status chain_steps_impl(dr_scene scene, const dr_config *cfgIn, double b, const uint64_t *seedIndex, const int32_t *depth,
+                                  const uint64_t *chainId, int64_t nChains, int64_t steps, dr_step_record *records, float *film,
+                                  const double *uniforms, int uniformDim);
+
 extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, double b, const uint64_t *seedIndex, const int32_t *depth,
                                     const uint64_t *chainId, int64_t nChains, int64_t steps, dr_step_record *records, float *film) {
+    if (nChains > 0 && (!seedIndex || !chainId)) { dr_set_error("dr_chain_steps: bad argument"); return DR_ERR_INVALID_ARG; }
+    return chain_steps_impl(scene, cfgIn, b, seedIndex, depth, chainId, nChains, steps, records, film, nullptr, 0);
+}
+
+// Chains of the reference replayed: every uniform comes from the caller's table (layout: include/drmlt_b200.h) instead of Philox.
+extern "C" dr_status dr_chain_replay(dr_scene scene, const dr_config *cfgIn, double b, const int32_t *depth, int64_t nChains, int64_t steps,
+                                     const double *uniforms, int32_t uniformDim, dr_step_record *records, float *film) {
+    if (nChains > 0 && (!uniforms || uniformDim <= 0 || (uniformDim & 1))) { dr_set_error("dr_chain_replay: a table of an even number of coordinates per sampler is required"); return DR_ERR_INVALID_ARG; }
+    if (nChains < 0 || nChains > (1 << 20)) { dr_set_error("dr_chain_replay: chain count out of range"); return DR_ERR_INVALID_ARG; }
+    std::vector<uint64_t> ids((size_t) nChains);
+    for (int64_t i = 0; i < nChains; ++i) ids[i] = (uint64_t) i;
+    return chain_steps_impl(scene, cfgIn, b, ids.data(), depth, ids.data(), nChains, steps, records, film, uniforms, uniformDim);
+}
+
+static dr_status chain_steps_impl(dr_scene scene, const dr_config *cfgIn, double b, const uint64_t *seedIndex, const int32_t *depth,
+                                  const uint64_t *chainId, int64_t nChains, int64_t steps, dr_step_record *records, float *film,
+                                  const double *uniforms, int uniformDim) {
     if (!scene || !cfgIn || nChains < 0 || steps < 0 || (nChains > 0 && (!seedIndex || !chainId))) { dr_set_error("dr_chain_steps: bad argument"); return DR_ERR_INVALID_ARG; }
     if (nChains == 0) { dr_config c = *cfgIn; return dr_config_validate(&c); }
     if (nChains > (1 << 24) || steps > (1 << 24)) { dr_set_error("dr_chain_steps: too large"); return DR_ERR_INVALID_ARG; }
@@ -1557,9 +1582,17 @@ extern "C" dr_status dr_chain_steps(dr_scene scene, const dr_config *cfgIn, doub
         if ((st = drec.alloc((size_t) n * steps * sizeof(dr_step_record)))) return done(st);
         cudaMemsetAsync(drec.p, 0, (size_t) n * steps * sizeof(dr_step_record), j->stream);
     }
+    DevBuf dtab;
+    const long long tabStride = 3ll * uniformDim + (long long) steps * (4 + 12ll * uniformDim);
+    if (uniforms) {
+        if ((st = dtab.alloc((size_t) n * tabStride * sizeof(double)))) return done(st);
+        if (cudaMemcpy(dtab.p, uniforms, (size_t) n * tabStride * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { dr_set_error("dr_chain_replay: table upload failed"); return done(DR_ERR_CUDA); }
+        j->replay = dtab.as<double>(); j->replayStride = tabStride; j->replayDim = uniformDim;
+    }
     JobParams job;
     memset(&job, 0, sizeof(job));
     job.type = JOB_CHAIN; job.mutTarget = 0;
+    job.replay = j->replay; job.replayStride = j->replayStride; job.replayDim = j->replayDim;
     if ((st = setup_lanes(j, job)) || (st = run_machine(j, job, j->counters, film != nullptr))) return done(st);   // seed replay
     j->seeded = true;
     if (steps > 0 && (st = run_chains(j, steps, records ? drec.as<dr_step_record>() : nullptr, (int) steps, film != nullptr))) return done(st);

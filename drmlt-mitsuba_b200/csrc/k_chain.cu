@@ -177,7 +177,10 @@ DR_D void chain_init(const Machine &M, int lane, Core &c, const int *depthIn, co
     for (int k = 0; k < M.lm.nU; ++k) ub[k] = 0.0;
     for (int s = 0; s < 3; ++s)
         for (int k = 0; k < alloc[s]; ++k)
-            ub[M.pp.off[s] + k] = (double) keyed_uniform(M.pp.seed, S_BOOT, sidx, (uint32_t) s, (uint32_t) k);
+            if (M.job.replay) {          // the recorded chain's seed state (a coordinate it never had reads 0.5)
+                const double v = k < M.job.replayDim ? M.job.replay[(size_t) lane * M.job.replayStride + (size_t) s * M.job.replayDim + k] : NAN;
+                ub[M.pp.off[s] + k] = isnan(v) ? 0.5 : v;
+            } else ub[M.pp.off[s] + k] = (double) keyed_uniform(M.pp.seed, S_BOOT, sidx, (uint32_t) s, (uint32_t) k);
     c.phase = PH_INIT;
     c.pstate = PS_START;
 }
@@ -208,7 +211,7 @@ k_chain(const __grid_constant__ Machine M) {
         for (;;) {
             long long item = 0;
             MutCtx mc;
-            mc.pp = &pp; mc.chain = c.chainId; mc.mut = c.mut; mc.largeStep = false; mc.lightTracing = false;
+            mc.pp = &pp; mc.chain = c.chainId; mc.mut = c.mut; mc.largeStep = false; mc.lightTracing = false; mc.table = replay_table(M, lane);
             if (job.type != JOB_CHAIN) item = (long long) lane + (long long) c.mut * M.lm.n;
             else {
                 mc.largeStep = c.phase != PH_INIT && c.large == 1u;
@@ -278,7 +281,7 @@ k_chain(const __grid_constant__ Machine M) {
                                 currentWeight = (1. - a) * cc.Lx / (cc.Lx / cp.b + cp.pLarge);
                                 proposedWeight = (a + (largeStep ? 1. : 0.)) * yL / (yL / cp.b + cp.pLarge);
                             } else { currentWeight = 1. - a; proposedWeight = a; }
-                            accept = (a == 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 1u) < a);
+                            accept = (a == 1.) || (chain_coin(M, lane, c, 1) < a);
                         } else {
                             currentWeight = cp.kelemenWeights ? cc.Lx / (cc.Lx / cp.b + cp.pLarge) : 1.;
                             proposedWeight = 0.; accept = false;
@@ -321,13 +324,13 @@ k_chain(const __grid_constant__ Machine M) {
                         if (cp.useMixture) {
                             if (!invalid_loose(cc.yL)) {
                                 cc.a1 = metropolis_clamp(cc.yL / cc.Lx);
-                                cc.acc1 = (cc.a1 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 1u) < cc.a1);
+                                cc.acc1 = (cc.a1 >= 1.) || (chain_coin(M, lane, c, 1) < cc.a1);
                             }
-                            doSecond = !largeStep && ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 3u) < 0.5);
+                            doSecond = !largeStep && (chain_coin(M, lane, c, 3) < 0.5);
                         } else {
                             if (!invalid_strict(cc.yL)) {
                                 cc.a1 = metropolis_clamp(cc.yL / cc.Lx);
-                                cc.acc1 = (cc.a1 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 1u) < cc.a1);
+                                cc.acc1 = (cc.a1 >= 1.) || (chain_coin(M, lane, c, 1) < cc.a1);
                             }
                             doSecond = !cc.acc1 && (cp.timidAfterLarge || !largeStep);
                         }
@@ -342,7 +345,7 @@ k_chain(const __grid_constant__ Machine M) {
                             cc.a1 = 0.; cc.acc1 = 0;
                             if (!invalid_loose(cc.zL)) {
                                 a2 = metropolis_clamp(cc.zL / cc.Lx);
-                                acc2 = (a2 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 2u) < a2);
+                                acc2 = (a2 >= 1.) || (chain_coin(M, lane, c, 2) < a2);
                             }
                         } else if (!invalid_strict(cc.zL)) {
                             if (pp.type == DR_TYPE_GREEN) { c.phase = PH_REVERSE; c.pstate = PS_START; mutationDone = false; }
@@ -353,7 +356,7 @@ k_chain(const __grid_constant__ Machine M) {
                                     const Real T = largeStep ? 1.0 : mira_transition_ratio(M, mc, ub, cc.posY, posZ);
                                     if (!invalid_strict(T)) {
                                         a2 = metropolis_clamp((cc.zL / cc.Lx) * T * (1.0 - aReverse) / (1.0 - cc.a1));
-                                        acc2 = (a2 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 2u) < a2);
+                                        acc2 = (a2 >= 1.) || (chain_coin(M, lane, c, 2) < a2);
                                     }
                                 }
                             } else {                               // orbital, drmlt_proc.cpp:655-669
@@ -361,7 +364,7 @@ k_chain(const __grid_constant__ Machine M) {
                                 else if (cc.zL >= cc.Lx) { a2 = 1.0; acc2 = true; }
                                 else {
                                     a2 = (cc.zL - cc.yL) / (cc.Lx - cc.yL);
-                                    acc2 = (a2 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 2u) < a2);
+                                    acc2 = (a2 >= 1.) || (chain_coin(M, lane, c, 2) < a2);
                                 }
                             }
                         }
@@ -370,7 +373,7 @@ k_chain(const __grid_constant__ Machine M) {
                         const Real aReverse = invalid_strict(Lr) ? 0. : metropolis_clamp(Lr / cc.zL);
                         if (aReverse != 1.) {
                             a2 = metropolis_clamp((cc.zL / cc.Lx) * (1. - aReverse) / (1. - cc.a1));
-                            acc2 = (a2 >= 1.) || ((Real) keyed_uniform(pp.seed, S_COIN, c.chainId, c.mut, 2u) < a2);
+                            acc2 = (a2 >= 1.) || (chain_coin(M, lane, c, 2) < a2);
                         }
                         mutationDone = true;
                     }

@@ -261,6 +261,10 @@ struct JobParams {
     unsigned int chainFirst, chainEnd;
     const int *qDepth;                  // [chains] MMLT depth | chain id (RNG key) | bootstrap sample of every chain
     const unsigned long long *qChainId, *qSeedIdx;
+    // JOB_CHAIN, replayed chains of the reference (dr_chain_replay): lane l reads its uniforms from replay + l * replayStride
+    const double *replay;
+    long long replayStride;
+    int replayDim;
 };
 
 struct FilmParams {
@@ -298,12 +302,26 @@ struct Machine {
     int traceRefill, traceDescend;   // k_trace tuning: refill below this many busy lanes / leave the descend phase below this many
 };
 
+// uniforms of a chain: the replay table of the lane (dr_chain_replay) or keyed Philox (S_COIN: 0 large step, 1 accept 1, 2 accept 2, 3 mixture)
+DR_D ReplayTable replay_table(const Machine &M, int lane) {
+    ReplayTable t;
+    t.base = M.job.replay ? M.job.replay + (size_t) lane * M.job.replayStride : nullptr;
+    t.dim = M.job.replayDim;
+    return t;
+}
+DR_D Real chain_coin(const Machine &M, int lane, const Core &c, int which);
+
 // ------------------------------------------------------------------ MIS arrays of a lane
 DR_D PredRec *geo_slot(const Machine &M, int lane, int side, int j) { return M.lm.geo + ((size_t) lane * 2 + side) * 2 + (j & 1); }
 DR_D double *misrec_slot(const Machine &M, int lane, int side, int j) { return M.lm.misrec + (((size_t) lane * 2 + side) * M.lm.mrSlots + j) * MR_WORDS; }
 DR_D void misrec_store(const Machine &M, int lane, int side, int j, Real fwdNext, Real bwdPrev, Real conv) {
     double4 v = make_double4(fwdNext, bwdPrev, conv, 0.0);
     *reinterpret_cast<double4 *>(misrec_slot(M, lane, side, j)) = v;      // one aligned 32-byte sector
+}
+
+DR_D Real chain_coin(const Machine &M, int lane, const Core &c, int which) {
+    if (M.job.replay) return replay_table(M, lane).coin(c.mut, which);
+    return (Real) keyed_uniform(M.pp.seed, S_COIN, c.chainId, c.mut, (uint32_t) which);
 }
 
 // findMaxDimensions (pssmlt_utils.h:27-77): MMLT vectors depend on the chain's depth

@@ -79,11 +79,35 @@ DR_D Real pssmlt_mutate(Real value, Real xi1, Real xi2, const PssParams &pp) {  
 DR_D R2 ub_load(const double *buf, int slot) { const double2 v = *reinterpret_cast<const double2 *>(buf + slot); return r2(v.x, v.y); }
 DR_D void ub_store(double *buf, int slot, R2 v) { *reinterpret_cast<double2 *>(buf + slot) = make_double2(v.x, v.y); }
 
+// Four uniforms of one coordinate pair: (coordinate 2p, draw 0), (2p, draw 1), (2p + 1, draw 0), (2p + 1, draw 1).
+struct U4 { Real x, y, z, w; };
+
+// Replay table of one chain (dr_chain_replay, include/drmlt_b200.h): the uniforms of a recorded chain of the reference in the
+// keyed address space.  D = dim coordinates per sampler; doubles; NaN = never drawn by the recorded chain:
+//   [3][D] seed state per sampler | per mutation: [4] coins (large step, accept 1, accept 2, mixture), [3][2 D] stage-1 draws
+//   (sampler; 2 * coordinate + draw), [3][2 D] stage-2 draws.
+struct ReplayTable {
+    const double *base;      // this chain's table (null: keyed Philox uniforms)
+    int dim;
+    DR_D size_t mut_stride() const { return 4 + 12 * (size_t) dim; }
+    DR_D const double *mut_block(uint32_t mut) const { return base + 3 * (size_t) dim + mut * mut_stride(); }
+    DR_D Real coin(uint32_t mut, int which) const { return mut_block(mut)[which]; }
+    DR_D U4 stage(uint32_t mut, int stage, int sampler, int pair) const {
+        U4 u = { NAN, NAN, NAN, NAN };
+        if (2 * pair + 1 < dim) {
+            const double *q = mut_block(mut) + 4 + (size_t) (stage * 3 + sampler) * 2 * dim + 4 * pair;
+            u.x = q[0]; u.y = q[1]; u.z = q[2]; u.w = q[3];
+        }
+        return u;
+    }
+};
+
 // What a proposal needs to know about the mutation it belongs to.
 struct MutCtx {
     const PssParams *pp;
     uint64_t chain;          // chain id
     uint32_t mut;            // mutation counter of the chain
+    ReplayTable table;       // replayed chain: uniforms come from the table
     bool largeStep;
     bool lightTracing;       // nextStage(current->t == 1): the emitter sampler keeps its real stage-2 kernel
     DR_D bool identity1(int s) const { return (pp->identity1 >> s) & 1u; }
@@ -92,18 +116,30 @@ struct MutCtx {
         if ((pp->identity2 >> s) & 1u) return !lightTracing;      // handleLightTracing: stage2 = Identity, stageLT = real kernel
         return false;
     }
+    // the uniforms of coordinate pair p of sampler s in stage `stage` (0 / 1)
+    DR_D U4 draws(int stage, int s, int p) const {
+        if (table.base) return table.stage(mut, stage, s, p);
+        const float4 f = keyed_uniform4(pp->seed, (stage == 0 ? S_STAGE1 : S_STAGE2) + s, chain, mut, (uint32_t) p);
+        U4 u = { (Real) f.x, (Real) f.y, (Real) f.z, (Real) f.w };
+        return u;
+    }
 };
+// A replayed chain did not draw what the reference's lazy, touch-driven fill never asked for (a sampler the path did not touch;
+// a dimension PSSMLTSampler created in that very step): NaN in the table = the coordinate keeps its current value.
+DR_D Real drawn_or(Real candidate, Real draw, Real current) { return isnan(draw) ? current : candidate; }
 
 // un-wrapped stage-1 proposal of the coordinate pair p of sampler s (drmlt_sampler.cpp:313-359, pssmlt_sampler.cpp:124-166)
 DR_D R2 propose_stage1(const MutCtx &m, int s, int p, R2 x) {
     const PssParams &pp = *m.pp;
     if (!m.largeStep && m.identity1(s)) return x;
-    const float4 u = keyed_uniform4(pp.seed, S_STAGE1 + s, m.chain, m.mut, (uint32_t) p);
-    if (m.largeStep) return r2(u.x, u.z);
+    const U4 u = m.draws(0, s, p);
+    if (m.largeStep) return r2(drawn_or(u.x, u.x, x.x), drawn_or(u.z, u.z, x.y));
     if (pp.integrator == DR_INTEGRATOR_PSSMLT)
-        return r2(pssmlt_mutate(x.x, u.x, u.y, pp), pssmlt_mutate(x.y, u.z, u.w, pp));
+        return r2(drawn_or(pssmlt_mutate(x.x, u.x, u.y, pp), u.x, x.x), drawn_or(pssmlt_mutate(x.y, u.z, u.w, pp), u.z, x.y));
     if (pp.type != DR_TYPE_ORBITAL)
-        return r2(x.x + kelemen_sample(u.x, pp.kel_s2, pp.kel_logRatio), x.y + kelemen_sample(u.z, pp.kel_s2, pp.kel_logRatio));
+        return r2(drawn_or(x.x + kelemen_sample(u.x, pp.kel_s2, pp.kel_logRatio), u.x, x.x),
+                  drawn_or(x.y + kelemen_sample(u.z, pp.kel_s2, pp.kel_logRatio), u.z, x.y));
+    if (isnan(u.x)) return x;
     const Real d = kelemen_sample(u.x, pp.kel_s2, pp.kel_logRatio);   // drmlt_sampler.cpp:351-359
     Real sa, ca;
     sincospi(2.0 * u.y, &sa, &ca);
@@ -113,10 +149,11 @@ DR_D R2 propose_stage1(const MutCtx &m, int s, int p, R2 x) {
 DR_D R2 propose_stage2(const MutCtx &m, int s, int p, R2 x, R2 y) {
     const PssParams &pp = *m.pp;
     if (!m.largeStep && m.identity2(s)) return x;
-    const float4 u = keyed_uniform4(pp.seed, S_STAGE2 + s, m.chain, m.mut, (uint32_t) p);
-    if (m.largeStep) return r2(u.x, u.z);   // release-build behaviour of fillSpace with m_largeStep still set
+    const U4 u = m.draws(1, s, p);
+    if (m.largeStep) return r2(drawn_or(u.x, u.x, x.x), drawn_or(u.z, u.z, x.y));   // fillSpace with m_largeStep still set (assertions aside)
     if (pp.type != DR_TYPE_ORBITAL)
-        return r2(x.x + gaussian_sample(u.x, u.y, pp.sigma2), x.y + gaussian_sample(u.z, u.w, pp.sigma2));
+        return r2(drawn_or(x.x + gaussian_sample(u.x, u.y, pp.sigma2), u.x, x.x), drawn_or(x.y + gaussian_sample(u.z, u.w, pp.sigma2), u.z, x.y));
+    if (isnan(u.x)) return x;
     const Real theta = cauchy_sample(u.x, pp.cauchy_disp);
     const Real du1 = y.x - x.x, du2 = y.y - x.y;
     const Real norm = sqrt(du1 * du1 + du2 * du2);

@@ -179,6 +179,20 @@ class Scene:
         return (rec, film) if want_film else rec
 
 
+    def chain_replay(self, cfg, b, depth, tables, dim, steps, want_film=False):
+        """Chains of the reference replayed from tables of keyed uniforms (dr_chain_replay): tables is [n_chains][3 dim + steps (4 + 12 dim)] float64."""
+        tables = np.ascontiguousarray(tables, np.float64)
+        n = tables.shape[0]
+        assert tables.shape[1] == 3 * dim + steps * (4 + 12 * dim)
+        depth = np.ascontiguousarray(depth, np.int32)
+        rec = (abi.dr_step_record * (n * max(steps, 1)))()
+        W, H = self.film_size(cfg)
+        film = np.zeros((H, W, 3), np.float32) if want_film else None
+        abi.check(self.lib, self.lib.dr_chain_replay(self.h, C.byref(cfg), b, _fp(depth, C.c_int32), n, steps, _fp(tables, C.c_double), dim,
+                                                     rec, _fp(film) if want_film else None))
+        return (rec, film) if want_film else rec
+
+
 class Job:
     """One rank's share of a render (dr_job): bootstrap -> [all-reduce] -> seed -> run* -> develop."""
 

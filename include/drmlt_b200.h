@@ -308,6 +308,22 @@ dr_status dr_chain_steps(dr_scene scene, const dr_config *cfg, double b,
                          const uint64_t *seed_index, const int32_t *depth, const uint64_t *chain_id,
                          int64_t n_chains, int64_t steps, dr_step_record *records, float *film);
 
+/* Chains of the REFERENCE replayed on a recorded uniform stream (SURVEY 8b `uniforms`; DRMLTRenderer::process
+ * src/integrators/drmlt/drmlt_proc.cpp:386-771, processMixture :161-380, PSSMLTRenderer::process
+ * src/integrators/pssmlt/pssmlt_proc.cpp:110-285): like dr_chain_steps, but every uniform -- the seed state, the large-step and
+ * acceptance coins, the samplers' proposal draws -- comes from the caller's table instead of the counter-based generator.
+ * A sequential stream does not say WHICH uniform a value is (the reference fills a sampler's proposal lazily, when the path first
+ * touches it); the table does: it is the stream sorted into the keyed address space.  Per chain, D = uniform_dim (even)
+ * coordinates per sampler (0 sensor, 1 emitter, 2 direct), doubles, NaN = never drawn by the recorded chain (the coordinate
+ * then keeps its value in that step):
+ *     [3][D]                    seed state: the replayed + padded current vector of each sampler (drmlt_proc.cpp:467-504)
+ *     per mutation m < steps:   [4] coins (0 large step, 1 accept 1, 2 accept 2, 3 mixture),
+ *                               [3][2 D] stage-1 draws, index 2 * coordinate + draw,  [3][2 D] stage-2 draws
+ * i.e. 3 D + steps (4 + 12 D) doubles per chain, chains back to back.  tests/ builds the table with the oracle
+ * (orc_chain_stream) from the streams of tests/golden/ref_chain.npz. */
+dr_status dr_chain_replay(dr_scene scene, const dr_config *cfg, double b, const int32_t *depth, int64_t n_chains, int64_t steps,
+                          const double *uniforms, int32_t uniform_dim, dr_step_record *records, float *film);
+
 /* Bootstrap luminances of samples [first, first+n) (before the x maxDepth MMLT scaling). */
 dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfg,
                                  uint64_t first, int64_t n, float *luminance, int32_t *depth);

@@ -831,3 +831,49 @@ def test_cuda_equal_mutation_relmse_against_the_reference_integrator():
     runs = gold["drmlt_orbital_mmlt_relmse_runs"]
     print("relMSE vs converged reference render: CUDA", errs, "reference", runs)
     assert np.median(errs) <= 1.25 * np.median(runs) and max(errs) <= 1.25 * runs.max()
+
+
+# tests/golden/ref_chain.npz holds whole chains of the reference's own DRMLTRenderer::process / PSSMLTRenderer::process
+# (oracle/ref/ref_sampler.cpp, ref_pssmlt_sampler.cpp; tools/make_ref_chain_golden.py) with the uniform streams they consumed.
+# The oracle sorts the streams into the keyed address space (replay table); dr_chain_replay runs the CUDA chain step on that
+# table.  north_star: "given identical uniform streams, accept / reject decisions must be bit-exact except where the acceptance
+# ratio lies within 1e-5 of the threshold".
+@pytest.mark.parametrize("case", RP.CHAIN_REPLAY_CASES, ids=lambda c: c[0])
+def test_cuda_chain_replays_reference_chain(case):
+    gold = dict(np.load(RP.GOLDEN_CHAIN))
+    name, scene_name, params = case
+    if ("chain", scene_name) not in _ref_gpu_scenes:
+        _ref_gpu_scenes[("chain", scene_name)] = Scene(RP.CHAIN_SCENES[scene_name]())
+    gpu = _ref_gpu_scenes[("chain", scene_name)]
+    orc = RP.chain_oracle_scene(scene_name)
+    pssmlt = params["integrator"] == "pssmlt"
+    cfg = RP.chain_case_config(params)
+    cfg.ray_epsilon, cfg.shadow_epsilon = 1e-7, 1e-5        # the reference's double build (constants.h:33-36)
+    refs = [RP.chain_from_golden(gold, case, pick) for pick in RP.CHAIN_PICKS]
+    orcs = [RP.run_chain_oracle(orc, case, r, want_table=True) for r in refs]
+    tables = np.stack([o["table"] for o in orcs])
+    depth = np.array([int(r["depth"]) for r in refs], np.int32)
+    K = RP.CHAIN_K
+    rec, film = gpu.chain_replay(cfg, RP.CHAIN_B if pssmlt else 1.0, depth, tables, RP.CHAIN_TABLE_DIM, K, want_film=True)
+    g = recs(rec).reshape(len(refs), K)
+    film_ref = sum(r["film"] for r in refs)
+    for i, r in enumerate(refs):
+        want = RP.chain_decisions_from_counters(r["counters"], pssmlt)
+        got = np.stack([g[i]["large"], g[i]["acc1"], g[i]["did2"], g[i]["acc2"]], axis=1).astype(np.int64)
+        if pssmlt:
+            got[:, 2:] = 0
+        bad = np.nonzero((want != got).any(axis=1))[0]
+        if len(bad):                   # a flip is only admissible where the acceptance ratio is within 1e-5 of the coin
+            m = bad[0]
+            o = orcs[i]["L"][m]        # the oracle's L_x, L_y, L_z, a1, a2 of that mutation
+            t = tables[i]
+            coins = t[3 * RP.CHAIN_TABLE_DIM + m * (4 + 12 * RP.CHAIN_TABLE_DIM):][:4]
+            near = min(abs(o[3] - coins[1]), abs(o[4] - coins[2])) if not np.isnan(coins[1:3]).all() else 1.0
+            assert near < 1e-5, (name, i, "first differing mutation", int(m), want[m], got[m])
+        # luminances of the states the decisions were taken on (float32 records)
+        ok = slice(0, bad[0] if len(bad) else K)
+        assert np.allclose(g[i]["L_y"][ok], orcs[i]["L"][ok, 1], rtol=2e-5, atol=1e-30), (name, i)
+        assert np.allclose(g[i]["a1"][ok], orcs[i]["L"][ok, 3], rtol=2e-5, atol=1e-6), (name, i)
+    # the work units' films: float atomics against the reference's double ImageBlock
+    scale = np.abs(film_ref).max()
+    assert np.abs(film.astype(np.float64) - film_ref).max() <= 2e-5 * scale, (name, np.abs(film - film_ref).max() / scale)
