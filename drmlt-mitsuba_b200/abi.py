@@ -18,7 +18,7 @@ DR_TRI_SMOOTH = 1
 DR_INTEGRATOR_PSSMLT, DR_INTEGRATOR_DRMLT = 0, 1
 DR_TECH_PATH, DR_TECH_BDPT, DR_TECH_MMLT = 0, 1, 2
 DR_TYPE_GREEN, DR_TYPE_MIRA, DR_TYPE_ORBITAL = 0, 1, 2
-DR_FILTER_GAUSSIAN, DR_FILTER_BOX = 0, 1
+DR_FILTER_GAUSSIAN, DR_FILTER_BOX, DR_FILTER_TABLE, DR_FILTER_TENT, DR_FILTER_MITCHELL, DR_FILTER_CATMULLROM, DR_FILTER_LANCZOS = range(7)
 DR_MAX_SPLATS = 12
 
 
@@ -66,7 +66,7 @@ class dr_config(C.Structure):
                 ("film_width", C.c_int32), ("film_height", C.c_int32),
                 ("crop_offset_x", C.c_int32), ("crop_offset_y", C.c_int32),
                 ("crop_width", C.c_int32), ("crop_height", C.c_int32), ("n_lanes", C.c_int32), ("_reserved0", C.c_int32),
-                ("importance_map", C.POINTER(C.c_float))]
+                ("importance_map", C.POINTER(C.c_float)), ("filter_radius", C.c_double), ("filter_table", C.c_double * 32)]
 
 
 class dr_stats(C.Structure):
@@ -109,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "dr_config_validate", "dr_scene_create", "dr_scene_destroy", "dr_scene_reupload", "dr_render", "dr_cancel",
     "dr_job_create", "dr_job_destroy", "dr_job_bootstrap", "dr_job_seed_chains", "dr_job_run",
     "dr_job_film_device", "dr_job_develop", "dr_job_stats", "dr_job_profile", "dr_job_direct", "dr_direct_image", "dr_job_num_chains", "dr_job_total_mutations",
-    "dr_trace_rays", "dr_eval_paths", "dr_chain_steps", "dr_chain_replay", "dr_bootstrap_luminance", "dr_max_dimensions",
+    "dr_trace_rays", "dr_eval_paths", "dr_chain_steps", "dr_chain_replay", "dr_splat_points", "dr_bootstrap_luminance", "dr_max_dimensions",
     "dr_render_progressive", "dr_film_size", "dr_first_stage_config", "dr_resample_luminance", "dr_importance_map",
 ]
 
@@ -171,6 +171,7 @@ def load_library(path=None):
                                    C.c_int64, C.c_int64, P(dr_step_record), P(C.c_float)]
     lib.dr_chain_replay.argtypes = [C.c_void_p, P(dr_config), C.c_double, P(C.c_int32), C.c_int64, C.c_int64, P(C.c_double), C.c_int32,
                                     P(dr_step_record), P(C.c_float)]
+    lib.dr_splat_points.argtypes = [C.c_int, P(dr_config), C.c_int32, C.c_int32, P(C.c_float), P(C.c_float), C.c_int64, P(C.c_float)]
     lib.dr_bootstrap_luminance.argtypes = [C.c_void_p, P(dr_config), C.c_uint64, C.c_int64, P(C.c_float), P(C.c_int32)]
     lib.dr_max_dimensions.argtypes = [P(dr_config), C.c_int, P(C.c_int), P(C.c_int), P(C.c_int)]
     lib.dr_max_dimensions.restype = None

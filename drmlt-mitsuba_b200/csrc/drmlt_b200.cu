@@ -161,7 +161,11 @@ extern "C" dr_status dr_config_set(dr_config *c, const char *key, const char *va
     if (!strcmp(key, "rfilter")) {
         if (!strcmp(value, "gaussian")) c->rfilter = DR_FILTER_GAUSSIAN;
         else if (!strcmp(value, "box")) c->rfilter = DR_FILTER_BOX;
-        else { dr_set_error("Unsupported reconstruction filter \"%s\" (gaussian|box)", value); return DR_ERR_UNSUPPORTED; }
+        else if (!strcmp(value, "tent")) c->rfilter = DR_FILTER_TENT;
+        else if (!strcmp(value, "mitchell")) c->rfilter = DR_FILTER_MITCHELL;
+        else if (!strcmp(value, "catmullrom")) c->rfilter = DR_FILTER_CATMULLROM;
+        else if (!strcmp(value, "lanczos")) c->rfilter = DR_FILTER_LANCZOS;
+        else { dr_set_error("Unsupported reconstruction filter \"%s\" (gaussian|box|tent|mitchell|catmullrom|lanczos)", value); return DR_ERR_UNSUPPORTED; }
         return DR_OK;
     }
     if (!strcmp(key, "seed")) {
@@ -222,10 +226,15 @@ extern "C" dr_status dr_config_validate(dr_config *c) {
         // the reference overflows its direct sampler in this mode
         dr_set_error("technique=bdpt requires directSampling=false on the GPU path"); return DR_ERR_UNSUPPORTED;
     }
-    if (c->acceptance_map && c->integrator == DR_INTEGRATOR_DRMLT && c->rfilter != DR_FILTER_BOX) {
-        dr_set_error("acceptanceMap requires the box reconstruction filter (drmlt_proc.cpp:75-79)"); return DR_ERR_INVALID_ARG;
+    if (c->rfilter < DR_FILTER_GAUSSIAN || c->rfilter > DR_FILTER_LANCZOS) { dr_set_error("Unsupported rfilter"); return DR_ERR_UNSUPPORTED; }
+    if (c->rfilter == DR_FILTER_TABLE && !(c->filter_radius > 0.0 && std::isfinite(c->filter_radius))) {
+        dr_set_error("rfilter: a filter table needs a positive radius"); return DR_ERR_INVALID_ARG;          // Assert(m_radius > 0), rfilter.cpp:38
     }
-    if (c->rfilter != DR_FILTER_GAUSSIAN && c->rfilter != DR_FILTER_BOX) { dr_set_error("Unsupported rfilter"); return DR_ERR_UNSUPPORTED; }
+    // "Hack to detect box filter" (drmlt_proc.cpp:75-79): radius - 0.500010f > 1e-6
+    if (c->acceptance_map && c->integrator == DR_INTEGRATOR_DRMLT &&
+        !(c->rfilter == DR_FILTER_BOX || (c->rfilter == DR_FILTER_TABLE && !(c->filter_radius - (double) 0.500010f > 1e-6)))) {
+        dr_set_error("Box filter required for acceptance map!"); return DR_ERR_INVALID_ARG;
+    }
     return DR_OK;
 }
 
@@ -534,22 +543,55 @@ static void make_params(const dr_config &c, int W, int H, double b, const int *e
     int off = 0;
     for (int s = 0; s < 3; ++s) { pp.off[s] = off; off += (lay[s] + 1) & ~1; }
     pp.nU = std::max(off, 2);
-    // reconstruction filter table (rfilter.cpp:37-55; gaussian.cpp:30-60 stddev 0.5 radius 2; box.cpp radius 0.5 + 1e-5)
+    // reconstruction filter: radius + the 32-entry table of ReconstructionFilter::configure (rfilter.cpp:37-55) -- from the caller
+    // (DR_FILTER_TABLE) or from the plugins' eval functions with their default parameters (src/rfilters/{gaussian,box,tent,
+    // mitchell,catmullrom,lanczos}.cpp)
     FilmParams &fp = p.fp;
     fp.w = W; fp.h = H;
-    const double stddev = 0.5, radius = c.rfilter == DR_FILTER_BOX ? 0.5 + (double) 1e-5f : 4 * stddev;   // Float 0.5 + a float literal (box.cpp:38)
-    double vals[32], sum = 0.0;
-    for (int i = 0; i < 31; ++i) {
-        const double x = (radius * i) / 31;
-        double v;
-        if (c.rfilter == DR_FILTER_BOX) v = std::fabs(x) <= radius ? 1.0 : 0.0;
-        else { const double alpha = -1.0 / (2.0 * stddev * stddev); v = std::max(0.0, std::exp(alpha * x * x) - std::exp(alpha * radius * radius)); }
-        vals[i] = v; sum += v;
+    double vals[32], radius;
+    if (c.rfilter == DR_FILTER_TABLE) {
+        radius = c.filter_radius;
+        for (int i = 0; i < 32; ++i) vals[i] = c.filter_table[i];
+    } else {
+        const double stddev = 0.5;
+        switch (c.rfilter) {
+            case DR_FILTER_BOX: radius = 0.5 + (double) 1e-5f; break;             // Float 0.5 + a float literal (box.cpp:38)
+            case DR_FILTER_TENT: radius = 1.0; break;
+            case DR_FILTER_LANCZOS: radius = 3.0; break;                             // lobes = 3
+            default: radius = 2.0; break;                                            // gaussian 4 stddev, mitchell, catmullrom
+        }
+        auto cubic = [](double x, double B, double C) {                              // mitchell.cpp:55-69, catmullrom.cpp:43-58
+            x = std::fabs(x);
+            const double x2 = x * x, x3 = x2 * x;
+            if (x < 1) return (double) (1.0f / 6.0f) * ((12 - 9 * B - 6 * C) * x3 + (-18 + 12 * B + 6 * C) * x2 + (6 - 2 * B));
+            if (x < 2) return (double) (1.0f / 6.0f) * ((-B - 6 * C) * x3 + (6 * B + 30 * C) * x2 + (-12 * B - 48 * C) * x + (8 * B + 24 * C));
+            return 0.0;
+        };
+        double sum = 0.0;
+        for (int i = 0; i < 31; ++i) {
+            const double x = (radius * i) / 31;
+            double v;
+            switch (c.rfilter) {
+                case DR_FILTER_BOX: v = std::fabs(x) <= radius ? 1.0 : 0.0; break;
+                case DR_FILTER_TENT: v = std::max(0.0, 1.0 - std::fabs(x / radius)); break;
+                case DR_FILTER_MITCHELL: v = cubic(x, (double) (1.0f / 3.0f), (double) (1.0f / 3.0f)); break;   // props.getFloat("B", 1.0f / 3.0f)
+                case DR_FILTER_CATMULLROM: v = cubic(x, 0.0, 0.5); break;
+                case DR_FILTER_LANCZOS: {                                          // lanczos.cpp:44-57 (Epsilon of the double build)
+                    const double ax = std::fabs(x);
+                    if (ax < 1e-7) v = 1.0;
+                    else if (ax > radius) v = 0.0;
+                    else { const double x1 = M_PI * ax, x2 = x1 / radius; v = (std::sin(x1) * std::sin(x2)) / (x1 * x2); }
+                    break;
+                }
+                default: { const double alpha = -1.0 / (2.0 * stddev * stddev); v = std::max(0.0, std::exp(alpha * x * x) - std::exp(alpha * radius * radius)); }
+            }
+            vals[i] = v; sum += v;
+        }
+        vals[31] = 0.0;
+        sum *= 2 * radius / 31;
+        const double normalization = 1.0 / sum;      // multiplied in, as rfilter.cpp:52-54
+        for (int i = 0; i < 31; ++i) vals[i] *= normalization;
     }
-    vals[31] = 0.0;
-    sum *= 2 * radius / 31;
-    const double normalization = 1.0 / sum;          // multiplied in, as rfilter.cpp:52-54
-    for (int i = 0; i < 31; ++i) vals[i] *= normalization;
     for (int i = 0; i < 32; ++i) fp.values[i] = (float) vals[i];
     fp.radius = (float) radius; fp.scaleFactor = (float) (31 / radius);
 }
@@ -1465,6 +1507,38 @@ extern "C" dr_status dr_direct_image(dr_scene scene, const dr_config *cfgIn, flo
     CKL();
     CK(cudaMemcpy(imageRgb, rgb.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
     if (li) CK(cudaMemcpy(li, dli.p, sizeof(double) * 3 * n * ps, cudaMemcpyDeviceToHost));
+    return DR_OK;
+}
+
+// The film by itself: `n` splats through the reconstruction filter of `cfg` into a w x h film (ImageBlock::put, imageblock.h:149-196).
+extern "C" dr_status dr_splat_points(int device, const dr_config *cfgIn, int32_t w, int32_t h, const float *pos, const float *rgb, int64_t n, float *filmRgb) {
+    if (!cfgIn || w <= 0 || h <= 0 || n < 0 || !filmRgb || (n > 0 && (!pos || !rgb))) { dr_set_error("dr_splat_points: bad argument"); return DR_ERR_INVALID_ARG; }
+    if (cfgIn->rfilter < DR_FILTER_GAUSSIAN || cfgIn->rfilter > DR_FILTER_LANCZOS || (cfgIn->rfilter == DR_FILTER_TABLE && !(cfgIn->filter_radius > 0.0))) {
+        dr_set_error("dr_splat_points: unsupported rfilter"); return DR_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); dr_set_error("no CUDA device available (there is no CPU fallback)"); return DR_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { dr_set_error("device %d out of range (%d devices)", device, ndev); return DR_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(device));
+    Machine M;
+    memset(&M, 0, sizeof(M));
+    dr_config c = *cfgIn;
+    if (c.max_depth <= 0) c.max_depth = 1;
+    make_params(c, w, h, 1.0, nullptr, M);
+    const size_t np = (size_t) w * h;
+    DevBuf film, dpos, drgb;
+    dr_status st;
+    if ((st = film.alloc(np * sizeof(float4))) || (st = dpos.alloc((size_t) n * 8)) || (st = drgb.alloc((size_t) n * 12))) return st;
+    CK(cudaMemset(film.p, 0, np * sizeof(float4)));
+    if (n) {
+        CK(cudaMemcpy(dpos.p, pos, (size_t) n * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(drgb.p, rgb, (size_t) n * 12, cudaMemcpyHostToDevice));
+        launch_splat_points(M.fp, film.as<float4>(), dpos.as<float>(), drgb.as<float>(), n, 0);
+        CKL();
+    }
+    std::vector<float4> f4(np);
+    CK(cudaMemcpy(f4.data(), film.p, np * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < np; ++i) { filmRgb[3 * i] = f4[i].x; filmRgb[3 * i + 1] = f4[i].y; filmRgb[3 * i + 2] = f4[i].z; }
     return DR_OK;
 }
 

@@ -522,6 +522,15 @@ __global__ void k_flush_pssmlt(const __grid_constant__ Machine M) {
     rec_store(M.lm.chain + lane, cc);
 }
 
+// dr_splat_points: the film alone -- ImageBlock::put of explicit (position, RGB) pairs (parity against the reference's own block)
+__global__ void k_splat_points(const __grid_constant__ FilmParams fp, float4 *film, const float2 *pos, const float3 *rgb, long long n) {
+    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (i < n) film_put(film, fp, pos[i], rgb[i]);
+}
+void launch_splat_points(const FilmParams &fp, float4 *film, const float *pos, const float *rgb, long long n, cudaStream_t s) {
+    k_splat_points<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(fp, film, reinterpret_cast<const float2 *>(pos), reinterpret_cast<const float3 *>(rgb), n);
+}
+
 static unsigned grid_for(int n, int threads) { return stage_grid(n, threads); }
 
 void launch_chain(const Machine &M, const LaunchCfg &lc) {

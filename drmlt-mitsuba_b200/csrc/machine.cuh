@@ -486,4 +486,5 @@ void launch_resume(const Machine &M, const LaunchCfg &lc);                // k_c
 void launch_flush_pssmlt(const Machine &M, const LaunchCfg &lc);          // k_chain.cu
 void launch_direct(const DevScene &sc, const FilmParams &fp, unsigned long long seed, int pixelSamples, int shadingSamples, float4 *film, float *rgb,
                    double *li, cudaStream_t stream);                       // k_direct.cu: weighted film -> normalised rgb
+void launch_splat_points(const FilmParams &fp, float4 *film, const float *pos, const float *rgb, long long n, cudaStream_t s);   // k_chain.cu
 void launch_trace_rays(const DevScene &sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits, cudaStream_t stream);

@@ -24,6 +24,9 @@
 #include <mitsuba/core/bitmap.h>
 #include <mitsuba/core/plugin.h>
 #include <mitsuba/core/sched.h>
+#include <mitsuba/core/rfilter.h>
+#include <mitsuba/core/statistics.h>
+#include <mitsuba/core/lock.h>
 #include <drmlt_b200.h>
 #include <cstdlib>
 #include <cstring>
@@ -153,14 +156,41 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why) {
 #if defined(DR_PLUGIN_PSSMLT)
 #define DR_CLASS PSSMLT
 #define DR_NAME "pssmlt"
+// the reference's statistics counters, under the reference's own names (pssmlt_proc.cpp:33-40): `mitsuba` prints the same table
+static StatsCounter largeStepRatio("Primary sample space MLT", "Accepted large steps", EPercentage);
+static StatsCounter smallStepRatio("Primary sample space MLT", "Accepted small steps", EPercentage);
+static StatsCounter acceptanceRate("Primary sample space MLT", "Overall acceptance rate", EPercentage);
+static void publishStats(const dr_stats &st) {
+    largeStepRatio += st.large_accept; largeStepRatio.incrementBase(st.large_base);
+    smallStepRatio += st.bold_accept; smallStepRatio.incrementBase(st.bold_base);
+    acceptanceRate += st.accept; acceptanceRate.incrementBase(st.accept_base);
+}
 #else
 #define DR_CLASS DRMLT
 #define DR_NAME "drmlt"
+// the reference's statistics counters, under the reference's own names (drmlt_proc.cpp:34-49)
+static StatsCounter firstLevelRatio("Delayed Rejection MLT", "Accepted 1st-stage mutations", EPercentage);
+static StatsCounter largeStepRatio("Delayed Rejection MLT", "Accepted large mutations in the 1st-stage mutations", EPercentage);
+static StatsCounter boldStepRatio("Delayed Rejection MLT", "Accepted bold mutation in the 1st-stage mutations", EPercentage);
+static StatsCounter secondLevelRatio("Delayed Rejection MLT", "Accepted 2nd-stage mutations", EPercentage);
+static StatsCounter secondLevelLargeRatio("Delayed Rejection MLT", "Accepted 2nd-stage mutations after large mutation", EPercentage);
+static StatsCounter secondLevelBoldRatio("Delayed Rejection MLT", "Accepted 2nd-stage mutations after bold mutation", EPercentage);
+static StatsCounter acceptanceRate("Delayed Rejection MLT", "Overall acceptance rate", EPercentage);
+static void publishStats(const dr_stats &st) {
+    firstLevelRatio += st.first_accept; firstLevelRatio.incrementBase(st.first_base);
+    largeStepRatio += st.large_accept; largeStepRatio.incrementBase(st.large_base);
+    boldStepRatio += st.bold_accept; boldStepRatio.incrementBase(st.bold_base);
+    secondLevelRatio += st.second_accept; secondLevelRatio.incrementBase(st.second_base);
+    secondLevelLargeRatio += st.second_large_accept; secondLevelLargeRatio.incrementBase(st.second_large_base);
+    secondLevelBoldRatio += st.second_bold_accept; secondLevelBoldRatio.incrementBase(st.second_bold_base);
+    acceptanceRate += st.accept; acceptanceRate.incrementBase(st.accept_base);
+}
 #endif
 
 class DR_CLASS : public Integrator {
 public:
     DR_CLASS(const Properties &props) : Integrator(props), m_scene(NULL) {
+        m_mutex = new Mutex();
         dr_config_default(&m_config);
         check(dr_config_set(&m_config, "integrator", DR_NAME));
         // forward every parameter under the reference's own name (drmlt.cpp:193-349, pssmlt.cpp:181-307)
@@ -204,9 +234,13 @@ public:
         m_config.crop_offset_x = film->getCropOffset().x; m_config.crop_offset_y = film->getCropOffset().y;
         m_config.crop_width = size.x; m_config.crop_height = size.y;
         m_config.sample_count = (int32_t) sensor->getSampler()->getSampleCount();   // drmlt.cpp:400
-        const std::string rf = film->getReconstructionFilter()->getClass()->getName();
-        check(dr_config_set(&m_config, "rfilter", rf == "BoxFilter" ? "box" : "gaussian"));
-        if (rf != "BoxFilter" && rf != "GaussianFilter") Log(EWarn, "Reconstruction filter %s: using gaussian", rf.c_str());
+        // the film's reconstruction filter, whatever plugin and parameters it was built from: after configure() it is a radius and
+        // a 32-entry table (src/libcore/rfilter.cpp:37-55), read back through evalDiscretized (include/mitsuba/core/rfilter.h:76-77)
+        const ReconstructionFilter *rf = film->getReconstructionFilter();
+        m_config.rfilter = DR_FILTER_TABLE;
+        m_config.filter_radius = (double) rf->getRadius();
+        for (int i = 0; i < 32; ++i)
+            m_config.filter_table[i] = (double) rf->evalDiscretized((i + (Float) 0.5) * rf->getRadius() / MTS_FILTER_RESOLUTION);
         check(dr_config_validate(&m_config));
 
         // ---- flatten Scene -> dr_scene_desc
@@ -267,7 +301,9 @@ public:
         desc.camera.film_width = film->getSize().x; desc.camera.film_height = film->getSize().y;
 
         const char *dev = getenv("DRMLT_DEVICE");
-        check(dr_scene_create(&desc, dev ? atoi(dev) : 0, &m_scene));
+        dr_scene created = NULL;
+        check(dr_scene_create(&desc, dev ? atoi(dev) : 0, &created));
+        { LockGuard lock(m_mutex); m_scene = created; }
 
         // ---- render on the GPU, hand the developed image to the film (drmlt_proc.cpp:850-853)
         std::vector<float> image((size_t) size.x * size.y * 3);
@@ -277,12 +313,12 @@ public:
         RefreshCtx ctx = { film.get(), queue, job, size };
         // (`mitsuba -r` marks the job interactive: mitsuba.cpp:395; non-interactive jobs only develop at the end, drmlt.cpp:608)
         const dr_status status = dr_render_progressive(m_scene, &m_config, image.data(), &st, job->isInteractive() ? 2.0 : 0.0, &DR_CLASS::refresh, &ctx);
-        dr_scene sceneHandle = m_scene;
-        m_scene = NULL;
-        dr_scene_destroy(sceneHandle);
+        { LockGuard lock(m_mutex); m_scene = NULL; }            // cancel() from another thread never sees a scene being destroyed
+        dr_scene_destroy(created);
         if (status == DR_ERR_CANCELLED) return false;
         check(status);
         refresh(image.data(), size.x, size.y, 0.0, &st, &ctx);
+        publishStats(st);
         // same figures as the reference's StatsCounters (drmlt_proc.cpp:34-49)
         Log(EInfo, "Normalization factor b = %f; %llu mutations, first stage accepted %.2f %%, second stage %.2f %%, %.1f ms on the GPU",
             st.luminance, (unsigned long long) st.mutations, st.first_base ? 100.0 * st.first_accept / st.first_base : 0.0,
@@ -303,13 +339,14 @@ public:
         return 0;
     }
 
-    void cancel() { if (m_scene) dr_cancel(m_scene); }           // Integrator::cancel (drmlt.cpp:386-391), any thread
+    void cancel() { LockGuard lock(m_mutex); if (m_scene) dr_cancel(m_scene); }   // Integrator::cancel (drmlt.cpp:386-391), any thread
 
     MTS_DECLARE_CLASS()
 private:
     void check(dr_status st) const { if (st != DR_OK) Log(EError, "%s", dr_last_error()); }   // EError throws (renderjob.cpp:110-114)
     dr_config m_config;
     dr_scene m_scene;
+    ref<Mutex> m_mutex;
 };
 
 MTS_IMPLEMENT_CLASS_S(DR_CLASS, false, Integrator)

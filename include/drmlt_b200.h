@@ -100,7 +100,11 @@ typedef struct dr_scene_desc {
 typedef enum dr_integrator { DR_INTEGRATOR_PSSMLT = 0, DR_INTEGRATOR_DRMLT = 1 } dr_integrator;
 typedef enum dr_technique  { DR_TECH_PATH = 0, DR_TECH_BDPT = 1, DR_TECH_MMLT = 2 } dr_technique;
 typedef enum dr_type       { DR_TYPE_GREEN = 0, DR_TYPE_MIRA = 1, DR_TYPE_ORBITAL = 2 } dr_type;
-typedef enum dr_filter     { DR_FILTER_GAUSSIAN = 0, DR_FILTER_BOX = 1 } dr_filter;
+/* reconstruction filter of the film (the plugins under src/rfilters with their default parameters); DR_FILTER_TABLE: the caller supplies
+ * what every ReconstructionFilter boils down to after configure() -- radius + the 32-entry discretisation (rfilter.cpp:37-55,
+ * include/mitsuba/core/rfilter.h:76-77) -- which covers non-default parameters (gaussian stddev, Mitchell B / C, lanczos lobes) */
+typedef enum dr_filter     { DR_FILTER_GAUSSIAN = 0, DR_FILTER_BOX = 1, DR_FILTER_TABLE = 2, DR_FILTER_TENT = 3, DR_FILTER_MITCHELL = 4,
+                             DR_FILTER_CATMULLROM = 5, DR_FILTER_LANCZOS = 6 } dr_filter;
 
 /* Parameter names, meaning and defaults follow DRMLT::DRMLT(props) (drmlt.cpp:178-351)
  * and PSSMLT::PSSMLT(props) (pssmlt.cpp:166-308).  Fill with dr_config_default()
@@ -132,7 +136,7 @@ typedef struct dr_config {
     float   mutation_size_high;     /* mutationSizeHigh = 1/64 (pssmlt) */
     /* carried by other scene objects in the reference */
     int32_t sample_count;      /* sensor sampler's sampleCount = mutations per pixel (drmlt.cpp:400) */
-    int32_t rfilter;           /* film reconstruction filter: gaussian (stddev .5) | box */
+    int32_t rfilter;           /* dr_filter: rfilter=gaussian (stddev .5) | box | tent | mitchell | catmullrom | lanczos; DR_FILTER_TABLE: see below */
     /* GPU execution knobs (no reference equivalent) */
     int32_t n_chains;          /* Markov chains (the reference's work units) per GPU; 0 = auto */
     uint64_t seed;             /* counter-based RNG key (reference: /dev/urandom, random.cpp:473-489) */
@@ -155,6 +159,9 @@ typedef struct dr_config {
     /* m_config.importanceMap (drmlt.h:57, internal): host pointer to crop_width*crop_height floats, or NULL.
      * With twoStage=true and NULL here, dr_render computes it with dr_importance_map first. */
     const float *importance_map;
+    /* rfilter = DR_FILTER_TABLE: ReconstructionFilter::getRadius() and m_values[0..31] (m_values[i] = evalDiscretized((i + .5) * radius / 31)) */
+    double filter_radius;
+    double filter_table[32];
 } dr_config;
 
 void      dr_config_default(dr_config *cfg);
@@ -323,6 +330,11 @@ dr_status dr_chain_steps(dr_scene scene, const dr_config *cfg, double b,
  * (orc_chain_stream) from the streams of tests/golden/ref_chain.npz. */
 dr_status dr_chain_replay(dr_scene scene, const dr_config *cfg, double b, const int32_t *depth, int64_t n_chains, int64_t steps,
                           const double *uniforms, int32_t uniform_dim, dr_step_record *records, float *film);
+
+/* The film by itself (parity entry point): `n` splats (pos [n][2] in pixel coordinates, rgb [n][3]) through the reconstruction
+ * filter of `cfg` into a w x h film (host, w*h*3) -- ImageBlock::put (include/mitsuba/render/imageblock.h:149-196) with the
+ * 32-entry table of ReconstructionFilter::configure (src/libcore/rfilter.cpp:37-55); non-finite or negative values are rejected. */
+dr_status dr_splat_points(int device, const dr_config *cfg, int32_t w, int32_t h, const float *pos, const float *rgb, int64_t n, float *film_rgb);
 
 /* Bootstrap luminances of samples [first, first+n) (before the x maxDepth MMLT scaling). */
 dr_status dr_bootstrap_luminance(dr_scene scene, const dr_config *cfg,

@@ -143,7 +143,7 @@ int orc_chain_steps(void *h, const dr_config *cfg, double b, const uint64_t *see
     unsigned nt = threads > 0 ? (unsigned) threads : std::max(1u, std::thread::hardware_concurrency());
     nt = (unsigned) std::min<int64_t>(nt, std::max<int64_t>(1, n_chains));
     std::vector<Film> films(film_out ? nt : 0);
-    for (auto &f : films) f.init(sc.cam.resX, sc.cam.resY, cfg->rfilter);
+    for (auto &f : films) f.init(sc.cam.resX, sc.cam.resY, *cfg);
     std::vector<ChainStats> tstats(nt);
     std::atomic<int64_t> next(0);
     auto work = [&](unsigned tid) {
@@ -205,7 +205,7 @@ long long orc_chain_stream(void *h, const dr_config *cfg, double b, int depth, c
     Scene &sc = ((OrcScene *) h)->sc;
     applyEps(sc, cfg);
     Film film;
-    film.init(sc.cam.resX, sc.cam.resY, cfg->rfilter);
+    film.init(sc.cam.resX, sc.cam.resY, *cfg);
     ChainRunner runner(sc, *cfg, b, film_out ? &film : nullptr);
     // the streams are read through padded copies, so that an (erroneous) over-read is detected instead of crashing
     std::vector<double> boot, work;
@@ -324,7 +324,7 @@ int orc_render(void *h, const dr_config *cfgIn, int64_t n_boot, int64_t n_chains
     auto t1 = std::chrono::steady_clock::now();
     if (seconds_chains) *seconds_chains = std::chrono::duration<double>(t1 - t0).count();
     if (image_rgb) {
-        Film f; f.init(sc.cam.resX, sc.cam.resY, cfg->rfilter);
+        Film f; f.init(sc.cam.resX, sc.cam.resY, *cfg);
         for (size_t i = 0; i < film.size(); ++i) f.data[i] = film[i];
         develop(f, b, cfg->acceptance_map != 0, image_rgb, cfg->first_stage ? nullptr : cfg->importance_map);
         if (cfg->direct_samples > 0 && !cfg->acceptance_map && !(cfg->two_stage && cfg->first_stage)) {   // `!nested` (drmlt.cpp:478)   // value += direct[i] (drmlt_proc.cpp:846-847)
@@ -544,7 +544,7 @@ int orc_direct_image(void *h, const dr_config *cfg, float *image_rgb, double *li
     int pixelSamples = std::max(cfg->direct_samples, 1), shadingSamples = 1;
     while (pixelSamples > 8) { pixelSamples /= 2; shadingSamples *= 2; }
     const int W = (int) sc.cam.resX, H = (int) sc.cam.resY;
-    Film f; f.init(W, H, cfg->rfilter);
+    Film f; f.init(W, H, *cfg);
     std::vector<Float> weight((size_t) W * H, 0.0);
     PathCtx ctx; ctx.scene = &sc;
     std::vector<Vec2> u(2 * shadingSamples);

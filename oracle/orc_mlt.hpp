@@ -336,20 +336,44 @@ struct Film {
     Float radius, scaleFactor;
     Float values[32];
     std::vector<Float> data;   // w*h*3
+    // the filter plugins' eval functions with their default parameters (src/rfilters/*.cpp) -> radius + 32-entry table (rfilter.cpp:37-55)
+    static Float evalFilter(int rfilter, Float x, Float radius) {
+        auto cubic = [](Float x, Float B, Float C) {   // mitchell.cpp:55-69, catmullrom.cpp:43-58
+            x = std::abs(x);
+            Float x2 = x * x, x3 = x2 * x;
+            if (x < 1) return 1.0f / 6.0f * ((12 - 9 * B - 6 * C) * x3 + (-18 + 12 * B + 6 * C) * x2 + (6 - 2 * B));
+            else if (x < 2) return 1.0f / 6.0f * ((-B - 6 * C) * x3 + (6 * B + 30 * C) * x2 + (-12 * B - 48 * C) * x + (8 * B + 24 * C));
+            return (Float) 0.0;
+        };
+        switch (rfilter) {
+        case DR_FILTER_BOX: return std::abs(x) <= radius ? 1.0 : 0.0;                              // box.cpp:43-45
+        case DR_FILTER_TENT: return std::max((Float) 0.0, 1.0f - std::abs(x / radius));               // tent.cpp:43-45
+        case DR_FILTER_MITCHELL: return cubic(x, 1.0f / 3.0f, 1.0f / 3.0f);
+        case DR_FILTER_CATMULLROM: return cubic(x, 0.0f, 0.5f);
+        case DR_FILTER_LANCZOS: {                                                                  // lanczos.cpp:44-57
+            x = std::abs(x);
+            if (x < 1e-7) return 1.0;
+            else if (x > radius) return 0.0;
+            Float x1 = M_PI * x, x2 = x1 / radius;
+            return (std::sin(x1) * std::sin(x2)) / (x1 * x2);
+        }
+        default: {                                                                                 // gaussian.cpp:52-57, stddev 0.5
+            const Float stddev = 0.5, alpha = -1.0 / (2.0 * stddev * stddev);
+            return std::max((Float) 0.0, std::exp(alpha * x * x) - std::exp(alpha * radius * radius));
+        }
+        }
+    }
     void init(int w_, int h_, int rfilter) {
         w = w_; h = h_; data.assign((size_t) w * h * 3, 0.0);
-        // gaussian.cpp:30-60 (stddev 0.5, radius 2) / box.cpp:30-46 (radius 0.5 + 1e-5); rfilter.cpp:37-55
-        Float stddev = 0.5;
-        radius = rfilter == DR_FILTER_BOX ? 0.5 + (Float) 1e-5f : 4 * stddev;   // a FLOAT literal added to Float 0.5 (box.cpp:38)
+        switch (rfilter) {
+        case DR_FILTER_BOX: radius = 0.5 + (Float) 1e-5f; break;      // a FLOAT literal added to Float 0.5 (box.cpp:38)
+        case DR_FILTER_TENT: radius = 1.0; break;
+        case DR_FILTER_LANCZOS: radius = 3.0; break;                  // lobes = 3
+        default: radius = 2.0; break;                                 // gaussian: 4 stddev; mitchell, catmullrom
+        }
         Float sum = 0.0;
         for (int i = 0; i < 31; ++i) {
-            Float x = (radius * i) / 31;
-            Float v;
-            if (rfilter == DR_FILTER_BOX) v = std::abs(x) <= radius ? 1.0 : 0.0;
-            else {
-                Float alpha = -1.0 / (2.0 * stddev * stddev);
-                v = std::max((Float) 0.0, std::exp(alpha * x * x) - std::exp(alpha * radius * radius));
-            }
+            Float v = evalFilter(rfilter, (radius * i) / 31, radius);
             values[i] = v; sum += v;
         }
         values[31] = 0.0;
@@ -357,6 +381,13 @@ struct Film {
         sum *= 2 * radius / 31;
         const Float normalization = 1.0 / sum;          // multiplied in, as rfilter.cpp:52-54
         for (int i = 0; i < 31; ++i) values[i] *= normalization;
+    }
+    // a job's film: the configuration's filter, or its explicit table (DR_FILTER_TABLE)
+    void init(int w_, int h_, const dr_config &c) {
+        if (c.rfilter != DR_FILTER_TABLE) { init(w_, h_, c.rfilter); return; }
+        w = w_; h = h_; data.assign((size_t) w * h * 3, 0.0);
+        radius = c.filter_radius; scaleFactor = 31 / radius;
+        for (int i = 0; i < 32; ++i) values[i] = c.filter_table[i];
     }
     Float evalDiscretized(Float x) const { return values[std::min((int) std::abs(x * scaleFactor), 31)]; }
     bool put(const Vec2 &_pos, const RGB &value) {

@@ -13,13 +13,18 @@ using namespace mitsuba;
 
 extern "C" void ref_init();     // ref_path.cpp
 
-extern "C" int ref_splat(int w, int h, int gaussian, const float *pos, const float *rgb, int64_t n, double *film_out /* [h][w][3] */,
-                         int *accepted /* [n] */) {
+/* filter: 0 box, 1 gaussian, 3 tent, 4 mitchell, 5 catmullrom, 6 lanczos (3.. = dr_filter); radius_out / table_out (optional):
+ * what the plugin boils down to after configure() -- getRadius() and the 32 discretised values read back through evalDiscretized */
+extern "C" int ref_splat(int w, int h, int filter, const float *pos, const float *rgb, int64_t n, double *film_out /* [h][w][3] */,
+                         int *accepted /* [n] */, double *radius_out, double *table_out /* [32] */) {
     try {
         ref_init();
+        const char *names[] = { "box", "gaussian", "gaussian", "tent", "mitchell", "catmullrom", "lanczos" };
         ref<ReconstructionFilter> rf = static_cast<ReconstructionFilter *>(
-            PluginManager::getInstance()->createObject(MTS_CLASS(ReconstructionFilter), Properties(gaussian ? "gaussian" : "box")));
+            PluginManager::getInstance()->createObject(MTS_CLASS(ReconstructionFilter), Properties(names[filter])));
         rf->configure();
+        if (radius_out) *radius_out = rf->getRadius();
+        if (table_out) for (int i = 0; i < 32; ++i) table_out[i] = rf->evalDiscretized((i + (Float) 0.5) * rf->getRadius() / MTS_FILTER_RESOLUTION);
         ref<ImageBlock> block = new ImageBlock(Bitmap::ESpectrum, Vector2i(w, h), rf.get());
         block->clear();
         for (int64_t i = 0; i < n; ++i) {

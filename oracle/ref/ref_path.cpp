@@ -39,6 +39,8 @@
 #include <map>
 #include <tuple>
 #include <execinfo.h>
+#include <dlfcn.h>
+#include <unistd.h>
 #include <signal.h>
 #include "../../include/drmlt_b200.h"
 #include "src/integrators/pssmlt_utils.h"     // findMaxDimensions, as the integrators include it (drmlt.cpp, pssmlt.cpp)
@@ -47,7 +49,7 @@ using namespace mitsuba;
 #define TR(msg) do { if (getenv("REF_TRACE")) fprintf(stderr, "[ref] %s\n", msg); } while (0)
 
 #define REF_PLUGINS(X) X(diffuse) X(dielectric) X(conductor) X(roughconductor) X(roughdielectric) X(plastic) X(twosided) \
-    X(area) X(perspective) X(gaussian) X(box) X(independent) X(path) X(drmlt) X(pssmlt)
+    X(area) X(perspective) X(gaussian) X(box) X(tent) X(mitchell) X(catmullrom) X(lanczos) X(independent) X(path) X(drmlt) X(pssmlt)
 #define X(name) extern "C" void *CreateInstance_##name(const Properties &props);
 REF_PLUGINS(X)
 #undef X
@@ -61,8 +63,31 @@ void PluginManager::staticInitialization() { m_instance = new PluginManager(); }
 void PluginManager::staticShutdown() { m_instance = NULL; }
 void PluginManager::ensurePluginLoaded(const std::string &) {}
 std::vector<std::string> PluginManager::getLoadedPlugins() const { return std::vector<std::string>(); }
+/* REF_PLUGIN_DIR=<dir>: a plugin file <dir>/<name>.so takes precedence over the table and is loaded exactly as the reference
+ * loads plugins/<name>.so -- dlopen(RTLD_LAZY | RTLD_LOCAL) + dlsym("CreateInstance") (libcore/plugin.cpp:62-96, 222-248).
+ * This is how the drop-in plugins built from drmlt-mitsuba_b200/shim/mts_plugin.cpp are exercised by the reference's own
+ * RenderJob -> Scene::render -> Integrator::render. */
+typedef void *(*CreateInstanceFn)(const Properties &);
+static CreateInstanceFn pluginFromDir(const std::string &name) {
+    static std::map<std::string, CreateInstanceFn> cache;
+    const char *dir = getenv("REF_PLUGIN_DIR");
+    if (!dir) return NULL;
+    const std::string path = std::string(dir) + "/" + name + ".so";
+    std::map<std::string, CreateInstanceFn>::iterator it = cache.find(path);
+    if (it != cache.end()) return it->second;
+    CreateInstanceFn fn = NULL;
+    if (access(path.c_str(), R_OK) == 0) {
+        void *handle = dlopen(path.c_str(), RTLD_LAZY | RTLD_LOCAL);
+        if (!handle) SLog(EError, "Error while loading plugin \"%s\": %s", path.c_str(), dlerror());
+        fn = (CreateInstanceFn) dlsym(handle, "CreateInstance");
+        if (!fn || !dlsym(handle, "GetDescription")) SLog(EError, "Could not resolve symbol \"CreateInstance\" / \"GetDescription\" in \"%s\"", path.c_str());
+    }
+    cache[path] = fn;
+    return fn;
+}
 ConfigurableObject *PluginManager::createObject(const Properties &props) {
     const std::string name = props.getPluginName();
+    if (CreateInstanceFn fn = pluginFromDir(name)) return (ConfigurableObject *) fn(props);
 #define X(n) if (name == #n) return (ConfigurableObject *) CreateInstance_##n(props);
     REF_PLUGINS(X)
 #undef X

@@ -442,16 +442,24 @@ def film_inputs():
     return pos, rgb
 
 
+FILM_FILTERS = (("gaussian", 1, abi.DR_FILTER_GAUSSIAN), ("box", 0, abi.DR_FILTER_BOX), ("tent", 3, abi.DR_FILTER_TENT),
+                ("mitchell", 4, abi.DR_FILTER_MITCHELL), ("catmullrom", 5, abi.DR_FILTER_CATMULLROM), ("lanczos", 6, abi.DR_FILTER_LANCZOS))
+
+
 def run_film(fn, is_ref):
-    """{gaussian, box} -> film [h][w][3] in double + the verdict of every put."""
-    fn.argtypes = [C.c_int, C.c_int, C.c_int, PF32, PF32, C.c_int64, PD, PI32]
+    """Every filter plugin -> film [h][w][3] in double + the verdict of every put (+ radius and 32-entry table of the reference's)."""
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, PF32, PF32, C.c_int64, PD, PI32] + ([PD, PD] if is_ref else [])
     pos, rgb = film_inputs()
     out = {}
-    for name, gaussian in (("gaussian", 1), ("box", 0)):
+    for name, ref_id, orc_id in FILM_FILTERS:
         film, ok = np.zeros((FILM_H, FILM_W, 3)), np.zeros(FILM_N, np.int32)
-        sel = gaussian if is_ref else (abi.DR_FILTER_GAUSSIAN if gaussian else abi.DR_FILTER_BOX)
-        assert fn(FILM_W, FILM_H, sel, pos.ctypes.data_as(PF32), rgb.ctypes.data_as(PF32), FILM_N, film.ctypes.data_as(PD), ok.ctypes.data_as(PI32)) == 0
+        radius, table = D(), np.zeros(32)
+        extra = [C.byref(radius), table.ctypes.data_as(PD)] if is_ref else []
+        assert fn(FILM_W, FILM_H, ref_id if is_ref else orc_id, pos.ctypes.data_as(PF32), rgb.ctypes.data_as(PF32), FILM_N, film.ctypes.data_as(PD),
+                  ok.ctypes.data_as(PI32), *extra) == 0
         out["film_" + name], out["ok_" + name] = film, ok
+        if is_ref:
+            out["table_" + name] = np.concatenate([[radius.value], table])
     return out
 
 

@@ -71,7 +71,7 @@ def test_config_parameter_names_of_the_reference(lib):
     (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, scaleSecond=1.5), "scaleSecond is bigger"),
     (dict(integrator="drmlt", technique="path", maxDepth=8), "Unknown implementation"),      # type is required
     (dict(integrator="drmlt", type="mira", maxDepth=8), "Unknown technique"),                # technique is required
-    (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, acceptanceMap=True), "box reconstruction filter"),
+    (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, acceptanceMap=True), "Box filter required for acceptance map!"),      # the reference's own text (drmlt_proc.cpp:78)
     (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, bogus=1), "Unknown parameter"),
     (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, twoStage=True, firstStageSizeReduction=0), "firstStageSizeReduction"),
     (dict(integrator="drmlt", technique="path", type="mira", maxDepth=8, cropOffsetX=-1), "Invalid crop window"),

@@ -877,3 +877,60 @@ def test_cuda_chain_replays_reference_chain(case):
     # the work units' films: float atomics against the reference's double ImageBlock
     scale = np.abs(film_ref).max()
     assert np.abs(film.astype(np.float64) - film_ref).max() <= 2e-5 * scale, (name, np.abs(film - film_ref).max() / scale)
+
+
+# The CUDA film against the reference's OWN ImageBlock::put (tests/golden/ref_film.npz, oracle/ref/ref_film.cpp): 4000 splats inside, on
+# pixel / half-pixel lattices and up to 3 pixels outside the film, NaN / inf / negative values, through every reconstruction filter
+# plugin -- by name (the library's restatement of the plugin's eval function) and as the explicit radius + 32-entry table the
+# reference's filter object hands out (DR_FILTER_TABLE, what the Mitsuba-side plugin passes).  Float atomics vs the block's doubles.
+@pytest.mark.parametrize("name", [f[0] for f in RP.FILM_FILTERS])
+@pytest.mark.parametrize("as_table", [False, True])
+def test_cuda_film_matches_reference_imageblock(lib, name, as_table):
+    gold = dict(np.load(RP.GOLDEN_FILM))
+    pos, rgb = RP.film_inputs()
+    cfg = make_config(integrator="drmlt", technique="path", type="mira", maxDepth=3, rfilter=name)
+    if as_table:
+        cfg.rfilter = abi.DR_FILTER_TABLE
+        cfg.filter_radius = float(gold["table_" + name][0])
+        for i in range(32):
+            cfg.filter_table[i] = float(gold["table_" + name][1 + i])
+    film = np.zeros((RP.FILM_H, RP.FILM_W, 3), np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))     # noqa: E731
+    abi.check(lib, lib.dr_splat_points(0, C.byref(cfg), RP.FILM_W, RP.FILM_H, fp(pos), fp(rgb), len(pos), fp(film)))
+    want = gold["film_" + name]
+    # every pixel sums <= a few hundred float products: the order of the atomics moves the last bits only
+    assert np.abs(film - want).max() <= 3e-6 * np.abs(want).max(), (name, np.abs(film - want).max() / np.abs(want).max())
+    assert np.isfinite(film).all()
+
+
+# The drop-in plugins themselves: oracle/_ref/plugins/drmlt.so and pssmlt.so are drmlt-mitsuba_b200/shim/mts_plugin.cpp compiled against
+# the reference's headers and linked with the reference's libcore / librender / libbidir (oracle/ref/Makefile).  With REF_PLUGIN_DIR
+# set, the plugin manager dlopen()s them (RTLD_LOCAL) and resolves CreateInstance / GetDescription exactly as the reference loads
+# plugins/<name>.so (plugin.cpp:62-96, 180-196); the job then runs through the reference's OWN RenderJob -> Scene::render ->
+# Integrator::render (the plugin flattens the mitsuba::Scene, renders on the GPU, hands the bitmap to the film and publishes the
+# reference's statistics counters).  Same bounds as the reference's integrators against themselves (check_rates_and_b).
+import os  # noqa: E402
+
+PLUGIN_DIR = os.path.join(RP.ROOT, "oracle", "_ref", "plugins")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(PLUGIN_DIR, "drmlt.so")), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", ["drmlt_orbital_mmlt", "drmlt_mira_path", "pssmlt_path"])
+def test_drop_in_plugin_under_the_references_render_job(name):
+    gold = dict(np.load(RP.GOLDEN_RENDER))
+    params, spp = RP.RENDER_CASES[name]
+    os.environ["REF_PLUGIN_DIR"] = PLUGIN_DIR
+    try:
+        img, sec, _, stats = RP.run_render_ref(C.CDLL(RP.REF_PATH), params, spp, threads=2)
+    finally:
+        del os.environ["REF_PLUGIN_DIR"]
+    assert np.isfinite(img).all() and img.shape == gold[name + "_image"].shape
+    names, runs = gold[name + "_stats_names"], gold[name + "_stats"]
+    assert set(str(k) for k in names) <= set(stats), (sorted(stats), names)      # the plugin publishes the reference's counters by name
+    for k, vals in zip(names, runs.T):
+        assert abs(stats[str(k)] - vals.mean()) <= 1.0 + (vals.max() - vals.min()), (name, str(k), stats[str(k)], vals)
+    b, bs = float(RP.luminance(img).mean()), gold[name + "_b"]
+    assert abs(b - bs.mean()) <= 0.005 * bs.mean() + (bs.max() - bs.min()) / 2, (name, b, bs)
+    if name == "drmlt_orbital_mmlt":
+        err, ref_errs = RP.rel_mse(img, gold["converged_drmlt_orbital_mmlt"]), gold["drmlt_orbital_mmlt_relmse_runs"]
+        assert err <= 1.25 * ref_errs.max(), (err, ref_errs)
