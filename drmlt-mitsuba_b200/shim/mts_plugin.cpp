@@ -349,6 +349,9 @@ private:
     ref<Mutex> m_mutex;
 };
 
-MTS_IMPLEMENT_CLASS_S(DR_CLASS, false, Integrator)
-MTS_EXPORT_PLUGIN(DR_CLASS, "B200 " DR_NAME " integrator");
+// (one more macro level, so that the class registers under its expanded name -- "DRMLT" / "PSSMLT", the reference's own)
+#define DR_IMPLEMENT(cls) MTS_IMPLEMENT_CLASS_S(cls, false, Integrator)
+#define DR_EXPORT(cls, descr) MTS_EXPORT_PLUGIN(cls, descr)
+DR_IMPLEMENT(DR_CLASS)
+DR_EXPORT(DR_CLASS, "B200 " DR_NAME " integrator");
 MTS_NAMESPACE_END

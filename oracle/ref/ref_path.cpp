@@ -81,6 +81,7 @@ static CreateInstanceFn pluginFromDir(const std::string &name) {
         if (!handle) SLog(EError, "Error while loading plugin \"%s\": %s", path.c_str(), dlerror());
         fn = (CreateInstanceFn) dlsym(handle, "CreateInstance");
         if (!fn || !dlsym(handle, "GetDescription")) SLog(EError, "Could not resolve symbol \"CreateInstance\" / \"GetDescription\" in \"%s\"", path.c_str());
+        Class::staticInitialization();     /* "New classes must be registered within the class hierarchy" (plugin.cpp:100-101) */
     }
     cache[path] = fn;
     return fn;
@@ -431,7 +432,15 @@ int ref_render(const dr_scene_desc *d, const dr_config *c, int sample_count, int
         memcpy(image_rgb, rs->film->image.data(), rs->film->image.size() * sizeof(float));
         delete rs;
         return 0;
-    } catch (const std::exception &e) { fprintf(stderr, "oracle/_ref: %s\n", e.what()); return 1; }
+    } catch (const std::exception &e) {
+        fprintf(stderr, "oracle/_ref: %s\n", e.what());
+        try {                                /* leave no worker thread behind: the calling process must be able to exit */
+            Scheduler *sched = Scheduler::getInstance();
+            if (sched->isRunning()) sched->stop();
+            for (size_t i = sched->getWorkerCount(); i-- > 0; ) sched->unregisterWorker(sched->getWorker((int) i));
+        } catch (...) {}
+        return 1;
+    }
 }
 
 /* BSDF::sample / eval / pdf of the reference's plugins in the local frame (what orc_bsdf_sample / orc_bsdf_eval

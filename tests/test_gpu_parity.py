@@ -914,16 +914,27 @@ import os  # noqa: E402
 PLUGIN_DIR = os.path.join(RP.ROOT, "oracle", "_ref", "plugins")
 
 
+def run_plugin_job(name, tmp_path, spp=None, timeout=300):
+    """tools/plugin_render.py in a process of its own (the reference's scheduler threads stay there) -> (image or None, info, stderr)."""
+    import json
+    import subprocess
+    import sys
+    out = str(tmp_path / (name + ".npy"))
+    cmd = [sys.executable, os.path.join(RP.ROOT, "tools", "plugin_render.py"), name, out] + ([str(spp)] if spp else [])
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("PLUGIN_RENDER ")]
+    assert line, (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
+    info = json.loads(line[-1][len("PLUGIN_RENDER "):])
+    return (np.load(out) if info["ok"] else None), info, p.stderr
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(PLUGIN_DIR, "drmlt.so")), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
 @pytest.mark.parametrize("name", ["drmlt_orbital_mmlt", "drmlt_mira_path", "pssmlt_path"])
-def test_drop_in_plugin_under_the_references_render_job(name):
+def test_drop_in_plugin_under_the_references_render_job(name, tmp_path):
     gold = dict(np.load(RP.GOLDEN_RENDER))
-    params, spp = RP.RENDER_CASES[name]
-    os.environ["REF_PLUGIN_DIR"] = PLUGIN_DIR
-    try:
-        img, sec, _, stats = RP.run_render_ref(C.CDLL(RP.REF_PATH), params, spp, threads=2)
-    finally:
-        del os.environ["REF_PLUGIN_DIR"]
+    img, info, err = run_plugin_job(name, tmp_path)
+    assert info["ok"], (info, err[-2000:])
+    stats = info["stats"]
     assert np.isfinite(img).all() and img.shape == gold[name + "_image"].shape
     names, runs = gold[name + "_stats_names"], gold[name + "_stats"]
     assert set(str(k) for k in names) <= set(stats), (sorted(stats), names)      # the plugin publishes the reference's counters by name

@@ -415,3 +415,31 @@ def test_reference_chain_fixture_is_current(golden_chain):
     assert sorted(live) == sorted(golden_chain)
     for k, v in live.items():
         assert np.array_equal(v, golden_chain[k]), k
+
+
+# ================================================================ the drop-in plugin under the reference's plugin manager
+# oracle/_ref/plugins/drmlt.so / pssmlt.so = drmlt-mitsuba_b200/shim/mts_plugin.cpp compiled against the reference (oracle/ref/Makefile).
+# Without a GPU the job must fail LOUDLY and the reference's way: dr_scene_create reports "no CUDA device", the plugin raises it as
+# Log(EError) and RenderJob::run catches the exception (renderjob.cpp:110-114) -- after the plugin was dlopen()ed, passed the
+# plugin manager's class check (plugin.cpp:188-193) and flattened the mitsuba::Scene.  (The GPU suite renders through it.)
+PLUGIN_SO = os.path.join(RP.ROOT, "oracle", "_ref", "plugins", "drmlt.so")
+
+
+@pytest.mark.skipif(not os.path.exists(PLUGIN_SO), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", ["drmlt_orbital_mmlt", "pssmlt_path"])
+def test_drop_in_plugin_loads_and_fails_loudly_without_a_gpu(name, tmp_path):
+    import json
+    import subprocess
+    import sys
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: covered by tests/test_gpu_parity.py")
+    except ImportError:
+        pass
+    p = subprocess.run([sys.executable, os.path.join(RP.ROOT, "tools", "plugin_render.py"), name, str(tmp_path / "x.npy"), "4"],
+                       capture_output=True, text=True, timeout=300)
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("PLUGIN_RENDER ")]
+    assert line and not json.loads(line[-1][len("PLUGIN_RENDER "):])["ok"], (p.stdout[-1000:], p.stderr[-1000:])
+    log = p.stdout + p.stderr           # Mitsuba's logger writes to stdout
+    assert "no CUDA device available (there is no CPU fallback)" in log and "caught exception" in log, log[-1500:]
