@@ -355,6 +355,11 @@ void orc_first_stage_config(void *h, const dr_config *cfg, dr_config *nested) {
     *nested = c;
 }
 void orc_resample_luminance(const float *image_rgb, int w, int h, int W, int H, float *map) { resampleLuminance(image_rgb, w, h, W, H, map); }
+// the resampling alone, double in / double out: held bit for bit against the reference's Bitmap::resample (tests/test_ref_pins.py)
+void orc_resample_map_f64(const double *lum, int w, int h, int W, int H, double *out) {
+    const std::vector<Float> r = resampleMap(std::vector<Float>(lum, lum + (size_t) w * h), w, h, W, H);
+    for (size_t i = 0; i < r.size(); ++i) out[i] = r[i];
+}
 // develop of an accumulated film (W*H*3 floats) with an optional importance map (drmlt_proc.cpp:813-854)
 void orc_develop(const float *film_rgb, int w, int h, double b, int acceptance_map, const float *importance, float *image_rgb) {
     Film f; f.init(w, h, DR_FILTER_BOX);

@@ -793,9 +793,8 @@ struct Resampler {
     }
 };
 // mltLuminancePass, last part (util.cpp:180-196): developed RGB -> luminance -> Bitmap::resample (bitmap.cpp:2230-2329)
-inline void resampleLuminance(const float *rgb, int w, int h, int W, int H, float *map) {
-    std::vector<Float> lum((size_t) w * h);
-    for (size_t i = 0; i < lum.size(); ++i) lum[i] = RGB(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]).luminance();
+// Bitmap::resample of a luminance bitmap (bitmap.cpp:2230-2329): along x first (into a [h][W] temporary), then along y
+inline std::vector<Float> resampleMap(const std::vector<Float> &lum, int w, int h, int W, int H) {
     std::vector<Float> tmp, out;
     const Float *cur = lum.data();
     int curW = w;
@@ -811,7 +810,13 @@ inline void resampleLuminance(const float *rgb, int w, int h, int W, int H, floa
         for (int x = 0; x < curW; ++x) r.resampleAndClamp(cur + x, curW, out.data() + x, curW);
         cur = out.data();
     }
-    for (size_t i = 0; i < (size_t) W * H; ++i) map[i] = (float) cur[i];
+    return std::vector<Float>(cur, cur + (size_t) W * H);
+}
+inline void resampleLuminance(const float *rgb, int w, int h, int W, int H, float *map) {
+    std::vector<Float> lum((size_t) w * h);
+    for (size_t i = 0; i < lum.size(); ++i) lum[i] = RGB(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]).luminance();
+    const std::vector<Float> out = resampleMap(lum, w, h, W, H);
+    for (size_t i = 0; i < (size_t) W * H; ++i) map[i] = (float) out[i];
 }
 
 } // namespace orc

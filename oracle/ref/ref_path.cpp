@@ -32,6 +32,7 @@
 #include <mitsuba/core/sched.h>
 #include <mitsuba/core/appender.h>
 #include <mitsuba/bidir/pathsampler.h>
+#include <mitsuba/bidir/util.h>
 #include <mitsuba/render/renderjob.h>
 #include <mitsuba/render/renderqueue.h>
 #include <mitsuba/core/bitmap.h>
@@ -49,7 +50,7 @@ using namespace mitsuba;
 #define TR(msg) do { if (getenv("REF_TRACE")) fprintf(stderr, "[ref] %s\n", msg); } while (0)
 
 #define REF_PLUGINS(X) X(diffuse) X(dielectric) X(conductor) X(roughconductor) X(roughdielectric) X(plastic) X(twosided) \
-    X(area) X(perspective) X(gaussian) X(box) X(tent) X(mitchell) X(catmullrom) X(lanczos) X(independent) X(path) X(drmlt) X(pssmlt)
+    X(area) X(perspective) X(gaussian) X(box) X(tent) X(mitchell) X(catmullrom) X(lanczos) X(independent) X(ldsampler) X(path) X(direct) X(drmlt) X(pssmlt)
 #define X(name) extern "C" void *CreateInstance_##name(const Properties &props);
 REF_PLUGINS(X)
 #undef X
@@ -63,6 +64,7 @@ void PluginManager::staticInitialization() { m_instance = new PluginManager(); }
 void PluginManager::staticShutdown() { m_instance = NULL; }
 void PluginManager::ensurePluginLoaded(const std::string &) {}
 std::vector<std::string> PluginManager::getLoadedPlugins() const { return std::vector<std::string>(); }
+static ConfigurableObject *ref_make_film(const Properties &props);
 /* REF_PLUGIN_DIR=<dir>: a plugin file <dir>/<name>.so takes precedence over the table and is loaded exactly as the reference
  * loads plugins/<name>.so -- dlopen(RTLD_LAZY | RTLD_LOCAL) + dlsym("CreateInstance") (libcore/plugin.cpp:62-96, 222-248).
  * This is how the drop-in plugins built from drmlt-mitsuba_b200/shim/mts_plugin.cpp are exercised by the reference's own
@@ -89,6 +91,7 @@ static CreateInstanceFn pluginFromDir(const std::string &name) {
 ConfigurableObject *PluginManager::createObject(const Properties &props) {
     const std::string name = props.getPluginName();
     if (CreateInstanceFn fn = pluginFromDir(name)) return (ConfigurableObject *) fn(props);
+    if (name == "hdrfilm") return ref_make_film(props);      /* the nested film of mltLuminancePass (util.cpp:120-130); hdrfilm itself needs OpenEXR */
 #define X(n) if (name == #n) return (ConfigurableObject *) CreateInstance_##n(props);
     REF_PLUGINS(X)
 #undef X
@@ -107,8 +110,10 @@ MTS_IMPLEMENT_CLASS(PluginManager, false, Object)
 class PinFilm : public Film {
 public:
     PinFilm(const Properties &props) : Film(props) {}
-    void clear() {}
-    void put(const ImageBlock *) {}
+    /* SamplingIntegrator::render accumulates weighted blocks into the film (hdrfilm.cpp:352, 388-393): the same storage here */
+    void configure() { m_storage = new ImageBlock(Bitmap::ESpectrumAlphaWeight, m_cropSize); m_storage->clear(); }
+    void clear() { if (m_storage) m_storage->clear(); }
+    void put(const ImageBlock *block) { m_storage->put(block); }
     /* what DRMLTProcess::develop / PSSMLTProcess::develop hand over (drmlt_proc.cpp:850-853): spectrum float pixels */
     void setBitmap(const Bitmap *bitmap, Float multiplier) {
         const Vector2i sz = bitmap->getSize();
@@ -120,12 +125,52 @@ public:
     void addBitmap(const Bitmap *, Float) {}
     void setDestinationFile(const fs::path &, uint32_t) {}
     void develop(const Scene *, Float) {}
-    bool develop(const Point2i &, const Vector2i &, const Point2i &, Bitmap *) const { return false; }
+    /* hdrfilm.cpp:425-470 for the two targets this path asks for: the weighted storage divided by its weight -> ESpectrum
+     * (renderDirectComponent, util.cpp:87-91) or ELuminance (mltLuminancePass, util.cpp:184-188) float pixels.  A film that was
+     * handed a developed bitmap (setBitmap: the nested MLT job) develops that instead. */
+    bool develop(const Point2i &so, const Vector2i &size, const Point2i &to, Bitmap *target) const {
+        if (target->getComponentFormat() != Bitmap::EFloat) return false;
+        const bool lum = target->getPixelFormat() == Bitmap::ELuminance;
+        if (!lum && target->getPixelFormat() != Bitmap::ESpectrum) return false;
+        Float *dst = target->getFloatData();
+        const int tw = target->getWidth(), tc = target->getChannelCount();
+        const Bitmap *src = m_storage->getBitmap();
+        const int border = m_storage->getBorderSize(), sw = src->getWidth(), sc = src->getChannelCount();
+        const Float *sdata = src->getFloatData();
+        for (int y = 0; y < size.y; ++y)
+            for (int x = 0; x < size.x; ++x) {
+                Spectrum value;
+                if (!image.empty()) {
+                    const float *p = &image[((size_t) (y + so.y) * m_cropSize.x + (x + so.x)) * 3];
+                    for (int q = 0; q < SPECTRUM_SAMPLES; ++q) value[q] = p[q];
+                } else {
+                    const Float *p = sdata + ((size_t) (y + so.y + border) * sw + (x + so.x + border)) * sc;
+                    const Float weight = p[sc - 1], inv = weight != 0 ? (Float) 1 / weight : (Float) 0;
+                    for (int q = 0; q < SPECTRUM_SAMPLES; ++q) value[q] = p[q] * inv;
+                }
+                Float *o = dst + ((size_t) (y + to.y) * tw + (x + to.x)) * tc;
+                if (lum) o[0] = value.getLuminance();
+                else for (int q = 0; q < SPECTRUM_SAMPLES; ++q) o[q] = value[q];
+            }
+        return true;
+    }
     bool destinationExists(const fs::path &) const { return false; }
     bool hasAlpha() const { return false; }
     MTS_DECLARE_CLASS()
+private:
+    ref<ImageBlock> m_storage;
 };
 MTS_IMPLEMENT_CLASS(PinFilm, false, Film)
+
+static ConfigurableObject *ref_make_film(const Properties &props) {
+    Properties fp(props);
+    ref<ConfigurableObject> rf = PluginManager::getInstance()->createObject(MTS_CLASS(ReconstructionFilter), Properties("gaussian"));   // hdrfilm's default
+    rf->configure();
+    PinFilm *film = new PinFilm(fp);
+    film->addChild(rf);
+    rf->setParent(film);
+    return film;
+}
 
 /* ---- replayed uniforms */
 class ReplaySampler : public Sampler {
@@ -441,6 +486,68 @@ int ref_render(const dr_scene_desc *d, const dr_config *c, int sample_count, int
         } catch (...) {}
         return 1;
     }
+}
+
+/* The separate direct-illumination image: BidirectionalUtils::renderDirectComponent (src/libbidir/util.cpp:30-94) itself -- the
+ * `direct` integrator (src/integrators/direct/direct.cpp) with the pixelSamples x shadingSamples split, an `ldsampler` per worker,
+ * SamplingIntegrator::render on `threads` local workers, film->develop.  The ldsampler scrambles from /dev/urandom: comparable
+ * statistically. */
+int ref_direct_image(const dr_scene_desc *d, int rfilter, int direct_samples, int threads, float *image_rgb) {
+    try {
+        initOnce();
+        Scheduler *sched = Scheduler::getInstance();
+        for (int i = 0; i < threads; ++i) sched->registerWorker(new LocalWorker(i, formatString("wrk%i", i)));
+        sched->start();
+        RefScene *rs = (RefScene *) scene_create(d, rfilter);
+        ref<RenderQueue> queue = new RenderQueue();
+        int sceneResID = sched->registerResource(rs->scene);
+        int sensorResID = sched->registerResource(rs->scene->getSensor());
+        ref<RenderJob> job = new RenderJob("dire", rs->scene, queue, sceneResID, sensorResID, -1, false, false);
+        rs->scene->getFilm()->clear();
+        ref<Bitmap> img = BidirectionalUtils::renderDirectComponent(rs->scene, sceneResID, sensorResID, queue, job, (size_t) direct_samples);
+        sched->unregisterResource(sceneResID);
+        sched->unregisterResource(sensorResID);
+        sched->stop();
+        for (size_t i = sched->getWorkerCount(); i-- > 0; ) sched->unregisterWorker(sched->getWorker((int) i));
+        if (!img) { delete rs; return 2; }
+        const Float *src = img->getFloatData();
+        const size_t n = (size_t) img->getWidth() * img->getHeight();
+        for (size_t i = 0; i < n; ++i) {
+            Spectrum sp; for (int q = 0; q < SPECTRUM_SAMPLES; ++q) sp[q] = src[i * SPECTRUM_SAMPLES + q];
+            Float R, G, B; sp.toLinearRGB(R, G, B);
+            image_rgb[3 * i] = (float) R; image_rgb[3 * i + 1] = (float) G; image_rgb[3 * i + 2] = (float) B;
+        }
+        delete rs;
+        return 0;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "oracle/_ref: %s\n", e.what());
+        try {
+            Scheduler *sched = Scheduler::getInstance();
+            if (sched->isRunning()) sched->stop();
+            for (size_t i = sched->getWorkerCount(); i-- > 0; ) sched->unregisterWorker(sched->getWorker((int) i));
+        } catch (...) {}
+        return 1;
+    }
+}
+
+/* The up-sampling of the first-stage luminance map, as mltLuminancePass does it (util.cpp:175-196): Bitmap::resample
+ * (src/libcore/bitmap.cpp:2230-2400) of an ELuminance float bitmap with the gaussian filter plugin, EClamp borders, clamped to
+ * [0, inf). */
+int ref_resample_luminance(const double *lum, int w, int h, int W, int H, double *out) {
+    try {
+        initOnce();
+        ref<ReconstructionFilter> rfilter = static_cast<ReconstructionFilter *>(
+            PluginManager::getInstance()->createObject(MTS_CLASS(ReconstructionFilter), Properties("gaussian")));
+        rfilter->configure();
+        ref<Bitmap> src = new Bitmap(Bitmap::ELuminance, Bitmap::EFloat, Vector2i(w, h));
+        Float *sd = src->getFloatData();
+        for (size_t i = 0; i < (size_t) w * h; ++i) sd[i] = (Float) lum[i];
+        ref<Bitmap> dst = src->resample(rfilter, ReconstructionFilter::EClamp, ReconstructionFilter::EClamp, Vector2i(W, H),
+                                        0.0f, std::numeric_limits<Float>::infinity());
+        const Float *dd = dst->getFloatData();
+        for (size_t i = 0; i < (size_t) W * H; ++i) out[i] = dd[i];
+        return 0;
+    } catch (const std::exception &e) { fprintf(stderr, "oracle/_ref: %s\n", e.what()); return 1; }
 }
 
 /* BSDF::sample / eval / pdf of the reference's plugins in the local frame (what orc_bsdf_sample / orc_bsdf_eval

@@ -657,3 +657,66 @@ def check_chain_oracle_vs_ref(case, ref):
     t = run_chain_oracle(orc, case, ref, table_in=o["table"])
     assert np.array_equal(t["decisions"], o["decisions"]) and np.abs(t["film"] - o["film"]).max() <= 1e-13 * scale, (case[0], "replay table")
     return o
+
+
+# ---------------------------------------------------------------- the direct pass and the importance-map resampling
+GOLDEN_DIRECT = os.path.join(ROOT, "tests", "golden", "ref_direct.npz")
+DIRECT_SCENES = {"cornell": lambda: scenes.cornell_box(film=(64, 64), tess=4), "glossy": lambda: scenes.glossy_scene(film=(64, 64), subdiv=2)}
+DIRECT_SAMPLES = 64
+RESAMPLE_SHAPES = [((20, 12), (160, 90)), ((64, 48), (16, 12)), ((33, 17), (33, 40)), ((8, 8), (128, 8)), ((5, 7), (5, 7)), ((1, 1), (16, 16)), ((20, 11), (320, 180))]
+
+
+def resample_input(shape):
+    (w, h), (W, H) = shape
+    rng = np.random.RandomState(w * 131 + H)
+    return (rng.rand(h, w) ** 3) * 4.0
+
+
+def run_direct_ref(lib):
+    """BidirectionalUtils::renderDirectComponent of the reference (ref_direct_image) on the test scenes, and Bitmap::resample
+    (ref_resample_luminance) on the test maps -> flat dict of arrays (tests/golden/ref_direct.npz)."""
+    P = C.POINTER
+    lib.ref_direct_image.argtypes = [P(abi.dr_scene_desc), C.c_int, C.c_int, C.c_int, PF32]
+    lib.ref_resample_luminance.argtypes = [PD, C.c_int, C.c_int, C.c_int, C.c_int, PD]
+    out = {}
+    for name, make in DIRECT_SCENES.items():
+        data = make()
+        d = data.desc()
+        W, H = data.film
+        img = np.zeros((H, W, 3), np.float32)
+        assert lib.ref_direct_image(C.byref(d), abi.DR_FILTER_GAUSSIAN, DIRECT_SAMPLES, 4, img.ctypes.data_as(PF32)) == 0
+        out["direct_" + name] = img
+    for i, shape in enumerate(RESAMPLE_SHAPES):
+        (w, h), (W, H) = shape
+        src, dst = np.ascontiguousarray(resample_input(shape)), np.zeros((H, W))
+        assert lib.ref_resample_luminance(src.ctypes.data_as(PD), w, h, W, H, dst.ctypes.data_as(PD)) == 0
+        out["resample_%d" % i] = dst
+    return out
+
+
+def run_resample_oracle(lib):
+    lib.orc_resample_map_f64.argtypes = [PD, C.c_int, C.c_int, C.c_int, C.c_int, PD]
+    out = {}
+    for i, shape in enumerate(RESAMPLE_SHAPES):
+        (w, h), (W, H) = shape
+        src, dst = np.ascontiguousarray(resample_input(shape)), np.zeros((H, W))
+        lib.orc_resample_map_f64(src.ctypes.data_as(PD), w, h, W, H, dst.ctypes.data_as(PD))
+        out["resample_%d" % i] = dst
+    return out
+
+
+def check_direct_image(img, ref, what):
+    """The separate direct-illumination image against the reference's (util.cpp:30-94), statistically: the reference draws its
+    pixel and shading samples from an ldsampler scrambled from /dev/urandom, the product from keyed uniforms.  The pixels that see
+    the area light (only 8 PIXEL samples land there, whatever directSamples: util.cpp:44-54) carry most of the image mean and all
+    of its noise; they are compared loosely, everything else within 1 % in the mean and a small relMSE."""
+    from scipy.ndimage import binary_dilation
+    a, b = luminance(np.asarray(img, np.float64)), luminance(np.asarray(ref, np.float64))
+    lit = binary_dilation(b > 1.0, iterations=3)
+    m = ~lit
+    assert m.sum() > 0.8 * m.size
+    assert abs(a[m].mean() / b[m].mean() - 1.0) < 0.01, (what, a[m].mean(), b[m].mean())
+    err = float(np.mean((a[m] - b[m]) ** 2 / (b[m] ** 2 + 1e-2)))
+    assert err < 1e-2, (what, err)     # both images carry their own sampling noise (measured 1e-3 .. 5e-3)
+    assert abs(a[lit].mean() / b[lit].mean() - 1.0) < 0.08, (what, a[lit].mean(), b[lit].mean())
+    return err

@@ -971,3 +971,28 @@ def test_drop_in_plugin_under_the_references_render_job(name, tmp_path):
     if name == "drmlt_orbital_mmlt":
         err, ref_errs = RP.rel_mse(img, gold["converged_drmlt_orbital_mmlt"]), gold["drmlt_orbital_mmlt_relmse_runs"]
         assert err <= 1.25 * ref_errs.max(), (err, ref_errs)
+
+
+# the CUDA direct pass against the reference's own renderDirectComponent (tests/golden/ref_direct.npz,
+# oracle/ref/ref_path.cpp ref_direct_image), statistically (ldsampler vs keyed uniforms); rank 3: the importance-map resampling
+# on the GPU against the reference's Bitmap::resample (same fixture; the GPU map is float32).
+@pytest.mark.parametrize("name", list(RP.DIRECT_SCENES))
+def test_cuda_direct_image_matches_reference_direct_integrator(name):
+    gold = dict(np.load(RP.GOLDEN_DIRECT))
+    gpu = Scene(RP.DIRECT_SCENES[name]())
+    cfg = make_config(integrator="drmlt", technique="mmlt", type="orbital", maxDepth=6, directSamples=RP.DIRECT_SAMPLES, seed=3)
+    cfg.ray_epsilon, cfg.shadow_epsilon = 1e-7, 1e-5
+    RP.check_direct_image(gpu.direct_image(cfg), gold["direct_" + name], name)
+
+
+def test_cuda_resampling_matches_reference_bitmap_resample():
+    gold = dict(np.load(RP.GOLDEN_DIRECT))
+    gpu, _, _ = pair("cornell")
+    for i, shape in enumerate(RP.RESAMPLE_SHAPES):
+        (w, h), (W, H) = shape
+        lum = RP.resample_input(shape).astype(np.float32)
+        # a grey image whose luminance is `lum` (the three weights sum to 1 in float up to 1e-7)
+        img = np.repeat(lum[..., None], 3, axis=2)
+        m = gpu.resample_luminance(img, (W, H))
+        want = gold["resample_%d" % i]
+        assert np.abs(m - want).max() <= 2e-6 * max(want.max(), 1e-30), (shape, np.abs(m - want).max())

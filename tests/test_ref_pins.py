@@ -443,3 +443,41 @@ def test_drop_in_plugin_loads_and_fails_loudly_without_a_gpu(name, tmp_path):
     assert line and not json.loads(line[-1][len("PLUGIN_RENDER "):])["ok"], (p.stdout[-1000:], p.stderr[-1000:])
     log = p.stdout + p.stderr           # Mitsuba's logger writes to stdout
     assert "no CUDA device available (there is no CPU fallback)" in log and "caught exception" in log, log[-1500:]
+
+
+# ================================================================ SURVEY 8f rank 1 / rank 3: the direct pass, the importance-map resampling
+# ref_direct_image runs BidirectionalUtils::renderDirectComponent itself (src/libbidir/util.cpp:30-94: the `direct` integrator with
+# the pixelSamples x shadingSamples split, an `ldsampler`, SamplingIntegrator::render on local workers, film->develop);
+# ref_resample_luminance the up-sampling step of mltLuminancePass (util.cpp:175-196): Bitmap::resample with the gaussian plugin,
+# clamped borders, clamped to [0, inf).  The resampling is deterministic -> bit for bit; the direct image is compared statistically.
+@needs_ref_path
+def test_oracle_resampling_equals_reference_bitmap_resample_bit_for_bit():
+    lib = C.CDLL(RP.REF_PATH)
+    lib.ref_resample_luminance.argtypes = [RP.PD, C.c_int, C.c_int, C.c_int, C.c_int, RP.PD]
+    got = RP.run_resample_oracle(C.CDLL(RP.ORACLE))
+    for i, shape in enumerate(RP.RESAMPLE_SHAPES):
+        (w, h), (W, H) = shape
+        src, dst = np.ascontiguousarray(RP.resample_input(shape)), np.zeros((H, W))
+        assert lib.ref_resample_luminance(src.ctypes.data_as(RP.PD), w, h, W, H, dst.ctypes.data_as(RP.PD)) == 0
+        assert np.array_equal(got["resample_%d" % i], dst), shape
+
+
+def test_oracle_resampling_reproduces_reference_fixture():
+    gold = dict(np.load(RP.GOLDEN_DIRECT))
+    got = RP.run_resample_oracle(C.CDLL(RP.ORACLE))
+    for k, v in got.items():
+        assert np.array_equal(v, gold[k]), k
+    assert (gold["resample_0"] >= 0).all()
+
+
+@pytest.mark.parametrize("name", list(RP.DIRECT_SCENES))
+def test_oracle_direct_image_matches_reference_direct_integrator(name):
+    from drmlt_mitsuba_b200 import abi
+    from drmlt_mitsuba_b200.integrator import make_config
+    gold = dict(np.load(RP.GOLDEN_DIRECT))
+    orc = oracle_lib.OracleScene(RP.DIRECT_SCENES[name]())
+    cfg = make_config(integrator="drmlt", technique="mmlt", type="orbital", maxDepth=6, directSamples=RP.DIRECT_SAMPLES, seed=3)
+    o = abi.dr_config.from_buffer_copy(cfg)
+    o.ray_epsilon = o.shadow_epsilon = 0.0
+    img = orc.direct_image(o)
+    RP.check_direct_image(img[0] if isinstance(img, tuple) else img, gold["direct_" + name], name)
