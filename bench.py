@@ -29,19 +29,34 @@ import numpy as np  # noqa: E402
 
 METRIC = "chain_mutations_per_sec"
 UNIT = "mutations/s"
-PARAMS = dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)
+# BASELINE.json configs[0..4] (C1..C5): scene generator, film, integrator parameters.  C5 is the headline workload.
+CONFIGS = {
+    "C1": ("cornell", dict(film=(256, 256)), dict(integrator="pssmlt", technique="path", sigma=1.0 / 64, maxDepth=8, directSamples=-1)),
+    "C2": ("cornell", dict(film=(256, 256)), dict(integrator="drmlt", type="mira", technique="path", scaleSecond=0.1, acceptanceMap=True,
+                                                  rfilter="box", maxDepth=8, directSamples=-1)),
+    "C3": ("glossy", dict(film=(512, 512)), dict(integrator="drmlt", type="green", technique="bdpt", directSampling=False, maxDepth=8, directSamples=-1)),
+    "C4": ("caustic", dict(film=(512, 512)), dict(integrator="drmlt", type="orbital", technique="mmlt", fixEmitterPath=True, maxDepth=8, directSamples=-1)),
+    "C5": ("door", dict(), dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+}
+PARAMS = CONFIGS["C5"][2]
 
 
-def workload_name(scene_name, data):
-    return "C5 %s scene %d tris %dx%d drmlt orbital mmlt maxDepth=8 directSamples=-1" % (
-        scene_name, data.n_triangles, data.film[0], data.film[1])
+def config_params(args):
+    return dict(CONFIGS[args.config][2])
+
+
+def workload_name(config, data):
+    scene_name, _, params = CONFIGS[config]
+    extra = " ".join("%s=%s" % (k, v) for k, v in params.items() if k not in ("integrator", "type", "technique", "maxDepth", "directSamples"))
+    return "%s %s scene %d tris %dx%d %s %s %s maxDepth=%d directSamples=%d%s" % (
+        config, scene_name, data.n_triangles, data.film[0], data.film[1], params["integrator"], params.get("type", ""), params["technique"],
+        params["maxDepth"], params["directSamples"], (" " + extra) if extra else "")
 
 
 def build_scene(args):
     from drmlt_mitsuba_b200 import scenes
-    if args.scene == "door":
-        return scenes.door_scene()
-    return scenes.SCENES[args.scene]()
+    scene_name, kw, _ = CONFIGS[args.config]
+    return scenes.SCENES[scene_name](**kw)
 
 
 def ray_bytes(n_tris):
@@ -139,13 +154,13 @@ def cpu_sample(orc, cfg, threads, target_s, n_boot=40000):
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_path.so")
 
 
-def reference_sample(scene, spp, timeout_s=600):
+def reference_sample(config, spp, timeout_s=900):
     """One bounded run of the REFERENCE'S OWN DRMLT integrator (oracle/_ref, compiled from the reference's sources) on all
     host cores, in a subprocess (tools/ref_sample.py).  None if oracle/_ref is absent or the run fails."""
     if not os.path.exists(REF_LIB):
         return None
     try:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_sample.py"), "--scene", scene, "--spp", str(spp)],
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_sample.py"), "--config", config, "--spp", str(spp)],
                              capture_output=True, text=True, timeout=timeout_s).stdout
         for ln in out.splitlines():                     # the reference's progress bar shares the line
             if "REF_SAMPLE " in ln:
@@ -157,7 +172,7 @@ def reference_sample(scene, spp, timeout_s=600):
 
 def reference_baseline(r):
     return {"value": r["mutations_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
-            "sample": "the reference's own DRMLT::render (oracle/_ref, double precision, SAH kd-tree) on the same scene: %d mutations/pixel = "
+            "sample": "the reference's own integrator (DRMLT::render / PSSMLT::render of oracle/_ref: the reference's sources, -O3 -march=nocona, double precision, SAH kd-tree) on the same scene and parameters: %d mutations/pixel = "
                       "%d mutations in %.1f s render time incl. its bootstrap, %d worker threads; kd-tree build %.1f s not counted"
                       % (r["spp"], r["mutations"], r["render_s"], r["threads"], r["scene_build_s"]),
             "acceptance_percent": r["stats_percent"]}
@@ -173,7 +188,7 @@ def run_reference(args):
         for i in range(args.warmup + args.steps):
             timed = i >= args.warmup
             spp = args.ref_spp if timed else 2
-            r = reference_sample(args.scene, spp)
+            r = reference_sample(args.config, spp)
             if r is None:
                 runs = None
                 break
@@ -186,7 +201,7 @@ def run_reference(args):
             base["value"] = value
             line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": 1e3 * float(np.mean([r["render_s"] for r in runs])), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                    "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.scene, data), "mutations_per_pixel_per_step": runs[-1]["spp"]},
+                    "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.config, data), "mutations_per_pixel_per_step": runs[-1]["spp"]},
                     "cpu_baseline": base,
                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
             print(json.dumps(line))
@@ -206,7 +221,7 @@ def run_reference(args):
     sample = "%d chains x %d mutations per step, oracle port (double precision) of DRMLTRenderer::process, %d threads" % (info[0], info[1], threads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * info[0] * info[1] / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.scene, data)},
+            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.config, data)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -251,7 +266,7 @@ def run_gpu(args):
     scene_create_s = time.perf_counter() - t0
     scene_bytes = scene.reupload()
 
-    params = dict(PARAMS, seed=args.seed, sampleCount=args.spp * world)   # weak scaling: W*H*spp mutations per GPU
+    params = dict(config_params(args), seed=args.seed, sampleCount=args.spp * world)   # weak scaling: W*H*spp mutations per GPU
     if args.chains:
         params["chains"] = args.chains
     if args.lanes:
@@ -339,18 +354,33 @@ def run_gpu(args):
     dom_launch_ms = stage_ms[dom] / max(1, stage_launches[dom])
     achieved = stages[dom]["achieved_gbs"] or 0.0
     step_gbs = b_mut * muts_rank / (dev_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+    # What ncu measured for the kernels (profiles/traffic.json, one --set full capture per kernel): the traversal kernel serves
+    # its BVH from L1 / L2, so the ALGORITHMIC bytes of SURVEY 8d (the `achieved` / `frac` of the contract) are not its DRAM bytes --
+    # its real DRAM utilisation is a few percent and its bound is L1 wavefronts + the latency of dependent node fetches under
+    # divergence.  Reported side by side.
+    ncu = traffic.get("ncu", {})
+    roofline = {"bound": ncu.get(dom, {}).get("bound", "hbm"), "bound_of_byte_model": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": scaled_traffic(traffic, dom, stages[dom]["units"] / max(1, stage_launches[dom])),
                 "traffic_source": traffic.get("source"), "ms_per_launch": dom_launch_ms,
                 "units_per_launch": stages[dom]["units"] / max(1, stage_launches[dom]), "bytes_per_unit": stages[dom]["bytes_per_unit"],
+                "ncu": ncu.get(dom),
                 "stages": stages, "whole_step": {"bytes_per_mutation": b_mut, "achieved": step_gbs, "frac": step_gbs / peak},
                 "paths_per_mutation": paths_per_mut, "rays_per_path": rays_per_path,
                 "mrays_per_s": (st1.rays - st0.rays) * world / (max_ms * 1e-3) / 1e6,
                 "rounds_per_step": prof_rounds, "profiled_step_mutations": int(prof_muts)}
+    # the stage group that moves the most DRAM bytes (ncu): its measured traffic per launch over its live launch time
+    dram_stage = max((k for k in stage_ms if k in traffic), key=lambda k: traffic[k] / max(1, traffic.get("paths_in_captured_launch" if k == "k_chain" else "rays_in_captured_launch", 1)) * stages[k]["units"], default=None)
+    if dram_stage:
+        t_launch = scaled_traffic(traffic, dram_stage, stages[dram_stage]["units"] / max(1, stage_launches[dram_stage]))
+        ms_launch = stage_ms[dram_stage] / max(1, stage_launches[dram_stage])
+        roofline["largest_dram_stage"] = {"kernel": dram_stage, "bound": "hbm", "dram_bytes_per_launch": t_launch, "ms_per_launch": ms_launch,
+                                          "achieved": t_launch / (ms_launch * 1e-3) / 1e9 if ms_launch > 0 else None,
+                                          "frac": t_launch / (ms_launch * 1e-3) / 1e9 / peak if ms_launch > 0 else None, "ncu": ncu.get(dram_stage)}
     job.close()
 
     # ---- e2e: whole job through the public API with host buffers
-    e2e_params = dict(PARAMS, seed=args.seed + 1, sampleCount=args.e2e_spp * world)
+    e2e_params = dict(config_params(args), seed=args.seed + 1, sampleCount=args.e2e_spp * world)
     if args.e2e_chains:
         e2e_params["chains"] = args.e2e_chains
     if args.e2e_lanes:
@@ -374,6 +404,25 @@ def run_gpu(args):
                                    device_bootstrap_and_seeding_ms=est.bootstrap_ms, device_chains_ms=est.chains_ms),
            "what": "dr_scene_reupload + bootstrap + b all-reduce + chains + film reduce + develop + image D2H; sampleCount=%d" % (args.e2e_spp * world)}
 
+    # ---- strong scaling: ONE job of W*H*strong_spp mutations in total, shared by the N GPUs (bootstrap, b all-reduce, chains,
+    #      film reduce, develop, image D2H; wall clock, max over ranks).  The driver's per-N runs give the curve.
+    strong = None
+    if args.strong_spp > 0:
+        sp = dict(config_params(args), seed=args.seed + 2, sampleCount=args.strong_spp)
+        barrier()
+        s0 = time.perf_counter()
+        _, sst, _ = distributed.render(scene, sp, dist if world > 1 else None, rank, world)
+        barrier()
+        s_wall = time.perf_counter() - s0
+        ts = torch.tensor([float(sst.mutations), s_wall], dtype=torch.float64, device=dev)
+        tm = ts.clone()
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "mutations_per_pixel_total": args.strong_spp, "mutations": int(ts[0].item()), "seconds": float(tm[1].item()),
+                  "value": float(ts[0].item()) / float(tm[1].item()), "unit": UNIT,
+                  "rank0_phases_ms": dict(getattr(distributed.render, "last_timing", {}))}
+
     def pct(a, b):
         return round(100.0 * a / max(1, b), 2)
     # the reference's statistics counters (drmlt_proc.cpp:34-49) of rank 0's job, comparable with cpu_baseline.acceptance_percent
@@ -389,7 +438,7 @@ def run_gpu(args):
         cpu = None
         if not args.no_cpu:
             try:
-                ref = reference_sample(args.scene, args.ref_spp)
+                ref = reference_sample(args.config, args.cpu_spp)
                 if ref is not None:
                     raise StopIteration
                 _, orc = oracle_scene(data)
@@ -404,10 +453,11 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.scene, data), "chains_per_gpu": int(n_chains), "mutations_per_chain_per_step": M,
+                "config": {"workload": workload_name(args.config, data), "chains_per_gpu": int(n_chains), "mutations_per_chain_per_step": M,
                            "l2": "flushed between timed steps (512 MiB device write)", "b": b, "scene_create_s": scene_create_s,
-                           "scene_bytes": int(scene_bytes), "wall_s_timed_region": wall},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
+                           "scene_bytes": int(scene_bytes), "wall_s_timed_region": wall, "e2e_mutations_per_pixel": args.e2e_spp,
+                           "cpu_baseline_mutations_per_pixel": args.cpu_spp, "reference_arm_mutations_per_pixel_per_step": args.ref_spp},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "strong_scaling": strong, "gpu_launches": launches, "clocks": clk.summary()}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -422,9 +472,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scene", default="door")
+    ap.add_argument("--config", default="C5", choices=sorted(CONFIGS), help="BASELINE.json configuration (C5 = the headline workload)")
     ap.add_argument("--mutations", type=int, default=64, help="mutations per chain per step")
-    ap.add_argument("--chains", type=int, default=4194304, help="chains resident per GPU in the timed steps (0 = auto)")
+    ap.add_argument("--chains", type=int, default=-1, help="chains resident per GPU in the timed steps (0 = auto; default: 4194304 for C5, auto otherwise)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes of the wavefront machine in the timed steps (0 = one per chain; fewer: work-unit queue)")
     ap.add_argument("--e2e-chains", type=int, default=0, dest="e2e_chains")
     ap.add_argument("--e2e-lanes", type=int, default=0, dest="e2e_lanes")
@@ -433,10 +483,17 @@ def main():
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
-    ap.add_argument("--ref-spp", type=int, default=16, dest="ref_spp", help="mutations per pixel of one bounded run of the reference's own integrator")
+    ap.add_argument("--ref-spp", type=int, default=16, dest="ref_spp",
+                    help="--impl reference: mutations per pixel of one timed step (a bounded sample: K steps must end within minutes)")
+    ap.add_argument("--cpu-spp", type=int, default=64, dest="cpu_spp",
+                    help="cpu_baseline leg of the GPU arm: mutations per pixel of the ONE run of the reference's integrator (64 = the e2e job's own)")
+    ap.add_argument("--strong-spp", type=int, default=512, dest="strong_spp",
+                    help="strong-scaling leg: a job of W*H*strong_spp mutations IN TOTAL, shared by the N GPUs (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    if args.chains < 0:
+        args.chains = 4194304 if args.config == "C5" else 0
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -487,6 +487,38 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     return DR_OK;
 }
 
+// A replica of a scene on another GPU (multi-GPU jobs hold one replica per device): the device buffers are filled from the
+// pinned staging copies the original keeps -- no second BVH build, no second flattening.
+extern "C" dr_status dr_scene_clone(dr_scene scene, int device, dr_scene *out) {
+    if (!scene || !out) { dr_set_error("dr_scene_clone: null argument"); return DR_ERR_INVALID_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); dr_set_error("no CUDA device available (there is no CPU fallback)"); return DR_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { dr_set_error("device %d out of range (%d devices)", device, ndev); return DR_ERR_INVALID_ARG; }
+    const SceneImpl *src = static_cast<const SceneImpl *>(scene);
+    CK(cudaSetDevice(device));
+    SceneImpl *s = new SceneImpl();
+    s->device = device; s->filmW = src->filmW; s->filmH = src->filmH; s->nTris = src->nTris; s->nNodes = src->nNodes; s->typeMask = src->typeMask;
+    s->dev = src->dev;
+    auto fail = [&](dr_status code) { dr_scene_destroy(s); return code; };
+    // the device pointers of DevScene, in the order dr_scene_create uploaded them
+    const void **slots[9] = { (const void **) &s->dev.nodes, (const void **) &s->dev.tris, (const void **) &s->dev.normals, (const void **) &s->dev.emTris,
+                              (const void **) &s->dev.emCdf, (const void **) &s->dev.emitterCdf, (const void **) &s->dev.emitters, (const void **) &s->dev.materials,
+                              (const void **) &s->dOrder };
+    if (src->uploads.size() != 9) { dr_set_error("dr_scene_clone: unexpected scene layout"); return fail(DR_ERR_INVALID_ARG); }
+    for (size_t i = 0; i < src->uploads.size(); ++i) {
+        HostUpload u = src->uploads[i];
+        u.host = nullptr;                                   // the staging copy stays with the original
+        if (cudaMalloc(&u.dev, u.bytes) != cudaSuccess) { dr_set_error("dr_scene_clone: cudaMalloc of %zu bytes failed", u.bytes); cudaGetLastError(); return fail(DR_ERR_CUDA); }
+        s->allocations.push_back(u.dev);
+        if (cudaMemcpy(u.dev, src->uploads[i].host, u.bytes, cudaMemcpyHostToDevice) != cudaSuccess) { dr_set_error("dr_scene_clone: upload failed"); cudaGetLastError(); return fail(DR_ERR_CUDA); }
+        *slots[i] = u.dev;
+        s->bytes += u.bytes;
+    }
+    *out = s;
+    return DR_OK;
+}
+
 // Repeat the host->device copies of the flattened scene (what a plugin pays per render job).
 extern "C" dr_status dr_scene_reupload(dr_scene scene, int64_t *bytes) {
     if (!scene) { dr_set_error("dr_scene_reupload: null scene"); return DR_ERR_INVALID_ARG; }

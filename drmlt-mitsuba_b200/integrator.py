@@ -110,6 +110,25 @@ class Scene:
         abi.check(self.lib, self.lib.dr_scene_reupload(self.h, C.byref(n)))
         return n.value
 
+    def clone(self, device):
+        """A replica of this scene on another GPU (dr_scene_clone: no second BVH build)."""
+        other = Scene.__new__(Scene)
+        other.lib, other.data, other.device = self.lib, self.data, device
+        h = C.c_void_p()
+        abi.check(self.lib, self.lib.dr_scene_clone(self.h, device, C.byref(h)))
+        other.h = h
+        return other
+
+    def render_multi(self, cfg, replicas):
+        """dr_render_multi: one job on this scene's GPU and on the GPUs of `replicas` (Scene.clone), NCCL inside the library."""
+        W, H = self.film_size(cfg)
+        img = np.zeros((H, W, 3), np.float32)
+        st = abi.dr_stats()
+        scenes_ = [self] + list(replicas)
+        arr = (C.c_void_p * len(scenes_))(*[s.h for s in scenes_])
+        abi.check(self.lib, self.lib.dr_render_multi(arr, len(scenes_), C.byref(cfg), _fp(img), C.byref(st)))
+        return img, st
+
     # ---- whole job, host buffers (DRMLT::render / PSSMLT::render)
     def render(self, cfg, out=None):
         W, H = self.film_size(cfg)

@@ -300,9 +300,17 @@ public:
         desc.camera.near_clip = (float) cam->getNearClip(); desc.camera.far_clip = (float) cam->getFarClip();
         desc.camera.film_width = film->getSize().x; desc.camera.film_height = film->getSize().y;
 
-        const char *dev = getenv("DRMLT_DEVICE");
+        // DRMLT_DEVICE=<g>: the GPU of the job; DRMLT_DEVICES=<g0>,<g1>,...: several GPUs of this node -- chains sharded across them,
+        // b all-reduced and the films reduced with NCCL inside the library (dr_render_multi)
+        std::vector<int> devices;
+        if (const char *list = getenv("DRMLT_DEVICES")) {
+            std::istringstream is(list);
+            std::string tok;
+            while (std::getline(is, tok, ',')) if (!tok.empty()) devices.push_back(atoi(tok.c_str()));
+        }
+        if (devices.empty()) { const char *dev = getenv("DRMLT_DEVICE"); devices.push_back(dev ? atoi(dev) : 0); }
         dr_scene created = NULL;
-        check(dr_scene_create(&desc, dev ? atoi(dev) : 0, &created));
+        check(dr_scene_create(&desc, devices[0], &created));
         { LockGuard lock(m_mutex); m_scene = created; }
 
         // ---- render on the GPU, hand the developed image to the film (drmlt_proc.cpp:850-853)
@@ -311,10 +319,22 @@ public:
         // interactive jobs and `mitsuba -r` see partial results: develop + signalRefresh every <= 2 s (drmlt_proc.cpp:856-867);
         // Scene::flush (scene.cpp:468-511) then dumps whatever bitmap the film holds, plus _time.csv / _stats.txt
         RefreshCtx ctx = { film.get(), queue, job, size };
-        // (`mitsuba -r` marks the job interactive: mitsuba.cpp:395; non-interactive jobs only develop at the end, drmlt.cpp:608)
-        const dr_status status = dr_render_progressive(m_scene, &m_config, image.data(), &st, job->isInteractive() ? 2.0 : 0.0, &DR_CLASS::refresh, &ctx);
+        dr_status status;
+        std::vector<dr_scene> replicas(1, created);
+        if (devices.size() > 1) {
+            for (size_t g = 1; g < devices.size(); ++g) {
+                dr_scene r = NULL;
+                const dr_status cs = dr_scene_clone(created, devices[g], &r);
+                if (cs != DR_OK) { for (size_t k = 1; k < replicas.size(); ++k) dr_scene_destroy(replicas[k]); check(cs); }
+                replicas.push_back(r);
+            }
+            status = dr_render_multi(replicas.data(), (int32_t) replicas.size(), &m_config, image.data(), &st);
+        } else {
+            // (`mitsuba -r` marks the job interactive: mitsuba.cpp:395; non-interactive jobs only develop at the end, drmlt.cpp:608)
+            status = dr_render_progressive(m_scene, &m_config, image.data(), &st, job->isInteractive() ? 2.0 : 0.0, &DR_CLASS::refresh, &ctx);
+        }
         { LockGuard lock(m_mutex); m_scene = NULL; }            // cancel() from another thread never sees a scene being destroyed
-        dr_scene_destroy(created);
+        for (size_t k = 0; k < replicas.size(); ++k) dr_scene_destroy(replicas[k]);
         if (status == DR_ERR_CANCELLED) return false;
         check(status);
         refresh(image.data(), size.x, size.y, 0.0, &st, &ctx);

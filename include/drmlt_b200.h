@@ -210,6 +210,8 @@ int         dr_device_count(void);
  * (scene.cpp:332-394, skdtree.cpp) for this path. */
 dr_status dr_scene_create(const dr_scene_desc *desc, int device, dr_scene *out);
 void      dr_scene_destroy(dr_scene scene);
+/* A replica of `scene` on another GPU, filled from the staging copies the original keeps (no second BVH build). */
+dr_status dr_scene_clone(dr_scene scene, int device, dr_scene *out);
 /* Repeat the host->device copies of the flattened scene buffers (BVH nodes, triangles, normals,
  * emitter tables, materials) from the staging copies kept by dr_scene_create; `bytes` receives
  * the number of bytes copied.  This is the per-job upload a plugin pays when the scene changed. */
@@ -229,6 +231,13 @@ typedef int (*dr_refresh_fn)(const float *image_rgb, int32_t width, int32_t heig
 dr_status dr_render_progressive(dr_scene scene, const dr_config *cfg, float *image_rgb, dr_stats *stats,
                                 double refresh_seconds, dr_refresh_fn fn, void *user);
 
+/* dr_render on `n` GPUs of one node: scenes[g] is the replica on its GPU (dr_scene_create + dr_scene_clone), scenes[0]'s GPU
+ * develops the image.  One host thread per GPU; chains, bootstrap samples and mutation budget are sharded by rank; ONE NCCL
+ * all-reduce of {sum luminance, count} gives the global b (the reference averages its initialisation threads' means,
+ * drmlt.cpp:498-546), ONE NCCL reduce sums the films onto the first GPU (DRMLTProcess::processResult, drmlt_proc.cpp:856-867).
+ * `stats`: counters summed over the GPUs, phase times of the slowest.  NCCL is loaded on first use (libnccl.so.2). */
+dr_status dr_render_multi(const dr_scene *scenes, int32_t n, const dr_config *cfg, float *image_rgb, dr_stats *stats);
+
 /* ---- staged API (multi-GPU drivers, tests, benchmarks) -------------------
  * One job = one rank's share of a render.  Sequence:
  *   dr_job_create -> dr_job_bootstrap -> [all-reduce sum_lum/count across ranks] ->
@@ -246,8 +255,8 @@ dr_status dr_job_run(dr_job job, int64_t mutations_per_chain);
  * BidirectionalUtils::renderDirectComponent, src/libbidir/util.cpp:30-94, with the `direct` integrator,
  * src/integrators/direct/direct.cpp:144-305); dr_job_develop adds it (drmlt_proc.cpp:846-847).  No-op for directSamples <= 0. */
 dr_status dr_job_direct(dr_job job);
-/* Device pointers of the accumulation film (W*H*3 floats, un-normalised) -- the buffer
- * a multi-GPU driver hands to ncclReduce. */
+/* Device pointer of the accumulation film: W*H*4 floats (RGB + one unused float per pixel: a splat is one 16-byte vector
+ * atomic), un-normalised; *n_floats = W*H*4 -- the buffer and count a multi-GPU driver hands to ncclReduce. */
 dr_status dr_job_film_device(dr_job job, float **film_dev, int64_t *n_floats);
 /* Develop: image = film * (b / mean pixel luminance)  (drmlt_proc.cpp:823-849).  Host out. */
 dr_status dr_job_develop(dr_job job, float *image_rgb);

@@ -1,6 +1,6 @@
 """The CPU arm of bench.py (`--impl reference`) prints the contract's JSON line.  With oracle/_ref present it times the
 reference's own DRMLT integrator (cpu_baseline.kind "reference"), otherwise the oracle port ("port").  Runs on the small
-Cornell scene so that the CPU suite stays short; the GPU arm is covered by the driver's own bench run."""
+Cornell configuration (C1) so that the CPU suite stays short; the GPU arm is covered by the driver's own bench run."""
 import json
 import os
 import subprocess
@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="0", WORLD_SIZE="1")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scene", "cornell", "--steps", "1", "--warmup", "0",
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C1", "--steps", "1", "--warmup", "0",
                           "--ref-spp", "16"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])

@@ -996,3 +996,36 @@ def test_cuda_resampling_matches_reference_bitmap_resample():
         m = gpu.resample_luminance(img, (W, H))
         want = gold["resample_%d" % i]
         assert np.abs(m - want).max() <= 2e-6 * max(want.max(), 1e-30), (shape, np.abs(m - want).max())
+
+
+# SURVEY 8e inside the library: dr_render_multi -- one host thread per GPU, NCCL all-reduce of {sum luminance, count} -> b,
+# NCCL reduce of the films -- against the same job on one GPU.  Chains and bootstrap samples are sharded by rank, so the images
+# are two independent estimates of the same picture: b within 0.5 %, acceptance rates within 1 %, counters add up.
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_gpu_count() < 2", reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("params", [dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1),
+                                    dict(integrator="pssmlt", technique="path", maxDepth=6, directSamples=4)])
+def test_render_multi_gpu_matches_single_gpu(params):
+    data = scenes.cornell_box(film=(128, 128), tess=8)
+    s0 = Scene(data, device=0)
+    s1 = s0.clone(1)
+    cfg = make_config(seed=11, sampleCount=256, **params)
+    img1, st1 = s0.render(cfg)
+    img2, st2 = s0.render_multi(cfg, [s1])
+    assert st2.mutations == pytest.approx(st1.mutations, rel=1e-3) and st2.mutations >= 128 * 128 * 256 * 0.999
+    assert st2.luminance == pytest.approx(st1.luminance, rel=5e-3)
+    for a, b in (("first_accept", "first_base"), ("second_accept", "second_base"), ("accept", "accept_base")):
+        if getattr(st1, b):
+            assert abs(getattr(st2, a) / max(1, getattr(st2, b)) - getattr(st1, a) / getattr(st1, b)) < 0.01
+    l1, l2 = RP.luminance(img1), RP.luminance(img2)
+    assert np.isfinite(img2).all() and abs(l2.mean() - l1.mean()) < 0.02 * l1.mean()
+    assert RP.rel_mse(img2, img1) < 0.05
+    # a GPU taking no part is an error, not a hang: a replica list with a null entry
+    import ctypes as C_
+    arr = (C_.c_void_p * 2)(s0.h, None)
+    out = np.zeros((128, 128, 3), np.float32)
+    assert s0.lib.dr_render_multi(arr, 2, C_.byref(cfg), out.ctypes.data_as(C_.POINTER(C_.c_float)), None) == 1      # DR_ERR_INVALID_ARG

@@ -18,24 +18,26 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--scene", default="door")
+    ap.add_argument("--config", default="C5", help="BASELINE.json configuration (bench.py CONFIGS)")
     ap.add_argument("--spp", type=int, default=8)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--film", default="", help="WxH (door scene only; default: the scene's own film)")
     ap.add_argument("--out-image", default="", dest="out_image", help="write the developed image to this .npy file")
     args = ap.parse_args()
     import ref_path_cases as RP
+    import bench
     from drmlt_mitsuba_b200 import scenes
-    film = tuple(int(x) for x in args.film.split("x")) if args.film else None
-    if args.scene == "door":
-        data = scenes.door_scene(film=film) if film else scenes.door_scene()
-    else:
-        data = scenes.SCENES[args.scene](film=film) if film else scenes.SCENES[args.scene]()
+    scene_name, kw, params = bench.CONFIGS[args.config]
+    kw = dict(kw)
+    if args.film:
+        kw["film"] = tuple(int(x) for x in args.film.split("x"))
+    data = scenes.SCENES[scene_name](**kw)
     W, H = data.film
-    # the reference hands out one seed per work unit of 1e5 mutations and floor(workUnits / cores) seeds per init thread
-    # (drmlt.cpp:430-450, 498-546): fewer work units than cores would render nothing
-    spp = max(args.spp, -(-(args.threads + 1) * 100000 // (W * H)))
-    params = dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)
+    # the reference hands out one seed per work unit of 1e5 mutations (2e5 for technique=path) and floor(workUnits / cores) seeds
+    # per init thread (drmlt.cpp:430-450, 498-546): fewer work units than cores would render nothing
+    unit = 200000 if params["technique"] == "path" else 100000
+    spp = max(args.spp, -(-(args.threads + 1) * unit // (W * H)))
+    params = dict(params)
     lib = C.CDLL(RP.REF_PATH)
     img, sec, scene_sec, stats = RP.run_render_ref(lib, params, spp, threads=args.threads, data=data)
     out = {"mutations_per_s": W * H * spp / sec, "render_s": sec, "scene_build_s": scene_sec, "spp": spp, "threads": args.threads,
