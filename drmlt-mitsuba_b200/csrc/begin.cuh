@@ -1,6 +1,8 @@
-// begin.cuh -- start of a path, fused into the chain kernel (k_chain.cu): the proposal is mutated into the lane's coordinate
-// buffer (pss.cuh) and the first ray of its path is emitted, in the same thread that has just finished the chain-level step
-// (one Core round trip, one queue hand-off and one dependent launch per path less than a kernel of its own).
+// begin.cuh -- start of a path (k_begin, k_chain.cu): the proposal is mutated into the lane's coordinate buffer (pss.cuh) and the
+// first ray of its path is emitted.  k_begin runs one class of this work per warp, fed by its own queue (machine.cuh Q_BEGIN).
+// (Fusing it into the chain kernel -- one Core round trip and one launch per round less -- was measured in round 2: the fused
+// kernel needs 164 registers instead of 126 and runs the three proposal classes divergently, 178 us against 75 + 76 us per
+// 120 k paths under ncu and 145 against 152 M mutations/s in the bench; profiles/r02_*.)
 //   stage 1   first-stage proposal  (large step: uniforms | Kelemen | orbital: radial Kelemen + angle)
 //   stage 2   second-stage proposal (Gaussian | orbital rotation by a wrapped-Cauchy angle)
 //   other     seed replay, Green's reverse state, bootstrap samples, replayed vectors

@@ -5,8 +5,8 @@
 // single MMLT splat, pathsampler.cpp:288-313), (2) runs the chain-level step: delayed-rejection acceptance
 // (DRMLTRenderer::process, src/integrators/drmlt/drmlt_proc.cpp:539-769; processMixture :161-380;
 // PSSMLTRenderer::process, src/integrators/pssmlt/pssmlt_proc.cpp:175-272), expectation-weighted film splats,
-// commit of the accepted primary-sample vector and statistics, and (3) mutates the lane's next proposal and
-// emits the first ray of the next path (begin.cuh).
+// commit of the accepted primary-sample vector and statistics, and (3) hands the lane to the k_begin class that mutates its
+// next proposal and emits the first ray of the next path (begin.cuh).
 #include "begin.cuh"
 
 namespace {
@@ -200,7 +200,6 @@ k_chain(const __grid_constant__ Machine M) {
     uint32_t st[ST_COUNT];
 #pragma unroll
     for (int i = 0; i < ST_COUNT; ++i) st[i] = 0;
-    queues_recycle(M.q);
     const uint32_t cnt = M.q.count[Q_CHAIN + M.parity];
     const uint32_t *items = M.q.items + (size_t) (Q_CHAIN + M.parity) * M.q.n;
     for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
@@ -464,12 +463,9 @@ k_chain(const __grid_constant__ Machine M) {
             break;
         }
         // ================= start the lane's next path: mutate the proposal, emit its first ray (begin.cuh) =================
-        if (c.pstate == PS_START) {
-            RayF ray;
-            dest = begin_path(M, lane, c, ray);
-            rec_store(M.lm.core + lane, c);
-            q_push_ray(M.q, dest, (uint32_t) lane, ray);
-        } else rec_store(M.lm.core + lane, c);
+        rec_store(M.lm.core + lane, c);
+        if (c.pstate == PS_START)
+            q_push(M.q, Q_BEGIN + (job.type != JOB_CHAIN ? BEGIN_OTHER : (c.phase == PH_STAGE1 ? BEGIN_STAGE1 : (c.phase == PH_STAGE2 ? BEGIN_STAGE2 : BEGIN_OTHER))), (uint32_t) lane);
     }
     stats_flush(st, M.counters);
 }
@@ -533,8 +529,36 @@ void launch_splat_points(const FilmParams &fp, float4 *film, const float *pos, c
 
 static unsigned grid_for(int n, int threads) { return stage_grid(n, threads); }
 
+template <int CLS>
+DR_D void begin_lane(const Machine &M, uint32_t qi) {
+    const int lane = (int) M.q.items[(size_t) (Q_BEGIN + CLS) * M.q.n + qi];
+    Core c;
+    rec_load(c, M.lm.core + lane);
+    if (CLS == BEGIN_STAGE1) c.phase = PH_STAGE1;             // compile-time phase for the proposal switch
+    if (CLS == BEGIN_STAGE2) c.phase = PH_STAGE2;
+    RayF ray;
+    const int dest = begin_path(M, lane, c, ray);
+    rec_store(M.lm.core + lane, c);
+    q_push_ray(M.q, dest, (uint32_t) lane, ray);
+}
+__global__ void __launch_bounds__(128, BEGIN_MINB)
+k_begin(const __grid_constant__ Machine M) {
+    queues_recycle(M.q);
+    const uint32_t cnt[3] = { M.q.count[Q_BEGIN + BEGIN_STAGE1], M.q.count[Q_BEGIN + BEGIN_STAGE2], M.q.count[Q_BEGIN + BEGIN_OTHER] };
+    const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;; w += nWarps) {
+        int cls; uint32_t qi;
+        if (!multiq_locate<3>(cnt, w, cls, qi)) break;
+        if (qi >= cnt[cls]) continue;
+        if (cls == BEGIN_STAGE1) begin_lane<BEGIN_STAGE1>(M, qi);
+        else if (cls == BEGIN_STAGE2) begin_lane<BEGIN_STAGE2>(M, qi);
+        else begin_lane<BEGIN_OTHER>(M, qi);
+    }
+}
+
 void launch_chain(const Machine &M, const LaunchCfg &lc) {
     k_chain<<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M);
+    k_begin<<<grid_for(lc.nLanes + 3 * 128, 128), 128, 0, lc.stream>>>(M);
 }
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId, const unsigned long long *seedIdx) {
     k_setup_lanes<<<(unsigned) ((lc.nLanes + 127) / 128), 128, 0, lc.stream>>>(M, depth, chainId, seedIdx);

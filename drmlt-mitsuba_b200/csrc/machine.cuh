@@ -15,10 +15,11 @@
 //   k_chain                  a path has ended: MIS weight, then the chain-level step fused in the same
 //                            thread -- delayed-rejection acceptance (mira / green / orbital / mixture, or
 //                            PSSMLT), expectation-weighted film splats, commit of the accepted
-//                            primary-sample vector, statistics -- then the NEXT proposal is mutated and
-//                            its first ray is emitted
+//                            primary-sample vector, statistics
+//   k_begin<class>           the NEXT proposal is mutated (one class of transition-kernel arithmetic per warp) and the
+//                            first ray of its path is emitted
 //
-// One round = { trace closest, trace shadow, walk x materials, connect, chain }; every ray emitted in
+// One round = { trace (closest + shadow), walk x materials, connect, chain, begin }; every ray emitted in
 // round r is traced in round r + 1.  Lanes progress at their own pace: a lane whose first stage was
 // accepted starts its next mutation while its neighbour traces a second-stage path.  The same machine
 // runs three kinds of jobs: Markov chains (JOB_CHAIN), the bootstrap (JOB_BOOT,
@@ -56,6 +57,9 @@
 #endif
 #ifndef CHAIN_MINB
 #define CHAIN_MINB 3
+#endif
+#ifndef BEGIN_MINB
+#define BEGIN_MINB 4
 #endif
 
 // ------------------------------------------------------------------ lane records (AoS: one record per lane per array,
@@ -170,9 +174,11 @@ template <class T> DR_D void rec_store(T *dst, const T &src) {
 
 // ------------------------------------------------------------------ work queues
 // Q_RAYC / Q_RAYS / Q_CHAIN are double-buffered by round parity: kernels of round r consume [r & 1] and
-// produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT and Q_PT
-// are produced and consumed inside one round.
-enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 6 */, Q_CONNECT = 12, Q_PT = 13, Q_COUNT = 14 };
+// produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT, Q_PT and
+// Q_BEGIN are produced and consumed inside one round.
+enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 6 */, Q_CONNECT = 12, Q_PT = 13, Q_BEGIN = 14 /* + class, 3 */, Q_COUNT = 17 };
+// classes of "start the next path" work: each runs one kind of proposal arithmetic on full warps
+enum { BEGIN_STAGE1 = 0, BEGIN_STAGE2 = 1, BEGIN_OTHER = 2 };
 struct RayF { float4 a, b; };                               // (o, tmin), (d, tmax): float32 cast of a ray, for the traversal
 struct Queues {
     uint32_t *items;          // [Q_COUNT][n]
@@ -211,17 +217,19 @@ DR_D void q_push_ray(const Queues &q, int which, uint32_t lane, const RayF &ray)
     }
 }
 
-// The queue counters are emptied by the kernels of the round themselves (no launch of its own).  k_chain, the last kernel
+// The queue counters are emptied by the kernels of the round themselves (no launch of its own).  k_begin, the last kernel
 // of round r, empties the in-round walk / connect / path-tracer queues (their consumers ran before it) and the head
 // counters of the dynamic ray fetch; k_trace, the first kernel of round r + 1, empties the ray / chain queues that round r
-// consumed -- the ones round r + 1 produces into once the traversal is done (trace_recycle).
+// consumed -- the ones round r + 1 produces into once the traversal is done -- and the begin-class queues k_chain fills later
+// in its round (trace_recycle).
 DR_D void queues_recycle(const Queues &q) {
     const int t = threadIdx.x;
-    if (blockIdx.x == 0 && t >= Q_WALK && t < Q_COUNT + 2) q.count[t] = 0;
+    if (blockIdx.x == 0 && t >= Q_WALK && t < Q_COUNT + 2 && !(t >= Q_BEGIN && t < Q_BEGIN + 3)) q.count[t] = 0;
 }
 DR_D void trace_recycle(const Queues &q, int parity) {
     const int t = threadIdx.x;
     if (blockIdx.x == 0 && t < Q_WALK && (t & 1) == (parity ^ 1)) q.count[t] = 0;
+    if (blockIdx.x == 0 && t >= Q_BEGIN && t < Q_BEGIN + 3) q.count[t] = 0;
 }
 
 // Several queues in ONE launch: the global warp index space is the concatenation of the queues, each rounded up to
@@ -479,7 +487,7 @@ void launch_trace(const Machine &M, const LaunchCfg &lc);                 // k_t
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask);   // k_walk.cu: walk queues of the BSDF types present, then connect
 void launch_pt(const Machine &M, const LaunchCfg &lc);                    // k_pt.cu
 void launch_bdpt(const Machine &M, const LaunchCfg &lc);                  // k_bdpt.cu
-void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu (chain step + start of the next path)
+void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu: k_chain (chain step), then k_begin (start of the next path, one class per warp)
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId,
                   const unsigned long long *seedIdx);                     // k_chain.cu: initialise lanes for M.job and queue them
 void launch_resume(const Machine &M, const LaunchCfg &lc);                // k_chain.cu: re-queue idle chains whose target was raised
