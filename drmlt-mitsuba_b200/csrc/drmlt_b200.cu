@@ -680,6 +680,7 @@ struct dr_job_t {
     // that the latency-bound tail of one group's stage kernels overlaps with the other groups' kernels.
     struct Group { Queues q; cudaStream_t stream = nullptr; cudaEvent_t evJoin = nullptr; uint32_t *countsHost = nullptr; int begin = 0, end = 0; };
     cudaEvent_t evFork = nullptr;
+    cudaGraphExec_t graphExec = nullptr;        // the captured rounds (run_machine), updated in place by later runs
     std::vector<Group> groups;
     float *bootLum = nullptr;
     float *bootLumTarget = nullptr;             // two-stage MLT: importance-re-weighted luminances, the seed CDF is built on these
@@ -753,6 +754,7 @@ extern "C" void dr_job_destroy(dr_job j) {
     for (void *p : j->allocations) cudaFreeAsync(p, j->stream);
     if (j->stream) cudaStreamSynchronize(j->stream);
     for (auto &g : j->groups) { if (g.countsHost) cudaFreeHost(g.countsHost); if (g.evJoin) cudaEventDestroy(g.evJoin); if (g.stream) cudaStreamDestroy(g.stream); }
+    if (j->graphExec) cudaGraphExecDestroy(j->graphExec);
     if (j->evFork) cudaEventDestroy(j->evFork);
     for (cudaEvent_t e : j->profEvents) cudaEventDestroy(e);
     if (j->ev0) cudaEventDestroy(j->ev0);
@@ -865,7 +867,7 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
         }
     }
     j->cfg.importance_map = nullptr;                       // the host buffer is not referenced after creation
-    CK(cudaStreamSynchronize(j->stream));
+    if (cudaStreamSynchronize(j->stream) != cudaSuccess) { dr_set_error("dr_job_create: %s", cudaGetErrorString(cudaGetLastError())); return fail(DR_ERR_CUDA); }
     *out = j;
     return DR_OK;
 }
@@ -918,7 +920,9 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     const bool useGraph = !j->profile && !getenv("DRMLT_NO_GRAPH");
-    auto cleanup = [&]() { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); };
+    // the executable graph lives with the job: every later run (bootstrap, seed replay, each dr_job_run, every progressive
+    // slice) captures the same topology with other kernel parameters and UPDATES it in place instead of instantiating anew
+    auto cleanup = [&]() { if (graph) cudaGraphDestroy(graph); };
     if (useGraph) {
         const uint64_t round0 = j->rounds;
         CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
@@ -932,11 +936,22 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
         for (int g = 0; g < G; ++g)
             cudaMemcpyAsync(j->groups[g].countsHost, j->groups[g].q.count, sizeof(uint32_t) * Q_COUNT, cudaMemcpyDeviceToHost, j->groups[g].stream);
         for (int g = 1; g < G; ++g) { cudaEventRecord(j->groups[g].evJoin, j->groups[g].stream); cudaStreamWaitEvent(s0, j->groups[g].evJoin, 0); }
-        if (cudaStreamEndCapture(s0, &graph) != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        bool ready = cudaStreamEndCapture(s0, &graph) == cudaSuccess;
+        if (ready && j->graphExec) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(j->graphExec, graph, &info) != cudaSuccess) {      // (another topology: start over)
+                cudaGetLastError();
+                cudaGraphExecDestroy(j->graphExec);
+                j->graphExec = nullptr;
+            }
+        }
+        if (ready && !j->graphExec) ready = cudaGraphInstantiate(&j->graphExec, graph, 0) == cudaSuccess;
+        if (!ready) {
             dr_set_error("CUDA graph capture of the wavefront rounds failed: %s", cudaGetErrorString(cudaGetLastError()));
             cleanup();
             return DR_ERR_CUDA;
         }
+        exec = j->graphExec;
     }
     for (;;) {
         if (j->scene->cancel) { join_groups(j); cleanup(); dr_set_error("cancelled"); return DR_ERR_CANCELLED; }
@@ -1018,7 +1033,7 @@ static long long bootstrap_samples(const dr_job j) {
     // The image is scaled by b, so the relative error of b is a floor of the image error.  On the GPU a bootstrap path
     // costs about as much as a mutation: spend 1/8 of the mutation budget on it (profiles/r01_g_chain_length_study.json:
     // 16 M instead of 0.8 M bootstrap paths lower relMSE 4-10x at 59 M mutations for +0.2 s).
-    n = std::max(n, total / 8);
+    n = std::max(n, std::min<long long>(total / 8, 1ll << 26));   // (capped: 64 M samples = 0.8 GB of luminances + CDF per GPU)
     return n;
 }
 
@@ -1094,7 +1109,9 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
     j->b = b;
     j->M.cp.b = b;
     const int n = j->nChains;
-    const unsigned long long firstChain = (unsigned long long) c.rank * (unsigned long long) n;
+    // chain ids key the mutation / coin streams: ranks (and work-unit batches) get disjoint 2^32-id ranges, whatever their chain
+    // counts (a stride of the rank-local count would overlap when W*H*sampleCount does not divide by the world size)
+    const unsigned long long firstChain = (unsigned long long) c.rank << 32;
     CK(cudaEventRecord(j->ev0, j->stream));
     resample_chains(j, firstChain);
     CKL();
@@ -1136,7 +1153,7 @@ static dr_status run_chain_range(dr_job j, long long first, long long count, lon
 static dr_status next_batch(dr_job j) {
     if (j->epoch > 0) {
         const dr_config &c = j->cfg;
-        const unsigned long long firstChain = ((unsigned long long) j->epoch * c.world_size + c.rank) * (unsigned long long) j->nChains;
+        const unsigned long long firstChain = ((unsigned long long) j->epoch * c.world_size + c.rank) << 32;
         resample_chains(j, firstChain);
         CKL();
     }

@@ -21,6 +21,7 @@
 #endif
 #include "common.cuh"
 #include "../../include/drmlt_b200.h"
+#include <atomic>
 #include <vector>
 #include <string>
 
@@ -96,7 +97,7 @@ struct dr_scene_t {
     int filmW = 0, filmH = 0;
     uint32_t nTris = 0, nNodes = 0;
     unsigned typeMask = 0;           // BSDF models present (bit = dr_bsdf_type)
-    volatile int cancel = 0;
+    std::atomic<int> cancel{0};       // set by dr_cancel from any thread, polled between graph replays
     size_t bytes = 0;
 };
 

@@ -91,15 +91,29 @@ def _render_cfg(scene, cfg, dist, rank, world_size, mutations_per_chain, all_ran
     dev = "cuda:%d" % scene.device
     b = all_reduce_normalization(s, c, cfg.technique == abi.DR_TECH_MMLT, cfg.max_depth, dist, dev)
     lap("allreduce_b_ms")
-    job.seed_chains(b)
-    lap("seed_chains_ms")
-    per = mutations_per_chain if mutations_per_chain is not None else max(1, job.total_mutations // job.num_chains)
-    job.run(per)
-    lap("chains_ms")
+    # a rank whose own seed pool is empty (or whose chains fail) must not leave the others waiting in the film reduce: every
+    # rank learns of the failure through one small all-reduce and raises together
+    failure = None
+    try:
+        job.seed_chains(b)
+        lap("seed_chains_ms")
+        per = mutations_per_chain if mutations_per_chain is not None else max(1, job.total_mutations // job.num_chains)
+        job.run(per)
+        lap("chains_ms")
+    except Exception as e:              # noqa: BLE001 -- re-raised below, on every rank
+        failure = e
     if world_size > 1:
+        flag = torch.tensor([1.0 if failure is not None else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        if float(flag.item()) > 0:
+            job.close()
+            raise failure if failure is not None else RuntimeError("another rank failed before the film reduce")
         film = torch.as_tensor(DeviceFilm(job), device=dev)
         reduce_film(film, dist, 0, all_ranks)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(dev)      # the job's streams are non-blocking: this host sync orders the reduce before develop
+    elif failure is not None:
+        job.close()
+        raise failure
     lap("film_reduce_ms")
     if rank == 0:
         job.direct()                       # separate direct-illumination image (directSamples > 0), added by develop

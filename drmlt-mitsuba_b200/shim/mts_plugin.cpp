@@ -250,14 +250,26 @@ public:
         std::vector<dr_material> mats;
         std::vector<dr_emitter> ems;
         bool anyNormals = false;
-        const std::vector<TriMesh *> &meshes = scene->getMeshes();
-        if (meshes.size() != scene->getShapes().size())
-            Log(EError, "Only triangle meshes are supported on the GPU path (tessellate analytic shapes)");
+        // triangle meshes as they are; analytic shapes (rectangle, sphere, disk, cylinder, heightfield: SURVEY 8f rank 4) through the
+        // shape's own tessellation (Shape::createTriMesh, include/mitsuba/render/shape.h:243 -- what the reference's preview uses)
+        std::vector<ref<TriMesh> > tessellated;
+        std::vector<std::pair<const TriMesh *, const Shape *> > meshes;          // geometry, owner of BSDF / emitter
+        const ref_vector<Shape> &shapes = scene->getShapes();
+        for (size_t si = 0; si < shapes.size(); ++si) {
+            const Shape *shape = shapes[si].get();
+            if (shape->getClass()->derivesFrom(MTS_CLASS(TriMesh))) { meshes.push_back(std::make_pair(static_cast<const TriMesh *>(shape), shape)); continue; }
+            ref<TriMesh> tm = const_cast<Shape *>(shape)->createTriMesh();          // NotImplemented for shapes without a tessellation
+            Log(EWarn, "Shape \"%s\" (%s) is tessellated into %u triangles for the GPU path", shape->getName().c_str(),
+                shape->getClass()->getName().c_str(), (unsigned) tm->getTriangleCount());
+            tessellated.push_back(tm);
+            meshes.push_back(std::make_pair(tm.get(), shape));
+        }
         for (size_t mi = 0; mi < meshes.size(); ++mi) {
-            const TriMesh *mesh = meshes[mi];
-            if (mesh->getVertexTexcoords()) Log(EWarn, "Mesh \"%s\" has texture coordinates: the shading tangent follows dpdu, not p1-p0", mesh->getName().c_str());
+            const TriMesh *mesh = meshes[mi].first;
+            const Shape *owner = meshes[mi].second;
+            if (mesh->getVertexTexcoords() && owner == mesh) Log(EWarn, "Mesh \"%s\" has texture coordinates: the shading tangent follows dpdu, not p1-p0", mesh->getName().c_str());
             dr_material mat; std::string why;
-            if (!mesh->getBSDF() || !flattenBSDF(mesh->getBSDF(), mat, why)) Log(EError, "Mesh \"%s\": %s", mesh->getName().c_str(), why.c_str());
+            if (!owner->getBSDF() || !flattenBSDF(owner->getBSDF(), mat, why)) Log(EError, "Mesh \"%s\": %s", owner->getName().c_str(), why.c_str());
             mats.push_back(mat);
             const uint32_t base = (uint32_t) (P.size() / 3), firstTri = (uint32_t) triMat.size();
             const Point *pos = mesh->getVertexPositions();
@@ -268,8 +280,8 @@ public:
             }
             anyNormals |= nrm != NULL;
             int32_t em = -1;
-            if (mesh->isEmitter()) {
-                const Emitter *e = mesh->getEmitter();
+            if (owner->isEmitter()) {
+                const Emitter *e = owner->getEmitter();
                 if (e->getClass()->getName() != "AreaLight") Log(EError, "Only area emitters are supported (pathsampler.cpp:65-71)");
                 dr_emitter de;
                 de.first_tri = firstTri; de.n_tris = (uint32_t) mesh->getTriangleCount();

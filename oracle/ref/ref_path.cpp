@@ -50,7 +50,7 @@ using namespace mitsuba;
 #define TR(msg) do { if (getenv("REF_TRACE")) fprintf(stderr, "[ref] %s\n", msg); } while (0)
 
 #define REF_PLUGINS(X) X(diffuse) X(dielectric) X(conductor) X(roughconductor) X(roughdielectric) X(plastic) X(twosided) \
-    X(area) X(perspective) X(gaussian) X(box) X(tent) X(mitchell) X(catmullrom) X(lanczos) X(independent) X(ldsampler) X(path) X(direct) X(drmlt) X(pssmlt)
+    X(area) X(rectangle) X(sphere) X(perspective) X(gaussian) X(box) X(tent) X(mitchell) X(catmullrom) X(lanczos) X(independent) X(ldsampler) X(path) X(direct) X(drmlt) X(pssmlt)
 #define X(name) extern "C" void *CreateInstance_##name(const Properties &props);
 REF_PLUGINS(X)
 #undef X
@@ -272,12 +272,36 @@ extern "C" {
 
 void ref_init() { initOnce(); }
 
-static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties *integrator = NULL, int sampleCount = 1);
+static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties *integrator = NULL, int sampleCount = 1, bool analytic = false);
 void *ref_scene_create(const dr_scene_desc *d, int rfilter) {
     try { return scene_create(d, rfilter); }
     catch (const std::exception &e) { fprintf(stderr, "oracle/_ref: %s\n", e.what()); return NULL; }
 }
-static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties *integrator, int sampleCount) {
+/* an analytic shape plugin (rectangle / sphere) with a diffuse BSDF and, optionally, an area emitter */
+static void addAnalytic(Scene *scene, const char *plugin, const Transform &toWorld, const Spectrum &reflectance, const Spectrum *radiance,
+                        const Point *center = NULL, Float radius = 0) {
+    PluginManager *pm = PluginManager::getInstance();
+    Properties sp(plugin);
+    if (center) { sp.setPoint("center", *center); sp.setFloat("radius", radius); } else sp.setTransform("toWorld", toWorld);
+    ref<Shape> shape = static_cast<Shape *>(pm->createObject(MTS_CLASS(Shape), sp));
+    Properties bp("diffuse");
+    bp.setSpectrum("reflectance", reflectance);
+    ref<ConfigurableObject> bsdf = pm->createObject(MTS_CLASS(BSDF), bp);
+    bsdf->configure();
+    shape->addChild(bsdf);
+    bsdf->setParent(shape);
+    if (radiance) {
+        Properties ep("area");
+        ep.setSpectrum("radiance", *radiance);
+        ref<ConfigurableObject> em = pm->createObject(MTS_CLASS(Emitter), ep);
+        shape->addChild(em);
+        em->setParent(shape);
+    }
+    shape->configure();
+    scene->addChild(shape);
+}
+
+static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties *integrator, int sampleCount, bool analytic) {
     initOnce();
     TR("init done");
     PluginManager *pm = PluginManager::getInstance();
@@ -322,10 +346,25 @@ static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties 
 
     for (uint32_t i = 0; i < d->n_materials; ++i) rs->bsdfs.push_back(makeBSDF(d->materials[i]));
 
+    if (analytic) {
+        /* the camera of `d`, but a room of ANALYTIC shapes instead of its triangles: floor, back wall and two side walls
+         * (rectangles), a sphere, and a rectangular area light under the ceiling */
+        const Float h = 1.0;
+        const Spectrum white(0.7f), red = rgbSpectrum((const float[3]) { 0.63f, 0.06f, 0.05f }), green = rgbSpectrum((const float[3]) { 0.12f, 0.45f, 0.1f });
+        const Spectrum light(15.0f);
+        addAnalytic(rs->scene, "rectangle", Transform::translate(Vector(0, -h, 0)) * Transform::rotate(Vector(1, 0, 0), -90), white, NULL);       // floor, normal +y
+        addAnalytic(rs->scene, "rectangle", Transform::translate(Vector(0, h, 0)) * Transform::rotate(Vector(1, 0, 0), 90), white, NULL);        // ceiling, normal -y
+        addAnalytic(rs->scene, "rectangle", Transform::translate(Vector(0, 0, -h)), white, NULL);                                                // back wall, normal +z
+        addAnalytic(rs->scene, "rectangle", Transform::translate(Vector(-h, 0, 0)) * Transform::rotate(Vector(0, 1, 0), 90), red, NULL);          // left, normal +x
+        addAnalytic(rs->scene, "rectangle", Transform::translate(Vector(h, 0, 0)) * Transform::rotate(Vector(0, 1, 0), -90), green, NULL);        // right, normal -x
+        const Point c0(0.2f, -0.55f, -0.1f);
+        addAnalytic(rs->scene, "sphere", Transform(), white, NULL, &c0, 0.45f);
+        addAnalytic(rs->scene, "rectangle", Transform::translate(Vector(0, h - 0.01f, 0)) * Transform::rotate(Vector(1, 0, 0), 90) * Transform::scale(Vector(0.25f, 0.25f, 1)), white, &light);
+    }
     /* one TriMesh per (material, emitter, smooth) group, in triangle order (trimesh.h:71-77) */
     typedef std::tuple<uint32_t, int32_t, bool> Key;
     std::map<Key, std::vector<uint32_t> > groups;
-    for (uint32_t t = 0; t < d->n_triangles; ++t) {
+    for (uint32_t t = 0; !analytic && t < d->n_triangles; ++t) {
         bool smooth = d->tri_flags && (d->tri_flags[t] & DR_TRI_SMOOTH) && d->normals;
         groups[Key(d->tri_material[t], d->tri_emitter[t], smooth)].push_back(t);
     }
@@ -453,7 +492,8 @@ int ref_render(const dr_scene_desc *d, const dr_config *c, int sample_count, int
         for (int i = 0; i < threads; ++i) sched->registerWorker(new LocalWorker(i, formatString("wrk%i", i)));
         sched->start();
         ref<Timer> timer = new Timer();
-        RefScene *rs = (RefScene *) scene_create(d, c->rfilter, &ip, sample_count);
+        /* REF_ANALYTIC_SCENE=1: the same job on a room of analytic shapes (scene_create) -- exercises the plugin's tessellation */
+        RefScene *rs = (RefScene *) scene_create(d, c->rfilter, &ip, sample_count, getenv("REF_ANALYTIC_SCENE") != NULL);
         *scene_seconds = timer->getMilliseconds() / 1000.0;
         Statistics::getInstance()->resetAll();
         ref<RenderQueue> queue = new RenderQueue();

@@ -1029,3 +1029,28 @@ def test_render_multi_gpu_matches_single_gpu(params):
     arr = (C_.c_void_p * 2)(s0.h, None)
     out = np.zeros((128, 128, 3), np.float32)
     assert s0.lib.dr_render_multi(arr, 2, C_.byref(cfg), out.ctypes.data_as(C_.POINTER(C_.c_float)), None) == 1      # DR_ERR_INVALID_ARG
+
+
+# SURVEY 8f rank 4, analytic shapes: a room of Mitsuba `rectangle` and `sphere` shapes (oracle/ref/ref_path.cpp, REF_ANALYTIC_SCENE)
+# rendered by the reference's own integrator on the analytic shapes (tests/golden/ref_analytic.npz, three runs) and by the plugin,
+# which tessellates them with the shapes' own createTriMesh (shim/mts_plugin.cpp).  The sphere becomes 1 482 triangles: b within 3 %.
+@pytest.mark.skipif(not os.path.exists(os.path.join(PLUGIN_DIR, "drmlt.so")), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
+def test_drop_in_plugin_tessellates_analytic_shapes(tmp_path):
+    import json
+    import subprocess
+    import sys
+    gold = dict(np.load(os.path.join(RP.ROOT, "tests", "golden", "ref_analytic.npz")))
+    out = str(tmp_path / "analytic.npy")
+    p = subprocess.run([sys.executable, os.path.join(RP.ROOT, "tools", "plugin_render.py"), "drmlt_orbital_mmlt", out, "--analytic"],
+                       capture_output=True, text=True, timeout=300)
+    line = [ln for ln in p.stdout.splitlines() if "PLUGIN_RENDER " in ln]
+    assert line, (p.stdout[-1500:], p.stderr[-1500:])
+    info = json.loads(line[-1][line[-1].index("PLUGIN_RENDER ") + len("PLUGIN_RENDER "):])
+    assert info["ok"], info
+    assert p.stdout.count("is tessellated into") == 7 and "(Sphere) is tessellated into 1482 triangles" in p.stdout
+    img = np.load(out)
+    b, bs = float(RP.luminance(img).mean()), gold["analytic_b"]
+    assert abs(b / bs.mean() - 1.0) < 0.03, (b, bs)
+    for k, vals in zip(gold["analytic_stats_names"], gold["analytic_stats"].T):
+        assert abs(info["stats"][str(k)] - vals.mean()) <= 2.0 + (vals.max() - vals.min()), (str(k), info["stats"][str(k)], vals)
+    assert RP.rel_mse(img, gold["analytic_image"]) < 0.05

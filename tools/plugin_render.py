@@ -18,11 +18,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ref_path_cases as RP  # noqa: E402
 
 name, out = sys.argv[1], sys.argv[2]
-spp = int(sys.argv[3]) if len(sys.argv) > 3 else None
-os.environ["REF_PLUGIN_DIR"] = os.path.join(ROOT, "oracle", "_ref", "plugins")
+spp = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else None
+if "--analytic" in sys.argv:            # a room of ANALYTIC shapes (rectangles, a sphere; ref_path.cpp scene_create): the plugin tessellates them
+    os.environ["REF_ANALYTIC_SCENE"] = "1"
+if "--reference" not in sys.argv:       # (--reference: the reference's own integrator instead of the plugin -- writes the fixture)
+    os.environ["REF_PLUGIN_DIR"] = os.path.join(ROOT, "oracle", "_ref", "plugins")
 params, case_spp = RP.RENDER_CASES[name]
 try:
-    img, sec, _, stats = RP.run_render_ref(C.CDLL(RP.REF_PATH), params, spp or case_spp, threads=2)
+    img, sec, _, stats = RP.run_render_ref(C.CDLL(RP.REF_PATH), params, spp or case_spp, threads=2 if "--reference" not in sys.argv else (os.cpu_count() or 2))
 except AssertionError as e:
     print("PLUGIN_RENDER " + json.dumps({"ok": False, "error": str(e)}), flush=True)
     os._exit(3)
