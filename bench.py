@@ -171,7 +171,8 @@ def reference_sample(config, spp, timeout_s=900):
 
 
 def reference_baseline(r):
-    return {"value": r["mutations_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+    return {"value": r["mutations_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference", "render_s": r["render_s"],
+            "scene_build_s": r["scene_build_s"], "cold_value": r["mutations"] / (r["render_s"] + r["scene_build_s"]),
             "sample": "the reference's own integrator (DRMLT::render / PSSMLT::render of oracle/_ref: the reference's sources, -O3 -march=nocona, double precision, SAH kd-tree) on the same scene and parameters: %d mutations/pixel = "
                       "%d mutations in %.1f s render time incl. its bootstrap, %d worker threads; kd-tree build %.1f s not counted"
                       % (r["spp"], r["mutations"], r["render_s"], r["threads"], r["scene_build_s"]),
@@ -422,6 +423,11 @@ def run_gpu(args):
         strong = {"scaling": "strong", "mutations_per_pixel_total": args.strong_spp, "mutations": int(ts[0].item()), "seconds": float(tm[1].item()),
                   "value": float(ts[0].item()) / float(tm[1].item()), "unit": UNIT,
                   "rank0_phases_ms": dict(getattr(distributed.render, "last_timing", {}))}
+
+    # cold start: the same job including dr_scene_create (flattening, host SAH BVH build, 4-wide collapse, upload) -- what
+    # `mitsuba scene.xml` pays once per scene; beside it (cpu_baseline.sample) the reference's kd-tree build + render
+    e2e["cold"] = {"scene_create_s": scene_create_s, "seconds": scene_create_s + e2e["seconds"],
+                   "value": e2e["mutations"] / (scene_create_s + e2e["seconds"]), "unit": UNIT}
 
     def pct(a, b):
         return round(100.0 * a / max(1, b), 2)
