@@ -8,9 +8,6 @@
 #include <limits>
 #include <atomic>
 #include <thread>
-#include <chrono>
-#include <cstdio>
-#include <functional>
 
 namespace {
 
@@ -30,45 +27,28 @@ float as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 } // namespace
 
 void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out) {
-    const auto t00 = std::chrono::steady_clock::now();
     const int NB = 16;
     const int LEAF = getenv("DRMLT_BVH_LEAF") ? std::max(1, std::min(4, atoi(getenv("DRMLT_BVH_LEAF")))) : 2;   // triangles per leaf (the leaf code holds count - 1 in two bits)
-    // Large ranges (the serial top of the tree) bin on all host threads: every thread bins a slice into private bins, the bins are
-    // merged in slice order (box union and integer counts: the result does not depend on the thread count).
-    const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    auto slices = [&](uint32_t count, const std::function<void(unsigned, uint32_t, uint32_t)> &fn) {
-        const unsigned T = count >= (1u << 16) ? nThreads : 1u;
-        if (T == 1) { fn(0, 0, count); return 1u; }
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < T; ++t)
-            th.emplace_back(fn, t, (uint32_t) ((uint64_t) count * t / T), (uint32_t) ((uint64_t) count * (t + 1) / T));
-        for (auto &x : th) x.join();
-        return T;
-    };
-    // the primitives travel WITH their boxes and centroids: a split partitions this array in place, so every pass over a
-    // range streams through memory (an index array into fixed boxes gathers at random once the range is partitioned)
-    struct Prim { Box b; float c[3]; uint32_t id; };
-    std::vector<Prim> prims(nTris), scratch;
-    slices(nTris, [&](unsigned, uint32_t b0, uint32_t e0) {
-        for (uint32_t i = b0; i < e0; ++i) {
-            Box b; b.reset();
-            for (int v = 0; v < 3; ++v)
-                for (int a = 0; a < 3; ++a) {
-                    float x = P[3 * (size_t) I[3 * (size_t) i + v] + a];
-                    b.lo[a] = std::min(b.lo[a], x); b.hi[a] = std::max(b.hi[a], x);
-                }
-            prims[i].b = b; prims[i].id = i;
-            for (int a = 0; a < 3; ++a) prims[i].c[a] = 0.5f * (b.lo[a] + b.hi[a]);
-        }
-    });
+    std::vector<Box> box(nTris);
+    std::vector<float> cen(3 * (size_t) nTris);
+    out.order.resize(nTris);
+    for (uint32_t i = 0; i < nTris; ++i) {
+        out.order[i] = i;
+        Box b; b.reset();
+        for (int v = 0; v < 3; ++v)
+            for (int a = 0; a < 3; ++a) {
+                float x = P[3 * (size_t) I[3 * (size_t) i + v] + a];
+                b.lo[a] = std::min(b.lo[a], x); b.hi[a] = std::max(b.hi[a], x);
+            }
+        box[i] = b;
+        for (int a = 0; a < 3; ++a) cen[3 * (size_t) i + a] = 0.5f * (b.lo[a] + b.hi[a]);
+    }
     out.nodes.clear();
     out.rootIsLeaf = nTris <= (uint32_t) LEAF;
     if (out.rootIsLeaf) {
         // one pseudo node whose child0 is the leaf and child1 an empty box
         Box b; b.reset();
-        for (uint32_t i = 0; i < nTris; ++i) b.grow(prims[i].b);
-        out.order.resize(nTris);
-        for (uint32_t i = 0; i < nTris; ++i) out.order[i] = i;
+        for (uint32_t i = 0; i < nTris; ++i) b.grow(box[i]);
         float inf = std::numeric_limits<float>::infinity();
         out.nodes.push_back(make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]));
         out.nodes.push_back(make_float4(b.hi[1], b.hi[2], inf, inf));
@@ -80,7 +60,7 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
     // Child boxes are padded by a few 1e-6 of the scene extent: the traversal tests them with the float-cast ray,
     // whose origin / direction differ from the double ray by one float ulp.
     Box sceneBox; sceneBox.reset();
-    for (uint32_t i = 0; i < nTris; ++i) sceneBox.grow(prims[i].b);
+    for (uint32_t i = 0; i < nTris; ++i) sceneBox.grow(box[i]);
     const float pad = 4e-6f * std::max(std::max(sceneBox.hi[0] - sceneBox.lo[0], sceneBox.hi[1] - sceneBox.lo[1]),
                                        std::max(sceneBox.hi[2] - sceneBox.lo[2], 1e-30f));
     struct Range { int node; uint32_t first, count; int depth; };
@@ -90,87 +70,42 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
     auto split = [&](const Range &r, std::vector<float4> &nodes, std::vector<Range> &work, int &maxDepth) {
         float clo[3], chi[3];
         for (int a = 0; a < 3; ++a) { clo[a] = std::numeric_limits<float>::infinity(); chi[a] = -clo[a]; }
-        {
-            float tlo[16][3], thi[16][3];
-            const unsigned T = slices(r.count, [&](unsigned t, uint32_t b, uint32_t e) {
-                for (int a = 0; a < 3; ++a) { tlo[t][a] = std::numeric_limits<float>::infinity(); thi[t][a] = -tlo[t][a]; }
-                for (uint32_t i = r.first + b; i < r.first + e; ++i) {
-                    const float *c = prims[i].c;
-                    for (int a = 0; a < 3; ++a) { tlo[t][a] = std::min(tlo[t][a], c[a]); thi[t][a] = std::max(thi[t][a], c[a]); }
-                }
-            });
-            for (unsigned t = 0; t < T; ++t)
-                for (int a = 0; a < 3; ++a) { clo[a] = std::min(clo[a], tlo[t][a]); chi[a] = std::max(chi[a], thi[t][a]); }
+        for (uint32_t i = r.first; i < r.first + r.count; ++i) {
+            const float *c = &cen[3 * (size_t) out.order[i]];
+            for (int a = 0; a < 3; ++a) { clo[a] = std::min(clo[a], c[a]); chi[a] = std::max(chi[a], c[a]); }
         }
         int bestAxis = -1, bestSplit = -1; float bestCost = std::numeric_limits<float>::infinity();
-        {
-            // bins of the three axes in one pass over the range
-            struct Bins { uint32_t cnt[3][NB]; Box bb[3][NB]; };
-            std::vector<Bins> tb(nThreads);
-            float scale[3];
-            for (int a = 0; a < 3; ++a) scale[a] = (chi[a] - clo[a]) > 0.f ? NB / (chi[a] - clo[a]) : 0.f;
-            const unsigned T = slices(r.count, [&](unsigned t, uint32_t b, uint32_t e) {
-                Bins &B = tb[t];
-                for (int a = 0; a < 3; ++a) for (int k = 0; k < NB; ++k) { B.cnt[a][k] = 0; B.bb[a][k].reset(); }
-                for (uint32_t i = r.first + b; i < r.first + e; ++i) {
-                    const Prim &p = prims[i];
-                    for (int a = 0; a < 3; ++a) {
-                        if (!(scale[a] > 0.f)) continue;
-                        const int k = std::min(NB - 1, (int) ((p.c[a] - clo[a]) * scale[a]));
-                        B.cnt[a][k]++; B.bb[a][k].grow(p.b);
-                    }
-                }
-            });
-            for (int a = 0; a < 3; ++a) {
-                if (!(scale[a] > 0.f)) continue;
-                uint32_t cnt[NB] = { 0 }; Box bb[NB];
-                for (int b = 0; b < NB; ++b) bb[b].reset();
-                for (unsigned t = 0; t < T; ++t) for (int b = 0; b < NB; ++b) { cnt[b] += tb[t].cnt[a][b]; if (tb[t].cnt[a][b]) bb[b].grow(tb[t].bb[a][b]); }
-                float rArea[NB]; uint32_t rCnt[NB];
-                Box acc; acc.reset(); uint32_t c2 = 0;
-                for (int b = NB - 1; b > 0; --b) { acc.grow(bb[b]); c2 += cnt[b]; rCnt[b] = c2; rArea[b] = c2 ? acc.area() : 0.f; }
-                acc.reset(); uint32_t c1 = 0;
-                for (int b = 0; b < NB - 1; ++b) {
-                    acc.grow(bb[b]); c1 += cnt[b];
-                    if (c1 == 0 || rCnt[b + 1] == 0) continue;
-                    float cost = c1 * acc.area() + rCnt[b + 1] * rArea[b + 1];
-                    if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = b; }
-                }
+        for (int a = 0; a < 3; ++a) {
+            float ext = chi[a] - clo[a];
+            if (!(ext > 0.f)) continue;
+            uint32_t cnt[NB] = { 0 }; Box bb[NB];
+            for (int b = 0; b < NB; ++b) bb[b].reset();
+            float scale = NB / ext;
+            for (uint32_t i = r.first; i < r.first + r.count; ++i) {
+                uint32_t p = out.order[i];
+                int b = std::min(NB - 1, (int) ((cen[3 * (size_t) p + a] - clo[a]) * scale));
+                cnt[b]++; bb[b].grow(box[p]);
+            }
+            float rArea[NB]; uint32_t rCnt[NB];
+            Box acc; acc.reset(); uint32_t c2 = 0;
+            for (int b = NB - 1; b > 0; --b) { acc.grow(bb[b]); c2 += cnt[b]; rCnt[b] = c2; rArea[b] = c2 ? acc.area() : 0.f; }
+            acc.reset(); uint32_t c1 = 0;
+            for (int b = 0; b < NB - 1; ++b) {
+                acc.grow(bb[b]); c1 += cnt[b];
+                if (c1 == 0 || rCnt[b + 1] == 0) continue;
+                float cost = c1 * acc.area() + rCnt[b + 1] * rArea[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = b; }
             }
         }
         uint32_t mid;
         if (bestAxis >= 0) {
             float ext = chi[bestAxis] - clo[bestAxis], scale = NB / ext;
-            auto left = [&](const Prim &p) { return std::min(NB - 1, (int) ((p.c[bestAxis] - clo[bestAxis]) * scale)) <= bestSplit; };
-            Prim *beg = prims.data() + r.first, *end = beg + r.count;
-            if (r.count >= (1u << 16) && nThreads > 1) {
-                // parallel partition: count per slice, then scatter the slices to their places in a scratch copy.  (The order
-                // inside the two halves differs from std::partition's; a split only depends on the SETS.)
-                uint32_t nl[16], base[16][2];
-                scratch.resize(r.count);
-                const unsigned T = slices(r.count, [&](unsigned t, uint32_t b, uint32_t e) {
-                    uint32_t c = 0;
-                    for (uint32_t i = b; i < e; ++i) c += left(beg[i]) ? 1u : 0u;
-                    nl[t] = c;
-                });
-                uint32_t totalLeft = 0;
-                for (unsigned t = 0; t < T; ++t) totalLeft += nl[t];
-                uint32_t l = 0, rr = totalLeft;
-                for (unsigned t = 0; t < T; ++t) {
-                    const uint32_t b = (uint32_t) ((uint64_t) r.count * t / T), e = (uint32_t) ((uint64_t) r.count * (t + 1) / T);
-                    base[t][0] = l; base[t][1] = rr;
-                    l += nl[t]; rr += (e - b) - nl[t];
-                }
-                slices(r.count, [&](unsigned t, uint32_t b, uint32_t e) {
-                    uint32_t l2 = base[t][0], r2 = base[t][1];
-                    for (uint32_t i = b; i < e; ++i) { if (left(beg[i])) scratch[l2++] = beg[i]; else scratch[r2++] = beg[i]; }
-                });
-                slices(r.count, [&](unsigned, uint32_t b, uint32_t e) { std::copy(scratch.begin() + b, scratch.begin() + e, beg + b); });
-                mid = r.first + totalLeft;
-            } else {
-                Prim *m = std::partition(beg, end, left);
-                mid = (uint32_t) (m - prims.data());
-            }
+            uint32_t *beg = out.order.data() + r.first, *end = beg + r.count;
+            uint32_t *m = std::partition(beg, end, [&](uint32_t p) {
+                int b = std::min(NB - 1, (int) ((cen[3 * (size_t) p + bestAxis] - clo[bestAxis]) * scale));
+                return b <= bestSplit;
+            });
+            mid = (uint32_t) (m - out.order.data());
         } else {
             mid = r.first + r.count / 2;
         }
@@ -179,12 +114,7 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
         Box cb[2]; int code[2];
         for (int c = 0; c < 2; ++c) {
             cb[c].reset();
-            Box tbx[16];
-            const unsigned T = slices(counts[c], [&](unsigned t, uint32_t b, uint32_t e) {
-                tbx[t].reset();
-                for (uint32_t i = firsts[c] + b; i < firsts[c] + e; ++i) tbx[t].grow(prims[i].b);
-            });
-            for (unsigned t = 0; t < T; ++t) cb[c].grow(tbx[t]);       // (an empty slice leaves its box inverted: growing by it changes nothing)
+            for (uint32_t i = firsts[c]; i < firsts[c] + counts[c]; ++i) cb[c].grow(box[out.order[i]]);
             if (counts[c] <= (uint32_t) LEAF) {
                 code[c] = ~(int) ((firsts[c] << 2) | (counts[c] - 1));
             } else {
@@ -212,7 +142,6 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
         if (r.count <= taskSize && r.node != 0) { tasks.push_back(r); continue; }
         split(r, out.nodes, work, out.maxDepth);
     }
-    const auto tA = std::chrono::steady_clock::now();
     // Phase B (parallel): every task builds its subtree into a private node array whose node 0 is the subtree root.
     struct Sub { std::vector<float4> nodes; int maxDepth = 1; };
     std::vector<Sub> subs(tasks.size());
@@ -229,12 +158,11 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
             while (!w.empty()) { Range r = w.back(); w.pop_back(); split(r, sb.nodes, w, sb.maxDepth); }
         }
     };
+    const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<std::thread> pool;
     for (unsigned t = 1; t < nThreads && t < tasks.size(); ++t) pool.emplace_back(worker);
     worker();
     for (auto &t : pool) t.join();
-    const auto tB = std::chrono::steady_clock::now();
-    if (getenv("DRMLT_BVH_TIMES")) fprintf(stderr, "bvh: phase A %.3f s (since start), phase B %.3f s, tasks %zu\n", std::chrono::duration<double>(tA - t00).count(), std::chrono::duration<double>(tB - tA).count(), tasks.size());
     // Stitch: the subtree root goes into the node reserved for it, its other nodes are appended; inner child codes move along.
     for (size_t k = 0; k < tasks.size(); ++k) {
         const Sub &sb = subs[k];
@@ -252,8 +180,6 @@ void build_bvh(const float *P, const uint32_t *I, uint32_t nTris, BuiltBVH &out)
         }
         out.maxDepth = std::max(out.maxDepth, sb.maxDepth);
     }
-    out.order.resize(nTris);
-    for (uint32_t i = 0; i < nTris; ++i) out.order[i] = prims[i].id;
 }
 
 // ------------------------------------------------------------------ BVH2 -> BVH4
