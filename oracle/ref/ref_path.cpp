@@ -152,6 +152,11 @@ public:
                 if (lum) o[0] = value.getLuminance();
                 else for (int q = 0; q < SPECTRUM_SAMPLES; ++q) o[q] = value[q];
             }
+        if (getenv("REF_TRACE") && lum) {
+            Float lo = 1e30, hi = -1e30; int zeros = 0;
+            for (int i = 0; i < size.x * size.y; ++i) { lo = std::min(lo, dst[i]); hi = std::max(hi, dst[i]); zeros += dst[i] == 0; }
+            fprintf(stderr, "[ref] PinFilm::develop luminance %dx%d: min %g max %g zeros %d (from %s)\n", size.x, size.y, lo, hi, zeros, image.empty() ? "storage" : "bitmap");
+        }
         return true;
     }
     bool destinationExists(const fs::path &) const { return false; }
@@ -487,6 +492,8 @@ int ref_render(const dr_scene_desc *d, const dr_config *c, int sample_count, int
         ip.setBoolean("lightImage", c->light_image != 0);
         ip.setFloat("sigma", (Float) c->sigma);
         ip.setInteger("timeout", c->timeout);
+        ip.setBoolean("twoStage", c->two_stage != 0);                      // mltLuminancePass: the nested film is the "hdrfilm" alias above
+        ip.setInteger("firstStageSizeReduction", c->first_stage_size_reduction);
 
         Scheduler *sched = Scheduler::getInstance();
         for (int i = 0; i < threads; ++i) sched->registerWorker(new LocalWorker(i, formatString("wrk%i", i)));

@@ -720,3 +720,9 @@ def check_direct_image(img, ref, what):
     assert err < 1e-2, (what, err)     # both images carry their own sampling noise (measured 1e-3 .. 5e-3)
     assert abs(a[lit].mean() / b[lit].mean() - 1.0) < 0.08, (what, a[lit].mean(), b[lit].mean())
     return err
+
+
+# ---------------------------------------------------------------- two-stage MLT, whole job
+GOLDEN_TWOSTAGE = os.path.join(ROOT, "tests", "golden", "ref_twostage.npz")
+TWOSTAGE_PARAMS = dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, twoStage=True, firstStageSizeReduction=4)
+TWOSTAGE_SPP = 512

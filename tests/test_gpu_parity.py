@@ -1054,3 +1054,24 @@ def test_drop_in_plugin_tessellates_analytic_shapes(tmp_path):
     for k, vals in zip(gold["analytic_stats_names"], gold["analytic_stats"].T):
         assert abs(info["stats"][str(k)] - vals.mean()) <= 2.0 + (vals.max() - vals.min()), (str(k), info["stats"][str(k)], vals)
     assert RP.rel_mse(img, gold["analytic_image"]) < 0.05
+
+
+# SURVEY 8f rank 3, whole job: the reference's OWN two-stage MLT -- mltLuminancePass (nested job on a film / 4, luminance map,
+# Bitmap::resample), SplatList::normalize(importanceMap), develop x importance -- run end to end in oracle/_ref
+# (tests/golden/ref_twostage.npz, tools/make_ref_twostage_golden.py, three runs) against dr_render with twoStage=true.
+# The reference's statistics counters cover the nested AND the main job; so does the sum formed here.
+def test_cuda_two_stage_job_matches_reference_two_stage_mlt():
+    gold = dict(np.load(RP.GOLDEN_TWOSTAGE))
+    gpu = Scene(RP.RENDER_SCENE())
+    cfg = make_config(seed=9, sampleCount=RP.TWOSTAGE_SPP, **RP.TWOSTAGE_PARAMS)
+    _, nst = gpu.importance_map(cfg)
+    img, st = gpu.render(cfg)
+    b, bs = float(RP.luminance(img).mean()), gold["twostage_b"]
+    assert abs(b - bs.mean()) <= 0.005 * bs.mean() + (bs.max() - bs.min()) / 2, (b, bs)
+    for k, vals in zip(gold["twostage_stats_names"], gold["twostage_stats"].T):
+        a_, base_ = RP.STATS_MAP[str(k)]
+        ours = 100.0 * (getattr(st, a_) + getattr(nst, a_)) / max(1, getattr(st, base_) + getattr(nst, base_))
+        assert abs(ours - vals.mean()) <= 1.5 + (vals.max() - vals.min()), (str(k), ours, vals)
+    lo = lambda im: RP.luminance(im.astype(np.float64)).reshape(8, 8, 8, 8).mean(axis=(1, 3))     # noqa: E731
+    l1, l2 = lo(img), lo(gold["twostage_image"])
+    assert np.abs(l1 - l2).sum() / l2.sum() < 0.05
