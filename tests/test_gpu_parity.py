@@ -1073,5 +1073,11 @@ def test_cuda_two_stage_job_matches_reference_two_stage_mlt():
         ours = 100.0 * (getattr(st, a_) + getattr(nst, a_)) / max(1, getattr(st, base_) + getattr(nst, base_))
         assert abs(ours - vals.mean()) <= 1.5 + (vals.max() - vals.min()), (str(k), ours, vals)
     lo = lambda im: RP.luminance(im.astype(np.float64)).reshape(8, 8, 8, 8).mean(axis=(1, 3))     # noqa: E731
+    # The picture itself is held against the reference's CONVERGED single-stage render: with MMLT a chain never leaves its depth, so
+    # the share of every depth is fixed by the seeds -- which the reference draws ~ L while its chains then sample L / importance.
+    # Its own two-stage image is 12 % (L1, 8x8 blocks) away from its own single-stage image (25-35 % too dark under the ceiling);
+    # the product seeds ~ the re-weighted luminance (deliberate deviation 3) and must land on the converged picture.
+    conv = lo(dict(np.load(RP.GOLDEN_RENDER))["converged_drmlt_orbital_mmlt"])
     l1, l2 = lo(img), lo(gold["twostage_image"])
-    assert np.abs(l1 - l2).sum() / l2.sum() < 0.05
+    assert np.abs(l1 - conv).sum() / conv.sum() < 0.05, np.abs(l1 - conv).sum() / conv.sum()
+    assert np.abs(l2 - conv).sum() / conv.sum() > 0.08          # (the fixture still shows the reference's bias)
