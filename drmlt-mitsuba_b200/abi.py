@@ -65,7 +65,7 @@ class dr_config(C.Structure):
                 ("first_stage", C.c_int32), ("first_stage_size_reduction", C.c_int32),
                 ("film_width", C.c_int32), ("film_height", C.c_int32),
                 ("crop_offset_x", C.c_int32), ("crop_offset_y", C.c_int32),
-                ("crop_width", C.c_int32), ("crop_height", C.c_int32), ("n_lanes", C.c_int32), ("_reserved0", C.c_int32),
+                ("crop_width", C.c_int32), ("crop_height", C.c_int32), ("n_lanes", C.c_int32), ("depth_balance", C.c_int32),
                 ("importance_map", C.POINTER(C.c_float)), ("filter_radius", C.c_double), ("filter_table", C.c_double * 32)]
 
 

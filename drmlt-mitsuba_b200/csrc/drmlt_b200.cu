@@ -87,6 +87,7 @@ extern "C" void dr_config_default(dr_config *c) {
     c->crop_width = c->crop_height = 0;
     c->importance_map = nullptr;
     c->n_lanes = 0;
+    c->depth_balance = 1;
 }
 
 static bool parse_bool(const char *v, int *out) {
@@ -120,6 +121,7 @@ extern "C" dr_status dr_config_set(dr_config *c, const char *key, const char *va
         { "acceptanceMap", &dr_config::acceptance_map }, { "timidAfterLarge", &dr_config::timid_after_large },
         { "fixEmitterPath", &dr_config::fix_emitter_path }, { "useMixture", &dr_config::use_mixture },
         { "kelemenStyleMutation", &dr_config::kelemen_style_mutation }, { "firstStage", &dr_config::first_stage },
+        { "depthBalance", &dr_config::depth_balance },
     };
     static const IntKey ints[] = {
         { "maxDepth", &dr_config::max_depth }, { "rrDepth", &dr_config::rr_depth }, { "directSamples", &dr_config::direct_samples },
@@ -667,6 +669,7 @@ static void resample_chains(dr_job_t *j, unsigned long long firstChain);
 
 struct dr_job_t {
     dr_scene scene = nullptr;
+    int device = 0;
     dr_config cfg;
     int W = 0, H = 0;                           // size of the rendered image = crop window of the film
     float *importance = nullptr;                // [W*H] two-stage importance map on the device (null: none)
@@ -703,6 +706,11 @@ struct dr_job_t {
     uint32_t epoch = 0;                         // work-unit queue: batches run so far (chain ids of batch e start at e * nChains * worldSize)
     long long totalMutations = 0, mutationsDone = 0;
     uint32_t mutTarget = 0;
+    // depth-balanced MMLT chains (dr_config.depth_balance): per-depth mutation factors, seed weights and bootstrap sums
+    uint32_t *mutScale = nullptr;               // [256] 16.16 fixed point, indexed by path depth
+    float *depthWeight = nullptr;               // [maxDepth] seed weight of depth d + 1
+    double *depthSums = nullptr;                // [32]
+    bool balanced = false;
     double b = 0.0;
     bool bootstrapped = false, seeded = false;
     cudaStream_t stream = nullptr;
@@ -749,7 +757,7 @@ static dr_status job_alloc(dr_job j, T **p, size_t count, bool zero = false) {
 
 extern "C" void dr_job_destroy(dr_job j) {
     if (!j) return;
-    cudaSetDevice(j->scene->device);
+    cudaSetDevice(j->device);                   // (not j->scene->device: a garbage collector may already have destroyed the scene)
     if (j->stream) cudaStreamSynchronize(j->stream);
     for (void *p : j->allocations) cudaFreeAsync(p, j->stream);
     if (j->stream) cudaStreamSynchronize(j->stream);
@@ -760,6 +768,7 @@ extern "C" void dr_job_destroy(dr_job j) {
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);
     if (j->stream) cudaStreamDestroy(j->stream);
+    cudaGetLastError();
     delete j;
 }
 
@@ -823,7 +832,7 @@ static dr_status job_create_common(dr_scene scene, const dr_config *cfgIn, int n
     if ((st = check_technique(cfg))) return st;
     CK(cudaSetDevice(scene->device));
     dr_job j = new dr_job_t();
-    j->scene = scene; j->cfg = cfg;
+    j->scene = scene; j->device = scene->device; j->cfg = cfg;
     memset(&j->M, 0, sizeof(j->M));
     FilmWindow fw;
     if ((st = film_window(scene, cfg, fw))) { delete j; return st; }
@@ -1084,6 +1093,61 @@ extern "C" dr_status dr_job_bootstrap(dr_job j, double *sumOut, double *countOut
     return DR_OK;
 }
 
+// Depth-balanced chain lengths (MMLT, resident chains; GPU execution knob dr_config.depth_balance, no reference equivalent).
+// A mutation of a depth-d path costs ~d rays and ~d rounds of the wavefront machine, so with equal chain lengths the
+// rounds of a job are set by its deepest chains while the lanes of the shallow ones idle.  Here a chain of depth d runs
+// m_d ~ per * dbar / d mutations (dbar = luminance-weighted mean depth of the bootstrap) and the seeds are resampled
+// ~ L / m_d: the expected number of mutations spent at depth d stays ~ B_d (the reference's allocation: chains ~ B_d,
+// equal lengths), every chain still starts in its stationary distribution, and the film's normalisation (b / mean film
+// luminance, drmlt_proc.cpp:813-854) does not depend on the chain count.  The m_d are integers; the seed weights use the
+// very same integers, so the per-depth energy is exact in expectation whatever the rounding.
+static dr_status balance_depths(dr_job j, long long per) {
+    const dr_config &c = j->cfg;
+    const int D = c.max_depth;
+    dr_status st;
+    if (!j->mutScale && ((st = job_alloc(j, &j->mutScale, 256)) || (st = job_alloc(j, &j->depthWeight, 32)) || (st = job_alloc(j, &j->depthSums, 32 + (size_t) depth_sums_scratch_doubles()))))
+        return st;
+    const float *src = j->bootLumTarget ? j->bootLumTarget : j->bootLum;
+    launch_depth_sums(src, j->nBoot, j->bootFirst, D, j->depthSums + 32, j->depthSums, j->stream);
+    double B[32];
+    CK(cudaMemcpyAsync(B, j->depthSums, 32 * sizeof(double), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    const double cost0 = getenv("DRMLT_DEPTH_COST0") ? atof(getenv("DRMLT_DEPTH_COST0")) : 0.0;
+    double sumB = 0.0, sumBd = 0.0;
+    for (int d = 0; d < D; ++d) { sumB += B[d]; sumBd += B[d] * (d + 1 + cost0); }
+    if (!(sumB > 0.0)) return DR_OK;
+    const double dbar = sumBd / sumB;
+    uint32_t scale[256];
+    long long m[32];
+    // smallest common factor for which the expected total N * sum B / sum (B_d / m_d) reaches the budget N * per
+    auto total = [&](double lambda) {
+        double q = 0.0;
+        for (int d = 0; d < D; ++d) {
+            scale[d + 1] = (uint32_t) std::min(4294967295.0, std::floor(65536.0 * lambda * dbar / (d + 1 + cost0) + 0.5));
+            m[d] = ((long long) per * scale[d + 1]) >> 16;
+            if (m[d] < 1) return -1.0;
+            q += B[d] / (double) m[d];
+        }
+        return sumB / q;
+    };
+    double lo = 0.25, hi = 4.0;
+    if (!(total(hi) >= (double) per)) return DR_OK;          // (degenerate budget: keep equal lengths)
+    for (int it = 0; it < 48; ++it) { const double mid = 0.5 * (lo + hi); if (total(mid) >= (double) per) hi = mid; else lo = mid; }
+    if (total(hi) < 0.0) return DR_OK;
+    float w[32] = { 0 };
+    for (int d = 0; d < D; ++d) w[d] = (float) ((double) per / (double) m[d]);
+    scale[0] = 65536u;
+    for (int d = D + 1; d < 256; ++d) scale[d] = 65536u;
+    CK(cudaMemcpyAsync(j->mutScale, scale, sizeof(scale), cudaMemcpyHostToDevice, j->stream));
+    CK(cudaMemcpyAsync(j->depthWeight, w, sizeof(w), cudaMemcpyHostToDevice, j->stream));
+    launch_scan(src, j->nBoot, j->cdf, j->blockSums, j->stream, j->depthWeight, j->bootFirst, D);
+    CK(cudaStreamSynchronize(j->stream));                     // (scale / w are stack arrays)
+    CKL();
+    j->launches += 5;
+    j->balanced = true;
+    return DR_OK;
+}
+
 // seedPDF.sample per chain (pathsampler.cpp:946-954)
 static void resample_chains(dr_job_t *j, unsigned long long firstChain) {
     const dr_config &c = j->cfg;
@@ -1113,6 +1177,12 @@ extern "C" dr_status dr_job_seed_chains(dr_job j, double b) {
     // counts (a stride of the rank-local count would overlap when W*H*sampleCount does not divide by the world size)
     const unsigned long long firstChain = (unsigned long long) c.rank << 32;
     CK(cudaEventRecord(j->ev0, j->stream));
+    j->balanced = false;
+    if (c.depth_balance && c.technique == DR_TECH_MMLT && !j->chainCursor && !j->replay && c.max_depth <= 32) {
+        const long long per = std::max<long long>(1, j->totalMutations / n);
+        dr_status st;
+        if (per >= 8 && (st = balance_depths(j, per))) return st;
+    }
     resample_chains(j, firstChain);
     CKL();
     j->epoch = 0;
@@ -1174,6 +1244,7 @@ static dr_status run_chains(dr_job j, long long steps, dr_step_record *records, 
     job.mutTarget = j->mutTarget;
     job.records = records; job.recordStride = recordStride;
     job.replay = j->replay; job.replayStride = j->replayStride; job.replayDim = j->replayDim;
+    job.mutScale = j->balanced && !records ? j->mutScale : nullptr;
     CK(cudaStreamSynchronize(j->stream));
     for (int g = 0; g < (int) j->groups.size(); ++g) {             // parked chains start their next mutation
         Machine M = machine_for(j, g, job, j->counters, withFilm);

@@ -266,7 +266,7 @@ k_chain(const __grid_constant__ Machine M) {
                         if (r.nl) splat_list_copy(M, lane, 0, 3, r.nl, inv_lum(r));
                         cc.cumW = 0.; c.tx = (int8_t) r.t;
                         c.phase = PH_STAGE1; c.large = 2u;
-                        c.pstate = c.mut < job.mutTarget ? PS_START : PS_IDLE;
+                        c.pstate = c.mut < mut_target(job, c.depth) ? PS_START : PS_IDLE;
                     } else if (!drmlt) {
                         // ---------------- PSSMLT (pssmlt_proc.cpp:175-272)
                         ++st[ST_MUT];
@@ -443,7 +443,7 @@ k_chain(const __grid_constant__ Machine M) {
                     if (mutationDone) {
                         ++c.mut;
                         c.phase = PH_STAGE1; c.large = 2u;
-                        c.pstate = c.mut < job.mutTarget ? PS_START : PS_IDLE;
+                        c.pstate = c.mut < mut_target(job, c.depth) ? PS_START : PS_IDLE;
                     }
                     if (c.pstate == PS_IDLE && job.chainCursor) {
                         // work-unit queue: this chain is complete; the lane takes the next one (generateWork, drmlt_proc.cpp:869-883)
@@ -499,7 +499,7 @@ __global__ void k_resume_lanes(const __grid_constant__ Machine M) {
     const int lane = M.laneBegin + blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= M.laneEnd) return;
     Core *c = M.lm.core + lane;
-    if (c->pstate == PS_IDLE && c->mut < M.job.mutTarget) {
+    if (c->pstate == PS_IDLE && c->mut < mut_target(M.job, c->depth)) {
         c->pstate = PS_START; c->phase = PH_STAGE1; c->large = 2u;
         q_push(M.q, Q_CHAIN + M.parity, (uint32_t) lane);
     }

@@ -40,7 +40,8 @@ __global__ void k_lum_final(const double *partial, double *out /* [2]: sum, coun
 #define SCAN_BLOCK 1024
 #define SCAN_ITEMS 4
 __global__ void __launch_bounds__(SCAN_BLOCK)
-k_scan_blocks(const float *lum, long long n, double *cdf /* n+1, cdf[0] = 0 */, double *blockSums) {
+k_scan_blocks(const float *lum, long long n, double *cdf /* n+1, cdf[0] = 0 */, double *blockSums,
+              const float *depthWeight, unsigned long long first, int maxDepth) {
     __shared__ double warpSums[32];
     const long long base = (long long) blockIdx.x * SCAN_BLOCK * SCAN_ITEMS + (long long) threadIdx.x * SCAN_ITEMS;
     double v[SCAN_ITEMS], run = 0.0;
@@ -49,7 +50,9 @@ k_scan_blocks(const float *lum, long long n, double *cdf /* n+1, cdf[0] = 0 */, 
         const long long i = base + k;
         float x = i < n ? lum[i] : 0.f;
         if (!(x > 0.f) || isinf(x)) x = 0.f;     // NaN / negative / inf samples carry no seed
-        run += (double) x; v[k] = run;
+        double xd = (double) x;
+        if (depthWeight && i < n) xd *= (double) depthWeight[(first + (unsigned long long) i) % (unsigned long long) maxDepth];
+        run += xd; v[k] = run;
     }
     double incl = run;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -123,6 +126,42 @@ __global__ void k_resample(const double *cdf, long long n, unsigned long long se
     depth[c] = technique == DR_TECH_MMLT ? (int) (s % (unsigned long long) maxDepth) + 1 : -1;
 }
 
+// per-depth sums of the bootstrap luminances (MMLT: sample i has depth (first + i) % maxDepth + 1, pathsampler.cpp:886-890);
+// out[d - 1] = sum.  maxDepth <= 32.  Fixed summation order (thread-strided, shared-memory tree, blocks in order), so a job
+// with the same seed gets the same per-depth chain lengths on every run.
+__global__ void __launch_bounds__(256)
+k_depth_sums(const float *lum, long long n, unsigned long long first, int maxDepth, double *partial /* [RED_BLOCKS][32] */) {
+    __shared__ double acc[256];
+    // thread t of the grid only sees samples of ONE depth when its stride is a multiple of maxDepth: pad the stride
+    const long long threads = (long long) gridDim.x * blockDim.x;
+    const long long stride = (threads + maxDepth - 1) / maxDepth * maxDepth;
+    const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    double s = 0.0;
+    for (long long i = t; i < n; i += stride) {
+        const float x = lum[i];
+        if (x > 0.f && !isinf(x)) s += (double) x;
+    }
+    acc[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = 0.0;
+        if ((int) threadIdx.x < maxDepth)
+            for (int k = 0; k < 256; ++k)
+                if ((int) ((first + (unsigned long long) (t - threadIdx.x + k)) % (unsigned long long) maxDepth) == (int) threadIdx.x) v += acc[k];
+        partial[blockIdx.x * 32 + threadIdx.x] = v;
+    }
+}
+__global__ void k_depth_final(const double *partial, int blocks, double *out) {
+    double v = 0.0;
+    for (int b = 0; b < blocks; ++b) v += partial[b * 32 + threadIdx.x];
+    out[threadIdx.x] = v;
+}
+int depth_sums_scratch_doubles() { return RED_BLOCKS * 32; }
+void launch_depth_sums(const float *lum, long long n, unsigned long long first, int maxDepth, double *scratch, double *out, cudaStream_t s) {
+    k_depth_sums<<<RED_BLOCKS, 256, 0, s>>>(lum, n, first, maxDepth, scratch);
+    k_depth_final<<<1, 32, 0, s>>>(scratch, RED_BLOCKS, out);
+}
+
 // ---------------------------------------------------------------- develop (drmlt_proc.cpp:813-854)
 __global__ void k_film_luminance(const float4 *film, const float *importance, long long n, double *out) {
     double s = 0.0;
@@ -178,9 +217,10 @@ void launch_lum_reduce(const float *lum, long long n, double *scratch, double *o
     k_lum_reduce<<<RED_BLOCKS, 256, 0, s>>>(lum, n, scratch);
     k_lum_final<<<1, 1, 0, s>>>(scratch, out);
 }
-void launch_scan(const float *lum, long long n, double *cdf, double *blockSums, cudaStream_t s) {
+void launch_scan(const float *lum, long long n, double *cdf, double *blockSums, cudaStream_t s,
+                 const float *depthWeight, unsigned long long first, int maxDepth) {
     const long long nb = scan_blocks(n);
-    k_scan_blocks<<<(unsigned) nb, SCAN_BLOCK, 0, s>>>(lum, n, cdf, blockSums);
+    k_scan_blocks<<<(unsigned) nb, SCAN_BLOCK, 0, s>>>(lum, n, cdf, blockSums, depthWeight, first, maxDepth);
     k_scan_sums<<<1, 1024, 0, s>>>(blockSums, (int) nb);
     k_scan_add<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(cdf, n, blockSums);
 }

@@ -273,7 +273,15 @@ struct JobParams {
     const double *replay;
     long long replayStride;
     int replayDim;
+    // JOB_CHAIN, depth-balanced MMLT chains (dr_config.depth_balance): 16.16 fixed-point factor per path depth; a chain of
+    // depth d runs (mutTarget * mutScale[d]) >> 16 mutations.  Null: every chain runs mutTarget mutations.
+    const uint32_t *mutScale;
 };
+// the number of mutations a chain of path depth `depth` has to reach
+__device__ __forceinline__ uint32_t mut_target(const JobParams &job, int depth) {
+    if (!job.mutScale || depth < 0) return job.mutTarget;
+    return (uint32_t) (((unsigned long long) job.mutTarget * __ldg(job.mutScale + depth)) >> 16);
+}
 
 struct FilmParams {
     int w, h;

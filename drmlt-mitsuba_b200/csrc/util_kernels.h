@@ -4,7 +4,11 @@
 long long scan_blocks(long long n);
 int lum_reduce_scratch_doubles();
 void launch_lum_reduce(const float *lum, long long n, double *scratch, double *out /* [2]: sum, count */, cudaStream_t s);   // 2 launches, bit-reproducible
-void launch_scan(const float *lum, long long n, double *cdf /* n + 1 */, double *blockSums, cudaStream_t s);   // 3 launches
+// 3 launches; depthWeight (optional, [maxDepth]): sample i is weighted by depthWeight[(first + i) % maxDepth]
+void launch_scan(const float *lum, long long n, double *cdf /* n + 1 */, double *blockSums, cudaStream_t s,
+                 const float *depthWeight = nullptr, unsigned long long first = 0, int maxDepth = 1);
+int depth_sums_scratch_doubles();
+void launch_depth_sums(const float *lum, long long n, unsigned long long first, int maxDepth, double *scratch, double *out /* [32] */, cudaStream_t s);   // 2 launches
 void launch_resample(const double *cdf, long long n, unsigned long long seed, unsigned long long firstChain, int nChains, unsigned long long bootFirst,
                      int maxDepth, int technique, unsigned long long *seedIdx, unsigned long long *chainId, int *depth, cudaStream_t s);
 void launch_film_luminance(const float4 *film, const float *importance /* or null */, long long n, double *out, cudaStream_t s);

@@ -155,7 +155,10 @@ typedef struct dr_config {
      * reference's DRMLTProcess::generateWork, drmlt_proc.cpp:869-883); every dr_job_run then runs a fresh batch of
      * n_chains chains, `mutations_per_chain` mutations each, from newly resampled seeds. */
     int32_t n_lanes;
-    int32_t _reserved0;
+    /* GPU execution knob (MMLT, resident chains): a chain of path depth d runs ~ mutations_per_chain * dbar / d mutations
+     * and the seeds are resampled ~ L * d, so that every lane finishes after about the same number of rays; the mutations
+     * spent per depth stay ~ the bootstrap's per-depth luminance as in the reference.  depthBalance = true. */
+    int32_t depth_balance;
     /* m_config.importanceMap (drmlt.h:57, internal): host pointer to crop_width*crop_height floats, or NULL.
      * With twoStage=true and NULL here, dr_render computes it with dr_importance_map first. */
     const float *importance_map;

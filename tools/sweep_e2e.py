@@ -4,7 +4,7 @@
   python tools/sweep_e2e.py "DRMLT_GROUPS=3" "DRMLT_GROUPS=6,DRMLT_TRACE_CTAS=3" ...
 
 Each argument is a comma-separated list of KEY=VALUE environment settings (the library reads its DRMLT_* knobs when a
-job is created); "chains=N" / "lanes=N" / "spp=N" are passed to the configuration instead.  Prints one JSON line per setting: device time of
+job is created); "chains=N" / "lanes=N" / "spp=N" / "balance=0|1" are passed to the configuration instead.  Prints one JSON line per setting: device time of
 the chain phase, whole-job wall time, mutations/s.  A tuning aid -- its numbers are not bench values.
 """
 import json
@@ -52,6 +52,8 @@ def main():
                 params["sampleCount"] = int(v)
             elif k in ("chains", "lanes"):
                 params[k] = int(v)
+            elif k == "balance":
+                params["depthBalance"] = bool(int(v))
             else:
                 os.environ[k] = v
         data = scene_data(scene_name)
