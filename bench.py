@@ -427,7 +427,20 @@ def run_gpu(args):
     # cold start: the same job including dr_scene_create (flattening, host SAH BVH build, 4-wide collapse, upload) -- what
     # `mitsuba scene.xml` pays once per scene; beside it (cpu_baseline.sample) the reference's kd-tree build + render
     e2e["cold"] = {"scene_create_s": scene_create_s, "seconds": scene_create_s + e2e["seconds"],
-                   "value": e2e["mutations"] / (scene_create_s + e2e["seconds"]), "unit": UNIT}
+                   "value": e2e["mutations"] / (scene_create_s + e2e["seconds"]), "unit": UNIT, "bvh": scene.bvh_info()}
+    # ... and with the tree built on the device (dr_scene_create_ex, DR_SCENE_BVH_GPU: what the plugin shim uses for its one-shot
+    # renders): scene creation + the same job on that scene, one GPU
+    if world == 1:
+        torch.cuda.synchronize()
+        c0 = time.perf_counter()
+        cold_scene = Scene(data, device=local, gpu_bvh=True)
+        c_create = time.perf_counter() - c0
+        _, cst, _ = distributed.render(cold_scene, e2e_params, None, rank, world)
+        torch.cuda.synchronize()
+        c_wall = time.perf_counter() - c0
+        e2e["cold_gpu_bvh"] = {"scene_create_s": c_create, "seconds": c_wall, "value": float(cst.mutations) / c_wall, "unit": UNIT,
+                               "bvh": cold_scene.bvh_info(), "device_chains_ms": cst.chains_ms}
+        cold_scene.close()
 
     def pct(a, b):
         return round(100.0 * a / max(1, b), 2)

@@ -106,7 +106,7 @@ dr_refresh_fn = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.c_int32, C.c_int32,
 # every symbol include/drmlt_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "dr_abi_version", "dr_last_error", "dr_device_count", "dr_config_default", "dr_config_set",
-    "dr_config_validate", "dr_scene_create", "dr_scene_destroy", "dr_scene_reupload", "dr_scene_clone", "dr_render_multi", "dr_render", "dr_cancel",
+    "dr_config_validate", "dr_scene_create", "dr_scene_create_ex", "dr_scene_bvh_info", "dr_scene_destroy", "dr_scene_reupload", "dr_scene_clone", "dr_render_multi", "dr_render", "dr_cancel",
     "dr_job_create", "dr_job_destroy", "dr_job_bootstrap", "dr_job_seed_chains", "dr_job_run",
     "dr_job_film_device", "dr_job_develop", "dr_job_stats", "dr_job_profile", "dr_job_direct", "dr_direct_image", "dr_job_num_chains", "dr_job_total_mutations",
     "dr_trace_rays", "dr_eval_paths", "dr_chain_steps", "dr_chain_replay", "dr_splat_points", "dr_bootstrap_luminance", "dr_max_dimensions",
@@ -141,6 +141,9 @@ def load_library(path=None):
     lib.dr_config_set.argtypes = [P(dr_config), C.c_char_p, C.c_char_p]
     lib.dr_config_validate.argtypes = [P(dr_config)]
     lib.dr_scene_create.argtypes = [P(dr_scene_desc), C.c_int, P(C.c_void_p)]
+    lib.dr_scene_create_ex.argtypes = [P(dr_scene_desc), C.c_int, C.c_uint32, P(C.c_void_p)]
+    lib.dr_scene_bvh_info.argtypes = [C.c_void_p, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_double)]
+    lib.dr_scene_bvh_info.restype = None
     lib.dr_scene_destroy.argtypes = [C.c_void_p]
     lib.dr_scene_destroy.restype = None
     lib.dr_scene_clone.argtypes = [C.c_void_p, C.c_int, P(C.c_void_p)]

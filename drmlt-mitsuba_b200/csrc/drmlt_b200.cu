@@ -264,19 +264,36 @@ struct SceneImpl : dr_scene_t {
 template <class T>
 static dr_status upload(SceneImpl *s, const std::vector<T> &v, const T **devOut) {
     HostUpload u;
-    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-    u.bytes = bytes;
-    CK(cudaMallocHost((void **) &u.host, bytes));
+    const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    u.bytes = bytes; u.host = nullptr;                       // (the pinned staging copy is made by the first dr_scene_reupload)
+    CK(cudaMalloc(&u.dev, bytes));
+    s->allocations.push_back(u.dev);
+    CK(cudaMemset(u.dev, 0, bytes));
+    if (!v.empty()) CK(cudaMemcpy(u.dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     s->uploads.push_back(u);
-    HostUpload &up = s->uploads.back();
-    memset(up.host, 0, bytes);
-    if (!v.empty()) memcpy(up.host, v.data(), v.size() * sizeof(T));
-    CK(cudaMalloc(&up.dev, bytes));
-    s->allocations.push_back(up.dev);
-    CK(cudaMemcpy(up.dev, up.host, bytes, cudaMemcpyHostToDevice));
     s->bytes += bytes;
     s->uploadBytes += bytes;
-    *devOut = (const T *) up.dev;
+    *devOut = (const T *) u.dev;
+    return DR_OK;
+}
+// an array that was produced on the device (build_scene_gpu): the scene takes ownership
+template <class T>
+static void adopt(SceneImpl *s, T *dev, size_t count, const T **devOut, bool own = true) {
+    HostUpload u;
+    u.bytes = std::max<size_t>(count * sizeof(T), 16); u.host = nullptr; u.dev = dev;
+    if (own) s->allocations.push_back(u.dev);
+    s->uploads.push_back(u);
+    s->bytes += u.bytes;
+    s->uploadBytes += u.bytes;
+    *devOut = dev;
+}
+// pinned host copies of the scene arrays, for dr_scene_reupload (made on first use: a one-shot render never needs them)
+static dr_status ensure_staging(SceneImpl *s) {
+    for (HostUpload &u : s->uploads)
+        if (!u.host) {
+            CK(cudaMallocHost((void **) &u.host, u.bytes));
+            CK(cudaMemcpy(u.host, u.dev, u.bytes, cudaMemcpyDeviceToHost));
+        }
     return DR_OK;
 }
 
@@ -314,6 +331,18 @@ extern "C" void dr_scene_destroy(dr_scene scene) {
 }
 
 extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scene *out) {
+    // (DRMLT_BVH=gpu|host overrides the default builder of this entry point: a tuning aid)
+    const char *env = getenv("DRMLT_BVH");
+    return dr_scene_create_ex(d, device, env && !strcmp(env, "gpu") ? DR_SCENE_BVH_GPU : DR_SCENE_BVH_HOST, out);
+}
+extern "C" void dr_scene_bvh_info(dr_scene scene, int32_t *builder, int32_t *nNodes, int32_t *stackBound, double *buildMs) {
+    if (!scene) return;
+    if (builder) *builder = scene->bvhBuilder;
+    if (nNodes) *nNodes = (int32_t) scene->nNodes;
+    if (stackBound) *stackBound = scene->bvhDepth;
+    if (buildMs) *buildMs = scene->bvhBuildMs;
+}
+extern "C" dr_status dr_scene_create_ex(const dr_scene_desc *d, int device, uint32_t flags, dr_scene *out) {
     if (!d || !out) { dr_set_error("dr_scene_create: null argument"); return DR_ERR_INVALID_ARG; }
     *out = nullptr;
     if (!d->positions || !d->indices || !d->tri_material || !d->tri_emitter || !d->materials || d->n_triangles == 0 ||
@@ -357,24 +386,41 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     dr_status st = DR_OK;
     auto fail = [&](dr_status code) { dr_scene_destroy(s); return code; };
 
-    BuiltBVH bvh;
-    build_bvh(d->positions, d->indices, d->n_triangles, bvh);
-#ifdef DR_BVH4
-    collapse_bvh4(bvh);
-#endif
-    if (bvh.maxDepth >= DR_STACK) { dr_set_error("dr_scene_create: BVH depth %d exceeds the traversal stack (%d)", bvh.maxDepth, DR_STACK); return fail(DR_ERR_UNSUPPORTED); }
-    s->nNodes = (uint32_t) (bvh.nodes.size() / DR_NODE_F4);
-
-    // triangles and shading normals in leaf order
     const size_t nT = d->n_triangles;
-    std::vector<float4> tris(3 * nT), normals;
     bool anySmooth = false;
     for (size_t i = 0; i < nT; ++i)
         if (d->normals && d->tri_flags && (d->tri_flags[i] & DR_TRI_SMOOTH)) { anySmooth = true; break; }
-    if (anySmooth) normals.assign(3 * nT, make_float4(0, 0, 0, 0));
+    BuiltBVH bvh;
+    GpuScene gpu;
+    struct GpuGuard { GpuScene &g; bool adopted = false; ~GpuGuard() { if (!adopted) g.release(); } } gpuGuard{ gpu };
+    const auto tBuild = std::chrono::steady_clock::now();
+    bool gpuBuilt = false;
+#ifdef DR_BVH4
+    if ((flags & DR_SCENE_BVH_GPU) && d->n_triangles >= 1024) {
+        bool tooDeep = false;
+        gpuBuilt = build_scene_gpu(d, anySmooth, DR_STACK, gpu, &tooDeep);
+        if (!gpuBuilt && !tooDeep) return fail(DR_ERR_CUDA);
+        if (gpuBuilt) { bvh.maxDepth = gpu.stackBound; s->nNodes = gpu.nNodes; }
+    }
+#endif
+    if (!gpuBuilt) {
+        build_bvh(d->positions, d->indices, d->n_triangles, bvh);
+#ifdef DR_BVH4
+        collapse_bvh4(bvh);
+#endif
+    }
+    s->bvhBuilder = gpuBuilt ? (int) DR_SCENE_BVH_GPU : (int) DR_SCENE_BVH_HOST;
+    s->bvhDepth = bvh.maxDepth;
+    s->bvhBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tBuild).count();
+    if (bvh.maxDepth >= DR_STACK) { dr_set_error("dr_scene_create: BVH depth %d exceeds the traversal stack (%d)", bvh.maxDepth, DR_STACK); return fail(DR_ERR_UNSUPPORTED); }
+    if (!gpuBuilt) s->nNodes = (uint32_t) (bvh.nodes.size() / DR_NODE_F4);
+
+    // triangles and shading normals in leaf order (device build: packed by build_scene_gpu)
+    std::vector<float4> tris(gpuBuilt ? 0 : 3 * nT), normals;
+    if (anySmooth && !gpuBuilt) normals.assign(3 * nT, make_float4(0, 0, 0, 0));
     auto P = [&](uint32_t v) { return f3(d->positions[3 * (size_t) v], d->positions[3 * (size_t) v + 1], d->positions[3 * (size_t) v + 2]); };
     auto N = [&](uint32_t v) { return f3(d->normals[3 * (size_t) v], d->normals[3 * (size_t) v + 1], d->normals[3 * (size_t) v + 2]); };
-    for (size_t slot = 0; slot < nT; ++slot) {
+    for (size_t slot = 0; slot < (gpuBuilt ? 0 : nT); ++slot) {
         const uint32_t prim = bvh.order[slot];
         const uint32_t i0 = d->indices[3 * (size_t) prim], i1 = d->indices[3 * (size_t) prim + 1], i2 = d->indices[3 * (size_t) prim + 2];
         const float3 p0 = P(i0), p1 = P(i1), p2 = P(i2);
@@ -457,10 +503,19 @@ extern "C" dr_status dr_scene_create(const dr_scene_desc *d, int device, dr_scen
     DevScene &ds = s->dev;
     memset(&ds, 0, sizeof(ds));
     const unsigned int *dOrder = nullptr;
-    if ((st = upload(s, bvh.nodes, &ds.nodes)) || (st = upload(s, tris, &ds.tris)) || (st = upload(s, normals, &ds.normals)) ||
-        (st = upload(s, emTris, &ds.emTris)) || (st = upload(s, emCdf, &ds.emCdf)) || (st = upload(s, emitterCdf, &ds.emitterCdf)) ||
-        (st = upload(s, emitters, &ds.emitters)) || (st = upload(s, mats, &ds.materials)) || (st = upload(s, bvh.order, &dOrder)))
+    if (gpuBuilt) {                          // (the same order of arrays as the host build: dr_scene_clone walks them)
+        gpuGuard.adopted = true;
+        s->allocations.push_back(gpu.order);               // (owned from here on; listed with the uploads below)
+        adopt(s, gpu.nodes, 8 * (size_t) gpu.nNodes, &ds.nodes);
+        adopt(s, gpu.tris, 3 * nT, &ds.tris);
+        adopt(s, gpu.normals, gpu.normalsCount, &ds.normals);
+    } else if ((st = upload(s, bvh.nodes, &ds.nodes)) || (st = upload(s, tris, &ds.tris)) || (st = upload(s, normals, &ds.normals)))
         return fail(st);
+    if ((st = upload(s, emTris, &ds.emTris)) || (st = upload(s, emCdf, &ds.emCdf)) || (st = upload(s, emitterCdf, &ds.emitterCdf)) ||
+        (st = upload(s, emitters, &ds.emitters)) || (st = upload(s, mats, &ds.materials)))
+        return fail(st);
+    if (gpuBuilt) adopt(s, (unsigned int *) gpu.order, nT, &dOrder, false);
+    else if ((st = upload(s, bvh.order, &dOrder))) return fail(st);
     s->dOrder = const_cast<unsigned int *>(dOrder);
     ds.nEmitters = (int) d->n_emitters; ds.nTris = (int) d->n_triangles; ds.nNodes = (int) s->nNodes; ds.rootIsLeaf = 0;
     ds.epsilon = 1e-4f; ds.shadowEpsilon = 1e-3f;     // constants.h:29-30 (single precision)
@@ -513,7 +568,7 @@ extern "C" dr_status dr_scene_clone(dr_scene scene, int device, dr_scene *out) {
         u.host = nullptr;                                   // the staging copy stays with the original
         if (cudaMalloc(&u.dev, u.bytes) != cudaSuccess) { dr_set_error("dr_scene_clone: cudaMalloc of %zu bytes failed", u.bytes); cudaGetLastError(); return fail(DR_ERR_CUDA); }
         s->allocations.push_back(u.dev);
-        if (cudaMemcpy(u.dev, src->uploads[i].host, u.bytes, cudaMemcpyHostToDevice) != cudaSuccess) { dr_set_error("dr_scene_clone: upload failed"); cudaGetLastError(); return fail(DR_ERR_CUDA); }
+        if (cudaMemcpyPeer(u.dev, device, src->uploads[i].dev, src->device, u.bytes) != cudaSuccess) { dr_set_error("dr_scene_clone: copy from device %d failed", src->device); cudaGetLastError(); return fail(DR_ERR_CUDA); }
         *slots[i] = u.dev;
         s->bytes += u.bytes;
     }
@@ -526,6 +581,8 @@ extern "C" dr_status dr_scene_reupload(dr_scene scene, int64_t *bytes) {
     if (!scene) { dr_set_error("dr_scene_reupload: null scene"); return DR_ERR_INVALID_ARG; }
     SceneImpl *s = static_cast<SceneImpl *>(scene);
     CK(cudaSetDevice(s->device));
+    dr_status st = ensure_staging(s);
+    if (st) return st;
     for (HostUpload &u : s->uploads) CK(cudaMemcpyAsync(u.dev, u.host, u.bytes, cudaMemcpyHostToDevice, 0));
     CK(cudaStreamSynchronize(0));
     if (bytes) *bytes = (int64_t) s->uploadBytes;

@@ -89,6 +89,16 @@ struct BuiltBVH {
 void build_bvh(const float *positions, const uint32_t *indices, uint32_t nTris, BuiltBVH &out);
 #define DR_NO_CHILD ((int) 0x80000000)       /* empty child slot of a 4-wide node */
 void collapse_bvh4(BuiltBVH &bvh);           // BVH2 (4 float4 per node) -> BVH4 (8 float4 per node); bvh_build.cpp
+// LBVH build + triangle packing on the current device (bvh_gpu.cu): the device-resident arrays of DevScene; false + tooDeep: fall back to build_bvh
+struct GpuScene {
+    float4 *nodes = nullptr, *tris = nullptr, *normals = nullptr;
+    uint32_t *order = nullptr;
+    uint32_t nNodes = 0;
+    size_t normalsCount = 0;         // float4s in `normals` (0: no smooth triangle, a 16-byte placeholder is allocated)
+    int stackBound = 0;
+    void release();
+};
+bool build_scene_gpu(const dr_scene_desc *d, bool anySmooth, int stackLimit, GpuScene &out, bool *tooDeep);
 
 struct dr_scene_t {
     int device = 0;
@@ -96,6 +106,8 @@ struct dr_scene_t {
     std::vector<void *> allocations;
     int filmW = 0, filmH = 0;
     uint32_t nTris = 0, nNodes = 0;
+    int bvhBuilder = 0, bvhDepth = 0;   // DR_SCENE_BVH_* that built the tree | its stack bound
+    double bvhBuildMs = 0.0;
     unsigned typeMask = 0;           // BSDF models present (bit = dr_bsdf_type)
     std::atomic<int> cancel{0};       // set by dr_cancel from any thread, polled between graph replays
     size_t bytes = 0;

@@ -53,14 +53,25 @@ def make_config(**params):
 class Scene:
     """GPU-resident flattened scene (dr_scene)."""
 
-    def __init__(self, data, device=0):
+    def __init__(self, data, device=0, gpu_bvh=None):
+        """gpu_bvh: True = LBVH built on the device (dr_scene_create_ex, DR_SCENE_BVH_GPU), False = the host's binned-SAH
+        build, None = dr_scene_create's default (host)."""
         self.lib = abi.load_library()
         self.data = data
         self.device = device
         desc = data.desc()
         h = C.c_void_p()
-        abi.check(self.lib, self.lib.dr_scene_create(C.byref(desc), device, C.byref(h)))
+        if gpu_bvh is None:
+            abi.check(self.lib, self.lib.dr_scene_create(C.byref(desc), device, C.byref(h)))
+        else:
+            abi.check(self.lib, self.lib.dr_scene_create_ex(C.byref(desc), device, 1 if gpu_bvh else 0, C.byref(h)))
         self.h = h
+
+    def bvh_info(self):
+        """dict(builder="gpu"|"host", nodes, stack_bound, build_ms) of dr_scene_bvh_info."""
+        b, n, d, ms = C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+        self.lib.dr_scene_bvh_info(self.h, C.byref(b), C.byref(n), C.byref(d), C.byref(ms))
+        return dict(builder="gpu" if b.value == 1 else "host", nodes=n.value, stack_bound=d.value, build_ms=ms.value)
 
     def close(self):
         if getattr(self, "h", None):

@@ -105,6 +105,67 @@ def test_ray_casting_matches_oracle(name):
     assert ((sg["prim"] >= 0) == (hc["prim"] >= 0)).mean() > 0.9999
 
 
+# a17 with the tree built on the device (dr_scene_create_ex, DR_SCENE_BVH_GPU; csrc/bvh_gpu.cu): another tree over the same triangles,
+# so the closest hits -- and with them whole jobs -- are those of the host's binned-SAH tree; the scene arrays never visit the host
+# (dr_scene_reupload makes its pinned staging copy on first use).
+HIT_DTYPE = [("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<i4")]
+
+
+@pytest.mark.parametrize("name", ["cornell", "glossy", "caustic", "door"])
+def test_device_built_bvh_gives_the_same_hits_and_jobs(name):
+    data = SCENE_MAKERS[name]()
+    host, dev = Scene(data, gpu_bvh=False), Scene(data, gpu_bvh=True)
+    ih, idv = host.bvh_info(), dev.bvh_info()
+    assert ih["builder"] == "host" and idv["builder"] == ("gpu" if data.n_triangles >= 1024 else "host")
+    assert 0 < idv["stack_bound"] < 64 and idv["nodes"] > 0
+    rays = _random_rays(data, 100000, 7)
+    a = np.frombuffer(host.trace(rays), dtype=HIT_DTYPE)
+    b = np.frombuffer(dev.trace(rays), dtype=HIT_DTYPE)
+    assert ((a["prim"] >= 0) == (b["prim"] >= 0)).all()
+    both = a["prim"] >= 0
+    assert (a["t"][both] == b["t"][both]).mean() > 0.9999 and (a["prim"][both] == b["prim"][both]).mean() > 0.9999   # (ties on shared edges)
+    sa = np.frombuffer(host.trace(rays, shadow=True), dtype=HIT_DTYPE)
+    sb = np.frombuffer(dev.trace(rays, shadow=True), dtype=HIT_DTYPE)
+    assert ((sa["prim"] >= 0) == (sb["prim"] >= 0)).all()
+    cfg = make_config(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1, sampleCount=8, seed=3)
+    img_h, st_h = host.render(cfg)
+    img_d, st_d = dev.render(cfg)
+    assert st_d.luminance == pytest.approx(st_h.luminance, rel=1e-6) and st_d.mutations == st_h.mutations
+    assert st_d.rays == pytest.approx(st_h.rays, rel=1e-3) and st_d.accept == pytest.approx(st_h.accept, rel=1e-3)
+    assert np.abs(img_d - img_h).sum() <= 1e-3 * img_h.sum()
+    # the device-resident scene through dr_scene_reupload (pinned staging copy made on first use): the same job again
+    assert dev.reupload() > 48 * data.n_triangles
+    img_d2, st_d2 = dev.render(cfg)
+    assert (st_d2.mutations, st_d2.rays, st_d2.accept) == (st_d.mutations, st_d.rays, st_d.accept)
+    host.close(); dev.close()
+
+
+def test_device_bvh_falls_back_to_the_host_build_when_too_deep():
+    """Triangles clustered at 40 scales towards a point: the radix tree of the Morton codes degenerates into a chain whose 4-wide
+    collapse would exceed the traversal stack; dr_scene_create_ex then uses the host's SAH build, which splits by count."""
+    data = scenes.SceneData("scales", (32, 32))
+    m = data.add_material(abi.DR_BSDF_DIFFUSE)
+    rng = np.random.RandomState(5)
+    for k in range(40):
+        s = 2.0 ** -k
+        for _ in range(40):
+            c = s * (1.0 + 0.25 * rng.rand(3))
+            e = 0.05 * s
+            data.add_quad(c + (-e, -e, 0), c + (e, -e, 0), c + (e, e, 0), c + (-e, e, 0), m)
+    light = data.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0, 0, 0))
+    data.add_quad((-1, 3, -1), (1, 3, -1), (1, 3, 1), (-1, 3, 1), light, radiance=(10, 10, 10))
+    data.set_camera((3, 3, 3), (0, 0, 0), (0, 1, 0), 40.0)
+    assert data.n_triangles >= 1024
+    dev, host = Scene(data, gpu_bvh=True), Scene(data, gpu_bvh=False)
+    info = dev.bvh_info()
+    rays = _random_rays(data, 50000, 9)
+    a = np.frombuffer(host.trace(rays), dtype=HIT_DTYPE)
+    b = np.frombuffer(dev.trace(rays), dtype=HIT_DTYPE)
+    assert info["stack_bound"] < 64
+    assert ((a["prim"] >= 0) == (b["prim"] >= 0)).all() and (a["t"] == b["t"])[a["prim"] >= 0].mean() > 0.9999
+    print("builder for the 40-scale scene:", info)
+
+
 def test_ray_edge_cases():
     gpu, orc, data = pair("cornell")
     rays = (abi.dr_ray * 4)()

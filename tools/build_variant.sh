@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../drmlt-mitsuba_b200/csrc"
 suffix=$1; shift
 mkdir -p build_$suffix
-for f in drmlt_b200.cu k_chain.cu k_walk.cu k_pt.cu k_bdpt.cu k_direct.cu k_trace.cu k_util.cu multi_gpu.cu bvh_build.cpp; do
+for f in drmlt_b200.cu k_chain.cu k_walk.cu k_pt.cu k_bdpt.cu k_direct.cu k_trace.cu k_util.cu multi_gpu.cu bvh_gpu.cu bvh_build.cpp; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c $f -o build_$suffix/${f%.*}.o &
 done
 wait
