@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DRMLT_B200_LIB") or os.path.join(_HERE, "csrc", "libdrmlt_b200.so")
 
 DR_OK = 0
-DR_BSDF_DIFFUSE, DR_BSDF_DIELECTRIC, DR_BSDF_CONDUCTOR, DR_BSDF_ROUGHCONDUCTOR, DR_BSDF_ROUGHDIELECTRIC, DR_BSDF_PLASTIC = 0, 1, 2, 3, 4, 5
+DR_BSDF_DIFFUSE, DR_BSDF_DIELECTRIC, DR_BSDF_CONDUCTOR, DR_BSDF_ROUGHCONDUCTOR, DR_BSDF_ROUGHDIELECTRIC, DR_BSDF_PLASTIC, DR_BSDF_ROUGHPLASTIC = 0, 1, 2, 3, 4, 5, 6
+DR_ROUGH_TABLE_THETA, DR_ROUGH_TABLE_DOUBLES = 100, 104
 DR_MAT_TWOSIDED, DR_MAT_GGX, DR_MAT_SAMPLE_VISIBLE, DR_MAT_NONLINEAR = 1, 2, 4, 8
 DR_TRI_SMOOTH = 1
 DR_INTEGRATOR_PSSMLT, DR_INTEGRATOR_DRMLT = 0, 1
@@ -26,7 +27,7 @@ class dr_material(C.Structure):
     _fields_ = [("type", C.c_int32), ("flags", C.c_uint32),
                 ("reflectance", C.c_float * 3), ("transmittance", C.c_float * 3),
                 ("eta", C.c_float * 3), ("k", C.c_float * 3),
-                ("alpha", C.c_float), ("_pad", C.c_float)]
+                ("alpha", C.c_float), ("table", C.c_uint32)]
 
 
 class dr_emitter(C.Structure):
@@ -47,7 +48,7 @@ class dr_scene_desc(C.Structure):
                 ("indices", C.POINTER(C.c_uint32)), ("tri_material", C.POINTER(C.c_uint32)),
                 ("tri_emitter", C.POINTER(C.c_int32)), ("tri_flags", C.POINTER(C.c_uint32)),
                 ("materials", C.POINTER(dr_material)), ("emitters", C.POINTER(dr_emitter)),
-                ("camera", dr_camera)]
+                ("camera", dr_camera), ("rough_tables", C.POINTER(C.c_double)), ("n_rough_tables", C.c_uint32)]
 
 
 class dr_config(C.Structure):

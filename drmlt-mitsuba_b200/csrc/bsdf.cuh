@@ -1,7 +1,8 @@
 // bsdf.cuh -- device BSDF models in the local shading frame (z = shading normal).
 //
 // Behavioural parity targets: src/bsdfs/diffuse.cpp:109-150, dielectric.cpp:227-330,
-// conductor.cpp:223-285, roughconductor.cpp:258-417, roughdielectric.cpp:270-611, plastic.cpp:240-420 with src/bsdfs/microfacet.h (Beckmann/GGX,
+// conductor.cpp:223-285, roughconductor.cpp:258-417, roughdielectric.cpp:270-611, plastic.cpp:240-420, roughplastic.cpp:325-470 (+ rtrans.h)
+// with src/bsdfs/microfacet.h (Beckmann/GGX,
 // isotropic, sampleAll and sampleVisible), wrapped by twosided.cpp:107-186 when DR_MAT_TWOSIDED.
 // Branching is on the material type (a small enum) -- no virtual dispatch.
 #pragma once
@@ -16,6 +17,7 @@ struct Mat {   // material fetched into registers
     int type; uint32_t flags;
     R3 refl, trans, eta, k;
     Real alpha;
+    const double *table;     // roughplastic: its rough-transmittance table
 };
 
 DR_D Mat load_material(const DevScene &sc, int id) {
@@ -26,9 +28,10 @@ DR_D Mat load_material(const DevScene &sc, int id) {
     m.refl = r3(a.z, a.w, b.x); m.trans = r3(b.y, b.z, b.w);
     m.eta = r3(c.x, c.y, c.z); m.k = r3(c.w, d.x, d.y);
     m.alpha = d.z;
+    m.table = m.type == DR_BSDF_ROUGHPLASTIC ? sc.roughTables + (size_t) __float_as_uint(d.w) * DR_ROUGH_TABLE_DOUBLES : nullptr;
     return m;
 }
-DR_D bool mat_has_smooth(int type) { return type == DR_BSDF_DIFFUSE || type == DR_BSDF_ROUGHCONDUCTOR || type == DR_BSDF_ROUGHDIELECTRIC || type == DR_BSDF_PLASTIC; }
+DR_D bool mat_has_smooth(int type) { return type == DR_BSDF_DIFFUSE || type == DR_BSDF_ROUGHCONDUCTOR || type == DR_BSDF_ROUGHDIELECTRIC || type == DR_BSDF_PLASTIC || type == DR_BSDF_ROUGHPLASTIC; }
 DR_D bool mat_non_symmetric(int type) { return type == DR_BSDF_DIELECTRIC || type == DR_BSDF_ROUGHDIELECTRIC; }
 DR_D bool mat_transmissive_or_backside(const Mat &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }
 // BSDF::EUsesSampler: sample() draws one more number from the vertex's sampler (roughdielectric.cpp:464, 555)
@@ -246,6 +249,52 @@ DR_D R3 plastic_diffuse(const Mat &m) {                             // :266-271
     return diff;
 }
 
+// ---- rough plastic (roughplastic.cpp): m.refl = diffuseReflectance, m.trans = specularReflectance, m.eta.x = eta, m.alpha; m.table =
+// the rough transmittance reduced to (eta, alpha) (include/drmlt_b200.h DR_ROUGH_TABLE_*), whose slot [102] the library fills with
+// m_specularSamplingWeight (roughplastic.cpp:273-277) when the scene is created.
+// RoughTransmittance::eval with eta and alpha fixed (rtrans.h:136-146) = evalCubicInterp1D (spline.cpp:23-60) of cos^(1/4)
+DR_D Real rough_transmittance(const double *tab, Real cosTheta) {
+    if (!(cosTheta >= 0.)) return 0.;
+    const Real x = pow(fabs(cosTheta), 0.25);
+    if (!(x >= 0. && x <= 1.)) return 0.;                      // (spline.cpp:25-26; the clamp below maps it to 0)
+    const int size = DR_ROUGH_TABLE_THETA;
+    Real t = (x - 0.) * (size - 1) / (1. - 0.);
+    const int k = max(0, min((int) t, size - 2));
+    const Real f0 = __ldg(tab + k), f1 = __ldg(tab + k + 1);
+    const Real d0 = k > 0 ? 0.5 * (f1 - __ldg(tab + k - 1)) : f1 - f0;
+    const Real d1 = k + 2 < size ? 0.5 * (__ldg(tab + k + 2) - f0) : f1 - f0;
+    t = t - (Real) k;
+    const Real t2 = t * t, t3 = t2 * t;
+    const Real result = (2 * t3 - 3 * t2 + 1) * f0 + (-2 * t3 + 3 * t2) * f1 + (t3 - 2 * t2 + t) * d0 + (t3 - t2) * d1;
+    return fmin(1., fmax(0., result));
+}
+DR_D Real roughplastic_prob_specular(const Mat &m, Real cosThetaI) {   // roughplastic.cpp:407-416
+    const Real p = 1. - rough_transmittance(m.table, cosThetaI), w = __ldg(m.table + 102);
+    return (p * w) / (p * w + (1. - p) * (1. - w));
+}
+DR_D R3 roughplastic_eval(const Mat &m, R3 wi, R3 wo) {               // :325-381 (both components enabled)
+    Microfacet distr(m);
+    const R3 H = normalize(wo + wi);
+    const Real D = distr.eval(H);
+    Real cosThetaT;
+    const Real F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, m.eta.x);
+    const Real G = distr.G(wi, wo, H);
+    R3 result = m.trans * (F * D * G / (4.0 * wi.z));
+    R3 diff = m.refl;
+    const Real T12 = rough_transmittance(m.table, wi.z), T21 = rough_transmittance(m.table, wo.z);
+    const Real Fdr = 1. - __ldg(m.table + DR_ROUGH_TABLE_THETA);
+    if (m.flags & DR_MAT_NONLINEAR) { diff.x /= 1. - diff.x * Fdr; diff.y /= 1. - diff.y * Fdr; diff.z /= 1. - diff.z * Fdr; }
+    else diff = diff / (1. - Fdr);
+    return result + diff * (R_INV_PI * wo.z * T12 * T21 * (1. / (m.eta.x * m.eta.x)));
+}
+DR_D Real roughplastic_pdf(const Mat &m, R3 wi, R3 wo) {              // :383-432
+    Microfacet distr(m);
+    const R3 H = normalize(wo + wi);
+    const Real probSpecular = roughplastic_prob_specular(m, wi.z);
+    const Real dwh_dwo = 1.0 / (4.0 * dot(wo, H));
+    return distr.pdf(wi, H) * dwh_dwo * probSpecular + (1. - probSpecular) * (R_INV_PI * wo.z);
+}
+
 // ---- nested (one-sided) evaluation
 DR_D R3 bsdf_eval_nested(const Mat &m, R3 wi, R3 wo, int mode, int measure) {
     switch (m.type) {
@@ -277,6 +326,9 @@ DR_D R3 bsdf_eval_nested(const Mat &m, R3 wi, R3 wo, int mode, int measure) {
         }
         return r3(0.);
     }
+    case DR_BSDF_ROUGHPLASTIC:
+        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0. || wo.z <= 0.) return r3(0.);
+        return roughplastic_eval(m, wi, wo);
     case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:270-348
         if (measure != MEAS_SOLID_ANGLE || wi.z == 0.) return r3(0.);
         const Real mEta = m.eta.x, mInvEta = 1. / mEta;
@@ -341,6 +393,9 @@ DR_D Real bsdf_pdf_nested(const Mat &m, R3 wi, R3 wo, int measure) {
         } else if (measure == MEAS_SOLID_ANGLE) return R_INV_PI * wo.z * (1. - probSpecular);
         return 0.;
     }
+    case DR_BSDF_ROUGHPLASTIC:
+        if (measure != MEAS_SOLID_ANGLE || wi.z <= 0. || wo.z <= 0.) return 0.;
+        return roughplastic_pdf(m, wi, wo);
     case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:350-420 (both components enabled)
         if (measure != MEAS_SOLID_ANGLE) return 0.;
         const Real mEta = m.eta.x, mInvEta = 1. / mEta;
@@ -405,6 +460,27 @@ DR_D void bsdf_sample_nested(const Mat &m, R3 wi, int mode, Real sx, Real sy, Re
             r.pdf = (1. - probSpecular) * (R_INV_PI * r.wo.z);
             r.weight = plastic_diffuse(m) * ((1. / (m.eta.x * m.eta.x)) * (1. - Fi) * (1. - Fo) / (1. - probSpecular));
         }
+        return;
+    }
+    case DR_BSDF_ROUGHPLASTIC: {                                     // roughplastic.cpp:434-491 (both components enabled)
+        if (wi.z <= 0.) return;
+        Microfacet distr(m);
+        const Real probSpecular = roughplastic_prob_specular(m, wi.z);
+        r.eta = 1.;
+        if (sy < probSpecular) {
+            Real tpdf = 0.;
+            const R3 mm = distr.sample(wi, sx, sy / probSpecular, tpdf, epsilon);
+            r.wo = mm * (2. * dot(wi, mm)) - wi;
+            r.sampledType = BT_GLOSSY_R;
+            if (r.wo.z <= 0.) return;
+        } else {
+            r.sampledType = BT_DIFFUSE_R;
+            r.wo = square_to_cosine_hemisphere(sx, (sy - probSpecular) / (1. - probSpecular));
+        }
+        const Real pdf = (wi.z <= 0. || r.wo.z <= 0.) ? 0. : roughplastic_pdf(m, wi, r.wo);      // "guard against numerical imprecisions" (:484-490)
+        if (pdf == 0.) return;
+        r.pdf = pdf;
+        r.weight = roughplastic_eval(m, wi, r.wo) / pdf;
         return;
     }
     case DR_BSDF_ROUGHDIELECTRIC: {                                  // roughdielectric.cpp:514-611 (both components enabled)

@@ -360,9 +360,20 @@ extern "C" dr_status dr_scene_create_ex(const dr_scene_desc *d, int device, uint
             if (d->indices[3 * (size_t) i + v] >= d->n_vertices) { dr_set_error("triangle %u: vertex index out of range", i); return DR_ERR_INVALID_ARG; }
     }
     for (uint32_t m = 0; m < d->n_materials; ++m)
-        if (d->materials[m].type < DR_BSDF_DIFFUSE || d->materials[m].type > DR_BSDF_PLASTIC) {
-            dr_set_error("material %u: unsupported BSDF type %d", m, d->materials[m].type); return DR_ERR_UNSUPPORTED;
+    {
+        const dr_material &mat = d->materials[m];
+        if (mat.type < DR_BSDF_DIFFUSE || mat.type > DR_BSDF_ROUGHPLASTIC) {
+            dr_set_error("material %u: unsupported BSDF type %d", m, mat.type); return DR_ERR_UNSUPPORTED;
         }
+        if (mat.type == DR_BSDF_ROUGHPLASTIC) {
+            if (!d->rough_tables || mat.table >= d->n_rough_tables) {
+                dr_set_error("material %u: roughplastic needs its rough-transmittance table (dr_scene_desc.rough_tables[%u])", m, mat.table);
+                return DR_ERR_INVALID_ARG;
+            }
+            // MicrofacetDistribution + RoughPlastic (roughplastic.cpp:210-230): eta != 1; the Phong distribution is not on this path
+            if (!(mat.eta[0] > 0.f) || mat.eta[0] == 1.f) { dr_set_error("The interior and exterior indices of refraction must be positive and differ!"); return DR_ERR_INVALID_ARG; }
+        }
+    }
     for (uint32_t e = 0; e < d->n_emitters; ++e) {
         const dr_emitter &em = d->emitters[e];
         if (em.n_tris == 0 || (uint64_t) em.first_tri + em.n_tris > d->n_triangles) { dr_set_error("emitter %u: triangle range out of bounds", e); return DR_ERR_INVALID_ARG; }
@@ -499,6 +510,22 @@ extern "C" dr_status dr_scene_create_ex(const dr_scene_desc *d, int device, uint
             for (int c = 0; c < 3; ++c) { dAvg += Y[c] * m.reflectance[c]; sAvg += Y[c] * m.transmittance[c]; }
             m.k[1] = (float) (sAvg / (dAvg + sAvg));
         }
+    // roughplastic: the caller's tables + m_specularSamplingWeight (roughplastic.cpp:273-277) in slot [102], in double
+    std::vector<double> roughTables(d->rough_tables ? d->rough_tables : nullptr,
+                                    d->rough_tables ? d->rough_tables + (size_t) d->n_rough_tables * DR_ROUGH_TABLE_DOUBLES : nullptr);
+    {
+        std::vector<int> owner(d->n_rough_tables, -1);
+        for (uint32_t i = 0; i < d->n_materials; ++i) {
+            const DevMaterial &m = mats[i];
+            if (m.type != DR_BSDF_ROUGHPLASTIC) continue;
+            if (owner[m.table] >= 0) { dr_set_error("materials %d and %u share rough table %u (one table per roughplastic material)", owner[m.table], i, m.table); return fail(DR_ERR_INVALID_ARG); }
+            owner[m.table] = (int) i;
+            const double Y[3] = { 0.212671f, 0.715160f, 0.072169f };
+            double dAvg = 0, sAvg = 0;
+            for (int c = 0; c < 3; ++c) { dAvg += Y[c] * m.reflectance[c]; sAvg += Y[c] * m.transmittance[c]; }
+            roughTables[(size_t) m.table * DR_ROUGH_TABLE_DOUBLES + 102] = sAvg / (dAvg + sAvg);
+        }
+    }
 
     DevScene &ds = s->dev;
     memset(&ds, 0, sizeof(ds));
@@ -512,7 +539,7 @@ extern "C" dr_status dr_scene_create_ex(const dr_scene_desc *d, int device, uint
     } else if ((st = upload(s, bvh.nodes, &ds.nodes)) || (st = upload(s, tris, &ds.tris)) || (st = upload(s, normals, &ds.normals)))
         return fail(st);
     if ((st = upload(s, emTris, &ds.emTris)) || (st = upload(s, emCdf, &ds.emCdf)) || (st = upload(s, emitterCdf, &ds.emitterCdf)) ||
-        (st = upload(s, emitters, &ds.emitters)) || (st = upload(s, mats, &ds.materials)))
+        (st = upload(s, emitters, &ds.emitters)) || (st = upload(s, mats, &ds.materials)) || (st = upload(s, roughTables, &ds.roughTables)))
         return fail(st);
     if (gpuBuilt) adopt(s, (unsigned int *) gpu.order, nT, &dOrder, false);
     else if ((st = upload(s, bvh.order, &dOrder))) return fail(st);
@@ -559,10 +586,10 @@ extern "C" dr_status dr_scene_clone(dr_scene scene, int device, dr_scene *out) {
     s->dev = src->dev;
     auto fail = [&](dr_status code) { dr_scene_destroy(s); return code; };
     // the device pointers of DevScene, in the order dr_scene_create uploaded them
-    const void **slots[9] = { (const void **) &s->dev.nodes, (const void **) &s->dev.tris, (const void **) &s->dev.normals, (const void **) &s->dev.emTris,
+    const void **slots[10] = { (const void **) &s->dev.nodes, (const void **) &s->dev.tris, (const void **) &s->dev.normals, (const void **) &s->dev.emTris,
                               (const void **) &s->dev.emCdf, (const void **) &s->dev.emitterCdf, (const void **) &s->dev.emitters, (const void **) &s->dev.materials,
-                              (const void **) &s->dOrder };
-    if (src->uploads.size() != 9) { dr_set_error("dr_scene_clone: unexpected scene layout"); return fail(DR_ERR_INVALID_ARG); }
+                              (const void **) &s->dev.roughTables, (const void **) &s->dOrder };
+    if (src->uploads.size() != 10) { dr_set_error("dr_scene_clone: unexpected scene layout"); return fail(DR_ERR_INVALID_ARG); }
     for (size_t i = 0; i < src->uploads.size(); ++i) {
         HostUpload u = src->uploads[i];
         u.host = nullptr;                                   // the staging copy stays with the original

@@ -193,24 +193,27 @@ static unsigned grid_for(int n, int threads) { return stage_grid(n, threads); }
 // the walk queues of all BSDF models in one launch, every warp on one model (multiq_locate)
 __global__ void __launch_bounds__(128, WALK_MINB)
 k_walk(const __grid_constant__ Machine M) {
-    const uint32_t cnt[6] = { M.q.count[Q_WALK + 0], M.q.count[Q_WALK + 1], M.q.count[Q_WALK + 2], M.q.count[Q_WALK + 3], M.q.count[Q_WALK + 4], M.q.count[Q_WALK + 5] };
+    static_assert(Q_WALK + N_WALK_CLASSES == Q_CONNECT && DR_BSDF_ROUGHPLASTIC == N_WALK_CLASSES - 1, "one walk queue per BSDF model");
+    const uint32_t cnt[N_WALK_CLASSES] = { M.q.count[Q_WALK + 0], M.q.count[Q_WALK + 1], M.q.count[Q_WALK + 2], M.q.count[Q_WALK + 3], M.q.count[Q_WALK + 4], M.q.count[Q_WALK + 5],
+                                           M.q.count[Q_WALK + 6] };
     const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;; w += nWarps) {
         int cls; uint32_t qi;
-        if (!multiq_locate<6>(cnt, w, cls, qi)) break;
+        if (!multiq_locate<N_WALK_CLASSES>(cnt, w, cls, qi)) break;
         if (qi >= cnt[cls]) continue;
         if (cls == DR_BSDF_DIFFUSE) walk_lane<DR_BSDF_DIFFUSE>(M, qi);
         else if (cls == DR_BSDF_DIELECTRIC) walk_lane<DR_BSDF_DIELECTRIC>(M, qi);
         else if (cls == DR_BSDF_CONDUCTOR) walk_lane<DR_BSDF_CONDUCTOR>(M, qi);
         else if (cls == DR_BSDF_ROUGHCONDUCTOR) walk_lane<DR_BSDF_ROUGHCONDUCTOR>(M, qi);
         else if (cls == DR_BSDF_ROUGHDIELECTRIC) walk_lane<DR_BSDF_ROUGHDIELECTRIC>(M, qi);
-        else walk_lane<DR_BSDF_PLASTIC>(M, qi);
+        else if (cls == DR_BSDF_PLASTIC) walk_lane<DR_BSDF_PLASTIC>(M, qi);
+        else walk_lane<DR_BSDF_ROUGHPLASTIC>(M, qi);
     }
 }
 
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask) {
     (void) typeMask;
-    const unsigned g = grid_for(lc.nLanes + 6 * 128, 128);
+    const unsigned g = grid_for(lc.nLanes + N_WALK_CLASSES * 128, 128);
     k_walk<<<g, 128, 0, lc.stream>>>(M);
     k_connect<<<g, 128, 0, lc.stream>>>(M);
 }

@@ -176,7 +176,8 @@ template <class T> DR_D void rec_store(T *dst, const T &src) {
 // Q_RAYC / Q_RAYS / Q_CHAIN are double-buffered by round parity: kernels of round r consume [r & 1] and
 // produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT, Q_PT and
 // Q_BEGIN are produced and consumed inside one round.
-enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 6 */, Q_CONNECT = 12, Q_PT = 13, Q_BEGIN = 14 /* + class, 3 */, Q_COUNT = 17 };
+enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 7 */, Q_CONNECT = 13, Q_PT = 14, Q_BEGIN = 15 /* + class, 3 */, Q_COUNT = 18 };
+#define N_WALK_CLASSES 7
 // classes of "start the next path" work: each runs one kind of proposal arithmetic on full warps
 enum { BEGIN_STAGE1 = 0, BEGIN_STAGE2 = 1, BEGIN_OTHER = 2 };
 struct RayF { float4 a, b; };                               // (o, tmin), (d, tmax): float32 cast of a ray, for the traversal

@@ -28,7 +28,7 @@
 struct DevMaterial {      // 64 B, mirrors dr_material
     int32_t type; uint32_t flags;
     float reflectance[3], transmittance[3], eta[3], k[3];
-    float alpha, pad;
+    float alpha; uint32_t table;
 };
 
 struct DevEmitter {       // 64 B
@@ -73,6 +73,7 @@ struct DevScene {
     const double *emitterCdf;       // nEmitters + 1 (selection by sampling weight)
     const DevEmitter *emitters;
     const DevMaterial *materials;
+    const double *roughTables;      // roughplastic: DR_ROUGH_TABLE_DOUBLES per table (include/drmlt_b200.h)
     int nEmitters, nTris, nNodes;
     int rootIsLeaf;                  // degenerate scenes with <= 4 triangles
     DevCamera cam;

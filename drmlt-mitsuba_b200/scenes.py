@@ -18,6 +18,7 @@ class SceneData:
         self.film = film
         self._P, self._N, self._I, self._mat, self._emi, self._flg = [], [], [], [], [], []
         self.materials, self.emitters = [], []
+        self.rough_tables = []
         self.n_vertices = 0
         self.n_triangles = 0
         self.camera = None
@@ -25,7 +26,9 @@ class SceneData:
 
     # ---- construction helpers
     def add_material(self, type_, flags=0, reflectance=(0.5, 0.5, 0.5), transmittance=(1, 1, 1),
-                     eta=(1.5, 0, 0), k=(0, 0, 0), alpha=0.1):
+                     eta=(1.5, 0, 0), k=(0, 0, 0), alpha=0.1, rough_table=None):
+        """rough_table (roughplastic): the DR_ROUGH_TABLE_DOUBLES doubles of include/drmlt_b200.h for this (distribution, eta, alpha)
+        -- rough_tables.reduce(path to data/microfacet/<distribution>.dat, eta, alpha), or the reference's own RoughTransmittance."""
         m = abi.dr_material()
         m.type, m.flags = type_, flags
         m.reflectance[:] = reflectance
@@ -33,6 +36,12 @@ class SceneData:
         m.eta[:] = eta
         m.k[:] = k
         m.alpha = alpha
+        if type_ == abi.DR_BSDF_ROUGHPLASTIC:
+            t = np.ascontiguousarray(rough_table, np.float64)
+            if t.shape != (abi.DR_ROUGH_TABLE_DOUBLES,):
+                raise ValueError("roughplastic needs a rough_table of %d doubles" % abi.DR_ROUGH_TABLE_DOUBLES)
+            m.table = len(self.rough_tables)
+            self.rough_tables.append(t)
         self.materials.append(m)
         return len(self.materials) - 1
 
@@ -117,11 +126,12 @@ class SceneData:
             flg = np.ascontiguousarray(np.concatenate(self._flg), np.uint32)
             mats = (abi.dr_material * len(self.materials))(*self.materials)
             emis = (abi.dr_emitter * max(1, len(self.emitters)))(*self.emitters)
-            self._keep = (P, N, I, mat, emi, flg, mats, emis)
+            rt = np.ascontiguousarray(np.concatenate(self.rough_tables) if self.rough_tables else np.zeros(0), np.float64)
+            self._keep = (P, N, I, mat, emi, flg, mats, emis, rt)
         return self._keep
 
     def desc(self):
-        P, N, I, mat, emi, flg, mats, emis = self.arrays()
+        P, N, I, mat, emi, flg, mats, emis, rt = self.arrays()
         d = abi.dr_scene_desc()
         d.n_vertices, d.n_triangles = P.shape[0], I.shape[0]
         d.n_materials, d.n_emitters = len(self.materials), len(self.emitters)
@@ -133,6 +143,9 @@ class SceneData:
         d.tri_flags = flg.ctypes.data_as(C.POINTER(C.c_uint32))
         d.materials = C.cast(mats, C.POINTER(abi.dr_material))
         d.emitters = C.cast(emis, C.POINTER(abi.dr_emitter))
+        if len(self.rough_tables):
+            d.rough_tables = rt.ctypes.data_as(C.POINTER(C.c_double))
+            d.n_rough_tables = len(self.rough_tables)
         d.camera = self.camera
         return d
 
@@ -174,10 +187,12 @@ def _room(s, white, red, green, tess, light_half=0.25, radiance=(15.0, 15.0, 15.
     s.add_quad((-h, 0.995, -h), (h, 0.995, -h), (h, 0.995, h), (-h, 0.995, h), light_mat, radiance=radiance)   # faces -y
 
 
-def cornell_box(film=(256, 256), tess=8, plastic=False):
+def cornell_box(film=(256, 256), tess=8, plastic=False, rough_tables=None):
     """C1 / C2: Cornell box, area light, one-sided diffuse walls, ~1k triangles.
-    plastic=True: the two boxes are `plastic` (one linear, one nonlinear + twosided)."""
-    s = SceneData("cornell-plastic" if plastic else "cornell", film)
+    plastic=True: the two boxes are `plastic` (one linear, one nonlinear + twosided).
+    rough_tables = (table of (beckmann, 1.49, 0.1), table of (ggx, 1.9, 0.3)): the boxes are `roughplastic` (Beckmann / GGX with
+    visible-normal sampling, nonlinear, twosided) -- the tables come from rough_tables.reduce or the reference (include/drmlt_b200.h)."""
+    s = SceneData("cornell-roughplastic" if rough_tables is not None else "cornell-plastic" if plastic else "cornell", film)
     white = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.73, 0.73, 0.73))
     red = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.63, 0.065, 0.05))
     green = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.14, 0.45, 0.091))
@@ -187,6 +202,11 @@ def cornell_box(film=(256, 256), tess=8, plastic=False):
         box1 = s.add_material(abi.DR_BSDF_PLASTIC, reflectance=(0.1, 0.27, 0.36), transmittance=(1, 1, 1), eta=(1.49, 0, 0))
         box2 = s.add_material(abi.DR_BSDF_PLASTIC, flags=abi.DR_MAT_NONLINEAR | abi.DR_MAT_TWOSIDED, reflectance=(0.6, 0.5, 0.2),
                               transmittance=(0.9, 0.9, 1.0), eta=(1.9, 0, 0))
+    if rough_tables is not None:
+        box1 = s.add_material(abi.DR_BSDF_ROUGHPLASTIC, reflectance=(0.1, 0.27, 0.36), transmittance=(1, 1, 1), eta=(1.49, 0, 0), alpha=0.1,
+                              rough_table=rough_tables[0])
+        box2 = s.add_material(abi.DR_BSDF_ROUGHPLASTIC, flags=abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE | abi.DR_MAT_NONLINEAR | abi.DR_MAT_TWOSIDED,
+                              reflectance=(0.6, 0.5, 0.2), transmittance=(0.9, 0.9, 1.0), eta=(1.9, 0, 0), alpha=0.3, rough_table=rough_tables[1])
     s.add_box((0.33, -0.7, 0.35), (0.3, 0.3, 0.3), -17.0, box1, tess=4)
     s.add_box((-0.33, -0.4, -0.3), (0.3, 0.6, 0.3), 17.0, box2, tess=4)
     s.set_camera((0, 0, 3.9), (0, 0, 0), (0, 1, 0), 39.0)

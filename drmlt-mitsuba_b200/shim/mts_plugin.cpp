@@ -28,6 +28,7 @@
 #include <mitsuba/core/statistics.h>
 #include <mitsuba/core/lock.h>
 #include <drmlt_b200.h>
+#include "src/bsdfs/rtrans.h"          // RoughTransmittance, as src/bsdfs/roughplastic.cpp includes it (compile with -I<mitsuba root>)
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -76,7 +77,28 @@ void toRGB(const Spectrum &sp, float out[3]) {
     out[0] = (float) r; out[1] = (float) g; out[2] = (float) b;
 }
 
-bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why) {
+// The rough-transmittance table of one roughplastic material (include/drmlt_b200.h, DR_ROUGH_TABLE_*), from the host's own
+// RoughTransmittance and data/microfacet/*.dat, reduced exactly as RoughPlastic::configure reduces it (roughplastic.cpp:283-301)
+void roughTable(bool ggx, Float eta, Float alpha, std::vector<double> &tables) {
+    ref<RoughTransmittance> ext = new RoughTransmittance(ggx ? MicrofacetDistribution::EGGX : MicrofacetDistribution::EBeckmann);
+    ext->checkEta(eta); ext->checkAlpha(alpha);
+    ref<RoughTransmittance> in = ext->clone();
+    ext->setEta(eta);
+    in->setEta(1 / eta);
+    struct Peek : public RoughTransmittance {
+        static const Float *trans(const RoughTransmittance *r) { return r->*(&Peek::m_trans); }
+        static size_t thetaSamples(const RoughTransmittance *r) { return r->*(&Peek::m_thetaSamples); }
+    };
+    const size_t base = tables.size();
+    tables.resize(base + DR_ROUGH_TABLE_DOUBLES, 0.0);
+    tables[base + 100] = in->evalDiffuse(alpha);
+    ext->setAlpha(alpha);
+    tables[base + 101] = ext->evalDiffuse(alpha);
+    if (Peek::thetaSamples(ext.get()) != DR_ROUGH_TABLE_THETA) SLog(EError, "Unexpected rough transmittance table size");
+    for (int k = 0; k < DR_ROUGH_TABLE_THETA; ++k) tables[base + k] = (double) Peek::trans(ext.get())[k];
+}
+
+bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector<double> &roughTables) {
     memset(&m, 0, sizeof(m));
     m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 1.f;
     m.transmittance[0] = m.transmittance[1] = m.transmittance[2] = 1.f;
@@ -131,6 +153,29 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why) {
         ts.spectrum("specularReflectance", from, m.transmittance);                      // dr_material: transmittance = specularReflectance
         size_t nl = str.find("nonlinear = ", from);
         if (nl != std::string::npos && str[nl + 12] == '1') m.flags |= DR_MAT_NONLINEAR;
+    } else if (model == "RoughPlastic") {                 // src/bsdfs/roughplastic.cpp (toString :600-615)
+        m.type = DR_BSDF_ROUGHPLASTIC;
+        float eta = 0.f, alpha = 0.f;
+        if (!ts.scalar("eta", from, eta)) { why = "cannot parse rough plastic eta"; return false; }
+        m.eta[0] = eta;                                   // intIOR / extIOR
+        size_t a = str.find("alpha = ConstantFloatTexture", from);
+        if (a == std::string::npos || !ts.scalar("alpha", from, alpha)) { why = "textured roughness"; return false; }
+        m.alpha = alpha;
+        m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 0.5f;                  // diffuseReflectance default (roughplastic.cpp:200)
+        if (!ts.spectrum("diffuseReflectance", from, m.reflectance)) { why = "textured rough plastic diffuseReflectance"; return false; }
+        if (!ts.spectrum("specularReflectance", from, m.transmittance)) { why = "textured rough plastic specularReflectance"; return false; }
+        size_t d = str.find("distribution = ", from);
+        if (d == std::string::npos) { why = "no distribution"; return false; }
+        if (str.compare(d + 15, 3, "ggx") == 0) m.flags |= DR_MAT_GGX;
+        else if (str.compare(d + 15, 8, "beckmann") != 0) { why = "phong distribution"; return false; }
+        size_t v = str.find("sampleVisible = ", from);
+        if (v != std::string::npos && str[v + 16] == '1') m.flags |= DR_MAT_SAMPLE_VISIBLE;
+        size_t nl = str.find("nonlinear = ", from);
+        if (nl != std::string::npos && str[nl + 12] == '1') m.flags |= DR_MAT_NONLINEAR;
+        // the reference averages the constant alpha texture's Spectrum with a float third before it reaches the tables (spectrum.h:481-486)
+        Float av = 0; av += (Float) m.alpha; av += (Float) m.alpha; av += (Float) m.alpha; av *= (1.0f / 3);
+        m.table = (uint32_t) (roughTables.size() / DR_ROUGH_TABLE_DOUBLES);
+        roughTable((m.flags & DR_MAT_GGX) != 0, (Float) m.eta[0], av, roughTables);
     } else if (model == "RoughDielectric") {              // src/bsdfs/roughdielectric.cpp (toString :659-672)
         if (nested) { why = "twosided rough dielectric"; return false; }
         m.type = DR_BSDF_ROUGHDIELECTRIC;
@@ -248,6 +293,7 @@ public:
         std::vector<uint32_t> I, triMat, triFlags;
         std::vector<int32_t> triEm;
         std::vector<dr_material> mats;
+        std::vector<double> roughTables;           // DR_ROUGH_TABLE_DOUBLES per roughplastic material
         std::vector<dr_emitter> ems;
         bool anyNormals = false;
         // triangle meshes as they are; analytic shapes (rectangle, sphere, disk, cylinder, heightfield: SURVEY 8f rank 4) through the
@@ -269,7 +315,7 @@ public:
             const Shape *owner = meshes[mi].second;
             if (mesh->getVertexTexcoords() && owner == mesh) Log(EWarn, "Mesh \"%s\" has texture coordinates: the shading tangent follows dpdu, not p1-p0", mesh->getName().c_str());
             dr_material mat; std::string why;
-            if (!owner->getBSDF() || !flattenBSDF(owner->getBSDF(), mat, why)) Log(EError, "Mesh \"%s\": %s", owner->getName().c_str(), why.c_str());
+            if (!owner->getBSDF() || !flattenBSDF(owner->getBSDF(), mat, why, roughTables)) Log(EError, "Mesh \"%s\": %s", owner->getName().c_str(), why.c_str());
             mats.push_back(mat);
             const uint32_t base = (uint32_t) (P.size() / 3), firstTri = (uint32_t) triMat.size();
             const Point *pos = mesh->getVertexPositions();
@@ -306,6 +352,7 @@ public:
         desc.positions = P.data(); desc.normals = anyNormals ? N.data() : NULL; desc.indices = I.data();
         desc.tri_material = triMat.data(); desc.tri_emitter = triEm.data(); desc.tri_flags = triFlags.data();
         desc.materials = mats.data(); desc.emitters = ems.empty() ? NULL : ems.data();
+        desc.rough_tables = roughTables.empty() ? NULL : roughTables.data(); desc.n_rough_tables = (uint32_t) (roughTables.size() / DR_ROUGH_TABLE_DOUBLES);
         const Matrix4x4 &tw = cam->getWorldTransform()->eval(0).getMatrix();
         for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) desc.camera.to_world[4 * r + c] = (float) tw(r, c);
         desc.camera.xfov_deg = (float) cam->getXFov();

@@ -44,7 +44,9 @@ typedef enum dr_bsdf_type {
     DR_BSDF_CONDUCTOR = 2,      /* src/bsdfs/conductor.cpp:223-285 */
     DR_BSDF_ROUGHCONDUCTOR = 3, /* src/bsdfs/roughconductor.cpp:250-412 */
     DR_BSDF_ROUGHDIELECTRIC = 4,/* src/bsdfs/roughdielectric.cpp:270-611 (isotropic alpha; uses one extra primary sample per BSDF sample) */
-    DR_BSDF_PLASTIC = 5         /* src/bsdfs/plastic.cpp:240-420: delta specular coating over a diffuse base */
+    DR_BSDF_PLASTIC = 5,        /* src/bsdfs/plastic.cpp:240-420: delta specular coating over a diffuse base */
+    DR_BSDF_ROUGHPLASTIC = 6    /* src/bsdfs/roughplastic.cpp:325-470: microfacet coating over a diffuse base (constant alpha; needs a rough-
+                                   transmittance table, dr_scene_desc.rough_tables) */
 } dr_bsdf_type;
 
 #define DR_MAT_TWOSIDED       1u  /* wrapped in <bsdf type="twosided"> (src/bsdfs/twosided.cpp) */
@@ -59,9 +61,20 @@ typedef struct dr_material {
     float    transmittance[3];  /* dielectric specularTransmittance | plastic: specularReflectance */
     float    eta[3];            /* conductor eta (RGB) | dielectric, roughdielectric, plastic: intIOR/extIOR in eta[0] */
     float    k[3];              /* conductor k (RGB) (plastic: ignored; the library derives its constants here) */
-    float    alpha;             /* roughconductor / roughdielectric alpha (isotropic) */
-    float    _pad;
+    float    alpha;             /* roughconductor / roughdielectric / roughplastic alpha (isotropic) */
+    uint32_t table;             /* roughplastic: index of its table in dr_scene_desc.rough_tables (others: 0) */
 } dr_material;                  /* 64 bytes */
+
+/* Rough Fresnel transmittance of a roughplastic material (src/bsdfs/rtrans.h), reduced to the material's (eta, alpha) as
+ * RoughPlastic::configure does (roughplastic.cpp:283-301): DR_ROUGH_TABLE_DOUBLES doubles per table --
+ *   [0, 100)  m_externalRoughTransmittance after setEta(eta) + setAlpha(alpha): the 100 cos-theta samples that
+ *             RoughTransmittance::eval interpolates (rtrans.h:136-146, evalCubicInterp1D, spline.cpp:23-60)
+ *   [100]     m_internalRoughTransmittance->evalDiffuse(alpha) (after setEta(1 / eta))       (roughplastic.cpp:369)
+ *   [101]     m_externalRoughTransmittance->evalDiffuse(alpha)                               (:307, informative)
+ * The reference reads these from data/microfacet/{beckmann,ggx}.dat; a Mitsuba host gets them from its own RoughTransmittance
+ * (shim/mts_plugin.cpp), other hosts from the .dat files (drmlt_mitsuba_b200/rough_tables.py). */
+#define DR_ROUGH_TABLE_THETA   100
+#define DR_ROUGH_TABLE_DOUBLES 104
 
 /* One area emitter = one emissive triangle mesh (src/emitters/area.cpp:67-215).
  * Its triangles are the contiguous range [first_tri, first_tri + n_tris). */
@@ -93,6 +106,8 @@ typedef struct dr_scene_desc {
     const dr_material *materials;
     const dr_emitter  *emitters;
     dr_camera camera;
+    const double *rough_tables;    /* n_rough_tables * DR_ROUGH_TABLE_DOUBLES, or NULL (no roughplastic material) */
+    uint32_t n_rough_tables;
 } dr_scene_desc;
 
 /* ------------------------------------------------------------------ config */

@@ -386,6 +386,22 @@ int orc_splat_f64(int w, int h, int rfilter, const float *pos, const float *rgb,
 }
 
 // BSDF leaf access for chi-square / consistency tests (modelled on src/tests/test_chisquare.cpp)
+/* roughplastic at leaf level: registers the material's table (DR_ROUGH_TABLE_DOUBLES doubles, as in dr_scene_desc.rough_tables) and
+ * returns the value to store in dr_material.table for the orc_bsdf_* calls below */
+/* RoughTransmittance::eval(cosTheta) of a reduced table (rtrans.h:136-146) */
+double orc_rough_transmittance(const double *table, double cosTheta) {
+    dr_material m{};
+    m.type = DR_BSDF_ROUGHPLASTIC; m.eta[0] = 1.5f; m.reflectance[0] = m.transmittance[0] = 0.5f;
+    m.table = 0;
+    detail::prepareRoughPlastic(m, table);
+    return detail::RoughPlastic(m).T(cosTheta);
+}
+uint32_t orc_rough_table_register(const dr_material *m, const double *table) {
+    dr_material mm = *m;
+    mm.table = 0;
+    detail::prepareRoughPlastic(mm, table);
+    return mm.table;
+}
 void orc_bsdf_sample(const dr_material *m, const double *wi, int mode, double u1, double u2, double *wo, double *weight, double *pdf, int *sampledType) {
     BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), mode);
     Float p = 0;

@@ -4,10 +4,13 @@
 // Restates src/bsdfs/diffuse.cpp:109-150, src/bsdfs/dielectric.cpp:220-340,
 // src/bsdfs/conductor.cpp:223-285, src/bsdfs/roughconductor.cpp:250-412,
 // src/bsdfs/microfacet.h:191-700 (Beckmann + GGX, sampleAll / sampleVisible),
-// src/bsdfs/twosided.cpp:107-195.
+// src/bsdfs/twosided.cpp:107-195; plastic.cpp:240-420; roughplastic.cpp:325-491 with rtrans.h:136-146 and spline.cpp:23-60.
 #pragma once
 #include "orc_math.hpp"
 #include "../include/drmlt_b200.h"
+#include <array>
+#include <deque>
+#include <mutex>
 
 namespace orc {
 
@@ -30,7 +33,7 @@ struct BSDFRecord {
 
 inline RGB rgb3(const float *v) { return RGB(v[0], v[1], v[2]); }
 
-inline bool bsdfHasSmooth(const dr_material &m) { return m.type == DR_BSDF_DIFFUSE || m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC || m.type == DR_BSDF_PLASTIC; }
+inline bool bsdfHasSmooth(const dr_material &m) { return m.type == DR_BSDF_DIFFUSE || m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC || m.type == DR_BSDF_PLASTIC || m.type == DR_BSDF_ROUGHPLASTIC; }
 inline bool bsdfNonSymmetric(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC; }   // dielectric.cpp:201, roughdielectric.cpp:253
 // BSDF::EUsesSampler: sample() draws one more number from the vertex's sampler (roughdielectric.cpp:464, 555)
 inline bool bsdfUsesSampler(const dr_material &m) { return m.type == DR_BSDF_ROUGHDIELECTRIC; }
@@ -242,6 +245,92 @@ struct Plastic {       // SmoothPlastic::configure (plastic.cpp:188-205); dr_mat
     }
 };
 
+// ---------------------------------------------------------------- rough plastic (roughplastic.cpp, rtrans.h)
+// The oracle keeps every table it was given in a process-wide, append-only registry; prepareRoughPlastic re-points
+// dr_material.table at the registry entry, so that the BSDF functions need nothing but the material.
+typedef std::array<double, DR_ROUGH_TABLE_DOUBLES> RoughTable;
+inline std::deque<RoughTable> &roughTableRegistry() { static std::deque<RoughTable> r; return r; }
+inline uint32_t registerRoughTable(const double *t) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    RoughTable a;
+    for (int i = 0; i < DR_ROUGH_TABLE_DOUBLES; ++i) a[i] = t[i];
+    roughTableRegistry().push_back(a);
+    return (uint32_t) (roughTableRegistry().size() - 1);
+}
+// RoughPlastic::configure (roughplastic.cpp:273-277): m_specularSamplingWeight -> slot [102] of the material's own copy of the table
+inline void prepareRoughPlastic(dr_material &m, const double *sceneTables) {
+    if (m.type != DR_BSDF_ROUGHPLASTIC) return;
+    RoughTable t;
+    for (int i = 0; i < DR_ROUGH_TABLE_DOUBLES; ++i) t[i] = sceneTables[(size_t) m.table * DR_ROUGH_TABLE_DOUBLES + i];
+    const Float dAvg = RGB(m.reflectance[0], m.reflectance[1], m.reflectance[2]).luminance();
+    const Float sAvg = RGB(m.transmittance[0], m.transmittance[1], m.transmittance[2]).luminance();
+    t[102] = sAvg / (dAvg + sAvg);
+    m.table = registerRoughTable(t.data());
+}
+// evalCubicInterp1D(x, values, size, min = 0, max = 1) (src/libcore/spline.cpp:23-60)
+inline Float evalCubicInterp1D(Float x, const double *values, size_t size, Float min, Float max) {
+    if (!(x >= min && x <= max)) return 0.0;
+    Float t = ((x - min) * (size - 1)) / (max - min);
+    size_t k = std::max((size_t) 0, std::min((size_t) t, size - 2));
+    Float f0 = values[k], f1 = values[k + 1], d0, d1;
+    if (k > 0) d0 = 0.5f * (values[k + 1] - values[k - 1]); else d0 = values[k + 1] - values[k];
+    if (k + 2 < size) d1 = 0.5f * (values[k + 2] - values[k]); else d1 = values[k + 1] - values[k];
+    t = t - (Float) k;
+    Float t2 = t * t, t3 = t2 * t;
+    return (2 * t3 - 3 * t2 + 1) * f0 + (-2 * t3 + 3 * t2) * f1 + (t3 - 2 * t2 + t) * d0 + (t3 - t2) * d1;
+}
+struct RoughPlastic {   // dr_material: reflectance = diffuse, transmittance = specular, eta[0], alpha, table
+    const double *tab;
+    Float eta, invEta2, specularSamplingWeight;
+    RGB diffuse, specular;
+    bool nonlinear;
+    explicit RoughPlastic(const dr_material &m) {
+        tab = roughTableRegistry()[m.table].data();
+        eta = m.eta[0]; invEta2 = 1.0f / (eta * eta);                  // roughplastic.cpp:279
+        specularSamplingWeight = tab[102];
+        diffuse = rgb3(m.reflectance); specular = rgb3(m.transmittance);
+        nonlinear = (m.flags & DR_MAT_NONLINEAR) != 0;
+    }
+    // m_externalRoughTransmittance->eval(cosTheta, alpha) with eta and alpha fixed (rtrans.h:136-146, 192)
+    Float T(Float cosTheta) const {
+        Float warpedCosTheta = std::pow(std::abs(cosTheta), (Float) 0.25f);
+        if (!(cosTheta >= 0)) return 0.0;
+        Float result = evalCubicInterp1D(warpedCosTheta, tab, DR_ROUGH_TABLE_THETA, 0.0f, 1.0f);
+        return std::min((Float) 1.0f, std::max((Float) 0.0f, result));
+    }
+    Float probSpecular(Float cosThetaI) const {                       // roughplastic.cpp:407-416
+        Float p = 1 - T(cosThetaI);
+        return (p * specularSamplingWeight) / (p * specularSamplingWeight + (1 - p) * (1 - specularSamplingWeight));
+    }
+    RGB eval(const dr_material &m, const Vec3 &wi, const Vec3 &wo) const {   // :339-381
+        Microfacet distr(m);
+        const Vec3 H = normalize(wo + wi);
+        const Float D = distr.eval(H);
+        Float ct;
+        const Float F = fresnelDielectricExt(dot(wi, H), ct, eta);
+        const Float G = distr.G(wi, wo, H);
+        Float value = F * D * G / (4.0f * Frame::cosTheta(wi));
+        RGB result = specular * value;
+        RGB diff = diffuse;
+        Float T12 = T(Frame::cosTheta(wi)), T21 = T(Frame::cosTheta(wo));
+        Float Fdr = 1 - tab[DR_ROUGH_TABLE_THETA];                     // 1 - m_internalRoughTransmittance->evalDiffuse(alpha)
+        if (nonlinear) diff = RGB(diff.r / (1 - diff.r * Fdr), diff.g / (1 - diff.g * Fdr), diff.b / (1 - diff.b * Fdr));
+        else diff = diff * (1.0 / (1 - Fdr));
+        return result + diff * (INV_PI * Frame::cosTheta(wo) * T12 * T21 * invEta2);
+    }
+    Float pdf(const dr_material &m, const Vec3 &wi, const Vec3 &wo) const {   // :396-432
+        Microfacet distr(m);
+        const Vec3 H = normalize(wo + wi);
+        Float pS = probSpecular(Frame::cosTheta(wi)), pD = 1 - pS;
+        const Float dwh_dwo = 1.0f / (4.0f * dot(wo, H));
+        const Float prob = distr.pdf(wi, H);
+        Float result = prob * dwh_dwo * pS;
+        result += pD * squareToCosineHemispherePdf(wo);
+        return result;
+    }
+};
+
 inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
     switch (m.type) {
     case DR_BSDF_DIFFUSE:   // diffuse.cpp:109-117
@@ -262,6 +351,9 @@ inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
         Float model = D * G / (4.0 * Frame::cosTheta(b.wi));
         return F * model;
     }
+    case DR_BSDF_ROUGHPLASTIC:   // roughplastic.cpp:325-381
+        if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
+        return RoughPlastic(m).eval(m, b.wi, b.wo);
     case DR_BSDF_PLASTIC: {   // plastic.cpp:240-277
         if (Frame::cosTheta(b.wo) <= 0 || Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
         Plastic p(m);
@@ -337,6 +429,9 @@ inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
         else
             return distr.pdf(b.wi, H) / (4 * absDot(b.wo, H));
     }
+    case DR_BSDF_ROUGHPLASTIC:   // roughplastic.cpp:383-432
+        if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return 0.0;
+        return RoughPlastic(m).pdf(m, b.wi, b.wo);
     case DR_BSDF_PLASTIC: {   // plastic.cpp:279-307
         if (Frame::cosTheta(b.wo) <= 0 || Frame::cosTheta(b.wi) <= 0) return 0.0;
         Plastic p(m);
@@ -392,6 +487,30 @@ inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
 // `extra`: the number sample() draws from bRec.sampler (EUsesSampler BSDFs; roughdielectric.cpp:555)
 inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const Vec2 &sample, Float epsilon, Float extra) {
     switch (m.type) {
+    case DR_BSDF_ROUGHPLASTIC: {   // roughplastic.cpp:434-491 (both components enabled)
+        if (Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
+        RoughPlastic p(m);
+        Microfacet distr(m);
+        Vec2 s2(sample);
+        const Float probSpecular = p.probSpecular(Frame::cosTheta(b.wi));
+        bool choseSpecular = true;
+        if (s2.y < probSpecular) s2.y /= probSpecular;
+        else { s2.y = (s2.y - probSpecular) / (1 - probSpecular); choseSpecular = false; }
+        if (choseSpecular) {
+            Float unusedPdf;
+            const Vec3 mm = distr.sample(b.wi, s2, unusedPdf, epsilon);
+            b.wo = reflectM(b.wi, mm);
+            b.sampledType = EGlossyReflection;
+            if (Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
+        } else {
+            b.sampledType = EDiffuseReflection;
+            b.wo = squareToCosineHemisphere(s2);
+        }
+        b.eta = 1.0;
+        pdf = (Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) ? 0.0 : p.pdf(m, b.wi, b.wo);
+        if (pdf == 0) return RGB(0.0);
+        return p.eval(m, b.wi, b.wo) * (1.0 / pdf);
+    }
     case DR_BSDF_PLASTIC: {   // plastic.cpp:368-412 (both components enabled)
         if (Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
         Plastic p(m);

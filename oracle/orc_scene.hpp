@@ -12,6 +12,7 @@
 #pragma once
 #include "orc_math.hpp"
 #include "../include/drmlt_b200.h"
+#include <stdexcept>
 
 namespace orc {
 
@@ -158,7 +159,7 @@ struct EmitterRec {
     RGB power() const { return radiance * (PI * area); }   // area.cpp:205
 };
 
-namespace detail { inline void preparePlastic(dr_material &m); }   // orc_bsdf.hpp: constants SmoothPlastic::configure derives
+namespace detail { inline void preparePlastic(dr_material &m); inline void prepareRoughPlastic(dr_material &m, const double *sceneTables); }   // orc_bsdf.hpp: constants SmoothPlastic::configure derives
 
 struct Scene {
     std::vector<Vec3> P, N;
@@ -240,6 +241,11 @@ inline void Scene::load(const dr_scene_desc &d) {
     else triFlags.assign(d.n_triangles, 0);
     mats.assign(d.materials, d.materials + d.n_materials);
     for (dr_material &m : mats) detail::preparePlastic(m);
+    for (dr_material &m : mats)
+        if (m.type == DR_BSDF_ROUGHPLASTIC) {
+            if (!d.rough_tables || m.table >= d.n_rough_tables) throw std::runtime_error("roughplastic material without a rough-transmittance table");
+            detail::prepareRoughPlastic(m, d.rough_tables);
+        }
     for (uint32_t i = 0; i < d.n_triangles; ++i) hasRoughDielectric |= mats[d.tri_material[i]].type == DR_BSDF_ROUGHDIELECTRIC;
     emitters.resize(d.n_emitters);
     emitterPDF.clear();

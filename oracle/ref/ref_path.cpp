@@ -44,12 +44,13 @@
 #include <unistd.h>
 #include <signal.h>
 #include "../../include/drmlt_b200.h"
+#include "src/bsdfs/rtrans.h"                   // RoughTransmittance, as roughplastic.cpp includes it
 #include "src/integrators/pssmlt_utils.h"     // findMaxDimensions, as the integrators include it (drmlt.cpp, pssmlt.cpp)
 
 using namespace mitsuba;
 #define TR(msg) do { if (getenv("REF_TRACE")) fprintf(stderr, "[ref] %s\n", msg); } while (0)
 
-#define REF_PLUGINS(X) X(diffuse) X(dielectric) X(conductor) X(roughconductor) X(roughdielectric) X(plastic) X(twosided) \
+#define REF_PLUGINS(X) X(diffuse) X(dielectric) X(conductor) X(roughconductor) X(roughdielectric) X(plastic) X(roughplastic) X(twosided) \
     X(area) X(rectangle) X(sphere) X(perspective) X(gaussian) X(box) X(tent) X(mitchell) X(catmullrom) X(lanczos) X(independent) X(ldsampler) X(path) X(direct) X(drmlt) X(pssmlt)
 #define X(name) extern "C" void *CreateInstance_##name(const Properties &props);
 REF_PLUGINS(X)
@@ -226,13 +227,15 @@ void initOnce() {
     Spectrum::staticInitialization();
     Scheduler::staticInitialization();
     Thread::getThread()->getLogger()->setLogLevel(getenv("REF_LOG") ? EDebug : EWarn);
+    /* data/microfacet/*.dat (roughplastic, rtrans.h:50-51) is resolved through the thread's FileResolver, as mitsuba.cpp sets it up */
+    Thread::getThread()->getFileResolver()->appendPath(getenv("REF_DATA_ROOT") ? getenv("REF_DATA_ROOT") : "/root/reference");
 }
 
 Spectrum rgbSpectrum(const float *v) { Spectrum s; s.fromLinearRGB(v[0], v[1], v[2]); return s; }
 
 ref<BSDF> makeBSDF(const dr_material &m) {
     PluginManager *pm = PluginManager::getInstance();
-    const char *names[] = { "diffuse", "dielectric", "conductor", "roughconductor", "roughdielectric", "plastic" };
+    const char *names[] = { "diffuse", "dielectric", "conductor", "roughconductor", "roughdielectric", "plastic", "roughplastic" };
     Properties p(names[m.type]);
     switch (m.type) {
         case DR_BSDF_DIFFUSE: p.setSpectrum("reflectance", rgbSpectrum(m.reflectance)); break;
@@ -249,13 +252,14 @@ ref<BSDF> makeBSDF(const dr_material &m) {
             p.setSpectrum("specularReflectance", rgbSpectrum(m.reflectance));
             break;
         case DR_BSDF_PLASTIC:
+        case DR_BSDF_ROUGHPLASTIC:
             p.setFloat("intIOR", (Float) m.eta[0]); p.setFloat("extIOR", 1.0);
             p.setSpectrum("diffuseReflectance", rgbSpectrum(m.reflectance));
             p.setSpectrum("specularReflectance", rgbSpectrum(m.transmittance));
             p.setBoolean("nonlinear", (m.flags & DR_MAT_NONLINEAR) != 0);
             break;
     }
-    if (m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC) {
+    if (m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC || m.type == DR_BSDF_ROUGHPLASTIC) {
         p.setString("distribution", (m.flags & DR_MAT_GGX) ? "ggx" : "beckmann");
         p.setFloat("alpha", (Float) m.alpha);
         p.setBoolean("sampleVisible", (m.flags & DR_MAT_SAMPLE_VISIBLE) != 0);
@@ -276,6 +280,33 @@ ref<BSDF> makeBSDF(const dr_material &m) {
 extern "C" {
 
 void ref_init() { initOnce(); }
+
+/* The reference's own RoughTransmittance (src/bsdfs/rtrans.h), reduced as RoughPlastic::configure reduces it (roughplastic.cpp:283-301):
+ * the DR_ROUGH_TABLE_DOUBLES doubles of include/drmlt_b200.h.  `probe`/`probe_out` (optional): eval(cosTheta) of the reduced
+ * external table at n_probe angles, for the pins of the 1-D interpolation. */
+int ref_rough_table(int ggx, double eta, double alpha, double *table, const double *probe, int n_probe, double *probe_out) {
+    initOnce();
+    try {
+        ref<RoughTransmittance> ext = new RoughTransmittance(ggx ? MicrofacetDistribution::EGGX : MicrofacetDistribution::EBeckmann);
+        ext->checkEta((Float) eta); ext->checkAlpha((Float) alpha);
+        ref<RoughTransmittance> in = ext->clone();
+        ext->setEta((Float) eta);
+        in->setEta(1 / (Float) eta);
+        for (int i = 0; i < DR_ROUGH_TABLE_DOUBLES; ++i) table[i] = 0.0;
+        table[100] = in->evalDiffuse((Float) alpha);
+        ext->setAlpha((Float) alpha);
+        table[101] = ext->evalDiffuse((Float) alpha);
+        /* after setEta + setAlpha the object holds exactly the 100 theta samples (rtrans.h:331-347): read the protected array itself */
+        struct Peek : public RoughTransmittance {
+            static const Float *trans(const RoughTransmittance *r) { return r->*(&Peek::m_trans); }
+            static size_t thetaSamples(const RoughTransmittance *r) { return r->*(&Peek::m_thetaSamples); }
+        };
+        if (Peek::thetaSamples(ext.get()) != DR_ROUGH_TABLE_THETA) throw std::runtime_error("unexpected number of theta samples");
+        for (int k = 0; k < DR_ROUGH_TABLE_THETA; ++k) table[k] = Peek::trans(ext.get())[k];
+        for (int i = 0; i < n_probe; ++i) probe_out[i] = ext->eval((Float) probe[i], (Float) alpha);
+        return 0;
+    } catch (const std::exception &e) { fprintf(stderr, "oracle/_ref: %s\n", e.what()); return 1; }
+}
 
 static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties *integrator = NULL, int sampleCount = 1, bool analytic = false);
 void *ref_scene_create(const dr_scene_desc *d, int rfilter) {

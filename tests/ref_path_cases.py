@@ -28,6 +28,21 @@ def material(type_, flags=0, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta
     return m
 
 
+# roughplastic: (ggx, eta, alpha) of the rough-transmittance tables in tests/golden/ref_rough_tables.npz -- made by the reference's own
+# RoughTransmittance (tools/make_ref_roughplastic_golden.py); eta / alpha are the float values the materials carry
+GOLDEN_ROUGH = os.path.join(ROOT, "tests", "golden", "ref_rough_tables.npz")
+ROUGH_TABLES = {"beckmann_1.49_0.1": (0, 1.49, 0.1), "ggx_1.9_0.3": (1, 1.9, 0.3), "beckmann_1.33_0.05": (0, 1.33, 0.05)}
+ROUGH_OF = {"roughplastic_beckmann": "beckmann_1.49_0.1", "roughplastic_ggx_visible_nonlinear": "ggx_1.9_0.3",
+            "roughplastic_beckmann_visible_twosided": "beckmann_1.33_0.05"}
+_rough_cache = {}
+
+
+def rough_table(key):
+    if not _rough_cache:
+        _rough_cache.update(dict(np.load(GOLDEN_ROUGH)))
+    return np.ascontiguousarray(_rough_cache[key], np.float64)
+
+
 def bsdf_materials():
     T, G, V, N = abi.DR_MAT_TWOSIDED, abi.DR_MAT_GGX, abi.DR_MAT_SAMPLE_VISIBLE, abi.DR_MAT_NONLINEAR
     cu = dict(eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421))
@@ -45,6 +60,9 @@ def bsdf_materials():
         "roughdielectric_beckmann_visible": material(4, V, eta=(1.5, 0, 0), alpha=0.3),
         "plastic": material(5, 0, reflectance=(0.5, 0.3, 0.2), transmittance=(1, 1, 1), eta=(1.49, 0, 0)),
         "plastic_nonlinear": material(5, N, reflectance=(0.2, 0.3, 0.7), transmittance=(0.9, 0.9, 0.9), eta=(1.9, 0, 0)),
+        "roughplastic_beckmann": material(6, 0, reflectance=(0.5, 0.3, 0.2), transmittance=(1, 1, 1), eta=(1.49, 0, 0), alpha=0.1),
+        "roughplastic_ggx_visible_nonlinear": material(6, G | V | N, reflectance=(0.2, 0.3, 0.7), transmittance=(0.9, 0.9, 0.9), eta=(1.9, 0, 0), alpha=0.3),
+        "roughplastic_beckmann_visible_twosided": material(6, V | T, reflectance=(0.4, 0.4, 0.1), transmittance=(1, 0.8, 0.6), eta=(1.33, 0, 0), alpha=0.05),
     }
 
 
@@ -67,6 +85,10 @@ def run_bsdf(lib, prefix, n=600, seed=7):
     ev.argtypes = [C.c_void_p, PD, PD, C.c_int, C.c_int, PD, PD]
     out = {}
     for name, m in bsdf_materials().items():
+        if m.type == abi.DR_BSDF_ROUGHPLASTIC and not is_ref:      # the oracle takes the table, the reference plugin reads its own data file
+            lib.orc_rough_table_register.restype = C.c_uint32
+            lib.orc_rough_table_register.argtypes = [C.c_void_p, PD]
+            m.table = lib.orc_rough_table_register(C.byref(m), rough_table(ROUGH_OF[name]).ctypes.data_as(PD))
         rng = np.random.default_rng(seed)
         two_sided_ok = m.type in (1, 4) or (m.flags & abi.DR_MAT_TWOSIDED)
         wi = _dirs(rng, n, both=bool(two_sided_ok))
@@ -103,6 +125,7 @@ SCENES = {
     "roughglass": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.15, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE)),
     "roughglass-beckmann": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.3, 0)),
     "plastic": lambda: scenes.cornell_box(film=(128, 128), tess=8, plastic=True),
+    "roughplastic": lambda: scenes.cornell_box(film=(128, 128), tess=8, rough_tables=(rough_table("beckmann_1.49_0.1"), rough_table("ggx_1.9_0.3"))),
     # the bench's C5 "door" scene at test size (occluded light, displaced floor, spheres)
     "door": lambda: scenes.door_scene(film=(160, 90), floor_grid=64, n_spheres=16, sphere_subdiv=2),
 }
@@ -112,7 +135,8 @@ PATH_CASES = [("cornell", "mmlt", 6), ("cornell", "bdpt", 5), ("cornell", "path"
               ("caustic", "mmlt", 8), ("caustic", "path", 8),
               ("roughglass", "mmlt", 8), ("roughglass", "path", 6), ("roughglass-beckmann", "bdpt", 5),
               ("plastic", "mmlt", 8), ("plastic", "bdpt", 6), ("plastic", "path", 8),
-              ("door", "mmlt", 8), ("door", "path", 8)]
+              ("door", "mmlt", 8), ("door", "path", 8),
+              ("roughplastic", "mmlt", 8), ("roughplastic", "bdpt", 6), ("roughplastic", "path", 8)]
 N_PATHS = 6000
 N_PATHS_OF = {"door": 48000}      # the door scene's light is occluded: ~1.5 % (MMLT) / 6 % (PT) of uniform vectors contribute
 

@@ -41,6 +41,8 @@ SCENE_MAKERS = {
     "roughglass": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.15, abi.DR_MAT_GGX | abi.DR_MAT_SAMPLE_VISIBLE)),
     "roughglass-beckmann": lambda: scenes.glossy_scene(film=(128, 128), subdiv=3, rough_glass=(0.3, 0)),
     "plastic": lambda: scenes.cornell_box(film=(128, 128), tess=8, plastic=True),
+    # microfacet coating over a diffuse base; the rough-transmittance tables are the reference's own (tests/golden/ref_rough_tables.npz)
+    "roughplastic": lambda: RP.SCENES["roughplastic"](),
     "door": lambda: scenes.door_scene(film=(160, 90), floor_grid=64, n_spheres=16, sphere_subdiv=2),
     # BASELINE.json's own sizes: C3 (~100 k triangles, 512x512), C4 (~97 k, 512x512), C5 (1.0 M triangles, 1280x720) -- the BVH depth and
     # film the bench runs (the oracle side is sampled: 1e5 rays, 4e4 primary-sample vectors)
@@ -208,6 +210,10 @@ CASES = [
     ("plastic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
     ("plastic", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=16)),
     ("plastic", dict(integrator="drmlt", type="mira", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
+    # roughplastic: Beckmann / GGX coating, rough Fresnel transmittance from the data tables (roughplastic.cpp:325-491, rtrans.h)
+    ("roughplastic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("roughplastic", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=16)),
+    ("roughplastic", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
     # film plugin parameters (film.cpp:30-48, perspective.cpp:126-173): crop window, and a film size other than dr_camera's
     ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1,
                      cropOffsetX=24, cropOffsetY=40, cropWidth=64, cropHeight=48)),
@@ -353,6 +359,9 @@ CHAIN_CASES = [
     ("plastic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
     ("plastic", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1)),
     ("plastic", dict(integrator="pssmlt", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False)),
+    ("roughplastic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("roughplastic", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1)),
+    ("roughplastic", dict(integrator="pssmlt", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False)),
 ]
 
 
@@ -681,7 +690,7 @@ def test_equal_mutation_relmse_is_indistinguishable_from_the_oracle(params):
     gpu.close()
 
 
-@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16), ("roughglass", 16), ("roughglass-beckmann", 4), ("plastic", 16)])
+@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16), ("roughglass", 16), ("roughglass-beckmann", 4), ("plastic", 16), ("roughplastic", 16)])
 def test_direct_illumination_pass(name, samples):
     """the separate direct image (renderDirectComponent + the `direct` integrator) on keyed samples."""
     gpu, orc, data = pair(name)

@@ -109,6 +109,8 @@ def _bsdf_tolerance(name):
     # delta, diffuse and Beckmann lobes: bit for bit.  GGX: 2 ulp.
     # Plastic: the reference integrates its internal diffuse reflectance to 1e-5 (util.cpp:864), and the material record
     # (dr_material.k) keeps the two derived constants as float: 1e-7 absolute in the re-scaled sample -> 1e-4 of 1e-3.
+    if "roughplastic" in name:      # tables, Fdr and the sampling weight travel in double: only pow() and summation order differ
+        return 1e-13
     if "plastic" in name:
         return 1e-4
     if "rough" in name:
@@ -481,3 +483,35 @@ def test_oracle_direct_image_matches_reference_direct_integrator(name):
     o.ray_epsilon = o.shadow_epsilon = 0.0
     img = orc.direct_image(o)
     RP.check_direct_image(img[0] if isinstance(img, tuple) else img, gold["direct_" + name], name)
+
+
+# ---------------------------------------------------------------- roughplastic: the rough-transmittance tables
+MICROFACET_DIR = "/root/reference/data/microfacet"
+
+
+@pytest.mark.skipif(not os.path.isdir(MICROFACET_DIR), reason="needs the reference's data/microfacet/*.dat")
+@pytest.mark.parametrize("key", sorted(RP.ROUGH_TABLES))
+def test_rough_table_reduction_equals_reference_rough_transmittance(key):
+    """drmlt_mitsuba_b200/rough_tables.py (what a non-Mitsuba host uses to fill dr_scene_desc.rough_tables) against the reference's own
+    RoughTransmittance::setEta / setAlpha / evalDiffuse (tests/golden/ref_rough_tables.npz): the 100 theta samples and both diffuse
+    transmittances to 1e-15."""
+    from drmlt_mitsuba_b200 import rough_tables
+    ggx, eta, alpha = RP.ROUGH_TABLES[key]
+    got = rough_tables.reduce(os.path.join(MICROFACET_DIR, "ggx.dat" if ggx else "beckmann.dat"), eta, alpha)
+    want = RP.rough_table(key)
+    assert np.abs(got[:102] - want[:102]).max() <= 1e-15
+    with pytest.raises(ValueError):
+        rough_tables.reduce(os.path.join(MICROFACET_DIR, "beckmann.dat"), 9.0, 0.1)       # checkEta (rtrans.h:356-364)
+
+
+@pytest.mark.parametrize("key", sorted(RP.ROUGH_TABLES))
+def test_oracle_rough_transmittance_equals_reference_eval(key):
+    """RoughTransmittance::eval(cosTheta) of the reduced table (rtrans.h:136-146 + evalCubicInterp1D) at 260 angles incl. the
+    out-of-range ones, through the oracle's roughplastic pdf: pdf(wi, wo) - the diffuse part isolates T(cos wi)."""
+    gold = dict(np.load(RP.GOLDEN_ROUGH))
+    lib = C.CDLL(RP.ORACLE)
+    lib.orc_rough_transmittance.restype = C.c_double
+    lib.orc_rough_transmittance.argtypes = [C.POINTER(C.c_double), C.c_double]
+    t = RP.rough_table(key)
+    got = np.array([lib.orc_rough_transmittance(t.ctypes.data_as(C.POINTER(C.c_double)), float(c)) for c in gold["probe"]])
+    assert np.abs(got - gold[key + "_probe"]).max() <= 2e-16
