@@ -626,6 +626,7 @@ static void make_params(const dr_config &c, int W, int H, double b, const int *e
     p.pc.hasRoughDielectric = (typeMask >> DR_BSDF_ROUGHDIELECTRIC) & 1u;
     p.pc.excludeDirect = c.direct_samples >= 0;        // separateDirect (drmlt.cpp:242)
     p.pc.lightImage = c.light_image != 0;
+    p.pc.bdBatch = 0;                                  // (alloc_lanes decides)
     PssParams &pp = p.pp;
     memset(&pp, 0, sizeof(pp));
     pp.seed = c.seed; pp.integrator = c.integrator; pp.type = c.type;
@@ -883,6 +884,14 @@ static dr_status alloc_lanes(dr_job j, int n) {
         ((st = job_alloc(j, &lm.bv, (size_t) 2 * BD_MAXV * n)) || (st = job_alloc(j, &lm.bx, (size_t) 2 * BD_MAXV * n)) ||
          (st = job_alloc(j, &lm.bacc, (size_t) n)) || (st = job_alloc(j, &lm.bsplat, (size_t) 4 * BD_MAXS * 2 * n))))
         return st;
+    // batched connections: all (s, t) pairs of a path in one round (k_bdpt.cu); DRMLT_BD_BATCH=0 keeps one pair per round
+    lm.bdStride = (j->cfg.max_depth + 1) * (j->cfg.max_depth + 2) / 2;
+    const bool bdBatch = j->cfg.technique == DR_TECH_BDPT && lm.bdStride <= BD_MAXC && !(getenv("DRMLT_BD_BATCH") && atoi(getenv("DRMLT_BD_BATCH")) == 0);
+    j->M.pc.bdBatch = bdBatch ? 1 : 0;
+    if (bdBatch &&
+        ((st = job_alloc(j, &lm.bconn, (size_t) lm.bdStride * n)) || (st = job_alloc(j, &lm.brayd, (size_t) 8 * lm.bdStride * n)) ||
+         (st = job_alloc(j, &lm.bvis, (size_t) n, true)) || (st = job_alloc(j, &lm.bpend, (size_t) n, true)) || (st = job_alloc(j, &lm.bcount, (size_t) n, true))))
+        return st;
     // groups of about 1 M lanes -- the persistent traversal kernel needs several rays per resident thread to amortise
     // its latency-bound tail, while >= 3 groups are needed for the stages of different groups to overlap (measured at
     // 4 M lanes: 1 group 110 M mutations/s, 2: 136, 3: 144, 4: 146, 6: 143, 8: 140; at 8 M lanes 8 groups: 148) --
@@ -898,6 +907,9 @@ static dr_status alloc_lanes(dr_job j, int n) {
         gr.q.n = gr.end - gr.begin;
         if ((st = job_alloc(j, &gr.q.items, (size_t) Q_COUNT * gr.q.n)) || (st = job_alloc(j, &gr.q.rays, (size_t) 4 * 2 * gr.q.n)) || (st = job_alloc(j, &gr.q.aux, (size_t) Q_COUNT * gr.q.n, true)) || (st = job_alloc(j, &gr.q.count, (size_t) Q_COUNT + 2, true)))   // + head counters of the two ray queues
             return st;
+        gr.q.bn = bdBatch ? gr.q.n * lm.bdStride : 0;
+        gr.q.bitems = nullptr; gr.q.brays = nullptr;
+        if (bdBatch && ((st = job_alloc(j, &gr.q.bitems, (size_t) 2 * gr.q.bn)) || (st = job_alloc(j, &gr.q.brays, (size_t) 2 * 2 * gr.q.bn)))) return st;
         if (cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&gr.evJoin, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost((void **) &gr.countsHost, sizeof(uint32_t) * Q_COUNT) != cudaSuccess) {
             dr_set_error("group stream creation failed: %s", cudaGetErrorString(cudaGetLastError())); return DR_ERR_CUDA;
         }
@@ -1006,7 +1018,7 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
     for (int g = 0; g < G; ++g) Ms.push_back(machine_for(j, g, job, counters, withFilm));
     const bool mmlt = j->cfg.technique == DR_TECH_MMLT;
     const unsigned typeMask = static_cast<SceneImpl *>(j->scene)->typeMask;
-    const int walkLaunches = mmlt ? 2 : 1;
+    const int walkLaunches = mmlt || j->M.pc.bdBatch ? 2 : 1;
     const int R = j->roundsPerPoll;                             // even: a replay starts at the parity it was captured with
     CK(cudaStreamSynchronize(j->stream));                       // everything queued on the main stream is visible to the groups
     cudaStream_t s0 = j->groups[0].stream;
@@ -1089,7 +1101,7 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
         bool busy = false;
         for (int g = 0; g < G; ++g) {
             const uint32_t *c = j->groups[g].countsHost;
-            busy |= c[Q_RAYC + p] != 0 || c[Q_RAYS + p] != 0 || c[Q_CHAIN + p] != 0;
+            busy |= c[Q_RAYC + p] != 0 || c[Q_RAYS + p] != 0 || c[Q_CHAIN + p] != 0 || c[Q_BDS + p] != 0;
         }
         if (!busy) break;
     }

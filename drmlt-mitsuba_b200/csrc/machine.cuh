@@ -65,7 +65,7 @@
 // ------------------------------------------------------------------ lane records (AoS: one record per lane per array,
 // every record a multiple of 16 bytes, so a lane picked from a queue is fetched with a few 128-bit loads)
 enum { PS_IDLE = 0, PS_START, PS_SENSOR_HIT, PS_EMITTER_HIT, PS_CONNECT, PS_CONNECT_SHADOW, PS_FINISH, PS_EMPTY,
-       PS_PT_HIT, PS_PT_NEE, PS_PT_DONE, PS_BD_EHIT, PS_BD_SHIT, PS_BD_SHADOW, PS_BD_DONE };
+       PS_PT_HIT, PS_PT_NEE, PS_PT_DONE, PS_BD_EHIT, PS_BD_SHIT, PS_BD_SHADOW, PS_BD_DONE, PS_BD_BATCH };
 enum { PH_STAGE1 = 0, PH_STAGE2 = 1, PH_REVERSE = 2, PH_INIT = 3 };
 enum { F_DELTA = 1u, F_ANYCONN = 2u, F_SPOS_FAIL = 4u, F_PT_FIRST = 8u, F_PT_EMITTED = 16u, F_PT_DIRECT = 32u, F_PT_NONSPEC = 64u };
 
@@ -123,7 +123,17 @@ struct alignas(16) BdAcc {            // 128 bytes: the splat list being built (
     Real pdfs[4];                     // the four densities next to the connection in flight (path.cpp:835-859)
     Real pad2[4];
 };
-static_assert(sizeof(BExtra) == 64 && sizeof(BdAcc) == 128, "bdpt records");
+// Batched connections (PathCfg::bdBatch): all (s, t) pairs of a path are evaluated in ONE round -- their shadow rays travel together
+// through the Q_BDS queue, tagged lane * BD_MAXC + connection index -- instead of one pair per round.
+#define BD_MAXC 64                    // connections per path: (maxDepth + 1)(maxDepth + 2) / 2 <= BD_MAXC (one visibility bit each)
+struct alignas(16) BdConn {           // 80 bytes: one evaluated connection waiting for its shadow ray
+    R3 value;                         // prefix_s prefix_t f_s f_t G, MIS weight not yet applied
+    Real pdfs[4];                     // the four densities next to the connection (path.cpp:835-859)
+    float2 spos;                      // t = 1: pixel of the light-image splat
+    uint8_t s, t, needsRay, pad[5];
+    Real pad2;
+};
+static_assert(sizeof(BExtra) == 64 && sizeof(BdAcc) == 128 && sizeof(BdConn) == 80, "bdpt records");
 
 // MIS bookkeeping of the MMLT walks: ONE 32-byte record per walk step, written as a whole sector.
 //   misrec[side][j] = { fwdNext, bwdPrev, conv, - }: written when vertex j of `side` (0 sensor, 1 emitter) has produced
@@ -150,6 +160,13 @@ struct LaneMem {
     BExtra *bx;               // [n][2][BD_MAXV]
     BdAcc *bacc;              // [n]
     float4 *bsplat;           // [n][4][BD_MAXS][2]: light-image splats (pos.xy | rgb) of the lists x, y, z and of the path in flight
+    // ... with batched connections only (else null)
+    BdConn *bconn;            // [n][bdStride] evaluated connections of the path in flight, in the reference's (s, t) order
+    double *brayd;            // [n][bdStride][8] their un-rounded shadow rays
+    unsigned long long *bvis; // [n] bit i: shadow ray of connection i found no occluder
+    uint32_t *bpend;          // [n] shadow rays still in flight
+    uint32_t *bcount;         // [n] connections recorded
+    int bdStride;             // (maxDepth + 1)(maxDepth + 2) / 2
     int n, nU;
     int ubCount, mrSlots;
 };
@@ -176,7 +193,8 @@ template <class T> DR_D void rec_store(T *dst, const T &src) {
 // Q_RAYC / Q_RAYS / Q_CHAIN are double-buffered by round parity: kernels of round r consume [r & 1] and
 // produce into [(r + 1) & 1] (Q_CHAIN is also fed in-round by trace / walk / connect).  Q_WALK, Q_CONNECT, Q_PT and
 // Q_BEGIN are produced and consumed inside one round.
-enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_WALK = 6 /* + bsdf type, 7 */, Q_CONNECT = 13, Q_PT = 14, Q_BEGIN = 15 /* + class, 3 */, Q_COUNT = 18 };
+enum { Q_RAYC = 0, Q_RAYS = 2, Q_CHAIN = 4, Q_BDS = 6 /* x2 parities: batched BDPT shadow rays */, Q_WALK = 8 /* + bsdf type, 7 */, Q_CONNECT = 15, Q_PT = 16,
+       Q_BEGIN = 17 /* + class, 3 */, Q_COUNT = 20 };
 #define N_WALK_CLASSES 7
 // classes of "start the next path" work: each runs one kind of proposal arithmetic on full warps
 enum { BEGIN_STAGE1 = 0, BEGIN_STAGE2 = 1, BEGIN_OTHER = 2 };
@@ -186,6 +204,9 @@ struct Queues {
     uint32_t *count;          // [Q_COUNT] (+ 2 head counters of the ray queues)
     float4 *rays;             // [4][n][2]: the float32 rays of the four ray queues (Q_RAYC x2, Q_RAYS x2), parallel to
                               // items -- the traversal kernels read their input with coalesced, independent loads
+    uint32_t *bitems;         // [2][bn] batched BDPT shadow rays (Q_BDS, by parity): lane * BD_MAXC + connection index
+    float4 *brays;            // [2][bn][2] their float32 rays
+    int bn;                   // capacity per parity: n * bdStride
     int *aux;                 // [Q_COUNT][n]: result of the traversal that queued the lane (leaf-order triangle, -1 = miss),
                               // parallel to items: the consumer reads it coalesced instead of gathering a per-lane record
     int n;
@@ -495,7 +516,7 @@ void trace_init();                                                        // k_t
 void launch_trace(const Machine &M, const LaunchCfg &lc);                 // k_trace.cu: closest + shadow queues
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask);   // k_walk.cu: walk queues of the BSDF types present, then connect
 void launch_pt(const Machine &M, const LaunchCfg &lc);                    // k_pt.cu
-void launch_bdpt(const Machine &M, const LaunchCfg &lc);                  // k_bdpt.cu
+void launch_bdpt(const Machine &M, const LaunchCfg &lc);                  // k_bdpt.cu: (k_bd_shadow: the batched shadow rays,) k_bdpt
 void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu: k_chain (chain step), then k_begin (start of the next path, one class per warp)
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId,
                   const unsigned long long *seedIdx);                     // k_chain.cu: initialise lanes for M.job and queue them

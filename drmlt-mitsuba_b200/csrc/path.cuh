@@ -20,6 +20,7 @@ struct PathCfg {
     int excludeDirect;        // separateDirect (directSamples >= 0)
     int lightImage;
     int hasRoughDielectric;   // some triangle's BSDF draws an extra number per sample (pssmlt_utils.h:35-45)
+    int bdBatch;              // technique=bdpt: all connections of a path in one round (machine.cuh BdConn)
 };
 
 struct PathResult {           // single-splat techniques (path, mmlt)
