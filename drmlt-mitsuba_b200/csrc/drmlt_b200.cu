@@ -840,8 +840,15 @@ static dr_status job_alloc(dr_job j, T **p, size_t count, bool zero = false) {
     return DR_OK;
 }
 
+#ifdef DR_FILM_MATCH_STATS
+void film_match_stats_print();
+#endif
 extern "C" void dr_job_destroy(dr_job j) {
     if (!j) return;
+#ifdef DR_FILM_MATCH_STATS
+    if (j->stream) cudaStreamSynchronize(j->stream);
+    film_match_stats_print();
+#endif
     cudaSetDevice(j->device);                   // (not j->scene->device: a garbage collector may already have destroyed the scene)
     if (j->stream) cudaStreamSynchronize(j->stream);
     for (void *p : j->allocations) cudaFreeAsync(p, j->stream);

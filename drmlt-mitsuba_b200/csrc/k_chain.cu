@@ -565,3 +565,12 @@ void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const
 }
 void launch_resume(const Machine &M, const LaunchCfg &lc) { k_resume_lanes<<<(unsigned) ((lc.nLanes + 127) / 128), 128, 0, lc.stream>>>(M); }
 void launch_flush_pssmlt(const Machine &M, const LaunchCfg &lc) { k_flush_pssmlt<<<(unsigned) ((lc.nLanes + 127) / 128), 128, 0, lc.stream>>>(M); }
+
+#ifdef DR_FILM_MATCH_STATS
+void film_match_stats_print() {
+    unsigned long long h[3] = { 0, 0, 0 };
+    cudaMemcpyFromSymbol(h, g_filmMatch, sizeof(h));
+    fprintf(stderr, "[film_put] %llu splats from k_chain, %llu (%.4f %%) share their filter footprint with another thread splatting at the same time; "
+            "%.1f of 32 threads active per splat\n", h[0], h[1], h[0] ? 100.0 * (double) h[1] / (double) h[0] : 0.0, h[0] ? (double) h[2] / (double) h[0] : 0.0);
+}
+#endif

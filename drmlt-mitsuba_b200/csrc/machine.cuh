@@ -415,11 +415,25 @@ DR_D void emit_ray(const Machine &M, int lane, Core &c, R3 o, R3 d, Real tmin, R
 // ------------------------------------------------------------------ film
 // Splat of one (position, RGB) pair through the tabulated reconstruction filter
 // (ImageBlock::put, include/mitsuba/render/imageblock.h:149-196): one 16-byte vector atomic per touched pixel.
+#ifdef DR_FILM_MATCH_STATS
+// measurement build (tools/build_variant.sh stats -DDR_FILM_MATCH_STATS): how often do two threads that splat at the same time share
+// a filter footprint -- i.e. what a warp-aggregated splat (north_star (e)) could merge?  Printed by dr_job_destroy.
+static __device__ unsigned long long g_filmMatch[3];      // film_put calls | calls whose footprint another active thread shares | threads active per call
+#endif
 static __device__ __noinline__ void film_put(float4 *film, const FilmParams &fp, float2 pos, float3 value) {
     if (!rgb_valid(value)) return;
     const float px = pos.x - 0.5f, py = pos.y - 0.5f;
     const int minx = max((int) ceilf(px - fp.radius), 0), miny = max((int) ceilf(py - fp.radius), 0);
     const int maxx = min((int) floorf(px + fp.radius), fp.w - 1), maxy = min((int) floorf(py + fp.radius), fp.h - 1);
+#ifdef DR_FILM_MATCH_STATS
+    {
+        const unsigned act = __activemask();
+        const unsigned peers = __match_any_sync(act, miny * fp.w + minx);
+        atomicAdd(&g_filmMatch[0], 1ull);
+        if (__popc(peers) > 1) atomicAdd(&g_filmMatch[1], 1ull);
+        atomicAdd(&g_filmMatch[2], (unsigned long long) __popc(act));
+    }
+#endif
     for (int y = miny; y <= maxy; ++y) {
         const float wy = fp.values[min((int) fabsf((y - py) * fp.scaleFactor), 31)];
         for (int x = minx; x <= maxx; ++x) {
