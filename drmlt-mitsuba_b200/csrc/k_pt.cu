@@ -5,7 +5,10 @@
 // the lane holds PtExtra, the sensor-side slot the current shading point.
 #include "machine.cuh"
 
-__global__ void __launch_bounds__(128)
+#ifndef PT_MINB
+#define PT_MINB 2
+#endif
+__global__ void __launch_bounds__(128, PT_MINB)
 k_pt(const __grid_constant__ Machine M) {
     const DevScene &sc = M.sc;
     const PathCfg &pc = M.pc;
