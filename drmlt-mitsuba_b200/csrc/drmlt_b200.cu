@@ -1215,9 +1215,13 @@ static dr_status balance_depths(dr_job j, long long per) {
     double B[32];
     CK(cudaMemcpyAsync(B, j->depthSums, 32 * sizeof(double), cudaMemcpyDeviceToHost, j->stream));
     CK(cudaStreamSynchronize(j->stream));
+    // cost model of a depth-d mutation: (d + c0)^e rays; c0 = 0, e = 1 measured best (DRMLT_DEPTH_COST0 / DRMLT_DEPTH_COST_EXP: tuning aids)
     const double cost0 = getenv("DRMLT_DEPTH_COST0") ? atof(getenv("DRMLT_DEPTH_COST0")) : 0.0;
+    const double costE = getenv("DRMLT_DEPTH_COST_EXP") ? atof(getenv("DRMLT_DEPTH_COST_EXP")) : 1.0;
+    double cost[32];
+    for (int d = 0; d < 32; ++d) cost[d] = std::pow(std::max(0.25, d + 1 + cost0), costE);
     double sumB = 0.0, sumBd = 0.0;
-    for (int d = 0; d < D; ++d) { sumB += B[d]; sumBd += B[d] * (d + 1 + cost0); }
+    for (int d = 0; d < D; ++d) { sumB += B[d]; sumBd += B[d] * cost[d]; }
     if (!(sumB > 0.0)) return DR_OK;
     const double dbar = sumBd / sumB;
     uint32_t scale[256];
@@ -1226,7 +1230,7 @@ static dr_status balance_depths(dr_job j, long long per) {
     auto total = [&](double lambda) {
         double q = 0.0;
         for (int d = 0; d < D; ++d) {
-            scale[d + 1] = (uint32_t) std::min(4294967295.0, std::floor(65536.0 * lambda * dbar / (d + 1 + cost0) + 0.5));
+            scale[d + 1] = (uint32_t) std::min(4294967295.0, std::floor(65536.0 * lambda * dbar / cost[d] + 0.5));
             m[d] = ((long long) per * scale[d + 1]) >> 16;
             if (m[d] < 1) return -1.0;
             q += B[d] / (double) m[d];
