@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DR_ABI_VERSION 4
+#define DR_ABI_VERSION 5     /* 5: dr_scene_desc.rough_tables, dr_material.table, dr_config.depth_balance, dr_scene_create_ex */
 
 /* ------------------------------------------------------------------ status */
 typedef enum dr_status {

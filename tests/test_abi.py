@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 from drmlt_mitsuba_b200 import abi
@@ -25,7 +26,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), "libdrmlt_b200.so does not export %s" % name
     assert sorted(abi.EXPORTED_SYMBOLS) == declared
-    assert lib.dr_abi_version() == 4
+    assert lib.dr_abi_version() == 5
 
 
 def test_struct_layouts_match_header(lib):
@@ -117,3 +118,16 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.dr_scene_create(C.byref(empty), 0, C.byref(h)) == 1
     assert lib.dr_trace_rays(None, None, 1, 0, None) == 1
     assert lib.dr_job_run(None, 1) == 1
+    # roughplastic (roughplastic.cpp:210-222, rtrans.h): needs its rough-transmittance table and eta != 1
+    from drmlt_mitsuba_b200 import scenes
+    for eta, table, needle in ((1.5, None, b"rough-transmittance table"), (1.0, np.zeros(abi.DR_ROUGH_TABLE_DOUBLES), b"must be positive and differ")):
+        data = scenes.SceneData("rp", (16, 16))
+        m = data.add_material(abi.DR_BSDF_ROUGHPLASTIC, eta=(eta, 0, 0), rough_table=np.zeros(abi.DR_ROUGH_TABLE_DOUBLES))
+        data.add_quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0), m)
+        data.set_camera((0, 0, 3), (0, 0, 0), (0, 1, 0), 40.0)
+        desc = data.desc()
+        if table is None:
+            desc.rough_tables = None
+            desc.n_rough_tables = 0
+        assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) == 1 and needle in lib.dr_last_error(), lib.dr_last_error()
+    assert lib.dr_scene_create_ex(None, 0, 1, C.byref(h)) == 1
