@@ -887,6 +887,7 @@ static dr_status alloc_lanes(dr_job j, int n) {
         (st = job_alloc(j, &lm.misrec, (size_t) 2 * lm.mrSlots * MR_WORDS * n)) || (st = job_alloc(j, &lm.conn, (size_t) 4 * n)) || (st = job_alloc(j, &lm.ubuf, (size_t) lm.ubCount * lm.nU * n)) ||
         (st = job_alloc(j, &lm.rayd, (size_t) 8 * n)))
         return st;
+    if (j->cfg.technique == DR_TECH_PATH && ((st = job_alloc(j, &lm.rayd2, (size_t) 8 * n)) || (st = job_alloc(j, &lm.neeOcc, (size_t) n, true)))) return st;
     if (j->cfg.technique == DR_TECH_BDPT &&      // both subpaths and the splat lists are kept per lane
         ((st = job_alloc(j, &lm.bv, (size_t) 2 * BD_MAXV * n)) || (st = job_alloc(j, &lm.bx, (size_t) 2 * BD_MAXV * n)) ||
          (st = job_alloc(j, &lm.bacc, (size_t) n)) || (st = job_alloc(j, &lm.bsplat, (size_t) 4 * BD_MAXS * 2 * n))))

@@ -27,12 +27,19 @@ k_pt(const __grid_constant__ Machine M) {
         Vtx v;
         int dest = Q_CHAIN + M.parity;
         RayF ray;
-        enum { GO_HIT, GO_SHADE, GO_BSDF, GO_DONE } go = c.pstate == PS_PT_NEE ? GO_BSDF : GO_HIT;
-        if (c.pstate == PS_PT_NEE) {                         // the shadow ray of the direct-illumination sample arrived
-            if (hit.tri < 0) px.Li += px.pending;
-            rec_load(v, M.lm.vt + lane);
-            c.d = px.dIn;                                    // incoming direction at v
+        // The direct-illumination sample of a vertex and the BSDF-sampled ray that continues the path leave in the SAME round
+        // (a path costs one round per vertex instead of two): the shadow ray is queued with Q_DEFERRED, the traversal writes its
+        // verdict to neeOcc[lane], and the lane -- back with its BSDF-sampled ray -- adds the pending contribution first, i.e. in
+        // the reference's order (path.cpp:196-221 before :222-290).  Only the shadow ray of a path's LAST vertex brings the lane back itself.
+        enum { GO_HIT, GO_SHADE, GO_BSDF, GO_DONE } go = c.pstate == PS_PT_NEE ? GO_DONE : GO_HIT;
+        if (c.flags & F_PT_NEEPEND) {
+            if (!M.lm.neeOcc[lane]) px.Li += px.pending;
+            c.flags &= ~F_PT_NEEPEND;
         }
+        if (c.pstate == PS_PT_NEE && hit.tri < 0) px.Li += px.pending;      // the last vertex's shadow ray arrived
+        bool haveShadow = false;                             // this vertex's direct-illumination sample needs its shadow ray
+        R3 shO = r3(0.), shD = r3(0.);
+        Real shMax = 0.;
         for (bool running = true; running;) {
             switch (go) {
             case GO_HIT: {                                   // the camera ray or a BSDF-sampled ray arrived
@@ -97,11 +104,7 @@ k_pt(const __grid_constant__ Machine M) {
                             const Real bp = bsdf_pdf(m, wi, wo, MEAS_SOLID_ANGLE);
                             px.pending = c.weight * value * bsdfVal * ((pdf * pdf) / (pdf * pdf + bp * bp));
                         }
-                        c.pstate = PS_PT_NEE;
-                        emit_ray(M, lane, c, v.p, dd, sc.epsilon, dist * (1. - sc.shadowEpsilon), ray);
-                        dest = Q_RAYS + (M.parity ^ 1);
-                        running = false;
-                        break;
+                        haveShadow = true; shO = v.p; shD = dd; shMax = dist * (1. - sc.shadowEpsilon);
                     }
                 }
                 go = GO_BSDF;
@@ -125,11 +128,28 @@ k_pt(const __grid_constant__ Machine M) {
                 c.pstate = PS_PT_HIT;
                 emit_ray(M, lane, c, v.p, to_world(v, bs.wo), sc.epsilon, INFINITY, ray);
                 dest = Q_RAYC + (M.parity ^ 1);
+                if (haveShadow) {                            // ... and the shadow ray beside it
+                    Real tmin = sc.epsilon;
+                    tmin *= fmax(fmax(fmax(fabs(shO.x), fabs(shO.y)), fabs(shO.z)), (Real) sc.epsilon);       // as emit_ray
+                    RayF sh;
+                    sh.a = make_float4((float) shO.x, (float) shO.y, (float) shO.z, (float) tmin);
+                    sh.b = make_float4((float) shD.x, (float) shD.y, (float) shD.z, (float) shMax);
+                    double2 *r2 = reinterpret_cast<double2 *>(M.lm.rayd2 + 8 * (size_t) lane);
+                    r2[0] = make_double2(shO.x, shO.y); r2[1] = make_double2(shO.z, shD.x); r2[2] = make_double2(shD.y, shD.z); r2[3] = make_double2(tmin, shMax);
+                    ++c.nrays;
+                    c.flags |= F_PT_NEEPEND;
+                    q_push_ray(M.q, Q_RAYS + (M.parity ^ 1), (uint32_t) lane | Q_DEFERRED, sh);
+                    haveShadow = false;
+                }
                 running = false;
                 break;
             }
             default:
-                c.pstate = PS_PT_DONE;
+                if (haveShadow) {                            // the path ends here, but its last direct-illumination sample is still to be resolved
+                    c.pstate = PS_PT_NEE;
+                    emit_ray(M, lane, c, shO, shD, sc.epsilon, shMax, ray);
+                    dest = Q_RAYS + (M.parity ^ 1);
+                } else c.pstate = PS_PT_DONE;
                 running = false;
                 break;
             }

@@ -43,8 +43,9 @@ k_trace(const __grid_constant__ Machine M) {
                         const uint32_t k = shadow ? qi - cntC : qi;
                         const float4 *rays = shadow ? raysS : raysC;
                         const float4 a = __ldcs(rays + 2 * (size_t) k), b = __ldcs(rays + 2 * (size_t) k + 1);
-                        lane = (int) __ldcs((shadow ? itemsS : itemsC) + k);
-                        tr.begin(stack, shadow, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, M.lm.rayd + 8 * (size_t) lane);
+                        lane = (int) __ldcs((shadow ? itemsS : itemsC) + k);      // (shadow queue of technique=path: may carry Q_DEFERRED)
+                        const double *rayd = (lane & Q_DEFERRED) ? M.lm.rayd2 + 8 * (size_t) (lane & ~Q_DEFERRED) : M.lm.rayd + 8 * (size_t) lane;
+                        tr.begin(stack, shadow, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, rayd);
                     }
                 }
                 exhausted = base + (uint32_t) __popc(idle) >= cnt;
@@ -72,7 +73,8 @@ k_trace(const __grid_constant__ Machine M) {
                     const uint32_t mf = (uint32_t) __float_as_int(__ldg(&M.sc.tris[3 * (size_t) tr.hit.tri + 2].z));
                     dest = Q_WALK + (int) ((mf >> 24) & 7u);
                 }
-                q_push_hit(M.q, dest, (uint32_t) lane, found ? tr.hit.tri : -1);
+                if (lane & Q_DEFERRED) M.lm.neeOcc[lane & ~Q_DEFERRED] = found ? 1 : 0;   // the lane comes back with its BSDF-sampled ray
+                else q_push_hit(M.q, dest, (uint32_t) lane, found ? tr.hit.tri : -1);
                 lane = -1;
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, lane >= 0));

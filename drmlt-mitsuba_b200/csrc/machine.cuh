@@ -67,7 +67,9 @@
 enum { PS_IDLE = 0, PS_START, PS_SENSOR_HIT, PS_EMITTER_HIT, PS_CONNECT, PS_CONNECT_SHADOW, PS_FINISH, PS_EMPTY,
        PS_PT_HIT, PS_PT_NEE, PS_PT_DONE, PS_BD_EHIT, PS_BD_SHIT, PS_BD_SHADOW, PS_BD_DONE, PS_BD_BATCH };
 enum { PH_STAGE1 = 0, PH_STAGE2 = 1, PH_REVERSE = 2, PH_INIT = 3 };
-enum { F_DELTA = 1u, F_ANYCONN = 2u, F_SPOS_FAIL = 4u, F_PT_FIRST = 8u, F_PT_EMITTED = 16u, F_PT_DIRECT = 32u, F_PT_NONSPEC = 64u };
+enum { F_DELTA = 1u, F_ANYCONN = 2u, F_SPOS_FAIL = 4u, F_PT_FIRST = 8u, F_PT_EMITTED = 16u, F_PT_DIRECT = 32u, F_PT_NONSPEC = 64u,
+       F_PT_NEEPEND = 128u /* the shadow ray of the previous vertex's direct-illumination sample travels beside the BSDF-sampled ray */ };
+#define Q_DEFERRED 0x40000000u        /* shadow-queue item: lane | Q_DEFERRED = the result goes to LaneMem::neeOcc, the lane is not queued (k_pt.cu) */
 
 struct alignas(16) Core {     // 128 bytes
     uint8_t pstate, s, t, j;          // path in flight: state, strategy, vertices walked on the current side
@@ -155,6 +157,9 @@ struct LaneMem {
     double *ubuf;             // [n][ubCount][nU] coordinate buffers X, Y (pssmlt), Z (drmlt), R (green): only the buffers the
                               //   integrator can touch are allocated
     double *rayd;             // [n][8] o, d, tmin, tmax of the same ray un-rounded (deciding triangle tests)
+    // technique=path only (else null): the deferred direct-illumination shadow ray of a lane (k_pt.cu)
+    double *rayd2;            // [n][8] its un-rounded ray
+    int *neeOcc;              // [n] 1: it found an occluder
     // technique=bdpt only (else null)
     Vtx *bv;                  // [n][2][BD_MAXV] subpath vertices
     BExtra *bx;               // [n][2][BD_MAXV]
