@@ -1146,7 +1146,8 @@ static long long bootstrap_samples(const dr_job j) {
     // The image is scaled by b, so the relative error of b is a floor of the image error.  On the GPU a bootstrap path
     // costs about as much as a mutation: spend 1/8 of the mutation budget on it (profiles/r01_g_chain_length_study.json:
     // 16 M instead of 0.8 M bootstrap paths lower relMSE 4-10x at 59 M mutations for +0.2 s).
-    n = std::max(n, std::min<long long>(total / 8, 1ll << 26));   // (capped: 64 M samples = 0.8 GB of luminances + CDF per GPU)
+    const long long div = getenv("DRMLT_BOOT_DIV") ? std::max(1, atoi(getenv("DRMLT_BOOT_DIV"))) : 8;   // (tuning aid)
+    n = std::max(n, std::min<long long>(total / div, 1ll << 26));   // (capped: 64 M samples = 0.8 GB of luminances + CDF per GPU)
     return n;
 }
 
