@@ -1092,7 +1092,7 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
             dr_status st = join_groups(j);
             if (st) return st;
         }
-        j->launches += (uint64_t) R * G * (1 + walkLaunches + 2);
+        for (int g = 0; g < G; ++g) j->launches += (uint64_t) R * (1 + walkLaunches + (chain_begin_fused(j->groups[g].end - j->groups[g].begin, j->cfg.integrator) ? 1 : 2));
         if (!j->profEvents.empty()) {
             for (size_t i = 0; i + 3 < j->profEvents.size(); i += 4)
                 for (int s = 0; s < STAGE_COUNT; ++s) {

@@ -189,6 +189,10 @@ DR_D void chain_init(const Machine &M, int lane, Core &c, const int *depthIn, co
 
 // ------------------------------------------------------------------ the chain kernel
 
+// FUSED: the lane's next path is started here instead of by k_begin -- one launch (and its ~20 us latency floor) less per round.  For
+// small PSSMLT groups only (one proposal class): C1 +6 %; with drmlt's three proposal classes diverging inside a warp it loses 2-3 % on
+// C2 / C3 / C4 and more at C5 size (164 registers).
+template <bool FUSED>
 __global__ void __launch_bounds__(128, CHAIN_MINB)
 k_chain(const __grid_constant__ Machine M) {
     const JobParams &job = M.job;
@@ -200,6 +204,7 @@ k_chain(const __grid_constant__ Machine M) {
     uint32_t st[ST_COUNT];
 #pragma unroll
     for (int i = 0; i < ST_COUNT; ++i) st[i] = 0;
+    if (FUSED) queues_recycle(M.q);                           // (the last kernel of the round empties the in-round queues)
     const uint32_t cnt = M.q.count[Q_CHAIN + M.parity];
     const uint32_t *items = M.q.items + (size_t) (Q_CHAIN + M.parity) * M.q.n;
     for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < cnt; qi += gridDim.x * blockDim.x) {
@@ -463,6 +468,13 @@ k_chain(const __grid_constant__ Machine M) {
             break;
         }
         // ================= start the lane's next path: mutate the proposal, emit its first ray (begin.cuh) =================
+        if (FUSED && c.pstate == PS_START) {
+            RayF ray;
+            const int dest = begin_path(M, lane, c, ray);
+            rec_store(M.lm.core + lane, c);
+            q_push_ray(M.q, dest, (uint32_t) lane, ray);
+            continue;
+        }
         rec_store(M.lm.core + lane, c);
         if (c.pstate == PS_START)
             q_push(M.q, Q_BEGIN + (job.type != JOB_CHAIN ? BEGIN_OTHER : (c.phase == PH_STAGE1 ? BEGIN_STAGE1 : (c.phase == PH_STAGE2 ? BEGIN_STAGE2 : BEGIN_OTHER))), (uint32_t) lane);
@@ -556,8 +568,15 @@ k_begin(const __grid_constant__ Machine M) {
     }
 }
 
+// groups of up to this many lanes start the next path inside k_chain (DRMLT_FUSE_BEGIN_LANES overrides; 0 = never)
+static int fuse_begin_lanes() {
+    static const int v = getenv("DRMLT_FUSE_BEGIN_LANES") ? atoi(getenv("DRMLT_FUSE_BEGIN_LANES")) : 131072;
+    return v;
+}
+bool chain_begin_fused(int nLanes, int integrator) { return integrator == DR_INTEGRATOR_PSSMLT && nLanes <= fuse_begin_lanes(); }
 void launch_chain(const Machine &M, const LaunchCfg &lc) {
-    k_chain<<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M);
+    if (chain_begin_fused(lc.nLanes, M.pp.integrator)) { k_chain<true><<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M); return; }
+    k_chain<false><<<grid_for(lc.nLanes, 128), 128, 0, lc.stream>>>(M);
     k_begin<<<grid_for(lc.nLanes + 3 * 128, 128), 128, 0, lc.stream>>>(M);
 }
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId, const unsigned long long *seedIdx) {

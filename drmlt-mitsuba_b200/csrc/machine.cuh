@@ -536,6 +536,7 @@ void launch_trace(const Machine &M, const LaunchCfg &lc);                 // k_t
 void launch_walk(const Machine &M, const LaunchCfg &lc, unsigned typeMask);   // k_walk.cu: walk queues of the BSDF types present, then connect
 void launch_pt(const Machine &M, const LaunchCfg &lc);                    // k_pt.cu
 void launch_bdpt(const Machine &M, const LaunchCfg &lc);                  // k_bdpt.cu: (k_bd_shadow: the batched shadow rays,) k_bdpt
+bool chain_begin_fused(int nLanes, int integrator);                       // k_chain.cu: small pssmlt groups start the next path inside k_chain (no k_begin launch)
 void launch_chain(const Machine &M, const LaunchCfg &lc);                 // k_chain.cu: k_chain (chain step), then k_begin (start of the next path, one class per warp)
 void launch_setup(const Machine &M, const LaunchCfg &lc, const int *depth, const unsigned long long *chainId,
                   const unsigned long long *seedIdx);                     // k_chain.cu: initialise lanes for M.job and queue them
