@@ -15,7 +15,17 @@ DR_OK = 0
 DR_BSDF_DIFFUSE, DR_BSDF_DIELECTRIC, DR_BSDF_CONDUCTOR, DR_BSDF_ROUGHCONDUCTOR, DR_BSDF_ROUGHDIELECTRIC, DR_BSDF_PLASTIC, DR_BSDF_ROUGHPLASTIC = 0, 1, 2, 3, 4, 5, 6
 DR_ROUGH_TABLE_THETA, DR_ROUGH_TABLE_DOUBLES = 100, 104
 DR_MAT_TWOSIDED, DR_MAT_GGX, DR_MAT_SAMPLE_VISIBLE, DR_MAT_NONLINEAR = 1, 2, 4, 8
-DR_TRI_SMOOTH = 1
+DR_TRI_SMOOTH, DR_TRI_UV_TANGENTS, DR_TRI_NO_TEXCOORDS = 1, 2, 4
+DR_WRAP_REPEAT, DR_WRAP_CLAMP, DR_WRAP_MIRROR, DR_WRAP_ZERO, DR_WRAP_ONE = range(5)
+DR_MAX_TEXTURES = 4095
+
+
+def DR_MAT_TEX_REFLECTANCE(i):
+    return ((i + 1) & 0xfff) << 8
+
+
+def DR_MAT_TEX_TRANSMITTANCE(i):
+    return ((i + 1) & 0xfff) << 20
 DR_INTEGRATOR_PSSMLT, DR_INTEGRATOR_DRMLT = 0, 1
 DR_TECH_PATH, DR_TECH_BDPT, DR_TECH_MMLT = 0, 1, 2
 DR_TYPE_GREEN, DR_TYPE_MIRA, DR_TYPE_ORBITAL = 0, 1, 2
@@ -28,6 +38,12 @@ class dr_material(C.Structure):
                 ("reflectance", C.c_float * 3), ("transmittance", C.c_float * 3),
                 ("eta", C.c_float * 3), ("k", C.c_float * 3),
                 ("alpha", C.c_float), ("table", C.c_uint32)]
+
+
+class dr_texture(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("texels", C.POINTER(C.c_float)),
+                ("wrap_u", C.c_uint32), ("wrap_v", C.c_uint32), ("nearest", C.c_uint32), ("pad", C.c_uint32),
+                ("uv_scale", C.c_double * 2), ("uv_offset", C.c_double * 2)]
 
 
 class dr_emitter(C.Structure):
@@ -48,7 +64,8 @@ class dr_scene_desc(C.Structure):
                 ("indices", C.POINTER(C.c_uint32)), ("tri_material", C.POINTER(C.c_uint32)),
                 ("tri_emitter", C.POINTER(C.c_int32)), ("tri_flags", C.POINTER(C.c_uint32)),
                 ("materials", C.POINTER(dr_material)), ("emitters", C.POINTER(dr_emitter)),
-                ("camera", dr_camera), ("rough_tables", C.POINTER(C.c_double)), ("n_rough_tables", C.c_uint32)]
+                ("camera", dr_camera), ("rough_tables", C.POINTER(C.c_double)), ("n_rough_tables", C.c_uint32),
+                ("n_textures", C.c_uint32), ("texcoords", C.POINTER(C.c_float)), ("textures", C.POINTER(dr_texture))]
 
 
 class dr_config(C.Structure):

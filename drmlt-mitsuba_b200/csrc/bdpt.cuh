@@ -20,7 +20,7 @@ DR_D bool bd_roulette(const Machine &M, Core &c, UReader &rd, int sampler, int i
 // BSDF sampling step at surface vertex j of `side`; emits the ray on success
 DR_D bool bd_sample_surface(const Machine &M, int lane, Core &c, UReader &rd, int side, int j, const Vtx &v, R3 predP, RayF &ray) {
     const int mode = side == BD_E ? MODE_IMPORTANCE : MODE_RADIANCE;
-    const Mat m = load_material(M.sc, v.mat);
+    const Mat m = load_material(M.sc, v.mat, v.uv);
     WalkStep ws;
     const R2 u = rd.next2D(side == BD_E ? SMP_EMITTER : SMP_SENSOR);
     const Real uz = mat_uses_sampler(m.type) ? rd.next1D(side == BD_E ? SMP_EMITTER : SMP_SENSOR) : 0.5;   // bRec.sampler->next1D()

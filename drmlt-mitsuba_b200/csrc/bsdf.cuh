@@ -31,6 +31,46 @@ DR_D Mat load_material(const DevScene &sc, int id) {
     m.table = m.type == DR_BSDF_ROUGHPLASTIC ? sc.roughTables + (size_t) __float_as_uint(d.w) * DR_ROUGH_TABLE_DOUBLES : nullptr;
     return m;
 }
+// Bitmap texture lookup without ray differentials: BitmapTexture::eval(uv) (bitmap.cpp:432-455) -> MIPMap::evalBilinear(0, uv) /
+// evalBox(0, uv) with evalTexel's boundary conditions (mipmap.h:503-596), after Texture2D::eval's scale and offset (texture.cpp:112-121).
+DR_D bool tex_wrap(uint32_t mode, int &x, int size, Real &constant) {      // false: the texel is the constant (zero / one)
+    if (x >= 0 && x < size) return true;
+    switch (mode) {
+        case DR_WRAP_REPEAT: { const int r = x % size; x = r < 0 ? r + size : r; return true; }
+        case DR_WRAP_CLAMP: x = min(max(x, 0), size - 1); return true;
+        case DR_WRAP_MIRROR: { const int r = x % (2 * size); x = r < 0 ? r + 2 * size : r; if (x >= size) x = 2 * size - x - 1; return true; }
+        case DR_WRAP_ZERO: constant = 0.; return false;
+        default: constant = 1.; return false;
+    }
+}
+DR_D R3 tex_texel(const DevScene &sc, const DevTexture &t, int x, int y) {
+    Real c = 0.;
+    if (!tex_wrap(t.wrapU, x, (int) t.w, c)) return r3(c);
+    if (!tex_wrap(t.wrapV, y, (int) t.h, c)) return r3(c);
+    const float4 v = __ldg(sc.texels + t.first + (size_t) y * t.w + (size_t) x);
+    return r3(v.x, v.y, v.z);
+}
+static __device__ __noinline__ R3 tex_eval(const DevScene &sc, uint32_t id, R2 uvIn) {
+    const DevTexture t = sc.textures[id];
+    const Real ux = uvIn.x * t.scaleU + t.offU, uy = uvIn.y * t.scaleV + t.offV;
+    if (t.nearest) return tex_texel(sc, t, (int) floor(ux * (Real) t.w), (int) floor(uy * (Real) t.h));
+    if (!isfinite(ux) || !isfinite(uy)) return r3(0.);
+    const Real u = ux * (Real) t.w - 0.5f, v = uy * (Real) t.h - 0.5f;
+    const int xPos = (int) floor(u), yPos = (int) floor(v);
+    const Real dx1 = u - xPos, dx2 = 1.0f - dx1, dy1 = v - yPos, dy2 = 1.0f - dy1;
+    return tex_texel(sc, t, xPos, yPos) * dx2 * dy2 + tex_texel(sc, t, xPos, yPos + 1) * dx2 * dy1
+         + tex_texel(sc, t, xPos + 1, yPos) * dx1 * dy2 + tex_texel(sc, t, xPos + 1, yPos + 1) * dx1 * dy1;
+}
+// the material of a surface vertex: textured colour parameters (DR_MAT_TEX_*) are looked up at the vertex' uv
+DR_D Mat load_material(const DevScene &sc, int id, R2 uv) {
+    Mat m = load_material(sc, id);
+    if (m.flags >> 8) {
+        const uint32_t tr = (m.flags >> 8) & 0xfffu, tt = m.flags >> 20;
+        if (tr) m.refl = tex_eval(sc, tr - 1u, uv);
+        if (tt) m.trans = tex_eval(sc, tt - 1u, uv);
+    }
+    return m;
+}
 DR_D bool mat_has_smooth(int type) { return type == DR_BSDF_DIFFUSE || type == DR_BSDF_ROUGHCONDUCTOR || type == DR_BSDF_ROUGHDIELECTRIC || type == DR_BSDF_PLASTIC || type == DR_BSDF_ROUGHPLASTIC; }
 DR_D bool mat_non_symmetric(int type) { return type == DR_BSDF_DIELECTRIC || type == DR_BSDF_ROUGHDIELECTRIC; }
 DR_D bool mat_transmissive_or_backside(const Mat &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC || (m.flags & DR_MAT_TWOSIDED); }

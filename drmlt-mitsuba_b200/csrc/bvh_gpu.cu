@@ -215,7 +215,7 @@ struct Arena {
 
 // triangle records of scene.h in leaf order, from the caller's arrays (what dr_scene_create's host loop does for the host build)
 __global__ void k_pack_triangles(const float *P, const float *N, const uint32_t *I, const uint32_t *order, const uint32_t *triMat, const int32_t *triEm,
-                                 const uint32_t *triFlags, const int32_t *matType, uint32_t n, int anySmooth, float4 *tris, float4 *normals) {
+                                 const uint32_t *triFlags, const int32_t *matType, uint32_t n, int anySmooth, int hasUV, float4 *tris, float4 *normals) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n) return;
     const uint32_t prim = order[slot];
@@ -223,7 +223,8 @@ __global__ void k_pack_triangles(const float *P, const float *N, const uint32_t 
     const float *p0 = P + 3 * (size_t) i0, *p1 = P + 3 * (size_t) i1, *p2 = P + 3 * (size_t) i2;
     const bool smooth = anySmooth && triFlags && (triFlags[prim] & DR_TRI_SMOOTH);
     const uint32_t m = triMat[prim];
-    const uint32_t mf = m | ((uint32_t) matType[m] << 24) | (smooth ? 0x80000000u : 0u);
+    const uint32_t mf = m | ((uint32_t) matType[m] << 24) | (smooth ? 0x80000000u : 0u) |
+                        (hasUV && !(triFlags && (triFlags[prim] & DR_TRI_NO_TEXCOORDS)) ? DR_MF_HAS_UV | (triFlags && (triFlags[prim] & DR_TRI_UV_TANGENTS) ? DR_MF_UV_TANGENTS : 0u) : 0u);
     tris[3 * (size_t) slot] = make_float4(p0[0], p0[1], p0[2], p1[0]);
     tris[3 * (size_t) slot + 1] = make_float4(p1[1], p1[2], p2[0], p2[1]);
     tris[3 * (size_t) slot + 2] = make_float4(p2[2], __int_as_float((int) prim), __int_as_float((int) mf), __int_as_float(triEm[prim]));
@@ -311,7 +312,7 @@ bool build_scene_gpu(const dr_scene_desc *d, bool anySmooth, int stackLimit, Gpu
     if (anySmooth) CKB(cudaMemcpyAsync(dN, d->normals, 3 * nVerts * sizeof(float), cudaMemcpyHostToDevice, 0));
     CKB(cudaMemcpyAsync(matType, types.data(), types.size() * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
     k_pack_triangles<<<blocks, 256>>>(dP, anySmooth ? dN : nullptr, dI, out.order, triMat, triEm, d->tri_flags ? triFlags : nullptr, matType, (uint32_t) n,
-                                      anySmooth ? 1 : 0, out.tris, out.normals);
+                                      anySmooth ? 1 : 0, d->texcoords ? 1 : 0, out.tris, out.normals);
     Bounds b;
     CKB(cudaMemcpy(&b, dBounds, sizeof(b), cudaMemcpyDeviceToHost));
     // child boxes are padded by a few 1e-6 of the scene extent, as in the host build (the traversal tests them with the float-cast ray)

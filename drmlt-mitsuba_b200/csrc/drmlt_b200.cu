@@ -298,6 +298,12 @@ static dr_status ensure_staging(SceneImpl *s) {
 }
 
 static float as_float_bits(int i) { float f; memcpy(&f, &i, 4); return f; }
+// texture-coordinate bits of a triangle record (scene.h): the mesh has texture coordinates | it carries UV tangents
+static uint32_t tri_uv_bits(const dr_scene_desc *d, size_t prim) {
+    const uint32_t f = d->tri_flags ? d->tri_flags[prim] : 0u;
+    if (!d->texcoords || (f & DR_TRI_NO_TEXCOORDS)) return 0u;
+    return DR_MF_HAS_UV | ((f & DR_TRI_UV_TANGENTS) ? DR_MF_UV_TANGENTS : 0u);
+}
 
 // fresnelDiffuseReflectance(eta, fast = false) (src/libcore/util.cpp:815-867): integral of the unpolarised Fresnel
 // reflectance F(sqrt(xi), eta) over xi in [0, 1].  The reference integrates with an adaptive Gauss-Lobatto rule to a relative
@@ -374,6 +380,24 @@ extern "C" dr_status dr_scene_create_ex(const dr_scene_desc *d, int device, uint
             if (!(mat.eta[0] > 0.f) || mat.eta[0] == 1.f) { dr_set_error("The interior and exterior indices of refraction must be positive and differ!"); return DR_ERR_INVALID_ARG; }
         }
     }
+    // bitmap textures (ABI 6)
+    if (d->n_textures > DR_MAX_TEXTURES || (d->n_textures && !d->textures)) { dr_set_error("dr_scene_create: bad texture table"); return DR_ERR_INVALID_ARG; }
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        const dr_texture &tx = d->textures[t];
+        if (!tx.texels || tx.width == 0 || tx.height == 0 || tx.width > (1u << 15) || tx.height > (1u << 15) || tx.wrap_u > DR_WRAP_ONE || tx.wrap_v > DR_WRAP_ONE) {
+            dr_set_error("texture %u: missing texels, bad size or wrap mode", t); return DR_ERR_INVALID_ARG;
+        }
+    }
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const uint32_t tr = (d->materials[m].flags >> 8) & 0xfffu, tt = d->materials[m].flags >> 20;
+        if (tr > d->n_textures || tt > d->n_textures) { dr_set_error("material %u: texture index out of range", m); return DR_ERR_INVALID_ARG; }
+    }
+    if (!d->texcoords && d->tri_flags)
+        for (uint32_t i = 0; i < d->n_triangles; ++i)
+            if (d->tri_flags[i] & DR_TRI_UV_TANGENTS) { dr_set_error("triangle %u: DR_TRI_UV_TANGENTS without texcoords", i); return DR_ERR_INVALID_ARG; }
+    if (d->tri_flags)
+        for (uint32_t i = 0; i < d->n_triangles; ++i)
+            if ((d->tri_flags[i] & DR_TRI_UV_TANGENTS) && (d->tri_flags[i] & DR_TRI_NO_TEXCOORDS)) { dr_set_error("triangle %u: DR_TRI_UV_TANGENTS on a mesh without texcoords", i); return DR_ERR_INVALID_ARG; }
     for (uint32_t e = 0; e < d->n_emitters; ++e) {
         const dr_emitter &em = d->emitters[e];
         if (em.n_tris == 0 || (uint64_t) em.first_tri + em.n_tris > d->n_triangles) { dr_set_error("emitter %u: triangle range out of bounds", e); return DR_ERR_INVALID_ARG; }
@@ -437,7 +461,8 @@ extern "C" dr_status dr_scene_create_ex(const dr_scene_desc *d, int device, uint
         const float3 p0 = P(i0), p1 = P(i1), p2 = P(i2);
         const bool smooth = anySmooth && (d->tri_flags[prim] & DR_TRI_SMOOTH);
         // material index | BSDF model << 24 (routes the hit to its walk queue) | smooth << 31
-        const uint32_t mf = d->tri_material[prim] | ((uint32_t) d->materials[d->tri_material[prim]].type << 24) | (smooth ? 0x80000000u : 0u);
+        const uint32_t mf = d->tri_material[prim] | ((uint32_t) d->materials[d->tri_material[prim]].type << 24) | (smooth ? 0x80000000u : 0u) |
+                            tri_uv_bits(d, prim);
         tris[3 * slot] = make_float4(p0.x, p0.y, p0.z, p1.x);
         tris[3 * slot + 1] = make_float4(p1.y, p1.z, p2.x, p2.y);
         tris[3 * slot + 2] = make_float4(p2.z, as_float_bits((int) prim), as_float_bits((int) mf), as_float_bits(d->tri_emitter[prim]));
@@ -544,6 +569,38 @@ extern "C" dr_status dr_scene_create_ex(const dr_scene_desc *d, int device, uint
     if (gpuBuilt) adopt(s, (unsigned int *) gpu.order, nT, &dOrder, false);
     else if ((st = upload(s, bvh.order, &dOrder))) return fail(st);
     s->dOrder = const_cast<unsigned int *>(dOrder);
+    {   // texture coordinates in leaf order, texel pool, texture table (16-byte placeholders when the scene has none)
+        std::vector<float4> uvs, texels;
+        std::vector<DevTexture> textures(d->n_textures);
+        if (d->texcoords) {
+            std::vector<uint32_t> orderHost;
+            if (gpuBuilt) {
+                orderHost.resize(nT);
+                if (cudaMemcpy(orderHost.data(), gpu.order, nT * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); dr_set_error("dr_scene_create: reading the leaf order failed"); return fail(DR_ERR_CUDA); }
+            }
+            const uint32_t *order = gpuBuilt ? orderHost.data() : bvh.order.data();
+            uvs.resize(2 * nT);
+            for (size_t slot = 0; slot < nT; ++slot) {
+                const uint32_t prim = order[slot];
+                const float *t0 = d->texcoords + 2 * (size_t) d->indices[3 * (size_t) prim], *t1 = d->texcoords + 2 * (size_t) d->indices[3 * (size_t) prim + 1],
+                            *t2 = d->texcoords + 2 * (size_t) d->indices[3 * (size_t) prim + 2];
+                uvs[2 * slot] = make_float4(t0[0], t0[1], t1[0], t1[1]);
+                uvs[2 * slot + 1] = make_float4(t2[0], t2[1], 0.f, 0.f);
+            }
+        }
+        for (uint32_t t = 0; t < d->n_textures; ++t) {
+            const dr_texture &tx = d->textures[t];
+            DevTexture &dt = textures[t];
+            memset(&dt, 0, sizeof(dt));
+            dt.w = tx.width; dt.h = tx.height; dt.wrapU = tx.wrap_u; dt.wrapV = tx.wrap_v; dt.nearest = tx.nearest ? 1u : 0u;
+            dt.first = texels.size();
+            dt.scaleU = tx.uv_scale[0]; dt.scaleV = tx.uv_scale[1]; dt.offU = tx.uv_offset[0]; dt.offV = tx.uv_offset[1];
+            const size_t n = (size_t) tx.width * tx.height;
+            texels.resize(dt.first + n);
+            for (size_t i = 0; i < n; ++i) texels[dt.first + i] = make_float4(tx.texels[3 * i], tx.texels[3 * i + 1], tx.texels[3 * i + 2], 0.f);
+        }
+        if ((st = upload(s, uvs, &ds.uvs)) || (st = upload(s, texels, &ds.texels)) || (st = upload(s, textures, &ds.textures))) return fail(st);
+    }
     ds.nEmitters = (int) d->n_emitters; ds.nTris = (int) d->n_triangles; ds.nNodes = (int) s->nNodes; ds.rootIsLeaf = 0;
     ds.epsilon = 1e-4f; ds.shadowEpsilon = 1e-3f;     // constants.h:29-30 (single precision)
 
@@ -586,10 +643,11 @@ extern "C" dr_status dr_scene_clone(dr_scene scene, int device, dr_scene *out) {
     s->dev = src->dev;
     auto fail = [&](dr_status code) { dr_scene_destroy(s); return code; };
     // the device pointers of DevScene, in the order dr_scene_create uploaded them
-    const void **slots[10] = { (const void **) &s->dev.nodes, (const void **) &s->dev.tris, (const void **) &s->dev.normals, (const void **) &s->dev.emTris,
+    const void **slots[13] = { (const void **) &s->dev.nodes, (const void **) &s->dev.tris, (const void **) &s->dev.normals, (const void **) &s->dev.emTris,
                               (const void **) &s->dev.emCdf, (const void **) &s->dev.emitterCdf, (const void **) &s->dev.emitters, (const void **) &s->dev.materials,
-                              (const void **) &s->dev.roughTables, (const void **) &s->dOrder };
-    if (src->uploads.size() != 10) { dr_set_error("dr_scene_clone: unexpected scene layout"); return fail(DR_ERR_INVALID_ARG); }
+                              (const void **) &s->dev.roughTables, (const void **) &s->dOrder,
+                              (const void **) &s->dev.uvs, (const void **) &s->dev.texels, (const void **) &s->dev.textures };
+    if (src->uploads.size() != 13) { dr_set_error("dr_scene_clone: unexpected scene layout"); return fail(DR_ERR_INVALID_ARG); }
     for (size_t i = 0; i < src->uploads.size(); ++i) {
         HostUpload u = src->uploads[i];
         u.host = nullptr;                                   // the staging copy stays with the original

@@ -183,7 +183,7 @@ DR_D int bd_eval_connection(const Machine &M, int s, int t, const EndPoint &es, 
         const Real dp = dot(-d, vs.ns);
         fs = r3(dp > 0. ? R_INV_PI : 0.);
     } else {
-        ms = load_material(sc, vs.mat);
+        ms = load_material(sc, vs.mat, vs.uv);
         fs = surface_eval(sc, vs, ms, normalize(es.predP - vs.p), -d, MODE_IMPORTANCE);
     }
     if (t == 1) {
@@ -191,7 +191,7 @@ DR_D int bd_eval_connection(const Machine &M, int s, int t, const EndPoint &es, 
         const Real dp = absdot(vt.ns, d);
         ft = r3(dp != 0. ? imp / dp : imp);
     } else {
-        mt = load_material(sc, vt.mat);
+        mt = load_material(sc, vt.mat, vt.uv);
         ft = surface_eval(sc, vt, mt, normalize(et.predP - vt.p), d, MODE_RADIANCE);
     }
     value = xs.prefix * xt.prefix * fs * ft;
@@ -386,7 +386,7 @@ k_bdpt(const __grid_constant__ Machine M) {
                 fill_vertex(sc, hit, v.p, c.d, nv, tHit);
                 if (tHit == 0.) walkEnded = true;
                 else {
-                    const Mat nm = load_material(sc, nv.mat);
+                    const Mat nm = load_material(sc, nv.mat, nv.uv);
                     nv.degenerate = !(mat_has_smooth(nm.type) || nv.emitter >= 0);
                     // solid angle -> area (vertex.cpp:334-347)
                     const Real cosNext = absdot(c.d, nv.ng);

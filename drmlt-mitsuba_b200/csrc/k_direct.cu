@@ -49,7 +49,7 @@ k_direct(const __grid_constant__ DevScene sc, const __grid_constant__ FilmParams
         Vtx v; Real tHit;
         fill_vertex(sc, hit, o, d, v, tHit);
         if (v.emitter >= 0 && dot(v.ns, -d) > 0.) Li += emitter_radiance(sc, v.emitter);      // its.Le(-ray.d)
-        const Mat m = load_material(sc, v.mat);
+        const Mat m = load_material(sc, v.mat, v.uv);
         const R3 wi = to_local(v, -d);
         const R3 refN = mat_transmissive_or_backside(m) ? r3(0.) : v.ns;                      // records.inl:160-164
         const int nE = shadingSamples, nB = shadingSamples;

@@ -76,7 +76,7 @@ k_pt(const __grid_constant__ Machine M) {
             }
             case GO_SHADE: {                                 // top of the loop body for the vertex v (in registers)
                 const R3 d = c.d;
-                const Mat m = load_material(sc, v.mat);
+                const Mat m = load_material(sc, v.mat, v.uv);
                 if (v.emitter >= 0 && (c.flags & F_PT_EMITTED) && (c.flags & F_PT_NONSPEC) && dot(v.ns, -d) > 0.)
                     px.Li += c.weight * emitter_radiance(sc, v.emitter);
                 if (c.j >= pc.maxDepth && pc.maxDepth > 0) { go = GO_DONE; break; }
@@ -112,7 +112,7 @@ k_pt(const __grid_constant__ Machine M) {
             }
             case GO_BSDF: {                                  // BSDF sampling (path.cpp:222-240)
                 const R3 d = c.d;
-                const Mat m = load_material(sc, v.mat);
+                const Mat m = load_material(sc, v.mat, v.uv);
                 const R3 wi = to_local(v, -d);
                 const R2 ub = rd.next2D(SMP_SENSOR);
                 const Real uz = mat_uses_sampler(m.type) ? rd.next1D(SMP_SENSOR) : 0.5;      // bRec.sampler->next1D() (roughdielectric.cpp:555)

@@ -31,7 +31,7 @@ DR_D void walk_lane(const Machine &M, uint32_t qi) {
             Vtx nv; Real tHit;
             fill_vertex(sc, hit, v.p, d, nv, tHit);
             if (tHit == 0.) { c.pstate = PS_EMPTY; break; }
-            Mat nm = load_material(sc, nv.mat);
+            Mat nm = load_material(sc, nv.mat, nv.uv);
             nm.type = BSDF;                                  // compile-time constant for the BSDF switch
             nv.degenerate = !(mat_has_smooth(BSDF) || nv.emitter >= 0);
             // solid angle -> area (vertex.cpp:334-347); delta interactions keep their discrete pdfs
@@ -140,7 +140,7 @@ k_connect(const __grid_constant__ Machine M) {
                 const Real dp = dot(-d, vs.ns);
                 fs = r3(dp > 0. ? R_INV_PI : 0.);
             } else {
-                ms = load_material(sc, vs.mat);
+                ms = load_material(sc, vs.mat, vs.uv);
                 fs = surface_eval(sc, vs, ms, normalize(vsp.p - vs.p), -d, MODE_IMPORTANCE);
             }
             if (t == 1) {
@@ -148,7 +148,7 @@ k_connect(const __grid_constant__ Machine M) {
                 const Real dp = absdot(vt.ns, d);
                 ft = r3(dp != 0. ? imp / dp : imp);
             } else {
-                mt = load_material(sc, vt.mat);
+                mt = load_material(sc, vt.mat, vt.uv);
                 ft = surface_eval(sc, vt, mt, normalize(vtp.p - vt.p), d, MODE_RADIANCE);
             }
             R3 value = c.weight * fs * ft;

@@ -40,7 +40,7 @@ struct Vtx {                  // 128 bytes (one cache line), stored verbatim in 
     int mat, emitter;
     int type;
     int degenerate;
-    int pad[4];
+    R2 uv;                    // its.uv: interpolated texture coordinates, or the barycentric pair (skdtree.h:399-405)
 };
 
 DR_D R3 to_local(const Vtx &v, R3 w) { return r3(dot(w, v.ss), dot(w, cross(v.ns, v.ss)), dot(w, v.ns)); }
@@ -112,7 +112,27 @@ DR_D void fill_vertex(const DevScene &sc, const Hit &hit, R3 o, R3 d, Vtx &v, Re
         v.ns = face;
     }
     v.ng = face;
-    v.ss = normalize(e1 - v.ns * dot(v.ns, e1));    // computeShadingFrame, dpdu = p1 - p0
+    R3 dpdu = e1;                                   // its.dpdu = p1 - p0 unless the mesh carries UV tangents (skdtree.h:373-380)
+    v.uv = r2(bu, bv);
+    if (mf & DR_MF_HAS_UV) {
+        const float4 *up = sc.uvs + 2 * (size_t) hit.tri;
+        const float4 ua = ldg4(up), ub = ldg4(up + 1);
+        const Real b0 = 1. - bu - bv;
+        v.uv = r2((Real) ua.x * b0 + (Real) ua.z * bu + (Real) ub.x * bv, (Real) ua.y * b0 + (Real) ua.w * bu + (Real) ub.y * bv);
+        if (mf & DR_MF_UV_TANGENTS) {               // TriMesh::computeUVTangents (trimesh.cpp:741-759), per triangle
+            const Real du1 = (Real) ua.z - (Real) ua.x, dv1 = (Real) ua.w - (Real) ua.y, du2 = (Real) ub.x - (Real) ua.x, dv2 = (Real) ub.y - (Real) ua.y;
+            const Real det = du1 * dv2 - dv1 * du2;
+            if (det == 0.) {
+                const R3 n = cross(e1, e2);
+                R3 dpdv;
+                coordinate_system(n / length(n), dpdu, dpdv);
+            } else {
+                const Real invDet = 1.0 / det;
+                dpdu = (dv2 * e1 - dv1 * e2) * invDet;
+            }
+        }
+    }
+    v.ss = normalize(dpdu - v.ns * dot(v.ns, dpdu));    // computeShadingFrame
     v.mat = (int) (mf & 0x00ffffffu);
     v.emitter = __float_as_int(t2.w);
     v.type = V_SURFACE;

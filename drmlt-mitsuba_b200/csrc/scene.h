@@ -10,7 +10,10 @@
 //               t0 = (p0.x p0.y p0.z p1.x) t1 = (p1.y p1.z p2.x p2.y) t2 = (p2.z, prim, matflags, emitter)
 //             the exact float vertices (edges are formed on the fly, so the double-precision
 //             re-intersection of the shading stage sees the same triangle as the reference);
-//             prim = index in the caller's triangle order, matflags = material | bsdf model << 24 | smooth << 31
+//             prim = index in the caller's triangle order, matflags = material | bsdf model << 24 | has texcoords << 29 |
+//             UV tangents << 30 | smooth << 31
+//   uvs     : 32 B / triangle in leaf order = (u0 v0 u1 v1) (u2 v2 - -): the vertices' texture coordinates (only scenes with texcoords)
+//   texels  : 16 B / texel (r g b -), all bitmap textures back to back, row y = 0 first; textures: one DevTexture each
 //   normals : 48 B / triangle in leaf order (only read for smooth triangles at the closest hit)
 //   em_tris : 96 B / emitter triangle in EMITTER order: p0,p1,p2,smooth + n0,n1,n2 (position sampling)
 //   em_cdf  : double prefix sums of the per-emitter triangle areas (pmf.h DiscreteDistribution)
@@ -30,6 +33,15 @@ struct DevMaterial {      // 64 B, mirrors dr_material
     float reflectance[3], transmittance[3], eta[3], k[3];
     float alpha; uint32_t table;
 };
+
+struct DevTexture {       // 64 B (src/textures/bitmap.cpp, include/mitsuba/render/mipmap.h: MIP level 0 only on this path)
+    uint32_t w, h, wrapU, wrapV;
+    uint32_t nearest, pad0;
+    uint64_t first;       // offset of texel (0, 0) in DevScene::texels
+    double scaleU, scaleV, offU, offV;   // Texture2D::m_uvScale / m_uvOffset
+};
+#define DR_MF_HAS_UV      0x20000000u
+#define DR_MF_UV_TANGENTS 0x40000000u
 
 struct DevEmitter {       // 64 B
     double area, invArea;
@@ -74,6 +86,9 @@ struct DevScene {
     const DevEmitter *emitters;
     const DevMaterial *materials;
     const double *roughTables;      // roughplastic: DR_ROUGH_TABLE_DOUBLES per table (include/drmlt_b200.h)
+    const float4 *uvs;              // 2 per triangle, leaf order (placeholder when the scene has no texcoords)
+    const float4 *texels;
+    const DevTexture *textures;
     int nEmitters, nTris, nNodes;
     int rootIsLeaf;                  // degenerate scenes with <= 4 triangles
     DevCamera cam;

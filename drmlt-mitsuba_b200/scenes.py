@@ -19,6 +19,8 @@ class SceneData:
         self._P, self._N, self._I, self._mat, self._emi, self._flg = [], [], [], [], [], []
         self.materials, self.emitters = [], []
         self.rough_tables = []
+        self._UV, self.textures, self._tex_keep = [], [], []
+        self.has_uv = False
         self.n_vertices = 0
         self.n_triangles = 0
         self.camera = None
@@ -26,10 +28,18 @@ class SceneData:
 
     # ---- construction helpers
     def add_material(self, type_, flags=0, reflectance=(0.5, 0.5, 0.5), transmittance=(1, 1, 1),
-                     eta=(1.5, 0, 0), k=(0, 0, 0), alpha=0.1, rough_table=None):
-        """rough_table (roughplastic): the DR_ROUGH_TABLE_DOUBLES doubles of include/drmlt_b200.h for this (distribution, eta, alpha)
+                     eta=(1.5, 0, 0), k=(0, 0, 0), alpha=0.1, rough_table=None, reflectance_tex=None, transmittance_tex=None):
+        """reflectance_tex / transmittance_tex: index (add_texture) of a bitmap texture bound to that colour parameter; the constant is
+        then the texture's average (only the sampling weights of plastic / roughplastic read it).
+        rough_table (roughplastic): the DR_ROUGH_TABLE_DOUBLES doubles of include/drmlt_b200.h for this (distribution, eta, alpha)
         -- rough_tables.reduce(path to data/microfacet/<distribution>.dat, eta, alpha), or the reference's own RoughTransmittance."""
         m = abi.dr_material()
+        if reflectance_tex is not None:
+            flags |= abi.DR_MAT_TEX_REFLECTANCE(reflectance_tex)
+            reflectance = self.textures[reflectance_tex]._avg
+        if transmittance_tex is not None:
+            flags |= abi.DR_MAT_TEX_TRANSMITTANCE(transmittance_tex)
+            transmittance = self.textures[transmittance_tex]._avg
         m.type, m.flags = type_, flags
         m.reflectance[:] = reflectance
         m.transmittance[:] = transmittance
@@ -45,8 +55,25 @@ class SceneData:
         self.materials.append(m)
         return len(self.materials) - 1
 
-    def add_mesh(self, P, I, material, N=None, radiance=None, sampling_weight=1.0):
-        """P [nv,3] float, I [nt,3] int, optional vertex normals N.  `radiance` makes it an area emitter."""
+    def add_texture(self, texels, wrap=abi.DR_WRAP_REPEAT, wrap_v=None, nearest=False, uv_scale=(1.0, 1.0), uv_offset=(0.0, 0.0)):
+        """A bitmap texture (dr_texture): texels [h, w, 3] linear RGB float32, row v = 0 first."""
+        arr = np.ascontiguousarray(texels, np.float32)
+        t = abi.dr_texture()
+        t.height, t.width = arr.shape[:2]
+        t.texels = arr.ctypes.data_as(C.POINTER(C.c_float))
+        t.wrap_u, t.wrap_v = wrap, wrap if wrap_v is None else wrap_v
+        t.nearest = int(nearest)
+        t.uv_scale[:] = uv_scale
+        t.uv_offset[:] = uv_offset
+        t._avg = tuple(float(x) for x in arr.reshape(-1, 3).astype(np.float64).mean(axis=0))
+        self._tex_keep.append(arr)
+        self.textures.append(t)
+        return len(self.textures) - 1
+
+    def add_mesh(self, P, I, material, N=None, radiance=None, sampling_weight=1.0, UV=None, uv_tangents=False):
+        """P [nv,3] float, I [nt,3] int, optional vertex normals N and texture coordinates UV [nv,2].  `radiance` makes it an
+        area emitter.  uv_tangents: the mesh carries UV tangents (DR_TRI_UV_TANGENTS; what Mitsuba does for meshes whose BSDF holds a
+        filtered bitmap texture)."""
         P = np.asarray(P, np.float32).reshape(-1, 3)
         I = np.asarray(I, np.uint32).reshape(-1, 3)
         nt = I.shape[0]
@@ -63,12 +90,15 @@ class SceneData:
         self._I.append(I + np.uint32(self.n_vertices))
         self._mat.append(np.full(nt, material, np.uint32))
         self._emi.append(np.full(nt, emitter, np.int32))
-        self._flg.append(np.full(nt, 0 if N is None else abi.DR_TRI_SMOOTH, np.uint32))
+        self._UV.append(np.zeros((P.shape[0], 2), np.float32) if UV is None else np.asarray(UV, np.float32).reshape(-1, 2))
+        self.has_uv |= UV is not None
+        self._flg.append(np.full(nt, (0 if N is None else abi.DR_TRI_SMOOTH) | (abi.DR_TRI_UV_TANGENTS if uv_tangents and UV is not None else 0), np.uint32))
         self.n_vertices += P.shape[0]
         self.n_triangles += nt
 
-    def add_quad(self, a, b, c, d, material, nu=1, nv=1, **kw):
-        """Quad a,b,c,d (counter-clockwise seen from the front side), tessellated nu x nv."""
+    def add_quad(self, a, b, c, d, material, nu=1, nv=1, uv=False, **kw):
+        """Quad a,b,c,d (counter-clockwise seen from the front side), tessellated nu x nv.  uv=True: texture coordinates (0,0) at a,
+        (1,0) at b, (1,1) at c, (0,1) at d."""
         a, b, c, d = [np.asarray(x, np.float64) for x in (a, b, c, d)]
         u = np.linspace(0, 1, nu + 1)[:, None, None]
         v = np.linspace(0, 1, nv + 1)[None, :, None]
@@ -76,9 +106,11 @@ class SceneData:
         idx = np.arange((nu + 1) * (nv + 1)).reshape(nu + 1, nv + 1)
         i00, i10, i11, i01 = idx[:-1, :-1], idx[1:, :-1], idx[1:, 1:], idx[:-1, 1:]
         I = np.concatenate([np.stack([i00, i10, i11], -1).reshape(-1, 3), np.stack([i00, i11, i01], -1).reshape(-1, 3)])
+        if uv:
+            kw["UV"] = np.stack(np.broadcast_arrays(u[..., 0], v[..., 0]), -1).reshape(-1, 2)
         self.add_mesh(P.reshape(-1, 3), I, material, **kw)
 
-    def add_box(self, center, half, yrot_deg, material, tess=1):
+    def add_box(self, center, half, yrot_deg, material, tess=1, **kw):
         c = np.asarray(center, np.float64)
         hx, hy, hz = half
         th = math.radians(yrot_deg)
@@ -93,7 +125,7 @@ class SceneData:
             (V(-1, 1, 1), V(1, 1, 1), V(1, 1, -1), V(-1, 1, -1)),      # +y
         ]
         for f in faces:
-            self.add_quad(*f, material, nu=tess, nv=tess)
+            self.add_quad(*f, material, nu=tess, nv=tess, **kw)
 
     def add_icosphere(self, center, radius, subdiv, material, smooth=True, **kw):
         P, I = _icosphere(subdiv)
@@ -127,6 +159,8 @@ class SceneData:
             mats = (abi.dr_material * len(self.materials))(*self.materials)
             emis = (abi.dr_emitter * max(1, len(self.emitters)))(*self.emitters)
             rt = np.ascontiguousarray(np.concatenate(self.rough_tables) if self.rough_tables else np.zeros(0), np.float64)
+            self._uv = np.ascontiguousarray(np.concatenate(self._UV), np.float32) if self.has_uv else None
+            self._texs = (abi.dr_texture * max(1, len(self.textures)))(*self.textures)
             self._keep = (P, N, I, mat, emi, flg, mats, emis, rt)
         return self._keep
 
@@ -146,6 +180,11 @@ class SceneData:
         if len(self.rough_tables):
             d.rough_tables = rt.ctypes.data_as(C.POINTER(C.c_double))
             d.n_rough_tables = len(self.rough_tables)
+        if self._uv is not None:
+            d.texcoords = self._uv.ctypes.data_as(C.POINTER(C.c_float))
+        if len(self.textures):
+            d.textures = C.cast(self._texs, C.POINTER(abi.dr_texture))
+            d.n_textures = len(self.textures)
         d.camera = self.camera
         return d
 
@@ -209,6 +248,52 @@ def cornell_box(film=(256, 256), tess=8, plastic=False, rough_tables=None):
                               reflectance=(0.6, 0.5, 0.2), transmittance=(0.9, 0.9, 1.0), eta=(1.9, 0, 0), alpha=0.3, rough_table=rough_tables[1])
     s.add_box((0.33, -0.7, 0.35), (0.3, 0.3, 0.3), -17.0, box1, tess=4)
     s.add_box((-0.33, -0.4, -0.3), (0.3, 0.6, 0.3), 17.0, box2, tess=4)
+    s.set_camera((0, 0, 3.9), (0, 0, 0), (0, 1, 0), 39.0)
+    return s
+
+
+def procedural_texels(w, h, seed, lo=0.05, hi=0.9, cell=4):
+    """A deterministic colour bitmap [h, w, 3] float32: blocky random colours (cell x cell texels) plus per-texel noise, so that
+    bilinear, nearest and the wrap modes all give visibly different answers."""
+    rng = np.random.RandomState(seed)
+    coarse = rng.uniform(lo, hi, ((h + cell - 1) // cell, (w + cell - 1) // cell, 3))
+    img = np.repeat(np.repeat(coarse, cell, axis=0), cell, axis=1)[:h, :w]
+    img = np.clip(img + rng.uniform(-0.04, 0.04, img.shape), 0.01, 0.95)
+    # rounded to half precision: the reference keeps its MIP levels as halfs (bitmap.cpp:175-177), so these texels are exactly
+    # what its texture holds
+    return np.ascontiguousarray(img.astype(np.float16), np.float32)
+
+
+def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
+    """The Cornell box with bitmap textures: floor = diffuse with a bilinear, repeating texture (uscale = vscale = 2.5,
+    offset), back wall = diffuse, mirror-wrapped, on a mesh with UV tangents, left wall = rough conductor with a textured
+    specularReflectance (clamp), one box = plastic with a textured diffuseReflectance, the other = diffuse with a nearest-filtered
+    texture (zero / one wrap); everything else as cornell_box.  uv_tangents=True flags every mesh DR_TRI_UV_TANGENTS -- what the
+    reference does for any mesh with texture coordinates (trimesh.cpp:400-402); False keeps the edge-based shading frames."""
+    s = SceneData("cornell-textured", film)
+    T = bool(uv_tangents)
+    t_floor = s.add_texture(procedural_texels(32, 24, 11), wrap=abi.DR_WRAP_REPEAT, uv_scale=(2.5, 2.5), uv_offset=(0.125, -0.3))
+    t_back = s.add_texture(procedural_texels(17, 29, 12), wrap=abi.DR_WRAP_MIRROR, uv_scale=(1.7, 1.3), uv_offset=(-0.2, 0.1))
+    t_left = s.add_texture(procedural_texels(16, 16, 13, lo=0.4, hi=0.95), wrap=abi.DR_WRAP_CLAMP, uv_scale=(1.5, 1.5), uv_offset=(-0.25, -0.25))
+    t_box1 = s.add_texture(procedural_texels(8, 8, 14, lo=0.1, hi=0.7, cell=2), wrap=abi.DR_WRAP_REPEAT)
+    t_box2 = s.add_texture(procedural_texels(12, 6, 15, cell=3), wrap=abi.DR_WRAP_ZERO, wrap_v=abi.DR_WRAP_ONE, nearest=True,
+                           uv_scale=(1.25, 1.25), uv_offset=(-0.125, -0.125))
+    white = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.73, 0.73, 0.73))
+    green = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.14, 0.45, 0.091))
+    floor = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance_tex=t_floor)
+    back = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance_tex=t_back)
+    left = s.add_material(abi.DR_BSDF_ROUGHCONDUCTOR, flags=abi.DR_MAT_GGX, reflectance_tex=t_left, eta=(0.2, 0.92, 1.1), k=(3.9, 2.45, 2.14), alpha=0.25)
+    box1 = s.add_material(abi.DR_BSDF_PLASTIC, reflectance_tex=t_box1, transmittance=(1, 1, 1), eta=(1.49, 0, 0))
+    box2 = s.add_material(abi.DR_BSDF_DIFFUSE, flags=abi.DR_MAT_TWOSIDED, reflectance_tex=t_box2)
+    s.add_quad((-1, -1, 1), (1, -1, 1), (1, -1, -1), (-1, -1, -1), floor, tess, tess, uv=True, uv_tangents=T)
+    s.add_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1), white, tess, tess, uv=True, uv_tangents=T)
+    s.add_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), back, tess, tess, uv=True, uv_tangents=T)
+    s.add_quad((-1, -1, 1), (-1, -1, -1), (-1, 1, -1), (-1, 1, 1), left, tess, tess, uv=True, uv_tangents=T)
+    s.add_quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1), green, tess, tess, uv=True, uv_tangents=T)
+    h = 0.25
+    s.add_quad((-h, 0.995, -h), (h, 0.995, -h), (h, 0.995, h), (-h, 0.995, h), white, radiance=(15.0, 15.0, 15.0), uv=True, uv_tangents=T)
+    s.add_box((0.33, -0.7, 0.35), (0.3, 0.3, 0.3), -17.0, box1, tess=4, uv=True, uv_tangents=T)
+    s.add_box((-0.33, -0.4, -0.3), (0.3, 0.6, 0.3), 17.0, box2, tess=4, uv=True, uv_tangents=T)
     s.set_camera((0, 0, 3.9), (0, 0, 0), (0, 1, 0), 39.0)
     return s
 

@@ -119,7 +119,9 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector
     }
     if (model == "SmoothDiffuse") {                       // src/bsdfs/diffuse.cpp
         m.type = DR_BSDF_DIFFUSE;
-        if (!nested) toRGB(props.getSpectrum(props.hasProperty("reflectance") ? "reflectance" : "diffuseReflectance", Spectrum(.5f)), m.reflectance);
+        // the exact constant when it was given as a property; a <texture> child (no property) must not fall back to the default silently
+        if (!nested && (props.hasProperty("reflectance") || props.hasProperty("diffuseReflectance")))
+            toRGB(props.getSpectrum(props.hasProperty("reflectance") ? "reflectance" : "diffuseReflectance", Spectrum(.5f)), m.reflectance);
         else if (!ts.spectrum("reflectance", from, m.reflectance)) { why = "textured diffuse reflectance"; return false; }
     } else if (model == "SmoothDielectric") {             // src/bsdfs/dielectric.cpp
         m.type = DR_BSDF_DIELECTRIC;
@@ -289,7 +291,8 @@ public:
         check(dr_config_validate(&m_config));
 
         // ---- flatten Scene -> dr_scene_desc
-        std::vector<float> P, N;
+        std::vector<float> P, N, UV;
+        bool anyTexcoords = false;
         std::vector<uint32_t> I, triMat, triFlags;
         std::vector<int32_t> triEm;
         std::vector<dr_material> mats;
@@ -313,7 +316,11 @@ public:
         for (size_t mi = 0; mi < meshes.size(); ++mi) {
             const TriMesh *mesh = meshes[mi].first;
             const Shape *owner = meshes[mi].second;
-            if (mesh->getVertexTexcoords() && owner == mesh) Log(EWarn, "Mesh \"%s\" has texture coordinates: the shading tangent follows dpdu, not p1-p0", mesh->getName().c_str());
+            // texture coordinates and UV tangents (skdtree.h:373-405; every mesh with texture coordinates has tangents, trimesh.cpp:400-402):
+            // its.uv and the shading frame of the GPU path then agree with the host's
+            const Point2 *tex = mesh->getVertexTexcoords();
+            const bool tangents = tex && mesh->getUVTangents() != NULL;
+            anyTexcoords |= tex != NULL;
             dr_material mat; std::string why;
             if (!owner->getBSDF() || !flattenBSDF(owner->getBSDF(), mat, why, roughTables)) Log(EError, "Mesh \"%s\": %s", owner->getName().c_str(), why.c_str());
             mats.push_back(mat);
@@ -323,6 +330,7 @@ public:
             for (size_t v = 0; v < mesh->getVertexCount(); ++v) {
                 P.push_back((float) pos[v].x); P.push_back((float) pos[v].y); P.push_back((float) pos[v].z);
                 N.push_back(nrm ? (float) nrm[v].x : 0.f); N.push_back(nrm ? (float) nrm[v].y : 0.f); N.push_back(nrm ? (float) nrm[v].z : 0.f);
+                UV.push_back(tex ? (float) tex[v].x : 0.f); UV.push_back(tex ? (float) tex[v].y : 0.f);
             }
             anyNormals |= nrm != NULL;
             int32_t em = -1;
@@ -339,7 +347,7 @@ public:
             const Triangle *tri = mesh->getTriangles();
             for (size_t t = 0; t < mesh->getTriangleCount(); ++t) {
                 for (int k = 0; k < 3; ++k) I.push_back(base + tri[t].idx[k]);
-                triMat.push_back((uint32_t) mi); triEm.push_back(em); triFlags.push_back(nrm ? DR_TRI_SMOOTH : 0u);
+                triMat.push_back((uint32_t) mi); triEm.push_back(em); triFlags.push_back((nrm ? DR_TRI_SMOOTH : 0u) | (tangents ? DR_TRI_UV_TANGENTS : 0u) | (tex ? 0u : DR_TRI_NO_TEXCOORDS));
             }
         }
         if (scene->getEmitters().size() != ems.size()) Log(EError, "Only area emitters attached to triangle meshes are supported");
@@ -352,6 +360,7 @@ public:
         desc.positions = P.data(); desc.normals = anyNormals ? N.data() : NULL; desc.indices = I.data();
         desc.tri_material = triMat.data(); desc.tri_emitter = triEm.data(); desc.tri_flags = triFlags.data();
         desc.materials = mats.data(); desc.emitters = ems.empty() ? NULL : ems.data();
+        desc.texcoords = anyTexcoords ? UV.data() : NULL;
         desc.rough_tables = roughTables.empty() ? NULL : roughTables.data(); desc.n_rough_tables = (uint32_t) (roughTables.size() / DR_ROUGH_TABLE_DOUBLES);
         const Matrix4x4 &tw = cam->getWorldTransform()->eval(0).getMatrix();
         for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) desc.camera.to_world[4 * r + c] = (float) tw(r, c);

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DR_ABI_VERSION 5     /* 5: dr_scene_desc.rough_tables, dr_material.table, dr_config.depth_balance, dr_scene_create_ex */
+#define DR_ABI_VERSION 6     /* 6: bitmap textures (dr_texture, dr_scene_desc.texcoords / textures, DR_MAT_TEX_*, DR_TRI_UV_TANGENTS); 5: dr_scene_desc.rough_tables, dr_material.table, dr_config.depth_balance, dr_scene_create_ex */
 
 /* ------------------------------------------------------------------ status */
 typedef enum dr_status {
@@ -53,6 +53,13 @@ typedef enum dr_bsdf_type {
 #define DR_MAT_GGX            2u  /* roughconductor / roughdielectric distribution=ggx (else beckmann) */
 #define DR_MAT_SAMPLE_VISIBLE 4u  /* roughconductor / roughdielectric sampleVisible=true */
 #define DR_MAT_NONLINEAR      8u  /* plastic nonlinear=true (plastic.cpp:162, 268-271) */
+/* Bitmap textures on the two colour parameters (src/textures/bitmap.cpp): bits 8-19 of `flags` hold 1 + the index in
+ * dr_scene_desc.textures of the texture bound to `reflectance`, bits 20-31 the same for `transmittance` (0 = constant).
+ * A textured parameter is looked up at every BSDF evaluation / sample; the constant in the struct is then the texture's
+ * average (Texture::getAverage), which only the sampling weights of plastic / roughplastic use (plastic.cpp:188-205). */
+#define DR_MAT_TEX_REFLECTANCE(i)   ((((uint32_t) (i) + 1u) & 0xfffu) << 8)
+#define DR_MAT_TEX_TRANSMITTANCE(i) ((((uint32_t) (i) + 1u) & 0xfffu) << 20)
+#define DR_MAX_TEXTURES 4095
 
 typedef struct dr_material {
     int32_t  type;              /* dr_bsdf_type */
@@ -76,6 +83,23 @@ typedef struct dr_material {
 #define DR_ROUGH_TABLE_THETA   100
 #define DR_ROUGH_TABLE_DOUBLES 104
 
+/* A bitmap texture as the bidirectional path code sees it (src/textures/bitmap.cpp:432-455, include/mitsuba/render/mipmap.h:503-596):
+ * without ray differentials (its.hasUVPartials is never set on this path) `eval` is a bilinear -- or, for filterType=nearest, a
+ * box -- lookup in MIP level 0 at uv' = uv * uv_scale + uv_offset (Texture2D::eval, texture.cpp:112-121), out-of-range texels
+ * resolved per axis by the wrap mode.  The reference keeps its MIP levels in half precision (bitmap.cpp:175-177), so a Mitsuba
+ * host passes exactly what its texture holds.  Texels are linear RGB float32 (the host has already applied gamma / sRGB decoding; a
+ * luminance bitmap repeats its channel), row y = 0 first.  The arithmetic of the lookup is double, like the reference's. */
+typedef enum dr_wrap { DR_WRAP_REPEAT = 0, DR_WRAP_CLAMP = 1, DR_WRAP_MIRROR = 2, DR_WRAP_ZERO = 3, DR_WRAP_ONE = 4 } dr_wrap;
+typedef struct dr_texture {
+    uint32_t width, height;
+    const float *texels;        /* 3 * width * height */
+    uint32_t wrap_u, wrap_v;    /* dr_wrap (wrapModeU / wrapModeV) */
+    uint32_t nearest;           /* filterType=nearest: MIPMap::evalBox instead of evalBilinear */
+    uint32_t pad;
+    double   uv_scale[2];       /* uscale, vscale (default 1; double: the reference parses them into Float = double) */
+    double   uv_offset[2];      /* uoffset, voffset (default 0) */
+} dr_texture;                   /* 64 bytes */
+
 /* One area emitter = one emissive triangle mesh (src/emitters/area.cpp:67-215).
  * Its triangles are the contiguous range [first_tri, first_tri + n_tris). */
 typedef struct dr_emitter {
@@ -86,6 +110,12 @@ typedef struct dr_emitter {
 } dr_emitter;
 
 #define DR_TRI_SMOOTH 1u        /* interpolate vertex normals (mesh has normals) */
+#define DR_TRI_UV_TANGENTS 2u  /* the mesh carries UV tangents (TriMesh::computeUVTangents, trimesh.cpp: requested by BSDFs whose textures
+                                  use ray differentials, i.e. any bitmap texture that is not filterType=nearest): the shading frame is built on
+                                  dp/du of the texture parameterisation instead of the edge p1 - p0 (skdtree.h:373-380); needs texcoords.
+                                  In this reference EVERY mesh with texture coordinates has them (TriMesh::configure, trimesh.cpp:400-402) */
+#define DR_TRI_NO_TEXCOORDS 4u /* this triangle's mesh has no texture coordinates although the scene passes `texcoords`: its.uv is the
+                                  barycentric pair, as for a scene without texcoords */
 
 /* Pinhole camera (src/sensors/perspective.cpp:107-460) */
 typedef struct dr_camera {
@@ -108,6 +138,9 @@ typedef struct dr_scene_desc {
     dr_camera camera;
     const double *rough_tables;    /* n_rough_tables * DR_ROUGH_TABLE_DOUBLES, or NULL (no roughplastic material) */
     uint32_t n_rough_tables;
+    uint32_t n_textures;           /* <= DR_MAX_TEXTURES */
+    const float *texcoords;        /* 2 * n_vertices, or NULL: its.uv is then the barycentric pair (b1, b2) (skdtree.h:399-405) */
+    const dr_texture *textures;    /* n_textures, referenced by DR_MAT_TEX_* */
 } dr_scene_desc;
 
 /* ------------------------------------------------------------------ config */

@@ -402,6 +402,20 @@ uint32_t orc_rough_table_register(const dr_material *m, const double *table) {
     detail::prepareRoughPlastic(mm, table);
     return mm.table;
 }
+/* Texture2D::eval of a dr_texture at n intersection uv pairs (no ray differentials): orc_scene.hpp Texture::eval */
+void orc_texture_eval(const dr_texture *t, const double *uv, int n, double *rgb) {
+    dr_scene_desc d{};
+    d.n_textures = 1; d.textures = t;
+    Texture tex;
+    tex.w = (int) t->width; tex.h = (int) t->height; tex.wrapU = (int) t->wrap_u; tex.wrapV = (int) t->wrap_v; tex.nearest = t->nearest != 0;
+    tex.scaleU = t->uv_scale[0]; tex.scaleV = t->uv_scale[1]; tex.offU = t->uv_offset[0]; tex.offV = t->uv_offset[1];
+    tex.texels.resize((size_t) tex.w * tex.h);
+    for (size_t i = 0; i < tex.texels.size(); ++i) tex.texels[i] = RGB(t->texels[3 * i], t->texels[3 * i + 1], t->texels[3 * i + 2]);
+    for (int i = 0; i < n; ++i) {
+        const RGB v = tex.eval(Vec2(uv[2 * i], uv[2 * i + 1]));
+        rgb[3 * i] = v.r; rgb[3 * i + 1] = v.g; rgb[3 * i + 2] = v.b;
+    }
+}
 void orc_bsdf_sample(const dr_material *m, const double *wi, int mode, double u1, double u2, double *wo, double *weight, double *pdf, int *sampledType) {
     BSDFRecord b(Vec3(wi[0], wi[1], wi[2]), mode);
     Float p = 0;

@@ -33,6 +33,22 @@ struct BSDFRecord {
 
 inline RGB rgb3(const float *v) { return RGB(v[0], v[1], v[2]); }
 
+// A material as the BSDF functions see it: the POD of the ABI plus its two colour parameters in Float -- the constants of the
+// struct, or, for a textured parameter (DR_MAT_TEX_*), the bitmap lookup at the intersection (Scene::material, orc_scene.hpp),
+// which must not be rounded to float32.
+struct Mat : dr_material {
+    RGB R, T;
+    Mat(const dr_material &m) : dr_material(m), R(rgb3(m.reflectance)), T(rgb3(m.transmittance)) {}
+};
+// the material at an intersection: m_reflectance->eval(bRec.its) etc. of the BSDF plugins
+template <class SceneT, class ItsT> inline Mat materialAt(const SceneT &sc, const ItsT &its) {
+    Mat m(sc.mats[its.material]);
+    const uint32_t tr = (m.flags >> 8) & 0xfffu, tt = m.flags >> 20;
+    if (tr) m.R = sc.textures[tr - 1].eval(its.uv);
+    if (tt) m.T = sc.textures[tt - 1].eval(its.uv);
+    return m;
+}
+
 inline bool bsdfHasSmooth(const dr_material &m) { return m.type == DR_BSDF_DIFFUSE || m.type == DR_BSDF_ROUGHCONDUCTOR || m.type == DR_BSDF_ROUGHDIELECTRIC || m.type == DR_BSDF_PLASTIC || m.type == DR_BSDF_ROUGHPLASTIC; }
 inline bool bsdfNonSymmetric(const dr_material &m) { return m.type == DR_BSDF_DIELECTRIC || m.type == DR_BSDF_ROUGHDIELECTRIC; }   // dielectric.cpp:201, roughdielectric.cpp:253
 // BSDF::EUsesSampler: sample() draws one more number from the vertex's sampler (roughdielectric.cpp:464, 555)
@@ -231,11 +247,11 @@ struct Plastic {       // SmoothPlastic::configure (plastic.cpp:188-205); dr_mat
     Float eta, invEta2, fdrInt, specularSamplingWeight;
     RGB diffuse, specular;
     bool nonlinear;
-    explicit Plastic(const dr_material &m) {
+    explicit Plastic(const Mat &m) {
         eta = m.eta[0]; invEta2 = 1 / (eta * eta);
         // derived once per material by preparePlastic (below), stored as floats like the library's device copy
         fdrInt = m.k[0]; specularSamplingWeight = m.k[1];
-        diffuse = rgb3(m.reflectance); specular = rgb3(m.transmittance);
+        diffuse = m.R; specular = m.T;
         nonlinear = (m.flags & DR_MAT_NONLINEAR) != 0;
     }
     Float probSpecular(Float Fi) const { return (Fi * specularSamplingWeight) / (Fi * specularSamplingWeight + (1 - Fi) * (1 - specularSamplingWeight)); }
@@ -285,11 +301,11 @@ struct RoughPlastic {   // dr_material: reflectance = diffuse, transmittance = s
     Float eta, invEta2, specularSamplingWeight;
     RGB diffuse, specular;
     bool nonlinear;
-    explicit RoughPlastic(const dr_material &m) {
+    explicit RoughPlastic(const Mat &m) {
         tab = roughTableRegistry()[m.table].data();
         eta = m.eta[0]; invEta2 = 1.0f / (eta * eta);                  // roughplastic.cpp:279
         specularSamplingWeight = tab[102];
-        diffuse = rgb3(m.reflectance); specular = rgb3(m.transmittance);
+        diffuse = m.R; specular = m.T;
         nonlinear = (m.flags & DR_MAT_NONLINEAR) != 0;
     }
     // m_externalRoughTransmittance->eval(cosTheta, alpha) with eta and alpha fixed (rtrans.h:136-146, 192)
@@ -331,22 +347,22 @@ struct RoughPlastic {   // dr_material: reflectance = diffuse, transmittance = s
     }
 };
 
-inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
+inline RGB evalNested(const Mat &m, const BSDFRecord &b, int measure) {
     switch (m.type) {
     case DR_BSDF_DIFFUSE:   // diffuse.cpp:109-117
         if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
-        return rgb3(m.reflectance) * (INV_PI * Frame::cosTheta(b.wo));
+        return m.R * (INV_PI * Frame::cosTheta(b.wo));
     case DR_BSDF_CONDUCTOR:   // conductor.cpp:223-237
         if (measure != EDiscrete || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0 ||
             std::abs(dot(reflectZ(b.wi), b.wo) - 1) > DELTA_EPSILON) return RGB(0.0);
-        return rgb3(m.reflectance) * fresnelConductorExact(Frame::cosTheta(b.wi), rgb3(m.eta), rgb3(m.k));
+        return m.R * fresnelConductorExact(Frame::cosTheta(b.wi), rgb3(m.eta), rgb3(m.k));
     case DR_BSDF_ROUGHCONDUCTOR: {   // roughconductor.cpp:258-297
         if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
         Vec3 H = normalize(b.wo + b.wi);
         Microfacet distr(m);
         const Float D = distr.eval(H);
         if (D == 0) return RGB(0.0);
-        const RGB F = fresnelConductorExact(dot(b.wi, H), rgb3(m.eta), rgb3(m.k)) * rgb3(m.reflectance);
+        const RGB F = fresnelConductorExact(dot(b.wi, H), rgb3(m.eta), rgb3(m.k)) * m.R;
         const Float G = distr.G(b.wi, b.wo, H);
         Float model = D * G / (4.0 * Frame::cosTheta(b.wi));
         return F * model;
@@ -383,13 +399,13 @@ inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
         const Float G = distr.G(b.wi, b.wo, H);
         if (reflect) {
             Float value = F * D * G / (4.0 * std::abs(Frame::cosTheta(b.wi)));
-            return rgb3(m.reflectance) * value;
+            return m.R * value;
         } else {
             Float eta = Frame::cosTheta(b.wi) > 0.0 ? mEta : mInvEta;
             Float sqrtDenom = dot(b.wi, H) + eta * dot(b.wo, H);
             Float value = ((1 - F) * D * G * eta * eta * dot(b.wi, H) * dot(b.wo, H)) / (Frame::cosTheta(b.wi) * sqrtDenom * sqrtDenom);
             Float factor = (b.mode == ERadiance) ? (Frame::cosTheta(b.wi) > 0 ? mInvEta : mEta) : 1.0;
-            return rgb3(m.transmittance) * std::abs(value * factor * factor);
+            return m.T * std::abs(value * factor * factor);
         }
     }
     case DR_BSDF_DIELECTRIC: {   // dielectric.cpp:227-253
@@ -398,20 +414,20 @@ inline RGB evalNested(const dr_material &m, const BSDFRecord &b, int measure) {
         Float F = fresnelDielectricExt(Frame::cosTheta(b.wi), cosThetaT, eta);
         if (Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) >= 0) {
             if (std::abs(dot(reflectZ(b.wi), b.wo) - 1) > DELTA_EPSILON) return RGB(0.0);
-            return rgb3(m.reflectance) * F;
+            return m.R * F;
         } else {
             Float scale = -(cosThetaT < 0 ? invEta : eta);
             Vec3 refr(scale * b.wi.x, scale * b.wi.y, cosThetaT);
             if (std::abs(dot(refr, b.wo) - 1) > DELTA_EPSILON) return RGB(0.0);
             Float factor = (b.mode == ERadiance) ? (cosThetaT < 0 ? invEta : eta) : 1.0;
-            return rgb3(m.transmittance) * (factor * factor * (1 - F));
+            return m.T * (factor * factor * (1 - F));
         }
     }
     }
     return RGB(0.0);
 }
 
-inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
+inline Float pdfNested(const Mat &m, const BSDFRecord &b, int measure) {
     switch (m.type) {
     case DR_BSDF_DIFFUSE:   // diffuse.cpp:119-126
         if (measure != ESolidAngle || Frame::cosTheta(b.wi) <= 0 || Frame::cosTheta(b.wo) <= 0) return 0.0;
@@ -485,7 +501,7 @@ inline Float pdfNested(const dr_material &m, const BSDFRecord &b, int measure) {
 }
 
 // `extra`: the number sample() draws from bRec.sampler (EUsesSampler BSDFs; roughdielectric.cpp:555)
-inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const Vec2 &sample, Float epsilon, Float extra) {
+inline RGB sampleNested(const Mat &m, BSDFRecord &b, Float &pdf, const Vec2 &sample, Float epsilon, Float extra) {
     switch (m.type) {
     case DR_BSDF_ROUGHPLASTIC: {   // roughplastic.cpp:434-491 (both components enabled)
         if (Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
@@ -549,7 +565,7 @@ inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const V
             b.wo = reflectM(b.wi, mm);
             b.eta = 1.0; b.sampledType = EGlossyReflection;
             if (Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
-            weight = weight * rgb3(m.reflectance);
+            weight = weight * m.R;
             dwh_dwo = 1.0 / (4.0 * dot(b.wo, mm));
         } else {
             if (cosThetaT == 0) return RGB(0.0);
@@ -559,7 +575,7 @@ inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const V
             b.sampledType = EGlossyTransmission;
             if (Frame::cosTheta(b.wi) * Frame::cosTheta(b.wo) >= 0) return RGB(0.0);
             Float factor = (b.mode == ERadiance) ? (cosThetaT < 0 ? mInvEta : mEta) : 1.0;
-            weight = weight * rgb3(m.transmittance) * (factor * factor);
+            weight = weight * m.T * (factor * factor);
             Float sqrtDenom = dot(b.wi, mm) + b.eta * dot(b.wo, mm);
             dwh_dwo = (b.eta * b.eta * dot(b.wo, mm)) / (sqrtDenom * sqrtDenom);
         }
@@ -574,11 +590,11 @@ inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const V
         b.wo = squareToCosineHemisphere(sample);
         b.eta = 1.0; b.sampledType = EDiffuseReflection;
         pdf = squareToCosineHemispherePdf(b.wo);
-        return rgb3(m.reflectance);
+        return m.R;
     case DR_BSDF_CONDUCTOR:   // conductor.cpp:270-285
         if (Frame::cosTheta(b.wi) <= 0) return RGB(0.0);
         b.sampledType = EDeltaReflection; b.wo = reflectZ(b.wi); b.eta = 1.0; pdf = 1;
-        return rgb3(m.reflectance) * fresnelConductorExact(Frame::cosTheta(b.wi), rgb3(m.eta), rgb3(m.k));
+        return m.R * fresnelConductorExact(Frame::cosTheta(b.wi), rgb3(m.eta), rgb3(m.k));
     case DR_BSDF_ROUGHCONDUCTOR: {   // roughconductor.cpp:371-417
         if (Frame::cosTheta(b.wi) < 0) return RGB(0.0);
         Microfacet distr(m);
@@ -588,7 +604,7 @@ inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const V
         b.wo = reflectM(b.wi, mm);
         b.eta = 1.0; b.sampledType = EGlossyReflection;
         if (Frame::cosTheta(b.wo) <= 0) return RGB(0.0);
-        RGB F = fresnelConductorExact(dot(b.wi, mm), rgb3(m.eta), rgb3(m.k)) * rgb3(m.reflectance);
+        RGB F = fresnelConductorExact(dot(b.wi, mm), rgb3(m.eta), rgb3(m.k)) * m.R;
         Float weight;
         if (distr.sampleVis) weight = distr.smithG1(b.wo, mm);
         else weight = distr.eval(mm) * distr.G(b.wi, b.wo, mm) * dot(b.wi, mm) / (temporaryPdf * Frame::cosTheta(b.wi));
@@ -603,7 +619,7 @@ inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const V
         Float F = fresnelDielectricExt(Frame::cosTheta(b.wi), cosThetaT, eta);
         if (sample.x <= F) {
             b.sampledType = EDeltaReflection; b.wo = reflectZ(b.wi); b.eta = 1.0; pdf = F;
-            return rgb3(m.reflectance);
+            return m.R;
         } else {
             b.sampledType = EDeltaTransmission;
             Float scale = -(cosThetaT < 0 ? invEta : eta);
@@ -611,7 +627,7 @@ inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const V
             b.eta = cosThetaT < 0 ? eta : invEta;
             pdf = 1 - F;
             Float factor = (b.mode == ERadiance) ? (cosThetaT < 0 ? invEta : eta) : 1.0;
-            return rgb3(m.transmittance) * (factor * factor);
+            return m.T * (factor * factor);
         }
     }
     }
@@ -621,7 +637,7 @@ inline RGB sampleNested(const dr_material &m, BSDFRecord &b, Float &pdf, const V
 } // namespace detail
 
 // ---------------------------------------------------------------- public: with the twosided adapter
-inline RGB bsdfEval(const dr_material &m, const BSDFRecord &bRec, int measure = ESolidAngle) {
+inline RGB bsdfEval(const Mat &m, const BSDFRecord &bRec, int measure = ESolidAngle) {
     if (m.flags & DR_MAT_TWOSIDED) {   // twosided.cpp:107-127
         BSDFRecord b(bRec);
         if (Frame::cosTheta(b.wi) > 0) return detail::evalNested(m, b, measure);
@@ -630,7 +646,7 @@ inline RGB bsdfEval(const dr_material &m, const BSDFRecord &bRec, int measure = 
     }
     return detail::evalNested(m, bRec, measure);
 }
-inline Float bsdfPdf(const dr_material &m, const BSDFRecord &bRec, int measure = ESolidAngle) {
+inline Float bsdfPdf(const Mat &m, const BSDFRecord &bRec, int measure = ESolidAngle) {
     if (m.flags & DR_MAT_TWOSIDED) {   // twosided.cpp:129-141
         BSDFRecord b(bRec);
         if (b.wi.z > 0) return detail::pdfNested(m, b, measure);
@@ -639,7 +655,7 @@ inline Float bsdfPdf(const dr_material &m, const BSDFRecord &bRec, int measure =
     }
     return detail::pdfNested(m, bRec, measure);
 }
-inline RGB bsdfSample(const dr_material &m, BSDFRecord &bRec, Float &pdf, const Vec2 &sample, Float epsilon, Float extra = 0.5) {
+inline RGB bsdfSample(const Mat &m, BSDFRecord &bRec, Float &pdf, const Vec2 &sample, Float epsilon, Float extra = 0.5) {
     pdf = 0;
     if (m.flags & DR_MAT_TWOSIDED) {   // twosided.cpp:166-186
         bool flipped = false;

@@ -189,7 +189,7 @@ inline bool edgeSampleNext(PathCtx &ctx, PathEdge &edge, const Ray &ray, PathVer
     bool surface = sc.rayIntersect(ray, succ.its, &ctx.rays);
     if (!surface) return false;
     succ.type = ESurfaceInteraction;
-    const dr_material &m = sc.mats[succ.its.material];
+    const Mat m = materialAt(sc, succ.its);
     succ.degenerate = !(bsdfHasSmooth(m) || succ.its.emitter >= 0);
     edge.length = succ.its.t;
     if (edge.length == 0) return false;
@@ -265,7 +265,7 @@ inline bool vertexSampleNext(PathCtx &ctx, PathVertex &cur, Sampler *sampler, co
     }
     case ESurfaceInteraction: {   // :153-271
         const Intersection &its = cur.its;
-        const dr_material &bsdf = sc.mats[its.material];
+        const Mat bsdf = materialAt(sc, its);
         Vec3 wi = normalize(pred->getPosition() - its.p);
         BSDFRecord bRec(its.toLocal(wi), mode);
         Vec2 rndPoint = sampler->next2D();
@@ -384,7 +384,7 @@ inline RGB vertexEval(const Scene &sc, const PathVertex &cur, const PathVertex *
     }
     case ESurfaceInteraction: {
         const Intersection &its = cur.its;
-        const dr_material &bsdf = sc.mats[its.material];
+        const Mat bsdf = materialAt(sc, its);
         Vec3 wi = normalize(pred->getPosition() - its.p);
         Vec3 wo = normalize(succ->getPosition() - its.p);
         BSDFRecord bRec(its.toLocal(wi), its.toLocal(wo), mode);
@@ -432,7 +432,7 @@ inline Float vertexEvalPdf(const Scene &sc, const PathVertex &cur, const PathVer
     }
     case ESurfaceInteraction: {
         const Intersection &its = cur.its;
-        const dr_material &bsdf = sc.mats[its.material];
+        const Mat bsdf = materialAt(sc, its);
         wo = succ->getPosition() - its.p; dist = length(wo); wo /= dist;
         Vec3 wi = normalize(pred->getPosition() - its.p);
         BSDFRecord bRec(its.toLocal(wi), its.toLocal(wo), mode);
@@ -630,7 +630,7 @@ inline RGB pathTracerLi(PathCtx &ctx, Sampler *sampler, Ray ray, int maxDepth, i
     Float eta = 1.0;
     while (depth <= maxDepth || maxDepth < 0) {
         if (!its.valid()) break;
-        const dr_material &bsdf = sc.mats[its.material];
+        const Mat bsdf = materialAt(sc, its);
         if (its.emitter >= 0 && typeEmitted && non_specular) {
             if (dot(its.sh.n, -ray.d) > 0) Li += throughput * sc.emitters[its.emitter].radiance;
         }
@@ -703,7 +703,7 @@ inline RGB directLi(PathCtx &ctx, Ray ray, int shadingSamples, const Vec2 *u, co
     RGB Li(0.0);
     if (!sc.rayIntersect(ray, its, &ctx.rays)) return Li;
     if (its.emitter >= 0 && dot(its.sh.n, -ray.d) > 0) Li += sc.emitters[its.emitter].radiance;   // its.Le(-ray.d), area.cpp:112-117
-    const dr_material &bsdf = sc.mats[its.material];
+    const Mat bsdf = materialAt(sc, its);
     const int nE = shadingSamples, nB = shadingSamples;
     const Float fracLum = nE / (Float) (nE + nB), fracBSDF = nB / (Float) (nE + nB), weightLum = 1.0 / nE, weightBSDF = 1.0 / nB;
     auto mi = [](Float a, Float b) { a *= a; b *= b; return a / (a + b); };

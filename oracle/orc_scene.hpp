@@ -6,7 +6,9 @@
 // include/mitsuba/render/skdtree.h:343-426 (fillIntersectionRecord),
 // src/librender/scene.cpp:879-904,1057-1087 (emitter sampling), src/emitters/area.cpp:98-200,
 // src/librender/trimesh.cpp:429-440, src/librender/shape.cpp:102-126, src/libcore/triangle.cpp:24-60,
-// include/mitsuba/core/pmf.h:60-200, src/sensors/perspective.cpp:126-428.
+// include/mitsuba/core/pmf.h:60-200, src/sensors/perspective.cpp:126-428,
+// src/textures/bitmap.cpp:432-455 + include/mitsuba/render/mipmap.h:503-596 + src/librender/texture.cpp:112-121 (bitmap lookup
+// without ray differentials), src/librender/trimesh.cpp:708-760 (UV tangents).
 // The acceleration structure is a plain SAH BVH: the reference's kd-tree only decides WHICH
 // triangles are tested, the closest hit it returns is the same.
 #pragma once
@@ -161,8 +163,52 @@ struct EmitterRec {
 
 namespace detail { inline void preparePlastic(dr_material &m); inline void prepareRoughPlastic(dr_material &m, const double *sceneTables); }   // orc_bsdf.hpp: constants SmoothPlastic::configure derives
 
+// A bitmap texture: MIP level 0 of the reference's TMIPMap<Spectrum, Color3> (texels in Float) with its boundary conditions.
+struct Texture {
+    int w = 0, h = 0, wrapU = 0, wrapV = 0;
+    bool nearest = false;
+    Float scaleU = 1, scaleV = 1, offU = 0, offV = 0;
+    std::vector<RGB> texels;
+    static int modulo(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }   // math::modulo
+    // mipmap.h:503-563 evalTexel
+    RGB texel(int x, int y) const {
+        if (x < 0 || x >= w) {
+            switch (wrapU) {
+                case DR_WRAP_REPEAT: x = modulo(x, w); break;
+                case DR_WRAP_CLAMP: x = std::min(std::max(x, 0), w - 1); break;
+                case DR_WRAP_MIRROR: x = modulo(x, 2 * w); if (x >= w) x = 2 * w - x - 1; break;
+                case DR_WRAP_ZERO: return RGB(0.0f);
+                default: return RGB(1.0f);
+            }
+        }
+        if (y < 0 || y >= h) {
+            switch (wrapV) {
+                case DR_WRAP_REPEAT: y = modulo(y, h); break;
+                case DR_WRAP_CLAMP: y = std::min(std::max(y, 0), h - 1); break;
+                case DR_WRAP_MIRROR: y = modulo(y, 2 * h); if (y >= h) y = 2 * h - y - 1; break;
+                case DR_WRAP_ZERO: return RGB(0.0f);
+                default: return RGB(1.0f);
+            }
+        }
+        return texels[(size_t) y * w + x];
+    }
+    // Texture2D::eval (texture.cpp:112-121) -> BitmapTexture::eval(uv) (bitmap.cpp:432-455) -> evalBilinear / evalBox (mipmap.h:566-596)
+    RGB eval(const Vec2 &itsUv) const {
+        const Vec2 uv(itsUv.x * scaleU + offU, itsUv.y * scaleV + offV);
+        if (nearest) return texel((int) std::floor(uv.x * w), (int) std::floor(uv.y * h));
+        if (!std::isfinite(uv.x) || !std::isfinite(uv.y)) return RGB(0.0f);
+        Float u = uv.x * w - 0.5f, v = uv.y * h - 0.5f;
+        int xPos = (int) std::floor(u), yPos = (int) std::floor(v);
+        Float dx1 = u - xPos, dx2 = 1.0f - dx1, dy1 = v - yPos, dy2 = 1.0f - dy1;
+        return texel(xPos, yPos) * dx2 * dy2 + texel(xPos, yPos + 1) * dx2 * dy1
+             + texel(xPos + 1, yPos) * dx1 * dy2 + texel(xPos + 1, yPos + 1) * dx1 * dy1;
+    }
+};
+
 struct Scene {
     std::vector<Vec3> P, N;
+    std::vector<Vec2> UV;              // vertex texture coordinates (empty: its.uv is the barycentric pair)
+    std::vector<Texture> textures;
     std::vector<uint32_t> idx, triMat, triFlags;
     std::vector<int32_t> triEmitter;
     std::vector<dr_material> mats;
@@ -233,6 +279,19 @@ inline void Scene::load(const dr_scene_desc &d) {
         N.resize(d.n_vertices);
         for (uint32_t i = 0; i < d.n_vertices; ++i)
             N[i] = Vec3(d.normals[3 * i], d.normals[3 * i + 1], d.normals[3 * i + 2]);
+    }
+    if (d.texcoords) {
+        UV.resize(d.n_vertices);
+        for (uint32_t i = 0; i < d.n_vertices; ++i) UV[i] = Vec2(d.texcoords[2 * i], d.texcoords[2 * i + 1]);
+    }
+    textures.resize(d.n_textures);
+    for (uint32_t t = 0; t < d.n_textures; ++t) {
+        const dr_texture &tx = d.textures[t];
+        Texture &o = textures[t];
+        o.w = (int) tx.width; o.h = (int) tx.height; o.wrapU = (int) tx.wrap_u; o.wrapV = (int) tx.wrap_v; o.nearest = tx.nearest != 0;
+        o.scaleU = tx.uv_scale[0]; o.scaleV = tx.uv_scale[1]; o.offU = tx.uv_offset[0]; o.offV = tx.uv_offset[1];
+        o.texels.resize((size_t) o.w * o.h);
+        for (size_t i = 0; i < o.texels.size(); ++i) o.texels[i] = RGB(tx.texels[3 * i], tx.texels[3 * i + 1], tx.texels[3 * i + 2]);
     }
     idx.assign(d.indices, d.indices + 3 * (size_t) d.n_triangles);
     triMat.assign(d.tri_material, d.tri_material + d.n_triangles);
@@ -422,11 +481,28 @@ inline void Scene::fillIntersection(const Ray &ray, Float t, Float u, Float v, i
         shN = faceNormal;
     }
     its.ng = faceNormal;
-    its.uv = Vec2(b.y, b.z);
+    Vec3 dpdu = side1;
+    if (!UV.empty() && !(triFlags[prim] & DR_TRI_NO_TEXCOORDS)) {
+        const Vec2 &t0 = UV[i0], &t1 = UV[i1], &t2 = UV[i2];
+        its.uv = Vec2(t0.x * b.x + t1.x * b.y + t2.x * b.z, t0.y * b.x + t1.y * b.y + t2.y * b.z);
+        if (triFlags[prim] & DR_TRI_UV_TANGENTS) {   // trimesh.cpp:741-759 (computed per mesh there, per hit here)
+            const Vec2 dUV1(t1.x - t0.x, t1.y - t0.y), dUV2(t2.x - t0.x, t2.y - t0.y);
+            const Float determinant = dUV1.x * dUV2.y - dUV1.y * dUV2.x;
+            if (determinant == 0) {
+                Vec3 n = cross(side1, side2), dpdv;
+                coordinateSystem(n / length(n), dpdu, dpdv);
+            } else {
+                const Float invDet = 1.0f / determinant;
+                dpdu = (side1 * dUV2.y - side2 * dUV1.y) * invDet;
+            }
+        }
+    } else {
+        its.uv = Vec2(b.y, b.z);
+    }
     its.prim = prim;
     its.material = (int) triMat[prim];
     its.emitter = triEmitter[prim];
-    computeShadingFrame(shN, side1, its.sh);
+    computeShadingFrame(shN, dpdu, its.sh);
     its.wi = its.toLocal(-ray.d);
 }
 

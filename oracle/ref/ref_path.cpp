@@ -37,6 +37,9 @@
 #include <mitsuba/render/renderqueue.h>
 #include <mitsuba/core/bitmap.h>
 #include <mitsuba/core/timer.h>
+#include <mitsuba/render/texture.h>
+#include <mitsuba/render/mipmap.h>
+#include <mitsuba/core/half.h>
 #include <map>
 #include <tuple>
 #include <execinfo.h>
@@ -233,7 +236,69 @@ void initOnce() {
 
 Spectrum rgbSpectrum(const float *v) { Spectrum s; s.fromLinearRGB(v[0], v[1], v[2]); return s; }
 
-ref<BSDF> makeBSDF(const dr_material &m) {
+/* A bitmap texture from the texels of a dr_texture.  The reference's own BitmapTexture (src/textures/bitmap.cpp) can only be
+ * made from an image FILE (and its format conversion needs Boost.MPL); everything below its file handling is the reference's:
+ * this class holds the same TMIPMap<Color3, Color3h> (include/mitsuba/render/mipmap.h: half-precision storage, evalTexel's
+ * boundary conditions, evalBilinear / evalBox), derives from the reference's Texture2D (texture.cpp:81-121: uv scale / offset,
+ * dispatch on its.hasUVPartials) and restates only the ten lines of BitmapTexture::eval(uv) (bitmap.cpp:432-455). */
+class PinTexture : public Texture2D {
+public:
+    /* bitmap.cpp:175-177 stores TSpectrum<half, 3>; this compiler rejects the explicit TSpectrum<half> -> Color3 conversion inside
+     * evalTexel, so the half triple gets the two conversions spelled out (same half class, include/mitsuba/core/half.h) */
+    struct Color3h {
+        half s[3];
+        Color3h() {}
+        Color3h(const Color3 &c) { for (int i = 0; i < 3; ++i) s[i] = half((float) c[i]); }
+        operator Color3() const { return Color3((Float) (float) s[0], (Float) (float) s[1], (Float) (float) s[2]); }
+    };
+    typedef TMIPMap<Color3, Color3h> MIPMap3;
+    using Texture2D::eval;                           // eval(its, filter): texture.cpp:112-121
+    static Properties props(const dr_texture &t) {
+        Properties p("pintexture");
+        p.setFloat("uscale", t.uv_scale[0]); p.setFloat("vscale", t.uv_scale[1]);
+        p.setFloat("uoffset", t.uv_offset[0]); p.setFloat("voffset", t.uv_offset[1]);
+        return p;
+    }
+    static ReconstructionFilter::EBoundaryCondition bc(uint32_t w) {
+        switch (w) {
+            case DR_WRAP_CLAMP: return ReconstructionFilter::EClamp;
+            case DR_WRAP_MIRROR: return ReconstructionFilter::EMirror;
+            case DR_WRAP_ZERO: return ReconstructionFilter::EZero;
+            case DR_WRAP_ONE: return ReconstructionFilter::EOne;
+            default: return ReconstructionFilter::ERepeat;
+        }
+    }
+    PinTexture(const dr_texture &t) : Texture2D(props(t)) {
+        ref<Bitmap> bitmap = new Bitmap(Bitmap::ERGB, Bitmap::EFloat, Vector2i((int) t.width, (int) t.height));
+        bitmap->setGamma(1.0f);
+        Float *dst = (Float *) bitmap->getData();
+        for (size_t i = 0; i < 3 * (size_t) t.width * t.height; ++i) dst[i] = (Float) t.texels[i];
+        m_mipmap = new MIPMap3(bitmap, Bitmap::ERGB, Bitmap::EFloat, NULL, bc(t.wrap_u), bc(t.wrap_v), t.nearest ? ENearest : EBilinear, 20.0f);
+    }
+    Spectrum eval(const Point2 &uv) const {          // bitmap.cpp:432-455 (the RGB branch)
+        Spectrum result;
+        Color3 value;
+        if (m_mipmap->getFilterType() != ENearest) value = m_mipmap->evalBilinear(0, uv);
+        else value = m_mipmap->evalBox(0, uv);
+        result.fromLinearRGB(value[0], value[1], value[2]);
+        return result;
+    }
+    Spectrum eval(const Point2 &uv, const Vector2 &, const Vector2 &) const { return eval(uv); }
+    Spectrum getAverage() const { Spectrum r; Color3 a = m_mipmap->getAverage(); r.fromLinearRGB(a[0], a[1], a[2]); return r; }   // bitmap.cpp getAverage
+    Spectrum getMaximum() const { Spectrum r; Color3 a = m_mipmap->getMaximum(); r.fromLinearRGB(a[0], a[1], a[2]); return r; }
+    Spectrum getMinimum() const { Spectrum r; Color3 a = m_mipmap->getMinimum(); r.fromLinearRGB(a[0], a[1], a[2]); return r; }
+    bool isConstant() const { return false; }
+    bool isMonochromatic() const { return false; }
+    bool usesRayDifferentials() const { return true; }   // bitmap.cpp:542-544
+    Vector3i getResolution() const { return Vector3i(m_mipmap->getWidth(), m_mipmap->getHeight(), 1); }
+    MTS_DECLARE_CLASS()
+private:
+    ref<MIPMap3> m_mipmap;
+};
+MTS_IMPLEMENT_CLASS(PinTexture, false, Texture2D)
+
+ref<BSDF> makeBSDF(const dr_material &m, const std::vector<ref<Texture> > *textures = NULL) {
+    const uint32_t texR = (m.flags >> 8) & 0xfffu, texT = m.flags >> 20;       // DR_MAT_TEX_*: 1 + texture index
     PluginManager *pm = PluginManager::getInstance();
     const char *names[] = { "diffuse", "dielectric", "conductor", "roughconductor", "roughdielectric", "plastic", "roughplastic" };
     Properties p(names[m.type]);
@@ -265,6 +330,13 @@ ref<BSDF> makeBSDF(const dr_material &m) {
         p.setBoolean("sampleVisible", (m.flags & DR_MAT_SAMPLE_VISIBLE) != 0);
     }
     ref<BSDF> bsdf = static_cast<BSDF *>(pm->createObject(MTS_CLASS(BSDF), p));
+    if (textures && (texR || texT)) {               // <texture name="..."> children replace the constant spectra (e.g. diffuse.cpp addChild)
+        const bool plastic = m.type == DR_BSDF_PLASTIC || m.type == DR_BSDF_ROUGHPLASTIC;
+        const char *nameR = m.type == DR_BSDF_DIFFUSE ? "reflectance" : plastic ? "diffuseReflectance" : "specularReflectance";
+        const char *nameT = plastic ? "specularReflectance" : "specularTransmittance";
+        if (texR) bsdf->addChild(nameR, const_cast<Texture *>((*textures)[texR - 1].get()));
+        if (texT) bsdf->addChild(nameT, const_cast<Texture *>((*textures)[texT - 1].get()));
+    }
     bsdf->configure();
     if (m.flags & DR_MAT_TWOSIDED) {
         ref<BSDF> two = static_cast<BSDF *>(pm->createObject(MTS_CLASS(BSDF), Properties("twosided")));
@@ -380,7 +452,9 @@ static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties 
     rs->scene->addChild(sensor);
     rs->filmW = c.film_width; rs->filmH = c.film_height;
 
-    for (uint32_t i = 0; i < d->n_materials; ++i) rs->bsdfs.push_back(makeBSDF(d->materials[i]));
+    std::vector<ref<Texture> > textures;
+    for (uint32_t i = 0; i < d->n_textures; ++i) { textures.push_back(new PinTexture(d->textures[i])); textures.back()->configure(); }
+    for (uint32_t i = 0; i < d->n_materials; ++i) rs->bsdfs.push_back(makeBSDF(d->materials[i], &textures));
 
     if (analytic) {
         /* the camera of `d`, but a room of ANALYTIC shapes instead of its triangles: floor, back wall and two side walls
@@ -410,8 +484,12 @@ static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties 
         const bool smooth = std::get<2>(g.first);
         std::map<uint32_t, uint32_t> remap;
         for (uint32_t t : tris) for (int k = 0; k < 3; ++k) { uint32_t v = d->indices[3 * t + k]; if (!remap.count(v)) { uint32_t n = (uint32_t) remap.size(); remap[v] = n; } }
-        ref<TriMesh> mesh = new TriMesh("mesh", tris.size(), remap.size(), smooth, false, false, false, !smooth);
+        /* a mesh with texture coordinates always gets UV tangents in this reference (TriMesh::configure, trimesh.cpp:400-402), which
+         * is what DR_TRI_UV_TANGENTS says: the caller must have flagged every triangle */
+        if (d->texcoords) for (uint32_t t : tris) if (!d->tri_flags || !(d->tri_flags[t] & DR_TRI_UV_TANGENTS)) { fprintf(stderr, "ref: texcoords without DR_TRI_UV_TANGENTS\n"); return NULL; }
+        ref<TriMesh> mesh = new TriMesh("mesh", tris.size(), remap.size(), smooth, d->texcoords != NULL, false, false, !smooth);
         for (auto &kv : remap) {
+            if (d->texcoords) mesh->getVertexTexcoords()[kv.second] = Point2(d->texcoords[2 * kv.first], d->texcoords[2 * kv.first + 1]);
             mesh->getVertexPositions()[kv.second] = Point(d->positions[3 * kv.first], d->positions[3 * kv.first + 1], d->positions[3 * kv.first + 2]);
             if (smooth) mesh->getVertexNormals()[kv.second] = Normal(d->normals[3 * kv.first], d->normals[3 * kv.first + 1], d->normals[3 * kv.first + 2]);
         }
@@ -443,6 +521,22 @@ static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties 
 }
 
 void ref_scene_destroy(void *h) { delete (RefScene *) h; }
+
+/* Texture2D::eval(its, filter) of a dr_texture at n intersection uv pairs (its.hasUVPartials = false, as on the bidirectional path) */
+int ref_texture_eval(const dr_texture *t, const double *uv, int n, double *rgb, double *average) {
+    initOnce();
+    ref<PinTexture> tex = new PinTexture(*t);
+    Intersection its;
+    its.hasUVPartials = false;
+    for (int i = 0; i < n; ++i) {
+        its.uv = Point2(uv[2 * i], uv[2 * i + 1]);
+        Float r, g, b;
+        tex->eval(its, true).toLinearRGB(r, g, b);
+        rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
+    }
+    if (average) { Float r, g, b; tex->getAverage().toLinearRGB(r, g, b); average[0] = r; average[1] = g; average[2] = b; }
+    return 0;
+}
 void *ref_scene_ptr(void *h) { return ((RefScene *) h)->scene.get(); }     // the mitsuba::Scene, for the drivers in other translation units
 
 // findMaxDimensions (pssmlt_utils.h:27-77) on the scene built from the caller's dr_scene_desc: the primary-sample space sizes of

@@ -137,6 +137,11 @@ PATH_CASES = [("cornell", "mmlt", 6), ("cornell", "bdpt", 5), ("cornell", "path"
               ("plastic", "mmlt", 8), ("plastic", "bdpt", 6), ("plastic", "path", 8),
               ("door", "mmlt", 8), ("door", "path", 8),
               ("roughplastic", "mmlt", 8), ("roughplastic", "bdpt", 6), ("roughplastic", "path", 8)]
+# bitmap textures: their own fixture, tests/golden/ref_texture.npz (tools/make_ref_texture_golden.py)
+SCENES["textured"] = lambda: scenes.cornell_box_textured(film=(128, 128), tess=8, uv_tangents=True)
+TEXTURE_CASES = [("textured", "mmlt", 8), ("textured", "bdpt", 6), ("textured", "path", 8)]
+ALL_CASES = PATH_CASES + TEXTURE_CASES
+GOLDEN_TEXTURE = os.path.join(ROOT, "tests", "golden", "ref_texture.npz")
 N_PATHS = 6000
 N_PATHS_OF = {"door": 48000}      # the door scene's light is occluded: ~1.5 % (MMLT) / 6 % (PT) of uniform vectors contribute
 
@@ -161,7 +166,7 @@ def case_inputs(case, n=None):
     """The replayed primary-sample vectors of a case: a pure function of (case, n)."""
     name, tech, md = case
     n = n or n_paths(case)
-    rng = np.random.RandomState(1234 + 17 * PATH_CASES.index(case))
+    rng = np.random.RandomState(1234 + 17 * ALL_CASES.index(case))
     depth = rng.randint(1, md + 1, n).astype(np.int32)
     ds, de, dd = (6 * (md + 2), 2, 2) if tech == "path" else (3 * (md + 2), 3 * (md + 2), 1)
     us, ue, ud = [rng.rand(n, k).astype(np.float32) for k in (ds, de, dd)]
@@ -229,6 +234,55 @@ def compare_paths(lum, st, pos0, value0, want_lum, want_st, want_pos0, want_valu
     okv = (np.abs(value0[both] - want_value0[both]) <= 1e-4 * np.abs(want_value0[both]) + 1e-6 * scale).all(axis=1)
     assert okv.mean() >= 0.999, what + ": splat RGB differs"
     return rel
+
+
+# ---------------------------------------------------------------- bitmap texture lookups (Texture2D::eval without ray differentials)
+def texture_leaf_cases():
+    """name -> (dr_texture, keep-alive array): every wrap mode, both filters, non-square sizes, scale / offset, a 1x1 texture."""
+    out = {}
+    W = dict(repeat=abi.DR_WRAP_REPEAT, clamp=abi.DR_WRAP_CLAMP, mirror=abi.DR_WRAP_MIRROR, zero=abi.DR_WRAP_ZERO, one=abi.DR_WRAP_ONE)
+
+    def add(name, w, h, seed, wu, wv, nearest, scale=(1.0, 1.0), offset=(0.0, 0.0)):
+        arr = scenes.procedural_texels(w, h, seed, cell=2)
+        t = abi.dr_texture()
+        t.width, t.height, t.texels = w, h, arr.ctypes.data_as(C.POINTER(C.c_float))
+        t.wrap_u, t.wrap_v, t.nearest = W[wu], W[wv], int(nearest)
+        t.uv_scale[:], t.uv_offset[:] = scale, offset
+        out[name] = (t, arr)
+    for i, wu in enumerate(W):
+        add("bilinear_" + wu, 7 + i, 5 + 2 * i, 40 + i, wu, wu, False)
+        add("nearest_" + wu, 9 - i, 4 + i, 50 + i, wu, wu, True)
+    add("bilinear_repeat_mirror_scaled", 16, 8, 60, "repeat", "mirror", False, scale=(3.7, 0.1), offset=(0.3, -2.25))
+    add("nearest_zero_clamp_scaled", 5, 12, 61, "zero", "clamp", True, scale=(0.5, 2.0), offset=(-0.2, 0.6))
+    add("bilinear_1x1", 1, 1, 62, "repeat", "clamp", False)
+    return out
+
+
+def texture_leaf_uv(n=4000, seed=99):
+    rng = np.random.RandomState(seed)
+    uv = rng.uniform(-2.5, 3.5, (n, 2))
+    uv[:200] = rng.uniform(0, 1, (200, 2))
+    uv[200:220] = np.array([[0, 0], [1, 1], [0.5, 0.5], [1, 0], [0, 1], [-1, -1], [2, 2], [1e-17, 1 - 1e-16], [0.25, 0.75], [-0.0, 1.0]] * 2)
+    return np.ascontiguousarray(uv, np.float64)
+
+
+def run_texture(lib, prefix):
+    """RGB of every leaf case at the uv set; -> dict name -> [n, 3] (double)."""
+    fn = getattr(lib, prefix + "texture_eval")
+    uv = texture_leaf_uv()
+    out = {}
+    for name, (t, _keep) in texture_leaf_cases().items():
+        rgb = np.zeros((len(uv), 3), np.float64)
+        if prefix == "ref_":
+            fn.argtypes = [C.c_void_p, PD, C.c_int, PD, PD]
+            avg = np.zeros(3, np.float64)
+            fn(C.byref(t), uv.ctypes.data_as(PD), len(uv), rgb.ctypes.data_as(PD), avg.ctypes.data_as(PD))
+            out["texavg_" + name] = avg
+        else:
+            fn.argtypes = [C.c_void_p, PD, C.c_int, PD]
+            fn(C.byref(t), uv.ctypes.data_as(PD), len(uv), rgb.ctypes.data_as(PD))
+        out["tex_" + name] = rgb
+    return out
 
 
 # ---------------------------------------------------------------- the reference's own integrators, end to end

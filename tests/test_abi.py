@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), "libdrmlt_b200.so does not export %s" % name
     assert sorted(abi.EXPORTED_SYMBOLS) == declared
-    assert lib.dr_abi_version() == 5
+    assert lib.dr_abi_version() == 6
 
 
 def test_struct_layouts_match_header(lib):

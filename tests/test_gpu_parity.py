@@ -44,6 +44,11 @@ SCENE_MAKERS = {
     # microfacet coating over a diffuse base; the rough-transmittance tables are the reference's own (tests/golden/ref_rough_tables.npz)
     "roughplastic": lambda: RP.SCENES["roughplastic"](),
     "door": lambda: scenes.door_scene(film=(160, 90), floor_grid=64, n_spheres=16, sphere_subdiv=2),
+    # bitmap textures on diffuse / roughconductor / plastic parameters: with UV tangents on every mesh (what the
+    # reference does for meshes with texture coordinates), with the edge-based shading frames, and fine enough for the device BVH build
+    "textured": lambda: RP.SCENES["textured"](),
+    "textured-edgeframes": lambda: scenes.cornell_box_textured(film=(128, 128), tess=8, uv_tangents=False),
+    "textured-fine": lambda: scenes.cornell_box_textured(film=(128, 128), tess=12, uv_tangents=True),
     # BASELINE.json's own sizes: C3 (~100 k triangles, 512x512), C4 (~97 k, 512x512), C5 (1.0 M triangles, 1280x720) -- the BVH depth and
     # film the bench runs (the oracle side is sampled: 1e5 rays, 4e4 primary-sample vectors)
     "glossy_full": lambda: scenes.glossy_scene(),
@@ -113,7 +118,7 @@ def test_ray_casting_matches_oracle(name):
 HIT_DTYPE = [("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<i4")]
 
 
-@pytest.mark.parametrize("name", ["cornell", "glossy", "caustic", "door"])
+@pytest.mark.parametrize("name", ["cornell", "glossy", "caustic", "door", "textured-fine"])
 def test_device_built_bvh_gives_the_same_hits_and_jobs(name):
     data = SCENE_MAKERS[name]()
     host, dev = Scene(data, gpu_bvh=False), Scene(data, gpu_bvh=True)
@@ -214,6 +219,11 @@ CASES = [
     ("roughplastic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
     ("roughplastic", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=16)),
     ("roughplastic", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
+    # bitmap textures (bitmap.cpp:432-455, mipmap.h:503-596), texture coordinates and UV tangents (skdtree.h:373-405, trimesh.cpp:708-760)
+    ("textured", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("textured", dict(integrator="pssmlt", technique="path", maxDepth=8, directSamples=16)),
+    ("textured", dict(integrator="drmlt", type="green", technique="bdpt", maxDepth=6, directSamples=-1, directSampling=False)),
+    ("textured-edgeframes", dict(integrator="drmlt", type="mira", technique="mmlt", maxDepth=6, directSamples=-1)),
     # film plugin parameters (film.cpp:30-48, perspective.cpp:126-173): crop window, and a film size other than dr_camera's
     ("cornell", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=6, directSamples=-1,
                      cropOffsetX=24, cropOffsetY=40, cropWidth=64, cropHeight=48)),
@@ -362,6 +372,9 @@ CHAIN_CASES = [
     ("roughplastic", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
     ("roughplastic", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1)),
     ("roughplastic", dict(integrator="pssmlt", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False)),
+    ("textured", dict(integrator="drmlt", type="orbital", technique="mmlt", maxDepth=8, directSamples=-1)),
+    ("textured", dict(integrator="drmlt", type="mira", technique="path", maxDepth=8, directSamples=-1)),
+    ("textured-edgeframes", dict(integrator="pssmlt", technique="bdpt", maxDepth=5, directSamples=-1, directSampling=False)),
 ]
 
 
@@ -690,7 +703,8 @@ def test_equal_mutation_relmse_is_indistinguishable_from_the_oracle(params):
     gpu.close()
 
 
-@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16), ("roughglass", 16), ("roughglass-beckmann", 4), ("plastic", 16), ("roughplastic", 16)])
+@pytest.mark.parametrize("name,samples", [("cornell", 16), ("glossy", 4), ("caustic", 16), ("roughglass", 16), ("roughglass-beckmann", 4), ("plastic", 16), ("roughplastic", 16),
+                                          ("textured", 16)])
 def test_direct_illumination_pass(name, samples):
     """the separate direct image (renderDirectComponent + the `direct` integrator) on keyed samples."""
     gpu, orc, data = pair(name)
@@ -888,9 +902,9 @@ compare_paths = RP.compare_paths
 _ref_gpu_scenes = {}
 
 
-@pytest.mark.parametrize("case", RP.PATH_CASES, ids=RP.case_key)
+@pytest.mark.parametrize("case", RP.ALL_CASES, ids=RP.case_key)
 def test_cuda_paths_match_reference_path_sampler(case):
-    gold = np.load(RP.GOLDEN)
+    gold = np.load(RP.GOLDEN_TEXTURE if case in RP.TEXTURE_CASES else RP.GOLDEN)
     k = RP.case_key(case)
     if case[0] not in _ref_gpu_scenes:
         _ref_gpu_scenes[case[0]] = Scene(RP.SCENES[case[0]]())

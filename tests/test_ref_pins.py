@@ -164,6 +164,55 @@ def _oracle_paths(case):
     return lum, np.stack([r["s"], r["t"], r["n_splats"]], 1), r["pos0"], r["value0"]
 
 
+@pytest.fixture(scope="module")
+def golden_texture():
+    return dict(np.load(RP.GOLDEN_TEXTURE))
+
+
+# ---- bitmap textures: Texture2D::eval -> TMIPMap::evalBilinear / evalBox / evalTexel (texture.cpp:112-121, mipmap.h:503-596)
+@needs_ref_path
+def test_oracle_textures_equal_reference_mipmap_bit_for_bit():
+    ref = RP.run_texture(C.CDLL(RP.REF_PATH), "ref_")
+    got = RP.run_texture(C.CDLL(RP.ORACLE), "orc_")
+    assert len(got) == len(RP.texture_leaf_cases())
+    for k, v in got.items():
+        assert np.array_equal(v, ref[k]), k
+
+
+def test_oracle_textures_reproduce_reference_fixture(golden_texture):
+    got = RP.run_texture(C.CDLL(RP.ORACLE), "orc_")
+    for k, v in got.items():
+        assert np.array_equal(v, golden_texture[k]), k
+    # the fixture sees every boundary condition: lookups outside [0, 1)^2 differ between the wrap modes of one filter
+    uv = RP.texture_leaf_uv()
+    outside = ((uv < 0) | (uv >= 1)).any(axis=1)
+    assert outside.sum() > 1000
+    assert (golden_texture["tex_bilinear_zero"][outside] == 0).all(axis=1).sum() > 500 and (golden_texture["tex_bilinear_one"][outside] == 1).all(axis=1).sum() > 500
+    # Texture::getAverage of the reference = the mean of the texels the host passes (what SceneData.add_texture stores in the material)
+    for name, (t, arr) in RP.texture_leaf_cases().items():
+        assert np.allclose(golden_texture["texavg_" + name], arr.reshape(-1, 3).astype(np.float64).mean(axis=0), rtol=1e-12), name
+
+
+@needs_ref_path
+def test_texture_fixture_is_what_the_reference_computes(golden_texture):
+    k = RP.case_key(RP.TEXTURE_CASES[0])
+    r = RP.run_paths_ref(C.CDLL(RP.REF_PATH), RP.TEXTURE_CASES[0])
+    assert np.allclose(r["lum"], golden_texture[k + "_lum"], rtol=1e-9, atol=0)
+    assert np.array_equal(np.stack([r["s"], r["t"], r["n_splats"]], 1), golden_texture[k + "_st"])
+
+
+@pytest.mark.parametrize("case", RP.TEXTURE_CASES, ids=RP.case_key)
+def test_oracle_textured_paths_reproduce_reference_fixture(case, golden_texture):
+    """The BSDF plugins with <texture> children, TriMesh texture coordinates and UV tangents, through PathSampler::sampleSplats."""
+    k = RP.case_key(case)
+    lum, st, pos0, value0 = _oracle_paths(case)
+    rel = compare_paths(lum, st, pos0, value0, golden_texture[k + "_lum"], golden_texture[k + "_st"].astype(np.int32),
+                        golden_texture[k + "_pos0"], golden_texture[k + "_value0"], k, case[1] == "mmlt")
+    assert np.median(rel) < 1e-12, k
+    # the textures matter: the same vectors on the scene with its textures replaced by their averages give other contributions
+    assert len(np.unique(np.round(value0[lum > 0], 3), axis=0)) > 200
+
+
 @pytest.mark.parametrize("case", RP.PATH_CASES, ids=RP.case_key)
 def test_oracle_paths_reproduce_reference_fixture(case, golden_path):
     k = RP.case_key(case)
