@@ -27,14 +27,28 @@
 #include <mitsuba/core/rfilter.h>
 #include <mitsuba/core/statistics.h>
 #include <mitsuba/core/lock.h>
+#include <mitsuba/core/mstream.h>
+#include <mitsuba/core/serialization.h>
+#include <mitsuba/core/half.h>
+#include <mitsuba/render/texture.h>
 #include <drmlt_b200.h>
 #include "src/bsdfs/rtrans.h"          // RoughTransmittance, as src/bsdfs/roughplastic.cpp includes it (compile with -I<mitsuba root>)
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <vector>
+#include <map>
+#include <algorithm>
 
 MTS_NAMESPACE_BEGIN
+
+// InstanceManager keeps the objects it has serialized in a private map (include/mitsuba/core/serialization.h:84-88).  A BSDF exposes
+// no getter for its textures, but it hands every one of them to the manager when it is serialized (e.g. diffuse.cpp:161-165) -- which is
+// the only enumeration of a BSDF's children Mitsuba offers.  Access to the private member through an explicit template instantiation
+// (the one place the standard lets a private member be named).
+template <typename Tag, typename Tag::type M> struct DrPrivateAccess { friend typename Tag::type get(Tag) { return M; } };
+struct DrObjToId { typedef std::map<const SerializableObject *, unsigned int> InstanceManager::*type; friend type get(DrObjToId); };
+template struct DrPrivateAccess<DrObjToId, &InstanceManager::m_objToId>;
 
 namespace {
 
@@ -98,7 +112,94 @@ void roughTable(bool ggx, Float eta, Float alpha, std::vector<double> &tables) {
     for (int k = 0; k < DR_ROUGH_TABLE_THETA; ++k) tables[base + k] = (double) Peek::trans(ext.get())[k];
 }
 
-bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector<double> &roughTables) {
+// ---- bitmap textures (include/drmlt_b200.h: dr_texture) --------------------------------------------------------------
+struct FlatTextures {
+    std::vector<dr_texture> textures;
+    std::vector<std::vector<float> > texels;              // one array per texture (stable addresses: filled, then pointers taken)
+    std::map<const Texture2D *, uint32_t> index;
+};
+
+// The non-constant 2D textures of a BSDF in the order it serializes them (see DrPrivateAccess above); false: a texture this path cannot take.
+bool texturesOf(const BSDF *bsdf, std::vector<const Texture2D *> &out, std::string &why) {
+    ref<MemoryStream> ms = new MemoryStream();
+    ref<InstanceManager> im = new InstanceManager();
+    im->serialize(ms, bsdf);
+    const std::map<const SerializableObject *, unsigned int> &objs = (*im).*get(DrObjToId());
+    std::vector<std::pair<unsigned int, const Texture2D *> > found;
+    for (std::map<const SerializableObject *, unsigned int>::const_iterator it = objs.begin(); it != objs.end(); ++it) {
+        const Class *cls = it->first->getClass();
+        if (!cls->derivesFrom(MTS_CLASS(Texture))) continue;
+        const Texture *t = static_cast<const Texture *>(it->first);
+        if (t->isConstant()) continue;
+        if (!cls->derivesFrom(MTS_CLASS(Texture2D)) || t->toString().find("TMIPMap[") == std::string::npos) {
+            why = "texture " + cls->getName() + " (only bitmap textures are flattened)"; return false;
+        }
+        found.push_back(std::make_pair(it->second, static_cast<const Texture2D *>(t)));
+    }
+    std::sort(found.begin(), found.end());
+    for (size_t i = 0; i < found.size(); ++i) out.push_back(found[i].second);
+    return true;
+}
+
+// One bitmap texture -> dr_texture: MIP level 0 as the texture holds it (BitmapTexture::getBitmap = TMIPMap::toBitmap, bitmap.cpp:483-485:
+// half precision), filter and boundary conditions from the mipmap's description (mipmap.h:718-740), Texture2D's uv scale / offset.
+bool flattenTexture(const Texture2D *t, FlatTextures &ft, uint32_t &idx, std::string &why) {
+    std::map<const Texture2D *, uint32_t>::const_iterator known = ft.index.find(t);
+    if (known != ft.index.end()) { idx = known->second; return true; }
+    struct Peek : public Texture2D {
+        static Point2 offset(const Texture2D *x) { return x->*(&Peek::m_uvOffset); }
+        static Vector2 scale(const Texture2D *x) { return x->*(&Peek::m_uvScale); }
+    };
+    const std::string str = t->toString();
+    ref<Bitmap> bmp = t->getBitmap();
+    const int ch = bmp->getChannelCount();
+    if (!(bmp->getPixelFormat() == Bitmap::ERGB || bmp->getPixelFormat() == Bitmap::ELuminance) || (ch != 1 && ch != 3)) { why = "bitmap texture with an unsupported pixel format"; return false; }
+    const size_t n = (size_t) bmp->getWidth() * (size_t) bmp->getHeight();
+    std::vector<float> texels(3 * n);
+    for (size_t i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) {
+            const size_t k = i * ch + (ch == 3 ? c : 0);
+            float v;
+            switch (bmp->getComponentFormat()) {
+                case Bitmap::EFloat16: v = (float) bmp->getFloat16Data()[k]; break;
+                case Bitmap::EFloat32: v = bmp->getFloat32Data()[k]; break;
+                case Bitmap::EFloat64: v = (float) bmp->getFloat64Data()[k]; break;
+                default: why = "bitmap texture with an unsupported component format"; return false;
+            }
+            texels[3 * i + c] = v;
+        }
+    dr_texture d;
+    memset(&d, 0, sizeof(d));
+    d.width = (uint32_t) bmp->getWidth(); d.height = (uint32_t) bmp->getHeight();
+    // "filterType = bilinear," and "bc = [repeat, mirror]," (ReconstructionFilter::EBoundaryCondition by name, rfilter.cpp operator<<)
+    size_t f = str.find("filterType = "), b = str.find("bc = [");
+    if (f == std::string::npos || b == std::string::npos) { why = "cannot parse the texture's MIP map description"; return false; }
+    d.nearest = str.compare(f + 13, 7, "nearest") == 0;      // ewa / trilinear / bilinear: bilinear in level 0 without ray differentials (bitmap.cpp:432-455)
+    const size_t comma = str.find(", ", b), close = str.find(']', b);
+    if (comma == std::string::npos || close == std::string::npos || comma > close) { why = "cannot parse the texture's wrap modes"; return false; }
+    const std::string names[2] = { str.substr(b + 6, comma - (b + 6)), str.substr(comma + 2, close - (comma + 2)) };
+    uint32_t wrap[2];
+    for (int a = 0; a < 2; ++a) {
+        if (names[a] == "repeat") wrap[a] = DR_WRAP_REPEAT;
+        else if (names[a] == "clamp") wrap[a] = DR_WRAP_CLAMP;
+        else if (names[a] == "mirror") wrap[a] = DR_WRAP_MIRROR;
+        else if (names[a] == "zero") wrap[a] = DR_WRAP_ZERO;
+        else if (names[a] == "one") wrap[a] = DR_WRAP_ONE;
+        else { why = "unknown texture wrap mode " + names[a]; return false; }
+    }
+    d.wrap_u = wrap[0]; d.wrap_v = wrap[1];
+    d.uv_scale[0] = (double) Peek::scale(t).x; d.uv_scale[1] = (double) Peek::scale(t).y;
+    d.uv_offset[0] = (double) Peek::offset(t).x; d.uv_offset[1] = (double) Peek::offset(t).y;
+    idx = (uint32_t) ft.textures.size();
+    if (idx >= DR_MAX_TEXTURES) { why = "too many textures"; return false; }
+    ft.textures.push_back(d);
+    ft.texels.push_back(std::vector<float>());
+    ft.texels.back().swap(texels);
+    ft.index[t] = idx;
+    return true;
+}
+
+bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector<double> &roughTables, FlatTextures &ft) {
     memset(&m, 0, sizeof(m));
     m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 1.f;
     m.transmittance[0] = m.transmittance[1] = m.transmittance[2] = 1.f;
@@ -115,14 +216,58 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector
         if (from == std::string::npos) { why = "cannot parse twosided"; return false; }
         from += strlen("nestedBRDF[0] = ");
         model = ts.className(from);
+        if (model.compare(0, 4, "ref<") == 0) {          // ref<T>::toString: "ref<SmoothDiffuse>[ref=2, ptr=SmoothDiffuse[..."
+            size_t ptr = str.find("ptr=", from);
+            if (ptr == std::string::npos) { why = "cannot parse twosided"; return false; }
+            from = ptr + 4;
+            model = ts.className(from);
+        }
         nested = true;
     }
+    // Textured colour parameters: the BSDF's non-constant textures, in the order it serializes them (diffuse.cpp:161-165, dielectric.cpp:176-182,
+    // conductor.cpp:201-205, roughconductor.cpp:215-224, roughdielectric.cpp:226-237, plastic.cpp:176-184, roughplastic.cpp:242-253), matched with
+    // the parameters toString() prints as something other than a Constant*Texture.  slot 0 = dr_material.reflectance, 1 = .transmittance.
+    struct Param { const char *name; int slot; };
+    static const Param pDiffuse[] = { { "reflectance", 0 }, { NULL, 0 } };
+    static const Param pDielectric[] = { { "specularReflectance", 0 }, { "specularTransmittance", 1 }, { NULL, 0 } };
+    static const Param pConductor[] = { { "specularReflectance", 0 }, { NULL, 0 } };
+    static const Param pRoughConductor[] = { { "alphaU", -1 }, { "alphaV", -1 }, { "specularReflectance", 0 }, { NULL, 0 } };
+    static const Param pRoughDielectric[] = { { "alphaU", -1 }, { "alphaV", -1 }, { "specularReflectance", 0 }, { "specularTransmittance", 1 }, { NULL, 0 } };
+    static const Param pPlastic[] = { { "specularReflectance", 1 }, { "diffuseReflectance", 0 }, { NULL, 0 } };
+    static const Param pRoughPlastic[] = { { "specularReflectance", 1 }, { "diffuseReflectance", 0 }, { "alpha", -1 }, { NULL, 0 } };
+    const Param *params = model == "SmoothDiffuse" ? pDiffuse : model == "SmoothDielectric" ? pDielectric : model == "SmoothConductor" ? pConductor :
+        model == "RoughConductor" ? pRoughConductor : model == "RoughDielectric" ? pRoughDielectric : model == "SmoothPlastic" ? pPlastic :
+        model == "RoughPlastic" ? pRoughPlastic : NULL;
+    std::vector<const Texture2D *> texs;
+    if (!texturesOf(bsdf, texs, why)) return false;
+    if (!texs.empty()) {
+        size_t k = 0;
+        bool texRset = false, texTset = false;
+        for (const Param *p = params; p && p->name; ++p) {
+            size_t pos = str.find(std::string(p->name) + " = ", from);
+            if (pos == std::string::npos) continue;
+            // constants print as "Constant*Texture[...]", a bare spectrum "[r, g, b]" or a bare number (ConstantFloatTexture, basicshader.h:125-129)
+            const size_t vpos = str.find_first_not_of(" \n\t", pos + strlen(p->name) + 3);
+            if (vpos == std::string::npos || str.compare(vpos, 8, "Constant") == 0 || strchr("[-+.0123456789", str[vpos])) continue;
+            if (p->slot < 0) { why = "textured roughness"; return false; }
+            if (k >= texs.size()) { why = "textures shared between parameters"; return false; }
+            const Texture2D *t = texs[k++];
+            uint32_t idx = 0;
+            if ((p->slot == 0 ? texRset : texTset)) { why = "two textures on one parameter slot"; return false; }
+            (p->slot == 0 ? texRset : texTset) = true;
+            if (!flattenTexture(t, ft, idx, why)) return false;
+            m.flags |= p->slot == 0 ? DR_MAT_TEX_REFLECTANCE(idx) : DR_MAT_TEX_TRANSMITTANCE(idx);
+            toRGB(t->getAverage(), p->slot == 0 ? m.reflectance : m.transmittance);   // what the sampling weights of plastic / roughplastic read
+        }
+        if (k != texs.size()) { why = "texture on a parameter of " + model + " this path does not take (scaled or nested textures): " + str.substr(0, 300); return false; }
+    }
+    const bool texR = ((m.flags >> 8) & 0xfffu) != 0, texT = (m.flags >> 20) != 0;
     if (model == "SmoothDiffuse") {                       // src/bsdfs/diffuse.cpp
         m.type = DR_BSDF_DIFFUSE;
         // the exact constant when it was given as a property; a <texture> child (no property) must not fall back to the default silently
         if (!nested && (props.hasProperty("reflectance") || props.hasProperty("diffuseReflectance")))
             toRGB(props.getSpectrum(props.hasProperty("reflectance") ? "reflectance" : "diffuseReflectance", Spectrum(.5f)), m.reflectance);
-        else if (!ts.spectrum("reflectance", from, m.reflectance)) { why = "textured diffuse reflectance"; return false; }
+        else if (!texR && !ts.spectrum("reflectance", from, m.reflectance)) { why = "cannot parse diffuse reflectance"; return false; }
     } else if (model == "SmoothDielectric") {             // src/bsdfs/dielectric.cpp
         m.type = DR_BSDF_DIELECTRIC;
         float eta = 0.f;
@@ -150,8 +295,8 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector
         float eta = 0.f;
         if (!ts.scalar("eta", from, eta)) { why = "cannot parse plastic eta"; return false; }
         m.eta[0] = eta;                                   // intIOR / extIOR
-        m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 0.5f;                  // diffuseReflectance default (plastic.cpp:160)
-        if (!ts.spectrum("diffuseReflectance", from, m.reflectance)) { why = "textured plastic diffuseReflectance"; return false; }
+        if (!texR) m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 0.5f;       // diffuseReflectance default (plastic.cpp:160)
+        if (!texR && !ts.spectrum("diffuseReflectance", from, m.reflectance)) { why = "cannot parse plastic diffuseReflectance"; return false; }
         ts.spectrum("specularReflectance", from, m.transmittance);                      // dr_material: transmittance = specularReflectance
         size_t nl = str.find("nonlinear = ", from);
         if (nl != std::string::npos && str[nl + 12] == '1') m.flags |= DR_MAT_NONLINEAR;
@@ -163,9 +308,9 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector
         size_t a = str.find("alpha = ConstantFloatTexture", from);
         if (a == std::string::npos || !ts.scalar("alpha", from, alpha)) { why = "textured roughness"; return false; }
         m.alpha = alpha;
-        m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 0.5f;                  // diffuseReflectance default (roughplastic.cpp:200)
-        if (!ts.spectrum("diffuseReflectance", from, m.reflectance)) { why = "textured rough plastic diffuseReflectance"; return false; }
-        if (!ts.spectrum("specularReflectance", from, m.transmittance)) { why = "textured rough plastic specularReflectance"; return false; }
+        if (!texR) m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 0.5f;       // diffuseReflectance default (roughplastic.cpp:200)
+        if (!texR && !ts.spectrum("diffuseReflectance", from, m.reflectance)) { why = "cannot parse rough plastic diffuseReflectance"; return false; }
+        if (!texT && !ts.spectrum("specularReflectance", from, m.transmittance)) { why = "cannot parse rough plastic specularReflectance"; return false; }
         size_t d = str.find("distribution = ", from);
         if (d == std::string::npos) { why = "no distribution"; return false; }
         if (str.compare(d + 15, 3, "ggx") == 0) m.flags |= DR_MAT_GGX;
@@ -297,6 +442,7 @@ public:
         std::vector<int32_t> triEm;
         std::vector<dr_material> mats;
         std::vector<double> roughTables;           // DR_ROUGH_TABLE_DOUBLES per roughplastic material
+        FlatTextures flatTextures;                 // bitmap textures bound to colour parameters (dr_texture)
         std::vector<dr_emitter> ems;
         bool anyNormals = false;
         // triangle meshes as they are; analytic shapes (rectangle, sphere, disk, cylinder, heightfield: SURVEY 8f rank 4) through the
@@ -322,7 +468,7 @@ public:
             const bool tangents = tex && mesh->getUVTangents() != NULL;
             anyTexcoords |= tex != NULL;
             dr_material mat; std::string why;
-            if (!owner->getBSDF() || !flattenBSDF(owner->getBSDF(), mat, why, roughTables)) Log(EError, "Mesh \"%s\": %s", owner->getName().c_str(), why.c_str());
+            if (!owner->getBSDF() || !flattenBSDF(owner->getBSDF(), mat, why, roughTables, flatTextures)) Log(EError, "Mesh \"%s\": %s", owner->getName().c_str(), why.c_str());
             mats.push_back(mat);
             const uint32_t base = (uint32_t) (P.size() / 3), firstTri = (uint32_t) triMat.size();
             const Point *pos = mesh->getVertexPositions();
@@ -361,6 +507,8 @@ public:
         desc.tri_material = triMat.data(); desc.tri_emitter = triEm.data(); desc.tri_flags = triFlags.data();
         desc.materials = mats.data(); desc.emitters = ems.empty() ? NULL : ems.data();
         desc.texcoords = anyTexcoords ? UV.data() : NULL;
+        for (size_t t = 0; t < flatTextures.textures.size(); ++t) flatTextures.textures[t].texels = flatTextures.texels[t].data();
+        desc.textures = flatTextures.textures.empty() ? NULL : flatTextures.textures.data(); desc.n_textures = (uint32_t) flatTextures.textures.size();
         desc.rough_tables = roughTables.empty() ? NULL : roughTables.data(); desc.n_rough_tables = (uint32_t) (roughTables.size() / DR_ROUGH_TABLE_DOUBLES);
         const Matrix4x4 &tw = cam->getWorldTransform()->eval(0).getMatrix();
         for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) desc.camera.to_world[4 * r + c] = (float) tw(r, c);

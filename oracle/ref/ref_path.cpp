@@ -246,6 +246,7 @@ public:
     /* bitmap.cpp:175-177 stores TSpectrum<half, 3>; this compiler rejects the explicit TSpectrum<half> -> Color3 conversion inside
      * evalTexel, so the half triple gets the two conversions spelled out (same half class, include/mitsuba/core/half.h) */
     struct Color3h {
+        typedef half Scalar;
         half s[3];
         Color3h() {}
         Color3h(const Color3 &c) { for (int i = 0; i < 3; ++i) s[i] = half((float) c[i]); }
@@ -275,6 +276,8 @@ public:
         for (size_t i = 0; i < 3 * (size_t) t.width * t.height; ++i) dst[i] = (Float) t.texels[i];
         m_mipmap = new MIPMap3(bitmap, Bitmap::ERGB, Bitmap::EFloat, NULL, bc(t.wrap_u), bc(t.wrap_v), t.nearest ? ENearest : EBilinear, 20.0f);
     }
+    /* serializable like BitmapTexture (the drop-in plugin enumerates a BSDF's textures by serializing it); never unserialized */
+    PinTexture(Stream *stream, InstanceManager *manager) : Texture2D(stream, manager) { SLog(EError, "PinTexture cannot be unserialized"); }
     Spectrum eval(const Point2 &uv) const {          // bitmap.cpp:432-455 (the RGB branch)
         Spectrum result;
         Color3 value;
@@ -291,11 +294,17 @@ public:
     bool isMonochromatic() const { return false; }
     bool usesRayDifferentials() const { return true; }   // bitmap.cpp:542-544
     Vector3i getResolution() const { return Vector3i(m_mipmap->getWidth(), m_mipmap->getHeight(), 1); }
+    ref<Bitmap> getBitmap(const Vector2i &) const { return m_mipmap->toBitmap(); }      // bitmap.cpp:483-485
+    std::string toString() const {                                                      // bitmap.cpp:566-578
+        std::ostringstream oss;
+        oss << "BitmapTexture[" << endl << "  filename = \"\"," << endl << "  mipmap = " << indent(m_mipmap.toString()) << endl << "]";
+        return oss.str();
+    }
     MTS_DECLARE_CLASS()
 private:
     ref<MIPMap3> m_mipmap;
 };
-MTS_IMPLEMENT_CLASS(PinTexture, false, Texture2D)
+MTS_IMPLEMENT_CLASS_S(PinTexture, false, Texture2D)
 
 ref<BSDF> makeBSDF(const dr_material &m, const std::vector<ref<Texture> > *textures = NULL) {
     const uint32_t texR = (m.flags >> 8) & 0xfffu, texT = m.flags >> 20;       // DR_MAT_TEX_*: 1 + texture index

@@ -1167,6 +1167,44 @@ def test_drop_in_plugin_tessellates_analytic_shapes(tmp_path):
     assert RP.rel_mse(img, gold["analytic_image"]) < 0.05
 
 
+# SURVEY 8f rank 4, bitmap textures through the plugin: the reference's own DRMLT integrator on the textured Cornell box (BSDF plugins with
+# <texture> children, tests/golden/ref_texture.npz, three runs) against the plugin's job on the same mitsuba::Scene -- the shim finds the BSDFs'
+# textures (the objects a BSDF hands to the InstanceManager when it is serialized), reads MIP level 0, filter, wrap modes, uv scale / offset,
+# and passes texture coordinates and UV-tangent flags of the meshes (shim/mts_plugin.cpp).  The twosided box exercises the nested parse.
+@pytest.mark.skipif(not os.path.exists(os.path.join(PLUGIN_DIR, "drmlt.so")), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
+def test_drop_in_plugin_flattens_bitmap_textures(tmp_path):
+    import json
+    import subprocess
+    import sys
+    gold = dict(np.load(RP.GOLDEN_TEXTURE))
+    out = str(tmp_path / "textured.npy")
+    p = subprocess.run([sys.executable, os.path.join(RP.ROOT, "tools", "plugin_render.py"), "drmlt_orbital_mmlt", out, "--textured"],
+                       capture_output=True, text=True, timeout=300)
+    line = [ln for ln in p.stdout.splitlines() if "PLUGIN_RENDER " in ln]
+    assert line, (p.stdout[-1500:], p.stderr[-1500:])
+    info = json.loads(line[-1][line[-1].index("PLUGIN_RENDER ") + len("PLUGIN_RENDER "):])
+    assert info["ok"], (info, p.stdout[-1500:])
+    img = np.load(out)
+    b, bs = float(RP.luminance(img).mean()), gold["textured_b"]
+    assert abs(b - bs.mean()) <= 0.005 * bs.mean() + (bs.max() - bs.min()) / 2, (b, bs)
+    for k, vals in zip(gold["textured_stats_names"], gold["textured_stats"].T):
+        assert abs(info["stats"][str(k)] - vals.mean()) <= 1.0 + (vals.max() - vals.min()), (str(k), info["stats"][str(k)], vals)
+    # the picture: the plugin's image against the reference's, and against the same scene rendered through the C ABI directly (what the
+    # flattening must reproduce) -- 8x8-pixel blocks, relative L1
+    lo = lambda im: im.astype(np.float64).reshape(8, 8, 8, 8, 3).mean(axis=(1, 3))     # noqa: E731
+    ref_img = lo(gold["textured_image"])
+    assert np.abs(lo(img) - ref_img).sum() / ref_img.sum() < 0.06        # (two independent 1 024-spp renders are ~3 % apart)
+    params, spp = RP.RENDER_CASES["drmlt_orbital_mmlt"]
+    direct, _ = Scene(scenes.cornell_box_textured(film=(64, 64), tess=4)).render(make_config(seed=5, sampleCount=spp, **params))
+    assert np.abs(lo(img) - lo(direct)).sum() / lo(direct).sum() < 0.06
+    # ... and the textures are in the picture: the same box with every texture replaced by its average is further away than that
+    flat = scenes.cornell_box_textured(film=(64, 64), tess=4)
+    for m in flat.materials:
+        m.flags &= 0xff
+    untextured, _ = Scene(flat).render(make_config(seed=5, sampleCount=spp, **params))
+    assert np.abs(lo(untextured) - ref_img).sum() / ref_img.sum() > 0.10  # (~16 %)
+
+
 # SURVEY 8f rank 3, whole job: the reference's OWN two-stage MLT -- mltLuminancePass (nested job on a film / 4, luminance map,
 # Bitmap::resample), SplatList::normalize(importanceMap), develop x importance -- run end to end in oracle/_ref
 # (tests/golden/ref_twostage.npz, tools/make_ref_twostage_golden.py, three runs) against dr_render with twoStage=true.

@@ -21,11 +21,15 @@ name, out = sys.argv[1], sys.argv[2]
 spp = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else None
 if "--analytic" in sys.argv:            # a room of ANALYTIC shapes (rectangles, a sphere; ref_path.cpp scene_create): the plugin tessellates them
     os.environ["REF_ANALYTIC_SCENE"] = "1"
+data = None
+if "--textured" in sys.argv:            # the Cornell box with bitmap textures: the plugin enumerates and flattens the BSDFs' textures
+    from drmlt_mitsuba_b200 import scenes
+    data = scenes.cornell_box_textured(film=(64, 64), tess=4)
 if "--reference" not in sys.argv:       # (--reference: the reference's own integrator instead of the plugin -- writes the fixture)
     os.environ["REF_PLUGIN_DIR"] = os.path.join(ROOT, "oracle", "_ref", "plugins")
 params, case_spp = RP.RENDER_CASES[name]
 try:
-    img, sec, _, stats = RP.run_render_ref(C.CDLL(RP.REF_PATH), params, spp or case_spp, threads=2 if "--reference" not in sys.argv else (os.cpu_count() or 2))
+    img, sec, _, stats = RP.run_render_ref(C.CDLL(RP.REF_PATH), params, spp or case_spp, threads=2 if "--reference" not in sys.argv else (os.cpu_count() or 2), data=data)
 except AssertionError as e:
     print("PLUGIN_RENDER " + json.dumps({"ok": False, "error": str(e)}), flush=True)
     os._exit(3)
