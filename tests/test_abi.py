@@ -34,6 +34,8 @@ def test_struct_layouts_match_header(lib):
     assert C.sizeof(abi.dr_ray) == 32 and C.sizeof(abi.dr_hit) == 16
     assert C.sizeof(abi.dr_step_record) == 24
     assert C.sizeof(abi.dr_emitter) == 24
+    assert C.sizeof(abi.dr_texture) == 64
+    assert abi.DR_MAT_TEX_REFLECTANCE(0) == 0x100 and abi.DR_MAT_TEX_TRANSMITTANCE(2) == 3 << 20      # 1 + index in bits 8-19 / 20-31
     # the library and the ctypes mirror agree on dr_config: defaults land in the right fields
     cfg = abi.dr_config()
     lib.dr_config_default(C.byref(cfg))
@@ -131,3 +133,21 @@ def test_argument_validation_needs_no_device(lib):
             desc.n_rough_tables = 0
         assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) == 1 and needle in lib.dr_last_error(), lib.dr_last_error()
     assert lib.dr_scene_create_ex(None, 0, 1, C.byref(h)) == 1
+    # bitmap textures (ABI 6): texture indices, texel pointers, wrap modes, UV tangents need texture coordinates
+    def textured():
+        data = scenes.SceneData("tex", (16, 16))
+        t = data.add_texture(scenes.procedural_texels(4, 4, 1))
+        m = data.add_material(abi.DR_BSDF_DIFFUSE, reflectance_tex=t)
+        data.add_quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0), m, uv=True, uv_tangents=True)
+        data.set_camera((0, 0, 3), (0, 0, 0), (0, 1, 0), 40.0)
+        return data
+    data = textured(); desc = data.desc(); desc.n_textures = 0
+    assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) == 1 and b"texture index out of range" in lib.dr_last_error()
+    data = textured(); desc = data.desc(); desc.texcoords = None
+    assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) == 1 and b"DR_TRI_UV_TANGENTS without texcoords" in lib.dr_last_error()
+    data = textured(); data.textures[0].wrap_u = 7; desc = data.desc()
+    assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) == 1 and b"wrap mode" in lib.dr_last_error()
+    data = textured(); data.textures[0].texels = None; desc = data.desc()
+    assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) == 1 and b"missing texels" in lib.dr_last_error()
+    data = textured(); desc = data.desc()                       # a valid textured scene passes validation (and then needs the device)
+    assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) in (0, 2)
