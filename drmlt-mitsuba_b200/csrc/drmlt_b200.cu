@@ -1085,6 +1085,10 @@ static dr_status run_machine(dr_job j, const JobParams &job, unsigned long long 
     const bool mmlt = j->cfg.technique == DR_TECH_MMLT;
     const unsigned typeMask = static_cast<SceneImpl *>(j->scene)->typeMask;
     const int walkLaunches = mmlt || j->M.pc.bdBatch ? 2 : 1;
+    if (const char *e = getenv("DRMLT_ROUNDS_PER_POLL")) {      // tuning aid: rounds per graph replay = per host poll of the queue counters
+        const int r = atoi(e);
+        if (r >= 2 && r <= 512) j->roundsPerPoll = r & ~1;
+    }
     const int R = j->roundsPerPoll;                             // even: a replay starts at the parity it was captured with
     CK(cudaStreamSynchronize(j->stream));                       // everything queued on the main stream is visible to the groups
     cudaStream_t s0 = j->groups[0].stream;

@@ -56,19 +56,6 @@ k_trace(const __grid_constant__ Machine M) {
         //      one wait, and the phase ends once fewer than TRACE_DESCEND lanes are still descending; (B) the lanes that
         //      hold a leaf intersect its triangles together.  Repeat until too few lanes are busy (refill) or all are done.
         for (;;) {
-#ifdef DR_TRACE_SPEC
-            // speculative while-while: a lane that reaches a leaf postpones it and keeps descending from its stack; the phase ends once
-            // fewer than TRACE_DESCEND lanes can still descend and some lane is stalled (second leaf, or nothing left to descend)
-            for (;;) {
-                const bool descending = lane >= 0 && !tr.done && tr.cur >= 0;
-                if (descending) { tr.node_step(M.sc); if (!tr.done) tr.postpone(); }
-                const unsigned still = __ballot_sync(0xffffffffu, lane >= 0 && !tr.done && tr.cur >= 0);
-                const unsigned stalled = __ballot_sync(0xffffffffu, lane >= 0 && !tr.done && tr.stalled());
-                if (still == 0 || (stalled != 0 && __popc(still) < M.traceDescend)) break;
-            }
-            if (lane >= 0 && !tr.done && tr.pending != 0) tr.pending_step(M.sc);
-            if (lane >= 0 && !tr.done) tr.postpone();      // a second leaf waiting in cur becomes the next postponed one
-#else
             for (;;) {
                 const bool descending = lane >= 0 && !tr.done && tr.cur >= 0;
                 if (descending) tr.node_step(M.sc);
@@ -77,7 +64,6 @@ k_trace(const __grid_constant__ Machine M) {
                 if (still == 0 || (leafy != 0 && __popc(still) < M.traceDescend)) break;
             }
             if (lane >= 0 && !tr.done && tr.cur < 0) tr.leaf_step(M.sc);
-#endif
             if (lane >= 0 && tr.done) {
                 const bool found = tr.hit.tri >= 0;
                 int dest;

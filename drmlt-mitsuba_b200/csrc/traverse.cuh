@@ -95,17 +95,10 @@ struct Traversal {
         inv = f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
                  1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
         oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-        sp = 0; cur = 0; pending = 0;
+        sp = 0; cur = 0;
         done = !(tmax > tmin);
     }
-    DR_D void pop() { if (sp == 0) { if (pending != 0) cur = DR_NO_CHILD; else done = true; } else cur = stack[--sp]; }
-    // speculative schedule (k_trace): a leaf the descent arrives at is POSTPONED -- the lane takes the next entry off its stack and goes on
-    // descending with the other lanes; the leaves are intersected together later.  cur == DR_NO_CHILD: nothing left to descend.
-    int pending;              // postponed leaf code (< 0), 0 = none
-    DR_D void postpone() {
-        if (cur < 0 && cur != DR_NO_CHILD && pending == 0) { pending = cur; cur = sp == 0 ? DR_NO_CHILD : stack[--sp]; }
-    }
-    DR_D bool stalled() const { return cur < 0 && (pending != 0 || cur == DR_NO_CHILD); }   // holds a leaf it cannot postpone, or ran out of nodes
+    DR_D void pop() { if (sp == 0) done = true; else cur = stack[--sp]; }
     DR_D void step(const DevScene &sc) { if (cur >= 0) node_step(sc); else leaf_step(sc); }
 #ifdef DR_BVH4
     // 4-wide node: seven 16-byte loads (six box planes x four children, four child codes), four independent slab tests,
@@ -165,16 +158,8 @@ struct Traversal {
         }
     }
 #endif
-    DR_D void leaf_step(const DevScene &sc) { leaf_test(sc, cur); if (!done) pop(); }
-    // the postponed leaf, then: done if the stack and the current slot are empty too
-    DR_D void pending_step(const DevScene &sc) {
-        const int leaf = pending;
-        pending = 0;
-        leaf_test(sc, leaf);
-        if (!done && cur == DR_NO_CHILD) done = true;
-    }
-    DR_D void leaf_test(const DevScene &sc, int leafCode) {
-        const int code = ~leafCode;
+    DR_D void leaf_step(const DevScene &sc) {
+        const int code = ~cur;
         const int first = code >> 2, count = (code & 3) + 1;
         for (int i = 0; i < count; ++i) {
             const float4 *tp = sc.tris + 3 * (size_t) (first + i);
@@ -203,6 +188,7 @@ struct Traversal {
                 }
             }
         }
+        pop();
     }
 };
 
