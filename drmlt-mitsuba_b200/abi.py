@@ -127,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "dr_config_validate", "dr_scene_create", "dr_scene_create_ex", "dr_scene_bvh_info", "dr_scene_destroy", "dr_scene_reupload", "dr_scene_clone", "dr_render_multi", "dr_render", "dr_cancel",
     "dr_job_create", "dr_job_destroy", "dr_job_bootstrap", "dr_job_seed_chains", "dr_job_run",
     "dr_job_film_device", "dr_job_develop", "dr_job_stats", "dr_job_profile", "dr_job_direct", "dr_direct_image", "dr_job_num_chains", "dr_job_total_mutations",
-    "dr_trace_rays", "dr_eval_paths", "dr_chain_steps", "dr_chain_replay", "dr_splat_points", "dr_bootstrap_luminance", "dr_max_dimensions",
+    "dr_trace_rays", "dr_texture_eval", "dr_eval_paths", "dr_chain_steps", "dr_chain_replay", "dr_splat_points", "dr_bootstrap_luminance", "dr_max_dimensions",
     "dr_render_progressive", "dr_film_size", "dr_first_stage_config", "dr_resample_luminance", "dr_importance_map",
 ]
 
@@ -188,6 +188,7 @@ def load_library(path=None):
     lib.dr_job_total_mutations.argtypes = [C.c_void_p]
     lib.dr_job_total_mutations.restype = C.c_int64
     lib.dr_trace_rays.argtypes = [C.c_void_p, P(dr_ray), C.c_int64, C.c_int, P(dr_hit)]
+    lib.dr_texture_eval.argtypes = [C.c_void_p, C.c_uint32, P(C.c_double), C.c_int64, P(C.c_double)]
     lib.dr_eval_paths.argtypes = [C.c_void_p, P(dr_config), P(C.c_float), C.c_int, P(C.c_float), C.c_int,
                                   P(C.c_float), C.c_int, P(C.c_int32), C.c_int64, P(dr_path_result)]
     lib.dr_chain_steps.argtypes = [C.c_void_p, P(dr_config), C.c_double, P(C.c_uint64), P(C.c_int32), P(C.c_uint64),

@@ -258,6 +258,7 @@ struct HostUpload { void *dev; char *host; size_t bytes; };   // host: pinned st
 struct SceneImpl : dr_scene_t {
     std::vector<HostUpload> uploads;     // host staging copies (kept for dr_scene_reupload)
     unsigned int *dOrder = nullptr;      // leaf order -> caller's triangle index
+    uint32_t nTextures = 0;
     size_t uploadBytes = 0;
 };
 
@@ -600,6 +601,7 @@ extern "C" dr_status dr_scene_create_ex(const dr_scene_desc *d, int device, uint
             for (size_t i = 0; i < n; ++i) texels[dt.first + i] = make_float4(tx.texels[3 * i], tx.texels[3 * i + 1], tx.texels[3 * i + 2], 0.f);
         }
         if ((st = upload(s, uvs, &ds.uvs)) || (st = upload(s, texels, &ds.texels)) || (st = upload(s, textures, &ds.textures))) return fail(st);
+        s->nTextures = d->n_textures;
     }
     ds.nEmitters = (int) d->n_emitters; ds.nTris = (int) d->n_triangles; ds.nNodes = (int) s->nNodes; ds.rootIsLeaf = 0;
     ds.epsilon = 1e-4f; ds.shadowEpsilon = 1e-3f;     // constants.h:29-30 (single precision)
@@ -639,7 +641,7 @@ extern "C" dr_status dr_scene_clone(dr_scene scene, int device, dr_scene *out) {
     const SceneImpl *src = static_cast<const SceneImpl *>(scene);
     CK(cudaSetDevice(device));
     SceneImpl *s = new SceneImpl();
-    s->device = device; s->filmW = src->filmW; s->filmH = src->filmH; s->nTris = src->nTris; s->nNodes = src->nNodes; s->typeMask = src->typeMask;
+    s->device = device; s->filmW = src->filmW; s->filmH = src->filmH; s->nTris = src->nTris; s->nNodes = src->nNodes; s->typeMask = src->typeMask; s->nTextures = src->nTextures;
     s->dev = src->dev;
     auto fail = [&](dr_status code) { dr_scene_destroy(s); return code; };
     // the device pointers of DevScene, in the order dr_scene_create uploaded them
@@ -1772,6 +1774,22 @@ extern "C" dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n
     launch_trace_rays(s->dev, dr.as<dr_ray>(), n, shadow, s->dOrder, dh.as<dr_hit>(), 0);
     CKL();
     CK(cudaMemcpy(hits, dh.p, n * sizeof(dr_hit), cudaMemcpyDeviceToHost));
+    return DR_OK;
+}
+
+extern "C" dr_status dr_texture_eval(dr_scene scene, uint32_t texture, const double *uv, int64_t n, double *rgb) {
+    if (!scene || (n > 0 && (!uv || !rgb)) || n < 0) { dr_set_error("dr_texture_eval: bad argument"); return DR_ERR_INVALID_ARG; }
+    SceneImpl *s = static_cast<SceneImpl *>(scene);
+    if (texture >= s->nTextures) { dr_set_error("dr_texture_eval: texture index %u out of range (%u textures)", texture, s->nTextures); return DR_ERR_INVALID_ARG; }
+    if (n == 0) return DR_OK;
+    CK(cudaSetDevice(s->device));
+    DevBuf du, dc;
+    dr_status st;
+    if ((st = du.alloc(n * 2 * sizeof(double))) || (st = dc.alloc(n * 3 * sizeof(double)))) return st;
+    CK(cudaMemcpy(du.p, uv, n * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    launch_texture_eval(s->dev, texture, du.as<double>(), n, dc.as<double>(), 0);
+    CKL();
+    CK(cudaMemcpy(rgb, dc.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
     return DR_OK;
 }
 

@@ -124,3 +124,14 @@ void launch_direct(const DevScene &sc, const FilmParams &fp, unsigned long long 
     k_direct<<<(unsigned) ((total + 127) / 128), 128, 0, stream>>>(sc, fp, seed, pixelSamples, shadingSamples, film, li);
     k_direct_normalize<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(film, n, rgb);
 }
+
+// ---------------------------------------------------------------- replay kernel of dr_texture_eval: the BSDF stage's texture lookup on its own
+__global__ void k_texture_eval(const __grid_constant__ DevScene sc, uint32_t texture, const double *uv, long long n, double *rgb) {
+    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const R3 v = tex_eval(sc, texture, r2(uv[2 * i], uv[2 * i + 1]));
+    rgb[3 * i] = v.x; rgb[3 * i + 1] = v.y; rgb[3 * i + 2] = v.z;
+}
+void launch_texture_eval(const DevScene &sc, uint32_t texture, const double *uv, long long n, double *rgb, cudaStream_t stream) {
+    k_texture_eval<<<(unsigned) ((n + 127) / 128), 128, 0, stream>>>(sc, texture, uv, n, rgb);
+}

@@ -546,3 +546,4 @@ void launch_direct(const DevScene &sc, const FilmParams &fp, unsigned long long 
                    double *li, cudaStream_t stream);                       // k_direct.cu: weighted film -> normalised rgb
 void launch_splat_points(const FilmParams &fp, float4 *film, const float *pos, const float *rgb, long long n, cudaStream_t s);   // k_chain.cu
 void launch_trace_rays(const DevScene &sc, const dr_ray *rays, long long n, int shadow, const unsigned int *order, dr_hit *hits, cudaStream_t stream);
+void launch_texture_eval(const DevScene &sc, uint32_t texture, const double *uv, long long n, double *rgb, cudaStream_t stream);   // k_direct.cu

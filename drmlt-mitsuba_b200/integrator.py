@@ -116,6 +116,13 @@ class Scene:
         abi.check(self.lib, self.lib.dr_importance_map(self.h, C.byref(cfg), _fp(out), C.byref(st)))
         return out, st
 
+    def texture_eval(self, texture, uv):
+        """Texture `texture` of the scene at intersection uv pairs [n, 2] (double) -> RGB [n, 3] (double), on the device."""
+        uv = np.ascontiguousarray(uv, np.float64)
+        rgb = np.zeros((len(uv), 3), np.float64)
+        abi.check(self.lib, self.lib.dr_texture_eval(self.h, texture, _fp(uv, C.c_double), len(uv), _fp(rgb, C.c_double)))
+        return rgb
+
     def reupload(self):
         n = C.c_int64(0)
         abi.check(self.lib, self.lib.dr_scene_reupload(self.h, C.byref(n)))

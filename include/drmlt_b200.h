@@ -350,6 +350,10 @@ typedef struct dr_hit { float t, u, v; int32_t prim; } dr_hit;   /* prim = -1: m
 /* Closest-hit over `n` rays (Scene::rayIntersect, skdtree.cpp:111-138).  Host buffers.
  * `shadow`!=0: any-hit only (t/u/v undefined, prim >= 0 means occluded). */
 dr_status dr_trace_rays(dr_scene scene, const dr_ray *rays, int64_t n, int shadow, dr_hit *hits);
+/* Replay entry point of the texture stage: texture `texture` of the scene evaluated on the device at n intersection uv pairs
+ * (uv[2i], uv[2i+1]) exactly as the BSDF stage does -- Texture2D::eval without ray differentials (texture.cpp:112-121) ->
+ * TMIPMap::evalBilinear / evalBox (mipmap.h:566-596); rgb gets 3 doubles per lookup. */
+dr_status dr_texture_eval(dr_scene scene, uint32_t texture, const double *uv, int64_t n, double *rgb);
 
 #define DR_MAX_SPLATS 12
 typedef struct dr_path_result {

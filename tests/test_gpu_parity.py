@@ -1167,6 +1167,33 @@ def test_drop_in_plugin_tessellates_analytic_shapes(tmp_path):
     assert RP.rel_mse(img, gold["analytic_image"]) < 0.05
 
 
+# SURVEY 8f rank 4, bitmap textures, leaf level: the CUDA lookup (dr_texture_eval: the BSDF stage's tex_eval on its own) against the
+# reference's own Texture2D::eval -> TMIPMap::evalBilinear / evalBox / evalTexel (tests/golden/ref_texture.npz) for every wrap mode, both
+# filters, scaled / offset coordinates, 4 000 uv pairs each.  nearest: bit for bit; bilinear: the device contracts a*b + c into FMAs, the
+# reference's x86-64 build does not -- the texel coordinate uv * size - 0.5 moves by an ulp (of a coordinate up to ~60), hence the
+# weights by ~1e-14: bound 1e-13 (measured 1.2e-15).
+def test_cuda_texture_lookups_match_reference_mipmap():
+    gold = dict(np.load(RP.GOLDEN_TEXTURE))
+    uv = RP.texture_leaf_uv()
+    cases = RP.texture_leaf_cases()
+    data = scenes.SceneData("texture-leaves", (16, 16))
+    for name, (t, arr) in cases.items():
+        data.add_texture(arr.reshape(t.height, t.width, 3), wrap=t.wrap_u, wrap_v=t.wrap_v, nearest=bool(t.nearest),
+                         uv_scale=tuple(t.uv_scale), uv_offset=tuple(t.uv_offset))
+    m = data.add_material(abi.DR_BSDF_DIFFUSE, reflectance_tex=0)
+    data.add_quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0), m, uv=True, uv_tangents=True)
+    data.set_camera((0, 0, 3), (0, 0, 0), (0, 1, 0), 40.0)
+    gpu = Scene(data)
+    for i, name in enumerate(cases):
+        got, want = gpu.texture_eval(i, uv), gold["tex_" + name]
+        if name.startswith("nearest"):
+            assert np.array_equal(got, want), name
+        else:
+            assert np.abs(got - want).max() <= 1e-13, (name, np.abs(got - want).max())
+    with pytest.raises(abi.DrmltError):
+        gpu.texture_eval(len(cases), uv)
+
+
 # SURVEY 8f rank 4, bitmap textures through the plugin: the reference's own DRMLT integrator on the textured Cornell box (BSDF plugins with
 # <texture> children, tests/golden/ref_texture.npz, three runs) against the plugin's job on the same mitsuba::Scene -- the shim finds the BSDFs'
 # textures (the objects a BSDF hands to the InstanceManager when it is serialized), reads MIP level 0, filter, wrap modes, uv scale / offset,
