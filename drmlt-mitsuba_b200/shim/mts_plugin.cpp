@@ -414,6 +414,9 @@ public:
             Log(EError, "Subsurface integrators are not supported by MLT!");
         if (scene->getSampler()->getClass()->getName() != "IndependentSampler")   // drmlt.cpp:380-381
             Log(EError, "Metropolis light transport requires the independent sampler");
+        // participating media are not built on the GPU path: fail, do not render the scene without them
+        if (!scene->getMedia().empty() || scene->getSensor()->getMedium() != NULL)
+            Log(EError, "Participating media are not supported by the B200 plugin");
         return true;
     }
 
