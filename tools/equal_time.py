@@ -95,7 +95,7 @@ def main():
 
     def ref_render(spp_, tag):
         path = os.path.join(tempfile.gettempdir(), "equal_time_ref_%s.npy" % tag)
-        outp = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_sample.py"), "--scene", args.scene, "--film", "%dx%d" % (W, H),
+        outp = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_sample.py"), "--config", {"door": "C5", "cornell": "C1", "glossy": "C3", "caustic": "C4"}.get(args.scene, "C5"), "--film", "%dx%d" % (W, H),
                                "--spp", str(spp_), "--out-image", path], capture_output=True, text=True, timeout=1200).stdout
         for ln in outp.splitlines():
             if "REF_SAMPLE " in ln:
