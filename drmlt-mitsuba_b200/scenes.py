@@ -267,7 +267,7 @@ def procedural_texels(w, h, seed, lo=0.05, hi=0.9, cell=4):
 def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
     """The Cornell box with bitmap textures: floor = diffuse with a bilinear, repeating texture (uscale = vscale = 2.5,
     offset), back wall = diffuse, mirror-wrapped, on a mesh with UV tangents, left wall = rough conductor with a textured
-    specularReflectance (clamp), one box = plastic with a textured diffuseReflectance, the other = diffuse with a nearest-filtered
+    specularReflectance (clamp), one box = plastic with textured diffuseReflectance AND specularReflectance, the other = diffuse with a nearest-filtered
     texture (zero / one wrap); everything else as cornell_box.  uv_tangents=True flags every mesh DR_TRI_UV_TANGENTS -- what the
     reference does for any mesh with texture coordinates (trimesh.cpp:400-402); False keeps the edge-based shading frames."""
     s = SceneData("cornell-textured", film)
@@ -276,6 +276,7 @@ def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
     t_back = s.add_texture(procedural_texels(17, 29, 12), wrap=abi.DR_WRAP_MIRROR, uv_scale=(1.7, 1.3), uv_offset=(-0.2, 0.1))
     t_left = s.add_texture(procedural_texels(16, 16, 13, lo=0.4, hi=0.95), wrap=abi.DR_WRAP_CLAMP, uv_scale=(1.5, 1.5), uv_offset=(-0.25, -0.25))
     t_box1 = s.add_texture(procedural_texels(8, 8, 14, lo=0.1, hi=0.7, cell=2), wrap=abi.DR_WRAP_REPEAT)
+    t_box1s = s.add_texture(procedural_texels(6, 10, 16, lo=0.5, hi=0.95, cell=2), wrap=abi.DR_WRAP_MIRROR, uv_scale=(2.0, 1.0))
     t_box2 = s.add_texture(procedural_texels(12, 6, 15, cell=3), wrap=abi.DR_WRAP_ZERO, wrap_v=abi.DR_WRAP_ONE, nearest=True,
                            uv_scale=(1.25, 1.25), uv_offset=(-0.125, -0.125))
     white = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.73, 0.73, 0.73))
@@ -283,7 +284,8 @@ def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
     floor = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance_tex=t_floor)
     back = s.add_material(abi.DR_BSDF_DIFFUSE, reflectance_tex=t_back)
     left = s.add_material(abi.DR_BSDF_ROUGHCONDUCTOR, flags=abi.DR_MAT_GGX, reflectance_tex=t_left, eta=(0.2, 0.92, 1.1), k=(3.9, 2.45, 2.14), alpha=0.25)
-    box1 = s.add_material(abi.DR_BSDF_PLASTIC, reflectance_tex=t_box1, transmittance=(1, 1, 1), eta=(1.49, 0, 0))
+    # plastic with BOTH colour parameters textured (diffuseReflectance -> `reflectance`, specularReflectance -> `transmittance`)
+    box1 = s.add_material(abi.DR_BSDF_PLASTIC, reflectance_tex=t_box1, transmittance_tex=t_box1s, eta=(1.49, 0, 0))
     box2 = s.add_material(abi.DR_BSDF_DIFFUSE, flags=abi.DR_MAT_TWOSIDED, reflectance_tex=t_box2)
     s.add_quad((-1, -1, 1), (1, -1, 1), (1, -1, -1), (-1, -1, -1), floor, tess, tess, uv=True, uv_tangents=T)
     s.add_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1), white, tess, tess, uv=True, uv_tangents=T)

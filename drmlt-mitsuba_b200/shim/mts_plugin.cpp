@@ -519,6 +519,28 @@ public:
         desc.camera.near_clip = (float) cam->getNearClip(); desc.camera.far_clip = (float) cam->getFarClip();
         desc.camera.film_width = film->getSize().x; desc.camera.film_height = film->getSize().y;
 
+        // DRMLT_DUMP_SCENE=<file>: the flattened description as raw arrays (tests compare it with what the scene was built from)
+        if (const char *dump = getenv("DRMLT_DUMP_SCENE")) {
+            FILE *f = fopen(dump, "wb");
+            if (f) {
+                const uint32_t head[6] = { desc.n_vertices, desc.n_triangles, desc.n_materials, desc.n_emitters, desc.n_textures, desc.texcoords ? 1u : 0u };
+                fwrite(head, sizeof(head), 1, f);
+                fwrite(desc.positions, sizeof(float), 3 * (size_t) desc.n_vertices, f);
+                if (desc.texcoords) fwrite(desc.texcoords, sizeof(float), 2 * (size_t) desc.n_vertices, f);
+                fwrite(desc.indices, sizeof(uint32_t), 3 * (size_t) desc.n_triangles, f);
+                fwrite(desc.tri_material, sizeof(uint32_t), desc.n_triangles, f);
+                fwrite(desc.tri_flags, sizeof(uint32_t), desc.n_triangles, f);
+                fwrite(desc.materials, sizeof(dr_material), desc.n_materials, f);
+                for (uint32_t t = 0; t < desc.n_textures; ++t) {
+                    const dr_texture &tx = desc.textures[t];
+                    const uint32_t th[5] = { tx.width, tx.height, tx.wrap_u, tx.wrap_v, tx.nearest };
+                    fwrite(th, sizeof(th), 1, f);
+                    fwrite(tx.uv_scale, sizeof(double), 2, f); fwrite(tx.uv_offset, sizeof(double), 2, f);
+                    fwrite(tx.texels, sizeof(float), 3 * (size_t) tx.width * tx.height, f);
+                }
+                fclose(f);
+            }
+        }
         // DRMLT_DEVICE=<g>: the GPU of the job; DRMLT_DEVICES=<g0>,<g1>,...: several GPUs of this node -- chains sharded across them,
         // b all-reduced and the films reduced with NCCL inside the library (dr_render_multi)
         std::vector<int> devices;

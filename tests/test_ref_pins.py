@@ -496,6 +496,82 @@ def test_drop_in_plugin_loads_and_fails_loudly_without_a_gpu(name, tmp_path):
     assert "no CUDA device available (there is no CPU fallback)" in log and "caught exception" in log, log[-1500:]
 
 
+def _read_scene_dump(path):
+    """DRMLT_DUMP_SCENE of shim/mts_plugin.cpp -> dict of arrays."""
+    from drmlt_mitsuba_b200 import abi
+    raw = open(path, "rb").read()
+    off = [0]
+
+    def take(dtype, n):
+        a = np.frombuffer(raw, dtype=dtype, count=n, offset=off[0])
+        off[0] += a.nbytes
+        return a
+    nv, nt, nm, ne, ntex, has_uv = (int(x) for x in take("<u4", 6))
+    d = dict(P=take("<f4", 3 * nv).reshape(nv, 3), UV=take("<f4", 2 * nv).reshape(nv, 2) if has_uv else None, I=take("<u4", 3 * nt).reshape(nt, 3),
+             mat=take("<u4", nt), flags=take("<u4", nt))
+    d["materials"] = [abi.dr_material.from_buffer_copy(take("u1", 64).tobytes()) for _ in range(nm)]
+    d["textures"] = []
+    for _ in range(ntex):
+        w, h, wu, wv, nearest = (int(x) for x in take("<u4", 5))
+        scale, offset = take("<f8", 2).copy(), take("<f8", 2).copy()
+        d["textures"].append(dict(w=w, h=h, wrap=(wu, wv), nearest=nearest, scale=scale, offset=offset, texels=take("<f4", 3 * w * h).reshape(h, w, 3)))
+    assert off[0] == len(raw)
+    return d
+
+
+# The plugin's flattening of a textured mitsuba::Scene, EXACTLY: the scene the reference driver assembles from the textured Cornell box
+# (TriMesh objects with texture coordinates, BSDF plugins with <texture> children) goes through shim/mts_plugin.cpp, which dumps the
+# dr_scene_desc it built (DRMLT_DUMP_SCENE) before it fails for want of a GPU.  Every triangle must come back with its positions, its
+# texture coordinates, the UV-tangent flag, and a material whose textured parameters point at textures with the original texels, filter,
+# wrap modes and uv transform -- i.e. the order in which a BSDF serializes its textures was matched to the right parameters.
+@pytest.mark.skipif(not os.path.exists(PLUGIN_SO), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
+def test_drop_in_plugin_flattens_textured_scene_exactly(tmp_path):
+    import subprocess
+    import sys
+    from drmlt_mitsuba_b200 import abi, scenes
+    dump = str(tmp_path / "scene.bin")
+    env = dict(os.environ, DRMLT_DUMP_SCENE=dump)
+    subprocess.run([sys.executable, os.path.join(RP.ROOT, "tools", "plugin_render.py"), "drmlt_orbital_mmlt", str(tmp_path / "x.npy"), "4", "--textured"],
+                   capture_output=True, text=True, timeout=300, env=env)
+    assert os.path.exists(dump), "the plugin did not reach the end of its flattening"
+    got = _read_scene_dump(dump)
+    data = scenes.cornell_box_textured(film=(64, 64), tess=4)
+    P, N, I, mat, emi, flg, mats, emis, rt = data.arrays()
+    UV = data._uv
+    assert got["I"].shape == I.shape and got["UV"] is not None and len(got["textures"]) == len(data.textures)
+
+    def tex_key(t):
+        return (t["w"], t["h"], t["wrap"], t["nearest"], tuple(t["scale"]), tuple(t["offset"]), t["texels"].tobytes())
+    want_tex = [tex_key(dict(w=t.width, h=t.height, wrap=(t.wrap_u, t.wrap_v), nearest=t.nearest, scale=np.array(t.uv_scale[:]), offset=np.array(t.uv_offset[:]),
+                             texels=arr)) for t, arr in zip(data.textures, data._tex_keep)]
+    got_tex = [tex_key(t) for t in got["textures"]]
+    assert sorted(map(hash, got_tex)) == sorted(map(hash, want_tex))          # the same textures (half-precision texels: exact), in whatever order
+
+    def mat_key(m, texs):
+        tr, tt = (m.flags >> 8) & 0xfff, m.flags >> 20
+        return (m.type, m.flags & 0xff, hash(texs[tr - 1]) if tr else tuple(np.float32(m.reflectance[:]).round(5)),
+                (hash(texs[tt - 1]) if tt else tuple(np.float32(m.transmittance[:]).round(5))) if m.type in (1, 4, 5, 6) else None,
+                tuple(np.float32(m.eta[:]).round(4)) if m.type in (2, 3) else round(m.eta[0], 5) if m.type != 0 else None,
+                tuple(np.float32(m.k[:]).round(4)) if m.type in (2, 3) else None, round(m.alpha, 6) if m.type in (3, 4, 6) else None)
+    original = {}
+    for t in range(len(I)):
+        key = tuple(np.round(P[I[t]].astype(np.float64), 6).reshape(-1))
+        original[key] = (UV[I[t]].copy(), int(flg[t]), mat_key(data.materials[mat[t]], want_tex))
+    assert len(original) == len(I)
+    for t in range(len(got["I"])):
+        tri = got["I"][t]
+        key = tuple(np.round(got["P"][tri].astype(np.float64), 6).reshape(-1))
+        uv, fl, mk = original[key]
+        assert np.array_equal(got["UV"][tri], uv), t
+        assert (got["flags"][t] & abi.DR_TRI_UV_TANGENTS) and not (got["flags"][t] & abi.DR_TRI_NO_TEXCOORDS)      # every mesh with texcoords has tangents
+        assert mat_key(got["materials"][got["mat"][t]], got_tex) == mk, (t, mat_key(got["materials"][got["mat"][t]], got_tex), mk)
+    # the constants of textured parameters are the textures' averages (Texture::getAverage)
+    for m in got["materials"]:
+        tr = (m.flags >> 8) & 0xfff
+        if tr:
+            assert np.allclose(m.reflectance[:], got["textures"][tr - 1]["texels"].reshape(-1, 3).astype(np.float64).mean(axis=0), rtol=2e-3)
+
+
 # ================================================================ SURVEY 8f rank 1 / rank 3: the direct pass, the importance-map resampling
 # ref_direct_image runs BidirectionalUtils::renderDirectComponent itself (src/libbidir/util.cpp:30-94: the `direct` integrator with
 # the pixelSamples x shadingSamples split, an `ldsampler`, SamplingIntegrator::render on local workers, film->develop);
