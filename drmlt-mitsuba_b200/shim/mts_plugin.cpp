@@ -305,8 +305,8 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector
         float eta = 0.f, alpha = 0.f;
         if (!ts.scalar("eta", from, eta)) { why = "cannot parse rough plastic eta"; return false; }
         m.eta[0] = eta;                                   // intIOR / extIOR
-        size_t a = str.find("alpha = ConstantFloatTexture", from);
-        if (a == std::string::npos || !ts.scalar("alpha", from, alpha)) { why = "textured roughness"; return false; }
+        // a constant alpha prints as a bare number (ConstantFloatTexture::toString, basicshader.h:125-129); a textured one was rejected above
+        if (!ts.scalar("alpha", from, alpha)) { why = "textured roughness"; return false; }
         m.alpha = alpha;
         if (!texR) m.reflectance[0] = m.reflectance[1] = m.reflectance[2] = 0.5f;       // diffuseReflectance default (roughplastic.cpp:200)
         if (!texR && !ts.spectrum("diffuseReflectance", from, m.reflectance)) { why = "cannot parse rough plastic diffuseReflectance"; return false; }
@@ -538,6 +538,9 @@ public:
                     fwrite(tx.uv_scale, sizeof(double), 2, f); fwrite(tx.uv_offset, sizeof(double), 2, f);
                     fwrite(tx.texels, sizeof(float), 3 * (size_t) tx.width * tx.height, f);
                 }
+                const uint32_t nrt = desc.n_rough_tables;
+                fwrite(&nrt, sizeof(nrt), 1, f);
+                if (nrt) fwrite(desc.rough_tables, sizeof(double), (size_t) nrt * DR_ROUGH_TABLE_DOUBLES, f);
                 fclose(f);
             }
         }

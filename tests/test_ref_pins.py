@@ -515,6 +515,8 @@ def _read_scene_dump(path):
         w, h, wu, wv, nearest = (int(x) for x in take("<u4", 5))
         scale, offset = take("<f8", 2).copy(), take("<f8", 2).copy()
         d["textures"].append(dict(w=w, h=h, wrap=(wu, wv), nearest=nearest, scale=scale, offset=offset, texels=take("<f4", 3 * w * h).reshape(h, w, 3)))
+    nrt = int(take("<u4", 1)[0])
+    d["rough_tables"] = take("<f8", nrt * abi.DR_ROUGH_TABLE_DOUBLES).reshape(nrt, abi.DR_ROUGH_TABLE_DOUBLES)
     assert off[0] == len(raw)
     return d
 
@@ -570,6 +572,52 @@ def test_drop_in_plugin_flattens_textured_scene_exactly(tmp_path):
         tr = (m.flags >> 8) & 0xfff
         if tr:
             assert np.allclose(m.reflectance[:], got["textures"][tr - 1]["texels"].reshape(-1, 3).astype(np.float64).mean(axis=0), rtol=2e-3)
+
+
+# ... and the same round trip for every BSDF model of the path: dr_scene_desc -> the reference's own objects (BSDF plugins, TriMesh, area
+# emitters; oracle/ref/ref_path.cpp) -> shim/mts_plugin.cpp -> dr_scene_desc.  Constants nested in `twosided` are parsed from toString()
+# (6 significant digits), the others come from the BSDF's Properties.
+@pytest.mark.skipif(not os.path.exists(PLUGIN_SO), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("scene_name", ["cornell", "glossy", "roughglass", "roughglass-beckmann", "plastic", "roughplastic"])
+def test_drop_in_plugin_flattening_round_trip(scene_name, tmp_path):
+    import subprocess
+    import sys
+    from drmlt_mitsuba_b200 import abi
+    dump = str(tmp_path / "scene.bin")
+    subprocess.run([sys.executable, os.path.join(RP.ROOT, "tools", "plugin_render.py"), "drmlt_orbital_mmlt", str(tmp_path / "x.npy"), "4", "--scene=" + scene_name],
+                   capture_output=True, text=True, timeout=600, env=dict(os.environ, DRMLT_DUMP_SCENE=dump))
+    assert os.path.exists(dump), "the plugin did not reach the end of its flattening"
+    got = _read_scene_dump(dump)
+    data = RP.SCENES[scene_name]()
+    P, N, I, mat, emi, flg, mats, emis, rt = data.arrays()
+    assert got["I"].shape == I.shape and got["UV"] is None and not got["textures"]
+
+    def close(a, b):
+        return np.allclose(np.float64(a[:]), np.float64(b[:]), rtol=2e-5, atol=1e-7)
+    original = {}
+    for t in range(len(I)):
+        original.setdefault(tuple(np.round(P[I[t]].astype(np.float64), 6).reshape(-1)), []).append(t)
+    for t in range(len(got["I"])):
+        cands = original[tuple(np.round(got["P"][got["I"][t]].astype(np.float64), 6).reshape(-1))]
+        g = got["materials"][got["mat"][t]]
+        ok = False
+        for o in cands:                      # (coincident triangles of different objects: any of them)
+            w = data.materials[mat[o]]
+            same = g.type == w.type and (g.flags & 0xff) == (w.flags & 0xff) and bool(got["flags"][t] & abi.DR_TRI_SMOOTH) == bool(flg[o] & abi.DR_TRI_SMOOTH)
+            if w.type in (0, 2, 3, 5, 6) or w.type in (1, 4):
+                same &= close(g.reflectance, w.reflectance)
+            if w.type in (1, 4, 5, 6):
+                same &= close(g.transmittance, w.transmittance)
+            if w.type in (2, 3):
+                same &= close(g.eta, w.eta) and close(g.k, w.k)
+            elif w.type != 0:
+                same &= abs(g.eta[0] - w.eta[0]) <= 2e-5 * w.eta[0]
+            if w.type in (3, 4, 6):
+                same &= abs(g.alpha - w.alpha) <= 2e-5 * w.alpha
+            if w.type == 6:                  # the rough-transmittance table the host's own RoughTransmittance produced ([102]: filled by the library)
+                same &= np.allclose(got["rough_tables"][g.table][:102], data.rough_tables[w.table][:102], rtol=1e-9, atol=1e-12)
+            ok |= bool(same)
+        assert ok, (scene_name, t, g.type, g.flags, g.reflectance[:], g.transmittance[:], g.eta[:], g.k[:], g.alpha)
 
 
 # ================================================================ SURVEY 8f rank 1 / rank 3: the direct pass, the importance-map resampling

@@ -25,6 +25,9 @@ data = None
 if "--textured" in sys.argv:            # the Cornell box with bitmap textures: the plugin enumerates and flattens the BSDFs' textures
     from drmlt_mitsuba_b200 import scenes
     data = scenes.cornell_box_textured(film=(64, 64), tess=4)
+for a in sys.argv:
+    if a.startswith("--scene="):        # any scene of tests/ref_path_cases.py SCENES (at its test size)
+        data = RP.SCENES[a[len("--scene="):]]()
 if "--reference" not in sys.argv:       # (--reference: the reference's own integrator instead of the plugin -- writes the fixture)
     os.environ["REF_PLUGIN_DIR"] = os.path.join(ROOT, "oracle", "_ref", "plugins")
 params, case_spp = RP.RENDER_CASES[name]
