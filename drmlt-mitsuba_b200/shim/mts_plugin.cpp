@@ -541,6 +541,15 @@ public:
                 const uint32_t nrt = desc.n_rough_tables;
                 fwrite(&nrt, sizeof(nrt), 1, f);
                 if (nrt) fwrite(desc.rough_tables, sizeof(double), (size_t) nrt * DR_ROUGH_TABLE_DOUBLES, f);
+                const uint32_t hasN = desc.normals ? 1u : 0u;
+                fwrite(&hasN, sizeof(hasN), 1, f);
+                if (hasN) fwrite(desc.normals, sizeof(float), 3 * (size_t) desc.n_vertices, f);
+                fwrite(desc.tri_emitter, sizeof(int32_t), desc.n_triangles, f);
+                if (desc.n_emitters) fwrite(desc.emitters, sizeof(dr_emitter), desc.n_emitters, f);
+                fwrite(&desc.camera, sizeof(dr_camera), 1, f);
+                const uint32_t cfgBytes = (uint32_t) sizeof(dr_config);
+                fwrite(&cfgBytes, sizeof(cfgBytes), 1, f);
+                fwrite(&m_config, sizeof(dr_config), 1, f);
                 fclose(f);
             }
         }

@@ -517,6 +517,13 @@ def _read_scene_dump(path):
         d["textures"].append(dict(w=w, h=h, wrap=(wu, wv), nearest=nearest, scale=scale, offset=offset, texels=take("<f4", 3 * w * h).reshape(h, w, 3)))
     nrt = int(take("<u4", 1)[0])
     d["rough_tables"] = take("<f8", nrt * abi.DR_ROUGH_TABLE_DOUBLES).reshape(nrt, abi.DR_ROUGH_TABLE_DOUBLES)
+    d["N"] = take("<f4", 3 * nv).reshape(nv, 3) if int(take("<u4", 1)[0]) else None
+    d["emi"] = take("<i4", nt)
+    d["emitters"] = [abi.dr_emitter.from_buffer_copy(take("u1", C.sizeof(abi.dr_emitter)).tobytes()) for _ in range(ne)]
+    d["camera"] = abi.dr_camera.from_buffer_copy(take("u1", C.sizeof(abi.dr_camera)).tobytes())
+    nb = int(take("<u4", 1)[0])
+    assert nb == C.sizeof(abi.dr_config), "dr_config of the plugin and of the ctypes mirror differ in size"
+    d["config"] = abi.dr_config.from_buffer_copy(take("u1", nb).tobytes())
     assert off[0] == len(raw)
     return d
 
@@ -578,7 +585,7 @@ def test_drop_in_plugin_flattens_textured_scene_exactly(tmp_path):
 # emitters; oracle/ref/ref_path.cpp) -> shim/mts_plugin.cpp -> dr_scene_desc.  Constants nested in `twosided` are parsed from toString()
 # (6 significant digits), the others come from the BSDF's Properties.
 @pytest.mark.skipif(not os.path.exists(PLUGIN_SO), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("scene_name", ["cornell", "glossy", "roughglass", "roughglass-beckmann", "plastic", "roughplastic"])
+@pytest.mark.parametrize("scene_name", ["cornell", "glossy", "caustic", "roughglass", "roughglass-beckmann", "plastic", "roughplastic"])
 def test_drop_in_plugin_flattening_round_trip(scene_name, tmp_path):
     import subprocess
     import sys
@@ -618,6 +625,55 @@ def test_drop_in_plugin_flattening_round_trip(scene_name, tmp_path):
                 same &= np.allclose(got["rough_tables"][g.table][:102], data.rough_tables[w.table][:102], rtol=1e-9, atol=1e-12)
             ok |= bool(same)
         assert ok, (scene_name, t, g.type, g.flags, g.reflectance[:], g.transmittance[:], g.eta[:], g.k[:], g.alpha)
+        # smooth triangles come back with their vertex normals; emissive ones with their emitter
+        o = cands[0]
+        if flg[o] & abi.DR_TRI_SMOOTH:
+            assert np.allclose(got["N"][got["I"][t]], N[I[o]], atol=1e-6)
+        assert (got["emi"][t] >= 0) == (emi[o] >= 0)
+        if emi[o] >= 0:
+            ge, we = got["emitters"][got["emi"][t]], data.emitters[emi[o]]
+            assert close(ge.radiance, we.radiance) and abs(ge.sampling_weight - we.sampling_weight) < 1e-6 and ge.n_tris == we.n_tris
+            assert ge.first_tri <= t < ge.first_tri + ge.n_tris
+    # the sensor and the film (perspective.cpp:125-187, film.cpp:30-48)
+    gc, wc = got["camera"], data.camera
+    assert np.allclose(gc.to_world[:], wc.to_world[:], atol=1e-6) and abs(gc.xfov_deg - wc.xfov_deg) < 1e-4
+    assert abs(gc.near_clip - wc.near_clip) <= 1e-6 * wc.near_clip and abs(gc.far_clip - wc.far_clip) <= 1e-6 * wc.far_clip
+    assert (gc.film_width, gc.film_height) == data.film
+    # the job's configuration: the reference's parameter names forwarded verbatim, film / crop / sampler / filter read off the scene
+    cfg, (params, _) = got["config"], RP.RENDER_CASES["drmlt_orbital_mmlt"]
+    assert (cfg.integrator, cfg.technique, cfg.type, cfg.max_depth, cfg.direct_samples) == (abi.DR_INTEGRATOR_DRMLT, abi.DR_TECH_MMLT, abi.DR_TYPE_ORBITAL, params["maxDepth"], -1)
+    assert cfg.sample_count == 4 and (cfg.film_width, cfg.film_height, cfg.crop_width, cfg.crop_height) == data.film + data.film
+    assert (cfg.crop_offset_x, cfg.crop_offset_y) == (0, 0) and cfg.rr_depth == 5 and abs(cfg.p_large - 0.3) < 1e-7 and abs(cfg.sigma - 1 / 64) < 1e-9
+    assert cfg.rfilter == abi.DR_FILTER_TABLE and abs(cfg.filter_radius - 2.0) < 1e-12            # gaussian: radius 2, table = evalDiscretized
+    table = np.array(cfg.filter_table[:])
+    assert table[0] > 0.9 * table.max() and (np.diff(table) <= 1e-12).all() and 0 <= table[-1] < 1e-2 * table[0]
+
+
+# ... and the parameters: for every integrator configuration of RENDER_CASES the dr_config the plugin hands to dr_render equals the one
+# dr_config_set builds from the same `-D key=value` names (integrator.make_config), field by field -- apart from what the plugin reads off
+# the scene (film, crop, sample count, reconstruction filter).
+@pytest.mark.skipif(not os.path.exists(PLUGIN_SO), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", list(RP.RENDER_CASES))
+def test_drop_in_plugin_forwards_the_references_parameters(name, tmp_path):
+    import subprocess
+    import sys
+    from drmlt_mitsuba_b200 import abi
+    from drmlt_mitsuba_b200.integrator import make_config
+    dump = str(tmp_path / "scene.bin")
+    subprocess.run([sys.executable, os.path.join(RP.ROOT, "tools", "plugin_render.py"), name, str(tmp_path / "x.npy"), "4"],
+                   capture_output=True, text=True, timeout=600, env=dict(os.environ, DRMLT_DUMP_SCENE=dump))
+    assert os.path.exists(dump), "the plugin did not reach the end of its flattening"
+    got = _read_scene_dump(dump)["config"]
+    params, _ = RP.RENDER_CASES[name]
+    want = make_config(**params)
+    from_scene = {"sample_count", "film_width", "film_height", "crop_offset_x", "crop_offset_y", "crop_width", "crop_height", "rfilter", "filter_radius", "filter_table",
+                  "importance_map", "seed"}
+    for field, _ty in abi.dr_config._fields_:
+        if field in from_scene:
+            continue
+        a, b = getattr(got, field), getattr(want, field)
+        assert (list(a) == list(b)) if hasattr(a, "__len__") else (a == b), (name, field, a, b)
+    assert got.sample_count == 4 and (got.film_width, got.film_height) == (64, 64)
 
 
 # ================================================================ SURVEY 8f rank 1 / rank 3: the direct pass, the importance-map resampling
