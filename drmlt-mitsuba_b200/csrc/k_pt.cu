@@ -40,6 +40,8 @@ k_pt(const __grid_constant__ Machine M) {
         bool haveShadow = false;                             // this vertex's direct-illumination sample needs its shadow ray
         R3 shO = r3(0.), shD = r3(0.);
         Real shMax = 0.;
+        Mat m;                                               // material of the vertex v: loaded (textures looked up) once, by GO_SHADE
+        m.type = 0; m.flags = 0; m.alpha = 0.; m.table = nullptr; m.refl = m.trans = m.eta = m.k = r3(0.);
         for (bool running = true; running;) {
             switch (go) {
             case GO_HIT: {                                   // the camera ray or a BSDF-sampled ray arrived
@@ -76,7 +78,7 @@ k_pt(const __grid_constant__ Machine M) {
             }
             case GO_SHADE: {                                 // top of the loop body for the vertex v (in registers)
                 const R3 d = c.d;
-                const Mat m = load_material(sc, v.mat, v.uv);
+                m = load_material(sc, v.mat, v.uv);
                 if (v.emitter >= 0 && (c.flags & F_PT_EMITTED) && (c.flags & F_PT_NONSPEC) && dot(v.ns, -d) > 0.)
                     px.Li += c.weight * emitter_radiance(sc, v.emitter);
                 if (c.j >= pc.maxDepth && pc.maxDepth > 0) { go = GO_DONE; break; }
@@ -110,9 +112,8 @@ k_pt(const __grid_constant__ Machine M) {
                 go = GO_BSDF;
                 break;
             }
-            case GO_BSDF: {                                  // BSDF sampling (path.cpp:222-240)
+            case GO_BSDF: {                                  // BSDF sampling (path.cpp:222-240); always entered from GO_SHADE: m is this vertex's
                 const R3 d = c.d;
-                const Mat m = load_material(sc, v.mat, v.uv);
                 const R3 wi = to_local(v, -d);
                 const R2 ub = rd.next2D(SMP_SENSOR);
                 const Real uz = mat_uses_sampler(m.type) ? rd.next1D(SMP_SENSOR) : 0.5;      // bRec.sampler->next1D() (roughdielectric.cpp:555)
