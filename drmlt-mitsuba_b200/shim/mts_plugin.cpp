@@ -117,6 +117,7 @@ struct FlatTextures {
     std::vector<dr_texture> textures;
     std::vector<std::vector<float> > texels;              // one array per texture (stable addresses: filled, then pointers taken)
     std::map<const Texture2D *, uint32_t> index;
+    std::map<const BSDF *, std::vector<const Texture2D *> > ofBsdf;   // a BSDF shared by many meshes is serialized once (BitmapTexture::serialize reads its file)
 };
 
 // The non-constant 2D textures of a BSDF in the order it serializes them (see DrPrivateAccess above); false: a texture this path cannot take.
@@ -239,7 +240,14 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector
         model == "RoughConductor" ? pRoughConductor : model == "RoughDielectric" ? pRoughDielectric : model == "SmoothPlastic" ? pPlastic :
         model == "RoughPlastic" ? pRoughPlastic : NULL;
     std::vector<const Texture2D *> texs;
-    if (!texturesOf(bsdf, texs, why)) return false;
+    {
+        std::map<const BSDF *, std::vector<const Texture2D *> >::const_iterator cached = ft.ofBsdf.find(bsdf);
+        if (cached != ft.ofBsdf.end()) texs = cached->second;
+        else {
+            if (!texturesOf(bsdf, texs, why)) return false;
+            ft.ofBsdf[bsdf] = texs;
+        }
+    }
     if (!texs.empty()) {
         size_t k = 0;
         bool texRset = false, texTset = false;
