@@ -92,7 +92,9 @@ class SceneData:
         self._emi.append(np.full(nt, emitter, np.int32))
         self._UV.append(np.zeros((P.shape[0], 2), np.float32) if UV is None else np.asarray(UV, np.float32).reshape(-1, 2))
         self.has_uv |= UV is not None
-        self._flg.append(np.full(nt, (0 if N is None else abi.DR_TRI_SMOOTH) | (abi.DR_TRI_UV_TANGENTS if uv_tangents and UV is not None else 0), np.uint32))
+        # (DR_TRI_NO_TEXCOORDS only matters in a scene where some other mesh has texture coordinates)
+        self._flg.append(np.full(nt, (0 if N is None else abi.DR_TRI_SMOOTH) | (abi.DR_TRI_UV_TANGENTS if uv_tangents and UV is not None else 0) |
+                                 (abi.DR_TRI_NO_TEXCOORDS if UV is None else 0), np.uint32))
         self.n_vertices += P.shape[0]
         self.n_triangles += nt
 
@@ -269,7 +271,8 @@ def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
     offset), back wall = diffuse, mirror-wrapped, on a mesh with UV tangents, left wall = rough conductor with a textured
     specularReflectance (clamp), one box = plastic with textured diffuseReflectance AND specularReflectance, the other = diffuse with a nearest-filtered
     texture (zero / one wrap); everything else as cornell_box.  uv_tangents=True flags every mesh DR_TRI_UV_TANGENTS -- what the
-    reference does for any mesh with texture coordinates (trimesh.cpp:400-402); False keeps the edge-based shading frames."""
+    reference does for any mesh with texture coordinates (trimesh.cpp:400-402); False keeps the edge-based shading frames.  The ceiling
+    and the right wall carry no texture coordinates (a mixed scene: DR_TRI_NO_TEXCOORDS, barycentric uv, edge-based frames)."""
     s = SceneData("cornell-textured", film)
     T = bool(uv_tangents)
     t_floor = s.add_texture(procedural_texels(32, 24, 11), wrap=abi.DR_WRAP_REPEAT, uv_scale=(2.5, 2.5), uv_offset=(0.125, -0.3))
@@ -288,10 +291,10 @@ def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
     box1 = s.add_material(abi.DR_BSDF_PLASTIC, reflectance_tex=t_box1, transmittance_tex=t_box1s, eta=(1.49, 0, 0))
     box2 = s.add_material(abi.DR_BSDF_DIFFUSE, flags=abi.DR_MAT_TWOSIDED, reflectance_tex=t_box2)
     s.add_quad((-1, -1, 1), (1, -1, 1), (1, -1, -1), (-1, -1, -1), floor, tess, tess, uv=True, uv_tangents=T)
-    s.add_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1), white, tess, tess, uv=True, uv_tangents=T)
+    s.add_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1), white, tess, tess)         # (no texture coordinates: DR_TRI_NO_TEXCOORDS)
     s.add_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), back, tess, tess, uv=True, uv_tangents=T)
     s.add_quad((-1, -1, 1), (-1, -1, -1), (-1, 1, -1), (-1, 1, 1), left, tess, tess, uv=True, uv_tangents=T)
-    s.add_quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1), green, tess, tess, uv=True, uv_tangents=T)
+    s.add_quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1), green, tess, tess)
     h = 0.25
     s.add_quad((-h, 0.995, -h), (h, 0.995, -h), (h, 0.995, h), (-h, 0.995, h), white, radiance=(15.0, 15.0, 15.0), uv=True, uv_tangents=T)
     s.add_box((0.33, -0.7, 0.35), (0.3, 0.3, 0.3), -17.0, box1, tess=4, uv=True, uv_tangents=T)

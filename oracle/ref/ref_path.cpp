@@ -481,24 +481,25 @@ static void *scene_create(const dr_scene_desc *d, int rfilter, const Properties 
         addAnalytic(rs->scene, "rectangle", Transform::translate(Vector(0, h - 0.01f, 0)) * Transform::rotate(Vector(1, 0, 0), 90) * Transform::scale(Vector(0.25f, 0.25f, 1)), white, &light);
     }
     /* one TriMesh per (material, emitter, smooth) group, in triangle order (trimesh.h:71-77) */
-    typedef std::tuple<uint32_t, int32_t, bool> Key;
+    typedef std::tuple<uint32_t, int32_t, bool, bool> Key;
     std::map<Key, std::vector<uint32_t> > groups;
     for (uint32_t t = 0; !analytic && t < d->n_triangles; ++t) {
         bool smooth = d->tri_flags && (d->tri_flags[t] & DR_TRI_SMOOTH) && d->normals;
-        groups[Key(d->tri_material[t], d->tri_emitter[t], smooth)].push_back(t);
+        bool hasUV = d->texcoords && !(d->tri_flags && (d->tri_flags[t] & DR_TRI_NO_TEXCOORDS));
+        groups[Key(d->tri_material[t], d->tri_emitter[t], smooth, hasUV)].push_back(t);
     }
     TR("bsdfs");
     for (auto &g : groups) {
         const std::vector<uint32_t> &tris = g.second;
-        const bool smooth = std::get<2>(g.first);
+        const bool smooth = std::get<2>(g.first), hasUV = std::get<3>(g.first);
         std::map<uint32_t, uint32_t> remap;
         for (uint32_t t : tris) for (int k = 0; k < 3; ++k) { uint32_t v = d->indices[3 * t + k]; if (!remap.count(v)) { uint32_t n = (uint32_t) remap.size(); remap[v] = n; } }
         /* a mesh with texture coordinates always gets UV tangents in this reference (TriMesh::configure, trimesh.cpp:400-402), which
          * is what DR_TRI_UV_TANGENTS says: the caller must have flagged every triangle */
-        if (d->texcoords) for (uint32_t t : tris) if (!d->tri_flags || !(d->tri_flags[t] & DR_TRI_UV_TANGENTS)) { fprintf(stderr, "ref: texcoords without DR_TRI_UV_TANGENTS\n"); return NULL; }
-        ref<TriMesh> mesh = new TriMesh("mesh", tris.size(), remap.size(), smooth, d->texcoords != NULL, false, false, !smooth);
+        if (hasUV) for (uint32_t t : tris) if (!d->tri_flags || !(d->tri_flags[t] & DR_TRI_UV_TANGENTS)) { fprintf(stderr, "ref: texcoords without DR_TRI_UV_TANGENTS\n"); return NULL; }
+        ref<TriMesh> mesh = new TriMesh("mesh", tris.size(), remap.size(), smooth, hasUV, false, false, !smooth);
         for (auto &kv : remap) {
-            if (d->texcoords) mesh->getVertexTexcoords()[kv.second] = Point2(d->texcoords[2 * kv.first], d->texcoords[2 * kv.first + 1]);
+            if (hasUV) mesh->getVertexTexcoords()[kv.second] = Point2(d->texcoords[2 * kv.first], d->texcoords[2 * kv.first + 1]);
             mesh->getVertexPositions()[kv.second] = Point(d->positions[3 * kv.first], d->positions[3 * kv.first + 1], d->positions[3 * kv.first + 2]);
             if (smooth) mesh->getVertexNormals()[kv.second] = Normal(d->normals[3 * kv.first], d->normals[3 * kv.first + 1], d->normals[3 * kv.first + 2]);
         }
