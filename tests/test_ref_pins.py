@@ -653,6 +653,31 @@ def test_drop_in_plugin_flattening_round_trip(scene_name, tmp_path):
     assert table[0] > 0.9 * table.max() and (np.diff(table) <= 1e-12).all() and 0 <= table[-1] < 1e-2 * table[0]
 
 
+# ... and analytic shapes: the room of Mitsuba `rectangle` / `sphere` shapes (ref_path.cpp, REF_ANALYTIC_SCENE) comes out of the plugin as the
+# shapes' own tessellations (Shape::createTriMesh): six rectangles of two triangles, a sphere of 1 482 triangles whose vertices lie on the
+# sphere, the emissive rectangle as the one area emitter -- with the texture coordinates and UV tangents those meshes carry.
+@pytest.mark.skipif(not os.path.exists(PLUGIN_SO), reason="oracle/_ref plugins not built (needs /root/reference at build time)")
+def test_drop_in_plugin_tessellates_analytic_shapes_into_the_description(tmp_path):
+    import subprocess
+    import sys
+    from drmlt_mitsuba_b200 import abi
+    dump = str(tmp_path / "scene.bin")
+    subprocess.run([sys.executable, os.path.join(RP.ROOT, "tools", "plugin_render.py"), "drmlt_orbital_mmlt", str(tmp_path / "x.npy"), "4", "--analytic"],
+                   capture_output=True, text=True, timeout=600, env=dict(os.environ, DRMLT_DUMP_SCENE=dump))
+    assert os.path.exists(dump), "the plugin did not reach the end of its flattening"
+    d = _read_scene_dump(dump)
+    counts = np.bincount(d["mat"], minlength=7)
+    assert sorted(counts.tolist()) == [2] * 6 + [1482] and len(d["materials"]) == 7
+    sphere = np.unique(d["I"][d["mat"] == int(np.argmax(counts))])
+    r = np.linalg.norm(d["P"][sphere] - np.array([0.2, -0.55, -0.1]), axis=1)
+    assert np.abs(r - 0.45).max() < 1e-6
+    assert len(d["emitters"]) == 1 and d["emitters"][0].n_tris == 2 and np.allclose(d["emitters"][0].radiance[:], 15.0)
+    assert (d["emi"] >= 0).sum() == 2 and all(m.type == abi.DR_BSDF_DIFFUSE for m in d["materials"])
+    assert d["UV"] is not None and (d["flags"] & abi.DR_TRI_UV_TANGENTS).all() and not (d["flags"] & abi.DR_TRI_NO_TEXCOORDS).any()
+    reds = [m for m in d["materials"] if abs(m.reflectance[0] - 0.63) < 1e-5]
+    assert len(reds) == 1 and abs(reds[0].reflectance[1] - 0.06) < 1e-5
+
+
 # ... and the parameters: for every integrator configuration of RENDER_CASES the dr_config the plugin hands to dr_render equals the one
 # dr_config_set builds from the same `-D key=value` names (integrator.make_config), field by field -- apart from what the plugin reads off
 # the scene (film, crop, sample count, reconstruction filter).
