@@ -188,7 +188,9 @@ def run_reference(args):
         runs = []
         for i in range(args.warmup + args.steps):
             timed = i >= args.warmup
-            spp = args.ref_spp if timed else 2
+            # the e2e job's own 64 mutations/pixel when the K timed steps then still end within minutes (K <= 5), a bounded sample otherwise
+            ref_spp = args.ref_spp if args.ref_spp > 0 else max(8, min(64, 320 // max(1, args.steps)))
+            spp = ref_spp if timed else 2
             r = reference_sample(args.config, spp)
             if r is None:
                 runs = None
@@ -475,7 +477,7 @@ def run_gpu(args):
                 "config": {"workload": workload_name(args.config, data), "chains_per_gpu": int(n_chains), "mutations_per_chain_per_step": M,
                            "l2": "flushed between timed steps (512 MiB device write)", "b": b, "scene_create_s": scene_create_s,
                            "scene_bytes": int(scene_bytes), "wall_s_timed_region": wall, "e2e_mutations_per_pixel": args.e2e_spp,
-                           "cpu_baseline_mutations_per_pixel": args.cpu_spp, "reference_arm_mutations_per_pixel_per_step": args.ref_spp},
+                           "cpu_baseline_mutations_per_pixel": args.cpu_spp, "reference_arm_mutations_per_pixel_per_step": args.ref_spp if args.ref_spp > 0 else max(8, min(64, 320 // max(1, args.steps)))},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "strong_scaling": strong, "gpu_launches": launches, "clocks": clk.summary()}
     if world > 1:
         dist.barrier()
@@ -502,8 +504,9 @@ def main():
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
-    ap.add_argument("--ref-spp", type=int, default=16, dest="ref_spp",
-                    help="--impl reference: mutations per pixel of one timed step (a bounded sample: K steps must end within minutes)")
+    ap.add_argument("--ref-spp", type=int, default=0, dest="ref_spp",
+                    help="--impl reference: mutations per pixel of one timed step; 0 = 64 (the e2e job's own) for K <= 5 steps, else 320 // K "
+                         "(a bounded sample: K steps must end within minutes)")
     ap.add_argument("--cpu-spp", type=int, default=64, dest="cpu_spp",
                     help="cpu_baseline leg of the GPU arm: mutations per pixel of the ONE run of the reference's integrator (64 = the e2e job's own)")
     ap.add_argument("--strong-spp", type=int, default=512, dest="strong_spp",
