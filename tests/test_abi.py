@@ -151,3 +151,24 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) == 1 and b"missing texels" in lib.dr_last_error()
     data = textured(); desc = data.desc()                       # a valid textured scene passes validation (and then needs the device)
     assert lib.dr_scene_create(C.byref(desc), 0, C.byref(h)) in (0, 2)
+
+
+# The header is C (not C++), and a plain C99 host drives the library through it: examples/render_box.c compiles with -std=c99 -pedantic,
+# links against libdrmlt_b200.so and -- without a GPU -- gets DR_ERR_NO_DEVICE from dr_scene_create after its textured scene passed validation.
+def build_c_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "render_box")
+    libdir = os.path.join(root, "drmlt-mitsuba_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O2", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "render_box.c"), "-L" + libdir, "-ldrmlt_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe])
+    return exe
+
+
+def test_c99_host_example_builds_and_fails_loudly_without_a_gpu(lib, tmp_path):
+    import subprocess
+    exe = build_c_example(tmp_path)
+    if lib.dr_device_count() > 0:
+        pytest.skip("a CUDA device is present: tests/test_gpu_parity.py runs the example")
+    p = subprocess.run([exe, str(tmp_path / "o.ppm"), "4"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 2 and "no CPU fallback" in p.stderr, (p.returncode, p.stderr)

@@ -1167,6 +1167,45 @@ def test_drop_in_plugin_tessellates_analytic_shapes(tmp_path):
     assert RP.rel_mse(img, gold["analytic_image"]) < 0.05
 
 
+# The C ABI from a plain C99 host (examples/render_box.c: a textured box, drmlt orbital mmlt): the job runs, the image's mean luminance is the
+# normalisation b, and the same scene built through the Python mirror of the ABI gives the same b.
+def test_c99_host_example_renders():
+    import subprocess
+    import tempfile
+    from test_abi import build_c_example
+    import pathlib
+    with tempfile.TemporaryDirectory() as td:
+        exe = build_c_example(pathlib.Path(td))
+        p = subprocess.run([exe, os.path.join(td, "o.ppm"), "64"], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, (p.returncode, p.stderr[-1000:])
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("RENDER_BOX ")][-1]
+        vals = dict(kv.split("=") for kv in line.split()[1:])
+        assert os.path.getsize(os.path.join(td, "o.ppm")) == 128 * 128 * 3 + len("P6\n128 128\n255\n")
+    b, mean = float(vals["b"]), float(vals["mean"])
+    assert abs(int(vals["mutations"]) / (128 * 128 * 64) - 1) < 0.02 and 0.2 < float(vals["accept"]) < 0.98
+    data = scenes.SceneData("box", (128, 128))
+    tex = np.zeros((8, 8, 3), np.float32)
+    for y in range(8):
+        for x in range(8):
+            v = np.float32(0.75 if ((x // 2 + y // 2) & 1) else 0.15)
+            tex[y, x] = (v, v * np.float32(0.9), v * np.float32(0.6))
+    t = data.add_texture(tex, wrap=abi.DR_WRAP_REPEAT, uv_scale=(3.0, 3.0))
+    white = data.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.73, 0.73, 0.73))
+    red = data.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.63, 0.065, 0.05))
+    green = data.add_material(abi.DR_BSDF_DIFFUSE, reflectance=(0.14, 0.45, 0.091))
+    floor = data.add_material(abi.DR_BSDF_DIFFUSE, reflectance_tex=t)
+    data.add_quad((-1, -1, 1), (1, -1, 1), (1, -1, -1), (-1, -1, -1), floor, uv=True, uv_tangents=True)
+    data.add_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1), white)
+    data.add_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), white)
+    data.add_quad((-1, -1, 1), (-1, -1, -1), (-1, 1, -1), (-1, 1, 1), red)
+    data.add_quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1), green)
+    data.add_quad((-0.25, 0.995, -0.25), (0.25, 0.995, -0.25), (0.25, 0.995, 0.25), (-0.25, 0.995, 0.25), white, radiance=(15.0, 15.0, 15.0))
+    data.set_camera((0, 0, 3.9), (0, 0, 0), (0, 1, 0), 39.0)
+    _, st = Scene(data).render(make_config(integrator="drmlt", technique="mmlt", type="orbital", maxDepth=8, directSamples=-1, sampleCount=64, seed=1))
+    assert abs(b / st.luminance - 1) < 0.01, (b, st.luminance)          # two bootstraps of the same scene
+    assert abs(mean / b - 1) < 2e-3, (mean, b)                          # develop normalises the film to mean luminance b
+
+
 # SURVEY 8f rank 4, bitmap textures, leaf level: the CUDA lookup (dr_texture_eval: the BSDF stage's tex_eval on its own) against the
 # reference's own Texture2D::eval -> TMIPMap::evalBilinear / evalBox / evalTexel (tests/golden/ref_texture.npz) for every wrap mode, both
 # filters, scaled / offset coordinates, 4 000 uv pairs each.  nearest: bit for bit; bilinear: the device contracts a*b + c into FMAs, the
