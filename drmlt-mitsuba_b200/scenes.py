@@ -270,7 +270,7 @@ def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
     """The Cornell box with bitmap textures: floor = diffuse with a bilinear, repeating texture (uscale = vscale = 2.5,
     offset), back wall = diffuse, mirror-wrapped, on a mesh with UV tangents, left wall = rough conductor with a textured
     specularReflectance (clamp), one box = plastic with textured diffuseReflectance AND specularReflectance, the other = diffuse with a nearest-filtered
-    texture (zero / one wrap); everything else as cornell_box.  uv_tangents=True flags every mesh DR_TRI_UV_TANGENTS -- what the
+    texture (zero / one wrap), a glass pane with both dielectric colours textured; everything else as cornell_box.  uv_tangents=True flags every mesh DR_TRI_UV_TANGENTS -- what the
     reference does for any mesh with texture coordinates (trimesh.cpp:400-402); False keeps the edge-based shading frames.  The ceiling
     and the right wall carry no texture coordinates (a mixed scene: DR_TRI_NO_TEXCOORDS, barycentric uv, edge-based frames)."""
     s = SceneData("cornell-textured", film)
@@ -290,6 +290,9 @@ def cornell_box_textured(film=(256, 256), tess=8, uv_tangents=True):
     # plastic with BOTH colour parameters textured (diffuseReflectance -> `reflectance`, specularReflectance -> `transmittance`)
     box1 = s.add_material(abi.DR_BSDF_PLASTIC, reflectance_tex=t_box1, transmittance_tex=t_box1s, eta=(1.49, 0, 0))
     box2 = s.add_material(abi.DR_BSDF_DIFFUSE, flags=abi.DR_MAT_TWOSIDED, reflectance_tex=t_box2)
+    # a glass pane whose specularReflectance AND specularTransmittance are textured (dielectric: `reflectance`, then `transmittance`)
+    pane = s.add_material(abi.DR_BSDF_DIELECTRIC, reflectance_tex=t_box1s, transmittance_tex=t_left, eta=(1.5, 0, 0))
+    s.add_quad((-0.95, -0.3, 0.75), (-0.35, -0.3, 0.75), (-0.35, 0.55, 0.75), (-0.95, 0.55, 0.75), pane, 2, 2, uv=True, uv_tangents=T)
     s.add_quad((-1, -1, 1), (1, -1, 1), (1, -1, -1), (-1, -1, -1), floor, tess, tess, uv=True, uv_tangents=T)
     s.add_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1), white, tess, tess)         # (no texture coordinates: DR_TRI_NO_TEXCOORDS)
     s.add_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), back, tess, tess, uv=True, uv_tangents=T)
