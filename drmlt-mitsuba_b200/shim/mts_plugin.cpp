@@ -34,6 +34,7 @@
 #include <drmlt_b200.h>
 #include "src/bsdfs/rtrans.h"          // RoughTransmittance, as src/bsdfs/roughplastic.cpp includes it (compile with -I<mitsuba root>)
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
 #include <sstream>
 #include <vector>
@@ -216,6 +217,16 @@ bool flattenBSDF(const BSDF *bsdf, dr_material &m, std::string &why, std::vector
         from = str.find("nestedBRDF[0] = ");
         if (from == std::string::npos) { why = "cannot parse twosided"; return false; }
         from += strlen("nestedBRDF[0] = ");
+        {   // a different BSDF on the back side (nestedBRDF[1], twosided.cpp:85-100) is not representable: fail instead of using the front's
+            const size_t second = str.find("nestedBRDF[1] = ", from);
+            if (second == std::string::npos) { why = "cannot parse twosided"; return false; }
+            std::string a, b;
+            for (size_t i = from; i < second; ++i) if (!isspace((unsigned char) str[i])) a += str[i];
+            for (size_t i = second + strlen("nestedBRDF[1] = "); i < str.size(); ++i) if (!isspace((unsigned char) str[i])) b += str[i];
+            if (!a.empty() && a[a.size() - 1] == ',') a.erase(a.size() - 1);          // "...]," before nestedBRDF[1]
+            if (!b.empty() && b[b.size() - 1] == ']') b.erase(b.size() - 1);          // the closing bracket of TwoSided[...]
+            if (a != b) { why = "twosided with different front and back BSDFs"; return false; }
+        }
         model = ts.className(from);
         if (model.compare(0, 4, "ref<") == 0) {          // ref<T>::toString: "ref<SmoothDiffuse>[ref=2, ptr=SmoothDiffuse[..."
             size_t ptr = str.find("ptr=", from);
