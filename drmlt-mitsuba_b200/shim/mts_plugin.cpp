@@ -532,6 +532,7 @@ public:
         for (size_t t = 0; t < flatTextures.textures.size(); ++t) flatTextures.textures[t].texels = flatTextures.texels[t].data();
         desc.textures = flatTextures.textures.empty() ? NULL : flatTextures.textures.data(); desc.n_textures = (uint32_t) flatTextures.textures.size();
         desc.rough_tables = roughTables.empty() ? NULL : roughTables.data(); desc.n_rough_tables = (uint32_t) (roughTables.size() / DR_ROUGH_TABLE_DOUBLES);
+        if (!cam->getWorldTransform()->isStatic()) Log(EError, "An animated sensor transform (motion blur) is not supported by the B200 plugin");
         const Matrix4x4 &tw = cam->getWorldTransform()->eval(0).getMatrix();
         for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) desc.camera.to_world[4 * r + c] = (float) tw(r, c);
         desc.camera.xfov_deg = (float) cam->getXFov();
