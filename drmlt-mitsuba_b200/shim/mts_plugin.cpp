@@ -465,6 +465,7 @@ public:
         std::vector<dr_material> mats;
         std::vector<double> roughTables;           // DR_ROUGH_TABLE_DOUBLES per roughplastic material
         FlatTextures flatTextures;                 // bitmap textures bound to colour parameters (dr_texture)
+        std::map<const BSDF *, uint32_t> materialOf;
         std::vector<dr_emitter> ems;
         bool anyNormals = false;
         // triangle meshes as they are; analytic shapes (rectangle, sphere, disk, cylinder, heightfield: SURVEY 8f rank 4) through the
@@ -489,9 +490,17 @@ public:
             const Point2 *tex = mesh->getVertexTexcoords();
             const bool tangents = tex && mesh->getUVTangents() != NULL;
             anyTexcoords |= tex != NULL;
-            dr_material mat; std::string why;
-            if (!owner->getBSDF() || !flattenBSDF(owner->getBSDF(), mat, why, roughTables, flatTextures)) Log(EError, "Mesh \"%s\": %s", owner->getName().c_str(), why.c_str());
-            mats.push_back(mat);
+            // one material per distinct BSDF object, however many meshes share it (a roughplastic's table costs a data-file reduction)
+            uint32_t matIndex;
+            std::map<const BSDF *, uint32_t>::const_iterator seen = materialOf.find(owner->getBSDF());
+            if (owner->getBSDF() && seen != materialOf.end()) matIndex = seen->second;
+            else {
+                dr_material mat; std::string why;
+                if (!owner->getBSDF() || !flattenBSDF(owner->getBSDF(), mat, why, roughTables, flatTextures)) Log(EError, "Mesh \"%s\": %s", owner->getName().c_str(), why.c_str());
+                matIndex = (uint32_t) mats.size();
+                mats.push_back(mat);
+                materialOf[owner->getBSDF()] = matIndex;
+            }
             const uint32_t base = (uint32_t) (P.size() / 3), firstTri = (uint32_t) triMat.size();
             const Point *pos = mesh->getVertexPositions();
             const Normal *nrm = mesh->getVertexNormals();
@@ -515,7 +524,7 @@ public:
             const Triangle *tri = mesh->getTriangles();
             for (size_t t = 0; t < mesh->getTriangleCount(); ++t) {
                 for (int k = 0; k < 3; ++k) I.push_back(base + tri[t].idx[k]);
-                triMat.push_back((uint32_t) mi); triEm.push_back(em); triFlags.push_back((nrm ? DR_TRI_SMOOTH : 0u) | (tangents ? DR_TRI_UV_TANGENTS : 0u) | (tex ? 0u : DR_TRI_NO_TEXCOORDS));
+                triMat.push_back(matIndex); triEm.push_back(em); triFlags.push_back((nrm ? DR_TRI_SMOOTH : 0u) | (tangents ? DR_TRI_UV_TANGENTS : 0u) | (tex ? 0u : DR_TRI_NO_TEXCOORDS));
             }
         }
         if (scene->getEmitters().size() != ems.size()) Log(EError, "Only area emitters attached to triangle meshes are supported");
